@@ -1,0 +1,218 @@
+"""ctypes binding of libdsdneo_b200.so (the C-ABI declared in include/dsdneo_b200.h).
+
+This is plumbing for tests and bench.py: PyTorch supplies device buffers and streams, the
+library supplies every kernel.  There is no Python or CPU implementation of any stage here;
+if the shared library is missing, or no sm_100 device is present, calls fail loudly.
+
+The directory name contains a hyphen, so import it through `load_package()` in
+`__graft_entry__.py` (module name `dsdneo_b200`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsdneo_b200.so")
+
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+CH_LPF_PROFILE_WIDE, CH_LPF_PROFILE_6K25, CH_LPF_PROFILE_12K5 = 0, 1, 2
+CH_LPF_PROFILE_PROVOICE, CH_LPF_PROFILE_P25_C4FM, CH_LPF_PROFILE_P25_CQPSK = 3, 4, 5
+FIR_ARITH_FMA, FIR_ARITH_NOFMA = 0, 1
+LPF_MAX_TAPS = 144
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class DemodBankConfig(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int),
+        ("rate_out_hz", C.c_int),
+        ("channel_lpf_enable", C.c_int),
+        ("channel_lpf_profile", C.POINTER(C.c_int)),
+        ("channel_squelch_level", C.POINTER(C.c_float)),
+        ("fir_arith", C.c_int),
+    ]
+
+
+class DemodChanState(C.Structure):
+    _fields_ = [
+        ("prev_i", C.c_float),
+        ("prev_q", C.c_float),
+        ("have_prev", C.c_int),
+        ("dc_est", C.c_float),
+        ("discriminator_peak_est", C.c_float),
+        ("channel_pwr", C.c_float),
+        ("channel_squelched", C.c_int),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the hot path)"
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    L.dsdneo_b200_abi_version.restype = ci
+    L.dsdneo_b200_last_error.restype = C.c_char_p
+    L.dsdneo_b200_init.argtypes = [ci]
+    L.dsdneo_b200_device_sm_count.restype = ci
+    L.dsdneo_b200_stream_sync.argtypes = [vp]
+    L.dsdneo_b200_launch_count.restype = C.c_ulonglong
+    L.dsdneo_b200_malloc_device.restype = vp
+    L.dsdneo_b200_malloc_device.argtypes = [sz]
+    L.dsdneo_b200_free_device.argtypes = [vp]
+    L.dsdneo_b200_malloc_pinned.restype = vp
+    L.dsdneo_b200_malloc_pinned.argtypes = [sz]
+    L.dsdneo_b200_free_pinned.argtypes = [vp]
+    L.dsdneo_b200_memcpy_h2d.argtypes = [vp, vp, sz, vp]
+    L.dsdneo_b200_memcpy_d2h.argtypes = [vp, vp, sz, vp]
+    L.dsdneo_b200_channel_lpf_design.argtypes = [ci, ci, C.POINTER(cf), ci]
+    L.dsdneo_b200_demod_bank_create.restype = vp
+    L.dsdneo_b200_demod_bank_create.argtypes = [C.POINTER(DemodBankConfig)]
+    L.dsdneo_b200_demod_bank_destroy.argtypes = [vp]
+    L.dsdneo_b200_demod_bank_reset.argtypes = [vp, vp]
+    L.dsdneo_b200_demod_bank_get_state.argtypes = [vp, ci, C.POINTER(DemodChanState)]
+    L.dsdneo_b200_demod_bank_get_taps.argtypes = [vp, ci, C.POINTER(cf), ci]
+    L.dsdneo_b200_full_demod_batch.argtypes = [vp, vp, sz, ci, ci, vp, sz, vp]
+    L.dsdneo_b200_full_demod_batch_host.argtypes = [vp, vp, sz, ci, ci, vp, sz]
+    _bind_optional(L)
+    _lib = L
+    return L
+
+
+def _bind_optional(L: C.CDLL) -> None:
+    """Prototypes for entry points added after ABI v1 bring-up (channelizer, symbol side, FEC)."""
+    from . import _protos  # noqa: WPS433  (kept separate so this file stays readable)
+
+    _protos.bind(L)
+
+
+def last_error() -> str:
+    return lib().dsdneo_b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        raise B200Error(f"{what or 'libdsdneo_b200'} failed ({rc}): {last_error()}")
+    return rc
+
+
+def init(device: int = 0) -> None:
+    check(lib().dsdneo_b200_init(device), "dsdneo_b200_init")
+
+
+def launch_count() -> int:
+    return int(lib().dsdneo_b200_launch_count())
+
+
+def channel_lpf_design(rate_out_hz: int, profile: int):
+    import numpy as np
+
+    buf = (C.c_float * LPF_MAX_TAPS)()
+    n = check(lib().dsdneo_b200_channel_lpf_design(rate_out_hz, profile, buf, LPF_MAX_TAPS), "channel_lpf_design")
+    return np.frombuffer(buf, dtype=np.float32, count=n).copy()
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+class DemodBank:
+    """N-channel twin of the reference's `struct demod_state` + full_demod() (FSK discriminator kind)."""
+
+    def __init__(
+        self,
+        n_channels: int,
+        rate_out_hz: int = 48000,
+        channel_lpf_enable: bool = True,
+        profiles: Optional[Sequence[int]] = None,
+        squelch_levels: Optional[Sequence[float]] = None,
+        fir_arith: int = FIR_ARITH_FMA,
+    ):
+        cfg = DemodBankConfig()
+        cfg.n_channels = n_channels
+        cfg.rate_out_hz = rate_out_hz
+        cfg.channel_lpf_enable = 1 if channel_lpf_enable else 0
+        self._prof = (C.c_int * n_channels)(*profiles) if profiles is not None else None
+        self._sq = (C.c_float * n_channels)(*squelch_levels) if squelch_levels is not None else None
+        cfg.channel_lpf_profile = self._prof if self._prof is not None else None
+        cfg.channel_squelch_level = self._sq if self._sq is not None else None
+        cfg.fir_arith = fir_arith
+        self.n_channels = n_channels
+        self._h = lib().dsdneo_b200_demod_bank_create(C.byref(cfg))
+        if not self._h:
+            raise B200Error(f"demod_bank_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_demod_bank_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_demod_bank_reset(self._h, _stream_ptr(stream)), "demod_bank_reset")
+
+    def state(self, channel: int) -> DemodChanState:
+        st = DemodChanState()
+        check(lib().dsdneo_b200_demod_bank_get_state(self._h, channel, C.byref(st)), "demod_bank_get_state")
+        return st
+
+    def taps(self, profile: int):
+        import numpy as np
+
+        buf = (C.c_float * LPF_MAX_TAPS)()
+        n = check(lib().dsdneo_b200_demod_bank_get_taps(self._h, profile, buf, LPF_MAX_TAPS), "get_taps")
+        return np.frombuffer(buf, dtype=np.float32, count=n).copy()
+
+    def full_demod(self, d_iq, block_pairs: int, n_blocks: int, d_result=None, stream=None):
+        """d_iq: torch cuda float32 tensor [n_channels, pitch_pairs, 2]; returns [n_channels, result_pitch] f32."""
+        import torch
+
+        assert d_iq.is_cuda and d_iq.dtype == torch.float32 and d_iq.is_contiguous()
+        assert d_iq.shape[0] == self.n_channels and d_iq.shape[-1] == 2
+        pitch = d_iq.shape[1]
+        if d_result is None:
+            d_result = torch.empty((self.n_channels, block_pairs * n_blocks), dtype=torch.float32, device=d_iq.device)
+        assert d_result.is_cuda and d_result.dtype == torch.float32 and d_result.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(d_iq.device)
+        check(
+            lib().dsdneo_b200_full_demod_batch(
+                self._h, d_iq.data_ptr(), pitch, block_pairs, n_blocks, d_result.data_ptr(), d_result.shape[1],
+                _stream_ptr(stream),
+            ),
+            "full_demod_batch",
+        )
+        return d_result
+
+    def full_demod_host(self, h_iq, block_pairs: int, n_blocks: int):
+        """h_iq: numpy float32 [n_channels, pitch_pairs, 2] (C order). Returns numpy [n_channels, n] f32."""
+        import numpy as np
+
+        h_iq = np.ascontiguousarray(h_iq, dtype=np.float32)
+        assert h_iq.shape[0] == self.n_channels and h_iq.shape[-1] == 2
+        out = np.empty((self.n_channels, block_pairs * n_blocks), dtype=np.float32)
+        check(
+            lib().dsdneo_b200_full_demod_batch_host(
+                self._h, h_iq.ctypes.data, h_iq.shape[1], block_pairs, n_blocks, out.ctypes.data, out.shape[1]
+            ),
+            "full_demod_batch_host",
+        )
+        return out

@@ -1,0 +1,22 @@
+"""ctypes prototypes for the later sections of include/dsdneo_b200.h (bound only if exported)."""
+import ctypes as C
+
+
+def _has(L, name):
+    try:
+        getattr(L, name)
+        return True
+    except AttributeError:
+        return False
+
+
+def bind(L):
+    vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    protos = {
+        "dsdneo_b200_selftest_atan2f": (ci, [vp, vp, vp, ci, vp]),
+    }
+    for name, (res, args) in protos.items():
+        if _has(L, name):
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args

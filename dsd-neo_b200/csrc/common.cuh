@@ -1,0 +1,46 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+// Shared helpers for libdsdneo_b200 (sm_100a only; no CPU fallback anywhere in this library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dsdneo_b200.h"
+
+namespace dsdneo {
+
+// Thread-local sticky error text returned by dsdneo_b200_last_error().
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define DSDNEO_CUDA(call)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) {                                                                                      \
+            return dsdneo::cuda_fail(e__, #call, __FILE__, __LINE__);                                                  \
+        }                                                                                                              \
+    } while (0)
+
+#define DSDNEO_KERNEL_CHECK()                                                                                          \
+    do {                                                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                                                          \
+        if (e__ != cudaSuccess) {                                                                                      \
+            return dsdneo::cuda_fail(e__, "kernel launch", __FILE__, __LINE__);                                        \
+        }                                                                                                              \
+    } while (0)
+
+static inline cudaStream_t
+as_stream(void* s) {
+    return reinterpret_cast<cudaStream_t>(s);
+}
+
+// Every kernel launched by this library bumps this (bench.py reports it as gpu_launches).
+extern unsigned long long g_launch_count;
+static inline void
+count_launch(int n = 1) {
+    g_launch_count += (unsigned long long)n;
+}
+
+int ensure_device();  // 0 when a usable sm_100 device is current, else error code
+
+}  // namespace dsdneo

@@ -1,0 +1,166 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+// Library/device plumbing of the C-ABI (include/dsdneo_b200.h, "library / device" section).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dsdneo {
+
+static thread_local char t_err[512] = "";
+unsigned long long g_launch_count = 0;
+
+void
+set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+int
+cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return (e == cudaErrorMemoryAllocation) ? DSDNEO_B200_ENOMEM : DSDNEO_B200_ECUDA;
+}
+
+int
+ensure_device() {
+    static thread_local int checked_dev = -1;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device available (%s); libdsdneo_b200 has no CPU fallback", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return DSDNEO_B200_ENODEV;
+    }
+    if (dev == checked_dev) {
+        return 0;
+    }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) {
+        set_error("cannot query CUDA device %d (%s)", dev, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return DSDNEO_B200_ENODEV;
+    }
+    if (major != 10) {
+        set_error("CUDA device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+        return DSDNEO_B200_ENODEV;
+    }
+    checked_dev = dev;
+    return 0;
+}
+
+}  // namespace dsdneo
+
+using namespace dsdneo;
+
+extern "C" {
+
+int
+dsdneo_b200_abi_version(void) {
+    return DSDNEO_B200_ABI_VERSION;
+}
+
+const char*
+dsdneo_b200_last_error(void) {
+    return t_err;
+}
+
+int
+dsdneo_b200_init(int device_ordinal) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no CUDA device available (%s); libdsdneo_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        (void)cudaGetLastError();
+        return DSDNEO_B200_ENODEV;
+    }
+    if (device_ordinal < 0 || device_ordinal >= n) {
+        set_error("device ordinal %d out of range [0,%d)", device_ordinal, n);
+        return DSDNEO_B200_EINVAL;
+    }
+    DSDNEO_CUDA(cudaSetDevice(device_ordinal));
+    return ensure_device();
+}
+
+int
+dsdneo_b200_device_sm_count(void) {
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    int dev = 0, sms = 0;
+    DSDNEO_CUDA(cudaGetDevice(&dev));
+    DSDNEO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return sms;
+}
+
+int
+dsdneo_b200_stream_sync(void* stream) {
+    DSDNEO_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return 0;
+}
+
+unsigned long long
+dsdneo_b200_launch_count(void) {
+    return g_launch_count;
+}
+
+void*
+dsdneo_b200_malloc_device(size_t bytes) {
+    if (ensure_device()) {
+        return NULL;
+    }
+    void* p = NULL;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+        return NULL;
+    }
+    return p;
+}
+
+void
+dsdneo_b200_free_device(void* d_ptr) {
+    if (d_ptr) {
+        cudaFree(d_ptr);
+    }
+}
+
+void*
+dsdneo_b200_malloc_pinned(size_t bytes) {
+    if (ensure_device()) {
+        return NULL;
+    }
+    void* p = NULL;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+        return NULL;
+    }
+    return p;
+}
+
+void
+dsdneo_b200_free_pinned(void* h_ptr) {
+    if (h_ptr) {
+        cudaFreeHost(h_ptr);
+    }
+}
+
+int
+dsdneo_b200_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    DSDNEO_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return 0;
+}
+
+int
+dsdneo_b200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
+    DSDNEO_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,171 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/**
+ * @file dsdneo_b200.h
+ * @brief C-ABI of libdsdneo_b200.so: the B200 (sm_100a) many-channel twin of dsd-neo's
+ *        demodulation hot path.
+ *
+ * Plain C, plain pointers and sizes.  Every entry point names the reference interface
+ * (file:line under arancormonk/dsd-neo @ 4d06905) that it replaces or batches.
+ *
+ * Conventions
+ *  - All functions return 0 on success and a negative DSDNEO_B200_E* code on failure unless
+ *    documented otherwise; the text of the last failure on the calling thread is available
+ *    from dsdneo_b200_last_error().  There is NO CPU fallback: without a CUDA device every
+ *    compute entry point fails with DSDNEO_B200_ENODEV.
+ *  - `stream` parameters are `cudaStream_t` passed as `void*` (NULL = default stream), so this
+ *    header needs no CUDA headers.
+ *  - Pointers prefixed `d_` are device pointers, `h_` host pointers.  `*_host` variants copy
+ *    host->device, run the same kernels, and copy the results back (synchronous on return).
+ *  - Carried per-channel DSP state lives in device arenas owned by the bank objects
+ *    (struct-of-arrays: one value per channel per field).
+ */
+#ifndef DSDNEO_B200_H_
+#define DSDNEO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSDNEO_B200_ABI_VERSION 1
+
+enum {
+    DSDNEO_B200_OK = 0,
+    DSDNEO_B200_EINVAL = -1,  /* bad argument (same cases where the reference early-returns) */
+    DSDNEO_B200_ENODEV = -2,  /* no usable CUDA device / wrong architecture */
+    DSDNEO_B200_ECUDA = -3,   /* CUDA runtime error (sticky text in last_error) */
+    DSDNEO_B200_ENOMEM = -4,
+    DSDNEO_B200_EUNSUPPORTED = -5,
+};
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+int dsdneo_b200_abi_version(void);
+const char* dsdneo_b200_last_error(void);
+/** Select the CUDA device used by the calling thread (cudaSetDevice) and verify it is sm_100. */
+int dsdneo_b200_init(int device_ordinal);
+int dsdneo_b200_device_sm_count(void);
+/** Blocks until all work queued on `stream` has finished. */
+int dsdneo_b200_stream_sync(void* stream);
+/** Number of CUDA kernels this library has launched in this process (bench.py reports it). */
+unsigned long long dsdneo_b200_launch_count(void);
+
+/* Raw device/pinned memory so a pure-C host needs no CUDA runtime of its own. */
+void* dsdneo_b200_malloc_device(size_t bytes);
+void dsdneo_b200_free_device(void* d_ptr);
+void* dsdneo_b200_malloc_pinned(size_t bytes);
+void dsdneo_b200_free_pinned(void* h_ptr);
+int dsdneo_b200_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+int dsdneo_b200_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+
+/* ---- K4 host helper: channel low-pass design ------------------------------------------- */
+
+/* Channel LPF profile ids: include/dsd-neo/dsp/demod_state.h:36-43 (same numeric values). */
+enum {
+    DSDNEO_CH_LPF_PROFILE_WIDE = 0,
+    DSDNEO_CH_LPF_PROFILE_6K25 = 1,
+    DSDNEO_CH_LPF_PROFILE_12K5 = 2,
+    DSDNEO_CH_LPF_PROFILE_PROVOICE = 3,
+    DSDNEO_CH_LPF_PROFILE_P25_C4FM = 4,
+    DSDNEO_CH_LPF_PROFILE_P25_CQPSK = 5,
+    DSDNEO_CH_LPF_PROFILE_COUNT = 6,
+};
+#define DSDNEO_B200_LPF_MAX_TAPS 144
+
+/**
+ * Host-side twin of channel_lpf_design_low_pass() + dsd_firdes_low_pass()
+ * (src/dsp/demod_pipeline.cpp:443-460,478-489; src/dsp/firdes.cpp low_pass/Blackman):
+ * Blackman-windowed sinc, 1200 Hz transition, profile cutoff clamped to [100, 0.45*fs], unit DC gain.
+ * @return number of taps written (odd), or a negative error when the design does not fit
+ *         `max_taps` (the reference then falls back to fixed 63-tap tables; this library
+ *         reports DSDNEO_B200_EUNSUPPORTED instead).
+ */
+int dsdneo_b200_channel_lpf_design(int rate_out_hz, int profile, float* taps_out, int max_taps);
+
+/* ---- block side: batched full_demod() for the FSK-discriminator output kind ------------- */
+
+/**
+ * A bank of N independent channels, each the twin of one reference `struct demod_state`
+ * (include/dsd-neo/dsp/demod_state.h:67-258) configured as
+ *   output_kind = DSD_DEMOD_OUTPUT_FSK_DISCRIMINATOR, cqpsk_enable = 0, downsample_passes = 0,
+ *   iq_dc_block_enable = 0, iqbal_enable = 0 (the reference defaults for 4FSK modes,
+ *   src/io/radio/rtl_demod_config.cpp:189-228,481,491-509).
+ * Carried per channel: channel-LPF history (last taps-1 inputs), discriminator state
+ * {prev_i, prev_q, have_prev, dc_est, discriminator_peak_est} (include/dsd-neo/dsp/fsk_modem.h:29-36),
+ * channel_pwr, channel_squelched.
+ */
+typedef struct dsdneo_b200_demod_bank dsdneo_b200_demod_bank;
+
+/* Which of the reference's FIR kernels the channel LPF reproduces bit-for-bit. */
+enum {
+    /* acc = fma(tap, x[-d] + x[+d], acc): simd_fir_complex_apply_avx2 (src/dsp/simd_fir_avx2.cpp:120-141),
+     * the kernel the reference dispatches to on AVX2+FMA x86-64 hosts (src/dsp/simd_fir.cpp:322-330). Default. */
+    DSDNEO_FIR_ARITH_FMA = 0,
+    /* acc = acc + tap * (x[-d] + x[+d]) with separate roundings: the scalar and SSE2 kernels
+     * (src/dsp/simd_fir.cpp:96-110, src/dsp/simd_fir_sse2.cpp:283-308). */
+    DSDNEO_FIR_ARITH_NOFMA = 1,
+};
+
+typedef struct dsdneo_b200_demod_bank_config {
+    int n_channels;
+    int rate_out_hz;        /* demod_state.rate_out; channel sample rate (e.g. 48000) */
+    int channel_lpf_enable; /* demod_state.channel_lpf_enable */
+    /* Per-channel arrays (length n_channels) or NULL for the default in parentheses. */
+    const int* channel_lpf_profile;     /* DSDNEO_CH_LPF_PROFILE_* (P25_C4FM) */
+    const float* channel_squelch_level; /* demod_state.channel_squelch_level (0 = squelch off) */
+    int fir_arith;                      /* DSDNEO_FIR_ARITH_* */
+} dsdneo_b200_demod_bank_config;
+
+/** Snapshot of one channel's carried state, for parity dumps ("sync state to host"). */
+typedef struct dsdneo_b200_demod_chan_state {
+    float prev_i, prev_q;
+    int have_prev;
+    float dc_est;
+    float discriminator_peak_est;
+    float channel_pwr;
+    int channel_squelched;
+} dsdneo_b200_demod_chan_state;
+
+dsdneo_b200_demod_bank* dsdneo_b200_demod_bank_create(const dsdneo_b200_demod_bank_config* cfg);
+void dsdneo_b200_demod_bank_destroy(dsdneo_b200_demod_bank* bank);
+/** Zero all carried state (twin of a fresh demod_state + dsd_fsk_modem_init, src/dsp/fsk_modem.c:75-82). */
+int dsdneo_b200_demod_bank_reset(dsdneo_b200_demod_bank* bank, void* stream);
+int dsdneo_b200_demod_bank_get_state(dsdneo_b200_demod_bank* bank, int channel, dsdneo_b200_demod_chan_state* out);
+int dsdneo_b200_demod_bank_get_taps(dsdneo_b200_demod_bank* bank, int profile, float* taps_out, int max_taps);
+
+/**
+ * Batched twin of `void full_demod(struct demod_state*)` (src/dsp/demod_pipeline.cpp:1330-1350;
+ * declared include/dsd-neo/dsp/demod_pipeline.h:106) for every channel of the bank:
+ *   channel_lpf_apply -> simd_fir_complex_apply   (demod_pipeline.cpp:526-555, simd_fir.cpp:55-133)
+ *   mean_power over the first <=512 floats + channel squelch (demod_pipeline.cpp:926-945,1003-1020)
+ *   dsd_fsk_modem_discriminator_process           (src/dsp/fsk_modem.c:135-164)
+ *
+ * Each channel receives `n_blocks` consecutive reference blocks of `block_pairs` complex samples;
+ * one reference block == one full_demod() call with lp_len = 2*block_pairs (so the FIR's
+ * "pad the right edge with the block's last sample" behaviour, simd_fir.cpp:65-84, is reproduced
+ * at every block boundary, and squelch is evaluated once per block).
+ *
+ * @param d_iq      [n_channels][iq_pitch_pairs] interleaved cf32 (float2); pitch >= n_blocks*block_pairs
+ * @param d_result  [n_channels][result_pitch] f32 discriminator samples (demod_state.result),
+ *                  result_len == block_pairs per block
+ * Results are bit-identical to the reference's float output for the selected `fir_arith`, with the rest of the
+ * chain compiled without -ffast-math / FMA contraction (the reference's default build type).
+ */
+int dsdneo_b200_full_demod_batch(dsdneo_b200_demod_bank* bank, const float* d_iq, size_t iq_pitch_pairs,
+                                 int block_pairs, int n_blocks, float* d_result, size_t result_pitch, void* stream);
+
+/** Same, with host buffers: H2D copy, kernels, D2H copy, synchronous. */
+int dsdneo_b200_full_demod_batch_host(dsdneo_b200_demod_bank* bank, const float* h_iq, size_t iq_pitch_pairs,
+                                      int block_pairs, int n_blocks, float* h_result, size_t result_pitch);
+
+/** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
+ *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
+int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DSDNEO_B200_H_ */

@@ -1,0 +1,76 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/*
+ * TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("oracle") of the reference algorithms on the accelerated hot path of
+ * arancormonk/dsd-neo @ 4d06905.  Plain C11, one channel / one codeword at a time, written for
+ * clarity.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this; the product library (libdsdneo_b200.so) never links or calls it.
+ *
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_*.py) against
+ *   (a) the reference's own known-answer vectors for the path, and
+ *   (b) the unmodified reference sources compiled in place into oracle/_ref/libdsdneo_ref.so
+ *       (oracle/Makefile), on seeded random inputs,
+ * except the polyphase channelizer, which has no reference implementation (its oracle is the
+ * mathematical direct form in float64) -- see DESIGN.md.
+ *
+ * Build: -O2 -fno-fast-math -ffp-contract=off (float results are order- and contraction-exact).
+ */
+#ifndef DSDNEO_ORACLE_H_
+#define DSDNEO_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------- block side ------------------------------------------ */
+
+#define ORACLE_LPF_MAX_TAPS 144
+
+typedef struct oracle_demod_chan {
+    /* configuration */
+    int rate_out_hz;
+    int lpf_enable;
+    int lpf_profile;
+    int fir_fma; /* 1: AVX2-kernel arithmetic (fused), 0: scalar/SSE2 arithmetic */
+    float squelch_level;
+    /* channel LPF plan + history (demod_state.channel_lpf_*) */
+    int taps_len;
+    float taps[ORACLE_LPF_MAX_TAPS];
+    float hist_i[ORACLE_LPF_MAX_TAPS];
+    float hist_q[ORACLE_LPF_MAX_TAPS];
+    /* dsd_fsk_modem_state */
+    float prev_i, prev_q;
+    int have_prev;
+    float dc_est;
+    float peak_est;
+    /* squelch */
+    float channel_pwr;
+    int channel_squelched;
+} oracle_demod_chan;
+
+int oracle_channel_lpf_design(int rate_out_hz, int profile, float* taps_out, int max_taps);
+void oracle_fir_complex(const float* in, int in_len, float* out, float* hist_i, float* hist_q, const float* taps,
+                        int taps_len, int fma);
+float oracle_mean_power(const float* samples, int len, int step);
+int oracle_demod_chan_init(oracle_demod_chan* c, int rate_out_hz, int profile, int lpf_enable, float squelch_level,
+                           int fir_fma);
+/* One full_demod() call: n_floats interleaved I/Q in, n_floats/2 discriminator samples out.
+ * `scratch` must hold n_floats floats. Returns result_len. */
+int oracle_full_demod_block(oracle_demod_chan* c, const float* iq, int n_floats, float* scratch, float* out);
+
+/* Polyphase channelizer, direct form in float64 (definition in DESIGN.md):
+ *   y_k[n] = sum_{m=0}^{L-1} h[m] x[t_n - m] exp(-j 2 pi k (t_n - m) / M),  t_n = n*D + M - 1 - (hist offset)
+ * x is preceded by `hist_len` = L - 1 (at least) earlier samples at x_with_hist[0..hist_len). */
+void oracle_pfb_direct(const float* x_with_hist, int hist_len, int n_in, const float* h, int L, int M, int D,
+                       const int* channels, int n_sel, double* out_re_im /* [n_sel][n_out][2] */, int n_out);
+
+void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

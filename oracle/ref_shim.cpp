@@ -1,0 +1,117 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+ *
+ * Thin extern "C" driver around the UNMODIFIED reference sources compiled from
+ * /root/reference by oracle/Makefile into oracle/_ref/libdsdneo_ref*.so.  It
+ * only allocates the reference's own structs and calls the reference's own
+ * entry points so that Python (ctypes) can run them:
+ *   - full_demod()                    include/dsd-neo/dsp/demod_pipeline.h:106
+ *   - simd_fir_complex_apply[_scalar] src/dsp/simd_fir.cpp:55,350
+ *   - ReedSolomon_63 wrappers / Golay24 / BCH  (C++ headers -> C symbols)
+ * Nothing here restates an algorithm; the restatement lives in oracle/*.c.
+ */
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include <dsd-neo/dsp/demod_pipeline.h>
+#include <dsd-neo/dsp/demod_state.h>
+#include <dsd-neo/dsp/fsk_modem.h>
+#include <dsd-neo/dsp/simd_fir.h>
+
+#include "dsp/simd_fir_internal.h"
+
+extern "C" {
+
+/* ---- block side: one reference demod_state per channel ----------------- */
+
+void*
+ref_demod_create(int sample_rate, int symbol_rate, int lpf_profile, int lpf_enable, float squelch_level) {
+    void* mem = NULL;
+    if (posix_memalign(&mem, 64, sizeof(demod_state)) != 0 || !mem) {
+        return NULL;
+    }
+    memset(mem, 0, sizeof(demod_state));
+    demod_state* s = (demod_state*)mem;
+    /* Same field set as the reference bench's FSK configuration
+     * (tests/dsp/bench_dsp.cpp:1022-1046). */
+    s->rate_in = sample_rate;
+    s->rate_out = sample_rate;
+    s->rate_out2 = 0;
+    s->lowpassed = s->input_cb_buf;
+    s->mode_demod = &dsd_fm_demod;
+    s->output_kind = DSD_DEMOD_OUTPUT_FSK_DISCRIMINATOR;
+    s->symbol_rate_hz = symbol_rate;
+    s->symbol_levels = 4;
+    s->ted_sps = sample_rate / symbol_rate;
+    s->sps_is_integer = (s->ted_sps * symbol_rate == sample_rate) ? 1 : 0;
+    s->channel_lpf_enable = lpf_enable;
+    s->channel_lpf_profile = lpf_profile;
+    s->channel_squelch_level = squelch_level;
+    s->squelch_env = 1.0f;
+    s->squelch_env_attack = 0.125f;
+    s->squelch_env_release = 0.03125f;
+    dsd_fsk_modem_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.sample_rate_hz = s->rate_out;
+    cfg.symbol_rate_hz = s->symbol_rate_hz;
+    cfg.levels = s->symbol_levels;
+    cfg.channel_profile = s->channel_lpf_profile;
+    dsd_fsk_modem_init(&s->fsk_modem_state, &cfg);
+    return s;
+}
+
+void
+ref_demod_destroy(void* h) {
+    free(h);
+}
+
+/* Feed one block (n_floats interleaved I/Q floats) exactly like the demod
+ * thread does (src/io/radio/rtl_sdr_fm.cpp:3419-3420) and copy result[]. */
+int
+ref_demod_block(void* h, const float* iq, int n_floats, float* out, int out_cap) {
+    demod_state* s = (demod_state*)h;
+    if (!s || n_floats > MAXIMUM_BUF_LENGTH) {
+        return -1;
+    }
+    memcpy(s->input_cb_buf, iq, (size_t)n_floats * sizeof(float));
+    s->lowpassed = s->input_cb_buf;
+    s->lp_len = n_floats;
+    full_demod(s);
+    int n = s->result_len < out_cap ? s->result_len : out_cap;
+    memcpy(out, s->result, (size_t)n * sizeof(float));
+    return s->result_len;
+}
+
+/* Carried state, for parity dumps: {prev_i, prev_q, have_prev, dc_est, peak, channel_pwr, squelched} */
+void
+ref_demod_get_state(void* h, float* out7) {
+    demod_state* s = (demod_state*)h;
+    out7[0] = s->fsk_modem_state.prev_i;
+    out7[1] = s->fsk_modem_state.prev_q;
+    out7[2] = (float)s->fsk_modem_state.have_prev;
+    out7[3] = s->fsk_modem_state.dc_est;
+    out7[4] = s->fsk_modem_state.discriminator_peak_est;
+    out7[5] = s->channel_pwr;
+    out7[6] = (float)s->channel_squelched;
+}
+
+int
+ref_demod_get_lpf_taps(void* h, float* taps_out, int cap) {
+    demod_state* s = (demod_state*)h;
+    int n = s->channel_lpf_plan_taps_len;
+    if (n > cap) {
+        n = cap;
+    }
+    memcpy(taps_out, s->channel_lpf_plan_taps, (size_t)n * sizeof(float));
+    return s->channel_lpf_plan_taps_len;
+}
+
+void
+ref_fir_complex_scalar(const float* in, int in_len, float* out, float* hist_i, float* hist_q, const float* taps,
+                       int taps_len) {
+    simd_fir_complex_apply_scalar(in, in_len, out, hist_i, hist_q, taps, taps_len);
+}
+
+} /* extern "C" */

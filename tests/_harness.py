@@ -1,0 +1,215 @@
+"""Test infrastructure: loaders for the oracle (oracle/liboracle.so), the compiled reference
+(oracle/_ref/*.so, when present) and seeded synthetic-signal generators.
+
+Nothing in here is product code; nothing in dsd-neo_b200/ imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+LPF_MAX_TAPS = 144
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int)
+u8p = C.POINTER(C.c_uint8)
+
+
+def _ptr(a, typ=f32p):
+    return a.ctypes.data_as(typ)
+
+
+# --------------------------------------------------------------------------- oracle (restatement)
+
+class OracleDemodChan(C.Structure):
+    _fields_ = [
+        ("rate_out_hz", C.c_int),
+        ("lpf_enable", C.c_int),
+        ("lpf_profile", C.c_int),
+        ("fir_fma", C.c_int),
+        ("squelch_level", C.c_float),
+        ("taps_len", C.c_int),
+        ("taps", C.c_float * LPF_MAX_TAPS),
+        ("hist_i", C.c_float * LPF_MAX_TAPS),
+        ("hist_q", C.c_float * LPF_MAX_TAPS),
+        ("prev_i", C.c_float),
+        ("prev_q", C.c_float),
+        ("have_prev", C.c_int),
+        ("dc_est", C.c_float),
+        ("peak_est", C.c_float),
+        ("channel_pwr", C.c_float),
+        ("channel_squelched", C.c_int),
+    ]
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            subprocess.run(["make", "oracle"], cwd=ORACLE_DIR, check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.oracle_channel_lpf_design.argtypes = [C.c_int, C.c_int, f32p, C.c_int]
+        L.oracle_fir_complex.argtypes = [f32p, C.c_int, f32p, f32p, f32p, f32p, C.c_int, C.c_int]
+        L.oracle_mean_power.restype = C.c_float
+        L.oracle_mean_power.argtypes = [f32p, C.c_int, C.c_int]
+        L.oracle_demod_chan_init.argtypes = [C.POINTER(OracleDemodChan), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
+        L.oracle_full_demod_block.argtypes = [C.POINTER(OracleDemodChan), f32p, C.c_int, f32p, f32p]
+        L.oracle_pfb_direct.argtypes = [f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, i32p, C.c_int,
+                                        C.POINTER(C.c_double), C.c_int]
+        L.oracle_libm_atan2f_array.argtypes = [f32p, f32p, f32p, C.c_long]
+        _oracle = L
+    return _oracle
+
+
+def oracle_lpf_taps(rate, profile):
+    buf = np.zeros(LPF_MAX_TAPS, dtype=np.float32)
+    n = oracle().oracle_channel_lpf_design(rate, profile, _ptr(buf), LPF_MAX_TAPS)
+    assert n > 0
+    return buf[:n].copy()
+
+
+def oracle_full_demod(iq_ch, block_pairs, n_blocks, fir_fma=1, rate=48000, profile=4, lpf_enable=1, squelch=0.0,
+                      chan=None, return_chan=False):
+    """iq_ch: [n, 2] float32 for one channel. Runs n_blocks full_demod() blocks through the oracle."""
+    L = oracle()
+    if chan is None:
+        chan = OracleDemodChan()
+        assert L.oracle_demod_chan_init(C.byref(chan), rate, profile, lpf_enable, squelch, fir_fma) == 0
+    iq_ch = np.ascontiguousarray(iq_ch, dtype=np.float32)
+    out = np.empty(block_pairs * n_blocks, dtype=np.float32)
+    scratch = np.empty(2 * block_pairs, dtype=np.float32)
+    for b in range(n_blocks):
+        blk = np.ascontiguousarray(iq_ch[b * block_pairs:(b + 1) * block_pairs]).reshape(-1)
+        o = out[b * block_pairs:(b + 1) * block_pairs]
+        n = L.oracle_full_demod_block(C.byref(chan), _ptr(blk), 2 * block_pairs, _ptr(scratch), _ptr(o))
+        assert n == block_pairs
+    return (out, chan) if return_chan else out
+
+
+# --------------------------------------------------------------------------- compiled reference
+
+_refs = {}
+
+
+def ref_available(variant="par"):
+    return os.path.exists(_ref_path(variant))
+
+
+def _ref_path(variant):
+    name = {"par": "libdsdneo_ref.so", "avx2": "libdsdneo_ref_avx2.so", "fast": "libdsdneo_ref_fast.so"}[variant]
+    return os.path.join(REF_DIR, name)
+
+
+def ref(variant="par"):
+    """The unmodified reference TUs compiled by oracle/Makefile (None when not built)."""
+    if variant not in _refs:
+        path = _ref_path(variant)
+        if not os.path.exists(path):
+            _refs[variant] = None
+        else:
+            L = C.CDLL(path)
+            L.ref_demod_create.restype = C.c_void_p
+            L.ref_demod_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+            L.ref_demod_destroy.argtypes = [C.c_void_p]
+            L.ref_demod_block.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+            L.ref_demod_get_state.argtypes = [C.c_void_p, f32p]
+            L.ref_demod_get_lpf_taps.argtypes = [C.c_void_p, f32p, C.c_int]
+            L.ref_fir_complex_scalar.argtypes = [f32p, C.c_int, f32p, f32p, f32p, f32p, C.c_int]
+            L.simd_fir_complex_apply.argtypes = [f32p, C.c_int, f32p, f32p, f32p, f32p, C.c_int]
+            L.simd_fir_get_impl_name.restype = C.c_char_p
+            L.mean_power.restype = C.c_float
+            L.mean_power.argtypes = [f32p, C.c_int, C.c_int]
+            _refs[variant] = L
+    return _refs[variant]
+
+
+class RefDemod:
+    """One reference `struct demod_state` driven through the reference's own full_demod()."""
+
+    def __init__(self, variant="par", rate=48000, symrate=4800, profile=4, lpf_enable=1, squelch=0.0):
+        self.L = ref(variant)
+        assert self.L is not None
+        self.h = self.L.ref_demod_create(rate, symrate, profile, lpf_enable, squelch)
+        assert self.h
+
+    def block(self, iq_block):
+        blk = np.ascontiguousarray(iq_block, dtype=np.float32).reshape(-1)
+        out = np.empty(blk.size // 2, dtype=np.float32)
+        n = self.L.ref_demod_block(self.h, _ptr(blk), blk.size, _ptr(out), out.size)
+        assert n == out.size, n
+        return out
+
+    def run(self, iq_ch, block_pairs, n_blocks):
+        return np.concatenate([self.block(iq_ch[b * block_pairs:(b + 1) * block_pairs]) for b in range(n_blocks)])
+
+    def state(self):
+        s = np.zeros(7, dtype=np.float32)
+        self.L.ref_demod_get_state(self.h, _ptr(s))
+        return dict(prev_i=s[0], prev_q=s[1], have_prev=int(s[2]), dc_est=s[3], peak=s[4], pwr=s[5], squelched=int(s[6]))
+
+    def taps(self):
+        buf = np.zeros(LPF_MAX_TAPS, dtype=np.float32)
+        n = self.L.ref_demod_get_lpf_taps(self.h, _ptr(buf), LPF_MAX_TAPS)
+        return buf[:n].copy()
+
+    def close(self):
+        if self.h:
+            self.L.ref_demod_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+# --------------------------------------------------------------------------- synthetic signals
+
+LEVELS = np.array([1.0, 3.0, -1.0, -3.0], dtype=np.float64)  # dibit 0,1,2,3 -> +1,+3,-1,-3 (dsd_dibit.c:963-976)
+
+
+def synth_fsk_iq(rng, n_symbols, sps=10, dev_per_level=0.0785, amp=0.85, snr_db=None, dibits=None, phase0=0.19,
+                 shape=True):
+    """Phase-integrated 4-level FSK at `sps` samples/symbol -> [n_symbols*sps, 2] float32 (cf32).
+
+    Same construction as the reference's synthesize_fsk_iq (tests/dsp/test_rtl_symbol_pipeline.cpp:39-54):
+    per-sample phase step = dev_per_level * level; default 0.0785 rad = 2*pi*600 Hz/48 kHz per level
+    (+-1.8 kHz at the outer levels, TIA-102 C4FM).  With shape=True the level sequence is smoothed with a
+    raised-cosine-ish 1-symbol Hann kernel so the spectrum stays inside a 12.5 kHz channel.
+    """
+    if dibits is None:
+        dibits = rng.integers(0, 4, size=n_symbols)
+    lv = LEVELS[np.asarray(dibits)]
+    f = np.repeat(lv, sps)
+    if shape:
+        k = np.hanning(sps + 2)[1:-1]
+        k /= k.sum()
+        f = np.convolve(f, k, mode="same")
+    ph = phase0 + np.cumsum(f * dev_per_level)
+    z = amp * np.exp(1j * ph)
+    if snr_db is not None:
+        sigma = amp * 10 ** (-snr_db / 20.0) / np.sqrt(2.0)
+        z = z + sigma * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+    out = np.empty((z.size, 2), dtype=np.float32)
+    out[:, 0] = z.real
+    out[:, 1] = z.imag
+    return out
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def first_mismatch(a, b):
+    d = np.nonzero(a.reshape(-1).view(np.uint32) != b.reshape(-1).view(np.uint32))[0]
+    return None if d.size == 0 else (int(d[0]), float(a.reshape(-1)[d[0]]), float(b.reshape(-1)[d[0]]), int(d.size))
