@@ -216,3 +216,64 @@ class DemodBank:
             "full_demod_batch_host",
         )
         return out
+
+
+class Channelizer:
+    """Polyphase FIR channelizer (K2, optionally fused K1 cu8 widening). See include/dsdneo_b200.h."""
+
+    def __init__(self, n_channels: int = 256, taps_per_branch: int = 8, input_is_cu8: bool = False, prototype=None):
+        import numpy as np
+
+        self.M, self.T, self.cu8 = n_channels, taps_per_branch, bool(input_is_cu8)
+        proto_ptr = None
+        if prototype is not None:
+            self._proto = np.ascontiguousarray(prototype, dtype=np.float32)
+            assert self._proto.size == n_channels * taps_per_branch
+            proto_ptr = self._proto.ctypes.data_as(C.POINTER(C.c_float))
+        self._h = lib().dsdneo_b200_channelizer_create(n_channels, taps_per_branch, 1 if input_is_cu8 else 0, proto_ptr)
+        if not self._h:
+            raise B200Error(f"channelizer_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_channelizer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_channelizer_reset(self._h, _stream_ptr(stream)), "channelizer_reset")
+
+    def prototype(self):
+        import numpy as np
+
+        buf = np.empty(self.M * self.T, dtype=np.float32)
+        check(lib().dsdneo_b200_channelizer_get_prototype(self._h, buf.ctypes.data_as(C.POINTER(C.c_float)), buf.size))
+        return buf
+
+    def channelize(self, d_in, d_out=None, stream=None):
+        """d_in: cuda tensor, float32 [n, 2] (cf32) or uint8 [n, 2] (cu8); returns float32 [M, n/M, 2]."""
+        import torch
+
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.shape[-1] == 2
+        assert d_in.dtype == (torch.uint8 if self.cu8 else torch.float32)
+        n = d_in.shape[0]
+        if d_out is None:
+            d_out = torch.empty((self.M, n // self.M, 2), dtype=torch.float32, device=d_in.device)
+        assert d_out.is_cuda and d_out.is_contiguous() and d_out.dtype == torch.float32
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(
+            lib().dsdneo_b200_channelize(self._h, d_in.data_ptr(), n, d_out.data_ptr(), d_out.shape[1], _stream_ptr(stream)),
+            "channelize",
+        )
+        return d_out
+
+    def channelize_host(self, h_in):
+        import numpy as np
+
+        h_in = np.ascontiguousarray(h_in, dtype=np.uint8 if self.cu8 else np.float32)
+        n = h_in.shape[0]
+        out = np.empty((self.M, n // self.M, 2), dtype=np.float32)
+        check(lib().dsdneo_b200_channelize_host(self._h, h_in.ctypes.data, n, out.ctypes.data, out.shape[1]), "channelize_host")
+        return out

@@ -12,7 +12,15 @@ def _has(L, name):
 
 def bind(L):
     vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    cd = C.c_double
     protos = {
+        "dsdneo_b200_channelizer_design_prototype": (ci, [ci, ci, cd, C.POINTER(cf)]),
+        "dsdneo_b200_channelizer_create": (vp, [ci, ci, ci, C.POINTER(cf)]),
+        "dsdneo_b200_channelizer_destroy": (None, [vp]),
+        "dsdneo_b200_channelizer_reset": (ci, [vp, vp]),
+        "dsdneo_b200_channelizer_get_prototype": (ci, [vp, C.POINTER(cf), ci]),
+        "dsdneo_b200_channelize": (ci, [vp, vp, sz, vp, sz, vp]),
+        "dsdneo_b200_channelize_host": (ci, [vp, vp, sz, vp, sz]),
         "dsdneo_b200_selftest_atan2f": (ci, [vp, vp, vp, ci, vp]),
     }
     for name, (res, args) in protos.items():

@@ -160,6 +160,39 @@ int dsdneo_b200_full_demod_batch(dsdneo_b200_demod_bank* bank, const float* d_iq
 int dsdneo_b200_full_demod_batch_host(dsdneo_b200_demod_bank* bank, const float* h_iq, size_t iq_pitch_pairs,
                                       int block_pairs, int n_blocks, float* h_result, size_t result_pitch);
 
+/* ---- K2 (+K1): polyphase FIR channelizer -------------------------------------------------------- */
+
+/**
+ * Wideband complex IQ -> n_channels narrowband channels (critically sampled: every channel runs at
+ * fs_in / n_channels).  The reference has no channelizer (it tunes ONE channel with a half-band cascade,
+ * src/dsp/demod_pipeline.cpp:983-1001); this is the many-channel front end the north star adds.  Definition
+ * (also the float64 oracle, oracle/oracle_dsp.c:oracle_pfb_direct):
+ *     y_k[n] = sum_{m<L} h[m] x[t_n - m] exp(-j 2 pi k (t_n - m) / M),  t_n = n M + M - 1,  L = M * taps_per_branch
+ * Channel k is centred at k * fs_in / M (k > M/2 are the negative frequencies).
+ * With input_is_cu8 the input is unsigned 8-bit I/Q pairs widened on load exactly like
+ * widen_u8_to_f32_bias127 (src/dsp/simd_widen.cpp:139-147): (u8 - 127.5f) * (1/127.5f).
+ * Carried state: the last (taps_per_branch-1)*M input samples.
+ */
+typedef struct dsdneo_b200_channelizer dsdneo_b200_channelizer;
+
+/** Default prototype: Blackman-windowed sinc, cutoff = cutoff_rel * fs_in/(2M), unit DC gain. Returns L. */
+int dsdneo_b200_channelizer_design_prototype(int n_channels, int taps_per_branch, double cutoff_rel, float* h_out);
+/** prototype == NULL selects the default design with cutoff_rel = 1.0. */
+dsdneo_b200_channelizer* dsdneo_b200_channelizer_create(int n_channels, int taps_per_branch, int input_is_cu8,
+                                                        const float* prototype);
+void dsdneo_b200_channelizer_destroy(dsdneo_b200_channelizer* c);
+int dsdneo_b200_channelizer_reset(dsdneo_b200_channelizer* c, void* stream);
+int dsdneo_b200_channelizer_get_prototype(dsdneo_b200_channelizer* c, float* h_out, int max_taps);
+/**
+ * @param d_in   n_in_samples wideband samples (cf32 pairs, or cu8 pairs), n_in_samples % n_channels == 0
+ * @param d_out  [n_channels][out_pitch_pairs] cf32; n_in_samples / n_channels outputs per channel -- the layout
+ *               dsdneo_b200_full_demod_batch() consumes directly.
+ */
+int dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, float* d_out,
+                           size_t out_pitch_pairs, void* stream);
+int dsdneo_b200_channelize_host(dsdneo_b200_channelizer* c, const void* h_in, size_t n_in_samples, float* h_out,
+                                size_t out_pitch_pairs);
+
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);

@@ -213,3 +213,38 @@ def bits_equal(a, b):
 def first_mismatch(a, b):
     d = np.nonzero(a.reshape(-1).view(np.uint32) != b.reshape(-1).view(np.uint32))[0]
     return None if d.size == 0 else (int(d[0]), float(a.reshape(-1)[d[0]]), float(b.reshape(-1)[d[0]]), int(d.size))
+
+
+def oracle_pfb(x_with_hist, hist_len, h, M, channels, n_out, D=None):
+    """Float64 direct-form channelizer oracle. x_with_hist: [hist_len + n, 2] float32. Returns complex128 [len(channels), n_out]."""
+    D = M if D is None else D
+    xh = np.ascontiguousarray(x_with_hist, dtype=np.float32).reshape(-1)
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    ch = np.ascontiguousarray(channels, dtype=np.int32)
+    out = np.zeros((ch.size, n_out, 2), dtype=np.float64)
+    oracle().oracle_pfb_direct(_ptr(xh), hist_len, xh.size // 2 - hist_len, _ptr(h), h.size, M, D, _ptr(ch, i32p), ch.size,
+                               out.ctypes.data_as(C.POINTER(C.c_double)), n_out)
+    return out[..., 0] + 1j * out[..., 1]
+
+
+def synth_wideband(rng, M, n_out, active, fs_ratio_dev=0.0785, snr_db=30.0, amp=0.5):
+    """Sum of FSK carriers on the channelizer grid: channel k at k/M cycles/sample, each a 4-level FSK at
+    10 samples/symbol of the CHANNEL rate.  Returns ([n_out*M, 2] float32, {k: dibits})."""
+    n = n_out * M
+    t = np.arange(n, dtype=np.float64)
+    x = np.zeros(n, dtype=np.complex128)
+    truth = {}
+    for k in active:
+        nsym = n_out // 10 + 2
+        dib = rng.integers(0, 4, size=nsym)
+        lv = np.repeat(LEVELS[dib], 10 * M)[:n]
+        ph = np.cumsum(lv * (fs_ratio_dev / M)) + rng.uniform(0, 2 * np.pi)
+        x += np.exp(1j * (ph + 2 * np.pi * (k / M) * t))
+        truth[k] = dib
+    x *= amp / max(1, len(active)) ** 0.5
+    sigma = amp * 10 ** (-snr_db / 20.0) / np.sqrt(2.0)
+    x += sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    out = np.empty((n, 2), dtype=np.float32)
+    out[:, 0] = x.real
+    out[:, 1] = x.imag
+    return out, truth

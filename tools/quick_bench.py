@@ -28,7 +28,13 @@ def time_it(fn, iters=10, warm=3):
 
 for n_ch, bp, nb in [(256, 8192, 6), (1024, 8192, 6), (4096, 8192, 2)]:
     for arith in (0, 1):
-        iq = torch.randn((n_ch, bp * nb, 2), device="cuda", dtype=torch.float32) * 0.3
+        # 4-level FSK (random symbols, 10 samples/symbol, +-1.8 kHz outer deviation at 48 kS/s) + noise, made on the GPU
+        nsym = bp * nb // 10 + 1
+        lv = torch.tensor([1.0, 3.0, -1.0, -3.0], device="cuda")[torch.randint(0, 4, (n_ch, nsym), device="cuda")]
+        ph = torch.cumsum(lv.repeat_interleave(10, dim=1)[:, : bp * nb] * 0.0785, dim=1)
+        iq = torch.stack([0.85 * torch.cos(ph), 0.85 * torch.sin(ph)], dim=-1) + 0.05 * torch.randn((n_ch, bp * nb, 2), device="cuda")
+        iq = iq.contiguous().float()
+        del ph, lv
         out = torch.empty((n_ch, bp * nb), device="cuda", dtype=torch.float32)
         bank = b200.DemodBank(n_ch, 48000, True, fir_arith=arith)
         med, mn = time_it(lambda: bank.full_demod(iq, bp, nb, out))
@@ -38,3 +44,21 @@ for n_ch, bp, nb in [(256, 8192, 6), (1024, 8192, 6), (4096, 8192, 2)]:
               f"{samples * 12 / med / 1e6:.1f} GB/s algorithmic, x{samples / med * 1e3 / (n_ch * 48000):.0f} real time")
         bank.close()
         del iq, out
+
+# channelizer: C2 shape, 256 channels x 49152 outputs (12.58 M wideband samples = 1.024 s at 12.288 MS/s)
+for T in (8, 16):
+    for cu8 in (False, True):
+        n_out = 49152
+        if cu8:
+            x = torch.randint(0, 256, (n_out * 256, 2), device="cuda", dtype=torch.uint8)
+        else:
+            x = torch.randn((n_out * 256, 2), device="cuda", dtype=torch.float32)
+        y = torch.empty((256, n_out, 2), device="cuda", dtype=torch.float32)
+        cz = b200.Channelizer(256, T, cu8)
+        med, mn = time_it(lambda: cz.channelize(x, y))
+        n = n_out * 256
+        bytes_alg = n * ((2 if cu8 else 8) + 8)
+        print(f"channelize T={T} cu8={cu8}: median {med:.3f} ms min {mn:.3f} ms -> {n / med / 1e6:.2f} GS/s, "
+              f"{bytes_alg / med / 1e6:.0f} GB/s algorithmic ({bytes_alg / mn / 1e6 / 6549.4 * 100:.1f}% of measured HBM peak)")
+        cz.close()
+        del x, y
