@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""bench.py -- the judged benchmark (contract in the task statement, section 4).
+
+Workload (BASELINE.json configs[1], "C2"): a 256-channel polyphase FIR channelizer + FM discriminator on
+synthetic 12.288 MS/s complex IQ, one B200 per 256-channel band.  One step = 1.024 s of wideband signal
+(12,582,912 cf32 samples = 100.7 MB) through
+    pfb256_kernel (channelizer) -> lpf_phase_kernel (135-tap channel LPF + phase discriminator)
+    -> disc_recurrence_kernel (dc/peak recurrences, scaling)          [= the reference's full_demod(), per channel]
+The metric is IQ MS/s (wideband complex samples consumed per second, whole job) and the channels that could be
+served in real time (`channels_at_realtime`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this framework (CUDA, through the C-ABI)
+  python bench.py --impl reference [...]                         the reference's own CPU code on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M = 256
+WIDEBAND_HZ = 12_288_000
+CHAN_HZ = WIDEBAND_HZ // M  # 48000
+BLOCK_PAIRS = 8192  # the reference's DEFAULT_BUF_LENGTH (16384 floats) per full_demod() call
+N_BLOCKS = 6
+N_OUT = BLOCK_PAIRS * N_BLOCKS  # 49152 channel samples = 1.024 s
+N_IN = N_OUT * M  # 12,582,912 wideband samples per step
+SYMBOL_HZ = 4800
+N_ROTATE = 3  # distinct input buffers: 3 x 100.7 MB > 126 MB L2
+WORKLOAD = ("C2: 256-channel polyphase FIR channelizer + FM discriminator (channel LPF + FSK discriminator = "
+            "reference full_demod) on synthetic 12.288 MS/s complex IQ, 1xB200 per 256-channel band")
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return self
+        names = {
+            "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(pynvml, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+
+        def run():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(self.period)
+
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+        return self
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------- data
+
+def make_wideband(torch, device, seed: int):
+    """Synthetic wideband band: 256 4-level FSK carriers (one per channelizer bin, 4800 sym/s, +-1.8 kHz outer
+    deviation, independent random dibits seeded per channel) + AWGN at 30 dB per-carrier SNR, 0.5 full scale.
+    Built on the GPU in float64 phase, stored cf32.  Returns [N_IN, 2] float32."""
+    g = torch.Generator(device=device)
+    g.manual_seed(0xD5D + seed)
+    sps = WIDEBAND_HZ // SYMBOL_HZ  # 2560 wideband samples per symbol
+    nsym = N_IN // sps + 1
+    t = torch.arange(N_IN, device=device, dtype=torch.int64)
+    acc = torch.zeros((N_IN, 2), device=device, dtype=torch.float32)
+    levels = torch.tensor([1, 3, -1, -3], device=device, dtype=torch.int64)
+    two_pi = 2.0 * torch.pi
+    # phase is accumulated EXACTLY in integers: one level step = 600 Hz = 600/12.288e6 cycles per sample, and the
+    # carrier k/M cycles per sample; 600/12288000 = 1/20480 -> work in units of 1/20480 cycle (M=256 divides 20480)
+    unit = WIDEBAND_HZ // 600  # 20480 phase units per cycle
+    for k in range(M):
+        dib = torch.randint(0, 4, (nsym,), device=device, generator=g)
+        lv = levels[dib].repeat_interleave(sps)[:N_IN]
+        ph_units = torch.cumsum(lv, 0) + (t * (k * (unit // M))) + int(torch.randint(0, unit, (1,), generator=g, device=device))
+        ph = (ph_units % unit).to(torch.float32) * (two_pi / unit)
+        acc[:, 0] += torch.cos(ph)
+        acc[:, 1] += torch.sin(ph)
+    acc *= 0.5 / (M ** 0.5 * 3.0)  # rms ~ 0.5/3: headroom for the sum of 256 carriers
+    sigma = float(0.5 / (M ** 0.5 * 3.0)) * 10 ** (-30.0 / 20.0) / 2 ** 0.5
+    acc += sigma * torch.randn((N_IN, 2), device=device, dtype=torch.float32, generator=g)
+    return acc.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+
+def _load_ref():
+    """The unmodified reference compiled by oracle/Makefile (perf-bench flags); None if it did not travel."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libdsdneo_ref_fast.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    f32p = C.POINTER(C.c_float)
+    L.ref_demod_create_wideband.restype = C.c_void_p
+    L.ref_demod_create_wideband.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+    L.ref_demod_destroy.argtypes = [C.c_void_p]
+    L.ref_demod_block.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+    L.simd_fir_get_impl_name.restype = C.c_char_p
+    return L
+
+
+def cpu_reference_run(seconds_per_thread=None, blocks_per_thread=None):
+    """Times the reference's own CPU path for this workload on all host cores.
+
+    One channel of the reference = one `struct demod_state` fed the WIDEBAND block: 8 half-band /2 stages
+    (12.288 MS/s -> 48 kS/s, src/dsp/demod_pipeline.cpp:983-1001) + 135-tap channel LPF + FSK discriminator
+    (full_demod, :1330-1350).  The tuner/mixer that would centre each of the 256 channels is NOT charged.
+    Each thread owns one demod_state and pushes 131072-pair blocks (the reference's MAXIMUM_BUF_LENGTH).
+    Whole-job IQ rate = aggregate wideband pairs/s over all threads / 256 channels.
+    Falls back to the oracle port (channel LPF + discriminator only, no decimation) if oracle/_ref is absent.
+    """
+    import numpy as np
+
+    cores = len(os.sched_getaffinity(0))
+    L = _load_ref()
+    rng = np.random.default_rng(1)
+    if L is not None:
+        kind = "reference"
+        blk_pairs = 131072
+        x = (rng.standard_normal(2 * blk_pairs) * 0.2).astype(np.float32)
+        handles = [L.ref_demod_create_wideband(WIDEBAND_HZ, 8, SYMBOL_HZ, 4, 1, 0.0) for _ in range(cores)]
+        outs = [np.empty(blk_pairs, np.float32) for _ in range(cores)]
+        f32p = C.POINTER(C.c_float)
+
+        def one_block(i):
+            L.ref_demod_block(handles[i], x.ctypes.data_as(f32p), 2 * blk_pairs, outs[i].ctypes.data_as(f32p), blk_pairs)
+
+        chan_div = M  # every channel consumes the whole wideband stream
+        what = ("%d threads, each one reference demod_state: full_demod with 8 half-band stages (12.288 MS/s->48 kS/s) + "
+                "135-tap channel LPF + FSK discriminator on 131072-pair wideband blocks, perf-bench flags, simd=%s; "
+                "whole-job rate = aggregate wideband pairs/s / 256 channels (per-channel tuner mixing not charged)"
+                % (cores, L.simd_fir_get_impl_name().decode()))
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _harness as H
+
+        blk_pairs = BLOCK_PAIRS
+        O = H.oracle()
+        x = (rng.standard_normal(2 * blk_pairs) * 0.2).astype(np.float32)
+        chans = []
+        for _ in range(cores):
+            ch = H.OracleDemodChan()
+            O.oracle_demod_chan_init(C.byref(ch), CHAN_HZ, 4, 1, 0.0, 1)
+            chans.append(ch)
+        outs = [np.empty(blk_pairs, np.float32) for _ in range(cores)]
+        scr = [np.empty(2 * blk_pairs, np.float32) for _ in range(cores)]
+
+        def one_block(i):
+            O.oracle_full_demod_block(C.byref(chans[i]), H._ptr(x), 2 * blk_pairs, H._ptr(scr[i]), H._ptr(outs[i]))
+
+        chan_div = 1.0 / M * M  # channel-rate samples: IQ rate = channel pairs/s * M / M channels
+        what = ("%d threads, oracle port of channel LPF + FSK discriminator on already-channelised 8192-pair blocks "
+                "(oracle/_ref absent: half-band channel selection NOT included, so this overstates the CPU)" % cores)
+
+    counts = [0] * cores
+    deadline = [0.0]
+
+    def worker(i):
+        n = 0
+        if blocks_per_thread is not None:
+            for _ in range(blocks_per_thread):
+                one_block(i)
+                n += 1
+        else:
+            while time.perf_counter() < deadline[0]:
+                one_block(i)
+                n += 1
+        counts[i] = n
+
+    for i in range(cores):
+        one_block(i)  # warm-up (plans the LPF, touches buffers)
+    deadline[0] = time.perf_counter() + (seconds_per_thread or 0.0)
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(cores)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    pairs = sum(counts) * blk_pairs
+    if kind == "reference":
+        iq_msps = pairs / dt / M / 1e6
+    else:
+        iq_msps = pairs / dt / 1e6  # channel-rate pairs/s * 256 channels-per-IQ-sample / 256 channels
+    if L is not None:
+        for h in handles:
+            L.ref_demod_destroy(h)
+    return {"value": iq_msps, "unit": "MS/s", "cores": cores, "kind": kind, "sample": what, "seconds": dt,
+            "blocks": sum(counts)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_blocks = 8
+    for _ in range(max(1, args.warmup)):
+        cpu_reference_run(blocks_per_thread=1)
+    t0 = time.perf_counter()
+    vals = []
+    last = None
+    for _ in range(args.steps):
+        last = cpu_reference_run(blocks_per_thread=per_step_blocks)
+        vals.append(last["value"])
+    dt = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "iq_msps", "value": value, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "channels_at_realtime": value * 1e6 / WIDEBAND_HZ * M,
+        "config": {"workload": WORKLOAD, "channels": M, "wideband_rate_hz": WIDEBAND_HZ,
+                   "step": "bounded sample: %d wideband blocks of 131072 pairs per thread" % per_step_blocks},
+        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b200 = g.load_package()
+    b200.init(local)
+
+    def barrier():
+        if world > 1:
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs resident in HBM (weak scaling: every rank owns one independent 256-channel band) ----
+    base = make_wideband(torch, dev, seed=rank)
+    bufs = [base, torch.roll(base, 777 * M + 13, 0).contiguous(), base.flip(0).contiguous()][:N_ROTATE]
+    out = torch.empty((M, N_OUT), device=dev, dtype=torch.float32)
+    fe = b200.Frontend(M, 8, False, WIDEBAND_HZ, BLOCK_PAIRS)
+    stream = torch.cuda.current_stream(dev)
+
+    clocks = ClockSampler(local).start()
+    for i in range(args.warmup):
+        fe.process_async(bufs[i % N_ROTATE], out, stream)
+    fe.join(stream)
+    barrier()
+    b200.timing_enable(True)
+    launches0 = b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        # pipelined C-ABI call: FIR-side kernels of step i+1 overlap the serial recurrence kernel of step i
+        fe.process_async(bufs[i % N_ROTATE], out, stream)
+    fe.join(stream)
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = b200.launch_count() - launches0
+    ktimes = b200.timing_report()
+    b200.timing_enable(False)
+    clk = clocks.stop()
+    ms_per_step = ms_total / args.steps
+    value = world * N_IN / (ms_per_step * 1e-3) / 1e6  # whole-job IQ MS/s
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per launch) ----
+    alg_bytes = {
+        "pfb256_kernel": 16.0 * N_IN,              # 8 B cf32 in + 8 B cf32 channel out per wideband sample
+        "lpf_phase_kernel": 12.0 * M * N_OUT,      # 8 B in + 4 B phase out per channel sample
+        "disc_recurrence_kernel": 8.0 * M * N_OUT  # 4 B phase in + 4 B discriminator out per channel sample
+    }
+    peak, peak_src = measured_hbm_peak()
+    kernels = {}
+    for name, rec in ktimes.items():
+        avg_ms = rec["ms"] / max(1, rec["launches"])
+        kernels[name] = {"launches": rec["launches"], "avg_ms": avg_ms,
+                         "share": rec["ms"] / max(1e-12, sum(r["ms"] for r in ktimes.values()))}
+        if name in alg_bytes:
+            kernels[name]["achieved_gbs"] = alg_bytes[name] / (avg_ms * 1e-3) / 1e9
+    dom = max(kernels, key=lambda k: ktimes[k]["ms"]) if kernels else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = None
+    if dom and dom in alg_bytes:
+        a = kernels[dom]["achieved_gbs"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
+                    "note": "per-kernel times from CUDA events recorded by the library on the launching stream during the timed region"}
+
+    # ---- e2e: same metric through the host-buffer C-ABI call (pinned host in/out, copies inside the timed region) ----
+    e2e_steps = max(3, min(args.steps, 20))
+    h_in = [torch.empty((N_IN, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_in[0].copy_(bufs[0])
+    h_in[1].copy_(bufs[1])
+    h_out = torch.empty((M, N_OUT), dtype=torch.float32).pin_memory()
+    fe_h = b200.Frontend(M, 8, False, WIDEBAND_HZ, BLOCK_PAIRS)
+    for i in range(2):
+        fe_h.process_host(h_in[i % 2], h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        fe_h.process_host(h_in[i % 2], h_out)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    barrier()
+    e2e = {"value": world * N_IN / (e2e_ms * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": N_IN * 8,
+           "d2h_bytes_per_step": M * N_OUT * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "timer": "host wall clock around the synchronous C-ABI call dsdneo_b200_frontend_process_host, max over ranks",
+           "channels_at_realtime": world * N_IN / (e2e_ms * 1e-3) / WIDEBAND_HZ * M}
+
+    # parity spot-check of the e2e output against the device-resident path (same state history => same bits)
+    fe_a = b200.Frontend(M, 8, False, WIDEBAND_HZ, BLOCK_PAIRS)
+    fe_b = b200.Frontend(M, 8, False, WIDEBAND_HZ, BLOCK_PAIRS)
+    oa = fe_a.process(bufs[0]).cpu()
+    ob = torch.from_numpy(fe_b.process_host(h_in[0].numpy()))
+    same = bool(torch.equal(oa.view(torch.int32), ob.view(torch.int32)))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        cb = cpu_reference_run(seconds_per_thread=1.5)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "iq_msps", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "channels_at_realtime": value * 1e6 / WIDEBAND_HZ * M,
+        "config": {"workload": WORKLOAD, "channels_per_gpu": M, "wideband_rate_hz": WIDEBAND_HZ, "channel_rate_hz": CHAN_HZ,
+                   "samples_per_step": N_IN, "block_pairs": BLOCK_PAIRS, "blocks_per_step": N_BLOCKS,
+                   "channelizer_taps_per_branch": 8, "fir_arith": "fma (reference AVX2 kernel order)",
+                   "parallelism": "bands sharded over GPUs, no data-path collective",
+                   "step_call": "dsdneo_b200_frontend_process_async (2-stream stage pipeline), joined before the stop event",
+                   "l2_policy": "%d rotating input buffers of %.1f MB (> 126 MB L2)" % (N_ROTATE, N_IN * 8 / 1e6)},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline, "e2e_matches_device_path": same,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

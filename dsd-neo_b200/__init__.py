@@ -277,3 +277,106 @@ class Channelizer:
         out = np.empty((self.M, n // self.M, 2), dtype=np.float32)
         check(lib().dsdneo_b200_channelize_host(self._h, h_in.ctypes.data, n, out.ctypes.data, out.shape[1]), "channelize_host")
         return out
+
+
+class FrontendConfig(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int),
+        ("taps_per_branch", C.c_int),
+        ("input_is_cu8", C.c_int),
+        ("wideband_rate_hz", C.c_int),
+        ("block_pairs", C.c_int),
+        ("prototype", C.POINTER(C.c_float)),
+        ("channel_lpf_enable", C.c_int),
+        ("channel_lpf_profile", C.POINTER(C.c_int)),
+        ("channel_squelch_level", C.POINTER(C.c_float)),
+        ("fir_arith", C.c_int),
+    ]
+
+
+def timing_enable(on: bool) -> None:
+    check(lib().dsdneo_b200_timing_enable(1 if on else 0))
+
+
+def timing_report() -> dict:
+    import json
+
+    buf = C.create_string_buffer(16384)
+    check(lib().dsdneo_b200_timing_report(buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+class Frontend:
+    """Wideband IQ -> per-channel discriminator samples (channelizer + full_demod) behind one C-ABI call."""
+
+    def __init__(self, n_channels=256, taps_per_branch=8, input_is_cu8=False, wideband_rate_hz=12_288_000,
+                 block_pairs=8192, channel_lpf_enable=True, profiles=None, squelch_levels=None, fir_arith=FIR_ARITH_FMA):
+        cfg = FrontendConfig()
+        cfg.n_channels = n_channels
+        cfg.taps_per_branch = taps_per_branch
+        cfg.input_is_cu8 = 1 if input_is_cu8 else 0
+        cfg.wideband_rate_hz = wideband_rate_hz
+        cfg.block_pairs = block_pairs
+        cfg.prototype = None
+        cfg.channel_lpf_enable = 1 if channel_lpf_enable else 0
+        self._prof = (C.c_int * n_channels)(*profiles) if profiles is not None else None
+        self._sq = (C.c_float * n_channels)(*squelch_levels) if squelch_levels is not None else None
+        cfg.channel_lpf_profile = self._prof if self._prof is not None else None
+        cfg.channel_squelch_level = self._sq if self._sq is not None else None
+        cfg.fir_arith = fir_arith
+        self.M, self.cu8, self.block_pairs = n_channels, bool(input_is_cu8), block_pairs
+        self._h = lib().dsdneo_b200_frontend_create(C.byref(cfg))
+        if not self._h:
+            raise B200Error(f"frontend_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_frontend_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_frontend_reset(self._h, _stream_ptr(stream)), "frontend_reset")
+
+    def process(self, d_in, d_result=None, stream=None):
+        import torch
+
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.shape[-1] == 2
+        assert d_in.dtype == (torch.uint8 if self.cu8 else torch.float32)
+        n = d_in.shape[0]
+        if d_result is None:
+            d_result = torch.empty((self.M, n // self.M), dtype=torch.float32, device=d_in.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(lib().dsdneo_b200_frontend_process(self._h, d_in.data_ptr(), n, d_result.data_ptr(), d_result.shape[1],
+                                                  _stream_ptr(stream)), "frontend_process")
+        return d_result
+
+    def process_async(self, d_in, d_result, stream=None):
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(lib().dsdneo_b200_frontend_process_async(self._h, d_in.data_ptr(), d_in.shape[0], d_result.data_ptr(),
+                                                        d_result.shape[1], _stream_ptr(stream)), "frontend_process_async")
+        return d_result
+
+    def join(self, stream=None) -> None:
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        check(lib().dsdneo_b200_frontend_join(self._h, _stream_ptr(stream)), "frontend_join")
+
+    def process_host(self, h_in, h_out=None):
+        """h_in / h_out: numpy arrays or pinned torch CPU tensors."""
+        import numpy as np
+
+        n = h_in.shape[0]
+        if h_out is None:
+            h_out = np.empty((self.M, n // self.M), dtype=np.float32)
+        pin = h_in.data_ptr() if hasattr(h_in, "data_ptr") else h_in.ctypes.data
+        pout = h_out.data_ptr() if hasattr(h_out, "data_ptr") else h_out.ctypes.data
+        check(lib().dsdneo_b200_frontend_process_host(self._h, pin, n, pout, h_out.shape[1]), "frontend_process_host")
+        return h_out

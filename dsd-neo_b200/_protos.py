@@ -14,6 +14,16 @@ def bind(L):
     vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
     cd = C.c_double
     protos = {
+        "dsdneo_b200_timing_enable": (ci, [ci]),
+        "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
+        "dsdneo_b200_frontend_create": (vp, [vp]),
+        "dsdneo_b200_frontend_destroy": (None, [vp]),
+        "dsdneo_b200_frontend_reset": (ci, [vp, vp]),
+        "dsdneo_b200_frontend_bank": (vp, [vp]),
+        "dsdneo_b200_frontend_process": (ci, [vp, vp, sz, vp, sz, vp]),
+        "dsdneo_b200_frontend_process_host": (ci, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_frontend_process_async": (ci, [vp, vp, sz, vp, sz, vp]),
+        "dsdneo_b200_frontend_join": (ci, [vp, vp]),
         "dsdneo_b200_channelizer_design_prototype": (ci, [ci, ci, cd, C.POINTER(cf)]),
         "dsdneo_b200_channelizer_create": (vp, [ci, ci, ci, C.POINTER(cf)]),
         "dsdneo_b200_channelizer_destroy": (None, [vp]),

@@ -289,7 +289,10 @@ launch_pfb(const PfbParams& p, int grid, cudaStream_t s) {
         DSDNEO_CUDA(cudaFuncSetAttribute(pfb256_kernel<T, CU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    pfb256_kernel<T, CU8><<<grid, kM, smem, s>>>(p);
+    {
+        KernelTimer kt("pfb256_kernel", s);
+        pfb256_kernel<T, CU8><<<grid, kM, smem, s>>>(p);
+    }
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;

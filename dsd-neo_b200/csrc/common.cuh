@@ -43,4 +43,31 @@ count_launch(int n = 1) {
 
 int ensure_device();  // 0 when a usable sm_100 device is current, else error code
 
+// Optional per-kernel device timing (dsdneo_b200_timing_enable): CUDA events recorded on the launching
+// stream around each kernel, accumulated per kernel name.  Off by default (no events, no overhead).
+extern bool g_timing_on;
+void timing_begin(const char* name, cudaStream_t s);
+void timing_end(cudaStream_t s);
+struct KernelTimer {
+    cudaStream_t s;
+    bool on;
+    KernelTimer(const char* name, cudaStream_t stream) : s(stream), on(g_timing_on) {
+        if (on) {
+            timing_begin(name, s);
+        }
+    }
+    ~KernelTimer() {
+        if (on) {
+            timing_end(s);
+        }
+    }
+};
+
 }  // namespace dsdneo
+
+/* library-internal stage entry points of the demod bank (demod_bank.cu), used by frontend.cu */
+struct dsdneo_b200_demod_bank;
+int dsdneo_demod_fir_stage(dsdneo_b200_demod_bank* b, const float* d_iq, size_t iq_pitch_pairs, int block_pairs,
+                           int n_blocks, int slot, cudaStream_t s);
+int dsdneo_demod_rec_stage(dsdneo_b200_demod_bank* b, int block_pairs, int n_blocks, float* d_result,
+                           size_t result_pitch, int slot, cudaStream_t s);

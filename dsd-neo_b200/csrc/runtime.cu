@@ -52,6 +52,82 @@ ensure_device() {
     return 0;
 }
 
+bool g_timing_on = false;
+
+namespace {
+struct TimingRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct TimingAcc {
+    const char* name;
+    unsigned long long launches;
+    double ms;
+};
+constexpr int kMaxRec = 4096, kMaxAcc = 64;
+TimingRec g_rec[kMaxRec];
+int g_n_rec = 0;
+TimingAcc g_acc[kMaxAcc];
+int g_n_acc = 0;
+cudaEvent_t g_ev_pool[2 * kMaxRec];
+int g_ev_pool_n = 0;
+int g_open = -1;
+
+cudaEvent_t
+pool_event(int idx) {
+    while (g_ev_pool_n <= idx) {
+        cudaEventCreate(&g_ev_pool[g_ev_pool_n++]);
+    }
+    return g_ev_pool[idx];
+}
+
+void
+timing_drain() {
+    for (int i = 0; i < g_n_rec; i++) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(g_rec[i].b) != cudaSuccess || cudaEventElapsedTime(&ms, g_rec[i].a, g_rec[i].b) != cudaSuccess) {
+            (void)cudaGetLastError();
+            continue;
+        }
+        int j = 0;
+        for (; j < g_n_acc; j++) {
+            if (g_acc[j].name == g_rec[i].name || strcmp(g_acc[j].name, g_rec[i].name) == 0) {
+                break;
+            }
+        }
+        if (j == g_n_acc) {
+            if (g_n_acc == kMaxAcc) {
+                continue;
+            }
+            g_acc[g_n_acc++] = TimingAcc{g_rec[i].name, 0ull, 0.0};
+        }
+        g_acc[j].launches++;
+        g_acc[j].ms += (double)ms;
+    }
+    g_n_rec = 0;
+}
+}  // namespace
+
+void
+timing_begin(const char* name, cudaStream_t s) {
+    if (g_n_rec == kMaxRec) {
+        timing_drain();
+    }
+    g_open = g_n_rec++;
+    g_rec[g_open].name = name;
+    g_rec[g_open].a = pool_event(2 * g_open);
+    g_rec[g_open].b = pool_event(2 * g_open + 1);
+    cudaEventRecord(g_rec[g_open].a, s);
+}
+
+void
+timing_end(cudaStream_t s) {
+    if (g_open >= 0) {
+        cudaEventRecord(g_rec[g_open].b, s);
+        g_open = -1;
+    }
+}
+
 }  // namespace dsdneo
 
 using namespace dsdneo;
@@ -107,6 +183,31 @@ dsdneo_b200_stream_sync(void* stream) {
 unsigned long long
 dsdneo_b200_launch_count(void) {
     return g_launch_count;
+}
+
+int
+dsdneo_b200_timing_enable(int on) {
+    timing_drain();
+    g_n_acc = 0;
+    g_timing_on = on != 0;
+    return 0;
+}
+
+int
+dsdneo_b200_timing_report(char* buf, size_t cap) {
+    if (!buf || cap < 3) {
+        set_error("timing_report: bad buffer");
+        return DSDNEO_B200_EINVAL;
+    }
+    timing_drain();
+    size_t off = 0;
+    off += (size_t)snprintf(buf + off, cap - off, "{");
+    for (int j = 0; j < g_n_acc && off + 160 < cap; j++) {
+        off += (size_t)snprintf(buf + off, cap - off, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", j ? ", " : "",
+                                g_acc[j].name, g_acc[j].launches, g_acc[j].ms);
+    }
+    snprintf(buf + off, cap - off, "}");
+    return g_n_acc;
 }
 
 void*

@@ -52,6 +52,14 @@ int dsdneo_b200_stream_sync(void* stream);
 /** Number of CUDA kernels this library has launched in this process (bench.py reports it). */
 unsigned long long dsdneo_b200_launch_count(void);
 
+/**
+ * Per-kernel device timing for bench.py's roofline: when enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its own stream and accumulated per kernel name.  `timing_report` synchronises
+ * the outstanding events and writes {"kernel": {"launches": n, "ms": total}, ...} as JSON text.
+ */
+int dsdneo_b200_timing_enable(int on);
+int dsdneo_b200_timing_report(char* buf, size_t cap);
+
 /* Raw device/pinned memory so a pure-C host needs no CUDA runtime of its own. */
 void* dsdneo_b200_malloc_device(size_t bytes);
 void dsdneo_b200_free_device(void* d_ptr);
@@ -192,6 +200,52 @@ int dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t 
                            size_t out_pitch_pairs, void* stream);
 int dsdneo_b200_channelize_host(dsdneo_b200_channelizer* c, const void* h_in, size_t n_in_samples, float* h_out,
                                 size_t out_pitch_pairs);
+
+/* ---- FSK front end: channelizer -> full_demod, one call ----------------------------------------- */
+
+/**
+ * The whole block side for N channels: what the reference's demod thread does per process
+ * (src/io/radio/rtl_sdr_fm.cpp:3458-3512: take a block, call full_demod(), publish result[]), fed from one
+ * shared wideband stream instead of one tuner per channel.
+ */
+typedef struct dsdneo_b200_frontend dsdneo_b200_frontend;
+
+typedef struct dsdneo_b200_frontend_config {
+    int n_channels;         /* M */
+    int taps_per_branch;    /* channelizer prototype length / M (4, 8, 12 or 16) */
+    int input_is_cu8;       /* 0: cf32 wideband input, 1: cu8 (RTL-SDR native), widened on load */
+    int wideband_rate_hz;   /* channel rate = wideband_rate_hz / n_channels (demod_state.rate_out) */
+    int block_pairs;        /* complex samples per channel per reference block (one full_demod() call) */
+    const float* prototype; /* optional M*taps_per_branch taps, NULL = default design */
+    int channel_lpf_enable;
+    const int* channel_lpf_profile;     /* per channel or NULL */
+    const float* channel_squelch_level; /* per channel or NULL */
+    int fir_arith;                      /* DSDNEO_FIR_ARITH_* */
+} dsdneo_b200_frontend_config;
+
+dsdneo_b200_frontend* dsdneo_b200_frontend_create(const dsdneo_b200_frontend_config* cfg);
+void dsdneo_b200_frontend_destroy(dsdneo_b200_frontend* fe);
+int dsdneo_b200_frontend_reset(dsdneo_b200_frontend* fe, void* stream);
+/** Borrow the demod bank (for dsdneo_b200_demod_bank_get_state). */
+dsdneo_b200_demod_bank* dsdneo_b200_frontend_bank(dsdneo_b200_frontend* fe);
+/**
+ * @param d_wideband n_in_samples wideband samples on the device; n_in_samples % (n_channels*block_pairs) == 0
+ * @param d_result   [n_channels][result_pitch] f32 discriminator samples, n_in_samples/n_channels per channel
+ */
+int dsdneo_b200_frontend_process(dsdneo_b200_frontend* fe, const void* d_wideband, size_t n_in_samples, float* d_result,
+                                 size_t result_pitch, void* stream);
+/**
+ * Pipelined form for back-to-back tiles: the time-parallel stages (channelizer, channel LPF + phase
+ * discriminator) of call i+1 overlap the time-serial recurrence stage of call i on internal streams.
+ * Inputs must be ready on `stream` when called; results are complete after dsdneo_b200_frontend_join()
+ * has been ordered into a stream (call it once after a run of process_async calls).  Bit-identical output.
+ */
+int dsdneo_b200_frontend_process_async(dsdneo_b200_frontend* fe, const void* d_wideband, size_t n_in_samples,
+                                       float* d_result, size_t result_pitch, void* stream);
+int dsdneo_b200_frontend_join(dsdneo_b200_frontend* fe, void* stream);
+/** Host buffers (pinned recommended): per-block H2D / kernels / D2H pipelined on three streams; synchronous. */
+int dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
+                                      float* h_result, size_t result_pitch);
 
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */

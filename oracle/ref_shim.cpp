@@ -62,6 +62,19 @@ ref_demod_create(int sample_rate, int symbol_rate, int lpf_profile, int lpf_enab
     return s;
 }
 
+/* Wideband variant: rate_in -> rate_out through `passes` half-band stages (demod_pipeline.cpp:983-1001),
+ * the reference's own way of selecting one channel from a wide capture. */
+void*
+ref_demod_create_wideband(int rate_in, int passes, int symbol_rate, int lpf_profile, int lpf_enable, float squelch_level) {
+    demod_state* s = (demod_state*)ref_demod_create(rate_in >> passes, symbol_rate, lpf_profile, lpf_enable, squelch_level);
+    if (!s) {
+        return NULL;
+    }
+    s->rate_in = rate_in;
+    s->downsample_passes = passes;
+    return s;
+}
+
 void
 ref_demod_destroy(void* h) {
     free(h);

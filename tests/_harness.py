@@ -121,6 +121,8 @@ def ref(variant="par"):
             L = C.CDLL(path)
             L.ref_demod_create.restype = C.c_void_p
             L.ref_demod_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+            L.ref_demod_create_wideband.restype = C.c_void_p
+            L.ref_demod_create_wideband.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
             L.ref_demod_destroy.argtypes = [C.c_void_p]
             L.ref_demod_block.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
             L.ref_demod_get_state.argtypes = [C.c_void_p, f32p]
