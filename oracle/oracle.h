@@ -67,6 +67,24 @@ int oracle_full_demod_block(oracle_demod_chan* c, const float* iq, int n_floats,
 void oracle_pfb_direct(const float* x_with_hist, int hist_len, int n_in, const float* h, int L, int M, int D,
                        const int* channels, int n_sel, double* out_re_im /* [n_sel][n_out][2] */, int n_out);
 
+/* ------------------------------- FEC leaves (oracle_fec.c) ----------------------------------- */
+
+enum { ORACLE_HAMMING_7_4 = 0, ORACLE_HAMMING_12_8, ORACLE_HAMMING_13_9, ORACLE_HAMMING_15_11, ORACLE_HAMMING_16_11_4 };
+
+void oracle_fec_init(void);
+int oracle_hamming_decode(int code, uint8_t* bits, uint8_t* decoded);
+int oracle_golay_24_12_decode(uint8_t* bits24);
+void oracle_golay_24_12_encode(const uint8_t* data12, uint8_t* out24);
+int oracle_golay_20_8_decode(uint8_t* bits20);
+int oracle_qr_16_7_6_decode(uint8_t* bits16);
+void oracle_bptc_deinterleave(const uint8_t* in196, uint8_t* out196);
+unsigned oracle_bptc_196x96_extract(const uint8_t* in196, uint8_t* out96, uint8_t* r3, int* undefined_out);
+int oracle_p25_12_soft_llr(const int16_t* llr196, uint8_t out12[12]);
+int oracle_p25_12_soft_llr_list(const int16_t* llr196, uint8_t* cand_bytes, uint32_t* cand_metric, int max_candidates);
+int oracle_rs63_decode(int tt, const int* in63, int* out63);
+void oracle_rs63_encode(int tt, const int* data, int* cw63);
+int oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits);
+
 void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n);
 
 #ifdef __cplusplus

@@ -1,0 +1,833 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement of the FEC leaves of the hot path (see oracle.h).
+ * Each decoder cites the reference code it restates (arancormonk/dsd-neo @ 4d06905) and is pinned against
+ * the reference's known-answer vectors and the compiled reference by tests/test_oracle_fec.py.
+ *
+ * Code definitions are generated from their generator polynomials instead of being stored as matrices:
+ *   Hamming(15,11) and its shortenings (13,9) (12,8): column j of H = x^(n-1-j) mod (x^4+x+1)
+ *   Hamming(7,4):   x^(6-j) mod (x^3+x+1);   Hamming(16,11,4): the (15,11) columns with an odd-weight
+ *   completion bit and a 16th column 00001     (src/fec/fec.c:25-69 are exactly these matrices)
+ *   Golay(24,12): parity row i = [x^(22-i) mod g23 , overall parity], g23 = x^11+x^10+x^6+x^5+x^4+x^2+1;
+ *   Golay(20,8) = the same shortened by 4 data bits; QR(16,7,6): g = x^8+x^5+x^4+x^3+1, same construction
+ *   (src/fec/fec.c:73-126).
+ */
+#include "oracle.h"
+
+#include <string.h>
+
+/* ------------------------------------------------------------------ Hamming family */
+
+typedef struct {
+    int n, r;              /* codeword bits, syndrome bits */
+    uint8_t col[16];       /* syndrome of a single error at position j */
+    uint8_t pos_of[32];    /* syndrome -> position, 0xFF = not a single-bit syndrome */
+    int stop_on_fail;      /* reference `break`s before copying info bits (all but 12_8) */
+} ham_code;
+
+static ham_code g_ham[5];
+static int g_ready = 0;
+
+static unsigned
+xpow_mod(int e, unsigned g, int deg) {
+    unsigned r = 1;
+    for (int i = 0; i < e; i++) {
+        r <<= 1;
+        if (r & (1u << deg)) {
+            r ^= g;
+        }
+    }
+    return r;
+}
+
+static void
+ham_build(ham_code* c, int n, int r, unsigned g, int deg, int extended) {
+    memset(c, 0, sizeof(*c));
+    c->n = n;
+    c->r = r;
+    memset(c->pos_of, 0xFF, sizeof(c->pos_of));
+    int ncyc = extended ? n - 1 : n;
+    for (int j = 0; j < ncyc; j++) {
+        unsigned s = xpow_mod(ncyc - 1 - j, g, deg);
+        if (extended) {
+            s = (s << 1) | ((__builtin_popcount(s) & 1) ? 0u : 1u);
+        }
+        c->col[j] = (uint8_t)s;
+    }
+    if (extended) {
+        c->col[n - 1] = 1;
+    }
+    for (int j = 0; j < n; j++) {
+        c->pos_of[c->col[j]] = (uint8_t)j;
+    }
+}
+
+/* ------------------------------------------------------------------ Golay / QR family */
+
+typedef struct {
+    int k, r, maxw;           /* data bits, parity bits, patterns enumerated up to this weight */
+    uint16_t pt[12];          /* row s of P^T: bit (k-1-j) set when data bit j feeds parity s */
+    uint8_t corr[4096][3];
+} gq_code;
+
+static gq_code g_golay24, g_golay20, g_qr16;
+
+static unsigned
+gq_data_syndrome(const gq_code* c, int j) { /* syndrome (r bits, row 0 = MSB) of a single data-bit error */
+    unsigned s = 0;
+    for (int row = 0; row < c->r; row++) {
+        s |= (unsigned)((c->pt[row] >> (c->k - 1 - j)) & 1u) << (c->r - 1 - row);
+    }
+    return s;
+}
+
+/* Reproduces the write order of Golay_20_8_init / Golay_24_12_init / QR_16_7_6_init (src/fec/fec.c:452-528,
+ * 591-667, 737-783) including the partial writes that leave stale higher slots untouched. */
+static void
+gq_build_table(gq_code* c) {
+    const int k = c->k, r = c->r;
+    memset(c->corr, 0xFF, sizeof(c->corr));
+#define PB(ip) (1u << (r - 1 - (ip)))
+    for (int i1 = 0; i1 < k; i1++) {
+        unsigned s1 = gq_data_syndrome(c, i1);
+        for (int i2 = i1 + 1; i2 < k; i2++) {
+            unsigned s2 = s1 ^ gq_data_syndrome(c, i2);
+            if (c->maxw >= 3) {
+                for (int i3 = i2 + 1; i3 < k; i3++) {
+                    unsigned s3 = s2 ^ gq_data_syndrome(c, i3);
+                    c->corr[s3][0] = (uint8_t)i1;
+                    c->corr[s3][1] = (uint8_t)i2;
+                    c->corr[s3][2] = (uint8_t)i3;
+                }
+            }
+            c->corr[s2][0] = (uint8_t)i1;
+            c->corr[s2][1] = (uint8_t)i2;
+            if (c->maxw >= 3) {
+                for (int ip = 0; ip < r; ip++) {
+                    unsigned s = s2 ^ PB(ip);
+                    c->corr[s][0] = (uint8_t)i1;
+                    c->corr[s][1] = (uint8_t)i2;
+                    c->corr[s][2] = (uint8_t)(k + ip);
+                }
+            }
+        }
+        c->corr[s1][0] = (uint8_t)i1;
+        for (int ip1 = 0; ip1 < r; ip1++) {
+            unsigned sa = s1 ^ PB(ip1);
+            c->corr[sa][0] = (uint8_t)i1;
+            c->corr[sa][1] = (uint8_t)(k + ip1);
+            if (c->maxw >= 3) {
+                for (int ip2 = ip1 + 1; ip2 < r; ip2++) {
+                    unsigned sb = sa ^ PB(ip2);
+                    c->corr[sb][0] = (uint8_t)i1;
+                    c->corr[sb][1] = (uint8_t)(k + ip1);
+                    c->corr[sb][2] = (uint8_t)(k + ip2);
+                }
+            }
+        }
+    }
+    for (int ip1 = 0; ip1 < r; ip1++) {
+        unsigned sa = PB(ip1);
+        c->corr[sa][0] = (uint8_t)(k + ip1);
+        for (int ip2 = ip1 + 1; ip2 < r; ip2++) {
+            unsigned sb = sa ^ PB(ip2);
+            c->corr[sb][0] = (uint8_t)(k + ip1);
+            c->corr[sb][1] = (uint8_t)(k + ip2);
+            if (c->maxw >= 3) {
+                for (int ip3 = ip2 + 1; ip3 < r; ip3++) {
+                    unsigned sc = sb ^ PB(ip3);
+                    c->corr[sc][0] = (uint8_t)(k + ip1);
+                    c->corr[sc][1] = (uint8_t)(k + ip2);
+                    c->corr[sc][2] = (uint8_t)(k + ip3);
+                }
+            }
+        }
+    }
+#undef PB
+}
+
+static void
+gq_build(gq_code* c, int k, int r, int maxw, unsigned g, int deg, int full_k) {
+    /* parity word of data bit i (of the unshortened code with full_k data bits):
+     * [x^(deg + full_k - 1 - i) mod g, overall parity]; shortening drops the first full_k - k data bits */
+    memset(c, 0, sizeof(*c));
+    c->k = k;
+    c->r = r;
+    c->maxw = maxw;
+    for (int j = 0; j < k; j++) {
+        int i = j + (full_k - k);
+        unsigned rem = xpow_mod(deg + full_k - 1 - i, g, deg);
+        unsigned word = (rem << 1) | ((__builtin_popcount(rem) + 1) & 1u);
+        for (int row = 0; row < r; row++) {
+            if ((word >> (r - 1 - row)) & 1u) {
+                c->pt[row] |= (uint16_t)(1u << (k - 1 - j));
+            }
+        }
+    }
+    gq_build_table(c);
+}
+
+void
+oracle_fec_init(void) {
+    if (g_ready) {
+        return;
+    }
+    ham_build(&g_ham[ORACLE_HAMMING_7_4], 7, 3, 0xB, 3, 0);
+    ham_build(&g_ham[ORACLE_HAMMING_12_8], 12, 4, 0x13, 4, 0);
+    ham_build(&g_ham[ORACLE_HAMMING_13_9], 13, 4, 0x13, 4, 0);
+    ham_build(&g_ham[ORACLE_HAMMING_15_11], 15, 4, 0x13, 4, 0);
+    ham_build(&g_ham[ORACLE_HAMMING_16_11_4], 16, 5, 0x13, 4, 1);
+    g_ham[ORACLE_HAMMING_13_9].stop_on_fail = 1;
+    g_ham[ORACLE_HAMMING_15_11].stop_on_fail = 1;
+    g_ham[ORACLE_HAMMING_16_11_4].stop_on_fail = 1;
+    gq_build(&g_golay24, 12, 12, 3, 0xC75, 11, 12);
+    gq_build(&g_golay20, 8, 12, 3, 0xC75, 11, 12);
+    gq_build(&g_qr16, 7, 9, 2, 0x139, 8, 7);
+    g_ready = 1;
+}
+
+static unsigned
+ham_syndrome(const ham_code* c, const uint8_t* bits) {
+    unsigned s = 0;
+    for (int j = 0; j < c->n; j++) {
+        if (bits[j] & 1) { /* the reference sums raw bytes mod 2: only the LSB matters (fec.c:150-157) */
+            s ^= c->col[j];
+        }
+    }
+    return s;
+}
+
+/* Hamming_7_4_decode (fec.c:145-168) and Hamming_{12_8,13_9,15_11,16_11_4}_decode with nbCodewords = 1
+ * (fec.c:188-450).  Returns the reference's bool.  `decoded` may be NULL; for the codes that stop on failure the
+ * info bits are NOT copied when the word is uncorrectable (the reference breaks out before the memcpy). */
+int
+oracle_hamming_decode(int code, uint8_t* bits, uint8_t* decoded) {
+    oracle_fec_init();
+    const ham_code* c = &g_ham[code];
+    unsigned s = ham_syndrome(c, bits);
+    int ok = 1;
+    if (s) {
+        if (c->pos_of[s] == 0xFF) {
+            ok = 0;
+            if (c->stop_on_fail || code == ORACLE_HAMMING_7_4) {
+                return 0;
+            }
+        } else {
+            bits[c->pos_of[s]] ^= 1;
+        }
+    }
+    if (decoded && code != ORACLE_HAMMING_7_4) {
+        memcpy(decoded, bits, (size_t)(c->n - c->r));
+    }
+    return ok;
+}
+
+static unsigned
+gq_syndrome(const gq_code* c, const uint8_t* bits) {
+    unsigned s = 0;
+    for (int row = 0; row < c->r; row++) {
+        unsigned par = bits[c->k + row] & 1u;
+        for (int j = 0; j < c->k; j++) {
+            par ^= (bits[j] & 1u) & ((c->pt[row] >> (c->k - 1 - j)) & 1u);
+        }
+        s |= par << (c->r - 1 - row);
+    }
+    return s;
+}
+
+/* Golay_24_12_decode (fec.c:682-733), Golay_20_8_decode (fec.c:543-587; more than 2 flips => false AFTER flipping),
+ * QR_16_7_6_decode (fec.c:787-824). */
+int
+oracle_golay_24_12_decode(uint8_t* bits) {
+    oracle_fec_init();
+    unsigned s = gq_syndrome(&g_golay24, bits);
+    if (!s) {
+        return 1;
+    }
+    int i = 0;
+    for (; i < 3 && g_golay24.corr[s][i] != 0xFF; i++) {
+        bits[g_golay24.corr[s][i]] ^= 1;
+    }
+    return i != 0;
+}
+
+void
+oracle_golay_24_12_encode(const uint8_t* data12, uint8_t* out24) {
+    oracle_fec_init();
+    for (int j = 0; j < 12; j++) {
+        out24[j] = data12[j] & 1;
+    }
+    for (int row = 0; row < 12; row++) {
+        unsigned par = 0;
+        for (int j = 0; j < 12; j++) {
+            par ^= (data12[j] & 1u) & ((g_golay24.pt[row] >> (11 - j)) & 1u);
+        }
+        out24[12 + row] = (uint8_t)par;
+    }
+}
+
+int
+oracle_golay_20_8_decode(uint8_t* bits) {
+    oracle_fec_init();
+    unsigned s = gq_syndrome(&g_golay20, bits);
+    if (!s) {
+        return 1;
+    }
+    int i = 0;
+    for (; i < 3 && g_golay20.corr[s][i] != 0xFF; i++) {
+        bits[g_golay20.corr[s][i]] ^= 1;
+    }
+    return (i != 0) && (i <= 2);
+}
+
+int
+oracle_qr_16_7_6_decode(uint8_t* bits) {
+    oracle_fec_init();
+    unsigned s = gq_syndrome(&g_qr16, bits);
+    if (!s) {
+        return 1;
+    }
+    int i = 0;
+    for (; i < 2 && g_qr16.corr[s][i] != 0xFF; i++) {
+        bits[g_qr16.corr[s][i]] ^= 1;
+    }
+    return i != 0;
+}
+
+/* ------------------------------------------------------------------ BPTC(196,96) */
+
+/* BPTCDeInterleaveDMRData (src/fec/bptc.c:22-59): out[(13 i) mod 196] = in[i] & 1 */
+void
+oracle_bptc_deinterleave(const uint8_t* in196, uint8_t* out196) {
+    for (int i = 0; i < 196; i++) {
+        out196[(13 * i) % 196] = in196[i] & 1;
+    }
+}
+
+/* BPTC_196x96_Extract_Data (src/fec/bptc.c:61-149).  Two row/column passes, only the second counted.
+ * Stale-buffer behaviour of the reference: when a Hamming(13,9) column is uncorrectable the callee returns before
+ * writing its output buffer, so the caller copies whatever that buffer held -- the previous successfully decoded
+ * column of the same pass.  For the first column of a pass the reference reads an uninitialised stack buffer;
+ * here the column is left unchanged and *undefined_out is set so tests can exclude the case.
+ * (Hamming(15,11) is perfect: a row can never be uncorrectable.) */
+unsigned
+oracle_bptc_196x96_extract(const uint8_t* in196, uint8_t* out96, uint8_t* r3, int* undefined_out) {
+    oracle_fec_init();
+    uint8_t m[13][15];
+    int k = 1;
+    if (undefined_out) {
+        *undefined_out = 0;
+    }
+    for (int i = 0; i < 13; i++) {
+        for (int j = 0; j < 15; j++) {
+            m[i][j] = in196[k++] & 1;
+        }
+    }
+    unsigned errs = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        unsigned e = 0;
+        for (int i = 0; i < 9; i++) {
+            uint8_t line[15], dec[11];
+            memcpy(line, m[i], 15);
+            (void)oracle_hamming_decode(ORACLE_HAMMING_15_11, line, dec); /* always correctable */
+            memcpy(m[i], dec, 11);
+        }
+        uint8_t last[9];
+        int have_last = 0;
+        for (int j = 0; j < 15; j++) {
+            uint8_t col[13], dec[9];
+            for (int i = 0; i < 13; i++) {
+                col[i] = m[i][j];
+            }
+            if (oracle_hamming_decode(ORACLE_HAMMING_13_9, col, dec)) {
+                memcpy(last, dec, 9);
+                have_last = 1;
+                for (int i = 0; i < 9; i++) {
+                    m[i][j] = dec[i];
+                }
+            } else {
+                e++;
+                if (have_last) {
+                    for (int i = 0; i < 9; i++) {
+                        m[i][j] = last[i];
+                    }
+                } else if (undefined_out) {
+                    *undefined_out = 1;
+                }
+            }
+        }
+        if (pass == 1) {
+            errs = e;
+        }
+    }
+    k = 0;
+    for (int j = 3; j < 11; j++) {
+        out96[k++] = m[0][j];
+    }
+    for (int i = 1; i < 9; i++) {
+        for (int j = 0; j < 11; j++) {
+            out96[k++] = m[i][j];
+        }
+    }
+    r3[0] = m[0][2];
+    r3[1] = m[0][1];
+    r3[2] = m[0][0];
+    return errs;
+}
+
+/* ------------------------------------------------------------------ P25 half-rate trellis */
+
+/* dibit-pair nibble expected on the transition prev -> next (src/protocol/p25/p25_12.c:19) */
+static const uint64_t k_p25_dtm_packed = 0x86B54A793D0EF1C2ull; /* nibble i = entry i, entry 0 in the low nibble */
+
+static inline unsigned
+p25_dtm(int prev, int next) {
+    return (unsigned)((k_p25_dtm_packed >> (4 * ((prev << 2) | next))) & 0xF);
+}
+
+/* position of received dibit i in the de-interleaved stream (src/fec/trellis34.c:8-13):
+ * four groups g = 0..3, each walking dibit pairs (j, j+1) for j = 2g, 2g+8, 2g+16, ... < 98 */
+static void
+p25_interleave_98(uint8_t* t) {
+    int n = 0;
+    for (int g = 0; g < 4; g++) {
+        for (int j = 2 * g; j < 98; j += 8) {
+            t[n++] = (uint8_t)j;
+            t[n++] = (uint8_t)(j + 1);
+        }
+    }
+}
+
+static inline uint32_t
+llr_cost(int16_t llr, unsigned bit) {
+    if (bit) {
+        return llr < 0 ? (uint32_t)(-(int)llr) : 0u;
+    }
+    return llr > 0 ? (uint32_t)llr : 0u;
+}
+
+static void
+p25_deinterleave_llr(const int16_t* llr196, int16_t* dei) {
+    uint8_t t[98];
+    p25_interleave_98(t);
+    memset(dei, 0, 196 * sizeof(int16_t));
+    for (int i = 0; i < 98; i++) {
+        dei[2 * t[i]] = llr196[2 * i];
+        dei[2 * t[i] + 1] = llr196[2 * i + 1];
+    }
+}
+
+static inline uint32_t
+p25_branch_cost(const int16_t* dei, int sym, int prev, int next) {
+    unsigned e = p25_dtm(prev, next);
+    const int16_t* l = dei + 4 * sym;
+    return llr_cost(l[0], (e >> 3) & 1) + llr_cost(l[1], (e >> 2) & 1) + llr_cost(l[2], (e >> 1) & 1) + llr_cost(l[3], e & 1);
+}
+
+/* p25_12_soft_llr (src/protocol/p25/p25_12.c:204-283) */
+int
+oracle_p25_12_soft_llr(const int16_t* llr196, uint8_t out12[12]) {
+    int16_t dei[196];
+    p25_deinterleave_llr(llr196, dei);
+    uint32_t pm[4] = {0, 256, 256, 256}, cm[4] = {0, 0, 0, 0};
+    uint8_t bp[49][4];
+    for (int i = 0; i < 49; i++) {
+        for (int nx = 0; nx < 4; nx++) {
+            uint32_t best = 0xFFFFFFFFu;
+            uint8_t bprev = 0;
+            for (int pv = 0; pv < 4; pv++) {
+                uint32_t m = pm[pv] + p25_branch_cost(dei, i, pv, nx);
+                if (m < best) {
+                    best = m;
+                    bprev = (uint8_t)pv;
+                }
+            }
+            cm[nx] = best;
+            bp[i][nx] = bprev;
+        }
+        memcpy(pm, cm, sizeof(pm));
+    }
+    int st = 0;
+    uint32_t bf = cm[0];
+    for (int j = 1; j < 4; j++) {
+        if (cm[j] < bf) {
+            bf = cm[j];
+            st = j;
+        }
+    }
+    uint8_t td[49];
+    for (int i = 49; i-- > 0;) {
+        td[i] = (uint8_t)st;
+        st = bp[i][st];
+    }
+    for (int i = 0; i < 12; i++) {
+        out12[i] = (uint8_t)((td[4 * i] << 6) | (td[4 * i + 1] << 4) | (td[4 * i + 2] << 2) | td[4 * i + 3]);
+    }
+    return (int)(bf >> 8);
+}
+
+/* p25_12_soft_llr_list (src/protocol/p25/p25_12.c:31-202): list Viterbi, <= 8 survivors per state */
+int
+oracle_p25_12_soft_llr_list(const int16_t* llr196, uint8_t* cand_bytes /*[max][12]*/, uint32_t* cand_metric, int max_candidates) {
+    enum { K = 8 };
+    if (!llr196 || !cand_bytes || !cand_metric || max_candidates <= 0) {
+        return 0;
+    }
+    if (max_candidates > K) {
+        max_candidates = K;
+    }
+    int16_t dei[196];
+    p25_deinterleave_llr(llr196, dei);
+    static uint32_t ma[4][K], mb[4][K];
+    static uint8_t bp[49][4][K];
+    uint32_t (*pm)[K] = ma;
+    uint32_t (*cm)[K] = mb;
+    memset(ma, 0xFF, sizeof(ma));
+    memset(mb, 0xFF, sizeof(mb));
+    memset(bp, 0, sizeof(bp));
+    for (int s = 0; s < 4; s++) {
+        pm[s][0] = s == 0 ? 0u : 256u;
+    }
+    for (int i = 0; i < 49; i++) {
+        memset(cm, 0xFF, sizeof(ma));
+        for (int pv = 0; pv < 4; pv++) {
+            for (int nx = 0; nx < 4; nx++) {
+                uint32_t cost = p25_branch_cost(dei, i, pv, nx);
+                for (int rk = 0; rk < K; rk++) {
+                    if (pm[pv][rk] == 0xFFFFFFFFu) {
+                        continue;
+                    }
+                    uint32_t m = pm[pv][rk] + cost;
+                    int at = -1;
+                    for (int q = 0; q < K; q++) {
+                        if (m < cm[nx][q]) {
+                            at = q;
+                            break;
+                        }
+                    }
+                    if (at < 0) {
+                        continue;
+                    }
+                    for (int q = K - 1; q > at; q--) {
+                        cm[nx][q] = cm[nx][q - 1];
+                        bp[i][nx][q] = bp[i][nx][q - 1];
+                    }
+                    cm[nx][at] = m;
+                    bp[i][nx][at] = (uint8_t)((pv << 3) | rk);
+                }
+            }
+        }
+        uint32_t (*t)[K] = pm;
+        pm = cm;
+        cm = t;
+    }
+    int count = 0;
+    for (int s = 0; s < 4; s++) {
+        for (int rk = 0; rk < K; rk++) {
+            if (pm[s][rk] == 0xFFFFFFFFu) {
+                continue;
+            }
+            uint8_t td[49], bytes[12];
+            int st = s, r = rk;
+            for (int i = 49; i-- > 0;) {
+                td[i] = (uint8_t)st;
+                uint8_t p = bp[i][st][r];
+                st = (p >> 3) & 3;
+                r = p & 7;
+            }
+            for (int i = 0; i < 12; i++) {
+                bytes[i] = (uint8_t)((td[4 * i] << 6) | (td[4 * i + 1] << 4) | (td[4 * i + 2] << 2) | td[4 * i + 3]);
+            }
+            int dup = 0;
+            for (int c = 0; c < count; c++) {
+                if (memcmp(cand_bytes + 12 * c, bytes, 12) == 0) {
+                    dup = 1;
+                }
+            }
+            if (dup) {
+                continue;
+            }
+            uint32_t metric = pm[s][rk];
+            int at = count;
+            for (int c = 0; c < count; c++) {
+                if (metric < cand_metric[c]) {
+                    at = c;
+                    break;
+                }
+            }
+            if (count < max_candidates) {
+                count++;
+            } else if (at >= max_candidates) {
+                continue;
+            }
+            for (int c = count - 1; c > at; c--) {
+                memcpy(cand_bytes + 12 * c, cand_bytes + 12 * (c - 1), 12);
+                cand_metric[c] = cand_metric[c - 1];
+            }
+            memcpy(cand_bytes + 12 * at, bytes, 12);
+            cand_metric[at] = metric;
+        }
+    }
+    return count;
+}
+
+/* ------------------------------------------------------------------ Reed-Solomon over GF(64) */
+
+static int gf_exp[64], gf_log[64];
+static int gf_ready = 0;
+
+static void
+gf_init(void) { /* GF(2^6), primitive polynomial x^6 + x + 1 (ReedSolomon.hpp:685-727) */
+    if (gf_ready) {
+        return;
+    }
+    int v = 1;
+    for (int i = 0; i < 63; i++) {
+        gf_exp[i] = v;
+        gf_log[v] = i;
+        v <<= 1;
+        if (v & 0x40) {
+            v ^= 0x43;
+        }
+    }
+    gf_exp[63] = 0;
+    gf_log[0] = -1;
+    gf_ready = 1;
+}
+
+/* ReedSolomon_63<TT>::decode (ReedSolomon.hpp:738-771 with :353-582): Berlekamp iteration in the index-form
+ * bookkeeping of Rockliff's rs.c.  in/out: 63 symbols in polynomial form.  Returns 0 = ok / corrected, 1 = irrecoverable
+ * (out == in). */
+int
+oracle_rs63_decode(int tt, const int* in63, int* out63) {
+    enum { NN = 63 };
+    gf_init();
+    const int n2t = 2 * tt;
+    int recd[NN], s[2 * 8 + 2];
+    for (int i = 0; i < NN; i++) {
+        recd[i] = gf_log[in63[i]];
+    }
+    int syn_err = 0;
+    s[0] = 0;
+    for (int i = 1; i <= n2t; i++) {
+        int acc = 0;
+        for (int j = 0; j < NN; j++) {
+            if (recd[j] != -1) {
+                acc ^= gf_exp[(recd[j] + i * j) % NN];
+            }
+        }
+        if (acc) {
+            syn_err = 1;
+        }
+        s[i] = gf_log[acc];
+    }
+    if (!syn_err) {
+        memcpy(out63, in63, NN * sizeof(int));
+        return 0;
+    }
+    int elp[2 * 8 + 2][2 * 8], d[2 * 8 + 2], l[2 * 8 + 2], u_lu[2 * 8 + 2];
+    d[0] = 0;
+    d[1] = s[1];
+    elp[0][0] = 0;
+    elp[1][0] = 1;
+    for (int i = 1; i < n2t; i++) {
+        elp[0][i] = -1;
+        elp[1][i] = 0;
+    }
+    l[0] = l[1] = 0;
+    u_lu[0] = -1;
+    u_lu[1] = 0;
+    int u = 0;
+    do {
+        u++;
+        if (d[u] == -1) {
+            l[u + 1] = l[u];
+            for (int i = 0; i <= l[u]; i++) {
+                elp[u + 1][i] = elp[u][i];
+                elp[u][i] = gf_log[elp[u][i]];
+            }
+        } else {
+            int q = u - 1;
+            while (q > 0 && d[q] == -1) {
+                q--;
+            }
+            if (q > 0) {
+                for (int j = q - 1; j > 0; j--) {
+                    if (d[j] != -1 && u_lu[q] < u_lu[j]) {
+                        q = j;
+                    }
+                }
+            }
+            l[u + 1] = (l[u] > l[q] + u - q) ? l[u] : l[q] + u - q;
+            for (int i = 0; i < n2t; i++) {
+                elp[u + 1][i] = 0;
+            }
+            for (int i = 0; i <= l[q]; i++) {
+                if (elp[q][i] != -1) {
+                    elp[u + 1][i + u - q] = gf_exp[(d[u] + NN - d[q] + elp[q][i]) % NN];
+                }
+            }
+            for (int i = 0; i <= l[u]; i++) {
+                elp[u + 1][i] ^= elp[u][i];
+                elp[u][i] = gf_log[elp[u][i]];
+            }
+        }
+        u_lu[u + 1] = u - l[u + 1];
+        if (u < n2t) {
+            int dd = (s[u + 1] != -1) ? gf_exp[s[u + 1]] : 0;
+            for (int i = 1; i <= l[u + 1]; i++) {
+                if (s[u + 1 - i] != -1 && elp[u + 1][i] != 0) {
+                    dd ^= gf_exp[(s[u + 1 - i] + gf_log[elp[u + 1][i]]) % NN];
+                }
+            }
+            d[u + 1] = gf_log[dd];
+        }
+    } while (u < n2t && l[u + 1] <= tt);
+    u++;
+    if (l[u] > tt) {
+        memcpy(out63, in63, NN * sizeof(int));
+        return 1;
+    }
+    int deg = l[u];
+    int loc_poly[9];
+    for (int i = 0; i <= deg; i++) {
+        loc_poly[i] = gf_log[elp[u][i]];
+    }
+    int reg[9], root[8], loc[8], count = 0;
+    for (int i = 1; i <= deg; i++) {
+        reg[i] = loc_poly[i];
+    }
+    for (int i = 1; i <= NN; i++) {
+        int q = 1;
+        for (int j = 1; j <= deg; j++) {
+            if (reg[j] != -1) {
+                reg[j] = (reg[j] + j) % NN;
+                q ^= gf_exp[reg[j]];
+            }
+        }
+        if (!q) {
+            if (count < 8) {
+                root[count] = i;
+                loc[count] = NN - i;
+            }
+            count++;
+        }
+    }
+    if (count != deg) {
+        memcpy(out63, in63, NN * sizeof(int));
+        return 1;
+    }
+    int z[9];
+    for (int i = 1; i <= deg; i++) {
+        int zi;
+        if (s[i] != -1 && loc_poly[i] != -1) {
+            zi = gf_exp[s[i]] ^ gf_exp[loc_poly[i]];
+        } else if (s[i] != -1) {
+            zi = gf_exp[s[i]];
+        } else if (loc_poly[i] != -1) {
+            zi = gf_exp[loc_poly[i]];
+        } else {
+            zi = 0;
+        }
+        for (int j = 1; j < i; j++) {
+            if (s[j] != -1 && loc_poly[i - j] != -1) {
+                zi ^= gf_exp[(loc_poly[i - j] + s[j]) % NN];
+            }
+        }
+        z[i] = gf_log[zi];
+    }
+    memcpy(out63, in63, NN * sizeof(int));
+    for (int i = 0; i < deg; i++) {
+        int num = 1;
+        for (int j = 1; j <= deg; j++) {
+            if (z[j] != -1) {
+                num ^= gf_exp[(z[j] + j * root[i]) % NN];
+            }
+        }
+        if (num != 0) {
+            int den = 0;
+            for (int j = 0; j < deg; j++) {
+                if (j != i) {
+                    den += gf_log[1 ^ gf_exp[(loc[j] + root[i]) % NN]];
+                }
+            }
+            den %= NN;
+            int e = gf_exp[(gf_log[num] - den + NN) % NN];
+            out63[loc[i]] ^= e;
+        }
+    }
+    return 0;
+}
+
+/* Systematic encoder for tests (the reference tree has no encoder for this code): parity symbols occupy positions
+ * 0..2t-1, data the following kk positions -- the layout the reference decoder expects (ReedSolomon.hpp:838-851).
+ * Generator g(x) = prod_{i=1..2t} (x + alpha^i); codeword polynomial c(x) = sum c[j] x^j has c(alpha^i) = 0. */
+void
+oracle_rs63_encode(int tt, const int* data /*[63-2tt]*/, int* cw63) {
+    gf_init();
+    const int n2t = 2 * tt, kk = 63 - n2t;
+    int g[17];
+    g[0] = 1;
+    for (int i = 1; i <= n2t; i++) {
+        g[i] = 0;
+    }
+    for (int i = 1; i <= n2t; i++) { /* multiply by (x + alpha^i) */
+        for (int j = i; j > 0; j--) {
+            int t = g[j - 1];
+            if (g[j]) {
+                t ^= gf_exp[(gf_log[g[j]] + i) % 63];
+            }
+            g[j] = t;
+        }
+        g[0] = gf_exp[(gf_log[g[0]] + i) % 63];
+    }
+    int par[16];
+    for (int i = 0; i < n2t; i++) {
+        par[i] = 0;
+    }
+    for (int i = kk - 1; i >= 0; i--) { /* LFSR division of data(x) x^{2t} by g(x) */
+        int fb = data[i] ^ par[n2t - 1];
+        for (int j = n2t - 1; j > 0; j--) {
+            par[j] = par[j - 1] ^ (fb && g[j] ? gf_exp[(gf_log[fb] + gf_log[g[j]]) % 63] : 0);
+        }
+        par[0] = (fb && g[0]) ? gf_exp[(gf_log[fb] + gf_log[g[0]]) % 63] : 0;
+    }
+    for (int i = 0; i < n2t; i++) {
+        cw63[i] = par[i];
+    }
+    for (int i = 0; i < kk; i++) {
+        cw63[n2t + i] = data[i];
+    }
+}
+
+/* check_and_fix_redsolomon_36_20_17 / _24_12_13 / _24_16_9 (phase1/p25p1_check_hdu.cpp:38-45, p25p1_check_ldu.cpp:37-71;
+ * wrappers ReedSolomon.hpp:821-877,918-955,1013-1050): byte-per-bit hex words, parity first in the codeword. */
+int
+oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits /*[n_data][6]*/, const uint8_t* parity_bits /*[n_par][6]*/) {
+    const int n_par = n_total - n_data, tt = n_par / 2;
+    int in[63], out[63];
+    for (int i = 0; i < 63; i++) {
+        in[i] = 0;
+    }
+    for (int i = 0; i < n_par; i++) {
+        int v = 0;
+        for (int b = 0; b < 6; b++) {
+            v = (v << 1) | (parity_bits[6 * i + b] != 0);
+        }
+        in[i] = v;
+    }
+    for (int i = 0; i < n_data; i++) {
+        int v = 0;
+        for (int b = 0; b < 6; b++) {
+            v = (v << 1) | (data_bits[6 * i + b] != 0);
+        }
+        in[n_par + i] = v;
+    }
+    int rc = oracle_rs63_decode(tt, in, out);
+    for (int i = 0; i < n_data; i++) {
+        for (int b = 0; b < 6; b++) {
+            data_bits[6 * i + b] = (uint8_t)((out[n_par + i] >> (5 - b)) & 1);
+        }
+    }
+    return rc;
+}

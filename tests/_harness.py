@@ -250,3 +250,100 @@ def synth_wideband(rng, M, n_out, active, fs_ratio_dev=0.0785, snr_db=30.0, amp=
     out[:, 0] = x.real
     out[:, 1] = x.imag
     return out, truth
+
+
+# --------------------------------------------------------------------------- FEC bindings
+
+class P25Candidate(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 12), ("metric", C.c_uint32)]
+
+
+_fec_bound = {}
+
+
+def oracle_fec():
+    L = oracle()
+    if "o" not in _fec_bound:
+        i16p, u32p = C.POINTER(C.c_int16), C.POINTER(C.c_uint32)
+        L.oracle_hamming_decode.argtypes = [C.c_int, u8p, u8p]
+        L.oracle_golay_24_12_decode.argtypes = [u8p]
+        L.oracle_golay_24_12_encode.argtypes = [u8p, u8p]
+        L.oracle_golay_20_8_decode.argtypes = [u8p]
+        L.oracle_qr_16_7_6_decode.argtypes = [u8p]
+        L.oracle_bptc_deinterleave.argtypes = [u8p, u8p]
+        L.oracle_bptc_196x96_extract.restype = C.c_uint
+        L.oracle_bptc_196x96_extract.argtypes = [u8p, u8p, u8p, i32p]
+        L.oracle_p25_12_soft_llr.argtypes = [i16p, u8p]
+        L.oracle_p25_12_soft_llr_list.argtypes = [i16p, u8p, u32p, C.c_int]
+        L.oracle_rs63_decode.argtypes = [C.c_int, i32p, i32p]
+        L.oracle_rs63_encode.argtypes = [C.c_int, i32p, i32p]
+        L.oracle_p25_rs_decode.argtypes = [C.c_int, C.c_int, u8p, u8p]
+        L.oracle_fec_init()
+        _fec_bound["o"] = True
+    return L
+
+
+def ref_fec(variant="par"):
+    L = ref(variant)
+    if L is None:
+        return None
+    key = "r" + variant
+    if key not in _fec_bound:
+        i16p = C.POINTER(C.c_int16)
+        L.Hamming_7_4_decode.restype = C.c_bool
+        L.Hamming_7_4_decode.argtypes = [u8p]
+        for nm in ("Hamming_12_8_decode", "Hamming_13_9_decode", "Hamming_15_11_decode", "Hamming_16_11_4_decode"):
+            getattr(L, nm).restype = C.c_bool
+            getattr(L, nm).argtypes = [u8p, u8p, C.c_int]
+        for nm in ("Golay_24_12_decode", "Golay_20_8_decode", "QR_16_7_6_decode"):
+            getattr(L, nm).restype = C.c_bool
+            getattr(L, nm).argtypes = [u8p]
+        L.Golay_24_12_encode.argtypes = [u8p, u8p]
+        L.BPTCDeInterleaveDMRData.argtypes = [u8p, u8p]
+        L.BPTC_196x96_Extract_Data.restype = C.c_uint32
+        L.BPTC_196x96_Extract_Data.argtypes = [u8p, u8p, u8p]
+        L.p25_12_soft_llr.argtypes = [u8p, i16p, u8p]
+        L.p25_12_soft_llr_list.argtypes = [u8p, i16p, C.POINTER(P25Candidate), C.c_int]
+        for nm in ("check_and_fix_redsolomon_36_20_17", "check_and_fix_reedsolomon_24_12_13", "check_and_fix_reedsolomon_24_16_9"):
+            getattr(L, nm).argtypes = [u8p, u8p]
+        L.ref_rs63_decode.argtypes = [C.c_int, i32p, i32p]
+        L.InitAllFecFunction()
+        _fec_bound[key] = True
+    return L
+
+
+def u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def p25_trellis_encode(rng, dibits49=None):
+    """Encode 49 dibits with the P25 half-rate trellis (p25_12.c:19 transition table) and interleave them
+    (trellis34.c:8-13).  Returns (dibits49, tx_dibits98)."""
+    dtm = [2, 12, 1, 15, 14, 0, 13, 3, 9, 7, 10, 4, 5, 11, 6, 8]
+    if dibits49 is None:
+        dibits49 = rng.integers(0, 4, 49)
+        dibits49[48] = 0
+    st = 0
+    dei = np.zeros(98, dtype=np.int64)
+    for i, d in enumerate(dibits49):
+        nib = dtm[(st << 2) | int(d)]
+        dei[2 * i] = (nib >> 2) & 3
+        dei[2 * i + 1] = nib & 3
+        st = int(d)
+    tbl = []
+    for g in range(4):
+        for j in range(2 * g, 98, 8):
+            tbl += [j, j + 1]
+    tx = np.zeros(98, dtype=np.int64)
+    for i in range(98):
+        tx[i] = dei[tbl[i]]
+    return np.asarray(dibits49), tx
+
+
+def dibits_to_llr(tx98, mag=200, rng=None, noise=0.0):
+    """int16 LLR pairs (positive = bit 1) for 98 dibits, optionally with Gaussian noise."""
+    bits = np.stack([(tx98 >> 1) & 1, tx98 & 1], axis=1).reshape(-1)
+    llr = np.where(bits == 1, mag, -mag).astype(np.float64)
+    if rng is not None and noise > 0:
+        llr = llr + rng.standard_normal(llr.size) * noise
+    return np.clip(np.rint(llr), -32768, 32767).astype(np.int16)
