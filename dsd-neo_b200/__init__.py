@@ -380,3 +380,72 @@ class Frontend:
         pout = h_out.data_ptr() if hasattr(h_out, "data_ptr") else h_out.ctypes.data
         check(lib().dsdneo_b200_frontend_process_host(self._h, pin, n, pout, h_out.shape[1]), "frontend_process_host")
         return h_out
+
+
+# ------------------------------------------------------------------------------------------ FEC (host-buffer entry points)
+
+FEC_HAMMING_7_4, FEC_HAMMING_12_8, FEC_HAMMING_13_9, FEC_HAMMING_15_11, FEC_HAMMING_16_11_4 = 0, 1, 2, 3, 4
+FEC_GOLAY_20_8, FEC_GOLAY_24_12, FEC_QR_16_7_6 = 5, 6, 7
+P25_RS_36_20_17, P25_RS_24_12_13, P25_RS_24_16_9 = 0, 1, 2
+
+
+class P25Candidate(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 12), ("metric", C.c_uint32)]
+
+
+def fec_block_decode(code: int, bits, decoded=None):
+    """bits: uint8 [n_words, n] corrected in place (numpy). Returns ok[n_words] uint8."""
+    import numpy as np
+
+    assert bits.dtype == np.uint8 and bits.flags.c_contiguous
+    n_words = bits.shape[0]
+    ok = np.zeros(n_words, dtype=np.uint8)
+    dptr = decoded.ctypes.data if decoded is not None else None
+    check(lib().dsdneo_b200_fec_block_decode_batch_host(code, bits.ctypes.data, dptr, ok.ctypes.data, n_words), "fec_block_decode")
+    return ok
+
+
+def bptc_196x96(bursts, interleaved: bool):
+    import numpy as np
+
+    bursts = np.ascontiguousarray(bursts, dtype=np.uint8)
+    n = bursts.shape[0]
+    out, r3, errs = np.zeros((n, 96), np.uint8), np.zeros((n, 3), np.uint8), np.zeros(n, np.uint32)
+    check(lib().dsdneo_b200_bptc_196x96_batch_host(bursts.ctypes.data, 1 if interleaved else 0, out.ctypes.data, r3.ctypes.data,
+                                                   errs.ctypes.data, n), "bptc_196x96")
+    return out, r3, errs
+
+
+def p25_12_soft_llr(llr):
+    import numpy as np
+
+    llr = np.ascontiguousarray(llr, dtype=np.int16)
+    n = llr.shape[0]
+    out, met = np.zeros((n, 12), np.uint8), np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_p25_12_soft_llr_batch_host(llr.ctypes.data, out.ctypes.data, met.ctypes.data, n), "p25_12_soft_llr")
+    return out, met
+
+
+def p25_12_soft_llr_list(llr, max_candidates=8):
+    import numpy as np
+
+    llr = np.ascontiguousarray(llr, dtype=np.int16)
+    n = llr.shape[0]
+    cands = (P25Candidate * (8 * n))()
+    cnt = np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_p25_12_soft_llr_list_batch_host(llr.ctypes.data, C.addressof(cands), cnt.ctypes.data, max_candidates, n),
+          "p25_12_soft_llr_list")
+    return cands, cnt
+
+
+def p25_rs_decode(variant: int, data_bits, parity_bits):
+    """data_bits uint8 [n, k*6] corrected in place; returns status[n]."""
+    import numpy as np
+
+    assert data_bits.dtype == np.uint8 and data_bits.flags.c_contiguous
+    parity_bits = np.ascontiguousarray(parity_bits, dtype=np.uint8)
+    n = data_bits.shape[0]
+    st = np.zeros(n, np.uint8)
+    check(lib().dsdneo_b200_p25_rs_decode_batch_host(variant, data_bits.ctypes.data, parity_bits.ctypes.data, st.ctypes.data, n),
+          "p25_rs_decode")
+    return st

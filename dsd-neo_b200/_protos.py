@@ -14,6 +14,19 @@ def bind(L):
     vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
     cd = C.c_double
     protos = {
+        "dsdneo_b200_fec_block_code_len": (ci, [ci]),
+        "dsdneo_b200_fec_block_code_k": (ci, [ci]),
+        "dsdneo_b200_fec_block_decode_batch": (ci, [ci, vp, vp, vp, ci, vp]),
+        "dsdneo_b200_fec_block_decode_batch_host": (ci, [ci, vp, vp, vp, ci]),
+        "dsdneo_b200_fec_golay_24_12_encode_batch": (ci, [vp, vp, ci, vp]),
+        "dsdneo_b200_bptc_196x96_batch": (ci, [vp, ci, vp, vp, vp, ci, vp]),
+        "dsdneo_b200_bptc_196x96_batch_host": (ci, [vp, ci, vp, vp, vp, ci]),
+        "dsdneo_b200_p25_12_soft_llr_batch": (ci, [vp, vp, vp, ci, vp]),
+        "dsdneo_b200_p25_12_soft_llr_batch_host": (ci, [vp, vp, vp, ci]),
+        "dsdneo_b200_p25_12_soft_llr_list_batch": (ci, [vp, vp, vp, ci, ci, vp]),
+        "dsdneo_b200_p25_12_soft_llr_list_batch_host": (ci, [vp, vp, vp, ci, ci]),
+        "dsdneo_b200_p25_rs_decode_batch": (ci, [ci, vp, vp, vp, ci, vp]),
+        "dsdneo_b200_p25_rs_decode_batch_host": (ci, [ci, vp, vp, vp, ci]),
         "dsdneo_b200_timing_enable": (ci, [ci]),
         "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
         "dsdneo_b200_frontend_create": (vp, [vp]),

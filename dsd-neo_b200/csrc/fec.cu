@@ -1,0 +1,1036 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+/*
+ * Batched FEC leaves of the hot path (K13, K16, K17, K19): one thread per codeword / burst / trellis block.
+ * Pure integer work, bit-exact with the reference (statuses, tie-breaks and in-place correction semantics
+ * included).  Reference entry points replaced, each by a `*_batch` twin over n independent items:
+ *   Hamming_{7_4,12_8,13_9,15_11,16_11_4}_decode, Golay_{20_8,24_12}_decode, QR_16_7_6_decode,
+ *   Golay_24_12_encode                                  src/fec/fec.c:145-824 (API include/dsd-neo/fec/block_codes.h:29-56)
+ *   BPTCDeInterleaveDMRData + BPTC_196x96_Extract_Data   src/fec/bptc.c:51-59,136-149
+ *   p25_12_soft_llr, p25_12_soft_llr_list                src/protocol/p25/p25_12.c:204-283,144-202
+ *   check_and_fix_redsolomon_36_20_17, check_and_fix_reedsolomon_24_12_13 / _24_16_9
+ *                                                        src/protocol/p25/phase1/p25p1_check_hdu.cpp:38-45, p25p1_check_ldu.cpp:37-62
+ *                                                        (engine include/dsd-neo/fec/ReedSolomon.hpp:61-816)
+ * Data layouts at the C-ABI are the reference's own (one bit per byte, hex words as 6 bytes MSB first, int16 LLRs);
+ * words are packed to registers on load.  These kernels move tens of bytes per item and are latency-bound; they
+ * are sized one thread per item so that thousands of channels' frames fill the machine.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "../host/fec_tables.h"
+#include "common.cuh"
+
+using namespace dsdneo;
+
+namespace {
+
+dsdneo_fec_tables* g_d_tables = nullptr; /* device copy */
+
+int
+ensure_tables() {
+    if (g_d_tables) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    dsdneo_fec_tables* h = (dsdneo_fec_tables*)malloc(sizeof(dsdneo_fec_tables));
+    if (!h) {
+        set_error("fec: out of host memory");
+        return DSDNEO_B200_ENOMEM;
+    }
+    dsdneo_fec_build_tables(h);
+    dsdneo_fec_tables* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, sizeof(dsdneo_fec_tables));
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(d, h, sizeof(dsdneo_fec_tables), cudaMemcpyHostToDevice);
+    }
+    free(h);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_fail(e, "fec tables upload", __FILE__, __LINE__);
+    }
+    g_d_tables = d;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ block codes */
+
+__device__ __forceinline__ unsigned
+pack_bits(const uint8_t* b, int n) {
+    unsigned w = 0;
+    for (int j = 0; j < n; j++) {
+        w |= (unsigned)(b[j] & 1u) << j; /* the reference's mod-2 sums see only the LSB of each byte */
+    }
+    return w;
+}
+
+__global__ void
+hamming_decode_kernel(const dsdneo_fec_tables* __restrict__ T, int code, uint8_t* bits, uint8_t* decoded, uint8_t* ok_out,
+                      int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) {
+        return;
+    }
+    const dsdneo_hamming_table& t = T->ham[code];
+    uint8_t* b = bits + (size_t)i * t.n;
+    const unsigned w = pack_bits(b, t.n);
+    unsigned s = 0;
+    for (int row = 0; row < t.r; row++) {
+        s |= (unsigned)(__popc(w & t.row_mask[row]) & 1) << (t.r - 1 - row);
+    }
+    int ok = 1;
+    if (s) {
+        const unsigned pos = t.pos_of[s];
+        if (pos == 0xFFu) {
+            ok = 0;
+        } else {
+            b[pos] ^= 1; /* in place, upper bits of the byte untouched like the reference */
+        }
+    }
+    ok_out[i] = (uint8_t)ok;
+    if (!ok && t.stop_on_fail) {
+        return; /* the reference breaks out before copying the information bits */
+    }
+    if (decoded && code != DSDNEO_FEC_HAMMING_7_4) {
+        uint8_t* d = decoded + (size_t)i * t.k;
+        for (int j = 0; j < t.k; j++) {
+            d[j] = b[j];
+        }
+    }
+}
+
+__global__ void
+gq_decode_kernel(const dsdneo_fec_tables* __restrict__ T, int which, uint8_t* bits, uint8_t* ok_out, int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) {
+        return;
+    }
+    const dsdneo_gq_table& t = T->gq[which];
+    uint8_t* b = bits + (size_t)i * t.n;
+    const unsigned w = pack_bits(b, t.n);
+    unsigned s = 0;
+    for (int row = 0; row < t.r; row++) {
+        s |= (unsigned)(__popc(w & t.row_mask[row]) & 1) << (t.r - 1 - row);
+    }
+    int ok = 1;
+    if (s) {
+        int flips = 0;
+        for (; flips < t.maxw; flips++) {
+            const unsigned pos = t.corr[s][flips];
+            if (pos == 0xFFu) {
+                break;
+            }
+            b[pos] ^= 1;
+        }
+        ok = flips != 0;
+        if (which == 0 && flips > 2) {
+            ok = 0; /* Golay_20_8_decode: three flips are applied but reported as failure (fec.c:578-584) */
+        }
+    }
+    ok_out[i] = (uint8_t)ok;
+}
+
+__global__ void
+golay_24_12_encode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* data, uint8_t* out, int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) {
+        return;
+    }
+    const dsdneo_gq_table& t = T->gq[1];
+    const unsigned w = pack_bits(data + (size_t)i * 12, 12);
+    uint8_t* o = out + (size_t)i * 24;
+    for (int j = 0; j < 12; j++) {
+        o[j] = (uint8_t)((w >> j) & 1u);
+    }
+    for (int row = 0; row < 12; row++) {
+        o[12 + row] = (uint8_t)(__popc(w & t.row_mask[row] & 0xFFFu) & 1);
+    }
+}
+
+/* ------------------------------------------------------------------ BPTC(196,96) */
+
+__device__ __forceinline__ int
+ham_fix_word(const dsdneo_hamming_table& t, unsigned& w) {
+    unsigned s = 0;
+    for (int row = 0; row < t.r; row++) {
+        s |= (unsigned)(__popc(w & t.row_mask[row]) & 1) << (t.r - 1 - row);
+    }
+    if (!s) {
+        return 1;
+    }
+    const unsigned pos = t.pos_of[s];
+    if (pos == 0xFFu) {
+        return 0;
+    }
+    w ^= 1u << pos;
+    return 1;
+}
+
+__global__ void
+bptc_196x96_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in, int interleaved, uint8_t* out96, uint8_t* r3,
+                   uint32_t* errs_out, int n_bursts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bursts) {
+        return;
+    }
+    const uint8_t* src = in + (size_t)i * 196;
+    unsigned rows[13]; /* bit j of rows[r] = matrix[r][j] */
+    for (int r = 0; r < 13; r++) {
+        rows[r] = 0;
+    }
+    /* matrix[r][j] = deinterleaved[1 + 15 r + j]; deinterleaved[(13 t) mod 196] = received[t] (bptc.c:51-59) */
+    for (int t = 0; t < 196; t++) {
+        const int pos = interleaved ? (13 * t) % 196 : t;
+        if (pos == 0) {
+            continue; /* reserved bit R(3) */
+        }
+        const int r = (pos - 1) / 15, j = (pos - 1) - 15 * r;
+        rows[r] |= (unsigned)(src[t] & 1u) << j;
+    }
+    const dsdneo_hamming_table& h15 = T->ham[DSDNEO_FEC_HAMMING_15_11];
+    const dsdneo_hamming_table& h13 = T->ham[DSDNEO_FEC_HAMMING_13_9];
+    unsigned errs = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        unsigned e = 0;
+        for (int r = 0; r < 9; r++) {
+            unsigned w = rows[r];
+            (void)ham_fix_word(h15, w); /* perfect code: always "correctable"; only bits 0..10 are written back */
+            rows[r] = (rows[r] & ~0x7FFu) | (w & 0x7FFu);
+        }
+        unsigned last = 0;
+        int have_last = 0;
+        for (int j = 0; j < 15; j++) {
+            unsigned c = 0;
+            for (int r = 0; r < 13; r++) {
+                c |= ((rows[r] >> j) & 1u) << r;
+            }
+            unsigned put;
+            if (ham_fix_word(h13, c)) {
+                last = c & 0x1FFu;
+                have_last = 1;
+                put = last;
+            } else {
+                e++;
+                if (!have_last) {
+                    continue; /* reference reads an uninitialised buffer here; column left unchanged (documented) */
+                }
+                put = last; /* stale output buffer of the callee: previous good column (bptc.c:100-113) */
+            }
+            for (int r = 0; r < 9; r++) {
+                rows[r] = (rows[r] & ~(1u << j)) | (((put >> r) & 1u) << j);
+            }
+        }
+        if (pass == 1) {
+            errs = e;
+        }
+    }
+    uint8_t* o = out96 + (size_t)i * 96;
+    int k = 0;
+    for (int j = 3; j < 11; j++) {
+        o[k++] = (uint8_t)((rows[0] >> j) & 1u);
+    }
+    for (int r = 1; r < 9; r++) {
+        for (int j = 0; j < 11; j++) {
+            o[k++] = (uint8_t)((rows[r] >> j) & 1u);
+        }
+    }
+    if (r3) {
+        r3[3 * i + 0] = (uint8_t)((rows[0] >> 2) & 1u);
+        r3[3 * i + 1] = (uint8_t)((rows[0] >> 1) & 1u);
+        r3[3 * i + 2] = (uint8_t)(rows[0] & 1u);
+    }
+    errs_out[i] = errs;
+}
+
+/* ------------------------------------------------------------------ P25 half-rate trellis */
+
+/* transition nibble table p25_12.c:19, entry i in nibble i */
+__device__ __forceinline__ unsigned
+p25_dtm(int prev, int next) {
+    return (unsigned)((0x86B54A793D0EF1C2ull >> (4 * ((prev << 2) | next))) & 0xFull);
+}
+
+/* de-interleaved position of received dibit i (trellis34.c:8-13): groups of dibit pairs with stride 8 */
+__device__ __forceinline__ int
+p25_deinterleave_pos(int i) {
+    /* group sizes in dibits: 26, 24, 24, 24 */
+    int g, o;
+    if (i < 26) {
+        g = 0, o = i;
+    } else {
+        g = 1 + (i - 26) / 24;
+        o = (i - 26) % 24;
+    }
+    return 2 * g + 8 * (o >> 1) + (o & 1);
+}
+
+__device__ __forceinline__ uint32_t
+llr_cost(int llr, unsigned bit) {
+    return bit ? (llr < 0 ? (uint32_t)(-llr) : 0u) : (llr > 0 ? (uint32_t)llr : 0u);
+}
+
+__device__ __forceinline__ void
+p25_load_deinterleaved(const int16_t* llr196, int16_t* dei) {
+    for (int i = 0; i < 98; i++) {
+        const int p = p25_deinterleave_pos(i);
+        dei[2 * p] = llr196[2 * i];
+        dei[2 * p + 1] = llr196[2 * i + 1];
+    }
+}
+
+__device__ __forceinline__ uint32_t
+p25_branch(const int16_t* dei, int sym, int pv, int nx) {
+    const unsigned e = p25_dtm(pv, nx);
+    const int16_t* l = dei + 4 * sym;
+    return llr_cost(l[0], (e >> 3) & 1u) + llr_cost(l[1], (e >> 2) & 1u) + llr_cost(l[2], (e >> 1) & 1u) + llr_cost(l[3], e & 1u);
+}
+
+__global__ void
+p25_12_soft_llr_kernel(const int16_t* llr, uint8_t* out12, int32_t* metric_out, int n_blocks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) {
+        return;
+    }
+    int16_t dei[196];
+    p25_load_deinterleaved(llr + (size_t)i * 196, dei);
+    uint32_t pm0 = 0, pm1 = 256, pm2 = 256, pm3 = 256; /* path metrics stay in registers */
+    uint8_t bp[49];                                    /* 4 x 2-bit predecessors per step */
+    for (int s = 0; s < 49; s++) {
+        uint32_t cm[4];
+        unsigned packed = 0;
+#pragma unroll
+        for (int nx = 0; nx < 4; nx++) {
+            uint32_t best = pm0 + p25_branch(dei, s, 0, nx);
+            unsigned bprev = 0;
+            uint32_t m = pm1 + p25_branch(dei, s, 1, nx);
+            if (m < best) { /* strict <: the lowest predecessor wins ties (p25_12.c:244-247) */
+                best = m, bprev = 1;
+            }
+            m = pm2 + p25_branch(dei, s, 2, nx);
+            if (m < best) {
+                best = m, bprev = 2;
+            }
+            m = pm3 + p25_branch(dei, s, 3, nx);
+            if (m < best) {
+                best = m, bprev = 3;
+            }
+            cm[nx] = best;
+            packed |= bprev << (2 * nx);
+        }
+        bp[s] = (uint8_t)packed;
+        pm0 = cm[0], pm1 = cm[1], pm2 = cm[2], pm3 = cm[3];
+    }
+    uint32_t bf = pm0;
+    int st = 0;
+    if (pm1 < bf) {
+        bf = pm1, st = 1;
+    }
+    if (pm2 < bf) {
+        bf = pm2, st = 2;
+    }
+    if (pm3 < bf) {
+        bf = pm3, st = 3;
+    }
+    uint8_t td[49];
+    for (int s = 49; s-- > 0;) {
+        td[s] = (uint8_t)st;
+        st = (bp[s] >> (2 * st)) & 3;
+    }
+    uint8_t* o = out12 + (size_t)i * 12;
+    for (int b = 0; b < 12; b++) {
+        o[b] = (uint8_t)((td[4 * b] << 6) | (td[4 * b + 1] << 4) | (td[4 * b + 2] << 2) | td[4 * b + 3]);
+    }
+    metric_out[i] = (int32_t)(bf >> 8);
+}
+
+constexpr int kListK = 8;
+
+__global__ void __launch_bounds__(64)
+p25_12_soft_llr_list_kernel(const int16_t* llr, dsdneo_b200_p25_12_candidate* cands, int32_t* count_out, int max_candidates,
+                            int n_blocks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) {
+        return;
+    }
+    int16_t dei[196];
+    p25_load_deinterleaved(llr + (size_t)i * 196, dei);
+    uint32_t ma[4][kListK], mb[4][kListK];
+    uint8_t bp[49][4][kListK];
+    for (int s = 0; s < 4; s++) {
+        for (int r = 0; r < kListK; r++) {
+            ma[s][r] = 0xFFFFFFFFu;
+        }
+        ma[s][0] = s == 0 ? 0u : 256u;
+    }
+    uint32_t (*pm)[kListK] = ma;
+    uint32_t (*cm)[kListK] = mb;
+    for (int sym = 0; sym < 49; sym++) {
+        for (int s = 0; s < 4; s++) {
+            for (int r = 0; r < kListK; r++) {
+                cm[s][r] = 0xFFFFFFFFu;
+                bp[sym][s][r] = 0;
+            }
+        }
+        for (int pv = 0; pv < 4; pv++) {
+            for (int nx = 0; nx < 4; nx++) {
+                const uint32_t cost = p25_branch(dei, sym, pv, nx);
+                for (int rk = 0; rk < kListK; rk++) {
+                    if (pm[pv][rk] == 0xFFFFFFFFu) {
+                        continue;
+                    }
+                    const uint32_t m = pm[pv][rk] + cost;
+                    int at = -1;
+                    for (int q = 0; q < kListK; q++) {
+                        if (m < cm[nx][q]) { /* stable insertion, strict < (p25_12.c:31-52) */
+                            at = q;
+                            break;
+                        }
+                    }
+                    if (at < 0) {
+                        continue;
+                    }
+                    for (int q = kListK - 1; q > at; q--) {
+                        cm[nx][q] = cm[nx][q - 1];
+                        bp[sym][nx][q] = bp[sym][nx][q - 1];
+                    }
+                    cm[nx][at] = m;
+                    bp[sym][nx][at] = (uint8_t)((pv << 3) | rk);
+                }
+            }
+        }
+        uint32_t (*t)[kListK] = pm;
+        pm = cm;
+        cm = t;
+    }
+    if (max_candidates > kListK) {
+        max_candidates = kListK;
+    }
+    dsdneo_b200_p25_12_candidate* out = cands + (size_t)i * kListK;
+    int count = 0;
+    for (int s = 0; s < 4; s++) {
+        for (int rk = 0; rk < kListK; rk++) {
+            if (pm[s][rk] == 0xFFFFFFFFu) {
+                continue;
+            }
+            uint8_t bytes[12];
+            for (int b = 0; b < 12; b++) {
+                bytes[b] = 0;
+            }
+            int st = s, r = rk;
+            for (int sym = 49; sym-- > 0;) {
+                if (sym < 48) {
+                    bytes[sym >> 2] |= (uint8_t)(st << (6 - 2 * (sym & 3)));
+                }
+                const uint8_t p = bp[sym][st][r];
+                st = (p >> 3) & 3;
+                r = p & 7;
+            }
+            bool dup = false;
+            for (int c = 0; c < count && !dup; c++) {
+                bool same = true;
+                for (int b = 0; b < 12; b++) {
+                    same = same && (out[c].bytes[b] == bytes[b]);
+                }
+                dup = same;
+            }
+            if (dup) {
+                continue;
+            }
+            const uint32_t metric = pm[s][rk];
+            int at = count;
+            for (int c = 0; c < count; c++) {
+                if (metric < out[c].metric) {
+                    at = c;
+                    break;
+                }
+            }
+            if (count < max_candidates) {
+                count++;
+            } else if (at >= max_candidates) {
+                continue;
+            }
+            for (int c = count - 1; c > at; c--) {
+                out[c] = out[c - 1];
+            }
+            for (int b = 0; b < 12; b++) {
+                out[at].bytes[b] = bytes[b];
+            }
+            out[at].metric = metric;
+        }
+    }
+    count_out[i] = count;
+}
+
+/* ------------------------------------------------------------------ RS(63,k) over GF(64) */
+
+struct RsShape {
+    int n_total, n_data, tt;
+};
+
+/* Berlekamp iteration in Rockliff's index-form bookkeeping, as ReedSolomon_63<TT>::decode
+ * (ReedSolomon.hpp:353-582,738-771): same failure conditions (degree > t, root count != degree), corrections may land
+ * in the zero padding of the shortened code exactly like the reference. */
+__global__ void __launch_bounds__(64)
+p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_t* data_bits, const uint8_t* parity_bits,
+                     uint8_t* status, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    constexpr int NN = 63;
+    const signed char* EXP = T->gf_exp;
+    const signed char* LOG = T->gf_log;
+    const int n_par = sh.n_total - sh.n_data, tt = sh.tt, n2t = 2 * sh.tt;
+    uint8_t* dbits = data_bits + (size_t)w * sh.n_data * 6;
+    const uint8_t* pbits = parity_bits + (size_t)w * n_par * 6;
+    signed char recd[NN]; /* index form, -1 = zero */
+    int used = sh.n_total;
+    for (int i = 0; i < NN; i++) {
+        int v = 0;
+        if (i < n_par) {
+            for (int b = 0; b < 6; b++) {
+                v = (v << 1) | (pbits[6 * i + b] != 0);
+            }
+        } else if (i < used) {
+            for (int b = 0; b < 6; b++) {
+                v = (v << 1) | (dbits[6 * (i - n_par) + b] != 0);
+            }
+        }
+        recd[i] = LOG[v];
+    }
+    int s[18];
+    int syn_err = 0;
+    s[0] = 0;
+    for (int i = 1; i <= n2t; i++) {
+        int acc = 0;
+        for (int j = 0; j < used; j++) {
+            if (recd[j] != -1) {
+                acc ^= EXP[(recd[j] + i * j) % NN];
+            }
+        }
+        syn_err |= acc;
+        s[i] = LOG[acc];
+    }
+    /* hex_to_bin of the (possibly corrected) data symbols is a no-op for 0/1 inputs; inputs with other non-zero
+     * byte values are normalised to 1 like the reference's bin_to_hex/hex_to_bin round trip */
+    int out_sym[36];
+    for (int i = 0; i < sh.n_data; i++) {
+        out_sym[i] = recd[n_par + i] == -1 ? 0 : EXP[recd[n_par + i]];
+    }
+    int rc = 0;
+    if (syn_err) {
+        int elp[18][16], d[18], l[18], u_lu[18];
+        d[0] = 0;
+        d[1] = s[1];
+        elp[0][0] = 0;
+        elp[1][0] = 1;
+        for (int i = 1; i < n2t; i++) {
+            elp[0][i] = -1;
+            elp[1][i] = 0;
+        }
+        l[0] = l[1] = 0;
+        u_lu[0] = -1;
+        u_lu[1] = 0;
+        int u = 0;
+        do {
+            u++;
+            if (d[u] == -1) {
+                l[u + 1] = l[u];
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] = elp[u][i];
+                    elp[u][i] = LOG[elp[u][i]];
+                }
+            } else {
+                int q = u - 1;
+                while (q > 0 && d[q] == -1) {
+                    q--;
+                }
+                if (q > 0) {
+                    for (int j = q - 1; j > 0; j--) {
+                        if (d[j] != -1 && u_lu[q] < u_lu[j]) {
+                            q = j;
+                        }
+                    }
+                }
+                l[u + 1] = (l[u] > l[q] + u - q) ? l[u] : l[q] + u - q;
+                for (int i = 0; i < n2t; i++) {
+                    elp[u + 1][i] = 0;
+                }
+                for (int i = 0; i <= l[q]; i++) {
+                    if (elp[q][i] != -1) {
+                        elp[u + 1][i + u - q] = EXP[(d[u] + NN - d[q] + elp[q][i]) % NN];
+                    }
+                }
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] ^= elp[u][i];
+                    elp[u][i] = LOG[elp[u][i]];
+                }
+            }
+            u_lu[u + 1] = u - l[u + 1];
+            if (u < n2t) {
+                int dd = (s[u + 1] != -1) ? EXP[s[u + 1]] : 0;
+                for (int i = 1; i <= l[u + 1]; i++) {
+                    if (s[u + 1 - i] != -1 && elp[u + 1][i] != 0) {
+                        dd ^= EXP[(s[u + 1 - i] + LOG[elp[u + 1][i]]) % NN];
+                    }
+                }
+                d[u + 1] = LOG[dd];
+            }
+        } while (u < n2t && l[u + 1] <= tt);
+        u++;
+        if (l[u] > tt) {
+            rc = 1;
+        } else {
+            const int deg = l[u];
+            int lp[9], reg[9], root[8], loc[8], count = 0;
+            for (int i = 0; i <= deg; i++) {
+                lp[i] = LOG[elp[u][i]];
+                reg[i] = lp[i];
+            }
+            for (int i = 1; i <= NN; i++) {
+                int q = 1;
+                for (int j = 1; j <= deg; j++) {
+                    if (reg[j] != -1) {
+                        reg[j] = (reg[j] + j) % NN;
+                        q ^= EXP[reg[j]];
+                    }
+                }
+                if (!q) {
+                    if (count < 8) {
+                        root[count] = i;
+                        loc[count] = NN - i;
+                    }
+                    count++;
+                }
+            }
+            if (count != deg) {
+                rc = 1;
+            } else {
+                int z[9];
+                for (int i = 1; i <= deg; i++) {
+                    int zi = 0;
+                    if (s[i] != -1) {
+                        zi ^= EXP[s[i]];
+                    }
+                    if (lp[i] != -1) {
+                        zi ^= EXP[lp[i]];
+                    }
+                    for (int j = 1; j < i; j++) {
+                        if (s[j] != -1 && lp[i - j] != -1) {
+                            zi ^= EXP[(lp[i - j] + s[j]) % NN];
+                        }
+                    }
+                    z[i] = LOG[zi];
+                }
+                for (int i = 0; i < deg; i++) {
+                    int num = 1;
+                    for (int j = 1; j <= deg; j++) {
+                        if (z[j] != -1) {
+                            num ^= EXP[(z[j] + j * root[i]) % NN];
+                        }
+                    }
+                    if (num != 0) {
+                        int den = 0;
+                        for (int j = 0; j < deg; j++) {
+                            if (j != i) {
+                                den += LOG[1 ^ EXP[(loc[j] + root[i]) % NN]];
+                            }
+                        }
+                        den %= NN;
+                        const int e = EXP[(LOG[num] - den + NN) % NN];
+                        const int pos = loc[i] - n_par;
+                        if (pos >= 0 && pos < sh.n_data) {
+                            out_sym[pos] ^= e;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    for (int i = 0; i < sh.n_data; i++) {
+        for (int b = 0; b < 6; b++) {
+            dbits[6 * i + b] = (uint8_t)((out_sym[i] >> (5 - b)) & 1);
+        }
+    }
+    status[w] = (uint8_t)rc;
+}
+
+/* RAII device scratch for the *_host entry points */
+struct DevBuf {
+    void* p = nullptr;
+    cudaError_t err = cudaSuccess;
+    explicit DevBuf(size_t bytes) { err = cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() { cudaFree(p); }
+    template <typename U> U* as() { return static_cast<U*>(p); }
+};
+
+inline int
+grid_for(int n, int block) {
+    return (n + block - 1) / block;
+}
+
+int
+block_code_shape(int code, int* n, int* k) {
+    static const int N[8] = {7, 12, 13, 15, 16, 20, 24, 16};
+    static const int K[8] = {4, 8, 9, 11, 11, 8, 12, 7};
+    if (code < 0 || code >= DSDNEO_FEC_BLOCK_CODE_COUNT) {
+        set_error("fec: unknown block code %d", code);
+        return DSDNEO_B200_EINVAL;
+    }
+    *n = N[code];
+    *k = K[code];
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int
+dsdneo_b200_fec_block_code_len(int code) {
+    int n, k;
+    int rc = block_code_shape(code, &n, &k);
+    return rc ? rc : n;
+}
+
+int
+dsdneo_b200_fec_block_code_k(int code) {
+    int n, k;
+    int rc = block_code_shape(code, &n, &k);
+    return rc ? rc : k;
+}
+
+int
+dsdneo_b200_fec_block_decode_batch(int code, uint8_t* d_bits, uint8_t* d_decoded, uint8_t* d_ok, int n_words, void* stream) {
+    int n, k;
+    int rc = block_code_shape(code, &n, &k);
+    if (rc) {
+        return rc;
+    }
+    if (!d_bits || !d_ok || n_words < 0) {
+        set_error("fec_block_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    if (code <= DSDNEO_FEC_HAMMING_16_11_4) {
+        KernelTimer kt("hamming_decode_kernel", s);
+        hamming_decode_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(g_d_tables, code, d_bits, d_decoded, d_ok, n_words);
+    } else {
+        KernelTimer kt("gq_decode_kernel", s);
+        gq_decode_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(g_d_tables, code - DSDNEO_FEC_GOLAY_20_8, d_bits, d_ok, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_fec_block_decode_batch_host(int code, uint8_t* h_bits, uint8_t* h_decoded, uint8_t* h_ok, int n_words) {
+    int n, k;
+    int rc = block_code_shape(code, &n, &k);
+    if (rc) {
+        return rc;
+    }
+    if (!h_bits || !h_ok || n_words < 0) {
+        set_error("fec_block_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    DevBuf bits((size_t)n_words * n), dec((size_t)n_words * k), ok((size_t)n_words);
+    DSDNEO_CUDA(bits.err);
+    DSDNEO_CUDA(dec.err);
+    DSDNEO_CUDA(ok.err);
+    DSDNEO_CUDA(cudaMemcpy(bits.p, h_bits, (size_t)n_words * n, cudaMemcpyHostToDevice));
+    if (h_decoded) {
+        DSDNEO_CUDA(cudaMemcpy(dec.p, h_decoded, (size_t)n_words * k, cudaMemcpyHostToDevice)); /* untouched-on-failure semantics */
+    }
+    rc = dsdneo_b200_fec_block_decode_batch(code, bits.as<uint8_t>(), h_decoded ? dec.as<uint8_t>() : NULL, ok.as<uint8_t>(),
+                                            n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_bits, bits.p, (size_t)n_words * n, cudaMemcpyDeviceToHost));
+    if (h_decoded) {
+        DSDNEO_CUDA(cudaMemcpy(h_decoded, dec.p, (size_t)n_words * k, cudaMemcpyDeviceToHost));
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_ok, ok.p, (size_t)n_words, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_fec_golay_24_12_encode_batch(const uint8_t* d_data, uint8_t* d_out, int n_words, void* stream) {
+    if (!d_data || !d_out || n_words < 0) {
+        set_error("golay_24_12_encode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("golay_24_12_encode_kernel", s);
+        golay_24_12_encode_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(g_d_tables, d_data, d_out, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_bptc_196x96_batch(const uint8_t* d_in, int interleaved, uint8_t* d_out96, uint8_t* d_r3, uint32_t* d_errs,
+                              int n_bursts, void* stream) {
+    if (!d_in || !d_out96 || !d_errs || n_bursts < 0) {
+        set_error("bptc_196x96_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_bursts == 0) {
+        return 0;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("bptc_196x96_kernel", s);
+        bptc_196x96_kernel<<<grid_for(n_bursts, 64), 64, 0, s>>>(g_d_tables, d_in, interleaved, d_out96, d_r3, d_errs, n_bursts);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_bptc_196x96_batch_host(const uint8_t* h_in, int interleaved, uint8_t* h_out96, uint8_t* h_r3, uint32_t* h_errs,
+                                   int n_bursts) {
+    if (!h_in || !h_out96 || !h_errs || n_bursts < 0) {
+        set_error("bptc_196x96_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_bursts == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_bursts;
+    DevBuf in(n * 196), out(n * 96), r3(n * 3), er(n * 4);
+    DSDNEO_CUDA(in.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(r3.err);
+    DSDNEO_CUDA(er.err);
+    DSDNEO_CUDA(cudaMemcpy(in.p, h_in, n * 196, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_bptc_196x96_batch(in.as<uint8_t>(), interleaved, out.as<uint8_t>(), r3.as<uint8_t>(), er.as<uint32_t>(),
+                                       n_bursts, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out96, out.p, n * 96, cudaMemcpyDeviceToHost));
+    if (h_r3) {
+        DSDNEO_CUDA(cudaMemcpy(h_r3, r3.p, n * 3, cudaMemcpyDeviceToHost));
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_errs, er.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_p25_12_soft_llr_batch(const int16_t* d_llr196, uint8_t* d_out12, int32_t* d_metric, int n_blocks, void* stream) {
+    if (!d_llr196 || !d_out12 || !d_metric || n_blocks < 0) {
+        set_error("p25_12_soft_llr_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25_12_soft_llr_kernel", s);
+        p25_12_soft_llr_kernel<<<grid_for(n_blocks, 64), 64, 0, s>>>(d_llr196, d_out12, d_metric, n_blocks);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_12_soft_llr_batch_host(const int16_t* h_llr196, uint8_t* h_out12, int32_t* h_metric, int n_blocks) {
+    if (!h_llr196 || !h_out12 || !h_metric || n_blocks < 0) {
+        set_error("p25_12_soft_llr_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_blocks;
+    DevBuf llr(n * 392), out(n * 12), met(n * 4);
+    DSDNEO_CUDA(llr.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(met.err);
+    DSDNEO_CUDA(cudaMemcpy(llr.p, h_llr196, n * 392, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_p25_12_soft_llr_batch(llr.as<int16_t>(), out.as<uint8_t>(), met.as<int32_t>(), n_blocks, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out12, out.p, n * 12, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_metric, met.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_p25_12_soft_llr_list_batch(const int16_t* d_llr196, dsdneo_b200_p25_12_candidate* d_cands, int32_t* d_count,
+                                       int max_candidates, int n_blocks, void* stream) {
+    if (!d_llr196 || !d_cands || !d_count || max_candidates <= 0 || n_blocks < 0) {
+        set_error("p25_12_soft_llr_list_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25_12_soft_llr_list_kernel", s);
+        p25_12_soft_llr_list_kernel<<<grid_for(n_blocks, 64), 64, 0, s>>>(d_llr196, d_cands, d_count, max_candidates, n_blocks);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_12_soft_llr_list_batch_host(const int16_t* h_llr196, dsdneo_b200_p25_12_candidate* h_cands, int32_t* h_count,
+                                            int max_candidates, int n_blocks) {
+    if (!h_llr196 || !h_cands || !h_count || n_blocks < 0) {
+        set_error("p25_12_soft_llr_list_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_blocks;
+    DevBuf llr(n * 392), cands(n * kListK * sizeof(dsdneo_b200_p25_12_candidate)), cnt(n * 4);
+    DSDNEO_CUDA(llr.err);
+    DSDNEO_CUDA(cands.err);
+    DSDNEO_CUDA(cnt.err);
+    DSDNEO_CUDA(cudaMemcpy(llr.p, h_llr196, n * 392, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemset(cands.p, 0, n * kListK * sizeof(dsdneo_b200_p25_12_candidate)));
+    rc = dsdneo_b200_p25_12_soft_llr_list_batch(llr.as<int16_t>(), cands.as<dsdneo_b200_p25_12_candidate>(), cnt.as<int32_t>(),
+                                                max_candidates, n_blocks, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_cands, cands.p, n * kListK * sizeof(dsdneo_b200_p25_12_candidate), cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_count, cnt.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int
+rs_shape(int variant, RsShape* sh) {
+    switch (variant) {
+        case DSDNEO_P25_RS_36_20_17: *sh = RsShape{36, 20, 8}; return 0;
+        case DSDNEO_P25_RS_24_12_13: *sh = RsShape{24, 12, 6}; return 0;
+        case DSDNEO_P25_RS_24_16_9: *sh = RsShape{24, 16, 4}; return 0;
+        default: set_error("p25_rs_decode: unknown variant %d", variant); return DSDNEO_B200_EINVAL;
+    }
+}
+
+int
+dsdneo_b200_p25_rs_decode_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits, uint8_t* d_status, int n_words,
+                                void* stream) {
+    RsShape sh;
+    int rc = rs_shape(variant, &sh);
+    if (rc) {
+        return rc;
+    }
+    if (!d_data_bits || !d_parity_bits || !d_status || n_words < 0) {
+        set_error("p25_rs_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25_rs_decode_kernel", s);
+        p25_rs_decode_kernel<<<grid_for(n_words, 64), 64, 0, s>>>(g_d_tables, sh, d_data_bits, d_parity_bits, d_status, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
+                                     int n_words) {
+    RsShape sh;
+    int rc = rs_shape(variant, &sh);
+    if (rc) {
+        return rc;
+    }
+    if (!h_data_bits || !h_parity_bits || !h_status || n_words < 0) {
+        set_error("p25_rs_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words, db = (size_t)sh.n_data * 6, pb = (size_t)(sh.n_total - sh.n_data) * 6;
+    DevBuf data(n * db), par(n * pb), st(n);
+    DSDNEO_CUDA(data.err);
+    DSDNEO_CUDA(par.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(cudaMemcpy(data.p, h_data_bits, n * db, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(par.p, h_parity_bits, n * pb, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_p25_rs_decode_batch(variant, data.as<uint8_t>(), par.as<uint8_t>(), st.as<uint8_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_data_bits, data.p, n * db, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+} /* extern "C" */

@@ -247,6 +247,84 @@ int dsdneo_b200_frontend_join(dsdneo_b200_frontend* fe, void* stream);
 int dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
                                       float* h_result, size_t result_pitch);
 
+/* ---- batched FEC leaves (K13, K16, K17, K19) ------------------------------------------------------ */
+
+/*
+ * Layouts are the reference's own: one bit per unsigned char (only the LSB is significant on input; in-place
+ * correction flips the LSB and leaves the other bits of the byte alone, as src/fec/fec.c does), P25 hex words as six
+ * bytes MSB first, LLRs as int16 (positive = bit 1).  Every item is decoded independently -- the reference's
+ * nbCodewords argument is always 1 at its call sites.  No table initialisation call is
+ * needed (the twin of InitAllFecFunction(), src/fec/fec.c:827, runs on first use).
+ */
+enum {
+    DSDNEO_FEC_HAMMING_7_4 = 0, /* Hamming_7_4_decode      src/fec/fec.c:145-168 */
+    DSDNEO_FEC_HAMMING_12_8,    /* Hamming_12_8_decode     src/fec/fec.c:188-230 (keeps going after a bad word) */
+    DSDNEO_FEC_HAMMING_13_9,    /* Hamming_13_9_decode     src/fec/fec.c:253-302 */
+    DSDNEO_FEC_HAMMING_15_11,   /* Hamming_15_11_decode    src/fec/fec.c:327-376 */
+    DSDNEO_FEC_HAMMING_16_11_4, /* Hamming_16_11_4_decode  src/fec/fec.c:402-450 */
+    DSDNEO_FEC_GOLAY_20_8,      /* Golay_20_8_decode       src/fec/fec.c:543-587 (3 flips are applied but reported false) */
+    DSDNEO_FEC_GOLAY_24_12,     /* Golay_24_12_decode      src/fec/fec.c:682-733 */
+    DSDNEO_FEC_QR_16_7_6,       /* QR_16_7_6_decode        src/fec/fec.c:787-824 */
+    DSDNEO_FEC_BLOCK_CODE_COUNT
+};
+int dsdneo_b200_fec_block_code_len(int code); /* n: bytes per codeword */
+int dsdneo_b200_fec_block_code_k(int code);   /* k: information bits */
+/**
+ * @param d_bits    [n_words][n] codewords, corrected in place
+ * @param d_decoded [n_words][k] information bits (Hamming codes other than 7_4; may be NULL).  Not written for a word
+ *                  the reference reports uncorrectable before its memcpy (13_9, 15_11, 16_11_4).
+ * @param d_ok      [n_words] the reference's bool return (1 = no error or corrected)
+ */
+int dsdneo_b200_fec_block_decode_batch(int code, uint8_t* d_bits, uint8_t* d_decoded, uint8_t* d_ok, int n_words, void* stream);
+int dsdneo_b200_fec_block_decode_batch_host(int code, uint8_t* h_bits, uint8_t* h_decoded, uint8_t* h_ok, int n_words);
+/** Golay_24_12_encode (src/fec/fec.c:670-680): [n][12] data bits -> [n][24] codeword bits. */
+int dsdneo_b200_fec_golay_24_12_encode_batch(const uint8_t* d_data, uint8_t* d_out, int n_words, void* stream);
+
+/**
+ * BPTCDeInterleaveDMRData + BPTC_196x96_Extract_Data (src/fec/bptc.c:51-59,136-149; include/dsd-neo/fec/bptc.h).
+ * @param d_in        [n][196] burst bits; interleaved != 0: as received (de-interleave fused), else already de-interleaved
+ * @param d_out96     [n][96] payload bits;  d_r3 [n][3] reserved bits R(2..0) (may be NULL)
+ * @param d_errs      [n] number of uncorrectable Hamming lines in the second pass (the reference's return value)
+ * The reference copies a stale callee buffer when a Hamming(13,9) column is uncorrectable: the previous good column
+ * of the same pass is reproduced; when there is none (first column) the reference reads uninitialised stack and this
+ * library leaves the column unchanged.
+ */
+int dsdneo_b200_bptc_196x96_batch(const uint8_t* d_in, int interleaved, uint8_t* d_out96, uint8_t* d_r3, uint32_t* d_errs,
+                                  int n_bursts, void* stream);
+int dsdneo_b200_bptc_196x96_batch_host(const uint8_t* h_in, int interleaved, uint8_t* h_out96, uint8_t* h_r3, uint32_t* h_errs,
+                                       int n_bursts);
+
+/** p25_12_candidate_t (include/dsd-neo/protocol/p25/p25_12.h:13-17), same layout. */
+typedef struct dsdneo_b200_p25_12_candidate {
+    uint8_t bytes[12];
+    uint32_t metric;
+} dsdneo_b200_p25_12_candidate;
+/** p25_12_soft_llr (src/protocol/p25/p25_12.c:204-283): [n][196] LLRs -> [n][12] bytes, [n] return values (metric >> 8). */
+int dsdneo_b200_p25_12_soft_llr_batch(const int16_t* d_llr196, uint8_t* d_out12, int32_t* d_metric, int n_blocks, void* stream);
+int dsdneo_b200_p25_12_soft_llr_batch_host(const int16_t* h_llr196, uint8_t* h_out12, int32_t* h_metric, int n_blocks);
+/** p25_12_soft_llr_list (src/protocol/p25/p25_12.c:144-202): d_cands is [n][8] (P25_12_MAX_CANDIDATES slots per block,
+ *  the first d_count[i] valid, sorted by metric); max_candidates is clamped to 8 like the reference. */
+int dsdneo_b200_p25_12_soft_llr_list_batch(const int16_t* d_llr196, dsdneo_b200_p25_12_candidate* d_cands, int32_t* d_count,
+                                           int max_candidates, int n_blocks, void* stream);
+int dsdneo_b200_p25_12_soft_llr_list_batch_host(const int16_t* h_llr196, dsdneo_b200_p25_12_candidate* h_cands,
+                                                int32_t* h_count, int max_candidates, int n_blocks);
+
+enum {
+    DSDNEO_P25_RS_36_20_17 = 0, /* check_and_fix_redsolomon_36_20_17   phase1/p25p1_check_hdu.cpp:38-45 */
+    DSDNEO_P25_RS_24_12_13 = 1, /* check_and_fix_reedsolomon_24_12_13  phase1/p25p1_check_ldu.cpp:37-44 */
+    DSDNEO_P25_RS_24_16_9 = 2,  /* check_and_fix_reedsolomon_24_16_9   phase1/p25p1_check_ldu.cpp:55-62 */
+};
+/**
+ * RS(63,k) over GF(64) shortened to the P25 sizes (engine include/dsd-neo/fec/ReedSolomon.hpp:61-816).
+ * @param d_data_bits   [n][k][6]  data hex words, corrected in place
+ * @param d_parity_bits [n][n-k][6]
+ * @param d_status      [n] 0 = ok / corrected, 1 = irrecoverable (data left as received)
+ */
+int dsdneo_b200_p25_rs_decode_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits, uint8_t* d_status,
+                                    int n_words, void* stream);
+int dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
+                                         int n_words);
+
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);

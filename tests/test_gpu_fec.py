@@ -1,0 +1,149 @@
+"""GPU parity tests for the batched FEC kernels: bit-exact against the oracle (pinned to the reference by
+tests/test_oracle_fec.py) on exhaustive / seeded random batches, through the host-buffer C-ABI."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+import _harness as H
+from test_oracle_fec import HAM, bptc_kat_bits, _rs_words
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("code", [0, 1, 2, 3, 4])
+def test_hamming_exhaustive(gpu, code):
+    O = H.oracle_fec()
+    n, k, _ = HAM[code]
+    words = np.arange(1 << n, dtype=np.uint32)
+    bits = ((words[:, None] >> (n - 1 - np.arange(n))[None, :]) & 1).astype(np.uint8)
+    bits[::7] |= 0xA4  # dirty upper bits must be ignored on input and preserved in place (fec.c sums raw bytes mod 2)
+    want_bits = bits.copy()
+    want_dec = np.full((bits.shape[0], k), 9, np.uint8)
+    want_ok = np.zeros(bits.shape[0], np.uint8)
+    for i in range(bits.shape[0]):
+        want_ok[i] = O.oracle_hamming_decode(code, H._ptr(want_bits[i], H.u8p), None if code == 0 else H._ptr(want_dec[i], H.u8p))
+    got_bits = bits.copy()
+    got_dec = np.full((bits.shape[0], k), 9, np.uint8)
+    got_ok = gpu.fec_block_decode(code, got_bits, None if code == 0 else got_dec)
+    assert np.array_equal(got_ok, want_ok)
+    assert np.array_equal(got_bits, want_bits)
+    assert np.array_equal(got_dec, want_dec)
+
+
+@pytest.mark.parametrize("code,n,fn", [(5, 20, "oracle_golay_20_8_decode"), (6, 24, "oracle_golay_24_12_decode"),
+                                        (7, 16, "oracle_qr_16_7_6_decode")])
+def test_golay_qr_all_light_patterns(gpu, code, n, fn):
+    O = H.oracle_fec()
+    pats = [p for w in range(0, 5) for p in itertools.combinations(range(n), w)]
+    bits = np.zeros((len(pats), n), np.uint8)
+    for i, p in enumerate(pats):
+        bits[i, list(p)] = 1
+    rng = np.random.default_rng(code)
+    rnd = rng.integers(0, 2, (5000, n)).astype(np.uint8)
+    bits = np.concatenate([bits, rnd])
+    want = bits.copy()
+    want_ok = np.array([getattr(O, fn)(H._ptr(want[i], H.u8p)) for i in range(want.shape[0])], np.uint8)
+    got = bits.copy()
+    got_ok = gpu.fec_block_decode(code, got)
+    assert np.array_equal(got_ok != 0, want_ok != 0)
+    assert np.array_equal(got, want)
+
+
+def test_golay_encode(gpu):
+    import torch
+
+    O = H.oracle_fec()
+    data = ((np.arange(4096)[:, None] >> (11 - np.arange(12))[None, :]) & 1).astype(np.uint8)
+    d = torch.from_numpy(data).cuda()
+    out = torch.empty((4096, 24), dtype=torch.uint8, device="cuda")
+    gpu.check(gpu.lib().dsdneo_b200_fec_golay_24_12_encode_batch(d.data_ptr(), out.data_ptr(), 4096, None))
+    got = out.cpu().numpy()
+    for i in range(0, 4096, 37):
+        want = np.zeros(24, np.uint8)
+        O.oracle_golay_24_12_encode(H._ptr(data[i], H.u8p), H._ptr(want, H.u8p))
+        assert np.array_equal(got[i], want)
+
+
+def test_bptc_batch(gpu):
+    O = H.oracle_fec()
+    rng = np.random.default_rng(61)
+    cw = bptc_kat_bits()
+    n = 6000
+    bursts = np.tile(cw, (n, 1))
+    for i in range(n):
+        if i % 3 == 0:
+            bursts[i] = rng.integers(0, 2, 196)
+        else:
+            bursts[i, rng.choice(196, size=int(rng.integers(0, 14)), replace=False)] ^= 1
+    want_out, want_r, want_e, undef = np.zeros((n, 96), np.uint8), np.zeros((n, 3), np.uint8), np.zeros(n, np.uint32), np.zeros(n, bool)
+    for i in range(n):
+        u = C.c_int(0)
+        want_e[i] = O.oracle_bptc_196x96_extract(H._ptr(bursts[i], H.u8p), H._ptr(want_out[i], H.u8p), H._ptr(want_r[i], H.u8p), C.byref(u))
+        undef[i] = bool(u.value)
+    out, r3, errs = gpu.bptc_196x96(bursts, interleaved=False)
+    assert np.array_equal(errs, want_e) and np.array_equal(out, want_out) and np.array_equal(r3, want_r)  # incl. the documented choice
+    # fused de-interleave: transmit order in, same answers out
+    inter = np.zeros_like(bursts)
+    inter[:, (np.arange(196) * 181) % 196] = bursts
+    out2, r32, errs2 = gpu.bptc_196x96(inter, interleaved=True)
+    assert np.array_equal(errs2, want_e) and np.array_equal(out2, want_out) and np.array_equal(r32, want_r)
+    assert (~undef).sum() > 3000
+
+
+def test_p25_12_batch(gpu):
+    O = H.oracle_fec()
+    rng = np.random.default_rng(71)
+    i16p, u32p = C.POINTER(C.c_int16), C.POINTER(C.c_uint32)
+    n = 512
+    llrs = np.zeros((n, 196), np.int16)
+    for t in range(n):
+        dib, tx = H.p25_trellis_encode(rng)
+        llrs[t] = H.dibits_to_llr(tx, 200, rng, [0.0, 60.0, 150.0, 260.0][t % 4])
+        if t % 10 == 9:
+            llrs[t] = rng.integers(-300, 300, 196)
+        if t % 25 == 0:
+            llrs[t] = 0
+        if t % 50 == 1:
+            llrs[t] = rng.integers(-32768, 32768, 196)  # full-range LLRs incl. -32768
+    out, met = gpu.p25_12_soft_llr(llrs)
+    for t in range(n):
+        w = np.zeros(12, np.uint8)
+        m = O.oracle_p25_12_soft_llr(llrs[t].ctypes.data_as(i16p), H._ptr(w, H.u8p))
+        assert m == met[t] and np.array_equal(out[t], w), t
+    for maxc in (8, 3):
+        cands, cnt = gpu.p25_12_soft_llr_list(llrs, maxc)
+        for t in range(n):
+            cb, cm = np.zeros((8, 12), np.uint8), np.zeros(8, np.uint32)
+            na = O.oracle_p25_12_soft_llr_list(llrs[t].ctypes.data_as(i16p), H._ptr(cb, H.u8p), cm.ctypes.data_as(u32p), maxc)
+            assert na == cnt[t], (t, na, cnt[t])
+            for c in range(na):
+                assert bytes(cb[c]) == bytes(cands[8 * t + c].bytes) and int(cm[c]) == cands[8 * t + c].metric, (t, c)
+
+
+@pytest.mark.parametrize("variant,n,k", [(0, 36, 20), (1, 24, 12), (2, 24, 16)])
+def test_p25_rs_batch(gpu, variant, n, k):
+    O = H.oracle_fec()
+    tt = (n - k) // 2
+    rng = np.random.default_rng(81 + variant)
+    nw = 3000
+    data_bits = np.zeros((nw, k * 6), np.uint8)
+    par_bits = np.zeros((nw, 2 * tt * 6), np.uint8)
+    for t in range(nw):
+        data = np.zeros(63 - 2 * tt, np.int32)
+        data[:k] = rng.integers(0, 64, k)
+        cw = np.zeros(63, np.int32)
+        O.oracle_rs63_encode(tt, data.ctypes.data_as(H.i32p), cw.ctypes.data_as(H.i32p))
+        nerr = int(rng.integers(0, tt + 5))
+        pos = rng.choice(n, size=nerr, replace=False)
+        cw[pos] ^= rng.integers(1, 64, pos.size).astype(np.int32)
+        par_bits[t] = _rs_words(cw[:2 * tt])
+        data_bits[t] = _rs_words(cw[2 * tt:2 * tt + k])
+    want = data_bits.copy()
+    want_st = np.array([O.oracle_p25_rs_decode(n, k, H._ptr(want[t], H.u8p), H._ptr(par_bits[t], H.u8p)) for t in range(nw)], np.uint8)
+    got = data_bits.copy()
+    st = gpu.p25_rs_decode(variant, got, par_bits)
+    assert np.array_equal(st, want_st)
+    assert np.array_equal(got, want)
+    assert (want_st == 0).sum() > nw // 3 and (want_st == 1).sum() > 50
