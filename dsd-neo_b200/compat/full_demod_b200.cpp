@@ -1,0 +1,103 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/*
+ * Drop-in `full_demod()` for dsd-neo (compiled INSIDE the dsd-neo tree as C++14, like src/dsp/demod_pipeline.cpp,
+ * against its own headers).
+ *
+ * Same signature and caller contract as src/dsp/demod_pipeline.cpp:1330-1350: the demod thread sets d->lowpassed /
+ * d->lp_len (interleaved I/Q floats) and reads d->result[0..d->result_len).  Covered configuration: output_kind ==
+ * DSD_DEMOD_OUTPUT_FSK_DISCRIMINATOR with cqpsk off, no half-band passes, IQ DC block / IQ balance off (the defaults of
+ * every 4FSK mode, src/io/radio/rtl_demod_config.cpp:189-228).  Anything else is handed back to the reference's own
+ * implementation, which the integrator renames to full_demod_cpu (one line in demod_pipeline.cpp).
+ *
+ * One demod_state == one bank of 1 channel: correctness shim, not the fast path (the fast path is
+ * dsdneo_b200_frontend_process* over hundreds of channels).
+ */
+#include <dsd-neo/dsp/demod_pipeline.h>
+#include <dsd-neo/dsp/demod_state.h>
+#include <string.h>
+
+#include "dsdneo_b200.h"
+
+extern "C" void full_demod_cpu(struct demod_state* d); /* the reference body, renamed */
+
+#define B200_MAX_STATES 64
+static struct {
+    const struct demod_state* key;
+    dsdneo_b200_demod_bank* bank;
+    int rate_out, profile, lpf_enable;
+    float squelch;
+} g_banks[B200_MAX_STATES];
+
+static dsdneo_b200_demod_bank*
+bank_for(const struct demod_state* d) {
+    int free_slot = -1;
+    for (int i = 0; i < B200_MAX_STATES; i++) {
+        if (g_banks[i].key == d) {
+            if (g_banks[i].rate_out == d->rate_out && g_banks[i].profile == d->channel_lpf_profile
+                && g_banks[i].lpf_enable == d->channel_lpf_enable && g_banks[i].squelch == d->channel_squelch_level) {
+                return g_banks[i].bank;
+            }
+            dsdneo_b200_demod_bank_destroy(g_banks[i].bank); /* plan changed: same as channel_lpf_ensure_plan re-design */
+            g_banks[i].key = NULL;
+            free_slot = i;
+            break;
+        }
+        if (!g_banks[i].key && free_slot < 0) {
+            free_slot = i;
+        }
+    }
+    if (free_slot < 0) {
+        return NULL;
+    }
+    int profile = d->channel_lpf_profile;
+    float squelch = d->channel_squelch_level;
+    dsdneo_b200_demod_bank_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.n_channels = 1;
+    cfg.rate_out_hz = d->rate_out;
+    cfg.channel_lpf_enable = d->channel_lpf_enable;
+    cfg.channel_lpf_profile = &profile;
+    cfg.channel_squelch_level = &squelch;
+    cfg.fir_arith = DSDNEO_FIR_ARITH_FMA;
+    dsdneo_b200_demod_bank* b = dsdneo_b200_demod_bank_create(&cfg);
+    if (!b) {
+        return NULL;
+    }
+    g_banks[free_slot].key = d;
+    g_banks[free_slot].bank = b;
+    g_banks[free_slot].rate_out = d->rate_out;
+    g_banks[free_slot].profile = d->channel_lpf_profile;
+    g_banks[free_slot].lpf_enable = d->channel_lpf_enable;
+    g_banks[free_slot].squelch = d->channel_squelch_level;
+    return b;
+}
+
+extern "C" void
+full_demod(struct demod_state* d) {
+    const int covered = d && d->output_kind == DSD_DEMOD_OUTPUT_FSK_DISCRIMINATOR && !d->cqpsk_enable
+                        && d->downsample_passes <= 0 && !d->iq_dc_block_enable && !d->iqbal_enable && d->lowpassed
+                        && d->lp_len >= 2 && d->lp_len <= MAXIMUM_BUF_LENGTH;
+    dsdneo_b200_demod_bank* bank = covered ? bank_for(d) : NULL;
+    if (!bank) {
+        full_demod_cpu(d);
+        return;
+    }
+    const int pairs = d->lp_len >> 1;
+    if (dsdneo_b200_full_demod_batch_host(bank, d->lowpassed, (size_t)pairs, pairs, 1, d->result, (size_t)pairs) != 0) {
+        /* No silent fallback on a GPU failure: surface it the way the reference surfaces a dead stream. */
+        d->result_len = 0;
+        return;
+    }
+    d->result_len = pairs;
+    dsdneo_b200_demod_chan_state st;
+    if (dsdneo_b200_demod_bank_get_state(bank, 0, &st) == 0) {
+        d->channel_pwr = st.channel_pwr;
+        d->channel_squelched = st.channel_squelched;
+        d->squelch_gate_open = !st.channel_squelched;
+        d->fsk_modem_state.prev_i = st.prev_i;
+        d->fsk_modem_state.prev_q = st.prev_q;
+        d->fsk_modem_state.have_prev = st.have_prev;
+        d->fsk_modem_state.dc_est = st.dc_est;
+        d->fsk_modem_state.discriminator_peak_est = st.discriminator_peak_est;
+    }
+}

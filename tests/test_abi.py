@@ -1,0 +1,73 @@
+"""CPU tests of the boundary: the shared library loads without a GPU, exports every symbol the header declares,
+fails loudly (no CPU fallback) when no device is present, and the reference-side glue compiles against the
+reference's own headers."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import _harness as H
+
+ROOT = H.ROOT
+HEADER = os.path.join(ROOT, "include", "dsdneo_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dsdneo_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(b200):
+    out = subprocess.run(["nm", "-D", "--defined-only", b200.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (dsdneo_b200_[a-z0-9_]+)", out))
+    declared = _declared_symbols()
+    assert len(declared) > 40
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+
+
+def test_library_has_no_oracle_or_torch_dependency(b200):
+    ldd = subprocess.run(["ldd", b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "oracle" not in ldd and "libdsdneo_ref" not in ldd
+    sym = subprocess.run(["nm", "-D", b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in sym
+
+
+def test_no_cpu_fallback_without_device(b200):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = b200.lib()
+    assert L.dsdneo_b200_init(0) == b200.ENODEV
+    assert b"no CPU fallback" in L.dsdneo_b200_last_error()
+    with pytest.raises(b200.B200Error):
+        b200.DemodBank(4)
+    import numpy as np
+    bits = np.zeros((2, 24), np.uint8)
+    with pytest.raises(b200.B200Error):
+        b200.fec_block_decode(b200.FEC_GOLAY_24_12, bits)
+
+
+def test_host_side_lpf_design_matches_oracle(b200):
+    import numpy as np
+
+    for rate in (48000, 24000, 50000):
+        for prof in range(6):
+            assert np.array_equal(b200.channel_lpf_design(rate, prof).view(np.uint32), H.oracle_lpf_taps(rate, prof).view(np.uint32))
+    with pytest.raises(b200.B200Error):
+        b200.channel_lpf_design(96000, 4)  # 269 taps > 144: the reference would use its 63-tap fallback; unsupported here
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="reference headers not present")
+def test_reference_side_glue_compiles_against_reference_headers():
+    R = "/root/reference"
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + R + "/include", "-I" + R + "/src"]
+    subprocess.run(["g++", "-std=c++14", "-fsyntax-only"] + inc + [os.path.join(ROOT, "dsd-neo_b200/compat/full_demod_b200.cpp")], check=True)
+    subprocess.run(["gcc", "-std=c11", "-fsyntax-only"] + inc + [os.path.join(ROOT, "dsd-neo_b200/compat/fec_b200.c")], check=True)
+    # signatures of the shim must agree with the reference's own prototypes
+    chk = ("#include <stdbool.h>\n#include <stdint.h>\n#include <dsd-neo/fec/block_codes.h>\n#include <dsd-neo/fec/bptc.h>\n"
+           "#include <dsd-neo/protocol/p25/p25_12.h>\n#include \"%s\"\n" % os.path.join(ROOT, "dsd-neo_b200/compat/fec_b200.c"))
+    subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-x", "c", "-"] + inc, input=chk, text=True, check=True)
