@@ -246,7 +246,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_blocks = 8
+    per_step_blocks = 24
     for _ in range(max(1, args.warmup)):
         cpu_reference_run(blocks_per_thread=1)
     t0 = time.perf_counter()
