@@ -85,6 +85,43 @@ int oracle_rs63_decode(int tt, const int* in63, int* out63);
 void oracle_rs63_encode(int tt, const int* data, int* cw63);
 int oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits);
 
+/* ------------------------------- sample side (oracle_symbol.c) --------------------------------- */
+
+#define ORACLE_SYM_MAX_TAPS 256
+typedef struct oracle_sym_chan {
+    /* configuration */
+    int output_rate_hz, symbol_rate_hz;
+    int use_filter;      /* matched filter selected by lastsynctype (dsd_symbol.c:301-337) and opts->use_cosine_filter */
+    int window_l;        /* left window edge: 2 (P25, NXDN96...) or 1 (YSF / DMR), dsd_symbol.c:197-211 */
+    int track_minmax;    /* use_symbol() threshold tracking: rf_mod 0 and lastsynctype is P25p1 (dsd_dibit.c:264) */
+    int negative;        /* is_four_level_neg_synctype(synctype) */
+    int ssize, msize;
+    int taps_len;
+    float taps[ORACLE_SYM_MAX_TAPS];
+    /* carried state */
+    float fir_hist[ORACLE_SYM_MAX_TAPS];
+    int fir_head;
+    int sps_num, sps_den, sps_accum;
+    int sps, center_idx, jitter;
+    float lastsample;
+    float min, max, center, umid, lmid, minref, maxref;
+    float sbuf[128];
+    int sidx;
+    float minbuf[1024], maxbuf[1024];
+    int midx, sum_window;
+    double minbuf_sum, maxbuf_sum;
+    long symbolcnt;
+} oracle_sym_chan;
+
+void oracle_sym_init(oracle_sym_chan* c, int output_rate_hz, int symbol_rate_hz, int use_filter, int window_l, int track_minmax,
+                     int negative, const float* taps, int taps_len, int ssize, int msize);
+float oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), void* ctx);
+int oracle_sym_get_dibit(oracle_sym_chan* c, float (*next)(void*), void* ctx, float* symbol_out, uint8_t* rel_out, int16_t llr_out[2]);
+long oracle_sym_run_symbols(oracle_sym_chan* c, int have_sync, const float* samples, long n, long reserve, float* out, long max_out,
+                            long* consumed);
+long oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, long reserve, uint8_t* dibits, uint8_t* rel,
+                           int16_t* llr2, float* symbols, long max_out, long* consumed);
+
 void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n);
 
 #ifdef __cplusplus

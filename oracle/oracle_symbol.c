@@ -1,0 +1,433 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement of the sample side of the hot path for the configuration the
+ * batched path covers: RTL FSK-discriminator input (output kind 1), 4-level C4FM family (rf_mod == 0), no SNR
+ * hooks installed (so the SNR weight is the reference's sentinel path, src/core/frames/dsd_dibit.c:504-546).
+ *
+ *   getSymbol            src/dsp/dsd_symbol.c:1853-1880 with :197-225 (window), :301-337 (matched filter choice),
+ *                        :347-358 (sync clip), :360-397 (jitter), :423-460 (accumulate), :489-516 (timing nudge),
+ *                        :1306-1387 (slicer reset, fractional samples-per-symbol)
+ *   apply_sps_fir        src/dsp/dsd_filters.c:172-201
+ *   use_symbol           src/core/frames/dsd_dibit.c:243-299 (+ :195-241 extrema, core/state.h:1388-1454 window sums)
+ *   digitize + soft      src/core/frames/dsd_dibit.c:455-721, 963-1041
+ *   getDibitSoft         src/core/frames/dsd_dibit.c:1043-1089
+ *
+ * Pinned against the compiled reference by tests/test_oracle_symbol.py (bit-exact symbols, dibits, LLRs).
+ */
+#include <math.h>
+#include <string.h>
+
+#include "oracle.h"
+
+void
+oracle_sym_init(oracle_sym_chan* c, int output_rate_hz, int symbol_rate_hz, int use_filter, int window_l, int track_minmax,
+                int negative, const float* taps, int taps_len, int ssize, int msize) {
+    memset(c, 0, sizeof(*c));
+    c->output_rate_hz = output_rate_hz;
+    c->symbol_rate_hz = symbol_rate_hz;
+    c->use_filter = use_filter && taps && taps_len > 0;
+    c->window_l = window_l;
+    c->track_minmax = track_minmax;
+    c->negative = negative;
+    c->ssize = ssize;
+    c->msize = msize;
+    c->taps_len = c->use_filter ? taps_len : 0;
+    if (c->use_filter) {
+        memcpy(c->taps, taps, (size_t)taps_len * sizeof(float));
+    }
+    c->fir_head = -1;
+    /* initState() values the path reads before the first-call reset (src/core/util/dsd_init.c:519-592) */
+    c->jitter = -1;
+    c->min = -15000.0f;
+    c->max = 15000.0f;
+    c->minref = -12000.0f;
+    c->maxref = 12000.0f;
+    for (int i = 0; i < 1024; i++) {
+        c->minbuf[i] = -15000.0f;
+        c->maxbuf[i] = 15000.0f;
+    }
+    c->sps = 10;
+    c->center_idx = 4;
+}
+
+static void
+reset_slicer(oracle_sym_chan* c) { /* dsd_symbol.c:1306-1326 */
+    c->center = 0.0f;
+    c->min = -30000.0f;
+    c->max = 30000.0f;
+    c->lmid = -20000.0f;
+    c->umid = 20000.0f;
+    c->minref = -24000.0f;
+    c->maxref = 24000.0f;
+    for (int i = 0; i < 1024; i++) {
+        c->minbuf[i] = c->min;
+        c->maxbuf[i] = c->max;
+    }
+    c->midx = 0;
+    c->sum_window = 0;
+}
+
+static int
+next_sps(oracle_sym_chan* c) { /* dsd_symbol.c:1328-1387 */
+    if (c->sps_num != c->output_rate_hz || c->sps_den != c->symbol_rate_hz) {
+        c->sps_num = c->output_rate_hz;
+        c->sps_den = c->symbol_rate_hz;
+        c->sps_accum = 0;
+        c->jitter = -1;
+        reset_slicer(c);
+    }
+    int whole = c->output_rate_hz / c->symbol_rate_hz;
+    int rem = c->output_rate_hz % c->symbol_rate_hz;
+    if (whole < 2) {
+        whole = 2, rem = 0;
+    }
+    if (whole > 64) {
+        whole = 64, rem = 0;
+    }
+    if (rem > 0 && c->sps_den > 0) {
+        int acc = c->sps_accum + rem;
+        if (acc >= c->sps_den) {
+            whole++;
+            acc -= c->sps_den;
+        }
+        c->sps_accum = acc;
+        if (whole > 64) {
+            whole = 64;
+        }
+    }
+    return whole;
+}
+
+static float
+matched_fir(oracle_sym_chan* c, float x) { /* dsd_filters.c:172-201 */
+    if (!c->use_filter) {
+        return x;
+    }
+    int head = c->fir_head + 1;
+    if (head >= c->taps_len) {
+        head = 0;
+    }
+    c->fir_hist[head] = x;
+    c->fir_head = head;
+    float acc = 0.0f;
+    int last = c->taps_len - 1;
+    for (int i = 0; i <= last; i++) {
+        int idx = head - (last - i);
+        if (idx < 0) {
+            idx += c->taps_len;
+        }
+        acc += c->taps[i] * c->fir_hist[idx];
+    }
+    return acc;
+}
+
+/* One getSymbol() call.  `next(ctx)` yields the next discriminator sample. */
+float
+oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), void* ctx) {
+    c->sps = next_sps(c);
+    c->center_idx = (c->sps - 1) / 2;
+    const int l_edge = c->window_l, r_edge = 2;
+    const int span = c->sps < 1 ? 1 : c->sps;
+    if (span <= 1) {
+        c->jitter = -1;
+    }
+    float sum = 0.0f;
+    int count = 0;
+    for (int i = 0; i < span; i++) {
+        /* timing nudge, only at the first sample of an unsynchronised symbol (dsd_symbol.c:498-516, C4FM rule :489-496;
+         * samples-per-symbol 20 uses the NXDN rule :462-468) */
+        if (span > 1 && i == 0 && have_sync == 0 && c->jitter >= 0) {
+            if (c->sps == 20) {
+                if (c->jitter >= 7 && c->jitter <= 10) {
+                    i--;
+                } else if (c->jitter >= 11 && c->jitter <= 14) {
+                    i++;
+                }
+            } else {
+                if (c->jitter > 0 && c->jitter <= c->center_idx) {
+                    i--;
+                } else if (c->jitter > c->center_idx && c->jitter < c->sps) {
+                    i++;
+                }
+            }
+            c->jitter = -1;
+        }
+        float s = next(ctx);
+        s = matched_fir(c, s);
+        if (have_sync == 1) { /* rf_mod == 0 */
+            if (s > c->max) {
+                s = c->max;
+            } else if (s < c->min) {
+                s = c->min;
+            }
+        }
+        /* first zero crossing of the symbol (dsd_symbol.c:360-397, rf_mod == 0 branches) */
+        if (s > c->center) {
+            if (!(s > c->maxref * 1.25f)) {
+                if (c->jitter < 0 && c->lastsample < c->center) {
+                    c->jitter = i;
+                }
+            }
+        } else {
+            if (!(s < c->minref * 1.25f)) {
+                if (c->jitter < 0 && c->lastsample > c->center) {
+                    c->jitter = i;
+                }
+            }
+        }
+        /* window accumulation (dsd_symbol.c:423-460) */
+        if (c->sps == 20 && i >= 7 && i <= 13) {
+            sum += s;
+            count++;
+        }
+        if (c->sps == 5 && i == 2) {
+            sum += s;
+            count++;
+        } else if (!(c->sps == 5 && i == 2)) {
+            if (i >= c->center_idx - l_edge && i <= c->center_idx + r_edge) {
+                sum += s;
+                count++;
+            }
+        }
+        c->lastsample = s;
+    }
+    float symbol = count > 0 ? sum / (float)count : 0.0f;
+    c->symbolcnt++;
+    return symbol;
+}
+
+static void
+extrema_avg2(const float* v, int n, float* omin, float* omax) { /* dsd_dibit.c:195-241 */
+    if (n < 2) {
+        *omin = *omax = 0.0f;
+        return;
+    }
+    float mn1 = v[0], mn2 = v[1];
+    if (mn2 < mn1) {
+        float t = mn1;
+        mn1 = mn2;
+        mn2 = t;
+    }
+    float mx1 = v[0], mx2 = v[1];
+    if (mx2 > mx1) {
+        float t = mx1;
+        mx1 = mx2;
+        mx2 = t;
+    }
+    for (int i = 2; i < n; i++) {
+        float x = v[i];
+        if (x < mn1) {
+            mn2 = mn1;
+            mn1 = x;
+        } else if (x < mn2) {
+            mn2 = x;
+        }
+        if (x > mx1) {
+            mx2 = mx1;
+            mx1 = x;
+        } else if (x > mx2) {
+            mx2 = x;
+        }
+    }
+    *omin = (mn1 + mn2) * 0.5f;
+    *omax = (mx1 + mx2) * 0.5f;
+}
+
+static void
+use_symbol(oracle_sym_chan* c) { /* dsd_dibit.c:243-299 */
+    int cap = c->ssize;
+    if (cap < 0) {
+        cap = 0;
+    }
+    if (cap > 128) {
+        cap = 128;
+    }
+    if (c->track_minmax) {
+        float lmin, lmax;
+        extrema_avg2(c->sbuf, cap, &lmin, &lmax);
+        int window = c->msize < 1 ? 1 : (c->msize > 1024 ? 1024 : c->msize);
+        if (c->sum_window != window) {
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < window; i++) {
+                a += (double)c->minbuf[i];
+                b += (double)c->maxbuf[i];
+            }
+            c->minbuf_sum = a;
+            c->maxbuf_sum = b;
+            c->sum_window = window;
+            if (c->midx < 0 || c->midx >= window) {
+                c->midx = 0;
+            }
+        }
+        int idx = c->midx;
+        if (idx < 0 || idx >= window) {
+            idx = 0;
+        }
+        c->minbuf_sum += (double)lmin - (double)c->minbuf[idx];
+        c->maxbuf_sum += (double)lmax - (double)c->maxbuf[idx];
+        c->minbuf[idx] = lmin;
+        c->maxbuf[idx] = lmax;
+        idx++;
+        c->midx = idx >= window ? 0 : idx;
+        c->min = (float)(c->minbuf_sum / (double)window);
+        c->max = (float)(c->maxbuf_sum / (double)window);
+        c->center = (c->max + c->min) / 2.0f;
+        c->umid = ((c->max - c->center) * 5.0f / 8.0f) + c->center;
+        c->lmid = ((c->min - c->center) * 5.0f / 8.0f) + c->center;
+        c->maxref = c->max * 0.80f;
+        c->minref = c->min * 0.80f;
+    } else {
+        c->maxref = c->max;
+        c->minref = c->min;
+    }
+    if (cap > 0) {
+        if (c->sidx >= cap - 1) {
+            c->sidx = 0;
+        } else {
+            c->sidx++;
+        }
+    }
+}
+
+static int
+clamp255(int v) {
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+static int
+bit_metric(float sym, const float ideal[4], int bit_index) { /* dsd_dibit.c:609-642 */
+    float best0 = 3.4028234663852886e38f, best1 = 3.4028234663852886e38f, min_spacing = 3.4028234663852886e38f;
+    for (int i = 0; i < 4; i++) {
+        float d = (sym - ideal[i]) * (sym - ideal[i]);
+        if (((i >> (1 - bit_index)) & 1) != 0) {
+            if (d < best1) {
+                best1 = d;
+            }
+        } else if (d < best0) {
+            best0 = d;
+        }
+        for (int j = i + 1; j < 4; j++) {
+            float sp = fabsf(ideal[i] - ideal[j]);
+            if (sp > 1e-6f && sp < min_spacing) {
+                min_spacing = sp;
+            }
+        }
+    }
+    if (min_spacing == 3.4028234663852886e38f) {
+        min_spacing = 2.0f;
+    }
+    float scale = 255.0f / (min_spacing * min_spacing);
+    return clamp255((int)lrintf(fabsf(best0 - best1) * scale));
+}
+
+static int
+reliability(const oracle_sym_chan* c, float sym) { /* dsd_dibit.c:455-502 then :504-546 with no SNR hooks */
+    const float eps = 1e-6f;
+    int rel;
+    if (sym > c->umid) {
+        float span = c->max - c->umid;
+        if (span < eps) {
+            span = eps;
+        }
+        rel = (int)lrintf(((sym - c->umid) * 255.0f) / span);
+    } else if (sym > c->center) {
+        float d1 = sym - c->center, d2 = c->umid - sym, span = c->umid - c->center;
+        if (span < eps) {
+            span = eps;
+        }
+        float m = d1 < d2 ? d1 : d2;
+        rel = (int)lrintf((m * 510.0f) / span);
+    } else if (sym >= c->lmid) {
+        float d1 = c->center - sym, d2 = sym - c->lmid, span = c->center - c->lmid;
+        if (span < eps) {
+            span = eps;
+        }
+        float m = d1 < d2 ? d1 : d2;
+        rel = (int)lrintf((m * 510.0f) / span);
+    } else {
+        float span = c->lmid - c->min;
+        if (span < eps) {
+            span = eps;
+        }
+        rel = (int)lrintf(((c->lmid - sym) * 255.0f) / span);
+    }
+    rel = clamp255(rel);
+    /* apply_c4fm_snr_weight with the hook sentinel (-100 dB): w256 = 0 => scale 204/256 */
+    int scaled = (rel * 204) >> 8;
+    return clamp255(scaled);
+}
+
+/* One getDibitSoft() call: returns the dibit (pre-inversion value, as the reference returns), fills symbol/soft. */
+int
+oracle_sym_get_dibit(oracle_sym_chan* c, float (*next)(void*), void* ctx, float* symbol_out, uint8_t* rel_out, int16_t llr_out[2]) {
+    float sym = oracle_sym_get_symbol(c, 1, next, ctx);
+    c->sbuf[c->sidx] = sym;
+    use_symbol(c);
+    /* digitize, four-level (dsd_dibit.c:963-976,1018-1041) */
+    int dibit;
+    if (sym > c->center) {
+        dibit = sym > c->umid ? (c->negative ? 3 : 1) : (c->negative ? 2 : 0);
+    } else {
+        dibit = sym < c->lmid ? (c->negative ? 1 : 3) : (c->negative ? 0 : 2);
+    }
+    /* compute_dibit_soft_metric with build_standard_dibit_ideals (dsd_dibit.c:644-721) */
+    float plus_one = 0.5f * (c->center + c->umid), minus_one = 0.5f * (c->lmid + c->center);
+    float ideal[4];
+    if (c->negative) {
+        ideal[0] = minus_one, ideal[1] = c->min, ideal[2] = plus_one, ideal[3] = c->max;
+    } else {
+        ideal[0] = plus_one, ideal[1] = c->max, ideal[2] = minus_one, ideal[3] = c->min;
+    }
+    int mag0 = bit_metric(sym, ideal, 0), mag1 = bit_metric(sym, ideal, 1);
+    int rel = reliability(c, sym);
+    int min_mag = mag0 < mag1 ? mag0 : mag1;
+    if (min_mag > 0 && rel < min_mag) {
+        mag0 = (mag0 * rel) / min_mag;
+        mag1 = (mag1 * rel) / min_mag;
+    }
+    mag0 = clamp255(mag0);
+    mag1 = clamp255(mag1);
+    llr_out[0] = (int16_t)(((dibit >> 1) & 1) ? mag0 : -mag0);
+    llr_out[1] = (int16_t)((dibit & 1) ? mag1 : -mag1);
+    int a0 = llr_out[0] < 0 ? -llr_out[0] : llr_out[0], a1 = llr_out[1] < 0 ? -llr_out[1] : llr_out[1];
+    *rel_out = (uint8_t)clamp255(a1 < a0 ? a1 : a0);
+    *symbol_out = sym;
+    return dibit;
+}
+
+/* array drivers for ctypes */
+typedef struct {
+    const float* p;
+    long n, pos;
+} arr_src;
+
+static float
+arr_next(void* v) {
+    arr_src* s = (arr_src*)v;
+    return s->pos < s->n ? s->p[s->pos++] : 0.0f;
+}
+
+long
+oracle_sym_run_symbols(oracle_sym_chan* c, int have_sync, const float* samples, long n, long reserve, float* out, long max_out,
+                       long* consumed) {
+    arr_src s = {samples, n, 0};
+    long k = 0;
+    while (k < max_out && (s.n - s.pos) >= reserve) {
+        out[k++] = oracle_sym_get_symbol(c, have_sync, arr_next, &s);
+    }
+    *consumed = s.pos;
+    return k;
+}
+
+long
+oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, long reserve, uint8_t* dibits, uint8_t* rel, int16_t* llr2,
+                      float* symbols, long max_out, long* consumed) {
+    arr_src s = {samples, n, 0};
+    long k = 0;
+    while (k < max_out && (s.n - s.pos) >= reserve) {
+        dibits[k] = (uint8_t)oracle_sym_get_dibit(c, arr_next, &s, &symbols[k], &rel[k], &llr2[2 * k]);
+        k++;
+    }
+    *consumed = s.pos;
+    return k;
+}

@@ -1,0 +1,249 @@
+/* SPDX-License-Identifier: GPL-3.0-or-later */
+/*
+ * TEST INFRASTRUCTURE ONLY.  Drives the UNMODIFIED reference sample side -- getSymbol() (src/dsp/dsd_symbol.c:1853-1880)
+ * and getDibitSoft() (src/core/frames/dsd_dibit.c:1078-1089) -- the way the reference's own tests do
+ * (tests/dsp/test_rtl_symbol_cache_generation.c): memset opts/state, install dsd_rtl_stream_io_hooks.read and
+ * dsd_rtl_stream_metrics_hooks that report an FSK-discriminator stream, then pull symbols.  The reference keeps the
+ * matched-filter state in process globals (src/dsp/dsd_filters.c:325-345), so only ONE handle may be live at a time.
+ */
+#include <dsd-neo/core/dibit.h>
+#include <dsd-neo/core/opts.h>
+#include <dsd-neo/core/state.h>
+#include <dsd-neo/core/synctype_ids.h>
+#include <dsd-neo/dsp/sps_filters.h>
+#include <dsd-neo/dsp/symbol.h>
+#include <dsd-neo/io/rtl_stream_c.h>
+#include <dsd-neo/runtime/rtl_stream_io_hooks.h>
+#include <dsd-neo/runtime/rtl_stream_metrics_hooks.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern int g_oracle_shutdown_requested;
+
+typedef struct ref_sym {
+    dsd_opts* opts;
+    dsd_state* state;
+    const float* src;
+    long n_src, pos;
+    int out_rate, sym_rate, profile;
+} ref_sym;
+
+static ref_sym* g_live = NULL;
+static int g_fake_ctx;
+
+static int
+hook_read(void* ctx, float* out, size_t count, int* out_got) {
+    (void)ctx;
+    ref_sym* h = g_live;
+    long left = h->n_src - h->pos;
+    long n = (long)count < left ? (long)count : left;
+    if (n <= 0) {
+        *out_got = 0;
+        return -1;
+    }
+    memcpy(out, h->src + h->pos, (size_t)n * sizeof(float));
+    h->pos += n;
+    *out_got = (int)n;
+    return 0;
+}
+
+static double
+hook_pwr(const void* ctx) {
+    (void)ctx;
+    return 0.0;
+}
+
+static int hook_output_kind(void) { return RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR; }
+static unsigned int hook_output_rate(void) { return (unsigned int)g_live->out_rate; }
+static uint32_t hook_generation(void) { return 1U; }
+
+static int
+hook_symbol_profile(int* rate, int* levels, int* profile) {
+    if (rate) {
+        *rate = g_live->sym_rate;
+    }
+    if (levels) {
+        *levels = 4;
+    }
+    if (profile) {
+        *profile = g_live->profile;
+    }
+    return 0;
+}
+
+void*
+ref_sym_create(int output_rate_hz, int symbol_rate_hz, int synctype, int lastsynctype, int use_cosine_filter, int ssize,
+               int msize) {
+    ref_sym* h = (ref_sym*)calloc(1, sizeof(*h));
+    h->opts = (dsd_opts*)calloc(1, sizeof(dsd_opts));
+    h->state = (dsd_state*)calloc(1, sizeof(dsd_state));
+    h->out_rate = output_rate_hz;
+    h->sym_rate = symbol_rate_hz;
+    h->profile = RTL_STREAM_CHANNEL_PROFILE_P25_C4FM;
+    dsd_opts* o = h->opts;
+    dsd_state* s = h->state;
+    /* the subset of initOpts()/initState() that the sample side reads (src/core/util/dsd_init.c:169-177,519-592) */
+    o->audio_in_type = AUDIO_IN_RTL;
+    o->ssize = ssize;
+    o->msize = msize;
+    o->use_cosine_filter = use_cosine_filter;
+    s->rf_mod = 0;
+    s->jitter = -1;
+    s->synctype = synctype;
+    s->lastsynctype = lastsynctype;
+    s->min = -15000;
+    s->max = 15000;
+    s->minref = -12000;
+    s->maxref = 12000;
+    for (int i = 0; i < 1024; i++) {
+        s->maxbuf[i] = 15000;
+        s->minbuf[i] = -15000;
+    }
+    s->samplesPerSymbol = 10;
+    s->symbolCenter = 4;
+    s->rtl_ctx = (struct RtlSdrContext*)&g_fake_ctx;
+    s->dibit_buf = (int*)calloc(1000000, sizeof(int));
+    s->dibit_buf_p = s->dibit_buf + 200;
+    s->dmr_payload_buf = (int*)calloc(1000000, sizeof(int));
+    s->dmr_payload_p = s->dmr_payload_buf + 200;
+    s->dmr_soft_buf = (dsd_dibit_soft_t*)calloc(1000000, sizeof(dsd_dibit_soft_t));
+    s->dmr_soft_p = s->dmr_soft_buf + 200;
+    g_live = h;
+    init_rrc_filter_memory();
+    dsd_rtl_stream_io_hooks io;
+    memset(&io, 0, sizeof(io));
+    io.read = hook_read;
+    io.return_pwr = hook_pwr;
+    dsd_rtl_stream_io_hooks_set(io);
+    dsd_rtl_stream_metrics_hooks mh;
+    memset(&mh, 0, sizeof(mh));
+    mh.output_kind = hook_output_kind;
+    mh.output_rate_hz = hook_output_rate;
+    mh.symbol_profile = hook_symbol_profile;
+    mh.stream_generation = hook_generation;
+    dsd_rtl_stream_metrics_hooks_set(&mh);
+    g_oracle_shutdown_requested = 0;
+    return h;
+}
+
+void
+ref_sym_destroy(void* hv) {
+    ref_sym* h = (ref_sym*)hv;
+    if (!h) {
+        return;
+    }
+    if (g_live == h) {
+        g_live = NULL;
+    }
+    free(h->state->dibit_buf);
+    free(h->state->dmr_payload_buf);
+    free(h->state->dmr_soft_buf);
+    free(h->state);
+    free(h->opts);
+    free(h);
+}
+
+void
+ref_sym_feed(void* hv, const float* samples, long n) {
+    ref_sym* h = (ref_sym*)hv;
+    h->src = samples;
+    h->n_src = n;
+    h->pos = 0;
+}
+
+/* samples the reference has not consumed yet = unread source + what sits in its 512-float symbol cache */
+static long
+samples_left(const ref_sym* h) {
+    long cached = h->state->rtl_symbol_cache_len - h->state->rtl_symbol_cache_pos;
+    if (cached < 0) {
+        cached = 0;
+    }
+    return (h->n_src - h->pos) + cached;
+}
+
+void
+ref_sym_set_sync(void* hv, int synctype, int lastsynctype) {
+    ref_sym* h = (ref_sym*)hv;
+    h->state->synctype = synctype;
+    h->state->lastsynctype = lastsynctype;
+}
+
+/* getSymbol(opts, state, have_sync) until fewer than `reserve` samples remain.  Returns symbols produced. */
+long
+ref_sym_get_symbols(void* hv, int have_sync, long max_symbols, long reserve, float* out) {
+    ref_sym* h = (ref_sym*)hv;
+    g_live = h;
+    long n = 0;
+    while (n < max_symbols && samples_left(h) >= reserve) {
+        out[n++] = getSymbol(h->opts, h->state, have_sync);
+        if (g_oracle_shutdown_requested) {
+            return -1;
+        }
+    }
+    return n;
+}
+
+/* getDibitSoft() loop (have_sync = 1 inside the reference).  soft5: {reliability, llr0 lo, llr0 hi, llr1 lo, llr1 hi}. */
+long
+ref_sym_get_dibits(void* hv, long max_symbols, long reserve, uint8_t* dibits, uint8_t* reliab, int16_t* llr2, float* symbols) {
+    ref_sym* h = (ref_sym*)hv;
+    g_live = h;
+    long n = 0;
+    while (n < max_symbols && samples_left(h) >= reserve) {
+        int sidx_before = h->state->sidx;
+        dsd_dibit_soft_t soft;
+        int d = getDibitSoft(h->opts, h->state, &soft);
+        if (g_oracle_shutdown_requested) {
+            return -1;
+        }
+        dibits[n] = (uint8_t)d;
+        reliab[n] = soft.reliability;
+        llr2[2 * n] = soft.llr[0];
+        llr2[2 * n + 1] = soft.llr[1];
+        symbols[n] = h->state->sbuf[sidx_before]; /* get_dibit_and_analog_signal stores the symbol at sbuf[sidx] first */
+        n++;
+    }
+    return n;
+}
+
+/* {min, max, center, umid, lmid, minref, maxref, lastsample} + {samplesPerSymbol, symbolCenter, jitter, sidx, midx} */
+void
+ref_sym_get_state(void* hv, float* f8, int* i5) {
+    const dsd_state* s = ((ref_sym*)hv)->state;
+    f8[0] = s->min, f8[1] = s->max, f8[2] = s->center, f8[3] = s->umid, f8[4] = s->lmid, f8[5] = s->minref, f8[6] = s->maxref;
+    f8[7] = s->lastsample;
+    i5[0] = s->samplesPerSymbol, i5[1] = s->symbolCenter, i5[2] = s->jitter, i5[3] = s->sidx, i5[4] = s->midx;
+}
+
+long
+ref_sym_consumed(void* hv) {
+    ref_sym* h = (ref_sym*)hv;
+    return h->n_src - samples_left(h);
+}
+
+/* Normalised taps of one of the reference's matched filters at `sps`, read out as an impulse response
+ * (apply_sps_fir, src/dsp/dsd_filters.c:172-201).  which: 0 p25, 1 dmr, 2 nxdn, 3 dpmr, 4 m17.  Returns the tap count. */
+int
+ref_sps_fir_taps(int which, int sps, float* taps_out, int cap) {
+    float (*fn)(float, int) = which == 0 ? p25_filter : which == 1 ? dmr_filter : which == 2 ? nxdn_filter : which == 3 ? dpmr_filter : m17_filter;
+    init_rrc_filter_memory();
+    float resp[2048];
+    int last_nz = -1;
+    for (int n = 0; n < 2048; n++) {
+        resp[n] = fn(n == 0 ? 1.0f : 0.0f, sps);
+        if (resp[n] != 0.0f) {
+            last_nz = n;
+        }
+    }
+    init_rrc_filter_memory();
+    int len = last_nz + 1;
+    /* output n of the impulse response = taps[len-1-n] (newest sample meets the LAST tap) */
+    if (len > cap) {
+        return -len;
+    }
+    for (int n = 0; n < len; n++) {
+        taps_out[len - 1 - n] = resp[n];
+    }
+    return len;
+}

@@ -347,3 +347,100 @@ def dibits_to_llr(tx98, mag=200, rng=None, noise=0.0):
     if rng is not None and noise > 0:
         llr = llr + rng.standard_normal(llr.size) * noise
     return np.clip(np.rint(llr), -32768, 32767).astype(np.int16)
+
+
+# --------------------------------------------------------------------------- sample side
+
+class OracleSymChan(C.Structure):
+    _fields_ = [
+        ("output_rate_hz", C.c_int), ("symbol_rate_hz", C.c_int), ("use_filter", C.c_int), ("window_l", C.c_int),
+        ("track_minmax", C.c_int), ("negative", C.c_int), ("ssize", C.c_int), ("msize", C.c_int), ("taps_len", C.c_int),
+        ("taps", C.c_float * 256), ("fir_hist", C.c_float * 256), ("fir_head", C.c_int),
+        ("sps_num", C.c_int), ("sps_den", C.c_int), ("sps_accum", C.c_int),
+        ("sps", C.c_int), ("center_idx", C.c_int), ("jitter", C.c_int), ("lastsample", C.c_float),
+        ("min", C.c_float), ("max", C.c_float), ("center", C.c_float), ("umid", C.c_float), ("lmid", C.c_float),
+        ("minref", C.c_float), ("maxref", C.c_float), ("sbuf", C.c_float * 128), ("sidx", C.c_int),
+        ("minbuf", C.c_float * 1024), ("maxbuf", C.c_float * 1024), ("midx", C.c_int), ("sum_window", C.c_int),
+        ("minbuf_sum", C.c_double), ("maxbuf_sum", C.c_double), ("symbolcnt", C.c_long),
+    ]
+
+
+# reference sync-type ids used by the tests (include/dsd-neo/core/synctype_ids.h:30-31,68,123)
+SYNC_NONE, SYNC_P25P1_POS, SYNC_P25P1_NEG, SYNC_DMR_BS_DATA_POS = -1, 0, 1, 10
+# which of the reference's matched filters a sync class selects (dsd_symbol.c:301-337) and its window / tracking
+SYNC_CLASS = {
+    SYNC_NONE: dict(filter=None, window_l=2, track=0, negative=0),
+    SYNC_P25P1_POS: dict(filter=0, window_l=2, track=1, negative=0),
+    SYNC_P25P1_NEG: dict(filter=0, window_l=2, track=1, negative=1),
+    SYNC_DMR_BS_DATA_POS: dict(filter=1, window_l=1, track=0, negative=0),
+}
+
+
+def oracle_sym():
+    L = oracle()
+    if "sym" not in _fec_bound:
+        i16p = C.POINTER(C.c_int16)
+        lp = C.POINTER(C.c_long)
+        L.oracle_sym_init.argtypes = [C.POINTER(OracleSymChan), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int,
+                                      C.c_int, C.c_int]
+        L.oracle_sym_run_symbols.restype = C.c_long
+        L.oracle_sym_run_symbols.argtypes = [C.POINTER(OracleSymChan), C.c_int, f32p, C.c_long, C.c_long, f32p, C.c_long, lp]
+        L.oracle_sym_run_dibits.restype = C.c_long
+        L.oracle_sym_run_dibits.argtypes = [C.POINTER(OracleSymChan), f32p, C.c_long, C.c_long, u8p, u8p, i16p, f32p, C.c_long, lp]
+        _fec_bound["sym"] = True
+    return L
+
+
+def ref_sym(variant="par"):
+    L = ref(variant)
+    if L is None:
+        return None
+    key = "s" + variant
+    if key not in _fec_bound:
+        i16p = C.POINTER(C.c_int16)
+        L.ref_sym_create.restype = C.c_void_p
+        L.ref_sym_create.argtypes = [C.c_int] * 7
+        L.ref_sym_destroy.argtypes = [C.c_void_p]
+        L.ref_sym_feed.argtypes = [C.c_void_p, f32p, C.c_long]
+        L.ref_sym_set_sync.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_sym_get_symbols.restype = C.c_long
+        L.ref_sym_get_symbols.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_long, f32p]
+        L.ref_sym_get_dibits.restype = C.c_long
+        L.ref_sym_get_dibits.argtypes = [C.c_void_p, C.c_long, C.c_long, u8p, u8p, i16p, f32p]
+        L.ref_sym_get_state.argtypes = [C.c_void_p, f32p, i32p]
+        L.ref_sym_consumed.restype = C.c_long
+        L.ref_sym_consumed.argtypes = [C.c_void_p]
+        L.ref_sps_fir_taps.argtypes = [C.c_int, C.c_int, f32p, C.c_int]
+        _fec_bound[key] = True
+    return L
+
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def sps_fir_taps(which, sps):
+    """Normalised matched-filter taps the reference uses for filter `which` at `sps` (0 p25, 1 dmr, ...).
+    From the compiled reference when present, else from the committed golden fixture (tests/golden/make_golden.py)."""
+    R = ref_sym()
+    if R is not None:
+        buf = np.zeros(1024, np.float32)
+        n = R.ref_sps_fir_taps(which, sps, _ptr(buf), 1024)
+        assert n > 0
+        return buf[:n].copy()
+    z = np.load(os.path.join(GOLDEN_DIR, "sps_fir_taps.npz"))
+    return z["f%d_sps%d" % (which, sps)]
+
+
+def synth_disc(rng, n_symbols, sps=10, level=9000.0, noise=0.0, drift=0.0, dibits=None):
+    """Discriminator-like sample stream (what full_demod emits): 4-level, Hann-smoothed transitions, +-3*level peaks."""
+    if dibits is None:
+        dibits = rng.integers(0, 4, n_symbols)
+    x = np.repeat(LEVELS[np.asarray(dibits)] * level, sps)
+    k = np.hanning(sps + 2)[1:-1]
+    k /= k.sum()
+    x = np.convolve(x, k, mode="same")
+    if drift:
+        x = x + drift * np.sin(np.arange(x.size) * 2e-4)
+    if noise:
+        x = x + rng.standard_normal(x.size) * noise
+    return x.astype(np.float32), np.asarray(dibits)

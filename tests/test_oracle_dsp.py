@@ -164,3 +164,14 @@ def test_atan2f_matches_libm(tmp_path):
     bad = np.zeros(2, np.float32)
     nbad = L.a2_check(20_000_000, 88172645463325252, H._ptr(bad))
     assert nbad == 0, (nbad, bad)
+
+
+def test_oracle_full_demod_matches_committed_golden_vectors():
+    """Reference full_demod() outputs captured by tests/golden/make_golden.py (both FIR arithmetic variants)."""
+    import os
+
+    g = np.load(os.path.join(H.GOLDEN_DIR, "full_demod.npz"))
+    bp, nb = int(g["block_pairs"]), int(g["n_blocks"])
+    assert H.bits_equal(H.oracle_full_demod(g["iq"], bp, nb, fir_fma=0), g["ref_par"])
+    if "ref_avx2" in g:
+        assert H.bits_equal(H.oracle_full_demod(g["iq"], bp, nb, fir_fma=1), g["ref_avx2"])

@@ -1,0 +1,122 @@
+"""CPU tests: pin the sample-side oracle (oracle/oracle_symbol.c) against the UNMODIFIED reference getSymbol() /
+getDibitSoft() driven through its own runtime hook seam (oracle/ref_shim_symbol.c)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _harness as H
+
+needs_ref = pytest.mark.skipif(not H.ref_available("par"), reason="oracle/_ref not built (no /root/reference)")
+
+
+def _oracle_chan(sync, lastsync, taps_by_filter, rate=48000, symrate=4800, use_cosine=1):
+    cls = H.SYNC_CLASS[lastsync]
+    neg = H.SYNC_CLASS[sync]["negative"]
+    ch = H.OracleSymChan()
+    taps = taps_by_filter.get(cls["filter"]) if (use_cosine and cls["filter"] is not None) else None
+    tp = H._ptr(taps) if taps is not None else None
+    H.oracle_sym().oracle_sym_init(C.byref(ch), rate, symrate, 1 if taps is not None else 0, cls["window_l"], cls["track"], neg, tp,
+                                   0 if taps is not None else 0 if taps is None else taps.size, 128, 1024) if taps is None else \
+        H.oracle_sym().oracle_sym_init(C.byref(ch), rate, symrate, 1, cls["window_l"], cls["track"], neg, tp, taps.size, 128, 1024)
+    return ch
+
+
+@needs_ref
+@pytest.mark.parametrize("sync,lastsync", [(H.SYNC_P25P1_POS, H.SYNC_P25P1_POS), (H.SYNC_P25P1_NEG, H.SYNC_P25P1_NEG),
+                                           (H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS), (H.SYNC_NONE, H.SYNC_NONE)])
+@pytest.mark.parametrize("noise", [0.0, 2500.0])
+def test_get_dibit_soft_matches_reference(sync, lastsync, noise):
+    R, O = H.ref_sym(), H.oracle_sym()
+    rng = np.random.default_rng(100 + sync * 7 + int(noise))
+    nsym = 6000
+    x, _ = H.synth_disc(rng, nsym, 10, 9000.0, noise, drift=1500.0)
+    taps = {0: H.sps_fir_taps(0, 10), 1: H.sps_fir_taps(1, 10)}
+    h = R.ref_sym_create(48000, 4800, sync, lastsync, 1, 128, 1024)
+    R.ref_sym_feed(h, H._ptr(x), x.size)
+    d = np.zeros(nsym, np.uint8); r = np.zeros(nsym, np.uint8); l = np.zeros(2 * nsym, np.int16); s = np.zeros(nsym, np.float32)
+    n = R.ref_sym_get_dibits(h, nsym, 600, H._ptr(d, H.u8p), H._ptr(r, H.u8p), l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s))
+    assert n > 5000
+    consumed_ref = R.ref_sym_consumed(h)
+    R.ref_sym_destroy(h)
+    ch = _oracle_chan(sync, lastsync, taps)
+    d2 = np.zeros(nsym, np.uint8); r2 = np.zeros(nsym, np.uint8); l2 = np.zeros(2 * nsym, np.int16); s2 = np.zeros(nsym, np.float32)
+    cons = C.c_long(0)
+    n2 = O.oracle_sym_run_dibits(C.byref(ch), H._ptr(x), x.size, 600, H._ptr(d2, H.u8p), H._ptr(r2, H.u8p),
+                                 l2.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s2), n, C.byref(cons))
+    assert n2 == n and cons.value == consumed_ref
+    assert H.bits_equal(s[:n], s2[:n]), H.first_mismatch(s[:n], s2[:n])
+    assert np.array_equal(d[:n], d2[:n])
+    assert np.array_equal(r[:n], r2[:n]) and np.array_equal(l[:2 * n], l2[:2 * n])
+
+
+@needs_ref
+@pytest.mark.parametrize("lastsync", [H.SYNC_P25P1_POS, H.SYNC_NONE, H.SYNC_DMR_BS_DATA_POS])
+def test_get_symbol_unsynced_timing_matches_reference(lastsync):
+    """have_sync = 0: the +-1 sample jitter nudge is active, so symbols consume 9, 10 or 11 samples."""
+    R, O = H.ref_sym(), H.oracle_sym()
+    rng = np.random.default_rng(300 + lastsync)
+    nsym = 5000
+    # sampling-clock offset: 10.02 samples per symbol so the tracker has to keep nudging
+    dib = rng.integers(0, 4, nsym)
+    t = np.arange(int(nsym * 10.02))
+    idx = np.minimum((t / 10.02).astype(np.int64), nsym - 1)
+    x = (H.LEVELS[dib][idx] * 9000.0 + rng.standard_normal(t.size) * 800.0).astype(np.float32)
+    k = np.hanning(12)[1:-1]; k /= k.sum()
+    x = np.convolve(x, k, mode="same").astype(np.float32)
+    taps = {0: H.sps_fir_taps(0, 10), 1: H.sps_fir_taps(1, 10)}
+    h = R.ref_sym_create(48000, 4800, lastsync, lastsync, 1, 128, 1024)
+    R.ref_sym_feed(h, H._ptr(x), x.size)
+    s = np.zeros(nsym, np.float32)
+    n = R.ref_sym_get_symbols(h, 0, nsym, 600, H._ptr(s))
+    consumed_ref = R.ref_sym_consumed(h)
+    R.ref_sym_destroy(h)
+    assert n > 4000
+    ch = _oracle_chan(lastsync, lastsync, taps)
+    s2 = np.zeros(nsym, np.float32)
+    cons = C.c_long(0)
+    n2 = O.oracle_sym_run_symbols(C.byref(ch), 0, H._ptr(x), x.size, 600, H._ptr(s2), n, C.byref(cons))
+    assert n2 == n and cons.value == consumed_ref, (n, n2, cons.value, consumed_ref)
+    assert consumed_ref != 10 * n  # the nudge really fired
+    assert H.bits_equal(s[:n], s2[:n]), H.first_mismatch(s[:n], s2[:n])
+
+
+@needs_ref
+def test_fractional_samples_per_symbol():
+    """50 kS/s / 4800 sym/s = 10 + 2000/4800: the remainder accumulator alternates 10- and 11-sample symbols."""
+    R, O = H.ref_sym(), H.oracle_sym()
+    rng = np.random.default_rng(400)
+    x, _ = H.synth_disc(rng, 3000, 10, 9000.0, 500.0)
+    h = R.ref_sym_create(50000, 4800, H.SYNC_NONE, H.SYNC_NONE, 1, 128, 1024)
+    R.ref_sym_feed(h, H._ptr(x), x.size)
+    s = np.zeros(3000, np.float32)
+    n = R.ref_sym_get_symbols(h, 1, 3000, 600, H._ptr(s))
+    consumed_ref = R.ref_sym_consumed(h)
+    R.ref_sym_destroy(h)
+    ch = _oracle_chan(H.SYNC_NONE, H.SYNC_NONE, {}, rate=50000)
+    s2 = np.zeros(3000, np.float32)
+    cons = C.c_long(0)
+    n2 = O.oracle_sym_run_symbols(C.byref(ch), 1, H._ptr(x), x.size, 600, H._ptr(s2), n, C.byref(cons))
+    assert n2 == n and cons.value == consumed_ref
+    assert H.bits_equal(s[:n], s2[:n])
+
+
+def test_oracle_matches_committed_golden_vectors():
+    """Reference outputs captured by tests/golden/make_golden.py: runs everywhere, also without oracle/_ref."""
+    import os
+
+    O = H.oracle_sym()
+    g = np.load(os.path.join(H.GOLDEN_DIR, "symbols.npz"))
+    t = np.load(os.path.join(H.GOLDEN_DIR, "sps_fir_taps.npz"))
+    taps = {0: t["f0_sps10"], 1: t["f1_sps10"]}
+    for name, sync in (("p25p1_pos", H.SYNC_P25P1_POS), ("dmr_bs_data", H.SYNC_DMR_BS_DATA_POS)):
+        x = g[name + "_x"]
+        n = g[name + "_dibits"].size
+        ch = _oracle_chan(sync, sync, taps)
+        d = np.zeros(n, np.uint8); r = np.zeros(n, np.uint8); l = np.zeros(2 * n, np.int16); s = np.zeros(n, np.float32)
+        cons = C.c_long(0)
+        k = O.oracle_sym_run_dibits(C.byref(ch), H._ptr(x), x.size, 600, H._ptr(d, H.u8p), H._ptr(r, H.u8p),
+                                    l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s), n, C.byref(cons))
+        assert k == n
+        assert np.array_equal(d, g[name + "_dibits"]) and np.array_equal(r, g[name + "_rel"]) and np.array_equal(l, g[name + "_llr"])
+        assert H.bits_equal(s, g[name + "_symbols"])
