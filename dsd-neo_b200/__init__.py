@@ -449,3 +449,96 @@ def p25_rs_decode(variant: int, data_bits, parity_bits):
     check(lib().dsdneo_b200_p25_rs_decode_batch_host(variant, data_bits.ctypes.data, parity_bits.ctypes.data, st.ctypes.data, n),
           "p25_rs_decode")
     return st
+
+
+# ------------------------------------------------------------------------------------------ sample side
+
+SYM_MODE_GET_SYMBOL, SYM_MODE_GET_DIBIT_SOFT = 0, 1
+SYM_FILTER_NONE, SYM_FILTER_P25, SYM_FILTER_DMR, SYM_FILTER_NXDN, SYM_FILTER_DPMR, SYM_FILTER_M17 = -1, 0, 1, 2, 3, 4
+
+
+class SymClass(C.Structure):
+    _fields_ = [("filter", C.c_int), ("window_l", C.c_int), ("track_minmax", C.c_int), ("negative", C.c_int)]
+
+
+class SymbolizerConfig(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int), ("output_rate_hz", C.c_int), ("symbol_rate_hz", C.c_int), ("ssize", C.c_int), ("msize", C.c_int),
+        ("use_cosine_filter", C.c_int), ("n_filters", C.c_int),
+        ("filter_taps", C.POINTER(C.c_float) * 8), ("filter_len", C.c_int * 8),
+    ]
+
+
+class SymbolOut(C.Structure):
+    _fields_ = [("d_symbols", C.c_void_p), ("d_dibits", C.c_void_p), ("d_reliability", C.c_void_p), ("d_llr", C.c_void_p),
+                ("d_count", C.c_void_p), ("pitch", C.c_size_t)]
+
+
+def sym_class_from_synctype(synctype: int, lastsynctype: int, use_cosine_filter: bool = True) -> SymClass:
+    out = SymClass()
+    check(lib().dsdneo_b200_sym_class_from_synctype(synctype, lastsynctype, 1 if use_cosine_filter else 0, C.byref(out)),
+          "sym_class_from_synctype")
+    return out
+
+
+class Symbolizer:
+    """Batched twin of getSymbol()/getDibitSoft() for n_channels discriminator streams."""
+
+    def __init__(self, n_channels, output_rate_hz=48000, symbol_rate_hz=4800, filters=None, ssize=0, msize=0, use_cosine_filter=True):
+        import numpy as np
+
+        cfg = SymbolizerConfig()
+        cfg.n_channels, cfg.output_rate_hz, cfg.symbol_rate_hz = n_channels, output_rate_hz, symbol_rate_hz
+        cfg.ssize, cfg.msize, cfg.use_cosine_filter = ssize, msize, 1 if use_cosine_filter else 0
+        self._taps = {}
+        filters = filters or {}
+        cfg.n_filters = (max(filters) + 1) if filters else 0
+        for idx, taps in filters.items():
+            a = np.ascontiguousarray(taps, dtype=np.float32)
+            self._taps[idx] = a
+            cfg.filter_taps[idx] = a.ctypes.data_as(C.POINTER(C.c_float))
+            cfg.filter_len[idx] = a.size
+        self.n_channels = n_channels
+        self.sps_floor = max(2, min(64, output_rate_hz // symbol_rate_hz))
+        self._h = lib().dsdneo_b200_symbolizer_create(C.byref(cfg))
+        if not self._h:
+            raise B200Error(f"symbolizer_create failed: {last_error()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_symbolizer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None):
+        check(lib().dsdneo_b200_symbolizer_reset(self._h, _stream_ptr(stream)), "symbolizer_reset")
+
+    def set_class(self, classes):
+        arr = (SymClass * self.n_channels)(*classes)
+        check(lib().dsdneo_b200_symbolizer_set_class(self._h, arr), "symbolizer_set_class")
+
+    def out_pitch(self, n_samples):
+        return (n_samples + 96) // (self.sps_floor - 1) + 2
+
+    def run(self, d_disc, n_samples, mode=SYM_MODE_GET_DIBIT_SOFT, have_sync=1, stream=None):
+        """d_disc: cuda float32 [n_channels, pitch]. Returns dict of cuda tensors + per-channel counts."""
+        import torch
+
+        assert d_disc.is_cuda and d_disc.dtype == torch.float32 and d_disc.is_contiguous() and d_disc.shape[0] == self.n_channels
+        pitch = self.out_pitch(n_samples)
+        dev = d_disc.device
+        res = {
+            "symbols": torch.zeros((self.n_channels, pitch), dtype=torch.float32, device=dev),
+            "dibits": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+            "reliability": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+            "llr": torch.zeros((self.n_channels, pitch, 2), dtype=torch.int16, device=dev),
+            "count": torch.zeros((self.n_channels,), dtype=torch.int32, device=dev),
+        }
+        out = SymbolOut(res["symbols"].data_ptr(), res["dibits"].data_ptr(), res["reliability"].data_ptr(), res["llr"].data_ptr(),
+                        res["count"].data_ptr(), pitch)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        check(lib().dsdneo_b200_symbolize_batch(self._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, mode, have_sync, C.byref(out),
+                                                _stream_ptr(stream)), "symbolize_batch")
+        return res

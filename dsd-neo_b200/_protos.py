@@ -14,6 +14,12 @@ def bind(L):
     vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
     cd = C.c_double
     protos = {
+        "dsdneo_b200_sym_class_from_synctype": (ci, [ci, ci, ci, vp]),
+        "dsdneo_b200_symbolizer_create": (vp, [vp]),
+        "dsdneo_b200_symbolizer_destroy": (None, [vp]),
+        "dsdneo_b200_symbolizer_reset": (ci, [vp, vp]),
+        "dsdneo_b200_symbolizer_set_class": (ci, [vp, vp]),
+        "dsdneo_b200_symbolize_batch": (ci, [vp, vp, sz, ci, ci, ci, vp, vp]),
         "dsdneo_b200_fec_block_code_len": (ci, [ci]),
         "dsdneo_b200_fec_block_code_k": (ci, [ci]),
         "dsdneo_b200_fec_block_decode_batch": (ci, [ci, vp, vp, vp, ci, vp]),

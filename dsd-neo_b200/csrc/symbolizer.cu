@@ -1,0 +1,883 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+/*
+ * Sample side of the hot path (K9 + K10 + K11), batched over channels: discriminator samples -> matched filter ->
+ * symbol (window mean + jitter timing) -> threshold tracking -> 4-level slice + soft metrics.
+ *
+ * Reference being replaced, per channel (4-level C4FM family, RTL FSK-discriminator input, rf_mod == 0):
+ *   p25_filter/dmr_filter/... -> apply_sps_fir   src/dsp/dsd_filters.c:172-201, selection src/dsp/dsd_symbol.c:301-337
+ *   getSymbol                                    src/dsp/dsd_symbol.c:1853-1880 (+ :197-225,:347-516,:1306-1387,:1769-1796)
+ *   use_symbol / dsd_state_push_minmax_window    src/core/frames/dsd_dibit.c:195-299, include/dsd-neo/core/state.h:1388-1454
+ *   digitize / compute_dibit_soft_metric         src/core/frames/dsd_dibit.c:455-721,963-1041
+ *   getDibitSoft                                 src/core/frames/dsd_dibit.c:1043-1089
+ *
+ * Two kernels:
+ *   sps_fir_kernel      time-parallel.  The matched filter is a plain causal FIR over the sample stream (the symbol
+ *                       timing never feeds back into it), so it is evaluated for every sample up front, in the
+ *                       reference's accumulation order (taps oldest -> newest, mul then add, no FMA).
+ *   symbolize_kernel    time-serial, one thread per channel (lane = channel, SoA state => coalesced): everything with a
+ *                       loop-carried dependence -- the +-1-sample jitter nudge, clip, window mean, the 128-symbol
+ *                       extrema scan (kept in shared memory), the 1024-entry running means, slicing and LLRs.
+ * Bit-exact with the reference (floats included); the SNR-dependent reliability weight uses the reference's value for
+ * "no SNR hook installed" (w256 = 0, dsd_dibit.c:520-537).
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+using namespace dsdneo;
+
+namespace {
+
+constexpr int kMaxTaps = DSDNEO_B200_SYM_MAX_TAPS; /* 256 */
+constexpr int kCarry = 96;                         /* leftover samples carried between launches (< longest symbol) */
+constexpr int kSbuf = 128;
+constexpr int kMinMax = 1024;
+constexpr int kSymThreads = 32;
+
+/* per-channel scalars, struct-of-arrays on the device */
+struct SymScalars {
+    int* filter;      /* index into the filter table, -1 = none */
+    int* window_l;
+    int* track;
+    int* negative;
+    int* sps_num;
+    int* sps_den;
+    int* sps_accum;
+    int* sps;
+    int* center_idx;
+    int* jitter;
+    float* lastsample;
+    float* vmin;
+    float* vmax;
+    float* center;
+    float* umid;
+    float* lmid;
+    float* minref;
+    float* maxref;
+    int* sidx;
+    int* midx;
+    int* sum_window;
+    double* minbuf_sum;
+    double* maxbuf_sum;
+    int* carry_n;
+    long long* symbolcnt;
+};
+
+struct FirParams {
+    const float* in;     /* [n_ch][in_pitch] discriminator samples */
+    size_t in_pitch;
+    float* out;          /* [n_ch][out_pitch] filtered */
+    size_t out_pitch;
+    const float* taps;   /* [n_filters][kMaxTaps] */
+    const int* taps_len; /* [n_filters] */
+    const int* filter;   /* [n_ch] */
+    const float* hist;   /* [n_ch][kMaxTaps] last taps_len-1 inputs */
+    int n;
+};
+
+constexpr int kFirTile = 1024;
+constexpr int kFirThreads = 256;
+
+__global__ void __launch_bounds__(kFirThreads)
+sps_fir_kernel(const FirParams p) {
+    __shared__ float W[kFirTile + kMaxTaps];
+    __shared__ float T[kMaxTaps];
+    const int ch = blockIdx.y;
+    const int t0 = blockIdx.x * kFirTile;
+    const int tid = threadIdx.x;
+    const int f = p.filter[ch];
+    const float* x = p.in + (size_t)ch * p.in_pitch;
+    float* y = p.out + (size_t)ch * p.out_pitch;
+    if (f < 0) { /* no matched filter selected (dsd_symbol.c:301-337 falls through): identity */
+        for (int j = tid; j < kFirTile; j += kFirThreads) {
+            const int n = t0 + j;
+            if (n < p.n) {
+                y[n] = x[n];
+            }
+        }
+        return;
+    }
+    const int L = p.taps_len[f];
+    for (int i = tid; i < L; i += kFirThreads) {
+        T[i] = p.taps[f * kMaxTaps + i];
+    }
+    const float* hist = p.hist + (size_t)ch * kMaxTaps;
+    for (int j = tid; j < kFirTile + L - 1; j += kFirThreads) {
+        const int g = t0 - (L - 1) + j; /* W[j] = x[g] */
+        float v = 0.0f;
+        if (g >= 0) {
+            v = g < p.n ? x[g] : 0.0f;
+        } else {
+            v = hist[(L - 1) + g]; /* hist[L-2] == x[-1] */
+        }
+        W[j] = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < L; i++) { /* taps oldest -> newest, separate multiply and add (dsd_filters.c:191-199) */
+        const float t = T[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            acc[j] = __fadd_rn(acc[j], __fmul_rn(t, W[tid + kFirThreads * j + i]));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int n = t0 + tid + kFirThreads * j;
+        if (n < p.n) {
+            y[n] = acc[j];
+        }
+    }
+}
+
+__global__ void
+sps_fir_hist_kernel(const float* in, size_t in_pitch, float* hist_all, const int* filter, const int* taps_len, int n_ch, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ch >= n_ch) {
+        return;
+    }
+    const int f = filter[ch];
+    if (f < 0) {
+        return;
+    }
+    const int hl = taps_len[f] - 1;
+    float* hist = hist_all + (size_t)ch * kMaxTaps;
+    const float* x = in + (size_t)ch * in_pitch;
+    if (n >= hl) {
+        for (int k = lane; k < hl; k += 32) {
+            hist[k] = x[n - hl + k];
+        }
+    } else {
+        float keep[kMaxTaps / 32];
+        int c = 0;
+        for (int k = lane; k < hl - n; k += 32) {
+            keep[c++] = hist[k + n];
+        }
+        __syncwarp();
+        c = 0;
+        for (int k = lane; k < hl - n; k += 32) {
+            hist[k] = keep[c++];
+        }
+        for (int k = lane; k < n; k += 32) {
+            hist[hl - n + k] = x[k];
+        }
+    }
+}
+
+struct SymParams {
+    SymScalars s;
+    const float* filt;   /* [n_ch][filt_pitch] matched-filter output for this launch */
+    size_t filt_pitch;
+    float* carry;        /* [kCarry][n_ch] */
+    float* sbuf;         /* [kSbuf][n_ch] */
+    float* minbuf;       /* [kMinMax][n_ch] */
+    float* maxbuf;       /* [kMinMax][n_ch] */
+    float* symbols;      /* outputs, [n_ch][out_pitch] */
+    uint8_t* dibits;
+    uint8_t* reliab;
+    int16_t* llr;        /* [n_ch][out_pitch][2] */
+    int* count;          /* [n_ch] */
+    size_t out_pitch;
+    int n_ch, n, mode, have_sync, rate, symrate, ssize, msize;
+};
+
+__device__ __forceinline__ int
+clamp255(int v) {
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+__device__ __forceinline__ int
+bit_metric(float sym, const float (&ideal)[4], int bit_index) {
+    /* dsd_dibit.c:609-642 */
+    float best0 = 3.4028234663852886e38f, best1 = 3.4028234663852886e38f, min_spacing = 3.4028234663852886e38f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float e = __fsub_rn(sym, ideal[i]);
+        const float d = __fmul_rn(e, e);
+        if (((i >> (1 - bit_index)) & 1) != 0) {
+            if (d < best1) {
+                best1 = d;
+            }
+        } else if (d < best0) {
+            best0 = d;
+        }
+#pragma unroll
+        for (int j = i + 1; j < 4; j++) {
+            const float sp = fabsf(__fsub_rn(ideal[i], ideal[j]));
+            if (sp > 1e-6f && sp < min_spacing) {
+                min_spacing = sp;
+            }
+        }
+    }
+    if (min_spacing == 3.4028234663852886e38f) {
+        min_spacing = 2.0f;
+    }
+    const float scale = __fdiv_rn(255.0f, __fmul_rn(min_spacing, min_spacing));
+    return clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(best0, best1)), scale))); /* lrintf: round to nearest even */
+}
+
+__global__ void __launch_bounds__(kSymThreads)
+symbolize_kernel(const SymParams p) {
+    __shared__ float s_sbuf[kSbuf][kSymThreads];
+    const int lane = threadIdx.x;
+    const int ch = blockIdx.x * kSymThreads + lane;
+    const bool valid = ch < p.n_ch;
+    const int c = valid ? ch : p.n_ch - 1; /* inactive lanes shadow the last channel but never store */
+    const int N = p.n_ch;
+
+    for (int k = 0; k < kSbuf; k++) {
+        s_sbuf[k][lane] = p.sbuf[(size_t)k * N + c];
+    }
+    /* state -> registers */
+    const int window_l = p.s.window_l[c], track = p.s.track[c], negative = p.s.negative[c];
+    int sps_num = p.s.sps_num[c], sps_den = p.s.sps_den[c], sps_accum = p.s.sps_accum[c];
+    int sps = p.s.sps[c], center_idx = p.s.center_idx[c], jitter = p.s.jitter[c];
+    float lastsample = p.s.lastsample[c];
+    float vmin = p.s.vmin[c], vmax = p.s.vmax[c], center = p.s.center[c], umid = p.s.umid[c], lmid = p.s.lmid[c];
+    float minref = p.s.minref[c], maxref = p.s.maxref[c];
+    int sidx = p.s.sidx[c], midx = p.s.midx[c], sum_window = p.s.sum_window[c];
+    double minbuf_sum = p.s.minbuf_sum[c], maxbuf_sum = p.s.maxbuf_sum[c];
+    const int carry_n = p.s.carry_n[c];
+    long long symbolcnt = p.s.symbolcnt[c];
+
+    const float* filt = p.filt + (size_t)c * p.filt_pitch;
+    const long avail = (long)carry_n + p.n;
+    long pos = 0;
+    auto sample_at = [&](long k) -> float { return k < carry_n ? p.carry[(size_t)k * N + c] : filt[k - carry_n]; };
+
+    const int whole0 = p.rate / p.symrate;
+    const long reserve = (long)(whole0 < 2 ? 2 : (whole0 > 64 ? 64 : whole0)) + 2; /* longest possible symbol */
+    float* o_sym = p.symbols + (size_t)c * p.out_pitch;
+    uint8_t* o_dib = p.dibits ? p.dibits + (size_t)c * p.out_pitch : nullptr;
+    uint8_t* o_rel = p.reliab ? p.reliab + (size_t)c * p.out_pitch : nullptr;
+    int16_t* o_llr = p.llr ? p.llr + (size_t)c * p.out_pitch * 2 : nullptr;
+    long nsym = 0;
+    const int have_sync = (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) ? 1 : p.have_sync;
+
+    while (nsym < (long)p.out_pitch && (avail - pos) >= reserve) {
+        /* ---- symbol_apply_rtl_fsk_discriminator_timing (dsd_symbol.c:1328-1387) ---- */
+        if (sps_num != p.rate || sps_den != p.symrate) {
+            sps_num = p.rate;
+            sps_den = p.symrate;
+            sps_accum = 0;
+            jitter = -1;
+            center = 0.0f, vmin = -30000.0f, vmax = 30000.0f, lmid = -20000.0f, umid = 20000.0f;
+            minref = -24000.0f, maxref = 24000.0f;
+            for (int k = 0; k < kMinMax; k++) {
+                if (valid) {
+                    p.minbuf[(size_t)k * N + c] = vmin;
+                    p.maxbuf[(size_t)k * N + c] = vmax;
+                }
+            }
+            midx = 0;
+            sum_window = 0;
+        }
+        {
+            int whole = p.rate / p.symrate, rem = p.rate % p.symrate;
+            if (whole < 2) {
+                whole = 2, rem = 0;
+            }
+            if (whole > 64) {
+                whole = 64, rem = 0;
+            }
+            if (rem > 0 && sps_den > 0) {
+                int acc = sps_accum + rem;
+                if (acc >= sps_den) {
+                    whole++;
+                    acc -= sps_den;
+                }
+                sps_accum = acc;
+                if (whole > 64) {
+                    whole = 64;
+                }
+            }
+            sps = whole;
+            center_idx = (sps - 1) / 2;
+        }
+        /* ---- symbol_process_live_samples (dsd_symbol.c:1769-1792) ---- */
+        float sum = 0.0f;
+        int cnt = 0;
+        for (int i = 0; i < sps; i++) {
+            if (i == 0 && have_sync == 0 && jitter >= 0) { /* dsd_symbol.c:462-516 */
+                if (sps == 20) {
+                    if (jitter >= 7 && jitter <= 10) {
+                        i--;
+                    } else if (jitter >= 11 && jitter <= 14) {
+                        i++;
+                    }
+                } else {
+                    if (jitter > 0 && jitter <= center_idx) {
+                        i--;
+                    } else if (jitter > center_idx && jitter < sps) {
+                        i++;
+                    }
+                }
+                jitter = -1;
+            }
+            float s = sample_at(pos++);
+            if (have_sync == 1) { /* symbol_apply_sync_clip, rf_mod == 0 */
+                s = s > vmax ? vmax : (s < vmin ? vmin : s);
+            }
+            if (s > center) { /* symbol_update_jitter, rf_mod == 0 branches */
+                if (!(s > __fmul_rn(maxref, 1.25f)) && jitter < 0 && lastsample < center) {
+                    jitter = i;
+                }
+            } else {
+                if (!(s < __fmul_rn(minref, 1.25f)) && jitter < 0 && lastsample > center) {
+                    jitter = i;
+                }
+            }
+            if (sps == 20 && i >= 7 && i <= 13) { /* symbol_accumulate_sample */
+                sum = __fadd_rn(sum, s);
+                cnt++;
+            }
+            if (sps == 5 && i == 2) {
+                sum = __fadd_rn(sum, s);
+                cnt++;
+            } else if (i >= center_idx - window_l && i <= center_idx + 2) {
+                sum = __fadd_rn(sum, s);
+                cnt++;
+            }
+            lastsample = s;
+        }
+        const float sym = cnt > 0 ? __fdiv_rn(sum, (float)cnt) : 0.0f;
+        symbolcnt++;
+        if (valid) {
+            o_sym[nsym] = sym;
+        }
+        if (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
+            /* ---- get_dibit_and_analog_signal: sbuf, use_symbol (dsd_dibit.c:243-299) ---- */
+            s_sbuf[sidx][lane] = sym;
+            int cap = p.ssize < 0 ? 0 : (p.ssize > kSbuf ? kSbuf : p.ssize);
+            if (track) {
+                float lmin = 0.0f, lmax = 0.0f;
+                if (cap >= 2) {
+                    float mn1 = s_sbuf[0][lane], mn2 = s_sbuf[1][lane];
+                    if (mn2 < mn1) {
+                        const float t = mn1;
+                        mn1 = mn2, mn2 = t;
+                    }
+                    float mx1 = s_sbuf[0][lane], mx2 = s_sbuf[1][lane];
+                    if (mx2 > mx1) {
+                        const float t = mx1;
+                        mx1 = mx2, mx2 = t;
+                    }
+                    for (int k = 2; k < cap; k++) {
+                        const float v = s_sbuf[k][lane];
+                        if (v < mn1) {
+                            mn2 = mn1, mn1 = v;
+                        } else if (v < mn2) {
+                            mn2 = v;
+                        }
+                        if (v > mx1) {
+                            mx2 = mx1, mx1 = v;
+                        } else if (v > mx2) {
+                            mx2 = v;
+                        }
+                    }
+                    lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
+                    lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
+                }
+                const int window = p.msize < 1 ? 1 : (p.msize > kMinMax ? kMinMax : p.msize);
+                if (sum_window != window) { /* dsd_state_recompute_minmax_sums */
+                    double a = 0.0, b = 0.0;
+                    for (int k = 0; k < window; k++) {
+                        a += (double)p.minbuf[(size_t)k * N + c];
+                        b += (double)p.maxbuf[(size_t)k * N + c];
+                    }
+                    minbuf_sum = a, maxbuf_sum = b, sum_window = window;
+                    if (midx < 0 || midx >= window) {
+                        midx = 0;
+                    }
+                }
+                int idx = (midx < 0 || midx >= window) ? 0 : midx;
+                minbuf_sum += (double)lmin - (double)p.minbuf[(size_t)idx * N + c];
+                maxbuf_sum += (double)lmax - (double)p.maxbuf[(size_t)idx * N + c];
+                if (valid) {
+                    p.minbuf[(size_t)idx * N + c] = lmin;
+                    p.maxbuf[(size_t)idx * N + c] = lmax;
+                }
+                idx++;
+                midx = idx >= window ? 0 : idx;
+                vmin = (float)(minbuf_sum / (double)window);
+                vmax = (float)(maxbuf_sum / (double)window);
+                center = __fdiv_rn(__fadd_rn(vmax, vmin), 2.0f);
+                umid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 8.0f), center);
+                lmid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 8.0f), center);
+                maxref = __fmul_rn(vmax, 0.80f);
+                minref = __fmul_rn(vmin, 0.80f);
+            } else {
+                maxref = vmax;
+                minref = vmin;
+            }
+            if (cap > 0) {
+                sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
+            }
+            /* ---- digitize (dsd_dibit.c:963-976,1018-1041) ---- */
+            int dibit;
+            if (sym > center) {
+                dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+            } else {
+                dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
+            }
+            /* ---- compute_dibit_soft_metric (dsd_dibit.c:644-721) ---- */
+            const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+            float ideal[4];
+            if (negative) {
+                ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+            } else {
+                ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+            }
+            int mag0 = bit_metric(sym, ideal, 0), mag1 = bit_metric(sym, ideal, 1);
+            /* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) */
+            const float eps = 1e-6f;
+            int rel;
+            if (sym > umid) {
+                float span = __fsub_rn(vmax, umid);
+                span = span < eps ? eps : span;
+                rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(sym, umid), 255.0f), span));
+            } else if (sym > center) {
+                const float d1 = __fsub_rn(sym, center), d2 = __fsub_rn(umid, sym);
+                float span = __fsub_rn(umid, center);
+                span = span < eps ? eps : span;
+                rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+            } else if (sym >= lmid) {
+                const float d1 = __fsub_rn(center, sym), d2 = __fsub_rn(sym, lmid);
+                float span = __fsub_rn(center, lmid);
+                span = span < eps ? eps : span;
+                rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+            } else {
+                float span = __fsub_rn(lmid, vmin);
+                span = span < eps ? eps : span;
+                rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
+            }
+            rel = clamp255(rel);
+            rel = clamp255((rel * 204) >> 8); /* apply_c4fm_snr_weight with no SNR hook: w256 = 0 (dsd_dibit.c:520-537) */
+            const int min_mag = mag0 < mag1 ? mag0 : mag1;
+            if (min_mag > 0 && rel < min_mag) {
+                mag0 = (mag0 * rel) / min_mag;
+                mag1 = (mag1 * rel) / min_mag;
+            }
+            mag0 = clamp255(mag0);
+            mag1 = clamp255(mag1);
+            const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
+            if (valid) {
+                o_dib[nsym] = (uint8_t)dibit;
+                o_rel[nsym] = (uint8_t)clamp255(mag1 < mag0 ? mag1 : mag0);
+                o_llr[2 * nsym] = (int16_t)l0;
+                o_llr[2 * nsym + 1] = (int16_t)l1;
+            }
+        }
+        nsym++;
+    }
+
+    /* leftover samples -> carry (read everything first: source and destination overlap in the carry array) */
+    const int left = (int)(avail - pos);
+    float keep[kCarry / 8];
+    for (int base = 0; base < left; base += kCarry / 8) {
+        const int m = min(kCarry / 8, left - base);
+        for (int k = 0; k < m; k++) {
+            keep[k] = sample_at(pos + base + k);
+        }
+        if (valid) {
+            for (int k = 0; k < m; k++) {
+                p.carry[(size_t)(base + k) * N + c] = keep[k]; /* base + k < pos + base + k: never overtakes the reads */
+            }
+        }
+    }
+    if (!valid) {
+        return;
+    }
+    for (int k = 0; k < kSbuf; k++) {
+        p.sbuf[(size_t)k * N + c] = s_sbuf[k][lane];
+    }
+    p.s.sps_num[c] = sps_num, p.s.sps_den[c] = sps_den, p.s.sps_accum[c] = sps_accum;
+    p.s.sps[c] = sps, p.s.center_idx[c] = center_idx, p.s.jitter[c] = jitter;
+    p.s.lastsample[c] = lastsample;
+    p.s.vmin[c] = vmin, p.s.vmax[c] = vmax, p.s.center[c] = center, p.s.umid[c] = umid, p.s.lmid[c] = lmid;
+    p.s.minref[c] = minref, p.s.maxref[c] = maxref;
+    p.s.sidx[c] = sidx, p.s.midx[c] = midx, p.s.sum_window[c] = sum_window;
+    p.s.minbuf_sum[c] = minbuf_sum, p.s.maxbuf_sum[c] = maxbuf_sum;
+    p.s.carry_n[c] = left;
+    p.s.symbolcnt[c] = symbolcnt;
+    p.count[c] = (int)nsym;
+}
+
+__global__ void
+sym_reset_kernel(SymScalars s, float* minbuf, float* maxbuf, float* sbuf, float* carry, float* hist, int n_ch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) {
+        return;
+    }
+    /* initState() values (src/core/util/dsd_init.c:519-592) */
+    s.sps_num[c] = 0, s.sps_den[c] = 0, s.sps_accum[c] = 0;
+    s.sps[c] = 10, s.center_idx[c] = 4, s.jitter[c] = -1;
+    s.lastsample[c] = 0.0f;
+    s.vmin[c] = -15000.0f, s.vmax[c] = 15000.0f, s.center[c] = 0.0f, s.umid[c] = 0.0f, s.lmid[c] = 0.0f;
+    s.minref[c] = -12000.0f, s.maxref[c] = 12000.0f;
+    s.sidx[c] = 0, s.midx[c] = 0, s.sum_window[c] = 0;
+    s.minbuf_sum[c] = 0.0, s.maxbuf_sum[c] = 0.0;
+    s.carry_n[c] = 0;
+    s.symbolcnt[c] = 0;
+    for (int k = 0; k < kMinMax; k++) {
+        minbuf[(size_t)k * n_ch + c] = -15000.0f;
+        maxbuf[(size_t)k * n_ch + c] = 15000.0f;
+    }
+    for (int k = 0; k < kSbuf; k++) {
+        sbuf[(size_t)k * n_ch + c] = 0.0f;
+    }
+    for (int k = 0; k < kCarry; k++) {
+        carry[(size_t)k * n_ch + c] = 0.0f;
+    }
+    for (int k = 0; k < kMaxTaps; k++) {
+        hist[(size_t)c * kMaxTaps + k] = 0.0f;
+    }
+}
+
+}  // namespace
+
+struct dsdneo_b200_symbolizer {
+    int n_ch, rate, symrate, ssize, msize, use_cosine_filter, n_filters;
+    int h_taps_len[DSDNEO_B200_SYM_MAX_FILTERS];
+    void* arena; /* one allocation for all scalar arrays */
+    SymScalars s;
+    float *d_minbuf, *d_maxbuf, *d_sbuf, *d_carry, *d_hist, *d_taps;
+    int* d_taps_len;
+    float* d_filt;
+    size_t filt_pitch;
+};
+
+extern "C" {
+
+int
+dsdneo_b200_sym_class_from_synctype(int synctype, int lastsynctype, int use_cosine_filter, dsdneo_b200_sym_class* out) {
+    /* sync-type ids: include/dsd-neo/core/synctype_ids.h:30-123 */
+    if (!out) {
+        set_error("sym_class_from_synctype: NULL output");
+        return DSDNEO_B200_EINVAL;
+    }
+    auto is_p25p1 = [](int s) { return s == 0 || s == 1; };
+    auto is_dmr_bs = [](int s) { return s >= 10 && s <= 13; };
+    auto is_dmr_ms = [](int s) { return s >= 32 && s <= 34; };
+    auto is_ysf = [](int s) { return s == 30 || s == 31; };
+    auto is_m17 = [](int s) { return s == 8 || s == 9 || s == 16 || s == 17 || s == 76 || s == 77 || s == 86 || s == 87 || (s >= 98 && s <= 101); };
+    auto two_level = [](int s) { return s == 6 || s == 7 || s == 14 || s == 15 || s == 18 || s == 19 || s == 37 || s == 38; };
+    if (two_level(synctype)) {
+        set_error("sym_class_from_synctype: two-level sync types (D-STAR, ProVoice, EDACS) are not built yet");
+        return DSDNEO_B200_EUNSUPPORTED;
+    }
+    if ((lastsynctype >= 20 && lastsynctype <= 29) || lastsynctype == 35 || lastsynctype == 36) {
+        set_error("sym_class_from_synctype: dPMR / NXDN / P25p2 matched-filter selection depends on decoder options; pass the class explicitly");
+        return DSDNEO_B200_EUNSUPPORTED;
+    }
+    /* matched filter (dsd_symbol.c:301-337) */
+    int filter = DSDNEO_SYM_FILTER_NONE;
+    if (use_cosine_filter) {
+        if (is_dmr_bs(lastsynctype) || is_dmr_ms(lastsynctype) || is_ysf(lastsynctype)) {
+            filter = DSDNEO_SYM_FILTER_DMR;
+        } else if (is_m17(lastsynctype)) {
+            filter = DSDNEO_SYM_FILTER_M17;
+        } else if (is_p25p1(lastsynctype)) {
+            filter = DSDNEO_SYM_FILTER_P25;
+        }
+    }
+    out->filter = filter;
+    /* window (dsd_symbol.c:197-211): YSF by synctype, DMR BS / MS voice+data by lastsynctype */
+    out->window_l = (is_ysf(synctype) || is_dmr_bs(lastsynctype) || lastsynctype == 32 || lastsynctype == 33) ? 1 : 2;
+    out->track_minmax = is_p25p1(lastsynctype) ? 1 : 0; /* dsd_dibit.c:264 (rf_mod == 0) */
+    /* is_four_level_neg_synctype (dsd_dibit.c:915-935) */
+    const int s = synctype;
+    out->negative = (s == 1 || s == 3 || s == 5 || s == 9 || s == 11 || s == 13 || s == 17 || s == 29 || s == 31 || s == 77 || s == 87
+                     || s == 36 || s == 99 || s == 101)
+                        ? 1
+                        : 0;
+    return 0;
+}
+
+void
+dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y) {
+    if (!y) {
+        return;
+    }
+    cudaFree(y->arena);
+    cudaFree(y->d_minbuf);
+    cudaFree(y->d_maxbuf);
+    cudaFree(y->d_sbuf);
+    cudaFree(y->d_carry);
+    cudaFree(y->d_hist);
+    cudaFree(y->d_taps);
+    cudaFree(y->d_taps_len);
+    cudaFree(y->d_filt);
+    free(y);
+}
+
+dsdneo_b200_symbolizer*
+dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
+    if (!cfg || cfg->n_channels <= 0 || cfg->output_rate_hz <= 0 || cfg->symbol_rate_hz <= 0 || cfg->n_filters < 0
+        || cfg->n_filters > DSDNEO_B200_SYM_MAX_FILTERS) {
+        set_error("symbolizer_create: bad config");
+        return NULL;
+    }
+    for (int f = 0; f < cfg->n_filters; f++) {
+        if (cfg->filter_len[f] < 0 || cfg->filter_len[f] > kMaxTaps || (cfg->filter_len[f] > 0 && !cfg->filter_taps[f])) {
+            set_error("symbolizer_create: filter %d has %d taps (max %d)", f, cfg->filter_len[f], kMaxTaps);
+            return NULL;
+        }
+    }
+    if (ensure_device()) {
+        return NULL;
+    }
+    dsdneo_b200_symbolizer* y = (dsdneo_b200_symbolizer*)calloc(1, sizeof(*y));
+    if (!y) {
+        set_error("symbolizer_create: out of host memory");
+        return NULL;
+    }
+    const size_t n = (size_t)cfg->n_channels;
+    y->n_ch = cfg->n_channels;
+    y->rate = cfg->output_rate_hz;
+    y->symrate = cfg->symbol_rate_hz;
+    y->ssize = cfg->ssize > 0 ? cfg->ssize : 128;   /* opts->ssize default, src/core/util/dsd_init.c:169 */
+    y->msize = cfg->msize > 0 ? cfg->msize : 1024;  /* opts->msize default, :170 */
+    y->use_cosine_filter = cfg->use_cosine_filter;
+    y->n_filters = cfg->n_filters;
+    /* scalar arena: 22 x 4-byte arrays, 3 x 8-byte arrays */
+    const size_t arena_bytes = n * (22 * 4 + 3 * 8) + 256;
+    cudaError_t e = cudaMalloc(&y->arena, arena_bytes);
+    if (e == cudaSuccess) {
+        e = cudaMemset(y->arena, 0, arena_bytes);
+    }
+    if (e == cudaSuccess) {
+        char* b = (char*)y->arena;
+        double* d8 = (double*)b;
+        y->s.minbuf_sum = d8;
+        y->s.maxbuf_sum = d8 + n;
+        y->s.symbolcnt = (long long*)(d8 + 2 * n);
+        int* i4 = (int*)(d8 + 3 * n);
+        int k = 0;
+        y->s.filter = i4 + n * k++;
+        y->s.window_l = i4 + n * k++;
+        y->s.track = i4 + n * k++;
+        y->s.negative = i4 + n * k++;
+        y->s.sps_num = i4 + n * k++;
+        y->s.sps_den = i4 + n * k++;
+        y->s.sps_accum = i4 + n * k++;
+        y->s.sps = i4 + n * k++;
+        y->s.center_idx = i4 + n * k++;
+        y->s.jitter = i4 + n * k++;
+        y->s.lastsample = (float*)(i4 + n * k++);
+        y->s.vmin = (float*)(i4 + n * k++);
+        y->s.vmax = (float*)(i4 + n * k++);
+        y->s.center = (float*)(i4 + n * k++);
+        y->s.umid = (float*)(i4 + n * k++);
+        y->s.lmid = (float*)(i4 + n * k++);
+        y->s.minref = (float*)(i4 + n * k++);
+        y->s.maxref = (float*)(i4 + n * k++);
+        y->s.sidx = i4 + n * k++;
+        y->s.midx = i4 + n * k++;
+        y->s.sum_window = i4 + n * k++;
+        y->s.carry_n = i4 + n * k++;
+    }
+#define SYM_ALLOC(ptr, bytes)                                                                                          \
+    if (e == cudaSuccess) {                                                                                            \
+        e = cudaMalloc((void**)&(ptr), (bytes));                                                                       \
+    }
+    SYM_ALLOC(y->d_minbuf, n * kMinMax * sizeof(float));
+    SYM_ALLOC(y->d_maxbuf, n * kMinMax * sizeof(float));
+    SYM_ALLOC(y->d_sbuf, n * kSbuf * sizeof(float));
+    SYM_ALLOC(y->d_carry, n * kCarry * sizeof(float));
+    SYM_ALLOC(y->d_hist, n * kMaxTaps * sizeof(float));
+    SYM_ALLOC(y->d_taps, (size_t)DSDNEO_B200_SYM_MAX_FILTERS * kMaxTaps * sizeof(float));
+    SYM_ALLOC(y->d_taps_len, DSDNEO_B200_SYM_MAX_FILTERS * sizeof(int));
+#undef SYM_ALLOC
+    if (e == cudaSuccess) {
+        float* h = (float*)calloc((size_t)DSDNEO_B200_SYM_MAX_FILTERS * kMaxTaps, sizeof(float));
+        for (int f = 0; f < cfg->n_filters; f++) {
+            y->h_taps_len[f] = cfg->filter_len[f];
+            if (cfg->filter_len[f] > 0) {
+                memcpy(h + (size_t)f * kMaxTaps, cfg->filter_taps[f], (size_t)cfg->filter_len[f] * sizeof(float));
+            }
+        }
+        e = cudaMemcpy(y->d_taps, h, (size_t)DSDNEO_B200_SYM_MAX_FILTERS * kMaxTaps * sizeof(float), cudaMemcpyHostToDevice);
+        free(h);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->d_taps_len, y->h_taps_len, sizeof(y->h_taps_len), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cuda_fail(e, "symbolizer_create", __FILE__, __LINE__);
+        dsdneo_b200_symbolizer_destroy(y);
+        return NULL;
+    }
+    if (dsdneo_b200_symbolizer_reset(y, NULL) != 0) {
+        dsdneo_b200_symbolizer_destroy(y);
+        return NULL;
+    }
+    /* default class: no sync seen yet => no matched filter, window 2/2, no tracking, positive polarity */
+    dsdneo_b200_sym_class* cls = (dsdneo_b200_sym_class*)malloc(n * sizeof(dsdneo_b200_sym_class));
+    for (size_t i = 0; i < n; i++) {
+        cls[i].filter = DSDNEO_SYM_FILTER_NONE, cls[i].window_l = 2, cls[i].track_minmax = 0, cls[i].negative = 0;
+    }
+    int rc = dsdneo_b200_symbolizer_set_class(y, cls);
+    free(cls);
+    if (rc) {
+        dsdneo_b200_symbolizer_destroy(y);
+        return NULL;
+    }
+    return y;
+}
+
+int
+dsdneo_b200_symbolizer_reset(dsdneo_b200_symbolizer* y, void* stream) {
+    if (!y) {
+        set_error("symbolizer_reset: NULL");
+        return DSDNEO_B200_EINVAL;
+    }
+    sym_reset_kernel<<<(y->n_ch + 127) / 128, 128, 0, as_stream(stream)>>>(y->s, y->d_minbuf, y->d_maxbuf, y->d_sbuf, y->d_carry,
+                                                                            y->d_hist, y->n_ch);
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sym_class* per_channel) {
+    if (!y || !per_channel) {
+        set_error("symbolizer_set_class: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    const size_t n = (size_t)y->n_ch;
+    int* h = (int*)malloc(4 * n * sizeof(int));
+    if (!h) {
+        set_error("symbolizer_set_class: out of host memory");
+        return DSDNEO_B200_ENOMEM;
+    }
+    for (size_t i = 0; i < n; i++) {
+        int f = per_channel[i].filter;
+        if (f >= y->n_filters || (f >= 0 && y->h_taps_len[f] <= 0)) {
+            free(h);
+            set_error("symbolizer_set_class: channel %zu selects filter %d which was not supplied at create", i, f);
+            return DSDNEO_B200_EINVAL;
+        }
+        h[i] = f < 0 ? -1 : f;
+        h[n + i] = per_channel[i].window_l;
+        h[2 * n + i] = per_channel[i].track_minmax ? 1 : 0;
+        h[3 * n + i] = per_channel[i].negative ? 1 : 0;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.filter, h, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.window_l, h + n, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.track, h + 2 * n, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.negative, h + 3 * n, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    free(h);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "symbolizer_set_class", __FILE__, __LINE__);
+    }
+    return 0;
+}
+
+int
+dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                            const dsdneo_b200_symbol_out* out, void* stream) {
+    if (!y || !d_disc || !out || n_samples < 0 || disc_pitch < (size_t)n_samples || !out->d_symbols || !out->d_count
+        || out->pitch == 0) {
+        set_error("symbolize_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (mode != DSDNEO_SYM_MODE_GET_SYMBOL && mode != DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
+        set_error("symbolize_batch: unknown mode %d", mode);
+        return DSDNEO_B200_EINVAL;
+    }
+    if (mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT && (!out->d_dibits || !out->d_reliability || !out->d_llr)) {
+        set_error("symbolize_batch: GET_DIBIT_SOFT needs dibit, reliability and llr outputs");
+        return DSDNEO_B200_EINVAL;
+    }
+    {
+        int whole = y->rate / y->symrate;
+        whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
+        const size_t need = ((size_t)n_samples + kCarry) / (size_t)(whole - 1) + 2;
+        if (out->pitch < need) {
+            set_error("symbolize_batch: output pitch %zu is too small for %d samples (need >= %zu)", out->pitch, n_samples, need);
+            return DSDNEO_B200_EINVAL;
+        }
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    const size_t pitch = ((size_t)n_samples + 3) & ~(size_t)3;
+    if (!y->d_filt || y->filt_pitch < pitch) {
+        DSDNEO_CUDA(cudaDeviceSynchronize());
+        cudaFree(y->d_filt);
+        y->d_filt = NULL;
+        DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt, (size_t)y->n_ch * (pitch ? pitch : 4) * sizeof(float)));
+        y->filt_pitch = pitch ? pitch : 4;
+    }
+    if (n_samples > 0) {
+        FirParams fp;
+        fp.in = d_disc;
+        fp.in_pitch = disc_pitch;
+        fp.out = y->d_filt;
+        fp.out_pitch = y->filt_pitch;
+        fp.taps = y->d_taps;
+        fp.taps_len = y->d_taps_len;
+        fp.filter = y->s.filter;
+        fp.hist = y->d_hist;
+        fp.n = n_samples;
+        dim3 grid((unsigned)((n_samples + kFirTile - 1) / kFirTile), (unsigned)y->n_ch);
+        {
+            KernelTimer kt("sps_fir_kernel", s);
+            sps_fir_kernel<<<grid, kFirThreads, 0, s>>>(fp);
+        }
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+        {
+            KernelTimer kt("sps_fir_hist_kernel", s);
+            sps_fir_hist_kernel<<<(y->n_ch + 7) / 8, 256, 0, s>>>(d_disc, disc_pitch, y->d_hist, y->s.filter, y->d_taps_len, y->n_ch,
+                                                                 n_samples);
+        }
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
+    SymParams sp;
+    sp.s = y->s;
+    sp.filt = y->d_filt;
+    sp.filt_pitch = y->filt_pitch;
+    sp.carry = y->d_carry;
+    sp.sbuf = y->d_sbuf;
+    sp.minbuf = y->d_minbuf;
+    sp.maxbuf = y->d_maxbuf;
+    sp.symbols = out->d_symbols;
+    sp.dibits = out->d_dibits;
+    sp.reliab = out->d_reliability;
+    sp.llr = out->d_llr;
+    sp.count = out->d_count;
+    sp.out_pitch = out->pitch;
+    sp.n_ch = y->n_ch;
+    sp.n = n_samples;
+    sp.mode = mode;
+    sp.have_sync = have_sync ? 1 : 0;
+    sp.rate = y->rate;
+    sp.symrate = y->symrate;
+    sp.ssize = y->ssize;
+    sp.msize = y->msize;
+    {
+        KernelTimer kt("symbolize_kernel", s);
+        symbolize_kernel<<<(y->n_ch + kSymThreads - 1) / kSymThreads, kSymThreads, 0, s>>>(sp);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+} /* extern "C" */

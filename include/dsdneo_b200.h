@@ -247,6 +247,72 @@ int dsdneo_b200_frontend_join(dsdneo_b200_frontend* fe, void* stream);
 int dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
                                       float* h_result, size_t result_pitch);
 
+/* ---- sample side: matched filter + getSymbol + use_symbol + digitize, batched over channels (K9-K11) ----- */
+
+#define DSDNEO_B200_SYM_MAX_TAPS 256
+#define DSDNEO_B200_SYM_MAX_FILTERS 8
+/* Slot convention for the matched filters (the reference's five sps_fir objects, src/dsp/dsd_filters.c:325-345). */
+enum {
+    DSDNEO_SYM_FILTER_NONE = -1,
+    DSDNEO_SYM_FILTER_P25 = 0,  /* p25_filter  */
+    DSDNEO_SYM_FILTER_DMR = 1,  /* dmr_filter (also YSF, NXDN96) */
+    DSDNEO_SYM_FILTER_NXDN = 2, /* nxdn_filter */
+    DSDNEO_SYM_FILTER_DPMR = 3, /* dpmr_filter */
+    DSDNEO_SYM_FILTER_M17 = 4,  /* m17_filter  */
+};
+enum {
+    DSDNEO_SYM_MODE_GET_SYMBOL = 0,     /* twin of getSymbol(opts, state, have_sync): float symbols only */
+    DSDNEO_SYM_MODE_GET_DIBIT_SOFT = 1, /* twin of getDibitSoft(): have_sync = 1, + use_symbol + digitize + soft metrics */
+};
+
+/** What the reference derives from state->synctype / state->lastsynctype for each symbol. */
+typedef struct dsdneo_b200_sym_class {
+    int filter;       /* DSDNEO_SYM_FILTER_*: symbol_apply_matched_filter, src/dsp/dsd_symbol.c:301-337 */
+    int window_l;     /* left edge of the averaging window, 2 or 1: select_window_c4fm, dsd_symbol.c:197-211 (right edge is 2) */
+    int track_minmax; /* use_symbol() threshold tracking (P25p1): src/core/frames/dsd_dibit.c:264 */
+    int negative;     /* is_four_level_neg_synctype(synctype): dsd_dibit.c:915-935 */
+} dsdneo_b200_sym_class;
+/** The reference's rules for P25p1 / DMR / YSF / M17 / X2-TDMA / none (ids: include/dsd-neo/core/synctype_ids.h). */
+int dsdneo_b200_sym_class_from_synctype(int synctype, int lastsynctype, int use_cosine_filter, dsdneo_b200_sym_class* out);
+
+typedef struct dsdneo_b200_symbolizer_config {
+    int n_channels;
+    int output_rate_hz;    /* discriminator sample rate (dsd_rtl_stream_metrics_hooks.output_rate_hz), e.g. 48000 */
+    int symbol_rate_hz;    /* symbol_profile rate, e.g. 4800; samples per symbol = rate/symbol rate with remainder accumulator */
+    int ssize, msize;      /* opts->ssize / opts->msize (0 = reference defaults 128 / 1024) */
+    int use_cosine_filter; /* opts->use_cosine_filter */
+    int n_filters;
+    /* NORMALISED taps exactly as the reference's design_sps_fir() leaves them for this samples-per-symbol
+     * (src/dsd_filters.c:94-170): dsd-neo passes its own coefficient tables; oldest tap first. */
+    const float* filter_taps[DSDNEO_B200_SYM_MAX_FILTERS];
+    int filter_len[DSDNEO_B200_SYM_MAX_FILTERS];
+} dsdneo_b200_symbolizer_config;
+
+typedef struct dsdneo_b200_symbol_out {
+    float* d_symbols;       /* [n_channels][pitch] */
+    uint8_t* d_dibits;      /* [n_channels][pitch]     (GET_DIBIT_SOFT) value returned by getDibitSoft */
+    uint8_t* d_reliability; /* [n_channels][pitch]     dsd_dibit_soft_t.reliability (include/dsd-neo/core/dibit.h:24-27) */
+    int16_t* d_llr;         /* [n_channels][pitch][2]  dsd_dibit_soft_t.llr */
+    int32_t* d_count;       /* [n_channels] symbols produced by this call */
+    size_t pitch;           /* capacity per channel; must be >= (n_samples + 96) / (samples_per_symbol - 1) + 2 */
+} dsdneo_b200_symbol_out;
+
+typedef struct dsdneo_b200_symbolizer dsdneo_b200_symbolizer;
+dsdneo_b200_symbolizer* dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg);
+void dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y);
+/** Back to initState() values (src/core/util/dsd_init.c:519-592) and empty matched-filter history. */
+int dsdneo_b200_symbolizer_reset(dsdneo_b200_symbolizer* y, void* stream);
+/** Per-channel class (host array of n_channels).  Synchronises the device. */
+int dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sym_class* per_channel);
+/**
+ * Consume n_samples discriminator samples per channel ([n_channels][disc_pitch] f32, the output layout of
+ * dsdneo_b200_full_demod_batch) and emit every complete symbol; an unfinished symbol's samples are carried to the next
+ * call.  With have_sync == 0 (GET_SYMBOL mode) the reference's +-1 sample jitter nudge is active, so channels may emit
+ * different symbol counts.  Bit-identical to the reference for 4-level C4FM-family modes (rf_mod == 0).
+ */
+int dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode,
+                                int have_sync, const dsdneo_b200_symbol_out* out, void* stream);
+
 /* ---- batched FEC leaves (K13, K16, K17, K19) ------------------------------------------------------ */
 
 /*
