@@ -542,3 +542,39 @@ class Symbolizer:
         check(lib().dsdneo_b200_symbolize_batch(self._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, mode, have_sync, C.byref(out),
                                                 _stream_ptr(stream)), "symbolize_batch")
         return res
+
+
+def viterbi_k5_decode(cost, in_len, punct=None, out_pitch=None, out_init=None):
+    """cost: uint16 [n, pitch]; returns (out uint8 [n, out_pitch], metric uint32 [n])."""
+    import numpy as np
+
+    cost = np.ascontiguousarray(cost, dtype=np.uint16)
+    n = cost.shape[0]
+    if out_pitch is None:
+        out_pitch = 80
+    out = np.zeros((n, out_pitch), np.uint8) if out_init is None else np.ascontiguousarray(out_init, dtype=np.uint8).copy()
+    met = np.zeros(n, np.uint32)
+    pp, pl = (None, 0)
+    if punct is not None:
+        punct = np.ascontiguousarray(punct, dtype=np.uint8)
+        pp, pl = punct.ctypes.data, punct.size
+    check(lib().dsdneo_b200_viterbi_k5_decode_batch_host(cost.ctypes.data, cost.shape[1], in_len, pp, pl, out.ctypes.data, out.shape[1],
+                                                         met.ctypes.data, n), "viterbi_k5_decode")
+    return out, met
+
+
+def nxdn_conv_decode(sym, rel, n_steps, n_bits_out, metrics, out_pitch=40, out_init=None):
+    """sym/rel: uint8 [n, pitch]; metrics: uint16 [n, 32] updated in place. Returns out uint8 [n, out_pitch]."""
+    import numpy as np
+
+    sym = np.ascontiguousarray(sym, dtype=np.uint8)
+    n = sym.shape[0]
+    out = np.zeros((n, out_pitch), np.uint8) if out_init is None else np.ascontiguousarray(out_init, dtype=np.uint8).copy()
+    rp = None
+    if rel is not None:
+        rel = np.ascontiguousarray(rel, dtype=np.uint8)
+        rp = rel.ctypes.data
+    assert metrics.dtype == np.uint16 and metrics.shape == (n, 32) and metrics.flags.c_contiguous
+    check(lib().dsdneo_b200_nxdn_conv_decode_batch_host(sym.ctypes.data, rp, sym.shape[1], n_steps, n_bits_out, metrics.ctypes.data,
+                                                        out.ctypes.data, out.shape[1], n), "nxdn_conv_decode")
+    return out

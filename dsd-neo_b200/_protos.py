@@ -14,6 +14,10 @@ def bind(L):
     vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
     cd = C.c_double
     protos = {
+        "dsdneo_b200_viterbi_k5_decode_batch": (ci, [vp, sz, ci, vp, ci, vp, sz, vp, ci, vp]),
+        "dsdneo_b200_viterbi_k5_decode_batch_host": (ci, [vp, sz, ci, vp, ci, vp, sz, vp, ci]),
+        "dsdneo_b200_nxdn_conv_decode_batch": (ci, [vp, vp, sz, ci, ci, vp, vp, sz, ci, vp]),
+        "dsdneo_b200_nxdn_conv_decode_batch_host": (ci, [vp, vp, sz, ci, ci, vp, vp, sz, ci]),
         "dsdneo_b200_sym_class_from_synctype": (ci, [ci, ci, ci, vp]),
         "dsdneo_b200_symbolizer_create": (vp, [vp]),
         "dsdneo_b200_symbolizer_destroy": (None, [vp]),

@@ -657,6 +657,197 @@ p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_
     status[w] = (uint8_t)rc;
 }
 
+/* ------------------------------------------------------------------ K = 5 convolutional decoders */
+
+constexpr int kVitMaxSteps = 244; /* viterbi_history[244], src/core/util/dsd_misc.c:108 */
+constexpr int kNxdnMaxSteps = 300; /* m_decisions[8 * 300], src/protocol/nxdn/nxdn_convolution.c:52 */
+
+/* viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182) with viterbi_decode_bit (:191-236) and
+ * viterbi_chainback (:246-275).  One thread per frame: 16 path metrics in registers, one 16-bit decision word per step. */
+__global__ void __launch_bounds__(64)
+viterbi_k5_kernel(const uint16_t* in, size_t in_pitch, int in_len, const uint8_t* punct, int p_len, uint8_t* out, size_t out_pitch,
+                  uint32_t* metric_out, int n_frames) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) {
+        return;
+    }
+    const uint16_t* src = in + (size_t)f * in_pitch;
+    uint32_t pm[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        pm[i] = 0;
+    }
+    uint16_t hist[kVitMaxSteps];
+    /* de-puncturing: erased positions carry the neutral cost 0x7FFF (dsd_misc.c:163-177) */
+    int p = 0, i_in = 0, u = 0, pos = 0;
+    auto next_cost = [&](bool& ok) -> uint16_t {
+        if (i_in >= in_len) {
+            ok = false;
+            return 0;
+        }
+        ok = true;
+        uint16_t v;
+        if (!punct || punct[p]) {
+            v = src[i_in++];
+        } else {
+            v = 0x7FFF;
+        }
+        u++;
+        if (punct) {
+            p = (p + 1) % p_len;
+        }
+        return v;
+    };
+    for (;;) {
+        bool ok0, ok1;
+        const uint16_t s0 = next_cost(ok0);
+        if (!ok0) {
+            break;
+        }
+        const uint16_t s1 = next_cost(ok1);
+        if (!ok1) {
+            break; /* odd tail element is ignored, as `i + 1 < len` does */
+        }
+        if (pos >= kVitMaxSteps) {
+            break;
+        }
+        uint32_t cm[16];
+        unsigned h = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t c0 = (k >= 4) ? 0xFFFFu : 0u;
+            const uint32_t c1 = ((0x66u >> k) & 1u) ? 0xFFFFu : 0u; /* {0,F,F,0,0,F,F,0} */
+            const uint32_t d0 = c0 > s0 ? c0 - s0 : s0 - c0;
+            const uint32_t d1 = c1 > s1 ? c1 - s1 : s1 - c1;
+            const uint32_t metric = d0 + d1;
+            const uint32_t m0 = pm[k] + metric, m1 = pm[k + 8] + (0x1FFFEu - metric);
+            const uint32_t m2 = pm[k] + (0x1FFFEu - metric), m3 = pm[k + 8] + metric;
+            if (m0 >= m1) { /* ties take the "1" predecessor */
+                h |= 1u << (2 * k);
+                cm[2 * k] = m1;
+            } else {
+                cm[2 * k] = m0;
+            }
+            if (m2 >= m3) {
+                h |= 1u << (2 * k + 1);
+                cm[2 * k + 1] = m3;
+            } else {
+                cm[2 * k + 1] = m2;
+            }
+        }
+        hist[pos++] = (uint16_t)h;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            pm[k] = cm[k];
+        }
+    }
+    const int total = u;             /* length of the de-punctured message */
+    const int nbits = total / 2;
+    uint8_t* o = out + (size_t)f * out_pitch;
+    const int clear = (nbits - 1) / 8 + 1; /* only these bytes are cleared; later ones are OR-ed into (dsd_misc.c:252) */
+    for (int k = 0; k < clear && k < (int)out_pitch; k++) {
+        o[k] = 0;
+    }
+    unsigned state = 0;
+    int bit_pos = nbits + 4;
+    while (pos > 0) {
+        bit_pos--;
+        pos--;
+        const unsigned bit = hist[pos] & (1u << (state >> 4));
+        state >>= 1;
+        if (bit) {
+            state |= 0x80u;
+            if (bit_pos / 8 < (int)out_pitch) {
+                o[bit_pos / 8] |= (uint8_t)(1u << (7 - (bit_pos % 8)));
+            }
+        }
+    }
+    uint32_t best = pm[0];
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        best = pm[k] < best ? pm[k] : best;
+    }
+    metric_out[f] = best - (uint32_t)(total - in_len) * 0x7FFFu;
+}
+
+/* CNXDNConvolution_start / _decode / _decode_soft / _chainback (src/protocol/nxdn/nxdn_convolution.c:58-164).
+ * metrics: [n][32] = the reference's two ping-pong arrays m_metrics1 | m_metrics2, carried from frame to frame. */
+__global__ void __launch_bounds__(64)
+nxdn_conv_kernel(const uint8_t* sym, const uint8_t* rel, size_t pitch, int n_steps, int n_bits_out, uint16_t* metrics, uint8_t* out,
+                 size_t out_pitch, int n_frames) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) {
+        return;
+    }
+    const uint8_t* s = sym + (size_t)f * pitch;
+    const uint8_t* r = rel ? rel + (size_t)f * pitch : nullptr;
+    uint16_t a[16], b[16];
+    uint16_t* mio = metrics + (size_t)f * 32;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        a[i] = mio[i];
+        b[i] = mio[16 + i];
+    }
+    unsigned short dec[kNxdnMaxSteps]; /* 16 decision bits per step (the reference keeps them in a uint64) */
+    for (int t = 0; t < n_steps; t++) {
+        const int s0 = s[2 * t], s1 = s[2 * t + 1];
+        const bool even = (t & 1) == 0; /* even steps read m_metrics1 (a) and write m_metrics2 (b) */
+        unsigned d = 0;
+        uint16_t nm[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int t1 = (i >= 4) ? 2 : 0, t2 = ((0x66 >> i) & 1) ? 2 : 0;
+            int d0 = t1 - s0, d1 = t2 - s1;
+            d0 = d0 < 0 ? -d0 : d0;
+            d1 = d1 < 0 ? -d1 : d1;
+            const uint32_t oi = even ? a[i] : b[i], oj = even ? a[i + 8] : b[i + 8];
+            uint32_t m0, m1, m2, m3;
+            if (!r) {
+                const uint16_t metric = (uint16_t)(d0 + d1);
+                m0 = (uint16_t)(oi + metric);
+                m1 = (uint16_t)(oj + (4u - metric));
+                m2 = (uint16_t)(oi + (4u - metric));
+                m3 = (uint16_t)(oj + metric);
+            } else {
+                uint32_t metric = ((uint32_t)d0 * r[2 * t] + (uint32_t)d1 * r[2 * t + 1]) / 128u;
+                metric = metric > 8u ? 8u : metric;
+                m0 = oi + metric;
+                m1 = oj + (8u - metric);
+                m2 = oi + (8u - metric);
+                m3 = oj + metric;
+            }
+            const unsigned dec0 = m0 >= m1, dec1 = m2 >= m3;
+            nm[2 * i] = (uint16_t)(dec0 ? m1 : m0);
+            nm[2 * i + 1] = (uint16_t)(dec1 ? m3 : m2);
+            d |= (dec1 << (2 * i + 1)) | (dec0 << (2 * i));
+        }
+        dec[t] = (unsigned short)d;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (even) {
+                b[i] = nm[i];
+            } else {
+                a[i] = nm[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        mio[i] = a[i];
+        mio[16 + i] = b[i];
+    }
+    uint8_t* o = out + (size_t)f * out_pitch;
+    unsigned state = 0;
+    int t = n_steps, nb = n_bits_out;
+    while (nb-- > 0) {
+        --t;
+        const unsigned bit = (dec[t] >> (state >> 4)) & 1u;
+        state = (bit << 7) | (state >> 1);
+        const uint8_t mask = (uint8_t)(0x80u >> (nb & 7));
+        o[nb >> 3] = bit ? (uint8_t)(o[nb >> 3] | mask) : (uint8_t)(o[nb >> 3] & ~mask);
+    }
+}
+
 /* RAII device scratch for the *_host entry points */
 struct DevBuf {
     void* p = nullptr;
@@ -1030,6 +1221,128 @@ dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const ui
     }
     DSDNEO_CUDA(cudaMemcpy(h_data_bits, data.p, n * db, cudaMemcpyDeviceToHost));
     DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_viterbi_k5_decode_batch(const uint16_t* d_cost, size_t cost_pitch, int in_len, const uint8_t* d_punct, int p_len,
+                                    uint8_t* d_out, size_t out_pitch, uint32_t* d_metric, int n_frames, void* stream) {
+    if (!d_cost || !d_out || !d_metric || in_len < 2 || n_frames < 0 || cost_pitch < (size_t)in_len || (d_punct && p_len <= 0)) {
+        set_error("viterbi_k5_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("viterbi_k5_kernel", s);
+        viterbi_k5_kernel<<<grid_for(n_frames, 64), 64, 0, s>>>(d_cost, cost_pitch, in_len, d_punct, p_len, d_out, out_pitch, d_metric,
+                                                                n_frames);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_viterbi_k5_decode_batch_host(const uint16_t* h_cost, size_t cost_pitch, int in_len, const uint8_t* h_punct, int p_len,
+                                         uint8_t* h_out, size_t out_pitch, uint32_t* h_metric, int n_frames) {
+    if (!h_cost || !h_out || !h_metric || n_frames < 0) {
+        set_error("viterbi_k5_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_frames;
+    DevBuf cost(n * cost_pitch * 2), out(n * out_pitch), met(n * 4), pun(h_punct ? (size_t)p_len : 1);
+    DSDNEO_CUDA(cost.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(met.err);
+    DSDNEO_CUDA(pun.err);
+    DSDNEO_CUDA(cudaMemcpy(cost.p, h_cost, n * cost_pitch * 2, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(out.p, h_out, n * out_pitch, cudaMemcpyHostToDevice)); /* bytes past the cleared prefix are OR-ed into */
+    if (h_punct) {
+        DSDNEO_CUDA(cudaMemcpy(pun.p, h_punct, (size_t)p_len, cudaMemcpyHostToDevice));
+    }
+    rc = dsdneo_b200_viterbi_k5_decode_batch(cost.as<uint16_t>(), cost_pitch, in_len, h_punct ? pun.as<uint8_t>() : NULL, p_len,
+                                             out.as<uint8_t>(), out_pitch, met.as<uint32_t>(), n_frames, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out, out.p, n * out_pitch, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_metric, met.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_nxdn_conv_decode_batch(const uint8_t* d_sym, const uint8_t* d_rel, size_t pitch, int n_steps, int n_bits_out,
+                                   uint16_t* d_metrics, uint8_t* d_out, size_t out_pitch, int n_frames, void* stream) {
+    if (!d_sym || !d_metrics || !d_out || n_steps < 1 || n_steps > kNxdnMaxSteps || n_bits_out < 0 || n_bits_out > n_steps
+        || pitch < (size_t)(2 * n_steps) || out_pitch * 8 < (size_t)n_bits_out || n_frames < 0) {
+        set_error("nxdn_conv_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("nxdn_conv_kernel", s);
+        nxdn_conv_kernel<<<grid_for(n_frames, 64), 64, 0, s>>>(d_sym, d_rel, pitch, n_steps, n_bits_out, d_metrics, d_out, out_pitch,
+                                                               n_frames);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_nxdn_conv_decode_batch_host(const uint8_t* h_sym, const uint8_t* h_rel, size_t pitch, int n_steps, int n_bits_out,
+                                        uint16_t* h_metrics, uint8_t* h_out, size_t out_pitch, int n_frames) {
+    if (!h_sym || !h_metrics || !h_out || n_frames < 0) {
+        set_error("nxdn_conv_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_frames;
+    DevBuf sym(n * pitch), rel(h_rel ? n * pitch : 1), met(n * 64), out(n * out_pitch);
+    DSDNEO_CUDA(sym.err);
+    DSDNEO_CUDA(rel.err);
+    DSDNEO_CUDA(met.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(cudaMemcpy(sym.p, h_sym, n * pitch, cudaMemcpyHostToDevice));
+    if (h_rel) {
+        DSDNEO_CUDA(cudaMemcpy(rel.p, h_rel, n * pitch, cudaMemcpyHostToDevice));
+    }
+    DSDNEO_CUDA(cudaMemcpy(met.p, h_metrics, n * 64, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(out.p, h_out, n * out_pitch, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_nxdn_conv_decode_batch(sym.as<uint8_t>(), h_rel ? rel.as<uint8_t>() : NULL, pitch, n_steps, n_bits_out,
+                                            met.as<uint16_t>(), out.as<uint8_t>(), out_pitch, n_frames, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_metrics, met.p, n * 64, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_out, out.p, n * out_pitch, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -391,6 +391,33 @@ int dsdneo_b200_p25_rs_decode_batch(int variant, uint8_t* d_data_bits, const uin
 int dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
                                          int n_words);
 
+/**
+ * viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182; include/dsd-neo/fec/viterbi.h:23-29), the
+ * K = 5 soft decoder used by M17 and YSF.  Costs are uint16 "probability of a 1" (0 / 0xFFFF strong, 0x7FFF erased).
+ * @param d_cost   [n][cost_pitch] received soft bits, in_len used per frame (after de-puncturing at most 488)
+ * @param d_punct  puncture pattern (1 = transmitted) of p_len entries on the device, or NULL for the unpunctured decoder
+ * @param d_out    [n][out_pitch] decoded bytes; like the reference only the first (bits-1)/8+1 bytes are cleared and later
+ *                 bytes are OR-ed into (the decoded message starts at bit 8); out_pitch >= (bits+4+7)/8
+ * @param d_metric [n] the reference's return value (minimum final metric, neutral puncture cost removed)
+ */
+int dsdneo_b200_viterbi_k5_decode_batch(const uint16_t* d_cost, size_t cost_pitch, int in_len, const uint8_t* d_punct, int p_len,
+                                        uint8_t* d_out, size_t out_pitch, uint32_t* d_metric, int n_frames, void* stream);
+int dsdneo_b200_viterbi_k5_decode_batch_host(const uint16_t* h_cost, size_t cost_pitch, int in_len, const uint8_t* h_punct,
+                                             int p_len, uint8_t* h_out, size_t out_pitch, uint32_t* h_metric, int n_frames);
+/**
+ * CNXDNConvolution_start + n_steps x CNXDNConvolution_decode[_soft] + CNXDNConvolution_chainback(out, n_bits_out)
+ * (src/protocol/nxdn/nxdn_convolution.c:58-164).
+ * @param d_sym     [n][pitch] symbol pairs s0,s1 (values 0 / 2, 1 = erased), 2*n_steps used; d_rel: reliabilities r0,r1 for the
+ *                  soft decoder or NULL for the hard one
+ * @param d_metrics [n][32] uint16: the reference's two ping-pong metric arrays (m_metrics1 | m_metrics2), which it zeroes once
+ *                  at start-up and then carries from frame to frame -- pass zeros for a fresh decoder, keep them per channel
+ * @param d_out     [n][out_pitch] n_bits_out decoded bits MSB first (other bits of the buffer untouched), n_steps <= 300
+ */
+int dsdneo_b200_nxdn_conv_decode_batch(const uint8_t* d_sym, const uint8_t* d_rel, size_t pitch, int n_steps, int n_bits_out,
+                                       uint16_t* d_metrics, uint8_t* d_out, size_t out_pitch, int n_frames, void* stream);
+int dsdneo_b200_nxdn_conv_decode_batch_host(const uint8_t* h_sym, const uint8_t* h_rel, size_t pitch, int n_steps, int n_bits_out,
+                                            uint16_t* h_metrics, uint8_t* h_out, size_t out_pitch, int n_frames);
+
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);

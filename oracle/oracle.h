@@ -84,6 +84,9 @@ int oracle_p25_12_soft_llr_list(const int16_t* llr196, uint8_t* cand_bytes, uint
 int oracle_rs63_decode(int tt, const int* in63, int* out63);
 void oracle_rs63_encode(int tt, const int* data, int* cw63);
 int oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits);
+uint32_t oracle_viterbi_k5_decode(uint8_t* out, const uint16_t* in, int len);
+uint32_t oracle_viterbi_k5_decode_punctured(uint8_t* out, const uint16_t* in, const uint8_t* punct, int in_len, int p_len);
+void oracle_nxdn_conv_decode(const uint8_t* sym, const uint8_t* rel, int n_steps, int n_bits_out, uint16_t* metrics_io, uint8_t* out);
 
 /* ------------------------------- sample side (oracle_symbol.c) --------------------------------- */
 

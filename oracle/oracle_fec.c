@@ -831,3 +831,147 @@ oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits /*[n_data][6]*/
     }
     return rc;
 }
+
+/* ------------------------------------------------------------------ K = 5 soft Viterbi (M17 / YSF) */
+
+/* viterbi_decode (src/core/util/dsd_misc.c:118-143) with viterbi_decode_bit (:191-236), viterbi_chainback (:246-275):
+ * costs are uint16 "probability of a 1" (0 = strong 0, 0xFFFF = strong 1); ties (m0 >= m1) take the "1" predecessor;
+ * chain-back starts in state 0 and writes bit `len/2 + 3 - step`; only the first (len/2-1)/8+1 output bytes are cleared,
+ * later bytes are OR-ed into.  Returns the minimum final path metric. */
+uint32_t
+oracle_viterbi_k5_decode(uint8_t* out, const uint16_t* in, int len) {
+    static const uint16_t C0[8] = {0, 0, 0, 0, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
+    static const uint16_t C1[8] = {0, 0xFFFF, 0xFFFF, 0, 0, 0xFFFF, 0xFFFF, 0};
+    uint32_t pm[16] = {0}, cm[16];
+    static uint16_t hist[244];
+    memset(hist, 0, sizeof(hist));
+    int pos = 0;
+    for (int i = 0; i + 1 < len; i += 2, pos++) {
+        uint16_t s0 = in[i], s1 = in[i + 1];
+        uint16_t h = 0;
+        for (int k = 0; k < 8; k++) {
+            uint32_t d0 = C0[k] > s0 ? (uint32_t)(C0[k] - s0) : (uint32_t)(s0 - C0[k]);
+            uint32_t d1 = C1[k] > s1 ? (uint32_t)(C1[k] - s1) : (uint32_t)(s1 - C1[k]);
+            uint32_t metric = (uint16_t)d0 + (uint32_t)(uint16_t)d1;
+            uint32_t m0 = pm[k] + metric, m1 = pm[k + 8] + (0x1FFFE - metric);
+            uint32_t m2 = pm[k] + (0x1FFFE - metric), m3 = pm[k + 8] + metric;
+            if (m0 >= m1) {
+                h |= (uint16_t)(1u << (2 * k));
+                cm[2 * k] = m1;
+            } else {
+                cm[2 * k] = m0;
+            }
+            if (m2 >= m3) {
+                h |= (uint16_t)(1u << (2 * k + 1));
+                cm[2 * k + 1] = m3;
+            } else {
+                cm[2 * k + 1] = m2;
+            }
+        }
+        hist[pos] = h;
+        memcpy(pm, cm, sizeof(pm));
+    }
+    int nbits = len / 2;
+    uint8_t state = 0;
+    int bit_pos = nbits + 4;
+    memset(out, 0, (size_t)((nbits - 1) / 8 + 1));
+    while (pos > 0) {
+        bit_pos--;
+        pos--;
+        uint16_t bit = hist[pos] & (uint16_t)(1u << (state >> 4));
+        state >>= 1;
+        if (bit) {
+            state |= 0x80;
+            out[bit_pos / 8] |= (uint8_t)(1u << (7 - (bit_pos % 8)));
+        }
+    }
+    uint32_t best = pm[0];
+    for (int i = 1; i < 16; i++) {
+        if (pm[i] < best) {
+            best = pm[i];
+        }
+    }
+    return best;
+}
+
+/* viterbi_decode_punctured (dsd_misc.c:156-182) */
+uint32_t
+oracle_viterbi_k5_decode_punctured(uint8_t* out, const uint16_t* in, const uint8_t* punct, int in_len, int p_len) {
+    uint16_t umsg[488];
+    memset(umsg, 0, sizeof(umsg));
+    int p = 0, u = 0, i = 0;
+    while (i < in_len) {
+        if (punct[p]) {
+            umsg[u] = in[i++];
+        } else {
+            umsg[u] = 0x7FFF;
+        }
+        u++;
+        p = (p + 1) % p_len;
+    }
+    return oracle_viterbi_k5_decode(out, umsg, u) - (uint32_t)(u - in_len) * 0x7FFFu;
+}
+
+/* ------------------------------------------------------------------ NXDN K = 5 convolution */
+
+/* CNXDNConvolution_start + decode / decode_soft per symbol pair + chainback (src/protocol/nxdn/nxdn_convolution.c:58-164).
+ * metrics_io (2 x 16 uint16) are the decoder's two ping-pong metric arrays m_metrics1 / m_metrics2: the reference zeroes
+ * them only once at start-up (CNXDNConvolution_init, engine.c:2808); CNXDNConvolution_start() merely points "old" back at
+ * m_metrics1, so a frame starts from whatever the last ODD step of the previous frame left there (stale by one step when
+ * the previous frame had an odd number of steps).  rel == NULL selects the hard decoder.  Returns nothing; out receives n_bits_out bits (MSB first), taken from the LAST n_bits_out steps. */
+void
+oracle_nxdn_conv_decode(const uint8_t* sym /*[2*n_steps]*/, const uint8_t* rel /*[2*n_steps] or NULL*/, int n_steps,
+                        int n_bits_out, uint16_t* metrics_io, uint8_t* out) {
+    static const uint8_t T1[8] = {0, 0, 0, 0, 2, 2, 2, 2}, T2[8] = {0, 2, 2, 0, 0, 2, 2, 0};
+    static uint64_t dec[300];
+    uint16_t* om = metrics_io;      /* m_metrics1 */
+    uint16_t* nm = metrics_io + 16; /* m_metrics2 */
+    for (int t = 0; t < n_steps; t++) {
+        uint8_t s0 = sym[2 * t], s1 = sym[2 * t + 1];
+        uint64_t d = 0;
+        for (int i = 0; i < 8; i++) {
+            int d0 = (int)T1[i] - (int)s0, d1 = (int)T2[i] - (int)s1;
+            d0 = d0 < 0 ? -d0 : d0;
+            d1 = d1 < 0 ? -d1 : d1;
+            uint32_t m0, m1, m2, m3;
+            if (!rel) {
+                uint16_t metric = (uint16_t)(d0 + d1);
+                m0 = (uint16_t)(om[i] + metric);
+                m1 = (uint16_t)(om[i + 8] + (4u - metric));
+                m2 = (uint16_t)(om[i] + (4u - metric));
+                m3 = (uint16_t)(om[i + 8] + metric);
+            } else {
+                uint32_t metric = ((uint32_t)d0 * rel[2 * t] + (uint32_t)d1 * rel[2 * t + 1]) / 128u;
+                if (metric > 8u) {
+                    metric = 8u;
+                }
+                m0 = om[i] + metric;
+                m1 = om[i + 8] + (8u - metric);
+                m2 = om[i] + (8u - metric);
+                m3 = om[i + 8] + metric;
+            }
+            unsigned dec0 = m0 >= m1, dec1 = m2 >= m3;
+            nm[2 * i] = (uint16_t)(dec0 ? m1 : m0);
+            nm[2 * i + 1] = (uint16_t)(dec1 ? m3 : m2);
+            d |= ((uint64_t)dec1 << (2 * i + 1)) | ((uint64_t)dec0 << (2 * i));
+        }
+        dec[t] = d;
+        uint16_t* tmp = om;
+        om = nm;
+        nm = tmp;
+    }
+    uint32_t state = 0;
+    int t = n_steps;
+    int nb = n_bits_out;
+    while (nb-- > 0) {
+        --t;
+        uint32_t i = state >> 4;
+        uint8_t bit = (uint8_t)((dec[t] >> i) & 1u);
+        state = ((uint32_t)bit << 7) | (state >> 1);
+        if (bit) {
+            out[nb >> 3] |= (uint8_t)(0x80u >> (nb & 7));
+        } else {
+            out[nb >> 3] &= (uint8_t)~(0x80u >> (nb & 7));
+        }
+    }
+}

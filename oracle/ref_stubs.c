@@ -47,9 +47,7 @@ STUB_VOID(sf_write_sync)
  * test (tests/dsp/test_rtl_symbol_cache_generation.c). */
 void agsm_f() {}
 void analog_gain_f() {}
-void hpf_f() {}
-void lpf_f() {}
-void pbf_f() {}
+/* hpf_f / lpf_f / pbf_f come from the reference's own src/core/util/dsd_misc.c (compiled for its Viterbi decoder) */
 
 void* dsd_fopen_existing_regular_file() { return NULL; }
 int dsd_frame_sync_active_nxdn_variant() { return 0; }

@@ -444,3 +444,15 @@ def synth_disc(rng, n_symbols, sps=10, level=9000.0, noise=0.0, drift=0.0, dibit
     if noise:
         x = x + rng.standard_normal(x.size) * noise
     return x.astype(np.float32), np.asarray(dibits)
+
+
+def conv_k5_encode(bits):
+    """Rate-1/2 K=5 encoder used by M17 / NXDN / YSF (G1 = 1+D^3+D^4, G2 = 1+D+D^2+D^4), returns 2*len(bits) bits."""
+    sr = 0
+    out = []
+    for b in bits:
+        sr = ((sr << 1) | int(b)) & 0x1F
+        g1 = ((sr >> 0) ^ (sr >> 3) ^ (sr >> 4)) & 1
+        g2 = ((sr >> 0) ^ (sr >> 1) ^ (sr >> 2) ^ (sr >> 4)) & 1
+        out += [g1, g2]
+    return np.array(out, dtype=np.uint8)

@@ -147,3 +147,58 @@ def test_p25_rs_batch(gpu, variant, n, k):
     assert np.array_equal(st, want_st)
     assert np.array_equal(got, want)
     assert (want_st == 0).sum() > nw // 3 and (want_st == 1).sum() > 50
+
+
+def test_viterbi_k5_batch(gpu):
+    from test_oracle_fec import _bind_conv_oracle, viterbi_cases
+
+    O = H.oracle_fec()
+    _bind_conv_oracle(O)
+    rng = np.random.default_rng(91)
+    u16p = C.POINTER(C.c_uint16)
+    cases = viterbi_cases(rng, 208)
+    for nbits in (240, 96, 40, 176):
+        grp = [c for c, m in cases if c.size == 2 * (nbits + 4)]
+        cost = np.stack(grp)
+        init = np.full((cost.shape[0], 64), 0x55, np.uint8)
+        out, met = gpu.viterbi_k5_decode(cost, cost.shape[1], out_pitch=64, out_init=init)
+        for i in range(cost.shape[0]):
+            w = np.full(64, 0x55, np.uint8)
+            m = O.oracle_viterbi_k5_decode(H._ptr(w, H.u8p), cost[i].ctypes.data_as(u16p), cost.shape[1])
+            assert m == met[i] and np.array_equal(out[i], w), (nbits, i)
+    for pattern in ([1, 1, 1, 0], [1] * 8, [1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1]):
+        punct = np.array(pattern, np.uint8)
+        in_len = 250
+        cost = rng.integers(0, 65536, (64, in_len)).astype(np.uint16)
+        out, met = gpu.viterbi_k5_decode(cost, in_len, punct=punct, out_pitch=80)
+        for i in range(64):
+            w = np.zeros(80, np.uint8)
+            m = O.oracle_viterbi_k5_decode_punctured(H._ptr(w, H.u8p), cost[i].ctypes.data_as(u16p), H._ptr(punct, H.u8p), in_len, punct.size)
+            assert m == met[i] and np.array_equal(out[i], w), (pattern, i)
+
+
+def test_nxdn_conv_batch_with_carried_metrics(gpu):
+    from test_oracle_fec import _bind_conv_oracle
+
+    O = H.oracle_fec()
+    _bind_conv_oracle(O)
+    rng = np.random.default_rng(92)
+    u16p = C.POINTER(C.c_uint16)
+    n = 96
+    g_metrics = np.zeros((n, 32), np.uint16)
+    o_metrics = np.zeros((n, 32), np.uint16)
+    for frame in range(6):  # consecutive frames per channel: the metric arrays carry over like the reference's statics
+        n_steps = [191, 300, 37, 96, 255, 20][frame]
+        n_out = [187, 296, 37, 92, 1, 16][frame]
+        soft = frame % 2 == 1
+        sym = (rng.integers(0, 2, (n, 2 * n_steps)) * 2).astype(np.uint8)
+        sym[rng.random(sym.shape) < 0.05] = 1
+        rel = rng.integers(0, 256, sym.shape).astype(np.uint8)
+        init = np.full((n, 40), 0xA5, np.uint8)
+        out = gpu.nxdn_conv_decode(sym, rel if soft else None, n_steps, n_out, g_metrics, out_pitch=40, out_init=init)
+        for i in range(n):
+            w = np.full(40, 0xA5, np.uint8)
+            O.oracle_nxdn_conv_decode(H._ptr(sym[i], H.u8p), H._ptr(rel[i], H.u8p) if soft else None, n_steps, n_out,
+                                      o_metrics[i].ctypes.data_as(u16p), H._ptr(w, H.u8p))
+            assert np.array_equal(out[i], w), (frame, i)
+        assert np.array_equal(g_metrics, o_metrics), frame

@@ -224,3 +224,105 @@ def test_rs63_vs_reference(n, k):
         r1 = O.oracle_rs63_decode(tt, rx2.ctypes.data_as(H.i32p), oa.ctypes.data_as(H.i32p))
         r2 = R.ref_rs63_decode(tt, rx2.ctypes.data_as(H.i32p), ob.ctypes.data_as(H.i32p))
         assert r1 == r2 and np.array_equal(oa, ob), (trial, pos2)
+
+
+def _bind_conv(R):
+    u16p = C.POINTER(C.c_uint16)
+    R.viterbi_decode.restype = C.c_uint32
+    R.viterbi_decode.argtypes = [H.u8p, u16p, C.c_uint16]
+    R.viterbi_decode_punctured.restype = C.c_uint32
+    R.viterbi_decode_punctured.argtypes = [H.u8p, u16p, H.u8p, C.c_uint16, C.c_uint16]
+    R.CNXDNConvolution_decode.argtypes = [C.c_uint8, C.c_uint8]
+    R.CNXDNConvolution_decode_soft.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8]
+    R.CNXDNConvolution_chainback.argtypes = [H.u8p, C.c_uint]
+
+
+def _bind_conv_oracle(O):
+    u16p = C.POINTER(C.c_uint16)
+    O.oracle_viterbi_k5_decode.restype = C.c_uint32
+    O.oracle_viterbi_k5_decode.argtypes = [H.u8p, u16p, C.c_int]
+    O.oracle_viterbi_k5_decode_punctured.restype = C.c_uint32
+    O.oracle_viterbi_k5_decode_punctured.argtypes = [H.u8p, u16p, H.u8p, C.c_int, C.c_int]
+    O.oracle_nxdn_conv_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, u16p, H.u8p]
+
+
+def viterbi_cases(rng, n_cases):
+    """(cost array uint16, len) test inputs: clean / noisy encodings of terminated messages and pure noise."""
+    cases = []
+    for t in range(n_cases):
+        nbits = [240, 96, 40, 176][t % 4]
+        msg = np.concatenate([rng.integers(0, 2, nbits), np.zeros(4, np.int64)])
+        enc = H.conv_k5_encode(msg).astype(np.float64)
+        soft = enc * 65535.0 + rng.standard_normal(enc.size) * [0.0, 9000.0, 20000.0, 30000.0][(t // 4) % 4]
+        cost = np.clip(np.rint(soft), 0, 65535).astype(np.uint16)
+        if t % 11 == 10:
+            cost = rng.integers(0, 65536, cost.size).astype(np.uint16)
+        if t % 13 == 12:
+            cost[:] = 0x7FFF  # all erasures: every ACS is a tie
+        cases.append((cost, msg))
+    return cases
+
+
+@needs_ref
+def test_viterbi_k5_vs_reference():
+    O, R = H.oracle_fec(), H.ref_fec()
+    _bind_conv(R)
+    _bind_conv_oracle(O)
+    rng = np.random.default_rng(21)
+    u16p = C.POINTER(C.c_uint16)
+    for t, (cost, msg) in enumerate(viterbi_cases(rng, 200)):
+        n = cost.size
+        a, b = np.full(64, 0x55, np.uint8), np.full(64, 0x55, np.uint8)
+        ma = O.oracle_viterbi_k5_decode(H._ptr(a, H.u8p), cost.ctypes.data_as(u16p), n)
+        mb = R.viterbi_decode(H._ptr(b, H.u8p), cost.ctypes.data_as(u16p), n)
+        assert ma == mb and np.array_equal(a, b), t
+        if t % 16 < 4 and t % 11 != 10 and t % 13 != 12:  # clean: decodes back to the message (first message bit lands at bit 8)
+            nb = n // 2
+            bits = np.unpackbits(a)[8:8 + nb]
+            assert np.array_equal(bits[: msg.size - 4], msg[: msg.size - 4]) and ma == 0
+    # punctured: M17-style 2-of-... pattern and "no puncture"
+    for pattern in ([1, 1, 1, 0], [1] * 8, [1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1]):
+        punct = np.array(pattern, np.uint8)
+        for t in range(40):
+            in_len = int(rng.integers(40, 300)) & ~1
+            cost = rng.integers(0, 65536, in_len).astype(np.uint16)
+            a, b = np.zeros(80, np.uint8), np.zeros(80, np.uint8)
+            ma = O.oracle_viterbi_k5_decode_punctured(H._ptr(a, H.u8p), cost.ctypes.data_as(u16p), H._ptr(punct, H.u8p), in_len, punct.size)
+            mb = R.viterbi_decode_punctured(H._ptr(b, H.u8p), cost.ctypes.data_as(u16p), H._ptr(punct, H.u8p), in_len, punct.size)
+            assert ma == mb and np.array_equal(a, b), (pattern, t)
+
+
+@needs_ref
+def test_nxdn_convolution_vs_reference():
+    O, R = H.oracle_fec(), H.ref_fec()
+    _bind_conv(R)
+    _bind_conv_oracle(O)
+    rng = np.random.default_rng(22)
+    u16p = C.POINTER(C.c_uint16)
+    R.CNXDNConvolution_init()
+    metrics = np.zeros(32, np.uint16)  # oracle-side carried ping-pong metric arrays; the reference carries its own statics
+    for t in range(120):
+        n_steps = int(rng.integers(20, 300))
+        n_out = int(rng.integers(1, n_steps + 1)) if t % 3 else n_steps - 4
+        n_out = max(1, n_out)
+        msg = rng.integers(0, 2, n_steps)
+        enc = H.conv_k5_encode(msg)
+        sym = (enc * 2).astype(np.uint8)
+        flip = rng.random(sym.size) < [0.0, 0.03, 0.1, 0.5][t % 4]
+        sym[flip] = 2 - sym[flip]
+        if t % 7 == 6:
+            sym[rng.random(sym.size) < 0.1] = 1  # erasure value used by the NXDN depuncturer
+        soft = (t % 2 == 1)
+        rel = rng.integers(0, 256, sym.size).astype(np.uint8)
+        R.CNXDNConvolution_start()
+        for i in range(n_steps):
+            if soft:
+                R.CNXDNConvolution_decode_soft(int(sym[2 * i]), int(sym[2 * i + 1]), int(rel[2 * i]), int(rel[2 * i + 1]))
+            else:
+                R.CNXDNConvolution_decode(int(sym[2 * i]), int(sym[2 * i + 1]))
+        b = np.full(40, 0xA5, np.uint8)
+        R.CNXDNConvolution_chainback(H._ptr(b, H.u8p), n_out)
+        a = np.full(40, 0xA5, np.uint8)
+        O.oracle_nxdn_conv_decode(H._ptr(sym, H.u8p), H._ptr(rel, H.u8p) if soft else None, n_steps, n_out,
+                                  metrics.ctypes.data_as(u16p), H._ptr(a, H.u8p))
+        assert np.array_equal(a, b), t
