@@ -55,6 +55,7 @@ def bind(L):
         "dsdneo_b200_channelize": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_channelize_host": (ci, [vp, vp, sz, vp, sz]),
         "dsdneo_b200_selftest_atan2f": (ci, [vp, vp, vp, ci, vp]),
+        "dsdneo_b200_selftest_scale": (ci, [vp, vp, vp, ci, vp]),
     }
     for name, (res, args) in protos.items():
         if _has(L, name):

@@ -422,6 +422,10 @@ int dsdneo_b200_nxdn_conv_decode_batch_host(const uint8_t* h_sym, const uint8_t*
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);
 
+/** Self-test hook: the discriminator's output scale 30000.0f / peak (fsk_modem.c:127-129) as the recurrence kernel
+ *  evaluates it (d_fast) next to the device's IEEE division (d_ieee), so tests can check they agree bit for bit. */
+int dsdneo_b200_selftest_scale(const float* d_pk, float* d_fast, float* d_ieee, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,6 +133,29 @@ def test_device_atan2f(gpu):
     assert ok.all(), (y[~ok][:3], x[~ok][:3], got[~ok][:3], want[~ok][:3])
 
 
+def test_device_scale_division(gpu):
+    """The branch-free 30000/peak of the recurrence kernel == IEEE division (device and host), bit for bit, on every
+    kind of peak the tracker can produce: log-uniform over (1e-7, 2^20), dense around typical values, exact powers of two."""
+    import torch
+
+    rng = np.random.default_rng(78)
+    n = 1 << 23
+    pk = np.exp(rng.uniform(np.log(1.0e-7), np.log(1048576.0), n)).astype(np.float32)
+    pk[: n // 4] = rng.uniform(0.01, 4.0, n // 4).astype(np.float32)
+    pk[n // 4: n // 4 + 64] = (2.0 ** np.arange(-23, 41, dtype=np.float64)).astype(np.float32)[:64]
+    lo = np.float32(0.3).view(np.uint32)
+    pk[n // 2: n // 2 + (1 << 20)] = (lo + np.arange(1 << 20, dtype=np.uint32)).view(np.float32)  # 2^20 consecutive floats
+    pk = np.clip(pk, np.nextafter(np.float32(1.0e-7), np.float32(1)), np.nextafter(np.float32(1048576.0), np.float32(0)))
+    dp = torch.from_numpy(pk).cuda()
+    df, di = torch.empty_like(dp), torch.empty_like(dp)
+    gpu.check(gpu.lib().dsdneo_b200_selftest_scale(dp.data_ptr(), df.data_ptr(), di.data_ptr(), n, None))
+    fast, ieee = df.cpu().numpy(), di.cpu().numpy()
+    host = (np.float32(30000.0) / pk).astype(np.float32)
+    assert np.array_equal(ieee.view(np.uint32), host.view(np.uint32))
+    bad = fast.view(np.uint32) != host.view(np.uint32)
+    assert not bad.any(), (pk[bad][:4], fast[bad][:4], host[bad][:4])
+
+
 def test_no_cpu_fallback_symbols(b200):
     """The product library exports no oracle symbols and links no oracle code."""
     import subprocess
