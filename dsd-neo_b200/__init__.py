@@ -381,6 +381,18 @@ class Frontend:
         check(lib().dsdneo_b200_frontend_process_host(self._h, pin, n, pout, h_out.shape[1]), "frontend_process_host")
         return h_out
 
+    def submit_host(self, h_in, h_out) -> int:
+        """Streaming form: queue one tile, return its ticket; both buffers must stay untouched until wait_host(ticket)."""
+        pin = h_in.data_ptr() if hasattr(h_in, "data_ptr") else h_in.ctypes.data
+        pout = h_out.data_ptr() if hasattr(h_out, "data_ptr") else h_out.ctypes.data
+        t = lib().dsdneo_b200_frontend_submit_host(self._h, pin, h_in.shape[0], pout, h_out.shape[1])
+        if t < 0:
+            check(int(t), "frontend_submit_host")
+        return int(t)
+
+    def wait_host(self, ticket: int) -> None:
+        check(lib().dsdneo_b200_frontend_wait_host(self._h, ticket), "frontend_wait_host")
+
 
 # ------------------------------------------------------------------------------------------ FEC (host-buffer entry points)
 

@@ -45,6 +45,8 @@ def bind(L):
         "dsdneo_b200_frontend_bank": (vp, [vp]),
         "dsdneo_b200_frontend_process": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_frontend_process_host": (ci, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_frontend_submit_host": (C.c_longlong, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_frontend_wait_host": (ci, [vp, C.c_longlong]),
         "dsdneo_b200_frontend_process_async": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_frontend_join": (ci, [vp, vp]),
         "dsdneo_b200_channelizer_design_prototype": (ci, [ci, ci, cd, C.POINTER(cf)]),

@@ -29,6 +29,9 @@ struct dsdneo_b200_frontend {
     float* d_out[2];
     size_t in_cap, out_cap;
     cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2], ev_in_free[2];
+    cudaEvent_t ev_ticket[4];          /* completion of the last four submit_host calls */
+    unsigned long long host_blocks;    /* blocks queued by submit_host so far (slot = host_blocks & 1) */
+    unsigned long long host_tickets;   /* submit_host calls so far */
     int streams_ready;
     /* device-side two-stage pipeline (process_async): FIR-side stream, recurrence stream */
     cudaStream_t s_fir, s_rec;
@@ -132,6 +135,9 @@ dsdneo_b200_frontend_destroy(dsdneo_b200_frontend* fe) {
             cudaEventDestroy(fe->ev_comp[i]);
             cudaEventDestroy(fe->ev_d2h[i]);
             cudaEventDestroy(fe->ev_in_free[i]);
+        }
+        for (int i = 0; i < 4; i++) {
+            cudaEventDestroy(fe->ev_ticket[i]);
         }
     }
     for (int i = 0; i < 2; i++) {
@@ -264,16 +270,23 @@ dsdneo_b200_frontend_join(dsdneo_b200_frontend* fe, void* stream) {
     return 0;
 }
 
-int
-dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
-                                  float* h_result, size_t result_pitch) {
+/*
+ * Streaming form for host buffers: queues the per-block H2D / kernels / D2H pipeline of one tile on the three internal
+ * streams and returns without waiting, so the transfers of consecutive tiles overlap (the reference's own demod thread
+ * streams blocks through a ring in the same way, src/io/radio/rtl_sdr_fm.cpp:3458-3512).  Returns a ticket >= 0; the
+ * caller's buffers must stay valid and untouched until dsdneo_b200_frontend_wait_host(ticket) has returned.  At most
+ * four tickets may be outstanding.
+ */
+long long
+dsdneo_b200_frontend_submit_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples, float* h_result,
+                                 size_t result_pitch) {
     if (!fe || !h_wideband || !h_result) {
-        set_error("frontend_process_host: bad argument");
+        set_error("frontend_submit_host: bad argument");
         return DSDNEO_B200_EINVAL;
     }
     const size_t per_block = (size_t)fe->M * (size_t)fe->block_pairs;
     if (n_in_samples == 0 || n_in_samples % per_block != 0) {
-        set_error("frontend_process_host: n_in_samples must be a positive multiple of n_channels*block_pairs (%zu)", per_block);
+        set_error("frontend_submit_host: n_in_samples must be a positive multiple of n_channels*block_pairs (%zu)", per_block);
         return DSDNEO_B200_EINVAL;
     }
     int rc = ensure_device();
@@ -282,7 +295,7 @@ dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideba
     }
     const int n_blocks = (int)(n_in_samples / per_block);
     if (result_pitch < (size_t)n_blocks * fe->block_pairs) {
-        set_error("frontend_process_host: result_pitch too small");
+        set_error("frontend_submit_host: result_pitch too small");
         return DSDNEO_B200_EINVAL;
     }
     if (!fe->streams_ready) {
@@ -295,10 +308,18 @@ dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideba
             DSDNEO_CUDA(cudaEventCreateWithFlags(&fe->ev_d2h[i], cudaEventDisableTiming));
             DSDNEO_CUDA(cudaEventCreateWithFlags(&fe->ev_in_free[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < 4; i++) {
+            DSDNEO_CUDA(cudaEventCreateWithFlags(&fe->ev_ticket[i], cudaEventDisableTiming));
+        }
         fe->streams_ready = 1;
+        fe->host_blocks = 0;
+        fe->host_tickets = 0;
     }
     const size_t in_bytes = per_block * (fe->cu8 ? 2 : 8);
     const size_t out_floats = (size_t)fe->M * fe->block_pairs;
+    if (fe->in_cap < in_bytes || fe->out_cap < out_floats || !fe->d_chan || fe->chan_pitch < (size_t)fe->block_pairs) {
+        DSDNEO_CUDA(cudaDeviceSynchronize()); /* (re)allocation: drain anything still queued on the old buffers */
+    }
     if (fe->in_cap < in_bytes) {
         for (int i = 0; i < 2; i++) {
             cudaFree(fe->d_in[i]);
@@ -320,16 +341,16 @@ dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideba
         return rc;
     }
     const unsigned char* src = (const unsigned char*)h_wideband;
-    for (int b = 0; b < n_blocks; b++) {
-        const int slot = b & 1;
-        if (b >= 2) {
-            DSDNEO_CUDA(cudaStreamWaitEvent(fe->s_h2d, fe->ev_in_free[slot], 0)); /* kernels of block b-2 consumed d_in[slot] */
+    for (int b = 0; b < n_blocks; b++, fe->host_blocks++) {
+        const int slot = (int)(fe->host_blocks & 1);
+        if (fe->host_blocks >= 2) {
+            DSDNEO_CUDA(cudaStreamWaitEvent(fe->s_h2d, fe->ev_in_free[slot], 0)); /* kernels two blocks back consumed d_in[slot] */
         }
         DSDNEO_CUDA(cudaMemcpyAsync(fe->d_in[slot], src + (size_t)b * in_bytes, in_bytes, cudaMemcpyHostToDevice, fe->s_h2d));
         DSDNEO_CUDA(cudaEventRecord(fe->ev_h2d[slot], fe->s_h2d));
 
         DSDNEO_CUDA(cudaStreamWaitEvent(fe->s_comp, fe->ev_h2d[slot], 0));
-        if (b >= 2) {
+        if (fe->host_blocks >= 2) {
             DSDNEO_CUDA(cudaStreamWaitEvent(fe->s_comp, fe->ev_d2h[slot], 0)); /* d_out[slot] drained */
         }
         rc = dsdneo_b200_channelize(fe->cz, fe->d_in[slot], per_block, fe->d_chan, fe->chan_pitch, fe->s_comp);
@@ -350,9 +371,33 @@ dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideba
                                       (size_t)fe->M, cudaMemcpyDeviceToHost, fe->s_d2h));
         DSDNEO_CUDA(cudaEventRecord(fe->ev_d2h[slot], fe->s_d2h));
     }
-    DSDNEO_CUDA(cudaStreamSynchronize(fe->s_d2h));
-    DSDNEO_CUDA(cudaStreamSynchronize(fe->s_comp));
+    const long long ticket = (long long)fe->host_tickets++;
+    DSDNEO_CUDA(cudaEventRecord(fe->ev_ticket[ticket & 3], fe->s_d2h)); /* the tile's last D2H copy */
+    return ticket;
+}
+
+/** Blocks until the tile queued under `ticket` is complete in the caller's result buffer. */
+int
+dsdneo_b200_frontend_wait_host(dsdneo_b200_frontend* fe, long long ticket) {
+    if (!fe || !fe->streams_ready || ticket < 0 || (unsigned long long)ticket >= fe->host_tickets) {
+        set_error("frontend_wait_host: unknown ticket");
+        return DSDNEO_B200_EINVAL;
+    }
+    if ((unsigned long long)ticket + 4 < fe->host_tickets) {
+        return 0; /* its event slot has been reused by a later tile, which completes after it (same streams) */
+    }
+    DSDNEO_CUDA(cudaEventSynchronize(fe->ev_ticket[ticket & 3]));
     return 0;
+}
+
+int
+dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
+                                  float* h_result, size_t result_pitch) {
+    const long long t = dsdneo_b200_frontend_submit_host(fe, h_wideband, n_in_samples, h_result, result_pitch);
+    if (t < 0) {
+        return (int)t;
+    }
+    return dsdneo_b200_frontend_wait_host(fe, t);
 }
 
 } /* extern "C" */

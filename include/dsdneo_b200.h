@@ -246,6 +246,16 @@ int dsdneo_b200_frontend_join(dsdneo_b200_frontend* fe, void* stream);
 /** Host buffers (pinned recommended): per-block H2D / kernels / D2H pipelined on three streams; synchronous. */
 int dsdneo_b200_frontend_process_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
                                       float* h_result, size_t result_pitch);
+/**
+ * Streaming form of process_host, the shape of the reference's demod thread (src/io/radio/rtl_sdr_fm.cpp:3458-3512:
+ * blocks stream from the input ring through full_demod into the output ring): queues one tile and returns a ticket
+ * (>= 0, or a negative DSDNEO_B200_E* code) without waiting, so the PCIe transfers and kernels of consecutive tiles
+ * overlap.  Both host buffers must stay valid and untouched until wait_host(ticket) returns.  At most four tickets may
+ * be outstanding.  Bit-identical to process_host.
+ */
+long long dsdneo_b200_frontend_submit_host(dsdneo_b200_frontend* fe, const void* h_wideband, size_t n_in_samples,
+                                           float* h_result, size_t result_pitch);
+int dsdneo_b200_frontend_wait_host(dsdneo_b200_frontend* fe, long long ticket);
 
 /* ---- sample side: matched filter + getSymbol + use_symbol + digitize, batched over channels (K9-K11) ----- */
 

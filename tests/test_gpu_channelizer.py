@@ -132,3 +132,29 @@ def test_frontend_sync_async_and_host_paths_agree(gpu):
     for a, b, c in zip(outs_a, outs_b, outs_c):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
         assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+def test_frontend_streaming_host_tickets(gpu):
+    """submit_host / wait_host (tiles in flight overlap) == the blocking process_host, bit for bit, over six tiles with
+    the consumer lagging one ticket behind; unknown tickets are rejected."""
+    import torch
+
+    rng = np.random.default_rng(35)
+    bp, nb = 512, 2
+    tiles = [torch.from_numpy(H.synth_wideband(rng, M, bp * nb, [9, 130], snr_db=25.0)[0]).pin_memory() for _ in range(6)]
+    fa = gpu.Frontend(M, 8, False, 12_288_000, bp)
+    fb = gpu.Frontend(M, 8, False, 12_288_000, bp)
+    want = [fa.process_host(t.numpy()).copy() for t in tiles]
+    outs = [torch.empty((M, bp * nb), dtype=torch.float32).pin_memory() for _ in tiles]
+    tickets = []
+    for i, t in enumerate(tiles):
+        tickets.append(fb.submit_host(t, outs[i]))
+        if i >= 1:
+            fb.wait_host(tickets[i - 1])
+            assert np.array_equal(outs[i - 1].numpy().view(np.uint32), want[i - 1].view(np.uint32))
+    fb.wait_host(tickets[-1])
+    assert np.array_equal(outs[-1].numpy().view(np.uint32), want[-1].view(np.uint32))
+    assert tickets == list(range(6))
+    fb.wait_host(tickets[0])  # an old ticket is already complete
+    with pytest.raises(gpu.B200Error):
+        fb.wait_host(99)
