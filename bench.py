@@ -453,15 +453,101 @@ def run_b200_arm(args):
     print(json.dumps(line))
 
 
+def run_channel_sharded(args):
+    """North-star multi-GPU shape: ONE wideband stream, one NCCL broadcast of each raw IQ tile
+    from rank 0, every rank runs the channelizer and demodulates its own contiguous channel range.  Strong scaling of a
+    fixed band; not the driver's default line (that is --shard bands)."""
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b200 = g.load_package()
+    b200.init(local)
+    from dsdneo_b200 import shard
+
+    if args.channels != M:
+        raise SystemExit("bench.py --shard channels: the channelizer kernel is built for %d channels" % M)
+    base = make_wideband(torch, dev, seed=0)
+    bufs = [base, torch.roll(base, 777 * M + 13, 0).contiguous(), base.flip(0).contiguous()]
+    if rank != 0:
+        for b in bufs:
+            b.zero_()  # only the ingest rank holds data; everyone else receives it through the broadcast
+    sf = shard.ShardedFrontend(b200, M, rank, world, 8, False, WIDEBAND_HZ, BLOCK_PAIRS)
+    out = torch.empty((sf.hi - sf.lo, N_OUT), device=dev, dtype=torch.float32)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local).start()
+    for i in range(max(3, args.warmup)):
+        sf.process(bufs[i % 3], out)
+    barrier()
+    launches0 = b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    sf.prefetch(bufs[0])
+    for i in range(args.steps):
+        cur = bufs[i % 3]
+        sf.process(cur, out)
+        if i + 1 < args.steps:
+            sf.prefetch(bufs[(i + 1) % 3])  # broadcast of tile i+1 on a side stream, under the kernels of tile i
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = b200.launch_count() - launches0
+    clk = clocks.stop()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms_per_step = ms / args.steps
+    value = N_IN / (ms_per_step * 1e-3) / 1e6
+    print(json.dumps({
+        "metric": "iq_msps", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "channels_at_realtime": value * 1e6 / WIDEBAND_HZ * M,
+        "config": {"workload": WORKLOAD + " -- ONE band, channel ranges sharded over GPUs", "channels": M,
+                   "channels_per_gpu": [shard.channel_range(r, world, M)[1] - shard.channel_range(r, world, M)[0] for r in range(world)],
+                   "samples_per_step": N_IN, "collective": "one NCCL broadcast of the raw cf32 tile per step (%d bytes), "
+                   "double-buffered on a side stream" % (N_IN * 8),
+                   "l2_policy": "3 rotating input buffers of %.1f MB" % (N_IN * 8 / 1e6)},
+        "clocks": clk, "gpu_launches": int(launches)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shard", default="bands", choices=["bands", "channels"],
+                    help="bands (default): one independent 256-channel band per GPU, weak scaling, no collective; "
+                         "channels: ONE wideband stream, raw IQ tile broadcast over NCCL, each GPU demodulates a channel range "
+                         "(--channels sets the channelizer size)")
+    ap.add_argument("--channels", type=int, default=M)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.shard == "channels":
+        run_channel_sharded(args)
     else:
         if args.warmup < 3:
             args.warmup = 3
