@@ -218,6 +218,49 @@ class DemodBank:
         return out
 
 
+class HalfbandCascade:
+    """N-channel twin of full_demod_apply_halfband_decimation (demod_pipeline.cpp:983-1001): `passes` half-band /2 stages."""
+
+    def __init__(self, n_channels: int, passes: int, fir_arith: int = FIR_ARITH_FMA):
+        self.n_channels, self.passes = n_channels, passes
+        self._h = lib().dsdneo_b200_hb_cascade_create(n_channels, passes, fir_arith)
+        if not self._h:
+            raise B200Error(f"hb_cascade_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_hb_cascade_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_hb_cascade_reset(self._h, _stream_ptr(stream)), "hb_cascade_reset")
+
+    def decimate(self, d_in, block_pairs: int, n_blocks: int, d_out=None, stream=None):
+        """d_in: cuda f32 [n_channels, pitch_pairs, 2]; returns [n_channels, (block_pairs >> passes) * n_blocks, 2]."""
+        import torch
+
+        assert d_in.is_cuda and d_in.dtype == torch.float32 and d_in.is_contiguous() and d_in.shape[0] == self.n_channels
+        n_out = (block_pairs >> self.passes) * n_blocks
+        if d_out is None:
+            d_out = torch.empty((self.n_channels, n_out, 2), dtype=torch.float32, device=d_in.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(lib().dsdneo_b200_hb_cascade_decim_batch(self._h, d_in.data_ptr(), d_in.shape[1], block_pairs, n_blocks,
+                                                       d_out.data_ptr(), d_out.shape[1], _stream_ptr(stream)), "hb_cascade_decim_batch")
+        return d_out
+
+    def decimate_host(self, h_in, block_pairs: int, n_blocks: int):
+        import numpy as np
+
+        h_in = np.ascontiguousarray(h_in, dtype=np.float32)
+        out = np.empty((self.n_channels, (block_pairs >> self.passes) * n_blocks, 2), dtype=np.float32)
+        check(lib().dsdneo_b200_hb_cascade_decim_batch_host(self._h, h_in.ctypes.data, h_in.shape[1], block_pairs, n_blocks,
+                                                            out.ctypes.data, out.shape[1]), "hb_cascade_decim_batch_host")
+        return out
+
+
 class Channelizer:
     """Polyphase FIR channelizer (K2, optionally fused K1 cu8 widening). See include/dsdneo_b200.h."""
 

@@ -39,6 +39,11 @@ def bind(L):
         "dsdneo_b200_p25_rs_decode_batch_host": (ci, [ci, vp, vp, vp, ci]),
         "dsdneo_b200_timing_enable": (ci, [ci]),
         "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
+        "dsdneo_b200_hb_cascade_create": (vp, [ci, ci, ci]),
+        "dsdneo_b200_hb_cascade_destroy": (None, [vp]),
+        "dsdneo_b200_hb_cascade_reset": (ci, [vp, vp]),
+        "dsdneo_b200_hb_cascade_decim_batch": (ci, [vp, vp, sz, ci, ci, vp, sz, vp]),
+        "dsdneo_b200_hb_cascade_decim_batch_host": (ci, [vp, vp, sz, ci, ci, vp, sz]),
         "dsdneo_b200_frontend_create": (vp, [vp]),
         "dsdneo_b200_frontend_destroy": (None, [vp]),
         "dsdneo_b200_frontend_reset": (ci, [vp, vp]),

@@ -257,6 +257,26 @@ long long dsdneo_b200_frontend_submit_host(dsdneo_b200_frontend* fe, const void*
                                            float* h_result, size_t result_pitch);
 int dsdneo_b200_frontend_wait_host(dsdneo_b200_frontend* fe, long long ticket);
 
+/* ---- K3: complex half-band decimator cascade, batched over channels ------------------------------------ */
+/*
+ * Replaces full_demod_apply_halfband_decimation (src/dsp/demod_pipeline.cpp:983-1001) = `passes` calls of
+ * simd_hb_decim2_complex (src/dsp/simd_fir.cpp:363-373; stage 0 uses hb31_q15_taps, later stages hb_q15_taps,
+ * src/dsp/halfband.cpp:35-74), with the per-stage histories of struct demod_state (hb_hist_i/q[10][30]) kept on the device.
+ * Input  [n_channels][in_pitch_pairs] cf32, n_blocks reference blocks of block_pairs each (the reference pads the right
+ * edge of every block with its last sample, so block boundaries are part of the result);
+ * output [n_channels][out_pitch_pairs] cf32, block_pairs >> passes pairs per block.
+ * fir_arith selects the reference kernel whose arithmetic is reproduced bit for bit (DSDNEO_FIR_ARITH_*); as in the
+ * reference, blocks shorter than the tap count always take the unfused kernel.  block_pairs must be a multiple of 2^passes.
+ */
+typedef struct dsdneo_b200_hb_cascade dsdneo_b200_hb_cascade;
+dsdneo_b200_hb_cascade* dsdneo_b200_hb_cascade_create(int n_channels, int passes, int fir_arith);
+void dsdneo_b200_hb_cascade_destroy(dsdneo_b200_hb_cascade* h);
+int dsdneo_b200_hb_cascade_reset(dsdneo_b200_hb_cascade* h, void* stream);
+int dsdneo_b200_hb_cascade_decim_batch(dsdneo_b200_hb_cascade* h, const float* d_in, size_t in_pitch_pairs, int block_pairs,
+                                       int n_blocks, float* d_out, size_t out_pitch_pairs, void* stream);
+int dsdneo_b200_hb_cascade_decim_batch_host(dsdneo_b200_hb_cascade* h, const float* h_in, size_t in_pitch_pairs,
+                                            int block_pairs, int n_blocks, float* h_out, size_t out_pitch_pairs);
+
 /* ---- sample side: matched filter + getSymbol + use_symbol + digitize, batched over channels (K9-K11) ----- */
 
 #define DSDNEO_B200_SYM_MAX_TAPS 256

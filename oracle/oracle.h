@@ -55,6 +55,11 @@ int oracle_channel_lpf_design(int rate_out_hz, int profile, float* taps_out, int
 void oracle_fir_complex(const float* in, int in_len, float* out, float* hist_i, float* hist_q, const float* taps,
                         int taps_len, int fma);
 float oracle_mean_power(const float* samples, int len, int step);
+extern const float oracle_hb15_taps[15];
+extern const float oracle_hb31_taps[31];
+int oracle_hb_decim2_complex(const float* in, int in_len, float* out, float* hist_i, float* hist_q, const float* taps,
+                             int taps_len, int fma);
+int oracle_hb_cascade(const float* in, int in_len, int passes, float* hist, float* work, float* out, int fma);
 int oracle_demod_chan_init(oracle_demod_chan* c, int rate_out_hz, int profile, int lpf_enable, float squelch_level,
                            int fir_fma);
 /* One full_demod() call: n_floats interleaved I/Q in, n_floats/2 discriminator samples out.

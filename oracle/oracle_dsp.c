@@ -73,6 +73,9 @@ oracle_fir_complex(const float* in, int in_len, float* out, float* hist_i, float
     if (taps_len < 3 || !(taps_len & 1) || in_len < 2) {
         return;
     }
+    if (in_len < taps_len * 2) {
+        fma = 0; /* simd_fir_prefer_scalar_for_block, src/dsp/simd_fir.cpp:302-305,353-356: short blocks take the scalar kernel */
+    }
     int N = in_len / 2;
     int H = taps_len - 1;
     int c = H / 2;
@@ -126,6 +129,109 @@ oracle_fir_complex(const float* in, int in_len, float* out, float* hist_i, float
             hist_q[keep + k] = in[2 * k + 1];
         }
     }
+}
+
+/* ---- complex half-band decimator by 2 and its cascade --------------------------------------- */
+/* Taps: src/dsp/halfband.cpp:35-74 (Q15-normalised; odd taps zero except the centre). */
+const float oracle_hb15_taps[15] = {-108.0f / 32768.0f, 0.0f, 1800.0f / 32768.0f, 0.0f, -500.0f / 32768.0f, 0.0f,
+                                    7000.0f / 32768.0f, 0.5f, 7000.0f / 32768.0f, 0.0f, -500.0f / 32768.0f, 0.0f,
+                                    1800.0f / 32768.0f, 0.0f, -108.0f / 32768.0f};
+const float oracle_hb31_taps[31] = {0.0f, 0.0f, 13.0f / 32768.0f, 0.0f, -73.0f / 32768.0f, 0.0f, 233.0f / 32768.0f, 0.0f,
+                                    -587.0f / 32768.0f, 0.0f, 1314.0f / 32768.0f, 0.0f, -2953.0f / 32768.0f, 0.0f,
+                                    10244.0f / 32768.0f, 16386.0f / 32768.0f, 10244.0f / 32768.0f, 0.0f,
+                                    -2953.0f / 32768.0f, 0.0f, 1314.0f / 32768.0f, 0.0f, -587.0f / 32768.0f, 0.0f,
+                                    233.0f / 32768.0f, 0.0f, -73.0f / 32768.0f, 0.0f, 13.0f / 32768.0f, 0.0f, 0.0f};
+
+/* fma == 0: simd_hb_decim2_complex_scalar, src/dsp/simd_fir.cpp:139-222 (the SSE2 kernel does the same per-output
+ *           operations): acc = 0; acc += cc*x[centre]; for even e: acc += taps[e] * (x[-d] + x[+d]), zero taps skipped.
+ * fma == 1: src/dsp/simd_fir_avx2.cpp:312-390: centre product, then acc = fma(tap, x[-d] + x[+d], acc).
+ * Input beyond the block is the block's last sample; input before it is the carried history (taps_len - 1 samples).
+ * Returns the number of floats written (2 * (pairs / 2)). */
+int
+oracle_hb_decim2_complex(const float* in, int in_len, float* out, float* hist_i, float* hist_q, const float* taps,
+                         int taps_len, int fma) {
+    if (taps_len < 3 || !(taps_len & 1)) {
+        return 0;
+    }
+    int N = in_len / 2;
+    if (N <= 0) {
+        return 0;
+    }
+    if (in_len < taps_len * 2) {
+        fma = 0; /* simd_fir_prefer_scalar_for_block, src/dsp/simd_fir.cpp:302-305,366-368 */
+    }
+    int n_out = N / 2;
+    int H = taps_len - 1;
+    int c = H / 2;
+#define HB_I(rel) ((rel) < 0 ? hist_i[H + (rel)] : ((rel) < N ? in[2 * (rel)] : in[2 * (N - 1)]))
+#define HB_Q(rel) ((rel) < 0 ? hist_q[H + (rel)] : ((rel) < N ? in[2 * (rel) + 1] : in[2 * (N - 1) + 1]))
+    for (int n = 0; n < n_out; n++) {
+        const int mid = 2 * n; /* the reference centres on src index (taps_len-1) + 2n of [hist | block | pad] */
+        float ai, aq;
+        if (fma) {
+            ai = taps[c] * HB_I(mid);
+            aq = taps[c] * HB_Q(mid);
+        } else {
+            ai = 0.0f;
+            aq = 0.0f;
+            ai += taps[c] * HB_I(mid);
+            aq += taps[c] * HB_Q(mid);
+        }
+        for (int e = 0; e < c; e += 2) {
+            float t = taps[e];
+            if (t == 0.0f) {
+                continue;
+            }
+            int d = c - e;
+            float si = HB_I(mid - d) + HB_I(mid + d);
+            float sq = HB_Q(mid - d) + HB_Q(mid + d);
+            if (fma) {
+                ai = fmaf(t, si, ai);
+                aq = fmaf(t, sq, aq);
+            } else {
+                ai += t * si;
+                aq += t * sq;
+            }
+        }
+        out[2 * n] = ai;
+        out[2 * n + 1] = aq;
+    }
+#undef HB_I
+#undef HB_Q
+    if (N >= H) {
+        for (int k = 0; k < H; k++) {
+            hist_i[k] = in[2 * (N - H + k)];
+            hist_q[k] = in[2 * (N - H + k) + 1];
+        }
+    } else {
+        int keep = H - N;
+        memmove(hist_i, hist_i + N, (size_t)keep * sizeof(float));
+        memmove(hist_q, hist_q + N, (size_t)keep * sizeof(float));
+        for (int k = 0; k < N; k++) {
+            hist_i[keep + k] = in[2 * k];
+            hist_q[keep + k] = in[2 * k + 1];
+        }
+    }
+    return 2 * n_out;
+}
+
+/* full_demod_apply_halfband_decimation, src/dsp/demod_pipeline.cpp:983-1001: `passes` stages, stage 0 = 31 taps, the rest
+ * 15; hist is [passes][2][30].  `work` must hold in_len floats.  Result (in_len >> passes floats) is written to `out`. */
+int
+oracle_hb_cascade(const float* in, int in_len, int passes, float* hist /* [passes][2][30] */, float* work, float* out,
+                  int fma) {
+    const float* src = in;
+    int len = in_len;
+    for (int i = 0; i < passes; i++) {
+        float* dst = (i == passes - 1) ? out : ((i & 1) ? work + in_len / 2 : work);
+        len = oracle_hb_decim2_complex(src, len, dst, hist + (size_t)i * 60, hist + (size_t)i * 60 + 30,
+                                       i == 0 ? oracle_hb31_taps : oracle_hb15_taps, i == 0 ? 31 : 15, fma);
+        src = dst;
+    }
+    if (passes == 0) {
+        memcpy(out, in, (size_t)in_len * sizeof(float));
+    }
+    return len;
 }
 
 /* ---- mean power ----------------------------------------------------------------------- */

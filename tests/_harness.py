@@ -97,6 +97,22 @@ def oracle_full_demod(iq_ch, block_pairs, n_blocks, fir_fma=1, rate=48000, profi
     return (out, chan) if return_chan else out
 
 
+def oracle_hb_cascade(x, block_pairs, n_blocks, passes, fma=1, hist=None):
+    """x: [n, 2] float32 of one channel; runs the oracle's half-band cascade block by block.  Returns [n >> passes, 2]."""
+    L = oracle()
+    L.oracle_hb_cascade.restype = C.c_int
+    if hist is None:
+        hist = np.zeros((passes, 2, 30), np.float32)
+    outs = []
+    work = np.zeros(2 * block_pairs + 8, np.float32)
+    for b in range(n_blocks):
+        blk = np.ascontiguousarray(x[b * block_pairs:(b + 1) * block_pairs], dtype=np.float32).reshape(-1)
+        out = np.zeros(max(2, (2 * block_pairs) >> passes), np.float32)
+        n = L.oracle_hb_cascade(_ptr(blk), C.c_int(blk.size), C.c_int(passes), _ptr(hist), _ptr(work), _ptr(out), C.c_int(fma))
+        outs.append(out[:n].reshape(-1, 2).copy())
+    return np.concatenate(outs)
+
+
 # --------------------------------------------------------------------------- compiled reference
 
 _refs = {}

@@ -4,6 +4,9 @@
   sps_fir_taps.npz   normalised matched-filter taps of the reference (impulse responses of p25/dmr/nxdn/dpmr/m17_filter)
   full_demod.npz     seeded 4FSK IQ -> reference full_demod() discriminator output (parity + avx2 builds), 3 blocks of 1024 pairs
   symbols.npz        seeded discriminator stream -> reference getDibitSoft() dibits / symbols / soft metrics (P25p1 +, DMR BS data)
+  halfband.npz       seeded cf32 -> the reference's half-band cascade (simd_hb_decim2_complex chained as
+                     full_demod_apply_halfband_decimation does), 3 passes, 3 blocks of 512 pairs, parity + avx2 builds
+                     (python tests/golden/make_golden.py halfband  regenerates only this file)
 """
 import ctypes as C
 import os
@@ -16,8 +19,40 @@ sys.path.insert(0, os.path.dirname(HERE))
 import _harness as H  # noqa: E402
 
 
+def ref_hb_cascade(variant, x, block_pairs, n_blocks, passes):
+    """Chains the reference's simd_hb_decim2_complex exactly like demod_pipeline.cpp:983-1001 (31 taps, then 15)."""
+    R = C.CDLL(H._ref_path(variant))
+    R.simd_hb_decim2_complex.restype = C.c_int
+    hb15 = (C.c_float * 15).in_dll(R, "hb_q15_taps")
+    hb31 = (C.c_float * 31).in_dll(R, "hb31_q15_taps")
+    hist = np.zeros((passes, 2, 30), np.float32)
+    outs = []
+    for b in range(n_blocks):
+        cur = np.ascontiguousarray(x[b * block_pairs:(b + 1) * block_pairs]).reshape(-1).copy()
+        for i in range(passes):
+            dst = np.zeros(cur.size // 2 + 2, np.float32)
+            n = R.simd_hb_decim2_complex(H._ptr(cur), cur.size, H._ptr(dst), H._ptr(hist[i, 0]), H._ptr(hist[i, 1]),
+                                         hb31 if i == 0 else hb15, 31 if i == 0 else 15)
+            cur = dst[:n].copy()
+        outs.append(cur.reshape(-1, 2))
+    return np.concatenate(outs)
+
+
+def halfband():
+    rng = np.random.default_rng(20261018)
+    bp, nb, passes = 512, 3, 3
+    x = rng.standard_normal((bp * nb, 2)).astype(np.float32)
+    out = {"x": x, "block_pairs": bp, "n_blocks": nb, "passes": passes, "ref_par": ref_hb_cascade("par", x, bp, nb, passes)}
+    if H.ref_available("avx2") and H.ref("avx2").simd_fir_get_impl_name() == b"avx2":
+        out["ref_avx2"] = ref_hb_cascade("avx2", x, bp, nb, passes)
+    np.savez_compressed(os.path.join(HERE, "halfband.npz"), **out)
+    print("halfband.npz written")
+
+
 def main():
     assert H.ref_available("par"), "build oracle/_ref first (make -C oracle ref)"
+    if len(sys.argv) > 1 and sys.argv[1] == "halfband":
+        return halfband()
     R = H.ref_sym()
     taps = {}
     for which in range(5):
@@ -51,6 +86,7 @@ def main():
         sym[name + "_llr"] = l[:2 * n]
         sym[name + "_symbols"] = s[:n]
     np.savez_compressed(os.path.join(HERE, "symbols.npz"), **sym)
+    halfband()
     print("golden fixtures written to", HERE)
 
 

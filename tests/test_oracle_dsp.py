@@ -59,7 +59,9 @@ def test_fir_scalar_matches_reference_scalar_and_sse2():
 
 @needs_ref_avx2
 def test_fir_fma_matches_reference_avx2():
-    """oracle FIR (fma=1) == simd_fir_complex_apply_avx2 for block sizes that are multiples of 4."""
+    """oracle FIR (fma=1) == what simd_fir_complex_apply runs on an AVX2 host: the AVX2 kernel (vector body and its
+    contracted scalar epilogue) for blocks of at least taps_len pairs, the scalar kernel for shorter ones
+    (simd_fir_prefer_scalar_for_block, src/dsp/simd_fir.cpp:302-305)."""
     L, R = H.oracle(), H.ref("avx2")
     if R.simd_fir_get_impl_name() != b"avx2":
         pytest.skip("host CPU has no AVX2")
@@ -67,7 +69,7 @@ def test_fir_fma_matches_reference_avx2():
     taps = H.oracle_lpf_taps(48000, 2)
     hi = [np.zeros(144, np.float32) for _ in range(2)]
     hq = [np.zeros(144, np.float32) for _ in range(2)]
-    for n in [4096, 512, 8192, 272]:
+    for n in [4096, 512, 8192, 272, 100, 134, 135, 137, 141, 1001, 64]:
         x = rng.standard_normal(2 * n).astype(np.float32)
         a, b = np.zeros(2 * n, np.float32), np.zeros(2 * n, np.float32)
         L.oracle_fir_complex(H._ptr(x), 2 * n, H._ptr(a), H._ptr(hi[0]), H._ptr(hq[0]), H._ptr(taps), taps.size, 1)
@@ -175,3 +177,42 @@ def test_oracle_full_demod_matches_committed_golden_vectors():
     assert H.bits_equal(H.oracle_full_demod(g["iq"], bp, nb, fir_fma=0), g["ref_par"])
     if "ref_avx2" in g:
         assert H.bits_equal(H.oracle_full_demod(g["iq"], bp, nb, fir_fma=1), g["ref_avx2"])
+
+
+@needs_ref
+@pytest.mark.parametrize("variant,fma", [("par", 0), ("avx2", 1)])
+def test_halfband_matches_reference(variant, fma):
+    """oracle_hb_decim2_complex == the reference's simd_hb_decim2_complex (src/dsp/simd_fir.cpp:363-373), bit for bit:
+    both tap sets, long/odd/tiny blocks (tiny ones take the scalar kernel even on AVX2 hosts), history carried over 4 blocks."""
+    if not H.ref_available(variant):
+        pytest.skip("variant not built")
+    R = C.CDLL(H._ref_path(variant))
+    R.simd_hb_decim2_complex.restype = C.c_int
+    O = H.oracle()
+    O.oracle_hb_decim2_complex.restype = C.c_int
+    rng = np.random.default_rng(3)
+    for name, tl in (("hb31_q15_taps", 31), ("hb_q15_taps", 15)):
+        taps = (C.c_float * tl).in_dll(R, name)
+        otaps = (C.c_float * tl).in_dll(O, "oracle_hb31_taps" if tl == 31 else "oracle_hb15_taps")
+        assert list(taps) == list(otaps)
+        for npairs in (4096, 1000, 37, 8, 62, 2, 30, 31, 32, 15, 14, 16):
+            hr = np.zeros((2, 30), np.float32)
+            ho = np.zeros((2, 30), np.float32)
+            for _ in range(4):
+                x = rng.standard_normal(2 * npairs).astype(np.float32)
+                out_r, out_o = np.zeros(npairs + 2, np.float32), np.zeros(npairs + 2, np.float32)
+                nr = R.simd_hb_decim2_complex(H._ptr(x), 2 * npairs, H._ptr(out_r), H._ptr(hr[0]), H._ptr(hr[1]), taps, tl)
+                no = O.oracle_hb_decim2_complex(H._ptr(x), 2 * npairs, H._ptr(out_o), H._ptr(ho[0]), H._ptr(ho[1]), otaps, tl, fma)
+                assert nr == no == 2 * (npairs // 2)
+                assert H.bits_equal(out_r, out_o) and H.bits_equal(hr, ho)
+
+
+def test_oracle_halfband_matches_committed_golden_vectors():
+    """Reference half-band cascade outputs captured by tests/golden/make_golden.py (3 passes: 31, 15, 15 taps)."""
+    import os
+
+    g = np.load(os.path.join(H.GOLDEN_DIR, "halfband.npz"))
+    bp, nb, passes = int(g["block_pairs"]), int(g["n_blocks"]), int(g["passes"])
+    assert H.bits_equal(H.oracle_hb_cascade(g["x"], bp, nb, passes, fma=0), g["ref_par"])
+    if "ref_avx2" in g:
+        assert H.bits_equal(H.oracle_hb_cascade(g["x"], bp, nb, passes, fma=1), g["ref_avx2"])
