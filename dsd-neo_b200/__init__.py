@@ -471,6 +471,29 @@ def bptc_196x96(bursts, interleaved: bool):
     return out, r3, errs
 
 
+def bptc_128x77(mats):
+    """mats: uint8 [n, 128] (8 x 16 byte-per-bit matrices). Returns (out77 [n, 77], errs [n])."""
+    import numpy as np
+
+    mats = np.ascontiguousarray(mats, dtype=np.uint8).reshape(-1, 128)
+    n = mats.shape[0]
+    out, errs = np.zeros((n, 77), np.uint8), np.zeros(n, np.uint32)
+    check(lib().dsdneo_b200_bptc_128x77_batch_host(mats.ctypes.data, out.ctypes.data, errs.ctypes.data, n), "bptc_128x77")
+    return out, errs
+
+
+def bptc_16x2(words, parity_odd: bool):
+    """words: uint8 [n, 32] interleaved bits. Returns (out32 [n, 32], errs [n])."""
+    import numpy as np
+
+    words = np.ascontiguousarray(words, dtype=np.uint8).reshape(-1, 32)
+    n = words.shape[0]
+    out, errs = np.zeros((n, 32), np.uint8), np.zeros(n, np.uint32)
+    check(lib().dsdneo_b200_bptc_16x2_batch_host(words.ctypes.data, out.ctypes.data, errs.ctypes.data, 1 if parity_odd else 0, n),
+          "bptc_16x2")
+    return out, errs
+
+
 def p25_12_soft_llr(llr):
     import numpy as np
 
@@ -510,6 +533,38 @@ def p25_rs_decode(variant: int, data_bits, parity_bits):
 
 SYM_MODE_GET_SYMBOL, SYM_MODE_GET_DIBIT_SOFT = 0, 1
 SYM_FILTER_NONE, SYM_FILTER_P25, SYM_FILTER_DMR, SYM_FILTER_NXDN, SYM_FILTER_DPMR, SYM_FILTER_M17 = -1, 0, 1, 2, 3, 4
+
+
+def p25_rs_decode_erasures(variant: int, data_bits, parity_bits, erasures, n_erasures):
+    """check_and_fix_*_soft twin. erasures: int32 [n, pitch]; n_erasures: int32 [n]. Returns (data_bits, status)."""
+    import numpy as np
+
+    data_bits = np.ascontiguousarray(data_bits, dtype=np.uint8).copy()
+    parity_bits = np.ascontiguousarray(parity_bits, dtype=np.uint8)
+    erasures = np.ascontiguousarray(erasures, dtype=np.int32)
+    n_erasures = np.ascontiguousarray(n_erasures, dtype=np.int32)
+    n = data_bits.shape[0]
+    status = np.zeros(n, np.uint8)
+    check(lib().dsdneo_b200_p25_rs_decode_erasures_batch_host(variant, data_bits.ctypes.data, parity_bits.ctypes.data,
+                                                              erasures.ctypes.data, erasures.shape[1], n_erasures.ctypes.data,
+                                                              status.ctypes.data, n), "p25_rs_decode_erasures")
+    return data_bits, status
+
+
+def p25_rs_soft_reliability(variant: int, data_bits, parity_bits, data_reliab, parity_reliab, threshold: int = 64):
+    """p25p1_rs_*_soft_reliability twin. Returns (data_bits, status)."""
+    import numpy as np
+
+    data_bits = np.ascontiguousarray(data_bits, dtype=np.uint8).copy()
+    parity_bits = np.ascontiguousarray(parity_bits, dtype=np.uint8)
+    data_reliab = np.ascontiguousarray(data_reliab, dtype=np.uint8)
+    parity_reliab = np.ascontiguousarray(parity_reliab, dtype=np.uint8)
+    n = data_bits.shape[0]
+    status = np.zeros(n, np.uint8)
+    check(lib().dsdneo_b200_p25_rs_soft_reliability_batch_host(variant, data_bits.ctypes.data, parity_bits.ctypes.data,
+                                                               data_reliab.ctypes.data, parity_reliab.ctypes.data, threshold,
+                                                               status.ctypes.data, n), "p25_rs_soft_reliability")
+    return data_bits, status
 
 
 class SymClass(C.Structure):

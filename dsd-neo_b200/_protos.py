@@ -31,12 +31,20 @@ def bind(L):
         "dsdneo_b200_fec_golay_24_12_encode_batch": (ci, [vp, vp, ci, vp]),
         "dsdneo_b200_bptc_196x96_batch": (ci, [vp, ci, vp, vp, vp, ci, vp]),
         "dsdneo_b200_bptc_196x96_batch_host": (ci, [vp, ci, vp, vp, vp, ci]),
+        "dsdneo_b200_bptc_128x77_batch": (ci, [vp, vp, vp, ci, vp]),
+        "dsdneo_b200_bptc_128x77_batch_host": (ci, [vp, vp, vp, ci]),
+        "dsdneo_b200_bptc_16x2_batch": (ci, [vp, vp, vp, ci, ci, vp]),
+        "dsdneo_b200_bptc_16x2_batch_host": (ci, [vp, vp, vp, ci, ci]),
         "dsdneo_b200_p25_12_soft_llr_batch": (ci, [vp, vp, vp, ci, vp]),
         "dsdneo_b200_p25_12_soft_llr_batch_host": (ci, [vp, vp, vp, ci]),
         "dsdneo_b200_p25_12_soft_llr_list_batch": (ci, [vp, vp, vp, ci, ci, vp]),
         "dsdneo_b200_p25_12_soft_llr_list_batch_host": (ci, [vp, vp, vp, ci, ci]),
         "dsdneo_b200_p25_rs_decode_batch": (ci, [ci, vp, vp, vp, ci, vp]),
         "dsdneo_b200_p25_rs_decode_batch_host": (ci, [ci, vp, vp, vp, ci]),
+        "dsdneo_b200_p25_rs_decode_erasures_batch": (ci, [ci, vp, vp, vp, ci, vp, vp, ci, vp]),
+        "dsdneo_b200_p25_rs_decode_erasures_batch_host": (ci, [ci, vp, vp, vp, ci, vp, vp, ci]),
+        "dsdneo_b200_p25_rs_soft_reliability_batch": (ci, [ci, vp, vp, vp, vp, ci, vp, ci, vp]),
+        "dsdneo_b200_p25_rs_soft_reliability_batch_host": (ci, [ci, vp, vp, vp, vp, ci, vp, ci]),
         "dsdneo_b200_timing_enable": (ci, [ci]),
         "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
         "dsdneo_b200_hb_cascade_create": (vp, [ci, ci, ci]),

@@ -244,6 +244,90 @@ bptc_196x96_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in, i
     errs_out[i] = errs;
 }
 
+/* BPTC_128x77_Extract_Data (src/fec/bptc.c:167-252): rows 0-6 Hamming(16,11,4), row 7 column parity; an
+ * uncorrectable row receives the information bits of the most recent correctable row (the callee's stale output
+ * buffer); with no correctable row before it the reference's result is undefined and the row is left unchanged. */
+__global__ void
+bptc_128x77_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in, uint8_t* out77, uint32_t* errs_out, int n_items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) {
+        return;
+    }
+    const uint8_t* src = in + (size_t)i * 128;
+    const dsdneo_hamming_table& h16 = T->ham[DSDNEO_FEC_HAMMING_16_11_4];
+    unsigned rows[8];
+    for (int r = 0; r < 8; r++) {
+        rows[r] = pack_bits(src + 16 * r, 16);
+    }
+    unsigned errs = 0, last = 0;
+    int have_last = 0;
+    for (int r = 0; r < 7; r++) {
+        unsigned w = rows[r];
+        if (ham_fix_word(h16, w)) {
+            last = w & 0x7FFu;
+            have_last = 1;
+            rows[r] = (rows[r] & ~0x7FFu) | last;
+        } else {
+            errs++;
+            if (have_last) {
+                rows[r] = (rows[r] & ~0x7FFu) | last;
+            }
+        }
+    }
+    uint8_t* o = out77 + (size_t)i * 77;
+    int k = 0;
+    for (int r = 0; r < 2; r++) {
+        for (int j = 0; j < 11; j++) {
+            o[k++] = (uint8_t)((rows[r] >> j) & 1u);
+        }
+    }
+    for (int r = 2; r < 7; r++) {
+        for (int j = 0; j < 10; j++) {
+            o[k++] = (uint8_t)((rows[r] >> j) & 1u);
+        }
+    }
+    for (int r = 2; r < 7; r++) {
+        o[k++] = (uint8_t)((rows[r] >> 10) & 1u);
+    }
+    unsigned par = 0;
+    for (int r = 0; r < 7; r++) {
+        par ^= rows[r];
+    }
+    errs += (unsigned)__popc((par ^ rows[7]) & 0xFFFFu);
+    errs_out[i] = errs;
+}
+
+/* BPTC_16x2_Extract_Data (src/fec/bptc.c:272-333) with the reverse-channel de-interleave tables (:33-38). */
+__global__ void
+bptc_16x2_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in, uint8_t* out32, uint32_t* errs_out, int parity_odd,
+                 int n_items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) {
+        return;
+    }
+    const uint8_t* src = in + (size_t)i * 32;
+    unsigned m = 0;
+    for (int t = 0; t < 32; t++) {
+        /* DeInterleaveReverseChannelBptc[t] = t + 16 * (t odd) mod 32 pattern; Placement[v] = v/2 + 16 * (v odd) */
+        const int v = (t & 1) ? ((t + 16) & 31) : t;
+        const int pos = (v >> 1) + ((v & 1) << 4);
+        m |= (unsigned)(src[t] & 1u) << pos;
+    }
+    const dsdneo_hamming_table& h16 = T->ham[DSDNEO_FEC_HAMMING_16_11_4];
+    unsigned w = m & 0xFFFFu, errs = 0;
+    if (ham_fix_word(h16, w)) {
+        m = (m & ~0x7FFu) | (w & 0x7FFu);
+    } else {
+        errs = 1; /* reference copies an uninitialised buffer here: left as de-interleaved (documented) */
+    }
+    uint8_t* o = out32 + (size_t)i * 32;
+    for (int j = 0; j < 32; j++) {
+        o[j] = (uint8_t)((m >> j) & 1u);
+    }
+    const unsigned same = (unsigned)__popc(~((m & 0xFFFFu) ^ (m >> 16)) & 0xFFFFu);
+    errs_out[i] = errs + (parity_odd ? same : 16u - same);
+}
+
 /* ------------------------------------------------------------------ P25 half-rate trellis */
 
 /* transition nibble table p25_12.c:19, entry i in nibble i */
@@ -472,33 +556,32 @@ struct RsShape {
 /* Berlekamp iteration in Rockliff's index-form bookkeeping, as ReedSolomon_63<TT>::decode
  * (ReedSolomon.hpp:353-582,738-771): same failure conditions (degree > t, root count != degree), corrections may land
  * in the zero padding of the shortened code exactly like the reference. */
-__global__ void __launch_bounds__(64)
-p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_t* data_bits, const uint8_t* parity_bits,
-                     uint8_t* status, int n_words) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) {
-        return;
-    }
-    constexpr int NN = 63;
-    const signed char* EXP = T->gf_exp;
-    const signed char* LOG = T->gf_log;
-    const int n_par = sh.n_total - sh.n_data, tt = sh.tt, n2t = 2 * sh.tt;
-    uint8_t* dbits = data_bits + (size_t)w * sh.n_data * 6;
-    const uint8_t* pbits = parity_bits + (size_t)w * n_par * 6;
-    signed char recd[NN]; /* index form, -1 = zero */
-    int used = sh.n_total;
-    for (int i = 0; i < NN; i++) {
+/* hex words (6 byte-per-bit chars, any non-zero byte = 1, MSB first: ReedSolomon.hpp:799-815) -> 6-bit symbols, parity
+ * first (ReedSolomon.hpp:838-851) */
+__device__ __forceinline__ void
+rs_pack_symbols(const RsShape& sh, const uint8_t* dbits, const uint8_t* pbits, uint8_t* sym) {
+    const int n_par = sh.n_total - sh.n_data;
+    for (int i = 0; i < sh.n_total; i++) {
+        const uint8_t* src = (i < n_par) ? pbits + 6 * i : dbits + 6 * (i - n_par);
         int v = 0;
-        if (i < n_par) {
-            for (int b = 0; b < 6; b++) {
-                v = (v << 1) | (pbits[6 * i + b] != 0);
-            }
-        } else if (i < used) {
-            for (int b = 0; b < 6; b++) {
-                v = (v << 1) | (dbits[6 * (i - n_par) + b] != 0);
-            }
+        for (int b = 0; b < 6; b++) {
+            v = (v << 1) | (src[b] != 0);
         }
-        recd[i] = LOG[v];
+        sym[i] = (uint8_t)v;
+    }
+}
+
+/* Hard decision decode of one shortened word: sym = n_total symbols in polynomial form (parity first); out_sym receives
+ * the n_data data symbols (corrected, or as received when the word is irrecoverable).  Returns 0 / 1. */
+__device__ int
+rs63_hard_decode(const signed char* __restrict__ EXP, const signed char* __restrict__ LOG, const RsShape& sh, const uint8_t* sym,
+                 int* out_sym) {
+    constexpr int NN = 63;
+    const int n_par = sh.n_total - sh.n_data, tt = sh.tt, n2t = 2 * sh.tt;
+    signed char recd[NN]; /* index form, -1 = zero */
+    const int used = sh.n_total;
+    for (int i = 0; i < NN; i++) {
+        recd[i] = LOG[i < used ? sym[i] : 0];
     }
     int s[18];
     int syn_err = 0;
@@ -515,7 +598,6 @@ p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_
     }
     /* hex_to_bin of the (possibly corrected) data symbols is a no-op for 0/1 inputs; inputs with other non-zero
      * byte values are normalised to 1 like the reference's bin_to_hex/hex_to_bin round trip */
-    int out_sym[36];
     for (int i = 0; i < sh.n_data; i++) {
         out_sym[i] = recd[n_par + i] == -1 ? 0 : EXP[recd[n_par + i]];
     }
@@ -649,9 +731,359 @@ p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_
             }
         }
     }
+    return rc;
+}
+
+__global__ void __launch_bounds__(64)
+p25_rs_decode_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, uint8_t* data_bits, const uint8_t* parity_bits,
+                     uint8_t* status, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    const int n_par = sh.n_total - sh.n_data;
+    uint8_t* dbits = data_bits + (size_t)w * sh.n_data * 6;
+    uint8_t sym[36];
+    int out_sym[36];
+    rs_pack_symbols(sh, dbits, parity_bits + (size_t)w * n_par * 6, sym);
+    const int rc = rs63_hard_decode(T->gf_exp, T->gf_log, sh, sym, out_sym);
     for (int i = 0; i < sh.n_data; i++) {
         for (int b = 0; b < 6; b++) {
             dbits[6 * i + b] = (uint8_t)((out_sym[i] >> (5 - b)) & 1);
+        }
+    }
+    status[w] = (uint8_t)rc;
+}
+
+/* ---- bounded errors-and-erasures decoding (ReedSolomon.hpp:621-683,773-795) and the ranked-erasure soft wrappers ---- */
+
+struct Gf64 {
+    const signed char* EXP;
+    const signed char* LOG;
+    __device__ __forceinline__ int mul(int a, int b) const { return (a == 0 || b == 0) ? 0 : EXP[(LOG[a] + LOG[b]) % 63]; }
+    __device__ __forceinline__ int div(int a, int b) const { return (a == 0 || b == 0) ? 0 : EXP[(LOG[a] - LOG[b] + 63) % 63]; }
+    __device__ __forceinline__ int apow(int e) const { return EXP[e % 63]; } /* e >= 0 everywhere below */
+};
+
+__device__ int
+rs63_syndromes(const Gf64& gf, const uint8_t* w, int used, int n2t, uint8_t* syn) {
+    int err = 0;
+    syn[0] = 0;
+    for (int i = 1; i <= n2t; i++) {
+        int acc = 0;
+        for (int j = 0; j < used; j++) {
+            if (w[j]) {
+                acc ^= gf.mul(w[j], gf.apow(i * j));
+            }
+        }
+        syn[i] = (uint8_t)acc;
+        err |= acc;
+    }
+    return err != 0;
+}
+
+/* word: n_total symbols (parity first), corrected in place on success.  Returns 0 / 1 (word restored on failure).
+ * Corrections that the reference would apply to the zero padding of the shortened code make its final syndrome
+ * re-check see a non-codeword only if they are non-zero there; that case is reproduced by tracking the padding. */
+__device__ int
+rs63_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63 /* [63], positions >= n_total are zero on entry */,
+                    const uint8_t* erasures, int n_er) {
+    const int n2t = 2 * sh.tt;
+    uint8_t saved[63];
+    for (int i = 0; i < 63; i++) {
+        saved[i] = word63[i];
+    }
+    uint8_t syn[17];
+    int status = 1;
+    do {
+        if (!rs63_syndromes(gf, word63, 63, n2t, syn)) {
+            status = 0;
+            break;
+        }
+        uint8_t el[17];
+        for (int i = 0; i <= n2t; i++) {
+            el[i] = 0;
+        }
+        el[0] = 1;
+        for (int e = 0, deg = 0; e < n_er; e++, deg++) {
+            const int f = gf.apow(erasures[e]);
+            for (int i = deg; i >= 0; i--) {
+                el[i + 1] ^= (uint8_t)gf.mul(el[i], f);
+            }
+        }
+        uint8_t ms[16];
+        for (int i = 0; i < n2t; i++) {
+            int v = 0;
+            for (int j = 0; j <= n_er && j <= i; j++) {
+                v ^= gf.mul(el[j], syn[(i - j) + 1]);
+            }
+            ms[i] = (uint8_t)v;
+        }
+        uint8_t c[17], b[17], t[17];
+        for (int i = 0; i <= n2t; i++) {
+            c[i] = b[i] = 0;
+        }
+        c[0] = b[0] = 1;
+        int l = 0, m = 1, bb = 1, fail = 0;
+        const uint8_t* sy = ms + n_er;
+        const int ns = n2t - n_er;
+        for (int n = 0; n < ns; n++) {
+            int disc = sy[n];
+            for (int i = 1; i <= l; i++) {
+                disc ^= gf.mul(c[i], sy[n - i]);
+            }
+            if (disc == 0) {
+                m++;
+                continue;
+            }
+            for (int i = 0; i <= n2t; i++) {
+                t[i] = c[i];
+            }
+            if (bb == 0) {
+                fail = 1;
+                break;
+            }
+            const int coef = gf.div(disc, bb);
+            for (int i = 0; i + m <= n2t; i++) {
+                if (b[i]) {
+                    c[i + m] ^= (uint8_t)gf.mul(coef, b[i]);
+                }
+            }
+            if (2 * l <= n) {
+                l = n + 1 - l;
+                for (int i = 0; i <= n2t; i++) {
+                    b[i] = t[i];
+                }
+                bb = disc;
+                m = 1;
+            } else {
+                m++;
+            }
+        }
+        if (fail) {
+            break;
+        }
+        int udeg = 0, edeg = 0;
+        for (int i = n2t; i >= 0; i--) {
+            if (c[i]) {
+                udeg = i;
+                break;
+            }
+        }
+        if (2 * udeg + n_er > n2t) {
+            break;
+        }
+        for (int i = n2t; i >= 0; i--) {
+            if (el[i]) {
+                edeg = i;
+                break;
+            }
+        }
+        if (edeg + udeg > n2t) {
+            break;
+        }
+        uint8_t comb[17];
+        for (int i = 0; i <= n2t; i++) {
+            comb[i] = 0;
+        }
+        for (int i = 0; i <= edeg; i++) {
+            for (int j = 0; j <= udeg; j++) {
+                comb[i + j] ^= (uint8_t)gf.mul(el[i], c[j]);
+            }
+        }
+        int cdeg = 0;
+        for (int i = n2t; i >= 0; i--) {
+            if (comb[i]) {
+                cdeg = i;
+                break;
+            }
+        }
+        uint8_t locs[16];
+        int n_loc = 0;
+        if (cdeg != 0) {
+            for (int pos = 0; pos < 63; pos++) {
+                const int x = gf.apow(63 - pos);
+                int v = 0, xp = 1;
+                for (int i = 0; i <= cdeg; i++) {
+                    v ^= gf.mul(comb[i], xp);
+                    xp = gf.mul(xp, x);
+                }
+                if (v == 0) {
+                    if (n_loc >= n2t) {
+                        n_loc++;
+                        break;
+                    }
+                    locs[n_loc++] = (uint8_t)pos;
+                }
+            }
+        }
+        if (n_loc != cdeg || n_loc > n2t) {
+            break;
+        }
+        int ok = 1;
+        for (int i = 0; i < n_er && ok; i++) {
+            int found = 0;
+            for (int k = 0; k < n_loc; k++) {
+                found |= locs[k] == erasures[i];
+            }
+            ok = found;
+        }
+        if (!ok) {
+            break;
+        }
+        uint8_t mat[16][17];
+        for (int r = 0; r < n_loc; r++) {
+            for (int k = 0; k < n_loc; k++) {
+                mat[r][k] = (uint8_t)gf.apow((r + 1) * locs[k]);
+            }
+            mat[r][n_loc] = syn[r + 1];
+        }
+        int singular = 0;
+        for (int col = 0; col < n_loc && !singular; col++) {
+            int piv = -1;
+            for (int r = col; r < n_loc; r++) {
+                if (mat[r][col]) {
+                    piv = r;
+                    break;
+                }
+            }
+            if (piv < 0) {
+                singular = 1;
+                break;
+            }
+            if (piv != col) {
+                for (int k = col; k <= n_loc; k++) {
+                    const uint8_t tmp = mat[col][k];
+                    mat[col][k] = mat[piv][k];
+                    mat[piv][k] = tmp;
+                }
+            }
+            const int pv = mat[col][col];
+            for (int k = col; k <= n_loc; k++) {
+                mat[col][k] = (uint8_t)gf.div(mat[col][k], pv);
+            }
+            for (int r = 0; r < n_loc; r++) {
+                if (r == col || mat[r][col] == 0) {
+                    continue;
+                }
+                const int f = mat[r][col];
+                for (int k = col; k <= n_loc; k++) {
+                    mat[r][k] ^= (uint8_t)gf.mul(f, mat[col][k]);
+                }
+            }
+        }
+        if (singular) {
+            break;
+        }
+        for (int i = 0; i < n_loc; i++) {
+            word63[locs[i]] ^= mat[i][n_loc];
+        }
+        if (rs63_syndromes(gf, word63, 63, n2t, syn)) {
+            break;
+        }
+        status = 0;
+    } while (0);
+    if (status) {
+        for (int i = 0; i < 63; i++) {
+            word63[i] = saved[i];
+        }
+    }
+    return status;
+}
+
+/* mode 0: DSDReedSolomon_*::decode_soft with a caller-supplied erasure list (check_and_fix_*_soft,
+ *         phase1/p25p1_check_hdu.cpp:47-54, p25p1_check_ldu.cpp:46-71): hard decode, then one erasure decode.
+ * mode 1: p25p1_rs_*_soft_reliability (p25p1_check_hdu.cpp:56-77, p25p1_check_ldu.cpp:73-94): rank all symbols by
+ *         (reliability, position) with parity positions first (p25p1_soft.cpp:83-170), try n = 1..ranked erasures.
+ * Data bits are rewritten (normalised 0/1) exactly where the reference rewrites them: always in mode 0 (its hard decoder
+ * writes back even on failure), only on success in mode 1 (it works on a copy). */
+__global__ void __launch_bounds__(64)
+p25_rs_soft_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, int mode, uint8_t* data_bits, const uint8_t* parity_bits,
+                   const int32_t* erasures_in, const int32_t* n_erasures_in, int erasure_pitch, const uint8_t* data_rel,
+                   const uint8_t* par_rel, int threshold, uint8_t* status, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    const Gf64 gf = {T->gf_exp, T->gf_log};
+    const int n_par = sh.n_total - sh.n_data, n2t = 2 * sh.tt;
+    uint8_t* dbits = data_bits + (size_t)w * sh.n_data * 6;
+    uint8_t word[63];
+    int out_sym[36];
+    for (int i = 0; i < 63; i++) {
+        word[i] = 0;
+    }
+    rs_pack_symbols(sh, dbits, parity_bits + (size_t)w * n_par * 6, word);
+    int rc = rs63_hard_decode(T->gf_exp, T->gf_log, sh, word, out_sym);
+    bool write_back = (rc == 0) || (mode == 0);
+    if (rc != 0) {
+        uint8_t er[16];
+        int n_list = 0;
+        if (mode == 0) {
+            const int n = n_erasures_in[w];
+            bool valid = (n > 0 && n <= n2t);
+            unsigned long long seen = 0;
+            for (int i = 0; valid && i < n; i++) {
+                const int pos = erasures_in[(size_t)w * erasure_pitch + i];
+                if (pos < 0 || pos >= 63 || ((seen >> pos) & 1ull)) {
+                    valid = false; /* validate_erasures, ReedSolomon.hpp:584-600 */
+                } else {
+                    seen |= 1ull << pos;
+                    er[i] = (uint8_t)pos;
+                }
+            }
+            n_list = valid ? n : 0;
+            if (n_list > 0 && rs63_erasure_decode(gf, sh, word, er, n_list) == 0) {
+                rc = 0;
+                for (int i = 0; i < sh.n_data; i++) {
+                    out_sym[i] = word[n_par + i];
+                }
+            }
+        } else {
+            /* selection-sort the n2t weakest of all symbols by (reliability, position): same order as the reference's
+             * full stable sort truncated to its first entries */
+            const uint8_t* dr = data_rel + (size_t)w * sh.n_data;
+            const uint8_t* pr = par_rel + (size_t)w * n_par;
+            int hits = 0;
+            for (int i = 0; i < sh.n_total; i++) {
+                hits += ((i < n_par) ? pr[i] : dr[i - n_par]) < threshold;
+            }
+            int ranked = hits > sh.tt ? hits : sh.tt;
+            if (ranked > n2t) {
+                ranked = n2t;
+            }
+            unsigned long long taken = 0;
+            for (int k = 0; k < ranked; k++) {
+                int best = -1, best_rel = 256;
+                for (int i = 0; i < sh.n_total; i++) {
+                    if ((taken >> i) & 1ull) {
+                        continue;
+                    }
+                    const int r = (i < n_par) ? pr[i] : dr[i - n_par];
+                    if (r < best_rel) {
+                        best_rel = r;
+                        best = i;
+                    }
+                }
+                taken |= 1ull << best;
+                er[k] = (uint8_t)best;
+            }
+            for (int n = 1; n <= ranked && rc != 0; n++) {
+                if (rs63_erasure_decode(gf, sh, word, er, n) == 0) {
+                    rc = 0;
+                    write_back = true;
+                    for (int i = 0; i < sh.n_data; i++) {
+                        out_sym[i] = word[n_par + i];
+                    }
+                }
+            }
+        }
+    }
+    if (write_back) {
+        for (int i = 0; i < sh.n_data; i++) {
+            for (int b = 0; b < 6; b++) {
+                dbits[6 * i + b] = (uint8_t)((out_sym[i] >> (5 - b)) & 1);
+            }
         }
     }
     status[w] = (uint8_t)rc;
@@ -1044,6 +1476,80 @@ dsdneo_b200_bptc_196x96_batch_host(const uint8_t* h_in, int interleaved, uint8_t
     return 0;
 }
 
+static int
+bptc_small_batch(int which, const uint8_t* d_in, uint8_t* d_out, uint32_t* d_errs, int parity_odd, int n_items, void* stream) {
+    if (!d_in || !d_out || !d_errs || n_items < 0) {
+        set_error("bptc_%s_batch: bad argument", which ? "16x2" : "128x77");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_items == 0) {
+        return 0;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    if (which == 0) {
+        KernelTimer kt("bptc_128x77_kernel", s);
+        bptc_128x77_kernel<<<grid_for(n_items, 128), 128, 0, s>>>(g_d_tables, d_in, d_out, d_errs, n_items);
+    } else {
+        KernelTimer kt("bptc_16x2_kernel", s);
+        bptc_16x2_kernel<<<grid_for(n_items, 128), 128, 0, s>>>(g_d_tables, d_in, d_out, d_errs, parity_odd ? 1 : 0, n_items);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+static int
+bptc_small_batch_host(int which, const uint8_t* h_in, uint8_t* h_out, uint32_t* h_errs, int parity_odd, int n_items) {
+    if (!h_in || !h_out || !h_errs || n_items < 0) {
+        set_error("bptc_%s_batch_host: bad argument", which ? "16x2" : "128x77");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_items == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_items, in_b = which ? 32 : 128, out_b = which ? 32 : 77;
+    DevBuf in(n * in_b), out(n * out_b), er(n * 4);
+    DSDNEO_CUDA(in.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(er.err);
+    DSDNEO_CUDA(cudaMemcpy(in.p, h_in, n * in_b, cudaMemcpyHostToDevice));
+    rc = bptc_small_batch(which, in.as<uint8_t>(), out.as<uint8_t>(), er.as<uint32_t>(), parity_odd, n_items, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out, out.p, n * out_b, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_errs, er.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_bptc_128x77_batch(const uint8_t* d_in128, uint8_t* d_out77, uint32_t* d_errs, int n_items, void* stream) {
+    return bptc_small_batch(0, d_in128, d_out77, d_errs, 0, n_items, stream);
+}
+
+int
+dsdneo_b200_bptc_128x77_batch_host(const uint8_t* h_in128, uint8_t* h_out77, uint32_t* h_errs, int n_items) {
+    return bptc_small_batch_host(0, h_in128, h_out77, h_errs, 0, n_items);
+}
+
+int
+dsdneo_b200_bptc_16x2_batch(const uint8_t* d_in32, uint8_t* d_out32, uint32_t* d_errs, int parity_odd, int n_items, void* stream) {
+    return bptc_small_batch(1, d_in32, d_out32, d_errs, parity_odd, n_items, stream);
+}
+
+int
+dsdneo_b200_bptc_16x2_batch_host(const uint8_t* h_in32, uint8_t* h_out32, uint32_t* h_errs, int parity_odd, int n_items) {
+    return bptc_small_batch_host(1, h_in32, h_out32, h_errs, parity_odd, n_items);
+}
+
 int
 dsdneo_b200_p25_12_soft_llr_batch(const int16_t* d_llr196, uint8_t* d_out12, int32_t* d_metric, int n_blocks, void* stream) {
     if (!d_llr196 || !d_out12 || !d_metric || n_blocks < 0) {
@@ -1222,6 +1728,123 @@ dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const ui
     DSDNEO_CUDA(cudaMemcpy(h_data_bits, data.p, n * db, cudaMemcpyDeviceToHost));
     DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+static int
+rs_soft_launch(int variant, int mode, uint8_t* d_data_bits, const uint8_t* d_parity_bits, const int32_t* d_erasures,
+               int erasure_pitch, const int32_t* d_n_erasures, const uint8_t* d_data_rel, const uint8_t* d_par_rel, int threshold,
+               uint8_t* d_status, int n_words, void* stream) {
+    RsShape sh;
+    int rc = rs_shape(variant, &sh);
+    if (rc) {
+        return rc;
+    }
+    const bool args_ok = d_data_bits && d_parity_bits && d_status && n_words >= 0 &&
+                         (mode == 0 ? (d_erasures && d_n_erasures && erasure_pitch >= 1) : (d_data_rel && d_par_rel));
+    if (!args_ok) {
+        set_error("p25_rs soft decode: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25_rs_soft_kernel", s);
+        p25_rs_soft_kernel<<<grid_for(n_words, 64), 64, 0, s>>>(g_d_tables, sh, mode, d_data_bits, d_parity_bits, d_erasures,
+                                                                d_n_erasures, erasure_pitch, d_data_rel, d_par_rel, threshold,
+                                                                d_status, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_rs_decode_erasures_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits, const int32_t* d_erasures,
+                                         int erasure_pitch, const int32_t* d_n_erasures, uint8_t* d_status, int n_words,
+                                         void* stream) {
+    return rs_soft_launch(variant, 0, d_data_bits, d_parity_bits, d_erasures, erasure_pitch, d_n_erasures, NULL, NULL, 0, d_status,
+                          n_words, stream);
+}
+
+int
+dsdneo_b200_p25_rs_soft_reliability_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits,
+                                          const uint8_t* d_data_reliab, const uint8_t* d_parity_reliab, int erasure_threshold,
+                                          uint8_t* d_status, int n_words, void* stream) {
+    return rs_soft_launch(variant, 1, d_data_bits, d_parity_bits, NULL, 0, NULL, d_data_reliab, d_parity_reliab, erasure_threshold,
+                          d_status, n_words, stream);
+}
+
+static int
+rs_soft_host(int variant, int mode, uint8_t* h_data_bits, const uint8_t* h_parity_bits, const int32_t* h_erasures, int erasure_pitch,
+             const int32_t* h_n_erasures, const uint8_t* h_data_rel, const uint8_t* h_par_rel, int threshold, uint8_t* h_status,
+             int n_words) {
+    RsShape sh;
+    int rc = rs_shape(variant, &sh);
+    if (rc) {
+        return rc;
+    }
+    const bool args_ok = h_data_bits && h_parity_bits && h_status && n_words >= 0 &&
+                         (mode == 0 ? (h_erasures && h_n_erasures && erasure_pitch >= 1) : (h_data_rel && h_par_rel));
+    if (!args_ok) {
+        set_error("p25_rs soft decode (host): bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words, n_par = (size_t)(sh.n_total - sh.n_data), db = (size_t)sh.n_data * 6, pb = n_par * 6;
+    DevBuf data(n * db), par(n * pb), st(n);
+    DevBuf a(mode == 0 ? n * (size_t)erasure_pitch * 4 : n * (size_t)sh.n_data), b(mode == 0 ? n * 4 : n * n_par);
+    DSDNEO_CUDA(data.err);
+    DSDNEO_CUDA(par.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(a.err);
+    DSDNEO_CUDA(b.err);
+    DSDNEO_CUDA(cudaMemcpy(data.p, h_data_bits, n * db, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(par.p, h_parity_bits, n * pb, cudaMemcpyHostToDevice));
+    if (mode == 0) {
+        DSDNEO_CUDA(cudaMemcpy(a.p, h_erasures, n * (size_t)erasure_pitch * 4, cudaMemcpyHostToDevice));
+        DSDNEO_CUDA(cudaMemcpy(b.p, h_n_erasures, n * 4, cudaMemcpyHostToDevice));
+        rc = rs_soft_launch(variant, 0, data.as<uint8_t>(), par.as<uint8_t>(), a.as<int32_t>(), erasure_pitch, b.as<int32_t>(), NULL,
+                            NULL, 0, st.as<uint8_t>(), n_words, NULL);
+    } else {
+        DSDNEO_CUDA(cudaMemcpy(a.p, h_data_rel, n * (size_t)sh.n_data, cudaMemcpyHostToDevice));
+        DSDNEO_CUDA(cudaMemcpy(b.p, h_par_rel, n * n_par, cudaMemcpyHostToDevice));
+        rc = rs_soft_launch(variant, 1, data.as<uint8_t>(), par.as<uint8_t>(), NULL, 0, NULL, a.as<uint8_t>(), b.as<uint8_t>(),
+                            threshold, st.as<uint8_t>(), n_words, NULL);
+    }
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_data_bits, data.p, n * db, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_p25_rs_decode_erasures_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits,
+                                              const int32_t* h_erasures, int erasure_pitch, const int32_t* h_n_erasures,
+                                              uint8_t* h_status, int n_words) {
+    return rs_soft_host(variant, 0, h_data_bits, h_parity_bits, h_erasures, erasure_pitch, h_n_erasures, NULL, NULL, 0, h_status,
+                        n_words);
+}
+
+int
+dsdneo_b200_p25_rs_soft_reliability_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits,
+                                               const uint8_t* h_data_reliab, const uint8_t* h_parity_reliab, int erasure_threshold,
+                                               uint8_t* h_status, int n_words) {
+    return rs_soft_host(variant, 1, h_data_bits, h_parity_bits, NULL, 0, NULL, h_data_reliab, h_parity_reliab, erasure_threshold,
+                        h_status, n_words);
 }
 
 int

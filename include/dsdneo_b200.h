@@ -390,6 +390,22 @@ int dsdneo_b200_bptc_196x96_batch(const uint8_t* d_in, int interleaved, uint8_t*
 int dsdneo_b200_bptc_196x96_batch_host(const uint8_t* h_in, int interleaved, uint8_t* h_out96, uint8_t* h_r3, uint32_t* h_errs,
                                        int n_bursts);
 
+/**
+ * BPTC_128x77_Extract_Data (src/fec/bptc.c:167-252): in = the 8 x 16 byte-per-bit matrix (row-major, only the LSB of
+ * each byte is used), out = 77 bytes (72 data + 5 CRC bits), errs = uncorrectable Hamming(16,11,4) rows + column-parity
+ * failures, exactly the reference's return value.  An uncorrectable row takes the information bits of the most recent
+ * correctable row, as the reference's stale callee buffer does; where the reference reads an uninitialised buffer (no
+ * correctable row before it) the row is left unchanged.
+ */
+int dsdneo_b200_bptc_128x77_batch(const uint8_t* d_in128, uint8_t* d_out77, uint32_t* d_errs, int n_items, void* stream);
+int dsdneo_b200_bptc_128x77_batch_host(const uint8_t* h_in128, uint8_t* h_out77, uint32_t* h_errs, int n_items);
+/**
+ * BPTC_16x2_Extract_Data (src/fec/bptc.c:272-333): in = 32 interleaved bits, out = 32 de-interleaved bits with the
+ * first 11 Hamming(16,11,4)-corrected, errs = (uncorrectable ? 1 : 0) + parity mismatches (odd or even rule).
+ */
+int dsdneo_b200_bptc_16x2_batch(const uint8_t* d_in32, uint8_t* d_out32, uint32_t* d_errs, int parity_odd, int n_items, void* stream);
+int dsdneo_b200_bptc_16x2_batch_host(const uint8_t* h_in32, uint8_t* h_out32, uint32_t* h_errs, int parity_odd, int n_items);
+
 /** p25_12_candidate_t (include/dsd-neo/protocol/p25/p25_12.h:13-17), same layout. */
 typedef struct dsdneo_b200_p25_12_candidate {
     uint8_t bytes[12];
@@ -420,6 +436,38 @@ int dsdneo_b200_p25_rs_decode_batch(int variant, uint8_t* d_data_bits, const uin
                                     int n_words, void* stream);
 int dsdneo_b200_p25_rs_decode_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
                                          int n_words);
+
+#define DSDNEO_P25P1_SOFT_ERASURE_THRESHOLD 64 /* P25P1_SOFT_ERASURE_THRESHOLD, phase1/p25p1_soft.cpp:20 */
+/**
+ * check_and_fix_redsolomon_36_20_17_soft / check_and_fix_reedsolomon_24_12_13_soft / _24_16_9_soft
+ * (phase1/p25p1_check_hdu.cpp:47-54, p25p1_check_ldu.cpp:46-71 -> DSDReedSolomon_*::decode_soft, ReedSolomon.hpp:879-913):
+ * hard decode first, then one bounded errors-and-erasures decode (ReedSolomon_63::decode_with_erasures, :621-683,773-795)
+ * with the caller's erasure positions in codeword space (parity symbols 0..n-k-1, data after them).
+ * @param d_erasures   [n][erasure_pitch] positions, @param d_n_erasures [n] how many of them are valid (1..2t)
+ * @param d_status     [n] 0 = ok / corrected, 1 = irrecoverable; data bits are rewritten as 0/1 either way, as the
+ *                     reference's hard decoder does
+ */
+int dsdneo_b200_p25_rs_decode_erasures_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits,
+                                             const int32_t* d_erasures, int erasure_pitch, const int32_t* d_n_erasures,
+                                             uint8_t* d_status, int n_words, void* stream);
+int dsdneo_b200_p25_rs_decode_erasures_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits,
+                                                  const int32_t* h_erasures, int erasure_pitch, const int32_t* h_n_erasures,
+                                                  uint8_t* h_status, int n_words);
+/**
+ * p25p1_rs_36_20_17_soft_reliability / p25p1_rs_24_16_9_soft_reliability (phase1/p25p1_check_hdu.cpp:56-77,
+ * p25p1_check_ldu.cpp:73-94; the same rule is offered for the (24,12,13) shape): every symbol is ranked by
+ * (reliability, position) with parity positions numbered first (p25p1_build_rs_ranked_erasures, p25p1_soft.cpp:140-170),
+ * the count is max(#symbols below erasure_threshold, t) capped at 2t, and n = 1..count weakest symbols are tried as
+ * erasures in order; the first success wins.  Reliabilities are the per-symbol minima of |LLR| clamped to 0..255
+ * (p25p1_llr_reliability, p25p1_soft.cpp:64-79).  On failure the data bits are left untouched, as in the reference.
+ * erasure_threshold: pass DSDNEO_P25P1_SOFT_ERASURE_THRESHOLD unless DSD_NEO_P25P1_SOFT_ERASURE_THRESHOLD overrides it.
+ */
+int dsdneo_b200_p25_rs_soft_reliability_batch(int variant, uint8_t* d_data_bits, const uint8_t* d_parity_bits,
+                                              const uint8_t* d_data_reliab, const uint8_t* d_parity_reliab, int erasure_threshold,
+                                              uint8_t* d_status, int n_words, void* stream);
+int dsdneo_b200_p25_rs_soft_reliability_batch_host(int variant, uint8_t* h_data_bits, const uint8_t* h_parity_bits,
+                                                   const uint8_t* h_data_reliab, const uint8_t* h_parity_reliab,
+                                                   int erasure_threshold, uint8_t* h_status, int n_words);
 
 /**
  * viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182; include/dsd-neo/fec/viterbi.h:23-29), the

@@ -84,11 +84,18 @@ int oracle_golay_20_8_decode(uint8_t* bits20);
 int oracle_qr_16_7_6_decode(uint8_t* bits16);
 void oracle_bptc_deinterleave(const uint8_t* in196, uint8_t* out196);
 unsigned oracle_bptc_196x96_extract(const uint8_t* in196, uint8_t* out96, uint8_t* r3, int* undefined_out);
+unsigned oracle_bptc_128x77_extract(const uint8_t* in128, uint8_t* out77, int* undefined_out);
+unsigned oracle_bptc_16x2_extract(const uint8_t* in32, uint8_t* out32, unsigned parity_odd, int* undefined_out);
 int oracle_p25_12_soft_llr(const int16_t* llr196, uint8_t out12[12]);
 int oracle_p25_12_soft_llr_list(const int16_t* llr196, uint8_t* cand_bytes, uint32_t* cand_metric, int max_candidates);
 int oracle_rs63_decode(int tt, const int* in63, int* out63);
 void oracle_rs63_encode(int tt, const int* data, int* cw63);
 int oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits);
+int oracle_rs63_decode_with_erasures(int tt, const int* in63, int* out63, const int* erasures, int n_erasures);
+int oracle_p25_rs_ranked_erasures(const uint8_t* data_rel, int n_data, const uint8_t* par_rel, int n_par, int min_er, int threshold,
+                                  int* erasures, int max_er);
+int oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits, const uint8_t* data_rel,
+                                   const uint8_t* par_rel, int threshold);
 uint32_t oracle_viterbi_k5_decode(uint8_t* out, const uint16_t* in, int len);
 uint32_t oracle_viterbi_k5_decode_punctured(uint8_t* out, const uint16_t* in, const uint8_t* punct, int in_len, int p_len);
 void oracle_nxdn_conv_decode(const uint8_t* sym, const uint8_t* rel, int n_steps, int n_bits_out, uint16_t* metrics_io, uint8_t* out);

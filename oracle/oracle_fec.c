@@ -375,6 +375,103 @@ oracle_bptc_196x96_extract(const uint8_t* in196, uint8_t* out96, uint8_t* r3, in
     return errs;
 }
 
+/* BPTC_128x77_Extract_Data (src/fec/bptc.c:167-252): 8 x 16 matrix, rows 0-6 Hamming(16,11,4), row 7 = column
+ * parity.  An uncorrectable row is overwritten with the callee's stale output buffer = the information bits of the
+ * most recent correctable row of this call; if there is none yet the reference reads an uninitialised stack buffer
+ * (undefined: row left unchanged here, *undefined_out set).  Return = uncorrectable rows + column-parity failures. */
+unsigned
+oracle_bptc_128x77_extract(const uint8_t* in128, uint8_t* out77, int* undefined_out) {
+    uint8_t m[8][16];
+    if (undefined_out) {
+        *undefined_out = 0;
+    }
+    for (int i = 0; i < 8; i++) {
+        for (int j = 0; j < 16; j++) {
+            m[i][j] = in128[16 * i + j] & 1u;
+        }
+    }
+    unsigned ham_err = 0, par_err = 0;
+    uint8_t last[11];
+    int have_last = 0;
+    for (int i = 0; i < 7; i++) {
+        uint8_t line[16], dec[11];
+        memcpy(line, m[i], 16);
+        if (oracle_hamming_decode(ORACLE_HAMMING_16_11_4, line, dec)) {
+            memcpy(last, dec, 11);
+            have_last = 1;
+            memcpy(m[i], dec, 11);
+        } else {
+            ham_err++;
+            if (have_last) {
+                memcpy(m[i], last, 11);
+            } else if (undefined_out) {
+                *undefined_out = 1;
+            }
+        }
+    }
+    int k = 0;
+    for (int i = 0; i < 2; i++) {
+        for (int j = 0; j < 11; j++) {
+            out77[k++] = m[i][j];
+        }
+    }
+    for (int i = 2; i < 7; i++) {
+        for (int j = 0; j < 10; j++) {
+            out77[k++] = m[i][j];
+        }
+    }
+    for (int i = 2; i < 7; i++) {
+        out77[k++] = m[i][10];
+    }
+    for (int j = 0; j < 16; j++) {
+        unsigned ones = 0;
+        for (int i = 0; i < 7; i++) {
+            ones += m[i][j];
+        }
+        if ((ones % 2) != m[7][j]) {
+            par_err++;
+        }
+    }
+    return ham_err + par_err;
+}
+
+/* BPTC_16x2_Extract_Data (src/fec/bptc.c:272-333): reverse-channel de-interleave (tables :33-38), first 16 bits
+ * Hamming(16,11,4), last 16 bits = parity of the first 16 (odd or even).  When the Hamming word is uncorrectable the
+ * reference copies an uninitialised buffer over out[0..10] (undefined: left as de-interleaved here, flag set). */
+unsigned
+oracle_bptc_16x2_extract(const uint8_t* in32, uint8_t* out32, unsigned parity_odd, int* undefined_out) {
+    static const uint8_t dei[32] = {0,  17, 2,  19, 4,  21, 6,  23, 8,  25, 10, 27, 12, 29, 14, 31,
+                                    16, 1,  18, 3,  20, 5,  22, 7,  24, 9,  26, 11, 28, 13, 30, 15};
+    static const uint8_t place[32] = {0,  16, 1,  17, 2,  18, 3,  19, 4,  20, 5,  21, 6,  22, 7,  23,
+                                      8,  24, 9,  25, 10, 26, 11, 27, 12, 28, 13, 29, 14, 30, 15, 31};
+    uint8_t m[32], line[16], dec[11];
+    if (undefined_out) {
+        *undefined_out = 0;
+    }
+    for (int i = 0; i < 32; i++) {
+        m[place[dei[i]]] = in32[i] & 1u;
+    }
+    memcpy(out32, m, 32);
+    memcpy(line, m, 16);
+    unsigned ham_err = 0, odd_err = 0, even_err = 0;
+    if (oracle_hamming_decode(ORACLE_HAMMING_16_11_4, line, dec)) {
+        memcpy(out32, dec, 11);
+    } else {
+        ham_err = 1;
+        if (undefined_out) {
+            *undefined_out = 1;
+        }
+    }
+    for (int i = 0; i < 16; i++) {
+        if (out32[i] == out32[i + 16]) {
+            odd_err++;
+        } else {
+            even_err++;
+        }
+    }
+    return ham_err + (parity_odd ? odd_err : even_err);
+}
+
 /* ------------------------------------------------------------------ P25 half-rate trellis */
 
 /* dibit-pair nibble expected on the transition prev -> next (src/protocol/p25/p25_12.c:19) */
@@ -830,6 +927,346 @@ oracle_p25_rs_decode(int n_total, int n_data, uint8_t* data_bits /*[n_data][6]*/
         }
     }
     return rc;
+}
+
+/* ---- bounded errors-and-erasures decoding + the P25p1 ranked-erasure soft wrappers ---------------------------- */
+
+static int
+gfm(int a, int b) { /* ReedSolomon.hpp:72-78 */
+    return (a == 0 || b == 0) ? 0 : gf_exp[(gf_log[a] + gf_log[b]) % 63];
+}
+
+static int
+gfd(int a, int b) { /* ReedSolomon.hpp:80-89 (division by zero yields 0) */
+    return (a == 0 || b == 0) ? 0 : gf_exp[(gf_log[a] - gf_log[b] + 63) % 63];
+}
+
+static int
+gfa(int e) { /* ReedSolomon.hpp:91-98 */
+    e %= 63;
+    if (e < 0) {
+        e += 63;
+    }
+    return gf_exp[e];
+}
+
+static int
+rs_syndromes(const int* w, int n2t, int* syn) { /* ReedSolomon.hpp:102-119; syn[1..2t], polynomial form */
+    int err = 0;
+    syn[0] = 0;
+    for (int i = 1; i <= n2t; i++) {
+        int acc = 0;
+        for (int j = 0; j < 63; j++) {
+            if (w[j]) {
+                acc ^= gfm(w[j], gfa(i * j));
+            }
+        }
+        syn[i] = acc;
+        err |= acc != 0;
+    }
+    return err;
+}
+
+/* ReedSolomon_63<TT>::decode_with_erasures (ReedSolomon.hpp:773-795) = run_decode_with_erasures (:621-683): erasure
+ * locator, modified syndromes, Berlekamp-Massey on the tail, combined locator, root search over all 63 positions,
+ * error values by Gauss-Jordan on the Vandermonde system (first non-zero pivot), re-check of the syndromes.
+ * Returns 0 ok (out corrected) / 1 failure (out == in). */
+int
+oracle_rs63_decode_with_erasures(int tt, const int* in63, int* out63, const int* erasures, int n_er) {
+    gf_init();
+    const int n2t = 2 * tt;
+    if (!in63 || !out63 || n_er < 0 || n_er > n2t) {
+        return 1;
+    }
+    memcpy(out63, in63, 63 * sizeof(int));
+    int syn[17];
+    if (n_er == 0) {
+        return rs_syndromes(out63, n2t, syn) ? 1 : 0;
+    }
+    if (!erasures) {
+        return 1;
+    }
+    {
+        int seen[63] = {0};
+        for (int i = 0; i < n_er; i++) {
+            if (erasures[i] < 0 || erasures[i] >= 63 || seen[erasures[i]]) {
+                return 1;
+            }
+            seen[erasures[i]] = 1;
+        }
+    }
+    int status = 1;
+    do {
+        if (!rs_syndromes(out63, n2t, syn)) {
+            status = 0;
+            break;
+        }
+        int el[17] = {0}; /* erasure locator */
+        el[0] = 1;
+        for (int e = 0, deg = 0; e < n_er; e++, deg++) {
+            int f = gfa(erasures[e]);
+            for (int i = deg; i >= 0; i--) {
+                el[i + 1] ^= gfm(el[i], f);
+            }
+        }
+        int ms[16]; /* modified syndromes */
+        for (int i = 0; i < n2t; i++) {
+            int v = 0;
+            for (int j = 0; j <= n_er && j <= i; j++) {
+                v ^= gfm(el[j], syn[(i - j) + 1]);
+            }
+            ms[i] = v;
+        }
+        /* Berlekamp-Massey on ms[n_er .. 2t) (ReedSolomon.hpp:204-262) */
+        int c[17] = {0}, b[17] = {0}, t[17];
+        c[0] = b[0] = 1;
+        int l = 0, m = 1, bb = 1, fail = 0;
+        const int* sy = ms + n_er;
+        const int ns = n2t - n_er;
+        for (int n = 0; n < ns; n++) {
+            int disc = sy[n];
+            for (int i = 1; i <= l; i++) {
+                disc ^= gfm(c[i], sy[n - i]);
+            }
+            if (disc == 0) {
+                m++;
+                continue;
+            }
+            memcpy(t, c, sizeof(t));
+            if (bb == 0) {
+                fail = 1;
+                break;
+            }
+            int coef = gfd(disc, bb);
+            for (int i = 0; i + m <= n2t; i++) {
+                if (b[i]) {
+                    c[i + m] ^= gfm(coef, b[i]);
+                }
+            }
+            if (2 * l <= n) {
+                l = n + 1 - l;
+                memcpy(b, t, sizeof(b));
+                bb = disc;
+                m = 1;
+            } else {
+                m++;
+            }
+        }
+        if (fail) {
+            break;
+        }
+        int udeg = 0;
+        for (int i = n2t; i >= 0; i--) {
+            if (c[i]) {
+                udeg = i;
+                break;
+            }
+        }
+        if (2 * udeg + n_er > n2t) {
+            break;
+        }
+        int edeg = 0;
+        for (int i = n2t; i >= 0; i--) {
+            if (el[i]) {
+                edeg = i;
+                break;
+            }
+        }
+        if (edeg + udeg > n2t) {
+            break;
+        }
+        int comb[17] = {0};
+        for (int i = 0; i <= edeg; i++) {
+            for (int j = 0; j <= udeg; j++) {
+                comb[i + j] ^= gfm(el[i], c[j]);
+            }
+        }
+        int cdeg = 0;
+        for (int i = n2t; i >= 0; i--) {
+            if (comb[i]) {
+                cdeg = i;
+                break;
+            }
+        }
+        int locs[16], n_loc = 0;
+        if (cdeg != 0) { /* find_error_locations (:280-303) */
+            for (int pos = 0; pos < 63; pos++) {
+                int x = gfa(63 - pos), v = 0, xp = 1;
+                for (int i = 0; i <= cdeg; i++) {
+                    v ^= gfm(comb[i], xp);
+                    xp = gfm(xp, x);
+                }
+                if (v == 0) {
+                    if (n_loc >= n2t) {
+                        n_loc++;
+                        break;
+                    }
+                    locs[n_loc++] = pos;
+                }
+            }
+        }
+        if (n_loc != cdeg || n_loc > n2t) {
+            break;
+        }
+        int ok = 1;
+        for (int i = 0; i < n_er && ok; i++) {
+            int found = 0;
+            for (int k = 0; k < n_loc; k++) {
+                found |= locs[k] == erasures[i];
+            }
+            ok = found;
+        }
+        if (!ok) {
+            break;
+        }
+        int mat[16][17];
+        memset(mat, 0, sizeof(mat));
+        for (int r = 0; r < n_loc; r++) {
+            for (int k = 0; k < n_loc; k++) {
+                mat[r][k] = gfa((r + 1) * locs[k]);
+            }
+            mat[r][n_loc] = syn[r + 1];
+        }
+        int singular = 0;
+        for (int col = 0; col < n_loc && !singular; col++) { /* solve_gf_linear_system (:121-161) */
+            int piv = -1;
+            for (int r = col; r < n_loc; r++) {
+                if (mat[r][col]) {
+                    piv = r;
+                    break;
+                }
+            }
+            if (piv < 0) {
+                singular = 1;
+                break;
+            }
+            if (piv != col) {
+                for (int k = col; k <= n_loc; k++) {
+                    int tmp = mat[col][k];
+                    mat[col][k] = mat[piv][k];
+                    mat[piv][k] = tmp;
+                }
+            }
+            int pv = mat[col][col];
+            for (int k = col; k <= n_loc; k++) {
+                mat[col][k] = gfd(mat[col][k], pv);
+            }
+            for (int r = 0; r < n_loc; r++) {
+                if (r == col || mat[r][col] == 0) {
+                    continue;
+                }
+                int f = mat[r][col];
+                for (int k = col; k <= n_loc; k++) {
+                    mat[r][k] ^= gfm(f, mat[col][k]);
+                }
+            }
+        }
+        if (singular) {
+            break;
+        }
+        for (int i = 0; i < n_loc; i++) {
+            out63[locs[i]] ^= mat[i][n_loc];
+        }
+        if (rs_syndromes(out63, n2t, syn)) {
+            break;
+        }
+        status = 0;
+    } while (0);
+    if (status) {
+        memcpy(out63, in63, 63 * sizeof(int));
+    }
+    return status;
+}
+
+/* p25p1_build_rs_ranked_erasures (src/protocol/p25/phase1/p25p1_soft.cpp:140-170 with :83-136): every symbol is a
+ * candidate (parity positions first), sorted ascending by (reliability, position); count = max(#below threshold,
+ * min_erasures) capped at max_erasures. */
+int
+oracle_p25_rs_ranked_erasures(const uint8_t* data_rel, int n_data, const uint8_t* par_rel, int n_par, int min_er, int threshold,
+                              int* erasures, int max_er) {
+    uint8_t rel[64];
+    int pos[64], n = 0, hits = 0;
+    for (int i = 0; i < n_par && n < 64; i++) {
+        hits += par_rel[i] < threshold;
+        rel[n] = par_rel[i];
+        pos[n++] = i;
+    }
+    for (int i = 0; i < n_data && n < 64; i++) {
+        hits += data_rel[i] < threshold;
+        rel[n] = data_rel[i];
+        pos[n++] = n_par + i;
+    }
+    for (int i = 0; i < n; i++) {
+        for (int j = i + 1; j < n; j++) {
+            if (rel[j] < rel[i] || (rel[j] == rel[i] && pos[j] < pos[i])) {
+                uint8_t tr = rel[i];
+                rel[i] = rel[j];
+                rel[j] = tr;
+                int tp = pos[i];
+                pos[i] = pos[j];
+                pos[j] = tp;
+            }
+        }
+    }
+    int cnt = hits > min_er ? hits : min_er;
+    if (cnt > n) {
+        cnt = n;
+    }
+    if (cnt > max_er) {
+        cnt = max_er;
+    }
+    for (int i = 0; i < cnt; i++) {
+        erasures[i] = pos[i];
+    }
+    return cnt;
+}
+
+/* p25p1_rs_{36_20_17,24_12_13,24_16_9}_soft_reliability (phase1/p25p1_check_hdu.cpp:56-77, p25p1_check_ldu.cpp:73-94 and
+ * the (24,12,13) twin) over DSDReedSolomon_*::decode_soft (ReedSolomon.hpp:879-913 ...): hard decode first; then the n
+ * weakest symbols as erasures for n = 1..ranked, first success wins.  Ranking: min_erasures = t, max = 2t.
+ * On success data_bits holds the corrected 0/1 bits; on failure data_bits is untouched.  Returns 0 / 1. */
+int
+oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits, const uint8_t* data_rel,
+                               const uint8_t* par_rel, int threshold) {
+    gf_init();
+    const int n_par = n_total - n_data, tt = n_par / 2;
+    int er[16];
+    int n_ranked = oracle_p25_rs_ranked_erasures(data_rel, n_data, par_rel, n_par, tt, threshold, er, 2 * tt);
+    uint8_t cand[36 * 6];
+    int in[63], out[63];
+    for (int i = 0; i < 63; i++) {
+        in[i] = 0;
+    }
+    for (int i = 0; i < n_par; i++) {
+        int v = 0;
+        for (int b = 0; b < 6; b++) {
+            v = (v << 1) | (parity_bits[6 * i + b] != 0);
+        }
+        in[i] = v;
+    }
+    for (int i = 0; i < n_data; i++) {
+        int v = 0;
+        for (int b = 0; b < 6; b++) {
+            v = (v << 1) | (data_bits[6 * i + b] != 0);
+        }
+        in[n_par + i] = v;
+    }
+    for (int n = 1; n <= n_ranked; n++) {
+        memcpy(cand, data_bits, (size_t)n_data * 6);
+        if (oracle_p25_rs_decode(n_total, n_data, cand, parity_bits) == 0) { /* decode_soft tries the hard decoder first */
+            memcpy(data_bits, cand, (size_t)n_data * 6);
+            return 0;
+        }
+        if (oracle_rs63_decode_with_erasures(tt, in, out, er, n) == 0) {
+            for (int i = 0; i < n_data; i++) {
+                for (int b = 0; b < 6; b++) {
+                    data_bits[6 * i + b] = (uint8_t)((out[n_par + i] >> (5 - b)) & 1);
+                }
+            }
+            return 0;
+        }
+    }
+    return 1;
 }
 
 /* ------------------------------------------------------------------ K = 5 soft Viterbi (M17 / YSF) */

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import _harness as H
-from test_oracle_fec import HAM, bptc_kat_bits, _rs_words
+from test_oracle_fec import HAM, bptc_kat_bits, _rs_words, make_rs_soft_cases, oracle_rs_erasures
 
 pytestmark = pytest.mark.gpu
 
@@ -202,3 +202,76 @@ def test_nxdn_conv_batch_with_carried_metrics(gpu):
                                       o_metrics[i].ctypes.data_as(u16p), H._ptr(w, H.u8p))
             assert np.array_equal(out[i], w), (frame, i)
         assert np.array_equal(g_metrics, o_metrics), frame
+
+
+def test_bptc_128x77_and_16x2_bit_exact(gpu):
+    """Batched BPTC 128x77 / 16x2 == oracle (== reference, tests/test_oracle_fec.py) on valid, corrupted and random
+    inputs; items on which the reference itself is undefined (uninitialised buffer) are excluded."""
+    O = H.oracle_fec()
+    O.oracle_bptc_128x77_extract.restype = C.c_uint
+    O.oracle_bptc_16x2_extract.restype = C.c_uint
+    rng = np.random.default_rng(91)
+    n = 4096
+    mats = rng.integers(0, 2, (n, 128)).astype(np.uint8)
+    # make three quarters of them near-valid: valid Hamming rows + consistent parity row + 0..4 flips
+    for i in range(n):
+        if i % 4:
+            for r in range(7):
+                line, dec = mats[i, 16 * r:16 * r + 16].copy(), np.zeros(11, np.uint8)
+                O.oracle_hamming_decode(4, H._ptr(line, H.u8p), H._ptr(dec, H.u8p))
+                mats[i, 16 * r:16 * r + 16] = line
+            mats[i, 112:] = mats[i, :112].reshape(7, 16).sum(axis=0) % 2
+            for e in rng.integers(0, 128, int(rng.integers(0, 5))):
+                mats[i, e] ^= 1
+    mats |= (rng.integers(0, 128, (n, 128)) * 2).astype(np.uint8)  # dirty upper bits, as callers pass them
+    out, errs = gpu.bptc_128x77(mats)
+    checked = 0
+    for i in range(n):
+        w, und = np.zeros(77, np.uint8), C.c_int(0)
+        e = O.oracle_bptc_128x77_extract(H._ptr(mats[i].copy(), H.u8p), H._ptr(w, H.u8p), C.byref(und))
+        if und.value:
+            continue
+        assert e == errs[i] and np.array_equal(out[i], w), i
+        checked += 1
+    assert checked > n // 2
+    words = rng.integers(0, 256, (n, 32)).astype(np.uint8)
+    for odd in (False, True):
+        out, errs = gpu.bptc_16x2(words, odd)
+        checked = 0
+        for i in range(n):
+            w, und = np.zeros(32, np.uint8), C.c_int(0)
+            e = O.oracle_bptc_16x2_extract(H._ptr(words[i].copy(), H.u8p), H._ptr(w, H.u8p), C.c_uint(1 if odd else 0), C.byref(und))
+            if und.value:
+                continue
+            assert e == errs[i] and np.array_equal(out[i], w), i
+            checked += 1
+        assert checked > n // 4
+
+
+@pytest.mark.parametrize("n,k,variant", [(36, 20, 0), (24, 12, 1), (24, 16, 2)])
+def test_rs_soft_decoders_bit_exact(gpu, n, k, variant):
+    """Batched errors-and-erasures RS decode and the ranked-erasure soft wrapper == oracle (== reference,
+    tests/test_oracle_fec.py::test_rs_soft_vs_reference): status and every data bit, incl. untouched dirty bytes on failure."""
+    O = H.oracle_fec()
+    rng = np.random.default_rng(300 + variant)
+    dat, par, rel_d, rel_p, ers, n_ers, truth = make_rs_soft_cases(rng, n, k, 1500)
+    got, st = gpu.p25_rs_decode_erasures(variant, dat, par, ers, n_ers)
+    for i in range(dat.shape[0]):
+        want, rc = oracle_rs_erasures(n, k, dat[i], par[i], ers[i], n_ers[i])
+        assert rc == st[i] and np.array_equal(got[i], want), i
+    got, st = gpu.p25_rs_soft_reliability(variant, dat, par, rel_d, rel_p, 64)
+    solved = 0
+    for i in range(dat.shape[0]):
+        b = dat[i].copy()
+        rc = O.oracle_p25_rs_soft_reliability(n, k, H._ptr(b, H.u8p), H._ptr(par[i], H.u8p), H._ptr(rel_d[i].copy(), H.u8p),
+                                              H._ptr(rel_p[i].copy(), H.u8p), 64)
+        assert rc == st[i] and np.array_equal(got[i], b), i
+        solved += rc == 0 and np.array_equal(b, truth[i])
+    assert solved > 400
+    # a different threshold changes the ranked count, not the order
+    got2, st2 = gpu.p25_rs_soft_reliability(variant, dat[:200], par[:200], rel_d[:200], rel_p[:200], 200)
+    for i in range(200):
+        b = dat[i].copy()
+        rc = O.oracle_p25_rs_soft_reliability(n, k, H._ptr(b, H.u8p), H._ptr(par[i], H.u8p), H._ptr(rel_d[i].copy(), H.u8p),
+                                              H._ptr(rel_p[i].copy(), H.u8p), 200)
+        assert rc == st2[i] and np.array_equal(got2[i], b), i

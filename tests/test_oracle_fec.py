@@ -326,3 +326,194 @@ def test_nxdn_convolution_vs_reference():
         O.oracle_nxdn_conv_decode(H._ptr(sym, H.u8p), H._ptr(rel, H.u8p) if soft else None, n_steps, n_out,
                                   metrics.ctypes.data_as(u16p), H._ptr(a, H.u8p))
         assert np.array_equal(a, b), t
+
+
+def _near_valid_128x77(rng, n_flips):
+    """A matrix whose 7 Hamming rows are valid codewords and whose parity row is consistent, with n_flips bit errors."""
+    O = H.oracle_fec()
+    m = rng.integers(0, 2, 128).astype(np.uint8)
+    for i in range(7):
+        line, dec = m[16 * i:16 * i + 16].copy(), np.zeros(11, np.uint8)
+        while not O.oracle_hamming_decode(4, H._ptr(line, H.u8p), H._ptr(dec, H.u8p)):
+            line = rng.integers(0, 2, 16).astype(np.uint8)
+        m[16 * i:16 * i + 16] = line
+    m[112:128] = m[:112].reshape(7, 16).sum(axis=0) % 2
+    for e in rng.integers(0, 128, n_flips):
+        m[e] ^= 1
+    return m
+
+
+@needs_ref
+def test_bptc_128x77_and_16x2_match_reference():
+    """oracle == BPTC_128x77_Extract_Data / BPTC_16x2_Extract_Data (src/fec/bptc.c:167-333) on clean, lightly corrupted
+    and random inputs with dirty upper bits; inputs on which the reference reads an uninitialised buffer are excluded."""
+    O, R = H.oracle_fec(), H.ref("par")
+    R.InitAllFecFunction()
+    R.BPTC_128x77_Extract_Data.restype = C.c_uint32
+    R.BPTC_16x2_Extract_Data.restype = C.c_uint32
+    O.oracle_bptc_128x77_extract.restype = C.c_uint
+    O.oracle_bptc_16x2_extract.restype = C.c_uint
+    rng = np.random.default_rng(5)
+    compared = 0
+    for t in range(3000):
+        x = _near_valid_128x77(rng, int(rng.integers(0, 5))) if t % 3 else rng.integers(0, 2, 128).astype(np.uint8)
+        x = x | (rng.integers(0, 128, 128) * 2).astype(np.uint8)
+        a, b, oa, ob, und = x.copy(), x.copy(), np.zeros(77, np.uint8), np.zeros(77, np.uint8), C.c_int(0)
+        rb = O.oracle_bptc_128x77_extract(H._ptr(b, H.u8p), H._ptr(ob, H.u8p), C.byref(und))
+        if und.value:
+            continue
+        ra = R.BPTC_128x77_Extract_Data(H._ptr(a, H.u8p), H._ptr(oa, H.u8p))
+        assert ra == rb and np.array_equal(oa, ob)
+        compared += 1
+    assert compared > 1500
+    compared = 0
+    for t in range(3000):
+        x = rng.integers(0, 256, 32).astype(np.uint8)
+        for odd in (0, 1):
+            a, b, oa, ob, und = x.copy(), x.copy(), np.zeros(32, np.uint8), np.zeros(32, np.uint8), C.c_int(0)
+            rb = O.oracle_bptc_16x2_extract(H._ptr(b, H.u8p), H._ptr(ob, H.u8p), C.c_uint(odd), C.byref(und))
+            if und.value:
+                continue
+            ra = R.BPTC_16x2_Extract_Data(H._ptr(a, H.u8p), H._ptr(oa, H.u8p), C.c_uint32(odd))
+            assert ra == rb and np.array_equal(oa, ob)
+            compared += 1
+    assert compared > 1500
+
+
+def test_bptc_128x77_reference_kat():
+    """The reference's own known-answer matrix (tests/fec/test_fec_bptc_rs.c:74-125): zero errors, payload = 0xA5 pattern
+    LSB first, CRC bits zero; a single flipped bit is corrected."""
+    O = H.oracle_fec()
+    O.oracle_bptc_128x77_extract.restype = C.c_uint
+    ref = np.array([[1, 0, 1, 0, 0, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 1], [0, 0, 1, 0, 1, 1, 0, 1, 0, 0, 1, 1, 0, 1, 0, 1],
+                    [0, 1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0], [1, 0, 1, 0, 0, 1, 0, 1, 1, 0, 0, 1, 0, 1, 1, 0],
+                    [1, 0, 0, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0], [0, 1, 0, 1, 1, 0, 1, 0, 0, 1, 0, 0, 1, 1, 1, 0],
+                    [0, 1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 1, 0, 0]], np.uint8)
+    want = np.array([(0xA5 >> (i % 8)) & 1 for i in range(72)] + [0] * 5, np.uint8)
+    for flip in (None, (1, 3)):
+        m = ref.copy()
+        if flip:
+            m[flip] ^= 1
+        out = np.zeros(77, np.uint8)
+        assert O.oracle_bptc_128x77_extract(H._ptr(np.ascontiguousarray(m.reshape(-1)), H.u8p), H._ptr(out, H.u8p), None) == 0
+        assert np.array_equal(out, want)
+
+
+RS_SHAPES = {(36, 20): 0, (24, 12): 1, (24, 16): 2}
+
+
+def make_rs_soft_cases(rng, n, k, count, dirty=True):
+    """Random shortened RS words with 0..2t+2 symbol errors and per-symbol reliabilities that mostly flag the errors."""
+    O = H.oracle_fec()
+    tt = (n - k) // 2
+    dat, par, rel_d, rel_p, ers, n_ers, truth = [], [], [], [], [], [], []
+    for trial in range(count):
+        data = np.zeros(63 - 2 * tt, np.int32)
+        data[:k] = rng.integers(0, 64, k)
+        cw = np.zeros(63, np.int32)
+        O.oracle_rs63_encode(tt, data.ctypes.data_as(H.i32p), cw.ctypes.data_as(H.i32p))
+        rx = cw.copy()
+        pos = rng.choice(n, int(rng.integers(0, 2 * tt + 3)), replace=False)
+        rx[pos] ^= rng.integers(1, 64, pos.size).astype(np.int32)
+        rel = np.full(n, 255, np.uint8)
+        for q in pos:
+            if rng.random() < 0.8:
+                rel[q] = rng.integers(0, 120)
+        for q in rng.choice(n, int(rng.integers(0, 4)), replace=False):
+            rel[q] = rng.integers(0, 255)
+        d = _rs_words(rx[2 * tt:n])
+        if dirty and trial % 5 == 0:
+            d = (d * rng.integers(1, 120, d.size)).astype(np.uint8)  # callers pass any non-zero byte as a 1
+        kk = int(rng.integers(1, 2 * tt + 1))
+        e = (list(pos[:kk]) + [q for q in rng.permutation(n) if q not in pos])[:kk]
+        dat.append(d); par.append(_rs_words(rx[:2 * tt])); rel_d.append(rel[2 * tt:]); rel_p.append(rel[:2 * tt])
+        ers.append(np.array(e + [0] * (16 - kk), np.int32)); n_ers.append(kk); truth.append(_rs_words(cw[2 * tt:n]))
+    return (np.array(dat), np.array(par), np.array(rel_d), np.array(rel_p), np.array(ers), np.array(n_ers, np.int32), np.array(truth))
+
+
+def oracle_rs_erasures(n, k, d, p, ers, n_er):
+    """check_and_fix_*_soft semantics from the oracle parts: hard decode (writes back), then one erasure decode."""
+    O = H.oracle_fec()
+    tt = (n - k) // 2
+    d = d.copy()
+    sym = lambda bits: [int("".join("1" if b else "0" for b in bits[6 * i:6 * i + 6]), 2) for i in range(len(bits) // 6)]
+    inn = np.zeros(63, np.int32)
+    inn[:2 * tt] = sym(p)
+    inn[2 * tt:n] = sym(d)
+    rc = O.oracle_p25_rs_decode(n, k, H._ptr(d, H.u8p), H._ptr(p, H.u8p))
+    if rc != 0:
+        out = np.zeros(63, np.int32)
+        e = np.ascontiguousarray(ers[:n_er], np.int32)
+        rc = O.oracle_rs63_decode_with_erasures(tt, inn.ctypes.data_as(H.i32p), out.ctypes.data_as(H.i32p), e.ctypes.data_as(H.i32p), int(n_er))
+        if rc == 0:
+            d = _rs_words(out[2 * tt:n])
+    return d, rc
+
+
+@needs_ref
+@pytest.mark.parametrize("n,k", [(36, 20), (24, 12), (24, 16)])
+def test_rs_soft_vs_reference(n, k):
+    """Erasure decoding and the ranked-erasure soft wrappers == the reference (check_and_fix_*_soft,
+    p25p1_rs_*_soft_reliability, p25p1_build_rs_ranked_erasures), return codes and corrected bits."""
+    O, R = H.oracle_fec(), H.ref_fec()
+    f_ers = {(36, 20): R.check_and_fix_redsolomon_36_20_17_soft, (24, 12): R.check_and_fix_reedsolomon_24_12_13_soft,
+             (24, 16): R.check_and_fix_reedsolomon_24_16_9_soft}[(n, k)]
+    f_soft = {(36, 20): R.p25p1_rs_36_20_17_soft_reliability, (24, 16): R.p25p1_rs_24_16_9_soft_reliability}.get((n, k))
+    rng = np.random.default_rng(70 + n + k)
+    dat, par, rel_d, rel_p, ers, n_ers, truth = make_rs_soft_cases(rng, n, k, 1200)
+    wins = 0
+    for i in range(dat.shape[0]):
+        a = dat[i].copy()
+        e = np.ascontiguousarray(ers[i, :n_ers[i]])
+        ra = f_ers(H._ptr(a, H.u8p), H._ptr(par[i], H.u8p), e.ctypes.data_as(H.i32p), int(n_ers[i]))
+        b, rb = oracle_rs_erasures(n, k, dat[i], par[i], ers[i], n_ers[i])
+        assert ra == rb and np.array_equal(a, b), i
+        if f_soft is not None:
+            a, b = dat[i].copy(), dat[i].copy()
+            ra = f_soft(H._ptr(a, H.u8p), H._ptr(par[i], H.u8p), H._ptr(rel_d[i].copy(), H.u8p), H._ptr(rel_p[i].copy(), H.u8p))
+            rb = O.oracle_p25_rs_soft_reliability(n, k, H._ptr(b, H.u8p), H._ptr(par[i], H.u8p), H._ptr(rel_d[i].copy(), H.u8p),
+                                                  H._ptr(rel_p[i].copy(), H.u8p), 64)
+            assert ra == rb and np.array_equal(a, b), i
+            wins += ra == 0 and np.array_equal(a, truth[i])
+        # ranking helper
+        want, got = np.zeros(16, np.int32), np.zeros(16, np.int32)
+        tt = (n - k) // 2
+        nw = R.p25p1_build_rs_ranked_erasures(H._ptr(rel_d[i].copy(), H.u8p), k, H._ptr(rel_p[i].copy(), H.u8p), n - k, tt,
+                                              want.ctypes.data_as(H.i32p), 2 * tt)
+        ng = O.oracle_p25_rs_ranked_erasures(H._ptr(rel_d[i].copy(), H.u8p), k, H._ptr(rel_p[i].copy(), H.u8p), n - k, tt, 64,
+                                             got.ctypes.data_as(H.i32p), 2 * tt)
+        assert nw == ng and np.array_equal(want[:nw], got[:ng])
+    if f_soft is not None:
+        assert wins > 300
+
+
+def test_rs_soft_reference_kats():
+    """The reference's pinned vectors (tests/protocol/p25/test_p25p1_soft_rs.cpp:44-59,83-160): parity of fill_data(seed)
+    words, ten erased data symbols corrected by RS(36,20,17) where the hard decoder fails, ranked-erasure mapping."""
+    O = H.oracle_fec()
+    fill = lambda count, seed: np.array([(seed + i * 7) & 0x3F for i in range(count)], np.int32)
+    kats = [(8, 20, 3, [0x1F, 0x01, 0x38, 0x24, 0x0C, 0x2B, 0x29, 0x35, 0x1C, 0x11, 0x2D, 0x0A, 0x11, 0x3D, 0x12, 0x32]),
+            (8, 20, 29, [0x19, 0x3C, 0x0A, 0x2A, 0x33, 0x2F, 0x23, 0x23, 0x08, 0x0C, 0x0F, 0x16, 0x12, 0x04, 0x17, 0x01]),
+            (6, 12, 11, [0x05, 0x08, 0x00, 0x2B, 0x10, 0x32, 0x1F, 0x0D, 0x03, 0x2F, 0x27, 0x22]),
+            (4, 16, 23, [0x25, 0x2A, 0x2C, 0x09, 0x0A, 0x0F, 0x06, 0x29])]
+    for tt, k, seed, parity in kats:
+        data = np.zeros(63 - 2 * tt, np.int32)
+        data[:k] = fill(k, seed)
+        cw = np.zeros(63, np.int32)
+        O.oracle_rs63_encode(tt, data.ctypes.data_as(H.i32p), cw.ctypes.data_as(H.i32p))
+        assert list(cw[:2 * tt]) == parity
+    # HDU: 10 corrupted data symbols, all flagged as erasures (positions 16..25)
+    data = fill(20, 3)
+    bad = data.copy()
+    for i in range(10):
+        bad[i] ^= (0x21 + i) & 0x3F
+    par = _rs_words(np.array(kats[0][3]))
+    hard = _rs_words(bad)
+    assert O.oracle_p25_rs_decode(36, 20, H._ptr(hard, H.u8p), H._ptr(par, H.u8p)) == 1
+    fixed, rc = oracle_rs_erasures(36, 20, _rs_words(bad), par, np.arange(16, 26, dtype=np.int32), 10)
+    assert rc == 0 and np.array_equal(fixed, _rs_words(data))
+    er = np.zeros(16, np.int32)
+    d, p = np.full(20, 255, np.uint8), np.full(16, 255, np.uint8)
+    p[3], d[4] = 10, 20
+    assert O.oracle_p25_rs_ranked_erasures(H._ptr(d, H.u8p), 20, H._ptr(p, H.u8p), 16, 2, 64, er.ctypes.data_as(H.i32p), 16) == 2
+    assert list(er[:2]) == [3, 20]
