@@ -218,6 +218,68 @@ class DemodBank:
         return out
 
 
+class SyncPattern(C.Structure):
+    _fields_ = [("symbols", C.c_char_p), ("sync_type", C.c_int)]
+
+
+class SyncHit(C.Structure):
+    _fields_ = [("position", C.c_int), ("sync_type", C.c_int)]
+
+
+# include/dsd-neo/core/sync_patterns.h:33-67 with the ids of include/dsd-neo/core/synctype_ids.h (non-inverted DMR setting)
+DEFAULT_SYNC_PATTERNS = [
+    ("111113113311333313133333", 0),   # P25P1_SYNC            -> DSD_SYNC_P25P1_POS
+    ("333331331133111131311111", 1),   # INV_P25P1_SYNC        -> DSD_SYNC_P25P1_NEG
+    ("313333111331131131331131", 10),  # DMR_BS_DATA_SYNC      -> DSD_SYNC_DMR_BS_DATA_POS
+    ("131111333113313313113313", 12),  # DMR_BS_VOICE_SYNC     -> DSD_SYNC_DMR_BS_VOICE_POS
+    ("311131133313133331131113", 33),  # DMR_MS_DATA_SYNC      -> DSD_SYNC_DMR_MS_DATA
+    ("133313311131311113313331", 32),  # DMR_MS_VOICE_SYNC     -> DSD_SYNC_DMR_MS_VOICE
+    ("331313111113131113331133", 2),   # X2TDMA_BS_DATA_SYNC   -> DSD_SYNC_X2TDMA_DATA_POS
+    ("113131333331313331113311", 4),   # X2TDMA_BS_VOICE_SYNC  -> DSD_SYNC_X2TDMA_VOICE_POS
+    ("31111311313113131131", 30),      # FUSION_SYNC           -> DSD_SYNC_YSF_POS
+    ("13333133131331313313", 31),      # INV_FUSION_SYNC       -> DSD_SYNC_YSF_NEG
+]
+
+
+class FrameSync:
+    """Batched twin of the per-symbol sync hunt of getFrameSync() (dsd_frame_sync.c:3098-3148)."""
+
+    def __init__(self, n_channels: int, patterns=None):
+        patterns = DEFAULT_SYNC_PATTERNS if patterns is None else patterns
+        self._keep = [p.encode() if isinstance(p, str) else p for p, _ in patterns]
+        arr = (SyncPattern * len(patterns))(*[SyncPattern(k, t) for k, (_, t) in zip(self._keep, patterns)])
+        self.n_channels = n_channels
+        self._h = lib().dsdneo_b200_frame_sync_create(n_channels, arr, len(patterns))
+        if not self._h:
+            raise B200Error(f"frame_sync_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_frame_sync_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_frame_sync_reset(self._h, _stream_ptr(stream)), "frame_sync_reset")
+
+    def search(self, d_symbols, d_n_symbols, max_hits: int = 64, stream=None):
+        """d_symbols: cuda f32 [n_channels, pitch]; d_n_symbols: cuda int32 [n_channels].
+        Returns (hits int32 [n_channels, max_hits, 2] = (position, sync_type), n_hits int32 [n_channels])."""
+        import torch
+
+        assert d_symbols.is_cuda and d_symbols.dtype == torch.float32 and d_symbols.is_contiguous()
+        assert d_n_symbols.is_cuda and d_n_symbols.dtype == torch.int32
+        hits = torch.zeros((self.n_channels, max_hits, 2), dtype=torch.int32, device=d_symbols.device)
+        n_hits = torch.zeros(self.n_channels, dtype=torch.int32, device=d_symbols.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_symbols.device)
+        check(lib().dsdneo_b200_frame_sync_search_batch(self._h, d_symbols.data_ptr(), d_symbols.shape[1], d_n_symbols.data_ptr(),
+                                                        hits.data_ptr(), max_hits, n_hits.data_ptr(), _stream_ptr(stream)),
+              "frame_sync_search_batch")
+        return hits, n_hits
+
+
 class HalfbandCascade:
     """N-channel twin of full_demod_apply_halfband_decimation (demod_pipeline.cpp:983-1001): `passes` half-band /2 stages."""
 

@@ -47,6 +47,10 @@ def bind(L):
         "dsdneo_b200_p25_rs_soft_reliability_batch_host": (ci, [ci, vp, vp, vp, vp, ci, vp, ci]),
         "dsdneo_b200_timing_enable": (ci, [ci]),
         "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
+        "dsdneo_b200_frame_sync_create": (vp, [ci, vp, ci]),
+        "dsdneo_b200_frame_sync_destroy": (None, [vp]),
+        "dsdneo_b200_frame_sync_reset": (ci, [vp, vp]),
+        "dsdneo_b200_frame_sync_search_batch": (ci, [vp, vp, sz, vp, vp, ci, vp, vp]),
         "dsdneo_b200_hb_cascade_create": (vp, [ci, ci, ci]),
         "dsdneo_b200_hb_cascade_destroy": (None, [vp]),
         "dsdneo_b200_hb_cascade_reset": (ci, [vp, vp]),

@@ -257,6 +257,38 @@ long long dsdneo_b200_frontend_submit_host(dsdneo_b200_frontend* fe, const void*
                                            float* h_result, size_t result_pitch);
 int dsdneo_b200_frontend_wait_host(dsdneo_b200_frontend* fe, long long ticket);
 
+/* ---- K12: frame-sync correlator, batched over channels ------------------------------------------------------- */
+/*
+ * The per-symbol part of getFrameSync() (src/dsp/dsd_frame_sync.c:3098-3148) for FSK inputs: hunt-time slice
+ * symbol > 0 -> '1' else '3' (:2110-2127), rolling window, strcmp against the sync strings of
+ * include/dsd-neo/core/sync_patterns.h:33-67.  Patterns are given as the reference's own strings ('1'/'3', 8..32 symbols,
+ * oldest first) with the DSD_SYNC_* id (include/dsd-neo/core/synctype_ids.h) to report; at one position the first
+ * matching pattern in table order wins, as in the reference's ordered matcher list.  A pattern can only match once as
+ * many symbols as its length have been seen since create/reset (history carries across launches).
+ * Everything else getFrameSync does (protocol gating by opts, threshold warm start, timeouts) is host control flow.
+ */
+#define DSDNEO_B200_SYNC_MAX_PATTERNS 32
+typedef struct {
+    const char* symbols; /* e.g. "111113113311333313133333" (P25P1_SYNC) */
+    int sync_type;       /* e.g. 0 (DSD_SYNC_P25P1_POS) */
+} dsdneo_b200_sync_pattern;
+typedef struct {
+    int position;  /* index (within the launch) of the symbol that completes the pattern */
+    int sync_type;
+} dsdneo_b200_sync_hit;
+typedef struct dsdneo_b200_frame_sync dsdneo_b200_frame_sync;
+dsdneo_b200_frame_sync* dsdneo_b200_frame_sync_create(int n_channels, const dsdneo_b200_sync_pattern* patterns, int n_patterns);
+void dsdneo_b200_frame_sync_destroy(dsdneo_b200_frame_sync* fs);
+int dsdneo_b200_frame_sync_reset(dsdneo_b200_frame_sync* fs, void* stream);
+/**
+ * @param d_symbols   [n_channels][pitch] symbol-rate floats (dsdneo_b200_symbolizer output, getSymbol() values)
+ * @param d_n_symbols [n_channels] valid symbols per channel in this launch
+ * @param d_hits      [n_channels][max_hits] hits in stream order; @param d_n_hits [n_channels] hits found (may exceed
+ *                    max_hits, in which case only the first max_hits were stored)
+ */
+int dsdneo_b200_frame_sync_search_batch(dsdneo_b200_frame_sync* fs, const float* d_symbols, size_t pitch, const int* d_n_symbols,
+                                        dsdneo_b200_sync_hit* d_hits, int max_hits, int* d_n_hits, void* stream);
+
 /* ---- K3: complex half-band decimator cascade, batched over channels ------------------------------------ */
 /*
  * Replaces full_demod_apply_halfband_decimation (src/dsp/demod_pipeline.cpp:983-1001) = `passes` calls of

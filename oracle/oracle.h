@@ -137,6 +137,8 @@ long oracle_sym_run_symbols(oracle_sym_chan* c, int have_sync, const float* samp
 long oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, long reserve, uint8_t* dibits, uint8_t* rel,
                            int16_t* llr2, float* symbols, long max_out, long* consumed);
 
+int oracle_frame_sync_search(const float* symbols, int n, const char* const* patterns, const int* sync_types, int n_patterns,
+                             char* hist32, int* hist_count, int* hit_pos, int* hit_type, int max_hits);
 void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n);
 
 #ifdef __cplusplus

@@ -431,3 +431,34 @@ oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, long res
     *consumed = s.pos;
     return k;
 }
+
+
+/* ---- frame-sync hunt (src/dsp/dsd_frame_sync.c:3098-3148): hunt-time slice (:2110-2127) symbol > 0 -> '1' else '3',
+ * rolling character history, strcmp of its last strlen(pattern) characters against each pattern in table order; a
+ * pattern is only tried once that many characters have been pushed (frame_sync_history_materialize).  Reports every
+ * position where some pattern completes (the reference returns at the first and resumes after the frame).
+ * hist (32 chars) / hist_count carry across calls; returns the number of hits found (only max_hits are stored). */
+int
+oracle_frame_sync_search(const float* symbols, int n, const char* const* patterns, const int* sync_types, int n_patterns,
+                         char* hist32, int* hist_count, int* hit_pos, int* hit_type, int max_hits) {
+    int found = 0;
+    for (int p = 0; p < n; p++) {
+        memmove(hist32, hist32 + 1, 31);
+        hist32[31] = symbols[p] > 0.0f ? '1' : '3';
+        if (*hist_count < 32) {
+            (*hist_count)++;
+        }
+        for (int k = 0; k < n_patterns; k++) {
+            int L = (int)strlen(patterns[k]);
+            if (*hist_count >= L && strncmp(hist32 + 32 - L, patterns[k], (size_t)L) == 0) {
+                if (found < max_hits) {
+                    hit_pos[found] = p;
+                    hit_type[found] = sync_types[k];
+                }
+                found++;
+                break;
+            }
+        }
+    }
+    return found;
+}

@@ -462,6 +462,35 @@ def synth_disc(rng, n_symbols, sps=10, level=9000.0, noise=0.0, drift=0.0, dibit
     return x.astype(np.float32), np.asarray(dibits)
 
 
+def c4fm_shaping_taps(ntaps=241, fs=48000.0, rs=4800.0, alpha=0.2):
+    """P25 C4FM transmit shaping (TIA-102.BAAA: raised cosine alpha 0.2 times x/sin(x) pre-emphasis), frequency-sampled;
+    the reference's p25_filter (de-emphasis sinc) brings it back to a raised cosine.  Gain 10 = one impulse per 10 samples."""
+    N = 4096
+    f = np.fft.rfftfreq(N, 1 / fs)
+    T = 1 / rs
+    f1, f2 = (1 - alpha) / (2 * T), (1 + alpha) / (2 * T)
+    rc = np.zeros_like(f)
+    rc[f <= f1] = 1.0
+    m = (f > f1) & (f <= f2)
+    rc[m] = 0.5 * (1 + np.cos(np.pi * T / alpha * (f[m] - f1)))
+    x = np.pi * f * T
+    shp = np.ones_like(f)
+    shp[x > 0] = x[x > 0] / np.sin(x[x > 0])
+    h = np.fft.irfft(rc * np.where(f <= f2, shp, 0.0), N)
+    return np.roll(h, ntaps // 2)[:ntaps] * 10.0
+
+
+def synth_c4fm_disc(rng, dibits, level=9000.0, noise=0.0, pre=9):
+    """Discriminator-level C4FM stream at 10 samples/symbol whose symbol centres line up with getSymbol's window after the
+    91-tap p25_filter (45-sample delay + `pre` = 54 = 5 symbols + centre index 4)."""
+    imp = np.zeros(len(dibits) * 10)
+    imp[::10] = LEVELS[np.asarray(dibits)] * level
+    x = np.convolve(imp, c4fm_shaping_taps(), mode="same")
+    if noise:
+        x = x + rng.standard_normal(x.size) * noise
+    return np.concatenate([np.zeros(pre), x]).astype(np.float32)
+
+
 def conv_k5_encode(bits):
     """Rate-1/2 K=5 encoder used by M17 / NXDN / YSF (G1 = 1+D^3+D^4, G2 = 1+D+D^2+D^4), returns 2*len(bits) bits."""
     sr = 0
