@@ -34,6 +34,22 @@ constexpr int kCarry = 96;                         /* leftover samples carried b
 constexpr int kSbuf = 128;
 constexpr int kMinMax = 1024;
 constexpr int kSymThreads = 32;
+constexpr int kScanBlk = 16;  /* use_symbol's 128-entry extrema scan is kept as 8 block summaries + the block being replaced */
+constexpr int kWin = 128;     /* samples per channel staged in shared memory per refill */
+
+/* two smallest / two largest elements of a multiset, order independent (the reference's scan, dsd_dibit.c:264-289,
+ * finds exactly these: duplicates count as separate elements) */
+__device__ __forceinline__ void
+two_min_push(float& m1, float& m2, float v) {
+    m2 = fminf(m2, fmaxf(m1, v));
+    m1 = fminf(m1, v);
+}
+
+__device__ __forceinline__ void
+two_max_push(float& m1, float& m2, float v) {
+    m2 = fmaxf(m2, fminf(m1, v));
+    m1 = fmaxf(m1, v);
+}
 
 /* per-channel scalars, struct-of-arrays on the device */
 struct SymScalars {
@@ -188,21 +204,16 @@ clamp255(int v) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-__device__ __forceinline__ int
-bit_metric(float sym, const float (&ideal)[4], int bit_index) {
-    /* dsd_dibit.c:609-642 */
-    float best0 = 3.4028234663852886e38f, best1 = 3.4028234663852886e38f, min_spacing = 3.4028234663852886e38f;
+/* compute_dibit_soft_metric's per-bit magnitudes (dsd_dibit.c:609-642) for both bits at once: the spacing scan and the
+ * scale 255 / min_spacing^2 do not depend on the bit index, so they are evaluated once. */
+__device__ __forceinline__ void
+bit_metrics(float sym, const float (&ideal)[4], int& mag0, int& mag1) {
+    const float big = 3.4028234663852886e38f;
+    float d[4], min_spacing = big;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float e = __fsub_rn(sym, ideal[i]);
-        const float d = __fmul_rn(e, e);
-        if (((i >> (1 - bit_index)) & 1) != 0) {
-            if (d < best1) {
-                best1 = d;
-            }
-        } else if (d < best0) {
-            best0 = d;
-        }
+        d[i] = __fmul_rn(e, e);
 #pragma unroll
         for (int j = i + 1; j < 4; j++) {
             const float sp = fabsf(__fsub_rn(ideal[i], ideal[j]));
@@ -211,16 +222,22 @@ bit_metric(float sym, const float (&ideal)[4], int bit_index) {
             }
         }
     }
-    if (min_spacing == 3.4028234663852886e38f) {
+    if (min_spacing == big) {
         min_spacing = 2.0f;
     }
     const float scale = __fdiv_rn(255.0f, __fmul_rn(min_spacing, min_spacing));
-    return clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(best0, best1)), scale))); /* lrintf: round to nearest even */
+    /* bit 0 = MSB of the dibit index: {0,1} vs {2,3}; bit 1 = LSB: {0,2} vs {1,3}; strict < keeps the first minimum */
+    const float b0_0 = d[1] < d[0] ? d[1] : d[0], b0_1 = d[3] < d[2] ? d[3] : d[2];
+    const float b1_0 = d[2] < d[0] ? d[2] : d[0], b1_1 = d[3] < d[1] ? d[3] : d[1];
+    mag0 = clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(b0_0, b0_1)), scale))); /* lrintf: round to nearest even */
+    mag1 = clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(b1_0, b1_1)), scale)));
 }
 
 __global__ void __launch_bounds__(kSymThreads)
 symbolize_kernel(const SymParams p) {
     __shared__ float s_sbuf[kSbuf][kSymThreads];
+    __shared__ float s_blk[kSbuf / kScanBlk][4][kSymThreads]; /* per 16-entry block of sbuf: two smallest, two largest */
+    __shared__ float s_win[kWin * (kSymThreads + 1)];          /* staged samples, [sample][channel], padded rows */
     const int lane = threadIdx.x;
     const int ch = blockIdx.x * kSymThreads + lane;
     const bool valid = ch < p.n_ch;
@@ -256,7 +273,65 @@ symbolize_kernel(const SymParams p) {
     long nsym = 0;
     const int have_sync = (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) ? 1 : p.have_sync;
 
-    while (nsym < (long)p.out_pitch && (avail - pos) >= reserve) {
+    const int cap = p.ssize < 0 ? 0 : (p.ssize > kSbuf ? kSbuf : p.ssize);
+    const int n_blk = (cap + kScanBlk - 1) / kScanBlk;
+    auto rescan_block = [&](int b) {
+        float mn1 = 3.4028234663852886e38f, mn2 = mn1, mx1 = -mn1, mx2 = -mn1;
+        const int k1 = min(cap, (b + 1) * kScanBlk);
+        for (int k = b * kScanBlk; k < k1; k++) {
+            const float v = s_sbuf[k][lane];
+            two_min_push(mn1, mn2, v);
+            two_max_push(mx1, mx2, v);
+        }
+        s_blk[b][0][lane] = mn1, s_blk[b][1][lane] = mn2, s_blk[b][2][lane] = mx1, s_blk[b][3][lane] = mx2;
+    };
+    if (track) {
+        for (int b = 0; b < n_blk; b++) {
+            rescan_block(b);
+        }
+    }
+
+    /* Samples are staged through shared memory: the warp loads kWin consecutive samples of its 32 channels with
+     * coalesced 128-byte reads and each lane then walks its own column.  Lanes drift apart only by the +-1 timing
+     * nudges; a lane that falls outside the staged window reads global memory directly for that symbol. */
+    long wbase = 0, wend = 0;
+    bool active = nsym < (long)p.out_pitch && (avail - pos) >= reserve;
+    while (__any_sync(0xffffffffu, active)) {
+        if (__any_sync(0xffffffffu, active && (pos < wbase || pos + reserve > wend))) {
+            long mp = active ? pos : 0x7fffffffffffffffL;
+            for (int o = 16; o > 0; o >>= 1) {
+                const long other = __shfl_xor_sync(0xffffffffu, mp, o);
+                mp = other < mp ? other : mp;
+            }
+            wbase = mp;
+            wend = wbase + kWin;
+            __syncwarp();
+            for (int r = 0; r < kSymThreads; r++) {
+                const int cr = __shfl_sync(0xffffffffu, c, r);
+                const int cn = __shfl_sync(0xffffffffu, carry_n, r);
+                const float* fr = p.filt + (size_t)cr * p.filt_pitch;
+#pragma unroll
+                for (int g = 0; g < kWin / 32; g++) {
+                    const long k = wbase + g * 32 + lane;
+                    float* dst = &s_win[(g * 32 + lane) * (kSymThreads + 1) + r];
+                    const float* src = nullptr;
+                    if (k < cn) {
+                        src = &p.carry[(size_t)k * N + cr];
+                    } else if (k - cn < p.n) {
+                        src = &fr[k - cn];
+                    }
+                    if (src) { /* all 128 copies of the refill are in flight before the single wait below */
+                        const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src) : "memory");
+                    } else {
+                        *dst = 0.0f;
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
+        if (active) {
         /* ---- symbol_apply_rtl_fsk_discriminator_timing (dsd_symbol.c:1328-1387) ---- */
         if (sps_num != p.rate || sps_den != p.symrate) {
             sps_num = p.rate;
@@ -299,6 +374,8 @@ symbolize_kernel(const SymParams p) {
         /* ---- symbol_process_live_samples (dsd_symbol.c:1769-1792) ---- */
         float sum = 0.0f;
         int cnt = 0;
+        const bool in_win = pos >= wbase && pos + sps + 1 <= wend; /* a nudge reads at most one extra sample */
+        const float* wp = s_win + (in_win ? (int)(pos - wbase) : 0) * (kSymThreads + 1) + lane;
         for (int i = 0; i < sps; i++) {
             if (i == 0 && have_sync == 0 && jitter >= 0) { /* dsd_symbol.c:462-516 */
                 if (sps == 20) {
@@ -316,7 +393,9 @@ symbolize_kernel(const SymParams p) {
                 }
                 jitter = -1;
             }
-            float s = sample_at(pos++);
+            float s = in_win ? *wp : sample_at(pos);
+            wp += kSymThreads + 1;
+            pos++;
             if (have_sync == 1) { /* symbol_apply_sync_clip, rf_mod == 0 */
                 s = s > vmax ? vmax : (s < vmin ? vmin : s);
             }
@@ -350,32 +429,21 @@ symbolize_kernel(const SymParams p) {
         if (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
             /* ---- get_dibit_and_analog_signal: sbuf, use_symbol (dsd_dibit.c:243-299) ---- */
             s_sbuf[sidx][lane] = sym;
-            int cap = p.ssize < 0 ? 0 : (p.ssize > kSbuf ? kSbuf : p.ssize);
             if (track) {
                 float lmin = 0.0f, lmax = 0.0f;
                 if (cap >= 2) {
-                    float mn1 = s_sbuf[0][lane], mn2 = s_sbuf[1][lane];
-                    if (mn2 < mn1) {
-                        const float t = mn1;
-                        mn1 = mn2, mn2 = t;
+                    /* avg of the two smallest / two largest entries of sbuf[0..cap) (dsd_dibit.c:264-289): only the
+                     * 16-entry block that received the new symbol is rescanned, the rest comes from block summaries */
+                    if (sidx >= 0 && sidx < cap) {
+                        rescan_block(sidx / kScanBlk);
                     }
-                    float mx1 = s_sbuf[0][lane], mx2 = s_sbuf[1][lane];
-                    if (mx2 > mx1) {
-                        const float t = mx1;
-                        mx1 = mx2, mx2 = t;
-                    }
-                    for (int k = 2; k < cap; k++) {
-                        const float v = s_sbuf[k][lane];
-                        if (v < mn1) {
-                            mn2 = mn1, mn1 = v;
-                        } else if (v < mn2) {
-                            mn2 = v;
-                        }
-                        if (v > mx1) {
-                            mx2 = mx1, mx1 = v;
-                        } else if (v > mx2) {
-                            mx2 = v;
-                        }
+                    float mn1 = s_blk[0][0][lane], mn2 = s_blk[0][1][lane], mx1 = s_blk[0][2][lane], mx2 = s_blk[0][3][lane];
+                    for (int b = 1; b < n_blk; b++) {
+                        const float a1 = s_blk[b][0][lane], a2 = s_blk[b][1][lane], z1 = s_blk[b][2][lane], z2 = s_blk[b][3][lane];
+                        mn2 = fminf(fmaxf(mn1, a1), fminf(mn2, a2));
+                        mn1 = fminf(mn1, a1);
+                        mx2 = fmaxf(fminf(mx1, z1), fmaxf(mx2, z2));
+                        mx1 = fmaxf(mx1, z1);
                     }
                     lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
                     lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
@@ -401,11 +469,17 @@ symbolize_kernel(const SymParams p) {
                 }
                 idx++;
                 midx = idx >= window ? 0 : idx;
-                vmin = (float)(minbuf_sum / (double)window);
-                vmax = (float)(maxbuf_sum / (double)window);
-                center = __fdiv_rn(__fadd_rn(vmax, vmin), 2.0f);
-                umid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 8.0f), center);
-                lmid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 8.0f), center);
+                if ((window & (window - 1)) == 0) { /* power of two (default 1024): x / w == x * (1 / w) exactly */
+                    const double inv = 1.0 / (double)window;
+                    vmin = (float)(minbuf_sum * inv);
+                    vmax = (float)(maxbuf_sum * inv);
+                } else {
+                    vmin = (float)(minbuf_sum / (double)window);
+                    vmax = (float)(maxbuf_sum / (double)window);
+                }
+                center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f); /* x / 2.0f, exact */
+                umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center); /* .. / 8.0f, exact */
+                lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
                 maxref = __fmul_rn(vmax, 0.80f);
                 minref = __fmul_rn(vmin, 0.80f);
             } else {
@@ -430,7 +504,8 @@ symbolize_kernel(const SymParams p) {
             } else {
                 ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
             }
-            int mag0 = bit_metric(sym, ideal, 0), mag1 = bit_metric(sym, ideal, 1);
+            int mag0, mag1;
+            bit_metrics(sym, ideal, mag0, mag1);
             /* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) */
             const float eps = 1e-6f;
             int rel;
@@ -471,6 +546,8 @@ symbolize_kernel(const SymParams p) {
             }
         }
         nsym++;
+        } /* active */
+        active = nsym < (long)p.out_pitch && (avail - pos) >= reserve;
     }
 
     /* leftover samples -> carry (read everything first: source and destination overlap in the carry array) */

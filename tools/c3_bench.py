@@ -1,0 +1,75 @@
+"""Developer benchmark for configuration C3 (BASELINE.json configs[2]): 1024 synthetic P25 Phase 1 channels at discriminator
+level -> matched filter + getSymbol + slicer -> frame-sync hunt -> half-rate trellis + RS(36,20,17).  Prints per-kernel
+CUDA-event times (library timers) and the derived rates; not the judged bench (that is bench.py = C2)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g
+import _harness as H
+
+b200 = g.load_package()
+b200.init(0)
+n_ch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+n_samp = 49150  # 1.024 s at 48 kS/s, whole symbols so the replayed tile stays aligned
+rng = np.random.default_rng(5)
+P25_SYNC = "111113113311333313133333"
+# 8 distinct channel signals tiled over the channels (synthesis on the host is the slow part; content does not affect timing)
+base = []
+for c in range(8):
+    dib = rng.integers(0, 4, n_samp // 10 + 2)
+    for at in range(300 + 17 * c, dib.size - 250, 246):
+        dib[at:at + 24] = [int(ch) for ch in P25_SYNC]
+    base.append(H.synth_c4fm_disc(rng, dib, 9000.0, 700.0)[:n_samp])
+x = torch.from_numpy(np.stack([base[c % 8] for c in range(n_ch)])).cuda()
+taps = {0: H.sps_fir_taps(0, 10)}
+sy = b200.Symbolizer(n_ch, 48000, 4800, filters=taps)
+sy.set_class([b200.sym_class_from_synctype(0, 0)] * n_ch)
+fs = b200.FrameSync(n_ch, [(P25_SYNC, 0)])
+lib = b200.lib()
+
+
+def step():
+    res = sy.run(x, n_samp)
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=32)
+    return res, hits, n_hits
+
+
+for _ in range(3):
+    res, hits, n_hits = step()
+torch.cuda.synchronize()
+# FEC batch sized like one step: every sync is followed by one trellis block and one RS word
+n_frames = int(torch.clamp(n_hits, max=32).sum().item())
+print("symbols/channel", int(res["count"][0].item()), "hits/channel", n_hits[:8].tolist(), "frames", n_frames, file=sys.stderr)
+assert n_frames > 0
+llr = torch.randint(-300, 300, (n_frames, 196), dtype=torch.int16, device="cuda")
+out12 = torch.zeros((n_frames, 12), dtype=torch.uint8, device="cuda")
+met = torch.zeros(n_frames, dtype=torch.int32, device="cuda")
+rsd = torch.randint(0, 2, (n_frames, 120), dtype=torch.uint8, device="cuda")
+rsp = torch.randint(0, 2, (n_frames, 96), dtype=torch.uint8, device="cuda")
+rst = torch.zeros(n_frames, dtype=torch.uint8, device="cuda")
+b200.timing_enable(True)
+iters = 10
+t0 = time.perf_counter()
+for _ in range(iters):
+    step()
+    b200.check(lib.dsdneo_b200_p25_12_soft_llr_batch(llr.data_ptr(), out12.data_ptr(), met.data_ptr(), n_frames, None))
+    b200.check(lib.dsdneo_b200_p25_rs_decode_batch(0, rsd.data_ptr(), rsp.data_ptr(), rst.data_ptr(), n_frames, None))
+torch.cuda.synchronize()
+wall = (time.perf_counter() - t0) / iters
+rep = b200.timing_report()
+b200.timing_enable(False)
+n_sym = int(res["count"].sum().item())
+out = {"channels": n_ch, "samples_per_channel": n_samp, "symbols": n_sym, "frames": n_frames, "wall_ms_per_step": wall * 1e3,
+       "x_realtime": 1.024 / wall, "kernels": {k: v["ms"] / v["launches"] for k, v in rep.items()}}
+alg = {"sps_fir_kernel": n_ch * n_samp * 8.0, "symbolize_kernel": n_ch * n_samp * 4.0 + n_sym * 10.0,
+       "frame_sync_search_kernel": n_sym * 4.0, "p25_12_soft_llr_kernel": n_frames * 408.0, "p25_rs_decode_kernel": n_frames * 336.0}
+out["achieved_gbs"] = {k: alg[k] / (out["kernels"][k] * 1e-3) / 1e9 for k in alg if k in out["kernels"]}
+print(json.dumps(out))
