@@ -629,6 +629,27 @@ def p25_rs_soft_reliability(variant: int, data_bits, parity_bits, data_reliab, p
     return data_bits, status
 
 
+class MbeParms(C.Structure):
+    """struct mbe_parameters of mbelib 1.3.0 (see include/dsdneo_b200.h: parity unpinned)."""
+
+    _fields_ = [("w0", C.c_float), ("L", C.c_int), ("K", C.c_int), ("Vl", C.c_int * 57), ("Ml", C.c_float * 57),
+                ("log2Ml", C.c_float * 57), ("PHIl", C.c_float * 57), ("PSIl", C.c_float * 57), ("gamma", C.c_float),
+                ("un", C.c_int), ("repeat", C.c_int)]
+
+
+def mbe_synth(cur, prev_enhanced, keys=None, uvquality: int = 3, want_int16: bool = True):
+    """cur / prev_enhanced: ctypes arrays (MbeParms * n), updated in place. Returns (pcm_f [n,160] f32, pcm_s [n,160] i16)."""
+    import numpy as np
+
+    n = len(cur)
+    pcm_f = np.zeros((n, 160), np.float32)
+    pcm_s = np.zeros((n, 160), np.int16) if want_int16 else None
+    k = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+    check(lib().dsdneo_b200_mbe_synth_batch_host(C.byref(cur), C.byref(prev_enhanced), None if k is None else k.ctypes.data, uvquality,
+                                                 pcm_f.ctypes.data, None if pcm_s is None else pcm_s.ctypes.data, n), "mbe_synth")
+    return pcm_f, pcm_s
+
+
 class SymClass(C.Structure):
     _fields_ = [("filter", C.c_int), ("window_l", C.c_int), ("track_minmax", C.c_int), ("negative", C.c_int)]
 

@@ -73,6 +73,8 @@ def bind(L):
         "dsdneo_b200_channelizer_get_prototype": (ci, [vp, C.POINTER(cf), ci]),
         "dsdneo_b200_channelize": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_channelize_host": (ci, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_mbe_synth_batch": (ci, [vp, vp, vp, ci, vp, vp, ci, vp]),
+        "dsdneo_b200_mbe_synth_batch_host": (ci, [vp, vp, vp, ci, vp, vp, ci]),
         "dsdneo_b200_selftest_atan2f": (ci, [vp, vp, vp, ci, vp]),
         "dsdneo_b200_selftest_scale": (ci, [vp, vp, vp, ci, vp]),
     }

@@ -528,6 +528,35 @@ int dsdneo_b200_nxdn_conv_decode_batch(const uint8_t* d_sym, const uint8_t* d_re
 int dsdneo_b200_nxdn_conv_decode_batch_host(const uint8_t* h_sym, const uint8_t* h_rel, size_t pitch, int n_steps, int n_bits_out,
                                             uint16_t* h_metrics, uint8_t* h_out, size_t out_pitch, int n_frames);
 
+/* ---- K21: MBE speech synthesis stage, batched over frames -- PARITY UNPINNED ---------------------------------- */
+/*
+ * dsd-neo obtains PCM from mbelib-neo 2.x (mbe_processImbe4400Dataf / mbe_processAmbe2450Dataf, call sites
+ * src/core/vocoder/dsd_mbe.c:268,296,581,617,685), an un-vendored dependency that is absent here, so this stage cannot be
+ * compared with the reference.  It follows the published algorithm of mbelib 1.3.0
+ * (mbe_spectralAmpEnhance + mbe_synthesizeSpeechf + mbe_floattoshort, then mbe_moveMbeParms(cur, prev_enhanced)) with one
+ * documented difference: random phases / noise come from a counter-based hash of (key, band, sample, index) instead of
+ * libc rand().  The struct is mbelib 1.3.0's `struct mbe_parameters` (mbelib.h); whether mbelib-neo 2.x kept that
+ * layout is unverified.  The bit-level parameter decode (quantiser tables) is not part of this stage.
+ * d_cur[i] is enhanced and phase-updated in place and copied to d_prev_enhanced[i]; d_keys may be NULL (key = index).
+ */
+typedef struct {
+    float w0;
+    int L;
+    int K;
+    int Vl[57];
+    float Ml[57];
+    float log2Ml[57];
+    float PHIl[57];
+    float PSIl[57];
+    float gamma;
+    int un;
+    int repeat;
+} dsdneo_b200_mbe_parms;
+int dsdneo_b200_mbe_synth_batch(dsdneo_b200_mbe_parms* d_cur, dsdneo_b200_mbe_parms* d_prev_enhanced, const uint64_t* d_keys,
+                                int uvquality, float* d_pcm_f, int16_t* d_pcm_s, int n_frames, void* stream);
+int dsdneo_b200_mbe_synth_batch_host(dsdneo_b200_mbe_parms* h_cur, dsdneo_b200_mbe_parms* h_prev_enhanced, const uint64_t* h_keys,
+                                     int uvquality, float* h_pcm_f, int16_t* h_pcm_s, int n_frames);
+
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);

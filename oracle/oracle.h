@@ -139,6 +139,27 @@ long oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, lon
 
 int oracle_frame_sync_search(const float* symbols, int n, const char* const* patterns, const int* sync_types, int n_patterns,
                              char* hist32, int* hist_count, int* hit_pos, int* hit_type, int max_hits);
+/* ------------------------------- MBE synthesis stage (oracle_mbe.c) -- PARITY UNPINNED, see its header --------- */
+typedef struct { /* struct mbe_parameters of mbelib 1.3.0 (mbelib.h) */
+    float w0;
+    int L;
+    int K;
+    int Vl[57];
+    float Ml[57];
+    float log2Ml[57];
+    float PHIl[57];
+    float PSIl[57];
+    float gamma;
+    int un;
+    int repeat;
+} oracle_mbe_parms;
+float oracle_mbe_uniform(uint64_t key, int band, int sample, int index, int stream);
+void oracle_mbe_spectral_amp_enhance(oracle_mbe_parms* cur);
+void oracle_mbe_synthesize_speechf(float* aout, oracle_mbe_parms* cur, oracle_mbe_parms* prev, int uvquality, uint64_t key);
+void oracle_mbe_floattoshort(const float* in, int16_t* out);
+void oracle_mbe_synth_frame(float* aout, int16_t* pcm, oracle_mbe_parms* cur, oracle_mbe_parms* prev_enhanced, int uvquality,
+                            uint64_t key);
+
 void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n);
 
 #ifdef __cplusplus
