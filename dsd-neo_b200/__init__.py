@@ -629,6 +629,34 @@ def p25_rs_soft_reliability(variant: int, data_bits, parity_bits, data_reliab, p
     return data_bits, status
 
 
+def symbol_capture_pack(dibits, reliability, llr, symbols, with_header: bool = True) -> bytes:
+    """One channel's symbolizer output -> the reference's DSDNSYM2 capture bytes (see include/dsdneo_b200.h)."""
+    import numpy as np
+
+    d = np.ascontiguousarray(dibits, np.uint8)
+    r = np.ascontiguousarray(reliability, np.uint8)
+    l = np.ascontiguousarray(llr, np.int16).reshape(-1, 2)
+    s = np.ascontiguousarray(symbols, np.float32)
+    n = d.size
+    out = np.zeros(lib().dsdneo_b200_symbol_capture_size(n, 1 if with_header else 0), np.uint8)
+    check(lib().dsdneo_b200_symbol_capture_pack(d.ctypes.data, r.ctypes.data, l.ctypes.data, s.ctypes.data, n, 1 if with_header else 0,
+                                                out.ctypes.data), "symbol_capture_pack")
+    return out.tobytes()
+
+
+def symbol_capture_unpack(data: bytes):
+    """DSDNSYM2 bytes (with or without header) -> (dibits u8, reliability u8, llr i16 [n,2], symbols f32)."""
+    import numpy as np
+
+    buf = np.frombuffer(data, np.uint8)
+    cap = buf.size // 10 + 1
+    d, r, l, s = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8), np.zeros((cap, 2), np.int16), np.zeros(cap, np.float32)
+    n = lib().dsdneo_b200_symbol_capture_unpack(buf.ctypes.data, buf.size, d.ctypes.data, r.ctypes.data, l.ctypes.data, s.ctypes.data, cap)
+    if n < 0:
+        check(int(n), "symbol_capture_unpack")
+    return d[:n], r[:n], l[:n], s[:n]
+
+
 class MbeParms(C.Structure):
     """struct mbe_parameters of mbelib 1.3.0 (see include/dsdneo_b200.h: parity unpinned)."""
 

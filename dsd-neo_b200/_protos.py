@@ -73,6 +73,10 @@ def bind(L):
         "dsdneo_b200_channelizer_get_prototype": (ci, [vp, C.POINTER(cf), ci]),
         "dsdneo_b200_channelize": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_channelize_host": (ci, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_symbol_capture_size": (sz, [sz, ci]),
+        "dsdneo_b200_symbol_capture_pack": (ci, [vp, vp, vp, vp, sz, ci, vp]),
+        "dsdneo_b200_symbol_capture_unpack": (C.c_longlong, [vp, sz, vp, vp, vp, vp, sz]),
+        "dsdneo_b200_symbol_capture_write_file": (ci, [C.c_char_p, ci, vp, vp, vp, vp, sz]),
         "dsdneo_b200_mbe_synth_batch": (ci, [vp, vp, vp, ci, vp, vp, ci, vp]),
         "dsdneo_b200_mbe_synth_batch_host": (ci, [vp, vp, vp, ci, vp, vp, ci]),
         "dsdneo_b200_selftest_atan2f": (ci, [vp, vp, vp, ci, vp]),

@@ -528,6 +528,24 @@ int dsdneo_b200_nxdn_conv_decode_batch(const uint8_t* d_sym, const uint8_t* d_re
 int dsdneo_b200_nxdn_conv_decode_batch_host(const uint8_t* h_sym, const uint8_t* h_rel, size_t pitch, int n_steps, int n_bits_out,
                                             uint16_t* h_metrics, uint8_t* h_out, size_t out_pitch, int n_frames);
 
+/* ---- the reference's soft symbol-capture format ("DSDNSYM2") as harness I/O (host side, no device work) ---------- */
+/*
+ * Written by `dsd-neo -c file.bin`, replayed by `dsd-neo -i file.bin`: header src/core/file/dsd_file.c:876-888, record
+ * writer src/core/frames/dsd_dibit.c:794-818, reader src/dsp/dsd_symbol.c:120-173, constants include/dsd-neo/core/dibit.h:35-37.
+ * Packing one channel's symbolizer output (dibits, reliability, llr[n][2], symbols) into this format lets the unmodified
+ * reference CLI decode what the GPU demodulated.  unpack accepts data with or without the 16-byte header and returns the
+ * number of records (negative DSDNEO_B200_E* on a bad header).
+ */
+#define DSDNEO_B200_SYMCAP_HEADER_SIZE 16
+#define DSDNEO_B200_SYMCAP_RECORD_SIZE 10
+size_t dsdneo_b200_symbol_capture_size(size_t n_records, int with_header);
+int dsdneo_b200_symbol_capture_pack(const uint8_t* dibits, const uint8_t* reliability, const int16_t* llr, const float* symbols,
+                                    size_t n_records, int with_header, uint8_t* out);
+long long dsdneo_b200_symbol_capture_unpack(const uint8_t* in, size_t len, uint8_t* dibits, uint8_t* reliability, int16_t* llr,
+                                            float* symbols, size_t max_records);
+int dsdneo_b200_symbol_capture_write_file(const char* path, int append, const uint8_t* dibits, const uint8_t* reliability,
+                                          const int16_t* llr, const float* symbols, size_t n_records);
+
 /* ---- K21: MBE speech synthesis stage, batched over frames -- PARITY UNPINNED ---------------------------------- */
 /*
  * dsd-neo obtains PCM from mbelib-neo 2.x (mbe_processImbe4400Dataf / mbe_processAmbe2450Dataf, call sites

@@ -247,3 +247,39 @@ ref_sps_fir_taps(int which, int sps, float* taps_out, int cap) {
     }
     return len;
 }
+
+
+/* Drives the reference's own capture writer (write_symbol_capture_record, src/core/frames/dsd_dibit.c:794-818) after the
+ * 16-byte header openSymbolOutFile emits (src/core/file/dsd_file.c:876-888; that TU needs libsndfile, so its header
+ * constant is rebuilt here from the same macros of include/dsd-neo/core/dibit.h:35-37). */
+int
+ref_symbol_capture_write(const char* path, const unsigned char* dibits, const unsigned char* reliab, const short* llr,
+                         const float* symbols, int n) {
+    dsd_opts* o = (dsd_opts*)calloc(1, sizeof(dsd_opts));
+    dsd_state* s = (dsd_state*)calloc(1, sizeof(dsd_state));
+    if (!o || !s) {
+        return -1;
+    }
+    o->symbol_out_f = fopen(path, "wb");
+    if (!o->symbol_out_f) {
+        return -1;
+    }
+    unsigned char header[DSD_SYMBOL_CAPTURE_SOFT_HEADER_SIZE];
+    memset(header, 0, sizeof(header));
+    memcpy(header, DSD_SYMBOL_CAPTURE_SOFT_MAGIC, 8);
+    header[8] = 2;
+    header[9] = DSD_SYMBOL_CAPTURE_SOFT_RECORD_SIZE;
+    fwrite(header, 1, sizeof(header), o->symbol_out_f);
+    for (int i = 0; i < n; i++) {
+        dsd_dibit_soft_t soft;
+        soft.reliability = reliab[i];
+        soft.llr[0] = llr[2 * i];
+        soft.llr[1] = llr[2 * i + 1];
+        write_symbol_capture_record(o, s, dibits[i], symbols[i], &soft);
+    }
+    fclose(o->symbol_out_f);
+    int written = (int)s->symbol_capture_soft_records;
+    free(o);
+    free(s);
+    return written;
+}
