@@ -73,6 +73,19 @@ def bind(L):
         "dsdneo_b200_channelizer_get_prototype": (ci, [vp, C.POINTER(cf), ci]),
         "dsdneo_b200_channelize": (ci, [vp, vp, sz, vp, sz, vp]),
         "dsdneo_b200_channelize_host": (ci, [vp, vp, sz, vp, sz]),
+        "dsdneo_b200_stream_server_create": (vp, [sz, C.c_uint, ci, ci, ci]),
+        "dsdneo_b200_stream_server_destroy": (None, [vp]),
+        "dsdneo_b200_stream_server_make_current": (None, [vp]),
+        "dsdneo_b200_stream_server_push": (sz, [vp, vp, sz, ci]),
+        "dsdneo_b200_stream_server_close": (None, [vp]),
+        "dsdneo_b200_stream_server_bump_generation": (None, [vp]),
+        "dsdneo_b200_stream_server_set_power": (None, [vp, C.c_double]),
+        "dsdneo_b200_stream_hook_read": (ci, [vp, vp, sz, vp]),
+        "dsdneo_b200_stream_hook_return_pwr": (C.c_double, [vp]),
+        "dsdneo_b200_stream_hook_output_rate_hz": (C.c_uint, []),
+        "dsdneo_b200_stream_hook_output_kind": (ci, []),
+        "dsdneo_b200_stream_hook_symbol_profile": (ci, [vp, vp, vp]),
+        "dsdneo_b200_stream_hook_stream_generation": (C.c_uint32, []),
         "dsdneo_b200_symbol_capture_size": (sz, [sz, ci]),
         "dsdneo_b200_symbol_capture_pack": (ci, [vp, vp, vp, vp, sz, ci, vp]),
         "dsdneo_b200_symbol_capture_unpack": (C.c_longlong, [vp, sz, vp, vp, vp, vp, sz]),

@@ -546,6 +546,32 @@ long long dsdneo_b200_symbol_capture_unpack(const uint8_t* in, size_t len, uint8
 int dsdneo_b200_symbol_capture_write_file(const char* path, int append, const uint8_t* dibits, const uint8_t* reliability,
                                           const int16_t* llr, const float* symbols, size_t n_records);
 
+/* ---- stream server for the reference's runtime hook seam (host side, no device work) -------------------------- */
+/*
+ * The unmodified reference decoder reads discriminator floats through dsd_rtl_stream_io_hooks {read, return_pwr}
+ * (include/dsd-neo/runtime/rtl_stream_io_hooks.h:25-28) and asks dsd_rtl_stream_metrics_hooks for output_rate_hz,
+ * output_kind, symbol_profile and stream_generation (rtl_stream_metrics_hooks.h:28-47).  The dsdneo_b200_stream_hook_*
+ * functions have exactly those signatures, so a maintainer installs them in the two tables
+ * (src/engine/rtl_stream_io_hooks_install.c:26-34) and passes the server handle as rtl_ctx; the ingest loop pushes one
+ * channel's rows of the front end's output.  read blocks until data or close, returns 0 with *out_got floats, < 0 once
+ * the stream is closed and drained.  The context-free metrics hooks answer for the server made current.
+ */
+typedef struct dsdneo_b200_stream_server dsdneo_b200_stream_server;
+dsdneo_b200_stream_server* dsdneo_b200_stream_server_create(size_t ring_floats, unsigned int output_rate_hz, int symbol_rate_hz,
+                                                            int levels, int channel_profile);
+void dsdneo_b200_stream_server_destroy(dsdneo_b200_stream_server* s);
+void dsdneo_b200_stream_server_make_current(dsdneo_b200_stream_server* s);
+size_t dsdneo_b200_stream_server_push(dsdneo_b200_stream_server* s, const float* samples, size_t n, int block);
+void dsdneo_b200_stream_server_close(dsdneo_b200_stream_server* s);
+void dsdneo_b200_stream_server_bump_generation(dsdneo_b200_stream_server* s);
+void dsdneo_b200_stream_server_set_power(dsdneo_b200_stream_server* s, double pwr);
+int dsdneo_b200_stream_hook_read(void* rtl_ctx, float* out, size_t count, int* out_got);
+double dsdneo_b200_stream_hook_return_pwr(const void* rtl_ctx);
+unsigned int dsdneo_b200_stream_hook_output_rate_hz(void);
+int dsdneo_b200_stream_hook_output_kind(void);
+int dsdneo_b200_stream_hook_symbol_profile(int* out_symbol_rate_hz, int* out_levels, int* out_channel_profile);
+uint32_t dsdneo_b200_stream_hook_stream_generation(void);
+
 /* ---- K21: MBE speech synthesis stage, batched over frames -- PARITY UNPINNED ---------------------------------- */
 /*
  * dsd-neo obtains PCM from mbelib-neo 2.x (mbe_processImbe4400Dataf / mbe_processAmbe2450Dataf, call sites

@@ -283,3 +283,47 @@ ref_symbol_capture_write(const char* path, const unsigned char* dibits, const un
     free(s);
     return written;
 }
+
+
+/* External stream server: installs caller-supplied functions into the reference's two runtime hook tables
+ * (include/dsd-neo/runtime/rtl_stream_io_hooks.h:25-32, rtl_stream_metrics_hooks.h:28-50) exactly as
+ * src/engine/rtl_stream_io_hooks_install.c does, and hands `ctx` to the reader through state->rtl_ctx. */
+void
+ref_sym_use_external_hooks(void* hv, void* read_fn, void* pwr_fn, void* ctx, void* rate_fn, void* kind_fn, void* profile_fn,
+                           void* generation_fn) {
+    ref_sym* h = (ref_sym*)hv;
+    h->state->rtl_ctx = (struct RtlSdrContext*)ctx;
+    dsd_rtl_stream_io_hooks io;
+    memset(&io, 0, sizeof(io));
+    io.read = (int (*)(void*, float*, size_t, int*))read_fn;
+    io.return_pwr = (double (*)(const void*))pwr_fn;
+    dsd_rtl_stream_io_hooks_set(io);
+    dsd_rtl_stream_metrics_hooks mh;
+    memset(&mh, 0, sizeof(mh));
+    mh.output_rate_hz = (unsigned int (*)(void))rate_fn;
+    mh.output_kind = (int (*)(void))kind_fn;
+    mh.symbol_profile = (int (*)(int*, int*, int*))profile_fn;
+    mh.stream_generation = (uint32_t (*)(void))generation_fn;
+    dsd_rtl_stream_metrics_hooks_set(&mh);
+}
+
+/* exactly n getDibitSoft() calls (the caller knows the stream holds enough samples) */
+long
+ref_sym_get_dibits_n(void* hv, long n_symbols, uint8_t* dibits, uint8_t* reliab, int16_t* llr2, float* symbols) {
+    ref_sym* h = (ref_sym*)hv;
+    g_live = h;
+    for (long n = 0; n < n_symbols; n++) {
+        int sidx_before = h->state->sidx;
+        dsd_dibit_soft_t soft;
+        int d = getDibitSoft(h->opts, h->state, &soft);
+        if (g_oracle_shutdown_requested) {
+            return -1;
+        }
+        dibits[n] = (uint8_t)d;
+        reliab[n] = soft.reliability;
+        llr2[2 * n] = soft.llr[0];
+        llr2[2 * n + 1] = soft.llr[1];
+        symbols[n] = h->state->sbuf[sidx_before];
+    }
+    return n_symbols;
+}
