@@ -657,6 +657,35 @@ def symbol_capture_unpack(data: bytes):
     return d[:n], r[:n], l[:n], s[:n]
 
 
+P25_WORD_GOLAY_24_6, P25_WORD_GOLAY_24_12, P25_WORD_HAMMING_10_6_3 = 0, 1, 2
+
+
+def p25_word_decode(code: int, data_bits, parity_bits):
+    """Golay(24,6)/(24,12)/Hamming(10,6,3) P25 words. Returns (data_bits corrected, status u8 [n], fixed i32 [n])."""
+    import numpy as np
+
+    data_bits = np.ascontiguousarray(data_bits, dtype=np.uint8).copy()
+    parity_bits = np.ascontiguousarray(parity_bits, dtype=np.uint8)
+    n = data_bits.shape[0]
+    st, fx = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_p25_word_decode_batch_host(code, data_bits.ctypes.data, parity_bits.ctypes.data, st.ctypes.data,
+                                                       fx.ctypes.data, n), "p25_word_decode")
+    return data_bits, st, fx
+
+
+def bch_63_16_decode(in63, out16_init=None):
+    """P25 NID BCH(63,16,11). Returns (out16 [n,16], ok u8 [n], err_count i32 [n])."""
+    import numpy as np
+
+    in63 = np.ascontiguousarray(in63, dtype=np.uint8).reshape(-1, 63)
+    n = in63.shape[0]
+    out = np.zeros((n, 16), np.uint8) if out16_init is None else np.ascontiguousarray(out16_init, dtype=np.uint8).copy()
+    ok, ec = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_bch_63_16_decode_batch_host(in63.ctypes.data, out.ctypes.data, ok.ctypes.data, ec.ctypes.data, n),
+          "bch_63_16_decode")
+    return out, ok, ec
+
+
 class MbeParms(C.Structure):
     """struct mbe_parameters of mbelib 1.3.0 (see include/dsdneo_b200.h: parity unpinned)."""
 

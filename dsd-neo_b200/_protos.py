@@ -45,6 +45,10 @@ def bind(L):
         "dsdneo_b200_p25_rs_decode_erasures_batch_host": (ci, [ci, vp, vp, vp, ci, vp, vp, ci]),
         "dsdneo_b200_p25_rs_soft_reliability_batch": (ci, [ci, vp, vp, vp, vp, ci, vp, ci, vp]),
         "dsdneo_b200_p25_rs_soft_reliability_batch_host": (ci, [ci, vp, vp, vp, vp, ci, vp, ci]),
+        "dsdneo_b200_p25_word_decode_batch": (ci, [ci, vp, vp, vp, vp, ci, vp]),
+        "dsdneo_b200_p25_word_decode_batch_host": (ci, [ci, vp, vp, vp, vp, ci]),
+        "dsdneo_b200_bch_63_16_decode_batch": (ci, [vp, vp, vp, vp, ci, vp]),
+        "dsdneo_b200_bch_63_16_decode_batch_host": (ci, [vp, vp, vp, vp, ci]),
         "dsdneo_b200_timing_enable": (ci, [ci]),
         "dsdneo_b200_timing_report": (ci, [C.c_char_p, sz]),
         "dsdneo_b200_frame_sync_create": (vp, [ci, vp, ci]),

@@ -1089,6 +1089,272 @@ p25_rs_soft_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, int mode
     status[w] = (uint8_t)rc;
 }
 
+/* ------------------------------------------------------------------ P25 word codes: Golay(24,6/12), Hamming(10,6,3), BCH(63,16,11) */
+
+__device__ __forceinline__ unsigned
+g23_syndrome(unsigned cw) { /* Golay24::syndrome, include/dsd-neo/fec/Golay24.hpp:58-72 (POLY 0xAE3) */
+    cw &= 0x7fffffu;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        cw = (cw & 1u) ? ((cw ^ 0xAE3u) >> 1) : (cw >> 1);
+    }
+    return cw << 12;
+}
+
+/* Golay24::correct (Golay24.hpp:108-169): *errs is the weight of the last syndrome examined, also on failure. */
+__device__ unsigned
+g23_correct(unsigned cw, int* errs) {
+    const unsigned saver = cw;
+    unsigned mask = 1;
+    int w = 3, j = -1;
+    *errs = 0;
+    while (j < 23) {
+        if (j != -1) {
+            if (j > 0) {
+                mask += mask;
+            }
+            cw = saver ^ mask;
+            w = 2;
+        }
+        unsigned s = g23_syndrome(cw);
+        if (!s) {
+            return cw;
+        }
+        for (int i = 0; i < 23; i++) {
+            *errs = __popc(s & 0x7fffffu);
+            if (*errs <= w) {
+                cw ^= s;
+                /* rotate right by i within 23 bits */
+                cw &= 0x7fffffu;
+                return i ? (((cw >> i) | (cw << (23 - i))) & 0x7fffffu) : cw;
+            }
+            cw = ((cw & 0x400000u) ? ((cw << 1) | 1u) : (cw << 1)) & 0x7fffffu;
+            s = g23_syndrome(cw);
+        }
+        j++;
+    }
+    return saver;
+}
+
+/* code 0/1: DSDGolay24::decode_6 / decode_12 (Golay24.hpp:336-405) = check_and_fix_golay_24_6 / _24_12
+ * (phase1/p25p1_check_hdu.cpp:26-36): status 0 ok / 1 uncorrectable or non-binary input (data untouched), fixed = errs.
+ * code 2: hamming_10_6_3_decode (src/fec/hamming_10_6_3.cpp:14-105): status 0 clean / 1 corrected / 2 uncorrectable. */
+__global__ void
+p25_word_decode_kernel(int code, uint8_t* data_bits, const uint8_t* parity_bits, uint8_t* status, int32_t* fixed, int n_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) {
+        return;
+    }
+    if (code == DSDNEO_P25_WORD_HAMMING_10_6_3) {
+        uint8_t* d = data_bits + (size_t)i * 6;
+        const uint8_t* p = parity_bits + (size_t)i * 4;
+        unsigned v = 0;
+        bool binary = true;
+        for (int k = 0; k < 6; k++) {
+            binary = binary && d[k] <= 1;
+            v = (v << 1) | (d[k] & 1u);
+        }
+        for (int k = 0; k < 4; k++) {
+            binary = binary && p[k] <= 1;
+            v = (v << 1) | (p[k] & 1u);
+        }
+        int st = 2;
+        if (binary) {
+            const int syn = ((__popc(v & 0x398u) & 1) << 3) | ((__popc(v & 0x354u) & 1) << 2) | ((__popc(v & 0x2E2u) & 1) << 1)
+                            | (__popc(v & 0x1E1u) & 1);
+            /* bad_bit_table {-2,0,1,5,2,-1,-1,6,3,-1,-1,7,4,8,9,-1} as nibbles, 0xF = uncorrectable */
+            const int b = (int)((0xF9847FF36FF2510Full >> (4 * syn)) & 0xFull);
+            if (syn == 0) {
+                st = 0;
+            } else if (b != 0xF) {
+                st = 1;
+                if (b >= 4) {
+                    v ^= 1u << b;
+                }
+                for (int k = 0; k < 6; k++) {
+                    d[k] = (uint8_t)((v >> (9 - k)) & 1u);
+                }
+            }
+        }
+        status[i] = (uint8_t)st;
+        if (fixed) {
+            fixed[i] = st == 1 ? 1 : 0;
+        }
+        return;
+    }
+    const int length = (code == DSDNEO_P25_WORD_GOLAY_24_6) ? 6 : 12;
+    uint8_t* w = data_bits + (size_t)i * length;
+    const uint8_t* p = parity_bits + (size_t)i * 12;
+    bool binary = true;
+    unsigned cw = 0;
+    for (int k = 0; k < 12; k++) {
+        binary = binary && p[11 - k] <= 1;
+        cw = (cw << 1) | (p[11 - k] & 1u);
+    }
+    for (int k = 0; k < length; k++) {
+        binary = binary && w[length - 1 - k] <= 1;
+        cw = (cw << 1) | (w[length - 1 - k] & 1u);
+    }
+    cw <<= (12 - length);
+    int errs = 0, st = 1;
+    if (binary) {
+        const unsigned pbit = cw & 0x800000u;
+        cw = g23_correct(cw & ~0x800000u, &errs) | pbit;
+        const int odd = __popc(cw & 0xffffffu) & 1;
+        if (!(odd && (cw & 0x3fu) != 0)) {
+            st = 0;
+            unsigned mask = 1u << (12 - length);
+            for (int k = 0; k < length; k++, mask <<= 1) {
+                w[k] = (cw & mask) ? 1 : 0;
+            }
+        }
+    }
+    status[i] = (uint8_t)st;
+    if (fixed) {
+        fixed[i] = errs;
+    }
+}
+
+/* BCH_63_16_11::decode_with_result (include/dsd-neo/fec/BCH_63_16.hpp:288-329), the P25 NID code: same Berlekamp
+ * bookkeeping as the RS(63,k) decoder above with t = 11 and binary error values. */
+__global__ void __launch_bounds__(64)
+bch_63_16_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in63, uint8_t* out16, uint8_t* ok_out, int32_t* err_count,
+                 int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    constexpr int NN = 63, TT = 11, N2T = 22;
+    const signed char* EXP = T->gf_exp;
+    const signed char* LOG = T->gf_log;
+    const uint8_t* in = in63 + (size_t)w * 63;
+    unsigned long long recd = 0; /* bit j = coefficient j */
+    for (int i = 0; i < NN; i++) {
+        recd |= (unsigned long long)(in[NN - 1 - i] ? 1 : 0) << i;
+    }
+    signed char s[N2T + 1];
+    int has_err = 0;
+    for (int i = 1; i <= N2T; i++) {
+        int syn = 0;
+        for (int j = 0; j < NN; j++) {
+            if ((recd >> j) & 1ull) {
+                syn ^= EXP[(i * j) % NN];
+            }
+        }
+        has_err |= syn;
+        s[i] = LOG[syn];
+    }
+    int ok = 1, count = 0;
+    if (has_err) {
+        signed char elp[N2T + 2][N2T];
+        signed char d[N2T + 2], l[N2T + 2], u_lu[N2T + 2];
+        d[0] = 0;
+        d[1] = s[1];
+        elp[0][0] = 0;
+        elp[1][0] = 1;
+        for (int i = 1; i < N2T; i++) {
+            elp[0][i] = -1;
+            elp[1][i] = 0;
+        }
+        l[0] = l[1] = 0;
+        u_lu[0] = -1;
+        u_lu[1] = 0;
+        int u = 0;
+        do {
+            u++;
+            if (d[u] == -1) {
+                l[u + 1] = l[u];
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] = elp[u][i];
+                }
+            } else {
+                int q = u - 1;
+                while (q > 0 && d[q] == -1) {
+                    q--;
+                }
+                if (q > 0) {
+                    for (int j = q - 1; j > 0; j--) {
+                        if (d[j] != -1 && u_lu[q] < u_lu[j]) {
+                            q = j;
+                        }
+                    }
+                }
+                const int cand = l[q] + u - q;
+                l[u + 1] = (signed char)(l[u] > cand ? l[u] : cand);
+                for (int i = 0; i < N2T; i++) {
+                    elp[u + 1][i] = 0;
+                }
+                for (int i = 0; i <= l[q]; i++) {
+                    if (elp[q][i] != -1) {
+                        elp[u + 1][i + u - q] = EXP[(d[u] + NN - d[q] + elp[q][i]) % NN];
+                    }
+                }
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] ^= elp[u][i];
+                }
+            }
+            for (int i = 0; i <= l[u]; i++) { /* index_elp_row(u): polynomial -> index form, in place */
+                if (elp[u][i] >= 0) {
+                    elp[u][i] = LOG[elp[u][i]];
+                }
+            }
+            u_lu[u + 1] = (signed char)(u - l[u + 1]);
+            if (u < N2T) {
+                int disc = (s[u + 1] != -1) ? EXP[s[u + 1]] : 0;
+                for (int i = 1; i <= l[u + 1]; i++) {
+                    if (s[u + 1 - i] != -1 && elp[u + 1][i] != 0) {
+                        disc ^= EXP[(s[u + 1 - i] + LOG[elp[u + 1][i]]) % NN];
+                    }
+                }
+                d[u + 1] = LOG[disc];
+            }
+        } while (u < N2T && l[u + 1] <= TT);
+        u++;
+        if (l[u] > TT) {
+            ok = 0;
+        } else {
+            const int deg = l[u];
+            int reg[TT + 1];
+            for (int i = 1; i <= deg; i++) {
+                reg[i] = elp[u][i] >= 0 ? LOG[elp[u][i]] : elp[u][i];
+            }
+            unsigned long long flips = 0;
+            for (int i = 1; i <= NN; i++) {
+                int q = 1;
+                for (int j = 1; j <= deg; j++) {
+                    if (reg[j] != -1) {
+                        reg[j] = (reg[j] + j) % NN;
+                        q ^= EXP[reg[j]];
+                    }
+                }
+                if (q == 0) {
+                    if (count >= TT) {
+                        break;
+                    }
+                    flips |= 1ull << (NN - i);
+                    count++;
+                }
+            }
+            if (count != deg) {
+                ok = 0;
+                count = 0;
+            } else {
+                recd ^= flips;
+            }
+        }
+    }
+    ok_out[w] = (uint8_t)ok;
+    if (err_count) {
+        err_count[w] = ok ? count : 0;
+    }
+    if (ok) {
+        uint8_t* o = out16 + (size_t)w * 16;
+        for (int i = 0; i < 16; i++) {
+            o[i] = (uint8_t)((recd >> (NN - 1 - i)) & 1ull);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ K = 5 convolutional decoders */
 
 constexpr int kVitMaxSteps = 244; /* viterbi_history[244], src/core/util/dsd_misc.c:108 */
@@ -1845,6 +2111,124 @@ dsdneo_b200_p25_rs_soft_reliability_batch_host(int variant, uint8_t* h_data_bits
                                                uint8_t* h_status, int n_words) {
     return rs_soft_host(variant, 1, h_data_bits, h_parity_bits, NULL, 0, NULL, h_data_reliab, h_parity_reliab, erasure_threshold,
                         h_status, n_words);
+}
+
+int
+dsdneo_b200_p25_word_decode_batch(int code, uint8_t* d_data_bits, const uint8_t* d_parity_bits, uint8_t* d_status, int32_t* d_fixed,
+                                  int n_words, void* stream) {
+    if (code < DSDNEO_P25_WORD_GOLAY_24_6 || code > DSDNEO_P25_WORD_HAMMING_10_6_3 || !d_data_bits || !d_parity_bits || !d_status
+        || n_words < 0) {
+        set_error("p25_word_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25_word_decode_kernel", s);
+        p25_word_decode_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(code, d_data_bits, d_parity_bits, d_status, d_fixed, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_word_decode_batch_host(int code, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
+                                       int32_t* h_fixed, int n_words) {
+    if (code < DSDNEO_P25_WORD_GOLAY_24_6 || code > DSDNEO_P25_WORD_HAMMING_10_6_3 || !h_data_bits || !h_parity_bits || !h_status
+        || n_words < 0) {
+        set_error("p25_word_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words, db = (code == DSDNEO_P25_WORD_GOLAY_24_12) ? 12 : 6,
+                 pb = (code == DSDNEO_P25_WORD_HAMMING_10_6_3) ? 4 : 12;
+    DevBuf data(n * db), par(n * pb), st(n), fx(n * 4);
+    DSDNEO_CUDA(data.err);
+    DSDNEO_CUDA(par.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(fx.err);
+    DSDNEO_CUDA(cudaMemcpy(data.p, h_data_bits, n * db, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(par.p, h_parity_bits, n * pb, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_p25_word_decode_batch(code, data.as<uint8_t>(), par.as<uint8_t>(), st.as<uint8_t>(), fx.as<int32_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_data_bits, data.p, n * db, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    if (h_fixed) {
+        DSDNEO_CUDA(cudaMemcpy(h_fixed, fx.p, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int
+dsdneo_b200_bch_63_16_decode_batch(const uint8_t* d_in63, uint8_t* d_out16, uint8_t* d_ok, int32_t* d_err_count, int n_words,
+                                   void* stream) {
+    if (!d_in63 || !d_out16 || !d_ok || n_words < 0) {
+        set_error("bch_63_16_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("bch_63_16_kernel", s);
+        bch_63_16_kernel<<<grid_for(n_words, 64), 64, 0, s>>>(g_d_tables, d_in63, d_out16, d_ok, d_err_count, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_out16, uint8_t* h_ok, int32_t* h_err_count, int n_words) {
+    if (!h_in63 || !h_out16 || !h_ok || n_words < 0) {
+        set_error("bch_63_16_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words;
+    DevBuf in(n * 63), out(n * 16), ok(n), ec(n * 4);
+    DSDNEO_CUDA(in.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(ok.err);
+    DSDNEO_CUDA(ec.err);
+    DSDNEO_CUDA(cudaMemcpy(in.p, h_in63, n * 63, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(out.p, h_out16, n * 16, cudaMemcpyHostToDevice)); /* failed words leave the caller's bits untouched */
+    rc = dsdneo_b200_bch_63_16_decode_batch(in.as<uint8_t>(), out.as<uint8_t>(), ok.as<uint8_t>(), ec.as<int32_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out16, out.p, n * 16, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_ok, ok.p, n, cudaMemcpyDeviceToHost));
+    if (h_err_count) {
+        DSDNEO_CUDA(cudaMemcpy(h_err_count, ec.p, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
 }
 
 int

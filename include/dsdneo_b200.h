@@ -501,6 +501,34 @@ int dsdneo_b200_p25_rs_soft_reliability_batch_host(int variant, uint8_t* h_data_
                                                    const uint8_t* h_data_reliab, const uint8_t* h_parity_reliab,
                                                    int erasure_threshold, uint8_t* h_status, int n_words);
 
+/* ---- P25 Phase 1 word codes around the RS decoders: Golay(24,6) / (24,12), Hamming(10,6,3), NID BCH(63,16,11) ---- */
+enum {
+    DSDNEO_P25_WORD_GOLAY_24_6 = 0,     /* check_and_fix_golay_24_6   phase1/p25p1_check_hdu.cpp:26-30, Golay24.hpp:336-368 */
+    DSDNEO_P25_WORD_GOLAY_24_12 = 1,    /* check_and_fix_golay_24_12  phase1/p25p1_check_hdu.cpp:32-36, Golay24.hpp:370-404 */
+    DSDNEO_P25_WORD_HAMMING_10_6_3 = 2, /* hamming_10_6_3_decode      src/fec/hamming_10_6_3.cpp:90-105 */
+};
+/**
+ * @param d_data_bits   [n][6 | 12 | 6] byte-per-bit words (MSB first), corrected in place exactly where the reference does
+ * @param d_parity_bits [n][12 | 12 | 4]
+ * @param d_status      Golay: 0 ok / 1 uncorrectable or non-binary input (word untouched); Hamming: 0 clean / 1 corrected /
+ *                      2 uncorrectable or non-binary input
+ * @param d_fixed       optional [n]: Golay = the reference's *fixed_errors (weight of the last syndrome examined, also on
+ *                      failure); Hamming = 1 when a bit was corrected
+ */
+int dsdneo_b200_p25_word_decode_batch(int code, uint8_t* d_data_bits, const uint8_t* d_parity_bits, uint8_t* d_status,
+                                      int32_t* d_fixed, int n_words, void* stream);
+int dsdneo_b200_p25_word_decode_batch_host(int code, uint8_t* h_data_bits, const uint8_t* h_parity_bits, uint8_t* h_status,
+                                           int32_t* h_fixed, int n_words);
+/**
+ * BCH_63_16_11::decode_with_result (include/dsd-neo/fec/BCH_63_16.hpp:288-329; caller p25p1_nid_decode,
+ * phase1/p25p1_check_nid.cpp:246-305): 63 byte-per-bit inputs (16 data bits MSB first, then 47 parity bits) -> 16 corrected
+ * data bits, ok flag (1 = success, up to 11 bit errors) and the number of corrected bits (0 on failure; output untouched).
+ */
+int dsdneo_b200_bch_63_16_decode_batch(const uint8_t* d_in63, uint8_t* d_out16, uint8_t* d_ok, int32_t* d_err_count, int n_words,
+                                       void* stream);
+int dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_out16, uint8_t* h_ok, int32_t* h_err_count,
+                                            int n_words);
+
 /**
  * viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182; include/dsd-neo/fec/viterbi.h:23-29), the
  * K = 5 soft decoder used by M17 and YSF.  Costs are uint16 "probability of a 1" (0 / 0xFFFF strong, 0x7FFF erased).

@@ -96,6 +96,9 @@ int oracle_p25_rs_ranked_erasures(const uint8_t* data_rel, int n_data, const uin
                                   int* erasures, int max_er);
 int oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, const uint8_t* parity_bits, const uint8_t* data_rel,
                                    const uint8_t* par_rel, int threshold);
+int oracle_p25_golay24_decode(int length, uint8_t* word, const uint8_t* parity, int* fixed_errors);
+int oracle_hamming_10_6_3_decode(uint8_t* data6, const uint8_t* parity4);
+int oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count);
 uint32_t oracle_viterbi_k5_decode(uint8_t* out, const uint16_t* in, int len);
 uint32_t oracle_viterbi_k5_decode_punctured(uint8_t* out, const uint16_t* in, const uint8_t* punct, int in_len, int p_len);
 void oracle_nxdn_conv_decode(const uint8_t* sym, const uint8_t* rel, int n_steps, int n_bits_out, uint16_t* metrics_io, uint8_t* out);

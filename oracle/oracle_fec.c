@@ -1269,6 +1269,286 @@ oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, cons
     return 1;
 }
 
+/* ------------------------------------------------------------------ P25 word codes: Golay(24,6/12), Hamming(10,6,3), BCH(63,16,11) */
+
+/* Golay24 (include/dsd-neo/fec/Golay24.hpp:17-222): Hank Wallace's (23,12) decoder + overall parity. */
+#define GOLAY_POLY 0xAE3u
+
+static unsigned
+g23_syndrome(unsigned cw) { /* :58-72 */
+    cw &= 0x7fffffu;
+    for (int i = 1; i <= 12; i++) {
+        if (cw & 1u) {
+            cw ^= GOLAY_POLY;
+        }
+        cw >>= 1;
+    }
+    return cw << 12;
+}
+
+static unsigned
+g23_rotl(unsigned cw) {
+    cw = (cw & 0x400000u) ? ((cw << 1) | 1u) : (cw << 1);
+    return cw & 0x7fffffu;
+}
+
+static unsigned
+g23_rotr(unsigned cw, int n) {
+    for (int i = 0; i < n; i++) {
+        cw = (cw & 1u) ? ((cw >> 1) | 0x400000u) : (cw >> 1);
+    }
+    return cw & 0x7fffffu;
+}
+
+static int
+parity32(unsigned cw) { /* Golay24::parity looks at the low 24 bits only */
+    unsigned p = cw ^ (cw >> 8) ^ (cw >> 16);
+    p ^= p >> 4;
+    p ^= p >> 2;
+    p ^= p >> 1;
+    return (int)(p & 1u);
+}
+
+/* Golay24::correct (:108-169): weight <= 3 syndrome over the 23 cyclic shifts, then 23 trial flips with threshold 2.
+ * *errs is whatever the last examined syndrome weighed, also when nothing could be corrected (the reference reports it). */
+static unsigned
+g23_correct(unsigned cw, int* errs) {
+    const unsigned saver = cw;
+    unsigned mask = 1;
+    int w = 3, j = -1;
+    *errs = 0;
+    while (j < 23) {
+        if (j != -1) {
+            if (j > 0) {
+                mask += mask;
+            }
+            cw = saver ^ mask;
+            w = 2;
+        }
+        unsigned s = g23_syndrome(cw);
+        if (!s) {
+            return cw;
+        }
+        for (int i = 0; i < 23; i++) {
+            *errs = __builtin_popcount(s & 0x7fffffu);
+            if (*errs <= w) {
+                return g23_rotr(cw ^ s, i);
+            }
+            cw = g23_rotl(cw);
+            s = g23_syndrome(cw);
+        }
+        j++;
+    }
+    return saver;
+}
+
+/* DSDGolay24::decode_6 / decode_12 (:336-405) = check_and_fix_golay_24_6 / _24_12 (phase1/p25p1_check_hdu.cpp:26-36).
+ * length = 6 or 12 data bits (MSB first) + 12 parity bits; returns 0 ok / 1 uncorrectable (data untouched). */
+int
+oracle_p25_golay24_decode(int length, uint8_t* word, const uint8_t* parity, int* fixed_errors) {
+    *fixed_errors = 0;
+    for (int i = 0; i < length; i++) {
+        if (word[i] > 1) {
+            return 1;
+        }
+    }
+    for (int i = 0; i < 12; i++) {
+        if (parity[i] > 1) {
+            return 1;
+        }
+    }
+    unsigned cw = 0;
+    for (int i = 0; i < 12; i++) {
+        cw = (cw << 1) | parity[11 - i];
+    }
+    for (int i = 0; i < length; i++) {
+        cw = (cw << 1) | word[length - 1 - i];
+    }
+    cw <<= (12 - length);
+    const unsigned pbit = cw & 0x800000u;
+    cw = g23_correct(cw & ~0x800000u, fixed_errors) | pbit;
+    int bad = parity32(cw);
+    if (bad && (cw & 0x3fu) != 0) {
+        return 1;
+    }
+    unsigned mask = 1u << (12 - length);
+    for (int i = 0; i < length; i++, mask <<= 1) {
+        word[i] = (cw & mask) ? 1 : 0;
+    }
+    return 0;
+}
+
+/* hamming_10_6_3_decode (src/fec/hamming_10_6_3.cpp:14-105): 0 clean, 1 corrected (data bits only), 2 uncorrectable or
+ * non-binary input. */
+int
+oracle_hamming_10_6_3_decode(uint8_t* data6, const uint8_t* parity4) {
+    static const int bad_bit[16] = {-2, 0, 1, 5, 2, -1, -1, 6, 3, -1, -1, 7, 4, 8, 9, -1};
+    unsigned v = 0;
+    for (int i = 0; i < 6; i++) {
+        if (data6[i] > 1) {
+            return 2;
+        }
+        v = (v << 1) | data6[i];
+    }
+    for (int i = 0; i < 4; i++) {
+        if (parity4[i] > 1) {
+            return 2;
+        }
+        v = (v << 1) | parity4[i];
+    }
+    const int syn = (__builtin_parity(v & 0x398u) << 3) | (__builtin_parity(v & 0x354u) << 2) | (__builtin_parity(v & 0x2E2u) << 1)
+                    | __builtin_parity(v & 0x1E1u);
+    if (!syn) {
+        return 0;
+    }
+    const int b = bad_bit[syn];
+    if (b < 0) {
+        return 2;
+    }
+    if (b >= 4) {
+        v ^= 1u << b;
+    }
+    for (int i = 0; i < 6; i++) {
+        data6[i] = (uint8_t)((v >> (9 - i)) & 1u);
+    }
+    return 1;
+}
+
+/* BCH_63_16_11::decode_with_result (include/dsd-neo/fec/BCH_63_16.hpp:288-329): input bit i is coefficient 62 - i,
+ * 22 syndromes over GF(64), Berlekamp iteration in Rockliff's index form, Chien search; the 16 data bits are coefficients
+ * 62..47.  Returns 1 success / 0 failure; *error_count = corrected bits (0 on failure, output untouched). */
+int
+oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count) {
+    enum { NN = 63, TT = 11, N2T = 22 };
+    gf_init();
+    int recd[NN], s[N2T + 1];
+    *error_count = 0;
+    for (int i = 0; i < NN; i++) {
+        recd[i] = in63[NN - 1 - i] ? 1 : 0;
+    }
+    int has_err = 0;
+    for (int i = 1; i <= N2T; i++) {
+        int syn = 0;
+        for (int j = 0; j < NN; j++) {
+            if (recd[j]) {
+                syn ^= gf_exp[(i * j) % NN];
+            }
+        }
+        has_err |= syn != 0;
+        s[i] = gf_log[syn];
+    }
+    if (has_err) {
+        int elp[N2T + 2][N2T], d[N2T + 2], l[N2T + 2], u_lu[N2T + 2];
+        d[0] = 0;
+        d[1] = s[1];
+        elp[0][0] = 0;
+        elp[1][0] = 1;
+        for (int i = 1; i < N2T; i++) {
+            elp[0][i] = -1;
+            elp[1][i] = 0;
+        }
+        l[0] = l[1] = 0;
+        u_lu[0] = -1;
+        u_lu[1] = 0;
+        int u = 0;
+        do {
+            u++;
+            if (d[u] == -1) {
+                l[u + 1] = l[u];
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] = elp[u][i];
+                }
+                for (int i = 0; i <= l[u]; i++) {
+                    if (elp[u][i] >= 0) {
+                        elp[u][i] = gf_log[elp[u][i]];
+                    }
+                }
+            } else {
+                int q = u - 1;
+                while (q > 0 && d[q] == -1) {
+                    q--;
+                }
+                if (q > 0) {
+                    for (int j = q - 1; j > 0; j--) {
+                        if (d[j] != -1 && u_lu[q] < u_lu[j]) {
+                            q = j;
+                        }
+                    }
+                }
+                const int cand = l[q] + u - q;
+                l[u + 1] = l[u] > cand ? l[u] : cand;
+                for (int i = 0; i < N2T; i++) {
+                    elp[u + 1][i] = 0;
+                }
+                for (int i = 0; i <= l[q]; i++) {
+                    if (elp[q][i] != -1) {
+                        elp[u + 1][i + u - q] = gf_exp[(d[u] + NN - d[q] + elp[q][i]) % NN];
+                    }
+                }
+                for (int i = 0; i <= l[u]; i++) {
+                    elp[u + 1][i] ^= elp[u][i];
+                }
+                for (int i = 0; i <= l[u]; i++) {
+                    if (elp[u][i] >= 0) {
+                        elp[u][i] = gf_log[elp[u][i]];
+                    }
+                }
+            }
+            u_lu[u + 1] = u - l[u + 1];
+            if (u < N2T) {
+                int disc = (s[u + 1] != -1) ? gf_exp[s[u + 1]] : 0;
+                for (int i = 1; i <= l[u + 1]; i++) {
+                    if (s[u + 1 - i] != -1 && elp[u + 1][i] != 0) {
+                        disc ^= gf_exp[(s[u + 1 - i] + gf_log[elp[u + 1][i]]) % NN];
+                    }
+                }
+                d[u + 1] = gf_log[disc];
+            }
+        } while (u < N2T && l[u + 1] <= TT);
+        u++;
+        if (l[u] > TT) {
+            return 0;
+        }
+        for (int i = 0; i <= l[u]; i++) {
+            if (elp[u][i] >= 0) {
+                elp[u][i] = gf_log[elp[u][i]];
+            }
+        }
+        int reg[TT + 1] = {0}, loc[TT], count = 0;
+        for (int i = 1; i <= l[u]; i++) {
+            reg[i] = elp[u][i];
+        }
+        for (int i = 1; i <= NN; i++) {
+            int q = 1;
+            for (int j = 1; j <= l[u]; j++) {
+                if (reg[j] != -1) {
+                    reg[j] = (reg[j] + j) % NN;
+                    q ^= gf_exp[reg[j]];
+                }
+            }
+            if (q == 0) {
+                if (count >= TT) {
+                    break;
+                }
+                loc[count++] = NN - i;
+            }
+        }
+        if (count != l[u]) {
+            return 0;
+        }
+        for (int i = 0; i < count; i++) {
+            if (loc[i] >= 0 && loc[i] < NN) {
+                recd[loc[i]] ^= 1;
+            }
+        }
+        *error_count = count;
+    }
+    for (int i = 0; i < 16; i++) {
+        out16[i] = (uint8_t)recd[NN - 1 - i];
+    }
+    return 1;
+}
+
 /* ------------------------------------------------------------------ K = 5 soft Viterbi (M17 / YSF) */
 
 /* viterbi_decode (src/core/util/dsd_misc.c:118-143) with viterbi_decode_bit (:191-236), viterbi_chainback (:246-275):

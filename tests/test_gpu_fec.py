@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import _harness as H
-from test_oracle_fec import HAM, bptc_kat_bits, _rs_words, make_rs_soft_cases, oracle_rs_erasures
+from test_oracle_fec import (HAM, bptc_kat_bits, _rs_words, make_rs_soft_cases, oracle_rs_erasures, bch_63_16_encode,
+                             make_p25_word_cases, oracle_p25_word)
 
 pytestmark = pytest.mark.gpu
 
@@ -275,3 +276,31 @@ def test_rs_soft_decoders_bit_exact(gpu, n, k, variant):
         rc = O.oracle_p25_rs_soft_reliability(n, k, H._ptr(b, H.u8p), H._ptr(par[i], H.u8p), H._ptr(rel_d[i].copy(), H.u8p),
                                               H._ptr(rel_p[i].copy(), H.u8p), 200)
         assert rc == st2[i] and np.array_equal(got2[i], b), i
+
+
+def test_p25_word_codes_and_nid_bch_bit_exact(gpu):
+    """Batched Golay(24,6)/(24,12), Hamming(10,6,3) and BCH(63,16,11) == oracle (== reference, tests/test_oracle_fec.py)."""
+    O = H.oracle_fec()
+    rng = np.random.default_rng(410)
+    for code in (0, 1, 2):
+        d, p = make_p25_word_cases(rng, code, 5000)
+        got, st, fx = gpu.p25_word_decode(code, d, p)
+        for i in range(d.shape[0]):
+            w, rc, f = oracle_p25_word(code, d[i], p[i])
+            assert rc == st[i] and np.array_equal(got[i], w), (code, i)
+            if code != 2:
+                assert f == fx[i], (code, i)
+    words = []
+    for t in range(3000):
+        x = bch_63_16_encode(rng.integers(0, 2, 16))
+        for e in rng.choice(63, int(rng.integers(0, 15)), replace=False):
+            x[e] ^= 1
+        words.append(rng.integers(0, 2, 63).astype(np.uint8) if t % 7 == 0 else x)
+    words = np.array(words)
+    init = np.full((words.shape[0], 16), 9, np.uint8)
+    out, ok, ec = gpu.bch_63_16_decode(words, init)
+    for i in range(words.shape[0]):
+        w, e = np.full(16, 9, np.uint8), C.c_int(-1)
+        r = O.oracle_bch_63_16_decode(H._ptr(words[i], H.u8p), H._ptr(w, H.u8p), C.byref(e))
+        assert r == ok[i] and e.value == ec[i] and np.array_equal(out[i], w), i
+    assert ok.sum() > 1800

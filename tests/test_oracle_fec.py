@@ -517,3 +517,116 @@ def test_rs_soft_reference_kats():
     p[3], d[4] = 10, 20
     assert O.oracle_p25_rs_ranked_erasures(H._ptr(d, H.u8p), 20, H._ptr(p, H.u8p), 16, 2, 64, er.ctypes.data_as(H.i32p), 16) == 2
     assert list(er[:2]) == [3, 20]
+
+
+# ---------------------------------------------------------------- P25 word codes: Golay(24,6/12), Hamming(10,6,3), BCH(63,16,11)
+
+def bch_63_16_encode(data16):
+    """Systematic BCH(63,16,11) codeword for 16 data bits (MSB first): input bit i is coefficient 62 - i, the generator is the
+    LCM of the minimal polynomials of alpha^1..alpha^22 over GF(64) (x^6 + x + 1)."""
+    exp, v = [], 1
+    for _ in range(63):
+        exp.append(v)
+        v <<= 1
+        if v & 0x40:
+            v ^= 0x43
+    log = {e: i for i, e in enumerate(exp)}
+    mul = lambda a, b: 0 if a == 0 or b == 0 else exp[(log[a] + log[b]) % 63]
+    roots, seen = [], set()
+    for i in range(1, 23):
+        c = i
+        while c not in seen:
+            seen.add(c)
+            roots.append(c)
+            c = (2 * c) % 63
+    g = [1]
+    for r in roots:  # g(x) *= (x + alpha^r), coefficients in GF(64), ends up binary
+        ng = [0] * (len(g) + 1)
+        for k, co in enumerate(g):
+            ng[k + 1] ^= co
+            ng[k] ^= mul(co, exp[r])
+        g = ng
+    assert len(g) == 48 and all(c in (0, 1) for c in g)
+    msg = [0] * 63
+    for i, b in enumerate(data16):
+        msg[62 - i] = int(b)
+    rem = msg[:]
+    for k in range(62, 46, -1):
+        if rem[k]:
+            for j, co in enumerate(g):
+                rem[k - 47 + j] ^= co
+    cw = [msg[k] if k >= 47 else rem[k] for k in range(63)]
+    return np.array([cw[62 - i] for i in range(63)], np.uint8)
+
+
+def make_p25_word_cases(rng, code, n):
+    """(data, parity) pairs: random words, about 2 % with non-binary bytes."""
+    db, pb = {0: (6, 12), 1: (12, 12), 2: (6, 4)}[code]
+    d = rng.integers(0, 2, (n, db)).astype(np.uint8)
+    p = rng.integers(0, 2, (n, pb)).astype(np.uint8)
+    d[::53, 0] = 2
+    p[7::61, 1] = 3
+    return d, p
+
+
+def oracle_p25_word(code, d, p):
+    O = H.oracle_fec()
+    d = d.copy()
+    if code == 2:
+        return d, O.oracle_hamming_10_6_3_decode(H._ptr(d, H.u8p), H._ptr(p, H.u8p)), None
+    fx = C.c_int(0)
+    rc = O.oracle_p25_golay24_decode(6 if code == 0 else 12, H._ptr(d, H.u8p), H._ptr(p, H.u8p), C.byref(fx))
+    return d, rc, fx.value
+
+
+@needs_ref
+def test_p25_word_codes_match_reference():
+    """Golay(24,6)/(24,12) (check_and_fix_golay_24_6/_12), Hamming(10,6,3) (exhaustive) and the NID BCH(63,16,11) decoder ==
+    the compiled reference: status, corrected bits, reported error counts, behaviour on non-binary input."""
+    O, R = H.oracle_fec(), H.ref_fec()
+    rng = np.random.default_rng(40)
+    for code, fn in ((0, R.check_and_fix_golay_24_6), (1, R.check_and_fix_golay_24_12)):
+        d, p = make_p25_word_cases(rng, code, 6000)
+        for i in range(d.shape[0]):
+            a, fa = d[i].copy(), C.c_int(-7)
+            ra = fn(H._ptr(a, H.u8p), H._ptr(p[i], H.u8p), C.byref(fa))
+            b, rb, fb = oracle_p25_word(code, d[i], p[i])
+            assert ra == rb and fa.value == fb and np.array_equal(a, b), (code, i)
+    for v in range(1024):
+        d = np.array([(v >> (9 - i)) & 1 for i in range(6)], np.uint8)
+        p = np.array([(v >> (3 - i)) & 1 for i in range(4)], np.uint8)
+        a = d.copy()
+        ra = R.hamming_10_6_3_decode(H._ptr(a, H.u8p), H._ptr(p, H.u8p))
+        b, rb, _ = oracle_p25_word(2, d, p)
+        assert ra == rb and np.array_equal(a, b), v
+    wins = 0
+    for t in range(4000):
+        cw = bch_63_16_encode(rng.integers(0, 2, 16))
+        x = cw.copy()
+        for e in rng.choice(63, int(rng.integers(0, 15)), replace=False):
+            x[e] ^= 1
+        if t % 7 == 0:
+            x = rng.integers(0, 2, 63).astype(np.uint8)
+        oa, ob, ea, eb = np.full(16, 9, np.uint8), np.full(16, 9, np.uint8), C.c_int(-1), C.c_int(-1)
+        ra = R.ref_bch_63_16_decode(H._ptr(x, H.u8p), H._ptr(oa, H.u8p), C.byref(ea))
+        rb = O.oracle_bch_63_16_decode(H._ptr(x, H.u8p), H._ptr(ob, H.u8p), C.byref(eb))
+        assert ra == rb and ea.value == eb.value and np.array_equal(oa, ob), t
+        wins += ra
+    assert wins > 2500
+
+
+def test_bch_63_16_corrects_up_to_eleven_errors():
+    """Property pin without the reference tree: every systematic codeword decodes to its data with error_count = number of
+    flipped bits for 0..11 errors."""
+    O = H.oracle_fec()
+    rng = np.random.default_rng(41)
+    for t in range(300):
+        data = rng.integers(0, 2, 16).astype(np.uint8)
+        cw = bch_63_16_encode(data)
+        ne = t % 12
+        x = cw.copy()
+        for e in rng.choice(63, ne, replace=False):
+            x[e] ^= 1
+        out, ec = np.zeros(16, np.uint8), C.c_int(-1)
+        assert O.oracle_bch_63_16_decode(H._ptr(x, H.u8p), H._ptr(out, H.u8p), C.byref(ec)) == 1
+        assert ec.value == ne and np.array_equal(out, data)
