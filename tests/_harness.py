@@ -491,6 +491,66 @@ def synth_c4fm_disc(rng, dibits, level=9000.0, noise=0.0, pre=9):
     return np.concatenate([np.zeros(pre), x]).astype(np.float32)
 
 
+def nyquist_tx_taps(rx_taps, box, ntaps=241, fs=48000.0, rs=4800.0, alpha=0.2):
+    """Transmit shaping that makes (tx * rx * box-average of `box` samples) a raised-cosine Nyquist pulse, so getSymbol's
+    window mean after the reference's matched filter `rx_taps` lands on the transmitted level.  Gain 10 = one impulse per
+    10 samples."""
+    N = 4096
+    f = np.fft.rfftfreq(N, 1 / fs)
+    T = 1 / rs
+    f1, f2 = (1 - alpha) / (2 * T), (1 + alpha) / (2 * T)
+    rc = np.zeros_like(f)
+    rc[f <= f1] = 1.0
+    m = (f > f1) & (f <= f2)
+    rc[m] = 0.5 * (1 + np.cos(np.pi * T / alpha * (f[m] - f1)))
+    RX = np.abs(np.fft.rfft(np.asarray(rx_taps, np.float64), N)) * np.abs(np.fft.rfft(np.ones(box) / box, N))
+    h = np.fft.irfft(np.where(f <= f2, rc / np.maximum(RX, 1e-3), 0.0), N)
+    return np.roll(h, ntaps // 2)[:ntaps] * 10.0
+
+
+def synth_dmr_disc(rng, dibits, rx_taps, level=10000.0, noise=0.0, pre=5):
+    """Discriminator-level 4FSK stream for the DMR/YSF class (61-tap RRC matched filter, window centre-1..centre+2, fixed
+    +-20000 thresholds): symbol centres aligned for `pre` = 5 leading samples."""
+    imp = np.zeros(len(dibits) * 10)
+    imp[::10] = LEVELS[np.asarray(dibits)] * level
+    x = np.convolve(imp, nyquist_tx_taps(rx_taps, 4), mode="same")
+    if noise:
+        x = x + rng.standard_normal(x.size) * noise
+    return np.concatenate([np.zeros(pre), x]).astype(np.float32)
+
+
+def hamming_parity_bruteforce(code, data_bits, n):
+    """Parity bits that make [data | parity] a codeword of the reference's Hamming code `code` (oracle_hamming_decode
+    accepts it unchanged); test-side encoder for BPTC construction."""
+    O = oracle_fec()
+    k = len(data_bits)
+    for v in range(1 << (n - k)):
+        word = np.array(list(data_bits) + [(v >> (n - k - 1 - i)) & 1 for i in range(n - k)], np.uint8)
+        probe, dec = word.copy(), np.zeros(k, np.uint8)
+        if oracle_fec().oracle_hamming_decode(code, _ptr(probe, u8p), _ptr(dec, u8p)) and np.array_equal(probe, word):
+            return word[k:]
+    raise AssertionError("no parity found")
+
+
+def bptc_196x96_encode(payload96, interleave=True):
+    """DMR BPTC(196,96): 13 x 15 product code (rows 0-8 Hamming(15,11), all columns Hamming(13,9)), reserved bits zero,
+    interleaved as the transmitter does (received[t] = deinterleaved[13 t mod 196], the inverse of bptc.c:51-59)."""
+    m = np.zeros((13, 15), np.uint8)
+    p = list(payload96)
+    m[0, 3:11] = p[:8]
+    for r in range(1, 9):
+        m[r, :11] = p[8 + 11 * (r - 1):8 + 11 * r]
+    for r in range(9):
+        m[r, 11:] = hamming_parity_bruteforce(3, m[r, :11], 15)   # ORACLE_HAMMING_15_11
+    for j in range(15):
+        m[9:, j] = hamming_parity_bruteforce(2, m[:9, j], 13)     # ORACLE_HAMMING_13_9
+    dei = np.zeros(196, np.uint8)
+    dei[1:] = m.reshape(-1)
+    if not interleave:
+        return dei
+    return np.array([dei[(13 * t) % 196] for t in range(196)], np.uint8)
+
+
 def conv_k5_encode(bits):
     """Rate-1/2 K=5 encoder used by M17 / NXDN / YSF (G1 = 1+D^3+D^4, G2 = 1+D+D^2+D^4), returns 2*len(bits) bits."""
     sr = 0

@@ -1,0 +1,79 @@
+"""Configuration C4 in miniature: synthetic DMR-class 4FSK channels (discriminator level) -> RRC matched filter + getSymbol +
+fixed-threshold slicer -> frame-sync hunt (DMR BS data sync) -> BPTC(196,96), every stage bit-exact against the CPU
+oracle chain and the payloads recovered; then the MBE synthesis stage on the side (parity unpinned, +-1 LSB vs its oracle,
+tests/test_mbe.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _harness as H
+from test_frame_sync import oracle_search
+from test_gpu_symbolizer import _oracle_dibits, _taps
+
+pytestmark = pytest.mark.gpu
+
+DMR_SYNC = "313333111331131131331131"
+WARMUP, GAP, N_FRAMES = 120, 14, 5
+
+
+def test_bptc_test_encoder_makes_valid_codewords():
+    O = H.oracle_fec()
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        payload = rng.integers(0, 2, 96).astype(np.uint8)
+        dei = H.bptc_196x96_encode(payload, interleave=False)
+        out, r3, und = np.zeros(96, np.uint8), np.zeros(3, np.uint8), C.c_int(0)
+        assert O.oracle_bptc_196x96_extract(H._ptr(dei, H.u8p), H._ptr(out, H.u8p), H._ptr(r3, H.u8p), C.byref(und)) == 0
+        assert np.array_equal(out, payload)
+
+
+def test_dmr_chain_bit_exact_and_payloads_recovered(gpu):
+    import torch
+
+    rng = np.random.default_rng(77)
+    n_ch = 24
+    taps = _taps()
+    chans, xs = [], []
+    for c in range(n_ch):
+        parts, payloads = [rng.integers(0, 4, WARMUP)], []
+        for _ in range(N_FRAMES):
+            payload = rng.integers(0, 2, 96).astype(np.uint8)
+            bits = H.bptc_196x96_encode(payload)
+            parts += [np.array([int(ch) for ch in DMR_SYNC]), (bits[0::2] << 1) | bits[1::2], rng.integers(0, 4, GAP)]
+            payloads.append(payload)
+        dib = np.concatenate(parts)
+        chans.append(payloads)
+        xs.append(H.synth_dmr_disc(rng, dib, taps[1], 10000.0, 0.0 if c % 2 == 0 else 500.0 + 40.0 * c))
+    xs = np.stack(xs)
+    n = xs.shape[1]
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([gpu.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), n)
+    fs = gpu.FrameSync(n_ch, [(DMR_SYNC, 10)])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=32)
+    torch.cuda.synchronize()
+    cnt, dib_g = res["count"].cpu().numpy(), res["dibits"].cpu().numpy()
+    sym_g, hits, n_hits = res["symbols"].cpu().numpy(), hits.cpu().numpy(), n_hits.cpu().numpy()
+    O = H.oracle_fec()
+    bursts, want_out, want_err, owner = [], [], [], []
+    for c in range(n_ch):
+        wd, wr, wl, ws = _oracle_dibits(xs[c], H.SYNC_DMR_BS_DATA_POS, taps)
+        assert cnt[c] == wd.size and np.array_equal(dib_g[c, :cnt[c]], wd) and H.bits_equal(sym_g[c, :cnt[c]], ws)
+        on, opos, otyp, _, _ = oracle_search(ws, [(DMR_SYNC, 10)], max_hits=32)
+        assert n_hits[c] == on and np.array_equal(hits[c, :on, 0], opos) and (hits[c, :on, 1] == 10).all()
+        frames = [p for p in opos.tolist() if p + 1 + 98 <= wd.size]
+        assert len(frames) >= N_FRAMES, (c, len(frames))
+        for i, p in enumerate(frames):
+            d = dib_g[c, p + 1:p + 99].astype(np.uint8)
+            bits = np.stack([(d >> 1) & 1, d & 1], axis=1).reshape(-1).astype(np.uint8)
+            bursts.append(bits)
+            dei, out, r3, und = np.zeros(196, np.uint8), np.zeros(96, np.uint8), np.zeros(3, np.uint8), C.c_int(0)
+            O.oracle_bptc_deinterleave(H._ptr(bits, H.u8p), H._ptr(dei, H.u8p))
+            want_err.append(O.oracle_bptc_196x96_extract(H._ptr(dei, H.u8p), H._ptr(out, H.u8p), H._ptr(r3, H.u8p), C.byref(und)))
+            want_out.append(out)
+            owner.append((c, i))
+    out, r3, errs = gpu.bptc_196x96(np.array(bursts), interleaved=True)
+    assert np.array_equal(out, np.array(want_out)) and np.array_equal(errs, np.array(want_err, np.uint32))
+    good = sum(int(errs[k] == 0 and i < N_FRAMES and np.array_equal(out[k], chans[c][i])) for k, (c, i) in enumerate(owner))
+    assert good >= n_ch * N_FRAMES - 2, (good, len(owner))  # every transmitted payload (a late false sync may add extras)

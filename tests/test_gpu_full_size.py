@@ -95,3 +95,41 @@ def test_c3_full_size_sample_side_replicas_and_spot_parity(gpu):
         wd, wr, wl, ws = _oracle_dibits(base[i], H.SYNC_P25P1_POS, taps)
         f = first[i]
         assert wd.size == k and np.array_equal(dib[f], wd) and np.array_equal(llr[f], wl) and H.bits_equal(sym[f], ws)
+
+
+def test_c5_channel_count_mixed_classes_replicas_and_spot_parity(gpu):
+    """8192 channels in one launch, protocol classes mixed per channel (P25 C4FM with threshold tracking, DMR/YSF class with
+    fixed thresholds, no matched filter): replicas of six base signals are identical wherever they land, and the six equal
+    the oracle."""
+    import torch
+
+    rng = np.random.default_rng(14)
+    n_ch, n_samp = 8192, 24570
+    taps = _taps()
+    syncs = [H.SYNC_P25P1_POS, H.SYNC_DMR_BS_DATA_POS, H.SYNC_NONE, H.SYNC_P25P1_NEG, H.SYNC_DMR_BS_DATA_POS, H.SYNC_P25P1_POS]
+    base = []
+    for i, s in enumerate(syncs):
+        dib = rng.integers(0, 4, n_samp // 10 + 2)
+        if s == H.SYNC_DMR_BS_DATA_POS:
+            base.append(H.synth_dmr_disc(rng, dib, taps[1], 10000.0, 300.0 * i)[:n_samp])
+        else:
+            base.append(H.synth_c4fm_disc(rng, dib, 9000.0, 250.0 * i)[:n_samp])
+    order = rng.integers(0, 6, n_ch)
+    x = torch.empty((n_ch, n_samp), dtype=torch.float32, device="cuda")
+    d_base = torch.from_numpy(np.stack(base)).cuda()
+    x.copy_(d_base[torch.from_numpy(order).cuda()])
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([gpu.sym_class_from_synctype(syncs[i], syncs[i]) for i in order])
+    res = sy.run(x, n_samp)
+    torch.cuda.synchronize()
+    cnt = res["count"].cpu().numpy()
+    k = int(cnt.min())
+    assert cnt.max() - k <= 1
+    sym, dib = res["symbols"][:, :k].cpu().numpy(), res["dibits"][:, :k].cpu().numpy()
+    first = {i: int(np.nonzero(order == i)[0][0]) for i in range(6)}
+    ref_rows = np.array([first[int(i)] for i in order])
+    assert np.array_equal(sym.view(np.uint32), sym[ref_rows].view(np.uint32)) and np.array_equal(dib, dib[ref_rows])
+    for i in range(6):
+        wd, wr, wl, ws = _oracle_dibits(base[i], syncs[i], taps)
+        f = first[i]
+        assert np.array_equal(dib[f], wd[:k]) and H.bits_equal(sym[f], ws[:k]), i
