@@ -134,6 +134,33 @@ def make_wideband(torch, device, seed: int):
     return acc.contiguous()
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank's host threads (and therefore its pinned-buffer pages) to the NUMA node its GPU hangs off, so the
+    end-to-end leg of several ranks does not cross the socket interconnect.  Best effort: returns the node or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 
 def _load_ref():
@@ -285,6 +312,7 @@ def run_b200_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path")
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -446,7 +474,8 @@ def run_b200_arm(args):
                    "channelizer_taps_per_branch": 8, "fir_arith": "fma (reference AVX2 kernel order)",
                    "parallelism": "bands sharded over GPUs, no data-path collective",
                    "step_call": "dsdneo_b200_frontend_process_async (2-stream stage pipeline), joined before the stop event",
-                   "l2_policy": "%d rotating input buffers of %.1f MB (> 126 MB L2)" % (N_ROTATE, N_IN * 8 / 1e6)},
+                   "l2_policy": "%d rotating input buffers of %.1f MB (> 126 MB L2)" % (N_ROTATE, N_IN * 8 / 1e6),
+                   "host_numa_binding": "rank 0 on node %s" % numa_node if numa_node is not None else "none"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline, "e2e_matches_device_path": same,
     }
