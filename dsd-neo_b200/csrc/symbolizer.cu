@@ -295,6 +295,13 @@ symbolize_kernel(const SymParams p) {
      * coalesced 128-byte reads and each lane then walks its own column.  Lanes drift apart only by the +-1 timing
      * nudges; a lane that falls outside the staged window reads global memory directly for that symbol. */
     long wbase = 0, wend = 0;
+    int pf_idx = -1; /* prefetched minbuf / maxbuf ring entry */
+    float pf_min = 0.0f, pf_max = 0.0f;
+    int cn_max = carry_n, cn_min = carry_n; /* carry lengths over the warp: bounds for the branch-free refill */
+    for (int o = 16; o > 0; o >>= 1) {
+        cn_max = max(cn_max, __shfl_xor_sync(0xffffffffu, cn_max, o));
+        cn_min = min(cn_min, __shfl_xor_sync(0xffffffffu, cn_min, o));
+    }
     bool active = nsym < (long)p.out_pitch && (avail - pos) >= reserve;
     while (__any_sync(0xffffffffu, active)) {
         if (__any_sync(0xffffffffu, active && (pos < wbase || pos + reserve > wend))) {
@@ -306,7 +313,22 @@ symbolize_kernel(const SymParams p) {
             wbase = mp;
             wend = wbase + kWin;
             __syncwarp();
-            for (int r = 0; r < kSymThreads; r++) {
+            const bool interior = wbase >= cn_max && wbase + kWin - cn_min <= (long)p.n;
+            if (interior) { /* the whole window lies inside this launch's filtered samples for every channel row */
+                const unsigned d0 = (unsigned)__cvta_generic_to_shared(&s_win[lane * (kSymThreads + 1)]);
+                for (int r = 0; r < kSymThreads; r++) {
+                    const int cr = min(blockIdx.x * kSymThreads + r, p.n_ch - 1);
+                    const int cn = __shfl_sync(0xffffffffu, carry_n, r);
+                    const float* src = p.filt + (size_t)cr * p.filt_pitch + (wbase - cn) + lane;
+#pragma unroll
+                    for (int g = 0; g < kWin / 32; g++) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (unsigned)(g * 32 * (kSymThreads + 1) + r)),
+                                     "l"(src + g * 32)
+                                     : "memory");
+                    }
+                }
+            }
+            for (int r = 0; r < (interior ? 0 : kSymThreads); r++) {
                 const int cr = __shfl_sync(0xffffffffu, c, r);
                 const int cn = __shfl_sync(0xffffffffu, carry_n, r);
                 const float* fr = p.filt + (size_t)cr * p.filt_pitch;
@@ -348,6 +370,7 @@ symbolize_kernel(const SymParams p) {
             }
             midx = 0;
             sum_window = 0;
+            pf_idx = -1;
         }
         {
             int whole = p.rate / p.symrate, rem = p.rate % p.symrate;
@@ -376,7 +399,23 @@ symbolize_kernel(const SymParams p) {
         int cnt = 0;
         const bool in_win = pos >= wbase && pos + sps + 1 <= wend; /* a nudge reads at most one extra sample */
         const float* wp = s_win + (in_win ? (int)(pos - wbase) : 0) * (kSymThreads + 1) + lane;
-        for (int i = 0; i < sps; i++) {
+        /* Synchronised steady state: no timing nudge (have_sync), and the zero-crossing detector is idle once it has
+         * fired (jitter >= 0 is only cleared by the nudge), so only the window samples and the symbol's last sample
+         * (which becomes lastsample) matter; same clip, same accumulation order. */
+        const bool quick = in_win && have_sync == 1 && jitter >= 0 && sps != 20 && sps != 5;
+        if (quick) {
+            const int lo = max(center_idx - window_l, 0), hi = min(center_idx + 2, sps - 1);
+            for (int i = lo; i <= hi; i++) {
+                float s = wp[i * (kSymThreads + 1)];
+                s = s > vmax ? vmax : (s < vmin ? vmin : s);
+                sum = __fadd_rn(sum, s);
+                cnt++;
+            }
+            float s = wp[(sps - 1) * (kSymThreads + 1)];
+            lastsample = s > vmax ? vmax : (s < vmin ? vmin : s);
+            pos += sps;
+        }
+        for (int i = quick ? sps : 0; i < sps; i++) {
             if (i == 0 && have_sync == 0 && jitter >= 0) { /* dsd_symbol.c:462-516 */
                 if (sps == 20) {
                     if (jitter >= 7 && jitter <= 10) {
@@ -461,14 +500,25 @@ symbolize_kernel(const SymParams p) {
                     }
                 }
                 int idx = (midx < 0 || midx >= window) ? 0 : midx;
-                minbuf_sum += (double)lmin - (double)p.minbuf[(size_t)idx * N + c];
-                maxbuf_sum += (double)lmax - (double)p.maxbuf[(size_t)idx * N + c];
+                /* the ring entry being replaced was requested one symbol ago (pf_*), so its latency is off the chain */
+                const float old_min = (pf_idx == idx) ? pf_min : p.minbuf[(size_t)idx * N + c];
+                const float old_max = (pf_idx == idx) ? pf_max : p.maxbuf[(size_t)idx * N + c];
+                minbuf_sum += (double)lmin - (double)old_min;
+                maxbuf_sum += (double)lmax - (double)old_max;
                 if (valid) {
                     p.minbuf[(size_t)idx * N + c] = lmin;
                     p.maxbuf[(size_t)idx * N + c] = lmax;
                 }
+                const int written = idx;
                 idx++;
                 midx = idx >= window ? 0 : idx;
+                pf_idx = midx;
+                if (midx == written) {
+                    pf_min = lmin, pf_max = lmax;
+                } else {
+                    pf_min = p.minbuf[(size_t)midx * N + c];
+                    pf_max = p.maxbuf[(size_t)midx * N + c];
+                }
                 if ((window & (window - 1)) == 0) { /* power of two (default 1024): x / w == x * (1 / w) exactly */
                     const double inv = 1.0 / (double)window;
                     vmin = (float)(minbuf_sum * inv);
