@@ -394,7 +394,7 @@ def run_b200_arm(args):
     # ---- e2e: same metric through the host-buffer C-ABI (pinned host in/out, every copy inside the timed region) ----
     # Streaming form, as the reference's demod thread consumes its input ring: tile i is queued (submit_host) while the
     # consumer waits for and reads tile i-1 (wait_host), so H2D, kernels and D2H of consecutive tiles overlap.
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 100))
 
     def e2e_leg(fe_x, h_in_x, h_out_x, streaming: bool):
         def run(n):
@@ -414,7 +414,7 @@ def run_b200_arm(args):
                 checksum += float(h_out_x[(n - 1) % 2][0, 0])
             return checksum
 
-        run(3)
+        run(5)
         barrier()
         t0 = time.perf_counter()
         run(e2e_steps)
