@@ -72,6 +72,47 @@ int oracle_full_demod_block(oracle_demod_chan* c, const float* iq, int n_floats,
 void oracle_pfb_direct(const float* x_with_hist, int hist_len, int n_in, const float* h, int L, int M, int D,
                        const int* channels, int n_sel, double* out_re_im /* [n_sel][n_out][2] */, int n_out);
 
+/* ------------------------------- CQPSK block side (oracle_cqpsk.c) --------------------------- */
+
+#define ORACLE_FLL_MAX_TAPS 48
+#define ORACLE_CQPSK_RING 64
+
+typedef struct oracle_cqpsk_chan {
+    /* configuration */
+    int rate_out_hz, sps;
+    float ted_gain;
+    int ted_gain_is_set;
+    /* cqpsk_rms_agc */
+    float agc_avg;
+    /* dsd_fll_band_edge_state_t */
+    int fll_ntaps;
+    float fll_alpha, fll_beta, fll_phase, fll_freq;
+    float fll_lower_r[ORACLE_FLL_MAX_TAPS], fll_lower_i[ORACLE_FLL_MAX_TAPS];
+    float fll_upper_r[ORACLE_FLL_MAX_TAPS], fll_upper_i[ORACLE_FLL_MAX_TAPS];
+    /* history of FLL outputs (serves as the FLL delay line and the Gardner delay line) */
+    float ring_r[ORACLE_CQPSK_RING], ring_j[ORACLE_CQPSK_RING];
+    long pushed, consumed;
+    /* ted_state_t */
+    float mu, omega, omega_mid, omega_rel, last_r, last_j, lock_accum, ted_effective_gain;
+    int lock_count, ted_span;
+    /* op25_diff_phasor_cc */
+    float diff_prev_r, diff_prev_j;
+    /* dsd_costas_loop_state_t + per-block metrics */
+    float costas_alpha, costas_beta, costas_phase, costas_freq, costas_err_smooth, costas_error;
+    float m_err_abs, m_err_raw_abs, m_conf_acc;
+    int m_zero_conf;
+    int costas_err_avg_q14, costas_err_raw_avg_q14, costas_conf_avg_q14, costas_zero_conf_pct;
+} oracle_cqpsk_chan;
+
+const float* oracle_cqpsk_mmse_table(void); /* [17][8] */
+int oracle_fll_band_edge_design(int sps, float* lower_r, float* lower_i, float* upper_r, float* upper_i, int max_taps);
+int oracle_cqpsk_chan_init(oracle_cqpsk_chan* q, int rate_out_hz, int sps, float ted_gain, int ted_gain_is_set);
+/* one un-squelched block of channel-filtered interleaved I/Q (>= 4 pairs) -> symbols near {-3,-1,+1,+3}; returns count */
+int oracle_cqpsk_block(oracle_cqpsk_chan* q, const float* lp, int n_floats, float* out);
+/* full_demod() with output_kind == SYMBOL_CQPSK: channel LPF + squelch (state in c) then the chain above */
+int oracle_full_demod_cqpsk_block(oracle_demod_chan* c, oracle_cqpsk_chan* q, const float* iq, int n_floats,
+                                  float* scratch, float* out);
+
 /* ------------------------------- FEC leaves (oracle_fec.c) ----------------------------------- */
 
 enum { ORACLE_HAMMING_7_4 = 0, ORACLE_HAMMING_12_8, ORACLE_HAMMING_13_9, ORACLE_HAMMING_15_11, ORACLE_HAMMING_16_11_4 };

@@ -19,6 +19,7 @@
 #include <dsd-neo/dsp/demod_state.h>
 #include <dsd-neo/dsp/fsk_modem.h>
 #include <dsd-neo/dsp/simd_fir.h>
+#include <dsd-neo/dsp/ted.h>
 
 #include "dsp/simd_fir_internal.h"
 
@@ -119,6 +120,76 @@ ref_demod_get_lpf_taps(void* h, float* taps_out, int cap) {
     }
     memcpy(taps_out, s->channel_lpf_plan_taps, (size_t)n * sizeof(float));
     return s->channel_lpf_plan_taps_len;
+}
+
+/* CQPSK symbol output kind, configured like the reference bench's configure_common_cqpsk_state
+ * (tests/dsp/bench_dsp.cpp:1073-1091) and the runtime defaults (src/io/radio/rtl_demod_config.cpp:364-366). */
+void*
+ref_demod_create_cqpsk(int sample_rate, int symbol_rate, int sps, int lpf_enable, float squelch_level, float ted_gain,
+                       int ted_gain_is_set) {
+    demod_state* s = (demod_state*)ref_demod_create(sample_rate, symbol_rate, DSD_CH_LPF_PROFILE_P25_CQPSK, lpf_enable,
+                                                    squelch_level);
+    if (!s) {
+        return NULL;
+    }
+    s->output_kind = DSD_DEMOD_OUTPUT_SYMBOL_CQPSK;
+    s->cqpsk_enable = 1;
+    s->ted_sps = sps;
+    s->sps_is_integer = 1;
+    s->ted_gain = ted_gain;
+    s->ted_gain_is_set = ted_gain_is_set;
+    s->cqpsk_diff_prev_r = 1.0f;
+    s->cqpsk_diff_prev_j = 0.0f;
+    s->cqpsk_agc_avg = 1.0f;
+    ted_init_state(&s->ted_state);
+    return s;
+}
+
+/* Carried CQPSK loop state for parity dumps (24 floats, ints converted):
+ * {agc_avg, fll.phase, fll.freq, fll.alpha, fll.beta, ted.mu, ted.omega, ted.last_r, ted.last_j, ted.lock_accum,
+ *  ted.lock_count, ted_effective_gain, diff_prev_r, diff_prev_j, costas.phase, costas.freq, costas.error,
+ *  costas.error_smooth, err_avg_q14, err_raw_avg_q14, conf_avg_q14, zero_conf_pct, channel_pwr, channel_squelched} */
+void
+ref_demod_get_cqpsk_state(void* h, float* out24) {
+    demod_state* s = (demod_state*)h;
+    out24[0] = s->cqpsk_agc_avg;
+    out24[1] = s->fll_band_edge_state.phase;
+    out24[2] = s->fll_band_edge_state.freq;
+    out24[3] = s->fll_band_edge_state.alpha;
+    out24[4] = s->fll_band_edge_state.beta;
+    out24[5] = s->ted_state.mu;
+    out24[6] = s->ted_state.omega;
+    out24[7] = s->ted_state.last_r;
+    out24[8] = s->ted_state.last_j;
+    out24[9] = s->ted_state.lock_accum;
+    out24[10] = (float)s->ted_state.lock_count;
+    out24[11] = s->ted_effective_gain;
+    out24[12] = s->cqpsk_diff_prev_r;
+    out24[13] = s->cqpsk_diff_prev_j;
+    out24[14] = s->costas_state.phase;
+    out24[15] = s->costas_state.freq;
+    out24[16] = s->costas_state.error;
+    out24[17] = s->costas_state.error_smooth;
+    out24[18] = (float)s->costas_err_avg_q14;
+    out24[19] = (float)s->costas_err_raw_avg_q14;
+    out24[20] = (float)s->costas_conf_avg_q14;
+    out24[21] = (float)s->costas_zero_conf_pct;
+    out24[22] = s->channel_pwr;
+    out24[23] = (float)s->channel_squelched;
+}
+
+int
+ref_demod_get_fll_taps(void* h, float* lower_r, float* lower_i, float* upper_r, float* upper_i, int cap) {
+    demod_state* s = (demod_state*)h;
+    int n = s->fll_band_edge_state.n_taps;
+    if (n > cap) {
+        n = cap;
+    }
+    memcpy(lower_r, s->fll_band_edge_state.taps_lower_r, (size_t)n * sizeof(float));
+    memcpy(lower_i, s->fll_band_edge_state.taps_lower_i, (size_t)n * sizeof(float));
+    memcpy(upper_r, s->fll_band_edge_state.taps_upper_r, (size_t)n * sizeof(float));
+    memcpy(upper_i, s->fll_band_edge_state.taps_upper_i, (size_t)n * sizeof(float));
+    return s->fll_band_edge_state.n_taps;
 }
 
 void

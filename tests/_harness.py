@@ -561,3 +561,183 @@ def conv_k5_encode(bits):
         g2 = ((sr >> 0) ^ (sr >> 1) ^ (sr >> 2) ^ (sr >> 4)) & 1
         out += [g1, g2]
     return np.array(out, dtype=np.uint8)
+
+
+# --------------------------------------------------------------------------- CQPSK block side (section 8f rank 3)
+
+FLL_MAX_TAPS = 48
+CQPSK_RING = 64
+
+
+class OracleCqpskChan(C.Structure):
+    _fields_ = [
+        ("rate_out_hz", C.c_int), ("sps", C.c_int), ("ted_gain", C.c_float), ("ted_gain_is_set", C.c_int),
+        ("agc_avg", C.c_float),
+        ("fll_ntaps", C.c_int),
+        ("fll_alpha", C.c_float), ("fll_beta", C.c_float), ("fll_phase", C.c_float), ("fll_freq", C.c_float),
+        ("fll_lower_r", C.c_float * FLL_MAX_TAPS), ("fll_lower_i", C.c_float * FLL_MAX_TAPS),
+        ("fll_upper_r", C.c_float * FLL_MAX_TAPS), ("fll_upper_i", C.c_float * FLL_MAX_TAPS),
+        ("ring_r", C.c_float * CQPSK_RING), ("ring_j", C.c_float * CQPSK_RING),
+        ("pushed", C.c_long), ("consumed", C.c_long),
+        ("mu", C.c_float), ("omega", C.c_float), ("omega_mid", C.c_float), ("omega_rel", C.c_float),
+        ("last_r", C.c_float), ("last_j", C.c_float), ("lock_accum", C.c_float), ("ted_effective_gain", C.c_float),
+        ("lock_count", C.c_int), ("ted_span", C.c_int),
+        ("diff_prev_r", C.c_float), ("diff_prev_j", C.c_float),
+        ("costas_alpha", C.c_float), ("costas_beta", C.c_float), ("costas_phase", C.c_float), ("costas_freq", C.c_float),
+        ("costas_err_smooth", C.c_float), ("costas_error", C.c_float),
+        ("m_err_abs", C.c_float), ("m_err_raw_abs", C.c_float), ("m_conf_acc", C.c_float), ("m_zero_conf", C.c_int),
+        ("costas_err_avg_q14", C.c_int), ("costas_err_raw_avg_q14", C.c_int), ("costas_conf_avg_q14", C.c_int),
+        ("costas_zero_conf_pct", C.c_int),
+    ]
+
+
+CQPSK_STATE_KEYS = ["agc_avg", "fll_phase", "fll_freq", "fll_alpha", "fll_beta", "mu", "omega", "last_r", "last_j",
+                    "lock_accum", "lock_count", "ted_effective_gain", "diff_prev_r", "diff_prev_j", "costas_phase",
+                    "costas_freq", "costas_error", "costas_err_smooth", "costas_err_avg_q14", "costas_err_raw_avg_q14",
+                    "costas_conf_avg_q14", "costas_zero_conf_pct", "channel_pwr", "channel_squelched"]
+
+
+def oracle_cqpsk():
+    L = oracle()
+    L.oracle_cqpsk_chan_init.argtypes = [C.POINTER(OracleCqpskChan), C.c_int, C.c_int, C.c_float, C.c_int]
+    L.oracle_cqpsk_block.argtypes = [C.POINTER(OracleCqpskChan), f32p, C.c_int, f32p]
+    L.oracle_full_demod_cqpsk_block.argtypes = [C.POINTER(OracleDemodChan), C.POINTER(OracleCqpskChan), f32p, C.c_int,
+                                                f32p, f32p]
+    L.oracle_fll_band_edge_design.argtypes = [C.c_int, f32p, f32p, f32p, f32p, C.c_int]
+    L.oracle_cqpsk_mmse_table.restype = C.POINTER(C.c_float)
+    return L
+
+
+class OracleCqpsk:
+    """One channel of the CQPSK oracle: full_demod() with output_kind == SYMBOL_CQPSK, block by block."""
+
+    def __init__(self, rate=24000, sps=5, lpf_enable=1, squelch=0.0, fir_fma=0, ted_gain=0.0, ted_gain_is_set=0):
+        self.L = oracle_cqpsk()
+        self.c, self.q = OracleDemodChan(), OracleCqpskChan()
+        assert self.L.oracle_demod_chan_init(C.byref(self.c), rate, 5, lpf_enable, squelch, fir_fma) == 0
+        assert self.L.oracle_cqpsk_chan_init(C.byref(self.q), rate, sps, ted_gain, ted_gain_is_set) == 0
+
+    def block(self, iq_block):
+        blk = np.ascontiguousarray(iq_block, dtype=np.float32).reshape(-1)
+        out = np.empty(blk.size // 2 + 2, dtype=np.float32)
+        scratch = np.empty(blk.size, dtype=np.float32)
+        n = self.L.oracle_full_demod_cqpsk_block(C.byref(self.c), C.byref(self.q), _ptr(blk), blk.size, _ptr(scratch),
+                                                 _ptr(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    def run(self, iq_ch, block_pairs, n_blocks):
+        outs = [self.block(iq_ch[b * block_pairs:(b + 1) * block_pairs]) for b in range(n_blocks)]
+        return np.concatenate(outs), np.array([o.size for o in outs], np.int32)
+
+    def state(self):
+        q, c = self.q, self.c
+        d = {k: getattr(q, k) for k in CQPSK_STATE_KEYS if hasattr(q, k)}
+        d["channel_pwr"], d["channel_squelched"] = c.channel_pwr, c.channel_squelched
+        return d
+
+
+class RefCqpsk:
+    """One reference `struct demod_state` in CQPSK symbol mode, driven through the reference's own full_demod()."""
+
+    def __init__(self, variant="par", rate=24000, symrate=4800, sps=5, lpf_enable=1, squelch=0.0, ted_gain=0.0,
+                 ted_gain_is_set=0):
+        self.L = ref(variant)
+        assert self.L is not None
+        self.L.ref_demod_create_cqpsk.restype = C.c_void_p
+        self.L.ref_demod_create_cqpsk.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+        self.L.ref_demod_get_cqpsk_state.argtypes = [C.c_void_p, f32p]
+        self.L.ref_demod_get_fll_taps.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, C.c_int]
+        self.h = self.L.ref_demod_create_cqpsk(rate, symrate, sps, lpf_enable, squelch, ted_gain, ted_gain_is_set)
+        assert self.h
+
+    def block(self, iq_block):
+        blk = np.ascontiguousarray(iq_block, dtype=np.float32).reshape(-1)
+        out = np.empty(blk.size // 2 + 2, dtype=np.float32)
+        n = self.L.ref_demod_block(self.h, _ptr(blk), blk.size, _ptr(out), out.size)
+        assert 0 <= n <= out.size, n
+        return out[:n].copy()
+
+    def run(self, iq_ch, block_pairs, n_blocks):
+        outs = [self.block(iq_ch[b * block_pairs:(b + 1) * block_pairs]) for b in range(n_blocks)]
+        return np.concatenate(outs), np.array([o.size for o in outs], np.int32)
+
+    def state(self):
+        s = np.zeros(24, dtype=np.float32)
+        self.L.ref_demod_get_cqpsk_state(self.h, _ptr(s))
+        d = dict(zip(CQPSK_STATE_KEYS, s.tolist()))
+        for k in ("lock_count", "costas_err_avg_q14", "costas_err_raw_avg_q14", "costas_conf_avg_q14",
+                  "costas_zero_conf_pct", "channel_squelched"):
+            d[k] = int(d[k])
+        return d
+
+    def fll_taps(self):
+        bufs = [np.zeros(FLL_MAX_TAPS, np.float32) for _ in range(4)]
+        n = self.L.ref_demod_get_fll_taps(self.h, *[_ptr(b) for b in bufs], FLL_MAX_TAPS)
+        return [b[:n].copy() for b in bufs]
+
+    def close(self):
+        if self.h:
+            self.L.ref_demod_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def cqpsk_state_equal(a, b):
+    """Bit-level comparison of two CQPSK state dicts (floats compared as float32 bit patterns)."""
+    bad = []
+    for k in CQPSK_STATE_KEYS:
+        if k not in a or k not in b:
+            continue
+        x, y = a[k], b[k]
+        if isinstance(x, int) and isinstance(y, int):
+            same = x == y
+        else:
+            same = np.float32(x).tobytes() == np.float32(y).tobytes()
+        if not same:
+            bad.append((k, x, y))
+    return bad
+
+
+def rrc_taps(sps, span=8, alpha=0.2):
+    """Root-raised-cosine pulse, unit energy (standard closed form; signal synthesis only)."""
+    n = np.arange(-span * sps, span * sps + 1, dtype=np.float64) / sps
+    h = np.zeros_like(n)
+    for i, t in enumerate(n):
+        if abs(t) < 1e-12:
+            h[i] = 1.0 - alpha + 4 * alpha / np.pi
+        elif abs(abs(t) - 1 / (4 * alpha)) < 1e-9:
+            h[i] = alpha / np.sqrt(2) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * alpha)) + (1 - 2 / np.pi) * np.cos(np.pi / (4 * alpha)))
+        else:
+            h[i] = (np.sin(np.pi * t * (1 - alpha)) + 4 * alpha * t * np.cos(np.pi * t * (1 + alpha))) / (np.pi * t * (1 - (4 * alpha * t) ** 2))
+    return h / np.sqrt((h ** 2).sum())
+
+
+def synth_cqpsk_iq(rng, n_symbols, sps=5, amp=0.6, snr_db=None, cfo=0.0, dibits=None, timing=0.0, phase0=0.3):
+    """pi/4-DQPSK (P25 LSM-like): each dibit advances the carrier phase by {+1,+3,-1,-3} x pi/4 (same dibit map as
+    the 4-level slicer), impulses shaped by a raised-cosine pulse (RRC twice), `cfo` rad/sample carrier offset, a
+    fractional `timing` offset in samples, complex AWGN at `snr_db` Es/N0.  Returns ([n, 2] float32, dibits)."""
+    if dibits is None:
+        dibits = rng.integers(0, 4, n_symbols)
+    steps = LEVELS[dibits] * (np.pi / 4)
+    ph = phase0 + np.cumsum(steps)
+    sym = np.exp(1j * ph)
+    up = np.zeros(n_symbols * sps, np.complex128)
+    up[::sps] = sym
+    h = rrc_taps(sps)
+    rc = np.convolve(h, h)
+    if timing:
+        # fractional delay by linear-phase interpolation of the pulse
+        t = np.arange(rc.size, dtype=np.float64)
+        rc = np.interp(t - timing, t, rc, left=0.0, right=0.0)
+    x = np.convolve(up, rc)[rc.size // 2: rc.size // 2 + n_symbols * sps]
+    x = x / np.sqrt(np.mean(np.abs(x) ** 2)) * amp
+    n = np.arange(x.size)
+    x = x * np.exp(1j * cfo * n)
+    if snr_db is not None:
+        es = amp * amp * sps
+        n0 = es / (10 ** (snr_db / 10))
+        x = x + (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size)) * np.sqrt(n0 / 2)
+    out = np.stack([x.real, x.imag], axis=1).astype(np.float32)
+    return out, dibits

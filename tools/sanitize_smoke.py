@@ -1,0 +1,55 @@
+"""Small pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck): tiny shapes, no timing."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g
+import _harness as H
+
+b200 = g.load_package()
+b200.init(0)
+rng = np.random.default_rng(1)
+M, bp, nb = 256, 512, 2
+x, _ = H.synth_wideband(rng, M, bp * nb, [5, 77], snr_db=25.0)
+fe = b200.Frontend(M, 8, False, 12_288_000, bp)
+out = torch.empty((M, bp * nb), device="cuda")
+for _ in range(2):
+    fe.process_async(torch.from_numpy(x).cuda(), out)
+fe.join()
+disc = fe.process(torch.from_numpy(x).cuda())
+bank = b200.DemodBank(40, 48000, True, squelch_levels=[0.0] * 20 + [1e-3] * 20)
+bank.full_demod(torch.randn((40, 700, 2), device="cuda") * 0.2, 350, 2)
+hb = b200.HalfbandCascade(3, 3)
+hb.decimate(torch.randn((3, 1024, 2), device="cuda"), 512, 2)
+taps = {0: H.sps_fir_taps(0, 10), 1: H.sps_fir_taps(1, 10)}
+sy = b200.Symbolizer(M, 48000, 4800, filters=taps)
+sy.set_class([b200.sym_class_from_synctype(0, 0) if c % 2 else b200.sym_class_from_synctype(10, 10) for c in range(M)])
+res = sy.run(disc, bp * nb)
+res = sy.run(disc, bp * nb, mode=b200.SYM_MODE_GET_SYMBOL, have_sync=0)
+fs = b200.FrameSync(M)
+fs.search(res["symbols"], res["count"])
+b200.bptc_196x96(rng.integers(0, 2, (64, 196)).astype(np.uint8), interleaved=True)
+b200.bptc_128x77(rng.integers(0, 2, (64, 128)).astype(np.uint8))
+b200.bptc_16x2(rng.integers(0, 2, (64, 32)).astype(np.uint8), True)
+b200.p25_12_soft_llr(rng.integers(-300, 300, (32, 196)).astype(np.int16))
+b200.p25_12_soft_llr_list(rng.integers(-300, 300, (32, 196)).astype(np.int16))
+d, p = rng.integers(0, 2, (32, 120)).astype(np.uint8), rng.integers(0, 2, (32, 96)).astype(np.uint8)
+b200.p25_rs_decode(0, d.copy(), p)
+b200.p25_rs_soft_reliability(0, d, p, rng.integers(0, 255, (32, 20)).astype(np.uint8), rng.integers(0, 255, (32, 16)).astype(np.uint8))
+b200.p25_word_decode(0, rng.integers(0, 2, (32, 6)).astype(np.uint8), rng.integers(0, 2, (32, 12)).astype(np.uint8))
+b200.bch_63_16_decode(rng.integers(0, 2, (32, 63)).astype(np.uint8))
+cur = (b200.MbeParms * 8)()
+prev = (b200.MbeParms * 8)()
+for i in range(8):
+    for q in (cur[i], prev[i]):
+        q.w0, q.L = 0.05 + 0.01 * i, 20 + i
+        for l in range(1, q.L + 1):
+            q.Vl[l], q.Ml[l] = l % 2, 10.0 + l
+b200.mbe_synth(cur, prev)
+torch.cuda.synchronize()
+print("sanitize_smoke done, launches =", b200.launch_count())
