@@ -218,6 +218,119 @@ class DemodBank:
         return out
 
 
+class CqpskBankConfig(C.Structure):
+    _fields_ = [
+        ("n_channels", C.c_int),
+        ("rate_out_hz", C.c_int),
+        ("ted_sps", C.POINTER(C.c_int)),
+        ("ted_gain", C.c_float),
+        ("ted_gain_is_set", C.c_int),
+    ]
+
+
+class CqpskChanState(C.Structure):
+    _fields_ = [
+        ("cqpsk_agc_avg", C.c_float),
+        ("fll_phase", C.c_float), ("fll_freq", C.c_float), ("fll_alpha", C.c_float), ("fll_beta", C.c_float),
+        ("ted_mu", C.c_float), ("ted_omega", C.c_float), ("ted_last_r", C.c_float), ("ted_last_j", C.c_float),
+        ("ted_lock_accum", C.c_float), ("ted_lock_count", C.c_int), ("ted_effective_gain", C.c_float),
+        ("cqpsk_diff_prev_r", C.c_float), ("cqpsk_diff_prev_j", C.c_float),
+        ("costas_phase", C.c_float), ("costas_freq", C.c_float), ("costas_error", C.c_float),
+        ("costas_error_smooth", C.c_float),
+        ("costas_err_avg_q14", C.c_int), ("costas_err_raw_avg_q14", C.c_int), ("costas_conf_avg_q14", C.c_int),
+        ("costas_zero_conf_pct", C.c_int), ("overflow", C.c_int),
+    ]
+
+
+class CqpskBank:
+    """N-channel twin of full_demod() for the CQPSK symbol output kind (AGC -> FLL -> Gardner -> diff -> Costas ->
+    4/pi atan): owns the channel-LPF bank (profile P25_CQPSK by default) and the per-channel loop state."""
+
+    def __init__(self, n_channels: int, rate_out_hz: int = 24000, ted_sps=None, channel_lpf_enable: bool = True,
+                 profiles=None, squelch_levels=None, fir_arith: int = FIR_ARITH_FMA, ted_gain: float = 0.0,
+                 ted_gain_is_set: bool = False):
+        self.lpf = DemodBank(n_channels, rate_out_hz, channel_lpf_enable,
+                             profiles if profiles is not None else [5] * n_channels, squelch_levels, fir_arith)
+        cfg = CqpskBankConfig()
+        cfg.n_channels = n_channels
+        cfg.rate_out_hz = rate_out_hz
+        self._sps = (C.c_int * n_channels)(*ted_sps) if ted_sps is not None else None
+        cfg.ted_sps = self._sps if self._sps is not None else None
+        cfg.ted_gain = ted_gain
+        cfg.ted_gain_is_set = 1 if ted_gain_is_set else 0
+        self.n_channels = n_channels
+        self.min_sps = min(ted_sps) if ted_sps is not None else 5
+        self._h = lib().dsdneo_b200_cqpsk_bank_create(C.byref(cfg))
+        if not self._h:
+            raise B200Error(f"cqpsk_bank_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().dsdneo_b200_cqpsk_bank_destroy(self._h)
+            self._h = None
+        if getattr(self, "lpf", None):
+            self.lpf.close()
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        self.lpf.reset(stream)
+        check(lib().dsdneo_b200_cqpsk_bank_reset(self._h, _stream_ptr(stream)), "cqpsk_bank_reset")
+
+    def state(self, channel: int) -> CqpskChanState:
+        st = CqpskChanState()
+        check(lib().dsdneo_b200_cqpsk_bank_get_state(self._h, channel, C.byref(st)), "cqpsk_bank_get_state")
+        return st
+
+    def fll_taps(self, channel: int):
+        import numpy as np
+
+        bufs = [np.zeros(48, np.float32) for _ in range(4)]
+        n = check(lib().dsdneo_b200_cqpsk_bank_get_fll_taps(self._h, channel, *[b.ctypes.data for b in bufs], 48), "fll_taps")
+        return [b[:n].copy() for b in bufs]
+
+    def block_capacity(self, block_pairs: int) -> int:
+        return check(lib().dsdneo_b200_cqpsk_block_capacity(block_pairs, self.min_sps), "cqpsk_block_capacity")
+
+    def full_demod(self, d_iq, block_pairs: int, n_blocks: int, stream=None):
+        """d_iq: torch cuda float32 [n_channels, pitch_pairs, 2].  Returns (symbols [n_channels, pitch] f32 with the
+        blocks' symbols back to back, counts [n_channels, n_blocks] int32)."""
+        import torch
+
+        assert d_iq.is_cuda and d_iq.dtype == torch.float32 and d_iq.is_contiguous()
+        assert d_iq.shape[0] == self.n_channels and d_iq.shape[-1] == 2
+        pitch = self.block_capacity(block_pairs) * n_blocks
+        sym = torch.zeros((self.n_channels, pitch), dtype=torch.float32, device=d_iq.device)
+        counts = torch.zeros((self.n_channels, n_blocks), dtype=torch.int32, device=d_iq.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_iq.device)
+        check(
+            lib().dsdneo_b200_full_demod_cqpsk_batch(
+                self.lpf._h, self._h, d_iq.data_ptr(), d_iq.shape[1], block_pairs, n_blocks, sym.data_ptr(), pitch,
+                counts.data_ptr(), _stream_ptr(stream),
+            ),
+            "full_demod_cqpsk_batch",
+        )
+        return sym, counts
+
+    def full_demod_host(self, h_iq, block_pairs: int, n_blocks: int):
+        import numpy as np
+
+        h_iq = np.ascontiguousarray(h_iq, dtype=np.float32)
+        assert h_iq.shape[0] == self.n_channels and h_iq.shape[-1] == 2
+        pitch = self.block_capacity(block_pairs) * n_blocks
+        sym = np.zeros((self.n_channels, pitch), np.float32)
+        counts = np.zeros((self.n_channels, n_blocks), np.int32)
+        check(
+            lib().dsdneo_b200_full_demod_cqpsk_batch_host(
+                self.lpf._h, self._h, h_iq.ctypes.data, h_iq.shape[1], block_pairs, n_blocks, sym.ctypes.data, pitch,
+                counts.ctypes.data,
+            ),
+            "full_demod_cqpsk_batch_host",
+        )
+        return sym, counts
+
+
 class SyncPattern(C.Structure):
     _fields_ = [("symbols", C.c_char_p), ("sync_type", C.c_int)]
 

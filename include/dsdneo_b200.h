@@ -168,6 +168,78 @@ int dsdneo_b200_full_demod_batch(dsdneo_b200_demod_bank* bank, const float* d_iq
 int dsdneo_b200_full_demod_batch_host(dsdneo_b200_demod_bank* bank, const float* h_iq, size_t iq_pitch_pairs,
                                       int block_pairs, int n_blocks, float* h_result, size_t result_pitch);
 
+/* ---- CQPSK symbol output kind of full_demod ------------------------ */
+
+/**
+ * The reference's OP25-style CQPSK chain for P25 LSM / simulcast and P25 Phase 2 channels, batched over a bank of
+ * channels.  Per channel and per block this is what full_demod() runs when `cqpsk_enable = 1` and
+ * `output_kind = DSD_DEMOD_OUTPUT_SYMBOL_CQPSK` (src/dsp/demod_pipeline.cpp:1100-1117,1330-1350):
+ *   cqpsk_rms_agc            src/dsp/demod_pipeline.cpp:796-842      (alpha 0.45, reference 0.85)
+ *   op25_fll_band_edge_cc    src/dsp/costas.cpp:1176-1224            (2 sps + 1 band-edge taps, loop_bw 2 pi / sps / 350)
+ *   op25_gardner_cc          src/dsp/costas.cpp:804-858              (8-tap MMSE interpolator, src/dsp/mmse_interp.cpp)
+ *   op25_diff_phasor_cc      src/dsp/costas.cpp:872-902
+ *   op25_costas_loop_cc      src/dsp/costas.cpp:935-961              (symbol rate, loop_bw 0.008, phase clamped to +-pi/2)
+ *   qpsk_differential_demod  src/dsp/demod_pipeline.cpp:742-764      (4/pi atan approximation -> {-3,-1,+1,+3})
+ * A squelched block yields ceil(block_pairs / sps) zero symbols and leaves every loop untouched (:1022-1040).
+ *
+ * Carried per channel: AGC average, FLL {phase, freq, delay line}, ted_state_t {mu, omega, last sample, lock
+ * accumulator, delay line}, cqpsk_diff_prev, dsd_costas_loop_state_t {phase, freq, error, error_smooth}; the FLL and
+ * Gardner delay lines are one ring of the FLL's outputs on the device.  Results (symbols, counts, state) are
+ * bit-identical to the reference built without -ffast-math / FMA contraction.
+ * Out of contract: non-finite input samples, blocks shorter than 4 pairs (the reference then skips timing recovery,
+ * costas.cpp:811-813), a change of sps on a live channel (create a new bank), sps outside 2..10.
+ */
+typedef struct dsdneo_b200_cqpsk_bank dsdneo_b200_cqpsk_bank;
+
+typedef struct dsdneo_b200_cqpsk_bank_config {
+    int n_channels;
+    int rate_out_hz;     /* demod_state.rate_out (24000 or 48000 in the reference's own configurations) */
+    const int* ted_sps;  /* per channel demod_state.ted_sps (NULL: 5 everywhere = P25p1 at 24 kHz) */
+    float ted_gain;      /* demod_state.ted_gain; <= 0 selects the OP25 default 0.025 (costas.cpp:145) */
+    int ted_gain_is_set; /* demod_state.ted_gain_is_set: 1 disables the locked-loop gain 0.018 at >= 5500 sym/s */
+} dsdneo_b200_cqpsk_bank_config;
+
+/** Snapshot of one channel's carried CQPSK state (field names follow the reference structs). */
+typedef struct dsdneo_b200_cqpsk_chan_state {
+    float cqpsk_agc_avg;
+    float fll_phase, fll_freq, fll_alpha, fll_beta;
+    float ted_mu, ted_omega, ted_last_r, ted_last_j, ted_lock_accum;
+    int ted_lock_count;
+    float ted_effective_gain;
+    float cqpsk_diff_prev_r, cqpsk_diff_prev_j;
+    float costas_phase, costas_freq, costas_error, costas_error_smooth;
+    int costas_err_avg_q14, costas_err_raw_avg_q14, costas_conf_avg_q14, costas_zero_conf_pct;
+    int overflow; /* 1 if a block produced more symbols than dsdneo_b200_cqpsk_block_capacity() allows (never on finite input) */
+} dsdneo_b200_cqpsk_chan_state;
+
+dsdneo_b200_cqpsk_bank* dsdneo_b200_cqpsk_bank_create(const dsdneo_b200_cqpsk_bank_config* cfg);
+void dsdneo_b200_cqpsk_bank_destroy(dsdneo_b200_cqpsk_bank* q);
+/** Fresh-channel state: ted_init_state + first-call initialisation of the FLL / Gardner / Costas blocks. */
+int dsdneo_b200_cqpsk_bank_reset(dsdneo_b200_cqpsk_bank* q, void* stream);
+int dsdneo_b200_cqpsk_bank_get_state(dsdneo_b200_cqpsk_bank* q, int channel, dsdneo_b200_cqpsk_chan_state* out);
+/** Band-edge filter taps of one channel (fll_band_edge_design_filter, costas.cpp:936-1024); returns n_taps. */
+int dsdneo_b200_cqpsk_bank_get_fll_taps(dsdneo_b200_cqpsk_bank* q, int channel, float* lower_r, float* lower_i,
+                                        float* upper_r, float* upper_i, int max_taps);
+/** Host-side band-edge filter design (same arithmetic as the reference, libm sinf/cosf); returns n_taps or <0. */
+int dsdneo_b200_fll_band_edge_design(int sps, float* lower_r, float* lower_i, float* upper_r, float* upper_i,
+                                     int max_taps);
+/** Symbols one block can produce per channel; `symbols_pitch` must be >= n_blocks * this value. */
+int dsdneo_b200_cqpsk_block_capacity(int block_pairs, int min_sps);
+
+/**
+ * Batched twin of full_demod() for the CQPSK symbol output kind: channel LPF (profile P25_CQPSK unless configured
+ * otherwise) + power / squelch from `bank`, then the chain above with the per-channel loop state of `q`.
+ * @param d_iq       [n_channels][iq_pitch_pairs] cf32, n_blocks consecutive blocks of block_pairs samples per channel
+ * @param d_symbols  [n_channels][symbols_pitch] f32: the blocks' symbols back to back (demod_state.result)
+ * @param d_counts   [n_channels][n_blocks] int: result_len of every block
+ */
+int dsdneo_b200_full_demod_cqpsk_batch(dsdneo_b200_demod_bank* bank, dsdneo_b200_cqpsk_bank* q, const float* d_iq,
+                                       size_t iq_pitch_pairs, int block_pairs, int n_blocks, float* d_symbols,
+                                       size_t symbols_pitch, int* d_counts, void* stream);
+int dsdneo_b200_full_demod_cqpsk_batch_host(dsdneo_b200_demod_bank* bank, dsdneo_b200_cqpsk_bank* q, const float* h_iq,
+                                            size_t iq_pitch_pairs, int block_pairs, int n_blocks, float* h_symbols,
+                                            size_t symbols_pitch, int* h_counts);
+
 /* ---- K2 (+K1): polyphase FIR channelizer -------------------------------------------------------- */
 
 /**

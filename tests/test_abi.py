@@ -71,3 +71,20 @@ def test_reference_side_glue_compiles_against_reference_headers():
     chk = ("#include <stdbool.h>\n#include <stdint.h>\n#include <dsd-neo/fec/block_codes.h>\n#include <dsd-neo/fec/bptc.h>\n"
            "#include <dsd-neo/protocol/p25/p25_12.h>\n#include \"%s\"\n" % os.path.join(ROOT, "dsd-neo_b200/compat/fec_b200.c"))
     subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-x", "c", "-"] + inc, input=chk, text=True, check=True)
+
+
+def test_host_side_fll_band_edge_design_matches_oracle(b200):
+    """dsdneo_b200_fll_band_edge_design (host/cqpsk_design.c) == the oracle's design (pinned to the reference's
+    fll_band_edge_design_filter by tests/test_oracle_cqpsk.py), bit for bit, for every supported sps."""
+    import numpy as np
+
+    L, O = b200.lib(), H.oracle_cqpsk()
+    for sps in range(2, 11):
+        got = [np.zeros(48, np.float32) for _ in range(4)]
+        want = [np.zeros(48, np.float32) for _ in range(4)]
+        n = L.dsdneo_b200_fll_band_edge_design(sps, *[g.ctypes.data for g in got], 48)
+        m = O.oracle_fll_band_edge_design(sps, *[H._ptr(w) for w in want], 48)
+        assert n == m == 2 * sps + 1
+        for g, w in zip(got, want):
+            assert H.bits_equal(g, w)
+    assert L.dsdneo_b200_cqpsk_block_capacity(2400, 5) >= 2400 // 5 + 2

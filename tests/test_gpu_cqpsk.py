@@ -1,0 +1,145 @@
+"""GPU parity tests (-m gpu): the batched CQPSK symbol output kind of full_demod (AGC -> FLL band-edge -> Gardner/MMSE ->
+diff phasor -> Costas -> 4/pi atan) through the C-ABI against the CPU oracle (oracle/oracle_cqpsk.c, itself pinned to
+the unmodified reference by tests/test_oracle_cqpsk.py) and the committed reference vectors (tests/golden/cqpsk.npz).
+Bar: bit-exact symbols, per-block counts and carried loop state."""
+import os
+
+import numpy as np
+import pytest
+
+import _harness as H
+
+pytestmark = pytest.mark.gpu
+
+STATE_MAP = [("agc_avg", "cqpsk_agc_avg"), ("fll_phase", "fll_phase"), ("fll_freq", "fll_freq"), ("fll_alpha", "fll_alpha"),
+             ("fll_beta", "fll_beta"), ("mu", "ted_mu"), ("omega", "ted_omega"), ("last_r", "ted_last_r"),
+             ("last_j", "ted_last_j"), ("lock_accum", "ted_lock_accum"), ("lock_count", "ted_lock_count"),
+             ("ted_effective_gain", "ted_effective_gain"), ("diff_prev_r", "cqpsk_diff_prev_r"),
+             ("diff_prev_j", "cqpsk_diff_prev_j"), ("costas_phase", "costas_phase"), ("costas_freq", "costas_freq"),
+             ("costas_error", "costas_error"), ("costas_err_smooth", "costas_error_smooth"),
+             ("costas_err_avg_q14", "costas_err_avg_q14"), ("costas_err_raw_avg_q14", "costas_err_raw_avg_q14"),
+             ("costas_conf_avg_q14", "costas_conf_avg_q14"), ("costas_zero_conf_pct", "costas_zero_conf_pct")]
+
+
+def _check_state(bank, c, orc):
+    st, lst, want = bank.state(c), bank.lpf.state(c), orc.state()
+    bad = []
+    for ok, gk in STATE_MAP:
+        a, b = want[ok], getattr(st, gk)
+        same = (a == b) if isinstance(a, int) else (np.float32(a).tobytes() == np.float32(b).tobytes())
+        if not same:
+            bad.append((ok, a, b))
+    if np.float32(want["channel_pwr"]).tobytes() != np.float32(lst.channel_pwr).tobytes():
+        bad.append(("channel_pwr", want["channel_pwr"], lst.channel_pwr))
+    if want["channel_squelched"] != lst.channel_squelched:
+        bad.append(("channel_squelched", want["channel_squelched"], lst.channel_squelched))
+    assert not bad, (c, bad)
+    assert st.overflow == 0
+
+
+def _compare(sym, counts, c, want_sym, want_counts):
+    assert np.array_equal(counts[c], want_counts), (c, counts[c], want_counts)
+    n = int(want_counts.sum())
+    assert H.bits_equal(sym[c, :n], want_sym), (c, H.first_mismatch(sym[c, :n], want_sym))
+
+
+def _signals(rng, n_ch, sps, n, snrs, cfos):
+    return np.stack([H.synth_cqpsk_iq(rng, n // sps + 2, sps=sps, snr_db=snrs[c % len(snrs)], cfo=cfos[c % len(cfos)],
+                                      timing=0.1 * c, phase0=0.2 * c)[0][:n] for c in range(n_ch)])
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("sps,rate,bp,nb", [(5, 24000, 2400, 4), (5, 24000, 997, 5), (4, 24000, 1600, 8), (10, 48000, 4800, 2),
+                                            (8, 48000, 3000, 5), (5, 24000, 36, 9), (5, 24000, 4, 40)])
+def test_cqpsk_bit_exact_vs_oracle(gpu, arith, sps, rate, bp, nb):
+    import torch
+
+    rng = np.random.default_rng(1000 + bp)
+    n_ch = 37  # two warps, the second one ragged
+    iq = _signals(rng, n_ch, sps, bp * nb, [None, 20.0, 12.0, 6.0, 2.0], [0.0, 0.02, -0.03, 0.08])
+    bank = gpu.CqpskBank(n_ch, rate, ted_sps=[sps] * n_ch, fir_arith=arith)
+    sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+    sym, counts = sym.cpu().numpy(), counts.cpu().numpy()
+    for c in range(n_ch):
+        orc = H.OracleCqpsk(rate=rate, sps=sps, fir_fma=1 - arith)
+        want_sym, want_counts = orc.run(iq[c], bp, nb)
+        _compare(sym, counts, c, want_sym, want_counts)
+        _check_state(bank, c, orc)
+
+
+def test_cqpsk_mixed_sps_squelch_and_launch_split(gpu):
+    """Channels of different sps in one warp, squelched blocks in some channels, and the same stream fed as three
+    launches: equals the oracle run block by block."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    n_ch, bp, nb, rate = 40, 1200, 6, 24000
+    sps = [5 if c % 3 else 4 for c in range(n_ch)]
+    iq = np.stack([H.synth_cqpsk_iq(rng, bp * nb // sps[c] + 2, sps=sps[c], snr_db=18.0, cfo=0.01 * (c % 5 - 2),
+                                    timing=0.07 * c)[0][:bp * nb] for c in range(n_ch)]).copy()
+    levels = [1e-3 if c % 4 == 1 else 0.0 for c in range(n_ch)]
+    for c in range(n_ch):
+        if c % 4 == 1:
+            iq[c, bp * (1 + c % 3):bp * (3 + c % 3)] *= np.float32(1e-4)
+    bank = gpu.CqpskBank(n_ch, rate, ted_sps=sps, squelch_levels=levels)
+    syms, cnts = [], []
+    for lo, hi in [(0, 1), (1, 4), (4, 6)]:
+        s, k = bank.full_demod(torch.from_numpy(np.ascontiguousarray(iq[:, lo * bp:hi * bp])).cuda(), bp, hi - lo)
+        syms.append(s.cpu().numpy())
+        cnts.append(k.cpu().numpy())
+    seen_sq = False
+    for c in range(n_ch):
+        orc = H.OracleCqpsk(rate=rate, sps=sps[c], squelch=levels[c], fir_fma=1)
+        for (lo, hi), s, k in zip([(0, 1), (1, 4), (4, 6)], syms, cnts):
+            want_sym, want_counts = orc.run(iq[c, lo * bp:hi * bp], bp, hi - lo)
+            _compare(s, k, c, want_sym, want_counts)
+            seen_sq = seen_sq or orc.state()["channel_squelched"] == 1 or bool((want_sym == 0).all() and want_sym.size)
+        _check_state(bank, c, orc)
+    assert seen_sq
+
+
+def test_cqpsk_golden_vectors(gpu):
+    """The committed outputs of the unmodified reference (tests/golden/cqpsk.npz), reference scalar/SSE2 FIR arithmetic."""
+    import torch
+
+    g = np.load(os.path.join(H.GOLDEN_DIR, "cqpsk.npz"))
+    for i in range(int(g["n_cases"])):
+        sps, rate, bp, nb = [int(v) for v in g[f"cfg{i}"]]
+        iq = g[f"iq{i}"].astype(np.float32)[None]
+        bank = gpu.CqpskBank(1, rate, ted_sps=[sps], squelch_levels=[float(g[f"squelch{i}"])], fir_arith=1)
+        sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+        _compare(sym.cpu().numpy(), counts.cpu().numpy(), 0, g[f"sym{i}"], g[f"counts{i}"])
+
+
+def test_cqpsk_host_entry_point_and_taps(gpu):
+    rng = np.random.default_rng(3)
+    n_ch, bp, nb = 3, 1000, 3
+    iq = _signals(rng, n_ch, 5, bp * nb, [15.0], [0.01])
+    bank = gpu.CqpskBank(n_ch, 24000)
+    sym, counts = bank.full_demod_host(iq, bp, nb)
+    L = H.oracle_cqpsk()
+    for c in range(n_ch):
+        orc = H.OracleCqpsk(fir_fma=1)
+        want_sym, want_counts = orc.run(iq[c], bp, nb)
+        _compare(sym, counts, c, want_sym, want_counts)
+    want = [np.zeros(H.FLL_MAX_TAPS, np.float32) for _ in range(4)]
+    n = L.oracle_fll_band_edge_design(5, *[H._ptr(w) for w in want], H.FLL_MAX_TAPS)
+    for got, w in zip(bank.fll_taps(0), want):
+        assert got.size == n and H.bits_equal(got, w[:n])
+
+
+def test_cqpsk_many_channels_independent(gpu):
+    """1024 channels (C3-sized bank): every channel equals the same channel run alone in a one-channel bank."""
+    import torch
+
+    rng = np.random.default_rng(9)
+    n_ch, bp, nb = 1024, 2400, 2
+    base = _signals(rng, 16, 5, bp * nb, [None, 14.0, 8.0], [0.0, 0.03, -0.02])
+    iq = np.ascontiguousarray(base[np.arange(n_ch) % 16] * (0.5 + (np.arange(n_ch) % 7)[:, None, None] * 0.1)).astype(np.float32)
+    bank = gpu.CqpskBank(n_ch, 24000)
+    sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+    sym, counts = sym.cpu().numpy(), counts.cpu().numpy()
+    for c in [0, 31, 32, 500, 777, 1023]:
+        orc = H.OracleCqpsk(fir_fma=1)
+        want_sym, want_counts = orc.run(iq[c], bp, nb)
+        _compare(sym, counts, c, want_sym, want_counts)
