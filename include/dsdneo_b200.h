@@ -709,6 +709,12 @@ int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out
  *  evaluates it (d_fast) next to the device's IEEE division (d_ieee), so tests can check they agree bit for bit. */
 int dsdneo_b200_selftest_scale(const float* d_pk, float* d_fast, float* d_ieee, int n, void* stream);
 
+/** Self-test hook: the CQPSK chain's branch-free division a / b and square root sqrt(a) (csrc/cqpsk.cu) next to the
+ *  device's IEEE operators; d_flags bit 0 / bit 1 = the sequence declared the division / square root operands inside its
+ *  safe range (outside it the kernel re-runs the symbol with the plain operators). */
+int dsdneo_b200_selftest_divsqrt(const float* d_a, const float* d_b, float* d_q_fast, float* d_q_ieee, float* d_s_fast,
+                                 float* d_s_ieee, unsigned char* d_flags, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,54 @@ def test_cqpsk_many_channels_independent(gpu):
         orc = H.OracleCqpsk(fir_fma=1)
         want_sym, want_counts = orc.run(iq[c], bp, nb)
         _compare(sym, counts, c, want_sym, want_counts)
+
+
+def test_cqpsk_slow_path_inputs(gpu):
+    """Inputs that push the speculative fast paths out of their safe range -- silent (all-zero) stretches, amplitudes
+    around 1e-20 and 1e15, a channel that is zero from the start -- still match the oracle bit for bit (the kernel
+    re-runs those chunks / symbols with the plain operators)."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    n_ch, bp, nb = 8, 1200, 5
+    iq = _signals(rng, n_ch, 5, bp * nb, [20.0, 10.0], [0.01, -0.02]).copy()
+    iq[1] *= np.float32(1e-20)
+    iq[2] *= np.float32(1e15)
+    iq[3][:] = 0.0
+    iq[4][1500:3200] = 0.0
+    iq[5][::7] = 0.0
+    iq[6] *= np.float32(3e-12)
+    iq[7][4000:] *= np.float32(1e-30)
+    bank = gpu.CqpskBank(n_ch, 24000, channel_lpf_enable=False)
+    sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+    sym, counts = sym.cpu().numpy(), counts.cpu().numpy()
+    for c in range(n_ch):
+        orc = H.OracleCqpsk(lpf_enable=0, fir_fma=1)
+        want_sym, want_counts = orc.run(iq[c], bp, nb)
+        _compare(sym, counts, c, want_sym, want_counts)
+        _check_state(bank, c, orc)
+
+
+def test_branch_free_div_sqrt_match_ieee(gpu):
+    """The kernel's branch-free a / b and sqrt(a) equal the IEEE operators bit for bit wherever they declare their
+    operands safe (2^24 random pairs across the whole exponent range plus the values the chain produces)."""
+    import torch
+
+    n = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bits = torch.randint(0, 2 ** 31 - 1, (2, n), generator=g, device="cuda", dtype=torch.int32)
+    a = bits[0].view(torch.float32).clone()
+    b = bits[1].view(torch.float32).clone()
+    a[: n // 2] = torch.rand(n // 2, generator=g, device="cuda") * 2.0          # the chain's own range
+    b[: n // 2] = torch.rand(n // 2, generator=g, device="cuda") * 2.0 + 1e-3
+    b[::2] = -b[::2]
+    outs = [torch.empty(n, device="cuda") for _ in range(4)]
+    flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    gpu.check(gpu.lib().dsdneo_b200_selftest_divsqrt(a.data_ptr(), b.data_ptr(), *[o.data_ptr() for o in outs],
+                                                     flags.data_ptr(), n, None))
+    torch.cuda.synchronize()
+    qf, qi, sf, si = [o.view(torch.int32) for o in outs]
+    ok_d, ok_s = (flags & 1) != 0, (flags & 2) != 0
+    assert int(ok_d.sum()) > n // 3 and int(ok_s.sum()) > n // 3
+    assert int(((qf != qi) & ok_d).sum()) == 0
+    assert int(((sf != si) & ok_s).sum()) == 0
