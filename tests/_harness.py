@@ -741,3 +741,31 @@ def synth_cqpsk_iq(rng, n_symbols, sps=5, amp=0.6, snr_db=None, cfo=0.0, dibits=
         x = x + (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size)) * np.sqrt(n0 / 2)
     out = np.stack([x.real, x.imag], axis=1).astype(np.float32)
     return out, dibits
+
+
+def synth_wideband_cqpsk(rng, M, n_out, active, sps=10, snr_db=30.0, amp=0.5, cfo_hz_frac=0.0):
+    """Sum of pi/4-DQPSK carriers on the channelizer grid: channel k at k/M cycles/sample, each shaped at `sps` samples
+    per symbol of the CHANNEL rate and interpolated to the wideband rate.  `cfo_hz_frac` offsets every carrier by that
+    fraction of the channel spacing.  Returns ([n_out*M, 2] float32, {k: dibits})."""
+    n = n_out * M
+    t = np.arange(n, dtype=np.float64)
+    x = np.zeros(n, dtype=np.complex128)
+    truth = {}
+    for k in active:
+        nsym = n_out // sps + 2
+        base, dib = synth_cqpsk_iq(rng, nsym, sps=sps, amp=1.0, snr_db=None, cfo=0.0, timing=0.0, phase0=rng.uniform(0, 6.28))
+        b = (base[:, 0] + 1j * base[:, 1])[:n_out + 1]
+        # linear interpolation from the channel rate to the wideband rate (the images fall outside the channel filter)
+        pos = np.arange(n, dtype=np.float64) / M
+        i0 = np.minimum(pos.astype(np.int64), b.size - 2)
+        fr = pos - i0
+        up = b[i0] * (1 - fr) + b[i0 + 1] * fr
+        x += up * np.exp(2j * np.pi * ((k + cfo_hz_frac) / M) * t)
+        truth[k] = dib
+    x *= amp / max(1, len(active)) ** 0.5
+    sigma = amp * 10 ** (-snr_db / 20.0) / np.sqrt(2.0)
+    x += sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    out = np.empty((n, 2), dtype=np.float32)
+    out[:, 0] = x.real
+    out[:, 1] = x.imag
+    return out, truth
