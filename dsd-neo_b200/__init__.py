@@ -160,7 +160,7 @@ class DemodBank:
             raise B200Error(f"demod_bank_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_demod_bank_destroy(self._h)
             self._h = None
 
@@ -265,7 +265,7 @@ class CqpskBank:
             raise B200Error(f"cqpsk_bank_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_cqpsk_bank_destroy(self._h)
             self._h = None
         if getattr(self, "lpf", None):
@@ -367,7 +367,7 @@ class FrameSync:
             raise B200Error(f"frame_sync_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_frame_sync_destroy(self._h)
             self._h = None
 
@@ -403,7 +403,7 @@ class HalfbandCascade:
             raise B200Error(f"hb_cascade_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_hb_cascade_destroy(self._h)
             self._h = None
 
@@ -453,7 +453,7 @@ class Channelizer:
             raise B200Error(f"channelizer_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_channelizer_destroy(self._h)
             self._h = None
 
@@ -548,7 +548,7 @@ class Frontend:
             raise B200Error(f"frontend_create failed: {last_error()}")
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_frontend_destroy(self._h)
             self._h = None
 
@@ -868,7 +868,7 @@ class Symbolizer:
             raise B200Error(f"symbolizer_create failed: {last_error()}")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # lib is None while the interpreter shuts down
             lib().dsdneo_b200_symbolizer_destroy(self._h)
             self._h = None
 

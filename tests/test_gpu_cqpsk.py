@@ -194,3 +194,28 @@ def test_branch_free_div_sqrt_match_ieee(gpu):
     assert int(ok_d.sum()) > n // 3 and int(ok_s.sum()) > n // 3
     assert int(((qf != qi) & ok_d).sum()) == 0
     assert int(((sf != si) & ok_s).sum()) == 0
+
+
+def test_cqpsk_vs_compiled_reference(gpu):
+    """Directly against the unmodified reference full_demod() (oracle/_ref) when it travelled with the snapshot: symbols,
+    counts and loop state, reference scalar/SSE2 FIR arithmetic."""
+    import torch
+
+    if not H.ref_available("par"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(31)
+    for sps, rate, bp, nb in [(5, 24000, 1500, 4), (8, 48000, 2000, 4)]:
+        n_ch = 4
+        iq = _signals(rng, n_ch, sps, bp * nb, [None, 15.0, 6.0], [0.0, 0.03, -0.01])
+        bank = gpu.CqpskBank(n_ch, rate, ted_sps=[sps] * n_ch, fir_arith=1)
+        sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+        sym, counts = sym.cpu().numpy(), counts.cpu().numpy()
+        for c in range(n_ch):
+            r = H.RefCqpsk("par", rate=rate, symrate=rate // sps, sps=sps)
+            want_sym, want_counts = r.run(iq[c], bp, nb)
+            _compare(sym, counts, c, want_sym, want_counts)
+            want, st = r.state(), bank.state(c)
+            for ok, gk in STATE_MAP:
+                a, b = want[ok], getattr(st, gk)
+                same = (a == b) if isinstance(a, int) else (np.float32(a).tobytes() == np.float32(b).tobytes())
+                assert same, (c, ok, a, b)

@@ -15,4 +15,10 @@ python tools/c3_bench.py 1024 2>/dev/null | grep '^{' > gpurun_out/c3_1024.json
 python tools/c3_bench.py 4096 2>/dev/null | grep '^{' > gpurun_out/c3_4096.json
 ncu --set full --clock-control none --import-source on -k regex:'symbolize_kernel|sps_fir_kernel' -s 6 -c 2 -f -o gpurun_out/ncu_symbolizer \
     python tools/c3_bench.py 1024 > gpurun_out/ncu_symbolizer.log 2>&1
+rm -f gpurun_out/cqpsk_bench.jsonl
+for n in 256 1024 4096 8192; do python tools/cqpsk_bench.py $n 2>/dev/null | grep '^{' >> gpurun_out/cqpsk_bench.jsonl; done
+python tools/cqpsk_bench.py 1024 48000 10 2>/dev/null | grep '^{' >> gpurun_out/cqpsk_bench.jsonl
+python tools/cqpsk_bench.py 1024 48000 8 2>/dev/null | grep '^{' >> gpurun_out/cqpsk_bench.jsonl
+ncu --set full --clock-control none --import-source on -k regex:'cqpsk_chain_kernel' -s 4 -c 1 -f -o gpurun_out/ncu_cqpsk_chain_kernel \
+    python tools/cqpsk_bench.py 1024 > gpurun_out/ncu_cqpsk_chain_kernel.log 2>&1
 ls -la gpurun_out/
