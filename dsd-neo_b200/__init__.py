@@ -773,6 +773,59 @@ def symbol_capture_unpack(data: bytes):
 P25_WORD_GOLAY_24_6, P25_WORD_GOLAY_24_12, P25_WORD_HAMMING_10_6_3 = 0, 1, 2
 
 
+def p25p1_nid_decode(code63, reliab63=None, observed_nac=None, parity=None, parity_reliab=None, threshold: int = 64):
+    """Batched p25p1_nid_decode on host arrays: code63 [n, 63] uint8 bits, reliab63 [n, 63] uint8 or None, observed_nac [n]
+    int32 or None, parity [n] uint8, parity_reliab [n] uint8 or None.  Returns (status int8, nac int32, duid uint8, errs int32)."""
+    import numpy as np
+
+    code63 = np.ascontiguousarray(code63, dtype=np.uint8)
+    n = code63.shape[0]
+    parity = np.ascontiguousarray(parity, dtype=np.uint8)
+    rel = None if reliab63 is None else np.ascontiguousarray(reliab63, dtype=np.uint8)
+    obs = None if observed_nac is None else np.ascontiguousarray(observed_nac, dtype=np.int32)
+    prel = None if parity_reliab is None else np.ascontiguousarray(parity_reliab, dtype=np.uint8)
+    st, nac, duid, errs = np.zeros(n, np.int8), np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros(n, np.int32)
+    check(
+        lib().dsdneo_b200_p25p1_nid_decode_batch_host(
+            code63.ctypes.data, None if rel is None else rel.ctypes.data, None if obs is None else obs.ctypes.data,
+            parity.ctypes.data, None if prel is None else prel.ctypes.data, threshold, st.ctypes.data, nac.ctypes.data,
+            duid.ctypes.data, errs.ctypes.data, n,
+        ),
+        "p25p1_nid_decode_batch_host",
+    )
+    return st, nac, duid, errs
+
+
+def p25p1_frame_cut(d_dibits, d_llr, d_counts, d_hits, d_n_hits, n_payload: int, stream=None):
+    """Device-side P25p1 frame cutter on the symbolizer / frame-sync outputs (torch cuda tensors).  Returns a dict of cuda
+    tensors indexed by slot = channel * max_hits + hit: nid_code63, nid_reliab63, nid_parity, nid_parity_reliab, nid_valid,
+    payload_dibits [slots, n_payload], payload_llr [slots, n_payload, 2], payload_valid."""
+    import torch
+
+    n_ch, max_hits = d_hits.shape[0], d_hits.shape[1]
+    slots = n_ch * max_hits
+    dev = d_dibits.device
+    u8 = lambda *shape: torch.zeros(shape, dtype=torch.uint8, device=dev)
+    out = {"nid_code63": u8(slots, 63), "nid_reliab63": u8(slots, 63), "nid_parity": u8(slots), "nid_parity_reliab": u8(slots),
+           "nid_valid": u8(slots), "payload_dibits": u8(slots, max(n_payload, 1)),
+           "payload_llr": torch.zeros((slots, max(n_payload, 1), 2), dtype=torch.int16, device=dev), "payload_valid": u8(slots)}
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    assert d_dibits.dtype == torch.uint8 and d_llr.dtype == torch.int16 and d_counts.dtype == torch.int32
+    assert d_hits.dtype == torch.int32 and d_n_hits.dtype == torch.int32 and d_hits.is_contiguous()
+    check(
+        lib().dsdneo_b200_p25p1_frame_cut_batch(
+            d_dibits.data_ptr(), d_dibits.shape[1], d_llr.data_ptr(), d_llr.shape[1], d_counts.data_ptr(), d_hits.data_ptr(),
+            d_n_hits.data_ptr(), n_ch, max_hits, n_payload, out["nid_code63"].data_ptr(), out["nid_reliab63"].data_ptr(),
+            out["nid_parity"].data_ptr(), out["nid_parity_reliab"].data_ptr(), out["nid_valid"].data_ptr(),
+            out["payload_dibits"].data_ptr(), out["payload_llr"].data_ptr(), out["payload_valid"].data_ptr(),
+            _stream_ptr(stream),
+        ),
+        "p25p1_frame_cut_batch",
+    )
+    return out
+
+
 def p25_word_decode(code: int, data_bits, parity_bits):
     """Golay(24,6)/(24,12)/Hamming(10,6,3) P25 words. Returns (data_bits corrected, status u8 [n], fixed i32 [n])."""
     import numpy as np

@@ -1216,22 +1216,14 @@ p25_word_decode_kernel(int code, uint8_t* data_bits, const uint8_t* parity_bits,
 }
 
 /* BCH_63_16_11::decode_with_result (include/dsd-neo/fec/BCH_63_16.hpp:288-329), the P25 NID code: same Berlekamp
- * bookkeeping as the RS(63,k) decoder above with t = 11 and binary error values. */
-__global__ void __launch_bounds__(64)
-bch_63_16_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in63, uint8_t* out16, uint8_t* ok_out, int32_t* err_count,
-                 int n_words) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) {
-        return;
-    }
+ * bookkeeping as the RS(63,k) decoder above with t = 11 and binary error values.  `recd` bit j = coefficient j (input bit i of
+ * the reference's byte-per-bit array is coefficient 62 - i); corrected in place on success.  Returns success; *count_out =
+ * corrected bits (0 on failure). */
+__device__ __forceinline__ int
+bch_63_16_decode_word(const dsdneo_fec_tables* __restrict__ T, unsigned long long& recd, int* count_out) {
     constexpr int NN = 63, TT = 11, N2T = 22;
     const signed char* EXP = T->gf_exp;
     const signed char* LOG = T->gf_log;
-    const uint8_t* in = in63 + (size_t)w * 63;
-    unsigned long long recd = 0; /* bit j = coefficient j */
-    for (int i = 0; i < NN; i++) {
-        recd |= (unsigned long long)(in[NN - 1 - i] ? 1 : 0) << i;
-    }
     signed char s[N2T + 1];
     int has_err = 0;
     for (int i = 1; i <= N2T; i++) {
@@ -1343,6 +1335,25 @@ bch_63_16_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in63, u
             }
         }
     }
+    *count_out = ok ? count : 0;
+    return ok;
+}
+
+__global__ void __launch_bounds__(64)
+bch_63_16_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in63, uint8_t* out16, uint8_t* ok_out, int32_t* err_count,
+                 int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    constexpr int NN = 63;
+    const uint8_t* in = in63 + (size_t)w * 63;
+    unsigned long long recd = 0; /* bit j = coefficient j */
+    for (int i = 0; i < NN; i++) {
+        recd |= (unsigned long long)(in[NN - 1 - i] ? 1 : 0) << i;
+    }
+    int count = 0;
+    const int ok = bch_63_16_decode_word(T, recd, &count);
     ok_out[w] = (uint8_t)ok;
     if (err_count) {
         err_count[w] = ok ? count : 0;
@@ -1352,6 +1363,232 @@ bch_63_16_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* in63, u
         for (int i = 0; i < 16; i++) {
             o[i] = (uint8_t)((recd >> (NN - 1 - i)) & 1ull);
         }
+    }
+}
+
+/* ------------------------------------------------------------------ P25 Phase 1 NID decode (p25p1_nid_decode) */
+
+struct NidDecoded {
+    int status, nac, duid, errs;
+};
+
+/* decode_nid_codeword (src/protocol/p25/phase1/p25p1_check_nid.cpp:250-303); word bit (62 - i) = reference bit i */
+__device__ __forceinline__ NidDecoded
+nid_codeword(const dsdneo_fec_tables* __restrict__ T, unsigned long long word, int parity, int* bch_failed) {
+    NidDecoded r = {0, 0, 0, 0};
+    int count = 0;
+    *bch_failed = 0;
+    if (!bch_63_16_decode_word(T, word, &count)) {
+        *bch_failed = 1;
+        return r;
+    }
+    r.errs = count;
+    r.nac = (int)((word >> 51) & 0xFFFull);
+    r.duid = (int)((word >> 47) & 0xFull);
+    /* TIA-102.BAAA-A Table 8-4: HDU 0, TDU 3, LDU1 5, TSDU 7, LDU2 A, PDU C, TDULC F */
+    if (!((0x94A9u >> r.duid) & 1u)) {
+        r.errs = 0;
+        return r;
+    }
+    const int want_parity = (r.duid == 0x5 || r.duid == 0xA) ? 1 : 0;
+    r.status = (want_parity == parity) ? 1 : 2;
+    return r;
+}
+
+/* p25p1_nid_decode (p25p1_check_nid.cpp:322-354): hard decode, one retry with the known NAC after a BCH failure, then the
+ * bounded Chase search over the (at most 8) least reliable positions.  One warp per NID: lane 0 does the hard decode (the
+ * common case ends there); for the search the lanes rank the 63 reliabilities, stride over the <= 2 x 256 flip masks, each
+ * running its own BCH decodes, and the winner is the minimum of the packed key {score, not-ok, corrections, flips, order of
+ * enumeration} -- the reference's replacement rule is exactly that lexicographic order with "first found" breaking ties. */
+__global__ void __launch_bounds__(128)
+p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* code63, const uint8_t* reliab63,
+                        const int32_t* observed_nac, const uint8_t* parity_in, const uint8_t* parity_reliab, int threshold,
+                        int8_t* status_out, int32_t* nac_out, uint8_t* duid_out, int32_t* errs_out, int n) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) {
+        return;
+    }
+    const uint8_t* in = code63 + (size_t)w * 63;
+    unsigned long long word = 0;
+    for (int i = 0; i < 63; i++) {
+        word |= (unsigned long long)(in[i] ? 1 : 0) << (62 - i);
+    }
+    const int parity = parity_in[w] ? 1 : 0;
+    const int prel = parity_reliab ? parity_reliab[w] : 0;
+    const int obs = observed_nac ? observed_nac[w] : 0;
+    const bool nac_ok = obs > 0 && obs <= 0xFFF && obs != 0xFFF;
+    const int rx_nac = (int)((word >> 51) & 0xFFFull);
+    const unsigned long long retry = (word & ~(0xFFFull << 51)) | ((unsigned long long)(obs & 0xFFF) << 51);
+    const bool have_retry = nac_ok && rx_nac != obs;
+
+    NidDecoded res = {0, 0, 0, 0};
+    if (lane == 0) {
+        int failed = 0;
+        res = nid_codeword(T, word, parity, &failed);
+        if (res.status == 0 && failed && have_retry) {
+            res = nid_codeword(T, retry, parity, &failed);
+        }
+    }
+    res.status = __shfl_sync(0xffffffffu, res.status, 0);
+    if (res.status <= 0 && reliab63) {
+        const uint8_t* rel = reliab63 + (size_t)w * 63;
+        /* rank of position i in the (reliability, index) order = number of positions that precede it */
+        __shared__ uint8_t s_order[4][64];
+        uint8_t* order = s_order[threadIdx.x >> 5];
+        for (int i = lane; i < 63; i += 32) {
+            const int ri = rel[i];
+            int rank = 0;
+            for (int j = 0; j < 63; j++) {
+                const int rj = rel[j];
+                rank += (rj < ri || (rj == ri && j < i)) ? 1 : 0;
+            }
+            order[rank] = (uint8_t)i;
+        }
+        __syncwarp();
+        /* build_soft_nid_pool (:123-153), every lane redundantly (at most 63 + 63 steps) */
+        int pool[8], n_pool = 0;
+        unsigned long long picked = 0;
+        for (int i = 0; i < 63 && n_pool < 8; i++) {
+            if ((int)rel[order[i]] < threshold) {
+                pool[n_pool++] = order[i];
+                picked |= 1ull << i;
+            }
+        }
+        for (int i = 0; i < 63 && n_pool < 6; i++) {
+            if (!((picked >> i) & 1ull)) {
+                pool[n_pool++] = order[i];
+            }
+        }
+        unsigned best_key = 0xffffffffu;
+        NidDecoded best = {0, 0, 0, 0};
+        const int n_masks = 1 << n_pool;
+        const int n_seq = n_pool > 0 ? (have_retry ? 2 : 1) * n_masks : 0;
+        for (int seq = lane; seq < n_seq; seq += 32) {
+            const int mask = seq & (n_masks - 1);
+            if (__popc(mask) > 3) {
+                continue;
+            }
+            unsigned long long cand = (seq >= n_masks) ? retry : word;
+            int score = 0;
+            for (int b = 0; b < n_pool; b++) {
+                if (mask & (1 << b)) {
+                    cand ^= 1ull << (62 - pool[b]);
+                    score += rel[pool[b]];
+                }
+            }
+            const int weight = __popc(mask);
+            if (weight > 0 && score > threshold * weight) { /* candidate_flip_allowed (:108-117) */
+                continue;
+            }
+            int failed = 0;
+            const NidDecoded d = nid_codeword(T, cand, parity, &failed);
+            if (d.status <= 0) {
+                continue;
+            }
+            if (d.status == 2) {
+                score += prel;
+            }
+            /* score <= 3 * 255 + 255 (11 bits), not-ok 1 bit, corrections <= 11 (4 bits), flips <= 3 (2 bits), seq < 512 */
+            const unsigned key = ((unsigned)score << 17) | ((d.status == 1 ? 0u : 1u) << 16) | ((unsigned)d.errs << 12)
+                                 | ((unsigned)weight << 10) | (unsigned)seq;
+            if (key < best_key) {
+                best_key = key;
+                best = d;
+            }
+        }
+        unsigned win = best_key;
+        for (int o = 16; o > 0; o >>= 1) {
+            win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
+        }
+        if (win != 0xffffffffu) {
+            const int src = __ffs(__ballot_sync(0xffffffffu, best_key == win)) - 1;
+            res.status = __shfl_sync(0xffffffffu, best.status, src);
+            res.nac = __shfl_sync(0xffffffffu, best.nac, src);
+            res.duid = __shfl_sync(0xffffffffu, best.duid, src);
+            res.errs = __shfl_sync(0xffffffffu, best.errs, src);
+        }
+    }
+    if (lane == 0) {
+        status_out[w] = (int8_t)res.status;
+        nac_out[w] = res.nac;
+        duid_out[w] = (uint8_t)res.duid;
+        errs_out[w] = res.errs;
+    }
+}
+
+/* ------------------------------------------------------------------ P25 Phase 1 frame cutter (status-symbol stripping) */
+
+/* Index (from the first sync dibit) of the k-th non-status dibit at or after frame offset `first`: the air interface inserts
+ * one status symbol after every 35 dibits, i.e. at frame offsets 35, 71, 107, ...  (the reference counts the same thing with
+ * `skipdibit`, src/protocol/p25/phase1/p25p1_tsbk.c:135-152 with skipdibit = 36 - 14 at offset 57, :1054). */
+__device__ __forceinline__ int
+p25p1_payload_offset(int first, int k) {
+    /* status symbols below offset `first`: first / 36 */
+    const int ordinal = first - first / 36 + k; /* 0-based ordinal among the non-status dibits of the frame */
+    return ordinal + ordinal / 35;
+}
+
+/* One thread block per (channel, hit) slot.  NID: the 32 dibits after the sync with the status symbol at frame offset 35
+ * dropped (p25p1_read_nid_fields, src/engine/dispatch/dispatch_p25p1.c:121-143): 63 BCH bits + reliabilities min(|llr|, 255)
+ * (:59-66) + the parity bit.  Payload: n_payload non-status dibits from frame offset 57 on, with their LLR pairs. */
+__global__ void __launch_bounds__(128)
+p25p1_frame_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const int16_t* llr, size_t llr_pitch, const int32_t* counts,
+                       const int32_t* hits /* [ch][max_hits][2] = {position of the last sync dibit, sync type} */,
+                       const int32_t* n_hits, int n_channels, int max_hits, int n_payload, uint8_t* nid_code63,
+                       uint8_t* nid_reliab63, uint8_t* nid_parity, uint8_t* nid_parity_reliab, uint8_t* nid_valid,
+                       uint8_t* payload_dibits, int16_t* payload_llr, uint8_t* payload_valid) {
+    const int slot = blockIdx.x;
+    const int ch = slot / max_hits, h = slot - ch * max_hits;
+    if (ch >= n_channels) {
+        return;
+    }
+    const int tid = threadIdx.x;
+    const bool present = h < min(n_hits[ch], max_hits);
+    const int count = counts[ch];
+    const long start = present ? (long)hits[((size_t)ch * max_hits + h) * 2] - 23 : 0; /* first sync dibit */
+    const uint8_t* d = dibits + (size_t)ch * dibit_pitch;
+    const int16_t* l = llr + (size_t)ch * llr_pitch * 2;
+    const bool nid_ok = present && start >= 0 && start + 57 <= count;
+    const int last_payload = p25p1_payload_offset(57, n_payload - 1);
+    const bool pay_ok = nid_ok && n_payload > 0 && start + last_payload + 1 <= count;
+    if (tid == 0) {
+        nid_valid[slot] = nid_ok ? 1 : 0;
+        payload_valid[slot] = pay_ok ? 1 : 0;
+    }
+    if (tid < 32) {
+        /* NID dibit k: frame offset 24 + k, skipping the status symbol at 35 */
+        const int off = 24 + tid + (tid >= 11 ? 1 : 0);
+        int dib = 0, l0 = 0, l1 = 0;
+        if (nid_ok) {
+            dib = d[start + off];
+            l0 = l[(start + off) * 2];
+            l1 = l[(start + off) * 2 + 1];
+        }
+        const int r0 = min(abs(l0), 255), r1 = min(abs(l1), 255);
+        uint8_t* code = nid_code63 + (size_t)slot * 63;
+        uint8_t* rel = nid_reliab63 + (size_t)slot * 63;
+        code[2 * tid] = (uint8_t)((dib >> 1) & 1);
+        rel[2 * tid] = (uint8_t)r0;
+        if (tid < 31) {
+            code[2 * tid + 1] = (uint8_t)(dib & 1);
+            rel[2 * tid + 1] = (uint8_t)r1;
+        } else {
+            nid_parity[slot] = (uint8_t)(dib & 1);
+            nid_parity_reliab[slot] = (uint8_t)r1;
+        }
+    }
+    for (int k = tid; k < n_payload; k += blockDim.x) {
+        int dib = 0, l0 = 0, l1 = 0;
+        if (pay_ok) {
+            const long pos = start + p25p1_payload_offset(57, k);
+            dib = d[pos];
+            l0 = l[pos * 2];
+            l1 = l[pos * 2 + 1];
+        }
+        payload_dibits[(size_t)slot * n_payload + k] = (uint8_t)dib;
+        payload_llr[((size_t)slot * n_payload + k) * 2] = (int16_t)l0;
+        payload_llr[((size_t)slot * n_payload + k) * 2 + 1] = (int16_t)l1;
     }
 }
 
@@ -2228,6 +2465,114 @@ dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_out16,
     if (h_err_count) {
         DSDNEO_CUDA(cudaMemcpy(h_err_count, ec.p, n * 4, cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+int
+dsdneo_b200_p25p1_nid_decode_batch(const uint8_t* d_code63, const uint8_t* d_reliab63, const int32_t* d_observed_nac,
+                                   const uint8_t* d_parity, const uint8_t* d_parity_reliab, int erasure_threshold,
+                                   int8_t* d_status, int32_t* d_nac, uint8_t* d_duid, int32_t* d_error_count, int n_words,
+                                   void* stream) {
+    if (!d_code63 || !d_parity || !d_status || !d_nac || !d_duid || !d_error_count || n_words < 0) {
+        set_error("p25p1_nid_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25p1_nid_decode_kernel", s);
+        p25p1_nid_decode_kernel<<<grid_for(n_words, 4), 128, 0, s>>>(g_d_tables, d_code63, d_reliab63, d_observed_nac, d_parity,
+                                                                    d_parity_reliab, erasure_threshold, d_status, d_nac, d_duid,
+                                                                    d_error_count, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8_t* h_reliab63, const int32_t* h_observed_nac,
+                                        const uint8_t* h_parity, const uint8_t* h_parity_reliab, int erasure_threshold,
+                                        int8_t* h_status, int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words) {
+    if (!h_code63 || !h_parity || !h_status || !h_nac || !h_duid || !h_error_count || n_words < 0) {
+        set_error("p25p1_nid_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words;
+    DevBuf code(n * 63), rel(n * 63), obs(n * 4), par(n), prel(n), st(n), nac(n * 4), duid(n), ec(n * 4);
+    DSDNEO_CUDA(code.err);
+    DSDNEO_CUDA(rel.err);
+    DSDNEO_CUDA(obs.err);
+    DSDNEO_CUDA(par.err);
+    DSDNEO_CUDA(prel.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(nac.err);
+    DSDNEO_CUDA(duid.err);
+    DSDNEO_CUDA(ec.err);
+    DSDNEO_CUDA(cudaMemcpy(code.p, h_code63, n * 63, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(par.p, h_parity, n, cudaMemcpyHostToDevice));
+    if (h_reliab63) {
+        DSDNEO_CUDA(cudaMemcpy(rel.p, h_reliab63, n * 63, cudaMemcpyHostToDevice));
+    }
+    if (h_observed_nac) {
+        DSDNEO_CUDA(cudaMemcpy(obs.p, h_observed_nac, n * 4, cudaMemcpyHostToDevice));
+    }
+    if (h_parity_reliab) {
+        DSDNEO_CUDA(cudaMemcpy(prel.p, h_parity_reliab, n, cudaMemcpyHostToDevice));
+    }
+    rc = dsdneo_b200_p25p1_nid_decode_batch(code.as<uint8_t>(), h_reliab63 ? rel.as<uint8_t>() : NULL,
+                                            h_observed_nac ? obs.as<int32_t>() : NULL, par.as<uint8_t>(),
+                                            h_parity_reliab ? prel.as<uint8_t>() : NULL, erasure_threshold, st.as<int8_t>(),
+                                            nac.as<int32_t>(), duid.as<uint8_t>(), ec.as<int32_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_nac, nac.p, n * 4, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_duid, duid.p, n, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_error_count, ec.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                  const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels,
+                                  int max_hits, int n_payload, uint8_t* d_nid_code63, uint8_t* d_nid_reliab63,
+                                  uint8_t* d_nid_parity, uint8_t* d_nid_parity_reliab, uint8_t* d_nid_valid,
+                                  uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid, void* stream) {
+    if (!d_dibits || !d_llr || !d_counts || !d_hits || !d_n_hits || n_channels <= 0 || max_hits <= 0 || n_payload < 0
+        || !d_nid_code63 || !d_nid_reliab63 || !d_nid_parity || !d_nid_parity_reliab || !d_nid_valid || !d_payload_valid
+        || (n_payload > 0 && (!d_payload_dibits || !d_payload_llr))) {
+        set_error("p25p1_frame_cut_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25p1_frame_cut_kernel", s);
+        p25p1_frame_cut_kernel<<<(unsigned)(n_channels * max_hits), 128, 0, s>>>(
+            d_dibits, dibit_pitch, d_llr, llr_pitch, d_counts, (const int32_t*)d_hits, d_n_hits, n_channels, max_hits, n_payload,
+            d_nid_code63, d_nid_reliab63, d_nid_parity, d_nid_parity_reliab, d_nid_valid, d_payload_dibits, d_payload_llr,
+            d_payload_valid);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
     return 0;
 }
 

@@ -602,6 +602,45 @@ int dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_ou
                                             int n_words);
 
 /**
+ * Batched twin of `struct p25p1_nid_result p25p1_nid_decode(const char bch_code[63], const uint8_t reliab63[63],
+ * int observed_nac, unsigned char parity, uint8_t parity_reliab)` (include/dsd-neo/protocol/p25/p25p1_check_nid.h:76,
+ * src/protocol/p25/phase1/p25p1_check_nid.cpp:322-354): hard BCH(63,16,11) decode + DUID / parity validation, one retry
+ * with the known NAC written over the received one after a BCH failure, then the bounded Chase search (at most 3 flips among
+ * the <= 8 least reliable positions, from the received word and from the NAC-rewritten word).
+ * d_reliab63 / d_observed_nac / d_parity_reliab may be NULL (hard decode only / no known NAC / reliability 0).
+ * `erasure_threshold` = p25p1_get_erasure_threshold() (64 unless configured, p25p1_soft.cpp:20-39).
+ * d_status[i] is enum NidResult (0 fail, 1 ok, 2 parity override); nac / duid / error_count as in the reference struct.
+ */
+int dsdneo_b200_p25p1_nid_decode_batch(const uint8_t* d_code63, const uint8_t* d_reliab63, const int32_t* d_observed_nac,
+                                       const uint8_t* d_parity, const uint8_t* d_parity_reliab, int erasure_threshold,
+                                       int8_t* d_status, int32_t* d_nac, uint8_t* d_duid, int32_t* d_error_count,
+                                       int n_words, void* stream);
+int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8_t* h_reliab63,
+                                            const int32_t* h_observed_nac, const uint8_t* h_parity,
+                                            const uint8_t* h_parity_reliab, int erasure_threshold, int8_t* h_status,
+                                            int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words);
+
+/**
+ * P25 Phase 1 frame cutter: what the reference does dibit by dibit between frame sync and the FEC leaves, for every sync
+ * hit of every channel at once, so that frames go from the slicer to the FEC kernels without a host round trip:
+ *   - NID fields: the 32 dibits after the sync with the status symbol at frame offset 35 dropped, as 63 BCH bits,
+ *     reliabilities min(|llr|, 255) and the final parity bit (p25p1_read_nid_fields + p25p1_append_bch_bits,
+ *     src/engine/dispatch/dispatch_p25p1.c:59-82,121-143) -- the inputs of dsdneo_b200_p25p1_nid_decode_batch;
+ *   - payload: `n_payload` dibits from frame offset 57 on with every 36th dibit of the frame (the status symbols) removed
+ *     (tsbk_read_repetition_samples, src/protocol/p25/phase1/p25p1_tsbk.c:135-152, skipdibit = 36 - 14 at :1054), with
+ *     their LLR pairs -- 98 dibits per half-rate trellis block, the input of dsdneo_b200_p25_12_soft_llr[_list]_batch.
+ * Slot s = channel * max_hits + hit.  d_hits is the hit array of dsdneo_b200_frame_sync_search_batch
+ * ({position of the last sync dibit, sync type} per hit).  nid_valid / payload_valid tell whether the stream of that channel
+ * (d_counts dibits) still holds the whole NID / payload; invalid slots are zero-filled.
+ */
+int dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                      const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels,
+                                      int max_hits, int n_payload, uint8_t* d_nid_code63, uint8_t* d_nid_reliab63,
+                                      uint8_t* d_nid_parity, uint8_t* d_nid_parity_reliab, uint8_t* d_nid_valid,
+                                      uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid,
+                                      void* stream);
+
+/**
  * viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182; include/dsd-neo/fec/viterbi.h:23-29), the
  * K = 5 soft decoder used by M17 and YSF.  Costs are uint16 "probability of a 1" (0 / 0xFFFF strong, 0x7FFF erased).
  * @param d_cost   [n][cost_pitch] received soft bits, in_len used per frame (after de-puncturing at most 488)

@@ -140,6 +140,13 @@ int oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, 
 int oracle_p25_golay24_decode(int length, uint8_t* word, const uint8_t* parity, int* fixed_errors);
 int oracle_hamming_10_6_3_decode(uint8_t* data6, const uint8_t* parity4);
 int oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count);
+/* p25p1_nid_decode (src/protocol/p25/phase1/p25p1_check_nid.cpp:322-354); returns NidResult status, fills nac / duid / errs */
+/* sequential P25p1 frame cutter (NID fields + status-stripped payload); bit 0 NID complete, bit 1 payload complete */
+int oracle_p25p1_frame_cut(const uint8_t* dibits, const int16_t* llr, int count, int pos_last_sync, int n_payload,
+                           uint8_t* code63, uint8_t* reliab63, uint8_t* parity, uint8_t* parity_reliab, uint8_t* payload_dibits,
+                           int16_t* payload_llr);
+int oracle_p25p1_nid_decode(const uint8_t* code63, const uint8_t* reliab63, int observed_nac, int parity, int parity_reliab,
+                            int threshold, int* nac, int* duid, int* errs);
 uint32_t oracle_viterbi_k5_decode(uint8_t* out, const uint16_t* in, int len);
 uint32_t oracle_viterbi_k5_decode_punctured(uint8_t* out, const uint16_t* in, const uint8_t* punct, int in_len, int p_len);
 void oracle_nxdn_conv_decode(const uint8_t* sym, const uint8_t* rel, int n_steps, int n_bits_out, uint16_t* metrics_io, uint8_t* out);

@@ -1692,3 +1692,231 @@ oracle_nxdn_conv_decode(const uint8_t* sym /*[2*n_steps]*/, const uint8_t* rel /
         }
     }
 }
+
+/* ------------------------------------------------------------------ P25 Phase 1 NID decode (hard + NAC retry + Chase search) */
+
+/* One 63-bit NID candidate through decode_nid_codeword (src/protocol/p25/phase1/p25p1_check_nid.cpp:250-303): BCH(63,16,11)
+ * correction, DUID membership in TIA-102.BAAA-A Table 8-4, final parity bit (1 for LDU1/LDU2 only).  status: 0 = fail, 1 = ok,
+ * 2 = parity override.  *bch_failed tells a BCH failure from an invalid DUID. */
+static int
+nid_codeword(const uint8_t* code63, int parity, int* nac, int* duid, int* errs, int* bch_failed) {
+    static const uint8_t duid_valid[16] = {1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 1, 0, 1, 0, 0, 1};
+    uint8_t dec[16];
+    int count = 0;
+    *nac = 0;
+    *duid = 0;
+    *errs = 0;
+    *bch_failed = 0;
+    if (!oracle_bch_63_16_decode(code63, dec, &count)) {
+        *bch_failed = 1;
+        return 0;
+    }
+    *errs = count;
+    for (int i = 0; i < 12; i++) {
+        *nac = (*nac << 1) | dec[i];
+    }
+    *duid = (dec[12] << 3) | (dec[13] << 2) | (dec[14] << 1) | dec[15];
+    if (!duid_valid[*duid]) {
+        *errs = 0;
+        return 0;
+    }
+    const int want_parity = (*duid == 0x5 || *duid == 0xA) ? 1 : 0;
+    return (want_parity == parity) ? 1 : 2;
+}
+
+static int
+nid_nac_of(const uint8_t* code63) {
+    int nac = 0;
+    for (int i = 0; i < 12; i++) {
+        nac = (nac << 1) | (code63[i] ? 1 : 0);
+    }
+    return nac;
+}
+
+/* p25p1_nid_decode (p25p1_check_nid.cpp:322-354).  reliab63 may be NULL (hard decode only).  `threshold` is
+ * p25p1_get_erasure_threshold() (64 unless configured, p25p1_soft.cpp:20-39).  Returns the status; nac / duid / errs as
+ * in struct p25p1_nid_result. */
+int
+oracle_p25p1_nid_decode(const uint8_t* code63, const uint8_t* reliab63, int observed_nac, int parity, int parity_reliab,
+                        int threshold, int* nac, int* duid, int* errs) {
+    int failed = 0;
+    const int nac_ok = observed_nac > 0 && observed_nac <= 0xFFF && observed_nac != 0xFFF;
+    const int rx_nac = nid_nac_of(code63);
+    uint8_t retry[63];
+    memcpy(retry, code63, 63);
+    for (int i = 0; i < 12; i++) {
+        retry[i] = (uint8_t)((observed_nac >> (11 - i)) & 1);
+    }
+    /* decode_nid_hard (:305-320): one retry with the known NAC written over the received one, after a BCH failure only */
+    int status = nid_codeword(code63, parity, nac, duid, errs, &failed);
+    if (status == 0 && failed && nac_ok && rx_nac != observed_nac) {
+        status = nid_codeword(retry, parity, nac, duid, errs, &failed);
+    }
+    if (status > 0 || !reliab63) {
+        return status;
+    }
+    /* build_soft_nid_pool (:123-153): positions by (reliability, index); those under the threshold first (at most 8), then
+     * filled up to 6 with the next weakest */
+    int order[63], pool[8], n_pool = 0;
+    for (int i = 0; i < 63; i++) {
+        order[i] = i;
+    }
+    for (int i = 0; i < 63; i++) {
+        for (int j = i + 1; j < 63; j++) {
+            const int a = order[j], b = order[i];
+            const int cmp = (reliab63[a] != reliab63[b]) ? (int)reliab63[a] - (int)reliab63[b] : a - b;
+            if (cmp < 0) {
+                order[i] = a;
+                order[j] = b;
+            }
+        }
+    }
+    uint8_t picked[63] = {0};
+    for (int i = 0; i < 63 && n_pool < 8; i++) {
+        if ((int)reliab63[order[i]] < threshold) {
+            pool[n_pool++] = order[i];
+            picked[i] = 1;
+        }
+    }
+    for (int i = 0; i < 63 && n_pool < 6; i++) {
+        if (!picked[i]) {
+            pool[n_pool++] = order[i];
+        }
+    }
+    if (n_pool <= 0) {
+        return status;
+    }
+    /* soft_nid_search_from_base (:200-228) from the received word, then from the NAC-rewritten word; candidates of at
+     * most 3 flips whose summed reliability stays within threshold x flips; best = lowest score (+ parity reliability on
+     * a parity override), then status ok, then fewer BCH corrections, then fewer flips, then first found */
+    int found = 0, b_status = 0, b_nac = 0, b_duid = 0, b_errs = 0, b_score = 0, b_changes = 0;
+    for (int base = 0; base < 2; base++) {
+        if (base == 1 && !(nac_ok && rx_nac != observed_nac)) {
+            break;
+        }
+        const uint8_t* from = base ? retry : code63;
+        for (int mask = 0; mask < (1 << n_pool); mask++) {
+            int weight = 0, score = 0;
+            uint8_t cand[63];
+            memcpy(cand, from, 63);
+            for (int b = 0; b < n_pool; b++) {
+                if (mask & (1 << b)) {
+                    weight++;
+                    cand[pool[b]] ^= 1;
+                    score += reliab63[pool[b]];
+                }
+            }
+            if (weight > 3 || (weight > 0 && score > threshold * weight)) {
+                continue;
+            }
+            int c_nac, c_duid, c_errs, c_failed;
+            const int c_status = nid_codeword(cand, parity, &c_nac, &c_duid, &c_errs, &c_failed);
+            if (c_status <= 0) {
+                continue;
+            }
+            if (c_status == 2) {
+                score += parity_reliab;
+            }
+            if (!found || score < b_score || (score == b_score && c_status == 1 && b_status != 1)
+                || (score == b_score && c_status == b_status && c_errs < b_errs)
+                || (score == b_score && c_status == b_status && c_errs == b_errs && weight < b_changes)) {
+                found = 1;
+                b_status = c_status;
+                b_nac = c_nac;
+                b_duid = c_duid;
+                b_errs = c_errs;
+                b_score = score;
+                b_changes = weight;
+            }
+        }
+    }
+    if (!found) {
+        return status;
+    }
+    *nac = b_nac;
+    *duid = b_duid;
+    *errs = b_errs;
+    return b_status;
+}
+
+/* ------------------------------------------------------------------ P25 Phase 1 frame cutter (sequential restatement) */
+
+/* Reads a frame the way the reference does, one dibit at a time after the sync:
+ *   NID   p25p1_read_nid_fields (src/engine/dispatch/dispatch_p25p1.c:121-143): 6 NAC dibits, 2 DUID dibits, 3 dibits, one
+ *         status symbol, 20 dibits, one last dibit whose low bit is the parity bit; bit reliabilities min(|llr|, 255) (:59-66)
+ *   data  tsbk_read_repetition_samples (src/protocol/p25/phase1/p25p1_tsbk.c:135-152) with skipdibit = 36 - 14 (:1054): a
+ *         dibit is payload while skipdibit / 36 == 0, else it is a status symbol and the counter restarts.
+ * PARITY UNPINNED for this function alone: both reference routines are static functions of translation units that need
+ * the whole decoder state (getDibitSoft), so they are restated here and checked by round trip instead -- frames built
+ * with the reference's own NID generator rule (tests/test_support/p25_nid_generator.hpp) and trellis table come back with
+ * their NAC / DUID / TSBK bytes through this cutter + the pinned decoders (tests/test_oracle_fec.py).
+ * `pos_last_sync` = index of the last sync dibit.  Returns bit 0: NID complete, bit 1: payload complete. */
+int
+oracle_p25p1_frame_cut(const uint8_t* dibits, const int16_t* llr /* [n][2] */, int count, int pos_last_sync, int n_payload,
+                       uint8_t* code63, uint8_t* reliab63, uint8_t* parity, uint8_t* parity_reliab, uint8_t* payload_dibits,
+                       int16_t* payload_llr) {
+    int p = pos_last_sync + 1; /* next dibit to read */
+    int flags = 0;
+    memset(code63, 0, 63);
+    memset(reliab63, 0, 63);
+    *parity = 0;
+    *parity_reliab = 0;
+    if (n_payload > 0) {
+        memset(payload_dibits, 0, (size_t)n_payload);
+        memset(payload_llr, 0, (size_t)n_payload * 2 * sizeof(int16_t));
+    }
+    if (pos_last_sync - 23 < 0 || p + 33 > count) {
+        return 0;
+    }
+    int idx = 0;
+    for (int k = 0; k < 33; k++) {
+        const int dib = dibits[p], l0 = llr[2 * p], l1 = llr[2 * p + 1];
+        p++;
+        if (k == 11) {
+            continue; /* status symbol between the 11th and 12th NID dibit */
+        }
+        const int r0 = (l0 < 0 ? -l0 : l0) > 255 ? 255 : (l0 < 0 ? -l0 : l0);
+        const int r1 = (l1 < 0 ? -l1 : l1) > 255 ? 255 : (l1 < 0 ? -l1 : l1);
+        code63[idx] = (uint8_t)((dib >> 1) & 1);
+        reliab63[idx] = (uint8_t)r0;
+        idx++;
+        if (idx < 63) {
+            code63[idx] = (uint8_t)(dib & 1);
+            reliab63[idx] = (uint8_t)r1;
+            idx++;
+        } else {
+            *parity = (uint8_t)(dib & 1);
+            *parity_reliab = (uint8_t)r1;
+        }
+    }
+    flags |= 1;
+    /* payload: does it fit?  walk with the reference's counter */
+    int skip = 36 - 14, k = 0, q = p;
+    while (k < n_payload && q < count) {
+        if (skip / 36 == 0) {
+            k++;
+        } else {
+            skip = 0;
+        }
+        skip++;
+        q++;
+    }
+    if (n_payload <= 0 || k < n_payload) {
+        return flags;
+    }
+    skip = 36 - 14;
+    k = 0;
+    while (k < n_payload) {
+        if (skip / 36 == 0) {
+            payload_dibits[k] = dibits[p];
+            payload_llr[2 * k] = llr[2 * p];
+            payload_llr[2 * k + 1] = llr[2 * p + 1];
+            k++;
+        } else {
+            skip = 0;
+        }
+        skip++;
+        p++;
+    }
+    return flags | 2;
+}

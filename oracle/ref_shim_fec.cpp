@@ -6,6 +6,8 @@
  */
 #include <dsd-neo/fec/BCH_63_16.hpp>
 #include <dsd-neo/fec/ReedSolomon.hpp>
+#include <dsd-neo/protocol/p25/p25p1_check_nid.h>
+#include <stdint.h>
 
 extern "C" {
 
@@ -29,6 +31,17 @@ ref_bch_63_16_decode(const char* in63, char* out16, int* error_count) {
         *error_count = r.error_count;
     }
     return r.success ? 1 : 0;
+}
+
+/* p25p1_nid_decode (include/dsd-neo/protocol/p25/p25p1_check_nid.h:76), flat arguments for ctypes */
+int
+ref_p25p1_nid_decode(const char* code63, const uint8_t* reliab63, int observed_nac, int parity, int parity_reliab, int* nac,
+                     int* duid, int* errs) {
+    const struct p25p1_nid_result r = p25p1_nid_decode(code63, reliab63, observed_nac, (unsigned char)parity, (uint8_t)parity_reliab);
+    *nac = r.nac;
+    *duid = r.duid;
+    *errs = r.error_count;
+    return (int)r.status;
 }
 
 } /* extern "C" */

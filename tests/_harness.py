@@ -769,3 +769,34 @@ def synth_wideband_cqpsk(rng, M, n_out, active, sps=10, snr_db=30.0, amp=0.5, cf
     out[:, 0] = x.real
     out[:, 1] = x.imag
     return out, truth
+
+
+# --------------------------------------------------------------------------- P25 Phase 1 air-interface framing (section 8f rank 4)
+
+P25P1_SYNC_DIBITS = [int(c) for c in "111113113311333313133333"]
+
+
+def p25p1_insert_status(frame_dibits_no_status, status_dibit=2):
+    """Insert a status symbol after every 35 dibits of a frame (frame offsets 35, 71, ...), as on the air interface."""
+    out = []
+    for i, d in enumerate(frame_dibits_no_status):
+        out.append(int(d))
+        if len(out) % 36 == 35:
+            out.append(status_dibit)
+    return np.array(out, dtype=np.int64)
+
+
+def p25p1_build_tsdu(rng, nac, n_blocks=3, bch_encode=None):
+    """One TSDU: sync + NID(NAC, DUID 7, BCH(63,16) + parity 0) + n_blocks half-rate trellis blocks, status symbols
+    inserted.  Returns (dibits incl. status, [49-dibit payloads])."""
+    duid = 0x7
+    info = np.array([(nac >> (11 - i)) & 1 for i in range(12)] + [(duid >> (3 - i)) & 1 for i in range(4)], np.uint8)
+    cw = bch_encode(info).astype(np.int64)
+    bits = np.concatenate([cw, [0]])  # parity bit 0 for TSDU
+    nid = bits[0::2] * 2 + bits[1::2]
+    body, payloads = [np.array(P25P1_SYNC_DIBITS), nid], []
+    for _ in range(n_blocks):
+        d49, tx98 = p25_trellis_encode(rng)
+        body.append(tx98)
+        payloads.append(d49)
+    return p25p1_insert_status(np.concatenate(body)), payloads

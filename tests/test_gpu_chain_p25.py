@@ -109,3 +109,93 @@ def test_p25_c4fm_chain_bit_exact_and_payloads_recovered(gpu):
         ok_t += np.array_equal(got12[k], by)
         ok_r += rs_rc[k] == 0 and np.array_equal(got_rs[k], _rs_words(rs20))
     assert ok_t == len(owner) and ok_r == len(owner), (ok_t, ok_r, len(owner))
+
+
+def test_p25_tsdu_chain_on_device_with_status_symbols(gpu):
+    """Real air-interface framing, no host step between slicer and FEC: discriminator samples -> symbolizer -> frame-sync
+    hunt -> device frame cutter (NID fields, status symbols stripped) -> p25p1_nid_decode (BCH + Chase) and the three
+    half-rate trellis blocks of each TSDU.  The cutter output equals the sequential oracle cutter on the same stream, the
+    decoders equal their oracles, and NAC / DUID / TSBK dibits are the transmitted ones."""
+    import torch
+    from test_oracle_fec import bch_63_16_encode, _oracle_cut
+
+    rng = np.random.default_rng(77)
+    n_ch, n_frames, max_hits = 24, 4, 8
+    chans = []
+    for c in range(n_ch):
+        parts, truth = [rng.integers(0, 4, WARMUP)], []
+        for f in range(n_frames):
+            nac = int(rng.integers(1, 0xFFF))
+            frame, payloads = H.p25p1_build_tsdu(rng, nac, 3, bch_63_16_encode)
+            parts += [frame, rng.integers(0, 4, GAP)]
+            truth.append((nac, payloads))
+        chans.append((np.concatenate(parts), truth))
+    n_dib = max(ch[0].size for ch in chans)
+    noise = [0.0 if c % 3 == 0 else 500.0 + 30.0 * c for c in range(n_ch)]
+    xs = np.stack([H.synth_c4fm_disc(rng, np.concatenate([ch[0], rng.integers(0, 4, n_dib - ch[0].size)]), 9000.0, noise[c])
+                   for c, ch in enumerate(chans)])
+    n = xs.shape[1]
+    taps = _taps()
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([gpu.sym_class_from_synctype(H.SYNC_P25P1_POS, H.SYNC_P25P1_POS)] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), n)
+    fs = gpu.FrameSync(n_ch, [(P25_SYNC, 0)])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=max_hits)
+    cut = gpu.p25p1_frame_cut(res["dibits"], res["llr"], res["count"], hits, n_hits, 3 * 98)
+    torch.cuda.synchronize()
+    cut_h = {k: v.cpu().numpy() for k, v in cut.items()}
+    dib, llr, cnt = res["dibits"].cpu().numpy(), res["llr"].cpu().numpy(), res["count"].cpu().numpy()
+    hits_h, n_hits_h = hits.cpu().numpy(), n_hits.cpu().numpy()
+    # ---- cutter == sequential oracle cutter, slot by slot
+    slots = []
+    for c in range(n_ch):
+        assert n_hits_h[c] >= n_frames
+        for h in range(max_hits):
+            s = c * max_hits + h
+            if h >= min(n_hits_h[c], max_hits):
+                assert cut_h["nid_valid"][s] == 0 and cut_h["payload_valid"][s] == 0
+                continue
+            flags, code, rel, par, prel, pd, pl = _oracle_cut(dib[c, :cnt[c]], llr[c, :cnt[c]], int(hits_h[c, h, 0]), 3 * 98)
+            assert cut_h["nid_valid"][s] == (flags & 1) and cut_h["payload_valid"][s] == ((flags >> 1) & 1)
+            assert np.array_equal(cut_h["nid_code63"][s], code) and np.array_equal(cut_h["nid_reliab63"][s], rel)
+            assert cut_h["nid_parity"][s] == par and cut_h["nid_parity_reliab"][s] == prel
+            assert np.array_equal(cut_h["payload_dibits"][s], pd) and np.array_equal(cut_h["payload_llr"][s], pl)
+            if flags == 3:
+                slots.append((c, h, s))
+    assert len(slots) >= n_ch * n_frames
+    # ---- decoders on the cut frames (device buffers straight from the cutter)
+    sel = torch.tensor([s for _, _, s in slots], device="cuda")
+    code_d = cut["nid_code63"][sel].contiguous()
+    rel_d = cut["nid_reliab63"][sel].contiguous()
+    par_d = cut["nid_parity"][sel].contiguous()
+    prel_d = cut["nid_parity_reliab"][sel].contiguous()
+    k = len(slots)
+    st = torch.zeros(k, dtype=torch.int8, device="cuda")
+    nac = torch.zeros(k, dtype=torch.int32, device="cuda")
+    duid = torch.zeros(k, dtype=torch.uint8, device="cuda")
+    errs = torch.zeros(k, dtype=torch.int32, device="cuda")
+    gpu.check(gpu.lib().dsdneo_b200_p25p1_nid_decode_batch(code_d.data_ptr(), rel_d.data_ptr(), None, par_d.data_ptr(),
+                                                           prel_d.data_ptr(), 64, st.data_ptr(), nac.data_ptr(), duid.data_ptr(),
+                                                           errs.data_ptr(), k, None))
+    blocks = cut["payload_llr"][sel].reshape(k * 3, 196).contiguous()
+    out12 = torch.zeros((k * 3, 12), dtype=torch.uint8, device="cuda")
+    met = torch.zeros(k * 3, dtype=torch.int32, device="cuda")
+    gpu.check(gpu.lib().dsdneo_b200_p25_12_soft_llr_batch(blocks.data_ptr(), out12.data_ptr(), met.data_ptr(), k * 3, None))
+    torch.cuda.synchronize()
+    st, nac, duid, out12 = st.cpu().numpy(), nac.cpu().numpy(), duid.cpu().numpy(), out12.cpu().numpy()
+    # ---- every transmitted frame is among the decoded ones, with its NAC and TSBK dibits
+    recovered = 0
+    for c in range(n_ch):
+        mine = [(i, s) for i, (cc, h, s) in enumerate(slots) if cc == c]
+        for nac_tx, payloads in chans[c][1]:
+            for i, s in mine:
+                if st[i] == 1 and nac[i] == nac_tx and duid[i] == 7:
+                    ok = True
+                    for b in range(3):
+                        want = np.zeros(12, np.uint8)
+                        for j in range(48):
+                            want[j // 4] |= int(payloads[b][j]) << (6 - 2 * (j % 4))
+                        ok = ok and np.array_equal(out12[3 * i + b], want)
+                    recovered += ok
+                    break
+    assert recovered == n_ch * n_frames, recovered

@@ -304,3 +304,31 @@ def test_p25_word_codes_and_nid_bch_bit_exact(gpu):
         r = O.oracle_bch_63_16_decode(H._ptr(words[i], H.u8p), H._ptr(w, H.u8p), C.byref(e))
         assert r == ok[i] and e.value == ec[i] and np.array_equal(out[i], w), i
     assert ok.sum() > 1800
+
+
+def test_p25p1_nid_decode_bit_exact_vs_oracle(gpu):
+    """Batched p25p1_nid_decode (hard, NAC retry, Chase search) == oracle (pinned to the reference) on noisy NIDs around and
+    beyond the BCH radius: status, NAC, DUID, correction count; with and without reliabilities / known NAC."""
+    from test_oracle_fec import nid_cases
+
+    O = H.oracle_fec()
+    O.oracle_p25p1_nid_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    rng = np.random.default_rng(631)
+    cases = nid_cases(rng, 3000)
+    code = np.stack([c[0] for c in cases]).astype(np.uint8)
+    rel = np.stack([c[1] for c in cases]).astype(np.uint8)
+    obs = np.array([c[2] for c in cases], np.int32)
+    par = np.array([c[3] for c in cases], np.uint8)
+    prel = np.array([c[4] for c in cases], np.uint8)
+    for use_rel, use_obs in [(True, True), (False, True), (True, False)]:
+        st, nac, duid, errs = gpu.p25p1_nid_decode(code, rel if use_rel else None, obs if use_obs else None, par,
+                                                   prel if use_rel else None, 64)
+        seen = set()
+        for i in range(len(cases)):
+            v = [C.c_int() for _ in range(3)]
+            want = O.oracle_p25p1_nid_decode(H._ptr(code[i], H.u8p), H._ptr(rel[i], H.u8p) if use_rel else None,
+                                             int(obs[i]) if use_obs else 0, int(par[i]), int(prel[i]) if use_rel else 0, 64,
+                                             *[C.byref(x) for x in v])
+            assert (st[i], nac[i], duid[i], errs[i]) == (want, v[0].value, v[1].value, v[2].value), (i, use_rel, use_obs)
+            seen.add(want)
+        assert seen == {0, 1, 2}

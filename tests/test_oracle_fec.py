@@ -630,3 +630,110 @@ def test_bch_63_16_corrects_up_to_eleven_errors():
         out, ec = np.zeros(16, np.uint8), C.c_int(-1)
         assert O.oracle_bch_63_16_decode(H._ptr(x, H.u8p), H._ptr(out, H.u8p), C.byref(ec)) == 1
         assert ec.value == ne and np.array_equal(out, data)
+
+
+# ---------------------------------------------------------------------------- P25p1 NID decode (hard + NAC retry + Chase)
+
+VALID_DUIDS = [0x0, 0x3, 0x5, 0x7, 0xA, 0xC, 0xF]
+
+
+def make_nid(rng, nac=None, duid=None):
+    """63 BCH bits + parity bit of one NID (TIA-102.BAAA-A: parity 1 for LDU1 / LDU2)."""
+    nac = int(rng.integers(1, 0xFFF)) if nac is None else nac
+    duid = int(rng.choice(VALID_DUIDS)) if duid is None else duid
+    info = np.array([(nac >> (11 - i)) & 1 for i in range(12)] + [(duid >> (3 - i)) & 1 for i in range(4)], np.uint8)
+    return bch_63_16_encode(info).astype(np.uint8), (1 if duid in (0x5, 0xA) else 0), nac, duid
+
+
+def nid_cases(rng, n):
+    """Noisy NIDs around the BCH radius with reliabilities that mostly (not always) mark the flipped bits as weak."""
+    cases = []
+    for k in range(n):
+        cw, par, nac, duid = make_nid(rng)
+        n_err = int(rng.choice([0, 3, 9, 11, 12, 13, 14, 15, 18, 25]))
+        pos = rng.choice(63, n_err, replace=False)
+        x = cw.copy()
+        x[pos] ^= 1
+        rel = rng.integers(60, 256, 63).astype(np.uint8)
+        weak = pos[rng.random(n_err) < 0.8]
+        rel[weak] = rng.integers(0, 90, weak.size)
+        if k % 5 == 0:
+            rel[rng.choice(63, 10, replace=False)] = rng.integers(0, 64, 10)  # ties and extra weak positions
+        if k % 7 == 0:
+            rel[:] = rng.integers(0, 3, 63) * 100                                # heavy ties
+        parity = par ^ int(rng.random() < 0.2)
+        observed = [0, nac, nac, int(rng.integers(1, 0xFFF)), 0xFFF][k % 5]
+        cases.append((x, rel, observed, parity, int(rng.integers(0, 256))))
+    return cases
+
+
+@needs_ref
+def test_p25p1_nid_decode_matches_reference():
+    """oracle_p25p1_nid_decode == the reference's p25p1_nid_decode (status, NAC, DUID, correction count) with and without
+    reliabilities, with / without a known NAC, around and beyond the BCH radius."""
+    O, R = H.oracle_fec(), H.ref_fec()
+    O.oracle_p25p1_nid_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    R.ref_p25p1_nid_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    rng = np.random.default_rng(63)
+    seen = set()
+    for x, rel, observed, parity, prel in nid_cases(rng, 1500):
+        for use_rel in (True, False):
+            a, b = [C.c_int() for _ in range(3)], [C.c_int() for _ in range(3)]
+            rp = H._ptr(rel, H.u8p) if use_rel else None
+            sa = R.ref_p25p1_nid_decode(H._ptr(x, H.u8p), rp, observed, parity, prel, *[C.byref(v) for v in a])
+            sb = O.oracle_p25p1_nid_decode(H._ptr(x, H.u8p), rp, observed, parity, prel, 64, *[C.byref(v) for v in b])
+            assert sa == sb, (sa, sb)
+            if sa > 0:
+                assert [v.value for v in a] == [v.value for v in b]
+            else:
+                assert a[2].value == b[2].value == 0
+            seen.add((sa, use_rel))
+    assert {(0, True), (1, True), (2, True), (1, False), (0, False)} <= seen
+
+
+def _oracle_cut(dib, llr, pos_last_sync, n_payload):
+    O = H.oracle_fec()
+    O.oracle_p25p1_frame_cut.argtypes = [H.u8p, C.POINTER(C.c_int16), C.c_int, C.c_int, C.c_int, H.u8p, H.u8p, H.u8p, H.u8p,
+                                         H.u8p, C.POINTER(C.c_int16)]
+    dib = np.ascontiguousarray(dib, np.uint8)
+    llr = np.ascontiguousarray(llr, np.int16)
+    code, rel = np.zeros(63, np.uint8), np.zeros(63, np.uint8)
+    par, prel = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    pd, pl = np.zeros(max(n_payload, 1), np.uint8), np.zeros((max(n_payload, 1), 2), np.int16)
+    flags = O.oracle_p25p1_frame_cut(H._ptr(dib, H.u8p), llr.ctypes.data_as(C.POINTER(C.c_int16)), dib.size, pos_last_sync,
+                                     n_payload, H._ptr(code, H.u8p), H._ptr(rel, H.u8p), H._ptr(par, H.u8p), H._ptr(prel, H.u8p),
+                                     H._ptr(pd, H.u8p), pl.ctypes.data_as(C.POINTER(C.c_int16)))
+    return flags, code, rel, int(par[0]), int(prel[0]), pd[:n_payload], pl[:n_payload]
+
+
+def test_p25p1_frame_cut_round_trip():
+    """A TSDU built with status symbols on the air-interface grid comes back through the sequential cutter + the pinned
+    decoders: NAC / DUID from the NID, the TSBK dibits from the three trellis blocks; truncated streams are flagged."""
+    O = H.oracle_fec()
+    O.oracle_p25p1_nid_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    rng = np.random.default_rng(8)
+    for trial in range(20):
+        nac = int(rng.integers(1, 0xFFF))
+        frame, payloads = H.p25p1_build_tsdu(rng, nac, 3, bch_63_16_encode)
+        assert frame.size == 24 + 33 + 3 * 98 + 8 + 1  # 9 status symbols up to frame offset 359
+        pre = int(rng.integers(0, 50))
+        dib = np.concatenate([rng.integers(0, 4, pre), frame, rng.integers(0, 4, 7)])
+        llr = np.stack([np.where(dib & 2, 200, -200), np.where(dib & 1, 300, -300)], axis=1).astype(np.int16)  # positive = bit 1
+        flags, code, rel, par, prel, pd, pl = _oracle_cut(dib, llr, pre + 23, 3 * 98)
+        assert flags == 3 and par == 0 and prel == 255 and set(rel.tolist()) <= {200, 255}
+        v = [C.c_int() for _ in range(3)]
+        st = O.oracle_p25p1_nid_decode(H._ptr(code, H.u8p), H._ptr(rel, H.u8p), 0, par, prel, 64, *[C.byref(x) for x in v])
+        assert st == 1 and v[0].value == nac and v[1].value == 7 and v[2].value == 0
+        for b in range(3):
+            blk = pd[98 * b:98 * (b + 1)]
+            out12 = np.zeros(12, np.uint8)
+            O.oracle_p25_12_soft_llr(pl[98 * b:98 * (b + 1)].reshape(-1).ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(out12, H.u8p))
+            want = np.zeros(12, np.uint8)
+            for j in range(48):
+                want[j // 4] |= int(payloads[b][j]) << (6 - 2 * (j % 4))
+            assert np.array_equal(out12, want), (trial, b)
+            assert np.array_equal(np.where(pl[98 * b:98 * (b + 1), 0] > 0, 2, 0) + np.where(pl[98 * b:98 * (b + 1), 1] > 0, 1, 0), blk)
+        # truncated: payload incomplete, then NID incomplete
+        assert _oracle_cut(dib[:pre + frame.size - 1], llr[:pre + frame.size - 1], pre + 23, 3 * 98)[0] == 3  # only the trailing status symbol is missing
+        assert _oracle_cut(dib[:pre + frame.size - 2], llr[:pre + frame.size - 2], pre + 23, 3 * 98)[0] == 1
+        assert _oracle_cut(dib[:pre + 40], llr[:pre + 40], pre + 23, 3 * 98)[0] == 0
