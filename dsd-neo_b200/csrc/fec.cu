@@ -1517,6 +1517,135 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
     }
 }
 
+/* ------------------------------------------------------------------ Hamming(10,6,3) soft decode */
+
+/* hamming_10_6_3_decode (src/fec/hamming_10_6_3.cpp:14-105) on a packed word v (bit 9 - i = reference bit i): returns the
+ * status (0 clean / 1 corrected / 2 uncorrectable) and leaves the corrected DATA bits in v (parity bits untouched). */
+__device__ __forceinline__ int
+ham1063_hard(unsigned& v) {
+    const int syn = ((__popc(v & 0x398u) & 1) << 3) | ((__popc(v & 0x354u) & 1) << 2) | ((__popc(v & 0x2E2u) & 1) << 1)
+                    | (__popc(v & 0x1E1u) & 1);
+    if (syn == 0) {
+        return 0;
+    }
+    const int b = (int)((0xF9847FF36FF2510Full >> (4 * syn)) & 0xFull);
+    if (b == 0xF) {
+        return 2;
+    }
+    if (b >= 4) {
+        v ^= 1u << b;
+    }
+    return 1;
+}
+
+/* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475), one thread per word */
+__global__ void
+hamming_10_6_3_soft_kernel(const uint8_t* bits10, const int32_t* reliab10, int hard_override, int threshold, uint8_t* out10,
+                           uint8_t* status, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    const uint8_t* in = bits10 + (size_t)w * 10;
+    const int32_t* rin = reliab10 + (size_t)w * 10;
+    int rel[10];
+    unsigned orig = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int r = rin[i];
+        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
+        orig = (orig << 1) | (in[i] & 1u);
+    }
+    auto penalty = [&](unsigned diff) {
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            p += ((diff >> (9 - i)) & 1u) ? rel[i] : 0;
+        }
+        return p;
+    };
+    int best_pen = 999999, best_flips = 99, found = 0, hard_valid = 0, hard_corrected = 0, hard_pen = 999999;
+    unsigned best = 0, hard = 0;
+    {
+        unsigned v = orig;
+        const int rc = ham1063_hard(v);
+        if (rc != 2) {
+            const unsigned d = v >> 4; /* data bits d0..d5 = bits 5..0 of d */
+            const unsigned d0 = (d >> 5) & 1u, d1 = (d >> 4) & 1u, d2 = (d >> 3) & 1u, d3 = (d >> 2) & 1u, d4 = (d >> 1) & 1u, d5 = d & 1u;
+            hard = (d << 4) | ((d0 ^ d1 ^ d2 ^ d5) << 3) | ((d0 ^ d1 ^ d3 ^ d5) << 2) | ((d0 ^ d2 ^ d3 ^ d4) << 1) | (d1 ^ d2 ^ d3 ^ d4);
+            hard_valid = 1;
+            hard_corrected = rc == 1;
+            hard_pen = penalty(hard ^ orig);
+            best_pen = hard_pen;
+            best_flips = __popc(hard ^ orig);
+            best = hard;
+            found = 1;
+        }
+    }
+    /* find_k_least_reliable (:174-206): rank by (reliability, index); positions under the threshold first */
+    int least[5], n_least = 0;
+    int order[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            rank += (rel[j] < rel[i] || (rel[j] == rel[i] && j < i)) ? 1 : 0;
+        }
+        order[rank] = i;
+    }
+    for (int i = 0; i < 10 && n_least < 5; i++) {
+        if (rel[order[i]] < threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int i = 0; i < 10 && n_least < 5; i++) {
+        if (rel[order[i]] >= threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int mask = 0; mask < 32; mask++) {
+        if (__popc(mask) > 2) {
+            continue;
+        }
+        unsigned cand = orig;
+        for (int b = 0; b < 5; b++) {
+            if (mask & (1 << b)) {
+                cand ^= 1u << (9 - least[b]);
+            }
+        }
+        unsigned v = cand;
+        if (ham1063_hard(v) != 0) {
+            continue;
+        }
+        const int pen = penalty(cand ^ orig);
+        const int flips = __popc(mask);
+        if (pen < best_pen || (pen == best_pen && flips < best_flips)) {
+            best_pen = pen;
+            best_flips = flips;
+            best = cand;
+            found = 1;
+        }
+    }
+    unsigned result = orig;
+    int st = 2;
+    if (found) {
+        if (hard_valid && hard_corrected && best != hard && (!hard_override || best_pen + 8 >= hard_pen)) {
+            result = hard;
+            st = 1;
+        } else {
+            result = best;
+            st = (best == orig) ? 0 : 1;
+        }
+    }
+    uint8_t* o = out10 + (size_t)w * 10;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        o[i] = (uint8_t)((result >> (9 - i)) & 1u);
+    }
+    status[w] = (uint8_t)st;
+}
+
 /* ------------------------------------------------------------------ P25 Phase 1 frame cutter (status-symbol stripping) */
 
 /* Index (from the first sync dibit) of the k-th non-status dibit at or after frame offset `first`: the air interface inserts
@@ -2465,6 +2594,63 @@ dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_out16,
     if (h_err_count) {
         DSDNEO_CUDA(cudaMemcpy(h_err_count, ec.p, n * 4, cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+int
+dsdneo_b200_hamming_10_6_3_soft_batch(const uint8_t* d_bits10, const int32_t* d_reliab10, int hard_override_enabled,
+                                      int erasure_threshold, uint8_t* d_out10, uint8_t* d_status, int n_words, void* stream) {
+    if (!d_bits10 || !d_reliab10 || !d_out10 || !d_status || n_words < 0) {
+        set_error("hamming_10_6_3_soft_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("hamming_10_6_3_soft_kernel", s);
+        hamming_10_6_3_soft_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(d_bits10, d_reliab10, hard_override_enabled,
+                                                                         erasure_threshold, d_out10, d_status, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_hamming_10_6_3_soft_batch_host(const uint8_t* h_bits10, const int32_t* h_reliab10, int hard_override_enabled,
+                                           int erasure_threshold, uint8_t* h_out10, uint8_t* h_status, int n_words) {
+    if (!h_bits10 || !h_reliab10 || !h_out10 || !h_status || n_words < 0) {
+        set_error("hamming_10_6_3_soft_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words;
+    DevBuf in(n * 10), rel(n * 40), out(n * 10), st(n);
+    DSDNEO_CUDA(in.err);
+    DSDNEO_CUDA(rel.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(cudaMemcpy(in.p, h_bits10, n * 10, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(rel.p, h_reliab10, n * 40, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_hamming_10_6_3_soft_batch(in.as<uint8_t>(), rel.as<int32_t>(), hard_override_enabled, erasure_threshold,
+                                               out.as<uint8_t>(), st.as<uint8_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out10, out.p, n * 10, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
     return 0;
 }
 

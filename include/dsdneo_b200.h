@@ -621,6 +621,21 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
                                             int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words);
 
 /**
+ * Batched twin of `int hamming_10_6_3_soft(const char* bits, const int* reliab, char* out_bits)`
+ * (include/dsd-neo/protocol/p25/p25p1_soft.h:40, src/protocol/p25/phase1/p25p1_soft.cpp:444-475): Hamming(10,6,3) with a
+ * bounded search over the 5 least reliable bits (at most 2 flips).  `hard_override_enabled` = p25_soft_hard_override_enabled()
+ * (1 unless configured, p25p1_soft.cpp:41-52), `erasure_threshold` = p25p1_get_erasure_threshold() (64 unless configured).
+ * d_bits10 / d_out10: [n][10] byte-per-bit (6 data + 4 parity); d_reliab10: [n][10] int (clamped to 0..255 like the reference);
+ * d_status[i]: 0 unchanged / 1 corrected / 2 failed (out = in).
+ */
+int dsdneo_b200_hamming_10_6_3_soft_batch(const uint8_t* d_bits10, const int32_t* d_reliab10, int hard_override_enabled,
+                                          int erasure_threshold, uint8_t* d_out10, uint8_t* d_status, int n_words,
+                                          void* stream);
+int dsdneo_b200_hamming_10_6_3_soft_batch_host(const uint8_t* h_bits10, const int32_t* h_reliab10,
+                                               int hard_override_enabled, int erasure_threshold, uint8_t* h_out10,
+                                               uint8_t* h_status, int n_words);
+
+/**
  * P25 Phase 1 frame cutter: what the reference does dibit by dibit between frame sync and the FEC leaves, for every sync
  * hit of every channel at once, so that frames go from the slicer to the FEC kernels without a host round trip:
  *   - NID fields: the 32 dibits after the sync with the status symbol at frame offset 35 dropped, as 63 BCH bits,

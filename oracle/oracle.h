@@ -139,6 +139,8 @@ int oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, 
                                    const uint8_t* par_rel, int threshold);
 int oracle_p25_golay24_decode(int length, uint8_t* word, const uint8_t* parity, int* fixed_errors);
 int oracle_hamming_10_6_3_decode(uint8_t* data6, const uint8_t* parity4);
+/* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475) */
+int oracle_hamming_10_6_3_soft(const uint8_t* bits10, const int* reliab10, int hard_override_enabled, int threshold, uint8_t* out10);
 int oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count);
 /* p25p1_nid_decode (src/protocol/p25/phase1/p25p1_check_nid.cpp:322-354); returns NidResult status, fills nac / duid / errs */
 /* sequential P25p1 frame cutter (NID fields + status-stripped payload); bit 0 NID complete, bit 1 payload complete */

@@ -1920,3 +1920,113 @@ oracle_p25p1_frame_cut(const uint8_t* dibits, const int16_t* llr /* [n][2] */, i
     }
     return flags | 2;
 }
+
+/* ------------------------------------------------------------------ Hamming(10,6,3) soft decode (P25p1 LDU hex words) */
+
+/* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475): the hard decode seeds the best candidate; then the 32
+ * flip masks over the 5 least reliable bits (find_k_least_reliable, :174-206: (reliability, index) order, those under the
+ * erasure threshold first) with at most 2 flips are tried, a candidate counts only if it is a clean codeword; lowest summed
+ * reliability of changed bits wins, then fewer flips; a hard single-bit correction is kept unless overriding is enabled and
+ * the soft winner is more than 8 cheaper.  Returns 0 unchanged / 1 corrected / 2 failed (out = in). */
+int
+oracle_hamming_10_6_3_soft(const uint8_t* bits10, const int* reliab10, int hard_override_enabled, int threshold, uint8_t* out10) {
+    int rel[10];
+    for (int i = 0; i < 10; i++) {
+        rel[i] = reliab10[i] < 0 ? 0 : (reliab10[i] > 255 ? 255 : reliab10[i]);
+    }
+    int best_pen = 999999, best_flips = 99, found = 0, hard_valid = 0, hard_corrected = 0, hard_pen = 999999;
+    uint8_t best[10] = {0}, hard[10] = {0};
+    {
+        uint8_t d[6], p[4];
+        memcpy(d, bits10, 6);
+        memcpy(p, bits10 + 6, 4);
+        const int rc = oracle_hamming_10_6_3_decode(d, p);
+        if (rc == 0 || rc == 1) {
+            memcpy(hard, d, 6);
+            hard[6] = d[0] ^ d[1] ^ d[2] ^ d[5];
+            hard[7] = d[0] ^ d[1] ^ d[3] ^ d[5];
+            hard[8] = d[0] ^ d[2] ^ d[3] ^ d[4];
+            hard[9] = d[1] ^ d[2] ^ d[3] ^ d[4];
+            hard_valid = 1;
+            hard_corrected = rc == 1;
+            hard_pen = 0;
+            int flips = 0;
+            for (int i = 0; i < 10; i++) {
+                if (hard[i] != bits10[i]) {
+                    hard_pen += rel[i];
+                    flips++;
+                }
+            }
+            best_pen = hard_pen;
+            best_flips = flips;
+            memcpy(best, hard, 10);
+            found = 1;
+        }
+    }
+    int order[10], least[5], n_least = 0;
+    for (int i = 0; i < 10; i++) {
+        order[i] = i;
+    }
+    for (int i = 0; i < 10; i++) {
+        for (int j = i + 1; j < 10; j++) {
+            const int a = order[j], b = order[i];
+            if (rel[a] < rel[b] || (rel[a] == rel[b] && a < b)) {
+                order[i] = a;
+                order[j] = b;
+            }
+        }
+    }
+    for (int i = 0; i < 10 && n_least < 5; i++) {
+        if (rel[order[i]] < threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int i = 0; i < 10 && n_least < 5; i++) {
+        if (rel[order[i]] >= threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int mask = 0; mask < 32; mask++) {
+        uint8_t cand[10];
+        memcpy(cand, bits10, 10);
+        int flips = 0;
+        for (int b = 0; b < 5; b++) {
+            if (mask & (1 << b)) {
+                cand[least[b]] ^= 1;
+                flips++;
+            }
+        }
+        if (flips > 2) {
+            continue;
+        }
+        uint8_t d[6];
+        memcpy(d, cand, 6);
+        if (oracle_hamming_10_6_3_decode(d, cand + 6) != 0) {
+            continue;
+        }
+        int pen = 0;
+        for (int i = 0; i < 10; i++) {
+            if (cand[i] != bits10[i]) {
+                pen += rel[i];
+            }
+        }
+        if (pen < best_pen || (pen == best_pen && flips < best_flips)) {
+            best_pen = pen;
+            best_flips = flips;
+            memcpy(best, cand, 10);
+            found = 1;
+        }
+    }
+    if (!found) {
+        memcpy(out10, bits10, 10);
+        return 2;
+    }
+    if (hard_valid && hard_corrected && memcmp(best, hard, 10) != 0) {
+        if (!hard_override_enabled || best_pen + 8 >= hard_pen) {
+            memcpy(out10, hard, 10);
+            return 1;
+        }
+    }
+    memcpy(out10, best, 10);
+    return memcmp(best, bits10, 10) == 0 ? 0 : 1;
+}

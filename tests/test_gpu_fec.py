@@ -332,3 +332,21 @@ def test_p25p1_nid_decode_bit_exact_vs_oracle(gpu):
             assert (st[i], nac[i], duid[i], errs[i]) == (want, v[0].value, v[1].value, v[2].value), (i, use_rel, use_obs)
             seen.add(want)
         assert seen == {0, 1, 2}
+
+
+def test_hamming_10_6_3_soft_bit_exact_vs_oracle(gpu):
+    from test_oracle_fec import hamming_soft_cases
+
+    O = H.oracle_fec()
+    O.oracle_hamming_10_6_3_soft.argtypes = [H.u8p, H.i32p, C.c_int, C.c_int, H.u8p]
+    rng = np.random.default_rng(1064)
+    bits, rel = hamming_soft_cases(rng, 8000)
+    for override in (1, 0):
+        out, st = np.zeros_like(bits), np.zeros(bits.shape[0], np.uint8)
+        gpu.check(gpu.lib().dsdneo_b200_hamming_10_6_3_soft_batch_host(bits.ctypes.data, rel.ctypes.data, override, 64,
+                                                                      out.ctypes.data, st.ctypes.data, bits.shape[0]))
+        for k in range(bits.shape[0]):
+            want = np.zeros(10, np.uint8)
+            rc = O.oracle_hamming_10_6_3_soft(H._ptr(bits[k], H.u8p), rel[k].ctypes.data_as(H.i32p), override, 64, H._ptr(want, H.u8p))
+            assert rc == st[k] and np.array_equal(out[k], want), (k, override)
+        assert set(st.tolist()) == {0, 1, 2}

@@ -737,3 +737,38 @@ def test_p25p1_frame_cut_round_trip():
         assert _oracle_cut(dib[:pre + frame.size - 1], llr[:pre + frame.size - 1], pre + 23, 3 * 98)[0] == 3  # only the trailing status symbol is missing
         assert _oracle_cut(dib[:pre + frame.size - 2], llr[:pre + frame.size - 2], pre + 23, 3 * 98)[0] == 1
         assert _oracle_cut(dib[:pre + 40], llr[:pre + 40], pre + 23, 3 * 98)[0] == 0
+
+
+def hamming_soft_cases(rng, n):
+    """10-bit words around Hamming(10,6,3) codewords with 0..3 flips and reliabilities that mostly mark the flips as weak."""
+    bits, rel = np.zeros((n, 10), np.uint8), np.zeros((n, 10), np.int32)
+    for k in range(n):
+        d = rng.integers(0, 2, 6).astype(np.uint8)
+        cw = np.concatenate([d, [d[0] ^ d[1] ^ d[2] ^ d[5], d[0] ^ d[1] ^ d[3] ^ d[5], d[0] ^ d[2] ^ d[3] ^ d[4],
+                                 d[1] ^ d[2] ^ d[3] ^ d[4]]]).astype(np.uint8)
+        pos = rng.choice(10, int(rng.integers(0, 4)), replace=False)
+        cw[pos] ^= 1
+        r = rng.integers(40, 300, 10)
+        weak = pos[rng.random(pos.size) < 0.75]
+        r[weak] = rng.integers(-5, 80, weak.size)
+        if k % 6 == 0:
+            r[:] = rng.integers(0, 3, 10) * 64  # ties on the threshold
+        bits[k], rel[k] = cw, r
+    return bits, rel
+
+
+@needs_ref
+def test_hamming_10_6_3_soft_matches_reference():
+    O, R = H.oracle_fec(), H.ref_fec()
+    O.oracle_hamming_10_6_3_soft.argtypes = [H.u8p, H.i32p, C.c_int, C.c_int, H.u8p]
+    R.hamming_10_6_3_soft.argtypes = [H.u8p, H.i32p, H.u8p]
+    rng = np.random.default_rng(1063)
+    bits, rel = hamming_soft_cases(rng, 6000)
+    seen = set()
+    for k in range(bits.shape[0]):
+        oa, ob = np.zeros(10, np.uint8), np.zeros(10, np.uint8)
+        ra = R.hamming_10_6_3_soft(H._ptr(bits[k], H.u8p), rel[k].ctypes.data_as(H.i32p), H._ptr(oa, H.u8p))
+        rb = O.oracle_hamming_10_6_3_soft(H._ptr(bits[k], H.u8p), rel[k].ctypes.data_as(H.i32p), 1, 64, H._ptr(ob, H.u8p))
+        assert ra == rb and np.array_equal(oa, ob), (k, ra, rb, bits[k], rel[k], oa, ob)
+        seen.add(ra)
+    assert seen == {0, 1, 2}
