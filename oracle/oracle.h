@@ -190,6 +190,17 @@ long oracle_sym_run_symbols(oracle_sym_chan* c, int have_sync, const float* samp
 long oracle_sym_run_dibits(oracle_sym_chan* c, const float* samples, long n, long reserve, uint8_t* dibits, uint8_t* rel,
                            int16_t* llr2, float* symbols, long max_out, long* consumed);
 
+/* symbol-rate CQPSK input (output kind 2): thresholds / tracker / CQPSK slicer / soft metric of the sample side */
+typedef struct oracle_cqpsk_slicer {
+    oracle_sym_chan base; /* tracker state (sbuf, minbuf / maxbuf, running sums), thresholds, negative flag */
+    int p25_slice;        /* is_cqpsk_active() && rf_mod == 1 && P25 sync type (dsd_dibit.c:950-961) */
+    int map_idx;          /* state->p25_cqpsk_dibit_map_idx */
+    double snr_db;        /* dsd_rtl_stream_metrics_hook_snr_cqpsk_db(); <= -50 = no hook */
+} oracle_cqpsk_slicer;
+void oracle_cqpsk_slicer_init(oracle_cqpsk_slicer* s, int negative, int p25_slice, int map_idx, double snr_db, int ssize, int msize);
+int oracle_cqpsk_slicer_dibit(oracle_cqpsk_slicer* s, float sample, uint8_t* rel_out, int16_t llr_out[2]);
+long oracle_cqpsk_slicer_run(oracle_cqpsk_slicer* s, const float* symbols, long n, uint8_t* dibits, uint8_t* rel, int16_t* llr2);
+
 int oracle_frame_sync_search(const float* symbols, int n, const char* const* patterns, const int* sync_types, int n_patterns,
                              char* hist32, int* hist_count, int* hit_pos, int* hit_type, int max_hits);
 /* ------------------------------- MBE synthesis stage (oracle_mbe.c) -- PARITY UNPINNED, see its header --------- */

@@ -462,3 +462,128 @@ oracle_frame_sync_search(const float* symbols, int n, const char* const* pattern
     }
     return found;
 }
+
+/* ---- symbol-rate CQPSK input (output kind 2): the sample side behind the CQPSK chain ------------------------------------
+ *
+ *   getSymbol fast path        src/dsp/dsd_symbol.c:1583-1625 (fixed +-2 / 0 thresholds before every take, :744-765; one
+ *                              stream float = one symbol)
+ *   use_symbol                 src/core/frames/dsd_dibit.c:243-299 with rf_mod == 1: the rolling min / max tracker always runs
+ *   digitize                   :1018-1041 -> select_four_level_dibit :978-1003: cqpsk_slice(symbol - center) (:329-349) through
+ *                              the OP25 dibit orientation map (include/dsd-neo/core/p25_cqpsk_dibit.h:28-52) when the CQPSK
+ *                              chain is active and the sync is a P25 one, else the threshold regions (:963-976)
+ *   soft metric                compute_dibit_soft_metric :685-721 with build_cqpsk_dibit_ideals (:660-683) or the standard
+ *                              ideals; reliability = cqpsk_reliability_raw (:376-401) weighted by the CQPSK SNR hook (:404-427)
+ * Not restated: the DSD_NEO_CQPSK_SYNC_INV / _NEG debug switches (cfg->cqpsk_sync_inv / neg, default off).
+ * Pinned against the compiled reference by tests/test_oracle_symbol.py (dibits, reliabilities, LLRs, thresholds). */
+void
+oracle_cqpsk_slicer_init(oracle_cqpsk_slicer* s, int negative, int p25_slice, int map_idx, double snr_db, int ssize, int msize) {
+    oracle_sym_init(&s->base, 4800, 4800, 0, 2, 1, negative, 0, 0, ssize, msize);
+    s->p25_slice = p25_slice;
+    s->map_idx = (map_idx >= 0 && map_idx < 5) ? map_idx : 0;
+    s->snr_db = snr_db;
+}
+
+static int
+cqpsk_map_correct(int map_idx, int dibit) {
+    static const uint8_t maps[5][4] = {{0, 1, 2, 3}, {2, 3, 0, 1}, {3, 2, 1, 0}, {1, 3, 0, 2}, {2, 0, 3, 1}};
+    return maps[map_idx][dibit & 3];
+}
+
+static int
+dibit_invert(int d) { /* dsd_dibit.c:300-311 */
+    return (d + 2) & 3;
+}
+
+int
+oracle_cqpsk_slicer_dibit(oracle_cqpsk_slicer* s, float sample, uint8_t* rel_out, int16_t llr_out[2]) {
+    oracle_sym_chan* c = &s->base;
+    /* symbol_try_rtl_symbol_rate_fast_path */
+    c->center = 0.0f;
+    c->min = -3.0f;
+    c->max = 3.0f;
+    c->lmid = -2.0f;
+    c->umid = 2.0f;
+    c->minref = -2.4f;
+    c->maxref = 2.4f;
+    const float sym = sample;
+    c->lastsample = sym;
+    c->symbolcnt++;
+    /* get_dibit_and_analog_signal */
+    c->sbuf[c->sidx] = sym;
+    use_symbol(c);
+    int dibit;
+    float ideal[4];
+    if (s->p25_slice) {
+        const float v = sym - c->center;
+        int raw = v >= 2.0f ? 1 : (v >= 0.0f ? 0 : (v >= -2.0f ? 2 : 3));
+        dibit = cqpsk_map_correct(s->map_idx, raw);
+        if (c->negative) {
+            dibit = dibit_invert(dibit);
+        }
+        static const float base_ideal[4] = {1.0f, 3.0f, -1.0f, -3.0f};
+        for (int d = 0; d < 4; d++) {
+            const int corrected = c->negative ? dibit_invert(d) : d;
+            int mapped = corrected;
+            for (int raw_d = 0; raw_d < 4; raw_d++) { /* dsd_p25_cqpsk_raw_dibit_for_corrected */
+                if (cqpsk_map_correct(s->map_idx, raw_d) == corrected) {
+                    mapped = raw_d;
+                    break;
+                }
+            }
+            ideal[d] = c->center + base_ideal[mapped];
+        }
+    } else {
+        if (sym > c->center) {
+            dibit = sym > c->umid ? (c->negative ? 3 : 1) : (c->negative ? 2 : 0);
+        } else {
+            dibit = sym < c->lmid ? (c->negative ? 1 : 3) : (c->negative ? 0 : 2);
+        }
+        const float plus_one = 0.5f * (c->center + c->umid), minus_one = 0.5f * (c->lmid + c->center);
+        if (c->negative) {
+            ideal[0] = minus_one, ideal[1] = c->min, ideal[2] = plus_one, ideal[3] = c->max;
+        } else {
+            ideal[0] = plus_one, ideal[1] = c->max, ideal[2] = minus_one, ideal[3] = c->min;
+        }
+    }
+    int mag0 = bit_metric(sym, ideal, 0), mag1 = bit_metric(sym, ideal, 1);
+    /* dmr_compute_reliability, rf_mod == 1 */
+    int rel;
+    {
+        const float sc = sym - c->center;
+        const float id = sc >= 2.0f ? 3.0f : (sc >= 0.0f ? 1.0f : (sc >= -2.0f ? -1.0f : -3.0f));
+        float err = fabsf(sc - id);
+        if (err > 1.0f) {
+            err = 1.0f;
+        }
+        rel = clamp255((int)((1.0f - err) * 255.0f + 0.5f));
+        if (!(s->snr_db <= -50.0)) {
+            int w256 = 0;
+            if (s->snr_db >= 25.0) {
+                w256 = 255;
+            } else if (s->snr_db > 0.0) {
+                w256 = (int)((s->snr_db / 25.0) * 255.0 + 0.5);
+            }
+            rel = clamp255((rel * (204 + (w256 >> 2))) >> 8);
+        }
+    }
+    const int min_mag = mag0 < mag1 ? mag0 : mag1;
+    if (min_mag > 0 && rel < min_mag) {
+        mag0 = (mag0 * rel) / min_mag;
+        mag1 = (mag1 * rel) / min_mag;
+    }
+    mag0 = clamp255(mag0);
+    mag1 = clamp255(mag1);
+    llr_out[0] = (int16_t)(((dibit >> 1) & 1) ? mag0 : -mag0);
+    llr_out[1] = (int16_t)((dibit & 1) ? mag1 : -mag1);
+    const int a0 = llr_out[0] < 0 ? -llr_out[0] : llr_out[0], a1 = llr_out[1] < 0 ? -llr_out[1] : llr_out[1];
+    *rel_out = (uint8_t)clamp255(a1 < a0 ? a1 : a0);
+    return dibit;
+}
+
+long
+oracle_cqpsk_slicer_run(oracle_cqpsk_slicer* s, const float* symbols, long n, uint8_t* dibits, uint8_t* rel, int16_t* llr2) {
+    for (long i = 0; i < n; i++) {
+        dibits[i] = (uint8_t)oracle_cqpsk_slicer_dibit(s, symbols[i], &rel[i], &llr2[2 * i]);
+    }
+    return n;
+}

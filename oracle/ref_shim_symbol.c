@@ -54,7 +54,20 @@ hook_pwr(const void* ctx) {
     return 0.0;
 }
 
-static int hook_output_kind(void) { return RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR; }
+static int g_kind = RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR, g_cqpsk_active = 0;
+static double g_snr_cqpsk = -100.0;
+static int hook_output_kind(void) { return g_kind; }
+static int
+hook_cqpsk_status(int* cqpsk, int* timing) {
+    if (cqpsk) {
+        *cqpsk = g_cqpsk_active;
+    }
+    if (timing) {
+        *timing = g_cqpsk_active;
+    }
+    return 0;
+}
+static double hook_snr_cqpsk(void) { return g_snr_cqpsk; }
 static unsigned int hook_output_rate(void) { return (unsigned int)g_live->out_rate; }
 static uint32_t hook_generation(void) { return 1U; }
 
@@ -122,8 +135,35 @@ ref_sym_create(int output_rate_hz, int symbol_rate_hz, int synctype, int lastsyn
     mh.output_rate_hz = hook_output_rate;
     mh.symbol_profile = hook_symbol_profile;
     mh.stream_generation = hook_generation;
+    g_kind = RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR;
+    g_cqpsk_active = 0;
+    g_snr_cqpsk = -100.0;
     dsd_rtl_stream_metrics_hooks_set(&mh);
     g_oracle_shutdown_requested = 0;
+    return h;
+}
+
+/* Symbol-rate CQPSK stream (output kind 2, src/dsp/dsd_symbol.c:1583-1625): the hooks report what the CQPSK block side
+ * reports (kind 2, profile P25_CQPSK, cqpsk_status, the CQPSK SNR), state->rf_mod = 1 as the modulation detector / -mq set it. */
+void*
+ref_sym_create_cqpsk(int symbol_rate_hz, int synctype, int lastsynctype, int ssize, int msize, int map_idx, int cqpsk_active,
+                     double snr_db) {
+    ref_sym* h = (ref_sym*)ref_sym_create(symbol_rate_hz, symbol_rate_hz, synctype, lastsynctype, 0, ssize, msize);
+    h->profile = RTL_STREAM_CHANNEL_PROFILE_P25_CQPSK;
+    h->state->rf_mod = 1;
+    h->state->p25_cqpsk_dibit_map_idx = (uint8_t)map_idx;
+    g_kind = RTL_STREAM_OUTPUT_SYMBOL_CQPSK;
+    g_cqpsk_active = cqpsk_active;
+    g_snr_cqpsk = snr_db;
+    dsd_rtl_stream_metrics_hooks mh;
+    memset(&mh, 0, sizeof(mh));
+    mh.output_kind = hook_output_kind;
+    mh.output_rate_hz = hook_output_rate;
+    mh.symbol_profile = hook_symbol_profile;
+    mh.stream_generation = hook_generation;
+    mh.cqpsk_status = hook_cqpsk_status;
+    mh.snr_cqpsk_db = hook_snr_cqpsk;
+    dsd_rtl_stream_metrics_hooks_set(&mh);
     return h;
 }
 

@@ -800,3 +800,23 @@ def p25p1_build_tsdu(rng, nac, n_blocks=3, bch_encode=None):
         body.append(tx98)
         payloads.append(d49)
     return p25p1_insert_status(np.concatenate(body)), payloads
+
+
+class OracleCqpskSlicer(C.Structure):
+    _fields_ = [("base", OracleSymChan), ("p25_slice", C.c_int), ("map_idx", C.c_int), ("snr_db", C.c_double)]
+
+
+def oracle_cqpsk_slicer_run(symbols, negative=0, p25_slice=1, map_idx=0, snr_db=-100.0, ssize=128, msize=1024, state=None):
+    """Symbol-rate CQPSK sample side (oracle/oracle_symbol.c): returns (dibits, reliability, llr [n, 2], state)."""
+    L = oracle()
+    L.oracle_cqpsk_slicer_init.argtypes = [C.POINTER(OracleCqpskSlicer), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+    L.oracle_cqpsk_slicer_run.restype = C.c_long
+    L.oracle_cqpsk_slicer_run.argtypes = [C.POINTER(OracleCqpskSlicer), f32p, C.c_long, u8p, u8p, C.POINTER(C.c_int16)]
+    if state is None:
+        state = OracleCqpskSlicer()
+        L.oracle_cqpsk_slicer_init(C.byref(state), negative, p25_slice, map_idx, snr_db, ssize, msize)
+    symbols = np.ascontiguousarray(symbols, np.float32)
+    n = symbols.size
+    d, r, l = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros((n, 2), np.int16)
+    L.oracle_cqpsk_slicer_run(C.byref(state), _ptr(symbols), n, _ptr(d, u8p), _ptr(r, u8p), l.ctypes.data_as(C.POINTER(C.c_int16)))
+    return d, r, l, state

@@ -120,3 +120,47 @@ def test_oracle_matches_committed_golden_vectors():
         assert k == n
         assert np.array_equal(d, g[name + "_dibits"]) and np.array_equal(r, g[name + "_rel"]) and np.array_equal(l, g[name + "_llr"])
         assert H.bits_equal(s, g[name + "_symbols"])
+
+
+def cqpsk_symbol_stream(rng, n, noise=0.25, offset=0.0):
+    """Symbol-rate CQPSK stream as the block side emits it: values near {-3,-1,+1,+3} (+ noise, + a slow centre drift)."""
+    lv = H.LEVELS[rng.integers(0, 4, n)]
+    drift = offset * np.sin(np.arange(n) / 700.0)
+    return (lv + noise * rng.standard_normal(n) + drift).astype(np.float32)
+
+
+@needs_ref
+@pytest.mark.parametrize("sync,active,map_idx,snr", [(H.SYNC_P25P1_POS, 1, 0, -100.0), (H.SYNC_P25P1_NEG, 1, 0, 18.0),
+                                                     (H.SYNC_P25P1_POS, 1, 3, 30.0), (H.SYNC_P25P1_POS, 1, 2, 7.5),
+                                                     (H.SYNC_P25P1_NEG, 1, 4, -100.0), (H.SYNC_P25P1_POS, 0, 0, 12.0),
+                                                     (H.SYNC_DMR_BS_DATA_POS, 1, 1, 3.0)])
+def test_cqpsk_symbol_rate_slicer_matches_reference(sync, active, map_idx, snr):
+    """Output kind 2 (symbol-rate CQPSK): the oracle's thresholds / tracker / CQPSK slicer / soft metric equal the unmodified
+    reference getDibitSoft() driven through its hook seam with rf_mod = 1: dibits, reliabilities, LLRs, symbols, thresholds."""
+    R = H.ref_sym()
+    R.ref_sym_create_cqpsk.restype = C.c_void_p
+    R.ref_sym_create_cqpsk.argtypes = [C.c_int] * 7 + [C.c_double]
+    R.ref_sym_get_dibits_n.restype = C.c_long
+    R.ref_sym_get_dibits_n.argtypes = [C.c_void_p, C.c_long, H.u8p, H.u8p, C.POINTER(C.c_int16), H.f32p]
+    rng = np.random.default_rng(500 + sync * 11 + map_idx)
+    n = 5000
+    x = cqpsk_symbol_stream(rng, n + 600, noise=0.35, offset=0.3)
+    h = R.ref_sym_create_cqpsk(4800, sync, sync, 128, 1024, map_idx, active, snr)
+    R.ref_sym_feed(h, H._ptr(x), x.size)
+    d = np.zeros(n, np.uint8); r = np.zeros(n, np.uint8); l = np.zeros(2 * n, np.int16); s = np.zeros(n, np.float32)
+    assert R.ref_sym_get_dibits_n(h, n, H._ptr(d, H.u8p), H._ptr(r, H.u8p), l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s)) == n
+    f8, i5 = np.zeros(8, np.float32), np.zeros(5, np.int32)
+    R.ref_sym_get_state(h, H._ptr(f8), i5.ctypes.data_as(H.i32p))
+    R.ref_sym_destroy(h)
+    assert H.bits_equal(s, x[:n])  # one stream float = one symbol
+    is_p25 = sync in (H.SYNC_P25P1_POS, H.SYNC_P25P1_NEG)
+    neg = H.SYNC_CLASS[sync]["negative"]
+    d2, r2, l2, st = H.oracle_cqpsk_slicer_run(x[:n], negative=neg, p25_slice=1 if (active and is_p25) else 0, map_idx=map_idx,
+                                               snr_db=snr)
+    assert np.array_equal(d, d2), int(np.argmax(d != d2))
+    assert np.array_equal(r, r2), int(np.argmax(r != r2))
+    assert np.array_equal(l, l2.reshape(-1))
+    b = st.base
+    want = np.array([b.min, b.max, b.center, b.umid, b.lmid, b.minref, b.maxref, b.lastsample], np.float32)
+    assert H.bits_equal(f8, want), (f8, want)
+    assert len(set(d.tolist())) == 4
