@@ -331,6 +331,58 @@ class CqpskBank:
         return sym, counts
 
 
+class CqpskSlicer:
+    """Symbol-rate CQPSK sample side (tracker + CQPSK slicer + soft metrics) behind CqpskBank.full_demod."""
+
+    def __init__(self, n_channels: int, ssize: int = 128, msize: int = 1024):
+        self.n_channels = n_channels
+        self._h = lib().dsdneo_b200_cqpsk_slicer_create(n_channels, ssize, msize)
+        if not self._h:
+            raise B200Error(f"cqpsk_slicer_create failed: {last_error()}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and lib is not None:
+            lib().dsdneo_b200_cqpsk_slicer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=None) -> None:
+        check(lib().dsdneo_b200_cqpsk_slicer_reset(self._h, _stream_ptr(stream)), "cqpsk_slicer_reset")
+
+    def set_class(self, negative=None, p25_slice=None, map_idx=None, snr_cqpsk_db: float = -100.0) -> None:
+        import numpy as np
+
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint8) for a in (negative, p25_slice, map_idx)]
+        check(lib().dsdneo_b200_cqpsk_slicer_set_class(self._h, *[None if a is None else a.ctypes.data for a in arrs],
+                                                       snr_cqpsk_db), "cqpsk_slicer_set_class")
+
+    def run(self, d_symbols, d_n_symbols, stream=None):
+        """d_symbols cuda f32 [n_channels, pitch], d_n_symbols cuda int32 [n_channels] -> dict(dibits, reliability, llr)."""
+        import torch
+
+        assert d_symbols.is_cuda and d_symbols.dtype == torch.float32 and d_symbols.is_contiguous()
+        assert d_n_symbols.dtype == torch.int32 and d_n_symbols.is_contiguous()
+        pitch = d_symbols.shape[1]
+        dev = d_symbols.device
+        out = {"dibits": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+               "reliability": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+               "llr": torch.zeros((self.n_channels, pitch, 2), dtype=torch.int16, device=dev)}
+        if stream is None:
+            stream = torch.cuda.current_stream(dev)
+        check(lib().dsdneo_b200_cqpsk_slice_batch(self._h, d_symbols.data_ptr(), pitch, d_n_symbols.data_ptr(),
+                                                  out["dibits"].data_ptr(), out["reliability"].data_ptr(), out["llr"].data_ptr(),
+                                                  pitch, _stream_ptr(stream)), "cqpsk_slice_batch")
+        return out
+
+    def state(self, channel: int):
+        import numpy as np
+
+        out = np.zeros(8, np.float32)
+        check(lib().dsdneo_b200_cqpsk_slicer_get_state(self._h, channel, out.ctypes.data), "cqpsk_slicer_get_state")
+        return out
+
+
 class SyncPattern(C.Structure):
     _fields_ = [("symbols", C.c_char_p), ("sync_type", C.c_int)]
 

@@ -663,6 +663,251 @@ sym_reset_kernel(SymScalars s, float* minbuf, float* maxbuf, float* sbuf, float*
     }
 }
 
+/* ---- symbol-rate CQPSK input (output kind 2): the sample side behind cqpsk_chain_kernel ---------------------------------
+ *
+ * Reference, per symbol (one stream float = one symbol):
+ *   symbol_try_rtl_symbol_rate_fast_path   src/dsp/dsd_symbol.c:1583-1625 (fixed thresholds :744-765, then take)
+ *   use_symbol, rf_mod == 1                src/core/frames/dsd_dibit.c:243-299: the min / max tracker always runs and
+ *                                           overwrites the fixed thresholds before digitize sees them
+ *   digitize                               :1018-1041: cqpsk_slice(symbol - center) (:329-349) through the OP25 dibit map
+ *                                           (core/p25_cqpsk_dibit.h) when the CQPSK chain is active on a P25 sync, else regions
+ *   compute_dibit_soft_metric              :685-721 with build_cqpsk_dibit_ideals (:660-683) / standard ideals,
+ *                                           reliability = cqpsk_reliability_raw (:376-401) x CQPSK SNR weight (:404-427)
+ * One lane per channel.  The symbol value does not feed back into anything but the tracker, so the per-channel chain is
+ * the 128-entry extrema scan (kept in shared memory, [entry][lane]) and the two f64 running sums. */
+struct CqSliceParams {
+    const float* symbols; /* [n_ch][sym_pitch] */
+    size_t sym_pitch;
+    const int* n_symbols; /* [n_ch] */
+    uint8_t* dibits;      /* [n_ch][out_pitch] */
+    uint8_t* reliab;
+    int16_t* llr;         /* [n_ch][out_pitch][2] */
+    size_t out_pitch;
+    /* per-channel class */
+    const uint8_t* negative;
+    const uint8_t* p25_slice;
+    const uint8_t* map_idx;
+    /* carried state */
+    float* sbuf;          /* [128][n_ch] */
+    float* minbuf;        /* [1024][n_ch] */
+    float* maxbuf;
+    int* sidx;
+    int* midx;
+    int* sum_window;
+    double* minbuf_sum;
+    double* maxbuf_sum;
+    float* thr;           /* [8][n_ch]: min, max, center, umid, lmid, minref, maxref, lastsample */
+    int n_ch, ssize, msize;
+    int snr_scale_num;    /* 204 + (w256 >> 2), or 0 when the SNR hook reports <= -50 dB (no weighting) */
+};
+
+__global__ void __launch_bounds__(32)
+cqpsk_slice_kernel(const CqSliceParams p) {
+    __shared__ float s_sbuf[128 * 32];
+    const int lane = threadIdx.x;
+    const int ch = blockIdx.x * 32 + lane;
+    const bool valid = ch < p.n_ch;
+    const int n_ch = p.n_ch;
+    int cap = p.ssize < 0 ? 0 : (p.ssize > 128 ? 128 : p.ssize);
+    const int window = p.msize < 1 ? 1 : (p.msize > 1024 ? 1024 : p.msize);
+    for (int k = 0; k < 128; k++) {
+        s_sbuf[k * 32 + lane] = valid ? p.sbuf[(size_t)k * n_ch + ch] : 0.0f;
+    }
+    int n = 0, sidx = 0, midx = 0, negative = 0, p25 = 0, map_idx = 0;
+    double min_sum = 0.0, max_sum = 0.0;
+    float vmin = 0.0f, vmax = 0.0f, center = 0.0f, umid = 0.0f, lmid = 0.0f, minref = 0.0f, maxref = 0.0f, last = 0.0f;
+    if (valid) {
+        n = p.n_symbols[ch];
+        sidx = p.sidx[ch];
+        midx = p.midx[ch];
+        negative = p.negative[ch];
+        p25 = p.p25_slice[ch];
+        map_idx = p.map_idx[ch] < 5 ? p.map_idx[ch] : 0;
+        min_sum = p.minbuf_sum[ch];
+        max_sum = p.maxbuf_sum[ch];
+        vmin = p.thr[0 * (size_t)n_ch + ch];
+        vmax = p.thr[1 * (size_t)n_ch + ch];
+        center = p.thr[2 * (size_t)n_ch + ch];
+        umid = p.thr[3 * (size_t)n_ch + ch];
+        lmid = p.thr[4 * (size_t)n_ch + ch];
+        minref = p.thr[5 * (size_t)n_ch + ch];
+        maxref = p.thr[6 * (size_t)n_ch + ch];
+        last = p.thr[7 * (size_t)n_ch + ch];
+        if (n > 0 && p.sum_window[ch] != window) { /* dsd_state_sync_minmax_sums, core/state.h:1388-1428 */
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < window; i++) {
+                a += (double)p.minbuf[(size_t)i * n_ch + ch];
+                b += (double)p.maxbuf[(size_t)i * n_ch + ch];
+            }
+            min_sum = a;
+            max_sum = b;
+            p.sum_window[ch] = window;
+            if (midx < 0 || midx >= window) {
+                midx = 0;
+            }
+        }
+    }
+    /* OP25 orientation maps (include/dsd-neo/core/p25_cqpsk_dibit.h:28-52), 2 bits per entry, and their inverses */
+    const unsigned fwd[5] = {0xE4u, 0x4Eu, 0x1Bu, 0x8Du, 0x72u};
+    const unsigned fmap = fwd[map_idx];
+    unsigned inv = 0;
+#pragma unroll
+    for (int raw = 3; raw >= 0; raw--) { /* lowest raw dibit wins, like dsd_p25_cqpsk_raw_dibit_for_corrected */
+        const unsigned c = (fmap >> (2 * raw)) & 3u;
+        inv = (inv & ~(3u << (2 * c))) | ((unsigned)raw << (2 * c));
+    }
+    const float* in = p.symbols + (size_t)(valid ? ch : 0) * p.sym_pitch;
+    uint8_t* od = p.dibits + (size_t)(valid ? ch : 0) * p.out_pitch;
+    uint8_t* orl = p.reliab + (size_t)(valid ? ch : 0) * p.out_pitch;
+    int16_t* ol = p.llr + (size_t)(valid ? ch : 0) * p.out_pitch * 2;
+    float* my_sbuf = s_sbuf + lane;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const float sym = in[i];
+        last = sym;
+        if (cap > 0) {
+            my_sbuf[sidx * 32] = sym; /* cap <= 0: the reference writes sbuf[sidx] with sidx stuck at its initial 0 */
+        } else {
+            my_sbuf[0] = sym;
+        }
+        /* use_symbol: average of the two smallest / two largest of sbuf[0..cap) (order independent, so exact) */
+        float lmin = 0.0f, lmax = 0.0f;
+        if (cap >= 2) {
+            const float a = my_sbuf[0], b = my_sbuf[32];
+            float mn1 = fminf(a, b), mn2 = fmaxf(a, b), mx1 = mn2, mx2 = mn1;
+#pragma unroll 8
+            for (int k = 2; k < cap; k++) {
+                const float v = my_sbuf[k * 32];
+                two_min_push(mn1, mn2, v);
+                two_max_push(mx1, mx2, v);
+            }
+            lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
+            lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
+        }
+        {
+            int idx = midx;
+            if (idx < 0 || idx >= window) {
+                idx = 0;
+            }
+            float* mb = p.minbuf + (size_t)idx * n_ch + ch;
+            float* xb = p.maxbuf + (size_t)idx * n_ch + ch;
+            min_sum += (double)lmin - (double)*mb;
+            max_sum += (double)lmax - (double)*xb;
+            *mb = lmin;
+            *xb = lmax;
+            idx++;
+            midx = idx >= window ? 0 : idx;
+        }
+        vmin = (float)(min_sum / (double)window);
+        vmax = (float)(max_sum / (double)window);
+        center = __fdiv_rn(__fadd_rn(vmax, vmin), 2.0f);
+        umid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 8.0f), center);
+        lmid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 8.0f), center);
+        maxref = __fmul_rn(vmax, 0.80f);
+        minref = __fmul_rn(vmin, 0.80f);
+        if (cap > 0) {
+            sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
+        }
+        /* digitize */
+        int dibit;
+        float ideal[4];
+        const float sc = __fsub_rn(sym, center);
+        if (p25) {
+            const int raw = sc >= 2.0f ? 1 : (sc >= 0.0f ? 0 : (sc >= -2.0f ? 2 : 3));
+            dibit = (int)((fmap >> (2 * raw)) & 3u);
+            if (negative) {
+                dibit = (dibit + 2) & 3;
+            }
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const int corrected = negative ? ((d + 2) & 3) : d;
+                const int mapped = (int)((inv >> (2 * corrected)) & 3u);
+                /* base levels {+1, +3, -1, -3} for raw dibits 0..3 */
+                const float level = (mapped == 0) ? 1.0f : ((mapped == 1) ? 3.0f : ((mapped == 2) ? -1.0f : -3.0f));
+                ideal[d] = __fadd_rn(center, level);
+            }
+        } else {
+            if (sym > center) {
+                dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+            } else {
+                dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
+            }
+            const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+            if (negative) {
+                ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+            } else {
+                ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+            }
+        }
+        int mag0, mag1;
+        bit_metrics(sym, ideal, mag0, mag1);
+        /* dmr_compute_reliability, rf_mod == 1 */
+        const float id = sc >= 2.0f ? 3.0f : (sc >= 0.0f ? 1.0f : (sc >= -2.0f ? -1.0f : -3.0f));
+        float err = fabsf(__fsub_rn(sc, id));
+        if (err > 1.0f) {
+            err = 1.0f;
+        }
+        int rel = clamp255(__float2int_rz(__fadd_rn(__fmul_rn(__fsub_rn(1.0f, err), 255.0f), 0.5f)));
+        if (p.snr_scale_num > 0) {
+            rel = clamp255((rel * p.snr_scale_num) >> 8);
+        }
+        const int min_mag = mag0 < mag1 ? mag0 : mag1;
+        if (min_mag > 0 && rel < min_mag) {
+            mag0 = (mag0 * rel) / min_mag;
+            mag1 = (mag1 * rel) / min_mag;
+        }
+        mag0 = clamp255(mag0);
+        mag1 = clamp255(mag1);
+        const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
+        od[i] = (uint8_t)dibit;
+        orl[i] = (uint8_t)clamp255(min(abs(l0), abs(l1)));
+        ol[2 * i] = (int16_t)l0;
+        ol[2 * i + 1] = (int16_t)l1;
+    }
+    if (valid) {
+        for (int k = 0; k < 128; k++) {
+            p.sbuf[(size_t)k * n_ch + ch] = s_sbuf[k * 32 + lane];
+        }
+        p.sidx[ch] = sidx;
+        p.midx[ch] = midx;
+        p.minbuf_sum[ch] = min_sum;
+        p.maxbuf_sum[ch] = max_sum;
+        p.thr[0 * (size_t)n_ch + ch] = vmin;
+        p.thr[1 * (size_t)n_ch + ch] = vmax;
+        p.thr[2 * (size_t)n_ch + ch] = center;
+        p.thr[3 * (size_t)n_ch + ch] = umid;
+        p.thr[4 * (size_t)n_ch + ch] = lmid;
+        p.thr[5 * (size_t)n_ch + ch] = minref;
+        p.thr[6 * (size_t)n_ch + ch] = maxref;
+        p.thr[7 * (size_t)n_ch + ch] = last;
+    }
+}
+
+__global__ void
+cqpsk_slicer_reset_kernel(float* sbuf, float* minbuf, float* maxbuf, int* sidx, int* midx, int* sum_window, double* a, double* b,
+                          float* thr, int n_ch) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_ch) {
+        return;
+    }
+    for (int k = 0; k < 128; k++) {
+        sbuf[(size_t)k * n_ch + ch] = 0.0f;
+    }
+    for (int k = 0; k < 1024; k++) { /* initState, src/core/util/dsd_init.c:519-592 */
+        minbuf[(size_t)k * n_ch + ch] = -15000.0f;
+        maxbuf[(size_t)k * n_ch + ch] = 15000.0f;
+    }
+    sidx[ch] = 0;
+    midx[ch] = 0;
+    sum_window[ch] = 0;
+    a[ch] = 0.0;
+    b[ch] = 0.0;
+    const float init[8] = {-15000.0f, 15000.0f, 0.0f, 0.0f, 0.0f, -12000.0f, 12000.0f, 0.0f};
+    for (int k = 0; k < 8; k++) {
+        thr[(size_t)k * n_ch + ch] = init[k];
+    }
+}
+
 }  // namespace
 
 struct dsdneo_b200_symbolizer {
@@ -1004,6 +1249,200 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
+    return 0;
+}
+
+} /* extern "C" */
+
+/* ---- symbol-rate CQPSK slicer ------------------------------------------------------------------------------------------ */
+
+struct dsdneo_b200_cqpsk_slicer {
+    int n_ch, ssize, msize, snr_scale_num;
+    uint8_t *d_negative, *d_p25, *d_map;
+    float *d_sbuf, *d_minbuf, *d_maxbuf, *d_thr;
+    int *d_sidx, *d_midx, *d_sum_window;
+    double *d_min_sum, *d_max_sum;
+};
+
+extern "C" {
+
+dsdneo_b200_cqpsk_slicer*
+dsdneo_b200_cqpsk_slicer_create(int n_channels, int ssize, int msize) {
+    if (n_channels <= 0) {
+        set_error("cqpsk_slicer_create: bad channel count");
+        return NULL;
+    }
+    if (ensure_device()) {
+        return NULL;
+    }
+    dsdneo_b200_cqpsk_slicer* q = (dsdneo_b200_cqpsk_slicer*)calloc(1, sizeof(*q));
+    if (!q) {
+        set_error("cqpsk_slicer_create: out of host memory");
+        return NULL;
+    }
+    const size_t n = (size_t)n_channels;
+    q->n_ch = n_channels;
+    q->ssize = ssize > 0 ? ssize : 128;   /* opts->ssize / msize defaults, src/core/util/dsd_init.c:169-170 */
+    q->msize = msize > 0 ? msize : 1024;
+    cudaError_t e = cudaMalloc((void**)&q->d_negative, n);
+#define CQS_ALLOC(ptr, bytes)                                                                                          \
+    if (e == cudaSuccess) {                                                                                            \
+        e = cudaMalloc((void**)&(ptr), (bytes));                                                                       \
+    }
+    CQS_ALLOC(q->d_p25, n);
+    CQS_ALLOC(q->d_map, n);
+    CQS_ALLOC(q->d_sbuf, n * 128 * sizeof(float));
+    CQS_ALLOC(q->d_minbuf, n * 1024 * sizeof(float));
+    CQS_ALLOC(q->d_maxbuf, n * 1024 * sizeof(float));
+    CQS_ALLOC(q->d_thr, n * 8 * sizeof(float));
+    CQS_ALLOC(q->d_sidx, n * sizeof(int));
+    CQS_ALLOC(q->d_midx, n * sizeof(int));
+    CQS_ALLOC(q->d_sum_window, n * sizeof(int));
+    CQS_ALLOC(q->d_min_sum, n * sizeof(double));
+    CQS_ALLOC(q->d_max_sum, n * sizeof(double));
+#undef CQS_ALLOC
+    if (e == cudaSuccess) {
+        e = cudaMemset(q->d_negative, 0, n);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemset(q->d_p25, 1, n);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemset(q->d_map, 0, n);
+    }
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cqpsk_slicer_create", __FILE__, __LINE__);
+        dsdneo_b200_cqpsk_slicer_destroy(q);
+        return NULL;
+    }
+    if (dsdneo_b200_cqpsk_slicer_reset(q, NULL) != 0 || cudaStreamSynchronize(0) != cudaSuccess) {
+        dsdneo_b200_cqpsk_slicer_destroy(q);
+        return NULL;
+    }
+    return q;
+}
+
+void
+dsdneo_b200_cqpsk_slicer_destroy(dsdneo_b200_cqpsk_slicer* q) {
+    if (!q) {
+        return;
+    }
+    cudaFree(q->d_negative);
+    cudaFree(q->d_p25);
+    cudaFree(q->d_map);
+    cudaFree(q->d_sbuf);
+    cudaFree(q->d_minbuf);
+    cudaFree(q->d_maxbuf);
+    cudaFree(q->d_thr);
+    cudaFree(q->d_sidx);
+    cudaFree(q->d_midx);
+    cudaFree(q->d_sum_window);
+    cudaFree(q->d_min_sum);
+    cudaFree(q->d_max_sum);
+    free(q);
+}
+
+int
+dsdneo_b200_cqpsk_slicer_reset(dsdneo_b200_cqpsk_slicer* q, void* stream) {
+    if (!q) {
+        set_error("cqpsk_slicer_reset: NULL slicer");
+        return DSDNEO_B200_EINVAL;
+    }
+    cqpsk_slicer_reset_kernel<<<(q->n_ch + 127) / 128, 128, 0, as_stream(stream)>>>(q->d_sbuf, q->d_minbuf, q->d_maxbuf, q->d_sidx,
+                                                                                  q->d_midx, q->d_sum_window, q->d_min_sum,
+                                                                                  q->d_max_sum, q->d_thr, q->n_ch);
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_cqpsk_slicer_set_class(dsdneo_b200_cqpsk_slicer* q, const uint8_t* h_negative, const uint8_t* h_p25_slice,
+                                   const uint8_t* h_map_idx, double snr_cqpsk_db) {
+    if (!q) {
+        set_error("cqpsk_slicer_set_class: NULL slicer");
+        return DSDNEO_B200_EINVAL;
+    }
+    const size_t n = (size_t)q->n_ch;
+    DSDNEO_CUDA(cudaDeviceSynchronize());
+    if (h_negative) {
+        DSDNEO_CUDA(cudaMemcpy(q->d_negative, h_negative, n, cudaMemcpyHostToDevice));
+    }
+    if (h_p25_slice) {
+        DSDNEO_CUDA(cudaMemcpy(q->d_p25, h_p25_slice, n, cudaMemcpyHostToDevice));
+    }
+    if (h_map_idx) {
+        DSDNEO_CUDA(cudaMemcpy(q->d_map, h_map_idx, n, cudaMemcpyHostToDevice));
+    }
+    /* apply_cqpsk_snr_weight, src/core/frames/dsd_dibit.c:404-427 */
+    q->snr_scale_num = 0;
+    if (!(snr_cqpsk_db <= -50.0)) {
+        int w256 = 0;
+        if (snr_cqpsk_db >= 25.0) {
+            w256 = 255;
+        } else if (snr_cqpsk_db > 0.0) {
+            w256 = (int)((snr_cqpsk_db / 25.0) * 255.0 + 0.5);
+        }
+        q->snr_scale_num = 204 + (w256 >> 2);
+    }
+    return 0;
+}
+
+int
+dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_symbols, size_t symbols_pitch, const int* d_n_symbols,
+                              uint8_t* d_dibits, uint8_t* d_reliability, int16_t* d_llr, size_t out_pitch, void* stream) {
+    if (!q || !d_symbols || !d_n_symbols || !d_dibits || !d_reliability || !d_llr) {
+        set_error("cqpsk_slice_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    CqSliceParams p;
+    p.symbols = d_symbols;
+    p.sym_pitch = symbols_pitch;
+    p.n_symbols = d_n_symbols;
+    p.dibits = d_dibits;
+    p.reliab = d_reliability;
+    p.llr = d_llr;
+    p.out_pitch = out_pitch;
+    p.negative = q->d_negative;
+    p.p25_slice = q->d_p25;
+    p.map_idx = q->d_map;
+    p.sbuf = q->d_sbuf;
+    p.minbuf = q->d_minbuf;
+    p.maxbuf = q->d_maxbuf;
+    p.sidx = q->d_sidx;
+    p.midx = q->d_midx;
+    p.sum_window = q->d_sum_window;
+    p.minbuf_sum = q->d_min_sum;
+    p.maxbuf_sum = q->d_max_sum;
+    p.thr = q->d_thr;
+    p.n_ch = q->n_ch;
+    p.ssize = q->ssize;
+    p.msize = q->msize;
+    p.snr_scale_num = q->snr_scale_num;
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("cqpsk_slice_kernel", s);
+        cqpsk_slice_kernel<<<(q->n_ch + 31) / 32, 32, 0, s>>>(p);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_cqpsk_slicer_get_state(dsdneo_b200_cqpsk_slicer* q, int channel, float* out8) {
+    if (!q || !out8 || channel < 0 || channel >= q->n_ch) {
+        set_error("cqpsk_slicer_get_state: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    DSDNEO_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < 8; k++) {
+        DSDNEO_CUDA(cudaMemcpy(out8 + k, q->d_thr + (size_t)k * q->n_ch + channel, sizeof(float), cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

@@ -240,6 +240,32 @@ int dsdneo_b200_full_demod_cqpsk_batch_host(dsdneo_b200_demod_bank* bank, dsdneo
                                             size_t iq_pitch_pairs, int block_pairs, int n_blocks, float* h_symbols,
                                             size_t symbols_pitch, int* h_counts);
 
+/**
+ * Sample side behind the CQPSK chain: the reference's symbol-rate input path (dsd_rtl_stream_metrics_hooks.output_kind == 2),
+ * i.e. what getDibitSoft() does per symbol when the stream already carries one float per symbol:
+ *   symbol_try_rtl_symbol_rate_fast_path   src/dsp/dsd_symbol.c:1583-1625
+ *   use_symbol with rf_mod == 1            src/core/frames/dsd_dibit.c:243-299 (rolling min / max tracker, ssize x msize windows)
+ *   digitize                               :1018-1041: cqpsk_slice(symbol - center) + OP25 dibit orientation map
+ *                                           (include/dsd-neo/core/p25_cqpsk_dibit.h) when `p25_slice`, else threshold regions
+ *   soft metric                            :685-721 (CQPSK or standard ideals), cqpsk_reliability_raw x CQPSK SNR weight
+ * Per channel: `negative` = is_four_level_neg_synctype(synctype), `p25_slice` = is_cqpsk_active() && P25 sync type
+ * (dsd_dibit.c:950-961), `map_idx` = state->p25_cqpsk_dibit_map_idx (0..4).  `snr_cqpsk_db` = the SNR hook's value for the
+ * weight (<= -50: none).  The DSD_NEO_CQPSK_SYNC_INV / _NEG debug switches are not supported.
+ * Outputs use the layout of dsdneo_b200_symbolize_batch (dibits, reliability, LLR pairs); bit-exact.
+ */
+typedef struct dsdneo_b200_cqpsk_slicer dsdneo_b200_cqpsk_slicer;
+dsdneo_b200_cqpsk_slicer* dsdneo_b200_cqpsk_slicer_create(int n_channels, int ssize, int msize);
+void dsdneo_b200_cqpsk_slicer_destroy(dsdneo_b200_cqpsk_slicer* q);
+int dsdneo_b200_cqpsk_slicer_reset(dsdneo_b200_cqpsk_slicer* q, void* stream);
+int dsdneo_b200_cqpsk_slicer_set_class(dsdneo_b200_cqpsk_slicer* q, const uint8_t* h_negative, const uint8_t* h_p25_slice,
+                                       const uint8_t* h_map_idx, double snr_cqpsk_db);
+/** @param d_symbols [n_channels][symbols_pitch] f32 (dsdneo_b200_full_demod_cqpsk_batch output), d_n_symbols [n_channels] */
+int dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_symbols, size_t symbols_pitch,
+                                  const int* d_n_symbols, uint8_t* d_dibits, uint8_t* d_reliability, int16_t* d_llr,
+                                  size_t out_pitch, void* stream);
+/** {min, max, center, umid, lmid, minref, maxref, lastsample} of one channel */
+int dsdneo_b200_cqpsk_slicer_get_state(dsdneo_b200_cqpsk_slicer* q, int channel, float* out8);
+
 /* ---- K2 (+K1): polyphase FIR channelizer -------------------------------------------------------- */
 
 /**

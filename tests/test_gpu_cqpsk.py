@@ -219,3 +219,71 @@ def test_cqpsk_vs_compiled_reference(gpu):
                 a, b = want[ok], getattr(st, gk)
                 same = (a == b) if isinstance(a, int) else (np.float32(a).tobytes() == np.float32(b).tobytes())
                 assert same, (c, ok, a, b)
+
+
+def test_cqpsk_symbol_rate_slicer_bit_exact_vs_oracle(gpu):
+    """The sample side behind the chain (output kind 2): tracker thresholds, CQPSK slicer with the OP25 orientation maps,
+    soft metrics -- dibits, reliabilities, LLRs and final thresholds equal the oracle (pinned to the reference's
+    getDibitSoft by tests/test_oracle_symbol.py) for every class, across two launches with ragged symbol counts."""
+    import torch
+    from test_oracle_symbol import cqpsk_symbol_stream
+
+    rng = np.random.default_rng(900)
+    n_ch, n = 70, 3000
+    neg = np.array([c % 2 for c in range(n_ch)], np.uint8)
+    p25 = np.array([0 if c % 7 == 3 else 1 for c in range(n_ch)], np.uint8)
+    mp = np.array([c % 5 for c in range(n_ch)], np.uint8)
+    x = np.stack([cqpsk_symbol_stream(rng, n, noise=0.2 + 0.01 * c, offset=0.02 * (c % 9)) for c in range(n_ch)])
+    x[5, 700:1400] = 0.0  # a squelched stretch: the block side emits exact zeros
+    for snr in (-100.0, 17.0):
+        sl = gpu.CqpskSlicer(n_ch)
+        sl.set_class(neg, p25, mp, snr)
+        counts = [np.array([n // 2 - (c % 13) for c in range(n_ch)], np.int32), None]
+        counts[1] = (n - counts[0]).astype(np.int32)
+        got_d, got_r, got_l = [], [], []
+        pos = np.zeros(n_ch, np.int64)
+        for part in range(2):
+            buf = np.zeros((n_ch, n), np.float32)
+            for c in range(n_ch):
+                buf[c, :counts[part][c]] = x[c, pos[c]:pos[c] + counts[part][c]]
+            res = sl.run(torch.from_numpy(buf).cuda(), torch.from_numpy(counts[part]).cuda())
+            got_d.append(res["dibits"].cpu().numpy()); got_r.append(res["reliability"].cpu().numpy()); got_l.append(res["llr"].cpu().numpy())
+            pos += counts[part]
+        for c in range(n_ch):
+            d, r, l, st = H.oracle_cqpsk_slicer_run(x[c], negative=int(neg[c]), p25_slice=int(p25[c]), map_idx=int(mp[c]), snr_db=snr)
+            a, b = counts[0][c], counts[1][c]
+            gd = np.concatenate([got_d[0][c, :a], got_d[1][c, :b]])
+            gr = np.concatenate([got_r[0][c, :a], got_r[1][c, :b]])
+            gl = np.concatenate([got_l[0][c, :a], got_l[1][c, :b]])
+            assert np.array_equal(gd, d), (c, int(np.argmax(gd != d)))
+            assert np.array_equal(gr, r) and np.array_equal(gl, l), c
+            bs = st.base
+            want = np.array([bs.min, bs.max, bs.center, bs.umid, bs.lmid, bs.minref, bs.maxref, bs.lastsample], np.float32)
+            assert H.bits_equal(sl.state(c), want), (c, sl.state(c), want)
+
+
+def test_cqpsk_iq_to_dibits(gpu):
+    """IQ -> CQPSK chain -> symbol-rate slicer on the device: the dibits equal the oracle chain's and, after acquisition, the
+    transmitted ones."""
+    import torch
+
+    rng = np.random.default_rng(901)
+    n_ch, bp, nb = 6, 2400, 5
+    sigs = [H.synth_cqpsk_iq(rng, bp * nb // 5 + 2, sps=5, snr_db=22.0, cfo=0.01 * (c - 2), timing=0.13 * c) for c in range(n_ch)]
+    iq = np.stack([s[0][:bp * nb] for s in sigs])
+    bank = gpu.CqpskBank(n_ch, 24000)
+    sym, counts = bank.full_demod(torch.from_numpy(iq).cuda(), bp, nb)
+    total = counts.sum(dim=1, dtype=torch.int32).contiguous()
+    sl = gpu.CqpskSlicer(n_ch)
+    res = sl.run(sym, total)
+    dib = res["dibits"].cpu().numpy()
+    tot = total.cpu().numpy()
+    for c in range(n_ch):
+        orc = H.OracleCqpsk(fir_fma=1)
+        want_sym, _ = orc.run(iq[c], bp, nb)
+        d, r, l, _ = H.oracle_cqpsk_slicer_run(want_sym)
+        assert tot[c] == want_sym.size and np.array_equal(dib[c, :tot[c]], d)
+        tx = sigs[c][1]
+        tail = dib[c, tot[c] - 600:tot[c]]
+        best = max(int((tx[tx.size - 600 - lag: tx.size - lag] == tail).sum()) for lag in range(0, 14))
+        assert best >= 594, (c, best)
