@@ -761,9 +761,53 @@ cqpsk_slice_kernel(const CqSliceParams p) {
     uint8_t* orl = p.reliab + (size_t)(valid ? ch : 0) * p.out_pitch;
     int16_t* ol = p.llr + (size_t)(valid ? ch : 0) * p.out_pitch * 2;
     float* my_sbuf = s_sbuf + lane;
+    /* Fast path of the extrema scan (full 128-entry window): eight 16-entry block summaries {two smallest, two largest} in
+     * registers; a new symbol only invalidates its own block, which is rescanned (two independent half chains), and the
+     * eight summaries are merged pairwise (depth 3).  The two smallest / largest of a multiset do not depend on the order of
+     * evaluation, so this is the reference's result exactly. */
+    const bool blocked = (cap == 128);
+    float bmn1[8], bmn2[8], bmx1[8], bmx2[8];
+    auto scan_block = [&](int b, float& mn1, float& mn2, float& mx1, float& mx2) {
+        const float* e = my_sbuf + b * 16 * 32;
+        const float a0 = e[0], a1 = e[32], c0 = e[8 * 32], c1 = e[9 * 32];
+        float p1 = fminf(a0, a1), p2 = fmaxf(a0, a1), q1 = fminf(c0, c1), q2 = fmaxf(c0, c1);
+        float P1 = p2, P2 = p1, Q1 = q2, Q2 = q1;
+#pragma unroll
+        for (int k = 2; k < 8; k++) {
+            const float v = e[k * 32], w = e[(8 + k) * 32];
+            two_min_push(p1, p2, v);
+            two_max_push(P1, P2, v);
+            two_min_push(q1, q2, w);
+            two_max_push(Q1, Q2, w);
+        }
+        mn1 = fminf(p1, q1);
+        mn2 = fminf(fmaxf(p1, q1), fminf(p2, q2));
+        mx1 = fmaxf(P1, Q1);
+        mx2 = fmaxf(fminf(P1, Q1), fmaxf(P2, Q2));
+    };
+    if (blocked) {
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            scan_block(b, bmn1[b], bmn2[b], bmx1[b], bmx2[b]);
+        }
+    }
+    const bool pow2_window = (window & (window - 1)) == 0;
+    const double inv_window = 1.0 / (double)window; /* exact for a power of two: x / 2^k == x * 2^-k */
+    /* the ring entries the next symbol replaces and the next symbol itself are requested one iteration early */
+    const bool prefetch = window >= 2;
+    float nxt_min = 0.0f, nxt_max = 0.0f, nxt_sym = 0.0f;
+    if (valid && n > 0) {
+        const int idx0 = (midx < 0 || midx >= window) ? 0 : midx;
+        nxt_min = p.minbuf[(size_t)idx0 * n_ch + ch];
+        nxt_max = p.maxbuf[(size_t)idx0 * n_ch + ch];
+        nxt_sym = in[0];
+    }
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
-        const float sym = in[i];
+        const float sym = nxt_sym;
+        if (i + 1 < n) {
+            nxt_sym = in[i + 1];
+        }
         last = sym;
         if (cap > 0) {
             my_sbuf[sidx * 32] = sym; /* cap <= 0: the reference writes sbuf[sidx] with sidx stuck at its initial 0 */
@@ -772,7 +816,36 @@ cqpsk_slice_kernel(const CqSliceParams p) {
         }
         /* use_symbol: average of the two smallest / two largest of sbuf[0..cap) (order independent, so exact) */
         float lmin = 0.0f, lmax = 0.0f;
-        if (cap >= 2) {
+        if (blocked) {
+            const int b = sidx >> 4;
+            float r1, r2, R1, R2;
+            scan_block(b, r1, r2, R1, R2);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { /* static indices keep the summaries in registers */
+                if (k == b) {
+                    bmn1[k] = r1;
+                    bmn2[k] = r2;
+                    bmx1[k] = R1;
+                    bmx2[k] = R2;
+                }
+            }
+            float t1[4], t2[4], T1[4], T2[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                t1[k] = fminf(bmn1[2 * k], bmn1[2 * k + 1]);
+                t2[k] = fminf(fmaxf(bmn1[2 * k], bmn1[2 * k + 1]), fminf(bmn2[2 * k], bmn2[2 * k + 1]));
+                T1[k] = fmaxf(bmx1[2 * k], bmx1[2 * k + 1]);
+                T2[k] = fmaxf(fminf(bmx1[2 * k], bmx1[2 * k + 1]), fmaxf(bmx2[2 * k], bmx2[2 * k + 1]));
+            }
+            const float u1a = fminf(t1[0], t1[1]), u2a = fminf(fmaxf(t1[0], t1[1]), fminf(t2[0], t2[1]));
+            const float u1b = fminf(t1[2], t1[3]), u2b = fminf(fmaxf(t1[2], t1[3]), fminf(t2[2], t2[3]));
+            const float U1a = fmaxf(T1[0], T1[1]), U2a = fmaxf(fminf(T1[0], T1[1]), fmaxf(T2[0], T2[1]));
+            const float U1b = fmaxf(T1[2], T1[3]), U2b = fmaxf(fminf(T1[2], T1[3]), fmaxf(T2[2], T2[3]));
+            const float mn1 = fminf(u1a, u1b), mn2 = fminf(fmaxf(u1a, u1b), fminf(u2a, u2b));
+            const float mx1 = fmaxf(U1a, U1b), mx2 = fmaxf(fminf(U1a, U1b), fmaxf(U2a, U2b));
+            lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
+            lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
+        } else if (cap >= 2) {
             const float a = my_sbuf[0], b = my_sbuf[32];
             float mn1 = fminf(a, b), mn2 = fmaxf(a, b), mx1 = mn2, mx2 = mn1;
 #pragma unroll 8
@@ -791,18 +864,29 @@ cqpsk_slice_kernel(const CqSliceParams p) {
             }
             float* mb = p.minbuf + (size_t)idx * n_ch + ch;
             float* xb = p.maxbuf + (size_t)idx * n_ch + ch;
-            min_sum += (double)lmin - (double)*mb;
-            max_sum += (double)lmax - (double)*xb;
+            const float old_min = prefetch ? nxt_min : *mb, old_max = prefetch ? nxt_max : *xb;
+            min_sum += (double)lmin - (double)old_min;
+            max_sum += (double)lmax - (double)old_max;
             *mb = lmin;
             *xb = lmax;
             idx++;
             midx = idx >= window ? 0 : idx;
+            if (prefetch && i + 1 < n) {
+                nxt_min = p.minbuf[(size_t)midx * n_ch + ch];
+                nxt_max = p.maxbuf[(size_t)midx * n_ch + ch];
+            }
         }
-        vmin = (float)(min_sum / (double)window);
-        vmax = (float)(max_sum / (double)window);
-        center = __fdiv_rn(__fadd_rn(vmax, vmin), 2.0f);
-        umid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 8.0f), center);
-        lmid = __fadd_rn(__fdiv_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 8.0f), center);
+        if (pow2_window) {
+            vmin = (float)(min_sum * inv_window);
+            vmax = (float)(max_sum * inv_window);
+        } else {
+            vmin = (float)(min_sum / (double)window);
+            vmax = (float)(max_sum / (double)window);
+        }
+        /* x / 2 and x / 8 are exact scalings: the same correctly rounded value as the reference's divisions */
+        center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
+        umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center);
+        lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
         maxref = __fmul_rn(vmax, 0.80f);
         minref = __fmul_rn(vmin, 0.80f);
         if (cap > 0) {

@@ -42,6 +42,18 @@ def step():
     return res, hits, n_hits
 
 
+def cut_and_nid(res, hits, n_hits):
+    # device frame cutter (NID fields + 3 trellis blocks per hit, status symbols stripped) and the NID decoder on every slot;
+    # the synthetic frames carry random dibits after the sync, so most NIDs fail the hard decode and take the Chase search:
+    # this is the decoder's worst case
+    cut = b200.p25p1_frame_cut(res["dibits"], res["llr"], res["count"], hits, n_hits, 3 * 98)
+    k = cut["nid_valid"].shape[0]
+    b200.check(lib.dsdneo_b200_p25p1_nid_decode_batch(cut["nid_code63"].data_ptr(), cut["nid_reliab63"].data_ptr(), None,
+                                                      cut["nid_parity"].data_ptr(), cut["nid_parity_reliab"].data_ptr(), 64,
+                                                      nid_st.data_ptr(), nid_nac.data_ptr(), nid_duid.data_ptr(), nid_err.data_ptr(), k, None))
+    return cut
+
+
 for _ in range(3):
     res, hits, n_hits = step()
 torch.cuda.synchronize()
@@ -55,11 +67,21 @@ met = torch.zeros(n_frames, dtype=torch.int32, device="cuda")
 rsd = torch.randint(0, 2, (n_frames, 120), dtype=torch.uint8, device="cuda")
 rsp = torch.randint(0, 2, (n_frames, 96), dtype=torch.uint8, device="cuda")
 rst = torch.zeros(n_frames, dtype=torch.uint8, device="cuda")
+nid_st = torch.zeros(n_ch * 32, dtype=torch.int8, device="cuda")
+nid_nac = torch.zeros(n_ch * 32, dtype=torch.int32, device="cuda")
+nid_duid = torch.zeros(n_ch * 32, dtype=torch.uint8, device="cuda")
+nid_err = torch.zeros(n_ch * 32, dtype=torch.int32, device="cuda")
+cut_and_nid(res, hits, n_hits)
+# first launches load the FEC kernels (lazy module loading): keep that out of the timed region
+b200.check(lib.dsdneo_b200_p25_12_soft_llr_batch(llr.data_ptr(), out12.data_ptr(), met.data_ptr(), n_frames, None))
+b200.check(lib.dsdneo_b200_p25_rs_decode_batch(0, rsd.data_ptr(), rsp.data_ptr(), rst.data_ptr(), n_frames, None))
+torch.cuda.synchronize()
 b200.timing_enable(True)
 iters = 10
 t0 = time.perf_counter()
 for _ in range(iters):
-    step()
+    res_i, hits_i, n_hits_i = step()
+    cut_and_nid(res_i, hits_i, n_hits_i)
     b200.check(lib.dsdneo_b200_p25_12_soft_llr_batch(llr.data_ptr(), out12.data_ptr(), met.data_ptr(), n_frames, None))
     b200.check(lib.dsdneo_b200_p25_rs_decode_batch(0, rsd.data_ptr(), rsp.data_ptr(), rst.data_ptr(), n_frames, None))
 torch.cuda.synchronize()
