@@ -686,6 +686,133 @@ def run_cqpsk_workload(args):
         "kernels": kern, "cpu_baseline": cpu}))
 
 
+# ----------------------------------------------------------------------------------------------- optional workload: FEC leaves
+
+def run_fec_workload(args):
+    """Developer line (NOT the judged C2 line): the batched FEC leaves on device-resident inputs (CUDA events) with the
+    reference's own functions timed natively beside them on ONE host core (they keep process-global state).
+    Inputs: valid codewords (the all-zero word of each linear code; encoded trellis paths) with a few channel errors."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _harness as H
+    import __graft_entry__ as g
+
+    b200 = g.load_package()
+    b200.init(0)
+    lib = b200.lib()
+    rng = np.random.default_rng(11)
+    N = 1 << 17
+    n_cpu = 4096
+
+    def flips(shape_n, width, k):
+        e = np.zeros((shape_n, width), np.uint8)
+        for _ in range(k):
+            e[np.arange(shape_n), rng.integers(0, width, shape_n)] ^= 1
+        return e
+
+    items = {}
+    # Golay(24,12): zero codeword + 2 errors
+    gol = flips(N, 24, 2)
+    # BPTC(196,96): zero burst + 3 errors
+    bptc = flips(N, 196, 3)
+    # P25 half-rate trellis: 64 encoded paths tiled, noisy LLRs
+    base = [H.p25_trellis_encode(rng)[1] for _ in range(64)]
+    tx = np.stack([base[i % 64] for i in range(N)])
+    bits = np.stack([(tx >> 1) & 1, tx & 1], axis=2).reshape(N, 196)
+    llr = np.clip(np.rint(np.where(bits == 1, 200.0, -200.0) + rng.standard_normal((N, 196)) * 70.0), -32768, 32767).astype(np.int16)
+    hard = ((llr[:, 0::2] > 0).astype(np.uint8) << 1) | (llr[:, 1::2] > 0).astype(np.uint8)
+    # RS(36,20,17): zero word + 4 symbol errors
+    rs = np.zeros((N, 36, 6), np.uint8)
+    for _ in range(4):
+        rs[np.arange(N), rng.integers(0, 36, N)] = rng.integers(0, 2, (N, 6))
+    rs_par, rs_dat = np.ascontiguousarray(rs[:, :16].reshape(N, 96)), np.ascontiguousarray(rs[:, 16:].reshape(N, 120))
+    # NID: zero codeword (NAC 0, DUID 0 = HDU, parity 0) + 4 errors, random reliabilities
+    nid = flips(N, 63, 4)
+    nid_rel = rng.integers(0, 256, (N, 63)).astype(np.uint8)
+    nid_par = np.zeros(N, np.uint8)
+    nid_prel = rng.integers(0, 256, N).astype(np.uint8)
+
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_gol, d_ok = dev(gol), torch.zeros(N, dtype=torch.uint8, device="cuda")
+    d_bptc, d_b96 = dev(bptc), torch.zeros((N, 96), dtype=torch.uint8, device="cuda")
+    d_bR, d_berr = torch.zeros((N, 3), dtype=torch.uint8, device="cuda"), torch.zeros(N, dtype=torch.int32, device="cuda")
+    d_llr, d_o12 = dev(llr), torch.zeros((N, 12), dtype=torch.uint8, device="cuda")
+    d_met = torch.zeros(N, dtype=torch.int32, device="cuda")
+    d_rsd, d_rsp, d_rst = dev(rs_dat), dev(rs_par), torch.zeros(N, dtype=torch.uint8, device="cuda")
+    d_nid, d_nrel, d_npar, d_nprel = dev(nid), dev(nid_rel), dev(nid_par), dev(nid_prel)
+    d_nst = torch.zeros(N, dtype=torch.int8, device="cuda")
+    d_nnac = torch.zeros(N, dtype=torch.int32, device="cuda")
+    d_nduid = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    d_nerr = torch.zeros(N, dtype=torch.int32, device="cuda")
+    d_gol0, d_rsd0 = d_gol.clone(), d_rsd.clone()
+
+    calls = {
+        "golay_24_12": (lambda: (d_gol.copy_(d_gol0), lib.dsdneo_b200_fec_block_decode_batch(b200.FEC_GOLAY_24_12, d_gol.data_ptr(), None, d_ok.data_ptr(), N, None))[1],
+                        48.0, "gq_decode_kernel"),
+        "bptc_196x96": (lambda: lib.dsdneo_b200_bptc_196x96_batch(d_bptc.data_ptr(), 1, d_b96.data_ptr(), d_bR.data_ptr(), d_berr.data_ptr(), N, None),
+                        299.0, "bptc_196x96_kernel"),
+        "p25_12_soft_llr": (lambda: lib.dsdneo_b200_p25_12_soft_llr_batch(d_llr.data_ptr(), d_o12.data_ptr(), d_met.data_ptr(), N, None),
+                            408.0, "p25_12_soft_llr_kernel"),
+        "rs_36_20_17": (lambda: (d_rsd.copy_(d_rsd0), lib.dsdneo_b200_p25_rs_decode_batch(0, d_rsd.data_ptr(), d_rsp.data_ptr(), d_rst.data_ptr(), N, None))[1],
+                        336.0, "p25_rs_decode_kernel"),
+        "p25p1_nid_decode": (lambda: lib.dsdneo_b200_p25p1_nid_decode_batch(d_nid.data_ptr(), d_nrel.data_ptr(), None, d_npar.data_ptr(), d_nprel.data_ptr(), 64,
+                                                                            d_nst.data_ptr(), d_nnac.data_ptr(), d_nduid.data_ptr(), d_nerr.data_ptr(), N, None),
+                             136.0, "p25p1_nid_decode_kernel"),
+    }
+    for fn_, _, _ in calls.values():
+        b200.check(fn_())
+    torch.cuda.synchronize()
+    b200.timing_enable(True)
+    launches0 = b200.launch_count()
+    steps = max(5, min(args.steps, 50))
+    for _ in range(steps):
+        for fn_, _, _ in calls.values():
+            b200.check(fn_())
+    torch.cuda.synchronize()
+    rep = b200.timing_report()
+    b200.timing_enable(False)
+    launches = b200.launch_count() - launches0
+
+    # reference functions, native loops on one core
+    path = os.path.join(ROOT, "oracle", "_ref", "libdsdneo_ref_fast.so")
+    cpu = {}
+    if os.path.exists(path):
+        L = C.CDLL(path)
+        L.InitAllFecFunction()
+        L.ref_fec_loop.restype = C.c_double
+        L.ref_fec_loop.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_long)]
+        packed = {
+            "golay_24_12": (0, gol[:n_cpu]),
+            "bptc_196x96": (1, bptc[:n_cpu]),
+            "p25_12_soft_llr": (2, np.concatenate([hard[:n_cpu], llr[:n_cpu].view(np.uint8)], axis=1)),
+            "rs_36_20_17": (3, np.concatenate([rs_dat[:n_cpu], rs_par[:n_cpu]], axis=1)),
+            "p25p1_nid_decode": (4, np.concatenate([nid[:n_cpu], nid_rel[:n_cpu], nid_par[:n_cpu, None], nid_prel[:n_cpu, None]], axis=1)),
+        }
+        for name, (kind, arr) in packed.items():
+            arr = np.ascontiguousarray(arr, np.uint8)
+            chk = C.c_long(0)
+            t1 = L.ref_fec_loop(kind, arr.ctypes.data, n_cpu, 1, C.byref(chk))
+            reps = max(1, int(1.5 / max(t1, 1e-6)))
+            t = L.ref_fec_loop(kind, arr.ctypes.data, n_cpu, reps, C.byref(chk))
+            cpu[name] = n_cpu * reps / t
+    out = {}
+    for name, (_, bytes_per_item, kname) in calls.items():
+        ms = rep[kname]["ms"] / rep[kname]["launches"]
+        out[name] = {"kernel": kname, "gpu_ms_per_launch": ms, "gpu_items_per_s": N / (ms * 1e-3), "items_per_launch": N,
+                     "algorithmic_bytes_per_item": bytes_per_item, "achieved_gbs": N * bytes_per_item / (ms * 1e-3) / 1e9,
+                     "cpu_items_per_s_one_core": cpu.get(name)}
+    peak, peak_src = measured_hbm_peak()
+    print(json.dumps({
+        "metric": "fec_items_per_s", "unit": "items/s", "n_gpus": 1, "steps": steps, "higher_is_better": True, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": "FEC leaves (section 8 rows a13-a16, f4; developer line): %d items per launch, "
+                                        "device-resident inputs, reference functions natively timed on one host core" % N},
+        "gpu_launches": int(launches), "hbm_peak_gbs": peak, "peak_source": peak_src, "kernels": out,
+        "cpu_baseline": {"kind": "reference", "cores": 1, "unit": "items/s", "value": cpu,
+                         "sample": "%d items per function, repeated for ~1.5 s each, perf-bench flags" % n_cpu}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -697,11 +824,13 @@ def main():
                          "channels: ONE wideband stream, raw IQ tile broadcast over NCCL, each GPU demodulates a channel range "
                          "(--channels sets the channelizer size)")
     ap.add_argument("--channels", type=int, default=M)
-    ap.add_argument("--workload", default="c2", choices=["c2", "cqpsk"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "cqpsk", "fec"],
                     help="c2 (default, the judged line) or cqpsk: developer line for the CQPSK chain with its own CPU baseline")
     args = ap.parse_args()
     if args.workload == "cqpsk":
         run_cqpsk_workload(args)
+    elif args.workload == "fec":
+        run_fec_workload(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     elif args.shard == "channels":

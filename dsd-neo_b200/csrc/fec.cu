@@ -1396,46 +1396,60 @@ nid_codeword(const dsdneo_fec_tables* __restrict__ T, unsigned long long word, i
 }
 
 /* p25p1_nid_decode (p25p1_check_nid.cpp:322-354): hard decode, one retry with the known NAC after a BCH failure, then the
- * bounded Chase search over the (at most 8) least reliable positions.  One warp per NID: lane 0 does the hard decode (the
- * common case ends there); for the search the lanes rank the 63 reliabilities, stride over the <= 2 x 256 flip masks, each
- * running its own BCH decodes, and the winner is the minimum of the packed key {score, not-ok, corrections, flips, order of
- * enumeration} -- the reference's replacement rule is exactly that lexicographic order with "first found" breaking ties. */
+ * bounded Chase search over the (at most 8) least reliable positions.  One warp per 32 NIDs: every lane hard-decodes its own
+ * NID (the common case ends there); the NIDs that still fail are then searched one after the other by the whole warp -- the
+ * lanes rank the 63 reliabilities, stride over the <= 2 x 256 flip masks, each running its own BCH decodes, and the winner is
+ * the minimum of the packed key {score, not-ok, corrections, flips, order of enumeration}: the reference's replacement rule
+ * is exactly that lexicographic order with "first found" breaking ties. */
 __global__ void __launch_bounds__(128)
 p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* code63, const uint8_t* reliab63,
                         const int32_t* observed_nac, const uint8_t* parity_in, const uint8_t* parity_reliab, int threshold,
                         int8_t* status_out, int32_t* nac_out, uint8_t* duid_out, int32_t* errs_out, int n) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n) {
+    const int warp_first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+    if (warp_first >= n) {
         return;
     }
-    const uint8_t* in = code63 + (size_t)w * 63;
+    const int w = warp_first + lane;
+    const bool valid = w < n;
     unsigned long long word = 0;
-    for (int i = 0; i < 63; i++) {
-        word |= (unsigned long long)(in[i] ? 1 : 0) << (62 - i);
+    int parity = 0, prel = 0, obs = 0;
+    if (valid) {
+        const uint8_t* in = code63 + (size_t)w * 63;
+        for (int i = 0; i < 63; i++) {
+            word |= (unsigned long long)(in[i] ? 1 : 0) << (62 - i);
+        }
+        parity = parity_in[w] ? 1 : 0;
+        prel = parity_reliab ? parity_reliab[w] : 0;
+        obs = observed_nac ? observed_nac[w] : 0;
     }
-    const int parity = parity_in[w] ? 1 : 0;
-    const int prel = parity_reliab ? parity_reliab[w] : 0;
-    const int obs = observed_nac ? observed_nac[w] : 0;
     const bool nac_ok = obs > 0 && obs <= 0xFFF && obs != 0xFFF;
     const int rx_nac = (int)((word >> 51) & 0xFFFull);
     const unsigned long long retry = (word & ~(0xFFFull << 51)) | ((unsigned long long)(obs & 0xFFF) << 51);
     const bool have_retry = nac_ok && rx_nac != obs;
 
     NidDecoded res = {0, 0, 0, 0};
-    if (lane == 0) {
+    if (valid) { /* decode_nid_hard (:305-320) */
         int failed = 0;
         res = nid_codeword(T, word, parity, &failed);
         if (res.status == 0 && failed && have_retry) {
             res = nid_codeword(T, retry, parity, &failed);
         }
     }
-    res.status = __shfl_sync(0xffffffffu, res.status, 0);
-    if (res.status <= 0 && reliab63) {
-        const uint8_t* rel = reliab63 + (size_t)w * 63;
+    unsigned todo = __ballot_sync(0xffffffffu, valid && res.status <= 0 && reliab63 != nullptr);
+    __shared__ uint8_t s_order[4][64];
+    uint8_t* order = s_order[threadIdx.x >> 5];
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned long long c_word = __shfl_sync(0xffffffffu, word, src);
+        const unsigned long long c_retry = __shfl_sync(0xffffffffu, retry, src);
+        const int c_parity = __shfl_sync(0xffffffffu, parity, src);
+        const int c_prel = __shfl_sync(0xffffffffu, prel, src);
+        const bool c_have_retry = __shfl_sync(0xffffffffu, have_retry ? 1 : 0, src) != 0;
+        const uint8_t* rel = reliab63 + (size_t)(warp_first + src) * 63;
         /* rank of position i in the (reliability, index) order = number of positions that precede it */
-        __shared__ uint8_t s_order[4][64];
-        uint8_t* order = s_order[threadIdx.x >> 5];
+        __syncwarp();
         for (int i = lane; i < 63; i += 32) {
             const int ri = rel[i];
             int rank = 0;
@@ -1463,18 +1477,18 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
         unsigned best_key = 0xffffffffu;
         NidDecoded best = {0, 0, 0, 0};
         const int n_masks = 1 << n_pool;
-        const int n_seq = n_pool > 0 ? (have_retry ? 2 : 1) * n_masks : 0;
+        const int n_seq = n_pool > 0 ? (c_have_retry ? 2 : 1) * n_masks : 0;
         for (int seq = lane; seq < n_seq; seq += 32) {
             const int mask = seq & (n_masks - 1);
             if (__popc(mask) > 3) {
                 continue;
             }
-            unsigned long long cand = (seq >= n_masks) ? retry : word;
+            unsigned long long cand = (seq >= n_masks) ? c_retry : c_word;
             int score = 0;
-            for (int b = 0; b < n_pool; b++) {
-                if (mask & (1 << b)) {
-                    cand ^= 1ull << (62 - pool[b]);
-                    score += rel[pool[b]];
+            for (int bq = 0; bq < n_pool; bq++) {
+                if (mask & (1 << bq)) {
+                    cand ^= 1ull << (62 - pool[bq]);
+                    score += rel[pool[bq]];
                 }
             }
             const int weight = __popc(mask);
@@ -1482,12 +1496,12 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
                 continue;
             }
             int failed = 0;
-            const NidDecoded d = nid_codeword(T, cand, parity, &failed);
+            const NidDecoded d = nid_codeword(T, cand, c_parity, &failed);
             if (d.status <= 0) {
                 continue;
             }
             if (d.status == 2) {
-                score += prel;
+                score += c_prel;
             }
             /* score <= 3 * 255 + 255 (11 bits), not-ok 1 bit, corrections <= 11 (4 bits), flips <= 3 (2 bits), seq < 512 */
             const unsigned key = ((unsigned)score << 17) | ((d.status == 1 ? 0u : 1u) << 16) | ((unsigned)d.errs << 12)
@@ -1502,14 +1516,20 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
             win = min(win, __shfl_xor_sync(0xffffffffu, win, o));
         }
         if (win != 0xffffffffu) {
-            const int src = __ffs(__ballot_sync(0xffffffffu, best_key == win)) - 1;
-            res.status = __shfl_sync(0xffffffffu, best.status, src);
-            res.nac = __shfl_sync(0xffffffffu, best.nac, src);
-            res.duid = __shfl_sync(0xffffffffu, best.duid, src);
-            res.errs = __shfl_sync(0xffffffffu, best.errs, src);
+            const int from = __ffs(__ballot_sync(0xffffffffu, best_key == win)) - 1;
+            const int b_status = __shfl_sync(0xffffffffu, best.status, from);
+            const int b_nac = __shfl_sync(0xffffffffu, best.nac, from);
+            const int b_duid = __shfl_sync(0xffffffffu, best.duid, from);
+            const int b_errs = __shfl_sync(0xffffffffu, best.errs, from);
+            if (lane == src) {
+                res.status = b_status;
+                res.nac = b_nac;
+                res.duid = b_duid;
+                res.errs = b_errs;
+            }
         }
     }
-    if (lane == 0) {
+    if (valid) {
         status_out[w] = (int8_t)res.status;
         nac_out[w] = res.nac;
         duid_out[w] = (uint8_t)res.duid;
@@ -2673,7 +2693,7 @@ dsdneo_b200_p25p1_nid_decode_batch(const uint8_t* d_code63, const uint8_t* d_rel
     cudaStream_t s = as_stream(stream);
     {
         KernelTimer kt("p25p1_nid_decode_kernel", s);
-        p25p1_nid_decode_kernel<<<grid_for(n_words, 4), 128, 0, s>>>(g_d_tables, d_code63, d_reliab63, d_observed_nac, d_parity,
+        p25p1_nid_decode_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(g_d_tables, d_code63, d_reliab63, d_observed_nac, d_parity,
                                                                     d_parity_reliab, erasure_threshold, d_status, d_nac, d_duid,
                                                                     d_error_count, n_words);
     }

@@ -15,7 +15,7 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__t_sector_hit_rate", "lts__t_sector_hit_rate", "sm__cycles_active.avg", "smsp__warp_issue_stalled",
         "smsp__average_warp", "sm__pipe_fma", "sm__inst_executed.avg.per_cycle", "gpu__dram_throughput", "dram__cycles_active")
 
-for name in ("bench.json", "bench_reference.json", "c3_1024.json", "c3_4096.json", "cqpsk_bench.jsonl"):
+for name in ("bench.json", "bench_reference.json", "c3_1024.json", "c3_4096.json", "cqpsk_bench.jsonl", "bench_cqpsk.json", "bench_fec.json"):
     src = os.path.join(OUT, name)
     if os.path.exists(src) and os.path.getsize(src) > 2:
         shutil.copy(src, os.path.join(PROF, f"{TAG}_{name}"))

@@ -21,4 +21,6 @@ python tools/cqpsk_bench.py 1024 48000 10 2>/dev/null | grep '^{' >> gpurun_out/
 python tools/cqpsk_bench.py 1024 48000 8 2>/dev/null | grep '^{' >> gpurun_out/cqpsk_bench.jsonl
 ncu --set full --clock-control none --import-source on -k regex:'cqpsk_chain_kernel' -s 4 -c 1 -f -o gpurun_out/ncu_cqpsk_chain_kernel \
     python tools/cqpsk_bench.py 1024 > gpurun_out/ncu_cqpsk_chain_kernel.log 2>&1
+python bench.py --workload cqpsk --steps 20 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_cqpsk.json
+python bench.py --workload fec --steps 20 2>/dev/null | tail -1 > gpurun_out/bench_fec.json
 ls -la gpurun_out/
