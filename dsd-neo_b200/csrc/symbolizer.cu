@@ -699,7 +699,17 @@ struct CqSliceParams {
     float* thr;           /* [8][n_ch]: min, max, center, umid, lmid, minref, maxref, lastsample */
     int n_ch, ssize, msize;
     int snr_scale_num;    /* 204 + (w256 >> 2), or 0 when the SNR hook reports <= -50 dB (no weighting) */
+    float2* minmax;       /* [n_ch][out_pitch] scratch: {min, max} after use_symbol, per symbol (tracker -> digitize kernel) */
 };
+
+/* thresholds from the tracked extremes (dsd_dibit.c:268-272); x / 2 and x / 8 are exact scalings, the same correctly
+ * rounded values as the reference's divisions */
+__device__ __forceinline__ void
+cq_thresholds(float vmin, float vmax, float& center, float& umid, float& lmid) {
+    center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
+    umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center);
+    lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
+}
 
 __global__ void __launch_bounds__(32)
 cqpsk_slice_kernel(const CqSliceParams p) {
@@ -713,16 +723,13 @@ cqpsk_slice_kernel(const CqSliceParams p) {
     for (int k = 0; k < 128; k++) {
         s_sbuf[k * 32 + lane] = valid ? p.sbuf[(size_t)k * n_ch + ch] : 0.0f;
     }
-    int n = 0, sidx = 0, midx = 0, negative = 0, p25 = 0, map_idx = 0;
+    int n = 0, sidx = 0, midx = 0;
     double min_sum = 0.0, max_sum = 0.0;
     float vmin = 0.0f, vmax = 0.0f, center = 0.0f, umid = 0.0f, lmid = 0.0f, minref = 0.0f, maxref = 0.0f, last = 0.0f;
     if (valid) {
         n = p.n_symbols[ch];
         sidx = p.sidx[ch];
         midx = p.midx[ch];
-        negative = p.negative[ch];
-        p25 = p.p25_slice[ch];
-        map_idx = p.map_idx[ch] < 5 ? p.map_idx[ch] : 0;
         min_sum = p.minbuf_sum[ch];
         max_sum = p.maxbuf_sum[ch];
         vmin = p.thr[0 * (size_t)n_ch + ch];
@@ -747,19 +754,8 @@ cqpsk_slice_kernel(const CqSliceParams p) {
             }
         }
     }
-    /* OP25 orientation maps (include/dsd-neo/core/p25_cqpsk_dibit.h:28-52), 2 bits per entry, and their inverses */
-    const unsigned fwd[5] = {0xE4u, 0x4Eu, 0x1Bu, 0x8Du, 0x72u};
-    const unsigned fmap = fwd[map_idx];
-    unsigned inv = 0;
-#pragma unroll
-    for (int raw = 3; raw >= 0; raw--) { /* lowest raw dibit wins, like dsd_p25_cqpsk_raw_dibit_for_corrected */
-        const unsigned c = (fmap >> (2 * raw)) & 3u;
-        inv = (inv & ~(3u << (2 * c))) | ((unsigned)raw << (2 * c));
-    }
     const float* in = p.symbols + (size_t)(valid ? ch : 0) * p.sym_pitch;
-    uint8_t* od = p.dibits + (size_t)(valid ? ch : 0) * p.out_pitch;
-    uint8_t* orl = p.reliab + (size_t)(valid ? ch : 0) * p.out_pitch;
-    int16_t* ol = p.llr + (size_t)(valid ? ch : 0) * p.out_pitch * 2;
+    float2* mm = p.minmax + (size_t)(valid ? ch : 0) * p.out_pitch;
     float* my_sbuf = s_sbuf + lane;
     /* Fast path of the extrema scan (full 128-entry window): eight 16-entry block summaries {two smallest, two largest} in
      * registers; a new symbol only invalidates its own block, which is rescanned (two independent half chains), and the
@@ -883,70 +879,17 @@ cqpsk_slice_kernel(const CqSliceParams p) {
             vmin = (float)(min_sum / (double)window);
             vmax = (float)(max_sum / (double)window);
         }
-        /* x / 2 and x / 8 are exact scalings: the same correctly rounded value as the reference's divisions */
-        center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
-        umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center);
-        lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
-        maxref = __fmul_rn(vmax, 0.80f);
-        minref = __fmul_rn(vmin, 0.80f);
         if (cap > 0) {
             sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
         }
-        /* digitize */
-        int dibit;
-        float ideal[4];
-        const float sc = __fsub_rn(sym, center);
-        if (p25) {
-            const int raw = sc >= 2.0f ? 1 : (sc >= 0.0f ? 0 : (sc >= -2.0f ? 2 : 3));
-            dibit = (int)((fmap >> (2 * raw)) & 3u);
-            if (negative) {
-                dibit = (dibit + 2) & 3;
-            }
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int corrected = negative ? ((d + 2) & 3) : d;
-                const int mapped = (int)((inv >> (2 * corrected)) & 3u);
-                /* base levels {+1, +3, -1, -3} for raw dibits 0..3 */
-                const float level = (mapped == 0) ? 1.0f : ((mapped == 1) ? 3.0f : ((mapped == 2) ? -1.0f : -3.0f));
-                ideal[d] = __fadd_rn(center, level);
-            }
-        } else {
-            if (sym > center) {
-                dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
-            } else {
-                dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
-            }
-            const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
-            if (negative) {
-                ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
-            } else {
-                ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
-            }
-        }
-        int mag0, mag1;
-        bit_metrics(sym, ideal, mag0, mag1);
-        /* dmr_compute_reliability, rf_mod == 1 */
-        const float id = sc >= 2.0f ? 3.0f : (sc >= 0.0f ? 1.0f : (sc >= -2.0f ? -1.0f : -3.0f));
-        float err = fabsf(__fsub_rn(sc, id));
-        if (err > 1.0f) {
-            err = 1.0f;
-        }
-        int rel = clamp255(__float2int_rz(__fadd_rn(__fmul_rn(__fsub_rn(1.0f, err), 255.0f), 0.5f)));
-        if (p.snr_scale_num > 0) {
-            rel = clamp255((rel * p.snr_scale_num) >> 8);
-        }
-        const int min_mag = mag0 < mag1 ? mag0 : mag1;
-        if (min_mag > 0 && rel < min_mag) {
-            mag0 = (mag0 * rel) / min_mag;
-            mag1 = (mag1 * rel) / min_mag;
-        }
-        mag0 = clamp255(mag0);
-        mag1 = clamp255(mag1);
-        const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
-        od[i] = (uint8_t)dibit;
-        orl[i] = (uint8_t)clamp255(min(abs(l0), abs(l1)));
-        ol[2 * i] = (int16_t)l0;
-        ol[2 * i + 1] = (int16_t)l1;
+        /* everything else of the symbol (thresholds, slicing, soft metric) only depends on {sym, min, max}: it is done by
+         * cqpsk_digitize_kernel, one thread per symbol */
+        mm[i] = make_float2(vmin, vmax);
+    }
+    if (n > 0) {
+        cq_thresholds(vmin, vmax, center, umid, lmid);
+        maxref = __fmul_rn(vmax, 0.80f);
+        minref = __fmul_rn(vmin, 0.80f);
     }
     if (valid) {
         for (int k = 0; k < 128; k++) {
@@ -965,6 +908,86 @@ cqpsk_slice_kernel(const CqSliceParams p) {
         p.thr[6 * (size_t)n_ch + ch] = maxref;
         p.thr[7 * (size_t)n_ch + ch] = last;
     }
+}
+
+/* digitize + compute_dibit_soft_metric for every symbol of every channel, one thread per symbol (time-parallel: the only
+ * state they read, {min, max} after use_symbol, was written per symbol by cqpsk_slice_kernel) */
+__global__ void __launch_bounds__(256)
+cqpsk_digitize_kernel(const CqSliceParams p) {
+    const int ch = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_symbols[ch]) {
+        return;
+    }
+    const float sym = p.symbols[(size_t)ch * p.sym_pitch + i];
+    const float2 mmv = p.minmax[(size_t)ch * p.out_pitch + i];
+    const float vmin = mmv.x, vmax = mmv.y;
+    const int negative = p.negative[ch], p25 = p.p25_slice[ch];
+    const int map_idx = p.map_idx[ch] < 5 ? p.map_idx[ch] : 0;
+    /* OP25 orientation maps (include/dsd-neo/core/p25_cqpsk_dibit.h:28-52), 2 bits per entry, and their inverses */
+    const unsigned fmap = (map_idx == 0) ? 0xE4u : (map_idx == 1) ? 0x4Eu : (map_idx == 2) ? 0x1Bu : (map_idx == 3) ? 0x8Du : 0x72u;
+    unsigned inv = 0;
+#pragma unroll
+    for (int raw = 3; raw >= 0; raw--) { /* lowest raw dibit wins, like dsd_p25_cqpsk_raw_dibit_for_corrected */
+        const unsigned c = (fmap >> (2 * raw)) & 3u;
+        inv = (inv & ~(3u << (2 * c))) | ((unsigned)raw << (2 * c));
+    }
+    float center, umid, lmid;
+    cq_thresholds(vmin, vmax, center, umid, lmid);
+    int dibit;
+    float ideal[4];
+    const float sc = __fsub_rn(sym, center);
+    if (p25) {
+        const int raw = sc >= 2.0f ? 1 : (sc >= 0.0f ? 0 : (sc >= -2.0f ? 2 : 3));
+        dibit = (int)((fmap >> (2 * raw)) & 3u);
+        if (negative) {
+            dibit = (dibit + 2) & 3;
+        }
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const int corrected = negative ? ((d + 2) & 3) : d;
+            const int mapped = (int)((inv >> (2 * corrected)) & 3u);
+            /* base levels {+1, +3, -1, -3} for raw dibits 0..3 */
+            const float level = (mapped == 0) ? 1.0f : ((mapped == 1) ? 3.0f : ((mapped == 2) ? -1.0f : -3.0f));
+            ideal[d] = __fadd_rn(center, level);
+        }
+    } else {
+        if (sym > center) {
+            dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+        } else {
+            dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
+        }
+        const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+        if (negative) {
+            ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+        } else {
+            ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+        }
+    }
+    int mag0, mag1;
+    bit_metrics(sym, ideal, mag0, mag1);
+    /* dmr_compute_reliability, rf_mod == 1 */
+    const float id = sc >= 2.0f ? 3.0f : (sc >= 0.0f ? 1.0f : (sc >= -2.0f ? -1.0f : -3.0f));
+    float err = fabsf(__fsub_rn(sc, id));
+    if (err > 1.0f) {
+        err = 1.0f;
+    }
+    int rel = clamp255(__float2int_rz(__fadd_rn(__fmul_rn(__fsub_rn(1.0f, err), 255.0f), 0.5f)));
+    if (p.snr_scale_num > 0) {
+        rel = clamp255((rel * p.snr_scale_num) >> 8);
+    }
+    const int min_mag = mag0 < mag1 ? mag0 : mag1;
+    if (min_mag > 0 && rel < min_mag) {
+        mag0 = (mag0 * rel) / min_mag;
+        mag1 = (mag1 * rel) / min_mag;
+    }
+    mag0 = clamp255(mag0);
+    mag1 = clamp255(mag1);
+    const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
+    const size_t o = (size_t)ch * p.out_pitch + i;
+    p.dibits[o] = (uint8_t)dibit;
+    p.reliab[o] = (uint8_t)clamp255(min(abs(l0), abs(l1)));
+    reinterpret_cast<short2*>(p.llr)[o] = make_short2((short)l0, (short)l1);
 }
 
 __global__ void
@@ -1346,6 +1369,8 @@ struct dsdneo_b200_cqpsk_slicer {
     float *d_sbuf, *d_minbuf, *d_maxbuf, *d_thr;
     int *d_sidx, *d_midx, *d_sum_window;
     double *d_min_sum, *d_max_sum;
+    float2* d_minmax; /* per-symbol {min, max} between the tracker and the digitize kernel, grown on demand */
+    size_t minmax_cap;
 };
 
 extern "C" {
@@ -1423,6 +1448,7 @@ dsdneo_b200_cqpsk_slicer_destroy(dsdneo_b200_cqpsk_slicer* q) {
     cudaFree(q->d_sum_window);
     cudaFree(q->d_min_sum);
     cudaFree(q->d_max_sum);
+    cudaFree(q->d_minmax);
     free(q);
 }
 
@@ -1483,7 +1509,21 @@ dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_symbol
     if (rc) {
         return rc;
     }
+    const size_t need = (size_t)q->n_ch * out_pitch;
+    if (q->minmax_cap < need) {
+        DSDNEO_CUDA(cudaDeviceSynchronize());
+        cudaFree(q->d_minmax);
+        q->d_minmax = NULL;
+        q->minmax_cap = 0;
+        DSDNEO_CUDA(cudaMalloc((void**)&q->d_minmax, need * sizeof(float2)));
+        q->minmax_cap = need;
+    }
+    if (symbols_pitch > out_pitch) {
+        set_error("cqpsk_slice_batch: out_pitch smaller than symbols_pitch");
+        return DSDNEO_B200_EINVAL;
+    }
     CqSliceParams p;
+    p.minmax = q->d_minmax;
     p.symbols = d_symbols;
     p.sym_pitch = symbols_pitch;
     p.n_symbols = d_n_symbols;
@@ -1511,6 +1551,13 @@ dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_symbol
     {
         KernelTimer kt("cqpsk_slice_kernel", s);
         cqpsk_slice_kernel<<<(q->n_ch + 31) / 32, 32, 0, s>>>(p);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    {
+        KernelTimer kt("cqpsk_digitize_kernel", s);
+        dim3 grid((unsigned)((symbols_pitch + 255) / 256), (unsigned)q->n_ch);
+        cqpsk_digitize_kernel<<<grid, 256, 0, s>>>(p);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
