@@ -197,6 +197,7 @@ struct SymParams {
     int* count;          /* [n_ch] */
     size_t out_pitch;
     int n_ch, n, mode, have_sync, rate, symrate, ssize, msize;
+    float2* minmax;      /* [n_ch][out_pitch] scratch: {min, max} after use_symbol per symbol (symbolize -> digitize kernel) */
 };
 
 __device__ __forceinline__ int
@@ -231,6 +232,15 @@ bit_metrics(float sym, const float (&ideal)[4], int& mag0, int& mag1) {
     const float b1_0 = d[2] < d[0] ? d[2] : d[0], b1_1 = d[3] < d[1] ? d[3] : d[1];
     mag0 = clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(b0_0, b0_1)), scale))); /* lrintf: round to nearest even */
     mag1 = clamp255(__float2int_rn(__fmul_rn(fabsf(__fsub_rn(b1_0, b1_1)), scale)));
+}
+
+/* thresholds from the tracked extremes (dsd_dibit.c:268-272); x / 2 and x / 8 are exact scalings, the same correctly
+ * rounded values as the reference's divisions */
+__device__ __forceinline__ void
+cq_thresholds(float vmin, float vmax, float& center, float& umid, float& lmid) {
+    center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
+    umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center);
+    lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
 }
 
 __global__ void __launch_bounds__(kSymThreads)
@@ -269,6 +279,7 @@ symbolize_kernel(const SymParams p) {
     float* o_sym = p.symbols + (size_t)c * p.out_pitch;
     uint8_t* o_dib = p.dibits ? p.dibits + (size_t)c * p.out_pitch : nullptr;
     uint8_t* o_rel = p.reliab ? p.reliab + (size_t)c * p.out_pitch : nullptr;
+    float2* o_mm = p.minmax ? p.minmax + (size_t)c * p.out_pitch : nullptr;
     int16_t* o_llr = p.llr ? p.llr + (size_t)c * p.out_pitch * 2 : nullptr;
     long nsym = 0;
     const int have_sync = (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) ? 1 : p.have_sync;
@@ -539,60 +550,11 @@ symbolize_kernel(const SymParams p) {
             if (cap > 0) {
                 sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
             }
-            /* ---- digitize (dsd_dibit.c:963-976,1018-1041) ---- */
-            int dibit;
-            if (sym > center) {
-                dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
-            } else {
-                dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
-            }
-            /* ---- compute_dibit_soft_metric (dsd_dibit.c:644-721) ---- */
-            const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
-            float ideal[4];
-            if (negative) {
-                ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
-            } else {
-                ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
-            }
-            int mag0, mag1;
-            bit_metrics(sym, ideal, mag0, mag1);
-            /* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) */
-            const float eps = 1e-6f;
-            int rel;
-            if (sym > umid) {
-                float span = __fsub_rn(vmax, umid);
-                span = span < eps ? eps : span;
-                rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(sym, umid), 255.0f), span));
-            } else if (sym > center) {
-                const float d1 = __fsub_rn(sym, center), d2 = __fsub_rn(umid, sym);
-                float span = __fsub_rn(umid, center);
-                span = span < eps ? eps : span;
-                rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
-            } else if (sym >= lmid) {
-                const float d1 = __fsub_rn(center, sym), d2 = __fsub_rn(sym, lmid);
-                float span = __fsub_rn(center, lmid);
-                span = span < eps ? eps : span;
-                rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
-            } else {
-                float span = __fsub_rn(lmid, vmin);
-                span = span < eps ? eps : span;
-                rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
-            }
-            rel = clamp255(rel);
-            rel = clamp255((rel * 204) >> 8); /* apply_c4fm_snr_weight with no SNR hook: w256 = 0 (dsd_dibit.c:520-537) */
-            const int min_mag = mag0 < mag1 ? mag0 : mag1;
-            if (min_mag > 0 && rel < min_mag) {
-                mag0 = (mag0 * rel) / min_mag;
-                mag1 = (mag1 * rel) / min_mag;
-            }
-            mag0 = clamp255(mag0);
-            mag1 = clamp255(mag1);
-            const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
-            if (valid) {
-                o_dib[nsym] = (uint8_t)dibit;
-                o_rel[nsym] = (uint8_t)clamp255(mag1 < mag0 ? mag1 : mag0);
-                o_llr[2 * nsym] = (int16_t)l0;
-                o_llr[2 * nsym + 1] = (int16_t)l1;
+            /* digitize and the soft metric only read {sym, thresholds}: sym_digitize_kernel does them one thread per symbol.
+             * Tracked channels hand over {min, max} per symbol (centre / mid thresholds follow from them); the others keep
+             * the same thresholds for the whole launch, which the second kernel reads from the carried state. */
+            if (valid && track) {
+                o_mm[nsym] = make_float2(vmin, vmax);
             }
         }
         nsym++;
@@ -630,6 +592,84 @@ symbolize_kernel(const SymParams p) {
     p.s.carry_n[c] = left;
     p.s.symbolcnt[c] = symbolcnt;
     p.count[c] = (int)nsym;
+}
+
+/* digitize (dsd_dibit.c:963-976,1018-1041) + compute_dibit_soft_metric (:644-721) + c4fm_reliability_from_thresholds
+ * (:455-502) for every symbol of every channel, one thread per symbol: they only read the symbol and the thresholds in
+ * force after use_symbol -- per symbol {min, max} from symbolize_kernel for tracked channels (centre and mid thresholds
+ * follow from them by the reference's own formulas), the carried thresholds for the others (constant over a launch:
+ * the only other writer is the first-call reset, which precedes the launch's first symbol). */
+__global__ void __launch_bounds__(256)
+sym_digitize_kernel(const SymParams p) {
+    const int c = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.count[c]) {
+        return;
+    }
+    const float sym = p.symbols[(size_t)c * p.out_pitch + i];
+    const int negative = p.s.negative[c];
+    float vmin, vmax, center, umid, lmid;
+    if (p.s.track[c]) {
+        const float2 mm = p.minmax[(size_t)c * p.out_pitch + i];
+        vmin = mm.x;
+        vmax = mm.y;
+        cq_thresholds(vmin, vmax, center, umid, lmid);
+    } else {
+        vmin = p.s.vmin[c], vmax = p.s.vmax[c], center = p.s.center[c], umid = p.s.umid[c], lmid = p.s.lmid[c];
+    }
+    /* ---- digitize (dsd_dibit.c:963-976,1018-1041) ---- */
+    int dibit;
+    if (sym > center) {
+        dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+    } else {
+        dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
+    }
+    /* ---- compute_dibit_soft_metric (dsd_dibit.c:644-721) ---- */
+    const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+    float ideal[4];
+    if (negative) {
+        ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+    } else {
+        ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+    }
+    int mag0, mag1;
+    bit_metrics(sym, ideal, mag0, mag1);
+    /* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) */
+    const float eps = 1e-6f;
+    int rel;
+    if (sym > umid) {
+        float span = __fsub_rn(vmax, umid);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(sym, umid), 255.0f), span));
+    } else if (sym > center) {
+        const float d1 = __fsub_rn(sym, center), d2 = __fsub_rn(umid, sym);
+        float span = __fsub_rn(umid, center);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+    } else if (sym >= lmid) {
+        const float d1 = __fsub_rn(center, sym), d2 = __fsub_rn(sym, lmid);
+        float span = __fsub_rn(center, lmid);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+    } else {
+        float span = __fsub_rn(lmid, vmin);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
+    }
+    rel = clamp255(rel);
+    rel = clamp255((rel * 204) >> 8); /* apply_c4fm_snr_weight with no SNR hook: w256 = 0 (dsd_dibit.c:520-537) */
+    const int min_mag = mag0 < mag1 ? mag0 : mag1;
+    if (min_mag > 0 && rel < min_mag) {
+        mag0 = (mag0 * rel) / min_mag;
+        mag1 = (mag1 * rel) / min_mag;
+    }
+    mag0 = clamp255(mag0);
+    mag1 = clamp255(mag1);
+    const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
+    const size_t o = (size_t)c * p.out_pitch + i;
+    p.dibits[o] = (uint8_t)dibit;
+    p.reliab[o] = (uint8_t)clamp255(mag1 < mag0 ? mag1 : mag0);
+    reinterpret_cast<short2*>(p.llr)[o] = make_short2((short)l0, (short)l1);
 }
 
 __global__ void
@@ -701,15 +741,6 @@ struct CqSliceParams {
     int snr_scale_num;    /* 204 + (w256 >> 2), or 0 when the SNR hook reports <= -50 dB (no weighting) */
     float2* minmax;       /* [n_ch][out_pitch] scratch: {min, max} after use_symbol, per symbol (tracker -> digitize kernel) */
 };
-
-/* thresholds from the tracked extremes (dsd_dibit.c:268-272); x / 2 and x / 8 are exact scalings, the same correctly
- * rounded values as the reference's divisions */
-__device__ __forceinline__ void
-cq_thresholds(float vmin, float vmax, float& center, float& umid, float& lmid) {
-    center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
-    umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center);
-    lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
-}
 
 __global__ void __launch_bounds__(32)
 cqpsk_slice_kernel(const CqSliceParams p) {
@@ -1026,6 +1057,8 @@ struct dsdneo_b200_symbolizer {
     int* d_taps_len;
     float* d_filt;
     size_t filt_pitch;
+    float2* d_minmax; /* per-symbol {min, max} between symbolize_kernel and sym_digitize_kernel, grown on demand */
+    size_t minmax_cap;
 };
 
 extern "C" {
@@ -1089,6 +1122,7 @@ dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y) {
     cudaFree(y->d_taps);
     cudaFree(y->d_taps_len);
     cudaFree(y->d_filt);
+    cudaFree(y->d_minmax);
     free(y);
 }
 
@@ -1350,12 +1384,32 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
     sp.symrate = y->symrate;
     sp.ssize = y->ssize;
     sp.msize = y->msize;
+    sp.minmax = NULL;
+    if (mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
+        const size_t need = (size_t)y->n_ch * out->pitch;
+        if (y->minmax_cap < need) {
+            DSDNEO_CUDA(cudaDeviceSynchronize());
+            cudaFree(y->d_minmax);
+            y->d_minmax = NULL;
+            y->minmax_cap = 0;
+            DSDNEO_CUDA(cudaMalloc((void**)&y->d_minmax, need * sizeof(float2)));
+            y->minmax_cap = need;
+        }
+        sp.minmax = y->d_minmax;
+    }
     {
         KernelTimer kt("symbolize_kernel", s);
         symbolize_kernel<<<(y->n_ch + kSymThreads - 1) / kSymThreads, kSymThreads, 0, s>>>(sp);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
+    if (mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT && out->pitch > 0) {
+        KernelTimer kt("sym_digitize_kernel", s);
+        dim3 grid((unsigned)((out->pitch + 255) / 256), (unsigned)y->n_ch);
+        sym_digitize_kernel<<<grid, 256, 0, s>>>(sp);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
     return 0;
 }
 
