@@ -1537,6 +1537,148 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
     }
 }
 
+/* ------------------------------------------------------------------ Golay(24,6) / (24,12) soft decode */
+
+/* check_and_fix_golay_24_6_soft / _24_12_soft (src/protocol/p25/phase1/p25p1_soft.cpp:477-593), one thread per word, on the
+ * packed codeword of DSDGolay24 (parity[i] = bit 12 + i, data[i] = bit 12 - length + i): hard decode as seed, then every
+ * combination of at most 4 flips among the 8 least reliable bits, each Golay-decoded and re-encoded; lowest summed
+ * reliability of changed bits wins, then fewer changed bits; hard-correction precedence as in the reference. */
+__global__ void
+p25_golay_soft_kernel(int length, uint8_t* data_bits, const uint8_t* parity_bits, const int32_t* reliab, int hard_override,
+                      int threshold, uint8_t* status, int32_t* fixed, int n_words) {
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n_words) {
+        return;
+    }
+    const int n = length + 12;
+    uint8_t* d = data_bits + (size_t)wi * length;
+    const uint8_t* pb = parity_bits + (size_t)wi * 12;
+    const int32_t* rin = reliab + (size_t)wi * n;
+    int rel[24];
+    auto bit_of = [&](int idx) { return idx < length ? (12 - length + idx) : (12 + idx - length); };
+    unsigned orig = 0;
+    bool binary = true;
+    for (int i = 0; i < n; i++) {
+        const int r = rin[i];
+        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
+        const unsigned b = i < length ? d[i] : pb[i - length];
+        binary = binary && b <= 1;
+        orig |= (b & 1u) << bit_of(i);
+    }
+    if (!binary) { /* word_bits_are_valid fails: every decode in the reference returns 1 and nothing is found */
+        status[wi] = 1;
+        fixed[wi] = 0;
+        return;
+    }
+    const unsigned data_mask = 0xfffu & ~((1u << (12 - length)) - 1u);
+    auto penalty = [&](unsigned diff, int& count) {
+        int pen = 0;
+        count = __popc(diff);
+        for (int i = 0; i < n; i++) {
+            pen += ((diff >> bit_of(i)) & 1u) ? rel[i] : 0;
+        }
+        return pen;
+    };
+    /* decode one packed candidate: returns false if uncorrectable; else the decoded data field and the diff vs orig of
+     * {decoded data, re-encoded parity} */
+    auto try_word = [&](unsigned cw, unsigned& dec_data, unsigned& diff, int& errs) {
+        const unsigned pbit = cw & 0x800000u;
+        cw = g23_correct(cw & ~0x800000u, &errs) | pbit;
+        const int odd = __popc(cw & 0xffffffu) & 1;
+        if (odd && (cw & 0x3fu) != 0) {
+            return false;
+        }
+        dec_data = cw & data_mask;
+        unsigned enc = g23_syndrome(dec_data) | dec_data; /* Golay24::golay + overall parity = Golay24::encode */
+        if (__popc(enc & 0xffffffu) & 1) {
+            enc ^= 0x800000u;
+        }
+        diff = ((dec_data ^ orig) & data_mask) | ((enc ^ orig) & 0xfff000u);
+        return true;
+    };
+    int best_pen = 999999, best_fixed = 0, found = 0, hard_valid = 0, hard_corrected = 0, hard_pen = 999999, hard_fixed = 0;
+    unsigned best = 0, hard = 0;
+    {
+        unsigned dd, diff;
+        int errs = 0;
+        if (try_word(orig, dd, diff, errs)) {
+            int cnt;
+            hard_fixed = errs;
+            hard_valid = 1;
+            hard_corrected = errs > 0;
+            hard_pen = penalty(diff, cnt);
+            best_pen = hard_pen;
+            best_fixed = cnt;
+            hard = dd;
+            best = dd;
+            found = 1;
+        }
+    }
+    int order[24], least[8], n_least = 0;
+    for (int i = 0; i < n; i++) {
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            rank += (rel[j] < rel[i] || (rel[j] == rel[i] && j < i)) ? 1 : 0;
+        }
+        order[rank] = i;
+    }
+    for (int i = 0; i < n && n_least < 8; i++) {
+        if (rel[order[i]] < threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int i = 0; i < n && n_least < 8; i++) {
+        if (rel[order[i]] >= threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    unsigned flip_bit[8];
+    for (int b = 0; b < 8; b++) {
+        flip_bit[b] = 1u << bit_of(least[b]);
+    }
+    for (int mask = 0; mask < 256; mask++) {
+        if (__popc(mask) > 4) {
+            continue;
+        }
+        unsigned cand = orig;
+        for (int b = 0; b < 8; b++) {
+            if (mask & (1 << b)) {
+                cand ^= flip_bit[b];
+            }
+        }
+        unsigned dd, diff;
+        int errs = 0;
+        if (!try_word(cand, dd, diff, errs)) {
+            continue;
+        }
+        int cnt;
+        const int pen = penalty(diff, cnt);
+        if (pen < best_pen || (pen == best_pen && cnt < best_fixed)) {
+            best_pen = pen;
+            best_fixed = cnt;
+            best = dd;
+            found = 1;
+        }
+    }
+    int st = 1, fx = 0;
+    unsigned result = 0;
+    if (found) {
+        st = 0;
+        if (hard_valid && hard_corrected && best != hard && (!hard_override || best_pen + 8 >= hard_pen)) {
+            result = hard;
+            fx = hard_fixed;
+        } else {
+            result = best;
+            fx = best_fixed;
+        }
+        for (int i = 0; i < length; i++) {
+            d[i] = (uint8_t)((result >> (12 - length + i)) & 1u);
+        }
+    }
+    status[wi] = (uint8_t)st;
+    fixed[wi] = fx;
+}
+
 /* ------------------------------------------------------------------ Hamming(10,6,3) soft decode */
 
 /* hamming_10_6_3_decode (src/fec/hamming_10_6_3.cpp:14-105) on a packed word v (bit 9 - i = reference bit i): returns the
@@ -2614,6 +2756,72 @@ dsdneo_b200_bch_63_16_decode_batch_host(const uint8_t* h_in63, uint8_t* h_out16,
     if (h_err_count) {
         DSDNEO_CUDA(cudaMemcpy(h_err_count, ec.p, n * 4, cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+int
+dsdneo_b200_p25_golay_soft_batch(int code, uint8_t* d_data_bits, const uint8_t* d_parity_bits, const int32_t* d_reliab,
+                                 int hard_override_enabled, int erasure_threshold, uint8_t* d_status, int32_t* d_fixed,
+                                 int n_words, void* stream) {
+    if ((code != DSDNEO_P25_WORD_GOLAY_24_6 && code != DSDNEO_P25_WORD_GOLAY_24_12) || !d_data_bits || !d_parity_bits || !d_reliab
+        || !d_status || !d_fixed || n_words < 0) {
+        set_error("p25_golay_soft_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int length = (code == DSDNEO_P25_WORD_GOLAY_24_6) ? 6 : 12;
+    {
+        KernelTimer kt("p25_golay_soft_kernel", s);
+        p25_golay_soft_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(length, d_data_bits, d_parity_bits, d_reliab,
+                                                                    hard_override_enabled, erasure_threshold, d_status, d_fixed,
+                                                                    n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25_golay_soft_batch_host(int code, uint8_t* h_data_bits, const uint8_t* h_parity_bits, const int32_t* h_reliab,
+                                      int hard_override_enabled, int erasure_threshold, uint8_t* h_status, int32_t* h_fixed,
+                                      int n_words) {
+    if ((code != DSDNEO_P25_WORD_GOLAY_24_6 && code != DSDNEO_P25_WORD_GOLAY_24_12) || !h_data_bits || !h_parity_bits || !h_reliab
+        || !h_status || !h_fixed || n_words < 0) {
+        set_error("p25_golay_soft_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words, length = (code == DSDNEO_P25_WORD_GOLAY_24_6) ? 6 : 12;
+    DevBuf dat(n * length), par(n * 12), rel(n * (length + 12) * 4), st(n), fx(n * 4);
+    DSDNEO_CUDA(dat.err);
+    DSDNEO_CUDA(par.err);
+    DSDNEO_CUDA(rel.err);
+    DSDNEO_CUDA(st.err);
+    DSDNEO_CUDA(fx.err);
+    DSDNEO_CUDA(cudaMemcpy(dat.p, h_data_bits, n * length, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(par.p, h_parity_bits, n * 12, cudaMemcpyHostToDevice));
+    DSDNEO_CUDA(cudaMemcpy(rel.p, h_reliab, n * (length + 12) * 4, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_p25_golay_soft_batch(code, dat.as<uint8_t>(), par.as<uint8_t>(), rel.as<int32_t>(), hard_override_enabled,
+                                          erasure_threshold, st.as<uint8_t>(), fx.as<int32_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_data_bits, dat.p, n * length, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_status, st.p, n, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_fixed, fx.p, n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -647,6 +647,21 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
                                             int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words);
 
 /**
+ * Batched twins of `int check_and_fix_golay_24_6_soft(char* data, const char* parity, const int* reliab, int* fixed)` and
+ * `check_and_fix_golay_24_12_soft` (include/dsd-neo/protocol/p25/p25p1_soft.h, src/protocol/p25/phase1/p25p1_soft.cpp:477-593):
+ * Golay(24,6) / (24,12) with a bounded search over the 8 least reliable bits (at most 4 flips).
+ * code = DSDNEO_P25_WORD_GOLAY_24_6 / _24_12; d_data_bits [n][6 | 12] corrected in place, d_parity_bits [n][12],
+ * d_reliab [n][18 | 24] int (data bits first, then parity; clamped to 0..255 like the reference);
+ * d_status[i]: 0 ok / 1 no valid candidate (data untouched); d_fixed[i] as the reference's *fixed.
+ */
+int dsdneo_b200_p25_golay_soft_batch(int code, uint8_t* d_data_bits, const uint8_t* d_parity_bits, const int32_t* d_reliab,
+                                     int hard_override_enabled, int erasure_threshold, uint8_t* d_status, int32_t* d_fixed,
+                                     int n_words, void* stream);
+int dsdneo_b200_p25_golay_soft_batch_host(int code, uint8_t* h_data_bits, const uint8_t* h_parity_bits,
+                                          const int32_t* h_reliab, int hard_override_enabled, int erasure_threshold,
+                                          uint8_t* h_status, int32_t* h_fixed, int n_words);
+
+/**
  * Batched twin of `int hamming_10_6_3_soft(const char* bits, const int* reliab, char* out_bits)`
  * (include/dsd-neo/protocol/p25/p25p1_soft.h:40, src/protocol/p25/phase1/p25p1_soft.cpp:444-475): Hamming(10,6,3) with a
  * bounded search over the 5 least reliable bits (at most 2 flips).  `hard_override_enabled` = p25_soft_hard_override_enabled()

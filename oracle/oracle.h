@@ -139,6 +139,9 @@ int oracle_p25_rs_soft_reliability(int n_total, int n_data, uint8_t* data_bits, 
                                    const uint8_t* par_rel, int threshold);
 int oracle_p25_golay24_decode(int length, uint8_t* word, const uint8_t* parity, int* fixed_errors);
 int oracle_hamming_10_6_3_decode(uint8_t* data6, const uint8_t* parity4);
+/* check_and_fix_golay_24_6_soft / _24_12_soft (src/protocol/p25/phase1/p25p1_soft.cpp:477-593); length = 6 or 12 */
+int oracle_p25_golay24_soft(int length, uint8_t* data, const uint8_t* parity, const int* reliab, int hard_override_enabled,
+                            int threshold, int* fixed);
 /* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475) */
 int oracle_hamming_10_6_3_soft(const uint8_t* bits10, const int* reliab10, int hard_override_enabled, int threshold, uint8_t* out10);
 int oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count);

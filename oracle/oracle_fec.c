@@ -2030,3 +2030,139 @@ oracle_hamming_10_6_3_soft(const uint8_t* bits10, const int* reliab10, int hard_
     memcpy(out10, best, 10);
     return memcmp(best, bits10, 10) == 0 ? 0 : 1;
 }
+
+/* ------------------------------------------------------------------ Golay(24,6) / (24,12) soft decode (P25p1 HDU / LDU words) */
+
+/* DSDGolay24::encode_6 / encode_12 (include/dsd-neo/fec/Golay24.hpp:407-434): 12 parity bits for `length` data bits */
+static void
+golay24_encode_parity(int length, const uint8_t* word, uint8_t* parity12) {
+    unsigned data = 0;
+    for (int i = 0; i < length; i++) {
+        data = (data << 1) | word[length - 1 - i];
+    }
+    data <<= (12 - length);
+    unsigned cw = g23_syndrome(data) | data; /* Golay24::golay (:22-37) */
+    if (parity32(cw)) {
+        cw ^= 0x800000u;
+    }
+    unsigned mask = 1u << 12;
+    for (int i = 0; i < 12; i++, mask <<= 1) {
+        parity12[i] = (cw & mask) ? 1 : 0;
+    }
+}
+
+/* check_and_fix_golay_24_6_soft / _24_12_soft (src/protocol/p25/phase1/p25p1_soft.cpp:477-593): hard decode seeds the best
+ * candidate; the 8 least reliable of the 6 + 12 / 12 + 12 bits (find_k_least_reliable, :174-206) are flipped in every
+ * combination of at most 4, each candidate is Golay-decoded and re-encoded, lowest summed reliability of changed bits
+ * wins, then fewer changed bits; a hard correction is kept unless overriding is enabled and the soft winner is more than
+ * 8 cheaper.  Returns 0 ok (data corrected in place, *fixed = changed bits or the hard count) / 1 no valid candidate. */
+int
+oracle_p25_golay24_soft(int length, uint8_t* data, const uint8_t* parity, const int* reliab, int hard_override_enabled,
+                        int threshold, int* fixed) {
+    *fixed = 0;
+    if (length != 6 && length != 12) {
+        return 1;
+    }
+    const int n = length + 12;
+    uint8_t orig[24], best[12] = {0}, hard[12] = {0};
+    int rel[24];
+    memcpy(orig, data, (size_t)length);
+    memcpy(orig + length, parity, 12);
+    for (int i = 0; i < n; i++) {
+        rel[i] = reliab[i] < 0 ? 0 : (reliab[i] > 255 ? 255 : reliab[i]);
+    }
+    int best_pen = 999999, best_fixed = 0, found = 0, hard_valid = 0, hard_corrected = 0, hard_pen = 999999, hard_fixed = 0;
+    {
+        uint8_t w[12];
+        memcpy(w, data, (size_t)length);
+        if (oracle_p25_golay24_decode(length, w, parity, &hard_fixed) == 0) {
+            uint8_t dec[24];
+            memcpy(dec, w, (size_t)length);
+            golay24_encode_parity(length, w, dec + length);
+            hard_valid = 1;
+            hard_corrected = hard_fixed > 0;
+            hard_pen = 0;
+            int diff = 0;
+            for (int i = 0; i < n; i++) {
+                if (dec[i] != orig[i]) {
+                    hard_pen += rel[i];
+                    diff++;
+                }
+            }
+            best_pen = hard_pen;
+            best_fixed = diff;
+            memcpy(hard, w, (size_t)length);
+            memcpy(best, w, (size_t)length);
+            found = 1;
+        }
+    }
+    int order[24], least[8], n_least = 0;
+    for (int i = 0; i < n; i++) {
+        order[i] = i;
+    }
+    for (int i = 0; i < n; i++) {
+        for (int j = i + 1; j < n; j++) {
+            const int a = order[j], b = order[i];
+            if (rel[a] < rel[b] || (rel[a] == rel[b] && a < b)) {
+                order[i] = a;
+                order[j] = b;
+            }
+        }
+    }
+    for (int i = 0; i < n && n_least < 8; i++) {
+        if (rel[order[i]] < threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int i = 0; i < n && n_least < 8; i++) {
+        if (rel[order[i]] >= threshold) {
+            least[n_least++] = order[i];
+        }
+    }
+    for (int mask = 0; mask < 256; mask++) {
+        if (__builtin_popcount((unsigned)mask) > 4) {
+            continue;
+        }
+        uint8_t cand[24];
+        memcpy(cand, orig, (size_t)n);
+        for (int b = 0; b < 8; b++) {
+            if (mask & (1 << b)) {
+                cand[least[b]] ^= 1;
+            }
+        }
+        uint8_t w[12];
+        int cf = 0;
+        memcpy(w, cand, (size_t)length);
+        if (oracle_p25_golay24_decode(length, w, cand + length, &cf) != 0) {
+            continue;
+        }
+        uint8_t dec[24];
+        memcpy(dec, w, (size_t)length);
+        golay24_encode_parity(length, w, dec + length);
+        int pen = 0, diff = 0;
+        for (int i = 0; i < n; i++) {
+            if (dec[i] != orig[i]) {
+                pen += rel[i];
+                diff++;
+            }
+        }
+        if (pen < best_pen || (pen == best_pen && diff < best_fixed)) {
+            best_pen = pen;
+            best_fixed = diff;
+            memcpy(best, w, (size_t)length);
+            found = 1;
+        }
+    }
+    if (!found) {
+        return 1;
+    }
+    if (hard_valid && hard_corrected && memcmp(best, hard, (size_t)length) != 0
+        && (!hard_override_enabled || best_pen + 8 >= hard_pen)) {
+        memcpy(data, hard, (size_t)length);
+        *fixed = hard_fixed;
+        return 0;
+    }
+    memcpy(data, best, (size_t)length);
+    *fixed = best_fixed;
+    return 0;
+}

@@ -350,3 +350,25 @@ def test_hamming_10_6_3_soft_bit_exact_vs_oracle(gpu):
             rc = O.oracle_hamming_10_6_3_soft(H._ptr(bits[k], H.u8p), rel[k].ctypes.data_as(H.i32p), override, 64, H._ptr(want, H.u8p))
             assert rc == st[k] and np.array_equal(out[k], want), (k, override)
         assert set(st.tolist()) == {0, 1, 2}
+
+
+@pytest.mark.parametrize("length", [6, 12])
+def test_p25_golay24_soft_bit_exact_vs_oracle(gpu, length):
+    from test_oracle_fec import golay_soft_cases
+
+    O = H.oracle_fec()
+    O.oracle_p25_golay24_soft.argtypes = [C.c_int, H.u8p, H.u8p, H.i32p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(2450 + length)
+    data, par, rel = golay_soft_cases(rng, length, 4000)
+    code = gpu.P25_WORD_GOLAY_24_6 if length == 6 else gpu.P25_WORD_GOLAY_24_12
+    for override in (1, 0):
+        got = data.copy()
+        st, fx = np.zeros(data.shape[0], np.uint8), np.zeros(data.shape[0], np.int32)
+        gpu.check(gpu.lib().dsdneo_b200_p25_golay_soft_batch_host(code, got.ctypes.data, par.ctypes.data, rel.ctypes.data, override, 64,
+                                                                 st.ctypes.data, fx.ctypes.data, data.shape[0]))
+        for k in range(data.shape[0]):
+            want = data[k].copy()
+            f = C.c_int(0)
+            rc = O.oracle_p25_golay24_soft(length, H._ptr(want, H.u8p), H._ptr(par[k], H.u8p), rel[k].ctypes.data_as(H.i32p), override, 64,
+                                           C.byref(f))
+            assert rc == st[k] and np.array_equal(got[k], want) and f.value == fx[k], (k, override, rc, st[k], f.value, fx[k])

@@ -772,3 +772,39 @@ def test_hamming_10_6_3_soft_matches_reference():
         assert ra == rb and np.array_equal(oa, ob), (k, ra, rb, bits[k], rel[k], oa, ob)
         seen.add(ra)
     assert seen == {0, 1, 2}
+
+
+def golay_soft_cases(rng, length, n):
+    """Noisy Golay(24,6) / (24,12) words (the zero codeword plus 0..6 flips: the code is linear) with reliabilities that mostly
+    mark the flips as weak; returns data [n, length], parity [n, 12], reliab [n, length + 12] int32."""
+    w = length + 12
+    bits = np.zeros((n, w), np.uint8)
+    rel = rng.integers(40, 300, (n, w)).astype(np.int32)
+    for k in range(n):
+        pos = rng.choice(w, int(rng.integers(0, 7)), replace=False)
+        bits[k, pos] ^= 1
+        weak = pos[rng.random(pos.size) < 0.8]
+        rel[k, weak] = rng.integers(-3, 90, weak.size)
+        if k % 6 == 0:
+            rel[k] = rng.integers(0, 3, w) * 64
+    return np.ascontiguousarray(bits[:, :length]), np.ascontiguousarray(bits[:, length:]), rel
+
+
+@needs_ref
+@pytest.mark.parametrize("length", [6, 12])
+def test_p25_golay24_soft_matches_reference(length):
+    O, R = H.oracle_fec(), H.ref_fec()
+    O.oracle_p25_golay24_soft.argtypes = [C.c_int, H.u8p, H.u8p, H.i32p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    fn = R.check_and_fix_golay_24_6_soft if length == 6 else R.check_and_fix_golay_24_12_soft
+    fn.argtypes = [H.u8p, H.u8p, H.i32p, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(2400 + length)
+    data, par, rel = golay_soft_cases(rng, length, 2500)
+    seen = set()
+    for k in range(data.shape[0]):
+        da, db = data[k].copy(), data[k].copy()
+        fa, fb = C.c_int(0), C.c_int(0)
+        ra = fn(H._ptr(da, H.u8p), H._ptr(par[k], H.u8p), rel[k].ctypes.data_as(H.i32p), C.byref(fa))
+        rb = O.oracle_p25_golay24_soft(length, H._ptr(db, H.u8p), H._ptr(par[k], H.u8p), rel[k].ctypes.data_as(H.i32p), 1, 64, C.byref(fb))
+        assert ra == rb and np.array_equal(da, db) and fa.value == fb.value, (k, ra, rb, fa.value, fb.value)
+        seen.add(ra)
+    assert 0 in seen
