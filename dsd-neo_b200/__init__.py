@@ -848,6 +848,32 @@ def p25p1_nid_decode(code63, reliab63=None, observed_nac=None, parity=None, pari
     return st, nac, duid, errs
 
 
+def dmr_burst_cut(d_dibits, d_reliability, d_counts, d_hits, d_n_hits, inverted_dmr: bool = False, stream=None):
+    """Device-side DMR BS data burst cutter on the symbolizer / frame-sync outputs (torch cuda tensors).  Returns a dict of cuda
+    uint8 tensors indexed by slot = channel * max_hits + hit: cach24, info196, rel98, slot_type20, valid."""
+    import torch
+
+    n_ch, max_hits = d_hits.shape[0], d_hits.shape[1]
+    slots = n_ch * max_hits
+    dev = d_dibits.device
+    u8 = lambda *shape: torch.zeros(shape, dtype=torch.uint8, device=dev)
+    out = {"cach24": u8(slots, 24), "info196": u8(slots, 196), "rel98": u8(slots, 98), "slot_type20": u8(slots, 20), "valid": u8(slots)}
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    assert d_dibits.dtype == torch.uint8 and d_reliability.dtype == torch.uint8 and d_counts.dtype == torch.int32
+    assert d_hits.dtype == torch.int32 and d_n_hits.dtype == torch.int32 and d_hits.is_contiguous()
+    check(
+        lib().dsdneo_b200_dmr_burst_cut_batch(
+            d_dibits.data_ptr(), d_dibits.shape[1], d_reliability.data_ptr(), d_reliability.shape[1], d_counts.data_ptr(),
+            d_hits.data_ptr(), d_n_hits.data_ptr(), n_ch, max_hits, 1 if inverted_dmr else 0, out["cach24"].data_ptr(),
+            out["info196"].data_ptr(), out["rel98"].data_ptr(), out["slot_type20"].data_ptr(), out["valid"].data_ptr(),
+            _stream_ptr(stream),
+        ),
+        "dmr_burst_cut_batch",
+    )
+    return out
+
+
 def p25p1_frame_cut(d_dibits, d_llr, d_counts, d_hits, d_n_hits, n_payload: int, stream=None):
     """Device-side P25p1 frame cutter on the symbolizer / frame-sync outputs (torch cuda tensors).  Returns a dict of cuda
     tensors indexed by slot = channel * max_hits + hit: nid_code63, nid_reliab63, nid_parity, nid_parity_reliab, nid_valid,

@@ -1883,6 +1883,74 @@ p25p1_frame_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const int16_t*
     }
 }
 
+/* ------------------------------------------------------------------ DMR BS data burst cutter */
+
+/* dmr_data_sync's collection phase (src/protocol/dmr/dmr_data.c:54-65,118-157,159-179,218-226,261-268) for every BS DATA
+ * sync hit of every channel: 90 dibits back from the dibit after the sync -- 12 CACH dibits de-interleaved with
+ * dmr_cach_interleave (src/protocol/dmr/dmr_cach.c:9-11), 49 info dibits, 5 slot-type dibits, the sync -- then 5 slot-type
+ * and 49 info dibits after it.  One thread block per (channel, hit) slot, one thread per dibit. */
+__global__ void __launch_bounds__(128)
+dmr_burst_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const uint8_t* reliab, size_t rel_pitch, const int32_t* counts,
+                     const int32_t* hits, const int32_t* n_hits, int n_channels, int max_hits, int inverted, uint8_t* cach24,
+                     uint8_t* info196, uint8_t* rel98, uint8_t* slot20, uint8_t* valid_out) {
+    const int slot = blockIdx.x;
+    const int ch = slot / max_hits, h = slot - ch * max_hits;
+    if (ch >= n_channels) {
+        return;
+    }
+    const int t = threadIdx.x;
+    const bool present = h < min(n_hits[ch], max_hits);
+    const long live = present ? (long)hits[((size_t)ch * max_hits + h) * 2] + 1 : 0;
+    const long start = live - 90;
+    const bool ok = present && start >= 0 && live + 54 <= counts[ch];
+    if (t == 0) {
+        valid_out[slot] = ok ? 1 : 0;
+    }
+    /* burst-relative dibit index: 0..11 CACH, 12..60 info, 61..65 slot type, 66..89 sync, 90..94 slot type, 95..143 info */
+    for (int k = t; k < 144; k += blockDim.x) {
+        if (k >= 66 && k < 90) {
+            continue;
+        }
+        int d = 0, r = 0;
+        if (ok) {
+            d = dibits[(size_t)ch * dibit_pitch + start + k];
+            r = reliab[(size_t)ch * rel_pitch + start + k];
+            if (inverted && k < 90) {
+                d ^= 2;
+            }
+        }
+        const uint8_t b1 = (uint8_t)((d >> 1) & 1), b0 = (uint8_t)(d & 1);
+        if (k < 12) {
+            /* dmr_cach_interleave {0,7,8,9,1,10,11,12,2,13,14,15,3,16,4,17,18,19,5,20,21,22,6,23}, 5 bits per entry */
+            const unsigned long long lo = 0x07B9A262D414A0E0ull; /* entries 0..11 */
+            const unsigned long long hi = 0x0B9AD5A167289203ull; /* entries 12..23 */
+            const int e0 = 2 * k, e1 = 2 * k + 1;
+            const int i0 = (int)(((e0 < 12 ? lo : hi) >> (5 * (e0 % 12))) & 31ull);
+            const int i1 = (int)(((e1 < 12 ? lo : hi) >> (5 * (e1 % 12))) & 31ull);
+            cach24[(size_t)slot * 24 + i0] = b1;
+            cach24[(size_t)slot * 24 + i1] = b0;
+        } else if (k < 61) {
+            const int i = k - 12;
+            info196[(size_t)slot * 196 + 2 * i] = b1;
+            info196[(size_t)slot * 196 + 2 * i + 1] = b0;
+            rel98[(size_t)slot * 98 + i] = (uint8_t)r;
+        } else if (k < 66) {
+            const int i = k - 61;
+            slot20[(size_t)slot * 20 + 2 * i] = b1;
+            slot20[(size_t)slot * 20 + 2 * i + 1] = b0;
+        } else if (k < 95) {
+            const int i = k - 90;
+            slot20[(size_t)slot * 20 + 10 + 2 * i] = b1;
+            slot20[(size_t)slot * 20 + 11 + 2 * i] = b0;
+        } else {
+            const int i = k - 95;
+            info196[(size_t)slot * 196 + 98 + 2 * i] = b1;
+            info196[(size_t)slot * 196 + 99 + 2 * i] = b0;
+            rel98[(size_t)slot * 98 + 49 + i] = (uint8_t)r;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ K = 5 convolutional decoders */
 
 constexpr int kVitMaxSteps = 244; /* viterbi_history[244], src/core/util/dsd_misc.c:108 */
@@ -2984,6 +3052,32 @@ dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, c
             d_dibits, dibit_pitch, d_llr, llr_pitch, d_counts, (const int32_t*)d_hits, d_n_hits, n_channels, max_hits, n_payload,
             d_nid_code63, d_nid_reliab63, d_nid_parity, d_nid_parity_reliab, d_nid_valid, d_payload_dibits, d_payload_llr,
             d_payload_valid);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_dmr_burst_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const uint8_t* d_reliability, size_t reliability_pitch,
+                                const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels, int max_hits,
+                                int inverted_dmr, uint8_t* d_cach24, uint8_t* d_info196, uint8_t* d_rel98, uint8_t* d_slot_type20,
+                                uint8_t* d_valid, void* stream) {
+    if (!d_dibits || !d_reliability || !d_counts || !d_hits || !d_n_hits || n_channels <= 0 || max_hits <= 0 || !d_cach24
+        || !d_info196 || !d_rel98 || !d_slot_type20 || !d_valid) {
+        set_error("dmr_burst_cut_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("dmr_burst_cut_kernel", s);
+        dmr_burst_cut_kernel<<<(unsigned)(n_channels * max_hits), 128, 0, s>>>(
+            d_dibits, dibit_pitch, d_reliability, reliability_pitch, d_counts, (const int32_t*)d_hits, d_n_hits, n_channels, max_hits,
+            inverted_dmr ? 1 : 0, d_cach24, d_info196, d_rel98, d_slot_type20, d_valid);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();

@@ -647,6 +647,21 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
                                             int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words);
 
 /**
+ * DMR base-station data burst cutter: the collection phase of `dmr_data_sync` (src/protocol/dmr/dmr_data.c:54-65,118-157,
+ * 159-179,218-226,261-268) for every BS DATA sync hit of every channel -- 90 dibits back from the dibit after the sync
+ * (12 CACH dibits de-interleaved with dmr_cach_interleave, 49 info dibits, 5 slot-type dibits, the sync) and 5 slot-type +
+ * 49 info dibits after it.  Outputs per slot (= channel * max_hits + hit): CACH bits [24] (bits 0..6 = the TACT word for
+ * Hamming(7,4)), info bits [196] in transmitted (interleaved) order = the input of dsdneo_b200_bptc_196x96_batch, per-dibit
+ * reliabilities of the 98 info dibits, slot-type bits [20] = the input of Golay(20,8), and whether the channel's stream
+ * (d_counts dibits) holds the whole burst.  `inverted_dmr` = opts->inverted_dmr (XOR 2 on the part before the sync's end).
+ */
+int dsdneo_b200_dmr_burst_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const uint8_t* d_reliability,
+                                    size_t reliability_pitch, const int32_t* d_counts, const void* d_hits,
+                                    const int32_t* d_n_hits, int n_channels, int max_hits, int inverted_dmr,
+                                    uint8_t* d_cach24, uint8_t* d_info196, uint8_t* d_rel98, uint8_t* d_slot_type20,
+                                    uint8_t* d_valid, void* stream);
+
+/**
  * Batched twins of `int check_and_fix_golay_24_6_soft(char* data, const char* parity, const int* reliab, int* fixed)` and
  * `check_and_fix_golay_24_12_soft` (include/dsd-neo/protocol/p25/p25p1_soft.h, src/protocol/p25/phase1/p25p1_soft.cpp:477-593):
  * Golay(24,6) / (24,12) with a bounded search over the 8 least reliable bits (at most 4 flips).

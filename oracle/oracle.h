@@ -146,6 +146,9 @@ int oracle_p25_golay24_soft(int length, uint8_t* data, const uint8_t* parity, co
 int oracle_hamming_10_6_3_soft(const uint8_t* bits10, const int* reliab10, int hard_override_enabled, int threshold, uint8_t* out10);
 int oracle_bch_63_16_decode(const uint8_t* in63, uint8_t* out16, int* error_count);
 /* p25p1_nid_decode (src/protocol/p25/phase1/p25p1_check_nid.cpp:322-354); returns NidResult status, fills nac / duid / errs */
+/* sequential DMR BS data burst cutter (CACH, 196 info bits + reliabilities, 20 slot-type bits); 1 = burst complete */
+int oracle_dmr_burst_cut(const uint8_t* dibits, const uint8_t* reliab, int count, int pos_last_sync, int inverted, uint8_t* cach24,
+                         uint8_t* info196, uint8_t* rel98, uint8_t* slot20);
 /* sequential P25p1 frame cutter (NID fields + status-stripped payload); bit 0 NID complete, bit 1 payload complete */
 int oracle_p25p1_frame_cut(const uint8_t* dibits, const int16_t* llr, int count, int pos_last_sync, int n_payload,
                            uint8_t* code63, uint8_t* reliab63, uint8_t* parity, uint8_t* parity_reliab, uint8_t* payload_dibits,

@@ -2166,3 +2166,57 @@ oracle_p25_golay24_soft(int length, uint8_t* data, const uint8_t* parity, const 
     *fixed = best_fixed;
     return 0;
 }
+
+/* ------------------------------------------------------------------ DMR BS data burst cutter (sequential restatement) */
+
+/* Collects one DMR base-station data burst around a BS DATA sync the way dmr_data_sync does (src/protocol/dmr/dmr_data.c:
+ * 54-65,118-157,159-179,218-226,261-268,321-340): 90 dibits back from the dibit after the sync -- 12 CACH dibits
+ * (de-interleaved with dmr_cach_interleave, src/protocol/dmr/dmr_cach.c:9-11), 49 info dibits, 5 slot-type dibits, the
+ * 24 sync dibits -- then, after the sync, 5 slot-type dibits and 49 info dibits.  `inverted` = opts->inverted_dmr (XOR 2
+ * on the cached part only, :87-89).  rel98 = per-dibit reliabilities of the 98 info dibits.
+ * PARITY UNPINNED for this function alone (static functions that need the whole decoder state); checked by round trip:
+ * bursts built from BPTC(196,96) / Golay(20,8) / Hamming(7,4) codewords come back through the pinned decoders.
+ * Returns 1 if the stream holds the whole burst. */
+int
+oracle_dmr_burst_cut(const uint8_t* dibits, const uint8_t* reliab, int count, int pos_last_sync, int inverted, uint8_t* cach24,
+                     uint8_t* info196, uint8_t* rel98, uint8_t* slot20) {
+    static const uint8_t cach_interleave[24] = {0, 7, 8, 9, 1, 10, 11, 12, 2, 13, 14, 15, 3, 16, 4, 17, 18, 19, 5, 20, 21, 22, 6, 23};
+    memset(cach24, 0, 24);
+    memset(info196, 0, 196);
+    memset(rel98, 0, 98);
+    memset(slot20, 0, 20);
+    const int live = pos_last_sync + 1; /* state->dmr_payload_p when dmr_data_sync starts */
+    int p = live - 90;
+    if (p < 0 || live + 54 > count) {
+        return 0;
+    }
+    for (int i = 0; i < 12; i++, p++) {
+        const int d = dibits[p] ^ (inverted ? 2 : 0);
+        cach24[cach_interleave[2 * i]] = (uint8_t)((d >> 1) & 1);
+        cach24[cach_interleave[2 * i + 1]] = (uint8_t)(d & 1);
+    }
+    for (int i = 0; i < 49; i++, p++) {
+        const int d = dibits[p] ^ (inverted ? 2 : 0);
+        info196[2 * i] = (uint8_t)((d >> 1) & 1);
+        info196[2 * i + 1] = (uint8_t)(d & 1);
+        rel98[i] = reliab[p];
+    }
+    for (int i = 0; i < 5; i++, p++) {
+        const int d = dibits[p] ^ (inverted ? 2 : 0);
+        slot20[2 * i] = (uint8_t)((d >> 1) & 1);
+        slot20[2 * i + 1] = (uint8_t)(d & 1);
+    }
+    p += 24; /* the sync itself */
+    for (int i = 0; i < 5; i++, p++) {
+        const int d = dibits[p];
+        slot20[2 * i + 10] = (uint8_t)((d >> 1) & 1);
+        slot20[2 * i + 11] = (uint8_t)(d & 1);
+    }
+    for (int i = 0; i < 49; i++, p++) {
+        const int d = dibits[p];
+        info196[2 * i + 98] = (uint8_t)((d >> 1) & 1);
+        info196[2 * i + 99] = (uint8_t)(d & 1);
+        rel98[i + 49] = reliab[p];
+    }
+    return 1;
+}

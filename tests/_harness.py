@@ -820,3 +820,58 @@ def oracle_cqpsk_slicer_run(symbols, negative=0, p25_slice=1, map_idx=0, snr_db=
     d, r, l = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros((n, 2), np.int16)
     L.oracle_cqpsk_slicer_run(C.byref(state), _ptr(symbols), n, _ptr(d, u8p), _ptr(r, u8p), l.ctypes.data_as(C.POINTER(C.c_int16)))
     return d, r, l, state
+
+
+# --------------------------------------------------------------------------- DMR BS data burst framing
+
+DMR_BS_DATA_SYNC_DIBITS = [int(c) for c in "313333111331131131331131"]
+DMR_CACH_INTERLEAVE = [0, 7, 8, 9, 1, 10, 11, 12, 2, 13, 14, 15, 3, 16, 4, 17, 18, 19, 5, 20, 21, 22, 6, 23]
+
+
+def golay_20_8_encode_bruteforce(data8):
+    """Golay(20,8) codeword for 8 data bits: the 12 parity bits the (pinned) oracle decoder accepts without a change."""
+    O = oracle_fec()
+    d = [int(b) for b in data8]
+    for par in range(4096):
+        w = np.array(d + [(par >> (11 - i)) & 1 for i in range(12)], np.uint8)
+        ref = w.copy()
+        if O.oracle_golay_20_8_decode(_ptr(w, u8p)) and np.array_equal(w, ref):
+            # a clean codeword is one whose single-bit flips all decode back to it
+            t = ref.copy()
+            t[3] ^= 1
+            if O.oracle_golay_20_8_decode(_ptr(t, u8p)) and np.array_equal(t, ref):
+                return ref
+    raise AssertionError("no Golay(20,8) codeword found")
+
+
+def hamming_7_4_encode_bruteforce(data4):
+    O = oracle_fec()
+    for par in range(8):
+        w = np.array([int(b) for b in data4] + [(par >> (2 - i)) & 1 for i in range(3)], np.uint8)
+        ref = w.copy()
+        dec = np.zeros(4, np.uint8)
+        t = ref.copy()
+        t[1] ^= 1
+        if O.oracle_hamming_decode(0, _ptr(t, u8p), _ptr(dec, u8p)) and np.array_equal(t, ref):
+            return ref
+    raise AssertionError("no Hamming(7,4) codeword found")
+
+
+def dmr_build_bs_data_burst(rng, payload96, color_code, data_type, tact4=(1, 0, 1, 0)):
+    """One DMR BS data burst in dibits: CACH (TACT Hamming(7,4) + 17 fragment bits, interleaved), 98 info bits, 10 slot-type
+    bits, BS DATA sync, 10 slot-type bits, 98 info bits.  Returns (144 dibits, dict of what was sent)."""
+    info = bptc_196x96_encode(payload96)
+    st8 = [(color_code >> (3 - i)) & 1 for i in range(4)] + [(data_type >> (3 - i)) & 1 for i in range(4)]
+    slot = golay_20_8_encode_bruteforce(st8)
+    cach = np.zeros(24, np.uint8)
+    cach[:7] = hamming_7_4_encode_bruteforce(tact4)
+    cach[7:] = rng.integers(0, 2, 17)
+    tx_cach = np.zeros(24, np.uint8)
+    for i in range(24):
+        tx_cach[i] = cach[DMR_CACH_INTERLEAVE[i]]
+    bits = np.concatenate([tx_cach, info[:98], slot[:10]])
+    first = (bits[0::2] << 1) | bits[1::2]
+    second_bits = np.concatenate([slot[10:], info[98:]])
+    second = (second_bits[0::2] << 1) | second_bits[1::2]
+    dib = np.concatenate([first, np.array(DMR_BS_DATA_SYNC_DIBITS), second]).astype(np.int64)
+    return dib, {"cach": cach, "info": info, "slot": slot}

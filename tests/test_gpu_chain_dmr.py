@@ -77,3 +77,83 @@ def test_dmr_chain_bit_exact_and_payloads_recovered(gpu):
     assert np.array_equal(out, np.array(want_out)) and np.array_equal(errs, np.array(want_err, np.uint32))
     good = sum(int(errs[k] == 0 and i < N_FRAMES and np.array_equal(out[k], chans[c][i])) for k, (c, i) in enumerate(owner))
     assert good >= n_ch * N_FRAMES - 2, (good, len(owner))  # every transmitted payload (a late false sync may add extras)
+
+
+def test_dmr_bs_data_bursts_on_device(gpu):
+    """Real DMR BS data burst framing (CACH + info + slot type around the sync), no host step between slicer and FEC:
+    symbolizer -> BS DATA sync hunt -> device burst cutter -> BPTC(196,96), Golay(20,8) slot type, Hamming(7,4) TACT.
+    The cutter equals the sequential oracle cutter on the same stream; payload, colour code and data type are recovered."""
+    import torch
+
+    rng = np.random.default_rng(99)
+    n_ch, n_bursts, max_hits = 16, 4, 8
+    taps = _taps()
+    chans, xs = [], []
+    for c in range(n_ch):
+        parts, sent = [rng.integers(0, 4, WARMUP)], []
+        for _ in range(n_bursts):
+            payload = rng.integers(0, 2, 96).astype(np.uint8)
+            cc, dt = int(rng.integers(0, 16)), int(rng.integers(0, 11))
+            burst, _ = H.dmr_build_bs_data_burst(rng, payload, cc, dt)
+            parts += [burst, rng.integers(0, 4, GAP)]
+            sent.append((payload, cc, dt))
+        chans.append(sent)
+        xs.append(H.synth_dmr_disc(rng, np.concatenate(parts), taps[1], 10000.0, 0.0 if c % 2 == 0 else 400.0 + 30.0 * c))
+    xs = np.stack(xs)
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([gpu.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), xs.shape[1])
+    fs = gpu.FrameSync(n_ch, [(DMR_SYNC, 10)])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=max_hits)
+    cut = gpu.dmr_burst_cut(res["dibits"], res["reliability"], res["count"], hits, n_hits)
+    torch.cuda.synchronize()
+    cut_h = {k: v.cpu().numpy() for k, v in cut.items()}
+    dib, rel, cnt = res["dibits"].cpu().numpy(), res["reliability"].cpu().numpy(), res["count"].cpu().numpy()
+    hits_h, n_hits_h = hits.cpu().numpy(), n_hits.cpu().numpy()
+    O = H.oracle_fec()
+    O.oracle_dmr_burst_cut.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, H.u8p, H.u8p, H.u8p, H.u8p]
+    good = []
+    for c in range(n_ch):
+        for h in range(max_hits):
+            s = c * max_hits + h
+            if h >= min(n_hits_h[c], max_hits):
+                assert cut_h["valid"][s] == 0
+                continue
+            cach, info, r98, slot = np.zeros(24, np.uint8), np.zeros(196, np.uint8), np.zeros(98, np.uint8), np.zeros(20, np.uint8)
+            ok = O.oracle_dmr_burst_cut(H._ptr(np.ascontiguousarray(dib[c, :cnt[c]]), H.u8p), H._ptr(np.ascontiguousarray(rel[c, :cnt[c]]), H.u8p),
+                                        int(cnt[c]), int(hits_h[c, h, 0]), 0, *[H._ptr(a, H.u8p) for a in (cach, info, r98, slot)])
+            assert cut_h["valid"][s] == ok
+            assert np.array_equal(cut_h["cach24"][s], cach) and np.array_equal(cut_h["info196"][s], info)
+            assert np.array_equal(cut_h["rel98"][s], r98) and np.array_equal(cut_h["slot_type20"][s], slot)
+            if ok:
+                good.append((c, s))
+    assert len(good) >= n_ch * n_bursts
+    sel = torch.tensor([s for _, s in good], device="cuda")
+    k = len(good)
+    info_d = cut["info196"][sel].contiguous()
+    out96 = torch.zeros((k, 96), dtype=torch.uint8, device="cuda")
+    r3 = torch.zeros((k, 3), dtype=torch.uint8, device="cuda")
+    errs = torch.zeros(k, dtype=torch.int32, device="cuda")
+    L = gpu.lib()
+    gpu.check(L.dsdneo_b200_bptc_196x96_batch(info_d.data_ptr(), 1, out96.data_ptr(), r3.data_ptr(), errs.data_ptr(), k, None))
+    slot_d = cut["slot_type20"][sel].contiguous()
+    ok_slot = torch.zeros(k, dtype=torch.uint8, device="cuda")
+    gpu.check(L.dsdneo_b200_fec_block_decode_batch(gpu.FEC_GOLAY_20_8, slot_d.data_ptr(), None, ok_slot.data_ptr(), k, None))
+    tact_d = cut["cach24"][sel][:, :7].contiguous()
+    tact_dec = torch.zeros((k, 4), dtype=torch.uint8, device="cuda")
+    ok_tact = torch.zeros(k, dtype=torch.uint8, device="cuda")
+    gpu.check(L.dsdneo_b200_fec_block_decode_batch(gpu.FEC_HAMMING_7_4, tact_d.data_ptr(), tact_dec.data_ptr(), ok_tact.data_ptr(), k, None))
+    torch.cuda.synchronize()
+    out96, errs, slot_h, ok_slot, ok_tact = out96.cpu().numpy(), errs.cpu().numpy(), slot_d.cpu().numpy(), ok_slot.cpu().numpy(), ok_tact.cpu().numpy()
+    tact_h = tact_d.cpu().numpy()
+    recovered = 0
+    for c in range(n_ch):
+        mine = [i for i, (cc_, s) in enumerate(good) if cc_ == c]
+        for payload, cc, dt in chans[c]:
+            for i in mine:
+                if errs[i] == 0 and np.array_equal(out96[i], payload) and ok_slot[i] and ok_tact[i] \
+                        and int("".join(map(str, slot_h[i, :4])), 2) == cc and int("".join(map(str, slot_h[i, 4:8])), 2) == dt \
+                        and list(tact_h[i, :4]) == [1, 0, 1, 0]:
+                    recovered += 1
+                    break
+    assert recovered == n_ch * n_bursts, recovered

@@ -808,3 +808,37 @@ def test_p25_golay24_soft_matches_reference(length):
         assert ra == rb and np.array_equal(da, db) and fa.value == fb.value, (k, ra, rb, fa.value, fb.value)
         seen.add(ra)
     assert 0 in seen
+
+
+def test_dmr_burst_cut_round_trip():
+    """A DMR BS data burst built from BPTC(196,96) / Golay(20,8) / Hamming(7,4) codewords comes back through the sequential
+    cutter + the pinned decoders; the inverted-DMR switch and truncated streams behave as in dmr_data_sync."""
+    O = H.oracle_fec()
+    O.oracle_dmr_burst_cut.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, H.u8p, H.u8p, H.u8p, H.u8p]
+    rng = np.random.default_rng(18)
+    for trial in range(6):
+        payload = rng.integers(0, 2, 96).astype(np.uint8)
+        cc, dt = int(rng.integers(0, 16)), int(rng.integers(0, 11))
+        burst, sent = H.dmr_build_bs_data_burst(rng, payload, cc, dt)
+        pre = int(rng.integers(0, 40))
+        dib = np.concatenate([rng.integers(0, 4, pre), burst, rng.integers(0, 4, 5)]).astype(np.uint8)
+        rel = rng.integers(0, 256, dib.size).astype(np.uint8)
+        pos = pre + 12 + 49 + 5 + 23
+        cach, info, rel98, slot = np.zeros(24, np.uint8), np.zeros(196, np.uint8), np.zeros(98, np.uint8), np.zeros(20, np.uint8)
+        args = [H._ptr(a, H.u8p) for a in (cach, info, rel98, slot)]
+        assert O.oracle_dmr_burst_cut(H._ptr(dib, H.u8p), H._ptr(rel, H.u8p), dib.size, pos, 0, *args) == 1
+        assert np.array_equal(cach, sent["cach"]) and np.array_equal(info, sent["info"]) and np.array_equal(slot, sent["slot"])
+        assert np.array_equal(rel98[:49], rel[pre + 12:pre + 61]) and np.array_equal(rel98[49:], rel[pos + 6:pos + 55])
+        dei, out, r3, und = np.zeros(196, np.uint8), np.zeros(96, np.uint8), np.zeros(3, np.uint8), C.c_int(0)
+        O.oracle_bptc_deinterleave(H._ptr(info, H.u8p), H._ptr(dei, H.u8p))
+        assert O.oracle_bptc_196x96_extract(H._ptr(dei, H.u8p), H._ptr(out, H.u8p), H._ptr(r3, H.u8p), C.byref(und)) == 0
+        assert np.array_equal(out, payload)
+        s2 = slot.copy()
+        assert O.oracle_golay_20_8_decode(H._ptr(s2, H.u8p))
+        assert int("".join(map(str, s2[:4])), 2) == cc and int("".join(map(str, s2[4:8])), 2) == dt
+        # inverted DMR: the part up to the sync's end is XORed with 2
+        dinv = dib.copy()
+        dinv[:pos + 1] ^= 2
+        assert O.oracle_dmr_burst_cut(H._ptr(dinv, H.u8p), H._ptr(rel, H.u8p), dib.size, pos, 1, *args) == 1
+        assert np.array_equal(info, sent["info"]) and np.array_equal(slot, sent["slot"])
+        assert O.oracle_dmr_burst_cut(H._ptr(dib, H.u8p), H._ptr(rel, H.u8p), pos + 54, pos, 0, *args) == 0
