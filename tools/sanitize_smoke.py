@@ -51,5 +51,34 @@ for i in range(8):
         for l in range(1, q.L + 1):
             q.Vl[l], q.Ml[l] = l % 2, 10.0 + l
 b200.mbe_synth(cur, prev)
+# CQPSK block side + symbol-rate slicer (ragged warp, mixed sps, a squelched stretch, two launches)
+n_cq = 37
+iq = np.stack([H.synth_cqpsk_iq(rng, 700, sps=5 if c % 3 else 4, snr_db=15.0, cfo=0.01)[0][:2400] for c in range(n_cq)]).copy()
+iq[3, 600:1800] *= np.float32(1e-4)
+iq[4, 1000:1400] = 0.0
+cq = b200.CqpskBank(n_cq, 24000, ted_sps=[5 if c % 3 else 4 for c in range(n_cq)], squelch_levels=[1e-3 if c == 3 else 0.0 for c in range(n_cq)])
+sl = b200.CqpskSlicer(n_cq)
+sl.set_class(np.arange(n_cq) % 2, np.ones(n_cq), np.arange(n_cq) % 5, 12.0)
+for lo in (0, 1200):
+    sym, counts = cq.full_demod(torch.from_numpy(np.ascontiguousarray(iq[:, lo:lo + 1200])).cuda(), 600, 2)
+    sl.run(sym, counts.sum(dim=1, dtype=torch.int32).contiguous())
+# P25p1 frame cutter + NID decode + soft word decoders, DMR burst cutter on the symbolizer outputs above
+res2 = sy.run(disc, bp * nb)
+hits, n_hits = fs.search(res2["symbols"], res2["count"], max_hits=8)
+cut = b200.p25p1_frame_cut(res2["dibits"], res2["llr"], res2["count"], hits, n_hits, 3 * 98)
+b200.dmr_burst_cut(res2["dibits"], res2["reliability"], res2["count"], hits, n_hits)
+k = cut["nid_valid"].shape[0]
+b200.p25p1_nid_decode(rng.integers(0, 2, (64, 63)).astype(np.uint8), rng.integers(0, 256, (64, 63)).astype(np.uint8),
+                      rng.integers(0, 4096, 64).astype(np.int32), rng.integers(0, 2, 64).astype(np.uint8), rng.integers(0, 256, 64).astype(np.uint8))
+b200.p25p1_nid_decode(rng.integers(0, 2, (5, 63)).astype(np.uint8), None, None, rng.integers(0, 2, 5).astype(np.uint8), None)
+L = b200.lib()
+bits10, rel10 = rng.integers(0, 2, (40, 10)).astype(np.uint8), rng.integers(0, 256, (40, 10)).astype(np.int32)
+out10, st10 = np.zeros_like(bits10), np.zeros(40, np.uint8)
+b200.check(L.dsdneo_b200_hamming_10_6_3_soft_batch_host(bits10.ctypes.data, rel10.ctypes.data, 1, 64, out10.ctypes.data, st10.ctypes.data, 40))
+for code, ln in ((b200.P25_WORD_GOLAY_24_6, 6), (b200.P25_WORD_GOLAY_24_12, 12)):
+    d, pbits = rng.integers(0, 2, (40, ln)).astype(np.uint8), rng.integers(0, 2, (40, 12)).astype(np.uint8)
+    r = rng.integers(0, 256, (40, ln + 12)).astype(np.int32)
+    stg, fxg = np.zeros(40, np.uint8), np.zeros(40, np.int32)
+    b200.check(L.dsdneo_b200_p25_golay_soft_batch_host(code, d.ctypes.data, pbits.ctypes.data, r.ctypes.data, 1, 64, stg.ctypes.data, fxg.ctypes.data, 40))
 torch.cuda.synchronize()
 print("sanitize_smoke done, launches =", b200.launch_count())
