@@ -88,3 +88,27 @@ def test_host_side_fll_band_edge_design_matches_oracle(b200):
         for g, w in zip(got, want):
             assert H.bits_equal(g, w)
     assert L.dsdneo_b200_cqpsk_block_capacity(2400, 5) >= 2400 // 5 + 2
+
+
+def test_new_entry_points_fail_loudly_without_device(b200):
+    """CQPSK bank / slicer, NID decode, soft word decoders and the frame cutters have no CPU fallback either."""
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(b200.B200Error):
+        b200.CqpskBank(4, 24000)
+    with pytest.raises(b200.B200Error):
+        b200.CqpskSlicer(4)
+    with pytest.raises(b200.B200Error):
+        b200.p25p1_nid_decode(np.zeros((2, 63), np.uint8), None, None, np.zeros(2, np.uint8), None)
+    L = b200.lib()
+    bits, rel = np.zeros((2, 10), np.uint8), np.zeros((2, 10), np.int32)
+    out, st = np.zeros((2, 10), np.uint8), np.zeros(2, np.uint8)
+    assert L.dsdneo_b200_hamming_10_6_3_soft_batch_host(bits.ctypes.data, rel.ctypes.data, 1, 64, out.ctypes.data, st.ctypes.data, 2) == b200.ENODEV
+    d, p, r = np.zeros((2, 6), np.uint8), np.zeros((2, 12), np.uint8), np.zeros((2, 18), np.int32)
+    fx = np.zeros(2, np.int32)
+    assert L.dsdneo_b200_p25_golay_soft_batch_host(b200.P25_WORD_GOLAY_24_6, d.ctypes.data, p.ctypes.data, r.ctypes.data, 1, 64,
+                                                   st.ctypes.data, fx.ctypes.data, 2) == b200.ENODEV
+    assert b"no CPU fallback" in L.dsdneo_b200_last_error()
