@@ -25,6 +25,9 @@ struct dsdneo_b200_stream_server {
     int closed;
     unsigned int output_rate_hz;
     int symbol_rate_hz, levels, channel_profile;
+    int output_kind;   /* 1 = FSK discriminator samples, 2 = symbol-rate CQPSK symbols */
+    int cqpsk_active;  /* what cqpsk_status reports for {cqpsk_enable, timing_active} */
+    double snr_cqpsk_db;
     uint32_t generation;
     double pwr;
     pthread_mutex_t mu;
@@ -53,6 +56,9 @@ dsdneo_b200_stream_server_create(size_t ring_floats, unsigned int output_rate_hz
     s->levels = levels;
     s->channel_profile = channel_profile;
     s->generation = 1;
+    s->output_kind = 1;
+    s->cqpsk_active = 0;
+    s->snr_cqpsk_db = -100.0;
     pthread_mutex_init(&s->mu, NULL);
     pthread_cond_init(&s->can_read, NULL);
     pthread_cond_init(&s->can_write, NULL);
@@ -209,7 +215,40 @@ dsdneo_b200_stream_hook_output_rate_hz(void) {
 
 int
 dsdneo_b200_stream_hook_output_kind(void) {
-    return 1; /* RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR, src/dsp/dsd_symbol.c:674-677 */
+    /* RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR = 1, RTL_STREAM_OUTPUT_SYMBOL_CQPSK = 2 (include/dsd-neo/io/rtl_stream_c.h:31-33) */
+    return (g_current && g_current->output_kind == 2) ? 2 : 1;
+}
+
+/* dsd_rtl_stream_metrics_hooks.cqpsk_status (rtl_stream_metrics_hooks.h:33): the sample side slices with cqpsk_slice() only
+ * when both flags are set (src/core/frames/dsd_dibit.c:829-844) */
+int
+dsdneo_b200_stream_hook_cqpsk_status(int* out_cqpsk_enable, int* out_cqpsk_timing_active) {
+    const int on = (g_current && g_current->output_kind == 2 && g_current->cqpsk_active) ? 1 : 0;
+    if (out_cqpsk_enable) {
+        *out_cqpsk_enable = on;
+    }
+    if (out_cqpsk_timing_active) {
+        *out_cqpsk_timing_active = on;
+    }
+    return 0;
+}
+
+/* dsd_rtl_stream_metrics_hooks.snr_cqpsk_db: <= -50 means "no estimate" to the reliability weighting (dsd_dibit.c:404-427) */
+double
+dsdneo_b200_stream_hook_snr_cqpsk_db(void) {
+    return g_current ? g_current->snr_cqpsk_db : -100.0;
+}
+
+void
+dsdneo_b200_stream_server_set_output_kind(dsdneo_b200_stream_server* s, int output_kind, int cqpsk_active, double snr_cqpsk_db) {
+    if (!s) {
+        return;
+    }
+    pthread_mutex_lock(&s->mu);
+    s->output_kind = (output_kind == 2) ? 2 : 1;
+    s->cqpsk_active = cqpsk_active ? 1 : 0;
+    s->snr_cqpsk_db = snr_cqpsk_db;
+    pthread_mutex_unlock(&s->mu);
 }
 
 int

@@ -774,6 +774,11 @@ void dsdneo_b200_stream_server_make_current(dsdneo_b200_stream_server* s);
 size_t dsdneo_b200_stream_server_push(dsdneo_b200_stream_server* s, const float* samples, size_t n, int block);
 void dsdneo_b200_stream_server_close(dsdneo_b200_stream_server* s);
 void dsdneo_b200_stream_server_bump_generation(dsdneo_b200_stream_server* s);
+/** output_kind 1 (default): FSK discriminator samples; 2: symbol-rate CQPSK symbols (the output of
+ *  dsdneo_b200_full_demod_cqpsk_batch), for which the decoder takes its symbol-rate fast path (src/dsp/dsd_symbol.c:1583-1625)
+ *  and, with `cqpsk_active`, slices with cqpsk_slice(); `snr_cqpsk_db` feeds the reliability weight (<= -50: none). */
+void dsdneo_b200_stream_server_set_output_kind(dsdneo_b200_stream_server* s, int output_kind, int cqpsk_active,
+                                               double snr_cqpsk_db);
 void dsdneo_b200_stream_server_set_power(dsdneo_b200_stream_server* s, double pwr);
 int dsdneo_b200_stream_hook_read(void* rtl_ctx, float* out, size_t count, int* out_got);
 double dsdneo_b200_stream_hook_return_pwr(const void* rtl_ctx);
@@ -781,6 +786,9 @@ unsigned int dsdneo_b200_stream_hook_output_rate_hz(void);
 int dsdneo_b200_stream_hook_output_kind(void);
 int dsdneo_b200_stream_hook_symbol_profile(int* out_symbol_rate_hz, int* out_levels, int* out_channel_profile);
 uint32_t dsdneo_b200_stream_hook_stream_generation(void);
+/* dsd_rtl_stream_metrics_hooks.cqpsk_status / .snr_cqpsk_db (rtl_stream_metrics_hooks.h:33,39) */
+int dsdneo_b200_stream_hook_cqpsk_status(int* out_cqpsk_enable, int* out_cqpsk_timing_active);
+double dsdneo_b200_stream_hook_snr_cqpsk_db(void);
 
 /* ---- K21: MBE speech synthesis stage, batched over frames -- PARITY UNPINNED ---------------------------------- */
 /*

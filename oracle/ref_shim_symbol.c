@@ -347,6 +347,31 @@ ref_sym_use_external_hooks(void* hv, void* read_fn, void* pwr_fn, void* ctx, voi
     dsd_rtl_stream_metrics_hooks_set(&mh);
 }
 
+/* Same, for a symbol-rate CQPSK stream: also installs the cqpsk_status and snr_cqpsk_db hooks and puts the decoder state
+ * where the modulation detector / -mq leave it (rf_mod = 1, orientation map). */
+void
+ref_sym_use_external_hooks_cqpsk(void* hv, void* read_fn, void* pwr_fn, void* ctx, void* rate_fn, void* kind_fn, void* profile_fn,
+                                 void* generation_fn, void* cqpsk_status_fn, void* snr_cqpsk_fn, int map_idx) {
+    ref_sym* h = (ref_sym*)hv;
+    h->state->rtl_ctx = (struct RtlSdrContext*)ctx;
+    h->state->rf_mod = 1;
+    h->state->p25_cqpsk_dibit_map_idx = (uint8_t)map_idx;
+    dsd_rtl_stream_io_hooks io;
+    memset(&io, 0, sizeof(io));
+    io.read = (int (*)(void*, float*, size_t, int*))read_fn;
+    io.return_pwr = (double (*)(const void*))pwr_fn;
+    dsd_rtl_stream_io_hooks_set(io);
+    dsd_rtl_stream_metrics_hooks mh;
+    memset(&mh, 0, sizeof(mh));
+    mh.output_rate_hz = (unsigned int (*)(void))rate_fn;
+    mh.output_kind = (int (*)(void))kind_fn;
+    mh.symbol_profile = (int (*)(int*, int*, int*))profile_fn;
+    mh.stream_generation = (uint32_t (*)(void))generation_fn;
+    mh.cqpsk_status = (int (*)(int*, int*))cqpsk_status_fn;
+    mh.snr_cqpsk_db = (double (*)(void))snr_cqpsk_fn;
+    dsd_rtl_stream_metrics_hooks_set(&mh);
+}
+
 /* exactly n getDibitSoft() calls (the caller knows the stream holds enough samples) */
 long
 ref_sym_get_dibits_n(void* hv, long n_symbols, uint8_t* dibits, uint8_t* reliab, int16_t* llr2, float* symbols) {

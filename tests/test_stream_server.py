@@ -158,3 +158,87 @@ def test_gpu_front_end_feeds_the_unmodified_reference_decoder(gpu):
     assert np.array_equal(res["dibits"][0, :n_sym].cpu().numpy(), got[0])
     assert np.array_equal(res["llr"][0, :n_sym].cpu().numpy(), got[2])
     assert H.bits_equal(res["symbols"][0, :n_sym].cpu().numpy(), got[3])
+
+
+def _ref_cqpsk_dibits_via_server(R, b, symbols, sync, map_idx, snr, n_sym):
+    """The unmodified reference getDibitSoft() with rf_mod = 1 pulling symbol-rate CQPSK symbols (output kind 2) through
+    the library's stream server and its cqpsk_status / snr_cqpsk_db hooks."""
+    L = b.lib()
+    srv = L.dsdneo_b200_stream_server_create(2048, 4800, 4800, 4, 5)  # profile 5 = P25_CQPSK
+    assert srv
+    L.dsdneo_b200_stream_server_set_output_kind(srv, 2, 1, snr)
+    L.dsdneo_b200_stream_server_make_current(srv)
+    assert L.dsdneo_b200_stream_hook_output_kind() == 2
+    R.ref_sym_use_external_hooks_cqpsk.argtypes = [C.c_void_p] * 10 + [C.c_int]
+    h = R.ref_sym_create(4800, 4800, sync, sync, 0, 128, 1024)
+    R.ref_sym_use_external_hooks_cqpsk(C.c_void_p(h), _fn(L, "dsdneo_b200_stream_hook_read"), _fn(L, "dsdneo_b200_stream_hook_return_pwr"),
+                                       C.c_void_p(srv), _fn(L, "dsdneo_b200_stream_hook_output_rate_hz"),
+                                       _fn(L, "dsdneo_b200_stream_hook_output_kind"), _fn(L, "dsdneo_b200_stream_hook_symbol_profile"),
+                                       _fn(L, "dsdneo_b200_stream_hook_stream_generation"), _fn(L, "dsdneo_b200_stream_hook_cqpsk_status"),
+                                       _fn(L, "dsdneo_b200_stream_hook_snr_cqpsk_db"), map_idx)
+
+    def produce():
+        for lo in range(0, symbols.size, 700):
+            chunk = np.ascontiguousarray(symbols[lo:lo + 700])
+            assert L.dsdneo_b200_stream_server_push(srv, chunk.ctypes.data, chunk.size, 1) == chunk.size
+        L.dsdneo_b200_stream_server_close(srv)
+
+    t = threading.Thread(target=produce)
+    t.start()
+    d = np.zeros(n_sym, np.uint8); r = np.zeros(n_sym, np.uint8); l = np.zeros(2 * n_sym, np.int16); s = np.zeros(n_sym, np.float32)
+    n = R.ref_sym_get_dibits_n(C.c_void_p(h), n_sym, H._ptr(d, H.u8p), H._ptr(r, H.u8p), l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s))
+    buf = np.zeros(4096, np.float32)
+    got = C.c_int(0)
+    while L.dsdneo_b200_stream_hook_read(srv, buf.ctypes.data, buf.size, C.byref(got)) == 0:
+        pass
+    t.join()
+    R.ref_sym_destroy(C.c_void_p(h))
+    L.dsdneo_b200_stream_server_destroy(srv)
+    assert n == n_sym
+    return d, r, l.reshape(-1, 2), s
+
+
+@needs_ref
+def test_reference_decoder_reads_cqpsk_symbols_through_the_stream_server():
+    """Output kind 2 at the seam: the reference decoder's symbol-rate path fed by the library's hooks produces exactly what the
+    oracle slicer (pinned to the same reference through the test shim's own hooks) produces."""
+    from test_oracle_symbol import cqpsk_symbol_stream
+
+    b = _b200()
+    R = C.CDLL(H._ref_path("par"))
+    _bind(R)
+    rng = np.random.default_rng(23)
+    x = cqpsk_symbol_stream(rng, 3200, noise=0.3, offset=0.2)
+    n_sym = 3000
+    for sync, map_idx, snr in [(H.SYNC_P25P1_POS, 0, -100.0), (H.SYNC_P25P1_NEG, 3, 14.0)]:
+        got = _ref_cqpsk_dibits_via_server(R, b, x, sync, map_idx, snr, n_sym)
+        d, r, l, _ = H.oracle_cqpsk_slicer_run(x[:n_sym], negative=H.SYNC_CLASS[sync]["negative"], p25_slice=1, map_idx=map_idx, snr_db=snr)
+        assert np.array_equal(got[0], d) and np.array_equal(got[1], r) and np.array_equal(got[2], l)
+        assert H.bits_equal(got[3], x[:n_sym])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_gpu_cqpsk_chain_feeds_the_unmodified_reference_decoder(gpu):
+    """Drop-in at the seam for CQPSK channels: IQ -> GPU channel LPF + CQPSK chain -> stream server (output kind 2) -> the
+    reference's own getDibitSoft; its dibits, reliabilities and LLRs equal the GPU symbol-rate slicer's on the same channel."""
+    import torch
+
+    R = C.CDLL(H._ref_path("par"))
+    _bind(R)
+    rng = np.random.default_rng(24)
+    bp, nb = 2400, 6
+    iq = H.synth_cqpsk_iq(rng, bp * nb // 5 + 2, sps=5, snr_db=20.0, cfo=0.015, timing=0.3)[0][:bp * nb][None]
+    bank = gpu.CqpskBank(1, 24000)
+    sym, counts = bank.full_demod(torch.from_numpy(np.ascontiguousarray(iq)).cuda(), bp, nb)
+    total = counts.sum(dim=1, dtype=torch.int32).contiguous()
+    n_all = int(total[0])
+    row = sym[0, :n_all].cpu().numpy().copy()
+    n_sym = n_all - 20
+    got = _ref_cqpsk_dibits_via_server(R, gpu, row, H.SYNC_P25P1_POS, 0, -100.0, n_sym)
+    sl = gpu.CqpskSlicer(1)
+    res = sl.run(sym, total)
+    torch.cuda.synchronize()
+    assert np.array_equal(res["dibits"][0, :n_sym].cpu().numpy(), got[0])
+    assert np.array_equal(res["reliability"][0, :n_sym].cpu().numpy(), got[1])
+    assert np.array_equal(res["llr"][0, :n_sym].cpu().numpy(), got[2])
