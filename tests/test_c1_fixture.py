@@ -125,3 +125,67 @@ def test_c1_gpu_chain_reproduces_the_reference_and_decodes_nac_140(gpu):
             w = np.zeros(12, np.uint8)
             O.oracle_p25_12_soft_llr(blocks_h[3 * f + b].ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(w, H.u8p))
             assert np.array_equal(out_h[3 * f + b], w)
+
+
+# ---- the reference's CQPSK / LSM control-channel fixture through the CQPSK chain ----------------------------------------------
+
+GQ = np.load(os.path.join(H.GOLDEN_DIR, "c1_p25p1_cqpsk_cc.npz"))
+
+
+def _nids_ok(dib, llr, n_dib, hit_pos, expected_nac):
+    from test_oracle_fec import _oracle_cut
+
+    Of = H.oracle_fec()
+    Of.oracle_p25p1_nid_decode.argtypes = [H.u8p, H.u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3
+    good = 0
+    for p in hit_pos:
+        flags, code, rel, par, prel, _, _ = _oracle_cut(dib[:n_dib], llr[:n_dib], int(p), 0)
+        if not (flags & 1):
+            continue
+        v = [C.c_int() for _ in range(3)]
+        st = Of.oracle_p25p1_nid_decode(H._ptr(code, H.u8p), H._ptr(rel, H.u8p), 0, par, prel, 64, *[C.byref(a) for a in v])
+        good += int(st == 1 and v[0].value == expected_nac and v[1].value == 7)
+    return good
+
+
+def test_c1_cqpsk_oracle_chain_reproduces_the_reference():
+    x = _widen(GQ["iq_cu8"])
+    bp = int(GQ["block_pairs"])
+    sym, counts = H.OracleCqpsk(rate=48000, sps=10, fir_fma=0).run(x, bp, x.shape[0] // bp)
+    assert np.array_equal(counts, GQ["counts"]) and _crc(sym) == GQ["symbols_crc"] and H.bits_equal(sym[:64], GQ["symbols_head"])
+    d, r, l, _ = H.oracle_cqpsk_slicer_run(sym)
+    m = GQ["dibits"].size
+    assert np.array_equal(d[:m], GQ["dibits"]) and np.array_equal(r[:m], GQ["reliab"]) and np.array_equal(l[:m], GQ["llr"])
+    sync = np.array(H.P25P1_SYNC_DIBITS)
+    hits = [i + 23 for i in range(d.size - 24) if np.array_equal(d[i:i + 24], sync)]
+    assert len(hits) >= 50 and _nids_ok(d, l, d.size, hits, int(GQ["expected_nac"])) >= len(hits) - 1
+
+
+@pytest.mark.gpu
+def test_c1_cqpsk_gpu_chain_reproduces_the_reference(gpu):
+    import torch
+
+    x = _widen(GQ["iq_cu8"])
+    bp = int(GQ["block_pairs"])
+    nb = x.shape[0] // bp
+    bank = gpu.CqpskBank(1, 48000, ted_sps=[10], fir_arith=gpu.FIR_ARITH_NOFMA)
+    sym, counts = bank.full_demod(torch.from_numpy(np.ascontiguousarray(x[None])).cuda(), bp, nb)
+    total = counts.sum(dim=1, dtype=torch.int32).contiguous()
+    n = int(total[0])
+    sym_h = sym[0, :n].cpu().numpy()
+    assert np.array_equal(counts[0].cpu().numpy(), GQ["counts"]) and _crc(sym_h) == GQ["symbols_crc"]
+    res = gpu.CqpskSlicer(1).run(sym, total)
+    m = GQ["dibits"].size
+    d, l = res["dibits"][0, :n].cpu().numpy(), res["llr"][0, :n].cpu().numpy()
+    assert np.array_equal(d[:m], GQ["dibits"]) and np.array_equal(res["reliability"][0, :m].cpu().numpy(), GQ["reliab"])
+    assert np.array_equal(l[:m], GQ["llr"])
+    # frames on the device: the sync hunt works on symbol signs, which CQPSK symbols near {-3,-1,+1,+3} satisfy as well
+    fs = gpu.FrameSync(1, [(SYNC, 0)])
+    hits, n_hits = fs.search(sym, total, max_hits=64)
+    cut = gpu.p25p1_frame_cut(res["dibits"], res["llr"], total, hits, n_hits, 3 * 98)
+    st, nac, duid, errs = gpu.p25p1_nid_decode(cut["nid_code63"].cpu().numpy(), cut["nid_reliab63"].cpu().numpy(), None,
+                                               cut["nid_parity"].cpu().numpy(), cut["nid_parity_reliab"].cpu().numpy())
+    nh = int(n_hits[0])
+    valid = cut["nid_valid"].cpu().numpy().astype(bool)
+    good = int(((st[:nh] == 1) & (nac[:nh] == int(GQ["expected_nac"])) & (duid[:nh] == 7) & valid[:nh]).sum())
+    assert nh >= 50 and good >= nh - 1, (nh, good)
