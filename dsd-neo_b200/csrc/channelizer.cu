@@ -284,10 +284,15 @@ template <int T, bool CU8>
 static int
 launch_pfb(const PfbParams& p, int grid, cudaStream_t s) {
     const size_t smem = (size_t)(kChunk * kFftPitch + kM * kOutPitch) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
+    /* the attribute is per device: one process may drive several GPUs, so the cache is keyed by device ordinal */
+    static bool attr_done[64] = {};
+    int dev = 0;
+    DSDNEO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         DSDNEO_CUDA(cudaFuncSetAttribute(pfb256_kernel<T, CU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) {
+            attr_done[dev] = true;
+        }
     }
     {
         KernelTimer kt("pfb256_kernel", s);

@@ -67,6 +67,7 @@ struct KernelTimer {
 
 /* library-internal stage entry points of the demod bank (demod_bank.cu), used by frontend.cu */
 struct dsdneo_b200_demod_bank;
+int dsdneo_demod_bank_channels(const dsdneo_b200_demod_bank* b);
 int dsdneo_demod_fir_stage(dsdneo_b200_demod_bank* b, const float* d_iq, size_t iq_pitch_pairs, int block_pairs,
                            int n_blocks, int slot, cudaStream_t s, int want_y = 0);
 int dsdneo_demod_rec_stage(dsdneo_b200_demod_bank* b, int block_pairs, int n_blocks, float* d_result,
@@ -74,6 +75,7 @@ int dsdneo_demod_rec_stage(dsdneo_b200_demod_bank* b, int block_pairs, int n_blo
 
 /* library-internal: the CQPSK chain (cqpsk.cu) behind the channel LPF of the demod bank */
 struct dsdneo_b200_cqpsk_bank;
+int dsdneo_cqpsk_bank_channels(const dsdneo_b200_cqpsk_bank* q);
 int dsdneo_cqpsk_stage(dsdneo_b200_cqpsk_bank* q, int n_channels, const float2* d_y, size_t y_pitch, const float* d_pwr,
                        const float* d_squelch_level, float* d_channel_pwr, int* d_squelched, int block_pairs,
                        int n_blocks, float* d_symbols, size_t symbols_pitch, int* d_counts, cudaStream_t s);

@@ -223,6 +223,10 @@ dsdneo_b200_frontend_process_async(dsdneo_b200_frontend* fe, const void* d_wideb
     }
     const size_t n_out = n_in_samples / (size_t)fe->M;
     const int n_blocks = (int)(n_out / (size_t)fe->block_pairs);
+    if (result_pitch < n_out) { /* the recurrence stage writes result + ch * result_pitch + n, n < n_out */
+        set_error("frontend_process_async: result_pitch %zu is smaller than the %zu samples produced per channel", result_pitch, n_out);
+        return DSDNEO_B200_EINVAL;
+    }
     const int slot = (int)(fe->async_seq & 1);
     rc = ensure_chan(fe, n_out, fe->s_fir);
     if (rc) {
@@ -383,9 +387,8 @@ dsdneo_b200_frontend_wait_host(dsdneo_b200_frontend* fe, long long ticket) {
         set_error("frontend_wait_host: unknown ticket");
         return DSDNEO_B200_EINVAL;
     }
-    if ((unsigned long long)ticket + 4 < fe->host_tickets) {
-        return 0; /* its event slot has been reused by a later tile, which completes after it (same streams) */
-    }
+    /* If the ticket's event slot was reused (> 4 tiles later), the slot now holds a LATER tile recorded on the same
+     * in-order D2H stream: waiting on it is conservative and still correct. */
     DSDNEO_CUDA(cudaEventSynchronize(fe->ev_ticket[ticket & 3]));
     return 0;
 }
