@@ -1012,6 +1012,16 @@ class Symbolizer:
         arr = (SymClass * self.n_channels)(*classes)
         check(lib().dsdneo_b200_symbolizer_set_class(self._h, arr), "symbolizer_set_class")
 
+    def set_snr(self, snr_db=None):
+        """Per-channel C4FM SNR (dB) as the metrics hook reports it; None = no hook installed (the default)."""
+        import numpy as np
+
+        if snr_db is None:
+            check(lib().dsdneo_b200_symbolizer_set_snr(self._h, None), "symbolizer_set_snr")
+            return
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (self.n_channels,)))
+        check(lib().dsdneo_b200_symbolizer_set_snr(self._h, a.ctypes.data), "symbolizer_set_snr")
+
     def out_pitch(self, n_samples):
         return (n_samples + 96) // (self.sps_floor - 1) + 2
 

@@ -14,11 +14,12 @@
  *   sps_fir_kernel      time-parallel.  The matched filter is a plain causal FIR over the sample stream (the symbol
  *                       timing never feeds back into it), so it is evaluated for every sample up front, in the
  *                       reference's accumulation order (taps oldest -> newest, mul then add, no FMA).
- *   symbolize_kernel    time-serial, one thread per channel (lane = channel, SoA state => coalesced): everything with a
- *                       loop-carried dependence -- the +-1-sample jitter nudge, clip, window mean, the 128-symbol
- *                       extrema scan (kept in shared memory), the 1024-entry running means, slicing and LLRs.
- * Bit-exact with the reference (floats included); the SNR-dependent reliability weight uses the reference's value for
- * "no SNR hook installed" (w256 = 0, dsd_dibit.c:520-537).
+ *   symbolize_kernel    time-serial, one WARP per channel: everything with a loop-carried dependence -- the +-1-sample
+ *                       jitter nudge, clip, window mean, the threshold tracker -- runs warp-uniform; the lanes share out the
+ *                       memory work (coalesced sample staging, the 128-symbol window and the ring chunks in registers)
+ *                       and digitize + store the outputs 32 symbols at a time.
+ * Bit-exact with the reference (floats included).  The SNR-dependent reliability weight (dsd_dibit.c:504-546) is a per-channel
+ * parameter (dsdneo_b200_symbolizer_set_snr); its default is the reference's value for "no SNR hook installed" (w256 = 0).
  */
 #include <stdlib.h>
 #include <string.h>
@@ -33,9 +34,6 @@ constexpr int kMaxTaps = DSDNEO_B200_SYM_MAX_TAPS; /* 256 */
 constexpr int kCarry = 96;                         /* leftover samples carried between launches (< longest symbol) */
 constexpr int kSbuf = 128;
 constexpr int kMinMax = 1024;
-constexpr int kSymThreads = 32;
-constexpr int kScanBlk = 16;  /* use_symbol's 128-entry extrema scan is kept as 8 block summaries + the block being replaced */
-constexpr int kWin = 128;     /* samples per channel staged in shared memory per refill */
 
 /* two smallest / two largest elements of a multiset, order independent (the reference's scan, dsd_dibit.c:264-289,
  * finds exactly these: duplicates count as separate elements) */
@@ -77,6 +75,7 @@ struct SymScalars {
     double* minbuf_sum;
     double* maxbuf_sum;
     int* carry_n;
+    int* snr_num;
     long long* symbolcnt;
 };
 
@@ -186,18 +185,18 @@ struct SymParams {
     SymScalars s;
     const float* filt;   /* [n_ch][filt_pitch] matched-filter output for this launch */
     size_t filt_pitch;
-    float* carry;        /* [kCarry][n_ch] */
-    float* sbuf;         /* [kSbuf][n_ch] */
-    float* minbuf;       /* [kMinMax][n_ch] */
-    float* maxbuf;       /* [kMinMax][n_ch] */
+    float* carry;        /* [n_ch][kCarry], right-aligned: the last carry_n entries are the unconsumed tail */
+    float* sbuf;         /* [n_ch][kSbuf] */
+    float* minbuf;       /* [n_ch][kMinMax] */
+    float* maxbuf;       /* [n_ch][kMinMax] */
     float* symbols;      /* outputs, [n_ch][out_pitch] */
     uint8_t* dibits;
     uint8_t* reliab;
     int16_t* llr;        /* [n_ch][out_pitch][2] */
     int* count;          /* [n_ch] */
+    const int* snr_num;  /* [n_ch] reliability weight numerator 204 + (w256 >> 2), dsd_dibit.c:504-546 */
     size_t out_pitch;
     int n_ch, n, mode, have_sync, rate, symrate, ssize, msize;
-    float2* minmax;      /* [n_ch][out_pitch] scratch: {min, max} after use_symbol per symbol (symbolize -> digitize kernel) */
 };
 
 __device__ __forceinline__ int
@@ -243,22 +242,366 @@ cq_thresholds(float vmin, float vmax, float& center, float& umid, float& lmid) {
     lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
 }
 
-__global__ void __launch_bounds__(kSymThreads)
-symbolize_kernel(const SymParams p) {
-    __shared__ float s_sbuf[kSbuf][kSymThreads];
-    __shared__ float s_blk[kSbuf / kScanBlk][4][kSymThreads]; /* per 16-entry block of sbuf: two smallest, two largest */
-    __shared__ float s_win[kWin * (kSymThreads + 1)];          /* staged samples, [sample][channel], padded rows */
-    const int lane = threadIdx.x;
-    const int ch = blockIdx.x * kSymThreads + lane;
-    const bool valid = ch < p.n_ch;
-    const int c = valid ? ch : p.n_ch - 1; /* inactive lanes shadow the last channel but never store */
-    const int N = p.n_ch;
-
-    for (int k = 0; k < kSbuf; k++) {
-        s_sbuf[k][lane] = p.sbuf[(size_t)k * N + c];
+/* digitize (dsd_dibit.c:963-976,1018-1041) + compute_dibit_soft_metric (:644-721) + c4fm_reliability_from_thresholds
+ * (:455-502) + apply_c4fm_snr_weight (:504-546, snr_num = 204 + (w256 >> 2)) for one symbol given the thresholds in force
+ * after use_symbol.  Reads nothing else, so the serial kernel hands 32 symbols at a time to its 32 lanes. */
+__device__ __forceinline__ void
+digitize_one(float sym, float vmin, float vmax, float center, float umid, float lmid, int negative, int snr_num, int& dibit_out,
+             int& rel_out, int& l0_out, int& l1_out) {
+    int dibit;
+    if (sym > center) {
+        dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+    } else {
+        dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
     }
-    /* state -> registers */
+    const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+    float ideal[4];
+    if (negative) {
+        ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+    } else {
+        ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+    }
+    int mag0, mag1;
+    bit_metrics(sym, ideal, mag0, mag1);
+    const float eps = 1e-6f;
+    int rel;
+    if (sym > umid) {
+        float span = __fsub_rn(vmax, umid);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(sym, umid), 255.0f), span));
+    } else if (sym > center) {
+        const float d1 = __fsub_rn(sym, center), d2 = __fsub_rn(umid, sym);
+        float span = __fsub_rn(umid, center);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+    } else if (sym >= lmid) {
+        const float d1 = __fsub_rn(center, sym), d2 = __fsub_rn(sym, lmid);
+        float span = __fsub_rn(center, lmid);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
+    } else {
+        float span = __fsub_rn(lmid, vmin);
+        span = span < eps ? eps : span;
+        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
+    }
+    rel = clamp255(rel);
+    rel = clamp255((rel * snr_num) >> 8);
+    const int min_mag = mag0 < mag1 ? mag0 : mag1;
+    if (min_mag > 0 && rel < min_mag) {
+        mag0 = (mag0 * rel) / min_mag;
+        mag1 = (mag1 * rel) / min_mag;
+    }
+    mag0 = clamp255(mag0);
+    mag1 = clamp255(mag1);
+    dibit_out = dibit;
+    l0_out = ((dibit >> 1) & 1) ? mag0 : -mag0;
+    l1_out = (dibit & 1) ? mag1 : -mag1;
+    rel_out = clamp255(mag1 < mag0 ? mag1 : mag0);
+}
+
+/* order-preserving map float -> int (an involution), so the warp-wide extrema can use redux.sync.min/max.s32 */
+__device__ __forceinline__ int
+fkey(float f) {
+    const int k = __float_as_int(f);
+    return k ^ ((k >> 31) & 0x7fffffff);
+}
+
+__device__ __forceinline__ float
+funkey(int k) {
+    return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
+}
+
+constexpr int kSymWarps = 4;    /* channels (warps) per CTA */
+constexpr int kRing = 1024;     /* staged samples per channel (shared-memory ring) */
+constexpr int kRingPad = 8;     /* slots 0..7 are mirrored behind the ring so a 5-sample window never wraps */
+constexpr int kLook = 704;      /* samples requested ahead of the read position */
+constexpr int kPending = 6;     /* cp.async groups (32 samples each) that may still be in flight after a refill */
+
+/* per-warp shared memory: the sample ring, the 128-symbol window, the cached chunk of the min / max rings and one group
+ * of 32 finished symbols waiting for digitize + store */
+struct WarpShared {
+    float ring[kRing + kRingPad];
+    float sbuf[kSbuf];
+    float mnr[32], mxr[32];
+    float o_sym[32], o_min[32], o_max[32], o_center[32], o_umid[32], o_lmid[32];
+};
+
+/*
+ * use_symbol's threshold tracker (dsd_dibit.c:243-299, core/state.h:1388-1454) for ONE channel held by ONE warp.
+ *
+ * The reference rescans sbuf[0..cap) for its two smallest and two largest entries on every symbol (126 compare-and-branch
+ * steps).  Here the two smallest / largest are carried: replacing entry e by v leaves them untouched unless e was one of
+ * them (e <= mn2 or e >= mx2), so the common case is one two_min_push / two_max_push; otherwise the warp rescans (4 entries
+ * per lane, then redux.sync on order-preserving keys).  The two smallest / largest of a multiset do not depend on
+ * evaluation order, so both paths give the reference's values.  The 1024-entry min / max rings stay in global memory
+ * ([channel][entry]); the 32-entry chunk being replaced is cached in shared memory and written back coalesced.
+ * Every lane carries the same scalar state and performs the same (same-value) shared-memory writes: control flow is
+ * warp-uniform, nothing diverges, and no lane ever reads a location it has not written itself.
+ */
+struct WarpTracker {
+    float mn1, mn2, mx1, mx2;  /* two smallest / largest of sbuf[0..cap) */
+    int cur_chunk, dirty;
+    int cap, window, lane;
+    double inv_window;
+    bool pow2;
+    float* minbuf;
+    float* maxbuf;
+    WarpShared* sh;
+
+    __device__ __forceinline__ void rescan() {
+        const float big = 3.4028234663852886e38f;
+        float a1 = big, a2 = big, z1 = -big, z2 = -big;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j * 32 + lane < cap) {
+                const float v = sh->sbuf[j * 32 + lane];
+                two_min_push(a1, a2, v);
+                two_max_push(z1, z2, v);
+            }
+        }
+        const int k1 = fkey(a1), k2 = fkey(a2), K1 = fkey(z1), K2 = fkey(z2);
+        const int m1 = __reduce_min_sync(0xffffffffu, k1);
+        const int M1 = __reduce_max_sync(0xffffffffu, K1);
+        const unsigned own_min = __ballot_sync(0xffffffffu, k1 == m1);
+        const unsigned own_max = __ballot_sync(0xffffffffu, K1 == M1);
+        const int m2 = __reduce_min_sync(0xffffffffu, lane == (__ffs(own_min) - 1) ? k2 : k1);
+        const int M2 = __reduce_max_sync(0xffffffffu, lane == (__ffs(own_max) - 1) ? K2 : K1);
+        mn1 = funkey(m1), mn2 = funkey(m2), mx1 = funkey(M1), mx2 = funkey(M2);
+    }
+
+    __device__ __forceinline__ void flush_chunk() {
+        if (dirty && cur_chunk >= 0 && cur_chunk * 32 + lane < kMinMax) {
+            minbuf[cur_chunk * 32 + lane] = sh->mnr[lane];
+            maxbuf[cur_chunk * 32 + lane] = sh->mxr[lane];
+        }
+        dirty = 0;
+    }
+
+    __device__ __forceinline__ void invalidate_cache() {
+        cur_chunk = -1, dirty = 0;
+    }
+
+    /* makes the chunk holding ring entry idx current */
+    __device__ __forceinline__ void seek(int idx) {
+        const int c = idx >> 5;
+        if (c == cur_chunk) {
+            return;
+        }
+        flush_chunk();
+        __syncwarp();
+        const float a = minbuf[c * 32 + lane], b = maxbuf[c * 32 + lane];
+        sh->mnr[lane] = a;
+        sh->mxr[lane] = b;
+        __syncwarp();
+        cur_chunk = c;
+    }
+
+    __device__ __forceinline__ void init(int lane_, int ssize, int msize, float* minbuf_row, float* maxbuf_row, const float* sbuf_row,
+                                         WarpShared* sh_, bool track) {
+        lane = lane_;
+        sh = sh_;
+        cap = ssize < 0 ? 0 : (ssize > kSbuf ? kSbuf : ssize);
+        window = msize < 1 ? 1 : (msize > kMinMax ? kMinMax : msize);
+        pow2 = (window & (window - 1)) == 0;
+        inv_window = 1.0 / (double)window; /* exact for a power of two: x / 2^k == x * 2^-k */
+        minbuf = minbuf_row, maxbuf = maxbuf_row;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sh->sbuf[j * 32 + lane] = sbuf_row[j * 32 + lane];
+        }
+        __syncwarp();
+        invalidate_cache();
+        mn1 = mn2 = mx1 = mx2 = 0.0f;
+        if (track && cap >= 2) {
+            rescan();
+        }
+    }
+
+    __device__ __forceinline__ void store_sbuf(float* sbuf_row) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sbuf_row[j * 32 + lane] = sh->sbuf[j * 32 + lane];
+        }
+    }
+
+    /* dsd_state_recompute_minmax_sums: sequential f64 sums over ring[0..window), the reference's order */
+    __device__ __forceinline__ void recompute_sums(double& min_sum, double& max_sum) {
+        flush_chunk();
+        __syncwarp();
+        double a = 0.0, b = 0.0;
+        for (int base = 0; base < window; base += 32) {
+            const float vm = base + lane < window ? minbuf[base + lane] : 0.0f;
+            const float vx = base + lane < window ? maxbuf[base + lane] : 0.0f;
+            const int m = min(32, window - base);
+            for (int k = 0; k < m; k++) {
+                a += (double)__shfl_sync(0xffffffffu, vm, k);
+                b += (double)__shfl_sync(0xffffffffu, vx, k);
+            }
+        }
+        min_sum = a, max_sum = b;
+    }
+
+    /* fills ring[0..count) with constants (slicer reset, warm start) */
+    __device__ __forceinline__ void fill_rings(float vmin, float vmax, int count) {
+        invalidate_cache();
+        for (int k = lane; k < count; k += 32) {
+            minbuf[k] = vmin;
+            maxbuf[k] = vmax;
+        }
+        __syncwarp();
+    }
+
+    /* the extrema part of use_symbol after sbuf[si] (old value e) was replaced by sym */
+    __device__ __forceinline__ void extrema(int si, float e, float sym, float& lmin, float& lmax) {
+        lmin = 0.0f, lmax = 0.0f;
+        if (cap >= 2) {
+            if (si < cap) {
+                if (e > mn2 && e < mx2) {
+                    two_min_push(mn1, mn2, sym);
+                    two_max_push(mx1, mx2, sym);
+                } else {
+                    rescan();
+                }
+            }
+            lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
+            lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
+        }
+    }
+
+    /* sbuf[sidx] = sym, then the tracker part of use_symbol (general form: any cap / window, lazily recomputed sums) */
+    __device__ __forceinline__ void push(float sym, int sidx, int& midx, int& sum_window, double& min_sum, double& max_sum,
+                                         float& vmin, float& vmax) {
+        /* get_dibit_and_analog_signal stores the symbol first (sidx may sit outside [0, cap) when ssize < 128) */
+        const int si = sidx & (kSbuf - 1);
+        const float e = sh->sbuf[si];
+        sh->sbuf[si] = sym;
+        float lmin, lmax;
+        extrema(si, e, sym, lmin, lmax);
+        if (sum_window != window) {
+            recompute_sums(min_sum, max_sum);
+            sum_window = window;
+            if (midx < 0 || midx >= window) {
+                midx = 0;
+            }
+            invalidate_cache();
+        }
+        const int idx = (midx < 0 || midx >= window) ? 0 : midx;
+        seek(idx);
+        const float old_min = sh->mnr[idx & 31], old_max = sh->mxr[idx & 31];
+        min_sum += (double)lmin - (double)old_min;
+        max_sum += (double)lmax - (double)old_max;
+        sh->mnr[idx & 31] = lmin;
+        sh->mxr[idx & 31] = lmax;
+        dirty = 1;
+        midx = idx + 1 >= window ? 0 : idx + 1;
+        if (pow2) {
+            vmin = (float)(min_sum * inv_window);
+            vmax = (float)(max_sum * inv_window);
+        } else {
+            vmin = (float)(min_sum / (double)window);
+            vmax = (float)(max_sum / (double)window);
+        }
+    }
+};
+
+/* x / 5 correctly rounded for the symbol mean: q = x * RN(1/5), one exact-remainder correction step.  Checked against the
+ * IEEE division on all 2^32 operands (dsdneo_b200_selftest_div5); operands outside the verified magnitude range take the
+ * IEEE operator. */
+__device__ __forceinline__ float
+div5_rn(float x) {
+    const float ax = fabsf(x);
+    if (ax > 1e-30f && ax < 1e30f) {
+        const float rc = 0.2f;
+        const float q = __fmul_rn(x, rc);
+        const float r = __fmaf_rn(-5.0f, q, x);
+        return __fmaf_rn(r, rc, q);
+    }
+    return __fdiv_rn(x, 5.0f);
+}
+
+/*
+ * One warp per channel.  Everything with a loop-carried dependence -- the +-1-sample jitter nudge, clip, window mean,
+ * the threshold tracker -- is evaluated by all 32 lanes redundantly (same registers, warp-uniform branches); what the
+ * lanes share out is memory: coalesced cp.async staging of the sample stream into a shared-memory ring, the rescan of
+ * the 128-entry symbol window, the ring chunks, and the per-symbol outputs, which are collected per group of 32 symbols
+ * and digitized + stored one symbol per lane (digitize and the soft metrics only read the symbol and the thresholds in
+ * force after use_symbol).  A single warp issues one dependent instruction every ~5 cycles, so the design minimises
+ * INSTRUCTIONS per symbol: the synchronised steady state (getDibitSoft on a locked channel: no timing nudge, zero-crossing
+ * detector idle) runs in a tight batch loop of up to 32 symbols with every invariant hoisted -- 5 shared-memory loads,
+ * clip, 5 adds, the constant division, the tracker update -- and everything else (hunting, fractional samples per symbol,
+ * the first symbols after a reset, unusual window sizes) takes the general per-sample path below it.
+ */
+template <int NW, bool TRACK>
+__device__ __forceinline__ int
+sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& pos, int& sidx, int midx0, int g0, float& vmin, float& vmax,
+               float& last_vmin, float& last_vmax, double& min_sum, double& max_sum) {
+    /* returns the number of symbols done (stops early only when vmin > vmax, which the general path handles) */
+    int k = 0;
+    int si = sidx;
+    float e = sh->sbuf[si];
+#pragma unroll 1
+    for (; k < nb; k++) {
+        if (!(vmin <= vmax)) {
+            break;
+        }
+        const float* b = sh->ring + ((pos + lo) & (kRing - 1));
+        const float r0 = b[0], r1 = b[1], r2 = b[2], r3 = b[3], r4 = NW > 4 ? b[4] : 0.0f;
+        last_vmin = vmin, last_vmax = vmax;
+        float sum = __fadd_rn(0.0f, fminf(fmaxf(r0, vmin), vmax));
+        sum = __fadd_rn(sum, fminf(fmaxf(r1, vmin), vmax));
+        sum = __fadd_rn(sum, fminf(fmaxf(r2, vmin), vmax));
+        sum = __fadd_rn(sum, fminf(fmaxf(r3, vmin), vmax));
+        float sym;
+        if (NW > 4) {
+            sum = __fadd_rn(sum, fminf(fmaxf(r4, vmin), vmax));
+            sym = div5_rn(sum);
+        } else {
+            sym = __fmul_rn(sum, 0.25f); /* exact scaling == the correctly rounded quotient */
+        }
+        sh->sbuf[si] = sym;
+        if (TRACK) {
+            if (e > tr.mn2 && e < tr.mx2) {
+                two_min_push(tr.mn1, tr.mn2, sym);
+                two_max_push(tr.mx1, tr.mx2, sym);
+            } else {
+                tr.rescan();
+            }
+            const float lmin = __fmul_rn(__fadd_rn(tr.mn1, tr.mn2), 0.5f);
+            const float lmax = __fmul_rn(__fadd_rn(tr.mx1, tr.mx2), 0.5f);
+            const int mi = (midx0 + k) & 31;
+            min_sum += (double)lmin - (double)sh->mnr[mi];
+            max_sum += (double)lmax - (double)sh->mxr[mi];
+            sh->mnr[mi] = lmin;
+            sh->mxr[mi] = lmax;
+            vmin = (float)(min_sum * tr.inv_window);
+            vmax = (float)(max_sum * tr.inv_window);
+            sh->o_min[g0 + k] = vmin;
+            sh->o_max[g0 + k] = vmax;
+        }
+        sh->o_sym[g0 + k] = sym;
+        si = (si + 1) & (kSbuf - 1);
+        e = sh->sbuf[si];
+        pos += sps;
+    }
+    sidx = si;
+    return k;
+}
+
+__global__ void __launch_bounds__(kSymWarps * 32)
+symbolize_kernel(const SymParams p) {
+    __shared__ WarpShared s_warp[kSymWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kSymWarps + warp;
+    if (c >= p.n_ch) {
+        return;
+    }
+    WarpShared* sh = &s_warp[warp];
+    float* ring = sh->ring;
+
+    /* state -> registers (every lane holds the same copy) */
     const int window_l = p.s.window_l[c], track = p.s.track[c], negative = p.s.negative[c];
+    const int snr_num = p.snr_num[c];
     int sps_num = p.s.sps_num[c], sps_den = p.s.sps_den[c], sps_accum = p.s.sps_accum[c];
     int sps = p.s.sps[c], center_idx = p.s.center_idx[c], jitter = p.s.jitter[c];
     float lastsample = p.s.lastsample[c];
@@ -266,106 +609,171 @@ symbolize_kernel(const SymParams p) {
     float minref = p.s.minref[c], maxref = p.s.maxref[c];
     int sidx = p.s.sidx[c], midx = p.s.midx[c], sum_window = p.s.sum_window[c];
     double minbuf_sum = p.s.minbuf_sum[c], maxbuf_sum = p.s.maxbuf_sum[c];
-    const int carry_n = p.s.carry_n[c];
+    int carry_n = p.s.carry_n[c];
+    carry_n = carry_n < 0 ? 0 : (carry_n > kCarry ? kCarry : carry_n);
     long long symbolcnt = p.s.symbolcnt[c];
+    const bool soft = p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT;
+    const int have_sync = soft ? 1 : p.have_sync;
 
+    WarpTracker tr;
+    tr.init(lane, p.ssize, p.msize, p.minbuf + (size_t)c * kMinMax, p.maxbuf + (size_t)c * kMinMax, p.sbuf + (size_t)c * kSbuf, sh,
+            soft && track);
+
+    /* sample stream in q-space: q in [kCarry - carry_n, kCarry) = carried tail, q >= kCarry = this launch's samples */
     const float* filt = p.filt + (size_t)c * p.filt_pitch;
-    const long avail = (long)carry_n + p.n;
-    long pos = 0;
-    auto sample_at = [&](long k) -> float { return k < carry_n ? p.carry[(size_t)k * N + c] : filt[k - carry_n]; };
+    float* carry = p.carry + (size_t)c * kCarry;
+    const int q0 = kCarry - carry_n;
+    const int q_end = kCarry + p.n;
+    const int q_fill_end = (q_end + 31) & ~31;
+    int pos = q0;
+    int whi = q0 & ~31;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    auto refill = [&]() {
+        while (whi < pos + kLook && whi < q_fill_end) {
+            const int q = whi + lane;
+            const float* src = filt;
+            unsigned bytes = 0;
+            if (q < kCarry) {
+                if (q >= q0) {
+                    src = carry + q, bytes = 4;
+                }
+            } else if (q < q_end) {
+                src = filt + (q - kCarry), bytes = 4;
+            }
+            const int slot = q & (kRing - 1);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ring_s + 4u * (unsigned)slot), "l"(src), "r"(bytes) : "memory");
+            if (slot < kRingPad) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ring_s + 4u * (unsigned)(slot + kRing)), "l"(src), "r"(bytes)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            whi += 32;
+        }
+        if (whi >= q_fill_end) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+        }
+        __syncwarp();
+    };
+    auto at = [&](int q) -> float { return ring[q & (kRing - 1)]; };
 
-    const int whole0 = p.rate / p.symrate;
-    const long reserve = (long)(whole0 < 2 ? 2 : (whole0 > 64 ? 64 : whole0)) + 2; /* longest possible symbol */
+    /* samples-per-symbol of the reference's fractional accumulator (dsd_symbol.c:1343-1387); invariant part hoisted */
+    int whole0 = p.rate / p.symrate, rem0 = p.rate % p.symrate;
+    if (whole0 < 2) {
+        whole0 = 2, rem0 = 0;
+    }
+    if (whole0 > 64) {
+        whole0 = 64, rem0 = 0;
+    }
+    const int reserve = whole0 + 2; /* longest possible symbol (one more sample when the accumulator wraps, one for a nudge) */
     float* o_sym = p.symbols + (size_t)c * p.out_pitch;
     uint8_t* o_dib = p.dibits ? p.dibits + (size_t)c * p.out_pitch : nullptr;
     uint8_t* o_rel = p.reliab ? p.reliab + (size_t)c * p.out_pitch : nullptr;
-    float2* o_mm = p.minmax ? p.minmax + (size_t)c * p.out_pitch : nullptr;
-    int16_t* o_llr = p.llr ? p.llr + (size_t)c * p.out_pitch * 2 : nullptr;
-    long nsym = 0;
-    const int have_sync = (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) ? 1 : p.have_sync;
+    short2* o_llr = p.llr ? reinterpret_cast<short2*>(p.llr) + (size_t)c * p.out_pitch : nullptr;
+    int nsym = 0;
+    const int out_cap = (int)(p.out_pitch > 0x7fffffffu ? 0x7fffffffu : p.out_pitch);
 
-    const int cap = p.ssize < 0 ? 0 : (p.ssize > kSbuf ? kSbuf : p.ssize);
-    const int n_blk = (cap + kScanBlk - 1) / kScanBlk;
-    auto rescan_block = [&](int b) {
-        float mn1 = 3.4028234663852886e38f, mn2 = mn1, mx1 = -mn1, mx2 = -mn1;
-        const int k1 = min(cap, (b + 1) * kScanBlk);
-        for (int k = b * kScanBlk; k < k1; k++) {
-            const float v = s_sbuf[k][lane];
-            two_min_push(mn1, mn2, v);
-            two_max_push(mx1, mx2, v);
+    /* one group of <= 32 finished symbols: lane k digitizes and stores symbol k */
+    auto flush_group = [&](int n_in_group) { /* symbols [nsym - n_in_group, nsym) */
+        __syncwarp();
+        const int base = nsym - n_in_group;
+        if (lane < n_in_group) {
+            const float g_sym = sh->o_sym[lane];
+            o_sym[base + lane] = g_sym;
+            if (soft) {
+                float g_min, g_max, g_center, g_umid, g_lmid;
+                if (track) { /* centre / mid thresholds follow from {min, max} by the reference's own formulas */
+                    g_min = sh->o_min[lane], g_max = sh->o_max[lane];
+                    cq_thresholds(g_min, g_max, g_center, g_umid, g_lmid);
+                } else {
+                    g_min = sh->o_min[lane], g_max = sh->o_max[lane], g_center = sh->o_center[lane];
+                    g_umid = sh->o_umid[lane], g_lmid = sh->o_lmid[lane];
+                }
+                int dibit, rel, l0, l1;
+                digitize_one(g_sym, g_min, g_max, g_center, g_umid, g_lmid, negative, snr_num, dibit, rel, l0, l1);
+                o_dib[base + lane] = (uint8_t)dibit;
+                o_rel[base + lane] = (uint8_t)rel;
+                o_llr[base + lane] = make_short2((short)l0, (short)l1);
+            }
         }
-        s_blk[b][0][lane] = mn1, s_blk[b][1][lane] = mn2, s_blk[b][2][lane] = mx1, s_blk[b][3][lane] = mx2;
+        __syncwarp();
     };
-    if (track) {
-        for (int b = 0; b < n_blk; b++) {
-            rescan_block(b);
-        }
-    }
 
-    /* Samples are staged through shared memory: the warp loads kWin consecutive samples of its 32 channels with
-     * coalesced 128-byte reads and each lane then walks its own column.  Lanes drift apart only by the +-1 timing
-     * nudges; a lane that falls outside the staged window reads global memory directly for that symbol. */
-    long wbase = 0, wend = 0;
-    int pf_idx = -1; /* prefetched minbuf / maxbuf ring entry */
-    float pf_min = 0.0f, pf_max = 0.0f;
-    int cn_max = carry_n, cn_min = carry_n; /* carry lengths over the warp: bounds for the branch-free refill */
-    for (int o = 16; o > 0; o >>= 1) {
-        cn_max = max(cn_max, __shfl_xor_sync(0xffffffffu, cn_max, o));
-        cn_min = min(cn_min, __shfl_xor_sync(0xffffffffu, cn_min, o));
-    }
-    bool active = nsym < (long)p.out_pitch && (avail - pos) >= reserve;
-    while (__any_sync(0xffffffffu, active)) {
-        if (__any_sync(0xffffffffu, active && (pos < wbase || pos + reserve > wend))) {
-            long mp = active ? pos : 0x7fffffffffffffffL;
-            for (int o = 16; o > 0; o >>= 1) {
-                const long other = __shfl_xor_sync(0xffffffffu, mp, o);
-                mp = other < mp ? other : mp;
+    const int lo0 = max((whole0 - 1) / 2 - window_l, 0), hi0 = min((whole0 - 1) / 2 + 2, whole0 - 1);
+    const int nw0 = hi0 - lo0 + 1;
+    const bool fast_cfg = soft && rem0 == 0 && whole0 != 20 && whole0 != 5 && (nw0 == 4 || nw0 == 5) && tr.cap == kSbuf
+                          && (!track || tr.pow2);
+
+    refill();
+    while (nsym < out_cap && (q_end - pos) >= reserve) {
+        refill();
+        /* ---- steady state of a locked channel: a batch of symbols through the tight loop ---- */
+        if (fast_cfg && jitter >= 0 && sps_num == p.rate && sps_den == p.symrate && (!track || sum_window == tr.window)) {
+            int nb = min(32 - (nsym & 31), out_cap - nsym);
+            nb = min(nb, (q_end - pos - reserve) / whole0 + 1);
+            /* every sample of the batch must have landed in the ring */
+            const int landed = (whi >= q_fill_end) ? whi : whi - 32 * kPending;
+            nb = min(nb, (landed - pos) / whole0);
+            int mi0 = 0;
+            if (track) {
+                const int idx = (midx < 0 || midx >= tr.window) ? 0 : midx;
+                nb = min(nb, min(32 - (idx & 31), tr.window - idx));
+                tr.seek(idx);
+                mi0 = idx;
             }
-            wbase = mp;
-            wend = wbase + kWin;
-            __syncwarp();
-            const bool interior = wbase >= cn_max && wbase + kWin - cn_min <= (long)p.n;
-            if (interior) { /* the whole window lies inside this launch's filtered samples for every channel row */
-                const unsigned d0 = (unsigned)__cvta_generic_to_shared(&s_win[lane * (kSymThreads + 1)]);
-                for (int r = 0; r < kSymThreads; r++) {
-                    const int cr = min(blockIdx.x * kSymThreads + r, p.n_ch - 1);
-                    const int cn = __shfl_sync(0xffffffffu, carry_n, r);
-                    const float* src = p.filt + (size_t)cr * p.filt_pitch + (wbase - cn) + lane;
-#pragma unroll
-                    for (int g = 0; g < kWin / 32; g++) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (unsigned)(g * 32 * (kSymThreads + 1) + r)),
-                                     "l"(src + g * 32)
-                                     : "memory");
+            if (nb > 0) {
+                const int g0 = nsym & 31;
+                if (!track) { /* thresholds do not move: hand them to digitize as they are */
+                    for (int k = lane; k < nb; k += 32) {
+                        sh->o_min[g0 + k] = vmin, sh->o_max[g0 + k] = vmax, sh->o_center[g0 + k] = center;
+                        sh->o_umid[g0 + k] = umid, sh->o_lmid[g0 + k] = lmid;
                     }
+                    __syncwarp();
                 }
-            }
-            for (int r = 0; r < (interior ? 0 : kSymThreads); r++) {
-                const int cr = __shfl_sync(0xffffffffu, c, r);
-                const int cn = __shfl_sync(0xffffffffu, carry_n, r);
-                const float* fr = p.filt + (size_t)cr * p.filt_pitch;
-#pragma unroll
-                for (int g = 0; g < kWin / 32; g++) {
-                    const long k = wbase + g * 32 + lane;
-                    float* dst = &s_win[(g * 32 + lane) * (kSymThreads + 1) + r];
-                    const float* src = nullptr;
-                    if (k < cn) {
-                        src = &p.carry[(size_t)k * N + cr];
-                    } else if (k - cn < p.n) {
-                        src = &fr[k - cn];
-                    }
-                    if (src) { /* all 128 copies of the refill are in flight before the single wait below */
-                        const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src) : "memory");
+                float lvmin = vmin, lvmax = vmax;
+                const int pos0 = pos;
+                int done;
+                if (track) {
+                    done = nw0 == 5 ? sym_fast_batch<5, true>(sh, tr, nb, whole0, lo0, pos, sidx, mi0, g0, vmin, vmax, lvmin, lvmax,
+                                                              minbuf_sum, maxbuf_sum)
+                                    : sym_fast_batch<4, true>(sh, tr, nb, whole0, lo0, pos, sidx, mi0, g0, vmin, vmax, lvmin, lvmax,
+                                                              minbuf_sum, maxbuf_sum);
+                } else {
+                    done = nw0 == 5 ? sym_fast_batch<5, false>(sh, tr, nb, whole0, lo0, pos, sidx, mi0, g0, vmin, vmax, lvmin, lvmax,
+                                                               minbuf_sum, maxbuf_sum)
+                                    : sym_fast_batch<4, false>(sh, tr, nb, whole0, lo0, pos, sidx, mi0, g0, vmin, vmax, lvmin, lvmax,
+                                                               minbuf_sum, maxbuf_sum);
+                }
+                if (done > 0) {
+                    (void)pos0;
+                    /* the symbol's last sample becomes lastsample, clipped with the thresholds that symbol saw */
+                    const float s = at(pos - 1);
+                    lastsample = s > lvmax ? lvmax : (s < lvmin ? lvmin : s);
+                    sps = whole0;
+                    center_idx = (sps - 1) / 2;
+                    symbolcnt += done;
+                    if (track) {
+                        tr.dirty = 1;
+                        midx = mi0 + done >= tr.window ? 0 : mi0 + done;
+                        center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f); /* x / 2.0f, exact */
+                        umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center); /* .. / 8.0f, exact */
+                        lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
+                        maxref = __fmul_rn(vmax, 0.80f);
+                        minref = __fmul_rn(vmin, 0.80f);
                     } else {
-                        *dst = 0.0f;
+                        maxref = vmax;
+                        minref = vmin;
                     }
+                    nsym += done;
+                    if ((nsym & 31) == 0) {
+                        flush_group(32);
+                    }
+                    continue;
                 }
             }
-            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
         }
-        if (active) {
-        /* ---- symbol_apply_rtl_fsk_discriminator_timing (dsd_symbol.c:1328-1387) ---- */
+        /* ---- general path, one symbol: symbol_apply_rtl_fsk_discriminator_timing (dsd_symbol.c:1328-1387) ---- */
         if (sps_num != p.rate || sps_den != p.symrate) {
             sps_num = p.rate;
             sps_den = p.symrate;
@@ -373,26 +781,14 @@ symbolize_kernel(const SymParams p) {
             jitter = -1;
             center = 0.0f, vmin = -30000.0f, vmax = 30000.0f, lmid = -20000.0f, umid = 20000.0f;
             minref = -24000.0f, maxref = 24000.0f;
-            for (int k = 0; k < kMinMax; k++) {
-                if (valid) {
-                    p.minbuf[(size_t)k * N + c] = vmin;
-                    p.maxbuf[(size_t)k * N + c] = vmax;
-                }
-            }
+            tr.fill_rings(vmin, vmax, kMinMax);
             midx = 0;
             sum_window = 0;
-            pf_idx = -1;
         }
         {
-            int whole = p.rate / p.symrate, rem = p.rate % p.symrate;
-            if (whole < 2) {
-                whole = 2, rem = 0;
-            }
-            if (whole > 64) {
-                whole = 64, rem = 0;
-            }
-            if (rem > 0 && sps_den > 0) {
-                int acc = sps_accum + rem;
+            int whole = whole0;
+            if (rem0 > 0 && sps_den > 0) {
+                int acc = sps_accum + rem0;
                 if (acc >= sps_den) {
                     whole++;
                     acc -= sps_den;
@@ -408,25 +804,7 @@ symbolize_kernel(const SymParams p) {
         /* ---- symbol_process_live_samples (dsd_symbol.c:1769-1792) ---- */
         float sum = 0.0f;
         int cnt = 0;
-        const bool in_win = pos >= wbase && pos + sps + 1 <= wend; /* a nudge reads at most one extra sample */
-        const float* wp = s_win + (in_win ? (int)(pos - wbase) : 0) * (kSymThreads + 1) + lane;
-        /* Synchronised steady state: no timing nudge (have_sync), and the zero-crossing detector is idle once it has
-         * fired (jitter >= 0 is only cleared by the nudge), so only the window samples and the symbol's last sample
-         * (which becomes lastsample) matter; same clip, same accumulation order. */
-        const bool quick = in_win && have_sync == 1 && jitter >= 0 && sps != 20 && sps != 5;
-        if (quick) {
-            const int lo = max(center_idx - window_l, 0), hi = min(center_idx + 2, sps - 1);
-            for (int i = lo; i <= hi; i++) {
-                float s = wp[i * (kSymThreads + 1)];
-                s = s > vmax ? vmax : (s < vmin ? vmin : s);
-                sum = __fadd_rn(sum, s);
-                cnt++;
-            }
-            float s = wp[(sps - 1) * (kSymThreads + 1)];
-            lastsample = s > vmax ? vmax : (s < vmin ? vmin : s);
-            pos += sps;
-        }
-        for (int i = quick ? sps : 0; i < sps; i++) {
+        for (int i = 0; i < sps; i++) {
             if (i == 0 && have_sync == 0 && jitter >= 0) { /* dsd_symbol.c:462-516 */
                 if (sps == 20) {
                     if (jitter >= 7 && jitter <= 10) {
@@ -443,8 +821,7 @@ symbolize_kernel(const SymParams p) {
                 }
                 jitter = -1;
             }
-            float s = in_win ? *wp : sample_at(pos);
-            wp += kSymThreads + 1;
+            float s = at(pos);
             pos++;
             if (have_sync == 1) { /* symbol_apply_sync_clip, rf_mod == 0 */
                 s = s > vmax ? vmax : (s < vmin ? vmin : s);
@@ -473,232 +850,122 @@ symbolize_kernel(const SymParams p) {
         }
         const float sym = cnt > 0 ? __fdiv_rn(sum, (float)cnt) : 0.0f;
         symbolcnt++;
-        if (valid) {
-            o_sym[nsym] = sym;
-        }
-        if (p.mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
+        if (soft) {
             /* ---- get_dibit_and_analog_signal: sbuf, use_symbol (dsd_dibit.c:243-299) ---- */
-            s_sbuf[sidx][lane] = sym;
             if (track) {
-                float lmin = 0.0f, lmax = 0.0f;
-                if (cap >= 2) {
-                    /* avg of the two smallest / two largest entries of sbuf[0..cap) (dsd_dibit.c:264-289): only the
-                     * 16-entry block that received the new symbol is rescanned, the rest comes from block summaries */
-                    if (sidx >= 0 && sidx < cap) {
-                        rescan_block(sidx / kScanBlk);
-                    }
-                    float mn1 = s_blk[0][0][lane], mn2 = s_blk[0][1][lane], mx1 = s_blk[0][2][lane], mx2 = s_blk[0][3][lane];
-                    for (int b = 1; b < n_blk; b++) {
-                        const float a1 = s_blk[b][0][lane], a2 = s_blk[b][1][lane], z1 = s_blk[b][2][lane], z2 = s_blk[b][3][lane];
-                        mn2 = fminf(fmaxf(mn1, a1), fminf(mn2, a2));
-                        mn1 = fminf(mn1, a1);
-                        mx2 = fmaxf(fminf(mx1, z1), fmaxf(mx2, z2));
-                        mx1 = fmaxf(mx1, z1);
-                    }
-                    lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
-                    lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
-                }
-                const int window = p.msize < 1 ? 1 : (p.msize > kMinMax ? kMinMax : p.msize);
-                if (sum_window != window) { /* dsd_state_recompute_minmax_sums */
-                    double a = 0.0, b = 0.0;
-                    for (int k = 0; k < window; k++) {
-                        a += (double)p.minbuf[(size_t)k * N + c];
-                        b += (double)p.maxbuf[(size_t)k * N + c];
-                    }
-                    minbuf_sum = a, maxbuf_sum = b, sum_window = window;
-                    if (midx < 0 || midx >= window) {
-                        midx = 0;
-                    }
-                }
-                int idx = (midx < 0 || midx >= window) ? 0 : midx;
-                /* the ring entry being replaced was requested one symbol ago (pf_*), so its latency is off the chain */
-                const float old_min = (pf_idx == idx) ? pf_min : p.minbuf[(size_t)idx * N + c];
-                const float old_max = (pf_idx == idx) ? pf_max : p.maxbuf[(size_t)idx * N + c];
-                minbuf_sum += (double)lmin - (double)old_min;
-                maxbuf_sum += (double)lmax - (double)old_max;
-                if (valid) {
-                    p.minbuf[(size_t)idx * N + c] = lmin;
-                    p.maxbuf[(size_t)idx * N + c] = lmax;
-                }
-                const int written = idx;
-                idx++;
-                midx = idx >= window ? 0 : idx;
-                pf_idx = midx;
-                if (midx == written) {
-                    pf_min = lmin, pf_max = lmax;
-                } else {
-                    pf_min = p.minbuf[(size_t)midx * N + c];
-                    pf_max = p.maxbuf[(size_t)midx * N + c];
-                }
-                if ((window & (window - 1)) == 0) { /* power of two (default 1024): x / w == x * (1 / w) exactly */
-                    const double inv = 1.0 / (double)window;
-                    vmin = (float)(minbuf_sum * inv);
-                    vmax = (float)(maxbuf_sum * inv);
-                } else {
-                    vmin = (float)(minbuf_sum / (double)window);
-                    vmax = (float)(maxbuf_sum / (double)window);
-                }
+                tr.push(sym, sidx, midx, sum_window, minbuf_sum, maxbuf_sum, vmin, vmax);
                 center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f); /* x / 2.0f, exact */
                 umid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmax, center), 5.0f), 0.125f), center); /* .. / 8.0f, exact */
                 lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
                 maxref = __fmul_rn(vmax, 0.80f);
                 minref = __fmul_rn(vmin, 0.80f);
             } else {
+                sh->sbuf[sidx & (kSbuf - 1)] = sym;
                 maxref = vmax;
                 minref = vmin;
             }
-            if (cap > 0) {
-                sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
+            if (tr.cap > 0) {
+                sidx = (sidx >= tr.cap - 1) ? 0 : sidx + 1;
             }
-            /* digitize and the soft metric only read {sym, thresholds}: sym_digitize_kernel does them one thread per symbol.
-             * Tracked channels hand over {min, max} per symbol (centre / mid thresholds follow from them); the others keep
-             * the same thresholds for the whole launch, which the second kernel reads from the carried state. */
-            if (valid && track) {
-                o_mm[nsym] = make_float2(vmin, vmax);
-            }
+        }
+        {
+            const int g = nsym & 31;
+            sh->o_sym[g] = sym, sh->o_min[g] = vmin, sh->o_max[g] = vmax;
+            sh->o_center[g] = center, sh->o_umid[g] = umid, sh->o_lmid[g] = lmid;
         }
         nsym++;
-        } /* active */
-        active = nsym < (long)p.out_pitch && (avail - pos) >= reserve;
+        if ((nsym & 31) == 0) {
+            flush_group(32);
+        }
+    }
+    if (nsym & 31) {
+        flush_group(nsym & 31);
     }
 
-    /* leftover samples -> carry (read everything first: source and destination overlap in the carry array) */
-    const int left = (int)(avail - pos);
-    float keep[kCarry / 8];
-    for (int base = 0; base < left; base += kCarry / 8) {
-        const int m = min(kCarry / 8, left - base);
-        for (int k = 0; k < m; k++) {
-            keep[k] = sample_at(pos + base + k);
+    /* leftover samples -> carry (right-aligned), through registers: the ring may be refilled first */
+    refill();
+    int left = q_end - pos;
+    left = left < 0 ? 0 : (left > kCarry ? kCarry : left);
+    float keep[kCarry / 32];
+#pragma unroll
+    for (int j = 0; j < kCarry / 32; j++) {
+        const int k = j * 32 + lane;
+        keep[j] = k < left ? at(q_end - left + k) : 0.0f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kCarry / 32; j++) {
+        const int k = j * 32 + lane;
+        if (k < left) {
+            carry[kCarry - left + k] = keep[j];
         }
-        if (valid) {
-            for (int k = 0; k < m; k++) {
-                p.carry[(size_t)(base + k) * N + c] = keep[k]; /* base + k < pos + base + k: never overtakes the reads */
-            }
-        }
     }
-    if (!valid) {
-        return;
+    tr.flush_chunk();
+    tr.store_sbuf(p.sbuf + (size_t)c * kSbuf);
+    if (lane == 0) {
+        p.s.sps_num[c] = sps_num, p.s.sps_den[c] = sps_den, p.s.sps_accum[c] = sps_accum;
+        p.s.sps[c] = sps, p.s.center_idx[c] = center_idx, p.s.jitter[c] = jitter;
+        p.s.lastsample[c] = lastsample;
+        p.s.vmin[c] = vmin, p.s.vmax[c] = vmax, p.s.center[c] = center, p.s.umid[c] = umid, p.s.lmid[c] = lmid;
+        p.s.minref[c] = minref, p.s.maxref[c] = maxref;
+        p.s.sidx[c] = sidx, p.s.midx[c] = midx, p.s.sum_window[c] = sum_window;
+        p.s.minbuf_sum[c] = minbuf_sum, p.s.maxbuf_sum[c] = maxbuf_sum;
+        p.s.carry_n[c] = left;
+        p.s.symbolcnt[c] = symbolcnt;
+        p.count[c] = nsym;
     }
-    for (int k = 0; k < kSbuf; k++) {
-        p.sbuf[(size_t)k * N + c] = s_sbuf[k][lane];
-    }
-    p.s.sps_num[c] = sps_num, p.s.sps_den[c] = sps_den, p.s.sps_accum[c] = sps_accum;
-    p.s.sps[c] = sps, p.s.center_idx[c] = center_idx, p.s.jitter[c] = jitter;
-    p.s.lastsample[c] = lastsample;
-    p.s.vmin[c] = vmin, p.s.vmax[c] = vmax, p.s.center[c] = center, p.s.umid[c] = umid, p.s.lmid[c] = lmid;
-    p.s.minref[c] = minref, p.s.maxref[c] = maxref;
-    p.s.sidx[c] = sidx, p.s.midx[c] = midx, p.s.sum_window[c] = sum_window;
-    p.s.minbuf_sum[c] = minbuf_sum, p.s.maxbuf_sum[c] = maxbuf_sum;
-    p.s.carry_n[c] = left;
-    p.s.symbolcnt[c] = symbolcnt;
-    p.count[c] = (int)nsym;
 }
 
-/* digitize (dsd_dibit.c:963-976,1018-1041) + compute_dibit_soft_metric (:644-721) + c4fm_reliability_from_thresholds
- * (:455-502) for every symbol of every channel, one thread per symbol: they only read the symbol and the thresholds in
- * force after use_symbol -- per symbol {min, max} from symbolize_kernel for tracked channels (centre and mid thresholds
- * follow from them by the reference's own formulas), the carried thresholds for the others (constant over a launch:
- * the only other writer is the first-call reset, which precedes the launch's first symbol). */
-__global__ void __launch_bounds__(256)
-sym_digitize_kernel(const SymParams p) {
-    const int c = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.count[c]) {
-        return;
+/* exhaustive check of div5_rn against the IEEE operator: every one of the 2^32 operands */
+__global__ void
+div5_selftest_kernel(unsigned long long* n_mismatch, unsigned* first_bad) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned long long it = 0; it < (1ull << 32) / stride; it++, i += stride) {
+        const float x = __uint_as_float(i);
+        const float a = div5_rn(x), b = __fdiv_rn(x, 5.0f);
+        const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+        if (!same) {
+            bad++;
+            atomicMin(first_bad, i);
+        }
     }
-    const float sym = p.symbols[(size_t)c * p.out_pitch + i];
-    const int negative = p.s.negative[c];
-    float vmin, vmax, center, umid, lmid;
-    if (p.s.track[c]) {
-        const float2 mm = p.minmax[(size_t)c * p.out_pitch + i];
-        vmin = mm.x;
-        vmax = mm.y;
-        cq_thresholds(vmin, vmax, center, umid, lmid);
-    } else {
-        vmin = p.s.vmin[c], vmax = p.s.vmax[c], center = p.s.center[c], umid = p.s.umid[c], lmid = p.s.lmid[c];
+    if (bad) {
+        atomicAdd(n_mismatch, bad);
     }
-    /* ---- digitize (dsd_dibit.c:963-976,1018-1041) ---- */
-    int dibit;
-    if (sym > center) {
-        dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
-    } else {
-        dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
-    }
-    /* ---- compute_dibit_soft_metric (dsd_dibit.c:644-721) ---- */
-    const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
-    float ideal[4];
-    if (negative) {
-        ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
-    } else {
-        ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
-    }
-    int mag0, mag1;
-    bit_metrics(sym, ideal, mag0, mag1);
-    /* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) */
-    const float eps = 1e-6f;
-    int rel;
-    if (sym > umid) {
-        float span = __fsub_rn(vmax, umid);
-        span = span < eps ? eps : span;
-        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(sym, umid), 255.0f), span));
-    } else if (sym > center) {
-        const float d1 = __fsub_rn(sym, center), d2 = __fsub_rn(umid, sym);
-        float span = __fsub_rn(umid, center);
-        span = span < eps ? eps : span;
-        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
-    } else if (sym >= lmid) {
-        const float d1 = __fsub_rn(center, sym), d2 = __fsub_rn(sym, lmid);
-        float span = __fsub_rn(center, lmid);
-        span = span < eps ? eps : span;
-        rel = __float2int_rn(__fdiv_rn(__fmul_rn(d1 < d2 ? d1 : d2, 510.0f), span));
-    } else {
-        float span = __fsub_rn(lmid, vmin);
-        span = span < eps ? eps : span;
-        rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
-    }
-    rel = clamp255(rel);
-    rel = clamp255((rel * 204) >> 8); /* apply_c4fm_snr_weight with no SNR hook: w256 = 0 (dsd_dibit.c:520-537) */
-    const int min_mag = mag0 < mag1 ? mag0 : mag1;
-    if (min_mag > 0 && rel < min_mag) {
-        mag0 = (mag0 * rel) / min_mag;
-        mag1 = (mag1 * rel) / min_mag;
-    }
-    mag0 = clamp255(mag0);
-    mag1 = clamp255(mag1);
-    const int l0 = ((dibit >> 1) & 1) ? mag0 : -mag0, l1 = (dibit & 1) ? mag1 : -mag1;
-    const size_t o = (size_t)c * p.out_pitch + i;
-    p.dibits[o] = (uint8_t)dibit;
-    p.reliab[o] = (uint8_t)clamp255(mag1 < mag0 ? mag1 : mag0);
-    reinterpret_cast<short2*>(p.llr)[o] = make_short2((short)l0, (short)l1);
 }
 
 __global__ void
 sym_reset_kernel(SymScalars s, float* minbuf, float* maxbuf, float* sbuf, float* carry, float* hist, int n_ch) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x;
+    const int t = threadIdx.x;
     if (c >= n_ch) {
         return;
     }
-    /* initState() values (src/core/util/dsd_init.c:519-592) */
-    s.sps_num[c] = 0, s.sps_den[c] = 0, s.sps_accum[c] = 0;
-    s.sps[c] = 10, s.center_idx[c] = 4, s.jitter[c] = -1;
-    s.lastsample[c] = 0.0f;
-    s.vmin[c] = -15000.0f, s.vmax[c] = 15000.0f, s.center[c] = 0.0f, s.umid[c] = 0.0f, s.lmid[c] = 0.0f;
-    s.minref[c] = -12000.0f, s.maxref[c] = 12000.0f;
-    s.sidx[c] = 0, s.midx[c] = 0, s.sum_window[c] = 0;
-    s.minbuf_sum[c] = 0.0, s.maxbuf_sum[c] = 0.0;
-    s.carry_n[c] = 0;
-    s.symbolcnt[c] = 0;
-    for (int k = 0; k < kMinMax; k++) {
-        minbuf[(size_t)k * n_ch + c] = -15000.0f;
-        maxbuf[(size_t)k * n_ch + c] = 15000.0f;
+    if (t == 0) {
+        /* initState() values (src/core/util/dsd_init.c:519-592) */
+        s.sps_num[c] = 0, s.sps_den[c] = 0, s.sps_accum[c] = 0;
+        s.sps[c] = 10, s.center_idx[c] = 4, s.jitter[c] = -1;
+        s.lastsample[c] = 0.0f;
+        s.vmin[c] = -15000.0f, s.vmax[c] = 15000.0f, s.center[c] = 0.0f, s.umid[c] = 0.0f, s.lmid[c] = 0.0f;
+        s.minref[c] = -12000.0f, s.maxref[c] = 12000.0f;
+        s.sidx[c] = 0, s.midx[c] = 0, s.sum_window[c] = 0;
+        s.minbuf_sum[c] = 0.0, s.maxbuf_sum[c] = 0.0;
+        s.carry_n[c] = 0;
+        s.symbolcnt[c] = 0;
     }
-    for (int k = 0; k < kSbuf; k++) {
-        sbuf[(size_t)k * n_ch + c] = 0.0f;
+    for (int k = t; k < kMinMax; k += blockDim.x) {
+        minbuf[(size_t)c * kMinMax + k] = -15000.0f;
+        maxbuf[(size_t)c * kMinMax + k] = 15000.0f;
     }
-    for (int k = 0; k < kCarry; k++) {
-        carry[(size_t)k * n_ch + c] = 0.0f;
+    for (int k = t; k < kSbuf; k += blockDim.x) {
+        sbuf[(size_t)c * kSbuf + k] = 0.0f;
     }
-    for (int k = 0; k < kMaxTaps; k++) {
+    for (int k = t; k < kCarry; k += blockDim.x) {
+        carry[(size_t)c * kCarry + k] = 0.0f;
+    }
+    for (int k = t; k < kMaxTaps; k += blockDim.x) {
         hist[(size_t)c * kMaxTaps + k] = 0.0f;
     }
 }
@@ -1057,8 +1324,6 @@ struct dsdneo_b200_symbolizer {
     int* d_taps_len;
     float* d_filt;
     size_t filt_pitch;
-    float2* d_minmax; /* per-symbol {min, max} between symbolize_kernel and sym_digitize_kernel, grown on demand */
-    size_t minmax_cap;
 };
 
 extern "C" {
@@ -1122,7 +1387,6 @@ dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y) {
     cudaFree(y->d_taps);
     cudaFree(y->d_taps_len);
     cudaFree(y->d_filt);
-    cudaFree(y->d_minmax);
     free(y);
 }
 
@@ -1155,8 +1419,8 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
     y->msize = cfg->msize > 0 ? cfg->msize : 1024;  /* opts->msize default, :170 */
     y->use_cosine_filter = cfg->use_cosine_filter;
     y->n_filters = cfg->n_filters;
-    /* scalar arena: 22 x 4-byte arrays, 3 x 8-byte arrays */
-    const size_t arena_bytes = n * (22 * 4 + 3 * 8) + 256;
+    /* scalar arena: 23 x 4-byte arrays, 3 x 8-byte arrays */
+    const size_t arena_bytes = n * (23 * 4 + 3 * 8) + 256;
     cudaError_t e = cudaMalloc(&y->arena, arena_bytes);
     if (e == cudaSuccess) {
         e = cudaMemset(y->arena, 0, arena_bytes);
@@ -1191,6 +1455,7 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
         y->s.midx = i4 + n * k++;
         y->s.sum_window = i4 + n * k++;
         y->s.carry_n = i4 + n * k++;
+        y->s.snr_num = i4 + n * k++;
     }
 #define SYM_ALLOC(ptr, bytes)                                                                                          \
     if (e == cudaSuccess) {                                                                                            \
@@ -1234,6 +1499,9 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
     }
     int rc = dsdneo_b200_symbolizer_set_class(y, cls);
     free(cls);
+    if (rc == 0) {
+        rc = dsdneo_b200_symbolizer_set_snr(y, NULL);
+    }
     if (rc) {
         dsdneo_b200_symbolizer_destroy(y);
         return NULL;
@@ -1247,8 +1515,7 @@ dsdneo_b200_symbolizer_reset(dsdneo_b200_symbolizer* y, void* stream) {
         set_error("symbolizer_reset: NULL");
         return DSDNEO_B200_EINVAL;
     }
-    sym_reset_kernel<<<(y->n_ch + 127) / 128, 128, 0, as_stream(stream)>>>(y->s, y->d_minbuf, y->d_maxbuf, y->d_sbuf, y->d_carry,
-                                                                            y->d_hist, y->n_ch);
+    sym_reset_kernel<<<y->n_ch, 128, 0, as_stream(stream)>>>(y->s, y->d_minbuf, y->d_maxbuf, y->d_sbuf, y->d_carry, y->d_hist, y->n_ch);
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;
@@ -1298,6 +1565,67 @@ dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sy
     return 0;
 }
 
+/* apply_c4fm_snr_weight (src/core/frames/dsd_dibit.c:504-546): the reliability of every dibit is scaled by
+ * (204 + (w256 >> 2)) / 256, w256 from the C4FM SNR the metrics hook reports (sentinel -100 dB => w256 = 0). */
+static int
+snr_scale_num(double snr_db) {
+    int w256 = 0;
+    if (snr_db > -13.0) {
+        if (snr_db >= 12.0) {
+            w256 = 255;
+        } else {
+            double w = (snr_db + 13.0) / 25.0;
+            w = w < 0.0 ? 0.0 : (w > 1.0 ? 1.0 : w);
+            w256 = (int)(w * 255.0 + 0.5);
+        }
+    }
+    return 204 + (w256 >> 2);
+}
+
+int
+dsdneo_b200_symbolizer_set_snr(dsdneo_b200_symbolizer* y, const double* h_snr_c4fm_db) {
+    if (!y) {
+        set_error("symbolizer_set_snr: NULL symbolizer");
+        return DSDNEO_B200_EINVAL;
+    }
+    const size_t n = (size_t)y->n_ch;
+    int* h = (int*)malloc(n * sizeof(int));
+    if (!h) {
+        set_error("symbolizer_set_snr: out of host memory");
+        return DSDNEO_B200_ENOMEM;
+    }
+    for (size_t i = 0; i < n; i++) {
+        h[i] = snr_scale_num(h_snr_c4fm_db ? h_snr_c4fm_db[i] : -100.0);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.snr_num, h, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    free(h);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "symbolizer_set_snr", __FILE__, __LINE__);
+    }
+    return 0;
+}
+
+int
+dsdneo_b200_selftest_div5(unsigned long long* d_n_mismatch, unsigned* d_first_bad, void* stream) {
+    if (!d_n_mismatch || !d_first_bad) {
+        set_error("selftest_div5: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemsetAsync(d_n_mismatch, 0, sizeof(unsigned long long), as_stream(stream)));
+    DSDNEO_CUDA(cudaMemsetAsync(d_first_bad, 0xff, sizeof(unsigned), as_stream(stream)));
+    div5_selftest_kernel<<<4096, 256, 0, as_stream(stream)>>>(d_n_mismatch, d_first_bad); /* 2^20 threads x 4096 operands */
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
 int
 dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
                             const dsdneo_b200_symbol_out* out, void* stream) {
@@ -1328,13 +1656,13 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
         return rc;
     }
     cudaStream_t s = as_stream(stream);
-    const size_t pitch = ((size_t)n_samples + 3) & ~(size_t)3;
+    const size_t pitch = (((size_t)n_samples + 31) & ~(size_t)31) + 32; /* rows start on 128-byte lines */
     if (!y->d_filt || y->filt_pitch < pitch) {
         DSDNEO_CUDA(cudaDeviceSynchronize());
         cudaFree(y->d_filt);
         y->d_filt = NULL;
-        DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt, (size_t)y->n_ch * (pitch ? pitch : 4) * sizeof(float)));
-        y->filt_pitch = pitch ? pitch : 4;
+        DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt, (size_t)y->n_ch * pitch * sizeof(float)));
+        y->filt_pitch = pitch;
     }
     if (n_samples > 0) {
         FirParams fp;
@@ -1384,32 +1712,13 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
     sp.symrate = y->symrate;
     sp.ssize = y->ssize;
     sp.msize = y->msize;
-    sp.minmax = NULL;
-    if (mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT) {
-        const size_t need = (size_t)y->n_ch * out->pitch;
-        if (y->minmax_cap < need) {
-            DSDNEO_CUDA(cudaDeviceSynchronize());
-            cudaFree(y->d_minmax);
-            y->d_minmax = NULL;
-            y->minmax_cap = 0;
-            DSDNEO_CUDA(cudaMalloc((void**)&y->d_minmax, need * sizeof(float2)));
-            y->minmax_cap = need;
-        }
-        sp.minmax = y->d_minmax;
-    }
+    sp.snr_num = y->s.snr_num;
     {
         KernelTimer kt("symbolize_kernel", s);
-        symbolize_kernel<<<(y->n_ch + kSymThreads - 1) / kSymThreads, kSymThreads, 0, s>>>(sp);
+        symbolize_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(sp);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
-    if (mode == DSDNEO_SYM_MODE_GET_DIBIT_SOFT && out->pitch > 0) {
-        KernelTimer kt("sym_digitize_kernel", s);
-        dim3 grid((unsigned)((out->pitch + 255) / 256), (unsigned)y->n_ch);
-        sym_digitize_kernel<<<grid, 256, 0, s>>>(sp);
-        DSDNEO_KERNEL_CHECK();
-        count_launch();
-    }
     return 0;
 }
 

@@ -465,6 +465,12 @@ int dsdneo_b200_symbolizer_reset(dsdneo_b200_symbolizer* y, void* stream);
 /** Per-channel class (host array of n_channels).  Synchronises the device. */
 int dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sym_class* per_channel);
 /**
+ * Per-channel C4FM SNR in dB as dsd_rtl_stream_metrics_hooks.snr_c4fm_db reports it (host array of n_channels, or NULL
+ * for the "no hook installed" sentinel of -100 dB on every channel, the default).  Selects the reliability weight
+ * (204 + (w256 >> 2)) / 256 of apply_c4fm_snr_weight (src/core/frames/dsd_dibit.c:504-546).  Synchronises the device.
+ */
+int dsdneo_b200_symbolizer_set_snr(dsdneo_b200_symbolizer* y, const double* h_snr_c4fm_db);
+/**
  * Consume n_samples discriminator samples per channel ([n_channels][disc_pitch] f32, the output layout of
  * dsdneo_b200_full_demod_batch) and emit every complete symbol; an unfinished symbol's samples are carried to the next
  * call.  With have_sync == 0 (GET_SYMBOL mode) the reference's +-1 sample jitter nudge is active, so channels may emit
@@ -822,6 +828,10 @@ int dsdneo_b200_mbe_synth_batch_host(dsdneo_b200_mbe_parms* h_cur, dsdneo_b200_m
 /** Self-test hook: the device atan2f used by the discriminator's large-angle branch (fsk_modem.c:34),
  *  evaluated on caller-supplied inputs so tests can compare it with the host libm bit for bit. */
 int dsdneo_b200_selftest_atan2f(const float* d_y, const float* d_x, float* d_out, int n, void* stream);
+
+/** Exhaustive check (all 2^32 operands) of the symbolizer's x / 5 sequence against the IEEE operator: writes the number of
+ * mismatching operands and the smallest mismatching bit pattern (0xffffffff if none). */
+int dsdneo_b200_selftest_div5(unsigned long long* d_n_mismatch, unsigned* d_first_bad, void* stream);
 
 /** Self-test hook: the discriminator's output scale 30000.0f / peak (fsk_modem.c:127-129) as the recurrence kernel
  *  evaluates it (d_fast) next to the device's IEEE division (d_ieee), so tests can check they agree bit for bit. */

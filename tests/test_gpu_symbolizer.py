@@ -175,3 +175,15 @@ def test_full_chain_channelizer_to_dibits(gpu):
             if ref.size == tail.size:
                 best = max(best, int((tail == ref).sum()))
         assert best > 0.97 * tail.size, best
+
+
+def test_div5_sequence_matches_ieee_on_every_operand(gpu):
+    """The symbol mean of a 5-sample window is sum / 5.0f; the kernel's 3-operation sequence is compared with the device's
+    IEEE division on all 2^32 bit patterns (exhaustive)."""
+    import torch
+
+    n_bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    first = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gpu.check(gpu.lib().dsdneo_b200_selftest_div5(n_bad.data_ptr(), first.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert int(n_bad.item()) == 0, (int(n_bad.item()), hex(int(first.item()) & 0xFFFFFFFF))
