@@ -431,15 +431,12 @@ p25_12_soft_llr_kernel(const int16_t* llr, uint8_t* out12, int32_t* metric_out, 
 
 constexpr int kListK = 8;
 
-__global__ void __launch_bounds__(64)
-p25_12_soft_llr_list_kernel(const int16_t* llr, dsdneo_b200_p25_12_candidate* cands, int32_t* count_out, int max_candidates,
-                            int n_blocks) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) {
-        return;
-    }
+/* p25_12_soft_llr_list (src/protocol/p25/p25_12.c:31-202) for one block: `out` receives up to min(max_candidates, 8)
+ * candidates sorted by metric (stable), returns their count.  llr196 = the 98 received dibits' LLR pairs in air order. */
+__device__ int
+p25_12_list_decode(const int16_t* llr196, dsdneo_b200_p25_12_candidate* out, int max_candidates) {
     int16_t dei[196];
-    p25_load_deinterleaved(llr + (size_t)i * 196, dei);
+    p25_load_deinterleaved(llr196, dei);
     uint32_t ma[4][kListK], mb[4][kListK];
     uint8_t bp[49][4][kListK];
     for (int s = 0; s < 4; s++) {
@@ -491,7 +488,6 @@ p25_12_soft_llr_list_kernel(const int16_t* llr, dsdneo_b200_p25_12_candidate* ca
     if (max_candidates > kListK) {
         max_candidates = kListK;
     }
-    dsdneo_b200_p25_12_candidate* out = cands + (size_t)i * kListK;
     int count = 0;
     for (int s = 0; s < 4; s++) {
         for (int rk = 0; rk < kListK; rk++) {
@@ -544,7 +540,17 @@ p25_12_soft_llr_list_kernel(const int16_t* llr, dsdneo_b200_p25_12_candidate* ca
             out[at].metric = metric;
         }
     }
-    count_out[i] = count;
+    return count;
+}
+
+__global__ void __launch_bounds__(64)
+p25_12_soft_llr_list_kernel(const int16_t* llr, dsdneo_b200_p25_12_candidate* cands, int32_t* count_out, int max_candidates,
+                            int n_blocks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) {
+        return;
+    }
+    count_out[i] = p25_12_list_decode(llr + (size_t)i * 196, cands + (size_t)i * kListK, max_candidates);
 }
 
 /* ------------------------------------------------------------------ RS(63,k) over GF(64) */
@@ -991,6 +997,52 @@ rs63_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63 /* [63], 
     return status;
 }
 
+/* The ranked-erasure retry of p25p1_rs_*_soft_reliability (p25p1_check_hdu.cpp:56-77, p25p1_check_ldu.cpp:73-94,
+ * p25p1_soft.cpp:83-170) for a word the hard decoder rejected: rank all symbols by (reliability, position) with parity
+ * positions first, erase the n = 1..ranked weakest, first success wins.  word63: parity first, zero padded; on success
+ * out_sym receives the n_data corrected data symbols.  Returns 0 / 1. */
+__device__ int
+rs63_ranked_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63, const uint8_t* dr, const uint8_t* pr, int threshold,
+                           int* out_sym) {
+    const int n_par = sh.n_total - sh.n_data, n2t = 2 * sh.tt;
+    uint8_t er[16];
+    /* selection-sort the n2t weakest of all symbols by (reliability, position): same order as the reference's
+     * full stable sort truncated to its first entries */
+    int hits = 0;
+    for (int i = 0; i < sh.n_total; i++) {
+        hits += ((i < n_par) ? pr[i] : dr[i - n_par]) < threshold;
+    }
+    int ranked = hits > sh.tt ? hits : sh.tt;
+    if (ranked > n2t) {
+        ranked = n2t;
+    }
+    unsigned long long taken = 0;
+    for (int k = 0; k < ranked; k++) {
+        int best = -1, best_rel = 256;
+        for (int i = 0; i < sh.n_total; i++) {
+            if ((taken >> i) & 1ull) {
+                continue;
+            }
+            const int r = (i < n_par) ? pr[i] : dr[i - n_par];
+            if (r < best_rel) {
+                best_rel = r;
+                best = i;
+            }
+        }
+        taken |= 1ull << best;
+        er[k] = (uint8_t)best;
+    }
+    for (int n = 1; n <= ranked; n++) {
+        if (rs63_erasure_decode(gf, sh, word63, er, n) == 0) {
+            for (int i = 0; i < sh.n_data; i++) {
+                out_sym[i] = word63[n_par + i];
+            }
+            return 0;
+        }
+    }
+    return 1;
+}
+
 /* mode 0: DSDReedSolomon_*::decode_soft with a caller-supplied erasure list (check_and_fix_*_soft,
  *         phase1/p25p1_check_hdu.cpp:47-54, p25p1_check_ldu.cpp:46-71): hard decode, then one erasure decode.
  * mode 1: p25p1_rs_*_soft_reliability (p25p1_check_hdu.cpp:56-77, p25p1_check_ldu.cpp:73-94): rank all symbols by
@@ -1040,42 +1092,11 @@ p25_rs_soft_kernel(const dsdneo_fec_tables* __restrict__ T, RsShape sh, int mode
                 }
             }
         } else {
-            /* selection-sort the n2t weakest of all symbols by (reliability, position): same order as the reference's
-             * full stable sort truncated to its first entries */
             const uint8_t* dr = data_rel + (size_t)w * sh.n_data;
             const uint8_t* pr = par_rel + (size_t)w * n_par;
-            int hits = 0;
-            for (int i = 0; i < sh.n_total; i++) {
-                hits += ((i < n_par) ? pr[i] : dr[i - n_par]) < threshold;
-            }
-            int ranked = hits > sh.tt ? hits : sh.tt;
-            if (ranked > n2t) {
-                ranked = n2t;
-            }
-            unsigned long long taken = 0;
-            for (int k = 0; k < ranked; k++) {
-                int best = -1, best_rel = 256;
-                for (int i = 0; i < sh.n_total; i++) {
-                    if ((taken >> i) & 1ull) {
-                        continue;
-                    }
-                    const int r = (i < n_par) ? pr[i] : dr[i - n_par];
-                    if (r < best_rel) {
-                        best_rel = r;
-                        best = i;
-                    }
-                }
-                taken |= 1ull << best;
-                er[k] = (uint8_t)best;
-            }
-            for (int n = 1; n <= ranked && rc != 0; n++) {
-                if (rs63_erasure_decode(gf, sh, word, er, n) == 0) {
-                    rc = 0;
-                    write_back = true;
-                    for (int i = 0; i < sh.n_data; i++) {
-                        out_sym[i] = word[n_par + i];
-                    }
-                }
+            if (rs63_ranked_erasure_decode(gf, sh, word, dr, pr, threshold, out_sym) == 0) {
+                rc = 0;
+                write_back = true;
             }
         }
     }
@@ -1543,33 +1564,10 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
  * packed codeword of DSDGolay24 (parity[i] = bit 12 + i, data[i] = bit 12 - length + i): hard decode as seed, then every
  * combination of at most 4 flips among the 8 least reliable bits, each Golay-decoded and re-encoded; lowest summed
  * reliability of changed bits wins, then fewer changed bits; hard-correction precedence as in the reference. */
-__global__ void
-p25_golay_soft_kernel(int length, uint8_t* data_bits, const uint8_t* parity_bits, const int32_t* reliab, int hard_override,
-                      int threshold, uint8_t* status, int32_t* fixed, int n_words) {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= n_words) {
-        return;
-    }
+__device__ int
+golay24_soft_word(unsigned orig, const int (&rel)[24], int length, int hard_override, int threshold, unsigned& result_out, int& fixed_out) {
     const int n = length + 12;
-    uint8_t* d = data_bits + (size_t)wi * length;
-    const uint8_t* pb = parity_bits + (size_t)wi * 12;
-    const int32_t* rin = reliab + (size_t)wi * n;
-    int rel[24];
     auto bit_of = [&](int idx) { return idx < length ? (12 - length + idx) : (12 + idx - length); };
-    unsigned orig = 0;
-    bool binary = true;
-    for (int i = 0; i < n; i++) {
-        const int r = rin[i];
-        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
-        const unsigned b = i < length ? d[i] : pb[i - length];
-        binary = binary && b <= 1;
-        orig |= (b & 1u) << bit_of(i);
-    }
-    if (!binary) { /* word_bits_are_valid fails: every decode in the reference returns 1 and nothing is found */
-        status[wi] = 1;
-        fixed[wi] = 0;
-        return;
-    }
     const unsigned data_mask = 0xfffu & ~((1u << (12 - length)) - 1u);
     auto penalty = [&](unsigned diff, int& count) {
         int pen = 0;
@@ -1671,6 +1669,57 @@ p25_golay_soft_kernel(int length, uint8_t* data_bits, const uint8_t* parity_bits
             result = best;
             fx = best_fixed;
         }
+    }
+    result_out = result;
+    fixed_out = fx;
+    return st;
+}
+
+/* DSDGolay24::decode_6 / decode_12 (Golay24.hpp:336-405) on the packed codeword (parity[i] = bit 12 + i, data[i] = bit
+ * 12 - length + i): returns 0 ok / 1 uncorrectable; cw_out = corrected word (valid when 0), errs = the decoder's count. */
+__device__ __forceinline__ int
+golay24_hard_word(unsigned cw, unsigned& cw_out, int& errs) {
+    const unsigned pbit = cw & 0x800000u;
+    cw = g23_correct(cw & ~0x800000u, &errs) | pbit;
+    const int odd = __popc(cw & 0xffffffu) & 1;
+    cw_out = cw;
+    return (odd && (cw & 0x3fu) != 0) ? 1 : 0;
+}
+
+__global__ void
+p25_golay_soft_kernel(int length, uint8_t* data_bits, const uint8_t* parity_bits, const int32_t* reliab, int hard_override,
+                      int threshold, uint8_t* status, int32_t* fixed, int n_words) {
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= n_words) {
+        return;
+    }
+    const int n = length + 12;
+    uint8_t* d = data_bits + (size_t)wi * length;
+    const uint8_t* pb = parity_bits + (size_t)wi * 12;
+    const int32_t* rin = reliab + (size_t)wi * n;
+    int rel[24];
+    auto bit_of = [&](int idx) { return idx < length ? (12 - length + idx) : (12 + idx - length); };
+    unsigned orig = 0;
+    bool binary = true;
+    for (int i = 0; i < 24; i++) {
+        rel[i] = 0;
+    }
+    for (int i = 0; i < n; i++) {
+        const int r = rin[i];
+        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
+        const unsigned b = i < length ? d[i] : pb[i - length];
+        binary = binary && b <= 1;
+        orig |= (b & 1u) << bit_of(i);
+    }
+    if (!binary) { /* word_bits_are_valid fails: every decode in the reference returns 1 and nothing is found */
+        status[wi] = 1;
+        fixed[wi] = 0;
+        return;
+    }
+    unsigned result = 0;
+    int fx = 0;
+    const int st = golay24_soft_word(orig, rel, length, hard_override, threshold, result, fx);
+    if (st == 0) {
         for (int i = 0; i < length; i++) {
             d[i] = (uint8_t)((result >> (12 - length + i)) & 1u);
         }
@@ -1700,24 +1749,10 @@ ham1063_hard(unsigned& v) {
     return 1;
 }
 
-/* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475), one thread per word */
-__global__ void
-hamming_10_6_3_soft_kernel(const uint8_t* bits10, const int32_t* reliab10, int hard_override, int threshold, uint8_t* out10,
-                           uint8_t* status, int n_words) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_words) {
-        return;
-    }
-    const uint8_t* in = bits10 + (size_t)w * 10;
-    const int32_t* rin = reliab10 + (size_t)w * 10;
-    int rel[10];
-    unsigned orig = 0;
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        const int r = rin[i];
-        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
-        orig = (orig << 1) | (in[i] & 1u);
-    }
+/* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475) on a packed word (bit 9 - i = reference bit i) with
+ * per-bit reliabilities already clamped to 0..255: returns 0 unchanged / 1 corrected / 2 failed, `result` = output word. */
+__device__ int
+ham1063_soft_word(unsigned orig, const int (&rel)[10], int hard_override, int threshold, unsigned& result_out) {
     auto penalty = [&](unsigned diff) {
         int p = 0;
 #pragma unroll
@@ -1800,6 +1835,30 @@ hamming_10_6_3_soft_kernel(const uint8_t* bits10, const int32_t* reliab10, int h
             st = (best == orig) ? 0 : 1;
         }
     }
+    result_out = result;
+    return st;
+}
+
+/* one thread per word */
+__global__ void
+hamming_10_6_3_soft_kernel(const uint8_t* bits10, const int32_t* reliab10, int hard_override, int threshold, uint8_t* out10,
+                           uint8_t* status, int n_words) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) {
+        return;
+    }
+    const uint8_t* in = bits10 + (size_t)w * 10;
+    const int32_t* rin = reliab10 + (size_t)w * 10;
+    int rel[10];
+    unsigned orig = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int r = rin[i];
+        rel[i] = r < 0 ? 0 : (r > 255 ? 255 : r);
+        orig = (orig << 1) | (in[i] & 1u);
+    }
+    unsigned result = orig;
+    const int st = ham1063_soft_word(orig, rel, hard_override, threshold, result);
     uint8_t* o = out10 + (size_t)w * 10;
 #pragma unroll
     for (int i = 0; i < 10; i++) {

@@ -236,4 +236,35 @@ void oracle_libm_atan2f_array(const float* y, const float* x, float* out, long n
 }
 #endif
 
+
+/* ---- P25 Phase 1 frame handlers over a dibit stream (oracle_p25p1_frame.c) ---- */
+/* same layout as dsdneo_b200_p25p1_frame / dsdneo_b200_p25p1_voice of include/dsdneo_b200.h */
+typedef struct oracle_p25p1_frame {
+    int64_t position;
+    int32_t channel;
+    int32_t voice_index;
+    int16_t nac;
+    int16_t nid_errs;
+    int8_t nid_status;
+    uint8_t duid;
+    uint8_t n_tsbk;
+    uint8_t tsbk_crc_ok;
+    uint8_t rs_kind;
+    uint8_t rs_status;
+    uint8_t lsd_ok;
+    uint8_t n_word_soft;
+    uint8_t lsd[2];
+    uint8_t reserved[6];
+    uint8_t tsbk[3][12];
+    uint8_t rs_data[20];
+    uint8_t rs_in_data[20];
+    uint8_t rs_in_parity[16];
+} oracle_p25p1_frame;
+typedef struct oracle_p25p1_voice {
+    uint32_t bits[9][8];
+    uint8_t reliab[9][8][23];
+} oracle_p25p1_voice;
+int oracle_p25p1_decode_frame(const uint8_t* dibits, const int16_t* llr, int count, int pos_last_sync, int observed_nac, int threshold,
+                              oracle_p25p1_frame* f, oracle_p25p1_voice* voice);
+
 #endif

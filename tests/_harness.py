@@ -875,3 +875,241 @@ def dmr_build_bs_data_burst(rng, payload96, color_code, data_type, tact4=(1, 0, 
     second = (second_bits[0::2] << 1) | second_bits[1::2]
     dib = np.concatenate([first, np.array(DMR_BS_DATA_SYNC_DIBITS), second]).astype(np.int64)
     return dib, {"cach": cach, "info": info, "slot": slot}
+
+
+# ---- P25 Phase 1 frames: record layouts (include/dsdneo_b200.h), reference frame harness, synthetic frame builders ----------
+
+P25_FRAME_DTYPE = np.dtype([
+    ("position", "<i8"), ("channel", "<i4"), ("voice_index", "<i4"), ("nac", "<i2"), ("nid_errs", "<i2"), ("nid_status", "i1"),
+    ("duid", "u1"), ("n_tsbk", "u1"), ("tsbk_crc_ok", "u1"), ("rs_kind", "u1"), ("rs_status", "u1"), ("lsd_ok", "u1"),
+    ("n_word_soft", "u1"), ("lsd", "u1", (2,)), ("reserved", "u1", (6,)), ("tsbk", "u1", (3, 12)), ("rs_data", "u1", (20,)),
+    ("rs_in_data", "u1", (20,)), ("rs_in_parity", "u1", (16,))])
+P25_VOICE_DTYPE = np.dtype([("bits", "<u4", (9, 8)), ("reliab", "u1", (9, 8, 23))])
+assert P25_FRAME_DTYPE.itemsize == 128 and P25_VOICE_DTYPE.itemsize == 1944
+
+REF_P25_DTYPE = np.dtype([
+    ("consumed", "<i4"), ("overrun", "<i4"), ("nid_status", "<i4"), ("nac", "<i4"), ("duid", "<i4"), ("nid_errs", "<i4"),
+    ("n_tsbk", "<i4"), ("tsbk_bytes", "u1", (3, 12)), ("tsbk_crc_err", "<i4", (3,)), ("tsbk_dibits", "u1", (3, 98)),
+    ("tsbk_llr", "<i2", (3, 196)), ("n_imbe", "<i4"), ("imbe_bit", "u1", (9, 8, 23)), ("imbe_rel", "u1", (9, 8, 23)),
+    ("n_words", "<i4"), ("word_code", "<i4", (48,)), ("word_rc", "<i4", (48,)), ("word_fixed", "<i4", (48,)),
+    ("word_in", "u1", (48, 24)), ("word_out", "u1", (48, 12)), ("word_soft_called", "<i4", (48,)), ("word_soft_rc", "<i4", (48,)),
+    ("rs_kind", "<i4"), ("rs_hard_rc", "<i4"), ("rs_soft_called", "<i4"), ("rs_soft_rc", "<i4"), ("rs_in_data", "u1", (120,)),
+    ("rs_in_parity", "u1", (96,)), ("rs_out_data", "u1", (120,)), ("rs_data_reliab", "u1", (20,)), ("rs_parity_reliab", "u1", (16,)),
+    ("n_lsd", "<i4"), ("lsd_in", "u1", (2, 16)), ("lsd_out", "u1", (2, 16)), ("lsd_llr", "<i2", (2, 16)), ("lsd_ok", "<i4", (2,))],
+    align=True)
+
+_ref_p25 = None
+
+
+def ref_p25_available():
+    return os.path.exists(os.path.join(REF_DIR, "libdsdneo_ref_p25.so"))
+
+
+def ref_p25():
+    """The UNMODIFIED reference P25p1 frame handlers replaying a dibit stream (oracle/ref_shim_p25.c)."""
+    global _ref_p25
+    if _ref_p25 is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libdsdneo_ref_p25.so"))
+        assert L.ref_p25_frame_size() == REF_P25_DTYPE.itemsize, (L.ref_p25_frame_size(), REF_P25_DTYPE.itemsize)
+        L.ref_p25_decode_frame.restype = C.c_long
+        L.ref_p25_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p]
+        _ref_p25 = L
+    return _ref_p25
+
+
+def ref_p25_decode(dibits, reliab, llr, pos_last_sync, observed_nac=0):
+    """One frame through dsd_dispatch_handle_p25p1; returns a REF_P25_DTYPE scalar."""
+    rec = np.zeros(1, REF_P25_DTYPE)
+    d, r, l = np.ascontiguousarray(dibits, np.uint8), np.ascontiguousarray(reliab, np.uint8), np.ascontiguousarray(llr, np.int16)
+    ref_p25().ref_p25_decode_frame(d.ctypes.data, r.ctypes.data, l.ctypes.data, d.size, pos_last_sync + 1, observed_nac, rec.ctypes.data)
+    return rec[0]
+
+
+def oracle_p25_decode(dibits, llr, pos_last_sync, observed_nac=0, threshold=64):
+    """oracle_p25p1_decode_frame; returns (consumed, frame record, voice record)."""
+    O = oracle_fec()
+    f, v = np.zeros(1, P25_FRAME_DTYPE), np.zeros(1, P25_VOICE_DTYPE)
+    d, l = np.ascontiguousarray(dibits, np.uint8), np.ascontiguousarray(llr, np.int16)
+    O.oracle_p25p1_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = O.oracle_p25p1_decode_frame(d.ctypes.data, l.ctypes.data, d.size, pos_last_sync, observed_nac, threshold, f.ctypes.data,
+                                    v.ctypes.data)
+    return n, f[0], v[0]
+
+
+def p25_words_from_bits(bits, n):
+    b = np.asarray(bits[:6 * n], np.int64).reshape(n, 6)
+    return (b * (1 << np.arange(5, -1, -1))).sum(axis=1).astype(np.uint8)
+
+
+def p25_frames_agree(ref, f, v):
+    """Field-by-field comparison of a reference harness record with an (oracle or device) frame + voice record.
+    Returns a list of mismatching field names (empty = equal)."""
+    bad = []
+    if int(ref["nid_status"]) != int(f["nid_status"]):
+        bad.append("nid_status")
+    if ref["nid_status"] > 0:
+        if int(ref["nac"]) != int(f["nac"]) or int(ref["duid"]) != int(f["duid"]) or int(ref["nid_errs"]) != int(f["nid_errs"]):
+            bad.append("nid")
+    else:
+        return bad + (["duid"] if int(f["duid"]) != 0xFF else [])
+    duid = int(ref["duid"])
+    if duid == 7:
+        n = int(ref["n_tsbk"])
+        if n != int(f["n_tsbk"]):
+            bad.append("n_tsbk")
+        for b in range(min(n, int(f["n_tsbk"]))):
+            if not np.array_equal(ref["tsbk_bytes"][b], f["tsbk"][b]):
+                bad.append("tsbk%d" % b)
+            if (ref["tsbk_crc_err"][b] == 0) != bool((f["tsbk_crc_ok"] >> b) & 1):
+                bad.append("tsbk_crc%d" % b)
+    if duid in (0x0, 0x5, 0xA):
+        kind = {0x0: 1, 0x5: 2, 0xA: 3}[duid]
+        n_data, n_par = {1: (20, 16), 2: (12, 12), 3: (16, 8)}[kind]
+        if int(ref["rs_kind"]) != kind or int(f["rs_kind"]) != kind:
+            bad.append("rs_kind")
+        if not np.array_equal(p25_words_from_bits(ref["rs_in_data"], n_data), f["rs_in_data"][:n_data]):
+            bad.append("rs_in_data")
+        if not np.array_equal(p25_words_from_bits(ref["rs_in_parity"], n_par), f["rs_in_parity"][:n_par]):
+            bad.append("rs_in_parity")
+        want = 0 if ref["rs_hard_rc"] == 0 else (1 if (ref["rs_soft_called"] and ref["rs_soft_rc"] == 0) else 2)
+        if want != int(f["rs_status"]):
+            bad.append("rs_status")
+        if not np.array_equal(p25_words_from_bits(ref["rs_out_data"], n_data), f["rs_data"][:n_data]):
+            bad.append("rs_data")
+    if duid in (0x5, 0xA):
+        if int(ref["n_imbe"]) != 9:
+            bad.append("n_imbe")
+        bits = ((v["bits"][:, :, None] >> np.arange(23, dtype=np.uint32)) & 1).astype(np.uint8)
+        if not np.array_equal(bits, ref["imbe_bit"]):
+            bad.append("imbe_bit")
+        if not np.array_equal(v["reliab"], ref["imbe_rel"]):
+            bad.append("imbe_rel")
+        for k in range(2):
+            val = int((ref["lsd_out"][k][:8].astype(np.int64) * (1 << np.arange(7, -1, -1))).sum())
+            if val != int(f["lsd"][k]) or bool(ref["lsd_ok"][k]) != bool((f["lsd_ok"] >> k) & 1):
+                bad.append("lsd%d" % k)
+    return bad
+
+
+IMBE_HI = [22, 66, 102, 43, 87, 115, 20, 64, 100, 41, 85, 151, 18, 62, 98, 39, 83, 149, 16, 60, 96, 37, 81, 147, 14, 58, 94, 35, 79,
+           145, 12, 56, 92, 33, 77, 143, 10, 54, 128, 31, 75, 141, 8, 52, 126, 29, 73, 139, 6, 50, 124, 27, 71, 167, 4, 48, 122, 25,
+           69, 165, 2, 46, 120, 23, 105, 163, 0, 90, 118, 67, 103, 161]
+IMBE_LO = [44, 88, 116, 21, 65, 101, 42, 86, 152, 19, 63, 99, 40, 84, 150, 17, 61, 97, 38, 82, 148, 15, 59, 95, 36, 80, 146, 13, 57,
+           93, 34, 78, 144, 11, 55, 129, 32, 76, 142, 9, 53, 127, 30, 74, 140, 7, 51, 125, 28, 72, 138, 5, 49, 123, 26, 70, 166, 3,
+           47, 121, 24, 106, 164, 1, 91, 119, 68, 104, 162, 45, 89, 117]
+
+
+def _bch_nid_encoder():
+    from test_oracle_fec import bch_63_16_encode
+
+    return bch_63_16_encode
+
+
+def p25p1_nid_dibits(nac, duid):
+    info = np.array([(nac >> (11 - i)) & 1 for i in range(12)] + [(duid >> (3 - i)) & 1 for i in range(4)], np.uint8)
+    cw = _bch_nid_encoder()(info).astype(np.int64)
+    parity = 1 if duid in (0x5, 0xA) else 0
+    bits = np.concatenate([cw, [parity]])
+    return bits[0::2] * 2 + bits[1::2]
+
+
+def hamming_10_6_3_encode(word6):
+    d = [(word6 >> (5 - i)) & 1 for i in range(6)]
+    p = [d[0] ^ d[1] ^ d[2] ^ d[5], d[0] ^ d[1] ^ d[3] ^ d[5], d[0] ^ d[2] ^ d[3] ^ d[4], d[1] ^ d[2] ^ d[3] ^ d[4]]
+    return d + p
+
+
+_golay6_parity = None
+
+
+def golay_24_6_encode(word6):
+    """6 data bits + the 12 parity bits the reference decoder accepts with zero corrections (found once by search)."""
+    global _golay6_parity
+    if _golay6_parity is None:
+        O = oracle_fec()
+        # linear code: find the parity of each unit data word, the rest follows by XOR
+        basis = []
+        for k in range(6):
+            data = np.zeros(6, np.uint8)
+            data[k] = 1
+            found = None
+            for par in range(4096):
+                p = np.array([(par >> (11 - i)) & 1 for i in range(12)], np.uint8)
+                d = data.copy()
+                fixed = C.c_int(0)
+                if O.oracle_p25_golay24_decode(6, _ptr(d, u8p), _ptr(p, u8p), C.byref(fixed)) == 0 and fixed.value == 0 \
+                        and np.array_equal(d, data):
+                    found = par
+                    break
+            assert found is not None
+            basis.append(found)
+        _golay6_parity = basis
+    par = 0
+    for k in range(6):
+        if (word6 >> (5 - k)) & 1:
+            par ^= _golay6_parity[k]
+    return [(word6 >> (5 - i)) & 1 for i in range(6)] + [(par >> (11 - i)) & 1 for i in range(12)]
+
+
+def rs63_shortened_encode(data_syms, n_par):
+    """Shortened RS(63, 63 - n_par) over GF(64): returns (parity symbols, data symbols) as the reference orders them."""
+    O = oracle_fec()
+    tt = n_par // 2
+    data = np.zeros(63 - n_par, np.int32)
+    data[:len(data_syms)] = data_syms
+    cw = np.zeros(63, np.int32)
+    O.oracle_rs63_encode(tt, data.ctypes.data_as(i32p), cw.ctypes.data_as(i32p))
+    return cw[:n_par].copy(), cw[n_par:n_par + len(data_syms)].copy()
+
+
+def _bits_to_dibits(bits):
+    b = np.asarray(bits, np.int64)
+    return b[0::2] * 2 + b[1::2]
+
+
+def lsd_16_8_encode(byte):
+    r = byte << 8
+    for i in range(15, 7, -1):
+        if (r >> i) & 1:
+            r ^= 0x139 << (i - 8)
+    par = r & 0xFF
+    return [(byte >> (7 - i)) & 1 for i in range(8)] + [(par >> (7 - i)) & 1 for i in range(8)]
+
+
+def p25p1_build_ldu(rng, nac, ldu2=False):
+    """One LDU1 / LDU2: sync + NID + 9 IMBE frames, 24 Hamming(10,6,3) hex words carrying an RS codeword, LSD.  Returns
+    (dibits incl. status, truth dict)."""
+    n_data = 16 if ldu2 else 12
+    n_par = 24 - n_data
+    data = rng.integers(0, 64, n_data)
+    par, dat = rs63_shortened_encode(data, n_par)
+    voice = rng.integers(0, 2, (9, 184)).astype(np.int64)
+    lsd = rng.integers(0, 256, 2)
+
+    def imbe(k):
+        return voice[k][IMBE_HI] * 2 + voice[k][IMBE_LO]
+
+    def words(block):  # four air words starting at air index 4 * block
+        out = []
+        for w in range(4 * block, 4 * block + 4):
+            sym = dat[n_data - 1 - w] if w < n_data else par[23 - w]
+            out.append(_bits_to_dibits(hamming_10_6_3_encode(int(sym))))
+        return np.concatenate(out)
+
+    body = [np.array(P25P1_SYNC_DIBITS), p25p1_nid_dibits(nac, 0xA if ldu2 else 0x5), imbe(0), imbe(1), words(0), imbe(2), words(1),
+            imbe(3), words(2), imbe(4), words(3), imbe(5), words(4), imbe(6), words(5), imbe(7),
+            _bits_to_dibits(lsd_16_8_encode(int(lsd[0])) + lsd_16_8_encode(int(lsd[1]))), imbe(8)]
+    mask = np.zeros(184, bool)
+    mask[IMBE_HI + IMBE_LO] = True
+    return p25p1_insert_status(np.concatenate(body)), {"rs_data": dat.astype(np.uint8), "voice": voice * mask, "lsd": lsd, "duid": 0xA if ldu2 else 0x5}
+
+
+def p25p1_build_hdu(rng, nac):
+    data = rng.integers(0, 64, 20)
+    par, dat = rs63_shortened_encode(data, 16)
+    out = []
+    for w in range(36):
+        sym = dat[19 - w] if w < 20 else par[35 - w]
+        out.append(_bits_to_dibits(golay_24_6_encode(int(sym))))
+    body = [np.array(P25P1_SYNC_DIBITS), p25p1_nid_dibits(nac, 0x0)] + out + [np.zeros(5, np.int64)]
+    return p25p1_insert_status(np.concatenate(body)), {"rs_data": dat.astype(np.uint8), "duid": 0}
