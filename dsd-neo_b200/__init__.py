@@ -874,6 +874,22 @@ def dmr_burst_cut(d_dibits, d_reliability, d_counts, d_hits, d_n_hits, inverted_
     return out
 
 
+def _p25_dtypes():
+    import numpy as np
+
+    frame = np.dtype([
+        ("position", "<i8"), ("channel", "<i4"), ("voice_index", "<i4"), ("nac", "<i2"), ("nid_errs", "<i2"), ("nid_status", "i1"),
+        ("duid", "u1"), ("n_tsbk", "u1"), ("tsbk_crc_ok", "u1"), ("rs_kind", "u1"), ("rs_status", "u1"), ("lsd_ok", "u1"),
+        ("n_word_soft", "u1"), ("lsd", "u1", (2,)), ("reserved", "u1", (6,)), ("tsbk", "u1", (3, 12)), ("rs_data", "u1", (20,)),
+        ("rs_in_data", "u1", (20,)), ("rs_in_parity", "u1", (16,))])
+    voice = np.dtype([("bits", "<u4", (9, 8)), ("reliab", "u1", (9, 8, 23))])
+    assert frame.itemsize == 128 and voice.itemsize == 1944
+    return frame, voice
+
+
+P25_FRAME_DTYPE, P25_VOICE_DTYPE = _p25_dtypes()
+
+
 def p25p1_frame_cut(d_dibits, d_llr, d_counts, d_hits, d_n_hits, n_payload: int, stream=None):
     """Device-side P25p1 frame cutter on the symbolizer / frame-sync outputs (torch cuda tensors).  Returns a dict of cuda
     tensors indexed by slot = channel * max_hits + hit: nid_code63, nid_reliab63, nid_parity, nid_parity_reliab, nid_valid,
@@ -902,6 +918,49 @@ def p25p1_frame_cut(d_dibits, d_llr, d_counts, d_hits, d_n_hits, n_payload: int,
         "p25p1_frame_cut_batch",
     )
     return out
+
+
+def p25p1_frames_decode(d_dibits, d_llr, d_counts, d_hits, d_n_hits, observed_nac=None, threshold=64, hard_override=True,
+                        region_offset=0, stream=None):
+    """Sync hits -> frame records, all on the device: NID cut + p25p1_nid_decode + the frame decoder (TSBK / HDU / LDU1 / LDU2).
+    Returns (frames, voices): numpy structured arrays (dsdneo_b200_p25p1_frame / _voice layouts), trimmed to the counts."""
+    import numpy as np
+    import torch
+
+    n_ch, max_hits = d_hits.shape[0], d_hits.shape[1]
+    slots = n_ch * max_hits
+    dev = d_dibits.device
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    assert region_offset == 0, "the python wrapper cuts from buffer index 0"
+    cut = p25p1_frame_cut(d_dibits, d_llr, d_counts, d_hits, d_n_hits, 0, stream)
+    st = torch.zeros(slots, dtype=torch.int8, device=dev)
+    nac = torch.zeros(slots, dtype=torch.int32, device=dev)
+    duid = torch.zeros(slots, dtype=torch.uint8, device=dev)
+    errs = torch.zeros(slots, dtype=torch.int32, device=dev)
+    obs = None
+    if observed_nac is not None:
+        obs = torch.as_tensor(np.repeat(np.asarray(observed_nac, np.int32), max_hits), device=dev).contiguous()
+    check(lib().dsdneo_b200_p25p1_nid_decode_batch(cut["nid_code63"].data_ptr(), cut["nid_reliab63"].data_ptr(),
+                                                   obs.data_ptr() if obs is not None else None, cut["nid_parity"].data_ptr(),
+                                                   cut["nid_parity_reliab"].data_ptr(), threshold, st.data_ptr(), nac.data_ptr(),
+                                                   duid.data_ptr(), errs.data_ptr(), slots, _stream_ptr(stream)), "p25p1_nid_decode_batch")
+    f_off = torch.zeros(n_ch, dtype=torch.int32, device=dev)
+    v_off = torch.zeros(n_ch, dtype=torch.int32, device=dev)
+    totals = torch.zeros(2, dtype=torch.int32, device=dev)
+    frames = torch.zeros((slots, 128), dtype=torch.uint8, device=dev)
+    voices = torch.zeros((slots, 1944), dtype=torch.uint8, device=dev)
+    check(lib().dsdneo_b200_p25p1_frames_decode_batch(
+        d_dibits.data_ptr(), d_dibits.shape[1], d_llr.data_ptr(), d_llr.shape[1], d_counts.data_ptr(), d_hits.data_ptr(),
+        d_n_hits.data_ptr(), n_ch, max_hits, region_offset, None, st.data_ptr(), cut["nid_valid"].data_ptr(), nac.data_ptr(),
+        duid.data_ptr(), errs.data_ptr(),
+        threshold, 1 if hard_override else 0, f_off.data_ptr(), v_off.data_ptr(), totals.data_ptr(), frames.data_ptr(), slots,
+        voices.data_ptr(), slots, _stream_ptr(stream)), "p25p1_frames_decode_batch")
+    torch.cuda.synchronize()
+    nf, nv = (int(x) for x in totals.cpu().numpy())
+    fr = frames[:nf].cpu().numpy().reshape(-1).view(P25_FRAME_DTYPE)
+    vo = voices[:nv].cpu().numpy().reshape(-1).view(P25_VOICE_DTYPE)
+    return fr, vo
 
 
 def p25_word_decode(code: int, data_bits, parity_bits):

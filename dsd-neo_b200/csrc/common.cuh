@@ -79,3 +79,11 @@ int dsdneo_cqpsk_bank_channels(const dsdneo_b200_cqpsk_bank* q);
 int dsdneo_cqpsk_stage(dsdneo_b200_cqpsk_bank* q, int n_channels, const float2* d_y, size_t y_pitch, const float* d_pwr,
                        const float* d_squelch_level, float* d_channel_pwr, int* d_squelched, int block_pairs,
                        int n_blocks, float* d_symbols, size_t symbols_pitch, int* d_counts, cudaStream_t s);
+
+/* library-internal: dsdneo_b200_p25p1_frame_cut_batch with hit positions relative to buffer index region_off (fec.cu) */
+extern "C" int dsdneo_p25p1_frame_cut_region(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                             const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels,
+                                             int max_hits, int n_payload, uint8_t* d_nid_code63, uint8_t* d_nid_reliab63,
+                                             uint8_t* d_nid_parity, uint8_t* d_nid_parity_reliab, uint8_t* d_nid_valid,
+                                             uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid,
+                                             int region_off, void* stream);

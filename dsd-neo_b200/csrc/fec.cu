@@ -371,14 +371,11 @@ p25_branch(const int16_t* dei, int sym, int pv, int nx) {
     return llr_cost(l[0], (e >> 3) & 1u) + llr_cost(l[1], (e >> 2) & 1u) + llr_cost(l[2], (e >> 1) & 1u) + llr_cost(l[3], e & 1u);
 }
 
-__global__ void
-p25_12_soft_llr_kernel(const int16_t* llr, uint8_t* out12, int32_t* metric_out, int n_blocks) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) {
-        return;
-    }
+/* p25_12_soft_llr (src/protocol/p25/p25_12.c:204-283) for one block: 12 bytes out, returns best_final >> 8 */
+__device__ __noinline__ int32_t
+p25_12_decode(const int16_t* llr196, uint8_t* o) {
     int16_t dei[196];
-    p25_load_deinterleaved(llr + (size_t)i * 196, dei);
+    p25_load_deinterleaved(llr196, dei);
     uint32_t pm0 = 0, pm1 = 256, pm2 = 256, pm3 = 256; /* path metrics stay in registers */
     uint8_t bp[49];                                    /* 4 x 2-bit predecessors per step */
     for (int s = 0; s < 49; s++) {
@@ -422,18 +419,26 @@ p25_12_soft_llr_kernel(const int16_t* llr, uint8_t* out12, int32_t* metric_out, 
         td[s] = (uint8_t)st;
         st = (bp[s] >> (2 * st)) & 3;
     }
-    uint8_t* o = out12 + (size_t)i * 12;
     for (int b = 0; b < 12; b++) {
         o[b] = (uint8_t)((td[4 * b] << 6) | (td[4 * b + 1] << 4) | (td[4 * b + 2] << 2) | td[4 * b + 3]);
     }
-    metric_out[i] = (int32_t)(bf >> 8);
+    return (int32_t)(bf >> 8);
+}
+
+__global__ void
+p25_12_soft_llr_kernel(const int16_t* llr, uint8_t* out12, int32_t* metric_out, int n_blocks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) {
+        return;
+    }
+    metric_out[i] = p25_12_decode(llr + (size_t)i * 196, out12 + (size_t)i * 12);
 }
 
 constexpr int kListK = 8;
 
 /* p25_12_soft_llr_list (src/protocol/p25/p25_12.c:31-202) for one block: `out` receives up to min(max_candidates, 8)
  * candidates sorted by metric (stable), returns their count.  llr196 = the 98 received dibits' LLR pairs in air order. */
-__device__ int
+__device__ __noinline__ int
 p25_12_list_decode(const int16_t* llr196, dsdneo_b200_p25_12_candidate* out, int max_candidates) {
     int16_t dei[196];
     p25_load_deinterleaved(llr196, dei);
@@ -579,7 +584,7 @@ rs_pack_symbols(const RsShape& sh, const uint8_t* dbits, const uint8_t* pbits, u
 
 /* Hard decision decode of one shortened word: sym = n_total symbols in polynomial form (parity first); out_sym receives
  * the n_data data symbols (corrected, or as received when the word is irrecoverable).  Returns 0 / 1. */
-__device__ int
+__device__ __noinline__ int
 rs63_hard_decode(const signed char* __restrict__ EXP, const signed char* __restrict__ LOG, const RsShape& sh, const uint8_t* sym,
                  int* out_sym) {
     constexpr int NN = 63;
@@ -791,7 +796,7 @@ rs63_syndromes(const Gf64& gf, const uint8_t* w, int used, int n2t, uint8_t* syn
 /* word: n_total symbols (parity first), corrected in place on success.  Returns 0 / 1 (word restored on failure).
  * Corrections that the reference would apply to the zero padding of the shortened code make its final syndrome
  * re-check see a non-codeword only if they are non-zero there; that case is reproduced by tracking the padding. */
-__device__ int
+__device__ __noinline__ int
 rs63_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63 /* [63], positions >= n_total are zero on entry */,
                     const uint8_t* erasures, int n_er) {
     const int n2t = 2 * sh.tt;
@@ -1001,7 +1006,7 @@ rs63_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63 /* [63], 
  * p25p1_soft.cpp:83-170) for a word the hard decoder rejected: rank all symbols by (reliability, position) with parity
  * positions first, erase the n = 1..ranked weakest, first success wins.  word63: parity first, zero padded; on success
  * out_sym receives the n_data corrected data symbols.  Returns 0 / 1. */
-__device__ int
+__device__ __noinline__ int
 rs63_ranked_erasure_decode(const Gf64& gf, const RsShape& sh, uint8_t* word63, const uint8_t* dr, const uint8_t* pr, int threshold,
                            int* out_sym) {
     const int n_par = sh.n_total - sh.n_data, n2t = 2 * sh.tt;
@@ -1123,7 +1128,7 @@ g23_syndrome(unsigned cw) { /* Golay24::syndrome, include/dsd-neo/fec/Golay24.hp
 }
 
 /* Golay24::correct (Golay24.hpp:108-169): *errs is the weight of the last syndrome examined, also on failure. */
-__device__ unsigned
+__device__ __noinline__ unsigned
 g23_correct(unsigned cw, int* errs) {
     const unsigned saver = cw;
     unsigned mask = 1;
@@ -1564,7 +1569,7 @@ p25p1_nid_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const uint8_t* 
  * packed codeword of DSDGolay24 (parity[i] = bit 12 + i, data[i] = bit 12 - length + i): hard decode as seed, then every
  * combination of at most 4 flips among the 8 least reliable bits, each Golay-decoded and re-encoded; lowest summed
  * reliability of changed bits wins, then fewer changed bits; hard-correction precedence as in the reference. */
-__device__ int
+__device__ __noinline__ int
 golay24_soft_word(unsigned orig, const int (&rel)[24], int length, int hard_override, int threshold, unsigned& result_out, int& fixed_out) {
     const int n = length + 12;
     auto bit_of = [&](int idx) { return idx < length ? (12 - length + idx) : (12 + idx - length); };
@@ -1751,7 +1756,7 @@ ham1063_hard(unsigned& v) {
 
 /* hamming_10_6_3_soft (src/protocol/p25/phase1/p25p1_soft.cpp:444-475) on a packed word (bit 9 - i = reference bit i) with
  * per-bit reliabilities already clamped to 0..255: returns 0 unchanged / 1 corrected / 2 failed, `result` = output word. */
-__device__ int
+__device__ __noinline__ int
 ham1063_soft_word(unsigned orig, const int (&rel)[10], int hard_override, int threshold, unsigned& result_out) {
     auto penalty = [&](unsigned diff) {
         int p = 0;
@@ -1887,7 +1892,7 @@ p25p1_frame_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const int16_t*
                        const int32_t* hits /* [ch][max_hits][2] = {position of the last sync dibit, sync type} */,
                        const int32_t* n_hits, int n_channels, int max_hits, int n_payload, uint8_t* nid_code63,
                        uint8_t* nid_reliab63, uint8_t* nid_parity, uint8_t* nid_parity_reliab, uint8_t* nid_valid,
-                       uint8_t* payload_dibits, int16_t* payload_llr, uint8_t* payload_valid) {
+                       uint8_t* payload_dibits, int16_t* payload_llr, uint8_t* payload_valid, int region_off) {
     const int slot = blockIdx.x;
     const int ch = slot / max_hits, h = slot - ch * max_hits;
     if (ch >= n_channels) {
@@ -1896,7 +1901,7 @@ p25p1_frame_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const int16_t*
     const int tid = threadIdx.x;
     const bool present = h < min(n_hits[ch], max_hits);
     const int count = counts[ch];
-    const long start = present ? (long)hits[((size_t)ch * max_hits + h) * 2] - 23 : 0; /* first sync dibit */
+    const long start = present ? (long)hits[((size_t)ch * max_hits + h) * 2] + region_off - 23 : 0; /* first sync dibit */
     const uint8_t* d = dibits + (size_t)ch * dibit_pitch;
     const int16_t* l = llr + (size_t)ch * llr_pitch * 2;
     const bool nid_ok = present && start >= 0 && start + 57 <= count;
@@ -2226,6 +2231,533 @@ block_code_shape(int code, int* n, int* k) {
     *n = N[code];
     *k = K[code];
     return 0;
+}
+
+
+/* ------------------------------------------------------------------ P25 Phase 1 frame decoder (one warp per frame) */
+
+/*
+ * Everything the reference's frame handlers do between the frame sync and the vocoder / message parsers, for every sync hit
+ * of every channel at once, straight from the slicer's dibit + LLR streams (no host step, no intermediate frame copies):
+ *   processTSBK   src/protocol/p25/phase1/p25p1_tsbk.c:108-161,1051-1081   1..3 half-rate blocks, list-8 + CRC-16 pick
+ *   processHDU    src/protocol/p25/phase1/p25p1_hdu.c:108-303              36 Golay(24,6) words hard + soft, RS(36,20,17)
+ *   processLDU1/2 src/protocol/p25/phase1/p25p1_ldu.c:89-222, p25p1_ldu1.c:54-245, p25p1_ldu2.c:54-280
+ *                                                                           9 IMBE de-interleaves, 24 Hamming(10,6,3) words hard
+ *                                                                           + soft, RS(24,12,13) / (24,16,9) hard + ranked
+ *                                                                           erasures, 2 LSD (16,8) words hard + soft
+ * The status symbol after every 35 dibits is skipped by index arithmetic (p25p1_payload_offset).  One warp per frame: lanes
+ * take one code word (or one trellis block, or one LSD word) each; lane 0 runs the Reed-Solomon decoder.
+ */
+struct P25FrameParams {
+    const uint8_t* dibits;
+    size_t dibit_pitch;
+    const int16_t* llr;
+    size_t llr_pitch; /* in dibits */
+    const int32_t* counts;
+    const int32_t* hits;   /* [ch][max_hits][2] = {position of the last sync dibit relative to region_off, sync type} */
+    const int32_t* n_hits;
+    int region_off;
+    const long long* stream_base; /* [ch] absolute stream index of buffer index 0, or NULL */
+    int n_channels, max_hits;
+    const int8_t* nid_status;
+    const uint8_t* nid_valid; /* optional: 0 = the NID did not fit in the stream (status forced to 0) */
+    const int32_t* nid_nac;
+    const uint8_t* nid_duid;
+    const int32_t* nid_errs;
+    int32_t* frame_off; /* [ch] first frame record of the channel (exclusive scan of min(n_hits, max_hits)) */
+    int32_t* voice_off; /* [ch] first voice record of the channel */
+    int32_t* totals;    /* {frames, voice records} */
+    dsdneo_b200_p25p1_frame* frames;
+    dsdneo_b200_p25p1_voice* voices;
+    int frame_capacity, voice_capacity;
+    int threshold, hard_override;
+};
+
+__device__ __forceinline__ bool
+p25_is_ldu(int status, int duid) {
+    return status > 0 && (duid == 0x5 || duid == 0xA);
+}
+
+__device__ __forceinline__ int
+p25_slot_status(const P25FrameParams& p, int slot) {
+    return (p.nid_valid && !p.nid_valid[slot]) ? 0 : p.nid_status[slot];
+}
+
+/* exclusive scans over the channels: frame records and voice records per channel (single CTA, n_channels in chunks) */
+__global__ void __launch_bounds__(1024)
+p25p1_frame_index_kernel(const P25FrameParams p) {
+    __shared__ int s_f[1024], s_v[1024];
+    __shared__ int carry_f, carry_v;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        carry_f = 0, carry_v = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < p.n_channels; base += 1024) {
+        const int c = base + t;
+        int nf = 0, nv = 0;
+        if (c < p.n_channels) {
+            nf = min(p.n_hits[c], p.max_hits);
+            for (int h = 0; h < nf; h++) {
+                const int slot = c * p.max_hits + h;
+                nv += p25_is_ldu(p25_slot_status(p, slot), p.nid_duid[slot]) ? 1 : 0;
+            }
+        }
+        s_f[t] = nf, s_v[t] = nv;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) { /* Hillis-Steele inclusive scan */
+            const int af = t >= o ? s_f[t - o] : 0, av = t >= o ? s_v[t - o] : 0;
+            __syncthreads();
+            s_f[t] += af, s_v[t] += av;
+            __syncthreads();
+        }
+        if (c < p.n_channels) {
+            p.frame_off[c] = carry_f + s_f[t] - nf;
+            p.voice_off[c] = carry_v + s_v[t] - nv;
+        }
+        __syncthreads();
+        if (t == 1023) {
+            carry_f += s_f[1023], carry_v += s_v[1023];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        p.totals[0] = carry_f, p.totals[1] = carry_v;
+    }
+}
+
+/* ComputeCrcCCITT16b + crc16_ok over the first 80 bits of a TSBK against its last 16 (src/protocol/p25/p25_crc.c:11-75) */
+__device__ __forceinline__ bool
+p25_crc16_ok(const uint8_t* bytes12) {
+    unsigned crc = 0;
+    for (int i = 0; i < 80; i++) {
+        const unsigned bit = (bytes12[i >> 3] >> (7 - (i & 7))) & 1u;
+        crc = (((crc >> 15) & 1u) ^ bit) ? (((crc << 1) ^ 0x1021u) & 0xFFFFu) : ((crc << 1) & 0xFFFFu);
+    }
+    return (crc ^ 0xFFFFu) == (((unsigned)bytes12[10] << 8) | bytes12[11]);
+}
+
+/* p25_lsd_fec_16x8 (src/protocol/p25/p25_lsd.c:27-78) on a packed word (bit 15 - i = reference bit i); the reference's
+ * lsd_parity[d] table is (d * x^8) mod (x^8 + x^5 + x^4 + x^3 + 1) */
+__device__ __forceinline__ unsigned
+lsd_parity_of(unsigned d) {
+    unsigned r = d << 8;
+#pragma unroll
+    for (int i = 15; i >= 8; i--) {
+        r ^= ((r >> i) & 1u) ? (0x139u << (i - 8)) : 0u;
+    }
+    return r & 0xFFu;
+}
+
+__device__ __noinline__ bool
+lsd_hard(unsigned& w) {
+    const unsigned synd = (w & 0xFFu) ^ lsd_parity_of(w >> 8);
+    if (synd == 0) {
+        return true;
+    }
+    if ((synd & (synd - 1)) == 0) {
+        w ^= synd; /* single parity bit */
+        return true;
+    }
+    for (int pos = 0; pos < 8; pos++) {
+        if (lsd_parity_of(1u << (7 - pos)) == synd) {
+            w ^= 1u << (15 - pos);
+            return true;
+        }
+    }
+    return false;
+}
+
+/* p25_lsd_fec_16x8_soft (p25_lsd.c:80-161): up to 6 bits under the erasure threshold, every flip subset, least penalty */
+__device__ __noinline__ bool
+lsd_soft(unsigned& w, const int (&rel)[16], int threshold) {
+    if (lsd_hard(w)) {
+        return true;
+    }
+    int cand[16], n = 0;
+    for (int i = 0; i < 16; i++) {
+        if (rel[i] < threshold) {
+            cand[n++] = i;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        for (int j = i + 1; j < n; j++) {
+            const int ri = rel[cand[i]], rj = rel[cand[j]];
+            if (rj < ri || (rj == ri && cand[j] < cand[i])) {
+                const int t = cand[i];
+                cand[i] = cand[j];
+                cand[j] = t;
+            }
+        }
+    }
+    n = n > 6 ? 6 : n;
+    if (n <= 0) {
+        return false;
+    }
+    unsigned best = 0;
+    int best_pen = 999999;
+    bool found = false;
+    for (int mask = 1; mask < (1 << n); mask++) {
+        unsigned tmp = w;
+        int pen = 0;
+        for (int b = 0; b < n; b++) {
+            if (mask & (1 << b)) {
+                tmp ^= 1u << (15 - cand[b]);
+                pen += rel[cand[b]];
+            }
+        }
+        if (pen >= best_pen) {
+            continue;
+        }
+        if (lsd_hard(tmp)) {
+            best = tmp, best_pen = pen, found = true;
+        }
+    }
+    if (found) {
+        w = best;
+    }
+    return found;
+}
+
+/* P25 Phase 1 IMBE interleave schedule (TIA-102.BAAA; include/dsd-neo/protocol/p25/p25p1_const.h:30-53) as the flat bit
+ * index row * 23 + column of imbe_fr[8][23] for the first / second bit of each of the 72 dibits of a voice frame */
+__constant__ uint8_t c_imbe_hi[72] = {22, 66, 102, 43, 87,  115, 20, 64, 100, 41, 85, 151, 18, 62, 98,  39, 83,  149,
+                                      16, 60, 96,  37, 81,  147, 14, 58, 94,  35, 79, 145, 12, 56, 92,  33, 77,  143,
+                                      10, 54, 128, 31, 75,  141, 8,  52, 126, 29, 73, 139, 6,  50, 124, 27, 71,  167,
+                                      4,  48, 122, 25, 69,  165, 2,  46, 120, 23, 105, 163, 0,  90, 118, 67, 103, 161};
+__constant__ uint8_t c_imbe_lo[72] = {44, 88, 116, 21, 65,  101, 42, 86, 152, 19, 63, 99,  40, 84, 150, 17, 61,  97,
+                                      38, 82, 148, 15, 59,  95,  36, 80, 146, 13, 57, 93,  34, 78, 144, 11, 55,  129,
+                                      32, 76, 142, 9,  53,  127, 30, 74, 140, 7,  51, 125, 28, 72, 138, 5,  49,  123,
+                                      26, 70, 166, 3,  47,  121, 24, 106, 164, 1,  91, 119, 68, 104, 162, 45, 89, 117};
+
+/* air layout of an LDU after the NID, in status-stripped dibits (p25p1_ldu1.c:176-213, p25p1_ldu2.c:206-234) */
+__constant__ short c_ldu_imbe_off[9] = {0, 72, 164, 256, 348, 440, 532, 624, 712};
+__constant__ short c_ldu_word_off[6] = {144, 236, 328, 420, 512, 604};
+constexpr int kLduLsdOff = 696;
+constexpr int kLduPayload = 784, kHduPayload = 329, kTsbkBlock = 98;
+
+struct P25Stream {
+    const uint8_t* d;
+    const int16_t* l;
+    int start; /* buffer index of the first sync dibit */
+    __device__ __forceinline__ int get(int k, int& l0, int& l1) const {
+        const int pos = start + p25p1_payload_offset(57, k);
+        l0 = l[2 * pos];
+        l1 = l[2 * pos + 1];
+        return d[pos] & 3;
+    }
+};
+
+__device__ __forceinline__ int
+clamp_rel(int l) {
+    const int a = l < 0 ? -l : l;
+    return a > 255 ? 255 : a;
+}
+
+/* check_and_fix_* then p25p1_rs_*_soft_reliability on 6-bit symbols (parity first), lane-serial.  Returns the record status:
+ * 0 hard decode ok, 1 recovered by ranked erasures, 2 irrecoverable; data_out = the n_data data symbols afterwards. */
+__device__ __noinline__ int
+p25_rs_frame_decode(const dsdneo_fec_tables* __restrict__ T, int n_total, int n_data, const uint8_t* sym, const uint8_t* data_rel,
+                    const uint8_t* par_rel, int threshold, uint8_t* data_out) {
+    const RsShape sh = {n_total, n_data, (n_total - n_data) / 2};
+    int out_sym[36];
+    int rc = rs63_hard_decode(T->gf_exp, T->gf_log, sh, sym, out_sym);
+    int status = rc == 0 ? 0 : 2;
+    if (rc != 0) {
+        const Gf64 gf = {T->gf_exp, T->gf_log};
+        uint8_t word[63];
+        for (int i = 0; i < 63; i++) {
+            word[i] = i < n_total ? sym[i] : 0;
+        }
+        if (rs63_ranked_erasure_decode(gf, sh, word, data_rel, par_rel, threshold, out_sym) == 0) {
+            status = 1;
+        }
+    }
+    for (int i = 0; i < n_data; i++) {
+        data_out[i] = (uint8_t)out_sym[i];
+    }
+    return status;
+}
+
+constexpr int kFrameWarps = 4;
+
+__global__ void __launch_bounds__(kFrameWarps * 32)
+p25p1_frame_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const P25FrameParams p) {
+    __shared__ uint8_t s_bit[kFrameWarps][184], s_rel[kFrameWarps][184];
+    __shared__ uint8_t s_word[kFrameWarps][36], s_wrel[kFrameWarps][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kFrameWarps + warp;
+    const int ch = slot / p.max_hits, h = slot - ch * p.max_hits;
+    if (ch >= p.n_channels || h >= min(p.n_hits[ch], p.max_hits)) {
+        return;
+    }
+    const int r = p.frame_off[ch] + h;
+    if (r >= p.frame_capacity) {
+        return;
+    }
+    const int status = p25_slot_status(p, slot);
+    const int duid = status > 0 ? p.nid_duid[slot] : 0xFF;
+    const int count = p.counts[ch];
+    const int pos_last = p.hits[2 * slot] + p.region_off;
+    P25Stream st;
+    st.d = p.dibits + (size_t)ch * p.dibit_pitch;
+    st.l = p.llr + (size_t)ch * p.llr_pitch * 2;
+    st.start = pos_last - 23;
+    /* voice record index: LDUs of this channel before this hit */
+    int vi = -1;
+    {
+        const bool mine = lane < h && p25_is_ldu(p25_slot_status(p, ch * p.max_hits + lane), p.nid_duid[ch * p.max_hits + lane]);
+        const unsigned before = __ballot_sync(0xffffffffu, mine);
+        if (duid == 0x5 || duid == 0xA) {
+            vi = p.voice_off[ch] + __popc(before);
+            if (vi >= p.voice_capacity) {
+                vi = -1;
+            }
+        }
+    }
+    dsdneo_b200_p25p1_frame* f = p.frames + r;
+    const int payload = (duid == 0x5 || duid == 0xA) ? kLduPayload : (duid == 0x0 ? kHduPayload : (duid == 0x7 ? 3 * kTsbkBlock : 0));
+    /* a TSDU is read block by block and ends at the block flagged last: only its first block must fit up front */
+    const int must_fit = duid == 0x7 ? kTsbkBlock : payload;
+    const bool fits = st.start >= 0 && (must_fit == 0 || st.start + p25p1_payload_offset(57, must_fit - 1) + 1 <= count);
+    /* header + cleared payload fields */
+    for (int i = lane; i < (int)sizeof(*f); i += 32) {
+        reinterpret_cast<uint8_t*>(f)[i] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        f->position = (p.stream_base ? p.stream_base[ch] : 0ll) + pos_last;
+        f->channel = ch;
+        f->voice_index = fits ? vi : -1;
+        f->nac = (int16_t)p.nid_nac[slot];
+        f->nid_errs = (int16_t)p.nid_errs[slot];
+        f->nid_status = (int8_t)status;
+        f->duid = (uint8_t)duid;
+        f->reserved[0] = fits ? 0 : 1; /* the stream ended inside the frame: payload fields not decoded */
+    }
+    if (!fits || payload == 0) {
+        return;
+    }
+    if (duid == 0x7) { /* ---- TSDU: one trellis block per lane ---- */
+        uint8_t out12[12];
+        bool crc = false, last = true;
+        const bool blk_fits = lane < 3 && st.start + p25p1_payload_offset(57, (lane + 1) * kTsbkBlock - 1) + 1 <= count;
+        if (blk_fits) {
+            int16_t llr196[196];
+            for (int i = 0; i < kTsbkBlock; i++) {
+                int l0, l1;
+                (void)st.get(lane * kTsbkBlock + i, l0, l1);
+                llr196[2 * i] = (int16_t)l0;
+                llr196[2 * i + 1] = (int16_t)l1;
+            }
+            dsdneo_b200_p25_12_candidate cands[kListK];
+            const int n = p25_12_list_decode(llr196, cands, kListK);
+            if (n > 0) {
+                int sel = 0;
+                for (int c = 0; c < n; c++) {
+                    if (p25_crc16_ok(cands[c].bytes)) {
+                        sel = c;
+                        break;
+                    }
+                }
+                for (int b = 0; b < 12; b++) {
+                    out12[b] = cands[sel].bytes[b];
+                }
+            } else {
+                (void)p25_12_decode(llr196, out12);
+            }
+            crc = p25_crc16_ok(out12);
+            last = (out12[0] >> 7) & 1;
+        }
+        const unsigned fitmask = __ballot_sync(0xffffffffu, blk_fits) & 7u;
+        const unsigned lastmask = __ballot_sync(0xffffffffu, blk_fits && last) & 7u;
+        const unsigned crcmask = __ballot_sync(0xffffffffu, blk_fits && crc) & 7u;
+        int n_blocks = lastmask ? __ffs(lastmask) : 3; /* processTSBK stops after the block flagged last */
+        const int n_avail = __ffs(~fitmask) - 1;       /* leading blocks that lie inside the stream */
+        if (n_blocks > n_avail) {                      /* the stream ended before the last block of this TSDU */
+            n_blocks = n_avail;
+            if (lane == 0) {
+                f->reserved[0] = 1;
+            }
+        }
+        if (lane < n_blocks) {
+            for (int b = 0; b < 12; b++) {
+                f->tsbk[lane][b] = out12[b];
+            }
+        }
+        if (lane == 0) {
+            f->n_tsbk = (uint8_t)n_blocks;
+            f->tsbk_crc_ok = (uint8_t)(crcmask & ((1u << n_blocks) - 1u));
+        }
+        return;
+    }
+    int soft_changed = 0;
+    if (duid == 0x0) { /* ---- HDU: 36 Golay(24,6) words, 9 dibits each ---- */
+        for (int w = lane; w < 36; w += 32) {
+            unsigned cw = 0;
+            int rel[24];
+            int minrel = 255;
+#pragma unroll
+            for (int i = 0; i < 24; i++) {
+                rel[i] = 0;
+            }
+            for (int d = 0; d < 9; d++) {
+                int l0, l1;
+                const int dib = st.get(w * 9 + d, l0, l1);
+                const int b0 = (dib >> 1) & 1, b1 = dib & 1;
+                /* bit index i of the word (data 0..5, parity 6..17) sits at packed bit 6 + i */
+                cw |= (unsigned)b0 << (6 + 2 * d);
+                cw |= (unsigned)b1 << (6 + 2 * d + 1);
+                rel[2 * d] = clamp_rel(l0);
+                rel[2 * d + 1] = clamp_rel(l1);
+                if (d < 3) {
+                    minrel = min(minrel, min(rel[2 * d], rel[2 * d + 1]));
+                }
+            }
+            unsigned fixed_cw = cw;
+            int errs = 0;
+            const int hard = golay24_hard_word(cw, fixed_cw, errs);
+            unsigned data = hard == 0 ? (fixed_cw & 0xFC0u) : (cw & 0xFC0u);
+            if (hard != 0 || errs > 0) {
+                unsigned sres = 0;
+                int sfx = 0;
+                if (golay24_soft_word(cw, rel, 6, p.hard_override, p.threshold, sres, sfx) == 0) {
+                    soft_changed += hard != 0 ? 1 : 0;
+                    data = sres & 0xFC0u;
+                }
+            }
+            int v = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                v = (v << 1) | (int)((data >> (6 + i)) & 1u);
+            }
+            s_word[warp][w] = (uint8_t)v;
+            s_wrel[warp][w] = (uint8_t)minrel;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            soft_changed += __shfl_xor_sync(0xffffffffu, soft_changed, o);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            uint8_t sym[36], dr[20], pr[16];
+            for (int i = 0; i < 20; i++) { /* hex_data[i] = air word 19 - i, hex_parity[i] = air word 35 - i */
+                f->rs_in_data[i] = s_word[warp][19 - i];
+                dr[i] = s_wrel[warp][19 - i];
+                sym[16 + i] = s_word[warp][19 - i];
+            }
+            for (int i = 0; i < 16; i++) {
+                f->rs_in_parity[i] = s_word[warp][35 - i];
+                pr[i] = s_wrel[warp][35 - i];
+                sym[i] = s_word[warp][35 - i];
+            }
+            f->rs_kind = 1;
+            f->rs_status = (uint8_t)p25_rs_frame_decode(T, 36, 20, sym, dr, pr, p.threshold, f->rs_data);
+            f->n_word_soft = (uint8_t)soft_changed;
+        }
+        return;
+    }
+    /* ---- LDU1 / LDU2 ---- */
+    const bool ldu2 = duid == 0xA;
+    const int n_data = ldu2 ? 16 : 12;
+    dsdneo_b200_p25p1_voice* voice = vi >= 0 ? p.voices + vi : nullptr;
+    for (int v = 0; v < 9; v++) {
+        for (int i = lane; i < 184; i += 32) {
+            s_bit[warp][i] = 0, s_rel[warp][i] = 0;
+        }
+        __syncwarp();
+        for (int j = lane; j < 72; j += 32) {
+            int l0, l1;
+            const int dib = st.get(c_ldu_imbe_off[v] + j, l0, l1);
+            s_bit[warp][c_imbe_hi[j]] = (uint8_t)((dib >> 1) & 1);
+            s_rel[warp][c_imbe_hi[j]] = (uint8_t)clamp_rel(l0);
+            s_bit[warp][c_imbe_lo[j]] = (uint8_t)(dib & 1);
+            s_rel[warp][c_imbe_lo[j]] = (uint8_t)clamp_rel(l1);
+        }
+        __syncwarp();
+        if (voice) {
+            if (lane < 8) {
+                unsigned w = 0;
+                for (int col = 0; col < 23; col++) {
+                    w |= (unsigned)s_bit[warp][lane * 23 + col] << col;
+                }
+                voice->bits[v][lane] = w;
+            }
+            uint8_t* rel_out = &voice->reliab[v][0][0];
+            for (int i = lane; i < 184; i += 32) {
+                rel_out[i] = s_rel[warp][i];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 24) { /* one Hamming(10,6,3) hex word per lane: read_and_correct_hex_word, p25p1_ldu.c:190-222 */
+        const int w = lane;
+        const int base = c_ldu_word_off[w >> 2] + (w & 3) * 5;
+        unsigned v10 = 0;
+        int rel[10], minrel = 255;
+        for (int d = 0; d < 5; d++) {
+            int l0, l1;
+            const int dib = st.get(base + d, l0, l1);
+            v10 = (v10 << 2) | (unsigned)dib;
+            rel[2 * d] = clamp_rel(l0);
+            rel[2 * d + 1] = clamp_rel(l1);
+            if (d < 3) {
+                minrel = min(minrel, min(rel[2 * d], rel[2 * d + 1]));
+            }
+        }
+        unsigned hv = v10;
+        const int hard = ham1063_hard(hv);
+        unsigned data = hv >> 4;
+        if (hard == 1 || hard == 2) {
+            unsigned sres = v10;
+            const int soft = ham1063_soft_word(v10, rel, p.hard_override, p.threshold, sres);
+            if (soft != 2) {
+                soft_changed += (hard == 2 || sres != hv) ? 1 : 0;
+                data = sres >> 4;
+            }
+        }
+        s_word[warp][w] = (uint8_t)(data & 0x3Fu);
+        s_wrel[warp][w] = (uint8_t)minrel;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        soft_changed += __shfl_xor_sync(0xffffffffu, soft_changed, o);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t sym[24], dr[16], pr[12];
+        const int n_par = 24 - n_data;
+        for (int i = 0; i < n_data; i++) { /* hex_data[i] = air word n_data - 1 - i, hex_parity[i] = air word 23 - i */
+            f->rs_in_data[i] = s_word[warp][n_data - 1 - i];
+            dr[i] = s_wrel[warp][n_data - 1 - i];
+            sym[n_par + i] = s_word[warp][n_data - 1 - i];
+        }
+        for (int i = 0; i < n_par; i++) {
+            f->rs_in_parity[i] = s_word[warp][23 - i];
+            pr[i] = s_wrel[warp][23 - i];
+            sym[i] = s_word[warp][23 - i];
+        }
+        f->rs_kind = ldu2 ? 3 : 2;
+        f->rs_status = (uint8_t)p25_rs_frame_decode(T, 24, n_data, sym, dr, pr, p.threshold, f->rs_data);
+        f->n_word_soft = (uint8_t)soft_changed;
+    }
+    bool lsd_good = false;
+    if (lane >= 30) { /* low speed data: two (16,8) words, 8 dibits each (p25p1_ldu1.c:128-175, 306-320) */
+        const int k = lane - 30;
+        unsigned w = 0;
+        int rel[16];
+        for (int d = 0; d < 8; d++) {
+            int l0, l1;
+            const int dib = st.get(kLduLsdOff + 8 * k + d, l0, l1);
+            w = (w << 2) | (unsigned)dib;
+            rel[2 * d] = l0 < 0 ? -l0 : l0; /* the LSD search compares unclamped |llr| with the threshold */
+            rel[2 * d + 1] = l1 < 0 ? -l1 : l1;
+        }
+        lsd_good = lsd_soft(w, rel, p.threshold);
+        f->lsd[k] = (uint8_t)(w >> 8);
+    }
+    const unsigned okmask = __ballot_sync(0xffffffffu, lsd_good);
+    if (lane == 1) {
+        f->lsd_ok = (uint8_t)((okmask >> 30) & 3u);
+    }
 }
 
 }  // namespace
@@ -3089,11 +3621,56 @@ dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8_t* 
 }
 
 int
-dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+dsdneo_b200_p25p1_frames_decode_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                      const int32_t* d_counts, const dsdneo_b200_sync_hit* d_hits, const int32_t* d_n_hits,
+                                      int n_channels, int max_hits, int region_offset, const long long* d_stream_base,
+                                      const int8_t* d_nid_status, const uint8_t* d_nid_valid, const int32_t* d_nid_nac,
+                                      const uint8_t* d_nid_duid, const int32_t* d_nid_errs, int erasure_threshold, int hard_override_enabled,
+                                      int32_t* d_frame_off, int32_t* d_voice_off, int32_t* d_totals,
+                                      dsdneo_b200_p25p1_frame* d_frames, int frame_capacity, dsdneo_b200_p25p1_voice* d_voices,
+                                      int voice_capacity, void* stream) {
+    if (!d_dibits || !d_llr || !d_counts || !d_hits || !d_n_hits || !d_nid_status || !d_nid_nac || !d_nid_duid || !d_nid_errs
+        || !d_frame_off || !d_voice_off || !d_totals || !d_frames || n_channels <= 0 || max_hits <= 0 || max_hits > 32
+        || frame_capacity < 0 || voice_capacity < 0 || (voice_capacity > 0 && !d_voices)) {
+        set_error("p25p1_frames_decode_batch: bad argument (max_hits must be 1..32)");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_tables();
+    if (rc) {
+        return rc;
+    }
+    P25FrameParams p;
+    p.dibits = d_dibits, p.dibit_pitch = dibit_pitch, p.llr = d_llr, p.llr_pitch = llr_pitch, p.counts = d_counts;
+    p.hits = reinterpret_cast<const int32_t*>(d_hits), p.n_hits = d_n_hits, p.region_off = region_offset;
+    p.stream_base = d_stream_base, p.n_channels = n_channels, p.max_hits = max_hits;
+    p.nid_status = d_nid_status, p.nid_valid = d_nid_valid, p.nid_nac = d_nid_nac, p.nid_duid = d_nid_duid, p.nid_errs = d_nid_errs;
+    p.frame_off = d_frame_off, p.voice_off = d_voice_off, p.totals = d_totals;
+    p.frames = d_frames, p.voices = d_voices, p.frame_capacity = frame_capacity, p.voice_capacity = voice_capacity;
+    p.threshold = erasure_threshold, p.hard_override = hard_override_enabled ? 1 : 0;
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("p25p1_frame_index_kernel", s);
+        p25p1_frame_index_kernel<<<1, 1024, 0, s>>>(p);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    {
+        KernelTimer kt("p25p1_frame_decode_kernel", s);
+        const int slots = n_channels * max_hits;
+        p25p1_frame_decode_kernel<<<(slots + kFrameWarps - 1) / kFrameWarps, kFrameWarps * 32, 0, s>>>(g_d_tables, p);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_p25p1_frame_cut_region(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
                                   const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels,
                                   int max_hits, int n_payload, uint8_t* d_nid_code63, uint8_t* d_nid_reliab63,
                                   uint8_t* d_nid_parity, uint8_t* d_nid_parity_reliab, uint8_t* d_nid_valid,
-                                  uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid, void* stream) {
+                                  uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid, int region_off,
+                                  void* stream) {
     if (!d_dibits || !d_llr || !d_counts || !d_hits || !d_n_hits || n_channels <= 0 || max_hits <= 0 || n_payload < 0
         || !d_nid_code63 || !d_nid_reliab63 || !d_nid_parity || !d_nid_parity_reliab || !d_nid_valid || !d_payload_valid
         || (n_payload > 0 && (!d_payload_dibits || !d_payload_llr))) {
@@ -3110,11 +3687,22 @@ dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, c
         p25p1_frame_cut_kernel<<<(unsigned)(n_channels * max_hits), 128, 0, s>>>(
             d_dibits, dibit_pitch, d_llr, llr_pitch, d_counts, (const int32_t*)d_hits, d_n_hits, n_channels, max_hits, n_payload,
             d_nid_code63, d_nid_reliab63, d_nid_parity, d_nid_parity_reliab, d_nid_valid, d_payload_dibits, d_payload_llr,
-            d_payload_valid);
+            d_payload_valid, region_off);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;
+}
+
+int
+dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                  const int32_t* d_counts, const void* d_hits, const int32_t* d_n_hits, int n_channels,
+                                  int max_hits, int n_payload, uint8_t* d_nid_code63, uint8_t* d_nid_reliab63,
+                                  uint8_t* d_nid_parity, uint8_t* d_nid_parity_reliab, uint8_t* d_nid_valid,
+                                  uint8_t* d_payload_dibits, int16_t* d_payload_llr, uint8_t* d_payload_valid, void* stream) {
+    return dsdneo_p25p1_frame_cut_region(d_dibits, dibit_pitch, d_llr, llr_pitch, d_counts, d_hits, d_n_hits, n_channels, max_hits,
+                                         n_payload, d_nid_code63, d_nid_reliab63, d_nid_parity, d_nid_parity_reliab, d_nid_valid,
+                                         d_payload_dibits, d_payload_llr, d_payload_valid, 0, stream);
 }
 
 int

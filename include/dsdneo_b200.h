@@ -718,6 +718,57 @@ int dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitc
                                       void* stream);
 
 /**
+ * P25 Phase 1 frame decoder: everything the reference's frame handlers do between the frame sync and the vocoder / message
+ * parsers, for every sync hit of every channel at once, straight from the slicer's dibit + LLR streams:
+ *   processTSBK  (src/protocol/p25/phase1/p25p1_tsbk.c:108-161,1051-1081)  1..3 half-rate trellis blocks, list-8 + CRC-16 pick
+ *   processHDU   (p25p1_hdu.c:108-303)                                     36 Golay(24,6) words hard + soft, RS(36,20,17)
+ *   processLDU1 / processLDU2 (p25p1_ldu.c:89-222, p25p1_ldu1.c:54-245, p25p1_ldu2.c:54-280)
+ *                                                                          9 IMBE de-interleaves (the imbe_fr[8][23] +
+ *                                                                          reliabilities handed to processMbeFrameSoft), 24
+ *                                                                          Hamming(10,6,3) words hard + soft, RS(24,12,13) /
+ *                                                                          (24,16,9) hard + ranked erasures, LSD (16,8) x 2
+ * NID results come from dsdneo_b200_p25p1_nid_decode_batch on the slots of dsdneo_b200_p25p1_frame_cut_batch (slot = channel
+ * * max_hits + hit; d_nid_valid = the cutter's nid_valid, may be NULL).  One frame record per hit, ordered by (channel, stream order): record index d_frame_off[channel] + hit;
+ * LDUs additionally get a voice record (frame.voice_index).  d_totals = {frames, voice records} written by the call.
+ * Hit positions are relative to buffer index region_offset of each channel row; frames that do not fit inside d_counts
+ * dibits keep their NID fields and are flagged (reserved[0] = 1).  TDU / TDULC / MPDU payloads are not decoded (NID only).
+ * Bit-exact with the reference handlers (tests/test_gpu_p25p1_frames.py; golden records from the unmodified handlers).
+ */
+typedef struct dsdneo_b200_p25p1_frame {
+    int64_t position;      /* stream index of the LAST sync dibit (d_stream_base[channel] + buffer index) */
+    int32_t channel;
+    int32_t voice_index;   /* LDU1 / LDU2: index into the voice records, else -1 */
+    int16_t nac;
+    int16_t nid_errs;
+    int8_t nid_status;     /* enum NidResult of p25p1_nid_decode (> 0 = decoded) */
+    uint8_t duid;          /* 0xFF when the NID failed */
+    uint8_t n_tsbk;        /* TSDU: blocks read (stops after the block flagged last) */
+    uint8_t tsbk_crc_ok;   /* bit b: block b passed crc16_lb_bridge */
+    uint8_t rs_kind;       /* 0 none, 1 RS(36,20,17) HDU, 2 RS(24,12,13) LDU1, 3 RS(24,16,9) LDU2 */
+    uint8_t rs_status;     /* 0 hard decode ok, 1 recovered by ranked erasures, 2 irrecoverable */
+    uint8_t lsd_ok;        /* bit k: p25_lsd_fec_16x8_soft accepted LSD word k */
+    uint8_t n_word_soft;   /* words whose soft decode changed the outcome (p25_p1_soft_hamming_ok / _golay_ok) */
+    uint8_t lsd[2];        /* corrected low speed data octets */
+    uint8_t reserved[6];   /* [0] = 1: the stream ended inside the frame */
+    uint8_t tsbk[3][12];
+    uint8_t rs_data[20];      /* hex_data[i] after Reed-Solomon (6-bit values) */
+    uint8_t rs_in_data[20];   /* hex_data[i] / hex_parity[i] after the word-level FEC, as handed to the RS decoder */
+    uint8_t rs_in_parity[16];
+} dsdneo_b200_p25p1_frame;
+typedef struct dsdneo_b200_p25p1_voice {
+    uint32_t bits[9][8];        /* imbe_fr[row][col] of voice frame v = bit col of bits[v][row] */
+    uint8_t reliab[9][8][23];   /* dsd_vocoder_soft_bit.reliability */
+} dsdneo_b200_p25p1_voice;
+int dsdneo_b200_p25p1_frames_decode_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int16_t* d_llr, size_t llr_pitch,
+                                          const int32_t* d_counts, const dsdneo_b200_sync_hit* d_hits, const int32_t* d_n_hits,
+                                          int n_channels, int max_hits, int region_offset, const long long* d_stream_base,
+                                          const int8_t* d_nid_status, const uint8_t* d_nid_valid, const int32_t* d_nid_nac,
+                                          const uint8_t* d_nid_duid, const int32_t* d_nid_errs, int erasure_threshold, int hard_override_enabled,
+                                          int32_t* d_frame_off, int32_t* d_voice_off, int32_t* d_totals,
+                                          dsdneo_b200_p25p1_frame* d_frames, int frame_capacity, dsdneo_b200_p25p1_voice* d_voices,
+                                          int voice_capacity, void* stream);
+
+/**
  * viterbi_decode / viterbi_decode_punctured (src/core/util/dsd_misc.c:118-182; include/dsd-neo/fec/viterbi.h:23-29), the
  * K = 5 soft decoder used by M17 and YSF.  Costs are uint16 "probability of a 1" (0 / 0xFFFF strong, 0x7FFF erased).
  * @param d_cost   [n][cost_pitch] received soft bits, in_len used per frame (after de-puncturing at most 488)
