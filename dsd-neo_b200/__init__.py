@@ -963,6 +963,121 @@ def p25p1_frames_decode(d_dibits, d_llr, d_counts, d_hits, d_n_hits, observed_na
     return fr, vo
 
 
+class P25p1RxConfig(C.Structure):
+    _fields_ = [("n_channels", C.c_int), ("rate_hz", C.c_int), ("block_pairs", C.c_int), ("max_pairs_per_call", C.c_int),
+                ("input_cu8", C.c_int), ("fir_arith", C.c_int), ("max_hits", C.c_int), ("erasure_threshold", C.c_int),
+                ("hard_override_disabled", C.c_int), ("track_nac", C.c_int), ("channel_squelch_level", C.POINTER(C.c_float)),
+                ("p25_filter_taps", C.POINTER(C.c_float)), ("p25_filter_len", C.c_int)]
+
+
+class P25p1RxOut(C.Structure):
+    _fields_ = [("d_frames", C.c_void_p), ("frame_capacity", C.c_int), ("d_voices", C.c_void_p), ("voice_capacity", C.c_int),
+                ("d_totals", C.c_void_p), ("d_dibits", C.c_void_p), ("dibit_pitch", C.c_size_t), ("d_counts", C.c_void_p)]
+
+
+class P25p1RxHostOut(C.Structure):
+    _fields_ = [("h_frames", C.c_void_p), ("frame_capacity", C.c_int), ("h_voices", C.c_void_p), ("voice_capacity", C.c_int),
+                ("h_totals", C.c_void_p), ("h_dibits", C.c_void_p), ("dibit_pitch", C.c_size_t), ("h_counts", C.c_void_p)]
+
+
+class P25p1Rx:
+    """P25 Phase 1 C4FM receiver bank (dsdneo_b200_p25p1_rx_*): per-channel IQ -> frames / voice records / dibits."""
+
+    def __init__(self, n_channels, p25_taps, rate_hz=48000, block_pairs=8192, max_pairs_per_call=49152, input_cu8=True,
+                 fir_arith=FIR_ARITH_FMA, max_hits=32, track_nac=False):
+        import numpy as np
+
+        self._taps = np.ascontiguousarray(p25_taps, dtype=np.float32)
+        cfg = P25p1RxConfig()
+        cfg.n_channels, cfg.rate_hz, cfg.block_pairs, cfg.max_pairs_per_call = n_channels, rate_hz, block_pairs, max_pairs_per_call
+        cfg.input_cu8, cfg.fir_arith, cfg.max_hits, cfg.track_nac = 1 if input_cu8 else 0, fir_arith, max_hits, 1 if track_nac else 0
+        cfg.p25_filter_taps = self._taps.ctypes.data_as(C.POINTER(C.c_float))
+        cfg.p25_filter_len = self._taps.size
+        self.n_channels, self.input_cu8 = n_channels, input_cu8
+        self._h = lib().dsdneo_b200_p25p1_rx_create(C.byref(cfg))
+        if not self._h:
+            raise B200Error(f"p25p1_rx_create failed: {last_error()}")
+        self.frame_capacity = lib().dsdneo_b200_p25p1_rx_frame_capacity(self._h)
+        self.voice_capacity = lib().dsdneo_b200_p25p1_rx_voice_capacity(self._h)
+        self.dibit_pitch = lib().dsdneo_b200_p25p1_rx_dibit_pitch(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib().dsdneo_b200_p25p1_rx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def alloc_device_out(self, device, with_dibits=True):
+        import torch
+
+        o = {"frames": torch.zeros((self.frame_capacity, 128), dtype=torch.uint8, device=device),
+             "voices": torch.zeros((self.voice_capacity, 1944), dtype=torch.uint8, device=device),
+             "totals": torch.zeros(2, dtype=torch.int32, device=device)}
+        if with_dibits:
+            o["dibits"] = torch.zeros((self.n_channels, self.dibit_pitch), dtype=torch.uint8, device=device)
+            o["counts"] = torch.zeros(self.n_channels, dtype=torch.int32, device=device)
+        return o
+
+    def process(self, d_iq, n_pairs, out, stream=None):
+        """d_iq: cuda uint8 [n_ch, pitch, 2] (cu8) or float32 [n_ch, pitch, 2]; out from alloc_device_out."""
+        import torch
+
+        assert d_iq.is_cuda and d_iq.is_contiguous() and d_iq.shape[0] == self.n_channels
+        assert d_iq.dtype == (torch.uint8 if self.input_cu8 else torch.float32)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_iq.device)
+        o = P25p1RxOut(out["frames"].data_ptr(), out["frames"].shape[0], out["voices"].data_ptr(), out["voices"].shape[0],
+                       out["totals"].data_ptr(), out["dibits"].data_ptr() if "dibits" in out else None,
+                       out["dibits"].shape[1] if "dibits" in out else 0, out["counts"].data_ptr() if "counts" in out else None)
+        check(lib().dsdneo_b200_p25p1_rx_process(self._h, d_iq.data_ptr(), d_iq.shape[1], n_pairs, C.byref(o), _stream_ptr(stream)),
+              "p25p1_rx_process")
+
+    @staticmethod
+    def records(out):
+        """(frames, voices) numpy structured arrays of a finished device call (synchronises)."""
+        import torch
+
+        torch.cuda.synchronize()
+        nf, nv = (int(x) for x in out["totals"].cpu().numpy())
+        fr = out["frames"][:nf].cpu().numpy().reshape(-1).view(P25_FRAME_DTYPE)
+        vo = out["voices"][:nv].cpu().numpy().reshape(-1).view(P25_VOICE_DTYPE)
+        return fr, vo
+
+    def alloc_host_out(self, with_dibits=True):
+        import torch
+
+        o = {"frames": torch.zeros((self.frame_capacity, 128), dtype=torch.uint8).pin_memory(),
+             "voices": torch.zeros((self.voice_capacity, 1944), dtype=torch.uint8).pin_memory(),
+             "totals": torch.zeros(2, dtype=torch.int32).pin_memory()}
+        if with_dibits:
+            o["dibits"] = torch.zeros((self.n_channels, self.dibit_pitch), dtype=torch.uint8).pin_memory()
+            o["counts"] = torch.zeros(self.n_channels, dtype=torch.int32).pin_memory()
+        return o
+
+    def _host_out(self, out):
+        return P25p1RxHostOut(out["frames"].data_ptr(), out["frames"].shape[0], out["voices"].data_ptr(), out["voices"].shape[0],
+                              out["totals"].data_ptr(), out["dibits"].data_ptr() if "dibits" in out else None,
+                              out["dibits"].shape[1] if "dibits" in out else 0, out["counts"].data_ptr() if "counts" in out else None)
+
+    def submit_host(self, h_iq, n_pairs, out):
+        """h_iq: host tensor [n_ch, pitch, 2] (pinned for overlap).  Returns a ticket."""
+        o = self._host_out(out)
+        t = lib().dsdneo_b200_p25p1_rx_submit_host(self._h, h_iq.data_ptr(), h_iq.shape[1], n_pairs, C.byref(o))
+        if t < 0:
+            check(int(t), "p25p1_rx_submit_host")
+        return t
+
+    def wait_host(self, ticket):
+        check(lib().dsdneo_b200_p25p1_rx_wait_host(self._h, ticket), "p25p1_rx_wait_host")
+
+    @staticmethod
+    def host_records(out):
+        nf, nv = (int(x) for x in out["totals"].numpy())
+        return (out["frames"][:nf].numpy().reshape(-1).view(P25_FRAME_DTYPE).copy(),
+                out["voices"][:nv].numpy().reshape(-1).view(P25_VOICE_DTYPE).copy())
+
+
 def p25_word_decode(code: int, data_bits, parity_bits):
     """Golay(24,6)/(24,12)/Hamming(10,6,3) P25 words. Returns (data_bits corrected, status u8 [n], fixed i32 [n])."""
     import numpy as np

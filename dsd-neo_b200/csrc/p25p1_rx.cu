@@ -1,0 +1,590 @@
+// SPDX-License-Identifier: GPL-3.0-or-later
+/*
+ * P25 Phase 1 C4FM receiver bank: the whole hot path of BASELINE.json's metric for N already-channelised streams as ONE
+ * C-ABI object, device-resident from IQ to frames:
+ *
+ *   cu8 | cf32 IQ (48 kS/s per channel)                       reference, per channel (one process each)
+ *     -> widen_u8_to_f32_bias127                               src/dsp/simd_widen.cpp:139-147
+ *     -> full_demod (channel LPF, squelch, FSK discriminator)  src/dsp/demod_pipeline.cpp:1330-1350
+ *     -> p25_filter + getDibitSoft (getSymbol, use_symbol,     src/dsp/dsd_symbol.c:1853-1880, src/core/frames/dsd_dibit.c:1043-1089
+ *        digitize, soft metrics)
+ *     -> frame sync                                            src/dsp/dsd_frame_sync.c:3098-3148
+ *     -> NID read + p25p1_nid_decode                           src/engine/dispatch/dispatch_p25p1.c:121-143,203-223
+ *     -> processTSBK / processHDU / processLDU1 / processLDU2  src/protocol/p25/phase1/
+ *   -> frame records (NAC, DUID, TSBK octets, link-control / encryption-sync hex words after RS, LSD) and voice records
+ *      (the imbe_fr[8][23] + reliabilities the reference hands to processMbeFrameSoft), plus the dibit stream.
+ *
+ * Streaming: every channel keeps the last kKeep symbols of its sliced stream on the device, and frames are decoded
+ * kDelay = 864 symbols (one LDU) behind the slicer, so a frame that straddles two process() calls is decoded exactly once,
+ * from a contiguous stream, on the call that completes it.
+ *
+ * This file only composes the batched stages (demod_bank.cu, symbolizer.cu, framesync.cu, fec.cu) on the device; every stage
+ * fails loudly without a CUDA device, and there is no CPU path.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+using namespace dsdneo;
+
+namespace {
+
+constexpr int kKeep = 1024;  /* symbols of history kept per channel (>= kDelay + the 90 dibits a DMR burst looks back) */
+constexpr int kDelay = 864;  /* frames are decoded this many symbols behind the slicer: the longest frame (LDU) */
+static const char kP25Sync[] = "111113113311333313133333"; /* P25P1_SYNC, include/dsd-neo/core/sync_patterns.h:34 */
+
+__global__ void
+widen_cu8_kernel(const uchar2* __restrict__ in, size_t in_pitch, float2* __restrict__ out, size_t out_pitch, int n_pairs) {
+    const int ch = blockIdx.y;
+    const float inv = 1.0f / 127.5f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const uchar2 u = in[(size_t)ch * in_pitch + i];
+        /* widen_u8_to_f32_bias127: (float(u8) - 127.5f) * (1.0f / 127.5f) */
+        out[(size_t)ch * out_pitch + i] = make_float2(__fmul_rn(__fsub_rn((float)u.x, 127.5f), inv), __fmul_rn(__fsub_rn((float)u.y, 127.5f), inv));
+    }
+}
+
+/* the last kKeep entries of the previous call's stream become the head of this call's stream (ping-pong buffers) */
+__global__ void
+stream_tail_kernel(const uint8_t* dib_prev, const uint8_t* rel_prev, const short2* llr_prev, const float* sym_prev, uint8_t* dib,
+                   uint8_t* rel, short2* llr, float* sym, const int* count_prev, size_t pitch) {
+    const int ch = blockIdx.x;
+    const int src0 = count_prev[ch]; /* previous valid length was kKeep + count_prev */
+    const size_t row = (size_t)ch * pitch;
+    for (int i = threadIdx.x; i < kKeep; i += blockDim.x) {
+        dib[row + i] = dib_prev[row + src0 + i];
+        rel[row + i] = rel_prev[row + src0 + i];
+        llr[row + i] = llr_prev[row + src0 + i];
+        sym[row + i] = sym_prev[row + src0 + i];
+    }
+}
+
+__global__ void
+stream_account_kernel(const int* count_new, int* valid, long long* stream_base, long long* total, int n_ch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) {
+        return;
+    }
+    /* buffer index 0 of this call = stream index (symbols before this call) - kKeep */
+    stream_base[c] = total[c] - kKeep;
+    total[c] += count_new[c];
+    valid[c] = kKeep + count_new[c];
+}
+
+/* per-slot observed NAC for the known-NAC retry of p25p1_nid_decode = the channel's last decoded NAC */
+__global__ void
+expand_nac_kernel(const int* chan_nac, int* slot_nac, int n_ch, int max_hits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ch * max_hits) {
+        slot_nac[i] = chan_nac[i / max_hits];
+    }
+}
+
+/* p25p1_apply_nac_update (dispatch_p25p1.c:145-157): the last valid decoded NAC of the call becomes the channel's NAC */
+__global__ void
+update_nac_kernel(const dsdneo_b200_p25p1_frame* frames, const int* frame_off, const int* n_hits, int max_hits, int* chan_nac,
+                  int n_ch, int frame_capacity) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) {
+        return;
+    }
+    const int n = min(n_hits[c], max_hits);
+    int nac = chan_nac[c];
+    for (int h = 0; h < n; h++) {
+        const int r = frame_off[c] + h;
+        if (r >= frame_capacity) {
+            break;
+        }
+        const int v = frames[r].nac;
+        if (frames[r].nid_status > 0 && v != 0 && v != 0xFFF) {
+            nac = v;
+        }
+    }
+    chan_nac[c] = nac;
+}
+
+}  // namespace
+
+struct dsdneo_b200_p25p1_rx {
+    dsdneo_b200_p25p1_rx_config cfg;
+    int n_ch, max_hits, cap_pairs, cap_new; /* cap_new = symbols one call can add per channel */
+    size_t pitch;                            /* stream row pitch = kKeep + cap_new */
+    dsdneo_b200_demod_bank* bank;
+    dsdneo_b200_symbolizer* sym;
+    dsdneo_b200_frame_sync* fs;
+    float2* d_iq;      /* widened input when the caller feeds cu8 */
+    float* d_disc;
+    int phase;         /* which of the two stream buffer sets receives this call */
+    uint8_t *d_dib[2], *d_rel[2];
+    int16_t* d_llr[2];
+    float* d_symv[2];
+    int *d_count[2], *d_valid;
+    long long *d_stream_base, *d_total;
+    int *d_hits, *d_n_hits;
+    uint8_t *d_code63, *d_rel63, *d_par, *d_prel, *d_nid_valid, *d_pay_dummy, *d_pay_valid;
+    int16_t* d_payllr_dummy;
+    int8_t* d_nid_status;
+    int *d_nid_nac, *d_nid_errs, *d_slot_nac, *d_chan_nac;
+    uint8_t* d_nid_duid;
+    int *d_frame_off, *d_voice_off;
+    /* host path */
+    int host_ready;
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_small[2], ev_in_free[2], ev_out_free[2];
+    void* d_in[2];
+    size_t in_cap;
+    dsdneo_b200_p25p1_frame* d_frames[2];
+    dsdneo_b200_p25p1_voice* d_voices[2];
+    int* d_totals[2];
+    int* h_totals; /* pinned, [2][2] */
+    unsigned long long tickets, waited;
+    dsdneo_b200_p25p1_rx_host_out pending[2];
+};
+
+extern "C" {
+
+void
+dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
+    if (!rx) {
+        return;
+    }
+    dsdneo_b200_demod_bank_destroy(rx->bank);
+    dsdneo_b200_symbolizer_destroy(rx->sym);
+    dsdneo_b200_frame_sync_destroy(rx->fs);
+    cudaFree(rx->d_iq);
+    cudaFree(rx->d_disc);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(rx->d_dib[i]);
+        cudaFree(rx->d_rel[i]);
+        cudaFree(rx->d_llr[i]);
+        cudaFree(rx->d_symv[i]);
+        cudaFree(rx->d_count[i]);
+        cudaFree(rx->d_in[i]);
+        cudaFree(rx->d_frames[i]);
+        cudaFree(rx->d_voices[i]);
+        cudaFree(rx->d_totals[i]);
+    }
+    cudaFree(rx->d_valid);
+    cudaFree(rx->d_stream_base);
+    cudaFree(rx->d_total);
+    cudaFree(rx->d_hits);
+    cudaFree(rx->d_n_hits);
+    cudaFree(rx->d_code63);
+    cudaFree(rx->d_rel63);
+    cudaFree(rx->d_par);
+    cudaFree(rx->d_prel);
+    cudaFree(rx->d_nid_valid);
+    cudaFree(rx->d_pay_dummy);
+    cudaFree(rx->d_pay_valid);
+    cudaFree(rx->d_payllr_dummy);
+    cudaFree(rx->d_nid_status);
+    cudaFree(rx->d_nid_nac);
+    cudaFree(rx->d_nid_errs);
+    cudaFree(rx->d_slot_nac);
+    cudaFree(rx->d_chan_nac);
+    cudaFree(rx->d_nid_duid);
+    cudaFree(rx->d_frame_off);
+    cudaFree(rx->d_voice_off);
+    if (rx->host_ready) {
+        cudaStreamDestroy(rx->s_h2d);
+        cudaStreamDestroy(rx->s_comp);
+        cudaStreamDestroy(rx->s_d2h);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(rx->ev_h2d[i]);
+            cudaEventDestroy(rx->ev_comp[i]);
+            cudaEventDestroy(rx->ev_small[i]);
+            cudaEventDestroy(rx->ev_in_free[i]);
+            cudaEventDestroy(rx->ev_out_free[i]);
+        }
+        cudaFreeHost(rx->h_totals);
+    }
+    free(rx);
+}
+
+int
+dsdneo_b200_p25p1_rx_frame_capacity(const dsdneo_b200_p25p1_rx* rx) {
+    return rx ? rx->n_ch * rx->max_hits : 0;
+}
+
+int
+dsdneo_b200_p25p1_rx_voice_capacity(const dsdneo_b200_p25p1_rx* rx) {
+    /* at most one LDU per 864 symbols of new stream, plus one that was pending */
+    return rx ? rx->n_ch * (rx->cap_new / kDelay + 2) : 0;
+}
+
+size_t
+dsdneo_b200_p25p1_rx_dibit_pitch(const dsdneo_b200_p25p1_rx* rx) {
+    return rx ? (size_t)rx->cap_new : 0;
+}
+
+dsdneo_b200_p25p1_rx*
+dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
+    if (!cfg || cfg->n_channels <= 0 || cfg->rate_hz <= 0 || cfg->block_pairs <= 0 || cfg->max_pairs_per_call < cfg->block_pairs
+        || cfg->max_pairs_per_call % cfg->block_pairs != 0 || !cfg->p25_filter_taps || cfg->p25_filter_len <= 0) {
+        set_error("p25p1_rx_create: bad config (max_pairs_per_call must be a positive multiple of block_pairs; the p25_filter taps "
+                  "for this sample rate are required)");
+        return NULL;
+    }
+    if (ensure_device()) {
+        return NULL;
+    }
+    dsdneo_b200_p25p1_rx* rx = (dsdneo_b200_p25p1_rx*)calloc(1, sizeof(*rx));
+    if (!rx) {
+        set_error("p25p1_rx_create: out of host memory");
+        return NULL;
+    }
+    rx->cfg = *cfg;
+    rx->n_ch = cfg->n_channels;
+    rx->max_hits = cfg->max_hits > 0 ? (cfg->max_hits > 32 ? 32 : cfg->max_hits) : 32;
+    rx->cap_pairs = cfg->max_pairs_per_call;
+    const int symrate = 4800;
+    int whole = cfg->rate_hz / symrate;
+    whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
+    rx->cap_new = (int)(((size_t)rx->cap_pairs + 96) / (size_t)(whole - 1) + 2);
+    rx->cap_new = (rx->cap_new + 31) & ~31;
+    rx->pitch = (size_t)kKeep + (size_t)rx->cap_new;
+    const size_t n = (size_t)rx->n_ch, slots = n * (size_t)rx->max_hits;
+
+    dsdneo_b200_demod_bank_config bc;
+    memset(&bc, 0, sizeof(bc));
+    bc.n_channels = rx->n_ch;
+    bc.rate_out_hz = cfg->rate_hz;
+    bc.channel_lpf_enable = 1;
+    bc.channel_lpf_profile = NULL; /* P25_C4FM */
+    bc.channel_squelch_level = cfg->channel_squelch_level;
+    bc.fir_arith = cfg->fir_arith;
+    rx->bank = dsdneo_b200_demod_bank_create(&bc);
+    dsdneo_b200_symbolizer_config sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.n_channels = rx->n_ch;
+    sc.output_rate_hz = cfg->rate_hz;
+    sc.symbol_rate_hz = symrate;
+    sc.use_cosine_filter = 1;
+    sc.n_filters = 1;
+    sc.filter_taps[0] = cfg->p25_filter_taps;
+    sc.filter_len[0] = cfg->p25_filter_len;
+    rx->sym = rx->bank ? dsdneo_b200_symbolizer_create(&sc) : NULL;
+    dsdneo_b200_sync_pattern pat = {kP25Sync, 0 /* DSD_SYNC_P25P1_POS */};
+    rx->fs = rx->sym ? dsdneo_b200_frame_sync_create(rx->n_ch, &pat, 1) : NULL;
+    if (!rx->bank || !rx->sym || !rx->fs) {
+        dsdneo_b200_p25p1_rx_destroy(rx);
+        return NULL;
+    }
+    /* every channel: P25 Phase 1 positive sync class (p25_filter, window 2/2, min / max tracking) */
+    {
+        dsdneo_b200_sym_class one;
+        dsdneo_b200_sym_class* cls = (dsdneo_b200_sym_class*)malloc(n * sizeof(*cls));
+        if (!cls || dsdneo_b200_sym_class_from_synctype(0, 0, 1, &one) != 0) {
+            free(cls);
+            dsdneo_b200_p25p1_rx_destroy(rx);
+            return NULL;
+        }
+        for (size_t i = 0; i < n; i++) {
+            cls[i] = one;
+        }
+        const int rc = dsdneo_b200_symbolizer_set_class(rx->sym, cls);
+        free(cls);
+        if (rc) {
+            dsdneo_b200_p25p1_rx_destroy(rx);
+            return NULL;
+        }
+    }
+    cudaError_t e = cudaSuccess;
+#define RX_ALLOC(ptr, bytes)                                                                                           \
+    if (e == cudaSuccess) {                                                                                            \
+        e = cudaMalloc((void**)&(ptr), (bytes));                                                                       \
+        if (e == cudaSuccess) {                                                                                        \
+            e = cudaMemset((ptr), 0, (bytes));                                                                         \
+        }                                                                                                              \
+    }
+    if (cfg->input_cu8) {
+        RX_ALLOC(rx->d_iq, n * (size_t)rx->cap_pairs * sizeof(float2));
+    }
+    RX_ALLOC(rx->d_disc, n * (size_t)rx->cap_pairs * sizeof(float));
+    for (int i = 0; i < 2; i++) {
+        RX_ALLOC(rx->d_dib[i], n * rx->pitch);
+        RX_ALLOC(rx->d_rel[i], n * rx->pitch);
+        RX_ALLOC(rx->d_llr[i], n * rx->pitch * 2 * sizeof(int16_t));
+        RX_ALLOC(rx->d_symv[i], n * rx->pitch * sizeof(float));
+        RX_ALLOC(rx->d_count[i], n * sizeof(int));
+    }
+    RX_ALLOC(rx->d_valid, n * sizeof(int));
+    RX_ALLOC(rx->d_stream_base, n * sizeof(long long));
+    RX_ALLOC(rx->d_total, n * sizeof(long long));
+    RX_ALLOC(rx->d_hits, slots * 2 * sizeof(int));
+    RX_ALLOC(rx->d_n_hits, n * sizeof(int));
+    RX_ALLOC(rx->d_code63, slots * 63);
+    RX_ALLOC(rx->d_rel63, slots * 63);
+    RX_ALLOC(rx->d_par, slots);
+    RX_ALLOC(rx->d_prel, slots);
+    RX_ALLOC(rx->d_nid_valid, slots);
+    RX_ALLOC(rx->d_pay_dummy, slots);
+    RX_ALLOC(rx->d_pay_valid, slots);
+    RX_ALLOC(rx->d_payllr_dummy, slots * 2 * sizeof(int16_t));
+    RX_ALLOC(rx->d_nid_status, slots);
+    RX_ALLOC(rx->d_nid_nac, slots * sizeof(int));
+    RX_ALLOC(rx->d_nid_errs, slots * sizeof(int));
+    RX_ALLOC(rx->d_slot_nac, slots * sizeof(int));
+    RX_ALLOC(rx->d_chan_nac, n * sizeof(int));
+    RX_ALLOC(rx->d_nid_duid, slots);
+    RX_ALLOC(rx->d_frame_off, n * sizeof(int));
+    RX_ALLOC(rx->d_voice_off, n * sizeof(int));
+#undef RX_ALLOC
+    if (e != cudaSuccess) {
+        cuda_fail(e, "p25p1_rx_create", __FILE__, __LINE__);
+        dsdneo_b200_p25p1_rx_destroy(rx);
+        return NULL;
+    }
+    return rx;
+}
+
+int
+dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
+                             const dsdneo_b200_p25p1_rx_out* out, void* stream) {
+    if (!rx || !d_iq || !out || !out->d_frames || !out->d_totals || n_pairs <= 0 || n_pairs > rx->cap_pairs
+        || n_pairs % rx->cfg.block_pairs != 0 || iq_pitch_pairs < (size_t)n_pairs || out->frame_capacity <= 0
+        || (out->voice_capacity > 0 && !out->d_voices)) {
+        set_error("p25p1_rx_process: bad argument (n_pairs must be a multiple of block_pairs, at most max_pairs_per_call)");
+        return DSDNEO_B200_EINVAL;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int n_ch = rx->n_ch, cur = rx->phase, prev = rx->phase ^ 1;
+    const float* iq = (const float*)d_iq;
+    size_t pitch_pairs = iq_pitch_pairs;
+    if (rx->cfg.input_cu8) {
+        KernelTimer kt("widen_cu8_kernel", s);
+        dim3 grid((unsigned)((n_pairs + 1023) / 1024), (unsigned)n_ch);
+        widen_cu8_kernel<<<grid, 256, 0, s>>>((const uchar2*)d_iq, iq_pitch_pairs, rx->d_iq, (size_t)rx->cap_pairs, n_pairs);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+        iq = (const float*)rx->d_iq;
+        pitch_pairs = (size_t)rx->cap_pairs;
+    }
+    int rc = dsdneo_b200_full_demod_batch(rx->bank, iq, pitch_pairs, rx->cfg.block_pairs, n_pairs / rx->cfg.block_pairs, rx->d_disc,
+                                          (size_t)rx->cap_pairs, stream);
+    if (rc) {
+        return rc;
+    }
+    {
+        KernelTimer kt("stream_tail_kernel", s);
+        stream_tail_kernel<<<n_ch, 256, 0, s>>>(rx->d_dib[prev], rx->d_rel[prev], (const short2*)rx->d_llr[prev], rx->d_symv[prev],
+                                               rx->d_dib[cur], rx->d_rel[cur], (short2*)rx->d_llr[cur], rx->d_symv[cur],
+                                               rx->d_count[prev], rx->pitch);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
+    dsdneo_b200_symbol_out so;
+    so.d_symbols = rx->d_symv[cur] + kKeep;
+    so.d_dibits = rx->d_dib[cur] + kKeep;
+    so.d_reliability = rx->d_rel[cur] + kKeep;
+    so.d_llr = rx->d_llr[cur] + 2 * kKeep;
+    so.d_count = rx->d_count[cur];
+    so.pitch = rx->pitch;
+    rc = dsdneo_b200_symbolize_batch(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, stream);
+    if (rc) {
+        return rc;
+    }
+    {
+        KernelTimer kt("stream_account_kernel", s);
+        stream_account_kernel<<<(n_ch + 127) / 128, 128, 0, s>>>(rx->d_count[cur], rx->d_valid, rx->d_stream_base, rx->d_total, n_ch);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
+    const int region = kKeep - kDelay;
+    rc = dsdneo_b200_frame_sync_search_batch(rx->fs, rx->d_symv[cur] + region, rx->pitch, rx->d_count[cur],
+                                             (dsdneo_b200_sync_hit*)rx->d_hits, rx->max_hits, rx->d_n_hits, stream);
+    if (rc) {
+        return rc;
+    }
+    rc = dsdneo_p25p1_frame_cut_region(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid, rx->d_hits, rx->d_n_hits, n_ch,
+                                       rx->max_hits, 0, rx->d_code63, rx->d_rel63, rx->d_par, rx->d_prel, rx->d_nid_valid,
+                                       rx->d_pay_dummy, rx->d_payllr_dummy, rx->d_pay_valid, region, stream);
+    if (rc) {
+        return rc;
+    }
+    const int slots = n_ch * rx->max_hits;
+    {
+        KernelTimer kt("expand_nac_kernel", s);
+        expand_nac_kernel<<<(slots + 255) / 256, 256, 0, s>>>(rx->d_chan_nac, rx->d_slot_nac, n_ch, rx->max_hits);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
+    const int threshold = rx->cfg.erasure_threshold > 0 ? rx->cfg.erasure_threshold : 64;
+    rc = dsdneo_b200_p25p1_nid_decode_batch(rx->d_code63, rx->d_rel63, rx->cfg.track_nac ? rx->d_slot_nac : NULL, rx->d_par, rx->d_prel,
+                                            threshold, rx->d_nid_status, rx->d_nid_nac, rx->d_nid_duid, rx->d_nid_errs, slots, stream);
+    if (rc) {
+        return rc;
+    }
+    rc = dsdneo_b200_p25p1_frames_decode_batch(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid,
+                                               (const dsdneo_b200_sync_hit*)rx->d_hits, rx->d_n_hits, n_ch, rx->max_hits, region,
+                                               rx->d_stream_base, rx->d_nid_status, rx->d_nid_valid, rx->d_nid_nac, rx->d_nid_duid,
+                                               rx->d_nid_errs, threshold, rx->cfg.hard_override_disabled ? 0 : 1, rx->d_frame_off,
+                                               rx->d_voice_off, out->d_totals, out->d_frames, out->frame_capacity, out->d_voices,
+                                               out->voice_capacity, stream);
+    if (rc) {
+        return rc;
+    }
+    if (rx->cfg.track_nac) {
+        KernelTimer kt("update_nac_kernel", s);
+        update_nac_kernel<<<(n_ch + 127) / 128, 128, 0, s>>>(out->d_frames, rx->d_frame_off, rx->d_n_hits, rx->max_hits, rx->d_chan_nac,
+                                                            n_ch, out->frame_capacity);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+    }
+    if (out->d_dibits) { /* the call's new dibits, [n_channels][dibit_pitch], + counts */
+        DSDNEO_CUDA(cudaMemcpy2DAsync(out->d_dibits, out->dibit_pitch, rx->d_dib[cur] + kKeep, rx->pitch,
+                                      (size_t)min((size_t)rx->cap_new, out->dibit_pitch), (size_t)n_ch, cudaMemcpyDeviceToDevice, s));
+    }
+    if (out->d_counts) {
+        DSDNEO_CUDA(cudaMemcpyAsync(out->d_counts, rx->d_count[cur], (size_t)n_ch * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+    rx->phase ^= 1;
+    return 0;
+}
+
+/*
+ * Host-buffer streaming form (the reference's demod thread consumes its input ring the same way, src/io/radio/rtl_sdr_fm.cpp:
+ * 3458-3512): submit(tile i) queues H2D, the whole chain and the D2H of the dibit stream on three internal streams and
+ * returns a ticket; wait(ticket) blocks until the tile's results are in the caller's buffers.  The record counts are only
+ * known after the tile ran, so wait() copies exactly totals[0] frame and totals[1] voice records.  At most two tiles may be
+ * in flight: submit() first completes the tile submitted two calls earlier if the caller has not waited for it yet.
+ */
+static int
+rx_host_init(dsdneo_b200_p25p1_rx* rx) {
+    if (rx->host_ready) {
+        return 0;
+    }
+    DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_h2d, cudaStreamNonBlocking));
+    DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_comp, cudaStreamNonBlocking));
+    DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_comp[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_small[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_in_free[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_out_free[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaMalloc((void**)&rx->d_frames[i], (size_t)dsdneo_b200_p25p1_rx_frame_capacity(rx) * sizeof(dsdneo_b200_p25p1_frame)));
+        DSDNEO_CUDA(cudaMalloc((void**)&rx->d_voices[i], (size_t)dsdneo_b200_p25p1_rx_voice_capacity(rx) * sizeof(dsdneo_b200_p25p1_voice)));
+        DSDNEO_CUDA(cudaMalloc((void**)&rx->d_totals[i], 2 * sizeof(int)));
+    }
+    DSDNEO_CUDA(cudaMallocHost((void**)&rx->h_totals, 4 * sizeof(int)));
+    rx->host_ready = 1;
+    return 0;
+}
+
+int
+dsdneo_b200_p25p1_rx_wait_host(dsdneo_b200_p25p1_rx* rx, long long ticket) {
+    if (!rx || !rx->host_ready || ticket < 0 || (unsigned long long)ticket >= rx->tickets) {
+        set_error("p25p1_rx_wait_host: unknown ticket");
+        return DSDNEO_B200_EINVAL;
+    }
+    if ((unsigned long long)ticket < rx->waited) {
+        return 0; /* already completed (by an earlier wait or by a later submit) */
+    }
+    for (unsigned long long t = rx->waited; t <= (unsigned long long)ticket; t++) {
+        const int slot = (int)(t & 1);
+        const dsdneo_b200_p25p1_rx_host_out* o = &rx->pending[slot];
+        DSDNEO_CUDA(cudaEventSynchronize(rx->ev_small[slot])); /* totals, dibits and counts are in host memory */
+        int nf = rx->h_totals[2 * slot], nv = rx->h_totals[2 * slot + 1];
+        nf = nf > o->frame_capacity ? o->frame_capacity : nf;
+        nv = nv > o->voice_capacity ? o->voice_capacity : nv;
+        if (nf > 0) {
+            DSDNEO_CUDA(cudaMemcpyAsync(o->h_frames, rx->d_frames[slot], (size_t)nf * sizeof(dsdneo_b200_p25p1_frame), cudaMemcpyDeviceToHost,
+                                        rx->s_d2h));
+        }
+        if (nv > 0 && o->h_voices) {
+            DSDNEO_CUDA(cudaMemcpyAsync(o->h_voices, rx->d_voices[slot], (size_t)nv * sizeof(dsdneo_b200_p25p1_voice), cudaMemcpyDeviceToHost,
+                                        rx->s_d2h));
+        }
+        DSDNEO_CUDA(cudaEventRecord(rx->ev_out_free[slot], rx->s_d2h));
+        DSDNEO_CUDA(cudaEventSynchronize(rx->ev_out_free[slot]));
+        if (o->h_totals) {
+            o->h_totals[0] = nf;
+            o->h_totals[1] = nv;
+        }
+        rx->waited = t + 1;
+    }
+    return 0;
+}
+
+long long
+dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
+                                 const dsdneo_b200_p25p1_rx_host_out* out) {
+    if (!rx || !h_iq || !out || !out->h_frames || out->frame_capacity <= 0 || n_pairs <= 0 || n_pairs > rx->cap_pairs
+        || iq_pitch_pairs < (size_t)n_pairs) {
+        set_error("p25p1_rx_submit_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = rx_host_init(rx);
+    if (rc) {
+        return rc;
+    }
+    if (rx->tickets >= 2 && rx->waited + 2 <= rx->tickets) { /* the slot about to be reused still holds an unread tile */
+        rc = dsdneo_b200_p25p1_rx_wait_host(rx, (long long)(rx->tickets - 2));
+        if (rc) {
+            return rc;
+        }
+    }
+    const int slot = (int)(rx->tickets & 1);
+    const size_t elt = rx->cfg.input_cu8 ? 2 : 8;
+    const size_t in_bytes = (size_t)rx->n_ch * iq_pitch_pairs * elt;
+    if (rx->in_cap < in_bytes) {
+        DSDNEO_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; i++) {
+            cudaFree(rx->d_in[i]);
+            rx->d_in[i] = NULL;
+            DSDNEO_CUDA(cudaMalloc(&rx->d_in[i], in_bytes));
+        }
+        rx->in_cap = in_bytes;
+    }
+    if (rx->tickets >= 2) {
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_h2d, rx->ev_in_free[slot], 0)); /* the chain two tiles back consumed d_in[slot] */
+    }
+    DSDNEO_CUDA(cudaMemcpyAsync(rx->d_in[slot], h_iq, in_bytes, cudaMemcpyHostToDevice, rx->s_h2d));
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_h2d[slot], rx->s_h2d));
+    DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_comp, rx->ev_h2d[slot], 0));
+    if (rx->tickets >= 2) {
+        /* the stream buffers this tile writes were last read by the dibit D2H of the tile two calls back (the tile in
+         * between only read them for its tail and wrote the other set) */
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_comp, rx->ev_small[slot], 0));
+    }
+    dsdneo_b200_p25p1_rx_out dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.d_frames = rx->d_frames[slot];
+    dev.frame_capacity = dsdneo_b200_p25p1_rx_frame_capacity(rx);
+    dev.d_voices = rx->d_voices[slot];
+    dev.voice_capacity = dsdneo_b200_p25p1_rx_voice_capacity(rx);
+    dev.d_totals = rx->d_totals[slot];
+    rc = dsdneo_b200_p25p1_rx_process(rx, rx->d_in[slot], iq_pitch_pairs, n_pairs, &dev, rx->s_comp);
+    if (rc) {
+        return rc;
+    }
+    const int cur = rx->phase ^ 1; /* the stream buffers this tile was written to */
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_in_free[slot], rx->s_comp));
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_comp[slot], rx->s_comp));
+    DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d2h, rx->ev_comp[slot], 0));
+    DSDNEO_CUDA(cudaMemcpyAsync(rx->h_totals + 2 * slot, rx->d_totals[slot], 2 * sizeof(int), cudaMemcpyDeviceToHost, rx->s_d2h));
+    if (out->h_dibits) {
+        DSDNEO_CUDA(cudaMemcpy2DAsync(out->h_dibits, out->dibit_pitch, rx->d_dib[cur] + kKeep, rx->pitch,
+                                      (size_t)min((size_t)rx->cap_new, out->dibit_pitch), (size_t)rx->n_ch, cudaMemcpyDeviceToHost, rx->s_d2h));
+    }
+    if (out->h_counts) {
+        DSDNEO_CUDA(cudaMemcpyAsync(out->h_counts, rx->d_count[cur], (size_t)rx->n_ch * sizeof(int), cudaMemcpyDeviceToHost, rx->s_d2h));
+    }
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_small[slot], rx->s_d2h));
+    rx->pending[slot] = *out;
+    return (long long)rx->tickets++;
+}
+
+int
+dsdneo_b200_p25p1_rx_process_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
+                                  const dsdneo_b200_p25p1_rx_host_out* out) {
+    const long long t = dsdneo_b200_p25p1_rx_submit_host(rx, h_iq, iq_pitch_pairs, n_pairs, out);
+    if (t < 0) {
+        return (int)t;
+    }
+    return dsdneo_b200_p25p1_rx_wait_host(rx, t);
+}
+
+} /* extern "C" */

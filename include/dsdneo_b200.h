@@ -847,6 +847,67 @@ uint32_t dsdneo_b200_stream_hook_stream_generation(void);
 int dsdneo_b200_stream_hook_cqpsk_status(int* out_cqpsk_enable, int* out_cqpsk_timing_active);
 double dsdneo_b200_stream_hook_snr_cqpsk_db(void);
 
+
+/* ---- P25 Phase 1 C4FM receiver bank: IQ -> frames in one object (the metric's chain, BASELINE.json configs[2]) ---------- */
+/*
+ * N already-channelised streams (48 kS/s cu8 or cf32 IQ, the reference's RTL ingest / --iq-replay format) through
+ *   widen_u8_to_f32_bias127 -> full_demod -> p25_filter + getDibitSoft -> frame sync -> NID -> TSBK / HDU / LDU1 / LDU2
+ * on the device, per channel what the reference runs as one process (dispatch: src/engine/dispatch/dispatch_p25p1.c:401-426).
+ * Every channel is configured as the reference is once it has seen a +P25p1 sync (synctype = lastsynctype = 0: p25_filter,
+ * window 2/2, min / max tracker).  Frames are decoded 864 symbols behind the slicer from a per-channel stream history kept
+ * on the device, so frames that straddle two calls are decoded once, from a contiguous stream.
+ */
+typedef struct dsdneo_b200_p25p1_rx_config {
+    int n_channels;
+    int rate_hz;             /* per-channel sample rate (48000) */
+    int block_pairs;         /* one full_demod() block (the reference's DEFAULT_BUF_LENGTH / 2 = 8192) */
+    int max_pairs_per_call;  /* capacity of one process call per channel; multiple of block_pairs */
+    int input_cu8;           /* 1 = cu8 IQ widened on the device, 0 = cf32 */
+    int fir_arith;           /* DSDNEO_FIR_ARITH_* */
+    int max_hits;            /* frame syncs kept per channel per call (<= 32; 0 = 32) */
+    int erasure_threshold;   /* p25p1_get_erasure_threshold() (0 = 64) */
+    int hard_override_disabled; /* !p25_soft_hard_override_enabled() */
+    int track_nac;           /* 1: the channel's last decoded NAC feeds the known-NAC retry of p25p1_nid_decode (state->nac) */
+    const float* channel_squelch_level; /* per channel or NULL (squelch off) */
+    const float* p25_filter_taps;       /* NORMALISED p25_filter taps for rate_hz as the reference's design_sps_fir leaves them */
+    int p25_filter_len;
+} dsdneo_b200_p25p1_rx_config;
+typedef struct dsdneo_b200_p25p1_rx_out { /* device buffers */
+    dsdneo_b200_p25p1_frame* d_frames;
+    int frame_capacity;
+    dsdneo_b200_p25p1_voice* d_voices;
+    int voice_capacity;
+    int32_t* d_totals;      /* {frame records, voice records} of this call */
+    uint8_t* d_dibits;      /* optional: the call's new dibits [n_channels][dibit_pitch] */
+    size_t dibit_pitch;
+    int32_t* d_counts;      /* optional: new dibits per channel */
+} dsdneo_b200_p25p1_rx_out;
+typedef struct dsdneo_b200_p25p1_rx_host_out { /* host buffers (pinned for overlap) */
+    dsdneo_b200_p25p1_frame* h_frames;
+    int frame_capacity;
+    dsdneo_b200_p25p1_voice* h_voices;
+    int voice_capacity;
+    int32_t* h_totals;
+    uint8_t* h_dibits;
+    size_t dibit_pitch;
+    int32_t* h_counts;
+} dsdneo_b200_p25p1_rx_host_out;
+typedef struct dsdneo_b200_p25p1_rx dsdneo_b200_p25p1_rx;
+dsdneo_b200_p25p1_rx* dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg);
+void dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx);
+int dsdneo_b200_p25p1_rx_frame_capacity(const dsdneo_b200_p25p1_rx* rx); /* records one call can produce at most */
+int dsdneo_b200_p25p1_rx_voice_capacity(const dsdneo_b200_p25p1_rx* rx);
+size_t dsdneo_b200_p25p1_rx_dibit_pitch(const dsdneo_b200_p25p1_rx* rx); /* dibits one call can add per channel at most */
+/** d_iq: [n_channels][iq_pitch_pairs] cu8 (uchar2) or cf32 (float2) per config; n_pairs a multiple of block_pairs. */
+int dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
+                                 const dsdneo_b200_p25p1_rx_out* out, void* stream);
+/** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned. */
+long long dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
+                                           const dsdneo_b200_p25p1_rx_host_out* out);
+int dsdneo_b200_p25p1_rx_wait_host(dsdneo_b200_p25p1_rx* rx, long long ticket);
+int dsdneo_b200_p25p1_rx_process_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
+                                      const dsdneo_b200_p25p1_rx_host_out* out);
+
 /* ---- K21: MBE speech synthesis stage, batched over frames -- PARITY UNPINNED ---------------------------------- */
 /*
  * dsd-neo obtains PCM from mbelib-neo 2.x (mbe_processImbe4400Dataf / mbe_processAmbe2450Dataf, call sites

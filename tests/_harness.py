@@ -1113,3 +1113,27 @@ def p25p1_build_hdu(rng, nac):
         out.append(_bits_to_dibits(golay_24_6_encode(int(sym))))
     body = [np.array(P25P1_SYNC_DIBITS), p25p1_nid_dibits(nac, 0x0)] + out + [np.zeros(5, np.int64)]
     return p25p1_insert_status(np.concatenate(body)), {"rs_data": dat.astype(np.uint8), "duid": 0}
+
+
+def synth_c4fm_iq(rng, dibits, snr_db=None, amp=0.6, pre=9, cu8=True):
+    """P25 C4FM on a complex carrier at 48 kS/s, 10 samples per symbol: TIA-102 shaping (raised cosine x inverse sinc), +-1.8 kHz
+    at the outer levels, phase-integrated, AWGN, optionally quantised like an RTL-SDR (cu8, the reference's --iq-replay
+    format).  `pre` = 9 lines the symbol centres up with getSymbol's window behind the 135-tap channel LPF (67 samples), the
+    discriminator and the 91-tap p25_filter (45 samples); found by scanning (the locked slicer never moves its window)."""
+    imp = np.zeros(len(dibits) * 10)
+    imp[::10] = LEVELS[np.asarray(dibits)]
+    f = np.concatenate([np.zeros(pre), np.convolve(imp, c4fm_shaping_taps(), mode="same")])
+    ph = 0.3 + np.cumsum(f * (2 * np.pi * 600.0 / 48000.0))
+    z = amp * np.exp(1j * ph)
+    if snr_db is not None:
+        sigma = amp * 10 ** (-snr_db / 20.0) / np.sqrt(2.0)
+        z = z + sigma * (rng.standard_normal(z.size) + 1j * rng.standard_normal(z.size))
+    iq = np.stack([z.real, z.imag], axis=1)
+    if cu8:
+        return np.clip(np.rint(iq * 127.5 + 127.5), 0, 255).astype(np.uint8)
+    return iq.astype(np.float32)
+
+
+def widen_cu8(u8):
+    """widen_u8_to_f32_bias127 (src/dsp/simd_widen.cpp:139-147)"""
+    return ((u8.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).astype(np.float32)

@@ -1,0 +1,138 @@
+"""The P25 Phase 1 receiver bank (dsdneo_b200_p25p1_rx_*, BASELINE.json configs[2] in miniature): cu8 IQ of several channels
+carrying HDU / LDU1 / LDU2 / TSDU frames -> frames, voice records and dibits through ONE C-ABI object, in several calls so
+that frames straddle call boundaries, device buffers and host buffers.  Expected values: the CPU oracle chain (widen ->
+full_demod -> p25_filter + getDibitSoft -> sync search -> frame handlers) run over each channel's WHOLE stream at once."""
+import numpy as np
+import pytest
+
+import _harness as H
+from test_frame_sync import oracle_search
+from test_gpu_symbolizer import _oracle_dibits, _taps
+
+pytestmark = pytest.mark.gpu
+P25_SYNC = "111113113311333313133333"
+BP = 4096
+
+
+def _channel(rng, n_sym_target, snr_db):
+    nac = int(rng.integers(1, 0xFFE))
+    parts, truth, n = [rng.integers(0, 4, 150)], [], 150
+    builders = [lambda: H.p25p1_build_hdu(rng, nac), lambda: H.p25p1_build_ldu(rng, nac, False), lambda: H.p25p1_build_ldu(rng, nac, True),
+                lambda: (H.p25p1_build_tsdu(rng, nac, 3, H._bch_nid_encoder())[0], {"duid": 7})]
+    k = 0
+    while n < n_sym_target - 900:
+        frame, t = builders[k % 4]()
+        k += 1
+        parts.append(frame)
+        truth.append((n + 23, nac, t))
+        n += frame.size
+    parts.append(rng.integers(0, 4, n_sym_target - n))
+    return H.synth_c4fm_iq(rng, np.concatenate(parts), snr_db=snr_db), truth
+
+
+def _oracle_chain(u8, taps):
+    x = H.widen_cu8(u8)
+    nb = x.shape[0] // BP
+    disc = H.oracle_full_demod(x[:nb * BP], BP, nb, fir_fma=1)
+    d, r, l, s = _oracle_dibits(disc, H.SYNC_P25P1_POS, taps)
+    n, pos, _, _, _ = oracle_search(s, [(P25_SYNC, 0)], max_hits=256)
+    return d, l, pos[:n]
+
+
+def _check(frames_by_ch, voices_all, chans, taps, n_calls_pairs):
+    recovered = 0
+    for c, (u8, truth) in enumerate(chans):
+        d, l, pos = _oracle_chain(u8[:n_calls_pairs], taps)
+        got = frames_by_ch[c]
+        # every sync the delayed search has passed (864 symbols behind the last slicer output) has a record, in stream order
+        want_pos = [int(p) for p in pos if p < d.size - 864]
+        assert [int(f["position"]) for f, _ in got] == want_pos, (c, [int(f["position"]) for f, _ in got][:6], want_pos[:6])
+        for (f, v), p in zip(got, want_pos):
+            n, of, ov = H.oracle_p25_decode(d, l, p, 0)
+            assert n != -1
+            for name in H.P25_FRAME_DTYPE.names:
+                if name in ("position", "channel", "voice_index", "reserved"):
+                    continue
+                assert np.array_equal(f[name], of[name]), (c, p, name, f[name], of[name])
+            if of["duid"] in (5, 10):
+                assert v is not None and np.array_equal(v["bits"], ov["bits"]) and np.array_equal(v["reliab"], ov["reliab"])
+        by_pos = {int(f["position"]): (f, v) for f, v in got}
+        for p0, nac, t in truth:
+            # the sliced stream lags the transmitted one by a few symbols (filter delays minus the shaping filter's advance)
+            for p in range(p0 + 3, p0 + 8):
+                if p not in by_pos:
+                    continue
+                f, v = by_pos[p]
+                ok = f["nid_status"] > 0 and f["nac"] == nac and f["duid"] == t["duid"]
+                if ok and "rs_data" in t:
+                    ok = f["rs_status"] in (0, 1) and np.array_equal(f["rs_data"][:t["rs_data"].size], t["rs_data"])
+                if ok and "voice" in t and c == 0:  # the noiseless channel: every vocoder bit is the transmitted one
+                    bits = ((v["bits"][:, :, None] >> np.arange(23, dtype=np.uint32)) & 1).reshape(9, 184)
+                    ok = np.array_equal(bits, t["voice"])
+                recovered += bool(ok)
+    return recovered
+
+
+def _split(frames, voices, n_ch):
+    out = [[] for _ in range(n_ch)]
+    for f in frames:
+        vi = int(f["voice_index"])
+        out[int(f["channel"])].append((f.copy(), voices[vi].copy() if vi >= 0 else None))
+    return out
+
+
+def test_rx_bank_device_buffers_frames_straddling_calls(gpu):
+    import torch
+
+    rng = np.random.default_rng(2525)
+    n_ch, n_sym = 6, 6200
+    taps = _taps()
+    chans = [_channel(rng, n_sym, snr_db=None if c == 0 else 22.0 - 2 * c) for c in range(n_ch)]
+    calls = [4 * BP, 2 * BP, 5 * BP, 3 * BP]  # 57344 of the 62000 pairs, uneven calls
+    rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=5 * BP, input_cu8=True)
+    out = rx.alloc_device_out("cuda")
+    per_ch = [[] for _ in range(n_ch)]
+    at = 0
+    for n_pairs in calls:
+        tile = np.stack([u8[at:at + n_pairs] for u8, _ in chans])
+        rx.process(torch.from_numpy(tile).cuda(), n_pairs, out)
+        fr, vo = rx.records(out)
+        for c, lst in enumerate(_split(fr, vo, n_ch)):
+            per_ch[c] += lst
+        at += n_pairs
+    recovered = _check(per_ch, None, chans, taps, at)
+    # the min / max tracker needs about 2000 symbols to settle from its +-30000 reset (the reference's sync warm start, not on
+    # this path, shortens that): frames after that must come out as transmitted
+    n_tx = sum(1 for _, truth in chans for p, _, _ in truth if 2200 < p < at // 10 - 900)
+    assert recovered >= 0.85 * n_tx and recovered >= 15, (recovered, n_tx)
+
+
+def test_rx_bank_host_streaming_equals_device_path(gpu):
+    import torch
+
+    rng = np.random.default_rng(77)
+    n_ch = 5
+    taps = _taps()
+    chans = [_channel(rng, 5000, snr_db=20.0) for c in range(n_ch)]
+    n_calls, n_pairs = 6, 2 * BP
+    dev = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=2 * BP)
+    host = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=2 * BP)
+    d_out = dev.alloc_device_out("cuda")
+    h_outs = [host.alloc_host_out() for _ in range(n_calls)]
+    tiles = [torch.from_numpy(np.stack([u8[i * n_pairs:(i + 1) * n_pairs] for u8, _ in chans])).pin_memory() for i in range(n_calls)]
+    # all tiles are submitted before the first wait: submit() itself completes tiles that would lose their slot
+    tickets = [host.submit_host(tiles[i], n_pairs, h_outs[i]) for i in range(n_calls)]
+    for t in tickets:
+        host.wait_host(t)
+    total = 0
+    for i in range(n_calls):
+        dev.process(tiles[i].cuda(), n_pairs, d_out)
+        fr_d, vo_d = dev.records(d_out)
+        fr_h, vo_h = host.host_records(h_outs[i])
+        assert fr_d.tobytes() == fr_h.tobytes() and vo_d.tobytes() == vo_h.tobytes()
+        assert torch.equal(d_out["counts"].cpu(), h_outs[i]["counts"])
+        cnt = h_outs[i]["counts"].numpy()
+        for c in range(n_ch):
+            assert torch.equal(d_out["dibits"][c, :cnt[c]].cpu(), h_outs[i]["dibits"][c, :cnt[c]])
+        total += fr_h.size
+    assert total >= n_ch * 6
