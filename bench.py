@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- the judged benchmark (contract in the task statement, section 4).
 
-Workload (BASELINE.json configs[1], "C2"): a 256-channel polyphase FIR channelizer + FM discriminator on
-synthetic 12.288 MS/s complex IQ, one B200 per 256-channel band.  One step = 1.024 s of wideband signal
-(12,582,912 cf32 samples = 100.7 MB) through
-    pfb256_kernel (channelizer) -> lpf_phase_kernel (135-tap channel LPF + phase discriminator)
-    -> disc_recurrence_kernel (dc/peak recurrences, scaling)          [= the reference's full_demod(), per channel]
-The metric is IQ MS/s (wideband complex samples consumed per second, whole job) and the channels that could be
-served in real time (`channels_at_realtime`).
+Default workload (BASELINE.json configs[2], "C3", the configuration the metric is quoted on): 1024 synthetic P25 Phase 1 C4FM
+channels per GPU, end to end.  One step = 1.024 s of signal on every channel (49152 cu8 IQ pairs at 48 kS/s = 100.7 MB per
+GPU, the reference's RTL ingest / --iq-replay sample format) through ONE C-ABI object, dsdneo_b200_p25p1_rx_*:
+    widen_u8_to_f32_bias127 -> full_demod (channel LPF + FSK discriminator) -> p25_filter + getDibitSoft (symbol timing,
+    threshold tracker, 4-level slicer, soft metrics) -> frame sync -> NID (BCH + Chase) -> processTSBK (half-rate trellis,
+    list-8 + CRC) / processHDU (Golay(24,6), RS(36,20,17)) / processLDU1,2 (IMBE de-interleave, Hamming(10,6,3),
+    RS(24,12,13) / RS(24,16,9), LSD)
+Outputs: frame records, the de-interleaved IMBE frames the reference hands to mbelib-neo, and the dibit stream.  (The
+vocoder itself is an un-vendored dependency of the reference: its parity cannot be pinned here, so it is not inside the
+judged step; `--workload mbe` times the synthesis stage separately.)
+The metric is IQ MS/s (complex channel samples consumed per second, whole job) and `channels_at_realtime`.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            this framework (CUDA, through the C-ABI)
-  python bench.py --impl reference [...]                         the reference's own CPU code on the host cores
+  python bench.py --impl reference [...]                         the reference's own CPU code on the host cores, same workload
+  python bench.py --workload c2 | cqpsk | fec [...]              developer lines (C2 = 256-channel channelizer + discriminator)
 """
 from __future__ import annotations
 
@@ -269,7 +274,7 @@ def cpu_reference_run(seconds_per_thread=None, blocks_per_thread=None):
             "blocks": sum(counts)}
 
 
-def run_reference_arm(args):
+def run_c2_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -300,7 +305,7 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------- our arm
 
-def run_b200_arm(args):
+def run_c2_b200_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -478,6 +483,416 @@ def run_b200_arm(args):
                    "host_numa_binding": "rank 0 on node %s" % numa_node if numa_node is not None else "none"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu_baseline, "e2e_matches_device_path": same,
+    }
+    print(json.dumps(line))
+
+
+# =============================================================================================== C3: the judged workload
+
+C3_CH = 1024            # channels per GPU
+C3_RATE = 48000
+C3_PAIRS = 49152        # IQ pairs per channel per step (1.024 s)
+C3_BLOCK = 8192         # one full_demod() block = the reference's DEFAULT_BUF_LENGTH (16384 floats)
+C3_TILES = 5            # rotating input tiles: 5 x 49152 samples = 24576 symbols, so the rotation closes on a whole symbol
+C3_SNR_DB = 20.0
+C3_WORKLOAD = ("C3: 1024 synthetic P25 Phase 1 C4FM channels per GPU, cu8 IQ at 48 kS/s -> full_demod -> p25_filter + "
+               "getDibitSoft -> frame sync -> NID -> TSBK half-rate trellis / HDU Golay + RS(36,20,17) / LDU1,2 IMBE "
+               "de-interleave + Hamming(10,6,3) + RS(24,12,13),(24,16,9) + LSD; frames, IMBE frames and dibits out")
+
+
+def c3_config():
+    """The SAME dictionary in both arms (driver: same_config)."""
+    return {"workload": C3_WORKLOAD, "channels_per_gpu": C3_CH, "channel_rate_hz": C3_RATE, "symbol_rate_hz": 4800,
+            "pairs_per_channel_per_step": C3_PAIRS, "block_pairs": C3_BLOCK, "input_format": "cu8 IQ (2 B per pair)",
+            "snr_db": C3_SNR_DB,
+            "traffic": "16 base channels tiled over the channels: 8 voice (HDU, 13 x {LDU1, LDU2}, TDU per 5.12 s) and 8 control "
+                       "(68 three-block TSDUs per 5.12 s), valid NID / trellis / Hamming / Golay / RS / LSD coding, random payloads",
+            "l2_policy": "5 rotating input tiles of 100.7 MB per GPU (503 MB > 126 MB L2); every step also streams about 0.9 GB of "
+                         "intermediates through HBM",
+            "parallelism": "channels sharded over GPUs (1024 per GPU), no data-path collective"}
+
+
+def _c4fm_shaping_taps(ntaps=241, fs=48000.0, rs=4800.0, alpha=0.2):
+    """P25 C4FM transmit shaping (TIA-102.BAAA: raised cosine alpha 0.2 times x / sin(x)), frequency-sampled."""
+    import numpy as np
+
+    N = 4096
+    f = np.fft.rfftfreq(N, 1 / fs)
+    T = 1 / rs
+    f1, f2 = (1 - alpha) / (2 * T), (1 + alpha) / (2 * T)
+    rc = np.zeros_like(f)
+    rc[f <= f1] = 1.0
+    m = (f > f1) & (f <= f2)
+    rc[m] = 0.5 * (1 + np.cos(np.pi * T / alpha * (f[m] - f1)))
+    x = np.pi * f * T
+    shp = np.ones_like(f)
+    shp[x > 0] = x[x > 0] / np.sin(x[x > 0])
+    h = np.fft.irfft(rc * np.where(f <= f2, shp, 0.0), N)
+    return np.roll(h, ntaps // 2)[:ntaps] * 10.0
+
+
+def c3_base_iq(seed=0):
+    """The 16 base channels as cu8 IQ, [16][5 * 49152][2]: the committed dibit streams (tests/golden/c3_p25_dibits.npz, frames
+    built by the test harness encoders) C4FM-shaped, FM-modulated at +-1.8 kHz outer deviation on a CIRCULAR time axis (the
+    rotation wraps without a symbol-timing jump), AWGN at C3_SNR_DB, quantised like an RTL-SDR."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c3_p25_dibits.npz"))
+    dib = g["dibits"]
+    levels = np.array([1.0, 3.0, -1.0, -3.0])
+    taps = _c4fm_shaping_taps()
+    rng = np.random.default_rng(0xC3 + seed)
+    n = dib.shape[1] * 10
+    assert n == C3_TILES * C3_PAIRS
+    out = np.empty((dib.shape[0], n, 2), np.uint8)
+    H = np.fft.rfft(np.roll(np.concatenate([taps, np.zeros(n - taps.size)]), -(taps.size // 2)))
+    for c in range(dib.shape[0]):
+        imp = np.zeros(n)
+        imp[::10] = levels[dib[c]]
+        f = np.roll(np.fft.irfft(np.fft.rfft(imp) * H, n), 9)  # 9 samples: symbol centres on the locked slicer's window
+        ph = np.cumsum(f * (2 * np.pi * 600.0 / 48000.0))
+        ph -= np.arange(1, n + 1) * (np.remainder(ph[-1], 2 * np.pi) / n)  # < 0.2 Hz offset: the phase closes over the rotation
+        z = 0.6 * np.exp(1j * (0.3 + ph))
+        sigma = 0.6 * 10 ** (-C3_SNR_DB / 20.0) / np.sqrt(2.0)
+        z = z + sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+        out[c, :, 0] = np.clip(np.rint(z.real * 127.5 + 127.5), 0, 255)
+        out[c, :, 1] = np.clip(np.rint(z.imag * 127.5 + 127.5), 0, 255)
+    return out
+
+
+def _p25_filter_taps():
+    """The reference's normalised p25_filter taps at 10 samples per symbol (read out of the unmodified reference by
+    tests/golden/make_golden.py; the dsd-neo glue passes its own table)."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sps_fir_taps.npz"))
+    return np.ascontiguousarray(g["f0_sps10"], np.float32)  # filter 0 = p25_filter
+
+
+# ----------------------------------------------------------------------------------------------- C3 reference arm
+
+class RefPool:
+    """The UNMODIFIED reference on the host cores, one forked worker per core (the reference keeps process-global state:
+    one channel per process).  Every worker owns one channel of the same synthetic workload and runs, per tile of 49152 cu8 pairs:
+    widen_u8_to_f32_bias127 -> full_demod (6 blocks of 8192 pairs, perf-bench flags, AVX2 dispatch) -> then per step
+    getDibitSoft over the step's discriminator samples through the reference's own hook seam -> frame sync search ->
+    dsd_dispatch_handle_p25p1 (NID, TSBK / HDU / LDU handlers, FEC leaves) on every sync.  States are created once; a step
+    is `tiles` tiles per worker, so steps measure steady state."""
+
+    def __init__(self, base_u8, cores=None):
+        import multiprocessing as mp
+
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.ctx = mp.get_context("fork")
+        self.base = base_u8
+        self.tiles = self.ctx.Value("i", 1)
+        self.stop = self.ctx.Value("i", 0)
+        self.b0 = self.ctx.Barrier(self.cores + 1)
+        self.b1 = self.ctx.Barrier(self.cores + 1)
+        self.frames = self.ctx.Array("l", self.cores)
+        self.kind = None
+        fast = os.path.join(ROOT, "oracle", "_ref", "libdsdneo_ref_fast.so")
+        p25 = os.path.join(ROOT, "oracle", "_ref", "libdsdneo_ref_p25.so")
+        if not (os.path.exists(fast) and os.path.exists(p25)):
+            raise SystemExit("bench.py: oracle/_ref is missing (run python __graft_entry__.py where /root/reference exists)")
+        self.paths = (fast, p25)
+        self.procs = [self.ctx.Process(target=self._worker, args=(i,), daemon=True) for i in range(self.cores)]
+        for p in self.procs:
+            p.start()
+
+    def _worker(self, idx):
+        import numpy as np
+
+        try:
+            os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[idx % len(os.sched_getaffinity(0))]})
+        except Exception:
+            pass
+        L, P = C.CDLL(self.paths[0]), C.CDLL(self.paths[1])
+        f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_ubyte)
+        L.ref_demod_create.restype = C.c_void_p
+        L.ref_demod_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.ref_demod_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.widen_u8_to_f32_bias127.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_sym_create.restype = C.c_void_p
+        L.ref_sym_create.argtypes = [C.c_int] * 7
+        L.ref_sym_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_long]
+        L.ref_sym_get_dibits.restype = C.c_long
+        L.ref_sym_get_dibits.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        P.ref_p25_decode_frame.restype = C.c_long
+        P.ref_p25_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_void_p]
+        rec = (C.c_ubyte * P.ref_p25_frame_size())()
+        demod = L.ref_demod_create(C3_RATE, 4800, 4, 1, 0.0)  # DSD_CH_LPF_PROFILE_P25_C4FM
+        sym = L.ref_sym_create(C3_RATE, 4800, 0, 0, 1, 128, 1024)
+        u8 = self.base[idx % self.base.shape[0]]
+        f32 = np.empty(2 * C3_PAIRS, np.float32)
+        sync = np.array([int(c) for c in "111113113311333313133333"], np.uint8)
+        tile_no = 0
+        disc = dib = rel = llr = symv = None
+        while True:
+            self.b0.wait()
+            if self.stop.value:
+                break
+            k_tiles = self.tiles.value
+            if disc is None or disc.size != k_tiles * C3_PAIRS:
+                disc = np.empty(k_tiles * C3_PAIRS, np.float32)
+                cap = disc.size // 9 + 16
+                dib, rel = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+                llr, symv = np.empty(2 * cap, np.int16), np.empty(cap, np.float32)
+            for k in range(k_tiles):
+                t = tile_no % C3_TILES
+                tile_no += 1
+                src = u8[t * C3_PAIRS:(t + 1) * C3_PAIRS]
+                L.widen_u8_to_f32_bias127(src.ctypes.data, f32.ctypes.data, 2 * C3_PAIRS)
+                for b in range(C3_PAIRS // C3_BLOCK):
+                    L.ref_demod_block(demod, f32.ctypes.data + 8 * b * C3_BLOCK, 2 * C3_BLOCK,
+                                      disc.ctypes.data + 4 * (k * C3_PAIRS + b * C3_BLOCK), C3_BLOCK)
+            L.ref_sym_feed(sym, disc.ctypes.data, disc.size)
+            nd = L.ref_sym_get_dibits(sym, dib.size, 12, dib.ctypes.data, rel.ctypes.data, llr.ctypes.data, symv.ctypes.data)
+            d = dib[:nd]
+            hits = np.nonzero((np.lib.stride_tricks.sliding_window_view(d, 24) == sync).all(axis=1))[0] + 23
+            n_fr = 0
+            for p in hits:
+                if p + 864 < nd:
+                    P.ref_p25_decode_frame(dib.ctypes.data, rel.ctypes.data, llr.ctypes.data, nd, int(p) + 1, 0, rec)
+                    n_fr += 1
+            self.frames[idx] = n_fr
+            self.b1.wait()
+
+    def step(self, tiles):
+        self.tiles.value = tiles
+        t0 = time.perf_counter()
+        self.b0.wait()
+        self.b1.wait()
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.stop.value = 1
+        try:
+            self.b0.wait(timeout=5)
+        except Exception:
+            pass
+        for p in self.procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+
+    def describe(self, tiles):
+        return ("%d forked workers (one per core), each ONE channel of the same synthetic workload through the unmodified reference: "
+                "widen_u8_to_f32_bias127 + full_demod (perf-bench flags, AVX2 FIR) + getDibitSoft (p25_filter, hook seam) + frame "
+                "sync + dsd_dispatch_handle_p25p1 (NID / TSBK / HDU / LDU handlers); states created once, %d tiles of 1.024 s per "
+                "worker per step" % (self.cores, tiles))
+
+
+def c3_reference_measure(steps, warmup, target_step_s=1.2):
+    base = c3_base_iq()
+    pool = RefPool(base)
+    try:
+        pool.step(1)  # plans the LPF, touches buffers
+        t1 = pool.step(2) / 2
+        tiles = int(max(4, min(256, round(target_step_s / max(t1, 1e-4)))))
+        for _ in range(max(0, warmup)):
+            pool.step(tiles)
+        times = [pool.step(tiles) for _ in range(steps)]
+        frames = sum(pool.frames[:])
+    finally:
+        pool.close()
+    dt = sum(times) / len(times)
+    value = pool.cores * tiles * C3_PAIRS / dt / 1e6
+    return {"value": value, "unit": "MS/s", "cores": pool.cores, "kind": "reference", "sample": pool.describe(tiles),
+            "ms_per_step": dt * 1e3, "tiles_per_worker_per_step": tiles, "frames_per_step": int(frames)}
+
+
+def run_c3_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    m = c3_reference_measure(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "iq_msps", "value": m["value"], "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "channels_at_realtime": m["value"] * 1e6 / C3_RATE, "config": c3_config(),
+        "cpu_baseline": {k: m[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": m["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "step": "bounded sample: %d tiles of 49152 pairs per worker per step, %d frames decoded in the last step"
+                                   % (m["tiles_per_worker_per_step"], m["frames_per_step"]),
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- C3 our arm
+
+def run_c3_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU path")
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None  # before any pinned allocation (first touch)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b200 = g.load_package()
+    b200.init(local)
+
+    def barrier():
+        if world > 1:
+            t = torch.zeros(1, device=dev)
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs: this rank's 1024 channels (channel c of the job = base channel c % 16, rotated per rank) ----
+    base = c3_base_iq(seed=rank)
+    idx = (np.arange(C3_CH) + 5 * rank) % base.shape[0]
+    h_tiles = []
+    for t in range(C3_TILES):
+        ht = torch.empty((C3_CH, C3_PAIRS, 2), dtype=torch.uint8).pin_memory()
+        ht.copy_(torch.from_numpy(np.ascontiguousarray(base[idx, t * C3_PAIRS:(t + 1) * C3_PAIRS])))
+        h_tiles.append(ht)
+    d_tiles = [t.to(dev) for t in h_tiles]
+    taps = _p25_filter_taps()
+    rx = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
+    out = rx.alloc_device_out(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    clocks = ClockSampler(local).start()
+    n_warm = max(args.warmup, C3_TILES)  # one full rotation: the threshold trackers settle, every code path is loaded
+    for i in range(n_warm):
+        rx.process(d_tiles[i % C3_TILES], C3_PAIRS, out, stream)
+    barrier()
+    b200.timing_enable(True)
+    launches0 = b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_frames = n_voice = n_good = 0
+    ev0.record(stream)
+    for i in range(args.steps):
+        rx.process(d_tiles[(i + n_warm) % C3_TILES], C3_PAIRS, out, stream)
+    ev1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = b200.launch_count() - launches0
+    ktimes = b200.timing_report()
+    b200.timing_enable(False)
+    clk = clocks.stop()
+    fr, vo = rx.records(out)  # the last step's records: how much real traffic the step decoded
+    n_frames, n_voice = int(fr.size), int(vo.size)
+    n_good = int(((fr["nid_status"] > 0) & (((fr["duid"] == 7) & (fr["n_tsbk"] > 0)) | ((fr["rs_kind"] > 0) & (fr["rs_status"] < 2))
+                                           | (fr["duid"] == 3))).sum())
+    n_sym = int(out["counts"].sum().item())
+    ms_per_step = ms_total / args.steps
+    value = world * C3_CH * C3_PAIRS / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: algorithmic bytes per launch (SURVEY.md section 8d, DESIGN.md section 5) ----
+    n_s = float(C3_CH * C3_PAIRS)
+    alg_bytes = {
+        "widen_cu8_kernel": 10.0 * n_s,              # 2 B cu8 in + 8 B cf32 out per pair
+        "lpf_phase_kernel": 12.0 * n_s,              # 8 B in + 4 B phase out per pair
+        "disc_recurrence_kernel": 8.0 * n_s,         # 4 B in + 4 B out
+        "sps_fir_kernel": 8.0 * n_s,                 # 4 B in + 4 B out per sample
+        "symbolize_kernel": 4.0 * n_s + 10.0 * n_sym,  # sps x 4 B in + 10 B out per symbol (the reference's .bin record)
+        "frame_sync_search_kernel": 4.0 * n_sym,
+    }
+    peak, peak_src = measured_hbm_peak()
+    tot = sum(r["ms"] for r in ktimes.values()) or 1e-12
+    kernels = {}
+    for name, rec in ktimes.items():
+        avg_ms = rec["ms"] / max(1, rec["launches"])
+        per_step = rec["ms"] / args.steps
+        kernels[name] = {"launches": rec["launches"], "avg_ms": avg_ms, "ms_per_step": per_step, "share": rec["ms"] / tot}
+        if name in alg_bytes:
+            kernels[name]["achieved_gbs"] = alg_bytes[name] / (avg_ms * 1e-3) / 1e9
+    dom = max((k for k in kernels if k in alg_bytes), key=lambda k: ktimes[k]["ms"]) if kernels else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = None
+    if dom:
+        a = kernels[dom]["achieved_gbs"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
+                    "note": "per-kernel times from CUDA events recorded by the library on the launching stream during the timed region"}
+
+    # ---- e2e: pinned host cu8 IQ in, host frames / IMBE frames / dibits out, every copy inside the timed region ----
+    e2e_steps = max(3, min(args.steps, 100))
+    rx_h = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
+    h_outs = [rx_h.alloc_host_out(), rx_h.alloc_host_out()]
+    d2h = [0]
+    seq = [0]  # tiles are fed in rotation order across calls of run(): the stream stays continuous (the locked slicer does not
+               # re-acquire symbol timing, so a repeated or skipped tile would slip it by a fraction of a symbol)
+
+    def run(n, count=False):
+        prev, chk, last = None, 0, None
+        for _ in range(n):
+            k = seq[0]
+            seq[0] += 1
+            t = rx_h.submit_host(h_tiles[k % C3_TILES], C3_PAIRS, h_outs[k % 2])
+            if prev is not None:
+                rx_h.wait_host(prev)
+                o = h_outs[(k - 1) % 2]
+                chk += int(o["totals"][0]) + int(o["dibits"][0, 0])  # the host reads the finished tile
+                if count:
+                    d2h[0] += int(o["totals"][0]) * 128 + int(o["totals"][1]) * 1944
+            prev, last = t, k
+        rx_h.wait_host(prev)
+        o = h_outs[last % 2]
+        if count:
+            d2h[0] += int(o["totals"][0]) * 128 + int(o["totals"][1]) * 1944
+        return chk + int(o["totals"][0])
+
+    run(C3_TILES + 1)
+    barrier()
+    t0 = time.perf_counter()
+    run(e2e_steps, count=True)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    barrier()
+    fixed_d2h = C3_CH * rx_h.dibit_pitch + C3_CH * 4 + 8
+    e2e = {"value": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": C3_CH * C3_PAIRS * 2,
+           "d2h_bytes_per_step": int(fixed_d2h + d2h[0] / e2e_steps), "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "channels_at_realtime": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / C3_RATE,
+           "timer": "host wall clock around K x {dsdneo_b200_p25p1_rx_submit_host(tile i); wait_host(tile i-1); host reads tile i-1} "
+                    "+ final wait, max over ranks",
+           "d2h_contents": "dibit stream + counts + frame records + IMBE frame records"}
+    # device path == host path (same state history => same bytes)
+    fr_h, vo_h = rx_h.host_records(h_outs[(seq[0] - 1) % 2])
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        try:
+            m = c3_reference_measure(steps=3, warmup=1, target_step_s=2.0)
+            cpu_baseline = {k: m[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except SystemExit as e:
+            cpu_baseline = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "iq_msps", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, C3_TILES),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "channels_at_realtime": value * 1e6 / C3_RATE, "config": c3_config(),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline,
+        "step_detail": {"call": "dsdneo_b200_p25p1_rx_process (device buffers) / _submit_host + _wait_host (host buffers)",
+                        "symbols_per_step": n_sym, "frames_per_step": n_frames, "frames_decoded_ok": n_good,
+                        "imbe_frames_per_step": 9 * n_voice, "host_numa_binding": ("node %s" % numa_node) if numa_node is not None else "none",
+                        "e2e_frames_last_step": int(fr_h.size), "e2e_voice_last_step": int(vo_h.size)},
     }
     print(json.dumps(line))
 
@@ -820,25 +1235,30 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shard", default="bands", choices=["bands", "channels"],
-                    help="bands (default): one independent 256-channel band per GPU, weak scaling, no collective; "
-                         "channels: ONE wideband stream, raw IQ tile broadcast over NCCL, each GPU demodulates a channel range "
-                         "(--channels sets the channelizer size)")
+                    help="(workload c2) bands: one independent 256-channel band per GPU; channels: ONE wideband stream, raw IQ tile "
+                         "broadcast over NCCL, each GPU demodulates a channel range")
     ap.add_argument("--channels", type=int, default=M)
-    ap.add_argument("--workload", default="c2", choices=["c2", "cqpsk", "fec"],
-                    help="c2 (default, the judged line) or cqpsk: developer line for the CQPSK chain with its own CPU baseline")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "cqpsk", "fec"],
+                    help="c3 (default, the judged line): 1024 P25 Phase 1 channels end to end; c2: 256-channel channelizer + "
+                         "discriminator; cqpsk / fec: developer lines")
     args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
     if args.workload == "cqpsk":
         run_cqpsk_workload(args)
     elif args.workload == "fec":
         run_fec_workload(args)
+    elif args.workload == "c2":
+        if args.impl == "reference":
+            run_c2_reference_arm(args)
+        elif args.shard == "channels":
+            run_channel_sharded(args)
+        else:
+            run_c2_b200_arm(args)
     elif args.impl == "reference":
-        run_reference_arm(args)
-    elif args.shard == "channels":
-        run_channel_sharded(args)
+        run_c3_reference_arm(args)
     else:
-        if args.warmup < 3:
-            args.warmup = 3
-        run_b200_arm(args)
+        run_c3_b200_arm(args)
 
 
 if __name__ == "__main__":

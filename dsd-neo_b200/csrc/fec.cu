@@ -373,7 +373,7 @@ p25_branch(const int16_t* dei, int sym, int pv, int nx) {
 
 /* p25_12_soft_llr (src/protocol/p25/p25_12.c:204-283) for one block: 12 bytes out, returns best_final >> 8 */
 __device__ __noinline__ int32_t
-p25_12_decode(const int16_t* llr196, uint8_t* o) {
+p25_12_decode(const int16_t* llr196, uint8_t* o, int* final_state = nullptr) {
     int16_t dei[196];
     p25_load_deinterleaved(llr196, dei);
     uint32_t pm0 = 0, pm1 = 256, pm2 = 256, pm3 = 256; /* path metrics stay in registers */
@@ -413,6 +413,9 @@ p25_12_decode(const int16_t* llr196, uint8_t* o) {
     }
     if (pm3 < bf) {
         bf = pm3, st = 3;
+    }
+    if (final_state) {
+        *final_state = st;
     }
     uint8_t td[49];
     for (int s = 49; s-- > 0;) {
@@ -2550,21 +2553,31 @@ p25p1_frame_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const P25Fram
                 llr196[2 * i] = (int16_t)l0;
                 llr196[2 * i + 1] = (int16_t)l1;
             }
-            dsdneo_b200_p25_12_candidate cands[kListK];
-            const int n = p25_12_list_decode(llr196, cands, kListK);
-            if (n > 0) {
-                int sel = 0;
-                for (int c = 0; c < n; c++) {
-                    if (p25_crc16_ok(cands[c].bytes)) {
-                        sel = c;
-                        break;
+            /* Shortcut for the common case.  Within one predecessor the rank-0 survivor of the list decoder has the smallest
+             * metric and equal metrics keep insertion order (predecessor, then rank, strict <), so rank 0 of every state is the
+             * plain Viterbi survivor (p25_12_soft_llr's tie rule).  The final candidates are inserted state by state and
+             * de-duplicated on the 48 packed symbols BEFORE comparing metrics, so a best path ending in state > 0 can be
+             * shadowed by a worse twin that ends in a lower state; a best path that ends in state 0 -- where every valid block
+             * ends, its 49th dibit is the flush -- is inserted first and nothing can displace it.  tsbk_select_crc_candidate
+             * takes the first candidate that passes the CRC: if the plain path ends in state 0 and passes, it is the answer.
+             * Everything else runs the full list decoder. */
+            int final_state = 0;
+            (void)p25_12_decode(llr196, out12, &final_state);
+            if (final_state != 0 || !p25_crc16_ok(out12)) {
+                dsdneo_b200_p25_12_candidate cands[kListK];
+                const int n = p25_12_list_decode(llr196, cands, kListK);
+                if (n > 0) {
+                    int sel = 0;
+                    for (int c = 0; c < n; c++) {
+                        if (p25_crc16_ok(cands[c].bytes)) {
+                            sel = c;
+                            break;
+                        }
+                    }
+                    for (int b = 0; b < 12; b++) {
+                        out12[b] = cands[sel].bytes[b];
                     }
                 }
-                for (int b = 0; b < 12; b++) {
-                    out12[b] = cands[sel].bytes[b];
-                }
-            } else {
-                (void)p25_12_decode(llr196, out12);
             }
             crc = p25_crc16_ok(out12);
             last = (out12[0] >> 7) & 1;

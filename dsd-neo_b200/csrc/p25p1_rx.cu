@@ -130,7 +130,7 @@ struct dsdneo_b200_p25p1_rx {
     int *d_frame_off, *d_voice_off;
     /* host path */
     int host_ready;
-    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaStream_t s_h2d, s_comp, s_d2h, s_rec; /* s_rec: the exact-size record copies of wait_host */
     cudaEvent_t ev_h2d[2], ev_comp[2], ev_small[2], ev_in_free[2], ev_out_free[2];
     void* d_in[2];
     size_t in_cap;
@@ -190,6 +190,7 @@ dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
         cudaStreamDestroy(rx->s_h2d);
         cudaStreamDestroy(rx->s_comp);
         cudaStreamDestroy(rx->s_d2h);
+        cudaStreamDestroy(rx->s_rec);
         for (int i = 0; i < 2; i++) {
             cudaEventDestroy(rx->ev_h2d[i]);
             cudaEventDestroy(rx->ev_comp[i]);
@@ -458,6 +459,7 @@ rx_host_init(dsdneo_b200_p25p1_rx* rx) {
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_h2d, cudaStreamNonBlocking));
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_comp, cudaStreamNonBlocking));
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_d2h, cudaStreamNonBlocking));
+    DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_rec, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
         DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_comp[i], cudaEventDisableTiming));
@@ -489,15 +491,16 @@ dsdneo_b200_p25p1_rx_wait_host(dsdneo_b200_p25p1_rx* rx, long long ticket) {
         int nf = rx->h_totals[2 * slot], nv = rx->h_totals[2 * slot + 1];
         nf = nf > o->frame_capacity ? o->frame_capacity : nf;
         nv = nv > o->voice_capacity ? o->voice_capacity : nv;
+        /* on their own stream: s_d2h may already hold the next tile's copies, which wait for that tile's kernels */
         if (nf > 0) {
             DSDNEO_CUDA(cudaMemcpyAsync(o->h_frames, rx->d_frames[slot], (size_t)nf * sizeof(dsdneo_b200_p25p1_frame), cudaMemcpyDeviceToHost,
-                                        rx->s_d2h));
+                                        rx->s_rec));
         }
         if (nv > 0 && o->h_voices) {
             DSDNEO_CUDA(cudaMemcpyAsync(o->h_voices, rx->d_voices[slot], (size_t)nv * sizeof(dsdneo_b200_p25p1_voice), cudaMemcpyDeviceToHost,
-                                        rx->s_d2h));
+                                        rx->s_rec));
         }
-        DSDNEO_CUDA(cudaEventRecord(rx->ev_out_free[slot], rx->s_d2h));
+        DSDNEO_CUDA(cudaEventRecord(rx->ev_out_free[slot], rx->s_rec));
         DSDNEO_CUDA(cudaEventSynchronize(rx->ev_out_free[slot]));
         if (o->h_totals) {
             o->h_totals[0] = nf;

@@ -786,17 +786,35 @@ def p25p1_insert_status(frame_dibits_no_status, status_dibit=2):
     return np.array(out, dtype=np.int64)
 
 
-def p25p1_build_tsdu(rng, nac, n_blocks=3, bch_encode=None):
+def p25_crc16_ccitt_inverted(bits):
+    """ComputeCrcCCITT16b (src/protocol/p25/p25_crc.c:11-29): polynomial 0x1021, zero preset, inverted."""
+    crc = 0
+    for b in bits:
+        crc = ((crc << 1) ^ 0x1021) & 0xFFFF if ((crc >> 15) & 1) ^ int(b) else (crc << 1) & 0xFFFF
+    return crc ^ 0xFFFF
+
+
+def p25_tsbk_dibits49(rng, last_block):
+    """One TSBK as the 49 trellis input dibits: 80 random bits with the last-block flag as bit 0, CRC-16 over them, flush."""
+    bits = rng.integers(0, 2, 80)
+    bits[0] = 1 if last_block else 0
+    crc = p25_crc16_ccitt_inverted(bits)
+    bits96 = np.concatenate([bits, [(crc >> (15 - i)) & 1 for i in range(16)]])
+    return np.concatenate([bits96[0::2] * 2 + bits96[1::2], [0]])
+
+
+def p25p1_build_tsdu(rng, nac, n_blocks=3, bch_encode=None, valid_crc=False):
     """One TSDU: sync + NID(NAC, DUID 7, BCH(63,16) + parity 0) + n_blocks half-rate trellis blocks, status symbols
-    inserted.  Returns (dibits incl. status, [49-dibit payloads])."""
+    inserted.  Returns (dibits incl. status, [49-dibit payloads]).  valid_crc: blocks carry a CRC-16 and the last-block flag
+    on the final block only (what a control channel sends); otherwise random dibits."""
     duid = 0x7
     info = np.array([(nac >> (11 - i)) & 1 for i in range(12)] + [(duid >> (3 - i)) & 1 for i in range(4)], np.uint8)
     cw = bch_encode(info).astype(np.int64)
     bits = np.concatenate([cw, [0]])  # parity bit 0 for TSDU
     nid = bits[0::2] * 2 + bits[1::2]
     body, payloads = [np.array(P25P1_SYNC_DIBITS), nid], []
-    for _ in range(n_blocks):
-        d49, tx98 = p25_trellis_encode(rng)
+    for b in range(n_blocks):
+        d49, tx98 = p25_trellis_encode(rng, p25_tsbk_dibits49(rng, b == n_blocks - 1) if valid_crc else None)
         body.append(tx98)
         payloads.append(d49)
     return p25p1_insert_status(np.concatenate(body)), payloads

@@ -37,9 +37,9 @@ def _voice_of(frames, voices, i):
     return voices[vi] if vi >= 0 else np.zeros(1, H.P25_VOICE_DTYPE)[0]
 
 
-@pytest.mark.parametrize("flip", [0.0, 0.02, 0.05])
-def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip):
-    rng = np.random.default_rng(int(flip * 100) + 11)
+@pytest.mark.parametrize("flip,coarse", [(0.0, False), (0.02, False), (0.05, False), (0.02, True), (0.06, True)])
+def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip, coarse):
+    rng = np.random.default_rng(int(flip * 100) + 11 + 50 * coarse)
     n_ch = 24
     streams, positions = [], []
     for c in range(n_ch):
@@ -47,7 +47,7 @@ def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip):
         nac = int(rng.integers(1, 0xFFE))
         builders = [lambda: H.p25p1_build_hdu(rng, nac)[0], lambda: H.p25p1_build_ldu(rng, nac, False)[0],
                     lambda: H.p25p1_build_ldu(rng, nac, True)[0],
-                    lambda: H.p25p1_build_tsdu(rng, nac, int(rng.integers(1, 4)), H._bch_nid_encoder())[0]]
+                    lambda: H.p25p1_build_tsdu(rng, nac, int(rng.integers(1, 4)), H._bch_nid_encoder(), valid_crc=c % 3 != 0)[0]]
         for k in rng.permutation(8):
             frame, gap = builders[k % 4](), rng.integers(0, 4, int(rng.integers(0, 12)))
             pos.append(at + 23)
@@ -59,7 +59,7 @@ def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip):
         parts.append(frame[:frame.size // 2])
         tx = np.concatenate(parts).astype(np.uint8)
         pos.insert(0, 25)  # a "sync" inside the leading noise: NID fails or decodes to garbage, both must match the oracle
-        d, rel, llr = _soft_from_dibits(rng, tx, flip=flip)
+        d, rel, llr = _soft_from_dibits(rng, tx, flip=flip, coarse=coarse)
         streams.append((d, llr))
         positions.append(pos)
     frames, voices = _run(gpu, streams, positions)
