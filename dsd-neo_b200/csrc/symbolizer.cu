@@ -146,6 +146,181 @@ sps_fir_kernel(const FirParams p) {
     }
 }
 
+/*
+ * Fast form of the matched filter: one CTA per (channel, 2048 outputs); every thread produces 8 consecutive outputs from a
+ * sliding register window (two LDS.128 of samples and two broadcast LDS.128 of taps per 8 taps and 128 FP32 operations), so the
+ * kernel runs at the FP32 pipe instead of the shared-memory port (the 4-outputs-per-thread form above does one LDS per 2 FP32
+ * operations).  The sample tile is staged with ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on an
+ * mbarrier, TMA unit) issued by thread 0; the few samples that come from the carried history or lie beyond the stream are
+ * patched in by the threads.  Same per-output operation order as the reference: taps oldest -> newest, multiply then add.
+ */
+constexpr int kFir8Threads = 256;
+constexpr int kFir8Tile = kFir8Threads * 8;
+
+__device__ __forceinline__ void
+mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void
+bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kFir8Threads)
+sps_fir8_kernel(const FirParams p) {
+    /* S[k] = x[a0 + k], a0 = the 16-byte aligned sample index at or below t0 - (L - 1); W[j] = S[j + extra] */
+    __shared__ __align__(128) float S[kFir8Tile + kMaxTaps + 16];
+    __shared__ float P[(kFir8Tile + kMaxTaps + 16) / 8 * 9 + 16];
+    __shared__ __align__(16) float T[kMaxTaps + 8];
+    __shared__ __align__(8) unsigned long long bar;
+    const int ch = blockIdx.y;
+    const int t0 = blockIdx.x * kFir8Tile;
+    const int tid = threadIdx.x;
+    const int f = p.filter[ch];
+    const float* x = p.in + (size_t)ch * p.in_pitch;
+    float* y = p.out + (size_t)ch * p.out_pitch;
+    if (f < 0) { /* no matched filter selected (dsd_symbol.c:301-337 falls through): identity */
+        for (int j = tid; j < kFir8Tile; j += kFir8Threads) {
+            const int n = t0 + j;
+            if (n < p.n) {
+                y[n] = x[n];
+            }
+        }
+        return;
+    }
+    const int L = p.taps_len[f];
+    const int g0 = t0 - (L - 1);
+    const int a0 = g0 & ~3;                       /* floor to a multiple of 4 (also for negative g0) */
+    const int extra = g0 - a0;                    /* 0..3 */
+    const int need = kFir8Tile + L - 1 + extra;   /* S entries the tile reads */
+    /* the part of [a0, a0 + need) that lies inside the row: [lo, hi), both multiples of 4 (the row pitch is one too) */
+    const int lo = a0 < 0 ? 0 : a0;
+    int hi = a0 + ((need + 3) & ~3);
+    const int row_end = (int)((p.n + 3) & ~3);
+    hi = hi > row_end ? row_end : hi;
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+    if (tid == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bytes = hi > lo ? (unsigned)(hi - lo) * 4u : 0u;
+        if (bytes) {
+            mbar_expect_tx(bar_s, bytes);
+            bulk_g2s((unsigned)__cvta_generic_to_shared(&S[lo - a0]), x + lo, bytes, bar_s);
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+        }
+    }
+    for (int i = tid; i < kMaxTaps + 8; i += kFir8Threads) {
+        T[i] = i < L ? p.taps[f * kMaxTaps + i] : 0.0f;
+    }
+    mbar_wait(bar_s, 0);
+    /* Re-layout into P with one pad word per 8 samples (index k -> k + k / 8): thread t then walks its window from 9 t, so the
+     * 32 lanes of every scalar LDS hit 32 different banks (the raw tile at stride 8 would be an 8-way conflict).  The same pass
+     * patches what the bulk copy could not supply: carried history left of the stream, zeros right of it. */
+    const float* hist = p.hist + (size_t)ch * kMaxTaps;
+    for (int k = tid; k < kFir8Tile + L - 1 + 8; k += kFir8Threads) {
+        const int g = g0 + k;
+        float v;
+        if (g < 0) {
+            const int h = (L - 1) + g; /* hist[L-2] == x[-1] */
+            v = h >= 0 ? hist[h] : 0.0f;
+        } else if (g >= p.n) {
+            v = 0.0f;
+        } else {
+            v = S[k + extra];
+        }
+        P[k + (k >> 3)] = v;
+    }
+    __syncthreads();
+    const float* W = P + 9 * tid; /* sample 8 t + i of the window sits at W[i + i / 8] */
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        acc[j] = 0.0f;
+    }
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        w[j] = W[j];
+    }
+    const int full = L >> 3;
+    for (int q = 0; q < full; q++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            w[8 + j] = W[9 * q + 9 + j];
+        }
+        const float4 ta = *reinterpret_cast<const float4*>(&T[8 * q]);
+        const float4 tb = *reinterpret_cast<const float4*>(&T[8 * q + 4]);
+        const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(t[i], w[i + j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            w[j] = w[8 + j];
+        }
+    }
+    const int rem = L & 7;
+    if (rem) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            w[8 + j] = W[9 * full + 9 + j];
+        }
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            if (i < rem) {
+                const float t = T[8 * full + i];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    acc[j] = __fadd_rn(acc[j], __fmul_rn(t, w[i + j]));
+                }
+            }
+        }
+    }
+    const int n0 = t0 + 8 * tid;
+    if (n0 + 8 <= p.n && (p.out_pitch & 3) == 0) {
+        reinterpret_cast<float4*>(y + n0)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<float4*>(y + n0)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (n0 + j < p.n) {
+                y[n0 + j] = acc[j];
+            }
+        }
+    }
+}
+
 __global__ void
 sps_fir_hist_kernel(const float* in, size_t in_pitch, float* hist_all, const int* filter, const int* taps_len, int n_ch, int n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1675,8 +1850,14 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
         fp.filter = y->s.filter;
         fp.hist = y->d_hist;
         fp.n = n_samples;
-        dim3 grid((unsigned)((n_samples + kFirTile - 1) / kFirTile), (unsigned)y->n_ch);
-        {
+        /* the bulk-copy form needs 16-byte aligned rows on both sides */
+        const bool aligned = (disc_pitch & 3) == 0 && (((uintptr_t)d_disc) & 15) == 0 && (y->filt_pitch & 3) == 0;
+        if (aligned) {
+            dim3 grid((unsigned)((n_samples + kFir8Tile - 1) / kFir8Tile), (unsigned)y->n_ch);
+            KernelTimer kt("sps_fir_kernel", s);
+            sps_fir8_kernel<<<grid, kFir8Threads, 0, s>>>(fp);
+        } else {
+            dim3 grid((unsigned)((n_samples + kFirTile - 1) / kFirTile), (unsigned)y->n_ch);
             KernelTimer kt("sps_fir_kernel", s);
             sps_fir_kernel<<<grid, kFirThreads, 0, s>>>(fp);
         }
