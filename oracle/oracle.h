@@ -169,6 +169,7 @@ typedef struct oracle_sym_chan {
     int window_l;        /* left window edge: 2 (P25, NXDN96...) or 1 (YSF / DMR), dsd_symbol.c:197-211 */
     int track_minmax;    /* use_symbol() threshold tracking: rf_mod 0 and lastsynctype is P25p1 (dsd_dibit.c:264) */
     int negative;        /* is_four_level_neg_synctype(synctype) */
+    int rf_mod;          /* 0 C4FM, 2 GFSK (window / accumulation / nudge rules, no sync clip) */
     int ssize, msize;
     int taps_len;
     float taps[ORACLE_SYM_MAX_TAPS];
@@ -207,6 +208,27 @@ void oracle_cqpsk_slicer_init(oracle_cqpsk_slicer* s, int negative, int p25_slic
 int oracle_cqpsk_slicer_dibit(oracle_cqpsk_slicer* s, float sample, uint8_t* rel_out, int16_t llr_out[2]);
 long oracle_cqpsk_slicer_run(oracle_cqpsk_slicer* s, const float* symbols, long n, uint8_t* dibits, uint8_t* rel, int16_t* llr2);
 
+/* acquisition = getFrameSync() from the never-synchronised state (oracle_symbol.c) */
+typedef struct oracle_acq_pattern {
+    const char* symbols; /* '1' / '3' string, oldest first */
+    int sync_type;
+    int kind;            /* 0 P25 Phase 1 (threshold warm start when rf_mod == 0), 1 DMR (warm start + resample-on-sync) */
+    int use_filter;      /* the decoder class from the sync on: matched filter, window, tracker, polarity */
+    const float* taps;
+    int taps_len;
+    int window_l, track_minmax, negative;
+} oracle_acq_pattern;
+typedef struct oracle_acq_result {
+    int sync_type;       /* -1: the samples ran out first */
+    int warm_start;      /* DSD_WARM_START_OK */
+    int resample_ok;
+    long hunt_symbols, consumed;
+    float lmin, lmax;
+    uint8_t resampled[66];
+} oracle_acq_result;
+int oracle_warm_start_thresholds(oracle_sym_chan* c, const float* newest_first, int len);
+long oracle_sym_acquire(oracle_sym_chan* c, const float* samples, long n, long reserve, const oracle_acq_pattern* pats, int n_pats,
+                        float* sym_out, uint8_t* dib_out, uint8_t* rel_out, long max_out, oracle_acq_result* res);
 int oracle_frame_sync_search(const float* symbols, int n, const char* const* patterns, const int* sync_types, int n_patterns,
                              char* hist32, int* hist_count, int* hit_pos, int* hit_type, int max_hits);
 /* ------------------------------- MBE synthesis stage (oracle_mbe.c) -- PARITY UNPINNED, see its header --------- */

@@ -15,6 +15,7 @@
  * Pinned against the compiled reference by tests/test_oracle_symbol.py (bit-exact symbols, dibits, LLRs).
  */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "oracle.h"
@@ -126,7 +127,8 @@ float
 oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), void* ctx) {
     c->sps = next_sps(c);
     c->center_idx = (c->sps - 1) / 2;
-    const int l_edge = c->window_l, r_edge = 2;
+    /* select_window_c4fm / _gfsk (dsd_symbol.c:197-225) */
+    const int l_edge = c->rf_mod == 2 ? 1 : c->window_l, r_edge = c->rf_mod == 2 ? 1 : 2;
     const int span = c->sps < 1 ? 1 : c->sps;
     if (span <= 1) {
         c->jitter = -1;
@@ -143,6 +145,12 @@ oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), v
                 } else if (c->jitter >= 11 && c->jitter <= 14) {
                     i++;
                 }
+            } else if (c->rf_mod == 2) { /* symbol_adjust_timing_gfsk (dsd_symbol.c:480-487) */
+                if (c->jitter >= c->center_idx - 1 && c->jitter <= c->center_idx) {
+                    i--;
+                } else if (c->jitter >= c->center_idx + 1 && c->jitter <= c->center_idx + 2) {
+                    i++;
+                }
             } else {
                 if (c->jitter > 0 && c->jitter <= c->center_idx) {
                     i--;
@@ -154,7 +162,7 @@ oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), v
         }
         float s = next(ctx);
         s = matched_fir(c, s);
-        if (have_sync == 1) { /* rf_mod == 0 */
+        if (have_sync == 1 && c->rf_mod == 0) { /* symbol_apply_sync_clip: C4FM only (dsd_symbol.c:347-358) */
             if (s > c->max) {
                 s = c->max;
             } else if (s < c->min) {
@@ -183,8 +191,14 @@ oracle_sym_get_symbol(oracle_sym_chan* c, int have_sync, float (*next)(void*), v
         if (c->sps == 5 && i == 2) {
             sum += s;
             count++;
-        } else if (!(c->sps == 5 && i == 2)) {
+        } else if (c->rf_mod == 0) {
             if (i >= c->center_idx - l_edge && i <= c->center_idx + r_edge) {
+                sum += s;
+                count++;
+            }
+        } else { /* symbol_accumulate_other_window (dsd_symbol.c:428-434): the two edge samples only */
+            const int hit = (c->sps <= 4) ? (i == c->center_idx) : (i == c->center_idx - l_edge || i == c->center_idx + r_edge);
+            if (hit) {
                 sum += s;
                 count++;
             }
@@ -461,6 +475,191 @@ oracle_frame_sync_search(const float* symbols, int n, const char* const* pattern
         }
     }
     return found;
+}
+
+/* ---- acquisition: getFrameSync() (src/dsp/dsd_frame_sync.c:3098-3148) from the never-synchronised state -------------------
+ *
+ * Per symbol, in the reference's order: getSymbol(have_sync = 0) (timing nudges on, no matched filter before the first sync:
+ * symbol_apply_matched_filter selects by lastsynctype, dsd_symbol.c:301-337); the 24-symbol level ring and sbuf write
+ * (frame_sync_update_symbol_ring, :1747-1764); the rolling DMR payload dibit + reliability with the thresholds in force
+ * (frame_sync_store_dmr_payload_symbol, :2161-2190, dmr_compute_reliability dsd_dibit.c:548-568); the hunt-time slice
+ * symbol > 0 -> '1' else '3' (:2110-2127); from the 8th symbol on frame_sync_eval_window (:2638-2676): sorted-window level
+ * estimate (frame_sync_level.c), maxref / minref = max / min for FSK profiles (:2332-2335), then the pattern compare.
+ * A call gives up after 1800 symbols without sync (:3039) and the next call starts with an empty window, which is restated
+ * here as a restart of the hunt context (the no-carrier hook of that moment is the host's business).
+ * On a match: frame_sync_set_basic_lock (:386-392), then for P25 Phase 1 dsd_sync_warm_start_thresholds_outer_only(24) when
+ * rf_mod == 0 (:611-622, src/dsp/sync_calibration.c:155-226), for DMR dmr_resample_on_sync (src/dsp/dmr_sync.c:108-126):
+ * the same warm start, then the 66 dibits in front of the sync re-sliced with the new thresholds.
+ * Pinned against the UNMODIFIED getFrameSync() by tests/test_oracle_symbol.py (ref_sym_frame_sync). */
+static int
+cmp_float(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+static void
+window_levels(const float* sorted, int count, float* omin, float* omax) { /* dsd_frame_sync_estimate_sorted_window_levels */
+    if (count <= 0) {
+        *omin = *omax = 0.0f;
+        return;
+    }
+    if (count < 3) {
+        float sum = 0.0f;
+        for (int i = 0; i < count; i++) {
+            sum += sorted[i];
+        }
+        *omin = *omax = sum / (float)count;
+        return;
+    }
+    int min_idx = 0, max_idx = count - 3;
+    if (count >= 13) {
+        min_idx = 2;
+        max_idx = count - 5;
+    }
+    if (max_idx + 2 >= count) {
+        max_idx = count - 3;
+    }
+    *omin = (sorted[min_idx] + sorted[min_idx + 1] + sorted[min_idx + 2]) / 3.0f;
+    *omax = (sorted[max_idx] + sorted[max_idx + 1] + sorted[max_idx + 2]) / 3.0f;
+}
+
+/* dsd_sync_warm_start_thresholds_outer_only over the newest `len` symbols (newest first, as the reference walks them).
+ * Returns 1 when the thresholds were replaced (DSD_WARM_START_OK). */
+int
+oracle_warm_start_thresholds(oracle_sym_chan* c, const float* newest_first, int len) {
+    float sum_pos = 0.0f, sum_neg = 0.0f;
+    int n_pos = 0, n_neg = 0;
+    for (int i = 0; i < len; i++) {
+        const float v = newest_first[i];
+        if (v > 0.0f) {
+            sum_pos += v;
+            n_pos++;
+        } else {
+            sum_neg += v;
+            n_neg++;
+        }
+    }
+    if (n_pos == 0 || n_neg == 0) {
+        return 0;
+    }
+    const float mean_pos = sum_pos / (float)n_pos, mean_neg = sum_neg / (float)n_neg;
+    if (fabsf(mean_pos - mean_neg) < 1.0f) {
+        return 0;
+    }
+    c->max = mean_pos;
+    c->min = mean_neg;
+    c->center = (c->max + c->min) / 2.0f;
+    c->umid = c->center + (c->max - c->center) * 0.625f;
+    c->lmid = c->center + (c->min - c->center) * 0.625f;
+    c->maxref = c->max * 0.80f;
+    c->minref = c->min * 0.80f;
+    int fill = c->msize > 1024 ? 1024 : c->msize;
+    for (int i = 0; i < fill; i++) {
+        c->maxbuf[i] = c->max;
+        c->minbuf[i] = c->min;
+    }
+    c->sum_window = 0; /* dsd_state_invalidate_minmax_sums */
+    return 1;
+}
+
+static int
+payload_dibit(const oracle_sym_chan* c, float symbol) {
+    if (symbol > c->center) {
+        return symbol > c->umid ? 1 : 0;
+    }
+    return symbol < c->lmid ? 3 : 2;
+}
+
+long
+oracle_sym_acquire(oracle_sym_chan* c, const float* samples, long n, long reserve, const oracle_acq_pattern* pats, int n_pats,
+                   float* sym_out, uint8_t* dib_out, uint8_t* rel_out, long max_out, oracle_acq_result* res) {
+    arr_src src = {samples, n, 0};
+    memset(res, 0, sizeof(*res));
+    res->sync_type = -1;
+    float lbuf[48], sorted[48];
+    int lidx = 0, level_count = 0, count = 0, since_start = 0;
+    float lmin = c->min, lmax = c->max;
+    char win[25];
+    memset(win, 0, sizeof(win));
+    long k = 0;
+    while (k < max_out && (src.n - src.pos) >= reserve) {
+        const float symbol = oracle_sym_get_symbol(c, 0, arr_next, &src);
+        /* frame_sync_update_symbol_ring */
+        lbuf[lidx] = symbol;
+        if (level_count < 24) {
+            level_count++;
+        }
+        c->sbuf[c->sidx] = symbol;
+        lidx = (lidx == 23) ? 0 : lidx + 1;
+        c->sidx = (c->sidx == c->ssize - 1) ? 0 : c->sidx + 1;
+        /* rolling DMR payload buffer */
+        sym_out[k] = symbol;
+        dib_out[k] = (uint8_t)payload_dibit(c, symbol);
+        rel_out[k] = (uint8_t)reliability(c, symbol);
+        k++;
+        memmove(win, win + 1, 23);
+        win[23] = symbol > 0.0f ? '1' : '3';
+        if (count < 24) {
+            count++;
+        }
+        since_start++;
+        if (since_start >= 8) { /* history_count >= 8: frame_sync_eval_window */
+            memcpy(sorted, lbuf, (size_t)level_count * sizeof(float));
+            qsort(sorted, (size_t)level_count, sizeof(float), cmp_float);
+            window_levels(sorted, level_count, &lmin, &lmax);
+            c->maxref = c->max;
+            c->minref = c->min;
+            for (int p = 0; p < n_pats; p++) {
+                const int L = (int)strlen(pats[p].symbols);
+                if (count < L || strncmp(win + 24 - L, pats[p].symbols, (size_t)L) != 0) {
+                    continue;
+                }
+                /* frame_sync_set_basic_lock */
+                c->max = (c->max + lmax) / 2;
+                c->min = (c->min + lmin) / 2;
+                float newest_first[24];
+                for (int i = 0; i < 24; i++) {
+                    newest_first[i] = (k - 1 - i) >= 0 ? sym_out[k - 1 - i] : 0.0f;
+                }
+                if (pats[p].kind == 1 || c->rf_mod == 0) {
+                    res->warm_start = oracle_warm_start_thresholds(c, newest_first, 24);
+                }
+                if (pats[p].kind == 1 && k >= 90) { /* dmr_resample_cach: symbols [-90 .. -25] */
+                    for (int i = 0; i < 66; i++) {
+                        const float sv = sym_out[k - 90 + i];
+                        res->resampled[i] = (uint8_t)payload_dibit(c, sv);
+                        dib_out[k - 90 + i] = res->resampled[i];
+                    }
+                    res->resample_ok = 1;
+                }
+                /* the decoder state the frame handlers see from here on */
+                c->use_filter = pats[p].use_filter && pats[p].taps && pats[p].taps_len > 0;
+                c->taps_len = c->use_filter ? pats[p].taps_len : 0;
+                if (c->use_filter) {
+                    memcpy(c->taps, pats[p].taps, (size_t)pats[p].taps_len * sizeof(float));
+                }
+                c->window_l = pats[p].window_l;
+                c->track_minmax = pats[p].track_minmax;
+                c->negative = pats[p].negative;
+                res->sync_type = pats[p].sync_type;
+                res->hunt_symbols = k;
+                res->consumed = src.pos;
+                res->lmin = lmin;
+                res->lmax = lmax;
+                return k;
+            }
+        }
+        if (since_start >= 1800) { /* frame_sync_handle_no_sync_timeout: the next getFrameSync() call starts afresh */
+            lidx = 0, level_count = 0, count = 0, since_start = 0;
+            lmin = c->min, lmax = c->max;
+            memset(win, 0, sizeof(win));
+        }
+    }
+    res->hunt_symbols = k;
+    res->consumed = src.pos;
+    res->lmin = lmin;
+    res->lmax = lmax;
+    return k;
 }
 
 /* ---- symbol-rate CQPSK input (output kind 2): the sample side behind the CQPSK chain ------------------------------------

@@ -12,6 +12,7 @@
 #include <dsd-neo/core/synctype_ids.h>
 #include <dsd-neo/dsp/sps_filters.h>
 #include <dsd-neo/dsp/symbol.h>
+#include <dsd-neo/dsp/sync_calibration.h>
 #include <dsd-neo/io/rtl_stream_c.h>
 #include <dsd-neo/runtime/rtl_stream_io_hooks.h>
 #include <dsd-neo/runtime/rtl_stream_metrics_hooks.h>
@@ -39,6 +40,8 @@ hook_read(void* ctx, float* out, size_t count, int* out_got) {
     long left = h->n_src - h->pos;
     long n = (long)count < left ? (long)count : left;
     if (n <= 0) {
+        extern volatile uint8_t exitflag;
+        exitflag = 1; /* getFrameSync() polls this and returns instead of hunting forever */
         *out_got = 0;
         return -1;
     }
@@ -391,4 +394,77 @@ ref_sym_get_dibits_n(void* hv, long n_symbols, uint8_t* dibits, uint8_t* reliab,
         symbols[n] = h->state->sbuf[sidx_before];
     }
     return n_symbols;
+}
+
+
+/* ---- acquisition: the UNMODIFIED getFrameSync() (src/dsp/dsd_frame_sync.c:3098-3148) on the hook-fed stream ------------------
+ * One call hunts symbol by symbol (getSymbol with have_sync = 0, hunt-time slicing, the rolling DMR payload buffer, pattern
+ * matching) and, on a match, runs the reference's own acquisition side effects: sync warm start of the slicer thresholds
+ * (dsd_sync_warm_start_thresholds_outer_only, src/dsp/sync_calibration.c:155-226) and, for DMR, the re-digitisation of the
+ * 66 dibits in front of the sync (dmr_resample_on_sync, src/dsp/dmr_sync.c:108-126). */
+extern volatile uint8_t exitflag;
+int getFrameSync(dsd_opts* opts, dsd_state* state);
+
+/* frame_mask: bit 0 P25 Phase 1, bit 1 DMR.  rf_mod: 0 C4FM, 2 GFSK (what the reference's -fs preset selects for DMR,
+ * src/runtime/decode_mode.c:242-266); the modulation is locked like -mc / -mg do, so the auto-detector stays out. */
+void
+ref_sym_configure_acquire(void* hv, int frame_mask, int rf_mod) {
+    ref_sym* h = (ref_sym*)hv;
+    dsd_opts* o = h->opts;
+    dsd_state* s = h->state;
+    o->frame_p25p1 = (frame_mask & 1) ? 1 : 0;
+    o->frame_dmr = (frame_mask & 2) ? 1 : 0;
+    o->mod_cli_lock = 1;
+    o->mod_c4fm = rf_mod == 0;
+    o->mod_gfsk = rf_mod == 2;
+    o->mod_qpsk = 0;
+    s->rf_mod = rf_mod;
+    s->synctype = DSD_SYNC_NONE;
+    s->lastsynctype = DSD_SYNC_NONE;
+    if (!s->symbol_history) {
+        s->symbol_history_size = DSD_SYMBOL_HISTORY_SIZE;
+        s->symbol_history = (float*)calloc((size_t)s->symbol_history_size, sizeof(float));
+        s->symbol_history_head = 0;
+        s->symbol_history_count = 0;
+    }
+}
+
+/* Returns the sync type getFrameSync() reported (DSD_SYNC_NONE / -1 when the samples ran out first). */
+int
+ref_sym_frame_sync(void* hv) {
+    ref_sym* h = (ref_sym*)hv;
+    g_live = h;
+    exitflag = 0;
+    const int st = getFrameSync(h->opts, h->state);
+    if (st >= 0) {
+        h->state->synctype = st;
+    }
+    exitflag = 0;
+    return st;
+}
+
+/* the most recent `n` entries of the reference's symbol history (oldest first) and of its rolling DMR payload / soft buffers */
+void
+ref_sym_recent(void* hv, int n, float* symbols, int32_t* payload_dibits, uint8_t* payload_reliab) {
+    ref_sym* h = (ref_sym*)hv;
+    const dsd_state* s = h->state;
+    for (int i = 0; i < n; i++) {
+        const int back = n - 1 - i;
+        float v = 0.0f;
+        if (s->symbol_history && back < s->symbol_history_count) {
+            int idx = s->symbol_history_head - 1 - back;
+            while (idx < 0) {
+                idx += s->symbol_history_size;
+            }
+            v = s->symbol_history[idx % s->symbol_history_size];
+        }
+        symbols[i] = v;
+        payload_dibits[i] = *(s->dmr_payload_p - n + i);
+        payload_reliab[i] = s->dmr_soft_p ? (s->dmr_soft_p - n + i)->reliability : 0;
+    }
+}
+
+long
+ref_sym_symbol_count(void* hv) {
+    return (long)((ref_sym*)hv)->state->symbol_history_count;
 }

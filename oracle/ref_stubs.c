@@ -58,3 +58,15 @@ uint64_t dsd_time_monotonic_ns(void) { return 0; }
 /* the harness checks this flag after every call: set when the reference gave up reading samples */
 int g_oracle_shutdown_requested = 0;
 void dsd_request_shutdown() { g_oracle_shutdown_requested = 1; }
+
+/* ---- getFrameSync (src/dsp/dsd_frame_sync.c) is compiled in for the acquisition harness (ref_sym_acquire): its UI, event,
+ * telemetry and trunking side calls are inert here; the frame-sync hook table (src/runtime/frame_sync_hooks.c) is the
+ * reference's own and stays empty, so its hooks are no-ops by the reference's design. ---- */
+void dsd_event_sync_slot() {}
+const char* dsd_format_local_datetime() { return ""; }
+int dsd_telemetry_is_active() { return 0; }
+void dsd_telemetry_publish_both_and_redraw() {}
+void printFrameInfo() {}
+void dsd_mark_cc_sync() {}
+uint64_t dsd_time_monotonic_ms(void) { return 0; }
+int dsd_rtl_channel_profile_for() { return 0; }

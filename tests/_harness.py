@@ -370,7 +370,7 @@ def dibits_to_llr(tx98, mag=200, rng=None, noise=0.0):
 class OracleSymChan(C.Structure):
     _fields_ = [
         ("output_rate_hz", C.c_int), ("symbol_rate_hz", C.c_int), ("use_filter", C.c_int), ("window_l", C.c_int),
-        ("track_minmax", C.c_int), ("negative", C.c_int), ("ssize", C.c_int), ("msize", C.c_int), ("taps_len", C.c_int),
+        ("track_minmax", C.c_int), ("negative", C.c_int), ("rf_mod", C.c_int), ("ssize", C.c_int), ("msize", C.c_int), ("taps_len", C.c_int),
         ("taps", C.c_float * 256), ("fir_hist", C.c_float * 256), ("fir_head", C.c_int),
         ("sps_num", C.c_int), ("sps_den", C.c_int), ("sps_accum", C.c_int),
         ("sps", C.c_int), ("center_idx", C.c_int), ("jitter", C.c_int), ("lastsample", C.c_float),
@@ -1155,3 +1155,45 @@ def synth_c4fm_iq(rng, dibits, snr_db=None, amp=0.6, pre=9, cu8=True):
 def widen_cu8(u8):
     """widen_u8_to_f32_bias127 (src/dsp/simd_widen.cpp:139-147)"""
     return ((u8.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).astype(np.float32)
+
+
+# ---- acquisition (getFrameSync from the never-synchronised state) -------------------------------------------------------------
+
+class OracleAcqPattern(C.Structure):
+    _fields_ = [("symbols", C.c_char_p), ("sync_type", C.c_int), ("kind", C.c_int), ("use_filter", C.c_int),
+                ("taps", C.POINTER(C.c_float)), ("taps_len", C.c_int), ("window_l", C.c_int), ("track_minmax", C.c_int),
+                ("negative", C.c_int)]
+
+
+class OracleAcqResult(C.Structure):
+    _fields_ = [("sync_type", C.c_int), ("warm_start", C.c_int), ("resample_ok", C.c_int), ("hunt_symbols", C.c_long),
+                ("consumed", C.c_long), ("lmin", C.c_float), ("lmax", C.c_float), ("resampled", C.c_uint8 * 66)]
+
+
+P25P1_SYNC_STR, P25P1_SYNC_INV_STR = "111113113311333313133333", "333331331133111131311111"
+DMR_BS_DATA_STR, DMR_BS_VOICE_STR = "313333111331131131331131", "131111333113313313113313"
+DMR_MS_DATA_STR, DMR_MS_VOICE_STR = "311131133313133331131113", "133313311131311113313331"
+
+
+def acquire_patterns(frame_p25p1, frame_dmr, taps, use_cosine_filter=True):
+    """The reference's matcher order for the enabled protocols (frame_sync_try_protocol_matches, dsd_frame_sync.c:1636-1700:
+    P25 Phase 1 before DMR; inside DMR: MS data, MS voice, BS data, BS voice) with the class each sync type gives the decoder.
+    Returns (ctypes array, keep-alive list)."""
+    pats, keep = [], []
+
+    def add(sym, st, kind, filt, window_l, track, negative):
+        tp = taps.get(filt) if (use_cosine_filter and filt is not None) else None
+        arr = np.ascontiguousarray(tp, np.float32) if tp is not None else None
+        keep.append(arr)
+        pats.append(OracleAcqPattern(sym.encode(), st, kind, 1 if arr is not None else 0, _ptr(arr) if arr is not None else None,
+                                     arr.size if arr is not None else 0, window_l, track, negative))
+
+    if frame_p25p1:
+        add(P25P1_SYNC_STR, 0, 0, 0, 2, 1, 0)
+        add(P25P1_SYNC_INV_STR, 1, 0, 0, 2, 1, 1)
+    if frame_dmr:  # inverted_dmr == 0: src/dsp/dsd_frame_sync.c:1108-1340
+        add(DMR_MS_DATA_STR, 33, 1, 1, 1, 0, 0)
+        add(DMR_MS_VOICE_STR, 32, 1, 1, 1, 0, 0)
+        add(DMR_BS_DATA_STR, 10, 1, 1, 1, 0, 0)
+        add(DMR_BS_VOICE_STR, 12, 1, 1, 1, 0, 0)
+    return (OracleAcqPattern * len(pats))(*pats), keep

@@ -2,6 +2,8 @@
 getDibitSoft() driven through its own runtime hook seam (oracle/ref_shim_symbol.c)."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -164,3 +166,98 @@ def test_cqpsk_symbol_rate_slicer_matches_reference(sync, active, map_idx, snr):
     want = np.array([b.min, b.max, b.center, b.umid, b.lmid, b.minref, b.maxref, b.lastsample], np.float32)
     assert H.bits_equal(f8, want), (f8, want)
     assert len(set(d.tolist())) == 4
+
+
+# ---- acquisition: the oracle's getFrameSync restatement against the UNMODIFIED getFrameSync() -------------------------------
+
+def _ref_acquire(disc, frame_mask, rf_mod, n_after=600):
+    """The real getFrameSync() once, then n_after getDibitSoft() calls.  Returns a dict of what the reference did."""
+    R = H.ref_sym()
+    R.ref_sym_configure_acquire.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    R.ref_sym_frame_sync.argtypes = [C.c_void_p]
+    R.ref_sym_frame_sync.restype = C.c_int
+    R.ref_sym_recent.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.ref_sym_symbol_count.restype = C.c_long
+    R.ref_sym_symbol_count.argtypes = [C.c_void_p]
+    h = R.ref_sym_create(48000, 4800, -1, -1, 1, 128, 1024)
+    R.ref_sym_configure_acquire(h, frame_mask, rf_mod)
+    R.ref_sym_feed(h, H._ptr(disc), disc.size)
+    st = -1
+    for _ in range(64):  # a call gives up after 1800 symbols without sync; the decoder loop simply calls again
+        st = R.ref_sym_frame_sync(h)
+        if st >= 0 or disc.size - R.ref_sym_consumed(h) < 2000:
+            break
+    out = {"sync_type": st, "hunted": int(R.ref_sym_symbol_count(h)), "consumed": int(R.ref_sym_consumed(h))}
+    f8, i5 = np.zeros(8, np.float32), np.zeros(5, np.int32)
+    R.ref_sym_get_state(h, H._ptr(f8), i5.ctypes.data_as(C.POINTER(C.c_int)))
+    out["f8"], out["i5"] = f8.copy(), i5.copy()
+    n = min(out["hunted"], 200)
+    sym, pd, pr = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    R.ref_sym_recent(h, n, H._ptr(sym), pd.ctypes.data, pr.ctypes.data)
+    out["recent_sym"], out["recent_dib"], out["recent_rel"] = sym, pd, pr
+    if st >= 0:
+        d, r = np.zeros(n_after, np.uint8), np.zeros(n_after, np.uint8)
+        l, s = np.zeros(2 * n_after, np.int16), np.zeros(n_after, np.float32)
+        k = R.ref_sym_get_dibits(h, n_after, 600, H._ptr(d, H.u8p), H._ptr(r, H.u8p), l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s))
+        out["after"] = (d[:k], r[:k], l[:2 * k].reshape(-1, 2), s[:k])
+    R.ref_sym_destroy(h)
+    return out
+
+
+def _oracle_acquire(disc, frame_mask, rf_mod, taps, n_after=600):
+    O = H.oracle_sym()
+    ch = H.OracleSymChan()
+    O.oracle_sym_init(C.byref(ch), 48000, 4800, 0, 2, 0, 0, None, 0, 128, 1024)
+    ch.rf_mod = rf_mod
+    pats, keep = H.acquire_patterns(frame_mask & 1, frame_mask & 2, taps)
+    n = disc.size // 8 + 8
+    sym, dib, rel = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    res = H.OracleAcqResult()
+    O.oracle_sym_acquire.restype = C.c_long
+    k = O.oracle_sym_acquire(C.byref(ch), H._ptr(disc), C.c_long(disc.size), C.c_long(600), pats, len(pats), H._ptr(sym),
+                             H._ptr(dib, H.u8p), H._ptr(rel, H.u8p), C.c_long(n), C.byref(res))
+    out = {"sync_type": res.sync_type, "hunted": int(k), "consumed": int(res.consumed), "ch": ch, "sym": sym[:k], "dib": dib[:k],
+           "rel": rel[:k], "warm": res.warm_start,
+           "f8": np.array([ch.min, ch.max, ch.center, ch.umid, ch.lmid, ch.minref, ch.maxref, ch.lastsample], np.float32)}
+    if res.sync_type >= 0:
+        d, r = np.zeros(n_after, np.uint8), np.zeros(n_after, np.uint8)
+        l, s = np.zeros(2 * n_after, np.int16), np.zeros(n_after, np.float32)
+        cons = C.c_long(0)
+        rest = np.ascontiguousarray(disc[res.consumed:])
+        kk = O.oracle_sym_run_dibits(C.byref(ch), H._ptr(rest), rest.size, 600, H._ptr(d, H.u8p), H._ptr(r, H.u8p),
+                                     l.ctypes.data_as(C.POINTER(C.c_int16)), H._ptr(s), n_after, C.byref(cons))
+        out["after"] = (d[:kk], r[:kk], l[:2 * kk].reshape(-1, 2), s[:kk])
+    return out
+
+
+def _compare_acquire(ref, got):
+    assert got["sync_type"] == ref["sync_type"], (got["sync_type"], ref["sync_type"])
+    # the reference's symbol history saturates at DSD_SYMBOL_HISTORY_SIZE = 2048 entries
+    assert min(got["hunted"], 2048) == ref["hunted"] and got["consumed"] == ref["consumed"], (got["hunted"], ref["hunted"], got["consumed"], ref["consumed"])
+    n = ref["recent_sym"].size
+    assert H.bits_equal(got["sym"][-n:], ref["recent_sym"])
+    assert np.array_equal(got["dib"][-n:], ref["recent_dib"].astype(np.uint8)) and np.array_equal(got["rel"][-n:], ref["recent_rel"])
+    assert H.bits_equal(got["f8"], ref["f8"]), (got["f8"], ref["f8"])
+    if ref["sync_type"] >= 0:
+        for a, b in zip(got["after"], ref["after"]):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+@needs_ref
+@pytest.mark.parametrize("fixture,mask,rf_mod,profile,want_sync", [
+    ("p25p1_c4fm_cc", 1, 0, 4, 0), ("p25p1_c4fm_vc", 1, 0, 4, 0), ("dmr_t3_cc", 2, 2, 2, 12), ("dmr_voice", 2, 2, 2, None),
+    ("dmr_t3_cc", 2, 0, 2, 12), ("dmr_t3_cc", 3, 0, 2, 12)])
+def test_acquisition_matches_the_unmodified_getframesync_on_the_reference_captures(fixture, mask, rf_mod, profile, want_sync):
+    path = "/root/reference/tests/fixtures/iq/%s.iq" % fixture
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    x = H.widen_cu8(np.fromfile(path, dtype=np.uint8)).reshape(-1, 2)
+    bp = 8000
+    disc = H.RefDemod("par", rate=48000, symrate=4800, profile=profile).run(x, bp, x.shape[0] // bp)
+    taps = {0: H.sps_fir_taps(0, 10), 1: H.sps_fir_taps(1, 10)}
+    ref = _ref_acquire(disc, mask, rf_mod)
+    got = _oracle_acquire(disc, mask, rf_mod, taps)
+    if want_sync is not None:
+        assert ref["sync_type"] == want_sync
+    assert ref["sync_type"] >= 0
+    _compare_acquire(ref, got)
