@@ -1126,7 +1126,7 @@ def mbe_synth(cur, prev_enhanced, keys=None, uvquality: int = 3, want_int16: boo
 
 
 class SymClass(C.Structure):
-    _fields_ = [("filter", C.c_int), ("window_l", C.c_int), ("track_minmax", C.c_int), ("negative", C.c_int)]
+    _fields_ = [("filter", C.c_int), ("window_l", C.c_int), ("track_minmax", C.c_int), ("negative", C.c_int), ("rf_mod", C.c_int)]
 
 
 class SymbolizerConfig(C.Structure):
@@ -1135,6 +1135,21 @@ class SymbolizerConfig(C.Structure):
         ("use_cosine_filter", C.c_int), ("n_filters", C.c_int),
         ("filter_taps", C.POINTER(C.c_float) * 8), ("filter_len", C.c_int * 8),
     ]
+
+
+class AcqPattern(C.Structure):
+    """dsdneo_b200_acq_pattern: one 24-symbol sync pattern of getFrameSync and the decoder class behind it."""
+    _fields_ = [("symbols", C.c_char_p), ("sync_type", C.c_int), ("kind", C.c_int), ("cls", SymClass)]
+
+
+ACQ_INFO_BYTES = 84
+
+
+def acq_info_dtype():
+    import numpy as np
+
+    return np.dtype([("acquired", "<i4"), ("sync_type", "<i4"), ("hit_index", "<i4"), ("hunt_symbols", "<i4"), ("warm_start", "u1"),
+                     ("resample_ok", "u1"), ("resampled", "u1", (66,))])
 
 
 class SymbolOut(C.Structure):
@@ -1197,7 +1212,53 @@ class Symbolizer:
         check(lib().dsdneo_b200_symbolizer_set_snr(self._h, a.ctypes.data), "symbolizer_set_snr")
 
     def out_pitch(self, n_samples):
-        return (n_samples + 96) // (self.sps_floor - 1) + 2
+        return (n_samples + 256) // (self.sps_floor - 1) + 2
+
+    def set_acquire_patterns(self, patterns):
+        """patterns: [(symbols '1'/'3' x 24, sync_type, kind 0 P25p1 / 1 DMR, SymClass)], compared in this order."""
+        self._pat_keep = [p[0].encode() if isinstance(p[0], str) else p[0] for p in patterns]
+        arr = (AcqPattern * len(patterns))()
+        for k, (sym, st, kind, cls) in enumerate(patterns):
+            arr[k].symbols, arr[k].sync_type, arr[k].kind, arr[k].cls = self._pat_keep[k], st, kind, cls
+        check(lib().dsdneo_b200_symbolizer_set_acquire_patterns(self._h, arr, len(patterns)), "symbolizer_set_acquire_patterns")
+
+    def set_acquired(self, flags=None):
+        import numpy as np
+
+        if flags is None:
+            check(lib().dsdneo_b200_symbolizer_set_acquired(self._h, None), "symbolizer_set_acquired")
+            return
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(flags, dtype=np.int32), (self.n_channels,)))
+        check(lib().dsdneo_b200_symbolizer_set_acquired(self._h, a.ctypes.data), "symbolizer_set_acquired")
+
+    def _alloc_out(self, dev, n_samples):
+        import torch
+
+        pitch = self.out_pitch(n_samples)
+        res = {
+            "symbols": torch.zeros((self.n_channels, pitch), dtype=torch.float32, device=dev),
+            "dibits": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+            "reliability": torch.zeros((self.n_channels, pitch), dtype=torch.uint8, device=dev),
+            "llr": torch.zeros((self.n_channels, pitch, 2), dtype=torch.int16, device=dev),
+            "count": torch.zeros((self.n_channels,), dtype=torch.int32, device=dev),
+        }
+        out = SymbolOut(res["symbols"].data_ptr(), res["dibits"].data_ptr(), res["reliability"].data_ptr(), res["llr"].data_ptr(),
+                        res["count"].data_ptr(), pitch)
+        return res, out
+
+    def run_acquire(self, d_disc, n_samples, stream=None):
+        """getFrameSync + getDibitSoft over one launch of RAW discriminator samples; adds res['info'] uint8 [n_channels, 84]
+        (view the host copy with acq_info_dtype())."""
+        import torch
+
+        assert d_disc.is_cuda and d_disc.dtype == torch.float32 and d_disc.is_contiguous() and d_disc.shape[0] == self.n_channels
+        res, out = self._alloc_out(d_disc.device, n_samples)
+        res["info"] = torch.zeros((self.n_channels, ACQ_INFO_BYTES), dtype=torch.uint8, device=d_disc.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_disc.device)
+        check(lib().dsdneo_b200_symbolize_acquire_batch(self._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, C.byref(out),
+                                                        res["info"].data_ptr(), _stream_ptr(stream)), "symbolize_acquire_batch")
+        return res
 
     def run(self, d_disc, n_samples, mode=SYM_MODE_GET_DIBIT_SOFT, have_sync=1, stream=None):
         """d_disc: cuda float32 [n_channels, pitch]. Returns dict of cuda tensors + per-channel counts."""

@@ -242,7 +242,7 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
     const int symrate = 4800;
     int whole = cfg->rate_hz / symrate;
     whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
-    rx->cap_new = (int)(((size_t)rx->cap_pairs + 96) / (size_t)(whole - 1) + 2);
+    rx->cap_new = (int)(((size_t)rx->cap_pairs + 256) / (size_t)(whole - 1) + 2);
     rx->cap_new = (rx->cap_new + 31) & ~31;
     rx->pitch = (size_t)kKeep + (size_t)rx->cap_new;
     const size_t n = (size_t)rx->n_ch, slots = n * (size_t)rx->max_hits;

@@ -31,7 +31,8 @@ using namespace dsdneo;
 namespace {
 
 constexpr int kMaxTaps = DSDNEO_B200_SYM_MAX_TAPS; /* 256 */
-constexpr int kCarry = 96;                         /* leftover samples carried between launches (< longest symbol) */
+constexpr int kCarry = 256;                        /* leftover samples carried between launches: the longest symbol, or the
+                                                      samples an unfinished acquisition still needs (kAcqMargin) */
 constexpr int kSbuf = 128;
 constexpr int kMinMax = 1024;
 
@@ -55,6 +56,7 @@ struct SymScalars {
     int* window_l;
     int* track;
     int* negative;
+    int* rf_mod;
     int* sps_num;
     int* sps_den;
     int* sps_accum;
@@ -370,6 +372,9 @@ struct SymParams {
     int16_t* llr;        /* [n_ch][out_pitch][2] */
     int* count;          /* [n_ch] */
     const int* snr_num;  /* [n_ch] reliability weight numerator 204 + (w256 >> 2), dsd_dibit.c:504-546 */
+    const int* start_off; /* optional [n_ch]: samples of this launch already consumed by the acquisition kernel */
+    const int* out_off;   /* optional [n_ch]: outputs already written by it */
+    const int* acquired;  /* optional [n_ch]: channels still hunting are skipped by symbolize_kernel */
     size_t out_pitch;
     int n_ch, n, mode, have_sync, rate, symrate, ssize, msize;
 };
@@ -417,27 +422,10 @@ cq_thresholds(float vmin, float vmax, float& center, float& umid, float& lmid) {
     lmid = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vmin, center), 5.0f), 0.125f), center);
 }
 
-/* digitize (dsd_dibit.c:963-976,1018-1041) + compute_dibit_soft_metric (:644-721) + c4fm_reliability_from_thresholds
- * (:455-502) + apply_c4fm_snr_weight (:504-546, snr_num = 204 + (w256 >> 2)) for one symbol given the thresholds in force
- * after use_symbol.  Reads nothing else, so the serial kernel hands 32 symbols at a time to its 32 lanes. */
-__device__ __forceinline__ void
-digitize_one(float sym, float vmin, float vmax, float center, float umid, float lmid, int negative, int snr_num, int& dibit_out,
-             int& rel_out, int& l0_out, int& l1_out) {
-    int dibit;
-    if (sym > center) {
-        dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
-    } else {
-        dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
-    }
-    const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
-    float ideal[4];
-    if (negative) {
-        ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
-    } else {
-        ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
-    }
-    int mag0, mag1;
-    bit_metrics(sym, ideal, mag0, mag1);
+/* c4fm_reliability_from_thresholds (dsd_dibit.c:455-502) + apply_c4fm_snr_weight (:504-546) = dmr_compute_reliability for
+ * rf_mod 0 / 2 (:548-568) */
+__device__ __forceinline__ int
+c4fm_reliability(float sym, float vmin, float vmax, float center, float umid, float lmid, int snr_num) {
     const float eps = 1e-6f;
     int rel;
     if (sym > umid) {
@@ -460,7 +448,31 @@ digitize_one(float sym, float vmin, float vmax, float center, float umid, float 
         rel = __float2int_rn(__fdiv_rn(__fmul_rn(__fsub_rn(lmid, sym), 255.0f), span));
     }
     rel = clamp255(rel);
-    rel = clamp255((rel * snr_num) >> 8);
+    return clamp255((rel * snr_num) >> 8);
+}
+
+/* digitize (dsd_dibit.c:963-976,1018-1041) + compute_dibit_soft_metric (:644-721) + c4fm_reliability_from_thresholds
+ * (:455-502) + apply_c4fm_snr_weight (:504-546, snr_num = 204 + (w256 >> 2)) for one symbol given the thresholds in force
+ * after use_symbol.  Reads nothing else, so the serial kernel hands 32 symbols at a time to its 32 lanes. */
+__device__ __forceinline__ void
+digitize_one(float sym, float vmin, float vmax, float center, float umid, float lmid, int negative, int snr_num, int& dibit_out,
+             int& rel_out, int& l0_out, int& l1_out) {
+    int dibit;
+    if (sym > center) {
+        dibit = sym > umid ? (negative ? 3 : 1) : (negative ? 2 : 0);
+    } else {
+        dibit = sym < lmid ? (negative ? 1 : 3) : (negative ? 0 : 2);
+    }
+    const float plus_one = __fmul_rn(0.5f, __fadd_rn(center, umid)), minus_one = __fmul_rn(0.5f, __fadd_rn(lmid, center));
+    float ideal[4];
+    if (negative) {
+        ideal[0] = minus_one, ideal[1] = vmin, ideal[2] = plus_one, ideal[3] = vmax;
+    } else {
+        ideal[0] = plus_one, ideal[1] = vmax, ideal[2] = minus_one, ideal[3] = vmin;
+    }
+    int mag0, mag1;
+    bit_metrics(sym, ideal, mag0, mag1);
+    int rel = c4fm_reliability(sym, vmin, vmax, center, umid, lmid, snr_num);
     const int min_mag = mag0 < mag1 ? mag0 : mag1;
     if (min_mag > 0 && rel < min_mag) {
         mag0 = (mag0 * rel) / min_mag;
@@ -773,9 +785,12 @@ symbolize_kernel(const SymParams p) {
     }
     WarpShared* sh = &s_warp[warp];
     float* ring = sh->ring;
+    if (p.acquired && !p.acquired[c]) {
+        return; /* still hunting: sym_acquire_kernel consumed this launch's samples and wrote the outputs and the count */
+    }
 
     /* state -> registers (every lane holds the same copy) */
-    const int window_l = p.s.window_l[c], track = p.s.track[c], negative = p.s.negative[c];
+    const int window_l = p.s.window_l[c], track = p.s.track[c], negative = p.s.negative[c], rf_mod = p.s.rf_mod[c];
     const int snr_num = p.snr_num[c];
     int sps_num = p.s.sps_num[c], sps_den = p.s.sps_den[c], sps_accum = p.s.sps_accum[c];
     int sps = p.s.sps[c], center_idx = p.s.center_idx[c], jitter = p.s.jitter[c];
@@ -800,8 +815,8 @@ symbolize_kernel(const SymParams p) {
     const int q0 = kCarry - carry_n;
     const int q_end = kCarry + p.n;
     const int q_fill_end = (q_end + 31) & ~31;
-    int pos = q0;
-    int whi = q0 & ~31;
+    int pos = q0 + (p.start_off ? p.start_off[c] : 0);
+    int whi = pos & ~31;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto refill = [&]() {
         while (whi < pos + kLook && whi < q_fill_end) {
@@ -846,10 +861,11 @@ symbolize_kernel(const SymParams p) {
     uint8_t* o_dib = p.dibits ? p.dibits + (size_t)c * p.out_pitch : nullptr;
     uint8_t* o_rel = p.reliab ? p.reliab + (size_t)c * p.out_pitch : nullptr;
     short2* o_llr = p.llr ? reinterpret_cast<short2*>(p.llr) + (size_t)c * p.out_pitch : nullptr;
-    int nsym = 0;
+    const int nsym0 = p.out_off ? p.out_off[c] : 0; /* outputs the acquisition kernel already wrote for this launch */
+    int nsym = nsym0;
     const int out_cap = (int)(p.out_pitch > 0x7fffffffu ? 0x7fffffffu : p.out_pitch);
 
-    /* one group of <= 32 finished symbols: lane k digitizes and stores symbol k */
+    /* one group of <= 32 finished symbols: lane k digitizes and stores symbol k (groups are relative to nsym0) */
     auto flush_group = [&](int n_in_group) { /* symbols [nsym - n_in_group, nsym) */
         __syncwarp();
         const int base = nsym - n_in_group;
@@ -877,7 +893,7 @@ symbolize_kernel(const SymParams p) {
 
     const int lo0 = max((whole0 - 1) / 2 - window_l, 0), hi0 = min((whole0 - 1) / 2 + 2, whole0 - 1);
     const int nw0 = hi0 - lo0 + 1;
-    const bool fast_cfg = soft && rem0 == 0 && whole0 != 20 && whole0 != 5 && (nw0 == 4 || nw0 == 5) && tr.cap == kSbuf
+    const bool fast_cfg = soft && rf_mod == 0 && rem0 == 0 && whole0 != 20 && whole0 != 5 && (nw0 == 4 || nw0 == 5) && tr.cap == kSbuf
                           && (!track || tr.pow2);
 
     refill();
@@ -885,7 +901,7 @@ symbolize_kernel(const SymParams p) {
         refill();
         /* ---- steady state of a locked channel: a batch of symbols through the tight loop ---- */
         if (fast_cfg && jitter >= 0 && sps_num == p.rate && sps_den == p.symrate && (!track || sum_window == tr.window)) {
-            int nb = min(32 - (nsym & 31), out_cap - nsym);
+            int nb = min(32 - ((nsym - nsym0) & 31), out_cap - nsym);
             nb = min(nb, (q_end - pos - reserve) / whole0 + 1);
             /* every sample of the batch must have landed in the ring */
             const int landed = (whi >= q_fill_end) ? whi : whi - 32 * kPending;
@@ -898,7 +914,7 @@ symbolize_kernel(const SymParams p) {
                 mi0 = idx;
             }
             if (nb > 0) {
-                const int g0 = nsym & 31;
+                const int g0 = (nsym - nsym0) & 31;
                 if (!track) { /* thresholds do not move: hand them to digitize as they are */
                     for (int k = lane; k < nb; k += 32) {
                         sh->o_min[g0 + k] = vmin, sh->o_max[g0 + k] = vmax, sh->o_center[g0 + k] = center;
@@ -941,7 +957,7 @@ symbolize_kernel(const SymParams p) {
                         minref = vmin;
                     }
                     nsym += done;
-                    if ((nsym & 31) == 0) {
+                    if (((nsym - nsym0) & 31) == 0) {
                         flush_group(32);
                     }
                     continue;
@@ -987,6 +1003,12 @@ symbolize_kernel(const SymParams p) {
                     } else if (jitter >= 11 && jitter <= 14) {
                         i++;
                     }
+                } else if (rf_mod == 2) { /* symbol_adjust_timing_gfsk */
+                    if (jitter >= center_idx - 1 && jitter <= center_idx) {
+                        i--;
+                    } else if (jitter >= center_idx + 1 && jitter <= center_idx + 2) {
+                        i++;
+                    }
                 } else {
                     if (jitter > 0 && jitter <= center_idx) {
                         i--;
@@ -998,7 +1020,7 @@ symbolize_kernel(const SymParams p) {
             }
             float s = at(pos);
             pos++;
-            if (have_sync == 1) { /* symbol_apply_sync_clip, rf_mod == 0 */
+            if (have_sync == 1 && rf_mod == 0) { /* symbol_apply_sync_clip: C4FM only */
                 s = s > vmax ? vmax : (s < vmin ? vmin : s);
             }
             if (s > center) { /* symbol_update_jitter, rf_mod == 0 branches */
@@ -1017,8 +1039,13 @@ symbolize_kernel(const SymParams p) {
             if (sps == 5 && i == 2) {
                 sum = __fadd_rn(sum, s);
                 cnt++;
-            } else if (i >= center_idx - window_l && i <= center_idx + 2) {
-                sum = __fadd_rn(sum, s);
+            } else if (rf_mod == 0) { /* symbol_accumulate_c4fm_window */
+                if (i >= center_idx - window_l && i <= center_idx + 2) {
+                    sum = __fadd_rn(sum, s);
+                    cnt++;
+                }
+            } else if (sps <= 4 ? (i == center_idx) : (i == center_idx - 1 || i == center_idx + 1)) {
+                sum = __fadd_rn(sum, s); /* symbol_accumulate_other_window with select_window_gfsk: the two edge samples */
                 cnt++;
             }
             lastsample = s;
@@ -1044,17 +1071,17 @@ symbolize_kernel(const SymParams p) {
             }
         }
         {
-            const int g = nsym & 31;
+            const int g = (nsym - nsym0) & 31;
             sh->o_sym[g] = sym, sh->o_min[g] = vmin, sh->o_max[g] = vmax;
             sh->o_center[g] = center, sh->o_umid[g] = umid, sh->o_lmid[g] = lmid;
         }
         nsym++;
-        if ((nsym & 31) == 0) {
+        if (((nsym - nsym0) & 31) == 0) {
             flush_group(32);
         }
     }
-    if (nsym & 31) {
-        flush_group(nsym & 31);
+    if ((nsym - nsym0) & 31) {
+        flush_group((nsym - nsym0) & 31);
     }
 
     /* leftover samples -> carry (right-aligned), through registers: the ring may be refilled first */
@@ -1088,6 +1115,475 @@ symbolize_kernel(const SymParams p) {
         p.s.carry_n[c] = left;
         p.s.symbolcnt[c] = symbolcnt;
         p.count[c] = nsym;
+    }
+}
+
+/* ------------------------------------------------------------------ acquisition: getFrameSync() on the device */
+
+constexpr int kAcqMaxPatterns = 8;
+constexpr int kAcqMargin = 208; /* hunting stops this many samples before the end of a launch: an acquisition always finishes
+                                   its matched-filter start-up (taps - 1 samples + one symbol) inside the launch; <= kCarry */
+
+struct AcqPattern {
+    unsigned bits;  /* last 24 hunt-sliced symbols, '1' -> 1, '3' -> 0, oldest in bit 23 */
+    int sync_type, kind;
+    int filter, window_l, track, negative;
+};
+
+struct AcqParams {
+    SymParams sp;          /* sp.filt = the RAW discriminator samples of this launch (no matched filter before the first sync) */
+    const float* taps;     /* [n_filters][kMaxTaps] */
+    const int* taps_len;
+    AcqPattern pat[kAcqMaxPatterns];
+    int n_pat;
+    int* acquired;         /* [n_ch] carried: 0 hunting, 1 synchronised */
+    int* hunt_since;       /* [n_ch] carried: symbols since the hunt context (re)started (getFrameSync gives up after 1800) */
+    unsigned* hunt_bits;   /* [n_ch] carried: hunt-sliced symbols, newest in bit 0 */
+    int* hunt_count;       /* [n_ch] carried: symbols in the window (<= 24) */
+    float* lbuf;           /* [n_ch][24] carried level ring */
+    int* lidx;             /* [n_ch] */
+    int* level_count;      /* [n_ch] */
+    float* hist;           /* [n_ch][128] carried symbol history ring (warm start, resample-on-sync) */
+    int* hist_head;        /* [n_ch] total symbols pushed */
+    int* start_off;        /* [n_ch] out: samples of this launch consumed here */
+    int* out_off;          /* [n_ch] out: outputs written here */
+    dsdneo_b200_acq_info* info; /* [n_ch] out */
+    float* fir_hist;       /* [n_ch][kMaxTaps] the matched filter's carried raw history (sps_fir_kernel) */
+};
+
+/*
+ * getFrameSync() from the never-synchronised state (src/dsp/dsd_frame_sync.c:3098-3148), one warp per hunting channel,
+ * warp-uniform like symbolize_kernel: getSymbol(have_sync = 0) with its timing nudges on the RAW samples; the level ring,
+ * sbuf and rolling payload dibit / reliability bookkeeping; hunt-time slice and 24-symbol pattern compare; on a match the
+ * basic lock, the sync warm start of the slicer thresholds (src/dsp/sync_calibration.c:155-226), for DMR the re-slicing of
+ * the 66 dibits in front of the sync (src/dsp/dmr_sync.c:60-126), and the switch to the decoder class of that sync type.
+ * The reference turns the matched filter on at that moment with an all-zero delay line; the first taps - 1 samples after the
+ * sync are therefore filtered here, directly and in the reference's accumulation order, and the first few synchronised
+ * symbols (getDibitSoft) are produced here too; symbolize_kernel takes over where the steady-state filter output is valid.
+ */
+__global__ void __launch_bounds__(kSymWarps * 32)
+sym_acquire_kernel(const AcqParams a) {
+    __shared__ WarpShared s_warp[kSymWarps];
+    __shared__ float s_hist[kSymWarps][128], s_lbuf[kSymWarps][24], s_sorted[kSymWarps][24];
+    const SymParams& p = a.sp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * kSymWarps + warp;
+    if (c >= p.n_ch) {
+        return;
+    }
+    if (a.acquired[c]) {
+        if (lane == 0) {
+            a.start_off[c] = 0, a.out_off[c] = 0;
+            a.info[c].acquired = 1, a.info[c].sync_type = -1, a.info[c].hit_index = -1, a.info[c].hunt_symbols = 0;
+            a.info[c].warm_start = 0, a.info[c].resample_ok = 0;
+        }
+        return;
+    }
+    WarpShared* sh = &s_warp[warp];
+    float* ring = sh->ring;
+    float* hist = s_hist[warp];
+    float* lbuf = s_lbuf[warp];
+    float* sorted = s_sorted[warp];
+    const unsigned full = 0xffffffffu;
+
+    int window_l = p.s.window_l[c], track = p.s.track[c], negative = p.s.negative[c];
+    const int rf_mod = p.s.rf_mod[c], snr_num = p.snr_num[c];
+    int sps_num = p.s.sps_num[c], sps_den = p.s.sps_den[c], sps_accum = p.s.sps_accum[c];
+    int sps = p.s.sps[c], center_idx = p.s.center_idx[c], jitter = p.s.jitter[c];
+    float lastsample = p.s.lastsample[c];
+    float vmin = p.s.vmin[c], vmax = p.s.vmax[c], center = p.s.center[c], umid = p.s.umid[c], lmid = p.s.lmid[c];
+    float minref = p.s.minref[c], maxref = p.s.maxref[c];
+    int sidx = p.s.sidx[c], midx = p.s.midx[c], sum_window = p.s.sum_window[c];
+    double minbuf_sum = p.s.minbuf_sum[c], maxbuf_sum = p.s.maxbuf_sum[c];
+    int carry_n = p.s.carry_n[c];
+    carry_n = carry_n < 0 ? 0 : (carry_n > kCarry ? kCarry : carry_n);
+    long long symbolcnt = p.s.symbolcnt[c];
+    int hunt_since = a.hunt_since[c], hunt_count = a.hunt_count[c], lidx = a.lidx[c], level_count = a.level_count[c];
+    unsigned hunt_bits = a.hunt_bits[c];
+    int hist_head = a.hist_head[c];
+    for (int k = lane; k < 128; k += 32) {
+        hist[k] = a.hist[(size_t)c * 128 + k];
+    }
+    if (lane < 24) {
+        lbuf[lane] = a.lbuf[(size_t)c * 24 + lane];
+    }
+    WarpTracker tr;
+    tr.init(lane, p.ssize, p.msize, p.minbuf + (size_t)c * kMinMax, p.maxbuf + (size_t)c * kMinMax, p.sbuf + (size_t)c * kSbuf, sh, false);
+
+    const float* raw = p.filt + (size_t)c * p.filt_pitch;
+    float* carry = p.carry + (size_t)c * kCarry;
+    const int q0 = kCarry - carry_n;
+    const int q_end = kCarry + p.n;
+    const int q_fill_end = (q_end + 31) & ~31;
+    int pos = q0;
+    int whi = q0 & ~31;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    auto refill = [&]() {
+        while (whi < pos + kLook && whi < q_fill_end) {
+            const int q = whi + lane;
+            const float* src = raw;
+            unsigned bytes = 0;
+            if (q < kCarry) {
+                if (q >= q0) {
+                    src = carry + q, bytes = 4;
+                }
+            } else if (q < q_end) {
+                src = raw + (q - kCarry), bytes = 4;
+            }
+            const int slot = q & (kRing - 1);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ring_s + 4u * (unsigned)slot), "l"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            whi += 32;
+        }
+        if (whi >= q_fill_end) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+        }
+        __syncwarp();
+    };
+    auto at = [&](int q) -> float { return ring[q & (kRing - 1)]; };
+
+    int whole0 = p.rate / p.symrate, rem0 = p.rate % p.symrate;
+    if (whole0 < 2) {
+        whole0 = 2, rem0 = 0;
+    }
+    if (whole0 > 64) {
+        whole0 = 64, rem0 = 0;
+    }
+    const int reserve = whole0 + 2;
+    float* o_sym = p.symbols + (size_t)c * p.out_pitch;
+    uint8_t* o_dib = p.dibits ? p.dibits + (size_t)c * p.out_pitch : nullptr;
+    uint8_t* o_rel = p.reliab ? p.reliab + (size_t)c * p.out_pitch : nullptr;
+    short2* o_llr = p.llr ? reinterpret_cast<short2*>(p.llr) + (size_t)c * p.out_pitch : nullptr;
+    const int out_cap = (int)(p.out_pitch > 0x7fffffffu ? 0x7fffffffu : p.out_pitch);
+    int nsym = 0;
+
+    /* matched filter of the acquired class, evaluated directly from the raw samples with a delay line that was all zero when
+     * the sync was accepted (apply_sps_fir, dsd_filters.c:172-201: taps oldest -> newest, multiply then add) */
+    int acq_pos = -1, filt_id = -1, filt_len = 0;
+    auto filtered = [&](int q) -> float {
+        if (filt_id < 0) {
+            return at(q);
+        }
+        const float* t = a.taps + (size_t)filt_id * kMaxTaps;
+        const int d = q - acq_pos; /* samples fed to the filter before this one */
+        float acc = 0.0f;
+        for (int i = max(0, filt_len - 1 - d); i < filt_len; i++) {
+            acc = __fadd_rn(acc, __fmul_rn(t[i], at(q - (filt_len - 1) + i)));
+        }
+        return acc;
+    };
+
+    /* one getSymbol(): dsd_symbol.c:1328-1387 (timing), :1769-1796 (samples) */
+    auto take_symbol = [&](int have_sync) -> float {
+        if (sps_num != p.rate || sps_den != p.symrate) {
+            sps_num = p.rate, sps_den = p.symrate, sps_accum = 0, jitter = -1;
+            center = 0.0f, vmin = -30000.0f, vmax = 30000.0f, lmid = -20000.0f, umid = 20000.0f;
+            minref = -24000.0f, maxref = 24000.0f;
+            tr.fill_rings(vmin, vmax, kMinMax);
+            midx = 0, sum_window = 0;
+        }
+        int whole = whole0;
+        if (rem0 > 0 && sps_den > 0) {
+            int acc = sps_accum + rem0;
+            if (acc >= sps_den) {
+                whole++;
+                acc -= sps_den;
+            }
+            sps_accum = acc;
+            whole = whole > 64 ? 64 : whole;
+        }
+        sps = whole;
+        center_idx = (sps - 1) / 2;
+        const int l_edge = rf_mod == 2 ? 1 : window_l;
+        float sum = 0.0f;
+        int cnt = 0;
+        for (int i = 0; i < sps; i++) {
+            if (i == 0 && have_sync == 0 && jitter >= 0) {
+                if (sps == 20) {
+                    if (jitter >= 7 && jitter <= 10) {
+                        i--;
+                    } else if (jitter >= 11 && jitter <= 14) {
+                        i++;
+                    }
+                } else if (rf_mod == 2) {
+                    if (jitter >= center_idx - 1 && jitter <= center_idx) {
+                        i--;
+                    } else if (jitter >= center_idx + 1 && jitter <= center_idx + 2) {
+                        i++;
+                    }
+                } else {
+                    if (jitter > 0 && jitter <= center_idx) {
+                        i--;
+                    } else if (jitter > center_idx && jitter < sps) {
+                        i++;
+                    }
+                }
+                jitter = -1;
+            }
+            float sv = filtered(pos);
+            pos++;
+            if (have_sync == 1 && rf_mod == 0) {
+                sv = sv > vmax ? vmax : (sv < vmin ? vmin : sv);
+            }
+            if (sv > center) {
+                if (!(sv > __fmul_rn(maxref, 1.25f)) && jitter < 0 && lastsample < center) {
+                    jitter = i;
+                }
+            } else {
+                if (!(sv < __fmul_rn(minref, 1.25f)) && jitter < 0 && lastsample > center) {
+                    jitter = i;
+                }
+            }
+            if (sps == 20 && i >= 7 && i <= 13) {
+                sum = __fadd_rn(sum, sv);
+                cnt++;
+            }
+            if (sps == 5 && i == 2) {
+                sum = __fadd_rn(sum, sv);
+                cnt++;
+            } else if (rf_mod == 0) {
+                if (i >= center_idx - l_edge && i <= center_idx + 2) {
+                    sum = __fadd_rn(sum, sv);
+                    cnt++;
+                }
+            } else if (sps <= 4 ? (i == center_idx) : (i == center_idx - 1 || i == center_idx + 1)) {
+                sum = __fadd_rn(sum, sv);
+                cnt++;
+            }
+            lastsample = sv;
+        }
+        symbolcnt++;
+        return cnt > 0 ? __fdiv_rn(sum, (float)cnt) : 0.0f;
+    };
+    auto payload_dibit = [&](float v) -> int { return v > center ? (v > umid ? 1 : 0) : (v < lmid ? 3 : 2); };
+
+    int acquired = 0, sync_type = -1, hit_index = -1, warm = 0, resample_ok = 0;
+    refill();
+    /* ---------------- hunt ---------------- */
+    while (!acquired && nsym < out_cap && (q_end - pos) >= kAcqMargin) {
+        refill();
+        const float symbol = take_symbol(0);
+        hist[hist_head & 127] = symbol; /* dsd_symbol_history_push */
+        hist_head++;
+        /* frame_sync_update_symbol_ring (dsd_frame_sync.c:1747-1764) */
+        lbuf[lidx] = symbol;
+        level_count = level_count < 24 ? level_count + 1 : 24;
+        sh->sbuf[sidx & (kSbuf - 1)] = symbol;
+        lidx = lidx == 23 ? 0 : lidx + 1;
+        sidx = (sidx == p.ssize - 1) ? 0 : sidx + 1;
+        /* rolling payload dibit + reliability (frame_sync_store_dmr_payload_symbol, :2161-2190) */
+        const int d = payload_dibit(symbol);
+        const int rel = c4fm_reliability(symbol, vmin, vmax, center, umid, lmid, snr_num);
+        if (lane == 0) {
+            o_sym[nsym] = symbol;
+            if (o_dib) {
+                o_dib[nsym] = (uint8_t)d;
+                o_rel[nsym] = (uint8_t)rel;
+                o_llr[nsym] = make_short2((short)(((d >> 1) & 1) ? rel : -rel), (short)((d & 1) ? rel : -rel));
+            }
+        }
+        nsym++;
+        hunt_bits = (hunt_bits << 1) | (symbol > 0.0f ? 1u : 0u);
+        hunt_count = hunt_count < 24 ? hunt_count + 1 : 24;
+        hunt_since++;
+        __syncwarp();
+        if (hunt_since >= 8) { /* frame_sync_eval_window (:2638-2676) */
+            /* sorted copy of the level ring: every lane ranks one entry (equal values are interchangeable) */
+            if (lane < level_count) {
+                const float v = lbuf[lane];
+                int rank = 0;
+                for (int j = 0; j < level_count; j++) {
+                    const float w = lbuf[j];
+                    rank += (w < v || (w == v && j < lane)) ? 1 : 0;
+                }
+                sorted[rank] = v;
+            }
+            __syncwarp();
+            float lmin, lmax;
+            { /* dsd_frame_sync_estimate_sorted_window_levels (src/dsp/frame_sync_level.c) */
+                const int n = level_count;
+                if (n < 3) {
+                    float sum = 0.0f;
+                    for (int i = 0; i < n; i++) {
+                        sum = __fadd_rn(sum, sorted[i]);
+                    }
+                    lmin = lmax = __fdiv_rn(sum, (float)n);
+                } else {
+                    int min_idx = 0, max_idx = n - 3;
+                    if (n >= 13) {
+                        min_idx = 2, max_idx = n - 5;
+                    }
+                    if (max_idx + 2 >= n) {
+                        max_idx = n - 3;
+                    }
+                    lmin = __fdiv_rn(__fadd_rn(__fadd_rn(sorted[min_idx], sorted[min_idx + 1]), sorted[min_idx + 2]), 3.0f);
+                    lmax = __fdiv_rn(__fadd_rn(__fadd_rn(sorted[max_idx], sorted[max_idx + 1]), sorted[max_idx + 2]), 3.0f);
+                }
+            }
+            maxref = vmax, minref = vmin; /* frame_sync_window_levels, FSK profiles (:2332-2335) */
+            int hit = -1;
+            if (hunt_count >= 24) {
+                for (int k = 0; k < a.n_pat && hit < 0; k++) {
+                    hit = ((hunt_bits & 0xFFFFFFu) == a.pat[k].bits) ? k : -1;
+                }
+            }
+            if (hit >= 0) {
+                const AcqPattern& pt = a.pat[hit];
+                vmax = __fmul_rn(__fadd_rn(vmax, lmax), 0.5f); /* frame_sync_set_basic_lock: (x + y) / 2 */
+                vmin = __fmul_rn(__fadd_rn(vmin, lmin), 0.5f);
+                if (pt.kind == 1 || rf_mod == 0) { /* dsd_sync_warm_start_thresholds_outer_only(24) */
+                    float sum_pos = 0.0f, sum_neg = 0.0f;
+                    int n_pos = 0, n_neg = 0;
+                    for (int i = 0; i < 24; i++) { /* newest first, the reference's order */
+                        const float v = hist[(hist_head - 1 - i) & 127];
+                        if (v > 0.0f) {
+                            sum_pos = __fadd_rn(sum_pos, v);
+                            n_pos++;
+                        } else {
+                            sum_neg = __fadd_rn(sum_neg, v);
+                            n_neg++;
+                        }
+                    }
+                    if (n_pos > 0 && n_neg > 0) {
+                        const float mp = __fdiv_rn(sum_pos, (float)n_pos), mn = __fdiv_rn(sum_neg, (float)n_neg);
+                        if (!(fabsf(__fsub_rn(mp, mn)) < 1.0f)) {
+                            vmax = mp, vmin = mn;
+                            center = __fmul_rn(__fadd_rn(vmax, vmin), 0.5f);
+                            umid = __fadd_rn(center, __fmul_rn(__fsub_rn(vmax, center), 0.625f));
+                            lmid = __fadd_rn(center, __fmul_rn(__fsub_rn(vmin, center), 0.625f));
+                            maxref = __fmul_rn(vmax, 0.80f);
+                            minref = __fmul_rn(vmin, 0.80f);
+                            tr.fill_rings(vmin, vmax, p.msize > kMinMax ? kMinMax : p.msize);
+                            sum_window = 0;
+                            warm = 1;
+                        }
+                    }
+                }
+                if (pt.kind == 1 && hist_head >= 90) { /* dmr_resample_cach: symbols [-90 .. -25] of the stream */
+                    for (int i = lane; i < 66; i += 32) {
+                        const int back = 89 - i; /* 0 = newest */
+                        const uint8_t d2 = (uint8_t)payload_dibit(hist[(hist_head - 1 - back) & 127]);
+                        a.info[c].resampled[i] = d2;
+                        const int at_out = nsym - 1 - back; /* the part that lies in this launch is rewritten in place */
+                        if (at_out >= 0 && o_dib) {
+                            o_dib[at_out] = d2;
+                        }
+                    }
+                    resample_ok = 1;
+                }
+                window_l = pt.window_l, track = pt.track, negative = pt.negative;
+                filt_id = pt.filter;
+                filt_len = filt_id >= 0 ? a.taps_len[filt_id] : 0;
+                if (filt_len <= 0) {
+                    filt_id = -1;
+                }
+                acq_pos = pos;
+                acquired = 1, sync_type = pt.sync_type, hit_index = nsym - 1;
+            }
+        }
+        if (!acquired && hunt_since >= 1800) { /* frame_sync_handle_no_sync_timeout: the next call starts with an empty window */
+            hunt_since = 0, hunt_count = 0, lidx = 0, level_count = 0, hunt_bits = 0;
+        }
+    }
+    /* ---------------- the first synchronised symbols, through the starting-up matched filter ---------------- */
+    if (acquired) {
+        if (track && tr.cap >= 2) {
+            tr.rescan();
+        }
+        while (nsym < out_cap && ((pos - acq_pos) < filt_len - 1 || pos < kCarry) && (q_end - pos) >= reserve) {
+            refill();
+            const float sym = take_symbol(1);
+            if (track) {
+                tr.push(sym, sidx, midx, sum_window, minbuf_sum, maxbuf_sum, vmin, vmax);
+                cq_thresholds(vmin, vmax, center, umid, lmid);
+                maxref = __fmul_rn(vmax, 0.80f);
+                minref = __fmul_rn(vmin, 0.80f);
+            } else {
+                sh->sbuf[sidx & (kSbuf - 1)] = sym;
+                maxref = vmax;
+                minref = vmin;
+            }
+            if (tr.cap > 0) {
+                sidx = (sidx >= tr.cap - 1) ? 0 : sidx + 1;
+            }
+            int dibit, rel, l0, l1;
+            digitize_one(sym, vmin, vmax, center, umid, lmid, negative, snr_num, dibit, rel, l0, l1);
+            if (lane == 0) {
+                o_sym[nsym] = sym;
+                if (o_dib) {
+                    o_dib[nsym] = (uint8_t)dibit;
+                    o_rel[nsym] = (uint8_t)rel;
+                    o_llr[nsym] = make_short2((short)l0, (short)l1);
+                }
+            }
+            nsym++;
+        }
+    }
+    /* ---------------- hand over ---------------- */
+    refill();
+    int left = 0;
+    if (!acquired) { /* still hunting: the unconsumed raw tail is carried */
+        left = q_end - pos;
+        left = left < 0 ? 0 : (left > kCarry ? kCarry : left);
+        float keep[kCarry / 32];
+#pragma unroll
+        for (int j = 0; j < kCarry / 32; j++) {
+            const int k = j * 32 + lane;
+            keep[j] = k < left ? at(q_end - left + k) : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kCarry / 32; j++) {
+            const int k = j * 32 + lane;
+            if (k < left) {
+                carry[kCarry - left + k] = keep[j];
+            }
+        }
+    }
+    if (acquired && filt_id >= 0) { /* sps_fir_kernel runs next over this launch: x[-1], x[-2] .. are the carried raw samples */
+        const int hl = filt_len - 1;
+        for (int k = lane; k < hl; k += 32) {
+            const int q = kCarry - hl + k;
+            a.fir_hist[(size_t)c * kMaxTaps + k] = q >= q0 ? carry[q] : 0.0f;
+        }
+    }
+    tr.flush_chunk();
+    tr.store_sbuf(p.sbuf + (size_t)c * kSbuf);
+    __syncwarp();
+    for (int k = lane; k < 128; k += 32) {
+        a.hist[(size_t)c * 128 + k] = hist[k];
+    }
+    if (lane < 24) {
+        a.lbuf[(size_t)c * 24 + lane] = lbuf[lane];
+    }
+    if (lane == 0) {
+        p.s.sps_num[c] = sps_num, p.s.sps_den[c] = sps_den, p.s.sps_accum[c] = sps_accum;
+        p.s.sps[c] = sps, p.s.center_idx[c] = center_idx, p.s.jitter[c] = jitter;
+        p.s.lastsample[c] = lastsample;
+        p.s.vmin[c] = vmin, p.s.vmax[c] = vmax, p.s.center[c] = center, p.s.umid[c] = umid, p.s.lmid[c] = lmid;
+        p.s.minref[c] = minref, p.s.maxref[c] = maxref;
+        p.s.sidx[c] = sidx, p.s.midx[c] = midx, p.s.sum_window[c] = sum_window;
+        p.s.minbuf_sum[c] = minbuf_sum, p.s.maxbuf_sum[c] = maxbuf_sum;
+        p.s.symbolcnt[c] = symbolcnt;
+        a.hunt_since[c] = hunt_since, a.hunt_count[c] = hunt_count, a.hunt_bits[c] = hunt_bits;
+        a.lidx[c] = lidx, a.level_count[c] = level_count, a.hist_head[c] = hist_head;
+        a.acquired[c] = acquired;
+        a.info[c].acquired = acquired, a.info[c].sync_type = sync_type, a.info[c].hit_index = hit_index;
+        a.info[c].hunt_symbols = acquired ? hit_index + 1 : nsym;
+        a.info[c].warm_start = (uint8_t)warm, a.info[c].resample_ok = (uint8_t)resample_ok;
+        a.out_off[c] = nsym;
+        if (acquired) {
+            p.s.window_l[c] = window_l, p.s.track[c] = track, p.s.negative[c] = negative;
+            p.s.filter[c] = filt_id;
+            p.s.carry_n[c] = 0;              /* symbolize_kernel continues inside this launch's filtered samples */
+            a.start_off[c] = pos - kCarry;   /* >= 0: the loop above ran until the carried raw samples were used up */
+        } else {
+            p.s.carry_n[c] = left;
+            a.start_off[c] = p.n;
+            p.count[c] = nsym;
+        }
     }
 }
 
@@ -1499,6 +1995,13 @@ struct dsdneo_b200_symbolizer {
     int* d_taps_len;
     float* d_filt;
     size_t filt_pitch;
+    /* acquisition (getFrameSync on the device): configured by dsdneo_b200_symbolizer_set_acquire_patterns */
+    int n_pat;
+    AcqPattern pat[kAcqMaxPatterns];
+    int *d_acquired, *d_hunt_since, *d_hunt_count, *d_lidx, *d_level_count, *d_hist_head, *d_start_off, *d_out_off;
+    unsigned* d_hunt_bits;
+    float *d_lbuf, *d_hist128;
+    dsdneo_b200_acq_info* d_info;
 };
 
 extern "C" {
@@ -1536,6 +2039,7 @@ dsdneo_b200_sym_class_from_synctype(int synctype, int lastsynctype, int use_cosi
         }
     }
     out->filter = filter;
+    out->rf_mod = 0;
     /* window (dsd_symbol.c:197-211): YSF by synctype, DMR BS / MS voice+data by lastsynctype */
     out->window_l = (is_ysf(synctype) || is_dmr_bs(lastsynctype) || lastsynctype == 32 || lastsynctype == 33) ? 1 : 2;
     out->track_minmax = is_p25p1(lastsynctype) ? 1 : 0; /* dsd_dibit.c:264 (rf_mod == 0) */
@@ -1562,6 +2066,18 @@ dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y) {
     cudaFree(y->d_taps);
     cudaFree(y->d_taps_len);
     cudaFree(y->d_filt);
+    cudaFree(y->d_acquired);
+    cudaFree(y->d_hunt_since);
+    cudaFree(y->d_hunt_count);
+    cudaFree(y->d_lidx);
+    cudaFree(y->d_level_count);
+    cudaFree(y->d_hist_head);
+    cudaFree(y->d_start_off);
+    cudaFree(y->d_out_off);
+    cudaFree(y->d_hunt_bits);
+    cudaFree(y->d_lbuf);
+    cudaFree(y->d_hist128);
+    cudaFree(y->d_info);
     free(y);
 }
 
@@ -1594,8 +2110,8 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
     y->msize = cfg->msize > 0 ? cfg->msize : 1024;  /* opts->msize default, :170 */
     y->use_cosine_filter = cfg->use_cosine_filter;
     y->n_filters = cfg->n_filters;
-    /* scalar arena: 23 x 4-byte arrays, 3 x 8-byte arrays */
-    const size_t arena_bytes = n * (23 * 4 + 3 * 8) + 256;
+    /* scalar arena: 24 x 4-byte arrays, 3 x 8-byte arrays */
+    const size_t arena_bytes = n * (24 * 4 + 3 * 8) + 256;
     cudaError_t e = cudaMalloc(&y->arena, arena_bytes);
     if (e == cudaSuccess) {
         e = cudaMemset(y->arena, 0, arena_bytes);
@@ -1612,6 +2128,7 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
         y->s.window_l = i4 + n * k++;
         y->s.track = i4 + n * k++;
         y->s.negative = i4 + n * k++;
+        y->s.rf_mod = i4 + n * k++;
         y->s.sps_num = i4 + n * k++;
         y->s.sps_den = i4 + n * k++;
         y->s.sps_accum = i4 + n * k++;
@@ -1670,7 +2187,7 @@ dsdneo_b200_symbolizer_create(const dsdneo_b200_symbolizer_config* cfg) {
     /* default class: no sync seen yet => no matched filter, window 2/2, no tracking, positive polarity */
     dsdneo_b200_sym_class* cls = (dsdneo_b200_sym_class*)malloc(n * sizeof(dsdneo_b200_sym_class));
     for (size_t i = 0; i < n; i++) {
-        cls[i].filter = DSDNEO_SYM_FILTER_NONE, cls[i].window_l = 2, cls[i].track_minmax = 0, cls[i].negative = 0;
+        cls[i].filter = DSDNEO_SYM_FILTER_NONE, cls[i].window_l = 2, cls[i].track_minmax = 0, cls[i].negative = 0, cls[i].rf_mod = 0;
     }
     int rc = dsdneo_b200_symbolizer_set_class(y, cls);
     free(cls);
@@ -1693,6 +2210,19 @@ dsdneo_b200_symbolizer_reset(dsdneo_b200_symbolizer* y, void* stream) {
     sym_reset_kernel<<<y->n_ch, 128, 0, as_stream(stream)>>>(y->s, y->d_minbuf, y->d_maxbuf, y->d_sbuf, y->d_carry, y->d_hist, y->n_ch);
     DSDNEO_KERNEL_CHECK();
     count_launch();
+    if (y->d_acquired) { /* every channel hunts again, with an empty window and an empty symbol history */
+        const size_t n = (size_t)y->n_ch;
+        cudaStream_t s = as_stream(stream);
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_acquired, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_hunt_since, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_hunt_count, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_lidx, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_level_count, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_hist_head, 0, n * sizeof(int), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_hunt_bits, 0, n * sizeof(unsigned), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_lbuf, 0, n * 24 * sizeof(float), s));
+        DSDNEO_CUDA(cudaMemsetAsync(y->d_hist128, 0, n * 128 * sizeof(float), s));
+    }
     return 0;
 }
 
@@ -1703,7 +2233,7 @@ dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sy
         return DSDNEO_B200_EINVAL;
     }
     const size_t n = (size_t)y->n_ch;
-    int* h = (int*)malloc(4 * n * sizeof(int));
+    int* h = (int*)malloc(5 * n * sizeof(int));
     if (!h) {
         set_error("symbolizer_set_class: out of host memory");
         return DSDNEO_B200_ENOMEM;
@@ -1719,6 +2249,7 @@ dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sy
         h[n + i] = per_channel[i].window_l;
         h[2 * n + i] = per_channel[i].track_minmax ? 1 : 0;
         h[3 * n + i] = per_channel[i].negative ? 1 : 0;
+        h[4 * n + i] = per_channel[i].rf_mod == 2 ? 2 : 0;
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) {
@@ -1732,6 +2263,9 @@ dsdneo_b200_symbolizer_set_class(dsdneo_b200_symbolizer* y, const dsdneo_b200_sy
     }
     if (e == cudaSuccess) {
         e = cudaMemcpy(y->s.negative, h + 3 * n, n * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(y->s.rf_mod, h + 4 * n, n * sizeof(int), cudaMemcpyHostToDevice);
     }
     free(h);
     if (e != cudaSuccess) {
@@ -1784,6 +2318,101 @@ dsdneo_b200_symbolizer_set_snr(dsdneo_b200_symbolizer* y, const double* h_snr_c4
 }
 
 int
+dsdneo_b200_symbolizer_set_acquire_patterns(dsdneo_b200_symbolizer* y, const dsdneo_b200_acq_pattern* patterns, int n_patterns) {
+    if (!y || !patterns || n_patterns < 1 || n_patterns > kAcqMaxPatterns) {
+        set_error("symbolizer_set_acquire_patterns: 1..%d patterns", kAcqMaxPatterns);
+        return DSDNEO_B200_EINVAL;
+    }
+    for (int k = 0; k < n_patterns; k++) {
+        const char* sym = patterns[k].symbols;
+        if (!sym || strlen(sym) != 24) {
+            set_error("symbolizer_set_acquire_patterns: pattern %d is not a 24-symbol '1' / '3' string", k);
+            return DSDNEO_B200_EUNSUPPORTED;
+        }
+        unsigned bits = 0;
+        for (int i = 0; i < 24; i++) {
+            if (sym[i] != '1' && sym[i] != '3') {
+                set_error("symbolizer_set_acquire_patterns: pattern %d has a symbol other than '1' / '3'", k);
+                return DSDNEO_B200_EINVAL;
+            }
+            bits = (bits << 1) | (sym[i] == '1' ? 1u : 0u);
+        }
+        const int f = patterns[k].cls.filter;
+        if (f >= y->n_filters || (f >= 0 && y->h_taps_len[f] <= 0)) {
+            set_error("symbolizer_set_acquire_patterns: pattern %d selects filter %d which was not supplied at create", k, f);
+            return DSDNEO_B200_EINVAL;
+        }
+        {
+            int whole = y->rate / y->symrate;
+            whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
+            if (f >= 0 && y->h_taps_len[f] - 1 + 2 * (whole + 2) > kAcqMargin) {
+                set_error("symbolizer_set_acquire_patterns: filter %d (%d taps) at %d samples per symbol does not start up within "
+                          "the %d-sample launch margin", f, y->h_taps_len[f], whole, kAcqMargin);
+                return DSDNEO_B200_EUNSUPPORTED;
+            }
+        }
+        y->pat[k].bits = bits;
+        y->pat[k].sync_type = patterns[k].sync_type;
+        y->pat[k].kind = patterns[k].kind;
+        y->pat[k].filter = f < 0 ? -1 : f;
+        y->pat[k].window_l = patterns[k].cls.window_l;
+        y->pat[k].track = patterns[k].cls.track_minmax ? 1 : 0;
+        y->pat[k].negative = patterns[k].cls.negative ? 1 : 0;
+    }
+    y->n_pat = n_patterns;
+    if (!y->d_acquired) {
+        const size_t n = (size_t)y->n_ch;
+        cudaError_t e = cudaSuccess;
+#define ACQ_ALLOC(ptr, bytes)                                                                                          \
+    if (e == cudaSuccess) {                                                                                            \
+        e = cudaMalloc((void**)&(ptr), (bytes));                                                                       \
+        if (e == cudaSuccess) {                                                                                        \
+            e = cudaMemset((ptr), 0, (bytes));                                                                         \
+        }                                                                                                              \
+    }
+        ACQ_ALLOC(y->d_acquired, n * sizeof(int));
+        ACQ_ALLOC(y->d_hunt_since, n * sizeof(int));
+        ACQ_ALLOC(y->d_hunt_count, n * sizeof(int));
+        ACQ_ALLOC(y->d_lidx, n * sizeof(int));
+        ACQ_ALLOC(y->d_level_count, n * sizeof(int));
+        ACQ_ALLOC(y->d_hist_head, n * sizeof(int));
+        ACQ_ALLOC(y->d_start_off, n * sizeof(int));
+        ACQ_ALLOC(y->d_out_off, n * sizeof(int));
+        ACQ_ALLOC(y->d_hunt_bits, n * sizeof(unsigned));
+        ACQ_ALLOC(y->d_lbuf, n * 24 * sizeof(float));
+        ACQ_ALLOC(y->d_hist128, n * 128 * sizeof(float));
+        ACQ_ALLOC(y->d_info, n * sizeof(dsdneo_b200_acq_info));
+#undef ACQ_ALLOC
+        if (e != cudaSuccess) {
+            return cuda_fail(e, "symbolizer_set_acquire_patterns", __FILE__, __LINE__);
+        }
+    }
+    return 0;
+}
+
+int
+dsdneo_b200_symbolizer_set_acquired(dsdneo_b200_symbolizer* y, const int* h_acquired) {
+    if (!y || !y->d_acquired) {
+        set_error("symbolizer_set_acquired: acquisition is not configured (set_acquire_patterns)");
+        return DSDNEO_B200_EINVAL;
+    }
+    const size_t n = (size_t)y->n_ch;
+    DSDNEO_CUDA(cudaDeviceSynchronize());
+    if (h_acquired) {
+        DSDNEO_CUDA(cudaMemcpy(y->d_acquired, h_acquired, n * sizeof(int), cudaMemcpyHostToDevice));
+    } else {
+        DSDNEO_CUDA(cudaMemset(y->d_acquired, 0, n * sizeof(int)));
+    }
+    /* a new hunt starts with an empty window */
+    DSDNEO_CUDA(cudaMemset(y->d_hunt_since, 0, n * sizeof(int)));
+    DSDNEO_CUDA(cudaMemset(y->d_hunt_count, 0, n * sizeof(int)));
+    DSDNEO_CUDA(cudaMemset(y->d_lidx, 0, n * sizeof(int)));
+    DSDNEO_CUDA(cudaMemset(y->d_level_count, 0, n * sizeof(int)));
+    DSDNEO_CUDA(cudaMemset(y->d_hunt_bits, 0, n * sizeof(unsigned)));
+    return 0;
+}
+
+int
 dsdneo_b200_selftest_div5(unsigned long long* d_n_mismatch, unsigned* d_first_bad, void* stream) {
     if (!d_n_mismatch || !d_first_bad) {
         set_error("selftest_div5: bad argument");
@@ -1801,9 +2430,9 @@ dsdneo_b200_selftest_div5(unsigned long long* d_n_mismatch, unsigned* d_first_ba
     return 0;
 }
 
-int
-dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
-                            const dsdneo_b200_symbol_out* out, void* stream) {
+static int
+symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                 const dsdneo_b200_symbol_out* out, bool acquire, dsdneo_b200_acq_info* d_info, void* stream) {
     if (!y || !d_disc || !out || n_samples < 0 || disc_pitch < (size_t)n_samples || !out->d_symbols || !out->d_count
         || out->pitch == 0) {
         set_error("symbolize_batch: bad argument");
@@ -1839,6 +2468,66 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
         DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt, (size_t)y->n_ch * pitch * sizeof(float)));
         y->filt_pitch = pitch;
     }
+    SymParams sp;
+    sp.s = y->s;
+    sp.filt = y->d_filt;
+    sp.filt_pitch = y->filt_pitch;
+    sp.carry = y->d_carry;
+    sp.sbuf = y->d_sbuf;
+    sp.minbuf = y->d_minbuf;
+    sp.maxbuf = y->d_maxbuf;
+    sp.symbols = out->d_symbols;
+    sp.dibits = out->d_dibits;
+    sp.reliab = out->d_reliability;
+    sp.llr = out->d_llr;
+    sp.count = out->d_count;
+    sp.out_pitch = out->pitch;
+    sp.n_ch = y->n_ch;
+    sp.n = n_samples;
+    sp.mode = mode;
+    sp.have_sync = have_sync ? 1 : 0;
+    sp.rate = y->rate;
+    sp.symrate = y->symrate;
+    sp.ssize = y->ssize;
+    sp.msize = y->msize;
+    sp.snr_num = y->s.snr_num;
+    sp.start_off = NULL;
+    sp.out_off = NULL;
+    sp.acquired = NULL;
+    if (acquire) { /* hunting channels first: they read the raw samples and may switch their class for the stages below */
+        AcqParams ap;
+        ap.sp = sp;
+        ap.sp.filt = d_disc;
+        ap.sp.filt_pitch = disc_pitch;
+        ap.taps = y->d_taps;
+        ap.taps_len = y->d_taps_len;
+        for (int k = 0; k < y->n_pat; k++) {
+            ap.pat[k] = y->pat[k];
+        }
+        ap.n_pat = y->n_pat;
+        ap.acquired = y->d_acquired;
+        ap.hunt_since = y->d_hunt_since;
+        ap.hunt_bits = y->d_hunt_bits;
+        ap.hunt_count = y->d_hunt_count;
+        ap.lbuf = y->d_lbuf;
+        ap.lidx = y->d_lidx;
+        ap.level_count = y->d_level_count;
+        ap.hist = y->d_hist128;
+        ap.hist_head = y->d_hist_head;
+        ap.start_off = y->d_start_off;
+        ap.out_off = y->d_out_off;
+        ap.info = d_info ? d_info : y->d_info;
+        ap.fir_hist = y->d_hist;
+        {
+            KernelTimer kt("sym_acquire_kernel", s);
+            sym_acquire_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(ap);
+        }
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+        sp.start_off = y->d_start_off;
+        sp.out_off = y->d_out_off;
+        sp.acquired = y->d_acquired;
+    }
     if (n_samples > 0) {
         FirParams fp;
         fp.in = d_disc;
@@ -1871,29 +2560,6 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
         DSDNEO_KERNEL_CHECK();
         count_launch();
     }
-    SymParams sp;
-    sp.s = y->s;
-    sp.filt = y->d_filt;
-    sp.filt_pitch = y->filt_pitch;
-    sp.carry = y->d_carry;
-    sp.sbuf = y->d_sbuf;
-    sp.minbuf = y->d_minbuf;
-    sp.maxbuf = y->d_maxbuf;
-    sp.symbols = out->d_symbols;
-    sp.dibits = out->d_dibits;
-    sp.reliab = out->d_reliability;
-    sp.llr = out->d_llr;
-    sp.count = out->d_count;
-    sp.out_pitch = out->pitch;
-    sp.n_ch = y->n_ch;
-    sp.n = n_samples;
-    sp.mode = mode;
-    sp.have_sync = have_sync ? 1 : 0;
-    sp.rate = y->rate;
-    sp.symrate = y->symrate;
-    sp.ssize = y->ssize;
-    sp.msize = y->msize;
-    sp.snr_num = y->s.snr_num;
     {
         KernelTimer kt("symbolize_kernel", s);
         symbolize_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(sp);
@@ -1901,6 +2567,26 @@ dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;
+}
+
+int
+dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                            const dsdneo_b200_symbol_out* out, void* stream) {
+    return symbolize_launch(y, d_disc, disc_pitch, n_samples, mode, have_sync, out, false, NULL, stream);
+}
+
+int
+dsdneo_b200_symbolize_acquire_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples,
+                                    const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, void* stream) {
+    if (!y || !y->d_acquired || y->n_pat < 1) {
+        set_error("symbolize_acquire_batch: acquisition is not configured (symbolizer_set_acquire_patterns)");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_samples < kAcqMargin) {
+        set_error("symbolize_acquire_batch: a launch must carry at least %d samples", kAcqMargin);
+        return DSDNEO_B200_EINVAL;
+    }
+    return symbolize_launch(y, d_disc, disc_pitch, n_samples, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, out, true, d_info, stream);
 }
 
 } /* extern "C" */

@@ -431,6 +431,8 @@ typedef struct dsdneo_b200_sym_class {
     int window_l;     /* left edge of the averaging window, 2 or 1: select_window_c4fm, dsd_symbol.c:197-211 (right edge is 2) */
     int track_minmax; /* use_symbol() threshold tracking (P25p1): src/core/frames/dsd_dibit.c:264 */
     int negative;     /* is_four_level_neg_synctype(synctype): dsd_dibit.c:915-935 */
+    int rf_mod;       /* state->rf_mod: 0 C4FM (default), 2 GFSK (two-sample window, GFSK timing nudge, no sync clip: dsd_symbol.c:213-225,
+                       * 347-358,428-434,480-487; what the reference's DMR / NXDN96 / M17 presets select, src/runtime/decode_mode.c) */
 } dsdneo_b200_sym_class;
 /** The reference's rules for P25p1 / DMR / YSF / M17 / X2-TDMA / none (ids: include/dsd-neo/core/synctype_ids.h). */
 int dsdneo_b200_sym_class_from_synctype(int synctype, int lastsynctype, int use_cosine_filter, dsdneo_b200_sym_class* out);
@@ -454,7 +456,7 @@ typedef struct dsdneo_b200_symbol_out {
     uint8_t* d_reliability; /* [n_channels][pitch]     dsd_dibit_soft_t.reliability (include/dsd-neo/core/dibit.h:24-27) */
     int16_t* d_llr;         /* [n_channels][pitch][2]  dsd_dibit_soft_t.llr */
     int32_t* d_count;       /* [n_channels] symbols produced by this call */
-    size_t pitch;           /* capacity per channel; must be >= (n_samples + 96) / (samples_per_symbol - 1) + 2 */
+    size_t pitch;           /* capacity per channel; must be >= (n_samples + 256) / (samples_per_symbol - 1) + 2 */
 } dsdneo_b200_symbol_out;
 
 typedef struct dsdneo_b200_symbolizer dsdneo_b200_symbolizer;
@@ -478,6 +480,52 @@ int dsdneo_b200_symbolizer_set_snr(dsdneo_b200_symbolizer* y, const double* h_sn
  */
 int dsdneo_b200_symbolize_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode,
                                 int have_sync, const dsdneo_b200_symbol_out* out, void* stream);
+
+/*
+ * Acquisition on the device: getFrameSync() from the never-synchronised state (src/dsp/dsd_frame_sync.c:3098-3148) for the
+ * FSK discriminator path, per channel and bit-exact.  A hunting channel takes RAW discriminator samples (no matched filter
+ * before the first sync, dsd_symbol.c:301-337) through getSymbol(have_sync = 0) with the timing nudges, keeps the 24-symbol
+ * level ring and the rolling payload dibits / reliabilities (:1747-1764, :2161-2190), slices the hunt window ('1' when the
+ * symbol is positive, else '3', :2110-2127) and compares it with the configured 24-symbol sync patterns from the 8th symbol on
+ * (:2638-2676).  On a match: frame_sync_set_basic_lock (:386-392); the sync warm start of the slicer thresholds
+ * (dsd_sync_warm_start_thresholds_outer_only(24), src/dsp/sync_calibration.c:155-226) for P25 Phase 1 when rf_mod == 0 and
+ * for DMR always; for DMR (kind 1) the 66 dibits in front of the sync re-sliced with the new thresholds
+ * (dmr_resample_on_sync, src/dsp/dmr_sync.c:60-126); then the channel switches to the pattern's decoder class and continues,
+ * inside the same launch, as a synchronised channel (getDibitSoft), with the matched filter starting from an all-zero delay
+ * line exactly where the reference turns it on.  A hunt that saw 1800 symbols without sync restarts with an empty window
+ * (:3039); the no-carrier housekeeping of that moment is the host's.
+ * Out of scope here: the other sync families of getFrameSync (NXDN, YSF, dPMR, M17, D-STAR, ProVoice, EDACS, P25p2), the
+ * CQPSK sync path, and re-acquisition policy after a lost sync (the host drops a channel back to hunting with _set_acquired).
+ */
+typedef struct dsdneo_b200_acq_pattern {
+    const char* symbols;       /* 24 characters '1' / '3' (include/dsd-neo/core/sync_patterns.h) */
+    int sync_type;             /* what getFrameSync returns for it (include/dsd-neo/core/synctype_ids.h) */
+    int kind;                  /* 0 P25 Phase 1 rules, 1 DMR rules (warm start always + resample-on-sync) */
+    dsdneo_b200_sym_class cls; /* decoder class in force after the sync (rf_mod is a channel property and is not switched) */
+} dsdneo_b200_acq_pattern;
+
+typedef struct dsdneo_b200_acq_info {
+    int32_t acquired;     /* 1 = synchronised (now or earlier) */
+    int32_t sync_type;    /* >= 0 only in the launch that found the sync */
+    int32_t hit_index;    /* output index (this launch) of the last sync symbol; the frame body starts at hit_index + 1 */
+    int32_t hunt_symbols; /* symbols this launch spent hunting */
+    uint8_t warm_start;   /* the sync warm start replaced the thresholds (DSD_WARM_START_OK) */
+    uint8_t resample_ok;  /* resampled[] is valid (DMR sync with >= 90 symbols of history) */
+    uint8_t resampled[66]; /* DMR: the 66 dibits in front of the sync, re-sliced (dmr_resample_cach); those of them that lie
+                            * in this launch's output are also rewritten in d_dibits */
+} dsdneo_b200_acq_info;
+
+/** Up to 8 patterns, compared in the given order (the reference tests P25p1 before DMR).  Allocates the hunt state. */
+int dsdneo_b200_symbolizer_set_acquire_patterns(dsdneo_b200_symbolizer* y, const dsdneo_b200_acq_pattern* patterns, int n_patterns);
+/** Per-channel hunting (0) / synchronised (1) flags, host array of n_channels or NULL for all hunting.  Synchronises. */
+int dsdneo_b200_symbolizer_set_acquired(dsdneo_b200_symbolizer* y, const int* h_acquired);
+/**
+ * dsdneo_b200_symbolize_batch(GET_DIBIT_SOFT) for a bank in which some channels still hunt for sync.  d_disc are the RAW
+ * discriminator samples; hunting channels emit their hunt symbols with the payload dibits / reliabilities of that moment,
+ * synchronised channels what getDibitSoft returns.  d_info: [n_channels] device records for this launch (may be NULL).
+ */
+int dsdneo_b200_symbolize_acquire_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples,
+                                        const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, void* stream);
 
 /* ---- batched FEC leaves (K13, K16, K17, K19) ------------------------------------------------------ */
 
