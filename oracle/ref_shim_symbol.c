@@ -414,6 +414,7 @@ ref_sym_configure_acquire(void* hv, int frame_mask, int rf_mod) {
     dsd_state* s = h->state;
     o->frame_p25p1 = (frame_mask & 1) ? 1 : 0;
     o->frame_dmr = (frame_mask & 2) ? 1 : 0;
+    o->inverted_dmr = (frame_mask & 4) ? 1 : 0; /* the -xr switch */
     o->mod_cli_lock = 1;
     o->mod_c4fm = rf_mod == 0;
     o->mod_gfsk = rf_mod == 2;

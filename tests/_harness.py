@@ -1175,7 +1175,7 @@ DMR_BS_DATA_STR, DMR_BS_VOICE_STR = "313333111331131131331131", "131111333113313
 DMR_MS_DATA_STR, DMR_MS_VOICE_STR = "311131133313133331131113", "133313311131311113313331"
 
 
-def acquire_patterns(frame_p25p1, frame_dmr, taps, use_cosine_filter=True):
+def acquire_patterns(frame_p25p1, frame_dmr, taps, use_cosine_filter=True, inverted_dmr=False):
     """The reference's matcher order for the enabled protocols (frame_sync_try_protocol_matches, dsd_frame_sync.c:1636-1700:
     P25 Phase 1 before DMR; inside DMR: MS data, MS voice, BS data, BS voice) with the class each sync type gives the decoder.
     Returns (ctypes array, keep-alive list)."""
@@ -1191,9 +1191,14 @@ def acquire_patterns(frame_p25p1, frame_dmr, taps, use_cosine_filter=True):
     if frame_p25p1:
         add(P25P1_SYNC_STR, 0, 0, 0, 2, 1, 0)
         add(P25P1_SYNC_INV_STR, 1, 0, 0, 2, 1, 1)
-    if frame_dmr:  # inverted_dmr == 0: src/dsp/dsd_frame_sync.c:1108-1340
+    if frame_dmr and not inverted_dmr:  # src/dsp/dsd_frame_sync.c:1108-1340
         add(DMR_MS_DATA_STR, 33, 1, 1, 1, 0, 0)
         add(DMR_MS_VOICE_STR, 32, 1, 1, 1, 0, 0)
         add(DMR_BS_DATA_STR, 10, 1, 1, 1, 0, 0)
         add(DMR_BS_VOICE_STR, 12, 1, 1, 1, 0, 0)
+    elif frame_dmr:  # opts->inverted_dmr == 1 (-xr): the same patterns name the opposite burst kind, BS ones with negative polarity
+        add(DMR_MS_DATA_STR, 32, 1, 1, 1, 0, 0)
+        add(DMR_MS_VOICE_STR, 33, 1, 1, 1, 0, 0)
+        add(DMR_BS_DATA_STR, 11, 1, 1, 1, 0, 1)
+        add(DMR_BS_VOICE_STR, 13, 1, 1, 1, 0, 1)
     return (OracleAcqPattern * len(pats))(*pats), keep

@@ -22,7 +22,8 @@ from test_oracle_symbol import _ref_acquire  # noqa: E402
 
 # name -> (capture, frame mask (1 P25p1, 2 DMR), rf_mod, channel LPF profile)
 CASES = {"p25p1_c4fm_cc": ("p25p1_c4fm_cc", 1, 0, 4), "p25p1_c4fm_vc": ("p25p1_c4fm_vc", 1, 0, 4),
-         "dmr_t3_cc": ("dmr_t3_cc", 2, 2, 2), "dmr_voice": ("dmr_voice", 2, 2, 2), "dmr_t3_cc_c4fm": ("dmr_t3_cc", 3, 0, 2)}
+         "dmr_t3_cc": ("dmr_t3_cc", 2, 2, 2), "dmr_voice": ("dmr_voice", 2, 2, 2), "dmr_t3_cc_c4fm": ("dmr_t3_cc", 3, 0, 2),
+         "dmr_t3_cc_xr": ("dmr_t3_cc", 6, 2, 2), "dmr_voice_xr": ("dmr_voice", 6, 2, 2)}  # mask 4 = opts->inverted_dmr (-xr)
 BP = 8000
 
 

@@ -209,7 +209,7 @@ def _oracle_acquire(disc, frame_mask, rf_mod, taps, n_after=600):
     ch = H.OracleSymChan()
     O.oracle_sym_init(C.byref(ch), 48000, 4800, 0, 2, 0, 0, None, 0, 128, 1024)
     ch.rf_mod = rf_mod
-    pats, keep = H.acquire_patterns(frame_mask & 1, frame_mask & 2, taps)
+    pats, keep = H.acquire_patterns(frame_mask & 1, frame_mask & 2, taps, inverted_dmr=bool(frame_mask & 4))
     n = disc.size // 8 + 8
     sym, dib, rel = np.zeros(n, np.float32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
     res = H.OracleAcqResult()
