@@ -2775,6 +2775,225 @@ p25p1_frame_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const P25Fram
 
 }  // namespace
 
+/* ---- DMR rate 3/4 trellis (dmr_r34_viterbi_decode / _soft, src/protocol/dmr/dmr_34_viterbi.c:402-474) ---------------------
+ * 8 lanes per codeword, lane = next state: 49 add-compare-select steps with the previous metrics exchanged by shuffles, the
+ * survivor's previous state kept three bits per step in registers, traceback by shuffles from end state 0.  Constellation and
+ * state tables: ETSI TS 102 361-1 B.2.5 (the reference's dsd_trellis34_constellation / _fsm, src/fec/trellis34.c:15-21). */
+__constant__ uint8_t c_r34_point_of_nibble[16] = {11, 12, 0, 7, 14, 9, 5, 2, 10, 13, 1, 6, 15, 8, 4, 3};
+__constant__ uint8_t c_r34_nibble_of_point[16] = {2, 10, 7, 15, 14, 6, 11, 3, 13, 5, 8, 0, 1, 9, 4, 12};
+__constant__ uint8_t c_r34_fsm[64] = {0, 8,  4, 12, 2, 10, 6, 14, 4, 12, 2, 10, 6, 14, 0, 8, 1, 9,  5, 13, 3, 11,
+                                      7, 15, 5, 13, 3, 11, 7, 15, 1, 9,  3, 11, 7, 15, 1, 9, 5, 13, 7, 15, 1, 9,
+                                      5, 13, 3, 11, 2, 10, 6, 14, 0, 8,  4, 12, 6, 14, 0, 8, 4, 12, 2, 10};
+
+__device__ __forceinline__ int
+r34_deinterleaved_source(int k) { /* inverse of dsd_trellis_interleave_98: which received dibit lands at position k */
+    /* table[i] = 8 * ((i % 26) / 2) + 2 * (i / 26) + (i & 1) for the 26/26/24/22 column walk (src/fec/trellis34.c:8-13) */
+    const int col = k >> 3, within = k & 7; /* k = 8 * col + 2 * row + parity */
+    const int row = within >> 1, par = within & 1;
+    const int base = row == 0 ? 0 : (row == 1 ? 26 : (row == 2 ? 50 : 74));
+    return base + 2 * col + par;
+}
+
+__global__ void __launch_bounds__(128)
+dmr_r34_kernel(const uint8_t* __restrict__ dibits, const uint8_t* __restrict__ reliab, uint8_t* __restrict__ out18, int n) {
+    __shared__ uint8_t s_dei[16][98], s_rel[16][98], s_states[16][49];
+    const int grp = threadIdx.x >> 3, ns = threadIdx.x & 7;
+    const int w = blockIdx.x * 16 + grp;
+    const bool live = w < n;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gbase = lane & ~7u;
+    if (live) {
+        for (int k = ns; k < 98; k += 8) {
+            const int src = r34_deinterleaved_source(k);
+            s_dei[grp][k] = dibits[(size_t)w * 98 + src] & 3;
+            s_rel[grp][k] = reliab ? reliab[(size_t)w * 98 + src] : 0;
+        }
+    }
+    __syncthreads();
+    const int INF = 1000000000;
+    int metric = ns == 0 ? 0 : INF;
+    unsigned long long bp0 = 0, bp1 = 0, bp2 = 0; /* 3 bits per step: steps 0..20, 21..41, 42..48 */
+    const bool soft = reliab != nullptr;
+    for (int t = 0; t < 49; t++) {
+        const int d0 = live ? s_dei[grp][2 * t] : 0, d1 = live ? s_dei[grp][2 * t + 1] : 0;
+        const int nib = (d0 << 2) | d1;
+        const int point = c_r34_point_of_nibble[nib];
+        const int rhi = live ? s_rel[grp][2 * t] : 0, rlo = live ? s_rel[grp][2 * t + 1] : 0;
+        int best = INF, best_ps = 0;
+#pragma unroll
+        for (int ps = 0; ps < 8; ps++) {
+            const int mp = __shfl_sync(0xffffffffu, metric, gbase + ps);
+            const int expect = c_r34_fsm[ps * 8 + ns];
+            int cost;
+            if (!soft) {
+                cost = __popc((unsigned)((expect ^ point) & 15));
+            } else {
+                const int x = c_r34_nibble_of_point[expect] ^ nib;
+                cost = (((x >> 3) & 1) + ((x >> 2) & 1)) * rhi + (((x >> 1) & 1) + (x & 1)) * rlo;
+            }
+            const int m = mp + cost;
+            if (mp < INF && m < best) {
+                best = m, best_ps = ps;
+            }
+        }
+        metric = best;
+        const unsigned long long v = (unsigned long long)best_ps;
+        if (t < 21) {
+            bp0 |= v << (3 * t);
+        } else if (t < 42) {
+            bp1 |= v << (3 * (t - 21));
+        } else {
+            bp2 |= v << (3 * (t - 42));
+        }
+    }
+    /* traceback: every lane follows the same path; lane `state` owns the back pointer */
+    int state = 0;
+    for (int t = 48; t >= 0; t--) {
+        if (ns == 0 && live) {
+            s_states[grp][t] = (uint8_t)state;
+        }
+        const unsigned long long word = t < 21 ? bp0 : (t < 42 ? bp1 : bp2);
+        const int sh = 3 * (t < 21 ? t : (t < 42 ? t - 21 : t - 42));
+        const int mine = (int)((word >> sh) & 7ull);
+        state = __shfl_sync(0xffffffffu, mine, gbase + state);
+    }
+    __syncthreads();
+    if (live && ns < 6) {
+        unsigned v = 0;
+        for (int k = 0; k < 8; k++) {
+            v = (v << 3) | (unsigned)(s_states[grp][ns * 8 + k] & 7);
+        }
+        out18[(size_t)w * 18 + 3 * ns] = (uint8_t)(v >> 16);
+        out18[(size_t)w * 18 + 3 * ns + 1] = (uint8_t)(v >> 8);
+        out18[(size_t)w * 18 + 3 * ns + 2] = (uint8_t)v;
+    }
+}
+
+/* ---- RS(12,9) over GF(2^8) (src/fec/rs-12-9.c:237-323): one thread per codeword; exp / log tables built per CTA ------------ */
+__device__ __forceinline__ uint8_t
+rs129_mul(const uint8_t* ex, const uint8_t* lg, uint8_t a, uint8_t b) {
+    return (a == 0 || b == 0) ? 0 : ex[(lg[a] + lg[b]) % 255];
+}
+
+__global__ void __launch_bounds__(128)
+rs_12_9_kernel(uint8_t* __restrict__ cw, uint8_t* __restrict__ syndrome3, uint8_t* __restrict__ result, uint8_t* __restrict__ errors_found,
+               int n) {
+    __shared__ uint8_t ex[256], lg[256];
+    if (threadIdx.x == 0) { /* x^8 + x^4 + x^3 + x^2 + 1; exp[255] = 1 and log[0] = 0 as in the reference's tables */
+        int v = 1;
+        lg[0] = 0;
+        for (int i = 0; i < 255; i++) {
+            ex[i] = (uint8_t)v;
+            lg[v] = (uint8_t)i;
+            v <<= 1;
+            if (v & 0x100) {
+                v ^= 0x11D;
+            }
+        }
+        ex[255] = 1;
+    }
+    __syncthreads();
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) {
+        return;
+    }
+    uint8_t c[12];
+    for (int i = 0; i < 12; i++) {
+        c[i] = cw[(size_t)w * 12 + i];
+    }
+    uint8_t S[3] = {0, 0, 0};
+    for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < 12; i++) {
+            S[j] = c[i] ^ rs129_mul(ex, lg, ex[j + 1], S[j]);
+        }
+    }
+    if (syndrome3) {
+        syndrome3[(size_t)w * 3] = S[0], syndrome3[(size_t)w * 3 + 1] = S[1], syndrome3[(size_t)w * 3 + 2] = S[2];
+    }
+    if (!(S[0] | S[1] | S[2])) {
+        result[w] = 0;
+        errors_found[w] = 0;
+        return;
+    }
+    uint8_t loc[6] = {1, 0, 0, 0, 0, 0}, D[6] = {0, 1, 0, 0, 0, 0}, psi2[6];
+    int L = 0, k = -1;
+    for (int nn = 0; nn < 3; nn++) {
+        uint8_t d = 0;
+        for (int i = 0; i <= L; i++) {
+            d ^= rs129_mul(ex, lg, loc[i], S[nn - i]);
+        }
+        if (d != 0) {
+            for (int i = 0; i < 6; i++) {
+                psi2[i] = loc[i] ^ rs129_mul(ex, lg, d, D[i]);
+            }
+            if (L < nn - k) {
+                const int L2 = nn - k;
+                k = nn - L;
+                const uint8_t di = ex[255 - lg[d]];
+                for (int i = 0; i < 6; i++) {
+                    D[i] = rs129_mul(ex, lg, loc[i], di);
+                }
+                L = L2;
+            }
+            for (int i = 0; i < 6; i++) {
+                loc[i] = psi2[i];
+            }
+        }
+        for (int i = 5; i > 0; i--) {
+            D[i] = D[i - 1];
+        }
+        D[0] = 0;
+    }
+    uint8_t ev[3] = {0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; i + j < 3; j++) {
+            ev[i + j] ^= rs129_mul(ex, lg, S[j], loc[i]);
+        }
+    }
+    uint8_t locs[4];
+    int nroots = 0;
+    for (int r = 1; r < 256; r++) {
+        uint8_t sum = 0;
+        for (int kk = 0; kk < 4; kk++) {
+            sum ^= rs129_mul(ex, lg, ex[(kk * r) % 255], loc[kk]);
+        }
+        if (sum == 0) {
+            if (nroots < 4) {
+                locs[nroots] = (uint8_t)(255 - r);
+            }
+            nroots++;
+        }
+    }
+    errors_found[w] = (uint8_t)nroots;
+    if (nroots == 0) {
+        result[w] = 1;
+        return;
+    }
+    bool bad = nroots > 3;
+    for (int r = 0; r < nroots && r < 4 && !bad; r++) {
+        bad = locs[r] >= 12;
+    }
+    if (bad) {
+        result[w] = 3;
+        return;
+    }
+    for (int r = 0; r < nroots; r++) {
+        const int i = locs[r];
+        uint8_t num = 0, den = 0;
+        for (int j = 0; j < 3; j++) {
+            num ^= rs129_mul(ex, lg, ev[j], ex[((255 - i) * j) % 255]);
+        }
+        for (int j = 1; j < 6; j += 2) {
+            den ^= rs129_mul(ex, lg, loc[j], ex[((255 - i) * (j - 1)) % 255]);
+        }
+        c[12 - i - 1] ^= rs129_mul(ex, lg, num, ex[255 - lg[den]]);
+    }
+    for (int i = 0; i < 12; i++) {
+        cw[(size_t)w * 12 + i] = c[i];
+    }
+    result[w] = 2;
+}
+
 extern "C" {
 
 int
@@ -2881,6 +3100,117 @@ dsdneo_b200_fec_golay_24_12_encode_batch(const uint8_t* d_data, uint8_t* d_out, 
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_dmr_r34_decode_batch(const uint8_t* d_dibits98, const uint8_t* d_reliab98, uint8_t* d_out18, int n_blocks, void* stream) {
+    if (!d_dibits98 || !d_out18 || n_blocks < 0) {
+        set_error("dmr_r34_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("dmr_r34_kernel", s);
+        dmr_r34_kernel<<<grid_for(n_blocks, 16), 128, 0, s>>>(d_dibits98, d_reliab98, d_out18, n_blocks);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_dmr_r34_decode_batch_host(const uint8_t* h_dibits98, const uint8_t* h_reliab98, uint8_t* h_out18, int n_blocks) {
+    if (!h_dibits98 || !h_out18 || n_blocks < 0) {
+        set_error("dmr_r34_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_blocks == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_blocks;
+    DevBuf in(n * 98), rel(n * 98), out(n * 18);
+    DSDNEO_CUDA(in.err);
+    DSDNEO_CUDA(rel.err);
+    DSDNEO_CUDA(out.err);
+    DSDNEO_CUDA(cudaMemcpy(in.p, h_dibits98, n * 98, cudaMemcpyHostToDevice));
+    if (h_reliab98) {
+        DSDNEO_CUDA(cudaMemcpy(rel.p, h_reliab98, n * 98, cudaMemcpyHostToDevice));
+    }
+    rc = dsdneo_b200_dmr_r34_decode_batch(in.as<uint8_t>(), h_reliab98 ? rel.as<uint8_t>() : NULL, out.as<uint8_t>(), n_blocks, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_out18, out.p, n * 18, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int
+dsdneo_b200_rs_12_9_decode_batch(uint8_t* d_codewords, uint8_t* d_syndrome3, uint8_t* d_result, uint8_t* d_errors_found, int n_words,
+                                 void* stream) {
+    if (!d_codewords || !d_result || !d_errors_found || n_words < 0) {
+        set_error("rs_12_9_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("rs_12_9_kernel", s);
+        rs_12_9_kernel<<<grid_for(n_words, 128), 128, 0, s>>>(d_codewords, d_syndrome3, d_result, d_errors_found, n_words);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_rs_12_9_decode_batch_host(uint8_t* h_codewords, uint8_t* h_syndrome3, uint8_t* h_result, uint8_t* h_errors_found,
+                                      int n_words) {
+    if (!h_codewords || !h_result || !h_errors_found || n_words < 0) {
+        set_error("rs_12_9_decode_batch_host: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_words == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    const size_t n = (size_t)n_words;
+    DevBuf cw(n * 12), syn(n * 3), res(n), ef(n);
+    DSDNEO_CUDA(cw.err);
+    DSDNEO_CUDA(syn.err);
+    DSDNEO_CUDA(res.err);
+    DSDNEO_CUDA(ef.err);
+    DSDNEO_CUDA(cudaMemcpy(cw.p, h_codewords, n * 12, cudaMemcpyHostToDevice));
+    rc = dsdneo_b200_rs_12_9_decode_batch(cw.as<uint8_t>(), syn.as<uint8_t>(), res.as<uint8_t>(), ef.as<uint8_t>(), n_words, NULL);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_codewords, cw.p, n * 12, cudaMemcpyDeviceToHost));
+    if (h_syndrome3) {
+        DSDNEO_CUDA(cudaMemcpy(h_syndrome3, syn.p, n * 3, cudaMemcpyDeviceToHost));
+    }
+    DSDNEO_CUDA(cudaMemcpy(h_result, res.p, n, cudaMemcpyDeviceToHost));
+    DSDNEO_CUDA(cudaMemcpy(h_errors_found, ef.p, n, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -561,6 +561,29 @@ int dsdneo_b200_fec_block_decode_batch_host(int code, uint8_t* h_bits, uint8_t* 
 int dsdneo_b200_fec_golay_24_12_encode_batch(const uint8_t* d_data, uint8_t* d_out, int n_words, void* stream);
 
 /**
+ * Batched twins of `int dmr_r34_viterbi_decode(const uint8_t* dibits98, uint8_t out_bytes18[18])` and
+ * `dmr_r34_viterbi_decode_soft(dibits98, reliab98, out_bytes18)` (include/dsd-neo/protocol/dmr/r34_viterbi.h:33,46;
+ * src/protocol/dmr/dmr_34_viterbi.c:402-474): DMR rate 3/4 trellis, 98 dibits -> 18 payload bytes.
+ * d_dibits98 [n][98] (0..3, as received); d_reliab98 [n][98] per-dibit reliabilities or NULL for the hard-decision decoder;
+ * d_out18 [n][18].  Bit-exact including the tie-break (lowest previous state).
+ */
+int dsdneo_b200_dmr_r34_decode_batch(const uint8_t* d_dibits98, const uint8_t* d_reliab98, uint8_t* d_out18, int n_blocks,
+                                     void* stream);
+int dsdneo_b200_dmr_r34_decode_batch_host(const uint8_t* h_dibits98, const uint8_t* h_reliab98, uint8_t* h_out18, int n_blocks);
+
+/**
+ * Batched twin of rs_12_9_calc_syndrome + rs_12_9_check_syndrome + rs_12_9_correct_errors (include/dsd-neo/fec/rs_12_9.h:41-44;
+ * src/fec/rs-12-9.c:237-323) as the reference's callers chain them: RS(12,9) over GF(2^8), 9 data + 3 checksum bytes.
+ * d_codewords [n][12] corrected in place; d_syndrome3 [n][3] (may be NULL); d_result[i]: 0 = syndrome zero (corrector not run),
+ * 1 = RS_12_9_CORRECT_ERRORS_RESULT_NO_ERRORS_FOUND, 2 = _ERRORS_CORRECTED, 3 = _ERRORS_CANT_BE_CORRECTED;
+ * d_errors_found[i] = the reference's *errors_found.
+ */
+int dsdneo_b200_rs_12_9_decode_batch(uint8_t* d_codewords, uint8_t* d_syndrome3, uint8_t* d_result, uint8_t* d_errors_found,
+                                     int n_words, void* stream);
+int dsdneo_b200_rs_12_9_decode_batch_host(uint8_t* h_codewords, uint8_t* h_syndrome3, uint8_t* h_result, uint8_t* h_errors_found,
+                                          int n_words);
+
+/**
  * BPTCDeInterleaveDMRData + BPTC_196x96_Extract_Data (src/fec/bptc.c:51-59,136-149; include/dsd-neo/fec/bptc.h).
  * @param d_in        [n][196] burst bits; interleaved != 0: as received (de-interleave fused), else already de-interleaved
  * @param d_out96     [n][96] payload bits;  d_r3 [n][3] reserved bits R(2..0) (may be NULL)

@@ -122,6 +122,8 @@ int oracle_hamming_decode(int code, uint8_t* bits, uint8_t* decoded);
 int oracle_golay_24_12_decode(uint8_t* bits24);
 void oracle_golay_24_12_encode(const uint8_t* data12, uint8_t* out24);
 int oracle_golay_20_8_decode(uint8_t* bits20);
+int oracle_dmr_r34_decode(const uint8_t* dibits98, const uint8_t* reliab98, uint8_t* out18);
+int oracle_rs_12_9_decode(uint8_t* cw12, uint8_t* syndrome3, uint8_t* errors_found);
 int oracle_qr_16_7_6_decode(uint8_t* bits16);
 void oracle_bptc_deinterleave(const uint8_t* in196, uint8_t* out196);
 unsigned oracle_bptc_196x96_extract(const uint8_t* in196, uint8_t* out96, uint8_t* r3, int* undefined_out);

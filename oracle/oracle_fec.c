@@ -2220,3 +2220,211 @@ oracle_dmr_burst_cut(const uint8_t* dibits, const uint8_t* reliab, int count, in
     }
     return 1;
 }
+
+/* ---- DMR rate 3/4 trellis: dmr_r34_viterbi_decode / _decode_soft (src/protocol/dmr/dmr_34_viterbi.c:402-474) -----------------
+ * 98 dibits -> de-interleave (dsd_trellis_interleave_98: received i lands at table[i], the table p25_interleave_98 above
+ * generates) -> 49 four-bit symbols (first dibit high) -> 8-state Viterbi over the ETSI TS 102 361-1 B.2.5 encoder (state =
+ * previous tribit, output point = fsm[prev * 8 + next]), start state 0, traceback from end state 0, the first 48 states packed
+ * three bits each into 18 bytes.  Hard: Hamming distance between constellation POINT indices (:213-236); soft: the expected
+ * point mapped back to its dibit pair and each differing bit charged the reliability of its dibit (:180-198, 238-263).
+ * Survivor choice: strict '<' with the previous state ascending (the lowest previous state wins ties).
+ * Pinned by tests/test_oracle_fec.py against the reference vectors (tests/protocol/dmr/dmr_r34_reference_vectors.h) and the
+ * compiled reference on random noisy inputs. */
+static const uint8_t r34_point_of_nibble[16] = {11, 12, 0, 7, 14, 9, 5, 2, 10, 13, 1, 6, 15, 8, 4, 3}; /* B.2.5 constellation */
+static const uint8_t r34_fsm[64] = {0, 8,  4, 12, 2, 10, 6, 14, 4, 12, 2, 10, 6, 14, 0, 8, 1, 9,  5, 13, 3, 11,
+                                    7, 15, 5, 13, 3, 11, 7, 15, 1, 9,  3, 11, 7, 15, 1, 9, 5, 13, 7, 15, 1, 9,
+                                    5, 13, 3, 11, 2, 10, 6, 14, 0, 8,  4, 12, 6, 14, 0, 8, 4, 12, 2, 10}; /* B.2.5 state table */
+
+int
+oracle_dmr_r34_decode(const uint8_t* dibits98, const uint8_t* reliab98, uint8_t* out18) {
+    uint8_t t98[98], dei[98], rdei[98], nib_of_point[16];
+    p25_interleave_98(t98);
+    for (int i = 0; i < 16; i++) {
+        nib_of_point[r34_point_of_nibble[i]] = (uint8_t)i;
+    }
+    for (int i = 0; i < 98; i++) {
+        dei[t98[i]] = dibits98[i] & 3;
+        rdei[t98[i]] = reliab98 ? reliab98[i] : 0;
+    }
+    const int INF = 1000000000;
+    int prev[8], cur[8];
+    uint8_t back[49][8];
+    memset(back, 0, sizeof(back));
+    for (int s = 0; s < 8; s++) {
+        prev[s] = INF;
+    }
+    prev[0] = 0;
+    for (int t = 0; t < 49; t++) {
+        const int nib = (dei[2 * t] << 2) | dei[2 * t + 1];
+        const int point = r34_point_of_nibble[nib];
+        for (int s = 0; s < 8; s++) {
+            cur[s] = INF;
+        }
+        for (int ps = 0; ps < 8; ps++) {
+            if (prev[ps] >= INF) {
+                continue;
+            }
+            for (int ns = 0; ns < 8; ns++) {
+                const int expect = r34_fsm[ps * 8 + ns];
+                int cost;
+                if (!reliab98) {
+                    cost = __builtin_popcount((unsigned)((expect ^ point) & 15));
+                } else {
+                    const int x = nib_of_point[expect] ^ nib;
+                    cost = ((x >> 3) & 1) * rdei[2 * t] + ((x >> 2) & 1) * rdei[2 * t] + ((x >> 1) & 1) * rdei[2 * t + 1]
+                           + (x & 1) * rdei[2 * t + 1];
+                }
+                const int m = prev[ps] + cost;
+                if (m < cur[ns]) {
+                    cur[ns] = m;
+                    back[t][ns] = (uint8_t)ps;
+                }
+            }
+        }
+        memcpy(prev, cur, sizeof(prev));
+    }
+    uint8_t states[49];
+    int s = 0;
+    for (int t = 48; t >= 0; t--) {
+        states[t] = (uint8_t)s;
+        s = back[t][s];
+    }
+    for (int g = 0; g < 6; g++) {
+        uint32_t v = 0;
+        for (int k = 0; k < 8; k++) {
+            v = (v << 3) | (uint32_t)(states[g * 8 + k] & 7);
+        }
+        out18[3 * g] = (uint8_t)(v >> 16), out18[3 * g + 1] = (uint8_t)(v >> 8), out18[3 * g + 2] = (uint8_t)v;
+    }
+    return 0;
+}
+
+/* ---- RS(12,9) over GF(2^8): rs_12_9_calc_syndrome / _check_syndrome / _correct_errors (src/fec/rs-12-9.c:237-323) -----------
+ * Field: x^8 + x^4 + x^3 + x^2 + 1, alpha = 2; exp[255] = 1, log[0] = 0, so the reference's inverse of 0 evaluates to 1.
+ * Syndromes S_j = Horner of the 12 bytes at alpha^(j+1), j = 0..2 (first byte = highest power).  The corrector runs
+ * Berlekamp-Massey over the three syndromes, finds the locator's roots by trying r = 1..255 (location = 255 - r), and applies
+ * Forney with the evaluator = (locator x syndrome) mod z^3; any location >= 12 => cannot correct; no roots => "no errors
+ * found" (result 0) even though the syndrome was not zero.
+ * Returns: 0 syndrome zero (nothing done), else 1 + the reference's result code (1 no roots, 2 corrected, 3 cannot correct);
+ * *errors_found as the reference reports it.  Pinned by tests/test_oracle_fec.py (reference codeword test_fec_bptc_rs.c:194 and
+ * the compiled reference on random corruptions). */
+static uint8_t rs129_exp[256], rs129_log[256];
+static int rs129_ready;
+
+static void
+rs129_init(void) {
+    if (rs129_ready) {
+        return;
+    }
+    int v = 1;
+    memset(rs129_log, 0, sizeof(rs129_log));
+    for (int i = 0; i < 255; i++) {
+        rs129_exp[i] = (uint8_t)v;
+        rs129_log[v] = (uint8_t)i;
+        v <<= 1;
+        if (v & 0x100) {
+            v ^= 0x11D;
+        }
+    }
+    rs129_exp[255] = 1;
+    rs129_ready = 1;
+}
+
+static uint8_t
+rs129_mul(uint8_t a, uint8_t b) {
+    return (a == 0 || b == 0) ? 0 : rs129_exp[(rs129_log[a] + rs129_log[b]) % 255];
+}
+
+static uint8_t
+rs129_inv(uint8_t a) {
+    return rs129_exp[255 - rs129_log[a]];
+}
+
+int
+oracle_rs_12_9_decode(uint8_t* cw12, uint8_t* syndrome3, uint8_t* errors_found) {
+    rs129_init();
+    uint8_t S[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < 12; i++) {
+            S[j] = cw12[i] ^ rs129_mul(rs129_exp[j + 1], S[j]);
+        }
+    }
+    if (syndrome3) {
+        syndrome3[0] = S[0], syndrome3[1] = S[1], syndrome3[2] = S[2];
+    }
+    *errors_found = 0;
+    if (!(S[0] | S[1] | S[2])) {
+        return 0;
+    }
+    /* Berlekamp-Massey, 3 iterations */
+    uint8_t loc[6] = {1, 0, 0, 0, 0, 0}, D[6] = {0, 1, 0, 0, 0, 0}, psi2[6];
+    int L = 0, k = -1;
+    for (int n = 0; n < 3; n++) {
+        uint8_t d = 0;
+        for (int i = 0; i <= L; i++) {
+            d ^= rs129_mul(loc[i], S[n - i]);
+        }
+        if (d != 0) {
+            for (int i = 0; i < 6; i++) {
+                psi2[i] = loc[i] ^ rs129_mul(d, D[i]);
+            }
+            if (L < n - k) {
+                const int L2 = n - k;
+                k = n - L;
+                const uint8_t di = rs129_inv(d);
+                for (int i = 0; i < 6; i++) {
+                    D[i] = rs129_mul(loc[i], di);
+                }
+                L = L2;
+            }
+            memcpy(loc, psi2, 6);
+        }
+        for (int i = 5; i > 0; i--) {
+            D[i] = D[i - 1];
+        }
+        D[0] = 0;
+    }
+    /* evaluator = (locator * syndrome) mod z^3 */
+    uint8_t ev[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; i + j < 3; j++) {
+            ev[i + j] ^= rs129_mul(S[j], loc[i]);
+        }
+    }
+    /* roots */
+    uint8_t locs[256];
+    int nroots = 0;
+    for (int r = 1; r < 256; r++) {
+        uint8_t sum = 0;
+        for (int kk = 0; kk < 4; kk++) {
+            sum ^= rs129_mul(rs129_exp[(kk * r) % 255], loc[kk]);
+        }
+        if (sum == 0) {
+            locs[nroots++] = (uint8_t)(255 - r);
+        }
+    }
+    *errors_found = (uint8_t)nroots;
+    if (nroots == 0) {
+        return 1;
+    }
+    if (nroots > 3) {
+        return 3;
+    }
+    for (int r = 0; r < nroots; r++) {
+        if (locs[r] >= 12) {
+            return 3;
+        }
+    }
+    for (int r = 0; r < nroots; r++) {
+        const int i = locs[r];
+        uint8_t num = 0, den = 0;
+        for (int j = 0; j < 6; j++) {
+            num ^= rs129_mul(ev[j], rs129_exp[((255 - i) * j) % 255]);
+        }
+        for (int j = 1; j < 6; j += 2) {
+            den ^= rs129_mul(loc[j], rs129_exp[((255 - i) * (j - 1)) % 255]);
+        }
+        cw12[12 - i - 1] ^= rs129_mul(num, rs129_inv(den));
+    }
+    return 2;
+}

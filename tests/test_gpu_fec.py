@@ -372,3 +372,35 @@ def test_p25_golay24_soft_bit_exact_vs_oracle(gpu, length):
             rc = O.oracle_p25_golay24_soft(length, H._ptr(want, H.u8p), H._ptr(par[k], H.u8p), rel[k].ctypes.data_as(H.i32p), override, 64,
                                            C.byref(f))
             assert rc == st[k] and np.array_equal(got[k], want) and f.value == fx[k], (k, override, rc, st[k], f.value, fx[k])
+
+
+def test_dmr_r34_hard_and_soft(gpu):
+    from test_oracle_fec import R34_VECTORS, make_r34_cases, oracle_r34
+
+    dib, rel = make_r34_cases(11, 3000)
+    for payload, dibits in R34_VECTORS:
+        d = np.array([[int(ch) for ch in dibits]], np.uint8)
+        out = np.zeros((1, 18), np.uint8)
+        gpu.check(gpu.lib().dsdneo_b200_dmr_r34_decode_batch_host(d.ctypes.data, None, out.ctypes.data, 1), "r34")
+        assert out.tobytes().hex().upper() == payload
+    n = dib.shape[0]
+    hard, soft = np.zeros((n, 18), np.uint8), np.zeros((n, 18), np.uint8)
+    gpu.check(gpu.lib().dsdneo_b200_dmr_r34_decode_batch_host(dib.ctypes.data, None, hard.ctypes.data, n), "r34")
+    gpu.check(gpu.lib().dsdneo_b200_dmr_r34_decode_batch_host(dib.ctypes.data, rel.ctypes.data, soft.ctypes.data, n), "r34 soft")
+    for i in range(n):
+        assert np.array_equal(hard[i], oracle_r34(dib[i])), i
+        assert np.array_equal(soft[i], oracle_r34(dib[i], rel[i])), i
+
+
+def test_rs_12_9(gpu):
+    from test_oracle_fec import make_rs129_cases, oracle_rs129
+
+    cw = make_rs129_cases(12, 5000)
+    n = cw.shape[0]
+    got = cw.copy()
+    syn, res, ef = np.zeros((n, 3), np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    gpu.check(gpu.lib().dsdneo_b200_rs_12_9_decode_batch_host(got.ctypes.data, syn.ctypes.data, res.ctypes.data, ef.ctypes.data, n), "rs129")
+    for i in range(n):
+        r, c, s, e = oracle_rs129(cw[i])
+        assert (int(res[i]), int(ef[i])) == (r, e) and np.array_equal(got[i], c) and np.array_equal(syn[i], s), i
+    assert set(res.tolist()) == {0, 1, 2, 3}

@@ -842,3 +842,119 @@ def test_dmr_burst_cut_round_trip():
         assert O.oracle_dmr_burst_cut(H._ptr(dinv, H.u8p), H._ptr(rel, H.u8p), dib.size, pos, 1, *args) == 1
         assert np.array_equal(info, sent["info"]) and np.array_equal(slot, sent["slot"])
         assert O.oracle_dmr_burst_cut(H._ptr(dib, H.u8p), H._ptr(rel, H.u8p), pos + 54, pos, 0, *args) == 0
+
+
+# ---- DMR rate 3/4 trellis and RS(12,9) ----------------------------------------------------------------------------------------
+
+# the reference's own known-answer vectors: tests/protocol/dmr/dmr_r34_reference_vectors.h (payload, transmitted dibits)
+R34_VECTORS = [
+    ("02550B350F9F838235DA49FB52ACE4645BA8",
+     "02222110323133223303302102023310133332322133102133130022101023022011033231112022112331223122222003"),
+    ("9032A5943D763939B97FE808AB2783BE51F8",
+     "13211222200320022021300302221311310212113322220010333303332301203103133220011101322110133223011123"),
+    ("3DD640810B98BC52429A00252F64BA72E596",
+     "31111320203033023023212313312133330001120220120303313232102332021322301123300222122032331132023303"),
+]
+RS129_CODEWORD = [3, 20, 37, 54, 71, 88, 105, 122, 139, 208, 63, 250]  # tests/fec/test_fec_bptc_rs.c:194
+
+
+def oracle_r34(dibits, reliab=None):
+    O = H.oracle_fec()
+    O.oracle_dmr_r34_decode.argtypes = [H.u8p, H.u8p, H.u8p]
+    out = np.zeros(18, np.uint8)
+    d = np.ascontiguousarray(dibits, np.uint8)
+    r = None if reliab is None else np.ascontiguousarray(reliab, np.uint8)
+    assert O.oracle_dmr_r34_decode(H._ptr(d, H.u8p), None if r is None else H._ptr(r, H.u8p), H._ptr(out, H.u8p)) == 0
+    return out
+
+
+def oracle_rs129(cw):
+    O = H.oracle_fec()
+    O.oracle_rs_12_9_decode.argtypes = [H.u8p, H.u8p, H.u8p]
+    c = np.ascontiguousarray(cw, np.uint8).copy()
+    syn, ef = np.zeros(3, np.uint8), np.zeros(1, np.uint8)
+    res = O.oracle_rs_12_9_decode(H._ptr(c, H.u8p), H._ptr(syn, H.u8p), H._ptr(ef, H.u8p))
+    return res, c, syn, int(ef[0])
+
+
+def make_r34_cases(seed, n):
+    """Valid codewords (the reference vectors) with 0..8 random dibit errors and random reliabilities, plus pure noise."""
+    rng = np.random.default_rng(seed)
+    base = [np.array([int(ch) for ch in d], np.uint8) for _, d in R34_VECTORS]
+    dib, rel = np.zeros((n, 98), np.uint8), rng.integers(0, 256, (n, 98)).astype(np.uint8)
+    for i in range(n):
+        if i % 5 == 4:
+            dib[i] = rng.integers(0, 4, 98)
+            continue
+        d = base[i % 3].copy()
+        pos = rng.choice(98, int(rng.integers(0, 9)), replace=False)
+        d[pos] = rng.integers(0, 4, pos.size)
+        rel[i, pos] = rng.integers(0, 64, pos.size)
+        dib[i] = d
+    return dib, rel
+
+
+def make_rs129_cases(seed, n):
+    rng = np.random.default_rng(seed)
+    cw = np.tile(np.array(RS129_CODEWORD, np.uint8), (n, 1))
+    for i in range(n):
+        k = i % 5  # 0 clean, 1..3 corrupted bytes, 4 random words
+        if k == 4:
+            cw[i] = rng.integers(0, 256, 12)
+        else:
+            pos = rng.choice(12, k, replace=False)
+            cw[i, pos] ^= rng.integers(1, 256, k).astype(np.uint8)
+    return cw
+
+
+def test_oracle_r34_reference_vectors():
+    for payload, dibits in R34_VECTORS:
+        d = np.array([int(ch) for ch in dibits], np.uint8)
+        assert oracle_r34(d).tobytes().hex().upper() == payload
+        assert oracle_r34(d, np.full(98, 200, np.uint8)).tobytes().hex().upper() == payload
+
+
+def test_oracle_rs129_reference_codeword():
+    res, c, syn, ef = oracle_rs129(RS129_CODEWORD)
+    assert res == 0 and not syn.any()
+    bad = np.array(RS129_CODEWORD, np.uint8)
+    bad[4] ^= 0x5A
+    res, c, syn, ef = oracle_rs129(bad)
+    assert res == 2 and ef == 1 and list(c) == RS129_CODEWORD and syn.any()
+
+
+@needs_ref
+def test_oracle_r34_matches_compiled_reference():
+    R = H.ref_fec("par")
+    R.dmr_r34_viterbi_decode.argtypes = [H.u8p, H.u8p]
+    R.dmr_r34_viterbi_decode_soft.argtypes = [H.u8p, H.u8p, H.u8p]
+    dib, rel = make_r34_cases(5, 400)
+    for i in range(dib.shape[0]):
+        out = np.zeros(18, np.uint8)
+        assert R.dmr_r34_viterbi_decode(H._ptr(dib[i], H.u8p), H._ptr(out, H.u8p)) == 0
+        assert np.array_equal(out, oracle_r34(dib[i])), i
+        assert R.dmr_r34_viterbi_decode_soft(H._ptr(dib[i], H.u8p), H._ptr(rel[i], H.u8p), H._ptr(out, H.u8p)) == 0
+        assert np.array_equal(out, oracle_r34(dib[i], rel[i])), i
+
+
+@needs_ref
+def test_oracle_rs129_matches_compiled_reference():
+    R = H.ref_fec("par")
+    R.rs_12_9_calc_syndrome.argtypes = [H.u8p, H.u8p]
+    R.rs_12_9_check_syndrome.argtypes = [H.u8p]
+    R.rs_12_9_check_syndrome.restype = C.c_uint8
+    R.rs_12_9_correct_errors.argtypes = [H.u8p, H.u8p, H.u8p]
+    R.rs_12_9_correct_errors.restype = C.c_uint8
+    cases = make_rs129_cases(6, 1500)
+    seen = set()
+    for i in range(cases.shape[0]):
+        c = cases[i].copy()
+        syn, ef = np.zeros(6, np.uint8), np.zeros(1, np.uint8)
+        R.rs_12_9_calc_syndrome(H._ptr(c, H.u8p), H._ptr(syn, H.u8p))
+        want = 0
+        if R.rs_12_9_check_syndrome(H._ptr(syn, H.u8p)):
+            want = 1 + R.rs_12_9_correct_errors(H._ptr(c, H.u8p), H._ptr(syn, H.u8p), H._ptr(ef, H.u8p))
+        res, oc, osyn, oef = oracle_rs129(cases[i])
+        assert (res, oef) == (want, int(ef[0])) and np.array_equal(oc, c) and np.array_equal(osyn, syn[:3]), i
+        seen.add(res)
+    assert seen == {0, 1, 2, 3}
