@@ -394,7 +394,10 @@ def run_c2_b200_arm(args):
         a = kernels[dom]["achieved_gbs"]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
-                    "note": "per-kernel times from CUDA events recorded by the library on the launching stream during the timed region"}
+                    "note": "per-kernel times from CUDA events recorded by the library on the launching stream during the timed region; "
+                            "the three pipeline stages of consecutive tiles run concurrently there, so a kernel's duration includes the time it "
+                            "shares the SMs with the other stages' kernels (kernels_serial: the same kernels one tile at a time)",
+                    "achieved_serial": (alg_bytes[dom] / (kserial[dom]["avg_ms"] * 1e-3) / 1e9) if dom in kserial else None}
 
     # ---- e2e: same metric through the host-buffer C-ABI (pinned host in/out, every copy inside the timed region) ----
     # Streaming form, as the reference's demod thread consumes its input ring: tile i is queued (submit_host) while the
@@ -769,8 +772,12 @@ def run_c3_b200_arm(args):
 
     clocks = ClockSampler(local).start()
     n_warm = max(args.warmup, C3_TILES)  # one full rotation: the threshold trackers settle, every code path is loaded
+    # Tiles are submitted to the bank's three-stage pipeline (channel filter | recurrences + matched filter | slicer + frames):
+    # consecutive tiles overlap on the device, every tile runs every stage, results complete in submission order.
+    last = -1
     for i in range(n_warm):
-        rx.process(d_tiles[i % C3_TILES], C3_PAIRS, out, stream)
+        last = rx.submit(d_tiles[i % C3_TILES], C3_PAIRS, out, stream)
+    rx.wait(last, stream)
     barrier()
     b200.timing_enable(True)
     launches0 = b200.launch_count()
@@ -778,12 +785,24 @@ def run_c3_b200_arm(args):
     n_frames = n_voice = n_good = 0
     ev0.record(stream)
     for i in range(args.steps):
-        rx.process(d_tiles[(i + n_warm) % C3_TILES], C3_PAIRS, out, stream)
+        last = rx.submit(d_tiles[(i + n_warm) % C3_TILES], C3_PAIRS, out, stream)
+    rx.wait(last, stream)
     ev1.record(stream)
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = b200.launch_count() - launches0
     ktimes = b200.timing_report()
+    # the same kernels one tile at a time (process = submit + wait): what each costs when it has the GPU to itself
+    n_serial = min(args.steps, 10)
+    b200.timing_enable(True)
+    evs0, evs1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs0.record(stream)
+    for i in range(n_serial):
+        rx.process(d_tiles[(i + n_warm + args.steps) % C3_TILES], C3_PAIRS, out, stream)
+    evs1.record(stream)
+    torch.cuda.synchronize()
+    serial_ms_per_step = evs0.elapsed_time(evs1) / n_serial
+    kserial = {k: {"avg_ms": v["ms"] / max(1, v["launches"])} for k, v in b200.timing_report().items()}
     b200.timing_enable(False)
     clk = clocks.stop()
     fr, vo = rx.records(out)  # the last step's records: how much real traffic the step decoded
@@ -830,29 +849,34 @@ def run_c3_b200_arm(args):
     # ---- e2e: pinned host cu8 IQ in, host frames / IMBE frames / dibits out, every copy inside the timed region ----
     e2e_steps = max(3, min(args.steps, 100))
     rx_h = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
-    h_outs = [rx_h.alloc_host_out(), rx_h.alloc_host_out()]
+    DEPTH = 4  # tiles in flight: the bank's four pipeline stages plus the copies either side (at most four tickets outstanding)
+    h_outs = [rx_h.alloc_host_out() for _ in range(DEPTH)]
     d2h = [0]
     seq = [0]  # tiles are fed in rotation order across calls of run(): the stream stays continuous (the locked slicer does not
                # re-acquire symbol timing, so a repeated or skipped tile would slip it by a fraction of a symbol)
 
     def run(n, count=False):
-        prev, chk, last = None, 0, None
+        chk = 0
+        pending = []  # (ticket, tile number)
+
+        def finish(entry):
+            nonlocal chk
+            t, k = entry
+            rx_h.wait_host(t)
+            o = h_outs[k % DEPTH]
+            chk += int(o["totals"][0]) + int(o["dibits"][0, 0])  # the host reads the finished tile
+            if count:
+                d2h[0] += int(o["totals"][0]) * 128 + int(o["totals"][1]) * 1944
+
         for _ in range(n):
             k = seq[0]
             seq[0] += 1
-            t = rx_h.submit_host(h_tiles[k % C3_TILES], C3_PAIRS, h_outs[k % 2])
-            if prev is not None:
-                rx_h.wait_host(prev)
-                o = h_outs[(k - 1) % 2]
-                chk += int(o["totals"][0]) + int(o["dibits"][0, 0])  # the host reads the finished tile
-                if count:
-                    d2h[0] += int(o["totals"][0]) * 128 + int(o["totals"][1]) * 1944
-            prev, last = t, k
-        rx_h.wait_host(prev)
-        o = h_outs[last % 2]
-        if count:
-            d2h[0] += int(o["totals"][0]) * 128 + int(o["totals"][1]) * 1944
-        return chk + int(o["totals"][0])
+            if len(pending) == DEPTH - 1:
+                finish(pending.pop(0))
+            pending.append((rx_h.submit_host(h_tiles[k % C3_TILES], C3_PAIRS, h_outs[k % DEPTH]), k))
+        while pending:
+            finish(pending.pop(0))
+        return chk
 
     run(C3_TILES + 1)
     barrier()
@@ -865,11 +889,11 @@ def run_c3_b200_arm(args):
     e2e = {"value": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": C3_CH * C3_PAIRS * 2,
            "d2h_bytes_per_step": int(fixed_d2h + d2h[0] / e2e_steps), "ms_per_step": e2e_ms, "steps": e2e_steps,
            "channels_at_realtime": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / C3_RATE,
-           "timer": "host wall clock around K x {dsdneo_b200_p25p1_rx_submit_host(tile i); wait_host(tile i-1); host reads tile i-1} "
-                    "+ final wait, max over ranks",
+           "timer": "host wall clock around K x {wait_host(tile i-3); host reads tile i-3; dsdneo_b200_p25p1_rx_submit_host(tile i)} "
+                    "+ final waits, max over ranks (three tiles in flight)",
            "d2h_contents": "dibit stream + counts + frame records + IMBE frame records"}
     # device path == host path (same state history => same bytes)
-    fr_h, vo_h = rx_h.host_records(h_outs[(seq[0] - 1) % 2])
+    fr_h, vo_h = rx_h.host_records(h_outs[(seq[0] - 1) % DEPTH])
 
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -888,8 +912,11 @@ def run_c3_b200_arm(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "channels_at_realtime": value * 1e6 / C3_RATE, "config": c3_config(),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "kernels_serial": {"ms_per_step": serial_ms_per_step, "steps": n_serial,
+                           "avg_ms": {k: v["avg_ms"] for k, v in kserial.items()},
+                           "note": "control: one tile at a time (dsdneo_b200_p25p1_rx_process), no overlap between the pipeline stages"},
         "cpu_baseline": cpu_baseline,
-        "step_detail": {"call": "dsdneo_b200_p25p1_rx_process (device buffers) / _submit_host + _wait_host (host buffers)",
+        "step_detail": {"call": "dsdneo_b200_p25p1_rx_submit + _wait (device buffers) / _submit_host + _wait_host (host buffers)",
                         "symbols_per_step": n_sym, "frames_per_step": n_frames, "frames_decoded_ok": n_good,
                         "imbe_frames_per_step": 9 * n_voice, "host_numa_binding": ("node %s" % numa_node) if numa_node is not None else "none",
                         "e2e_frames_last_step": int(fr_h.size), "e2e_voice_last_step": int(vo_h.size)},

@@ -1019,8 +1019,7 @@ class P25p1Rx:
             o["counts"] = torch.zeros(self.n_channels, dtype=torch.int32, device=device)
         return o
 
-    def process(self, d_iq, n_pairs, out, stream=None):
-        """d_iq: cuda uint8 [n_ch, pitch, 2] (cu8) or float32 [n_ch, pitch, 2]; out from alloc_device_out."""
+    def _dev_out(self, d_iq, out, stream):
         import torch
 
         assert d_iq.is_cuda and d_iq.is_contiguous() and d_iq.shape[0] == self.n_channels
@@ -1030,8 +1029,36 @@ class P25p1Rx:
         o = P25p1RxOut(out["frames"].data_ptr(), out["frames"].shape[0], out["voices"].data_ptr(), out["voices"].shape[0],
                        out["totals"].data_ptr(), out["dibits"].data_ptr() if "dibits" in out else None,
                        out["dibits"].shape[1] if "dibits" in out else 0, out["counts"].data_ptr() if "counts" in out else None)
+        return o, stream
+
+    def process(self, d_iq, n_pairs, out, stream=None):
+        """d_iq: cuda uint8 [n_ch, pitch, 2] (cu8) or float32 [n_ch, pitch, 2]; out from alloc_device_out."""
+        o, stream = self._dev_out(d_iq, out, stream)
         check(lib().dsdneo_b200_p25p1_rx_process(self._h, d_iq.data_ptr(), d_iq.shape[1], n_pairs, C.byref(o), _stream_ptr(stream)),
               "p25p1_rx_process")
+
+    def submit(self, d_iq, n_pairs, out, stream=None):
+        """Pipelined form of process(): queues the tile and returns a ticket; consecutive tiles overlap on the device."""
+        o, stream = self._dev_out(d_iq, out, stream)
+        t = lib().dsdneo_b200_p25p1_rx_submit(self._h, d_iq.data_ptr(), d_iq.shape[1], n_pairs, C.byref(o), _stream_ptr(stream))
+        if t < 0:
+            check(int(t), "p25p1_rx_submit")
+        return t
+
+    def wait(self, ticket, stream=None):
+        """Orders `stream` (default: torch's current stream) behind the tile's outputs; the host does not block."""
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        check(lib().dsdneo_b200_p25p1_rx_wait(self._h, ticket, _stream_ptr(stream)), "p25p1_rx_wait")
+
+    def input_consumed(self, ticket, stream=None):
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        check(lib().dsdneo_b200_p25p1_rx_input_consumed(self._h, ticket, _stream_ptr(stream)), "p25p1_rx_input_consumed")
 
     @staticmethod
     def records(out):

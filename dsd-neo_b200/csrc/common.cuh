@@ -73,6 +73,13 @@ int dsdneo_demod_fir_stage(dsdneo_b200_demod_bank* b, const float* d_iq, size_t 
 int dsdneo_demod_rec_stage(dsdneo_b200_demod_bank* b, int block_pairs, int n_blocks, float* d_result,
                            size_t result_pitch, int slot, cudaStream_t s);
 
+/* library-internal stage entry points of the symbolizer (symbolizer.cu), used by p25p1_rx.cu */
+struct dsdneo_b200_symbolizer;
+struct dsdneo_b200_symbol_out;
+int dsdneo_symbolize_fir_stage(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int slot, cudaStream_t s);
+int dsdneo_symbolize_sym_stage(dsdneo_b200_symbolizer* y, int n_samples, int mode, int have_sync, const dsdneo_b200_symbol_out* out,
+                               int slot, cudaStream_t s);
+
 /* library-internal: the CQPSK chain (cqpsk.cu) behind the channel LPF of the demod bank */
 struct dsdneo_b200_cqpsk_bank;
 int dsdneo_cqpsk_bank_channels(const dsdneo_b200_cqpsk_bank* q);

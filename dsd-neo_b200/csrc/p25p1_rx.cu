@@ -30,6 +30,8 @@ using namespace dsdneo;
 
 namespace {
 
+constexpr int kTraceTiles = 32;
+constexpr int kHostSlots = 4; /* host-buffer tiles in flight: the four pipeline stages plus the copies either side */
 constexpr int kKeep = 1024;  /* symbols of history kept per channel (>= kDelay + the 90 dibits a DMR burst looks back) */
 constexpr int kDelay = 864;  /* frames are decoded this many symbols behind the slicer: the longest frame (LDU) */
 static const char kP25Sync[] = "111113113311333313133333"; /* P25P1_SYNC, include/dsd-neo/core/sync_patterns.h:34 */
@@ -119,8 +121,8 @@ struct dsdneo_b200_p25p1_rx {
     uint8_t *d_dib[2], *d_rel[2];
     int16_t* d_llr[2];
     float* d_symv[2];
-    int *d_count[2], *d_valid;
-    long long *d_stream_base, *d_total;
+    int *d_count[2], *d_valid[2];
+    long long *d_stream_base[2], *d_total;
     int *d_hits, *d_n_hits;
     uint8_t *d_code63, *d_rel63, *d_par, *d_prel, *d_nid_valid, *d_pay_dummy, *d_pay_valid;
     int16_t* d_payllr_dummy;
@@ -128,18 +130,27 @@ struct dsdneo_b200_p25p1_rx {
     int *d_nid_nac, *d_nid_errs, *d_slot_nac, *d_chan_nac;
     uint8_t* d_nid_duid;
     int *d_frame_off, *d_voice_off;
+    /* the three-stage tile pipeline */
+    int pipe_ready;
+    cudaStream_t s_a, s_b, s_c, s_d;
+    cudaEvent_t ev_fork, ev_a[2], ev_b[2], ev_c[2], ev_d[2];
+    cudaEvent_t c_gate; /* optional extra dependency of the next tile's stage C (host path) */
+    int c_gate_set;
+    unsigned long long tiles;
+    cudaEvent_t* trace; /* DSDNEO_B200_RX_TRACE=1: [kTraceTiles][8] stage start / end events of the first tiles after trace_reset */
+    unsigned long long trace_base;
     /* host path */
     int host_ready;
-    cudaStream_t s_h2d, s_comp, s_d2h, s_rec; /* s_rec: the exact-size record copies of wait_host */
-    cudaEvent_t ev_h2d[2], ev_comp[2], ev_small[2], ev_in_free[2], ev_out_free[2];
-    void* d_in[2];
+    cudaStream_t s_h2d, s_d2h, s_rec; /* s_rec: the exact-size record copies of wait_host */
+    cudaEvent_t ev_small[kHostSlots], ev_out_free[kHostSlots];
+    void* d_in[kHostSlots];
     size_t in_cap;
-    dsdneo_b200_p25p1_frame* d_frames[2];
-    dsdneo_b200_p25p1_voice* d_voices[2];
-    int* d_totals[2];
-    int* h_totals; /* pinned, [2][2] */
+    dsdneo_b200_p25p1_frame* d_frames[kHostSlots];
+    dsdneo_b200_p25p1_voice* d_voices[kHostSlots];
+    int* d_totals[kHostSlots];
+    int* h_totals; /* pinned, [kHostSlots][2] */
     unsigned long long tickets, waited;
-    dsdneo_b200_p25p1_rx_host_out pending[2];
+    dsdneo_b200_p25p1_rx_host_out pending[kHostSlots];
 };
 
 extern "C" {
@@ -148,6 +159,20 @@ void
 dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
     if (!rx) {
         return;
+    }
+    cudaDeviceSynchronize(); /* tiles may still be in flight on the pipeline streams */
+    if (rx->pipe_ready) {
+        cudaStreamDestroy(rx->s_a);
+        cudaStreamDestroy(rx->s_b);
+        cudaStreamDestroy(rx->s_c);
+        cudaStreamDestroy(rx->s_d);
+        cudaEventDestroy(rx->ev_fork);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(rx->ev_a[i]);
+            cudaEventDestroy(rx->ev_b[i]);
+            cudaEventDestroy(rx->ev_c[i]);
+            cudaEventDestroy(rx->ev_d[i]);
+        }
     }
     dsdneo_b200_demod_bank_destroy(rx->bank);
     dsdneo_b200_symbolizer_destroy(rx->sym);
@@ -160,13 +185,17 @@ dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
         cudaFree(rx->d_llr[i]);
         cudaFree(rx->d_symv[i]);
         cudaFree(rx->d_count[i]);
+    }
+    for (int i = 0; i < kHostSlots; i++) {
         cudaFree(rx->d_in[i]);
         cudaFree(rx->d_frames[i]);
         cudaFree(rx->d_voices[i]);
         cudaFree(rx->d_totals[i]);
     }
-    cudaFree(rx->d_valid);
-    cudaFree(rx->d_stream_base);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(rx->d_valid[i]);
+        cudaFree(rx->d_stream_base[i]);
+    }
     cudaFree(rx->d_total);
     cudaFree(rx->d_hits);
     cudaFree(rx->d_n_hits);
@@ -188,14 +217,10 @@ dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
     cudaFree(rx->d_voice_off);
     if (rx->host_ready) {
         cudaStreamDestroy(rx->s_h2d);
-        cudaStreamDestroy(rx->s_comp);
         cudaStreamDestroy(rx->s_d2h);
         cudaStreamDestroy(rx->s_rec);
-        for (int i = 0; i < 2; i++) {
-            cudaEventDestroy(rx->ev_h2d[i]);
-            cudaEventDestroy(rx->ev_comp[i]);
+        for (int i = 0; i < kHostSlots; i++) {
             cudaEventDestroy(rx->ev_small[i]);
-            cudaEventDestroy(rx->ev_in_free[i]);
             cudaEventDestroy(rx->ev_out_free[i]);
         }
         cudaFreeHost(rx->h_totals);
@@ -310,8 +335,10 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
         RX_ALLOC(rx->d_symv[i], n * rx->pitch * sizeof(float));
         RX_ALLOC(rx->d_count[i], n * sizeof(int));
     }
-    RX_ALLOC(rx->d_valid, n * sizeof(int));
-    RX_ALLOC(rx->d_stream_base, n * sizeof(long long));
+    for (int i = 0; i < 2; i++) {
+        RX_ALLOC(rx->d_valid[i], n * sizeof(int));
+        RX_ALLOC(rx->d_stream_base[i], n * sizeof(long long));
+    }
     RX_ALLOC(rx->d_total, n * sizeof(long long));
     RX_ALLOC(rx->d_hits, slots * 2 * sizeof(int));
     RX_ALLOC(rx->d_n_hits, n * sizeof(int));
@@ -340,17 +367,81 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
     return rx;
 }
 
-int
-dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
-                             const dsdneo_b200_p25p1_rx_out* out, void* stream) {
+/*
+ * One tile through the chain as four pipeline stages on the bank's own streams, so that consecutive tiles overlap on the
+ * device: the latency-bound per-channel recurrences (discriminator, slicer) of one tile run under the throughput-bound
+ * filters of the next.
+ *   stage A (s_a)  widen cu8 -> channel LPF + phase (lpf_phase_kernel), FIR state          -> bank phase buffer [slot]
+ *   stage B (s_b)  discriminator recurrences -> d_disc -> matched filter (sps_fir_kernel)    -> symbolizer filter buffer [slot]
+ *   stage C (s_c)  stream tail, slicer (symbolize_kernel), stream accounting                   -> stream buffers [tile & 1]
+ *   stage D (s_d)  sync hunt, frame cut, NID, frame decode, NAC tracking, output copies
+ * Every stage owns its carried state, so the order inside a stream is the tile order and the only cross-stream edges are
+ * A(i) -> B(i) -> C(i) -> D(i) and the buffer-reuse edges B(i) -> A(i + 2), C(i) -> B(i + 2), D(i) -> C(i + 2).
+ */
+static int
+rx_pipeline_init(dsdneo_b200_p25p1_rx* rx) {
+    if (rx->pipe_ready) {
+        return 0;
+    }
+    int prio_least = 0, prio_greatest = 0;
+    DSDNEO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    /* the slicer is the longest serial chain of a tile: its CTAs (and the short frame kernels behind it) get SM slots first,
+     * the wide filter grids fill what is left */
+    const int p_hi = prio_greatest, p_mid = prio_greatest < prio_least ? prio_greatest + 1 : prio_least, p_lo = prio_least;
+    DSDNEO_CUDA(cudaStreamCreateWithPriority(&rx->s_a, cudaStreamNonBlocking, p_lo));
+    DSDNEO_CUDA(cudaStreamCreateWithPriority(&rx->s_b, cudaStreamNonBlocking, p_mid));
+    DSDNEO_CUDA(cudaStreamCreateWithPriority(&rx->s_c, cudaStreamNonBlocking, p_hi));
+    DSDNEO_CUDA(cudaStreamCreateWithPriority(&rx->s_d, cudaStreamNonBlocking, p_hi));
+    DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_a[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_b[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_c[i], cudaEventDisableTiming));
+        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_d[i], cudaEventDisableTiming));
+    }
+    const char* tr = getenv("DSDNEO_B200_RX_TRACE");
+    if (tr && tr[0] == '1') {
+        rx->trace = (cudaEvent_t*)calloc((size_t)kTraceTiles * 8, sizeof(cudaEvent_t));
+        for (int i = 0; rx->trace && i < kTraceTiles * 8; i++) {
+            DSDNEO_CUDA(cudaEventCreate(&rx->trace[i]));
+        }
+        rx->trace_base = ~0ull;
+    }
+    rx->pipe_ready = 1;
+    return 0;
+}
+
+static void
+rx_trace(dsdneo_b200_p25p1_rx* rx, unsigned long long tile, int what, cudaStream_t s) {
+    if (rx->trace && rx->trace_base != ~0ull && tile >= rx->trace_base && tile < rx->trace_base + kTraceTiles) {
+        cudaEventRecord(rx->trace[(tile - rx->trace_base) * 8 + what], s);
+    }
+}
+
+long long
+dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
+                            const dsdneo_b200_p25p1_rx_out* out, void* stream) {
     if (!rx || !d_iq || !out || !out->d_frames || !out->d_totals || n_pairs <= 0 || n_pairs > rx->cap_pairs
         || n_pairs % rx->cfg.block_pairs != 0 || iq_pitch_pairs < (size_t)n_pairs || out->frame_capacity <= 0
         || (out->voice_capacity > 0 && !out->d_voices)) {
         set_error("p25p1_rx_process: bad argument (n_pairs must be a multiple of block_pairs, at most max_pairs_per_call)");
         return DSDNEO_B200_EINVAL;
     }
-    cudaStream_t s = as_stream(stream);
+    int rc = rx_pipeline_init(rx);
+    if (rc) {
+        return rc;
+    }
+    const unsigned long long tile = rx->tiles;
+    const int slot = (int)(tile & 1);
     const int n_ch = rx->n_ch, cur = rx->phase, prev = rx->phase ^ 1;
+    /* ---- stage A ---- */
+    cudaStream_t s = rx->s_a;
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_fork, as_stream(stream))); /* the caller's input is ready on its stream */
+    DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_fork, 0));
+    if (tile >= 2) {
+        DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_b[slot], 0)); /* the recurrences two tiles back have read phase buffer [slot] */
+    }
+    rx_trace(rx, tile, 0, s);
     const float* iq = (const float*)d_iq;
     size_t pitch_pairs = iq_pitch_pairs;
     if (rx->cfg.input_cu8) {
@@ -362,11 +453,41 @@ dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t 
         iq = (const float*)rx->d_iq;
         pitch_pairs = (size_t)rx->cap_pairs;
     }
-    int rc = dsdneo_b200_full_demod_batch(rx->bank, iq, pitch_pairs, rx->cfg.block_pairs, n_pairs / rx->cfg.block_pairs, rx->d_disc,
-                                          (size_t)rx->cap_pairs, stream);
+    const int n_blocks = n_pairs / rx->cfg.block_pairs;
+    rc = dsdneo_demod_fir_stage(rx->bank, iq, pitch_pairs, rx->cfg.block_pairs, n_blocks, slot, s);
     if (rc) {
         return rc;
     }
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_a[slot], s)); /* also: the caller's input buffer is consumed */
+    rx_trace(rx, tile, 1, s);
+    /* ---- stage B ---- */
+    s = rx->s_b;
+    DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_a[slot], 0));
+    if (tile >= 2) {
+        DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_c[slot], 0)); /* the slicer two tiles back has read filter buffer [slot] */
+    }
+    rx_trace(rx, tile, 2, s);
+    rc = dsdneo_demod_rec_stage(rx->bank, rx->cfg.block_pairs, n_blocks, rx->d_disc, (size_t)rx->cap_pairs, slot, s);
+    if (rc) {
+        return rc;
+    }
+    rc = dsdneo_symbolize_fir_stage(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, slot, s);
+    if (rc) {
+        return rc;
+    }
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_b[slot], s));
+    rx_trace(rx, tile, 3, s);
+    /* ---- stage C ---- */
+    s = rx->s_c;
+    DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_b[slot], 0));
+    if (tile >= 2) {
+        DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_d[slot], 0)); /* the frame stage two tiles back has read stream buffers [cur] */
+    }
+    if (rx->c_gate_set) { /* host path: the stream buffers this tile writes were last read by a device-to-host copy */
+        DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->c_gate, 0));
+        rx->c_gate_set = 0;
+    }
+    rx_trace(rx, tile, 4, s);
     {
         KernelTimer kt("stream_tail_kernel", s);
         stream_tail_kernel<<<n_ch, 256, 0, s>>>(rx->d_dib[prev], rx->d_rel[prev], (const short2*)rx->d_llr[prev], rx->d_symv[prev],
@@ -382,25 +503,32 @@ dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t 
     so.d_llr = rx->d_llr[cur] + 2 * kKeep;
     so.d_count = rx->d_count[cur];
     so.pitch = rx->pitch;
-    rc = dsdneo_b200_symbolize_batch(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, stream);
+    rc = dsdneo_symbolize_sym_stage(rx->sym, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, slot, s);
     if (rc) {
         return rc;
     }
     {
         KernelTimer kt("stream_account_kernel", s);
-        stream_account_kernel<<<(n_ch + 127) / 128, 128, 0, s>>>(rx->d_count[cur], rx->d_valid, rx->d_stream_base, rx->d_total, n_ch);
+        stream_account_kernel<<<(n_ch + 127) / 128, 128, 0, s>>>(rx->d_count[cur], rx->d_valid[cur], rx->d_stream_base[cur], rx->d_total,
+                                                                 n_ch);
         DSDNEO_KERNEL_CHECK();
         count_launch();
     }
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_c[slot], s));
+    rx_trace(rx, tile, 5, s);
+    /* ---- stage D ---- */
+    s = rx->s_d;
+    DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_c[slot], 0));
+    rx_trace(rx, tile, 6, s);
     const int region = kKeep - kDelay;
     rc = dsdneo_b200_frame_sync_search_batch(rx->fs, rx->d_symv[cur] + region, rx->pitch, rx->d_count[cur],
-                                             (dsdneo_b200_sync_hit*)rx->d_hits, rx->max_hits, rx->d_n_hits, stream);
+                                             (dsdneo_b200_sync_hit*)rx->d_hits, rx->max_hits, rx->d_n_hits, s);
     if (rc) {
         return rc;
     }
-    rc = dsdneo_p25p1_frame_cut_region(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid, rx->d_hits, rx->d_n_hits, n_ch,
+    rc = dsdneo_p25p1_frame_cut_region(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid[cur], rx->d_hits, rx->d_n_hits, n_ch,
                                        rx->max_hits, 0, rx->d_code63, rx->d_rel63, rx->d_par, rx->d_prel, rx->d_nid_valid,
-                                       rx->d_pay_dummy, rx->d_payllr_dummy, rx->d_pay_valid, region, stream);
+                                       rx->d_pay_dummy, rx->d_payllr_dummy, rx->d_pay_valid, region, s);
     if (rc) {
         return rc;
     }
@@ -413,16 +541,16 @@ dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t 
     }
     const int threshold = rx->cfg.erasure_threshold > 0 ? rx->cfg.erasure_threshold : 64;
     rc = dsdneo_b200_p25p1_nid_decode_batch(rx->d_code63, rx->d_rel63, rx->cfg.track_nac ? rx->d_slot_nac : NULL, rx->d_par, rx->d_prel,
-                                            threshold, rx->d_nid_status, rx->d_nid_nac, rx->d_nid_duid, rx->d_nid_errs, slots, stream);
+                                            threshold, rx->d_nid_status, rx->d_nid_nac, rx->d_nid_duid, rx->d_nid_errs, slots, s);
     if (rc) {
         return rc;
     }
-    rc = dsdneo_b200_p25p1_frames_decode_batch(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid,
+    rc = dsdneo_b200_p25p1_frames_decode_batch(rx->d_dib[cur], rx->pitch, rx->d_llr[cur], rx->pitch, rx->d_valid[cur],
                                                (const dsdneo_b200_sync_hit*)rx->d_hits, rx->d_n_hits, n_ch, rx->max_hits, region,
-                                               rx->d_stream_base, rx->d_nid_status, rx->d_nid_valid, rx->d_nid_nac, rx->d_nid_duid,
+                                               rx->d_stream_base[cur], rx->d_nid_status, rx->d_nid_valid, rx->d_nid_nac, rx->d_nid_duid,
                                                rx->d_nid_errs, threshold, rx->cfg.hard_override_disabled ? 0 : 1, rx->d_frame_off,
                                                rx->d_voice_off, out->d_totals, out->d_frames, out->frame_capacity, out->d_voices,
-                                               out->voice_capacity, stream);
+                                               out->voice_capacity, s);
     if (rc) {
         return rc;
     }
@@ -440,16 +568,75 @@ dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t 
     if (out->d_counts) {
         DSDNEO_CUDA(cudaMemcpyAsync(out->d_counts, rx->d_count[cur], (size_t)n_ch * sizeof(int), cudaMemcpyDeviceToDevice, s));
     }
+    DSDNEO_CUDA(cudaEventRecord(rx->ev_d[slot], s));
+    rx_trace(rx, tile, 7, s);
     rx->phase ^= 1;
+    return (long long)rx->tiles++;
+}
+
+int
+dsdneo_b200_p25p1_rx_wait(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream) {
+    if (!rx || !rx->pipe_ready || ticket < 0 || (unsigned long long)ticket >= rx->tiles) {
+        set_error("p25p1_rx_wait: unknown ticket");
+        return DSDNEO_B200_EINVAL;
+    }
+    /* stage C runs the tiles in order: the event of a later tile in the same slot covers this one as well */
+    DSDNEO_CUDA(cudaStreamWaitEvent(as_stream(stream), rx->ev_d[(int)(ticket & 1)], 0));
     return 0;
+}
+
+int
+dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream) {
+    if (!rx || !rx->pipe_ready || ticket < 0 || (unsigned long long)ticket >= rx->tiles) {
+        set_error("p25p1_rx_input_consumed: unknown ticket");
+        return DSDNEO_B200_EINVAL;
+    }
+    DSDNEO_CUDA(cudaStreamWaitEvent(as_stream(stream), rx->ev_a[(int)(ticket & 1)], 0));
+    return 0;
+}
+
+/* Debug aid (DSDNEO_B200_RX_TRACE=1): start tracing at the next tile / read the stage start and end times (ms, relative to the
+ * first traced tile's stage A start) of the traced tiles: ms[tile][8] = {A0, A1, B0, B1, C0, C1, D0, D1}.  Synchronises. */
+int
+dsdneo_b200_p25p1_rx_trace(dsdneo_b200_p25p1_rx* rx, float* ms, int max_tiles) {
+    if (!rx || !rx->trace) {
+        return 0;
+    }
+    if (!ms) {
+        rx->trace_base = rx->tiles;
+        return 0;
+    }
+    cudaDeviceSynchronize();
+    const unsigned long long done = rx->tiles - rx->trace_base;
+    const int n = (int)(done < (unsigned long long)kTraceTiles ? done : kTraceTiles);
+    int k = 0;
+    for (; k < n && k < max_tiles; k++) {
+        for (int w = 0; w < 8; w++) {
+            float t = 0.0f;
+            cudaEventElapsedTime(&t, rx->trace[0], rx->trace[k * 8 + w]);
+            ms[k * 8 + w] = t;
+        }
+    }
+    return k;
+}
+
+int
+dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
+                             const dsdneo_b200_p25p1_rx_out* out, void* stream) {
+    const long long t = dsdneo_b200_p25p1_rx_submit(rx, d_iq, iq_pitch_pairs, n_pairs, out, stream);
+    if (t < 0) {
+        return (int)t;
+    }
+    return dsdneo_b200_p25p1_rx_wait(rx, t, stream);
 }
 
 /*
  * Host-buffer streaming form (the reference's demod thread consumes its input ring the same way, src/io/radio/rtl_sdr_fm.cpp:
  * 3458-3512): submit(tile i) queues H2D, the whole chain and the D2H of the dibit stream on three internal streams and
  * returns a ticket; wait(ticket) blocks until the tile's results are in the caller's buffers.  The record counts are only
- * known after the tile ran, so wait() copies exactly totals[0] frame and totals[1] voice records.  At most two tiles may be
- * in flight: submit() first completes the tile submitted two calls earlier if the caller has not waited for it yet.
+ * known after the tile ran, so wait() copies exactly totals[0] frame and totals[1] voice records.  At most kHostSlots (4) tiles
+ * may be in flight -- the depth of the four-stage pipeline plus the copies either side: submit() first completes the tile
+ * submitted four calls earlier if the caller has not waited for it yet.
  */
 static int
 rx_host_init(dsdneo_b200_p25p1_rx* rx) {
@@ -457,20 +644,16 @@ rx_host_init(dsdneo_b200_p25p1_rx* rx) {
         return 0;
     }
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_h2d, cudaStreamNonBlocking));
-    DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_comp, cudaStreamNonBlocking));
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_d2h, cudaStreamNonBlocking));
     DSDNEO_CUDA(cudaStreamCreateWithFlags(&rx->s_rec, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_h2d[i], cudaEventDisableTiming));
-        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_comp[i], cudaEventDisableTiming));
+    for (int i = 0; i < kHostSlots; i++) {
         DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_small[i], cudaEventDisableTiming));
-        DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_in_free[i], cudaEventDisableTiming));
         DSDNEO_CUDA(cudaEventCreateWithFlags(&rx->ev_out_free[i], cudaEventDisableTiming));
         DSDNEO_CUDA(cudaMalloc((void**)&rx->d_frames[i], (size_t)dsdneo_b200_p25p1_rx_frame_capacity(rx) * sizeof(dsdneo_b200_p25p1_frame)));
         DSDNEO_CUDA(cudaMalloc((void**)&rx->d_voices[i], (size_t)dsdneo_b200_p25p1_rx_voice_capacity(rx) * sizeof(dsdneo_b200_p25p1_voice)));
         DSDNEO_CUDA(cudaMalloc((void**)&rx->d_totals[i], 2 * sizeof(int)));
     }
-    DSDNEO_CUDA(cudaMallocHost((void**)&rx->h_totals, 4 * sizeof(int)));
+    DSDNEO_CUDA(cudaMallocHost((void**)&rx->h_totals, 2 * kHostSlots * sizeof(int)));
     rx->host_ready = 1;
     return 0;
 }
@@ -485,7 +668,7 @@ dsdneo_b200_p25p1_rx_wait_host(dsdneo_b200_p25p1_rx* rx, long long ticket) {
         return 0; /* already completed (by an earlier wait or by a later submit) */
     }
     for (unsigned long long t = rx->waited; t <= (unsigned long long)ticket; t++) {
-        const int slot = (int)(t & 1);
+        const int slot = (int)(t % kHostSlots);
         const dsdneo_b200_p25p1_rx_host_out* o = &rx->pending[slot];
         DSDNEO_CUDA(cudaEventSynchronize(rx->ev_small[slot])); /* totals, dibits and counts are in host memory */
         int nf = rx->h_totals[2 * slot], nv = rx->h_totals[2 * slot + 1];
@@ -523,34 +706,35 @@ dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, siz
     if (rc) {
         return rc;
     }
-    if (rx->tickets >= 2 && rx->waited + 2 <= rx->tickets) { /* the slot about to be reused still holds an unread tile */
-        rc = dsdneo_b200_p25p1_rx_wait_host(rx, (long long)(rx->tickets - 2));
+    if (rx->tickets >= kHostSlots && rx->waited + kHostSlots <= rx->tickets) { /* the slot about to be reused still holds an unread tile */
+        rc = dsdneo_b200_p25p1_rx_wait_host(rx, (long long)(rx->tickets - kHostSlots));
         if (rc) {
             return rc;
         }
     }
-    const int slot = (int)(rx->tickets & 1);
+    const int slot = (int)(rx->tickets % kHostSlots);
     const size_t elt = rx->cfg.input_cu8 ? 2 : 8;
     const size_t in_bytes = (size_t)rx->n_ch * iq_pitch_pairs * elt;
     if (rx->in_cap < in_bytes) {
         DSDNEO_CUDA(cudaDeviceSynchronize());
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kHostSlots; i++) {
             cudaFree(rx->d_in[i]);
             rx->d_in[i] = NULL;
             DSDNEO_CUDA(cudaMalloc(&rx->d_in[i], in_bytes));
         }
         rx->in_cap = in_bytes;
     }
-    if (rx->tickets >= 2) {
-        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_h2d, rx->ev_in_free[slot], 0)); /* the chain two tiles back consumed d_in[slot] */
+    if (rx->tickets >= kHostSlots) {
+        /* d_in[slot] was consumed by stage A of the tile kHostSlots back; stage A runs the tiles in order, so the event of the
+         * newest tile that shares its pipeline slot covers it */
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_h2d, rx->ev_a[(int)(rx->tiles & 1)], 0));
     }
     DSDNEO_CUDA(cudaMemcpyAsync(rx->d_in[slot], h_iq, in_bytes, cudaMemcpyHostToDevice, rx->s_h2d));
-    DSDNEO_CUDA(cudaEventRecord(rx->ev_h2d[slot], rx->s_h2d));
-    DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_comp, rx->ev_h2d[slot], 0));
     if (rx->tickets >= 2) {
         /* the stream buffers this tile writes were last read by the dibit D2H of the tile two calls back (the tile in
          * between only read them for its tail and wrote the other set) */
-        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_comp, rx->ev_small[slot], 0));
+        rx->c_gate = rx->ev_small[(int)((rx->tickets - 2) % kHostSlots)];
+        rx->c_gate_set = 1;
     }
     dsdneo_b200_p25p1_rx_out dev;
     memset(&dev, 0, sizeof(dev));
@@ -559,14 +743,12 @@ dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, siz
     dev.d_voices = rx->d_voices[slot];
     dev.voice_capacity = dsdneo_b200_p25p1_rx_voice_capacity(rx);
     dev.d_totals = rx->d_totals[slot];
-    rc = dsdneo_b200_p25p1_rx_process(rx, rx->d_in[slot], iq_pitch_pairs, n_pairs, &dev, rx->s_comp);
-    if (rc) {
-        return rc;
+    const long long tile = dsdneo_b200_p25p1_rx_submit(rx, rx->d_in[slot], iq_pitch_pairs, n_pairs, &dev, rx->s_h2d);
+    if (tile < 0) {
+        return tile;
     }
     const int cur = rx->phase ^ 1; /* the stream buffers this tile was written to */
-    DSDNEO_CUDA(cudaEventRecord(rx->ev_in_free[slot], rx->s_comp));
-    DSDNEO_CUDA(cudaEventRecord(rx->ev_comp[slot], rx->s_comp));
-    DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d2h, rx->ev_comp[slot], 0));
+    DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d2h, rx->ev_d[(int)(tile & 1)], 0));
     DSDNEO_CUDA(cudaMemcpyAsync(rx->h_totals + 2 * slot, rx->d_totals[slot], 2 * sizeof(int), cudaMemcpyDeviceToHost, rx->s_d2h));
     if (out->h_dibits) {
         DSDNEO_CUDA(cudaMemcpy2DAsync(out->h_dibits, out->dibit_pitch, rx->d_dib[cur] + kKeep, rx->pitch,

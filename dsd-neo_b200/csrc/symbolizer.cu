@@ -1993,8 +1993,8 @@ struct dsdneo_b200_symbolizer {
     SymScalars s;
     float *d_minbuf, *d_maxbuf, *d_sbuf, *d_carry, *d_hist, *d_taps;
     int* d_taps_len;
-    float* d_filt;
-    size_t filt_pitch;
+    float* d_filt[2]; /* matched-filter output, one buffer per pipeline slot */
+    size_t filt_pitch[2];
     /* acquisition (getFrameSync on the device): configured by dsdneo_b200_symbolizer_set_acquire_patterns */
     int n_pat;
     AcqPattern pat[kAcqMaxPatterns];
@@ -2065,7 +2065,8 @@ dsdneo_b200_symbolizer_destroy(dsdneo_b200_symbolizer* y) {
     cudaFree(y->d_hist);
     cudaFree(y->d_taps);
     cudaFree(y->d_taps_len);
-    cudaFree(y->d_filt);
+    cudaFree(y->d_filt[0]);
+    cudaFree(y->d_filt[1]);
     cudaFree(y->d_acquired);
     cudaFree(y->d_hunt_since);
     cudaFree(y->d_hunt_count);
@@ -2431,10 +2432,8 @@ dsdneo_b200_selftest_div5(unsigned long long* d_n_mismatch, unsigned* d_first_ba
 }
 
 static int
-symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
-                 const dsdneo_b200_symbol_out* out, bool acquire, dsdneo_b200_acq_info* d_info, void* stream) {
-    if (!y || !d_disc || !out || n_samples < 0 || disc_pitch < (size_t)n_samples || !out->d_symbols || !out->d_count
-        || out->pitch == 0) {
+symbolize_check(dsdneo_b200_symbolizer* y, int n_samples, int mode, const dsdneo_b200_symbol_out* out) {
+    if (!y || !out || n_samples < 0 || !out->d_symbols || !out->d_count || out->pitch == 0) {
         set_error("symbolize_batch: bad argument");
         return DSDNEO_B200_EINVAL;
     }
@@ -2446,32 +2445,22 @@ symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pit
         set_error("symbolize_batch: GET_DIBIT_SOFT needs dibit, reliability and llr outputs");
         return DSDNEO_B200_EINVAL;
     }
-    {
-        int whole = y->rate / y->symrate;
-        whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
-        const size_t need = ((size_t)n_samples + kCarry) / (size_t)(whole - 1) + 2;
-        if (out->pitch < need) {
-            set_error("symbolize_batch: output pitch %zu is too small for %d samples (need >= %zu)", out->pitch, n_samples, need);
-            return DSDNEO_B200_EINVAL;
-        }
+    int whole = y->rate / y->symrate;
+    whole = whole < 2 ? 2 : (whole > 64 ? 64 : whole);
+    const size_t need = ((size_t)n_samples + kCarry) / (size_t)(whole - 1) + 2;
+    if (out->pitch < need) {
+        set_error("symbolize_batch: output pitch %zu is too small for %d samples (need >= %zu)", out->pitch, n_samples, need);
+        return DSDNEO_B200_EINVAL;
     }
-    int rc = ensure_device();
-    if (rc) {
-        return rc;
-    }
-    cudaStream_t s = as_stream(stream);
-    const size_t pitch = (((size_t)n_samples + 31) & ~(size_t)31) + 32; /* rows start on 128-byte lines */
-    if (!y->d_filt || y->filt_pitch < pitch) {
-        DSDNEO_CUDA(cudaDeviceSynchronize());
-        cudaFree(y->d_filt);
-        y->d_filt = NULL;
-        DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt, (size_t)y->n_ch * pitch * sizeof(float)));
-        y->filt_pitch = pitch;
-    }
+    return 0;
+}
+
+static SymParams
+symbolize_params(dsdneo_b200_symbolizer* y, int n_samples, int mode, int have_sync, const dsdneo_b200_symbol_out* out, int slot) {
     SymParams sp;
     sp.s = y->s;
-    sp.filt = y->d_filt;
-    sp.filt_pitch = y->filt_pitch;
+    sp.filt = y->d_filt[slot];
+    sp.filt_pitch = y->filt_pitch[slot];
     sp.carry = y->d_carry;
     sp.sbuf = y->d_sbuf;
     sp.minbuf = y->d_minbuf;
@@ -2494,72 +2483,151 @@ symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pit
     sp.start_off = NULL;
     sp.out_off = NULL;
     sp.acquired = NULL;
-    if (acquire) { /* hunting channels first: they read the raw samples and may switch their class for the stages below */
-        AcqParams ap;
-        ap.sp = sp;
-        ap.sp.filt = d_disc;
-        ap.sp.filt_pitch = disc_pitch;
-        ap.taps = y->d_taps;
-        ap.taps_len = y->d_taps_len;
-        for (int k = 0; k < y->n_pat; k++) {
-            ap.pat[k] = y->pat[k];
-        }
-        ap.n_pat = y->n_pat;
-        ap.acquired = y->d_acquired;
-        ap.hunt_since = y->d_hunt_since;
-        ap.hunt_bits = y->d_hunt_bits;
-        ap.hunt_count = y->d_hunt_count;
-        ap.lbuf = y->d_lbuf;
-        ap.lidx = y->d_lidx;
-        ap.level_count = y->d_level_count;
-        ap.hist = y->d_hist128;
-        ap.hist_head = y->d_hist_head;
-        ap.start_off = y->d_start_off;
-        ap.out_off = y->d_out_off;
-        ap.info = d_info ? d_info : y->d_info;
-        ap.fir_hist = y->d_hist;
-        {
-            KernelTimer kt("sym_acquire_kernel", s);
-            sym_acquire_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(ap);
-        }
-        DSDNEO_KERNEL_CHECK();
-        count_launch();
-        sp.start_off = y->d_start_off;
-        sp.out_off = y->d_out_off;
-        sp.acquired = y->d_acquired;
+    return sp;
+}
+
+} /* extern "C" */
+
+/*
+ * The two halves of dsdneo_b200_symbolize_batch as separate stages, so that a caller which pipelines consecutive launches
+ * (csrc/p25p1_rx.cu) can run the matched filter of launch i+1 under the slicer of launch i: fir_stage writes the filter output
+ * of one launch into buffer `slot` (0 / 1) and advances the filter history; sym_stage consumes that buffer.  Each stage keeps
+ * its own carried state, so the only ordering a caller owes is fir(i) -> sym(i) and sym(i) -> fir(i + 2).
+ */
+int
+dsdneo_symbolize_fir_stage(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int slot, cudaStream_t s) {
+    if (!y || !d_disc || n_samples < 0 || disc_pitch < (size_t)n_samples || slot < 0 || slot > 1) {
+        set_error("symbolize fir stage: bad argument");
+        return DSDNEO_B200_EINVAL;
     }
-    if (n_samples > 0) {
-        FirParams fp;
-        fp.in = d_disc;
-        fp.in_pitch = disc_pitch;
-        fp.out = y->d_filt;
-        fp.out_pitch = y->filt_pitch;
-        fp.taps = y->d_taps;
-        fp.taps_len = y->d_taps_len;
-        fp.filter = y->s.filter;
-        fp.hist = y->d_hist;
-        fp.n = n_samples;
-        /* the bulk-copy form needs 16-byte aligned rows on both sides */
-        const bool aligned = (disc_pitch & 3) == 0 && (((uintptr_t)d_disc) & 15) == 0 && (y->filt_pitch & 3) == 0;
-        if (aligned) {
-            dim3 grid((unsigned)((n_samples + kFir8Tile - 1) / kFir8Tile), (unsigned)y->n_ch);
-            KernelTimer kt("sps_fir_kernel", s);
-            sps_fir8_kernel<<<grid, kFir8Threads, 0, s>>>(fp);
-        } else {
-            dim3 grid((unsigned)((n_samples + kFirTile - 1) / kFirTile), (unsigned)y->n_ch);
-            KernelTimer kt("sps_fir_kernel", s);
-            sps_fir_kernel<<<grid, kFirThreads, 0, s>>>(fp);
-        }
-        DSDNEO_KERNEL_CHECK();
-        count_launch();
-        {
-            KernelTimer kt("sps_fir_hist_kernel", s);
-            sps_fir_hist_kernel<<<(y->n_ch + 7) / 8, 256, 0, s>>>(d_disc, disc_pitch, y->d_hist, y->s.filter, y->d_taps_len, y->n_ch,
-                                                                 n_samples);
-        }
-        DSDNEO_KERNEL_CHECK();
-        count_launch();
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
     }
+    const size_t pitch = (((size_t)n_samples + 31) & ~(size_t)31) + 32; /* rows start on 128-byte lines */
+    if (!y->d_filt[slot] || y->filt_pitch[slot] < pitch) {
+        DSDNEO_CUDA(cudaDeviceSynchronize());
+        cudaFree(y->d_filt[slot]);
+        y->d_filt[slot] = NULL;
+        DSDNEO_CUDA(cudaMalloc((void**)&y->d_filt[slot], (size_t)y->n_ch * pitch * sizeof(float)));
+        y->filt_pitch[slot] = pitch;
+    }
+    if (n_samples == 0) {
+        return 0;
+    }
+    FirParams fp;
+    fp.in = d_disc;
+    fp.in_pitch = disc_pitch;
+    fp.out = y->d_filt[slot];
+    fp.out_pitch = y->filt_pitch[slot];
+    fp.taps = y->d_taps;
+    fp.taps_len = y->d_taps_len;
+    fp.filter = y->s.filter;
+    fp.hist = y->d_hist;
+    fp.n = n_samples;
+    /* the bulk-copy form needs 16-byte aligned rows on both sides */
+    const bool aligned = (disc_pitch & 3) == 0 && (((uintptr_t)d_disc) & 15) == 0 && (y->filt_pitch[slot] & 3) == 0;
+    if (aligned) {
+        dim3 grid((unsigned)((n_samples + kFir8Tile - 1) / kFir8Tile), (unsigned)y->n_ch);
+        KernelTimer kt("sps_fir_kernel", s);
+        sps_fir8_kernel<<<grid, kFir8Threads, 0, s>>>(fp);
+    } else {
+        dim3 grid((unsigned)((n_samples + kFirTile - 1) / kFirTile), (unsigned)y->n_ch);
+        KernelTimer kt("sps_fir_kernel", s);
+        sps_fir_kernel<<<grid, kFirThreads, 0, s>>>(fp);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    {
+        KernelTimer kt("sps_fir_hist_kernel", s);
+        sps_fir_hist_kernel<<<(y->n_ch + 7) / 8, 256, 0, s>>>(d_disc, disc_pitch, y->d_hist, y->s.filter, y->d_taps_len, y->n_ch, n_samples);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_symbolize_sym_stage(dsdneo_b200_symbolizer* y, int n_samples, int mode, int have_sync, const dsdneo_b200_symbol_out* out, int slot,
+                           cudaStream_t s) {
+    int rc = symbolize_check(y, n_samples, mode, out);
+    if (rc) {
+        return rc;
+    }
+    if (slot < 0 || slot > 1 || !y->d_filt[slot]) {
+        set_error("symbolize sym stage: no filter output in slot %d", slot);
+        return DSDNEO_B200_EINVAL;
+    }
+    const SymParams sp = symbolize_params(y, n_samples, mode, have_sync, out, slot);
+    {
+        KernelTimer kt("symbolize_kernel", s);
+        symbolize_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(sp);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+extern "C" {
+
+static int
+symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                 const dsdneo_b200_symbol_out* out, bool acquire, dsdneo_b200_acq_info* d_info, void* stream) {
+    int rc = symbolize_check(y, n_samples, mode, out);
+    if (rc) {
+        return rc;
+    }
+    if (!d_disc || disc_pitch < (size_t)n_samples) {
+        set_error("symbolize_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    cudaStream_t s = as_stream(stream);
+    if (!acquire) {
+        rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, 0, s);
+        return rc ? rc : dsdneo_symbolize_sym_stage(y, n_samples, mode, have_sync, out, 0, s);
+    }
+    rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    /* hunting channels first: they read the raw samples and may switch their class for the stages below */
+    AcqParams ap;
+    ap.sp = symbolize_params(y, n_samples, mode, have_sync, out, 0);
+    ap.sp.filt = d_disc;
+    ap.sp.filt_pitch = disc_pitch;
+    ap.taps = y->d_taps;
+    ap.taps_len = y->d_taps_len;
+    for (int k = 0; k < y->n_pat; k++) {
+        ap.pat[k] = y->pat[k];
+    }
+    ap.n_pat = y->n_pat;
+    ap.acquired = y->d_acquired;
+    ap.hunt_since = y->d_hunt_since;
+    ap.hunt_bits = y->d_hunt_bits;
+    ap.hunt_count = y->d_hunt_count;
+    ap.lbuf = y->d_lbuf;
+    ap.lidx = y->d_lidx;
+    ap.level_count = y->d_level_count;
+    ap.hist = y->d_hist128;
+    ap.hist_head = y->d_hist_head;
+    ap.start_off = y->d_start_off;
+    ap.out_off = y->d_out_off;
+    ap.info = d_info ? d_info : y->d_info;
+    ap.fir_hist = y->d_hist;
+    {
+        KernelTimer kt("sym_acquire_kernel", s);
+        sym_acquire_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(ap);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, 0, s);
+    if (rc) {
+        return rc;
+    }
+    SymParams sp = symbolize_params(y, n_samples, mode, have_sync, out, 0);
+    sp.start_off = y->d_start_off;
+    sp.out_off = y->d_out_off;
+    sp.acquired = y->d_acquired;
     {
         KernelTimer kt("symbolize_kernel", s);
         symbolize_kernel<<<(y->n_ch + kSymWarps - 1) / kSymWarps, kSymWarps * 32, 0, s>>>(sp);

@@ -972,6 +972,20 @@ size_t dsdneo_b200_p25p1_rx_dibit_pitch(const dsdneo_b200_p25p1_rx* rx); /* dibi
 /** d_iq: [n_channels][iq_pitch_pairs] cu8 (uchar2) or cf32 (float2) per config; n_pairs a multiple of block_pairs. */
 int dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
                                  const dsdneo_b200_p25p1_rx_out* out, void* stream);
+/**
+ * Pipelined form.  Inside the bank a tile passes three stages on three streams (channel filter | discriminator recurrences +
+ * matched filter | slicer + frames), and consecutive tiles overlap on the device: the latency-bound per-channel recurrences of
+ * one tile run under the throughput-bound filters of the next.  _submit queues one tile (its input must be complete on
+ * `stream` at call time) and returns a ticket without waiting; _wait makes `stream` wait (on the device, the host does not
+ * block) until that tile's outputs are complete; _input_consumed does the same for "d_iq may be overwritten".  Tiles complete
+ * in submission order.  _process == _submit + _wait on the same stream (no overlap between consecutive calls, because the
+ * next tile's input is only known to be ready after the wait).  Outputs of tile i must be consumed before they are handed to
+ * a later _submit again.
+ */
+long long dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t iq_pitch_pairs, int n_pairs,
+                                      const dsdneo_b200_p25p1_rx_out* out, void* stream);
+int dsdneo_b200_p25p1_rx_wait(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
+int dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
 /** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned. */
 long long dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
                                            const dsdneo_b200_p25p1_rx_host_out* out);
