@@ -723,17 +723,23 @@ template <int NW, bool TRACK>
 __device__ __forceinline__ int
 sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& pos, int& sidx, int midx0, int g0, float& vmin, float& vmax,
                float& last_vmin, float& last_vmax, double& min_sum, double& max_sum) {
-    /* returns the number of symbols done (stops early only when vmin > vmax, which the general path handles) */
+    /* returns the number of symbols done (stops early only when vmin > vmax, which the general path handles).
+     * Everything that does not depend on the previous symbol's thresholds -- the five window samples, the ring entries
+     * about to be replaced, the symbol about to leave the 128-entry window -- is loaded one symbol ahead, so the loop-carried
+     * chain is clip -> five adds -> divide -> extrema -> two f64 updates -> thresholds and nothing else. */
     int k = 0;
     int si = sidx;
     float e = sh->sbuf[si];
+    int off = (pos + lo) & (kRing - 1);
+    const float* b = sh->ring + off; /* the ring is mirrored kRingPad entries past its end: b[0..4] never wraps */
+    float r0 = b[0], r1 = b[1], r2 = b[2], r3 = b[3], r4 = NW > 4 ? b[4] : 0.0f;
+    int mi = TRACK ? (midx0 & 31) : 0;
+    float old_min = TRACK ? sh->mnr[mi] : 0.0f, old_max = TRACK ? sh->mxr[mi] : 0.0f;
 #pragma unroll 1
     for (; k < nb; k++) {
         if (!(vmin <= vmax)) {
             break;
         }
-        const float* b = sh->ring + ((pos + lo) & (kRing - 1));
-        const float r0 = b[0], r1 = b[1], r2 = b[2], r3 = b[3], r4 = NW > 4 ? b[4] : 0.0f;
         last_vmin = vmin, last_vmax = vmax;
         float sum = __fadd_rn(0.0f, fminf(fmaxf(r0, vmin), vmax));
         sum = __fadd_rn(sum, fminf(fmaxf(r1, vmin), vmax));
@@ -746,6 +752,15 @@ sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& po
         } else {
             sym = __fmul_rn(sum, 0.25f); /* exact scaling == the correctly rounded quotient */
         }
+        /* next symbol's operands (independent of this symbol's result) */
+        off = (off + sps) & (kRing - 1);
+        b = sh->ring + off;
+        r0 = b[0], r1 = b[1], r2 = b[2], r3 = b[3];
+        if (NW > 4) {
+            r4 = b[4];
+        }
+        const int si_next = (si + 1) & (kSbuf - 1);
+        const float e_next = sh->sbuf[si_next]; /* si_next != si: read before this symbol's store, same value either way */
         sh->sbuf[si] = sym;
         if (TRACK) {
             if (e > tr.mn2 && e < tr.mx2) {
@@ -756,19 +771,21 @@ sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& po
             }
             const float lmin = __fmul_rn(__fadd_rn(tr.mn1, tr.mn2), 0.5f);
             const float lmax = __fmul_rn(__fadd_rn(tr.mx1, tr.mx2), 0.5f);
-            const int mi = (midx0 + k) & 31;
-            min_sum += (double)lmin - (double)sh->mnr[mi];
-            max_sum += (double)lmax - (double)sh->mxr[mi];
+            min_sum += (double)lmin - (double)old_min;
+            max_sum += (double)lmax - (double)old_max;
+            const int mi_next = (mi + 1) & 31;
+            old_min = sh->mnr[mi_next], old_max = sh->mxr[mi_next]; /* a different entry than the one stored below */
             sh->mnr[mi] = lmin;
             sh->mxr[mi] = lmax;
             vmin = (float)(min_sum * tr.inv_window);
             vmax = (float)(max_sum * tr.inv_window);
             sh->o_min[g0 + k] = vmin;
             sh->o_max[g0 + k] = vmax;
+            mi = mi_next;
         }
         sh->o_sym[g0 + k] = sym;
-        si = (si + 1) & (kSbuf - 1);
-        e = sh->sbuf[si];
+        si = si_next;
+        e = e_next;
         pos += sps;
     }
     sidx = si;
@@ -814,35 +831,40 @@ symbolize_kernel(const SymParams p) {
     float* carry = p.carry + (size_t)c * kCarry;
     const int q0 = kCarry - carry_n;
     const int q_end = kCarry + p.n;
-    const int q_fill_end = (q_end + 31) & ~31;
     int pos = q0 + (p.start_off ? p.start_off[c] : 0);
-    int whi = pos & ~31;
+    /* staging: 16 bytes per lane and step (128 samples), at most kFillPending steps in flight.  Rows of the filter buffer
+     * and of the carry start on 128-byte lines and kCarry is a multiple of 4, so every 4-sample chunk is 16-byte aligned
+     * on both sides and lies wholly in the carry or wholly in this launch's samples */
+    constexpr int kFill = 128, kFillPending = 2;
+    const int q_fill_end = (q_end + kFill - 1) & ~(kFill - 1);
+    int whi = pos & ~(kFill - 1);
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto refill = [&]() {
         while (whi < pos + kLook && whi < q_fill_end) {
-            const int q = whi + lane;
+            const int q = whi + 4 * lane;
             const float* src = filt;
-            unsigned bytes = 0;
+            int bytes = 0;
             if (q < kCarry) {
-                if (q >= q0) {
-                    src = carry + q, bytes = 4;
+                if (q + 4 > q0) {
+                    src = carry + q, bytes = 16; /* entries before q0 are stale carry slots nobody reads */
                 }
             } else if (q < q_end) {
-                src = filt + (q - kCarry), bytes = 4;
+                src = filt + (q - kCarry);
+                bytes = min(16, 4 * (q_end - q));
             }
             const int slot = q & (kRing - 1);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ring_s + 4u * (unsigned)slot), "l"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + 4u * (unsigned)slot), "l"(src), "r"(bytes) : "memory");
             if (slot < kRingPad) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ring_s + 4u * (unsigned)(slot + kRing)), "l"(src), "r"(bytes)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(ring_s + 4u * (unsigned)(slot + kRing)), "l"(src), "r"(bytes)
                              : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            whi += 32;
+            whi += kFill;
         }
         if (whi >= q_fill_end) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
-            asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kFillPending) : "memory");
         }
         __syncwarp();
     };
@@ -865,13 +887,21 @@ symbolize_kernel(const SymParams p) {
     int nsym = nsym0;
     const int out_cap = (int)(p.out_pitch > 0x7fffffffu ? 0x7fffffffu : p.out_pitch);
 
-    /* one group of <= 32 finished symbols: lane k digitizes and stores symbol k (groups are relative to nsym0) */
-    auto flush_group = [&](int n_in_group) { /* symbols [nsym - n_in_group, nsym) */
+    /* finished symbols wait in a 32-slot group buffer; when a group is complete lane k digitizes and stores the symbol in
+     * slot k.  With the threshold tracker on, slot = position in the tracker's 32-entry ring chunk, so a batch of the fast
+     * loop ends at a group boundary and at a chunk boundary at the same time */
+    const int gphase = (soft && track && (tr.window & 31) == 0) ? (((midx < 0 || midx >= tr.window) ? 0 : midx) & 31) : 0;
+    int flushed = nsym0;
+    auto slot_of = [&](int ns) -> int { return (ns - nsym0 + gphase) & 31; };
+    auto flush_group = [&]() { /* symbols [flushed, nsym) sit in slots [end - n, end) */
         __syncwarp();
-        const int base = nsym - n_in_group;
-        if (lane < n_in_group) {
+        const int n_in_group = nsym - flushed;
+        const int end = slot_of(nsym) == 0 ? 32 : slot_of(nsym);
+        const int start = end - n_in_group;
+        if (n_in_group > 0 && lane >= start && lane < end) {
+            const int o = flushed + (lane - start);
             const float g_sym = sh->o_sym[lane];
-            o_sym[base + lane] = g_sym;
+            o_sym[o] = g_sym;
             if (soft) {
                 float g_min, g_max, g_center, g_umid, g_lmid;
                 if (track) { /* centre / mid thresholds follow from {min, max} by the reference's own formulas */
@@ -883,11 +913,12 @@ symbolize_kernel(const SymParams p) {
                 }
                 int dibit, rel, l0, l1;
                 digitize_one(g_sym, g_min, g_max, g_center, g_umid, g_lmid, negative, snr_num, dibit, rel, l0, l1);
-                o_dib[base + lane] = (uint8_t)dibit;
-                o_rel[base + lane] = (uint8_t)rel;
-                o_llr[base + lane] = make_short2((short)l0, (short)l1);
+                o_dib[o] = (uint8_t)dibit;
+                o_rel[o] = (uint8_t)rel;
+                o_llr[o] = make_short2((short)l0, (short)l1);
             }
         }
+        flushed = nsym;
         __syncwarp();
     };
 
@@ -901,10 +932,10 @@ symbolize_kernel(const SymParams p) {
         refill();
         /* ---- steady state of a locked channel: a batch of symbols through the tight loop ---- */
         if (fast_cfg && jitter >= 0 && sps_num == p.rate && sps_den == p.symrate && (!track || sum_window == tr.window)) {
-            int nb = min(32 - ((nsym - nsym0) & 31), out_cap - nsym);
+            int nb = min(32 - slot_of(nsym), out_cap - nsym);
             nb = min(nb, (q_end - pos - reserve) / whole0 + 1);
             /* every sample of the batch must have landed in the ring */
-            const int landed = (whi >= q_fill_end) ? whi : whi - 32 * kPending;
+            const int landed = (whi >= q_fill_end) ? whi : whi - kFill * kFillPending;
             nb = min(nb, (landed - pos) / whole0);
             int mi0 = 0;
             if (track) {
@@ -914,7 +945,7 @@ symbolize_kernel(const SymParams p) {
                 mi0 = idx;
             }
             if (nb > 0) {
-                const int g0 = (nsym - nsym0) & 31;
+                const int g0 = slot_of(nsym);
                 if (!track) { /* thresholds do not move: hand them to digitize as they are */
                     for (int k = lane; k < nb; k += 32) {
                         sh->o_min[g0 + k] = vmin, sh->o_max[g0 + k] = vmax, sh->o_center[g0 + k] = center;
@@ -957,8 +988,8 @@ symbolize_kernel(const SymParams p) {
                         minref = vmin;
                     }
                     nsym += done;
-                    if (((nsym - nsym0) & 31) == 0) {
-                        flush_group(32);
+                    if (slot_of(nsym) == 0) {
+                        flush_group();
                     }
                     continue;
                 }
@@ -1071,18 +1102,16 @@ symbolize_kernel(const SymParams p) {
             }
         }
         {
-            const int g = (nsym - nsym0) & 31;
+            const int g = slot_of(nsym);
             sh->o_sym[g] = sym, sh->o_min[g] = vmin, sh->o_max[g] = vmax;
             sh->o_center[g] = center, sh->o_umid[g] = umid, sh->o_lmid[g] = lmid;
         }
         nsym++;
-        if (((nsym - nsym0) & 31) == 0) {
-            flush_group(32);
+        if (slot_of(nsym) == 0) {
+            flush_group();
         }
     }
-    if ((nsym - nsym0) & 31) {
-        flush_group((nsym - nsym0) & 31);
-    }
+    flush_group();
 
     /* leftover samples -> carry (right-aligned), through registers: the ring may be refilled first */
     refill();
