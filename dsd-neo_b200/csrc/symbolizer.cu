@@ -1680,8 +1680,8 @@ sym_reset_kernel(SymScalars s, float* minbuf, float* maxbuf, float* sbuf, float*
  *                                           (core/p25_cqpsk_dibit.h) when the CQPSK chain is active on a P25 sync, else regions
  *   compute_dibit_soft_metric              :685-721 with build_cqpsk_dibit_ideals (:660-683) / standard ideals,
  *                                           reliability = cqpsk_reliability_raw (:376-401) x CQPSK SNR weight (:404-427)
- * One lane per channel.  The symbol value does not feed back into anything but the tracker, so the per-channel chain is
- * the 128-entry extrema scan (kept in shared memory, [entry][lane]) and the two f64 running sums. */
+ * The symbol value does not feed back into anything but the tracker, so the per-channel chain is the extrema of the
+ * 128-entry symbol window and the two f64 running sums (one warp per channel, see cqpsk_slice_kernel). */
 struct CqSliceParams {
     const float* symbols; /* [n_ch][sym_pitch] */
     size_t sym_pitch;
@@ -1695,8 +1695,8 @@ struct CqSliceParams {
     const uint8_t* p25_slice;
     const uint8_t* map_idx;
     /* carried state */
-    float* sbuf;          /* [128][n_ch] */
-    float* minbuf;        /* [1024][n_ch] */
+    float* sbuf;          /* [n_ch][128] */
+    float* minbuf;        /* [n_ch][1024] */
     float* maxbuf;
     int* sidx;
     int* midx;
@@ -1709,192 +1709,71 @@ struct CqSliceParams {
     float2* minmax;       /* [n_ch][out_pitch] scratch: {min, max} after use_symbol, per symbol (tracker -> digitize kernel) */
 };
 
-__global__ void __launch_bounds__(32)
+/*
+ * One WARP per channel (round 1: one lane per channel, 2.9 ms per 4800 symbols): the tracker of use_symbol is the only
+ * loop-carried state, and WarpTracker runs it the way symbolize_kernel does -- every lane holds the same scalars, the lanes
+ * share out the 128-entry window rescan (needed only when the symbol that leaves was one of the four extremes) and the
+ * 32-entry chunks of the 1024-entry f64-averaged rings.  Symbols are read 32 at a time (one per lane, coalesced) and handed
+ * round by shuffle; {min, max} after every symbol are collected one per lane and stored coalesced for the digitize kernel.
+ */
+constexpr int kCqWarps = 4;
+
+__global__ void __launch_bounds__(kCqWarps * 32)
 cqpsk_slice_kernel(const CqSliceParams p) {
-    __shared__ float s_sbuf[128 * 32];
-    const int lane = threadIdx.x;
-    const int ch = blockIdx.x * 32 + lane;
-    const bool valid = ch < p.n_ch;
+    __shared__ WarpShared s_warp[kCqWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * kCqWarps + warp;
+    if (ch >= p.n_ch) {
+        return;
+    }
+    WarpShared* sh = &s_warp[warp];
     const int n_ch = p.n_ch;
-    int cap = p.ssize < 0 ? 0 : (p.ssize > 128 ? 128 : p.ssize);
-    const int window = p.msize < 1 ? 1 : (p.msize > 1024 ? 1024 : p.msize);
-    for (int k = 0; k < 128; k++) {
-        s_sbuf[k * 32 + lane] = valid ? p.sbuf[(size_t)k * n_ch + ch] : 0.0f;
-    }
-    int n = 0, sidx = 0, midx = 0;
-    double min_sum = 0.0, max_sum = 0.0;
-    float vmin = 0.0f, vmax = 0.0f, center = 0.0f, umid = 0.0f, lmid = 0.0f, minref = 0.0f, maxref = 0.0f, last = 0.0f;
-    if (valid) {
-        n = p.n_symbols[ch];
-        sidx = p.sidx[ch];
-        midx = p.midx[ch];
-        min_sum = p.minbuf_sum[ch];
-        max_sum = p.maxbuf_sum[ch];
-        vmin = p.thr[0 * (size_t)n_ch + ch];
-        vmax = p.thr[1 * (size_t)n_ch + ch];
-        center = p.thr[2 * (size_t)n_ch + ch];
-        umid = p.thr[3 * (size_t)n_ch + ch];
-        lmid = p.thr[4 * (size_t)n_ch + ch];
-        minref = p.thr[5 * (size_t)n_ch + ch];
-        maxref = p.thr[6 * (size_t)n_ch + ch];
-        last = p.thr[7 * (size_t)n_ch + ch];
-        if (n > 0 && p.sum_window[ch] != window) { /* dsd_state_sync_minmax_sums, core/state.h:1388-1428 */
-            double a = 0.0, b = 0.0;
-            for (int i = 0; i < window; i++) {
-                a += (double)p.minbuf[(size_t)i * n_ch + ch];
-                b += (double)p.maxbuf[(size_t)i * n_ch + ch];
-            }
-            min_sum = a;
-            max_sum = b;
-            p.sum_window[ch] = window;
-            if (midx < 0 || midx >= window) {
-                midx = 0;
-            }
+    const int n = p.n_symbols[ch];
+    int sidx = p.sidx[ch], midx = p.midx[ch], sum_window = p.sum_window[ch];
+    double min_sum = p.minbuf_sum[ch], max_sum = p.maxbuf_sum[ch];
+    float vmin = p.thr[0 * (size_t)n_ch + ch], vmax = p.thr[1 * (size_t)n_ch + ch];
+    float center = p.thr[2 * (size_t)n_ch + ch], umid = p.thr[3 * (size_t)n_ch + ch], lmid = p.thr[4 * (size_t)n_ch + ch];
+    float minref = p.thr[5 * (size_t)n_ch + ch], maxref = p.thr[6 * (size_t)n_ch + ch], last = p.thr[7 * (size_t)n_ch + ch];
+    WarpTracker tr;
+    tr.init(lane, p.ssize, p.msize, p.minbuf + (size_t)ch * kMinMax, p.maxbuf + (size_t)ch * kMinMax, p.sbuf + (size_t)ch * kSbuf, sh, true);
+    const float* in = p.symbols + (size_t)ch * p.sym_pitch;
+    float2* mm = p.minmax + (size_t)ch * p.out_pitch;
+    float nxt = (lane < n) ? in[lane] : 0.0f;
+    for (int base = 0; base < n; base += 32) {
+        const float cur = nxt;
+        if (base + 32 + lane < n) {
+            nxt = in[base + 32 + lane]; /* the next group's symbols are requested while this group runs */
         }
-    }
-    const float* in = p.symbols + (size_t)(valid ? ch : 0) * p.sym_pitch;
-    float2* mm = p.minmax + (size_t)(valid ? ch : 0) * p.out_pitch;
-    float* my_sbuf = s_sbuf + lane;
-    /* Fast path of the extrema scan (full 128-entry window): eight 16-entry block summaries {two smallest, two largest} in
-     * registers; a new symbol only invalidates its own block, which is rescanned (two independent half chains), and the
-     * eight summaries are merged pairwise (depth 3).  The two smallest / largest of a multiset do not depend on the order of
-     * evaluation, so this is the reference's result exactly. */
-    const bool blocked = (cap == 128);
-    float bmn1[8], bmn2[8], bmx1[8], bmx2[8];
-    auto scan_block = [&](int b, float& mn1, float& mn2, float& mx1, float& mx2) {
-        const float* e = my_sbuf + b * 16 * 32;
-        const float a0 = e[0], a1 = e[32], c0 = e[8 * 32], c1 = e[9 * 32];
-        float p1 = fminf(a0, a1), p2 = fmaxf(a0, a1), q1 = fminf(c0, c1), q2 = fmaxf(c0, c1);
-        float P1 = p2, P2 = p1, Q1 = q2, Q2 = q1;
-#pragma unroll
-        for (int k = 2; k < 8; k++) {
-            const float v = e[k * 32], w = e[(8 + k) * 32];
-            two_min_push(p1, p2, v);
-            two_max_push(P1, P2, v);
-            two_min_push(q1, q2, w);
-            two_max_push(Q1, Q2, w);
-        }
-        mn1 = fminf(p1, q1);
-        mn2 = fminf(fmaxf(p1, q1), fminf(p2, q2));
-        mx1 = fmaxf(P1, Q1);
-        mx2 = fmaxf(fminf(P1, Q1), fmaxf(P2, Q2));
-    };
-    if (blocked) {
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            scan_block(b, bmn1[b], bmn2[b], bmx1[b], bmx2[b]);
-        }
-    }
-    const bool pow2_window = (window & (window - 1)) == 0;
-    const double inv_window = 1.0 / (double)window; /* exact for a power of two: x / 2^k == x * 2^-k */
-    /* the ring entries the next symbol replaces and the next symbol itself are requested one iteration early */
-    const bool prefetch = window >= 2;
-    float nxt_min = 0.0f, nxt_max = 0.0f, nxt_sym = 0.0f;
-    if (valid && n > 0) {
-        const int idx0 = (midx < 0 || midx >= window) ? 0 : midx;
-        nxt_min = p.minbuf[(size_t)idx0 * n_ch + ch];
-        nxt_max = p.maxbuf[(size_t)idx0 * n_ch + ch];
-        nxt_sym = in[0];
-    }
+        const int m = min(32, n - base);
+        float my_min = 0.0f, my_max = 0.0f;
 #pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const float sym = nxt_sym;
-        if (i + 1 < n) {
-            nxt_sym = in[i + 1];
-        }
-        last = sym;
-        if (cap > 0) {
-            my_sbuf[sidx * 32] = sym; /* cap <= 0: the reference writes sbuf[sidx] with sidx stuck at its initial 0 */
-        } else {
-            my_sbuf[0] = sym;
-        }
-        /* use_symbol: average of the two smallest / two largest of sbuf[0..cap) (order independent, so exact) */
-        float lmin = 0.0f, lmax = 0.0f;
-        if (blocked) {
-            const int b = sidx >> 4;
-            float r1, r2, R1, R2;
-            scan_block(b, r1, r2, R1, R2);
-#pragma unroll
-            for (int k = 0; k < 8; k++) { /* static indices keep the summaries in registers */
-                if (k == b) {
-                    bmn1[k] = r1;
-                    bmn2[k] = r2;
-                    bmx1[k] = R1;
-                    bmx2[k] = R2;
-                }
+        for (int k = 0; k < m; k++) {
+            const float sym = __shfl_sync(0xffffffffu, cur, k);
+            last = sym;
+            /* sbuf[sidx] = symbol (sidx stays 0 when ssize <= 0), then use_symbol's tracker: dsd_dibit.c:243-299 */
+            tr.push(sym, sidx, midx, sum_window, min_sum, max_sum, vmin, vmax);
+            if (tr.cap > 0) {
+                sidx = (sidx >= tr.cap - 1) ? 0 : sidx + 1;
             }
-            float t1[4], t2[4], T1[4], T2[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                t1[k] = fminf(bmn1[2 * k], bmn1[2 * k + 1]);
-                t2[k] = fminf(fmaxf(bmn1[2 * k], bmn1[2 * k + 1]), fminf(bmn2[2 * k], bmn2[2 * k + 1]));
-                T1[k] = fmaxf(bmx1[2 * k], bmx1[2 * k + 1]);
-                T2[k] = fmaxf(fminf(bmx1[2 * k], bmx1[2 * k + 1]), fmaxf(bmx2[2 * k], bmx2[2 * k + 1]));
-            }
-            const float u1a = fminf(t1[0], t1[1]), u2a = fminf(fmaxf(t1[0], t1[1]), fminf(t2[0], t2[1]));
-            const float u1b = fminf(t1[2], t1[3]), u2b = fminf(fmaxf(t1[2], t1[3]), fminf(t2[2], t2[3]));
-            const float U1a = fmaxf(T1[0], T1[1]), U2a = fmaxf(fminf(T1[0], T1[1]), fmaxf(T2[0], T2[1]));
-            const float U1b = fmaxf(T1[2], T1[3]), U2b = fmaxf(fminf(T1[2], T1[3]), fmaxf(T2[2], T2[3]));
-            const float mn1 = fminf(u1a, u1b), mn2 = fminf(fmaxf(u1a, u1b), fminf(u2a, u2b));
-            const float mx1 = fmaxf(U1a, U1b), mx2 = fmaxf(fminf(U1a, U1b), fmaxf(U2a, U2b));
-            lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
-            lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
-        } else if (cap >= 2) {
-            const float a = my_sbuf[0], b = my_sbuf[32];
-            float mn1 = fminf(a, b), mn2 = fmaxf(a, b), mx1 = mn2, mx2 = mn1;
-#pragma unroll 8
-            for (int k = 2; k < cap; k++) {
-                const float v = my_sbuf[k * 32];
-                two_min_push(mn1, mn2, v);
-                two_max_push(mx1, mx2, v);
-            }
-            lmin = __fmul_rn(__fadd_rn(mn1, mn2), 0.5f);
-            lmax = __fmul_rn(__fadd_rn(mx1, mx2), 0.5f);
-        }
-        {
-            int idx = midx;
-            if (idx < 0 || idx >= window) {
-                idx = 0;
-            }
-            float* mb = p.minbuf + (size_t)idx * n_ch + ch;
-            float* xb = p.maxbuf + (size_t)idx * n_ch + ch;
-            const float old_min = prefetch ? nxt_min : *mb, old_max = prefetch ? nxt_max : *xb;
-            min_sum += (double)lmin - (double)old_min;
-            max_sum += (double)lmax - (double)old_max;
-            *mb = lmin;
-            *xb = lmax;
-            idx++;
-            midx = idx >= window ? 0 : idx;
-            if (prefetch && i + 1 < n) {
-                nxt_min = p.minbuf[(size_t)midx * n_ch + ch];
-                nxt_max = p.maxbuf[(size_t)midx * n_ch + ch];
+            if (lane == k) {
+                my_min = vmin, my_max = vmax;
             }
         }
-        if (pow2_window) {
-            vmin = (float)(min_sum * inv_window);
-            vmax = (float)(max_sum * inv_window);
-        } else {
-            vmin = (float)(min_sum / (double)window);
-            vmax = (float)(max_sum / (double)window);
+        if (lane < m) {
+            mm[base + lane] = make_float2(my_min, my_max);
         }
-        if (cap > 0) {
-            sidx = (sidx >= cap - 1) ? 0 : sidx + 1;
-        }
-        /* everything else of the symbol (thresholds, slicing, soft metric) only depends on {sym, min, max}: it is done by
-         * cqpsk_digitize_kernel, one thread per symbol */
-        mm[i] = make_float2(vmin, vmax);
     }
     if (n > 0) {
         cq_thresholds(vmin, vmax, center, umid, lmid);
         maxref = __fmul_rn(vmax, 0.80f);
         minref = __fmul_rn(vmin, 0.80f);
     }
-    if (valid) {
-        for (int k = 0; k < 128; k++) {
-            p.sbuf[(size_t)k * n_ch + ch] = s_sbuf[k * 32 + lane];
-        }
+    tr.flush_chunk();
+    tr.store_sbuf(p.sbuf + (size_t)ch * kSbuf);
+    if (lane == 0) {
         p.sidx[ch] = sidx;
         p.midx[ch] = midx;
+        p.sum_window[ch] = sum_window;
         p.minbuf_sum[ch] = min_sum;
         p.maxbuf_sum[ch] = max_sum;
         p.thr[0 * (size_t)n_ch + ch] = vmin;
@@ -1996,11 +1875,11 @@ cqpsk_slicer_reset_kernel(float* sbuf, float* minbuf, float* maxbuf, int* sidx, 
         return;
     }
     for (int k = 0; k < 128; k++) {
-        sbuf[(size_t)k * n_ch + ch] = 0.0f;
+        sbuf[(size_t)ch * 128 + k] = 0.0f;
     }
     for (int k = 0; k < 1024; k++) { /* initState, src/core/util/dsd_init.c:519-592 */
-        minbuf[(size_t)k * n_ch + ch] = -15000.0f;
-        maxbuf[(size_t)k * n_ch + ch] = 15000.0f;
+        minbuf[(size_t)ch * 1024 + k] = -15000.0f;
+        maxbuf[(size_t)ch * 1024 + k] = 15000.0f;
     }
     sidx[ch] = 0;
     midx[ch] = 0;
@@ -2877,7 +2756,7 @@ dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_symbol
     cudaStream_t s = as_stream(stream);
     {
         KernelTimer kt("cqpsk_slice_kernel", s);
-        cqpsk_slice_kernel<<<(q->n_ch + 31) / 32, 32, 0, s>>>(p);
+        cqpsk_slice_kernel<<<(q->n_ch + kCqWarps - 1) / kCqWarps, kCqWarps * 32, 0, s>>>(p);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
