@@ -69,7 +69,7 @@ struct KernelTimer {
 struct dsdneo_b200_demod_bank;
 int dsdneo_demod_bank_channels(const dsdneo_b200_demod_bank* b);
 int dsdneo_demod_fir_stage(dsdneo_b200_demod_bank* b, const float* d_iq, size_t iq_pitch_pairs, int block_pairs,
-                           int n_blocks, int slot, cudaStream_t s, int want_y = 0);
+                           int n_blocks, int slot, cudaStream_t s, int want_y = 0, int input_cu8 = 0);
 int dsdneo_demod_rec_stage(dsdneo_b200_demod_bank* b, int block_pairs, int n_blocks, float* d_result,
                            size_t result_pitch, int slot, cudaStream_t s);
 

@@ -36,17 +36,6 @@ constexpr int kKeep = 1024;  /* symbols of history kept per channel (>= kDelay +
 constexpr int kDelay = 864;  /* frames are decoded this many symbols behind the slicer: the longest frame (LDU) */
 static const char kP25Sync[] = "111113113311333313133333"; /* P25P1_SYNC, include/dsd-neo/core/sync_patterns.h:34 */
 
-__global__ void
-widen_cu8_kernel(const uchar2* __restrict__ in, size_t in_pitch, float2* __restrict__ out, size_t out_pitch, int n_pairs) {
-    const int ch = blockIdx.y;
-    const float inv = 1.0f / 127.5f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
-        const uchar2 u = in[(size_t)ch * in_pitch + i];
-        /* widen_u8_to_f32_bias127: (float(u8) - 127.5f) * (1.0f / 127.5f) */
-        out[(size_t)ch * out_pitch + i] = make_float2(__fmul_rn(__fsub_rn((float)u.x, 127.5f), inv), __fmul_rn(__fsub_rn((float)u.y, 127.5f), inv));
-    }
-}
-
 /* the last kKeep entries of the previous call's stream become the head of this call's stream (ping-pong buffers) */
 __global__ void
 stream_tail_kernel(const uint8_t* dib_prev, const uint8_t* rel_prev, const short2* llr_prev, const float* sym_prev, uint8_t* dib,
@@ -115,7 +104,6 @@ struct dsdneo_b200_p25p1_rx {
     dsdneo_b200_demod_bank* bank;
     dsdneo_b200_symbolizer* sym;
     dsdneo_b200_frame_sync* fs;
-    float2* d_iq;      /* widened input when the caller feeds cu8 */
     float* d_disc;
     int phase;         /* which of the two stream buffer sets receives this call */
     uint8_t *d_dib[2], *d_rel[2];
@@ -177,7 +165,6 @@ dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
     dsdneo_b200_demod_bank_destroy(rx->bank);
     dsdneo_b200_symbolizer_destroy(rx->sym);
     dsdneo_b200_frame_sync_destroy(rx->fs);
-    cudaFree(rx->d_iq);
     cudaFree(rx->d_disc);
     for (int i = 0; i < 2; i++) {
         cudaFree(rx->d_dib[i]);
@@ -324,9 +311,6 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
             e = cudaMemset((ptr), 0, (bytes));                                                                         \
         }                                                                                                              \
     }
-    if (cfg->input_cu8) {
-        RX_ALLOC(rx->d_iq, n * (size_t)rx->cap_pairs * sizeof(float2));
-    }
     RX_ALLOC(rx->d_disc, n * (size_t)rx->cap_pairs * sizeof(float));
     for (int i = 0; i < 2; i++) {
         RX_ALLOC(rx->d_dib[i], n * rx->pitch);
@@ -371,7 +355,7 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
  * One tile through the chain as four pipeline stages on the bank's own streams, so that consecutive tiles overlap on the
  * device: the latency-bound per-channel recurrences (discriminator, slicer) of one tile run under the throughput-bound
  * filters of the next.
- *   stage A (s_a)  widen cu8 -> channel LPF + phase (lpf_phase_kernel), FIR state          -> bank phase buffer [slot]
+ *   stage A (s_a)  channel LPF + phase (lpf_phase_kernel; cu8 widened in its staging), FIR state -> bank phase buffer [slot]
  *   stage B (s_b)  discriminator recurrences -> d_disc -> matched filter (sps_fir_kernel)    -> symbolizer filter buffer [slot]
  *   stage C (s_c)  stream tail, slicer (symbolize_kernel), stream accounting                   -> stream buffers [tile & 1]
  *   stage D (s_d)  sync hunt, frame cut, NID, frame decode, NAC tracking, output copies
@@ -442,19 +426,10 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
         DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_b[slot], 0)); /* the recurrences two tiles back have read phase buffer [slot] */
     }
     rx_trace(rx, tile, 0, s);
-    const float* iq = (const float*)d_iq;
-    size_t pitch_pairs = iq_pitch_pairs;
-    if (rx->cfg.input_cu8) {
-        KernelTimer kt("widen_cu8_kernel", s);
-        dim3 grid((unsigned)((n_pairs + 1023) / 1024), (unsigned)n_ch);
-        widen_cu8_kernel<<<grid, 256, 0, s>>>((const uchar2*)d_iq, iq_pitch_pairs, rx->d_iq, (size_t)rx->cap_pairs, n_pairs);
-        DSDNEO_KERNEL_CHECK();
-        count_launch();
-        iq = (const float*)rx->d_iq;
-        pitch_pairs = (size_t)rx->cap_pairs;
-    }
+    /* cu8 input is widened inside the channel filter's staging (widen_u8_to_f32_bias127 fused into lpf_phase_kernel) */
     const int n_blocks = n_pairs / rx->cfg.block_pairs;
-    rc = dsdneo_demod_fir_stage(rx->bank, iq, pitch_pairs, rx->cfg.block_pairs, n_blocks, slot, s);
+    rc = dsdneo_demod_fir_stage(rx->bank, (const float*)d_iq, iq_pitch_pairs, rx->cfg.block_pairs, n_blocks, slot, s, 0,
+                                rx->cfg.input_cu8 ? 1 : 0);
     if (rc) {
         return rc;
     }

@@ -4,7 +4,7 @@
 # Usage: tools/profile_run_r02.sh [quick]   (quick: only the --set full captures of the kernels named in $KERNELS)
 set -u
 mkdir -p gpurun_out
-KERNELS=${KERNELS:-"lpf_phase_kernel symbolize_kernel sps_fir8_kernel disc_recurrence_kernel p25p1_frame_decode_kernel frame_sync_search_kernel widen_cu8_kernel"}
+KERNELS=${KERNELS:-"lpf_phase_kernel symbolize_kernel sps_fir8_kernel disc_recurrence_kernel p25p1_frame_decode_kernel frame_sync_search_kernel"}
 if [ "${1:-full}" != "quick" ]; then
     python bench.py --impl reference --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_reference.json
     python bench.py --steps 200 --warmup 5 2>/dev/null | tail -1 > gpurun_out/bench.json
