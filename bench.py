@@ -850,7 +850,7 @@ def run_c3_b200_arm(args):
     # ---- e2e: pinned host cu8 IQ in, host frames / IMBE frames / dibits out, every copy inside the timed region ----
     e2e_steps = max(3, min(args.steps, 100))
     rx_h = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
-    DEPTH = 4  # tiles in flight: the bank's four pipeline stages plus the copies either side (at most four tickets outstanding)
+    DEPTH = 6  # host tiles in flight = DEPTH - 1: H2D, the bank's four pipeline stages, D2H (at most six tickets outstanding)
     h_outs = [rx_h.alloc_host_out() for _ in range(DEPTH)]
     d2h = [0]
     seq = [0]  # tiles are fed in rotation order across calls of run(): the stream stays continuous (the locked slicer does not
@@ -890,8 +890,8 @@ def run_c3_b200_arm(args):
     e2e = {"value": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": C3_CH * C3_PAIRS * 2,
            "d2h_bytes_per_step": int(fixed_d2h + d2h[0] / e2e_steps), "ms_per_step": e2e_ms, "steps": e2e_steps,
            "channels_at_realtime": world * C3_CH * C3_PAIRS / (e2e_ms * 1e-3) / C3_RATE,
-           "timer": "host wall clock around K x {wait_host(tile i-3); host reads tile i-3; dsdneo_b200_p25p1_rx_submit_host(tile i)} "
-                    "+ final waits, max over ranks (three tiles in flight)",
+           "timer": "host wall clock around K x {wait_host(tile i-5); host reads tile i-5; dsdneo_b200_p25p1_rx_submit_host(tile i)} "
+                    "+ final waits, max over ranks (five tiles in flight)",
            "d2h_contents": "dibit stream + counts + frame records + IMBE frame records"}
     # device path == host path (same state history => same bytes)
     fr_h, vo_h = rx_h.host_records(h_outs[(seq[0] - 1) % DEPTH])

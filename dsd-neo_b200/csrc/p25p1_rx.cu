@@ -31,7 +31,8 @@ using namespace dsdneo;
 namespace {
 
 constexpr int kTraceTiles = 32;
-constexpr int kHostSlots = 4; /* host-buffer tiles in flight: the four pipeline stages plus the copies either side */
+constexpr int kTraceEvents = 10; /* A0 A1 B0 B1 C0 C1 D0 D1 + host path: H2D start, H2D end */
+constexpr int kHostSlots = 6; /* host-buffer tiles in flight: H2D + the four pipeline stages + D2H */
 constexpr int kKeep = 1024;  /* symbols of history kept per channel (>= kDelay + the 90 dibits a DMR burst looks back) */
 constexpr int kDelay = 864;  /* frames are decoded this many symbols behind the slicer: the longest frame (LDU) */
 static const char kP25Sync[] = "111113113311333313133333"; /* P25P1_SYNC, include/dsd-neo/core/sync_patterns.h:34 */
@@ -385,8 +386,8 @@ rx_pipeline_init(dsdneo_b200_p25p1_rx* rx) {
     }
     const char* tr = getenv("DSDNEO_B200_RX_TRACE");
     if (tr && tr[0] == '1') {
-        rx->trace = (cudaEvent_t*)calloc((size_t)kTraceTiles * 8, sizeof(cudaEvent_t));
-        for (int i = 0; rx->trace && i < kTraceTiles * 8; i++) {
+        rx->trace = (cudaEvent_t*)calloc((size_t)kTraceTiles * kTraceEvents, sizeof(cudaEvent_t));
+        for (int i = 0; rx->trace && i < kTraceTiles * kTraceEvents; i++) {
             DSDNEO_CUDA(cudaEventCreate(&rx->trace[i]));
         }
         rx->trace_base = ~0ull;
@@ -398,7 +399,7 @@ rx_pipeline_init(dsdneo_b200_p25p1_rx* rx) {
 static void
 rx_trace(dsdneo_b200_p25p1_rx* rx, unsigned long long tile, int what, cudaStream_t s) {
     if (rx->trace && rx->trace_base != ~0ull && tile >= rx->trace_base && tile < rx->trace_base + kTraceTiles) {
-        cudaEventRecord(rx->trace[(tile - rx->trace_base) * 8 + what], s);
+        cudaEventRecord(rx->trace[(tile - rx->trace_base) * kTraceEvents + what], s);
     }
 }
 
@@ -571,7 +572,8 @@ dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long ticket, 
 }
 
 /* Debug aid (DSDNEO_B200_RX_TRACE=1): start tracing at the next tile / read the stage start and end times (ms, relative to the
- * first traced tile's stage A start) of the traced tiles: ms[tile][8] = {A0, A1, B0, B1, C0, C1, D0, D1}.  Synchronises. */
+ * first traced tile's stage A start) of the traced tiles: ms[tile][10] = {A0, A1, B0, B1, C0, C1, D0, D1, H2D0, H2D1} (the last
+ * two only on the host path).  Synchronises. */
 int
 dsdneo_b200_p25p1_rx_trace(dsdneo_b200_p25p1_rx* rx, float* ms, int max_tiles) {
     if (!rx || !rx->trace) {
@@ -586,10 +588,13 @@ dsdneo_b200_p25p1_rx_trace(dsdneo_b200_p25p1_rx* rx, float* ms, int max_tiles) {
     const int n = (int)(done < (unsigned long long)kTraceTiles ? done : kTraceTiles);
     int k = 0;
     for (; k < n && k < max_tiles; k++) {
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < kTraceEvents; w++) {
             float t = 0.0f;
-            cudaEventElapsedTime(&t, rx->trace[0], rx->trace[k * 8 + w]);
-            ms[k * 8 + w] = t;
+            if (cudaEventElapsedTime(&t, rx->trace[0], rx->trace[k * kTraceEvents + w]) != cudaSuccess) {
+                (void)cudaGetLastError(); /* an event that was never recorded (device path: no H2D) */
+                t = -1.0f;
+            }
+            ms[k * kTraceEvents + w] = t;
         }
     }
     return k;
@@ -609,9 +614,9 @@ dsdneo_b200_p25p1_rx_process(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t 
  * Host-buffer streaming form (the reference's demod thread consumes its input ring the same way, src/io/radio/rtl_sdr_fm.cpp:
  * 3458-3512): submit(tile i) queues H2D, the whole chain and the D2H of the dibit stream on three internal streams and
  * returns a ticket; wait(ticket) blocks until the tile's results are in the caller's buffers.  The record counts are only
- * known after the tile ran, so wait() copies exactly totals[0] frame and totals[1] voice records.  At most kHostSlots (4) tiles
+ * known after the tile ran, so wait() copies exactly totals[0] frame and totals[1] voice records.  At most kHostSlots (6) tiles
  * may be in flight -- the depth of the four-stage pipeline plus the copies either side: submit() first completes the tile
- * submitted four calls earlier if the caller has not waited for it yet.
+ * submitted six calls earlier if the caller has not waited for it yet.
  */
 static int
 rx_host_init(dsdneo_b200_p25p1_rx* rx) {
@@ -704,7 +709,13 @@ dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, siz
          * newest tile that shares its pipeline slot covers it */
         DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_h2d, rx->ev_a[(int)(rx->tiles & 1)], 0));
     }
+    if (rx->pipe_ready) {
+        rx_trace(rx, rx->tiles, 8, rx->s_h2d);
+    }
     DSDNEO_CUDA(cudaMemcpyAsync(rx->d_in[slot], h_iq, in_bytes, cudaMemcpyHostToDevice, rx->s_h2d));
+    if (rx->pipe_ready) {
+        rx_trace(rx, rx->tiles, 9, rx->s_h2d);
+    }
     if (rx->tickets >= 2) {
         /* the stream buffers this tile writes were last read by the dibit D2H of the tile two calls back (the tile in
          * between only read them for its tail and wrote the other set) */

@@ -986,7 +986,9 @@ long long dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq
                                       const dsdneo_b200_p25p1_rx_out* out, void* stream);
 int dsdneo_b200_p25p1_rx_wait(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
 int dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
-/** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned. */
+/** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned.
+ * Up to six tickets may be outstanding (H2D, the four pipeline stages and D2H of consecutive tiles overlap); a seventh submit
+ * first completes the oldest one.  Input and output buffers of a ticket must stay untouched until its wait_host returned. */
 long long dsdneo_b200_p25p1_rx_submit_host(dsdneo_b200_p25p1_rx* rx, const void* h_iq, size_t iq_pitch_pairs, int n_pairs,
                                            const dsdneo_b200_p25p1_rx_host_out* out);
 int dsdneo_b200_p25p1_rx_wait_host(dsdneo_b200_p25p1_rx* rx, long long ticket);
