@@ -1202,3 +1202,43 @@ def acquire_patterns(frame_p25p1, frame_dmr, taps, use_cosine_filter=True, inver
         add(DMR_BS_DATA_STR, 11, 1, 1, 1, 0, 1)
         add(DMR_BS_VOICE_STR, 13, 1, 1, 1, 0, 1)
     return (OracleAcqPattern * len(pats))(*pats), keep
+
+
+# ---- the UNMODIFIED dmr_data_sync() on a replayed dibit stream (oracle/ref_shim_dmr.c -> oracle/_ref/libdsdneo_ref_dmr.so) ----
+REF_DMR_DTYPE = np.dtype([("handler_called", "<i4"), ("cach_called", "<i4"), ("burst", "<i4"), ("color_code", "<i4"),
+                          ("color_code_ok", "<i4"), ("dmr_color_code", "<i4"), ("currentslot", "<i4"), ("live_dibits", "<i4"),
+                          ("info", "u1", (196,)), ("rel98", "u1", (98,)), ("cach", "u1", (25,)), ("stereo_payload", "u1", (144,)),
+                          ("_pad", "u1", (1,))])
+_ref_dmr_lib = None
+
+
+def ref_dmr():
+    global _ref_dmr_lib
+    if _ref_dmr_lib is None:
+        path = os.path.join(ROOT, "oracle", "_ref", "libdsdneo_ref_dmr.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        assert L.ref_dmr_burst_size() == REF_DMR_DTYPE.itemsize
+        L.ref_dmr_data_sync.restype = C.c_long
+        L.ref_dmr_data_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p]
+        _ref_dmr_lib = L
+    return _ref_dmr_lib
+
+
+def ref_dmr_bursts(dib, rel, sync_ends, inverted_dmr, first_is_raw=True):
+    """dmr_data_sync on every burst of a CONTINUOUS, polarity-corrected dibit stream (what the device slicer produces after
+    acquisition).  The reference reads the 90 dibits up to the sync from its raw rolling buffer and corrects their polarity
+    itself; for bursts behind the first the stream is already corrected, so it is un-corrected here before the call.  The
+    colour-code confidence gate persists over the bursts, as in the reference.  Returns a REF_DMR_DTYPE array."""
+    L = ref_dmr()
+    L.ref_dmr_reset(1 if inverted_dmr else 0)
+    out = np.zeros(len(sync_ends), REF_DMR_DTYPE)
+    rel = np.ascontiguousarray(rel, np.uint8)
+    for k, p in enumerate(sync_ends):
+        raw = np.ascontiguousarray(dib, np.uint8).copy()
+        if inverted_dmr and not (k == 0 and first_is_raw):
+            raw[p - 89:p + 1] ^= 2
+        rc = L.ref_dmr_data_sync(raw.ctypes.data, rel.ctypes.data, raw.size, int(p), out[k:k + 1].ctypes.data)
+        assert rc >= 0
+    return out

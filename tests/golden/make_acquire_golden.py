@@ -9,7 +9,8 @@ DMR preset (rf_mod 2, 12.5 kHz channel filter) -- are stored here).  Run in the 
 Stored per case: sync type, symbols hunted (saturating at the reference's 2048-entry history), samples consumed, the slicer
 state right after the sync (min, max, center, umid, lmid, minref, maxref, lastsample), the newest <= 200 hunt symbols with their
 rolling payload dibits / reliabilities (after resample-on-sync), and the first 600 synchronised dibits / reliabilities / LLRs /
-symbols."""
+symbols; for the -xr cases one record of the UNMODIFIED dmr_data_sync() per burst of the stream (what it hands
+to dmr_data_burst_handler / dmr_cach, the slot-type colour code and the colour code its confidence gate locks)."""
 import os
 import sys
 
@@ -45,6 +46,20 @@ def main():
         d, r, l, s = ref["after"]
         out[name + "_after_dib"], out[name + "_after_rel"], out[name + "_after_llr"], out[name + "_after_sym"] = d, r, l, s
         print(name, "sync", ref["sync_type"], "hunted", ref["hunted"], "consumed", ref["consumed"], "after", d.size)
+        if name.endswith("_xr"):
+            # the UNMODIFIED dmr_data_sync() (oracle/ref_shim_dmr.c) on every burst of the whole (pinned) oracle stream
+            import test_acquire as T
+            from test_frame_sync import oracle_search
+            o = T._oracle_acquire(disc, mask, rf_mod, disc.size // 9)
+            dib = np.concatenate([o["dib"], o["after"][0]])
+            rel = np.concatenate([o["rel"], o["after"][1]])
+            sym = np.concatenate([o["sym"], o["after"][3]])
+            n, pos, _, _, _ = oracle_search(sym, [(H.DMR_BS_VOICE_STR, 13)], max_hits=80)
+            pos = [int(p) for p in pos[:n] if p >= 89 and p + 55 <= dib.size]
+            recs = H.ref_dmr_bursts(dib, rel, pos, True)
+            out[name + "_burst_pos"] = np.array(pos, np.int32)
+            out[name + "_burst_ref"] = recs.view(np.uint8).reshape(len(pos), -1)
+            print("   bursts", len(pos), "handled", int(recs["handler_called"].sum()), "colour codes", sorted(set(recs["dmr_color_code"].tolist())))
     path = os.path.join(HERE, "acquire.npz")
     np.savez_compressed(path, **out)
     print(os.path.getsize(path), "bytes")
