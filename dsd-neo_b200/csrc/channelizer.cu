@@ -23,6 +23,16 @@
  * free), then a shared-memory transpose so every channel receives 16 consecutive outputs = one full 128-byte
  * line per store.  HBM traffic is the algorithmic minimum: 8 B in + 8 B out per input sample.
  *
+ * General kernel (M = 512 ... 8192, and bin-pruned outputs for multi-GPU channel sharding), pfbn_kernel:
+ * a rank that owns the channels k = r0 (mod R) needs only those DFT bins.  One decimation-in-frequency step
+ * taken analytically prunes the transform to N = M / R points:
+ *     y_{R k' + r0}[n] = sum_{n'=0}^{N-1} W_N^{n' k'} * ( W_M^{n' r0} * sum_{j=0}^{R-1} W_R^{j r0} v_{n' + j N}[n] )
+ * so every rank still reads the whole wideband tile and runs all M branch filters (8 + 8/R bytes per input
+ * sample of HBM traffic), but its transform and its output shrink by R.  One CTA walks chunks of C output
+ * times: branch FIRs + fold from a sliding register window straight into padded shared memory, an in-place
+ * mixed-radix FFT (one radix-2/4/8 pass, then radix-16 passes, twiddles from a W_N table), and a transposed
+ * store so each channel receives C consecutive outputs (C * 8 contiguous bytes).  R = 1 is the plain M-channel case.
+ *
  * Compiled with -fmad=true (nothing here is bit-pinned to a CPU path; tolerance is stated in the tests).
  */
 #include <math.h>
@@ -242,28 +252,234 @@ pfb256_kernel(const PfbParams p) {
     }
 }
 
-template <bool CU8>
-__global__ void __launch_bounds__(1024)
-pfb_save_hist_kernel(const void* in, long n_in, float2* hist, int hist_len) {
-    /* hist := last hist_len input samples (older entries shift down when n_in < hist_len).
-     * Single CTA; read everything, barrier, then write, so the in-place shift is race-free. */
-    constexpr int kPer = (kMaxT - 1) * kM / 1024 + 1;
-    float2 v[kPer];
+
+/* ---------------------------------------------------------------------------------------------------------
+ * General M, pruned bins.
+ * ------------------------------------------------------------------------------------------------------- */
+constexpr int kMaxFold = 32; /* R <= 32 */
+
+struct PfbNParams {
+    const void* in;       /* cf32 / cu8, n_out * M samples */
+    const float2* hist;   /* (T-1) * M samples preceding `in` */
+    const float* proto;   /* T * M prototype taps */
+    const float2* twN;    /* W_N^m = exp(-j 2 pi m / N), m < N */
+    float2* out;          /* [N][out_pitch]: row k' = channel R k' + r0 */
+    size_t out_pitch;
+    long n_out;
+    int M, N, R, r0;
+    int C;                /* output times per chunk: 2, 4, 8 or 16 */
+    int rho;              /* radix of the first pass: 1 (none), 2, 4 or 8; N / rho is a power of 16 */
+    int chunks_per_cta;
+    float2 wR[kMaxFold];  /* W_R^{j r0} */
+};
+
+__device__ __forceinline__ int
+pad16(int i) {
+    return i + (i >> 4);
+}
+
+template <int RHO>
+__device__ __forceinline__ void
+dft_small(float2 (&a)[8]) {
+    if (RHO == 2) {
+        const float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    } else if (RHO == 4) {
+        dft4(a[0], a[1], a[2], a[3]);
+    } else {
+        constexpr float h = 0.70710678118654752f;
+        dft4(a[0], a[2], a[4], a[6]); /* even part: a[0], a[2], a[4], a[6] = E[0..3] */
+        dft4(a[1], a[3], a[5], a[7]); /* odd part:  a[1], a[3], a[5], a[7] = O[0..3] */
+        const float2 o0 = a[1], o1 = cmul(a[3], make_float2(h, -h)), o2 = mul_mj(a[5]), o3 = cmul(a[7], make_float2(-h, -h));
+        const float2 e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+        a[0] = cadd(e0, o0);
+        a[1] = cadd(e1, o1);
+        a[2] = cadd(e2, o2);
+        a[3] = cadd(e3, o3);
+        a[4] = csub(e0, o0);
+        a[5] = csub(e1, o1);
+        a[6] = csub(e2, o2);
+        a[7] = csub(e3, o3);
+    }
+}
+
+/* first pass of the in-place DIF transform: radix RHO over the whole row (S = N) */
+template <int RHO>
+__device__ __forceinline__ void
+pfbn_first_pass(float2* X, const PfbNParams& p, int pitchT) {
+    const int sub = p.N / RHO;
+    const int total = p.C * sub;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int row = t / sub, j = t - row * sub;
+        float2* Xr = X + row * pitchT;
+        float2 a[8];
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        const int i = threadIdx.x + 1024 * k;
-        if (i < hist_len) {
-            const long src = n_in - hist_len + i;
-            v[k] = (src >= 0) ? load_sample<CU8>(in, src) : hist[i + n_in];
+        for (int q = 0; q < RHO; q++) {
+            a[q] = Xr[pad16(j + q * sub)];
+        }
+        dft_small<RHO>(a);
+#pragma unroll
+        for (int k = 1; k < RHO; k++) {
+            a[k] = cmul(a[k], __ldg(p.twN + j * k));
+        }
+#pragma unroll
+        for (int k = 0; k < RHO; k++) {
+            Xr[pad16(j + k * sub)] = a[k];
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        const int i = threadIdx.x + 1024 * k;
-        if (i < hist_len) {
-            hist[i] = v[k];
+}
+
+template <int T, bool CU8>
+__global__ void __launch_bounds__(512, 1)
+pfbn_kernel(const PfbNParams p) {
+    extern __shared__ __align__(16) unsigned char pfb_smem[];
+    float2* X = reinterpret_cast<float2*>(pfb_smem); /* [C][pitchT], element n of a row at pad16(n) */
+    const int N = p.N, C = p.C, M = p.M, R = p.R;
+    const int pitchT = N + (N >> 4) + 16 / C; /* = 16 / C (mod 16): the transposed read of the store phase is conflict-free */
+    const int n16 = N >> 4;
+
+    const long chunk0 = (long)blockIdx.x * p.chunks_per_cta;
+    for (int c = 0; c < p.chunks_per_cta; c++) {
+        const long n0 = (chunk0 + c) * C;
+        if (n0 >= p.n_out) {
+            break;
         }
+        const int nv = (int)min((long)C, p.n_out - n0);
+
+        /* ---- branch FIRs + fold: thread owns fold index n' and walks its R branches ---- */
+        for (int np = threadIdx.x; np < N; np += blockDim.x) {
+            float2 wM = make_float2(1.0f, 0.0f);
+            if (p.r0) {
+                float sn, cs;
+                sincospif(-2.0f * (float)(np * p.r0) / (float)M, &sn, &cs);
+                wM = make_float2(cs, sn);
+            }
+            const int pn = pad16(np);
+            for (int j = 0; j < R; j++) {
+                const int b = np + j * N;
+                float g[T];
+#pragma unroll
+                for (int q = 0; q < T; q++) {
+                    g[q] = __ldg(p.proto + q * M + (M - 1 - b));
+                }
+                const float2 w = cmul(p.wR[j], wM);
+                float2 xs[T + 3];
+#pragma unroll
+                for (int q = 1; q < T; q++) {
+                    const long blk = n0 - q;
+                    xs[T - 1 - q] = (blk >= 0) ? load_sample<CU8>(p.in, blk * M + b) : p.hist[(long)(T - 1 + blk) * M + b];
+                }
+                for (int s = 0; s < C; s += 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        xs[T - 1 + i] = (s + i < nv) ? load_sample<CU8>(p.in, (n0 + s + i) * M + b) : make_float2(0.0f, 0.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float2 v = make_float2(0.0f, 0.0f);
+#pragma unroll
+                        for (int q = 0; q < T; q++) {
+                            v.x = fmaf(g[q], xs[T - 1 + i - q].x, v.x);
+                            v.y = fmaf(g[q], xs[T - 1 + i - q].y, v.y);
+                        }
+                        if (s + i < C) {
+                            float2* dst = X + (s + i) * pitchT + pn;
+                            if (R > 1) {
+                                v = cmul(v, w);
+                                if (j > 0) {
+                                    v = cadd(v, *dst);
+                                }
+                            }
+                            *dst = v;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < T - 1; q++) {
+                        xs[q] = xs[4 + q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- in-place decimation-in-frequency transform of the C rows ---- */
+        if (p.rho == 2) {
+            pfbn_first_pass<2>(X, p, pitchT);
+        } else if (p.rho == 4) {
+            pfbn_first_pass<4>(X, p, pitchT);
+        } else if (p.rho == 8) {
+            pfbn_first_pass<8>(X, p, pitchT);
+        }
+        for (int S = N / p.rho; S >= 16; S >>= 4) {
+            const int sub = S >> 4;          /* butterflies per block of size S */
+            const int tw_step = N / S;
+            const int total = C * n16;
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                const int row = t / n16, u = t - row * n16;
+                const int g = u / sub, j = u - g * sub;
+                float2* Xr = X + row * pitchT;
+                const int base = g * S + j;
+                float2 a[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    a[q] = Xr[pad16(base + q * sub)];
+                }
+                dft16(a);
+                if (S > 16) {
+#pragma unroll
+                    for (int k = 1; k < 16; k++) {
+                        a[k] = cmul(a[k], __ldg(p.twN + j * k * tw_step));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    Xr[pad16(base + k * sub)] = a[k];
+                }
+            }
+            __syncthreads();
+        }
+
+        /* ---- transposed store: C consecutive lanes = C consecutive times of one channel ---- */
+        {
+            const int total = N * C;
+            for (int t = threadIdx.x; t < total; t += blockDim.x) {
+                const int i = t & (C - 1);
+                const int pos = t / C;
+                /* position -> bin: the digits of pos (most significant first: radix rho, then 16s) are the bin's digits
+                 * least significant first */
+                int rem = pos, bin = 0, mul = 1, size = N;
+                if (p.rho > 1) {
+                    size = N / p.rho;
+                    bin = rem / size;
+                    rem -= bin * size;
+                    mul = p.rho;
+                }
+                while (size > 1) {
+                    size >>= 4;
+                    const int d = rem / size;
+                    rem -= d * size;
+                    bin += d * mul;
+                    mul <<= 4;
+                }
+                if (i < nv) {
+                    __stcs(&p.out[(size_t)bin * p.out_pitch + n0 + i], X[i * pitchT + pad16(pos)]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* hist_new := the last hist_len samples of (hist_old ++ in) */
+template <bool CU8>
+__global__ void __launch_bounds__(256)
+pfb_hist_kernel(const void* in, long n_in, const float2* hist_old, float2* hist_new, int hist_len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hist_len) {
+        const long src = n_in - hist_len + i;
+        hist_new[i] = (src >= 0) ? load_sample<CU8>(in, src) : hist_old[i + n_in];
     }
 }
 
@@ -272,7 +488,9 @@ pfb_save_hist_kernel(const void* in, long n_in, float2* hist, int hist_len) {
 struct dsdneo_b200_channelizer {
     int M, T, cu8;
     float* d_proto;
-    float2* d_hist;
+    float2* d_hist;      /* current history: the (T-1) * M samples before the next tile */
+    float2* d_hist_alt;  /* written by the next history update, then the two swap */
+    float2* d_tw[6];     /* W_N tables for N = M >> i (bin strides 1, 2, ... 32), made on first use */
     float* h_proto;
     void* d_stage_in;
     size_t stage_in_cap;
@@ -300,6 +518,62 @@ launch_pfb(const PfbParams& p, int grid, cudaStream_t s) {
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
+    return 0;
+}
+
+static int
+pfbn_chunk_times(int N) {
+    /* C * N elements of shared memory per CTA: 8192 (70 KB, two or three CTAs per SM) up to N = 1024, 16384 above */
+    int c = (N <= 1024 ? 8192 : 16384) / N;
+    return c > 16 ? 16 : (c < 2 ? 2 : c);
+}
+
+template <int T, bool CU8>
+static int
+launch_pfbn(const PfbNParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    DSDNEO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        DSDNEO_CUDA(cudaFuncSetAttribute(pfbn_kernel<T, CU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (dev >= 0 && dev < 64) {
+            attr_done[dev] = true;
+        }
+    }
+    {
+        KernelTimer kt("pfbn_kernel", s);
+        pfbn_kernel<T, CU8><<<grid, threads, smem, s>>>(p);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+/* W_N table for bin stride R = 1 << lg (N = M >> lg), built in float64 on first use */
+static int
+ensure_twiddles(dsdneo_b200_channelizer* c, int lg) {
+    if (c->d_tw[lg]) {
+        return 0;
+    }
+    const int N = c->M >> lg;
+    float2* h = (float2*)malloc(sizeof(float2) * (size_t)N);
+    if (!h) {
+        set_error("channelize: out of host memory");
+        return DSDNEO_B200_ENOMEM;
+    }
+    const double pi = 3.14159265358979323846;
+    for (int m = 0; m < N; m++) {
+        const double a = -2.0 * pi * (double)m / (double)N;
+        h[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    cudaError_t e = cudaMalloc((void**)&c->d_tw[lg], sizeof(float2) * (size_t)N);
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(c->d_tw[lg], h, sizeof(float2) * (size_t)N, cudaMemcpyHostToDevice);
+    }
+    free(h);
+    if (e != cudaSuccess) {
+        return cuda_fail(e, "channelize (twiddle table)", __FILE__, __LINE__);
+    }
     return 0;
 }
 
@@ -343,8 +617,8 @@ dsdneo_b200_channelizer_create(int n_channels, int taps_per_branch, int input_is
     if (ensure_device()) {
         return NULL;
     }
-    if (n_channels != kM) {
-        set_error("channelizer_create: only M = %d channels is built in this round (got %d)", kM, n_channels);
+    if (n_channels < 256 || n_channels > 8192 || (n_channels & (n_channels - 1)) != 0) {
+        set_error("channelizer_create: n_channels must be a power of two in 256 ... 8192 (got %d)", n_channels);
         return NULL;
     }
     if (taps_per_branch != 4 && taps_per_branch != 8 && taps_per_branch != 12 && taps_per_branch != 16) {
@@ -381,6 +655,9 @@ dsdneo_b200_channelizer_create(int n_channels, int taps_per_branch, int input_is
         e = cudaMemcpy(c->d_proto, c->h_proto, sizeof(float) * (size_t)L, cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess) {
+        e = cudaMalloc((void**)&c->d_hist_alt, sizeof(float2) * (size_t)(c->T - 1) * c->M);
+    }
+    if (e == cudaSuccess) {
         e = cudaMemset(c->d_hist, 0, sizeof(float2) * (size_t)(c->T - 1) * c->M);
     }
     if (e != cudaSuccess) {
@@ -398,6 +675,10 @@ dsdneo_b200_channelizer_destroy(dsdneo_b200_channelizer* c) {
     }
     cudaFree(c->d_proto);
     cudaFree(c->d_hist);
+    cudaFree(c->d_hist_alt);
+    for (int i = 0; i < 6; i++) {
+        cudaFree(c->d_tw[i]);
+    }
     cudaFree(c->d_stage_in);
     cudaFree(c->d_stage_out);
     free(c->h_proto);
@@ -425,10 +706,21 @@ dsdneo_b200_channelizer_get_prototype(dsdneo_b200_channelizer* c, float* h_out, 
 }
 
 int
-dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, float* d_out,
-                       size_t out_pitch_pairs, void* stream) {
+dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride, int bin_first,
+                            int advance, float* d_out, size_t out_pitch_pairs, void* stream) {
     if (!c || !d_in || !d_out || n_in_samples == 0 || (n_in_samples % (size_t)c->M) != 0) {
         set_error("channelize: bad argument (n_in_samples must be a positive multiple of n_channels)");
+        return DSDNEO_B200_EINVAL;
+    }
+    int lg = 0;
+    while ((1 << lg) < bin_stride) {
+        lg++;
+    }
+    if (bin_stride < 1 || bin_stride > kMaxFold || (1 << lg) != bin_stride || c->M / bin_stride < 256 || bin_first < 0 ||
+        bin_first >= bin_stride) {
+        set_error("channelize_bins: bin_stride must be a power of two <= %d that leaves >= 256 channels, 0 <= bin_first < "
+                  "bin_stride (got %d, %d; M = %d)",
+                  kMaxFold, bin_stride, bin_first, c->M);
         return DSDNEO_B200_EINVAL;
     }
     const long n_out = (long)(n_in_samples / (size_t)c->M);
@@ -441,15 +733,6 @@ dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in
         return rc;
     }
     cudaStream_t s = as_stream(stream);
-    PfbParams p;
-    p.in = d_in;
-    p.hist = c->d_hist;
-    p.proto = c->d_proto;
-    p.out = reinterpret_cast<float2*>(d_out);
-    p.out_pitch = out_pitch_pairs;
-    p.n_out = n_out;
-    const long n_chunks = (n_out + kChunk - 1) / kChunk;
-    /* one resident wave (2 CTAs per SM), at least 4 chunks each so the (T-1)-block window preload is amortised */
     int sms = 148;
     {
         int dev = 0;
@@ -457,34 +740,109 @@ dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in
             (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
     }
-    long cpc = (n_chunks + sms * 2 - 1) / (sms * 2);
-    if (cpc < 4) {
-        cpc = 4;
-    }
-    p.chunks_per_cta = (int)cpc;
-    const int grid = (int)((n_chunks + cpc - 1) / cpc);
+    if (c->M == kM && bin_stride == 1) {
+        PfbParams p;
+        p.in = d_in;
+        p.hist = c->d_hist;
+        p.proto = c->d_proto;
+        p.out = reinterpret_cast<float2*>(d_out);
+        p.out_pitch = out_pitch_pairs;
+        p.n_out = n_out;
+        const long n_chunks = (n_out + kChunk - 1) / kChunk;
+        /* one resident wave (2 CTAs per SM), at least 4 chunks each so the (T-1)-block window preload is amortised */
+        long cpc = (n_chunks + sms * 2 - 1) / (sms * 2);
+        if (cpc < 4) {
+            cpc = 4;
+        }
+        p.chunks_per_cta = (int)cpc;
+        const int grid = (int)((n_chunks + cpc - 1) / cpc);
 #define PFB_CASE(TT)                                                                                                   \
     case TT: rc = c->cu8 ? launch_pfb<TT, true>(p, grid, s) : launch_pfb<TT, false>(p, grid, s); break;
-    switch (c->T) {
-        PFB_CASE(4)
-        PFB_CASE(8)
-        PFB_CASE(12)
-        PFB_CASE(16)
-        default: set_error("channelize: unsupported taps_per_branch"); return DSDNEO_B200_EUNSUPPORTED;
-    }
+        switch (c->T) {
+            PFB_CASE(4)
+            PFB_CASE(8)
+            PFB_CASE(12)
+            PFB_CASE(16)
+            default: set_error("channelize: unsupported taps_per_branch"); return DSDNEO_B200_EUNSUPPORTED;
+        }
 #undef PFB_CASE
+    } else {
+        rc = ensure_twiddles(c, lg);
+        if (rc) {
+            return rc;
+        }
+        PfbNParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = d_in;
+        p.hist = c->d_hist;
+        p.proto = c->d_proto;
+        p.twN = c->d_tw[lg];
+        p.out = reinterpret_cast<float2*>(d_out);
+        p.out_pitch = out_pitch_pairs;
+        p.n_out = n_out;
+        p.M = c->M;
+        p.R = bin_stride;
+        p.r0 = bin_first;
+        p.N = c->M / bin_stride;
+        p.C = pfbn_chunk_times(p.N);
+        int lgN = 0;
+        while ((1 << lgN) < p.N) {
+            lgN++;
+        }
+        p.rho = 1 << (lgN & 3);
+        const double pi = 3.14159265358979323846;
+        for (int j = 0; j < bin_stride; j++) {
+            const double a = -2.0 * pi * (double)((j * bin_first) % bin_stride) / (double)bin_stride;
+            p.wR[j] = make_float2((float)cos(a), (float)sin(a));
+        }
+        const int pitchT = p.N + p.N / 16 + 16 / p.C;
+        const size_t smem = (size_t)p.C * pitchT * sizeof(float2);
+        const int threads = (p.C * p.N <= 8192) ? 256 : 512;
+        const int per_sm = (p.C * p.N <= 8192) ? 2 : 1;
+        const long n_chunks = (n_out + p.C - 1) / p.C;
+        long cpc = (n_chunks + (long)sms * per_sm - 1) / ((long)sms * per_sm);
+        if (cpc < 1) {
+            cpc = 1;
+        }
+        p.chunks_per_cta = (int)cpc;
+        const int grid = (int)((n_chunks + cpc - 1) / cpc);
+#define PFBN_CASE(TT)                                                                                                  \
+    case TT:                                                                                                           \
+        rc = c->cu8 ? launch_pfbn<TT, true>(p, grid, threads, smem, s) : launch_pfbn<TT, false>(p, grid, threads, smem, s); \
+        break;
+        switch (c->T) {
+            PFBN_CASE(4)
+            PFBN_CASE(8)
+            PFBN_CASE(12)
+            PFBN_CASE(16)
+            default: set_error("channelize: unsupported taps_per_branch"); return DSDNEO_B200_EUNSUPPORTED;
+        }
+#undef PFBN_CASE
+    }
     if (rc) {
         return rc;
     }
-    const int hist_len = (c->T - 1) * c->M;
-    if (c->cu8) {
-        pfb_save_hist_kernel<true><<<1, 1024, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, hist_len);
-    } else {
-        pfb_save_hist_kernel<false><<<1, 1024, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, hist_len);
+    if (advance) {
+        const int hist_len = (c->T - 1) * c->M;
+        const int grid_h = (hist_len + 255) / 256;
+        if (c->cu8) {
+            pfb_hist_kernel<true><<<grid_h, 256, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, c->d_hist_alt, hist_len);
+        } else {
+            pfb_hist_kernel<false><<<grid_h, 256, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, c->d_hist_alt, hist_len);
+        }
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
+        float2* t = c->d_hist;
+        c->d_hist = c->d_hist_alt;
+        c->d_hist_alt = t;
     }
-    DSDNEO_KERNEL_CHECK();
-    count_launch();
     return 0;
+}
+
+int
+dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, float* d_out,
+                       size_t out_pitch_pairs, void* stream) {
+    return dsdneo_b200_channelize_bins(c, d_in, n_in_samples, 1, 0, 1, d_out, out_pitch_pairs, stream);
 }
 
 int

@@ -278,6 +278,8 @@ int dsdneo_b200_cqpsk_slicer_get_state(dsdneo_b200_cqpsk_slicer* q, int channel,
  * With input_is_cu8 the input is unsigned 8-bit I/Q pairs widened on load exactly like
  * widen_u8_to_f32_bias127 (src/dsp/simd_widen.cpp:139-147): (u8 - 127.5f) * (1/127.5f).
  * Carried state: the last (taps_per_branch-1)*M input samples.
+ * n_channels: a power of two, 256 ... 8192 (4096 x 12.5 kHz = 51.2 MHz, 8192 x 6.25 kHz = 51.2 MHz: BASELINE configs
+ * C4 / C5); taps_per_branch 4, 8, 12 or 16.
  */
 typedef struct dsdneo_b200_channelizer dsdneo_b200_channelizer;
 
@@ -298,6 +300,16 @@ int dsdneo_b200_channelize(dsdneo_b200_channelizer* c, const void* d_in, size_t 
                            size_t out_pitch_pairs, void* stream);
 int dsdneo_b200_channelize_host(dsdneo_b200_channelizer* c, const void* h_in, size_t n_in_samples, float* h_out,
                                 size_t out_pitch_pairs);
+/**
+ * Bin-pruned form for channel sharding (one wideband stream, the raw tile broadcast to every GPU, each
+ * GPU demodulates its own channels): computes only the channels k = bin_first (mod bin_stride), bin_stride a power of
+ * two <= 32 with n_channels / bin_stride >= 256.  Row k' of d_out ([n_channels / bin_stride][out_pitch_pairs]) is channel
+ * bin_stride * k' + bin_first.  The branch filters still see the whole tile; the transform and the output shrink by
+ * bin_stride.  advance != 0 moves the carried history past this tile (pass 0 for all but the last call when one GPU
+ * computes several bin classes of the same tile).  dsdneo_b200_channelize() == bin_stride 1, bin_first 0, advance 1.
+ */
+int dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride,
+                                int bin_first, int advance, float* d_out, size_t out_pitch_pairs, void* stream);
 
 /* ---- FSK front end: channelizer -> full_demod, one call ----------------------------------------- */
 

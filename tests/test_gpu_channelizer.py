@@ -158,3 +158,84 @@ def test_frontend_streaming_host_tickets(gpu):
     fb.wait_host(tickets[0])  # an old ticket is already complete
     with pytest.raises(gpu.B200Error):
         fb.wait_host(99)
+
+
+# ---- general kernel: M = 512 ... 8192 and bin-pruned outputs (per-GPU channel classes of one broadcast tile) ----
+
+def _noise_plus_tones(rng, Mx, n_out, tones):
+    n = n_out * Mx
+    t = np.arange(n, dtype=np.float64)
+    x = 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    for k, off in tones:
+        x += 0.3 * np.exp(2j * np.pi * ((k + off) / Mx) * t + 1j * rng.uniform(0, 2 * np.pi))
+    out = np.empty((n, 2), np.float32)
+    out[:, 0], out[:, 1] = x.real, x.imag
+    return out
+
+
+@pytest.mark.parametrize("Mx,R,T", [(512, 1, 8), (512, 2, 4), (1024, 1, 8), (1024, 4, 16), (2048, 2, 8), (2048, 8, 12),
+                                    (4096, 1, 8), (4096, 4, 4), (8192, 8, 8), (8192, 1, 4), (8192, 32, 8), (256, 1, 8)])
+def test_general_channelizer_matches_direct_form(gpu, Mx, R, T):
+    import torch
+
+    rng = np.random.default_rng(1000 + Mx + 7 * R + T)
+    n_out = 37  # ragged against every chunk length (2, 4, 8, 16)
+    tones = [(3, 0.1), (Mx // 2 + 5, -0.2), (Mx - 2, 0.05), (R * 9 + (R - 1), 0.0)]
+    x = _noise_plus_tones(rng, Mx, n_out, tones)
+    cz = gpu.Channelizer(Mx, T)
+    xd = torch.from_numpy(x).cuda()
+    xh = np.concatenate([np.zeros(((T - 1) * Mx, 2), np.float32), x])
+    for r0 in sorted({0, R - 1, R // 2}):
+        y = cz.channelize_bins(xd, R, r0, advance=False).cpu().numpy()
+        got = y[..., 0] + 1j * y[..., 1]
+        assert got.shape == (Mx // R, n_out)
+        rows = sorted({0, 1, 9, (Mx // R) // 2, Mx // R - 1, int(rng.integers(0, Mx // R))})
+        want = H.oracle_pfb(xh, (T - 1) * Mx, cz.prototype(), Mx, [R * k + r0 for k in rows], n_out)
+        _check(got[rows], want)
+        # a tone sits in its own channel: energy check on the pruned row that holds it
+        for k, _ in tones:
+            if k % R == r0:
+                p_all = (np.abs(got) ** 2).mean(axis=1)
+                assert p_all[k // R] > 20 * np.median(p_all)
+
+
+@pytest.mark.parametrize("Mx,R", [(1024, 1), (2048, 2), (4096, 4)])
+def test_general_channelizer_streaming_and_cu8(gpu, Mx, R):
+    """Launch splits (history carried, double-buffered) and the fused cu8 widening, bit for bit."""
+    import torch
+
+    rng = np.random.default_rng(77 + Mx)
+    T, n_out = 8, 45
+    u8 = rng.integers(0, 256, size=(n_out * Mx, 2), dtype=np.uint8)
+    widened = ((u8.astype(np.float32) - np.float32(127.5)) * np.float32(1.0 / 127.5)).astype(np.float32)
+    r0 = R - 1
+    one = gpu.Channelizer(Mx, T).channelize_bins(torch.from_numpy(widened).cuda(), R, r0).cpu().numpy()
+    cz = gpu.Channelizer(Mx, T, input_is_cu8=True)
+    cuts = [0, 3, 20, 21, n_out]  # includes launches shorter than the history
+    parts = [cz.channelize_bins(torch.from_numpy(u8[a * Mx:b * Mx]).cuda(), R, r0).cpu().numpy() for a, b in zip(cuts, cuts[1:])]
+    two = np.concatenate(parts, axis=1)
+    assert np.array_equal(one.view(np.uint32), two.view(np.uint32))
+
+
+def test_bin_classes_tile_the_band(gpu):
+    """The R classes computed one after the other on one GPU (advance only on the last) cover every channel once and agree
+    with the unpruned transform within the stated tolerance."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    Mx, T, R, n_out = 1024, 8, 4, 24
+    x = torch.from_numpy(_noise_plus_tones(rng, Mx, n_out, [(17, 0.0), (600, 0.1)])).cuda()
+    full = gpu.Channelizer(Mx, T).channelize(x).cpu().numpy()
+    cz = gpu.Channelizer(Mx, T)
+    out = np.zeros_like(full)
+    for r0 in range(R):
+        out[r0::R] = cz.channelize_bins(x, R, r0, advance=(r0 == R - 1)).cpu().numpy()
+    scale = np.abs(full).max()
+    assert np.abs(out - full).max() <= 2e-5 * scale + 1e-7
+    # the history moved exactly once: a second tile still agrees
+    x2 = torch.from_numpy(_noise_plus_tones(rng, Mx, n_out, [(17, 0.0)])).cuda()
+    full2 = gpu.Channelizer(Mx, T)
+    full2.channelize(x)
+    want2 = full2.channelize(x2).cpu().numpy()
+    got2 = cz.channelize_bins(x2, R, 1).cpu().numpy()
+    assert np.abs(got2 - want2[1::R]).max() <= 2e-5 * np.abs(want2).max() + 1e-7
