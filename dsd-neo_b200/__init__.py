@@ -539,6 +539,15 @@ class Channelizer:
         )
         return d_out
 
+    def prime(self, d_in, stream=None) -> None:
+        """Carry the history over d_in ([n, 2] in the input format, on the GPU) without producing output."""
+        import torch
+
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.dtype == (torch.uint8 if self.cu8 else torch.float32)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(lib().dsdneo_b200_channelizer_prime(self._h, d_in.data_ptr(), d_in.shape[0], _stream_ptr(stream)), "channelizer_prime")
+
     def channelize_bins(self, d_in, bin_stride: int, bin_first: int, d_out=None, advance: bool = True, stream=None):
         """Only the channels k = bin_first (mod bin_stride): returns float32 [M / bin_stride, n/M, 2], row k' = channel
         bin_stride * k' + bin_first (the per-GPU share of one broadcast wideband tile)."""

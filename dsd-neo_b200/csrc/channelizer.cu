@@ -66,14 +66,25 @@ cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+#ifndef PFB_PACKED_ADD
+#define PFB_PACKED_ADD 1
+#endif
 __device__ __forceinline__ float2
 cadd(float2 a, float2 b) {
+#if PFB_PACKED_ADD
+    return __fadd2_rn(a, b);
+#else
     return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
 
 __device__ __forceinline__ float2
 csub(float2 a, float2 b) {
+#if PFB_PACKED_ADD
+    return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); /* exact: a - b */
+#else
     return make_float2(a.x - b.x, a.y - b.y);
+#endif
 }
 
 __device__ __forceinline__ float2
@@ -261,7 +272,8 @@ constexpr int kMaxFold = 32; /* R <= 32 */
 struct PfbNParams {
     const void* in;       /* cf32 / cu8, n_out * M samples */
     const float2* hist;   /* (T-1) * M samples preceding `in` */
-    const float* proto;   /* T * M prototype taps */
+    const float* proto;   /* T * M prototype taps (cu8 input: pre-scaled by 1/127.5) */
+    const float* bias;    /* cu8 input: -127.5 * sum_q proto[q M + M-1-b] per branch b (the widening's offset after the filter) */
     const float2* twN;    /* W_N^m = exp(-j 2 pi m / N), m < N */
     float2* out;          /* [N][out_pitch]: row k' = channel R k' + r0 */
     size_t out_pitch;
@@ -269,6 +281,7 @@ struct PfbNParams {
     int M, N, R, r0;
     int C;                /* output times per chunk: 2, 4, 8 or 16 */
     int rho;              /* radix of the first pass: 1 (none), 2, 4 or 8; N / rho is a power of 16 */
+    int lgN, lgC;
     int chunks_per_cta;
     float2 wR[kMaxFold];  /* W_R^{j r0} */
 };
@@ -304,34 +317,44 @@ dft_small(float2 (&a)[8]) {
     }
 }
 
-/* first pass of the in-place DIF transform: radix RHO over the whole row (S = N) */
+/* first pass of the in-place DIF transform: radix RHO over the whole row (S = N).  A thread keeps one butterfly
+ * column (its twiddles stay in registers) and walks the rows of the chunk. */
 template <int RHO>
 __device__ __forceinline__ void
 pfbn_first_pass(float2* X, const PfbNParams& p, int pitchT) {
     const int sub = p.N / RHO;
-    const int total = p.C * sub;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        const int row = t / sub, j = t - row * sub;
-        float2* Xr = X + row * pitchT;
-        float2 a[8];
-#pragma unroll
-        for (int q = 0; q < RHO; q++) {
-            a[q] = Xr[pad16(j + q * sub)];
-        }
-        dft_small<RHO>(a);
+    const int U = min(sub, (int)blockDim.x), rows_par = blockDim.x / U;
+    for (int j = threadIdx.x % U; j < sub; j += U) {
+        float2 tw[RHO];
 #pragma unroll
         for (int k = 1; k < RHO; k++) {
-            a[k] = cmul(a[k], __ldg(p.twN + j * k));
+            tw[k] = __ldg(p.twN + j * k);
         }
+        const int pstride = sub + (sub >> 4); /* sub is a multiple of 16 */
+        for (int row = threadIdx.x / U; row < p.C; row += rows_par) {
+            float2* Xr = X + row * pitchT + pad16(j);
+            float2 a[8];
 #pragma unroll
-        for (int k = 0; k < RHO; k++) {
-            Xr[pad16(j + k * sub)] = a[k];
+            for (int q = 0; q < RHO; q++) {
+                a[q] = Xr[q * pstride];
+            }
+            dft_small<RHO>(a);
+#pragma unroll
+            for (int k = 1; k < RHO; k++) {
+                a[k] = cmul(a[k], tw[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < RHO; k++) {
+                Xr[k * pstride] = a[k];
+            }
         }
     }
     __syncthreads();
 }
 
-template <int T, bool CU8>
+/* SC = output times per register window (4 or 8): the T - 1 + SC samples of one branch are requested together, then
+ * filtered out of registers. */
+template <int T, bool CU8, int SC>
 __global__ void __launch_bounds__(512, 1)
 pfbn_kernel(const PfbNParams p) {
     extern __shared__ __align__(16) unsigned char pfb_smem[];
@@ -339,6 +362,28 @@ pfbn_kernel(const PfbNParams p) {
     const int N = p.N, C = p.C, M = p.M, R = p.R;
     const int pitchT = N + (N >> 4) + 16 / C; /* = 16 / C (mod 16): the transposed read of the store phase is conflict-free */
     const int n16 = N >> 4;
+    unsigned short* binOf = reinterpret_cast<unsigned short*>(X + C * pitchT); /* [N]: position -> output row */
+
+    /* position -> bin: the digits of pos (most significant first: radix rho, then 16s) are the bin's digits, least
+     * significant first */
+    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+        int rem = pos, bin = 0, mul = 1, size = N;
+        if (p.rho > 1) {
+            size = N / p.rho;
+            bin = rem / size;
+            rem -= bin * size;
+            mul = p.rho;
+        }
+        while (size > 1) {
+            size >>= 4;
+            const int d = rem / size;
+            rem -= d * size;
+            bin += d * mul;
+            mul <<= 4;
+        }
+        binOf[pos] = (unsigned short)bin;
+    }
+    __syncthreads();
 
     const long chunk0 = (long)blockIdx.x * p.chunks_per_cta;
     for (int c = 0; c < p.chunks_per_cta; c++) {
@@ -348,59 +393,207 @@ pfbn_kernel(const PfbNParams p) {
         }
         const int nv = (int)min((long)C, p.n_out - n0);
 
-        /* ---- branch FIRs + fold: thread owns fold index n' and walks its R branches ---- */
-        for (int np = threadIdx.x; np < N; np += blockDim.x) {
+        /* ---- branch FIRs + fold: a task = (fold index n', window s); the R branches of n' accumulate in place.
+         * cu8 input is filtered as raw byte values (exact in f32); the widening (u - 127.5) / 127.5 of
+         * widen_u8_to_f32_bias127 is affine, so it is applied once per output: taps pre-scaled, bias as the
+         * accumulator's start value. ---- */
+        const int n_win = (C + SC - 1) / SC;
+        if constexpr (T <= 8) {
+            /* two adjacent branches per thread: one 4-byte (cu8) / 16-byte (cf32) request feeds both windows */
+            for (int task = threadIdx.x; task < (N >> 1) * n_win; task += blockDim.x) {
+                const int s = (task >> (p.lgN - 1)) * SC, np = (task & ((N >> 1) - 1)) * 2;
+                float2 wMa = make_float2(1.0f, 0.0f), wMb = wMa;
+                if (p.r0) {
+                    float sn, cs;
+                    sincospif(-2.0f * (float)(np * p.r0) / (float)M, &sn, &cs);
+                    wMa = make_float2(cs, sn);
+                    sincospif(-2.0f * (float)((np + 1) * p.r0) / (float)M, &sn, &cs);
+                    wMb = make_float2(cs, sn);
+                }
+                float2* dst0 = X + s * pitchT + pad16(np); /* np even: np + 1 is the next padded slot */
+                const bool interior = (n0 + s >= T - 1) && (s + SC <= nv);
+                const long first = (n0 + s - (T - 1)) * (long)M;
+                for (int j = 0; j < R; j++) {
+                    const int b = np + j * N;
+                    float2 ga[T], gb[T];
+#pragma unroll
+                    for (int q = 0; q < T; q++) {
+                        const float2 t = __ldg(reinterpret_cast<const float2*>(p.proto + q * M + (M - 2 - b)));
+                        ga[q] = make_float2(t.y, t.y); /* branch b:     proto[q M + M-1-b] */
+                        gb[q] = make_float2(t.x, t.x); /* branch b + 1: proto[q M + M-2-b] */
+                    }
+                    float2 xa[T - 1 + SC], xb[T - 1 + SC];
+                    if (interior) {
+                        if (CU8) {
+                            const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + first;
+#pragma unroll
+                            for (int i = 0; i < T - 1 + SC; i++) {
+                                const unsigned raw = __ldg(reinterpret_cast<const unsigned*>(src + (b + i * M)));
+                                xa[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
+                                                    __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7441)));
+                                xb[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7442)),
+                                                    __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7443)));
+                            }
+#pragma unroll
+                            for (int i = 0; i < T - 1 + SC; i++) {
+                                xa[i] = __fadd2_rn(xa[i], make_float2(-8388608.0f, -8388608.0f));
+                                xb[i] = __fadd2_rn(xb[i], make_float2(-8388608.0f, -8388608.0f));
+                            }
+                        } else {
+                            const float2* src = reinterpret_cast<const float2*>(p.in) + first;
+#pragma unroll
+                            for (int i = 0; i < T - 1 + SC; i++) {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (b + i * M)));
+                                xa[i] = make_float2(v.x, v.y);
+                                xb[i] = make_float2(v.z, v.w);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < T - 1 + SC; i++) {
+                            const long blk = n0 + s + i - (T - 1);
+                            float2 va = make_float2(0.0f, 0.0f), vb = va;
+                            if (blk < 0) {
+                                va = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
+                                vb = p.hist[(long)(T - 1 + blk) * M + b + 1];
+                                if (CU8) {
+                                    va = make_float2(fmaf(va.x, 127.5f, 127.5f), fmaf(va.y, 127.5f, 127.5f));
+                                    vb = make_float2(fmaf(vb.x, 127.5f, 127.5f), fmaf(vb.y, 127.5f, 127.5f));
+                                }
+                            } else if (blk < p.n_out) {
+                                if (CU8) {
+                                    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uchar2*>(p.in) + blk * M + b));
+                                    va = make_float2((float)u.x, (float)u.y);
+                                    vb = make_float2((float)u.z, (float)u.w);
+                                } else {
+                                    const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.in) + blk * M + b));
+                                    va = make_float2(v.x, v.y);
+                                    vb = make_float2(v.z, v.w);
+                                }
+                            }
+                            xa[i] = va;
+                            xb[i] = vb;
+                        }
+                    }
+                    const float2 wa = cmul(p.wR[j], wMa), wb = cmul(p.wR[j], wMb);
+                    float2 va0 = make_float2(0.0f, 0.0f), vb0 = va0;
+                    if (CU8) {
+                        const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + b));
+                        va0 = make_float2(bias.x, bias.x);
+                        vb0 = make_float2(bias.y, bias.y);
+                    }
+#pragma unroll
+                    for (int i = 0; i < SC; i++) {
+                        float2 va = va0, vb = vb0;
+#pragma unroll
+                        for (int q = 0; q < T; q++) {
+                            va = __ffma2_rn(ga[q], xa[T - 1 + i - q], va);
+                            vb = __ffma2_rn(gb[q], xb[T - 1 + i - q], vb);
+                        }
+                        if (s + i < C) {
+                            float2* dst = dst0 + i * pitchT;
+                            if (R > 1) {
+                                va = cmul(va, wa);
+                                vb = cmul(vb, wb);
+                                if (j > 0) {
+                                    va = __fadd2_rn(va, dst[0]);
+                                    vb = __fadd2_rn(vb, dst[1]);
+                                }
+                            }
+                            dst[0] = va;
+                            dst[1] = vb;
+                        }
+                    }
+                }
+            }
+        } else {
+        for (int task = threadIdx.x; task < N * n_win; task += blockDim.x) {
+            const int s = (task >> p.lgN) * SC, np = task & (N - 1);
             float2 wM = make_float2(1.0f, 0.0f);
             if (p.r0) {
                 float sn, cs;
                 sincospif(-2.0f * (float)(np * p.r0) / (float)M, &sn, &cs);
                 wM = make_float2(cs, sn);
             }
-            const int pn = pad16(np);
+            float2* dst0 = X + s * pitchT + pad16(np);
+            const bool interior = (n0 + s >= T - 1) && (s + SC <= nv);
+            const long first = (n0 + s - (T - 1)) * (long)M; /* oldest sample of the window, branch 0 */
             for (int j = 0; j < R; j++) {
                 const int b = np + j * N;
-                float g[T];
+                float2 g2[T];
 #pragma unroll
                 for (int q = 0; q < T; q++) {
-                    g[q] = __ldg(p.proto + q * M + (M - 1 - b));
+                    const float g = __ldg(p.proto + q * M + (M - 1 - b));
+                    g2[q] = make_float2(g, g);
+                }
+                float2 xs[T - 1 + SC];
+                if (interior) {
+                    if (CU8) {
+                        const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + first;
+#pragma unroll
+                        for (int i = 0; i < T - 1 + SC; i++) {
+                            const unsigned raw = __ldg(src + (b + i * M));
+                            xs[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
+                                                __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7441)));
+                        }
+#pragma unroll
+                        for (int i = 0; i < T - 1 + SC; i++) {
+                            xs[i] = __fadd2_rn(xs[i], make_float2(-8388608.0f, -8388608.0f));
+                        }
+                    } else {
+                        const float2* src = reinterpret_cast<const float2*>(p.in) + first;
+#pragma unroll
+                        for (int i = 0; i < T - 1 + SC; i++) {
+                            xs[i] = __ldg(src + (b + i * M));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < T - 1 + SC; i++) {
+                        const long blk = n0 + s + i - (T - 1);
+                        float2 v = make_float2(0.0f, 0.0f);
+                        if (blk < 0) {
+                            v = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
+                            if (CU8) {
+                                v = make_float2(fmaf(v.x, 127.5f, 127.5f), fmaf(v.y, 127.5f, 127.5f));
+                            }
+                        } else if (blk < p.n_out) {
+                            if (CU8) {
+                                const uchar2 u = __ldg(reinterpret_cast<const uchar2*>(p.in) + blk * M + b);
+                                v = make_float2((float)u.x, (float)u.y);
+                            } else {
+                                v = __ldg(reinterpret_cast<const float2*>(p.in) + blk * M + b);
+                            }
+                        }
+                        xs[i] = v;
+                    }
                 }
                 const float2 w = cmul(p.wR[j], wM);
-                float2 xs[T + 3];
-#pragma unroll
-                for (int q = 1; q < T; q++) {
-                    const long blk = n0 - q;
-                    xs[T - 1 - q] = (blk >= 0) ? load_sample<CU8>(p.in, blk * M + b) : p.hist[(long)(T - 1 + blk) * M + b];
+                float2 v0 = make_float2(0.0f, 0.0f);
+                if (CU8) {
+                    const float bias = __ldg(p.bias + b);
+                    v0 = make_float2(bias, bias);
                 }
-                for (int s = 0; s < C; s += 4) {
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        xs[T - 1 + i] = (s + i < nv) ? load_sample<CU8>(p.in, (n0 + s + i) * M + b) : make_float2(0.0f, 0.0f);
+                for (int i = 0; i < SC; i++) {
+                    float2 v = v0;
+#pragma unroll
+                    for (int q = 0; q < T; q++) {
+                        v = __ffma2_rn(g2[q], xs[T - 1 + i - q], v);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        float2 v = make_float2(0.0f, 0.0f);
-#pragma unroll
-                        for (int q = 0; q < T; q++) {
-                            v.x = fmaf(g[q], xs[T - 1 + i - q].x, v.x);
-                            v.y = fmaf(g[q], xs[T - 1 + i - q].y, v.y);
-                        }
-                        if (s + i < C) {
-                            float2* dst = X + (s + i) * pitchT + pn;
-                            if (R > 1) {
-                                v = cmul(v, w);
-                                if (j > 0) {
-                                    v = cadd(v, *dst);
-                                }
+                    if (s + i < C) {
+                        float2* dst = dst0 + i * pitchT;
+                        if (R > 1) {
+                            v = cmul(v, w);
+                            if (j > 0) {
+                                v = __fadd2_rn(v, *dst);
                             }
-                            *dst = v;
                         }
-                    }
-#pragma unroll
-                    for (int q = 0; q < T - 1; q++) {
-                        xs[q] = xs[4 + q];
+                        *dst = v;
                     }
                 }
             }
+        }
         }
         __syncthreads();
 
@@ -412,59 +605,57 @@ pfbn_kernel(const PfbNParams p) {
         } else if (p.rho == 8) {
             pfbn_first_pass<8>(X, p, pitchT);
         }
-        for (int S = N / p.rho; S >= 16; S >>= 4) {
-            const int sub = S >> 4;          /* butterflies per block of size S */
-            const int tw_step = N / S;
-            const int total = C * n16;
-            for (int t = threadIdx.x; t < total; t += blockDim.x) {
-                const int row = t / n16, u = t - row * n16;
-                const int g = u / sub, j = u - g * sub;
-                float2* Xr = X + row * pitchT;
-                const int base = g * S + j;
-                float2 a[16];
+        {
+            const int U = min(n16, (int)blockDim.x), rows_par = blockDim.x / U;
+            for (int S = N / p.rho; S >= 16; S >>= 4) {
+                const int sub = S >> 4; /* butterflies per block of size S */
+                const int tw_step = N / S;
+                for (int u = threadIdx.x % U; u < n16; u += U) {
+                    const int g = u / sub, j = u - g * sub;
+                    const int base = g * S + j;
+                    float2 tw[16];
+                    if (S > 16) {
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    a[q] = Xr[pad16(base + q * sub)];
-                }
-                dft16(a);
-                if (S > 16) {
+                        for (int k = 1; k < 16; k++) {
+                            tw[k] = __ldg(p.twN + j * k * tw_step);
+                        }
+                    }
+                    /* sub is 1 (base a multiple of 16) or a multiple of 16: the padded index is linear in q */
+                    const int pstride = sub + (sub >> 4);
+                    for (int row = threadIdx.x / U; row < C; row += rows_par) {
+                        float2* Xr = X + row * pitchT + pad16(base);
+                        float2 a[16];
 #pragma unroll
-                    for (int k = 1; k < 16; k++) {
-                        a[k] = cmul(a[k], __ldg(p.twN + j * k * tw_step));
+                        for (int q = 0; q < 16; q++) {
+                            a[q] = Xr[q * pstride];
+                        }
+                        dft16(a);
+                        if (S > 16) {
+#pragma unroll
+                            for (int k = 1; k < 16; k++) {
+                                a[k] = cmul(a[k], tw[k]);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            Xr[k * pstride] = a[k];
+                        }
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    Xr[pad16(base + k * sub)] = a[k];
-                }
+                __syncthreads();
             }
-            __syncthreads();
         }
 
         /* ---- transposed store: C consecutive lanes = C consecutive times of one channel ---- */
         {
-            const int total = N * C;
-            for (int t = threadIdx.x; t < total; t += blockDim.x) {
-                const int i = t & (C - 1);
-                const int pos = t / C;
-                /* position -> bin: the digits of pos (most significant first: radix rho, then 16s) are the bin's digits
-                 * least significant first */
-                int rem = pos, bin = 0, mul = 1, size = N;
-                if (p.rho > 1) {
-                    size = N / p.rho;
-                    bin = rem / size;
-                    rem -= bin * size;
-                    mul = p.rho;
-                }
-                while (size > 1) {
-                    size >>= 4;
-                    const int d = rem / size;
-                    rem -= d * size;
-                    bin += d * mul;
-                    mul <<= 4;
-                }
-                if (i < nv) {
-                    __stcs(&p.out[(size_t)bin * p.out_pitch + n0 + i], X[i * pitchT + pad16(pos)]);
+            const int i = threadIdx.x & (C - 1); /* blockDim is a multiple of C */
+            const int pstep = blockDim.x >> p.lgC;
+            float2* dst = p.out + n0 + i;
+            const float2* src = X + i * pitchT;
+            if (i < nv) {
+#pragma unroll 4
+                for (int pos = threadIdx.x >> p.lgC; pos < N; pos += pstep) {
+                    __stcs(dst + (size_t)binOf[pos] * p.out_pitch, src[pad16(pos)]);
                 }
             }
         }
@@ -491,6 +682,8 @@ struct dsdneo_b200_channelizer {
     float2* d_hist;      /* current history: the (T-1) * M samples before the next tile */
     float2* d_hist_alt;  /* written by the next history update, then the two swap */
     float2* d_tw[6];     /* W_N tables for N = M >> i (bin strides 1, 2, ... 32), made on first use */
+    float* d_proto_u8;   /* cu8 input: prototype * (1 / 127.5) ... */
+    float* d_bias_u8;    /* ... and -127.5 * (branch tap sum of it), per branch */
     float* h_proto;
     void* d_stage_in;
     size_t stage_in_cap;
@@ -528,21 +721,21 @@ pfbn_chunk_times(int N) {
     return c > 16 ? 16 : (c < 2 ? 2 : c);
 }
 
-template <int T, bool CU8>
+template <int T, bool CU8, int SC>
 static int
 launch_pfbn(const PfbNParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
     static bool attr_done[64] = {};
     int dev = 0;
     DSDNEO_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        DSDNEO_CUDA(cudaFuncSetAttribute(pfbn_kernel<T, CU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        DSDNEO_CUDA(cudaFuncSetAttribute(pfbn_kernel<T, CU8, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
         if (dev >= 0 && dev < 64) {
             attr_done[dev] = true;
         }
     }
     {
         KernelTimer kt("pfbn_kernel", s);
-        pfbn_kernel<T, CU8><<<grid, threads, smem, s>>>(p);
+        pfbn_kernel<T, CU8, SC><<<grid, threads, smem, s>>>(p);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
@@ -657,6 +850,36 @@ dsdneo_b200_channelizer_create(int n_channels, int taps_per_branch, int input_is
     if (e == cudaSuccess) {
         e = cudaMalloc((void**)&c->d_hist_alt, sizeof(float2) * (size_t)(c->T - 1) * c->M);
     }
+    if (e == cudaSuccess && c->cu8) {
+        /* the general kernel filters raw bytes: fold widen_u8_to_f32_bias127's scale into the taps and its offset into a
+         * per-branch start value (float64 here, f32 on the device) */
+        float* hs = (float*)malloc(sizeof(float) * (size_t)(L + c->M));
+        if (!hs) {
+            e = cudaErrorMemoryAllocation;
+        } else {
+            for (int m = 0; m < L; m++) {
+                hs[m] = (float)((double)c->h_proto[m] / 127.5);
+            }
+            for (int b = 0; b < c->M; b++) {
+                double acc = 0.0;
+                for (int q = 0; q < c->T; q++) {
+                    acc += (double)hs[q * c->M + (c->M - 1 - b)];
+                }
+                hs[L + b] = (float)(-127.5 * acc);
+            }
+            e = cudaMalloc((void**)&c->d_proto_u8, sizeof(float) * (size_t)L);
+            if (e == cudaSuccess) {
+                e = cudaMalloc((void**)&c->d_bias_u8, sizeof(float) * (size_t)c->M);
+            }
+            if (e == cudaSuccess) {
+                e = cudaMemcpy(c->d_proto_u8, hs, sizeof(float) * (size_t)L, cudaMemcpyHostToDevice);
+            }
+            if (e == cudaSuccess) {
+                e = cudaMemcpy(c->d_bias_u8, hs + L, sizeof(float) * (size_t)c->M, cudaMemcpyHostToDevice);
+            }
+            free(hs);
+        }
+    }
     if (e == cudaSuccess) {
         e = cudaMemset(c->d_hist, 0, sizeof(float2) * (size_t)(c->T - 1) * c->M);
     }
@@ -676,6 +899,8 @@ dsdneo_b200_channelizer_destroy(dsdneo_b200_channelizer* c) {
     cudaFree(c->d_proto);
     cudaFree(c->d_hist);
     cudaFree(c->d_hist_alt);
+    cudaFree(c->d_proto_u8);
+    cudaFree(c->d_bias_u8);
     for (int i = 0; i < 6; i++) {
         cudaFree(c->d_tw[i]);
     }
@@ -692,6 +917,32 @@ dsdneo_b200_channelizer_reset(dsdneo_b200_channelizer* c, void* stream) {
         return DSDNEO_B200_EINVAL;
     }
     DSDNEO_CUDA(cudaMemsetAsync(c->d_hist, 0, sizeof(float2) * (size_t)(c->T - 1) * c->M, as_stream(stream)));
+    return 0;
+}
+
+int
+dsdneo_b200_channelizer_prime(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, void* stream) {
+    if (!c || !d_in || n_in_samples == 0) {
+        set_error("channelizer_prime: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int hist_len = (c->T - 1) * c->M;
+    const int grid_h = (hist_len + 255) / 256;
+    if (c->cu8) {
+        pfb_hist_kernel<true><<<grid_h, 256, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, c->d_hist_alt, hist_len);
+    } else {
+        pfb_hist_kernel<false><<<grid_h, 256, 0, s>>>(d_in, (long)n_in_samples, c->d_hist, c->d_hist_alt, hist_len);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    float2* t = c->d_hist;
+    c->d_hist = c->d_hist_alt;
+    c->d_hist_alt = t;
     return 0;
 }
 
@@ -775,7 +1026,8 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
         memset(&p, 0, sizeof(p));
         p.in = d_in;
         p.hist = c->d_hist;
-        p.proto = c->d_proto;
+        p.proto = c->cu8 ? c->d_proto_u8 : c->d_proto;
+        p.bias = c->d_bias_u8;
         p.twN = c->d_tw[lg];
         p.out = reinterpret_cast<float2*>(d_out);
         p.out_pitch = out_pitch_pairs;
@@ -790,13 +1042,18 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
             lgN++;
         }
         p.rho = 1 << (lgN & 3);
+        p.lgN = lgN;
+        p.lgC = 0;
+        while ((1 << p.lgC) < p.C) {
+            p.lgC++;
+        }
         const double pi = 3.14159265358979323846;
         for (int j = 0; j < bin_stride; j++) {
             const double a = -2.0 * pi * (double)((j * bin_first) % bin_stride) / (double)bin_stride;
             p.wR[j] = make_float2((float)cos(a), (float)sin(a));
         }
         const int pitchT = p.N + p.N / 16 + 16 / p.C;
-        const size_t smem = (size_t)p.C * pitchT * sizeof(float2);
+        const size_t smem = (size_t)p.C * pitchT * sizeof(float2) + (size_t)p.N * sizeof(unsigned short);
         const int threads = (p.C * p.N <= 8192) ? 256 : 512;
         const int per_sm = (p.C * p.N <= 8192) ? 2 : 1;
         const long n_chunks = (n_out + p.C - 1) / p.C;
@@ -808,7 +1065,13 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
         const int grid = (int)((n_chunks + cpc - 1) / cpc);
 #define PFBN_CASE(TT)                                                                                                  \
     case TT:                                                                                                           \
-        rc = c->cu8 ? launch_pfbn<TT, true>(p, grid, threads, smem, s) : launch_pfbn<TT, false>(p, grid, threads, smem, s); \
+        if (p.C >= 8) {                                                                                                \
+            rc = c->cu8 ? launch_pfbn<TT, true, 8>(p, grid, threads, smem, s)                                          \
+                        : launch_pfbn<TT, false, 8>(p, grid, threads, smem, s);                                        \
+        } else {                                                                                                       \
+            rc = c->cu8 ? launch_pfbn<TT, true, 4>(p, grid, threads, smem, s)                                          \
+                        : launch_pfbn<TT, false, 4>(p, grid, threads, smem, s);                                        \
+        }                                                                                                              \
         break;
         switch (c->T) {
             PFBN_CASE(4)

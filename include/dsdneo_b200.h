@@ -291,6 +291,9 @@ dsdneo_b200_channelizer* dsdneo_b200_channelizer_create(int n_channels, int taps
 void dsdneo_b200_channelizer_destroy(dsdneo_b200_channelizer* c);
 int dsdneo_b200_channelizer_reset(dsdneo_b200_channelizer* c, void* stream);
 int dsdneo_b200_channelizer_get_prototype(dsdneo_b200_channelizer* c, float* h_out, int max_taps);
+/** Moves the carried history over n_in_samples input samples (device, the channelizer's input format) without producing
+ *  output: resuming a stream whose preceding samples are known, so that the first outputs carry no filter start-up. */
+int dsdneo_b200_channelizer_prime(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, void* stream);
 /**
  * @param d_in   n_in_samples wideband samples (cf32 pairs, or cu8 pairs), n_in_samples % n_channels == 0
  * @param d_out  [n_channels][out_pitch_pairs] cf32; n_in_samples / n_channels outputs per channel -- the layout
