@@ -1134,6 +1134,59 @@ class P25p1Rx:
                 out["voices"][:nv].numpy().reshape(-1).view(P25_VOICE_DTYPE).copy())
 
 
+def ambe3600x2450_decode(ambe_fr):
+    """ambe_fr uint8 [n, 4, 24] -> (ambe_d [n, 49], c0_errors [n], total_errors [n]); host arrays."""
+    import numpy as np
+
+    fr = np.ascontiguousarray(ambe_fr, dtype=np.uint8).reshape(-1, 96)
+    n = fr.shape[0]
+    d, c0, tot = np.zeros((n, 49), np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_ambe3600x2450_decode_batch_host(fr.ctypes.data, d.ctypes.data, c0.ctypes.data, tot.ctypes.data, n),
+          "ambe3600x2450_decode")
+    return d, c0, tot
+
+
+def imbe7200x4400_decode(imbe_fr):
+    """imbe_fr uint8 [n, 8, 23] -> (imbe_d [n, 88], c0_errors [n], total_errors [n]); host arrays."""
+    import numpy as np
+
+    fr = np.ascontiguousarray(imbe_fr, dtype=np.uint8).reshape(-1, 184)
+    n = fr.shape[0]
+    d, c0, tot = np.zeros((n, 88), np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    check(lib().dsdneo_b200_imbe7200x4400_decode_batch_host(fr.ctypes.data, d.ctypes.data, c0.ctypes.data, tot.ctypes.data, n),
+          "imbe7200x4400_decode")
+    return d, c0, tot
+
+
+def ambe_2450_dibit_map():
+    import numpy as np
+
+    m = np.zeros((36, 4), np.uint8)
+    check(lib().dsdneo_b200_ambe_2450_dibit_map(m.ctypes.data), "ambe_2450_dibit_map")
+    return m
+
+
+def dmr_voice_cut(d_dibits, d_counts, d_hits, d_n_hits, max_hits: int, n_bursts: int, inverted_dmr: bool = False, stream=None):
+    """Device tensors in (dibits uint8 [n_ch, pitch], counts int32 [n_ch], hits int32 [n_ch, max_hits, 2], n_hits int32 [n_ch]);
+    returns device tensors (cach24 [R, 24], ambe_fr [R, 3, 4, 24], sync48 [R, 48], valid [R]), R = n_ch * max_hits * n_bursts."""
+    import torch
+
+    n_ch = d_dibits.shape[0]
+    R = n_ch * max_hits * n_bursts
+    dev = d_dibits.device
+    cach = torch.zeros((R, 24), dtype=torch.uint8, device=dev)
+    fr = torch.zeros((R, 3, 4, 24), dtype=torch.uint8, device=dev)
+    sync = torch.zeros((R, 48), dtype=torch.uint8, device=dev)
+    valid = torch.zeros(R, dtype=torch.uint8, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    check(lib().dsdneo_b200_dmr_voice_cut_batch(d_dibits.data_ptr(), d_dibits.shape[1], d_counts.data_ptr(), d_hits.data_ptr(),
+                                                d_n_hits.data_ptr(), n_ch, max_hits, n_bursts, 1 if inverted_dmr else 0,
+                                                cach.data_ptr(), fr.data_ptr(), sync.data_ptr(), valid.data_ptr(), _stream_ptr(stream)),
+          "dmr_voice_cut")
+    return cach, fr, sync, valid
+
+
 def p25_word_decode(code: int, data_bits, parity_bits):
     """Golay(24,6)/(24,12)/Hamming(10,6,3) P25 words. Returns (data_bits corrected, status u8 [n], fixed i32 [n])."""
     import numpy as np

@@ -754,6 +754,43 @@ int dsdneo_b200_dmr_burst_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch,
                                     uint8_t* d_valid, void* stream);
 
 /**
+ * DMR base-station VOICE burst cutter: the collection phase of dmrBSBootstrap / dmrBS (src/protocol/dmr/dmr_bs.c:137-148,
+ * 150-170, 182-187, 711-722, 745-746, 838-848) for every BS VOICE sync hit of every channel.  Burst j = 0 is the hit's own
+ * burst (90 dibits back from the dibit after the sync: 12 CACH, 36 + 18 vocoder dibits, the sync, then 18 + 36 vocoder dibits
+ * after it); bursts j = 1 .. n_bursts-1 are the following 144-dibit bursts of the stream (the two TDMA slots alternate; the
+ * TACT word in the CACH names the slot).  Per record (= (channel * max_hits + hit) * n_bursts + j): CACH bits [24] (bits 0..6 =
+ * the TACT word for Hamming(7,4)), ambe_fr[3][4][24] (the three `char ambe_fr[4][24]` the reference hands to
+ * processMbeFrame, de-interleaved with dsd_ambe_2450_dibit_map, unreached cells 0), the 48 sync / EMB bits, and whether the
+ * channel's stream (d_counts dibits) holds the whole burst.  `inverted_dmr` = opts->inverted_dmr: XOR 2 on the first 90
+ * dibits of burst 0 (the part the reference takes from its rolling buffer).
+ */
+int dsdneo_b200_dmr_voice_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const int32_t* d_counts, const void* d_hits,
+                                    const int32_t* d_n_hits, int n_channels, int max_hits, int n_bursts, int inverted_dmr,
+                                    uint8_t* d_cach24, uint8_t* d_ambe_fr, uint8_t* d_sync48, uint8_t* d_valid, void* stream);
+/** dsd_ambe_2450_dibit_map (include/dsd-neo/core/ambe_interleave.h:25-32) as this library generates it:
+ *  out[i] = {high_row, high_col, low_row, low_col}, i < 36. */
+int dsdneo_b200_ambe_2450_dibit_map(uint8_t* out36x4);
+
+/**
+ * Vocoder frame ECC, batched: what `int mbe_decodeAmbe3600x2450Frame(const char ambe_fr[4][24], char ambe_d[49],
+ * mbe_process_result*)` and `int mbe_decodeImbe7200x4400Frame(const char imbe_fr[8][23], char imbe_d[88],
+ * mbe_process_result*)` do for the reference (mbelib-neo API, contract CMakeLists.txt:622-655; call sites
+ * src/core/vocoder/dsd_mbe.c:168,188): [23,12] Golay on C0, pseudo-random demodulation seeded with C0's data, Golay /
+ * [15,11] Hamming on the protected words, output bits in priority order.  d_c0_errors / d_total_errors = the `errs` / `errs2`
+ * the reference stores in its state (result.c0_errors / result.total_errors).  PARITY UNPINNED: mbelib-neo is not in the
+ * reference tree; this follows the published mbelib 1.3.0 / TIA-102.BABA algorithm.
+ * Frames are the reference's own arrays as bytes: ambe_fr [n][4][24], imbe_fr [n][8][23], values 0 / 1.
+ */
+int dsdneo_b200_ambe3600x2450_decode_batch(const uint8_t* d_ambe_fr, uint8_t* d_ambe_d, int32_t* d_c0_errors,
+                                           int32_t* d_total_errors, int n_frames, void* stream);
+int dsdneo_b200_ambe3600x2450_decode_batch_host(const uint8_t* h_ambe_fr, uint8_t* h_ambe_d, int32_t* h_c0_errors,
+                                                int32_t* h_total_errors, int n_frames);
+int dsdneo_b200_imbe7200x4400_decode_batch(const uint8_t* d_imbe_fr, uint8_t* d_imbe_d, int32_t* d_c0_errors,
+                                           int32_t* d_total_errors, int n_frames, void* stream);
+int dsdneo_b200_imbe7200x4400_decode_batch_host(const uint8_t* h_imbe_fr, uint8_t* h_imbe_d, int32_t* h_c0_errors,
+                                                int32_t* h_total_errors, int n_frames);
+
+/**
  * Batched twins of `int check_and_fix_golay_24_6_soft(char* data, const char* parity, const int* reliab, int* fixed)` and
  * `check_and_fix_golay_24_12_soft` (include/dsd-neo/protocol/p25/p25p1_soft.h, src/protocol/p25/phase1/p25p1_soft.cpp:477-593):
  * Golay(24,6) / (24,12) with a bounded search over the 8 least reliable bits (at most 4 flips).

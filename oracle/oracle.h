@@ -291,4 +291,14 @@ typedef struct oracle_p25p1_voice {
 int oracle_p25p1_decode_frame(const uint8_t* dibits, const int16_t* llr, int count, int pos_last_sync, int observed_nac, int threshold,
                               oracle_p25p1_frame* f, oracle_p25p1_voice* voice);
 
+
+/* ---- vocoder frame ECC + DMR voice burst cutter (oracle_mbe.c) -- PARITY UNPINNED for the ECC, see its header ---- */
+int oracle_mbe_golay2312(const uint8_t* in23, uint8_t* out23);
+unsigned oracle_mbe_golay2312_encode(unsigned data12);
+int oracle_mbe_hamming1511(const uint8_t* in15, uint8_t* out15);
+unsigned oracle_mbe_hamming1511_encode(unsigned data11);
+void oracle_ambe3600x2450_decode(const uint8_t* ambe_fr, uint8_t* ambe_d, int* c0_errs, int* total_errs);
+void oracle_imbe7200x4400_decode(const uint8_t* imbe_fr, uint8_t* imbe_d, int* c0_errs, int* total_errs);
+void oracle_dmr_voice_cut(const uint8_t* burst144, int invert_first90, uint8_t* cach24, uint8_t* ambe_fr3, uint8_t* sync48);
+
 #endif
