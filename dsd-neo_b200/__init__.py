@@ -1158,6 +1158,22 @@ def imbe7200x4400_decode(imbe_fr):
     return d, c0, tot
 
 
+def p25p1_voice_imbe_decode(d_voices, n_records: int, stream=None):
+    """d_voices: device uint8 [>= n_records, 1944] (the bank's voice records).  Returns device tensors
+    (imbe_d uint8 [n, 9, 88], c0_errors int32 [n, 9], total_errors int32 [n, 9])."""
+    import torch
+
+    dev = d_voices.device
+    d = torch.zeros((n_records, 9, 88), dtype=torch.uint8, device=dev)
+    c0 = torch.zeros((n_records, 9), dtype=torch.int32, device=dev)
+    tot = torch.zeros((n_records, 9), dtype=torch.int32, device=dev)
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    check(lib().dsdneo_b200_p25p1_voice_imbe_decode_batch(d_voices.data_ptr(), n_records, d.data_ptr(), c0.data_ptr(), tot.data_ptr(),
+                                                          _stream_ptr(stream)), "p25p1_voice_imbe_decode")
+    return d, c0, tot
+
+
 def ambe_2450_dibit_map():
     import numpy as np
 

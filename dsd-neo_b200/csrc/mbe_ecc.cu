@@ -162,6 +162,47 @@ imbe7200x4400_decode_kernel(const uint8_t* __restrict__ imbe_fr, uint8_t* __rest
     total_errs[f] = errs2;
 }
 
+/* the same on the receive bank's voice records (dsdneo_b200_p25p1_voice: nine frames, row r of frame v = the low 23 bits of
+ * bits[v][r]); one thread per (record, frame) */
+__global__ void __launch_bounds__(128)
+imbe7200x4400_decode_packed_kernel(const uint32_t* __restrict__ voices, int words_per_record, uint8_t* __restrict__ imbe_d,
+                                   int32_t* __restrict__ c0_errs, int32_t* __restrict__ total_errs, int n) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) {
+        return;
+    }
+    const uint32_t* w = voices + (size_t)(f / 9) * words_per_record + (f % 9) * 8;
+    int errs = 0;
+    const unsigned u0 = golay2312(w[0] & 0x7fffffu, &errs);
+    int errs2 = errs;
+    unsigned pr = 16u * u0;
+    uint8_t* o = imbe_d + (size_t)f * 88;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        o[j] = (uint8_t)((u0 >> (11 - j)) & 1u);
+    }
+    for (int i = 1; i < 4; i++) {
+        const unsigned u = golay2312((w[i] & 0x7fffffu) ^ pn_word(pr, 23), &errs2);
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            o[12 * i + j] = (uint8_t)((u >> (11 - j)) & 1u);
+        }
+    }
+    for (int i = 4; i < 7; i++) {
+        const unsigned h = hamming1511((w[i] & 0x7fffu) ^ pn_word(pr, 15), &errs2);
+#pragma unroll
+        for (int j = 0; j < 11; j++) {
+            o[48 + 11 * (i - 4) + j] = (uint8_t)((h >> (14 - j)) & 1u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        o[81 + j] = (uint8_t)((w[7] >> (6 - j)) & 1u);
+    }
+    c0_errs[f] = errs;
+    total_errs[f] = errs2;
+}
+
 /* dsd_ambe_2450_dibit_map[i] (include/dsd-neo/core/ambe_interleave.h:25-32), generated: packed (row << 5 | col) for the
  * dibit's high bit (low 8 bits of the result) and low bit (next 8 bits) */
 __host__ __device__ __forceinline__ unsigned
@@ -216,6 +257,9 @@ dmr_voice_cut_kernel(const uint8_t* dibits, size_t dibit_pitch, const int32_t* c
     const size_t rec = (size_t)slot * n_bursts + j;
     if (k == 0) {
         valid_out[rec] = ok ? 1 : 0;
+    }
+    if (!present) {
+        return; /* unused hit slot: its record stays as the caller initialised it */
     }
     uint8_t* fr = ambe_fr + rec * 288;
     /* the positions no dibit reaches stay 0, as after the reference's memset (dmr_bs.c:121-123) */
@@ -434,6 +478,35 @@ dsdneo_b200_imbe7200x4400_decode_batch(const uint8_t* d_imbe_fr, uint8_t* d_imbe
     {
         KernelTimer kt("imbe7200x4400_decode_kernel", s);
         imbe7200x4400_decode_kernel<<<grid_for(n_frames, 128), 128, 0, s>>>(d_imbe_fr, d_imbe_d, d_c0_errors, d_total_errors, n_frames);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_p25p1_voice_imbe_decode_batch(const dsdneo_b200_p25p1_voice* d_voices, int n_records, uint8_t* d_imbe_d,
+                                          int32_t* d_c0_errors, int32_t* d_total_errors, void* stream) {
+    if (!d_voices || !d_imbe_d || !d_c0_errors || !d_total_errors || n_records < 0) {
+        set_error("p25p1_voice_imbe_decode_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_records == 0) {
+        return 0;
+    }
+    int rc = ensure_device();
+    if (!rc) {
+        rc = ensure_tables();
+    }
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int n = n_records * 9;
+    {
+        KernelTimer kt("imbe7200x4400_decode_packed_kernel", s);
+        imbe7200x4400_decode_packed_kernel<<<grid_for(n, 128), 128, 0, s>>>(
+            reinterpret_cast<const uint32_t*>(d_voices), (int)(sizeof(dsdneo_b200_p25p1_voice) / 4), d_imbe_d, d_c0_errors, d_total_errors, n);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();

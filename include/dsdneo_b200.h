@@ -789,6 +789,11 @@ int dsdneo_b200_imbe7200x4400_decode_batch(const uint8_t* d_imbe_fr, uint8_t* d_
                                            int32_t* d_total_errors, int n_frames, void* stream);
 int dsdneo_b200_imbe7200x4400_decode_batch_host(const uint8_t* h_imbe_fr, uint8_t* h_imbe_d, int32_t* h_c0_errors,
                                                 int32_t* h_total_errors, int n_frames);
+/** The same straight from the receive bank's voice records (below): nine IMBE frames per record -> d_imbe_d [n_records][9][88],
+ *  d_c0_errors / d_total_errors [n_records][9]: what processMbeFrame -> mbe_decodeImbe7200x4400Frame sees for every LDU. */
+struct dsdneo_b200_p25p1_voice;
+int dsdneo_b200_p25p1_voice_imbe_decode_batch(const struct dsdneo_b200_p25p1_voice* d_voices, int n_records, uint8_t* d_imbe_d,
+                                              int32_t* d_c0_errors, int32_t* d_total_errors, void* stream);
 
 /**
  * Batched twins of `int check_and_fix_golay_24_6_soft(char* data, const char* parity, const int* reliab, int* fixed)` and

@@ -253,3 +253,28 @@ def test_gpu_voice_cut_equals_oracle(gpu):
         body = txt[txt.index("dsd_ambe_2450_dibit_map[DSD_AMBE_2450_DIBITS] = {"):]
         ref = np.array([[int(x) for x in mm] for mm in re.findall(r"\{(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\}", body)][:36], np.uint8)
         assert np.array_equal(m, ref)
+
+
+@pytest.mark.gpu
+def test_gpu_imbe_decode_from_voice_records(gpu):
+    """The bank's packed voice records (nine IMBE frames per LDU) decode like the unpacked imbe_fr arrays."""
+    import torch
+
+    L = _o()
+    rng = np.random.default_rng(6)
+    n = 40
+    rec = np.zeros(n, dtype=gpu.P25_VOICE_DTYPE)
+    fr = rng.integers(0, 2, (n, 9, 8, 23)).astype(np.uint8)
+    for k in range(0, n, 2):
+        for v in range(9):
+            fr[k, v] = imbe_encode(L, rng.integers(0, 2, 88).astype(np.uint8))
+            fr[k, v, rng.integers(0, 7), rng.integers(0, 15)] ^= 1
+    fr[:, :, 4:7, 15:] = 0
+    fr[:, :, 7, 7:] = 0
+    rec["bits"] = (fr.astype(np.uint32) << np.arange(23, dtype=np.uint32)).sum(axis=-1)
+    d, c0, tot = gpu.p25p1_voice_imbe_decode(torch.from_numpy(rec.view(np.uint8).reshape(n, -1)).cuda(), n)
+    d, c0, tot = d.cpu().numpy(), c0.cpu().numpy(), tot.cpu().numpy()
+    for k in range(n):
+        for v in range(9):
+            wd, w0, wt = _oracle_imbe(L, fr[k, v])
+            assert np.array_equal(d[k, v], wd) and c0[k, v] == w0 and tot[k, v] == wt, (k, v)
