@@ -165,6 +165,72 @@ ref_dmr_data_sync(const uint8_t* dibits, const uint8_t* reliab, long n, long syn
     return g.pos - (sync_end + 1);
 }
 
+/* ---- voice: the UNMODIFIED dmrBSBootstrap() / dmrBS() (src/protocol/dmr/dmr_bs.c:898-990) on a replayed stream.  processMbeFrame
+ * (the vocoder entry, src/core/vocoder/dsd_mbe.c) is replaced through --wrap by a recorder of the ambe_fr[4][24] it is handed;
+ * every burst the loop reads is logged through its own dmr_stereo_payload copy. ---- */
+void dmrBSBootstrap(dsd_opts* opts, dsd_state* state);
+volatile uint8_t exitflag = 0; /* include/dsd-neo/runtime/exitflag.h:28 (read by the loop of dmrBS) */
+
+static struct {
+    uint8_t* frames; /* [max][96] */
+    long* at;        /* [max]: live dibits consumed when the frame was handed over (names the burst) */
+    int max, n;
+} v;
+
+void
+__wrap_processMbeFrame(dsd_opts* opts, dsd_state* state, char imbe_fr[8][23], char ambe_fr[4][24], char imbe7100_fr[7][24]) {
+    (void)opts;
+    (void)state;
+    (void)imbe_fr;
+    (void)imbe7100_fr;
+    if (ambe_fr && v.frames && v.n < v.max) {
+        memcpy(v.frames + (size_t)v.n * 96, ambe_fr, 96);
+        v.at[v.n] = g.pos;
+    }
+    v.n++;
+}
+
+/*
+ * dibits[sync_end - 89 .. sync_end]: the 90 buffered dibits of the first voice burst (raw), the rest comes through getDibitSoft.
+ * Records up to max_frames ambe_fr arrays in call order (frame_pos[i] = stream position after the burst that carried frame i); returns the number of processMbeFrame calls; *consumed = live dibits read.
+ */
+int
+ref_dmr_voice_run(const uint8_t* dibits, const uint8_t* reliab, long n, long sync_end, uint8_t* frames96, long* frame_pos, int max_frames,
+                  long* consumed) {
+    if (!s_opts || sync_end < 89 || sync_end >= n) {
+        return -1;
+    }
+    for (int i = 0; i < 90; i++) {
+        s_payload[1000 + i] = dibits[sync_end - 89 + i] & 3;
+        s_soft[1000 + i].reliability = reliab[sync_end - 89 + i];
+    }
+    s_state->dmr_payload_buf = s_payload;
+    s_state->dmr_payload_p = s_payload + 1090;
+    s_state->dmr_soft_buf = s_soft;
+    s_state->dmr_soft_p = s_soft + 1090;
+    g.dibits = dibits, g.reliab = reliab, g.n = n, g.pos = sync_end + 1;
+    g.rec = NULL;
+    v.frames = frames96, v.at = frame_pos, v.max = max_frames, v.n = 0;
+    fflush(stderr);
+    const int saved = dup(2);
+    FILE* devnull = fopen("/dev/null", "w");
+    if (devnull) {
+        dup2(fileno(devnull), 2);
+    }
+    dmrBSBootstrap(s_opts, s_state);
+    fflush(stderr);
+    if (devnull) {
+        dup2(saved, 2);
+        fclose(devnull);
+    }
+    close(saved);
+    if (consumed) {
+        *consumed = g.pos - (sync_end + 1);
+    }
+    v.frames = NULL;
+    return v.n;
+}
+
 int
 ref_dmr_burst_size(void) {
     return (int)sizeof(ref_dmr_burst);

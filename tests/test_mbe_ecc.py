@@ -278,3 +278,98 @@ def test_gpu_imbe_decode_from_voice_records(gpu):
         for v in range(9):
             wd, w0, wt = _oracle_imbe(L, fr[k, v])
             assert np.array_equal(d[k, v], wd) and c0[k, v] == w0 and tot[k, v] == wt, (k, v)
+
+
+# ---- the voice burst cutter against the UNMODIFIED dmrBSBootstrap() / dmrBS() (oracle/ref_shim_dmr.c) ----
+
+def _ref_dmr_voice():
+    import _harness as HH
+
+    if not os.path.exists(os.path.join(HH.REF_DIR, "libdsdneo_ref_dmr.so")):
+        return None
+    R = HH.ref_dmr()
+    if not hasattr(R, "ref_dmr_voice_run"):
+        return None
+    R.ref_dmr_voice_run.argtypes = [u8p, u8p, C.c_long, C.c_long, u8p, C.POINTER(C.c_long), C.c_int, C.POINTER(C.c_long)]
+    R.ref_dmr_voice_run.restype = C.c_int
+    return R
+
+
+def _qr_16_7_6_encode(data7):
+    O = H.oracle_fec()
+    for par in range(512):
+        w = np.array(list(data7) + [(par >> (8 - i)) & 1 for i in range(9)], np.uint8)
+        t = w.copy()
+        if O.oracle_qr_16_7_6_decode(t.ctypes.data_as(u8p)) and np.array_equal(t, w):
+            return w
+    raise AssertionError("no QR(16,7,6) codeword")
+
+
+def _bs_voice_stream(rng, n_super=3, cc=5):
+    """BS stream in dibits: bursts alternate slot 0 / slot 1, both slots carry voice superframes A..F: A has the voice sync,
+    B..F a valid EMB (colour code, PI, LCSS under QR(16,7,6)) around 32 arbitrary embedded-signalling bits."""
+    L = _o()
+    m = np.array([[int(x) for x in e] for e in re.findall(r"\{(\d+),\s*(\d+),\s*(\d+),\s*(\d+)\}",
+                  open(REF_MAP).read().split("dsd_ambe_2450_dibit_map[DSD_AMBE_2450_DIBITS] = {")[1])][:36])
+    emb = [_qr_16_7_6_encode([(cc >> 3) & 1, (cc >> 2) & 1, (cc >> 1) & 1, cc & 1, 0, (l >> 1) & 1, l & 1]) for l in range(4)]
+    parts, sent = [rng.integers(0, 4, 30)], []
+    for b in range(12 * n_super):
+        slot, vc = b % 2, (b // 2) % 6
+        cach = np.zeros(24, np.uint8)
+        cach[:7] = H.hamming_7_4_encode_bruteforce((1, slot, 0, 0))
+        cach[7:] = rng.integers(0, 2, 17)
+        tx = np.array([cach[H.DMR_CACH_INTERLEAVE[i]] for i in range(24)], np.uint8)
+        dib = np.zeros(144, np.int64)
+        dib[:12] = (tx[0::2] << 1) | tx[1::2]
+        frames = rng.integers(0, 2, (3, 49)).astype(np.uint8)
+        frs = [ambe_encode(L, d) for d in frames]
+        for f, off, cnt, m0 in [(0, 12, 36, 0), (1, 48, 18, 0), (1, 90, 18, 18), (2, 108, 36, 0)]:
+            for i in range(cnt):
+                hr, hc, lr, lc = m[m0 + i]
+                dib[off + i] = (int(frs[f][hr, hc]) << 1) | int(frs[f][lr, lc])
+        if vc == 0:
+            dib[66:90] = [int(c) for c in "131111333113313313113313"]
+        else:
+            e = emb[int(rng.integers(0, 4))]
+            bits = np.concatenate([e[:8], rng.integers(0, 2, 32).astype(np.uint8), e[8:]])
+            dib[66:90] = (bits[0::2] << 1) | bits[1::2]
+        parts.append(dib)
+        sent.append(frs)
+    return np.concatenate(parts).astype(np.uint8), sent
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MAP), reason="reference tree not present")
+def test_voice_cutter_pinned_to_unmodified_dmrbs():
+    """Every ambe_fr[4][24] the unmodified dmrBSBootstrap() + dmrBS() loop hands to processMbeFrame on a replayed BS voice stream
+    (its colour-code confidence gate opens after a few valid EMBs) equals the oracle cutter's frame for the same burst."""
+    R = _ref_dmr_voice()
+    if R is None:
+        pytest.skip("oracle/_ref/libdsdneo_ref_dmr.so not built")
+    L = _o()
+    rng = np.random.default_rng(8)
+    for inverted in (0, 1):
+        dib, sent = _bs_voice_stream(rng)
+        stream = dib.copy()
+        sync_end = 30 + 89
+        if inverted:
+            stream[:sync_end + 1] ^= 2  # the hunt's buffer holds the raw dibits; the reference un-inverts the 90 it takes from it
+        rel = np.full(stream.size, 200, np.uint8)
+        R.ref_dmr_reset(inverted)
+        frames = np.zeros((400, 96), np.uint8)
+        at = (C.c_long * 400)()
+        consumed = C.c_long(0)
+        n_calls = R.ref_dmr_voice_run(stream.ctypes.data_as(u8p), rel.ctypes.data_as(u8p), stream.size, sync_end,
+                                      frames.ctypes.data_as(u8p), at, 400, C.byref(consumed))
+        assert n_calls >= 3 * 12, n_calls
+        seen = set()
+        for k in range(0, min(n_calls, 400), 3):
+            assert at[k] == at[k + 1] == at[k + 2] and (at[k] - 30) % 144 == 0
+            j = (at[k] - 30) // 144 - 1  # the burst that ended at this stream position
+            cach, fr, sync = np.zeros(24, np.uint8), np.zeros((3, 4, 24), np.uint8), np.zeros(48, np.uint8)
+            start = 30 + 144 * j
+            L.oracle_dmr_voice_cut(np.ascontiguousarray(stream[start:start + 144]).ctypes.data_as(u8p), int(inverted and j == 0),
+                                   cach.ctypes.data_as(u8p), fr.ctypes.data_as(u8p), sync.ctypes.data_as(u8p))
+            assert np.array_equal(frames[k:k + 3].reshape(3, 4, 24), fr), (inverted, j, k)
+            assert np.array_equal(fr, np.stack(sent[j])), (inverted, j)  # and it is what was transmitted
+            seen.add(int(j))
+        assert len(seen) >= 12 and {0, 1} & seen or len(seen) >= 12
