@@ -319,11 +319,11 @@ dft_small(float2 (&a)[8]) {
 
 /* first pass of the in-place DIF transform: radix RHO over the whole row (S = N).  A thread keeps one butterfly
  * column (its twiddles stay in registers) and walks the rows of the chunk. */
-template <int RHO>
+template <int RHO, int NT>
 __device__ __forceinline__ void
 pfbn_first_pass(float2* X, const PfbNParams& p, int pitchT) {
     const int sub = p.N / RHO;
-    const int U = min(sub, (int)blockDim.x), rows_par = blockDim.x / U;
+    const int U = min(sub, NT), rows_par = NT / U;
     for (int j = threadIdx.x % U; j < sub; j += U) {
         float2 tw[RHO];
 #pragma unroll
@@ -354,8 +354,8 @@ pfbn_first_pass(float2* X, const PfbNParams& p, int pitchT) {
 
 /* SC = output times per register window (4 or 8): the T - 1 + SC samples of one branch are requested together, then
  * filtered out of registers. */
-template <int T, bool CU8, int SC>
-__global__ void __launch_bounds__(512, 1)
+template <int T, bool CU8, int SC, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 pfbn_kernel(const PfbNParams p) {
     extern __shared__ __align__(16) unsigned char pfb_smem[];
     float2* X = reinterpret_cast<float2*>(pfb_smem); /* [C][pitchT], element n of a row at pad16(n) */
@@ -366,7 +366,7 @@ pfbn_kernel(const PfbNParams p) {
 
     /* position -> bin: the digits of pos (most significant first: radix rho, then 16s) are the bin's digits, least
      * significant first */
-    for (int pos = threadIdx.x; pos < N; pos += blockDim.x) {
+    for (int pos = threadIdx.x; pos < N; pos += NT) {
         int rem = pos, bin = 0, mul = 1, size = N;
         if (p.rho > 1) {
             size = N / p.rho;
@@ -385,6 +385,26 @@ pfbn_kernel(const PfbNParams p) {
     }
     __syncthreads();
 
+    /* cu8 pair path: every thread stages the window of its NEXT (task, branch) step with 4-byte cp.async copies into its own
+     * column of stage[2][T-1+SC][blockDim] while it filters the current one (no cross-thread sharing, so no barrier: only
+     * cp.async.wait_group); the first step of a chunk is requested before the previous chunk's transform and store */
+    constexpr bool kStaged = CU8 && (T <= 8);
+    unsigned* stage = reinterpret_cast<unsigned*>(pfb_smem + (((size_t)C * pitchT * sizeof(float2) + (size_t)N * 2 + 15) & ~(size_t)15));
+    unsigned qi = 0; /* steps taken by this thread: stage buffer = qi & 1 */
+    auto stage_window = [&](long n0s, int nvs, int task, int j, unsigned buf) {
+        const int s = (task >> (p.lgN - 1)) * SC, np = (task & ((N >> 1) - 1)) * 2;
+        if (!((n0s + s >= T - 1) && (s + SC <= nvs))) {
+            return; /* start-up / ragged windows are read directly */
+        }
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + (n0s + s - (T - 1)) * (long)M + np + j * N;
+        unsigned d32 = (unsigned)__cvta_generic_to_shared(stage + (size_t)buf * (T - 1 + SC) * NT + threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < T - 1 + SC; i++) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + (size_t)i * M) : "memory");
+            d32 += NT * 4;
+        }
+    };
+
     const long chunk0 = (long)blockIdx.x * p.chunks_per_cta;
     for (int c = 0; c < p.chunks_per_cta; c++) {
         const long n0 = (chunk0 + c) * C;
@@ -392,6 +412,8 @@ pfbn_kernel(const PfbNParams p) {
             break;
         }
         const int nv = (int)min((long)C, p.n_out - n0);
+        const bool more = (c + 1 < p.chunks_per_cta) && (n0 + C < p.n_out);
+        const int nv_next = more ? (int)min((long)C, p.n_out - (n0 + C)) : 0;
 
         /* ---- branch FIRs + fold: a task = (fold index n', window s); the R branches of n' accumulate in place.
          * cu8 input is filtered as raw byte values (exact in f32); the widening (u - 127.5) / 127.5 of
@@ -400,7 +422,14 @@ pfbn_kernel(const PfbNParams p) {
         const int n_win = (C + SC - 1) / SC;
         if constexpr (T <= 8) {
             /* two adjacent branches per thread: one 4-byte (cu8) / 16-byte (cf32) request feeds both windows */
-            for (int task = threadIdx.x; task < (N >> 1) * n_win; task += blockDim.x) {
+            const int n_tasks = (N >> 1) * n_win;
+            if (kStaged && c == 0) {
+                if ((int)threadIdx.x < n_tasks) {
+                    stage_window(n0, nv, threadIdx.x, 0, qi & 1u);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            for (int task = threadIdx.x; task < n_tasks; task += NT) {
                 const int s = (task >> (p.lgN - 1)) * SC, np = (task & ((N >> 1) - 1)) * 2;
                 float2 wMa = make_float2(1.0f, 0.0f), wMb = wMa;
                 if (p.r0) {
@@ -415,6 +444,17 @@ pfbn_kernel(const PfbNParams p) {
                 const long first = (n0 + s - (T - 1)) * (long)M;
                 for (int j = 0; j < R; j++) {
                     const int b = np + j * N;
+                    if (kStaged) {
+                        /* request the next step's window, then wait for this step's */
+                        if (j + 1 < R) {
+                            stage_window(n0, nv, task, j + 1, (qi + 1u) & 1u);
+                        } else if (task + NT < n_tasks) {
+                            stage_window(n0, nv, task + NT, 0, (qi + 1u) & 1u);
+                        } else if (more) {
+                            stage_window(n0 + C, nv_next, threadIdx.x, 0, (qi + 1u) & 1u);
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
                     float2 ga[T], gb[T];
 #pragma unroll
                     for (int q = 0; q < T; q++) {
@@ -422,92 +462,131 @@ pfbn_kernel(const PfbNParams p) {
                         ga[q] = make_float2(t.y, t.y); /* branch b:     proto[q M + M-1-b] */
                         gb[q] = make_float2(t.x, t.x); /* branch b + 1: proto[q M + M-2-b] */
                     }
-                    float2 xa[T - 1 + SC], xb[T - 1 + SC];
-                    if (interior) {
+                    const float2 wa = cmul(p.wR[j], wMa), wb = cmul(p.wR[j], wMb);
+                    float2 va[SC], vb[SC];
+                    {
+                        float2 va0 = make_float2(0.0f, 0.0f), vb0 = va0;
                         if (CU8) {
-                            const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + first;
+                            const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + b));
+                            va0 = make_float2(bias.x, bias.x);
+                            vb0 = make_float2(bias.y, bias.y);
+                        }
 #pragma unroll
-                            for (int i = 0; i < T - 1 + SC; i++) {
-                                const unsigned raw = __ldg(reinterpret_cast<const unsigned*>(src + (b + i * M)));
-                                xa[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
+                        for (int o = 0; o < SC; o++) {
+                            va[o] = va0;
+                            vb[o] = vb0;
+                        }
+                    }
+                    if (kStaged) {
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    }
+                    if (kStaged && interior) {
+                        /* stream the staged rows through the accumulators: row i feeds outputs i-(T-1) .. i with taps
+                         * T-1 .. 0 (every output sums its taps from the oldest sample to the newest, as the direct path) */
+                        const unsigned* mine = stage + (size_t)(qi & 1u) * (T - 1 + SC) * NT + threadIdx.x;
+#pragma unroll
+                        for (int i = 0; i < T - 1 + SC; i++) {
+                            const unsigned raw = mine[i * NT];
+                            float2 xa = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
                                                     __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7441)));
-                                xb[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7442)),
+                            float2 xb = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7442)),
                                                     __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7443)));
-                            }
+                            xa = __fadd2_rn(xa, make_float2(-8388608.0f, -8388608.0f));
+                            xb = __fadd2_rn(xb, make_float2(-8388608.0f, -8388608.0f));
 #pragma unroll
-                            for (int i = 0; i < T - 1 + SC; i++) {
-                                xa[i] = __fadd2_rn(xa[i], make_float2(-8388608.0f, -8388608.0f));
-                                xb[i] = __fadd2_rn(xb[i], make_float2(-8388608.0f, -8388608.0f));
-                            }
-                        } else {
-                            const float2* src = reinterpret_cast<const float2*>(p.in) + first;
-#pragma unroll
-                            for (int i = 0; i < T - 1 + SC; i++) {
-                                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (b + i * M)));
-                                xa[i] = make_float2(v.x, v.y);
-                                xb[i] = make_float2(v.z, v.w);
+                            for (int o = 0; o < SC; o++) {
+                                const int q = T - 1 + o - i;
+                                if (q >= 0 && q < T) {
+                                    va[o] = __ffma2_rn(ga[q], xa, va[o]);
+                                    vb[o] = __ffma2_rn(gb[q], xb, vb[o]);
+                                }
                             }
                         }
                     } else {
+                        float2 xa[T - 1 + SC], xb[T - 1 + SC];
+                        if (interior) {
+                            if (CU8) {
+                                const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + first;
 #pragma unroll
-                        for (int i = 0; i < T - 1 + SC; i++) {
-                            const long blk = n0 + s + i - (T - 1);
-                            float2 va = make_float2(0.0f, 0.0f), vb = va;
-                            if (blk < 0) {
-                                va = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
-                                vb = p.hist[(long)(T - 1 + blk) * M + b + 1];
-                                if (CU8) {
-                                    va = make_float2(fmaf(va.x, 127.5f, 127.5f), fmaf(va.y, 127.5f, 127.5f));
-                                    vb = make_float2(fmaf(vb.x, 127.5f, 127.5f), fmaf(vb.y, 127.5f, 127.5f));
+                                for (int i = 0; i < T - 1 + SC; i++) {
+                                    const unsigned raw = __ldg(reinterpret_cast<const unsigned*>(src + (b + i * M)));
+                                    xa[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
+                                                        __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7441)));
+                                    xb[i] = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7442)),
+                                                        __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7443)));
                                 }
-                            } else if (blk < p.n_out) {
-                                if (CU8) {
-                                    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uchar2*>(p.in) + blk * M + b));
-                                    va = make_float2((float)u.x, (float)u.y);
-                                    vb = make_float2((float)u.z, (float)u.w);
-                                } else {
-                                    const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.in) + blk * M + b));
-                                    va = make_float2(v.x, v.y);
-                                    vb = make_float2(v.z, v.w);
+#pragma unroll
+                                for (int i = 0; i < T - 1 + SC; i++) {
+                                    xa[i] = __fadd2_rn(xa[i], make_float2(-8388608.0f, -8388608.0f));
+                                    xb[i] = __fadd2_rn(xb[i], make_float2(-8388608.0f, -8388608.0f));
+                                }
+                            } else {
+                                const float2* src = reinterpret_cast<const float2*>(p.in) + first;
+#pragma unroll
+                                for (int i = 0; i < T - 1 + SC; i++) {
+                                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (b + i * M)));
+                                    xa[i] = make_float2(v.x, v.y);
+                                    xb[i] = make_float2(v.z, v.w);
                                 }
                             }
-                            xa[i] = va;
-                            xb[i] = vb;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < T - 1 + SC; i++) {
+                                const long blk = n0 + s + i - (T - 1);
+                                float2 xva = make_float2(0.0f, 0.0f), xvb = xva;
+                                if (blk < 0) {
+                                    xva = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
+                                    xvb = p.hist[(long)(T - 1 + blk) * M + b + 1];
+                                    if (CU8) {
+                                        xva = make_float2(fmaf(xva.x, 127.5f, 127.5f), fmaf(xva.y, 127.5f, 127.5f));
+                                        xvb = make_float2(fmaf(xvb.x, 127.5f, 127.5f), fmaf(xvb.y, 127.5f, 127.5f));
+                                    }
+                                } else if (blk < p.n_out) {
+                                    if (CU8) {
+                                        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uchar2*>(p.in) + blk * M + b));
+                                        xva = make_float2((float)u.x, (float)u.y);
+                                        xvb = make_float2((float)u.z, (float)u.w);
+                                    } else {
+                                        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(p.in) + blk * M + b));
+                                        xva = make_float2(v.x, v.y);
+                                        xvb = make_float2(v.z, v.w);
+                                    }
+                                }
+                                xa[i] = xva;
+                                xb[i] = xvb;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 0; o < SC; o++) {
+#pragma unroll
+                            for (int q = T - 1; q >= 0; q--) {
+                                va[o] = __ffma2_rn(ga[q], xa[T - 1 + o - q], va[o]);
+                                vb[o] = __ffma2_rn(gb[q], xb[T - 1 + o - q], vb[o]);
+                            }
                         }
                     }
-                    const float2 wa = cmul(p.wR[j], wMa), wb = cmul(p.wR[j], wMb);
-                    float2 va0 = make_float2(0.0f, 0.0f), vb0 = va0;
-                    if (CU8) {
-                        const float2 bias = __ldg(reinterpret_cast<const float2*>(p.bias + b));
-                        va0 = make_float2(bias.x, bias.x);
-                        vb0 = make_float2(bias.y, bias.y);
-                    }
 #pragma unroll
-                    for (int i = 0; i < SC; i++) {
-                        float2 va = va0, vb = vb0;
-#pragma unroll
-                        for (int q = 0; q < T; q++) {
-                            va = __ffma2_rn(ga[q], xa[T - 1 + i - q], va);
-                            vb = __ffma2_rn(gb[q], xb[T - 1 + i - q], vb);
-                        }
-                        if (s + i < C) {
-                            float2* dst = dst0 + i * pitchT;
+                    for (int o = 0; o < SC; o++) {
+                        if (s + o < C) {
+                            float2* dst = dst0 + o * pitchT;
+                            float2 ra = va[o], rb = vb[o];
                             if (R > 1) {
-                                va = cmul(va, wa);
-                                vb = cmul(vb, wb);
+                                ra = cmul(ra, wa);
+                                rb = cmul(rb, wb);
                                 if (j > 0) {
-                                    va = __fadd2_rn(va, dst[0]);
-                                    vb = __fadd2_rn(vb, dst[1]);
+                                    ra = __fadd2_rn(ra, dst[0]);
+                                    rb = __fadd2_rn(rb, dst[1]);
                                 }
                             }
-                            dst[0] = va;
-                            dst[1] = vb;
+                            dst[0] = ra;
+                            dst[1] = rb;
                         }
                     }
+                    qi++;
                 }
             }
         } else {
-        for (int task = threadIdx.x; task < N * n_win; task += blockDim.x) {
+        for (int task = threadIdx.x; task < N * n_win; task += NT) {
             const int s = (task >> p.lgN) * SC, np = task & (N - 1);
             float2 wM = make_float2(1.0f, 0.0f);
             if (p.r0) {
@@ -599,14 +678,14 @@ pfbn_kernel(const PfbNParams p) {
 
         /* ---- in-place decimation-in-frequency transform of the C rows ---- */
         if (p.rho == 2) {
-            pfbn_first_pass<2>(X, p, pitchT);
+            pfbn_first_pass<2, NT>(X, p, pitchT);
         } else if (p.rho == 4) {
-            pfbn_first_pass<4>(X, p, pitchT);
+            pfbn_first_pass<4, NT>(X, p, pitchT);
         } else if (p.rho == 8) {
-            pfbn_first_pass<8>(X, p, pitchT);
+            pfbn_first_pass<8, NT>(X, p, pitchT);
         }
         {
-            const int U = min(n16, (int)blockDim.x), rows_par = blockDim.x / U;
+            const int U = min(n16, NT), rows_par = NT / U;
             for (int S = N / p.rho; S >= 16; S >>= 4) {
                 const int sub = S >> 4; /* butterflies per block of size S */
                 const int tw_step = N / S;
@@ -649,7 +728,7 @@ pfbn_kernel(const PfbNParams p) {
         /* ---- transposed store: C consecutive lanes = C consecutive times of one channel ---- */
         {
             const int i = threadIdx.x & (C - 1); /* blockDim is a multiple of C */
-            const int pstep = blockDim.x >> p.lgC;
+            const int pstep = NT >> p.lgC;
             float2* dst = p.out + n0 + i;
             const float2* src = X + i * pitchT;
             if (i < nv) {
@@ -721,25 +800,31 @@ pfbn_chunk_times(int N) {
     return c > 16 ? 16 : (c < 2 ? 2 : c);
 }
 
-template <int T, bool CU8, int SC>
+template <int T, bool CU8, int SC, int NT>
 static int
-launch_pfbn(const PfbNParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
+launch_pfbn_nt(const PfbNParams& p, int grid, size_t smem, cudaStream_t s) {
     static bool attr_done[64] = {};
     int dev = 0;
     DSDNEO_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        DSDNEO_CUDA(cudaFuncSetAttribute(pfbn_kernel<T, CU8, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+        DSDNEO_CUDA(cudaFuncSetAttribute(pfbn_kernel<T, CU8, SC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         if (dev >= 0 && dev < 64) {
             attr_done[dev] = true;
         }
     }
     {
         KernelTimer kt("pfbn_kernel", s);
-        pfbn_kernel<T, CU8, SC><<<grid, threads, smem, s>>>(p);
+        pfbn_kernel<T, CU8, SC, NT><<<grid, NT, smem, s>>>(p);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;
+}
+
+template <int T, bool CU8, int SC>
+static int
+launch_pfbn(const PfbNParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
+    return threads == 256 ? launch_pfbn_nt<T, CU8, SC, 256>(p, grid, smem, s) : launch_pfbn_nt<T, CU8, SC, 512>(p, grid, smem, s);
 }
 
 /* W_N table for bin stride R = 1 << lg (N = M >> lg), built in float64 on first use */
@@ -1053,8 +1138,11 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
             p.wR[j] = make_float2((float)cos(a), (float)sin(a));
         }
         const int pitchT = p.N + p.N / 16 + 16 / p.C;
-        const size_t smem = (size_t)p.C * pitchT * sizeof(float2) + (size_t)p.N * sizeof(unsigned short);
         const int threads = (p.C * p.N <= 8192) ? 256 : 512;
+        size_t smem = (((size_t)p.C * pitchT * sizeof(float2) + (size_t)p.N * sizeof(unsigned short)) + 15) & ~(size_t)15;
+        if (c->cu8 && c->T <= 8) {
+            smem += (size_t)2 * (c->T - 1 + (p.C >= 8 ? 8 : 4)) * threads * sizeof(unsigned); /* per-thread window staging */
+        }
         const int per_sm = (p.C * p.N <= 8192) ? 2 : 1;
         const long n_chunks = (n_out + p.C - 1) / p.C;
         long cpc = (n_chunks + (long)sms * per_sm - 1) / ((long)sms * per_sm);
