@@ -919,7 +919,8 @@ def run_c3_b200_arm(args):
         "cpu_baseline": cpu_baseline,
         "step_detail": {"call": "dsdneo_b200_p25p1_rx_submit + _wait (device buffers) / _submit_host + _wait_host (host buffers)",
                         "symbols_per_step": n_sym, "frames_per_step": n_frames, "frames_decoded_ok": n_good,
-                        "imbe_frames_per_step": 9 * n_voice, "host_numa_binding": ("node %s" % numa_node) if numa_node is not None else "none",
+                        "imbe_frames_per_step": 9 * n_voice, "host_numa_binding": ("node %s" % numa_node) if numa_node is not None else
+                        ("none (one rank)" if world == 1 else "none (the host exposes no NUMA node for the GPU)"),
                         "e2e_frames_last_step": int(fr_h.size), "e2e_voice_last_step": int(vo_h.size)},
     }
     print(json.dumps(line))
