@@ -397,11 +397,12 @@ pfbn_kernel(const PfbNParams p) {
             return; /* start-up / ragged windows are read directly */
         }
         const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + (n0s + s - (T - 1)) * (long)M + np + j * N;
-        unsigned d32 = (unsigned)__cvta_generic_to_shared(stage + (size_t)buf * (T - 1 + SC) * NT + threadIdx.x);
+        const unsigned d32 = (unsigned)__cvta_generic_to_shared(stage + (size_t)buf * (T - 1 + SC) * NT + threadIdx.x);
 #pragma unroll
         for (int i = 0; i < T - 1 + SC; i++) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(src + (size_t)i * M) : "memory");
-            d32 += NT * 4;
+            /* shared address = base + constant; the global pointer advances by one row (a 64-bit add) per copy */
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + i * NT * 4), "l"(src) : "memory");
+            src += M;
         }
     };
 
