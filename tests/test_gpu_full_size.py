@@ -184,3 +184,36 @@ def test_c5_channel_count_cqpsk_streaming_and_spot_parity(gpu):
         assert np.array_equal(c1[0][c], want_counts) and H.bits_equal(s1[0][c, :n], want_sym)
         d, _, _, _ = H.oracle_cqpsk_slicer_run(want_sym)
         assert np.array_equal(d1[0][c, :n], d)
+
+
+def test_c5_size_channelizer_classes_agree_with_the_unpruned_transform(gpu):
+    """C5 size: one 8192-channel cu8 tile (6144 rows = 50.3 M wideband samples).  Two of the eight per-GPU channel classes equal
+    the unpruned 8192-point transform within the stage's tolerance, every tone sits in its own channel, and streaming the tile
+    in three launches is bit-identical to one launch."""
+    import torch
+
+    Mx, R, T, n_out = 8192, 8, 8, 6144
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((n_out * Mx, 2), device="cuda", generator=g) * 0.08
+    t = torch.arange(n_out * Mx, device="cuda", dtype=torch.float64)
+    tones = [11, 1234, 4096 + 77, 8190, 2 * 8 + 5, 777 * 8 + 5]
+    for k in tones:
+        ph = (2 * torch.pi * ((k / Mx) * t % 1.0)).to(torch.float32)
+        x[:, 0] += 0.12 * torch.cos(ph)
+        x[:, 1] += 0.12 * torch.sin(ph)
+    u8 = torch.clamp(torch.round(x * 127.5 + 127.5), 0, 255).to(torch.uint8).contiguous()
+    del x, t
+    full = gpu.Channelizer(Mx, T, True).channelize(u8)
+    scale = float(full.abs().max())
+    for r0 in (5, 0):
+        cz = gpu.Channelizer(Mx, T, True)
+        y = cz.channelize_bins(u8, R, r0)
+        assert float((y - full[r0::R]).abs().max()) <= 2e-5 * scale + 1e-7
+        cz2 = gpu.Channelizer(Mx, T, True)
+        parts = [cz2.channelize_bins(u8[a * Mx:b * Mx], R, r0) for a, b in ((0, 1000), (1000, 1003), (1003, n_out))]
+        assert _crc(torch.cat(parts, dim=1)) == _crc(y)
+        p = (y[..., 0] ** 2 + y[..., 1] ** 2).mean(dim=1)
+        med = float(p.median())
+        for k in tones:
+            if k % R == r0:
+                assert float(p[k // R]) > 30 * med, (k, float(p[k // R]), med)
