@@ -291,6 +291,13 @@ pad16(int i) {
     return i + (i >> 4);
 }
 
+/* a carried history sample (kept widened) back in the byte domain: (k - 127.5) / 127.5 re-expands to exactly k; the reset
+ * state 0.0 (never a widened byte: k - 127.5 is a half-integer) stays 127.5 */
+__device__ __forceinline__ float
+hist_byte(float x) {
+    return x == 0.0f ? 127.5f : rintf(fmaf(x, 127.5f, 127.5f));
+}
+
 template <int RHO>
 __device__ __forceinline__ void
 dft_small(float2 (&a)[8]) {
@@ -539,8 +546,8 @@ pfbn_kernel(const PfbNParams p) {
                                     xva = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
                                     xvb = p.hist[(long)(T - 1 + blk) * M + b + 1];
                                     if (CU8) {
-                                        xva = make_float2(fmaf(xva.x, 127.5f, 127.5f), fmaf(xva.y, 127.5f, 127.5f));
-                                        xvb = make_float2(fmaf(xvb.x, 127.5f, 127.5f), fmaf(xvb.y, 127.5f, 127.5f));
+                                        xva = make_float2(hist_byte(xva.x), hist_byte(xva.y));
+                                        xvb = make_float2(hist_byte(xvb.x), hist_byte(xvb.y));
                                     }
                                 } else if (blk < p.n_out) {
                                     if (CU8) {
@@ -635,7 +642,7 @@ pfbn_kernel(const PfbNParams p) {
                         if (blk < 0) {
                             v = p.hist[(long)(T - 1 + blk) * M + b]; /* kept widened */
                             if (CU8) {
-                                v = make_float2(fmaf(v.x, 127.5f, 127.5f), fmaf(v.y, 127.5f, 127.5f));
+                                v = make_float2(hist_byte(v.x), hist_byte(v.y));
                             }
                         } else if (blk < p.n_out) {
                             if (CU8) {
