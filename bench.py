@@ -1038,10 +1038,11 @@ def run_c3_one_stream(args):
 
     # ---- e2e: every rank feeds 1/N of each tile from pinned host memory; all-gather; records + dibits back to the host ----
     e2e_steps = max(3, min(args.steps, 60))
-    DEPTH = 3
+    DEPTH = 5
     outs = [sr.rx.alloc_device_out(dev) for _ in range(DEPTH)]
     h_outs = [sr.rx.alloc_host_out() for _ in range(DEPTH)]
     d2h_stream = torch.cuda.Stream(device=dev)
+    d2h_records = torch.cuda.Stream(device=dev)
     done = [None] * DEPTH
     d2h_bytes = [0]
 
@@ -1049,10 +1050,10 @@ def run_c3_one_stream(args):
         o, h = outs[k % DEPTH], h_outs[k % DEPTH]
         done[k % DEPTH].synchronize()
         nf, nv = int(h["totals"][0]), int(h["totals"][1])
-        with torch.cuda.stream(d2h_stream):
+        with torch.cuda.stream(d2h_records):  # its own stream: the other copy stream is already waiting for a later tile
             h["frames"][:nf].copy_(o["frames"][:nf], non_blocking=True)
             h["voices"][:nv].copy_(o["voices"][:nv], non_blocking=True)
-        d2h_stream.synchronize()
+        d2h_records.synchronize()
         d2h_bytes[0] += nf * 128 + nv * 1944
         return nf + int(h["dibits"][0, 0])
 
@@ -1065,13 +1066,8 @@ def run_c3_one_stream(args):
             if k + 1 < n:
                 sr.distribute(h_slices[(seq + 1) % C3_TILES], "allgather")
             o, h = outs[k % DEPTH], h_outs[k % DEPTH]
-            if k >= DEPTH:
-                pass
             t = sr.submit(o, stream)
-            sr.rx.wait(t, stream)
-            evk = torch.cuda.Event()
-            evk.record(stream)
-            d2h_stream.wait_event(evk)
+            sr.rx.wait(t, d2h_stream)  # only the copy stream waits for the tile: the next tile's kernels follow at once
             with torch.cuda.stream(d2h_stream):
                 h["totals"].copy_(o["totals"], non_blocking=True)
                 h["counts"].copy_(o["counts"], non_blocking=True)
