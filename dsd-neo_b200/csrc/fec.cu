@@ -2437,7 +2437,7 @@ __constant__ uint8_t c_imbe_lo[72] = {44, 88, 116, 21, 65,  101, 42, 86, 152, 19
 __constant__ short c_ldu_imbe_off[9] = {0, 72, 164, 256, 348, 440, 532, 624, 712};
 __constant__ short c_ldu_word_off[6] = {144, 236, 328, 420, 512, 604};
 constexpr int kLduLsdOff = 696;
-constexpr int kLduPayload = 784, kHduPayload = 329, kTsbkBlock = 98;
+constexpr int kLduPayload = 784, kHduPayload = 329, kTsbkBlock = 98, kTdulcPayload = 154; /* TDULC: 12 x 12 dibits + 10 nulls */
 
 struct P25Stream {
     const uint8_t* d;
@@ -2519,7 +2519,8 @@ p25p1_frame_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const P25Fram
         }
     }
     dsdneo_b200_p25p1_frame* f = p.frames + r;
-    const int payload = (duid == 0x5 || duid == 0xA) ? kLduPayload : (duid == 0x0 ? kHduPayload : (duid == 0x7 ? 3 * kTsbkBlock : 0));
+    const int payload = (duid == 0x5 || duid == 0xA) ? kLduPayload
+                        : (duid == 0x0 ? kHduPayload : (duid == 0x7 ? 3 * kTsbkBlock : (duid == 0xF ? kTdulcPayload : 0)));
     /* a TSDU is read block by block and ends at the block flagged last: only its first block must fit up front */
     const int must_fit = duid == 0x7 ? kTsbkBlock : payload;
     const bool fits = st.start >= 0 && (must_fit == 0 || st.start + p25p1_payload_offset(57, must_fit - 1) + 1 <= count);
@@ -2665,6 +2666,68 @@ p25p1_frame_decode_kernel(const dsdneo_fec_tables* __restrict__ T, const P25Fram
             }
             f->rs_kind = 1;
             f->rs_status = (uint8_t)p25_rs_frame_decode(T, 36, 20, sym, dr, pr, p.threshold, f->rs_data);
+            f->n_word_soft = (uint8_t)soft_changed;
+        }
+        return;
+    }
+    if (duid == 0xF) { /* ---- TDULC: 12 Golay(24,12) dodeca words, 12 dibits each (p25p1_tdulc.c:75-157,198-238) ---- */
+        if (lane < 12) {
+            const int k = lane; /* air order: data word 5 .. 0, parity word 5 .. 0 */
+            unsigned cw = 0;
+            int rel[24], half_rel[2] = {255, 255};
+            for (int d = 0; d < 12; d++) {
+                int l0, l1;
+                const int dib = st.get(k * 12 + d, l0, l1);
+                /* bit index i of the word (data 0..11, parity 12..23) sits at packed bit i */
+                cw |= (unsigned)((dib >> 1) & 1) << (2 * d);
+                cw |= (unsigned)(dib & 1) << (2 * d + 1);
+                rel[2 * d] = clamp_rel(l0);
+                rel[2 * d + 1] = clamp_rel(l1);
+                if (d < 6) {
+                    half_rel[d / 3] = min(half_rel[d / 3], min(rel[2 * d], rel[2 * d + 1]));
+                }
+            }
+            unsigned fixed_cw = cw;
+            int errs = 0;
+            const int hard = golay24_hard_word(cw, fixed_cw, errs);
+            unsigned data = hard == 0 ? (fixed_cw & 0xFFFu) : (cw & 0xFFFu);
+            if (hard != 0 || errs > 0) {
+                unsigned sres = 0;
+                int sfx = 0;
+                if (golay24_soft_word(cw, rel, 12, p.hard_override, p.threshold, sres, sfx) == 0) {
+                    soft_changed += hard != 0 ? 1 : 0;
+                    data = sres & 0xFFFu;
+                }
+            }
+            /* swap_hex_words: the dodeca word becomes two hex symbols, bits 6..11 first (reference bit 0 = MSB of a symbol) */
+            int lo = 0, hi = 0;
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                lo = (lo << 1) | (int)((data >> b) & 1u);
+                hi = (hi << 1) | (int)((data >> (6 + b)) & 1u);
+            }
+            const int i = 5 - (k % 6), base = k < 6 ? 0 : 12;
+            s_word[warp][base + 2 * i] = (uint8_t)hi;
+            s_word[warp][base + 2 * i + 1] = (uint8_t)lo;
+            s_wrel[warp][base + 2 * i] = (uint8_t)half_rel[1];
+            s_wrel[warp][base + 2 * i + 1] = (uint8_t)half_rel[0];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            soft_changed += __shfl_xor_sync(0xffffffffu, soft_changed, o);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            uint8_t sym[24], dr[12], pr[12];
+            for (int j = 0; j < 12; j++) {
+                f->rs_in_data[j] = s_word[warp][j];
+                dr[j] = s_wrel[warp][j];
+                sym[12 + j] = s_word[warp][j];
+                f->rs_in_parity[j] = s_word[warp][12 + j];
+                pr[j] = s_wrel[warp][12 + j];
+                sym[j] = s_word[warp][12 + j];
+            }
+            f->rs_kind = 2;
+            f->rs_status = (uint8_t)p25_rs_frame_decode(T, 24, 12, sym, dr, pr, p.threshold, f->rs_data);
             f->n_word_soft = (uint8_t)soft_changed;
         }
         return;

@@ -855,11 +855,15 @@ int dsdneo_b200_p25p1_frame_cut_batch(const uint8_t* d_dibits, size_t dibit_pitc
  *                                                                          reliabilities handed to processMbeFrameSoft), 24
  *                                                                          Hamming(10,6,3) words hard + soft, RS(24,12,13) /
  *                                                                          (24,16,9) hard + ranked erasures, LSD (16,8) x 2
+ *   processTDULC (p25p1_tdulc.c:75-238,284-300)                            12 Golay(24,12) dodeca words hard + soft, each two
+ *                                                                          RS symbols (bits 6..11 first, swap_hex_words),
+ *                                                                          RS(24,12,13) hard + ranked erasures; the link
+ *                                                                          control word is dodeca 5..0 = rs_data[11], [10], ...
  * NID results come from dsdneo_b200_p25p1_nid_decode_batch on the slots of dsdneo_b200_p25p1_frame_cut_batch (slot = channel
  * * max_hits + hit; d_nid_valid = the cutter's nid_valid, may be NULL).  One frame record per hit, ordered by (channel, stream order): record index d_frame_off[channel] + hit;
  * LDUs additionally get a voice record (frame.voice_index).  d_totals = {frames, voice records} written by the call.
  * Hit positions are relative to buffer index region_offset of each channel row; frames that do not fit inside d_counts
- * dibits keep their NID fields and are flagged (reserved[0] = 1).  TDU / TDULC / MPDU payloads are not decoded (NID only).
+ * dibits keep their NID fields and are flagged (reserved[0] = 1).  TDU has no payload; MPDU payloads are not decoded (NID only).
  * Bit-exact with the reference handlers (tests/test_gpu_p25p1_frames.py; golden records from the unmodified handlers).
  */
 typedef struct dsdneo_b200_p25p1_frame {
@@ -872,7 +876,7 @@ typedef struct dsdneo_b200_p25p1_frame {
     uint8_t duid;          /* 0xFF when the NID failed */
     uint8_t n_tsbk;        /* TSDU: blocks read (stops after the block flagged last) */
     uint8_t tsbk_crc_ok;   /* bit b: block b passed crc16_lb_bridge */
-    uint8_t rs_kind;       /* 0 none, 1 RS(36,20,17) HDU, 2 RS(24,12,13) LDU1, 3 RS(24,16,9) LDU2 */
+    uint8_t rs_kind;       /* 0 none, 1 RS(36,20,17) HDU, 2 RS(24,12,13) LDU1 and TDULC, 3 RS(24,16,9) LDU2 */
     uint8_t rs_status;     /* 0 hard decode ok, 1 recovered by ranked erasures, 2 irrecoverable */
     uint8_t lsd_ok;        /* bit k: p25_lsd_fec_16x8_soft accepted LSD word k */
     uint8_t n_word_soft;   /* words whose soft decode changed the outcome (p25_p1_soft_hamming_ok / _golay_ok) */

@@ -7,6 +7,7 @@
  *   processTSBK (1..3 half-rate blocks)  src/protocol/p25/phase1/p25p1_tsbk.c:108-161,1051-1081
  *   processHDU                           src/protocol/p25/phase1/p25p1_hdu.c:54-96,108-210,270-303
  *   processLDU1 / processLDU2            src/protocol/p25/phase1/p25p1_ldu.c:89-222, p25p1_ldu1.c:54-240, p25p1_ldu2.c:54-280
+ *   processTDULC                         src/protocol/p25/phase1/p25p1_tdulc.c:75-238,284-300
  *   LSD (16,8) cyclic code               src/protocol/p25/p25_lsd.c:27-161
  *   crc16_lb_bridge                      src/protocol/p25/p25_crc.c:11-75
  *
@@ -382,6 +383,81 @@ decode_ldu(cursor* c, oracle_p25p1_frame* f, oracle_p25p1_voice* v, int ldu2, in
     c->pos++; /* trailing status symbol (p25p1_ldu1.c:218-226) */
 }
 
+/* read_and_correct_dodeca_word (p25p1_tdulc.c:75-157): 6 data + 6 parity dibits, Golay(24,12) hard, then the soft decoder on the
+ * raw word when the hard decode failed or corrected anything.  half_rel[h] = dodeca_half_reliability (:159-169): the weakest
+ * clamped |LLR| of data dibits 3h .. 3h+2. */
+static void
+read_golay12_word(cursor* c, int threshold, uint8_t* data12, int* half_rel, int* soft_changed) {
+    uint8_t parity[12], raw[12];
+    int rel[24];
+    half_rel[0] = half_rel[1] = 255;
+    for (int d = 0; d < 12; d++) {
+        int l0, l1;
+        const int dib = next_dibit(c, &l0, &l1);
+        uint8_t* dst = d < 6 ? data12 + 2 * d : parity + 2 * (d - 6);
+        dst[0] = (uint8_t)((dib >> 1) & 1);
+        dst[1] = (uint8_t)(dib & 1);
+        rel[2 * d] = iabs(l0);
+        rel[2 * d + 1] = iabs(l1);
+        if (d < 6) {
+            int* h = &half_rel[d / 3];
+            if (clamp255(iabs(l0)) < *h) {
+                *h = clamp255(iabs(l0));
+            }
+            if (clamp255(iabs(l1)) < *h) {
+                *h = clamp255(iabs(l1));
+            }
+        }
+    }
+    memcpy(raw, data12, 12);
+    int fixed = 0;
+    const int hard = oracle_p25_golay24_decode(12, data12, parity, &fixed);
+    if (hard != 0 || fixed > 0) {
+        uint8_t sd[12];
+        int sfixed = 0;
+        memcpy(sd, raw, 12);
+        if (oracle_p25_golay24_soft(12, sd, parity, rel, 1, threshold, &sfixed) == 0) {
+            if (hard != 0) {
+                (*soft_changed)++;
+            }
+            memcpy(data12, sd, 12);
+        }
+    }
+}
+
+/* processTDULC (p25p1_tdulc.c:198-238,284-300): six data dodeca words 5..0, six parity dodeca words 5..0; swap_hex_words turns
+ * every dodeca word into two hex symbols (bits 6..11 first), RS(24,12,13) hard then ranked erasures, ten null dibits and the
+ * trailing status symbol.  Record: rs_in_* / rs_data hold the 12 + 12 hex symbols in that (swapped) order; the link control
+ * word is dodeca 5..0, i.e. rs_data[11], rs_data[10], rs_data[9] ... read as (2i+1, 2i) pairs. */
+static void
+decode_tdulc(cursor* c, oracle_p25p1_frame* f, int threshold) {
+    uint8_t word[12][12], data_rel[12], par_rel[12];
+    int soft_changed = 0;
+    for (int k = 0; k < 12; k++) { /* air order: data[5] .. data[0], parity[5] .. parity[0] */
+        const int i = 5 - (k % 6);
+        int hr[2];
+        read_golay12_word(c, threshold, word[k], hr, &soft_changed);
+        uint8_t* in = k < 6 ? f->rs_in_data : f->rs_in_parity;
+        uint8_t* rl = k < 6 ? data_rel : par_rel;
+        int hi = 0, lo = 0;
+        for (int b = 0; b < 6; b++) {
+            lo = (lo << 1) | (word[k][b] & 1);      /* bits 0..5 */
+            hi = (hi << 1) | (word[k][6 + b] & 1);  /* bits 6..11 */
+        }
+        in[2 * i] = (uint8_t)hi;
+        in[2 * i + 1] = (uint8_t)lo;
+        rl[2 * i] = (uint8_t)hr[1];
+        rl[2 * i + 1] = (uint8_t)hr[0];
+    }
+    f->n_word_soft = (uint8_t)soft_changed;
+    run_rs(f, 2, 24, 12, data_rel, par_rel, threshold);
+    for (int i = 0; i < 10; i++) { /* read_zeros(20): ten dibits */
+        int l0, l1;
+        (void)next_dibit(c, &l0, &l1);
+    }
+    c->pos++; /* trailing status symbol (p25p1_tdulc.c:249-251) */
+}
+
 static void
 decode_hdu(cursor* c, oracle_p25p1_frame* f, int threshold) {
     uint8_t data_rel[20], par_rel[16];
@@ -490,7 +566,8 @@ oracle_p25p1_decode_frame(const uint8_t* dibits, const int16_t* llr, int count, 
         case 0x5: decode_ldu(&c, f, voice, 0, threshold); break;
         case 0xA: decode_ldu(&c, f, voice, 1, threshold); break;
         case 0x7: decode_tsbk(&c, f); break;
-        default: break; /* TDU / TDULC / MPDU payloads are not decoded here */
+        case 0xF: decode_tdulc(&c, f, threshold); break;
+        default: break; /* TDU has no payload; MPDU payloads are not decoded here */
     }
     if (c.overrun || c.pos > count) {
         return -1;

@@ -980,8 +980,8 @@ def p25_frames_agree(ref, f, v):
                 bad.append("tsbk%d" % b)
             if (ref["tsbk_crc_err"][b] == 0) != bool((f["tsbk_crc_ok"] >> b) & 1):
                 bad.append("tsbk_crc%d" % b)
-    if duid in (0x0, 0x5, 0xA):
-        kind = {0x0: 1, 0x5: 2, 0xA: 3}[duid]
+    if duid in (0x0, 0x5, 0xA, 0xF):
+        kind = {0x0: 1, 0x5: 2, 0xA: 3, 0xF: 2}[duid]  # TDULC: RS(24,12,13) like LDU1, over Golay(24,12) dodeca words
         n_data, n_par = {1: (20, 16), 2: (12, 12), 3: (16, 8)}[kind]
         if int(ref["rs_kind"]) != kind or int(f["rs_kind"]) != kind:
             bad.append("rs_kind")
@@ -1120,6 +1120,52 @@ def p25p1_build_ldu(rng, nac, ldu2=False):
     mask = np.zeros(184, bool)
     mask[IMBE_HI + IMBE_LO] = True
     return p25p1_insert_status(np.concatenate(body)), {"rs_data": dat.astype(np.uint8), "voice": voice * mask, "lsd": lsd, "duid": 0xA if ldu2 else 0x5}
+
+
+_golay12_parity = None
+
+
+def golay_24_12_encode(word12):
+    """12 data bits + the 12 parity bits check_and_fix_golay_24_12 accepts with zero corrections (basis found once by search)."""
+    global _golay12_parity
+    if _golay12_parity is None:
+        O = oracle_fec()
+        basis = []
+        for k in range(12):
+            data = np.zeros(12, np.uint8)
+            data[k] = 1
+            found = None
+            for par in range(4096):
+                p = np.array([(par >> (11 - i)) & 1 for i in range(12)], np.uint8)
+                d = data.copy()
+                fixed = C.c_int(0)
+                # the decoder also accepts a word whose only error sits in a parity bit: a true codeword of the extended Golay
+                # code has a weight divisible by four
+                if (1 + bin(par).count("1")) % 4 == 0 and O.oracle_p25_golay24_decode(12, _ptr(d, u8p), _ptr(p, u8p), C.byref(fixed)) == 0 \
+                        and fixed.value == 0 and np.array_equal(d, data):
+                    found = par
+                    break
+            assert found is not None
+            basis.append(found)
+        _golay12_parity = basis
+    par = 0
+    for k in range(12):
+        if (word12 >> (11 - k)) & 1:
+            par ^= _golay12_parity[k]
+    return [(word12 >> (11 - i)) & 1 for i in range(12)] + [(par >> (11 - i)) & 1 for i in range(12)]
+
+
+def p25p1_build_tdulc(rng, nac):
+    """Terminator with link control: sync + NID(0xF) + 12 Golay(24,12) dodeca words (six data, six parity, each two RS hex
+    symbols with the halves swapped) + ten null dibits."""
+    data = rng.integers(0, 64, 12)
+    par, dat = rs63_shortened_encode(data, 12)
+    out = []
+    for syms in (dat, par):
+        for i in range(5, -1, -1):  # air order: word 5 first; hex 2i = bits 6..11, hex 2i+1 = bits 0..5
+            out.append(_bits_to_dibits(golay_24_12_encode((int(syms[2 * i + 1]) << 6) | int(syms[2 * i]))))
+    body = [np.array(P25P1_SYNC_DIBITS), p25p1_nid_dibits(nac, 0xF)] + out + [np.zeros(10, np.int64)]
+    return p25p1_insert_status(np.concatenate(body)), {"rs_data": dat.astype(np.uint8), "duid": 0xF}
 
 
 def p25p1_build_hdu(rng, nac):

@@ -46,15 +46,15 @@ def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip, coarse):
         parts, pos, at = [rng.integers(0, 4, 30 + c)], [], 30 + c
         nac = int(rng.integers(1, 0xFFE))
         builders = [lambda: H.p25p1_build_hdu(rng, nac)[0], lambda: H.p25p1_build_ldu(rng, nac, False)[0],
-                    lambda: H.p25p1_build_ldu(rng, nac, True)[0],
+                    lambda: H.p25p1_build_ldu(rng, nac, True)[0], lambda: H.p25p1_build_tdulc(rng, nac)[0],
                     lambda: H.p25p1_build_tsdu(rng, nac, int(rng.integers(1, 4)), H._bch_nid_encoder(), valid_crc=c % 3 != 0)[0]]
-        for k in rng.permutation(8):
-            frame, gap = builders[k % 4](), rng.integers(0, 4, int(rng.integers(0, 12)))
+        for k in rng.permutation(10):
+            frame, gap = builders[k % 5](), rng.integers(0, 4, int(rng.integers(0, 12)))
             pos.append(at + 23)
             at += frame.size + gap.size
             parts += [frame, gap]
         # one frame cut short by the end of the stream, one bogus hit in noise
-        frame = builders[c % 4]()
+        frame = builders[c % 5]()
         pos.append(at + 23)
         parts.append(frame[:frame.size // 2])
         tx = np.concatenate(parts).astype(np.uint8)
@@ -91,7 +91,7 @@ def test_frames_equal_the_oracle_on_synthetic_channels(gpu, flip, coarse):
                 kinds[int(of["duid"])] = kinds.get(int(of["duid"]), 0) + 1
             k += 1
     if flip == 0.0:
-        assert all(kinds.get(d, 0) >= 2 * n_ch for d in (0, 5, 7, 10)), kinds
+        assert all(kinds.get(d, 0) >= 2 * n_ch for d in (0, 5, 7, 10, 15)), kinds
 
 
 @pytest.mark.parametrize("name", ["c1_p25p1_c4fm_cc", "c1_p25p1_c4fm_vc"])

@@ -47,7 +47,7 @@ def _compare_stream(d, rel, llr, observed_nac=0, min_frames=1, positions=None):
             continue
         bad = H.p25_frames_agree(ref, f, v)
         assert not bad, (p, bad, int(ref["duid"]), int(ref["nid_status"]))
-        if ref["nid_status"] > 0 and int(ref["duid"]) in (0, 5, 7, 10):
+        if ref["nid_status"] > 0 and int(ref["duid"]) in (0, 5, 7, 10, 15):
             assert n == int(ref["consumed"]), (p, n, int(ref["consumed"]))
         kinds[int(f["duid"])] = kinds.get(int(f["duid"]), 0) + 1
         n_ok += 1
@@ -64,7 +64,7 @@ def test_synthetic_frames_oracle_equals_reference_handlers(flip, coarse):
     for rep in range(3):
         nac = int(rng.integers(1, 0xFFE))
         for build in (lambda: H.p25p1_build_hdu(rng, nac)[0], lambda: H.p25p1_build_ldu(rng, nac, False)[0],
-                      lambda: H.p25p1_build_ldu(rng, nac, True)[0],
+                      lambda: H.p25p1_build_ldu(rng, nac, True)[0], lambda: H.p25p1_build_tdulc(rng, nac)[0],
                       lambda: H.p25p1_build_tsdu(rng, nac, int(rng.integers(1, 4)), H._bch_nid_encoder(), valid_crc=rep != 1)[0]):
             frame, gap = build(), rng.integers(0, 4, int(rng.integers(0, 20)))
             positions.append(at + 23)
@@ -73,15 +73,16 @@ def test_synthetic_frames_oracle_equals_reference_handlers(flip, coarse):
     parts.append(rng.integers(0, 4, 900))
     tx = np.concatenate(parts).astype(np.uint8)
     d, rel, llr = _soft_from_dibits(rng, tx, flip=flip, coarse=coarse)
-    kinds = _compare_stream(d, rel, llr, min_frames=12, positions=positions)
+    kinds = _compare_stream(d, rel, llr, min_frames=15, positions=positions)
     if flip == 0.0:
         assert kinds.get(0, 0) == 3 and kinds.get(5, 0) == 3 and kinds.get(10, 0) == 3 and kinds.get(7, 0) == 3, kinds
+        assert kinds.get(15, 0) == 3, kinds
 
 
 def test_clean_frames_decode_to_the_transmitted_payloads():
     rng = np.random.default_rng(99)
     for build in (lambda: H.p25p1_build_hdu(rng, 0x293), lambda: H.p25p1_build_ldu(rng, 0x293, False),
-                  lambda: H.p25p1_build_ldu(rng, 0x293, True)):
+                  lambda: H.p25p1_build_ldu(rng, 0x293, True), lambda: H.p25p1_build_tdulc(rng, 0x293)):
         frame, truth = build()
         tx = np.concatenate([rng.integers(0, 4, 40), frame, rng.integers(0, 4, 40)]).astype(np.uint8)
         d, rel, llr = _soft_from_dibits(rng, tx, flip=0.0, weak=0.0)
@@ -89,7 +90,7 @@ def test_clean_frames_decode_to_the_transmitted_payloads():
         assert n > 0 and f["nid_status"] == 1 and f["nac"] == 0x293 and f["duid"] == truth["duid"]
         k = truth["rs_data"].size
         assert f["rs_status"] == 0 and np.array_equal(f["rs_data"][:k], truth["rs_data"])
-        if truth["duid"] != 0:
+        if truth["duid"] in (5, 10):
             bits = ((v["bits"][:, :, None] >> np.arange(23, dtype=np.uint32)) & 1).reshape(9, 184)
             assert np.array_equal(bits, truth["voice"]) and f["lsd_ok"] == 3 and np.array_equal(f["lsd"], truth["lsd"])
 
