@@ -266,6 +266,32 @@ int dsdneo_b200_cqpsk_slice_batch(dsdneo_b200_cqpsk_slicer* q, const float* d_sy
 /** {min, max, center, umid, lmid, minref, maxref, lastsample} of one channel */
 int dsdneo_b200_cqpsk_slicer_get_state(dsdneo_b200_cqpsk_slicer* q, int channel, float* out8);
 
+/* ---- IQ capture sidecar ("dsd-neo-iq" metadata of --iq-capture / --iq-replay): harness I/O for the block side ---- */
+
+enum { DSDNEO_B200_IQ_CU8 = 1, DSDNEO_B200_IQ_CF32 = 2 }; /* dsd_iq_sample_format, include/dsd-neo/io/iq_types.h:37-41 */
+/** The fields of dsd_iq_replay_config (include/dsd-neo/io/iq_replay.h:26-64) an ingest needs. */
+typedef struct dsdneo_b200_iq_info {
+    uint32_t version;                    /* 1: single segment, 2: with an "events" replay timeline */
+    int32_t sample_format;               /* DSDNEO_B200_IQ_CU8 / _CF32 */
+    uint32_t sample_rate_hz;
+    uint64_t center_frequency_hz, capture_center_frequency_hz, data_bytes;
+    uint32_t base_decimation, post_downsample, demod_rate_hz;
+    int32_t offset_tuning_enabled, fs4_shift_enabled, historical_cu8_two_pass /* combine_rotate_enabled == false */;
+    int32_t muted_bytes_excluded, contains_retunes, size_limit_reached;
+    uint32_t capture_retune_count, event_count;
+    char data_file[256];
+    char capture_stage[64];
+} dsdneo_b200_iq_info;
+/**
+ * Parses sidecar JSON text the way dsd_iq_replay_read_metadata does (src/io/iq/iq_replay.c:1520-1790: one flat object, the
+ * required fields, the value checks of :675-720; the v2 "events" array is counted, not interpreted).  0 on success,
+ * DSDNEO_B200_EINVAL for malformed / incomplete / inconsistent metadata, DSDNEO_B200_EUNSUPPORTED for a sample format no
+ * kernel here takes (cs16).  Host code; no device needed.
+ */
+int dsdneo_b200_iq_sidecar_parse(const char* json, size_t len, dsdneo_b200_iq_info* out);
+/** dsd_iq_replay_compute_effective_bytes (iq_replay.c:1859-1882): the replayable byte count, whole samples only. */
+long long dsdneo_b200_iq_effective_bytes(const dsdneo_b200_iq_info* info, uint64_t actual_file_size, int* size_mismatch);
+
 /* ---- K2 (+K1): polyphase FIR channelizer -------------------------------------------------------- */
 
 /**
