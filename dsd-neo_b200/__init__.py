@@ -996,7 +996,7 @@ class P25p1RxConfig(C.Structure):
     _fields_ = [("n_channels", C.c_int), ("rate_hz", C.c_int), ("block_pairs", C.c_int), ("max_pairs_per_call", C.c_int),
                 ("input_cu8", C.c_int), ("fir_arith", C.c_int), ("max_hits", C.c_int), ("erasure_threshold", C.c_int),
                 ("hard_override_disabled", C.c_int), ("track_nac", C.c_int), ("channel_squelch_level", C.POINTER(C.c_float)),
-                ("p25_filter_taps", C.POINTER(C.c_float)), ("p25_filter_len", C.c_int)]
+                ("p25_filter_taps", C.POINTER(C.c_float)), ("p25_filter_len", C.c_int), ("acquire_tiles", C.c_int)]
 
 
 class P25p1RxOut(C.Structure):
@@ -1013,7 +1013,7 @@ class P25p1Rx:
     """P25 Phase 1 C4FM receiver bank (dsdneo_b200_p25p1_rx_*): per-channel IQ -> frames / voice records / dibits."""
 
     def __init__(self, n_channels, p25_taps, rate_hz=48000, block_pairs=8192, max_pairs_per_call=49152, input_cu8=True,
-                 fir_arith=FIR_ARITH_FMA, max_hits=32, track_nac=False):
+                 fir_arith=FIR_ARITH_FMA, max_hits=32, track_nac=False, acquire_tiles=0):
         import numpy as np
 
         self._taps = np.ascontiguousarray(p25_taps, dtype=np.float32)
@@ -1022,6 +1022,7 @@ class P25p1Rx:
         cfg.input_cu8, cfg.fir_arith, cfg.max_hits, cfg.track_nac = 1 if input_cu8 else 0, fir_arith, max_hits, 1 if track_nac else 0
         cfg.p25_filter_taps = self._taps.ctypes.data_as(C.POINTER(C.c_float))
         cfg.p25_filter_len = self._taps.size
+        cfg.acquire_tiles = acquire_tiles
         self.n_channels, self.input_cu8 = n_channels, input_cu8
         self._h = lib().dsdneo_b200_p25p1_rx_create(C.byref(cfg))
         if not self._h:
@@ -1371,7 +1372,7 @@ class Symbolizer:
                         res["count"].data_ptr(), pitch)
         return res, out
 
-    def run_acquire(self, d_disc, n_samples, stream=None):
+    def run_acquire(self, d_disc, n_samples, stream=None, filtered=False):
         """getFrameSync + getDibitSoft over one launch of RAW discriminator samples; adds res['info'] uint8 [n_channels, 84]
         (view the host copy with acq_info_dtype())."""
         import torch
@@ -1381,8 +1382,9 @@ class Symbolizer:
         res["info"] = torch.zeros((self.n_channels, ACQ_INFO_BYTES), dtype=torch.uint8, device=d_disc.device)
         if stream is None:
             stream = torch.cuda.current_stream(d_disc.device)
-        check(lib().dsdneo_b200_symbolize_acquire_batch(self._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, C.byref(out),
-                                                        res["info"].data_ptr(), _stream_ptr(stream)), "symbolize_acquire_batch")
+        fn = lib().dsdneo_b200_symbolize_reacquire_batch if filtered else lib().dsdneo_b200_symbolize_acquire_batch
+        check(fn(self._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, C.byref(out), res["info"].data_ptr(), _stream_ptr(stream)),
+              "symbolize_acquire_batch")
         return res
 
     def run(self, d_disc, n_samples, mode=SYM_MODE_GET_DIBIT_SOFT, have_sync=1, stream=None):

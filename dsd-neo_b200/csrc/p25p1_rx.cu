@@ -107,6 +107,7 @@ struct dsdneo_b200_p25p1_rx {
     dsdneo_b200_frame_sync* fs;
     float* d_disc;
     int phase;         /* which of the two stream buffer sets receives this call */
+    int acq_left;      /* tiles still to run through the acquisition form (cfg.acquire_tiles at start) */
     uint8_t *d_dib[2], *d_rel[2];
     int16_t* d_llr[2];
     float* d_symv[2];
@@ -297,8 +298,22 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
         for (size_t i = 0; i < n; i++) {
             cls[i] = one;
         }
-        const int rc = dsdneo_b200_symbolizer_set_class(rx->sym, cls);
+        int rc = dsdneo_b200_symbolizer_set_class(rx->sym, cls);
         free(cls);
+        if (!rc && cfg->acquire_tiles > 0) {
+            /* start never-synchronised: getFrameSync's hunt for the P25 Phase 1 sync (hunting rules, timing nudges, basic lock,
+             * sync warm start, matched-filter start-up) runs on the device for the first acquire_tiles tiles */
+            dsdneo_b200_acq_pattern ap;
+            ap.symbols = kP25Sync;
+            ap.sync_type = 0; /* DSD_SYNC_P25P1_POS */
+            ap.kind = 0;
+            ap.cls = one;
+            rc = dsdneo_b200_symbolizer_set_acquire_patterns(rx->sym, &ap, 1);
+            if (!rc) {
+                rc = dsdneo_b200_symbolizer_set_acquired(rx->sym, NULL);
+            }
+            rx->acq_left = cfg->acquire_tiles;
+        }
         if (rc) {
             dsdneo_b200_p25p1_rx_destroy(rx);
             return NULL;
@@ -419,8 +434,18 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     const unsigned long long tile = rx->tiles;
     const int slot = (int)(tile & 1);
     const int n_ch = rx->n_ch, cur = rx->phase, prev = rx->phase ^ 1;
+    /* An acquiring tile runs its four stages one after the other on ONE stream, behind everything the previous tile queued:
+     * hunting channels read the raw discriminator samples, so the matched filter cannot run ahead of the slicer.  Only the
+     * first cfg.acquire_tiles tiles of a stream pay for that. */
+    const bool acq = rx->acq_left > 0;
+    const cudaStream_t st_a = acq ? rx->s_d : rx->s_a, st_b = acq ? rx->s_d : rx->s_b, st_c = acq ? rx->s_d : rx->s_c, st_d = rx->s_d;
+    if (acq && tile >= 1) {
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d, rx->ev_a[slot ^ 1], 0));
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d, rx->ev_b[slot ^ 1], 0));
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_d, rx->ev_c[slot ^ 1], 0));
+    }
     /* ---- stage A ---- */
-    cudaStream_t s = rx->s_a;
+    cudaStream_t s = st_a;
     DSDNEO_CUDA(cudaEventRecord(rx->ev_fork, as_stream(stream))); /* the caller's input is ready on its stream */
     DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_fork, 0));
     if (tile >= 2) {
@@ -437,7 +462,7 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     DSDNEO_CUDA(cudaEventRecord(rx->ev_a[slot], s)); /* also: the caller's input buffer is consumed */
     rx_trace(rx, tile, 1, s);
     /* ---- stage B ---- */
-    s = rx->s_b;
+    s = st_b;
     DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_a[slot], 0));
     if (tile >= 2) {
         DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_c[slot], 0)); /* the slicer two tiles back has read filter buffer [slot] */
@@ -447,14 +472,16 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     if (rc) {
         return rc;
     }
-    rc = dsdneo_symbolize_fir_stage(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, slot, s);
-    if (rc) {
-        return rc;
+    if (!acq) {
+        rc = dsdneo_symbolize_fir_stage(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, slot, s);
+        if (rc) {
+            return rc;
+        }
     }
     DSDNEO_CUDA(cudaEventRecord(rx->ev_b[slot], s));
     rx_trace(rx, tile, 3, s);
     /* ---- stage C ---- */
-    s = rx->s_c;
+    s = st_c;
     DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_b[slot], 0));
     if (tile >= 2) {
         DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_d[slot], 0)); /* the frame stage two tiles back has read stream buffers [cur] */
@@ -479,7 +506,16 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     so.d_llr = rx->d_llr[cur] + 2 * kKeep;
     so.d_count = rx->d_count[cur];
     so.pitch = rx->pitch;
-    rc = dsdneo_symbolize_sym_stage(rx->sym, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, slot, s);
+    if (acq) {
+        /* getFrameSync's hunt + getDibitSoft on this tile.  The hunt runs on the matched filter's output, as every hunt of the
+         * reference after a channel's first sync does (lastsynctype known): a cold hunt on raw samples locks half a symbol off
+         * once the 91-tap p25_filter (45 samples = 4.5 symbols of delay) switches on, and the reference only recovers from
+         * that by losing the frame and hunting again -- with the filter on. */
+        rc = dsdneo_symbolize_acquire_stage(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, NULL,
+                                            slot, 1, s);
+    } else {
+        rc = dsdneo_symbolize_sym_stage(rx->sym, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, slot, s);
+    }
     if (rc) {
         return rc;
     }
@@ -493,7 +529,7 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     DSDNEO_CUDA(cudaEventRecord(rx->ev_c[slot], s));
     rx_trace(rx, tile, 5, s);
     /* ---- stage D ---- */
-    s = rx->s_d;
+    s = st_d;
     DSDNEO_CUDA(cudaStreamWaitEvent(s, rx->ev_c[slot], 0));
     rx_trace(rx, tile, 6, s);
     const int region = kKeep - kDelay;
@@ -546,6 +582,12 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     }
     DSDNEO_CUDA(cudaEventRecord(rx->ev_d[slot], s));
     rx_trace(rx, tile, 7, s);
+    if (acq) { /* the stage streams pick up their carried state behind this tile */
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_a, rx->ev_d[slot], 0));
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_b, rx->ev_d[slot], 0));
+        DSDNEO_CUDA(cudaStreamWaitEvent(rx->s_c, rx->ev_d[slot], 0));
+        rx->acq_left--;
+    }
     rx->phase ^= 1;
     return (long long)rx->tiles++;
 }

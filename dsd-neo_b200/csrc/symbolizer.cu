@@ -1178,6 +1178,8 @@ struct AcqParams {
     int* out_off;          /* [n_ch] out: outputs written here */
     dsdneo_b200_acq_info* info; /* [n_ch] out */
     float* fir_hist;       /* [n_ch][kMaxTaps] the matched filter's carried raw history (sps_fir_kernel) */
+    int filtered_input;    /* the samples are already matched-filtered (a hunt after the first sync: lastsynctype known): no
+                            * filter start-up at the sync, the filter history is not touched */
 };
 
 /*
@@ -1571,7 +1573,7 @@ sym_acquire_kernel(const AcqParams a) {
             }
         }
     }
-    if (acquired && filt_id >= 0) { /* sps_fir_kernel runs next over this launch: x[-1], x[-2] .. are the carried raw samples */
+    if (acquired && filt_id >= 0 && !a.filtered_input) { /* sps_fir_kernel runs next over this launch: x[-1], x[-2] .. are the carried raw samples */
         const int hl = filt_len - 1;
         for (int k = lane; k < hl; k += 32) {
             const int q = kCarry - hl + k;
@@ -2476,33 +2478,34 @@ dsdneo_symbolize_sym_stage(dsdneo_b200_symbolizer* y, int n_samples, int mode, i
     return 0;
 }
 
-extern "C" {
-
-static int
-symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
-                 const dsdneo_b200_symbol_out* out, bool acquire, dsdneo_b200_acq_info* d_info, void* stream) {
-    int rc = symbolize_check(y, n_samples, mode, out);
-    if (rc) {
-        return rc;
-    }
-    if (!d_disc || disc_pitch < (size_t)n_samples) {
-        set_error("symbolize_batch: bad argument");
+/* The acquisition form of the two stages as one step on one stream (hunting channels read the RAW samples, so the matched
+ * filter of the launch cannot run ahead of them): sym_acquire_kernel, then the matched filter into buffer `slot`, then the
+ * slicer for the synchronised part of every channel.  Used by dsdneo_b200_symbolize_acquire_batch and by the receive bank
+ * while it acquires (csrc/p25p1_rx.cu). */
+int
+dsdneo_symbolize_acquire_stage(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                               const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, int slot, int hunt_filtered,
+                               cudaStream_t s) {
+    if (!y || !y->d_acquired || y->n_pat < 1 || slot < 0 || slot > 1) {
+        set_error("symbolize acquire stage: acquisition is not configured (symbolizer_set_acquire_patterns)");
         return DSDNEO_B200_EINVAL;
     }
-    cudaStream_t s = as_stream(stream);
-    if (!acquire) {
-        rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, 0, s);
-        return rc ? rc : dsdneo_symbolize_sym_stage(y, n_samples, mode, have_sync, out, 0, s);
-    }
-    rc = ensure_device();
+    int rc = ensure_device();
     if (rc) {
         return rc;
     }
-    /* hunting channels first: they read the raw samples and may switch their class for the stages below */
+    if (hunt_filtered) { /* the matched filter already runs (every hunt after a channel's first sync): hunt on its output */
+        rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, slot, s);
+        if (rc) {
+            return rc;
+        }
+    }
+    /* hunting channels first: they read the samples and may switch their class for the stages below */
     AcqParams ap;
-    ap.sp = symbolize_params(y, n_samples, mode, have_sync, out, 0);
-    ap.sp.filt = d_disc;
-    ap.sp.filt_pitch = disc_pitch;
+    ap.sp = symbolize_params(y, n_samples, mode, have_sync, out, slot);
+    ap.sp.filt = hunt_filtered ? y->d_filt[slot] : d_disc;
+    ap.sp.filt_pitch = hunt_filtered ? y->filt_pitch[slot] : disc_pitch;
+    ap.filtered_input = hunt_filtered ? 1 : 0;
     ap.taps = y->d_taps;
     ap.taps_len = y->d_taps_len;
     for (int k = 0; k < y->n_pat; k++) {
@@ -2528,11 +2531,13 @@ symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pit
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
-    rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, 0, s);
-    if (rc) {
-        return rc;
+    if (!hunt_filtered) {
+        rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, slot, s);
+        if (rc) {
+            return rc;
+        }
     }
-    SymParams sp = symbolize_params(y, n_samples, mode, have_sync, out, 0);
+    SymParams sp = symbolize_params(y, n_samples, mode, have_sync, out, slot);
     sp.start_off = y->d_start_off;
     sp.out_off = y->d_out_off;
     sp.acquired = y->d_acquired;
@@ -2543,6 +2548,50 @@ symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pit
     DSDNEO_KERNEL_CHECK();
     count_launch();
     return 0;
+}
+
+extern "C" {
+
+static int
+symbolize_launch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
+                 const dsdneo_b200_symbol_out* out, bool acquire, dsdneo_b200_acq_info* d_info, void* stream) {
+    int rc = symbolize_check(y, n_samples, mode, out);
+    if (rc) {
+        return rc;
+    }
+    if (!d_disc || disc_pitch < (size_t)n_samples) {
+        set_error("symbolize_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    cudaStream_t s = as_stream(stream);
+    if (!acquire) {
+        rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, 0, s);
+        return rc ? rc : dsdneo_symbolize_sym_stage(y, n_samples, mode, have_sync, out, 0, s);
+    }
+    return dsdneo_symbolize_acquire_stage(y, d_disc, disc_pitch, n_samples, mode, have_sync, out, d_info, 0, 0, s);
+}
+
+int
+dsdneo_b200_symbolize_reacquire_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples,
+                                      const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, void* stream) {
+    if (!y || !y->d_acquired || y->n_pat < 1) {
+        set_error("symbolize_reacquire_batch: acquisition is not configured (symbolizer_set_acquire_patterns)");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (n_samples < kAcqMargin) {
+        set_error("symbolize_reacquire_batch: a launch must carry at least %d samples", kAcqMargin);
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = symbolize_check(y, n_samples, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, out);
+    if (rc) {
+        return rc;
+    }
+    if (!d_disc || disc_pitch < (size_t)n_samples) {
+        set_error("symbolize_reacquire_batch: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    return dsdneo_symbolize_acquire_stage(y, d_disc, disc_pitch, n_samples, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, out, d_info, 0, 1,
+                                          as_stream(stream));
 }
 
 int

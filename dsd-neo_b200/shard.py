@@ -146,7 +146,8 @@ class ShardedP25Rx:
     runs on a side stream under the kernels of tile i."""
 
     def __init__(self, b200, n_channels: int, rank: int, world: int, p25_taps, pairs_per_tile: int, rate_hz: int = 48000,
-                 block_pairs: int = 8192, taps_per_branch: int = 8, root: int = 0, group=None, max_hits: int = 32, device=None):
+                 block_pairs: int = 8192, taps_per_branch: int = 8, root: int = 0, group=None, max_hits: int = 32, device=None,
+                 acquire_tiles: int = 0):
         import torch
 
         self.b200, self.M, self.rank, self.world, self.root, self.group = b200, n_channels, rank, world, root, group
@@ -155,7 +156,7 @@ class ShardedP25Rx:
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.cz = b200.Channelizer(n_channels, taps_per_branch, input_is_cu8=True)
         self.rx = b200.P25p1Rx(self.n_local, p25_taps, rate_hz=rate_hz, block_pairs=block_pairs, max_pairs_per_call=pairs_per_tile,
-                               input_cu8=False, max_hits=max_hits)
+                               input_cu8=False, max_hits=max_hits, acquire_tiles=acquire_tiles)
         self.chan = [torch.empty((self.n_local, pairs_per_tile, 2), dtype=torch.float32, device=self.dev) for _ in range(2)]
         self.raw = [torch.empty((pairs_per_tile * n_channels, 2), dtype=torch.uint8, device=self.dev) for _ in range(2)]
         self._side = torch.cuda.Stream(device=self.dev)

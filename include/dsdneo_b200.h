@@ -567,6 +567,17 @@ int dsdneo_b200_symbolizer_set_acquired(dsdneo_b200_symbolizer* y, const int* h_
  */
 int dsdneo_b200_symbolize_acquire_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples,
                                         const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, void* stream);
+/**
+ * The same for a hunt AFTER a channel's first sync: the reference keeps the sample-side matched filter of the last sync type
+ * running while it hunts again (dsd_symbol.c:301-337 selects the filter from lastsynctype), so hunting channels read the
+ * matched filter's output and nothing is restarted at the sync.  This is the form a stream should be acquired with in
+ * practice: a cold hunt on raw samples locks onto symbol centres that move by the filter's group delay -- 4.5 symbols for the
+ * 91-tap p25_filter at 10 samples per symbol -- the moment the filter switches on, and the reference itself only recovers from
+ * that by losing the first frame and hunting again with the filter on.  Built from the hunting and hand-over rules pinned by
+ * the cold form; not separately pinned.
+ */
+int dsdneo_b200_symbolize_reacquire_batch(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples,
+                                          const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, void* stream);
 
 /* ---- batched FEC leaves (K13, K16, K17, K19) ------------------------------------------------------ */
 
@@ -1029,6 +1040,11 @@ typedef struct dsdneo_b200_p25p1_rx_config {
     const float* channel_squelch_level; /* per channel or NULL (squelch off) */
     const float* p25_filter_taps;       /* NORMALISED p25_filter taps for rate_hz as the reference's design_sps_fir leaves them */
     int p25_filter_len;
+    int acquire_tiles;       /* 0: every channel starts synchronised (the stream must start symbol-aligned); k > 0: every channel
+                              * starts never-synchronised and the first k tiles run getFrameSync()'s acquisition on the device
+                              * (dsdneo_b200_symbolize_reacquire_batch: hunt on the matched filter's output, timing nudges, sync
+                              * warm start), one tile at a time; a channel that has not found the P25 Phase 1 sync by then continues
+                              * with the synchronised rules */
 } dsdneo_b200_p25p1_rx_config;
 typedef struct dsdneo_b200_p25p1_rx_out { /* device buffers */
     dsdneo_b200_p25p1_frame* d_frames;
