@@ -18,6 +18,7 @@
  */
 #include <dsd-neo/dsp/demod_pipeline.h>
 #include <dsd-neo/dsp/demod_state.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "dsdneo_b200.h"
@@ -32,7 +33,31 @@ static struct {
     int rate_out, profile, lpf_enable;
     float squelch;
     int cqpsk_sps;
+    int mirrored_have_prev; /* fsk_modem_state.have_prev as this shim last wrote it: a 0 found there since is a host-side reset */
 } g_banks[B200_MAX_STATES];
+
+/* Drop the device state kept for `d` (call where the reference frees or re-initialises a demod_state, so that a later state
+ * at the same address does not inherit it). */
+extern "C" void
+full_demod_b200_forget(const struct demod_state* d) {
+    for (int i = 0; i < B200_MAX_STATES; i++) {
+        if (g_banks[i].key == d) {
+            dsdneo_b200_demod_bank_destroy(g_banks[i].bank);
+            dsdneo_b200_cqpsk_bank_destroy(g_banks[i].cqpsk);
+            memset(&g_banks[i], 0, sizeof(g_banks[i]));
+        }
+    }
+}
+
+static int
+slot_of(const struct demod_state* d) {
+    for (int i = 0; i < B200_MAX_STATES; i++) {
+        if (g_banks[i].key == d) {
+            return i;
+        }
+    }
+    return -1;
+}
 
 static dsdneo_b200_demod_bank*
 bank_for(const struct demod_state* d) {
@@ -167,10 +192,25 @@ full_demod(struct demod_state* d) {
     const int covered = d && d->output_kind == DSD_DEMOD_OUTPUT_FSK_DISCRIMINATOR && !d->cqpsk_enable
                         && d->downsample_passes <= 0 && !d->iq_dc_block_enable && !d->iqbal_enable && d->lowpassed
                         && d->lp_len >= 2 && d->lp_len <= MAXIMUM_BUF_LENGTH;
-    dsdneo_b200_demod_bank* bank = covered ? bank_for(d) : NULL;
-    if (!bank) {
-        full_demod_cpu(d);
+    if (!covered) {
+        full_demod_cpu(d); /* configurations this library does not build stay on the reference's own code */
         return;
+    }
+    dsdneo_b200_demod_bank* bank = bank_for(d);
+    if (!bank) {
+        /* no silent fallback for a covered configuration: the table is full (full_demod_b200_forget was never called) or the
+         * device refused the bank */
+        static int warned = 0;
+        if (!warned++) {
+            fprintf(stderr, "full_demod (b200): no device bank for demod_state %p: %s\n", (const void*)d, dsdneo_b200_last_error());
+        }
+        d->result_len = 0;
+        return;
+    }
+    const int slot = slot_of(d);
+    /* the reference resets the modem on retune (dsd_fsk_modem_reset clears have_prev, dc and peak estimates): mirror it */
+    if (slot >= 0 && g_banks[slot].mirrored_have_prev && !d->fsk_modem_state.have_prev) {
+        (void)dsdneo_b200_demod_bank_reset(bank, NULL);
     }
     const int pairs = d->lp_len >> 1;
     if (dsdneo_b200_full_demod_batch_host(bank, d->lowpassed, (size_t)pairs, pairs, 1, d->result, (size_t)pairs) != 0) {
@@ -187,6 +227,9 @@ full_demod(struct demod_state* d) {
         d->fsk_modem_state.prev_i = st.prev_i;
         d->fsk_modem_state.prev_q = st.prev_q;
         d->fsk_modem_state.have_prev = st.have_prev;
+        if (slot >= 0) {
+            g_banks[slot].mirrored_have_prev = st.have_prev;
+        }
         d->fsk_modem_state.dc_est = st.dc_est;
         d->fsk_modem_state.discriminator_peak_est = st.discriminator_peak_est;
     }
