@@ -783,6 +783,11 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
  * Hamming(7,4)), info bits [196] in transmitted (interleaved) order = the input of dsdneo_b200_bptc_196x96_batch, per-dibit
  * reliabilities of the 98 info dibits, slot-type bits [20] = the input of Golay(20,8), and whether the channel's stream
  * (d_counts dibits) holds the whole burst.  `inverted_dmr` = opts->inverted_dmr (XOR 2 on the part before the sync's end).
+ * The cutters see one launch's dibit buffer: a burst that straddles two launches is reported valid = 0 by both (it needs 90
+ * dibits before the end of its sync and 54 after).  A streaming caller keeps the last 143 dibits (and reliabilities) of
+ * every channel in front of the next launch's dibits -- the layout the P25 receive bank uses for its own stream history
+ * (dsdneo_b200_p25p1_rx_*: 1024 symbols kept, frames decoded 864 symbols behind the slicer) -- and drops hits it has
+ * already cut; a DMR bank that does this on the device is not built.
  */
 int dsdneo_b200_dmr_burst_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const uint8_t* d_reliability,
                                     size_t reliability_pitch, const int32_t* d_counts, const void* d_hits,
