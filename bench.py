@@ -970,7 +970,8 @@ def run_c3_one_stream(args):
     Mw = C3_CH * world
     T = 8
     taps = _p25_filter_taps()
-    sr = shard.ShardedP25Rx(b200, Mw, rank, world, taps, C3_PAIRS, rate_hz=C3_RATE, block_pairs=C3_BLOCK, taps_per_branch=T, device=dev)
+    sr = shard.ShardedP25Rx(b200, Mw, rank, world, taps, C3_PAIRS, rate_hz=C3_RATE, block_pairs=C3_BLOCK, taps_per_branch=T, device=dev,
+                            channels_cu8=args.channels_cu8)
     n_tile = C3_PAIRS * Mw  # wideband samples per tile
     n_slice = n_tile // world
     # ---- the wideband stream: synthesised on every rank's GPU from the same 16 base channels (deterministic), so the ingest
@@ -1107,7 +1108,7 @@ def run_c3_one_stream(args):
     roofline = None
     if "pfbn_kernel" in kernels or "pfb256_kernel" in kernels:
         kn = "pfbn_kernel" if "pfbn_kernel" in kernels else "pfb256_kernel"
-        algb = n_tile * 2.0 + sr.n_local * C3_PAIRS * 8.0  # the whole cu8 tile in, this rank's cf32 channels out
+        algb = n_tile * 2.0 + sr.n_local * C3_PAIRS * (2.0 if args.channels_cu8 else 8.0)  # the whole cu8 tile in, this rank's channels out
         a = algb / (kernels[kn]["avg_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kn, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algb}
@@ -1118,6 +1119,7 @@ def run_c3_one_stream(args):
     cfg["parallelism"] = ("channel class k = rank (mod N) per GPU; the only collective is one NCCL broadcast (device-resident leg) / "
                           "all-gather (e2e leg, every rank ingests 1/N of the tile) of the raw tile per step, on a side stream")
     cfg["l2_policy"] = "5 rotating wideband tiles of %.1f MB" % (n_tile * 2 / 1e6)
+    cfg["channel_format"] = "cu8 (re-quantised by the channelizer, gain sqrt(M))" if args.channels_cu8 else "cf32"
     print(json.dumps({
         "metric": "iq_msps", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -1468,6 +1470,8 @@ def main():
                     help="bands (default): every GPU has its own channels, no collective; channels: ONE wideband stream, the raw IQ "
                          "tile reaches every GPU through one NCCL collective, each GPU channelizes and decodes its channel class")
     ap.add_argument("--channels", type=int, default=M)
+    ap.add_argument("--channels-cu8", action="store_true",
+                    help="(--shard channels) the channelizer hands the receive bank cu8 rows instead of cf32")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "cqpsk", "fec"],
                     help="c3 (default, the judged line): 1024 P25 Phase 1 channels end to end; c2: 256-channel channelizer + "
                          "discriminator; cqpsk / fec: developer lines")

@@ -568,6 +568,25 @@ class Channelizer:
         )
         return d_out
 
+    def channelize_bins_cu8(self, d_in, bin_stride: int, bin_first: int, gain: float, d_out=None, advance: bool = True, stream=None):
+        """channelize_bins with the rows re-quantised to cu8 (uint8 [M / bin_stride, n/M, 2]): the receive bank's native input."""
+        import torch
+
+        assert d_in.is_cuda and d_in.is_contiguous() and d_in.shape[-1] == 2
+        assert d_in.dtype == (torch.uint8 if self.cu8 else torch.float32)
+        n = d_in.shape[0]
+        if d_out is None:
+            d_out = torch.empty((self.M // bin_stride, n // self.M, 2), dtype=torch.uint8, device=d_in.device)
+        assert d_out.is_cuda and d_out.is_contiguous() and d_out.dtype == torch.uint8 and d_out.shape[0] == self.M // bin_stride
+        if stream is None:
+            stream = torch.cuda.current_stream(d_in.device)
+        check(
+            lib().dsdneo_b200_channelize_bins_cu8(self._h, d_in.data_ptr(), n, bin_stride, bin_first, 1 if advance else 0, float(gain),
+                                                  d_out.data_ptr(), d_out.shape[1], _stream_ptr(stream)),
+            "channelize_bins_cu8",
+        )
+        return d_out
+
     def channelize_host(self, h_in):
         import numpy as np
 

@@ -276,6 +276,8 @@ struct PfbNParams {
     const float* bias;    /* cu8 input: -127.5 * sum_q proto[q M + M-1-b] per branch b (the widening's offset after the filter) */
     const float2* twN;    /* W_N^m = exp(-j 2 pi m / N), m < N */
     float2* out;          /* [N][out_pitch]: row k' = channel R k' + r0 */
+    uchar2* out_u8;       /* instead of `out`: the same rows re-quantised to cu8, round(v * out_gain * 127.5 + 127.5) clamped */
+    float out_gain;
     size_t out_pitch;
     long n_out;
     int M, N, R, r0;
@@ -734,7 +736,36 @@ pfbn_kernel(const PfbNParams p) {
         }
 
         /* ---- transposed store: C consecutive lanes = C consecutive times of one channel ---- */
-        {
+        if (p.out_u8) {
+            /* cu8 rows (the receive bank's native input format: 2 B per sample instead of 8): a lane packs four consecutive
+             * times of one channel into one 8-byte store; a chunk that is cut short by the end of the launch stores bytes */
+            const int G = C >> 2, lgG = p.lgC - 2; /* C >= 4 */
+            const float sc = p.out_gain * 127.5f;
+            for (int t = threadIdx.x; t < N * G; t += NT) {
+                const int g = t & (G - 1), pos = t >> lgG, i0 = 4 * g;
+                if (i0 >= nv) {
+                    continue;
+                }
+                const float2* src = X + i0 * pitchT + pad16(pos);
+                unsigned w[2] = {0u, 0u};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 v = src[k * pitchT];
+                    const unsigned qx = (unsigned)__float2int_rn(fminf(fmaxf(fmaf(v.x, sc, 127.5f), 0.0f), 255.0f));
+                    const unsigned qy = (unsigned)__float2int_rn(fminf(fmaxf(fmaf(v.y, sc, 127.5f), 0.0f), 255.0f));
+                    w[k >> 1] |= (qx | (qy << 8)) << (16 * (k & 1));
+                }
+                uchar2* dst = p.out_u8 + (size_t)binOf[pos] * p.out_pitch + n0 + i0;
+                if (i0 + 4 <= nv) {
+                    __stcs(reinterpret_cast<uint2*>(dst), make_uint2(w[0], w[1]));
+                } else {
+                    for (int k = 0; i0 + k < nv; k++) {
+                        const unsigned q = w[k >> 1] >> (16 * (k & 1));
+                        dst[k] = make_uchar2((unsigned char)(q & 0xffu), (unsigned char)((q >> 8) & 0xffu));
+                    }
+                }
+            }
+        } else {
             const int i = threadIdx.x & (C - 1); /* blockDim is a multiple of C */
             const int pstep = NT >> p.lgC;
             float2* dst = p.out + n0 + i;
@@ -1049,10 +1080,10 @@ dsdneo_b200_channelizer_get_prototype(dsdneo_b200_channelizer* c, float* h_out, 
     return c->M * c->T;
 }
 
-int
-dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride, int bin_first,
-                            int advance, float* d_out, size_t out_pitch_pairs, void* stream) {
-    if (!c || !d_in || !d_out || n_in_samples == 0 || (n_in_samples % (size_t)c->M) != 0) {
+static int
+channelize_impl(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride, int bin_first, int advance,
+                float* d_out, uint8_t* d_out_u8, float out_gain, size_t out_pitch_pairs, void* stream) {
+    if (!c || !d_in || (!d_out && !d_out_u8) || n_in_samples == 0 || (n_in_samples % (size_t)c->M) != 0) {
         set_error("channelize: bad argument (n_in_samples must be a positive multiple of n_channels)");
         return DSDNEO_B200_EINVAL;
     }
@@ -1084,7 +1115,11 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
             (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
     }
-    if (c->M == kM && bin_stride == 1) {
+    if (d_out_u8 && (c->M / bin_stride > 4096 || (out_pitch_pairs & 3) != 0 || !(out_gain > 0.0f))) {
+        set_error("channelize_bins_cu8: needs at most 4096 output channels, out_pitch_pairs a multiple of 4 and a positive gain");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (c->M == kM && bin_stride == 1 && !d_out_u8) {
         PfbParams p;
         p.in = d_in;
         p.hist = c->d_hist;
@@ -1123,6 +1158,8 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
         p.bias = c->d_bias_u8;
         p.twN = c->d_tw[lg];
         p.out = reinterpret_cast<float2*>(d_out);
+        p.out_u8 = reinterpret_cast<uchar2*>(d_out_u8);
+        p.out_gain = out_gain;
         p.out_pitch = out_pitch_pairs;
         p.n_out = n_out;
         p.M = c->M;
@@ -1196,6 +1233,22 @@ dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t
         c->d_hist_alt = t;
     }
     return 0;
+}
+
+int
+dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride, int bin_first,
+                            int advance, float* d_out, size_t out_pitch_pairs, void* stream) {
+    return channelize_impl(c, d_in, n_in_samples, bin_stride, bin_first, advance, d_out, NULL, 0.0f, out_pitch_pairs, stream);
+}
+
+int
+dsdneo_b200_channelize_bins_cu8(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride, int bin_first,
+                                int advance, float gain, uint8_t* d_out, size_t out_pitch_pairs, void* stream) {
+    if (!d_out) {
+        set_error("channelize_bins_cu8: NULL output");
+        return DSDNEO_B200_EINVAL;
+    }
+    return channelize_impl(c, d_in, n_in_samples, bin_stride, bin_first, advance, NULL, d_out, gain, out_pitch_pairs, stream);
 }
 
 int

@@ -147,7 +147,7 @@ class ShardedP25Rx:
 
     def __init__(self, b200, n_channels: int, rank: int, world: int, p25_taps, pairs_per_tile: int, rate_hz: int = 48000,
                  block_pairs: int = 8192, taps_per_branch: int = 8, root: int = 0, group=None, max_hits: int = 32, device=None,
-                 acquire_tiles: int = 0):
+                 acquire_tiles: int = 0, channels_cu8: bool = False, channel_gain: Optional[float] = None):
         import torch
 
         self.b200, self.M, self.rank, self.world, self.root, self.group = b200, n_channels, rank, world, root, group
@@ -155,9 +155,14 @@ class ShardedP25Rx:
         self.pairs = pairs_per_tile
         self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.cz = b200.Channelizer(n_channels, taps_per_branch, input_is_cu8=True)
+        # channels_cu8: the channelizer hands the bank cu8 rows (its native capture format, 2 B per sample through HBM instead of
+        # 8), scaled by channel_gain (default sqrt(M): a channel of an evenly loaded band back at the wideband level)
+        self.channels_cu8 = channels_cu8
+        self.channel_gain = float(channel_gain) if channel_gain is not None else float(n_channels) ** 0.5
         self.rx = b200.P25p1Rx(self.n_local, p25_taps, rate_hz=rate_hz, block_pairs=block_pairs, max_pairs_per_call=pairs_per_tile,
-                               input_cu8=False, max_hits=max_hits, acquire_tiles=acquire_tiles)
-        self.chan = [torch.empty((self.n_local, pairs_per_tile, 2), dtype=torch.float32, device=self.dev) for _ in range(2)]
+                               input_cu8=channels_cu8, max_hits=max_hits, acquire_tiles=acquire_tiles)
+        self.chan = [torch.empty((self.n_local, pairs_per_tile, 2), dtype=torch.uint8 if channels_cu8 else torch.float32, device=self.dev)
+                     for _ in range(2)]
         self.raw = [torch.empty((pairs_per_tile * n_channels, 2), dtype=torch.uint8, device=self.dev) for _ in range(2)]
         self._side = torch.cuda.Stream(device=self.dev)
         self._arrived = [None, None]    # event: raw[b] holds its tile
@@ -212,7 +217,10 @@ class ShardedP25Rx:
         stream.wait_event(self._arrived[b])
         if self._tickets[b] is not None:
             self.rx.input_consumed(self._tickets[b], stream)  # the bank's first stage has read chan[b]
-        self.cz.channelize_bins(self.raw[b], self.world, self.rank, self.chan[b], stream=stream)
+        if self.channels_cu8:
+            self.cz.channelize_bins_cu8(self.raw[b], self.world, self.rank, self.channel_gain, self.chan[b], stream=stream)
+        else:
+            self.cz.channelize_bins(self.raw[b], self.world, self.rank, self.chan[b], stream=stream)
         ev = torch.cuda.Event()
         ev.record(stream)
         self._raw_free[b] = ev

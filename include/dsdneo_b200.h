@@ -339,6 +339,16 @@ int dsdneo_b200_channelize_host(dsdneo_b200_channelizer* c, const void* h_in, si
  */
 int dsdneo_b200_channelize_bins(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride,
                                 int bin_first, int advance, float* d_out, size_t out_pitch_pairs, void* stream);
+/**
+ * The same with the channels re-quantised to cu8 on the way out -- u8 = clamp(round(y * gain * 127.5 + 127.5), 0, 255), the
+ * inverse of widen_u8_to_f32_bias127 -- i.e. in the reference's native per-channel capture format: d_out is
+ * [n_channels / bin_stride][out_pitch_pairs] uchar2, the input dsdneo_b200_p25p1_rx_* / dsdneo_b200_full_demod_* take with
+ * input_cu8 = 1 (2 B per sample through HBM instead of 8).  `gain` scales a channel into the 8-bit range (a channel of a
+ * band of M equally loaded channels sits 1/sqrt(M) below the wideband level).  At most 4096 output channels,
+ * out_pitch_pairs a multiple of 4.
+ */
+int dsdneo_b200_channelize_bins_cu8(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_samples, int bin_stride,
+                                    int bin_first, int advance, float gain, uint8_t* d_out, size_t out_pitch_pairs, void* stream);
 
 /* ---- FSK front end: channelizer -> full_demod, one call ----------------------------------------- */
 

@@ -245,3 +245,34 @@ def test_bin_classes_tile_the_band(gpu):
     want2 = full2.channelize(x2).cpu().numpy()
     got2 = cz.channelize_bins(x2, R, 1).cpu().numpy()
     assert np.abs(got2 - want2[1::R]).max() <= 2e-5 * np.abs(want2).max() + 1e-7
+
+
+@pytest.mark.parametrize("Mx,R", [(1024, 1), (2048, 2), (4096, 1), (256, 1)])
+def test_cu8_output_is_the_requantised_cf32_output(gpu, Mx, R):
+    """channelize_bins_cu8 == clamp(round(channelize_bins * gain * 127.5 + 127.5)), including a ragged last chunk."""
+    import torch
+
+    rng = np.random.default_rng(Mx + R)
+    T, n_out = 8, 44 if Mx != 4096 else 20  # the row pitch must be a multiple of 4; 44 is ragged against 8- and 16-row chunks
+    x = torch.from_numpy(_noise_plus_tones(rng, Mx, n_out, [(5, 0.0), (Mx // 3, 0.1)])).cuda()
+    r0 = R - 1
+    gain = 1.7
+    ref = gpu.Channelizer(Mx, T).channelize_bins(x, R, r0) if not (Mx == 256 and R == 1) else None
+    got = gpu.Channelizer(Mx, T).channelize_bins_cu8(x, R, r0, gain)
+    assert got.shape == (Mx // R, n_out, 2) and got.dtype == torch.uint8
+    if ref is not None:
+        want = torch.clamp(torch.round(ref * (gain * 127.5) + 127.5), 0, 255).to(torch.uint8)
+        diff = (got.int() - want.int()).abs()
+        # float32 rounding of y * gain * 127.5 + 127.5 may differ from torch's by one ulp at an exact .5: allow isolated off-by-ones
+        assert int(diff.max()) <= 1 and float((diff != 0).float().mean()) < 1e-4
+    else:  # M = 256: the cf32 form runs the 256-channel kernel, the cu8 form the general one
+        full = gpu.Channelizer(Mx, T).channelize(x)
+        want = torch.clamp(torch.round(full * (gain * 127.5) + 127.5), 0, 255).to(torch.uint8)
+        assert int((got.int() - want.int()).abs().max()) <= 1
+    if Mx == 1024:  # a launch whose length is not a multiple of 4 into rows with a larger pitch: the last group stores bytes
+        n2 = 42
+        buf = torch.full((Mx // R, 48, 2), 77, dtype=torch.uint8, device="cuda")
+        cz2 = gpu.Channelizer(Mx, T)
+        gpu.check(gpu.lib().dsdneo_b200_channelize_bins_cu8(cz2._h, x.data_ptr(), n2 * Mx, R, r0, 1, gain, buf.data_ptr(), 48, None))
+        torch.cuda.synchronize()
+        assert torch.equal(buf[:, :n2], got[:, :n2]) and bool((buf[:, n2:] == 77).all())
