@@ -80,5 +80,31 @@ for code, ln in ((b200.P25_WORD_GOLAY_24_6, 6), (b200.P25_WORD_GOLAY_24_12, 12))
     r = rng.integers(0, 256, (40, ln + 12)).astype(np.int32)
     stg, fxg = np.zeros(40, np.uint8), np.zeros(40, np.int32)
     b200.check(L.dsdneo_b200_p25_golay_soft_batch_host(code, d.ctypes.data, pbits.ctypes.data, r.ctypes.data, 1, 64, stg.ctypes.data, fxg.ctypes.data, 40))
+# round 2: general / bin-pruned channelizer (cu8 and cf32, ragged launch lengths, cu8 output), vocoder frame ECC, DMR voice cutter,
+# acquisition and the P25 receive bank (frames incl. TDULC, acquisition at stream start)
+for Mx, R, cu8 in ((512, 2, True), (1024, 1, False), (2048, 8, True)):
+    cz = b200.Channelizer(Mx, 8, cu8)
+    for n_o in (37, 5):
+        xin = (torch.randint(0, 256, (n_o * Mx, 2), dtype=torch.uint8, device="cuda") if cu8 else torch.randn((n_o * Mx, 2), device="cuda"))
+        cz.channelize_bins(xin, R, R - 1)
+    cz.prime(xin)
+    xin = (torch.randint(0, 256, (40 * Mx, 2), dtype=torch.uint8, device="cuda") if cu8 else torch.randn((40 * Mx, 2), device="cuda"))
+    cz.channelize_bins_cu8(xin, R, 0, 2.0)
+b200.ambe3600x2450_decode(rng.integers(0, 2, (70, 4, 24)).astype(np.uint8))
+b200.imbe7200x4400_decode(rng.integers(0, 2, (70, 8, 23)).astype(np.uint8))
+b200.p25p1_voice_imbe_decode(torch.randint(0, 256, (5, 1944), dtype=torch.uint8, device="cuda"), 5)
+b200.dmr_voice_cut(res2["dibits"], res2["count"], hits, n_hits, 8, 3)
+import test_gpu_p25p1_rx as T
+
+chans = [T._channel(rng, 3400, snr_db=22.0) for _ in range(3)]
+p25_taps = H.sps_fir_taps(0, 10)
+for acq in (0, 1):
+    rx = b200.P25p1Rx(3, p25_taps, block_pairs=T.BP, max_pairs_per_call=4 * T.BP, acquire_tiles=acq)
+    rx_out = rx.alloc_device_out("cuda")
+    for kk in range(2):
+        tile = np.stack([u8[kk * 4 * T.BP:(kk + 1) * 4 * T.BP] for u8, _ in chans])
+        tk = rx.submit(torch.from_numpy(tile).cuda(), 4 * T.BP, rx_out)
+        rx.wait(tk)
+    torch.cuda.synchronize()
 torch.cuda.synchronize()
 print("sanitize_smoke done, launches =", b200.launch_count())
