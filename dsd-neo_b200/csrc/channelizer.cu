@@ -35,6 +35,7 @@
  *
  * Compiled with -fmad=true (nothing here is bit-pinned to a CPU path; tolerance is stated in the tests).
  */
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -268,6 +269,40 @@ pfb256_kernel(const PfbParams p) {
  * General M, pruned bins.
  * ------------------------------------------------------------------------------------------------------- */
 constexpr int kMaxFold = 32; /* R <= 32 */
+constexpr int kTmaBox = 256;  /* inner box width of the tensor-map copies (elements; the hardware limit per dimension) */
+
+__device__ __forceinline__ void
+pfb_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void
+pfb_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+pfb_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PFB_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni PFB_WAIT_DONE;\n"
+        "bra.uni PFB_WAIT_LOOP;\n"
+        "PFB_WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+/* one 2-D tensor-map copy (TMA): box {kTmaBox x rows} of 32-bit elements at element column c0, row c1 -> dense shared memory */
+__device__ __forceinline__ void
+pfb_tma_load_2d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
 
 struct PfbNParams {
     const void* in;       /* cf32 / cu8, n_out * M samples */
@@ -284,6 +319,7 @@ struct PfbNParams {
     int C;                /* output times per chunk: 2, 4, 8 or 16 */
     int rho;              /* radix of the first pass: 1 (none), 2, 4 or 8; N / rho is a power of 16 */
     int lgN, lgC;
+    int use_tma;          /* cu8 pair path: the step's window is ONE tensor-map copy per 256 pairs instead of 15 cp.async per thread */
     int chunks_per_cta;
     float2 wR[kMaxFold];  /* W_R^{j r0} */
 };
@@ -365,7 +401,7 @@ pfbn_first_pass(float2* X, const PfbNParams& p, int pitchT) {
  * filtered out of registers. */
 template <int T, bool CU8, int SC, int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
-pfbn_kernel(const PfbNParams p) {
+pfbn_kernel(const PfbNParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(16) unsigned char pfb_smem[];
     float2* X = reinterpret_cast<float2*>(pfb_smem); /* [C][pitchT], element n of a row at pad16(n) */
     const int N = p.N, C = p.C, M = p.M, R = p.R;
@@ -398,12 +434,39 @@ pfbn_kernel(const PfbNParams p) {
      * column of stage[2][T-1+SC][blockDim] while it filters the current one (no cross-thread sharing, so no barrier: only
      * cp.async.wait_group); the first step of a chunk is requested before the previous chunk's transform and store */
     constexpr bool kStaged = CU8 && (T <= 8);
-    unsigned* stage = reinterpret_cast<unsigned*>(pfb_smem + (((size_t)C * pitchT * sizeof(float2) + (size_t)N * 2 + 15) & ~(size_t)15));
+    unsigned* stage = reinterpret_cast<unsigned*>(pfb_smem + (((size_t)C * pitchT * sizeof(float2) + (size_t)N * 2 + 127) & ~(size_t)127));
     unsigned qi = 0; /* steps taken by this thread: stage buffer = qi & 1 */
+    /* TMA form of the staging (p.use_tma): thread 0 requests the whole CTA's window of a step as 2-D tensor-map copies
+     * (rows x 256 pairs each) that complete on an mbarrier per stage buffer; a block barrier per step keeps a buffer from being
+     * refilled while a warp still reads it.  Layout: stage[buf][half = t >> 8][row][t & 255]. */
+    constexpr int kRows = T - 1 + SC, kHalves = NT / kTmaBox;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(stage + 2 * kRows * NT);
+    unsigned tma_uses[2] = {0u, 0u};
+    if (kStaged && p.use_tma) {
+        if (threadIdx.x == 0) {
+            pfb_mbar_init(bar0, 1);
+            pfb_mbar_init(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     auto stage_window = [&](long n0s, int nvs, int task, int j, unsigned buf) {
         const int s = (task >> (p.lgN - 1)) * SC, np = (task & ((N >> 1) - 1)) * 2;
         if (!((n0s + s >= T - 1) && (s + SC <= nvs))) {
             return; /* start-up / ragged windows are read directly */
+        }
+        if (p.use_tma) {
+            if (threadIdx.x == 0) { /* its pair is the first of the step's NT pairs */
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const unsigned bar = bar0 + 8u * buf;
+                pfb_mbar_expect_tx(bar, (unsigned)(kRows * NT * 4));
+#pragma unroll
+                for (int h = 0; h < kHalves; h++) {
+                    pfb_tma_load_2d((unsigned)__cvta_generic_to_shared(stage + ((size_t)buf * kHalves + h) * kRows * kTmaBox), &tmap, bar,
+                                    ((np + j * N) >> 1) + h * kTmaBox, (int)(n0s + s - (T - 1)));
+                }
+            }
+            return;
         }
         const unsigned short* src = reinterpret_cast<const unsigned short*>(p.in) + (n0s + s - (T - 1)) * (long)M + np + j * N;
         const unsigned d32 = (unsigned)__cvta_generic_to_shared(stage + (size_t)buf * (T - 1 + SC) * NT + threadIdx.x);
@@ -437,7 +500,9 @@ pfbn_kernel(const PfbNParams p) {
                 if ((int)threadIdx.x < n_tasks) {
                     stage_window(n0, nv, threadIdx.x, 0, qi & 1u);
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (!p.use_tma) {
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                }
             }
             for (int task = threadIdx.x; task < n_tasks; task += NT) {
                 const int s = (task >> (p.lgN - 1)) * SC, np = (task & ((N >> 1) - 1)) * 2;
@@ -456,6 +521,9 @@ pfbn_kernel(const PfbNParams p) {
                     const int b = np + j * N;
                     if (kStaged) {
                         /* request the next step's window, then wait for this step's */
+                        if (p.use_tma) {
+                            __syncthreads(); /* every warp is done with the buffer the next copy fills */
+                        }
                         if (j + 1 < R) {
                             stage_window(n0, nv, task, j + 1, (qi + 1u) & 1u);
                         } else if (task + NT < n_tasks) {
@@ -463,7 +531,9 @@ pfbn_kernel(const PfbNParams p) {
                         } else if (more) {
                             stage_window(n0 + C, nv_next, threadIdx.x, 0, (qi + 1u) & 1u);
                         }
-                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        if (!p.use_tma) {
+                            asm volatile("cp.async.commit_group;" ::: "memory");
+                        }
                     }
                     float2 ga[T], gb[T];
 #pragma unroll
@@ -488,15 +558,25 @@ pfbn_kernel(const PfbNParams p) {
                         }
                     }
                     if (kStaged) {
-                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        if (!p.use_tma) {
+                            asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        } else if (interior) {
+                            const unsigned bsel = qi & 1u;
+                            pfb_mbar_wait(bar0 + 8u * bsel, tma_uses[bsel] & 1u);
+                            tma_uses[bsel]++;
+                        }
                     }
                     if (kStaged && interior) {
                         /* stream the staged rows through the accumulators: row i feeds outputs i-(T-1) .. i with taps
                          * T-1 .. 0 (every output sums its taps from the oldest sample to the newest, as the direct path) */
-                        const unsigned* mine = stage + (size_t)(qi & 1u) * (T - 1 + SC) * NT + threadIdx.x;
+                        /* cp.async form: stage[buf][row][t]; TMA form: stage[buf][t >> 8][row][t & 255] */
+                        const unsigned* mine = p.use_tma ? stage + ((size_t)(qi & 1u) * kHalves + (threadIdx.x / kTmaBox)) * kRows * kTmaBox
+                                                               + (threadIdx.x % kTmaBox)
+                                                         : stage + (size_t)(qi & 1u) * kRows * NT + threadIdx.x;
+                        const int row_pitch = p.use_tma ? kTmaBox : NT;
 #pragma unroll
                         for (int i = 0; i < T - 1 + SC; i++) {
-                            const unsigned raw = mine[i * NT];
+                            const unsigned raw = mine[i * row_pitch];
                             float2 xa = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7440)),
                                                     __uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7441)));
                             float2 xb = make_float2(__uint_as_float(__byte_perm(raw, 0x4B000000u, 0x7442)),
@@ -841,7 +921,7 @@ pfbn_chunk_times(int N) {
 
 template <int T, bool CU8, int SC, int NT>
 static int
-launch_pfbn_nt(const PfbNParams& p, int grid, size_t smem, cudaStream_t s) {
+launch_pfbn_nt(const PfbNParams& p, const CUtensorMap& tmap, int grid, size_t smem, cudaStream_t s) {
     static bool attr_done[64] = {};
     int dev = 0;
     DSDNEO_CUDA(cudaGetDevice(&dev));
@@ -853,7 +933,7 @@ launch_pfbn_nt(const PfbNParams& p, int grid, size_t smem, cudaStream_t s) {
     }
     {
         KernelTimer kt("pfbn_kernel", s);
-        pfbn_kernel<T, CU8, SC, NT><<<grid, NT, smem, s>>>(p);
+        pfbn_kernel<T, CU8, SC, NT><<<grid, NT, smem, s>>>(p, tmap);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();
@@ -862,8 +942,38 @@ launch_pfbn_nt(const PfbNParams& p, int grid, size_t smem, cudaStream_t s) {
 
 template <int T, bool CU8, int SC>
 static int
-launch_pfbn(const PfbNParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
-    return threads == 256 ? launch_pfbn_nt<T, CU8, SC, 256>(p, grid, smem, s) : launch_pfbn_nt<T, CU8, SC, 512>(p, grid, smem, s);
+launch_pfbn(const PfbNParams& p, const CUtensorMap& tmap, int grid, int threads, size_t smem, cudaStream_t s) {
+    return threads == 256 ? launch_pfbn_nt<T, CU8, SC, 256>(p, tmap, grid, smem, s) : launch_pfbn_nt<T, CU8, SC, 512>(p, tmap, grid, smem, s);
+}
+
+/* Tensor map over a cu8 tile seen as [rows][M / 2] 32-bit elements (two adjacent branches per element), box = 256 elements x
+ * `box_rows` rows.  The driver entry point is looked up once (no link against libcuda).  Returns false when the map cannot be
+ * made (alignment, old driver): the caller keeps the cp.async staging. */
+static bool
+make_tile_map(CUtensorMap* map, const void* d_in, int M, long n_rows, int box_rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = NULL;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* ptr = NULL;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) {
+            fn = (encode_fn)ptr;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    if (!fn || (((uintptr_t)d_in) & 15) != 0 || ((size_t)M * 2) % 16 != 0 || n_rows < box_rows) {
+        return false;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)(M / 2), (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)M * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kTmaBox, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(d_in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 /* W_N table for bin stride R = 1 << lg (N = M >> lg), built in float64 on first use */
@@ -1184,9 +1294,19 @@ channelize_impl(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_sample
         }
         const int pitchT = p.N + p.N / 16 + 16 / p.C;
         const int threads = (p.C * p.N <= 8192) ? 256 : 512;
-        size_t smem = (((size_t)p.C * pitchT * sizeof(float2) + (size_t)p.N * sizeof(unsigned short)) + 15) & ~(size_t)15;
+        size_t smem = (((size_t)p.C * pitchT * sizeof(float2) + (size_t)p.N * sizeof(unsigned short)) + 127) & ~(size_t)127;
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
         if (c->cu8 && c->T <= 8) {
-            smem += (size_t)2 * (c->T - 1 + (p.C >= 8 ? 8 : 4)) * threads * sizeof(unsigned); /* per-thread window staging */
+            const int rows = c->T - 1 + (p.C >= 8 ? 8 : 4);
+            smem += (size_t)2 * rows * threads * sizeof(unsigned) + 16; /* window staging (two buffers) + two mbarriers */
+            /* tensor-map staging when a step's pairs are one contiguous run of the row: N / 2 a multiple of the block size */
+            static int tma_env = -1;
+            if (tma_env < 0) {
+                const char* e = getenv("DSDNEO_B200_PFB_TMA");
+                tma_env = e ? atoi(e) : 1;
+            }
+            p.use_tma = tma_env && ((p.N / 2) % threads == 0) && make_tile_map(&tmap, d_in, c->M, n_out, rows) ? 1 : 0;
         }
         const int per_sm = (p.C * p.N <= 8192) ? 2 : 1;
         const long n_chunks = (n_out + p.C - 1) / p.C;
@@ -1199,11 +1319,11 @@ channelize_impl(dsdneo_b200_channelizer* c, const void* d_in, size_t n_in_sample
 #define PFBN_CASE(TT)                                                                                                  \
     case TT:                                                                                                           \
         if (p.C >= 8) {                                                                                                \
-            rc = c->cu8 ? launch_pfbn<TT, true, 8>(p, grid, threads, smem, s)                                          \
-                        : launch_pfbn<TT, false, 8>(p, grid, threads, smem, s);                                        \
+            rc = c->cu8 ? launch_pfbn<TT, true, 8>(p, tmap, grid, threads, smem, s)                                          \
+                        : launch_pfbn<TT, false, 8>(p, tmap, grid, threads, smem, s);                                        \
         } else {                                                                                                       \
-            rc = c->cu8 ? launch_pfbn<TT, true, 4>(p, grid, threads, smem, s)                                          \
-                        : launch_pfbn<TT, false, 4>(p, grid, threads, smem, s);                                        \
+            rc = c->cu8 ? launch_pfbn<TT, true, 4>(p, tmap, grid, threads, smem, s)                                          \
+                        : launch_pfbn<TT, false, 4>(p, tmap, grid, threads, smem, s);                                        \
         }                                                                                                              \
         break;
         switch (c->T) {
