@@ -157,3 +157,102 @@ def test_dmr_bs_data_bursts_on_device(gpu):
                     recovered += 1
                     break
     assert recovered == n_ch * n_bursts, recovered
+
+
+def _voice_burst(rng, gpu, L, frames49, first, slot_bit):
+    """One BS voice burst in dibits: CACH (TACT with the slot bit), three AMBE+2 frames (Golay-protected, PN-modulated) through the
+    reference's interleave schedule, the BS VOICE sync (burst A) or an arbitrary EMB field."""
+    from test_mbe_ecc import ambe_encode
+
+    amap = gpu.ambe_2450_dibit_map()
+    cach = np.zeros(24, np.uint8)
+    cach[:7] = H.hamming_7_4_encode_bruteforce((1, slot_bit, 0, 0))
+    cach[7:] = rng.integers(0, 2, 17)
+    tx = np.array([cach[H.DMR_CACH_INTERLEAVE[i]] for i in range(24)], np.uint8)
+    dib = np.zeros(144, np.int64)
+    dib[:12] = (tx[0::2] << 1) | tx[1::2]
+    frs = [ambe_encode(L, d) for d in frames49]
+    for f, off, cnt, m0 in [(0, 12, 36, 0), (1, 48, 18, 0), (1, 90, 18, 18), (2, 108, 36, 0)]:
+        for i in range(cnt):
+            hr, hc, lr, lc = amap[m0 + i]
+            dib[off + i] = (int(frs[f][hr, hc]) << 1) | int(frs[f][lr, lc])
+    dib[66:90] = [int(c) for c in "131111333113313313113313"] if first else rng.integers(0, 4, 24)
+    return dib
+
+
+def test_c4_chain_voice_and_data_on_device(gpu):
+    """BASELINE config C4 in miniature, no host step between slicer and vocoder bits: DMR base-station traffic (slot 1 voice
+    superframes A..F, slot 2 data bursts, noise) at discriminator level -> dmr matched filter + slicer -> BS DATA / BS VOICE sync
+    hunt -> data burst cutter -> BPTC(196,96) + Golay(20,8); voice burst cutter (6 bursts per superframe) -> AMBE+2 3600x2450
+    frame ECC.  Every transmitted payload and every transmitted 49-bit parameter vector comes back."""
+    import torch
+    from test_mbe_ecc import _o
+
+    L = _o()
+    rng = np.random.default_rng(404)
+    n_ch, n_bursts, max_hits, voice_hits, vb = 12, 26, 24, 4, 11
+    taps = _taps()
+    xs, sent_v, sent_d = [], [], []
+    for c in range(n_ch):
+        parts, sv, sd, k = [rng.integers(0, 4, 60)], [], [], 0
+        for b in range(n_bursts):
+            if b % 2 == 0:
+                frames = rng.integers(0, 2, (3, 49)).astype(np.uint8)
+                parts.append(_voice_burst(rng, gpu, L, frames, k % 6 == 0, 0))
+                sv.append(frames)
+                k += 1
+            else:
+                payload = rng.integers(0, 2, 96).astype(np.uint8)
+                parts.append(H.dmr_build_bs_data_burst(rng, payload, 7, 3, tact4=(1, 1, 0, 0))[0])
+                sd.append(payload)
+        parts.append(rng.integers(0, 4, 40))
+        xs.append(H.synth_dmr_disc(rng, np.concatenate(parts), taps[1], 10000.0, 0.0 if c % 3 == 0 else 300.0 + 25.0 * c))
+        sent_v.append(sv)
+        sent_d.append(sd)
+    xs = np.stack(xs)
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([gpu.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), xs.shape[1])
+    fs = gpu.FrameSync(n_ch, [(DMR_SYNC, 10), ("131111333113313313113313", 12)])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=max_hits)
+    ar = torch.arange(max_hits, device="cuda")[None, :]
+
+    def split(typ, keep):
+        m = (hits[..., 1] == typ) & (ar < n_hits[:, None])
+        order = torch.argsort((~m).to(torch.int8), dim=1, stable=True)
+        h = torch.gather(hits, 1, order[..., None].expand(-1, -1, 2))[:, :keep].contiguous()
+        return h, m.sum(1).to(torch.int32).clamp(max=keep)
+
+    dh, dn = split(10, max_hits)
+    vh, vn = split(12, voice_hits)
+    cut = gpu.dmr_burst_cut(res["dibits"], res["reliability"], res["count"], dh, dn)
+    k = cut["valid"].shape[0]
+    out96 = torch.zeros((k, 96), dtype=torch.uint8, device="cuda")
+    r3 = torch.zeros((k, 3), dtype=torch.uint8, device="cuda")
+    errs = torch.zeros(k, dtype=torch.int32, device="cuda")
+    Lb = gpu.lib()
+    gpu.check(Lb.dsdneo_b200_bptc_196x96_batch(cut["info196"].data_ptr(), 1, out96.data_ptr(), r3.data_ptr(), errs.data_ptr(), k, None))
+    cach, fr, sync, valid = gpu.dmr_voice_cut(res["dibits"], res["count"], vh, vn, voice_hits, vb)
+    n_fr = fr.shape[0] * 3
+    ambe_d = torch.zeros((n_fr, 49), dtype=torch.uint8, device="cuda")
+    c0 = torch.zeros(n_fr, dtype=torch.int32, device="cuda")
+    tot = torch.zeros(n_fr, dtype=torch.int32, device="cuda")
+    gpu.check(Lb.dsdneo_b200_ambe3600x2450_decode_batch(fr.data_ptr(), ambe_d.data_ptr(), c0.data_ptr(), tot.data_ptr(), n_fr, None))
+    torch.cuda.synchronize()
+    ok_d = ((cut["valid"] == 1) & (errs == 0)).view(n_ch, max_hits).cpu().numpy()
+    out96 = out96.view(n_ch, max_hits, 96).cpu().numpy()
+    v = (valid.view(n_ch, voice_hits, vb).bool() & (torch.arange(vb, device="cuda") % 2 == 0)
+         & (ar[:, :voice_hits] < vn[:, None])[..., None]).cpu().numpy()
+    ambe_d = ambe_d.view(n_ch, voice_hits, vb, 3, 49).cpu().numpy()
+    tot = tot.view(n_ch, voice_hits, vb, 3).cpu().numpy()
+    # the TACT of a voice burst names slot 0 and decodes under Hamming(7,4)
+    tact = cach.view(n_ch, voice_hits, vb, 24)[..., :7].cpu().numpy()
+    for c in range(n_ch):
+        got_p = {out96[c, h].tobytes() for h in range(max_hits) if ok_d[c, h]}
+        assert {p.tobytes() for p in sent_d[c]} <= got_p, c
+        got_f = {ambe_d[c, h, j, f].tobytes() for h in range(voice_hits) for j in range(vb) for f in range(3) if v[c, h, j] and tot[c, h, j, f] <= 3}
+        want_f = {f.tobytes() for fr3 in sent_v[c] for f in fr3}
+        assert len(want_f & got_f) >= len(want_f) - 3, (c, len(want_f & got_f), len(want_f))  # a superframe cut short by the stream's end
+        for h in range(voice_hits):
+            if v[c, h, 0]:
+                assert np.array_equal(tact[c, h, 0], H.hamming_7_4_encode_bruteforce((1, 0, 0, 0)))
