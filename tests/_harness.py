@@ -1094,14 +1094,14 @@ def lsd_16_8_encode(byte):
     return [(byte >> (7 - i)) & 1 for i in range(8)] + [(par >> (7 - i)) & 1 for i in range(8)]
 
 
-def p25p1_build_ldu(rng, nac, ldu2=False):
+def p25p1_build_ldu(rng, nac, ldu2=False, voice=None):
     """One LDU1 / LDU2: sync + NID + 9 IMBE frames, 24 Hamming(10,6,3) hex words carrying an RS codeword, LSD.  Returns
     (dibits incl. status, truth dict)."""
     n_data = 16 if ldu2 else 12
     n_par = 24 - n_data
     data = rng.integers(0, 64, n_data)
     par, dat = rs63_shortened_encode(data, n_par)
-    voice = rng.integers(0, 2, (9, 184)).astype(np.int64)
+    voice = rng.integers(0, 2, (9, 184)).astype(np.int64) if voice is None else np.asarray(voice, np.int64).reshape(9, 184)
     lsd = rng.integers(0, 256, 2)
 
     def imbe(k):

@@ -212,3 +212,60 @@ def test_rx_bank_acquires_an_unaligned_stream(gpu):
     assert got >= 0.5 * n_tx and got >= 12, (got, n_tx)
     blind, _ = run_bank(acquire_tiles=0)
     assert recovered(blind) < got, (recovered(blind), got)
+
+
+def test_rx_bank_voice_records_decode_to_the_transmitted_imbe_vectors(gpu):
+    """The metric's chain up to the vocoder's input: cu8 IQ of voice channels whose LDUs carry VALID IMBE 7200x4400 codewords
+    (Golay / Hamming protected, PN-modulated) -> receive bank -> voice records -> dsdneo_b200_p25p1_voice_imbe_decode_batch:
+    the 88-bit parameter vectors of every decoded LDU are the transmitted ones, with the error counts the reference would store."""
+    import torch
+    from test_mbe_ecc import _o, imbe_encode
+
+    L = _o()
+    rng = np.random.default_rng(88)
+    n_ch, pairs = 4, 5 * BP
+    taps = _taps()
+    chans, sent = [], []
+    for c in range(n_ch):
+        nac = int(rng.integers(1, 0xFFE))
+        parts, vecs, n = [rng.integers(0, 4, 150)], {}, 150
+        k = 0
+        while n < 6200 - 900:
+            d88 = rng.integers(0, 2, (9, 88)).astype(np.uint8)
+            voice = np.zeros((9, 184), np.int64)
+            for v in range(9):
+                voice[v] = imbe_encode(L, d88[v]).reshape(-1)  # imbe_fr[8][23], row-major
+            frame, _ = H.p25p1_build_ldu(rng, nac, ldu2=bool(k % 2), voice=voice)
+            vecs[n + 23] = d88
+            parts.append(frame)
+            n += frame.size
+            k += 1
+        parts.append(rng.integers(0, 4, 6200 - n))
+        chans.append(H.synth_c4fm_iq(rng, np.concatenate(parts), snr_db=None if c == 0 else 26.0))
+        sent.append(vecs)
+    rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=pairs, input_cu8=True)
+    out = rx.alloc_device_out("cuda")
+    n_ldu = n_match = 0
+    for k in range(3):
+        tile = np.stack([u8[k * pairs:(k + 1) * pairs] for u8 in chans])
+        rx.process(torch.from_numpy(tile).cuda(), pairs, out)
+        fr, vo = rx.records(out)
+        if vo.size == 0:
+            continue
+        d, c0, tot = gpu.p25p1_voice_imbe_decode(out["voices"], int(vo.size))
+        d, tot = d.cpu().numpy(), tot.cpu().numpy()
+        for f in fr:
+            if f["voice_index"] < 0 or f["nid_status"] <= 0:
+                continue
+            c, p = int(f["channel"]), int(f["position"])
+            # the sliced stream lags the transmitted one by a few symbols (filter delays)
+            want = next((sent[c][q] for q in range(p - 8, p - 2) if q in sent[c]), None)
+            if want is None or p < 2300:  # before the slicer's thresholds have settled from their reset
+                continue
+            n_ldu += 1
+            vi = int(f["voice_index"])
+            if np.array_equal(d[vi], want):
+                n_match += 1
+                if c == 0:
+                    assert (tot[vi] == 0).all()  # the noiseless channel: nothing to correct
+    assert n_ldu >= 6 and n_match >= n_ldu - 1, (n_ldu, n_match)
