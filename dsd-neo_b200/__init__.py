@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.dsdneo_b200_demod_bank_get_state.argtypes = [vp, ci, C.POINTER(DemodChanState)]
     L.dsdneo_b200_demod_bank_get_taps.argtypes = [vp, ci, C.POINTER(cf), ci]
     L.dsdneo_b200_full_demod_batch.argtypes = [vp, vp, sz, ci, ci, vp, sz, vp]
+    L.dsdneo_b200_full_demod_batch_cu8.argtypes = [vp, vp, sz, ci, ci, vp, sz, vp]
     L.dsdneo_b200_full_demod_batch_host.argtypes = [vp, vp, sz, ci, ci, vp, sz]
     _bind_optional(L)
     _lib = L
@@ -200,6 +201,20 @@ class DemodBank:
             ),
             "full_demod_batch",
         )
+        return d_result
+
+    def full_demod_cu8(self, d_iq_u8, block_pairs: int, n_blocks: int, d_result=None, stream=None):
+        """d_iq_u8: torch cuda uint8 tensor [n_channels, pitch_pairs, 2] (widened on the device); returns [n_channels, n] f32."""
+        import torch
+
+        assert d_iq_u8.is_cuda and d_iq_u8.dtype == torch.uint8 and d_iq_u8.is_contiguous()
+        assert d_iq_u8.shape[0] == self.n_channels and d_iq_u8.shape[-1] == 2
+        if d_result is None:
+            d_result = torch.empty((self.n_channels, block_pairs * n_blocks), dtype=torch.float32, device=d_iq_u8.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_iq_u8.device)
+        check(lib().dsdneo_b200_full_demod_batch_cu8(self._h, d_iq_u8.data_ptr(), d_iq_u8.shape[1], block_pairs, n_blocks,
+                                                     d_result.data_ptr(), d_result.shape[1], _stream_ptr(stream)), "full_demod_batch_cu8")
         return d_result
 
     def full_demod_host(self, h_iq, block_pairs: int, n_blocks: int):

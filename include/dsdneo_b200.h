@@ -163,6 +163,10 @@ int dsdneo_b200_demod_bank_get_taps(dsdneo_b200_demod_bank* bank, int profile, f
  */
 int dsdneo_b200_full_demod_batch(dsdneo_b200_demod_bank* bank, const float* d_iq, size_t iq_pitch_pairs,
                                  int block_pairs, int n_blocks, float* d_result, size_t result_pitch, void* stream);
+/** The same on cu8 IQ ([n_channels][iq_pitch_pairs] uchar2): widen_u8_to_f32_bias127 (src/dsp/simd_widen.cpp:139-147) fused into
+ *  the channel filter's loads, bit-identical to widening first (2 B per pair through HBM instead of 8). */
+int dsdneo_b200_full_demod_batch_cu8(dsdneo_b200_demod_bank* bank, const uint8_t* d_iq_u8, size_t iq_pitch_pairs, int block_pairs,
+                                     int n_blocks, float* d_result, size_t result_pitch, void* stream);
 
 /** Same, with host buffers: H2D copy, kernels, D2H copy, synchronous. */
 int dsdneo_b200_full_demod_batch_host(dsdneo_b200_demod_bank* bank, const float* h_iq, size_t iq_pitch_pairs,

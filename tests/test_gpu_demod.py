@@ -102,6 +102,20 @@ def test_full_demod_vs_compiled_reference(gpu):
         assert H.bits_equal(got[c], want), H.first_mismatch(got[c], want)
 
 
+def test_cu8_entry_equals_widen_then_full_demod(gpu):
+    """dsdneo_b200_full_demod_batch_cu8 == widen_u8_to_f32_bias127 + dsdneo_b200_full_demod_batch, bit for bit, state included."""
+    import torch
+
+    rng = np.random.default_rng(61)
+    n_ch, bp, nb = 7, 1024, 3
+    u8 = np.stack([H.synth_c4fm_iq(rng, rng.integers(0, 4, bp * nb // 10 + 4), snr_db=18.0)[:bp * nb] for _ in range(n_ch)])
+    a, b = gpu.DemodBank(n_ch, 48000, True), gpu.DemodBank(n_ch, 48000, True)
+    for k in range(2):
+        want = a.full_demod(torch.from_numpy(np.stack([H.widen_cu8(x) for x in u8])).cuda(), bp, nb).cpu().numpy()
+        got = b.full_demod_cu8(torch.from_numpy(u8).cuda(), bp, nb).cpu().numpy()
+        assert H.bits_equal(got, want), k
+
+
 def test_host_buffer_entry_point(gpu):
     rng = np.random.default_rng(10)
     bp, nb = 2048, 2
