@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.dsdneo_b200_memcpy_h2d.argtypes = [vp, vp, sz, vp]
     L.dsdneo_b200_memcpy_d2h.argtypes = [vp, vp, sz, vp]
     L.dsdneo_b200_channel_lpf_design.argtypes = [ci, ci, C.POINTER(cf), ci]
+    L.dsdneo_b200_sps_fir_design.argtypes = [ci, vp, ci, ci, cf, ci, vp, ci]
     L.dsdneo_b200_demod_bank_create.restype = vp
     L.dsdneo_b200_demod_bank_create.argtypes = [C.POINTER(DemodBankConfig)]
     L.dsdneo_b200_demod_bank_destroy.argtypes = [vp]
@@ -126,6 +127,21 @@ def channel_lpf_design(rate_out_hz: int, profile: int):
     buf = (C.c_float * LPF_MAX_TAPS)()
     n = check(lib().dsdneo_b200_channel_lpf_design(rate_out_hz, profile, buf, LPF_MAX_TAPS), "channel_lpf_design")
     return np.frombuffer(buf, dtype=np.float32, count=n).copy()
+
+
+SPS_FIR_DESIGN_INTERP, SPS_FIR_DESIGN_RRC = 0, 1
+
+
+def sps_fir_design(design_kind: int, base, base_sps: int, rrc_alpha: float, sps: int):
+    """design_sps_fir() (src/dsp/dsd_filters.c:94-170): normalised matched-filter taps of the reference's coefficient table
+    `base` (designed at `base_sps`) for `sps` samples per symbol."""
+    import numpy as np
+
+    b = np.ascontiguousarray(base, dtype=np.float32)
+    out = np.zeros(1024, np.float32)
+    n = check(lib().dsdneo_b200_sps_fir_design(design_kind, b.ctypes.data, b.size, base_sps, float(rrc_alpha), sps, out.ctypes.data,
+                                               out.size), "sps_fir_design")
+    return out[:n].copy()
 
 
 def _stream_ptr(stream) -> Optional[int]:

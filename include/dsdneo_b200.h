@@ -92,6 +92,26 @@ enum {
  */
 int dsdneo_b200_channel_lpf_design(int rate_out_hz, int profile, float* taps_out, int max_taps);
 
+enum {
+    DSDNEO_SPS_FIR_DESIGN_INTERP = 0, /* base table re-sampled linearly (p25_filter, nxdn_filter) */
+    DSDNEO_SPS_FIR_DESIGN_RRC = 1,    /* closed-form root-raised cosine (dmr 0.7, dpmr 0.2, m17 0.5) */
+};
+#define DSDNEO_B200_SPS_FIR_MAX_TAPS 1024
+
+/**
+ * Host-side twin of design_sps_fir() (src/dsp/dsd_filters.c:94-170), the lazy per-sps redesign behind p25_filter /
+ * dmr_filter / nxdn_filter / dpmr_filter / m17_filter (:347-370): the base table as it is at its own samples per symbol,
+ * otherwise a filter of the same span in symbols (odd length, <= 1023 taps) re-sampled from the table or evaluated from the
+ * RRC closed form, then scaled to unit DC gain.  `base` is the reference's coefficient table of the filter
+ * (dsd_filters.c:204-323), `design_kind` / `base_sps` / `rrc_alpha` the fields of its sps_fir descriptor (:325-345).
+ * The result is what dsdneo_b200_symbolizer_config::filter_taps and dsdneo_b200_p25p1_rx_config::p25_filter_taps expect,
+ * bit-identical to the taps the reference's filter holds after its first sample at `sps`.
+ * @return the tap count, DSDNEO_B200_EINVAL for arguments the reference would leave the filter unready on (sps <= 1, empty
+ *         table), DSDNEO_B200_EUNSUPPORTED when the taps do not fit `max_taps`.
+ */
+int dsdneo_b200_sps_fir_design(int design_kind, const float* base, int base_len, int base_sps, float rrc_alpha, int sps,
+                               float* taps_out, int max_taps);
+
 /* ---- block side: batched full_demod() for the FSK-discriminator output kind ------------- */
 
 /**
