@@ -1,6 +1,7 @@
 // SPDX-License-Identifier: GPL-3.0-or-later
 // Shared helpers for libdsdneo_b200 (sm_100a only; no CPU fallback anywhere in this library).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,10 +36,10 @@ as_stream(void* s) {
 }
 
 // Every kernel launched by this library bumps this (bench.py reports it as gpu_launches).
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 static inline void
 count_launch(int n = 1) {
-    g_launch_count += (unsigned long long)n;
+    g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed);
 }
 
 int ensure_device();  // 0 when a usable sm_100 device is current, else error code

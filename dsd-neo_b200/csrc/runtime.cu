@@ -3,12 +3,14 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace dsdneo {
 
 static thread_local char t_err[512] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 void
 set_error(const char* fmt, ...) {
@@ -72,6 +74,10 @@ int g_n_acc = 0;
 cudaEvent_t g_ev_pool[2 * kMaxRec];
 int g_ev_pool_n = 0;
 int g_open = -1;
+/* The recorder is process-wide (one table, one event pool, created on the device current at the first timed launch): a
+ * bench facility for ONE device.  The mutex makes it safe against launches from several host threads: it is held from
+ * timing_begin to timing_end, i.e. across the launch the pair brackets (only while timing is enabled). */
+std::mutex g_timing_mu;
 
 cudaEvent_t
 pool_event(int idx) {
@@ -110,6 +116,7 @@ timing_drain() {
 
 void
 timing_begin(const char* name, cudaStream_t s) {
+    g_timing_mu.lock();
     if (g_n_rec == kMaxRec) {
         timing_drain();
     }
@@ -126,6 +133,7 @@ timing_end(cudaStream_t s) {
         cudaEventRecord(g_rec[g_open].b, s);
         g_open = -1;
     }
+    g_timing_mu.unlock();
 }
 
 }  // namespace dsdneo
@@ -182,11 +190,12 @@ dsdneo_b200_stream_sync(void* stream) {
 
 unsigned long long
 dsdneo_b200_launch_count(void) {
-    return g_launch_count;
+    return g_launch_count.load(std::memory_order_relaxed);
 }
 
 int
 dsdneo_b200_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     timing_drain();
     g_n_acc = 0;
     g_timing_on = on != 0;
@@ -199,6 +208,7 @@ dsdneo_b200_timing_report(char* buf, size_t cap) {
         set_error("timing_report: bad buffer");
         return DSDNEO_B200_EINVAL;
     }
+    std::lock_guard<std::mutex> lk(g_timing_mu);
     timing_drain();
     size_t off = 0;
     off += (size_t)snprintf(buf + off, cap - off, "{");

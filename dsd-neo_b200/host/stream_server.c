@@ -14,6 +14,7 @@
  * context argument in the reference, so they answer for the server made current with ..._make_current().
  */
 #include <pthread.h>
+#include <stdatomic.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,7 +35,13 @@ struct dsdneo_b200_stream_server {
     pthread_cond_t can_read, can_write;
 };
 
-static dsdneo_b200_stream_server* g_current = NULL;
+/* One current server per process, as the reference has one decoder per process.  The pointer is atomic so the ingest thread
+ * can switch it while the decoder thread's hooks read it; a hook loads it once per call. */
+static _Atomic(dsdneo_b200_stream_server*) g_current_srv = NULL;
+static inline dsdneo_b200_stream_server*
+current_srv(void) {
+    return atomic_load_explicit(&g_current_srv, memory_order_acquire);
+}
 
 dsdneo_b200_stream_server*
 dsdneo_b200_stream_server_create(size_t ring_floats, unsigned int output_rate_hz, int symbol_rate_hz, int levels, int channel_profile) {
@@ -70,8 +77,9 @@ dsdneo_b200_stream_server_destroy(dsdneo_b200_stream_server* s) {
     if (!s) {
         return;
     }
-    if (g_current == s) {
-        g_current = NULL;
+    {
+        dsdneo_b200_stream_server* expect = s;
+        atomic_compare_exchange_strong(&g_current_srv, &expect, NULL);
     }
     pthread_mutex_destroy(&s->mu);
     pthread_cond_destroy(&s->can_read);
@@ -82,7 +90,7 @@ dsdneo_b200_stream_server_destroy(dsdneo_b200_stream_server* s) {
 
 void
 dsdneo_b200_stream_server_make_current(dsdneo_b200_stream_server* s) {
-    g_current = s;
+    atomic_store_explicit(&g_current_srv, s, memory_order_release);
 }
 
 /* producer side: blocks while the ring is full (back-pressure on the ingest loop) unless `block` is 0 */
@@ -210,20 +218,23 @@ dsdneo_b200_stream_hook_return_pwr(const void* rtl_ctx) {
 
 unsigned int
 dsdneo_b200_stream_hook_output_rate_hz(void) {
-    return g_current ? g_current->output_rate_hz : 0u;
+    dsdneo_b200_stream_server* const cur = current_srv();
+    return cur ? cur->output_rate_hz : 0u;
 }
 
 int
 dsdneo_b200_stream_hook_output_kind(void) {
+    dsdneo_b200_stream_server* const cur = current_srv();
     /* RTL_STREAM_OUTPUT_FSK_DISCRIMINATOR = 1, RTL_STREAM_OUTPUT_SYMBOL_CQPSK = 2 (include/dsd-neo/io/rtl_stream_c.h:31-33) */
-    return (g_current && g_current->output_kind == 2) ? 2 : 1;
+    return (cur && cur->output_kind == 2) ? 2 : 1;
 }
 
 /* dsd_rtl_stream_metrics_hooks.cqpsk_status (rtl_stream_metrics_hooks.h:33): the sample side slices with cqpsk_slice() only
  * when both flags are set (src/core/frames/dsd_dibit.c:829-844) */
 int
 dsdneo_b200_stream_hook_cqpsk_status(int* out_cqpsk_enable, int* out_cqpsk_timing_active) {
-    const int on = (g_current && g_current->output_kind == 2 && g_current->cqpsk_active) ? 1 : 0;
+    dsdneo_b200_stream_server* const cur = current_srv();
+    const int on = (cur && cur->output_kind == 2 && cur->cqpsk_active) ? 1 : 0;
     if (out_cqpsk_enable) {
         *out_cqpsk_enable = on;
     }
@@ -236,7 +247,8 @@ dsdneo_b200_stream_hook_cqpsk_status(int* out_cqpsk_enable, int* out_cqpsk_timin
 /* dsd_rtl_stream_metrics_hooks.snr_cqpsk_db: <= -50 means "no estimate" to the reliability weighting (dsd_dibit.c:404-427) */
 double
 dsdneo_b200_stream_hook_snr_cqpsk_db(void) {
-    return g_current ? g_current->snr_cqpsk_db : -100.0;
+    dsdneo_b200_stream_server* const cur = current_srv();
+    return cur ? cur->snr_cqpsk_db : -100.0;
 }
 
 void
@@ -253,22 +265,24 @@ dsdneo_b200_stream_server_set_output_kind(dsdneo_b200_stream_server* s, int outp
 
 int
 dsdneo_b200_stream_hook_symbol_profile(int* out_symbol_rate_hz, int* out_levels, int* out_channel_profile) {
-    if (!g_current) {
+    dsdneo_b200_stream_server* const cur = current_srv();
+    if (!cur) {
         return -1;
     }
     if (out_symbol_rate_hz) {
-        *out_symbol_rate_hz = g_current->symbol_rate_hz;
+        *out_symbol_rate_hz = cur->symbol_rate_hz;
     }
     if (out_levels) {
-        *out_levels = g_current->levels;
+        *out_levels = cur->levels;
     }
     if (out_channel_profile) {
-        *out_channel_profile = g_current->channel_profile;
+        *out_channel_profile = cur->channel_profile;
     }
     return 0;
 }
 
 uint32_t
 dsdneo_b200_stream_hook_stream_generation(void) {
-    return g_current ? g_current->generation : 0u;
+    dsdneo_b200_stream_server* const cur = current_srv();
+    return cur ? cur->generation : 0u;
 }
