@@ -160,6 +160,27 @@ def test_frontend_streaming_host_tickets(gpu):
         fb.wait_host(99)
 
 
+def test_frontend_six_tiles_ahead_of_the_first_wait(gpu):
+    """A caller that runs six tiles ahead of its first wait (more than the four event slots): waiting for ticket 0 then
+    synchronises on the later tile that reuses its slot, so tile 0's host rows are complete and correct when the wait
+    returns, and so is every tile up to the one waited for."""
+    import torch
+
+    rng = np.random.default_rng(36)
+    bp, nb = 512, 2
+    tiles = [torch.from_numpy(H.synth_wideband(rng, M, bp * nb, [17, 201], snr_db=25.0)[0]).pin_memory() for _ in range(6)]
+    fa = gpu.Frontend(M, 8, False, 12_288_000, bp)
+    fb = gpu.Frontend(M, 8, False, 12_288_000, bp)
+    want = [fa.process_host(t.numpy()).copy() for t in tiles]
+    outs = [torch.zeros((M, bp * nb), dtype=torch.float32).pin_memory() for _ in tiles]
+    tickets = [fb.submit_host(t, outs[i]) for i, t in enumerate(tiles)]
+    fb.wait_host(tickets[0])
+    for i in range(5):  # slot of ticket 0 is held by ticket 4: everything up to tile 4 has landed
+        assert np.array_equal(outs[i].numpy().view(np.uint32), want[i].view(np.uint32)), i
+    fb.wait_host(tickets[5])
+    assert np.array_equal(outs[5].numpy().view(np.uint32), want[5].view(np.uint32))
+
+
 # ---- general kernel: M = 512 ... 8192 and bin-pruned outputs (per-GPU channel classes of one broadcast tile) ----
 
 def _noise_plus_tones(rng, Mx, n_out, tones):
