@@ -740,7 +740,6 @@ sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& po
         if (!(vmin <= vmax)) {
             break;
         }
-        last_vmin = vmin, last_vmax = vmax;
         float sum = __fadd_rn(0.0f, fminf(fmaxf(r0, vmin), vmax));
         sum = __fadd_rn(sum, fminf(fmaxf(r1, vmin), vmax));
         sum = __fadd_rn(sum, fminf(fmaxf(r2, vmin), vmax));
@@ -748,10 +747,20 @@ sym_fast_batch(WarpShared* sh, WarpTracker& tr, int nb, int sps, int lo, int& po
         float sym;
         if (NW > 4) {
             sum = __fadd_rn(sum, fminf(fmaxf(r4, vmin), vmax));
-            sym = div5_rn(sum);
+            /* div5_rn's multiply + correction step, unconditionally; its operand-range test runs beside it (off the carried
+             * chain) and only decides whether this symbol leaves the batch for the general path, which divides with the IEEE
+             * operator.  A sum of exactly +0 (squelched channel; the sum starts from +0 and can never be -0) stays here:
+             * q = +0, remainder +0, result +0 == +0 / 5. */
+            const float q = __fmul_rn(sum, 0.2f);
+            sym = __fmaf_rn(__fmaf_rn(-5.0f, q, sum), 0.2f, q);
+            const float ax = fabsf(sum);
+            if (__builtin_expect(!(ax < 1e30f && (ax > 1e-30f || ax == 0.0f)), 0)) {
+                break;
+            }
         } else {
             sym = __fmul_rn(sum, 0.25f); /* exact scaling == the correctly rounded quotient */
         }
+        last_vmin = vmin, last_vmax = vmax;
         /* next symbol's operands (independent of this symbol's result) */
         off = (off + sps) & (kRing - 1);
         b = sh->ring + off;
