@@ -1133,6 +1133,18 @@ class P25p1Rx:
             stream = torch.cuda.current_stream()
         check(lib().dsdneo_b200_p25p1_rx_wait(self._h, ticket, _stream_ptr(stream)), "p25p1_rx_wait")
 
+    def reacquire(self, synchronised=None, tiles=1):
+        """Sends the channels whose flag is 0 (None: all) back to the sync hunt for the next `tiles` tiles."""
+        import numpy as np
+
+        if synchronised is None:
+            ptr = None
+        else:
+            flags = np.ascontiguousarray(synchronised, dtype=np.int32)
+            assert flags.size == self.n_channels
+            ptr = flags.ctypes.data
+        check(lib().dsdneo_b200_p25p1_rx_reacquire(self._h, ptr, int(tiles)), "p25p1_rx_reacquire")
+
     def input_consumed(self, ticket, stream=None):
         import torch
 

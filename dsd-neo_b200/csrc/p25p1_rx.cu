@@ -107,7 +107,8 @@ struct dsdneo_b200_p25p1_rx {
     dsdneo_b200_frame_sync* fs;
     float* d_disc;
     int phase;         /* which of the two stream buffer sets receives this call */
-    int acq_left;      /* tiles still to run through the acquisition form (cfg.acquire_tiles at start) */
+    int acq_left;      /* tiles still to run through the acquisition form (cfg.acquire_tiles at start, or after _reacquire) */
+    int acq_ready;     /* hunt state allocated, sync pattern set */
     uint8_t *d_dib[2], *d_rel[2];
     int16_t* d_llr[2];
     float* d_symv[2];
@@ -233,6 +234,26 @@ dsdneo_b200_p25p1_rx_dibit_pitch(const dsdneo_b200_p25p1_rx* rx) {
     return rx ? (size_t)rx->cap_new : 0;
 }
 
+/* hunt state + the P25 Phase 1 sync pattern for getFrameSync's acquisition on the device (once per bank) */
+static int
+rx_enable_acquire(dsdneo_b200_p25p1_rx* rx) {
+    if (rx->acq_ready) {
+        return 0;
+    }
+    dsdneo_b200_acq_pattern ap;
+    ap.symbols = kP25Sync;
+    ap.sync_type = 0; /* DSD_SYNC_P25P1_POS */
+    ap.kind = 0;
+    if (dsdneo_b200_sym_class_from_synctype(0, 0, 1, &ap.cls) != 0) {
+        return DSDNEO_B200_EINVAL;
+    }
+    const int rc = dsdneo_b200_symbolizer_set_acquire_patterns(rx->sym, &ap, 1);
+    if (!rc) {
+        rx->acq_ready = 1;
+    }
+    return rc;
+}
+
 dsdneo_b200_p25p1_rx*
 dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
     if (!cfg || cfg->n_channels <= 0 || cfg->rate_hz <= 0 || cfg->block_pairs <= 0 || cfg->max_pairs_per_call < cfg->block_pairs
@@ -303,12 +324,7 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
         if (!rc && cfg->acquire_tiles > 0) {
             /* start never-synchronised: getFrameSync's hunt for the P25 Phase 1 sync (hunting rules, timing nudges, basic lock,
              * sync warm start, matched-filter start-up) runs on the device for the first acquire_tiles tiles */
-            dsdneo_b200_acq_pattern ap;
-            ap.symbols = kP25Sync;
-            ap.sync_type = 0; /* DSD_SYNC_P25P1_POS */
-            ap.kind = 0;
-            ap.cls = one;
-            rc = dsdneo_b200_symbolizer_set_acquire_patterns(rx->sym, &ap, 1);
+            rc = rx_enable_acquire(rx);
             if (!rc) {
                 rc = dsdneo_b200_symbolizer_set_acquired(rx->sym, NULL);
             }
@@ -590,6 +606,25 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     }
     rx->phase ^= 1;
     return (long long)rx->tiles++;
+}
+
+int
+dsdneo_b200_p25p1_rx_reacquire(dsdneo_b200_p25p1_rx* rx, const int* h_synchronised, int tiles) {
+    if (!rx || tiles < 1) {
+        set_error("p25p1_rx_reacquire: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = rx_enable_acquire(rx);
+    if (rc) {
+        return rc;
+    }
+    /* drains the pipeline (device synchronise), then the flagged channels hunt from an empty window */
+    rc = dsdneo_b200_symbolizer_set_acquired(rx->sym, h_synchronised);
+    if (rc) {
+        return rc;
+    }
+    rx->acq_left = tiles;
+    return 0;
 }
 
 int

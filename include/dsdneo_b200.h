@@ -1128,6 +1128,17 @@ long long dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq
                                       const dsdneo_b200_p25p1_rx_out* out, void* stream);
 int dsdneo_b200_p25p1_rx_wait(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
 int dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream);
+/**
+ * Mid-stream loss of sync: sends channels back to getFrameSync()'s hunt (src/dsp/dsd_frame_sync.c, the warm form the
+ * reference runs after a channel's first sync: matched filter kept, hunting rules with the +-1-sample timing nudges, basic
+ * lock, sync warm start) for the next `tiles` tiles.  `h_synchronised`: host array of n_channels flags, 1 = the channel
+ * keeps its lock and runs the synchronised rules as before (its outputs are bit-identical to a stream without this call),
+ * 0 = the channel hunts from an empty window; NULL = every channel hunts.  The reference takes this decision per frame
+ * inside its decode loop (no valid NID -> back to getFrameSync); here the caller takes it from the frame records of the
+ * tiles it has seen (e.g. no frame with nid_status > 0 for a few tiles).  Drains the pipeline (device synchronise); the
+ * acquiring tiles run their stages one after the other, as at stream start (cfg.acquire_tiles).
+ */
+int dsdneo_b200_p25p1_rx_reacquire(dsdneo_b200_p25p1_rx* rx, const int* h_synchronised, int tiles);
 /** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned.
  * Up to six tickets may be outstanding (H2D, the four pipeline stages and D2H of consecutive tiles overlap); a seventh submit
  * first completes the oldest one.  Input and output buffers of a ticket must stay untouched until its wait_host returned. */

@@ -269,3 +269,67 @@ def test_rx_bank_voice_records_decode_to_the_transmitted_imbe_vectors(gpu):
                 if c == 0:
                     assert (tot[vi] == 0).all()  # the noiseless channel: nothing to correct
     assert n_ldu >= 6 and n_match >= n_ldu - 1, (n_ldu, n_match)
+
+
+def test_rx_bank_reacquires_channels_mid_stream(gpu):
+    """dsdneo_b200_p25p1_rx_reacquire: two of four channels lose their symbol phase mid-stream (a stretch of noise that is not
+    a whole number of symbols, then a new transmission).  Left alone the bank keeps slicing them off-phase and loses every frame
+    behind the gap; sent back to the sync hunt for two tiles they lock again and their frames decode with the transmitted NAC /
+    DUID, while the two channels that keep their lock produce bit-identical dibits and frame records in both runs."""
+    import torch
+
+    rng = np.random.default_rng(5151)
+    n_ch, n_tiles, pairs = 4, 6, 3 * BP
+    total = n_tiles * pairs
+    taps = _taps()
+    chans, after = [], {}
+    for c in range(n_ch):
+        u8, truth = _channel(rng, total // 10 + 200, snr_db=24.0)
+        if c >= 2:
+            cut = 2 * pairs
+            lead = int(rng.integers(20, 60)) * 10 + (5 if c == 2 else 7)
+            noise = rng.integers(96, 160, size=(lead, 2), dtype=np.uint8)
+            u8b, truth_b = _channel(rng, (total - cut) // 10 + 200, snr_db=24.0)
+            u8 = np.concatenate([u8[:cut], noise, u8b])
+            after[c] = [(p + (cut + lead) / 10.0, nac, t) for p, nac, t in truth_b if p + (cut + lead) / 10.0 < total // 10 - 900]
+        chans.append(u8[:total])
+
+    def run_bank(reacquire):
+        rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=pairs, input_cu8=True)
+        out = rx.alloc_device_out("cuda")
+        frames, dibs = [], [[] for _ in range(n_ch)]
+        for k in range(n_tiles):
+            if reacquire and k == 2:
+                rx.reacquire([1, 1, 0, 0], tiles=2)
+            tile = np.stack([u8[k * pairs:(k + 1) * pairs] for u8 in chans])
+            tk = rx.submit(torch.from_numpy(tile).cuda(), pairs, out)
+            rx.wait(tk)
+            fr, _ = rx.records(out)
+            frames += [f.copy() for f in fr]
+            cnt = out["counts"].cpu().numpy()
+            d = out["dibits"].cpu().numpy()
+            for c in range(n_ch):
+                dibs[c].append(d[c, :cnt[c]].copy())
+        return frames, [np.concatenate(x) for x in dibs]
+
+    def recovered(frames, c):
+        ok = 0
+        for f in frames:
+            if int(f["channel"]) == c and f["nid_status"] > 0 and any(
+                    f["nac"] == nac and f["duid"] == t["duid"] and abs(int(f["position"]) - p) < 40 for p, nac, t in after[c]):
+                ok += 1
+        return ok
+
+    plain, dibs_plain = run_bank(False)
+    again, dibs_again = run_bank(True)
+    for c in (0, 1):  # channels that keep their lock: nothing moves
+        assert np.array_equal(dibs_plain[c], dibs_again[c]), c
+        fp = [f for f in plain if int(f["channel"]) == c]
+        fa = [f for f in again if int(f["channel"]) == c]
+        assert len(fp) == len(fa) and len(fp) >= 4
+        for x, y in zip(fp, fa):
+            assert x.tobytes() == y.tobytes(), (c, x, y)
+    for c in (2, 3):
+        n_tx = len(after[c])
+        got, lost = recovered(again, c), recovered(plain, c)
+        assert n_tx >= 3 and got >= 2 and got > lost, (c, n_tx, got, lost)
