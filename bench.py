@@ -768,7 +768,9 @@ def run_c3_b200_arm(args):
         h_tiles.append(ht)
     d_tiles = [t.to(dev) for t in h_tiles]
     taps = _p25_filter_taps()
-    rx = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
+    watch = int(getattr(args, "auto_reacquire", 0))  # developer switch: the loss-of-sync watch on the device (default off)
+    rx = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32,
+                      auto_reacquire_tiles=watch)
     out = rx.alloc_device_out(dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -849,7 +851,8 @@ def run_c3_b200_arm(args):
 
     # ---- e2e: pinned host cu8 IQ in, host frames / IMBE frames / dibits out, every copy inside the timed region ----
     e2e_steps = max(3, min(args.steps, 100))
-    rx_h = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32)
+    rx_h = b200.P25p1Rx(C3_CH, taps, rate_hz=C3_RATE, block_pairs=C3_BLOCK, max_pairs_per_call=C3_PAIRS, input_cu8=True, max_hits=32,
+                        auto_reacquire_tiles=watch)
     DEPTH = 6  # host tiles in flight = DEPTH - 1: H2D, the bank's four pipeline stages, D2H (at most six tickets outstanding)
     h_outs = [rx_h.alloc_host_out() for _ in range(DEPTH)]
     d2h = [0]
@@ -921,7 +924,8 @@ def run_c3_b200_arm(args):
                         "symbols_per_step": n_sym, "frames_per_step": n_frames, "frames_decoded_ok": n_good,
                         "imbe_frames_per_step": 9 * n_voice, "host_numa_binding": ("node %s" % numa_node) if numa_node is not None else
                         ("none (one rank)" if world == 1 else "none (the host exposes no NUMA node for the GPU)"),
-                        "e2e_frames_last_step": int(fr_h.size), "e2e_voice_last_step": int(vo_h.size)},
+                        "e2e_frames_last_step": int(fr_h.size), "e2e_voice_last_step": int(vo_h.size),
+                        "auto_reacquire_tiles": watch},
     }
     print(json.dumps(line))
 
@@ -1506,6 +1510,8 @@ def main():
     ap.add_argument("--channels", type=int, default=M)
     ap.add_argument("--channels-cu8", action="store_true",
                     help="(--shard channels) the channelizer hands the receive bank cu8 rows instead of cf32")
+    ap.add_argument("--auto-reacquire", type=int, default=0,
+                    help="(c3) developer switch: cfg.auto_reacquire_tiles of the receive bank (loss-of-sync watch on the device)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "cqpsk", "fec"],
                     help="c3 (default, the judged line): 1024 P25 Phase 1 channels end to end; c2: 256-channel channelizer + "
                          "discriminator; cqpsk / fec: developer lines")

@@ -1046,7 +1046,8 @@ class P25p1RxConfig(C.Structure):
     _fields_ = [("n_channels", C.c_int), ("rate_hz", C.c_int), ("block_pairs", C.c_int), ("max_pairs_per_call", C.c_int),
                 ("input_cu8", C.c_int), ("fir_arith", C.c_int), ("max_hits", C.c_int), ("erasure_threshold", C.c_int),
                 ("hard_override_disabled", C.c_int), ("track_nac", C.c_int), ("channel_squelch_level", C.POINTER(C.c_float)),
-                ("p25_filter_taps", C.POINTER(C.c_float)), ("p25_filter_len", C.c_int), ("acquire_tiles", C.c_int)]
+                ("p25_filter_taps", C.POINTER(C.c_float)), ("p25_filter_len", C.c_int), ("acquire_tiles", C.c_int),
+                ("auto_reacquire_tiles", C.c_int)]
 
 
 class P25p1RxOut(C.Structure):
@@ -1063,7 +1064,7 @@ class P25p1Rx:
     """P25 Phase 1 C4FM receiver bank (dsdneo_b200_p25p1_rx_*): per-channel IQ -> frames / voice records / dibits."""
 
     def __init__(self, n_channels, p25_taps, rate_hz=48000, block_pairs=8192, max_pairs_per_call=49152, input_cu8=True,
-                 fir_arith=FIR_ARITH_FMA, max_hits=32, track_nac=False, acquire_tiles=0):
+                 fir_arith=FIR_ARITH_FMA, max_hits=32, track_nac=False, acquire_tiles=0, auto_reacquire_tiles=0):
         import numpy as np
 
         self._taps = np.ascontiguousarray(p25_taps, dtype=np.float32)
@@ -1073,6 +1074,7 @@ class P25p1Rx:
         cfg.p25_filter_taps = self._taps.ctypes.data_as(C.POINTER(C.c_float))
         cfg.p25_filter_len = self._taps.size
         cfg.acquire_tiles = acquire_tiles
+        cfg.auto_reacquire_tiles = auto_reacquire_tiles
         self.n_channels, self.input_cu8 = n_channels, input_cu8
         self._h = lib().dsdneo_b200_p25p1_rx_create(C.byref(cfg))
         if not self._h:

@@ -83,6 +83,7 @@ int dsdneo_symbolize_sym_stage(dsdneo_b200_symbolizer* y, int n_samples, int mod
 int dsdneo_symbolize_acquire_stage(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode,
                                    int have_sync, const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, int slot,
                                    int hunt_filtered, cudaStream_t s);
+int dsdneo_symbolize_drop_stage(dsdneo_b200_symbolizer* y, int* d_drop, cudaStream_t s);
 
 /* library-internal: the CQPSK chain (cqpsk.cu) behind the channel LPF of the demod bank */
 struct dsdneo_b200_cqpsk_bank;

@@ -96,6 +96,29 @@ update_nac_kernel(const dsdneo_b200_p25p1_frame* frames, const int* frame_off, c
     chan_nac[c] = nac;
 }
 
+/* Loss-of-sync watch (cfg.auto_reacquire_tiles = k): a channel none of whose sync hits of the last k tiles decoded to a valid
+ * NID is flagged; the slicer stage two tiles later sends it back to the sync hunt (the reference returns to getFrameSync()
+ * whenever a frame's NID fails; here the decision is taken per tile, on the device, in stream order -> deterministic). */
+__global__ void
+sync_watch_kernel(const int* n_hits, const int8_t* nid_status, const uint8_t* nid_valid, int max_hits, int* idle, int* drop, int k,
+                  int n_ch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) {
+        return;
+    }
+    const int n = min(n_hits[c], max_hits);
+    bool ok = false;
+    for (int h = 0; h < n; h++) {
+        ok = ok || (nid_valid[c * max_hits + h] && nid_status[c * max_hits + h] > 0);
+    }
+    int v = ok ? 0 : idle[c] + 1;
+    if (v >= k) {
+        drop[c] = 1;
+        v = -2; /* the drop takes effect two tiles from here; from then on k tiles to lock again before the next one */
+    }
+    idle[c] = v;
+}
+
 }  // namespace
 
 struct dsdneo_b200_p25p1_rx {
@@ -109,6 +132,7 @@ struct dsdneo_b200_p25p1_rx {
     int phase;         /* which of the two stream buffer sets receives this call */
     int acq_left;      /* tiles still to run through the acquisition form (cfg.acquire_tiles at start, or after _reacquire) */
     int acq_ready;     /* hunt state allocated, sync pattern set */
+    int *d_idle, *d_drop[2]; /* auto re-acquisition: tiles without a valid NID per channel, drop flags per pipeline slot */
     uint8_t *d_dib[2], *d_rel[2];
     int16_t* d_llr[2];
     float* d_symv[2];
@@ -189,6 +213,9 @@ dsdneo_b200_p25p1_rx_destroy(dsdneo_b200_p25p1_rx* rx) {
     cudaFree(rx->d_total);
     cudaFree(rx->d_hits);
     cudaFree(rx->d_n_hits);
+    cudaFree(rx->d_idle);
+    cudaFree(rx->d_drop[0]);
+    cudaFree(rx->d_drop[1]);
     cudaFree(rx->d_code63);
     cudaFree(rx->d_rel63);
     cudaFree(rx->d_par);
@@ -321,6 +348,22 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
         }
         int rc = dsdneo_b200_symbolizer_set_class(rx->sym, cls);
         free(cls);
+        if (!rc && cfg->auto_reacquire_tiles > 0) {
+            /* every tile runs the hunt kernel in front of the slicer (it returns at once for synchronised channels) */
+            rc = rx_enable_acquire(rx);
+            if (!rc && cfg->acquire_tiles <= 0) {
+                int* ones = (int*)malloc(n * sizeof(int));
+                if (!ones) {
+                    rc = DSDNEO_B200_ENOMEM;
+                } else {
+                    for (size_t i = 0; i < n; i++) {
+                        ones[i] = 1;
+                    }
+                    rc = dsdneo_b200_symbolizer_set_acquired(rx->sym, ones); /* the stream starts symbol-aligned */
+                    free(ones);
+                }
+            }
+        }
         if (!rc && cfg->acquire_tiles > 0) {
             /* start never-synchronised: getFrameSync's hunt for the P25 Phase 1 sync (hunting rules, timing nudges, basic lock,
              * sync warm start, matched-filter start-up) runs on the device for the first acquire_tiles tiles */
@@ -358,6 +401,11 @@ dsdneo_b200_p25p1_rx_create(const dsdneo_b200_p25p1_rx_config* cfg) {
     RX_ALLOC(rx->d_total, n * sizeof(long long));
     RX_ALLOC(rx->d_hits, slots * 2 * sizeof(int));
     RX_ALLOC(rx->d_n_hits, n * sizeof(int));
+    if (cfg->auto_reacquire_tiles > 0) {
+        RX_ALLOC(rx->d_idle, n * sizeof(int));
+        RX_ALLOC(rx->d_drop[0], n * sizeof(int));
+        RX_ALLOC(rx->d_drop[1], n * sizeof(int));
+    }
     RX_ALLOC(rx->d_code63, slots * 63);
     RX_ALLOC(rx->d_rel63, slots * 63);
     RX_ALLOC(rx->d_par, slots);
@@ -522,7 +570,19 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
     so.d_llr = rx->d_llr[cur] + 2 * kKeep;
     so.d_count = rx->d_count[cur];
     so.pitch = rx->pitch;
-    if (acq) {
+    const bool watch = rx->cfg.auto_reacquire_tiles > 0;
+    if (watch && tile >= 2) { /* decisions of the frame stage two tiles back (stage C already waits for it) */
+        rc = dsdneo_symbolize_drop_stage(rx->sym, rx->d_drop[slot], s);
+        if (rc) {
+            return rc;
+        }
+    }
+    if (watch && !acq) {
+        /* the pipelined form of the acquisition tile: the matched filter has run in stage B, the hunt kernel takes the channels
+         * that are hunting, the slicer the others (neither touches state of the stages in front) */
+        rc = dsdneo_symbolize_acquire_stage(rx->sym, rx->d_disc, (size_t)rx->cap_pairs, n_pairs, DSDNEO_SYM_MODE_GET_DIBIT_SOFT, 1, &so, NULL,
+                                            slot, 2, s);
+    } else if (acq) {
         /* getFrameSync's hunt + getDibitSoft on this tile.  The hunt runs on the matched filter's output, as every hunt of the
          * reference after a channel's first sync does (lastsynctype known): a cold hunt on raw samples locks half a symbol off
          * once the 91-tap p25_filter (45 samples = 4.5 symbols of delay) switches on, and the reference only recovers from
@@ -581,6 +641,13 @@ dsdneo_b200_p25p1_rx_submit(dsdneo_b200_p25p1_rx* rx, const void* d_iq, size_t i
                                                out->voice_capacity, s);
     if (rc) {
         return rc;
+    }
+    if (watch) {
+        KernelTimer kt("sync_watch_kernel", s);
+        sync_watch_kernel<<<(n_ch + 127) / 128, 128, 0, s>>>(rx->d_n_hits, rx->d_nid_status, rx->d_nid_valid, rx->max_hits, rx->d_idle,
+                                                            rx->d_drop[slot], rx->cfg.auto_reacquire_tiles, n_ch);
+        DSDNEO_KERNEL_CHECK();
+        count_launch();
     }
     if (rx->cfg.track_nac) {
         KernelTimer kt("update_nac_kernel", s);

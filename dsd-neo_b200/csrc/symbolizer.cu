@@ -2491,6 +2491,37 @@ dsdneo_symbolize_sym_stage(dsdneo_b200_symbolizer* y, int n_samples, int mode, i
  * filter of the launch cannot run ahead of them): sym_acquire_kernel, then the matched filter into buffer `slot`, then the
  * slicer for the synchronised part of every channel.  Used by dsdneo_b200_symbolize_acquire_batch and by the receive bank
  * while it acquires (csrc/p25p1_rx.cu). */
+/* Channels flagged in drop[] leave the synchronised state: they hunt from an empty window, exactly as after
+ * dsdneo_b200_symbolizer_set_acquired() with their flag at 0.  The flags are consumed. */
+__global__ void
+sym_drop_kernel(int* drop, int* acquired, int* hunt_since, int* hunt_count, int* lidx, int* level_count, unsigned* hunt_bits, int n_ch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch || !drop[c]) {
+        return;
+    }
+    drop[c] = 0;
+    if (acquired[c]) {
+        acquired[c] = 0;
+        hunt_since[c] = 0, hunt_count[c] = 0, lidx[c] = 0, level_count[c] = 0, hunt_bits[c] = 0u;
+    }
+}
+
+int
+dsdneo_symbolize_drop_stage(dsdneo_b200_symbolizer* y, int* d_drop, cudaStream_t s) {
+    if (!y || !y->d_acquired || !d_drop) {
+        set_error("symbolize drop stage: acquisition is not configured");
+        return DSDNEO_B200_EINVAL;
+    }
+    {
+        KernelTimer kt("sym_drop_kernel", s);
+        sym_drop_kernel<<<(y->n_ch + 127) / 128, 128, 0, s>>>(d_drop, y->d_acquired, y->d_hunt_since, y->d_hunt_count, y->d_lidx,
+                                                              y->d_level_count, y->d_hunt_bits, y->n_ch);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
 int
 dsdneo_symbolize_acquire_stage(dsdneo_b200_symbolizer* y, const float* d_disc, size_t disc_pitch, int n_samples, int mode, int have_sync,
                                const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, int slot, int hunt_filtered,
@@ -2503,7 +2534,8 @@ dsdneo_symbolize_acquire_stage(dsdneo_b200_symbolizer* y, const float* d_disc, s
     if (rc) {
         return rc;
     }
-    if (hunt_filtered) { /* the matched filter already runs (every hunt after a channel's first sync): hunt on its output */
+    if (hunt_filtered == 1) { /* the matched filter already runs (every hunt after a channel's first sync): hunt on its output
+                               * (2: the caller has run the filter stage for this slot itself, on another stream) */
         rc = dsdneo_symbolize_fir_stage(y, d_disc, disc_pitch, n_samples, slot, s);
         if (rc) {
             return rc;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DSDNEO_B200_ABI_VERSION 1
+#define DSDNEO_B200_ABI_VERSION 2 /* 2: dsdneo_b200_p25p1_rx_config grew auto_reacquire_tiles */
 
 enum {
     DSDNEO_B200_OK = 0,
@@ -1084,6 +1084,12 @@ typedef struct dsdneo_b200_p25p1_rx_config {
                               * (dsdneo_b200_symbolize_reacquire_batch: hunt on the matched filter's output, timing nudges, sync
                               * warm start), one tile at a time; a channel that has not found the P25 Phase 1 sync by then continues
                               * with the synchronised rules */
+    int auto_reacquire_tiles; /* 0: off; k > 0: loss-of-sync watch on the device -- a channel none of whose sync hits of the
+                               * last k tiles decoded to a valid NID goes back to getFrameSync()'s hunt (warm form, on the matched
+                               * filter's output) two tiles later, inside the tile pipeline (no serialised tiles, no host step) and
+                               * in stream order, so a stream decodes the same way however it is cut into calls of the same size;
+                               * it hunts until it finds the sync again.  The reference takes this decision per frame (NID failure
+                               * -> getFrameSync); k * tile length should exceed the longest gap between frames of a live channel */
 } dsdneo_b200_p25p1_rx_config;
 typedef struct dsdneo_b200_p25p1_rx_out { /* device buffers */
     dsdneo_b200_p25p1_frame* d_frames;

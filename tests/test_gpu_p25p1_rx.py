@@ -287,7 +287,7 @@ def test_rx_bank_reacquires_channels_mid_stream(gpu):
         u8, truth = _channel(rng, total // 10 + 200, snr_db=24.0)
         if c >= 2:
             cut = 2 * pairs
-            lead = int(rng.integers(20, 60)) * 10 + (5 if c == 2 else 7)
+            lead = int(rng.integers(20, 60)) * 10 + ((5 if c == 2 else 4) - cut) % 10  # new symbol phase: 5 / 4 samples off
             noise = rng.integers(96, 160, size=(lead, 2), dtype=np.uint8)
             u8b, truth_b = _channel(rng, (total - cut) // 10 + 200, snr_db=24.0)
             u8 = np.concatenate([u8[:cut], noise, u8b])
@@ -333,3 +333,74 @@ def test_rx_bank_reacquires_channels_mid_stream(gpu):
         n_tx = len(after[c])
         got, lost = recovered(again, c), recovered(plain, c)
         assert n_tx >= 3 and got >= 2 and got > lost, (c, n_tx, got, lost)
+
+
+def test_rx_bank_auto_reacquire_on_the_device(gpu):
+    """cfg.auto_reacquire_tiles: the loss-of-sync watch on the device.  Same scenario as above (two of four channels lose their
+    symbol phase behind a stretch of noise), no host step: the bank alone sends them back to the sync hunt once their sync hits
+    stop decoding, they lock again and their frames decode; the channels that keep decoding are never dropped and stay
+    bit-identical to a bank without the watch; the pipelined (submit / wait behind) and the tile-by-tile form give the same
+    records (the decisions are taken in stream order)."""
+    import torch
+
+    rng = np.random.default_rng(6161)
+    n_ch, n_tiles, pairs = 4, 10, 3 * BP
+    total = n_tiles * pairs
+    taps = _taps()
+    chans, after = [], {}
+    for c in range(n_ch):
+        u8, truth = _channel(rng, total // 10 + 200, snr_db=24.0)
+        if c >= 2:
+            cut = 2 * pairs
+            lead = int(rng.integers(20, 60)) * 10 + ((5 if c == 2 else 4) - cut) % 10  # new symbol phase: 5 / 4 samples off
+            noise = rng.integers(96, 160, size=(lead, 2), dtype=np.uint8)
+            u8b, truth_b = _channel(rng, (total - cut) // 10 + 200, snr_db=24.0)
+            u8 = np.concatenate([u8[:cut], noise, u8b])
+            after[c] = [(p + (cut + lead) / 10.0, nac, t) for p, nac, t in truth_b if p + (cut + lead) / 10.0 < total // 10 - 900]
+        chans.append(u8[:total])
+
+    def run_bank(auto, pipelined):
+        rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=pairs, input_cu8=True, auto_reacquire_tiles=auto)
+        outs = [rx.alloc_device_out("cuda") for _ in range(n_tiles)]
+        tiles = [torch.from_numpy(np.stack([u8[k * pairs:(k + 1) * pairs] for u8 in chans])).cuda() for k in range(n_tiles)]
+        frames, dibs = [], [[] for _ in range(n_ch)]
+        tickets = []
+        for k in range(n_tiles):
+            tickets.append(rx.submit(tiles[k], pairs, outs[k]))
+            if not pipelined:
+                rx.wait(tickets[-1])
+                torch.cuda.synchronize()
+        for k in range(n_tiles):
+            rx.wait(tickets[k])
+            torch.cuda.synchronize()
+            fr, _ = rx.records(outs[k])
+            frames += [f.copy() for f in fr]
+            cnt = outs[k]["counts"].cpu().numpy()
+            d = outs[k]["dibits"].cpu().numpy()
+            for c in range(n_ch):
+                dibs[c].append(d[c, :cnt[c]].copy())
+        return frames, [np.concatenate(x) for x in dibs]
+
+    def recovered(frames, c):
+        ok = 0
+        for f in frames:
+            if int(f["channel"]) == c and f["nid_status"] > 0 and any(
+                    f["nac"] == nac and f["duid"] == t["duid"] and abs(int(f["position"]) - p) < 40 for p, nac, t in after[c]):
+                ok += 1
+        return ok
+
+    plain, dibs_plain = run_bank(0, True)
+    auto, dibs_auto = run_bank(2, True)
+    auto_serial, dibs_serial = run_bank(2, False)
+    assert len(auto) == len(auto_serial) and all(x.tobytes() == y.tobytes() for x, y in zip(auto, auto_serial))
+    for c in range(n_ch):
+        assert np.array_equal(dibs_auto[c], dibs_serial[c]), c
+    for c in (0, 1):  # live channels are never dropped
+        assert np.array_equal(dibs_plain[c], dibs_auto[c]), c
+        fp = [f for f in plain if int(f["channel"]) == c]
+        fa = [f for f in auto if int(f["channel"]) == c]
+        assert len(fp) == len(fa) and len(fp) >= 8 and all(x.tobytes() == y.tobytes() for x, y in zip(fp, fa)), c
+    for c in (2, 3):
+        n_tx = len(after[c])
+        got, lost = recovered(auto, c), recovered(plain, c)
+        assert n_tx >= 6 and got >= 3 and got > lost, (c, n_tx, got, lost)
