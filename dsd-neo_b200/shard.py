@@ -147,7 +147,7 @@ class ShardedP25Rx:
 
     def __init__(self, b200, n_channels: int, rank: int, world: int, p25_taps, pairs_per_tile: int, rate_hz: int = 48000,
                  block_pairs: int = 8192, taps_per_branch: int = 8, root: int = 0, group=None, max_hits: int = 32, device=None,
-                 acquire_tiles: int = 0, channels_cu8: bool = False, channel_gain: Optional[float] = None):
+                 acquire_tiles: int = 0, auto_reacquire_tiles: int = 0, channels_cu8: bool = False, channel_gain: Optional[float] = None):
         import torch
 
         self.b200, self.M, self.rank, self.world, self.root, self.group = b200, n_channels, rank, world, root, group
@@ -160,7 +160,8 @@ class ShardedP25Rx:
         self.channels_cu8 = channels_cu8
         self.channel_gain = float(channel_gain) if channel_gain is not None else float(n_channels) ** 0.5
         self.rx = b200.P25p1Rx(self.n_local, p25_taps, rate_hz=rate_hz, block_pairs=block_pairs, max_pairs_per_call=pairs_per_tile,
-                               input_cu8=channels_cu8, max_hits=max_hits, acquire_tiles=acquire_tiles)
+                               input_cu8=channels_cu8, max_hits=max_hits, acquire_tiles=acquire_tiles,
+                               auto_reacquire_tiles=auto_reacquire_tiles)
         self.chan = [torch.empty((self.n_local, pairs_per_tile, 2), dtype=torch.uint8 if channels_cu8 else torch.float32, device=self.dev)
                      for _ in range(2)]
         self.raw = [torch.empty((pairs_per_tile * n_channels, 2), dtype=torch.uint8, device=self.dev) for _ in range(2)]

@@ -98,12 +98,20 @@ import test_gpu_p25p1_rx as T
 
 chans = [T._channel(rng, 3400, snr_db=22.0) for _ in range(3)]
 p25_taps = H.sps_fir_taps(0, 10)
-for acq in (0, 1):
-    rx = b200.P25p1Rx(3, p25_taps, block_pairs=T.BP, max_pairs_per_call=4 * T.BP, acquire_tiles=acq)
+for acq, watch in ((0, 0), (1, 0), (0, 1)):
+    # watch = 1 with a channel of noise: the loss-of-sync watch drops it (sync_watch_kernel, sym_drop_kernel) and the hunt kernel
+    # runs inside the pipeline
+    rx = b200.P25p1Rx(3, p25_taps, block_pairs=T.BP, max_pairs_per_call=2 * T.BP, acquire_tiles=acq, auto_reacquire_tiles=watch)
     rx_out = rx.alloc_device_out("cuda")
-    for kk in range(2):
-        tile = np.stack([u8[kk * 4 * T.BP:(kk + 1) * 4 * T.BP] for u8, _ in chans])
-        tk = rx.submit(torch.from_numpy(tile).cuda(), 4 * T.BP, rx_out)
+    for kk in range(4):
+        tile = np.stack([u8[kk * 2 * T.BP:(kk + 1) * 2 * T.BP] for u8, _ in chans])
+        if watch:
+            tile[2] = rng.integers(96, 160, size=tile[2].shape, dtype=np.uint8)
+        tk = rx.submit(torch.from_numpy(tile).cuda(), 2 * T.BP, rx_out)
+        rx.wait(tk)
+    if watch:
+        rx.reacquire([1, 0, 1], tiles=1)
+        tk = rx.submit(torch.from_numpy(tile).cuda(), 2 * T.BP, rx_out)
         rx.wait(tk)
     torch.cuda.synchronize()
 torch.cuda.synchronize()
