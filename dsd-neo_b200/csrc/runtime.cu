@@ -77,7 +77,7 @@ int g_open = -1;
 /* The recorder is process-wide (one table, one event pool, created on the device current at the first timed launch): a
  * bench facility for ONE device.  The mutex makes it safe against launches from several host threads: it is held from
  * timing_begin to timing_end, i.e. across the launch the pair brackets (only while timing is enabled). */
-std::mutex g_timing_mu;
+std::recursive_mutex g_timing_mu; /* recursive: a nested bracket (none today) must not deadlock */
 
 cudaEvent_t
 pool_event(int idx) {
@@ -195,7 +195,7 @@ dsdneo_b200_launch_count(void) {
 
 int
 dsdneo_b200_timing_enable(int on) {
-    std::lock_guard<std::mutex> lk(g_timing_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_timing_mu);
     timing_drain();
     g_n_acc = 0;
     g_timing_on = on != 0;
@@ -208,7 +208,7 @@ dsdneo_b200_timing_report(char* buf, size_t cap) {
         set_error("timing_report: bad buffer");
         return DSDNEO_B200_EINVAL;
     }
-    std::lock_guard<std::mutex> lk(g_timing_mu);
+    std::lock_guard<std::recursive_mutex> lk(g_timing_mu);
     timing_drain();
     size_t off = 0;
     off += (size_t)snprintf(buf + off, cap - off, "{");
