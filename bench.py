@@ -367,6 +367,14 @@ def run_c2_b200_arm(args):
     clk = clocks.stop()
     ms_per_step = ms_total / args.steps
     value = world * N_IN / (ms_per_step * 1e-3) / 1e6  # whole-job IQ MS/s
+    # control: the same kernels one tile at a time (no overlap between the stages of consecutive tiles)
+    b200.timing_enable(True)
+    for i in range(min(10, args.steps)):
+        fe.process_async(bufs[i % N_ROTATE], out, stream)
+        fe.join(stream)
+        torch.cuda.synchronize()
+    kserial = {k: {"avg_ms": v["ms"] / max(1, v["launches"])} for k, v in b200.timing_report().items()}
+    b200.timing_enable(False)
 
     # ---- roofline of the dominant kernel (algorithmic bytes per launch) ----
     alg_bytes = {
@@ -485,6 +493,8 @@ def run_c2_b200_arm(args):
                    "l2_policy": "%d rotating input buffers of %.1f MB (> 126 MB L2)" % (N_ROTATE, N_IN * 8 / 1e6),
                    "host_numa_binding": "rank 0 on node %s" % numa_node if numa_node is not None else "none"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "kernels_serial": {"avg_ms": {k: v["avg_ms"] for k, v in kserial.items()},
+                           "note": "control: one tile at a time, no overlap between the stages of consecutive tiles"},
         "cpu_baseline": cpu_baseline, "e2e_matches_device_path": same,
     }
     print(json.dumps(line))
