@@ -1474,6 +1474,61 @@ class Symbolizer:
         return res
 
 
+class SymbolStreamView(C.Structure):
+    _fields_ = [("d_symbols", C.c_void_p), ("d_dibits", C.c_void_p), ("d_reliability", C.c_void_p), ("d_llr", C.c_void_p),
+                ("pitch", C.c_size_t), ("d_valid", C.c_void_p), ("d_new", C.c_void_p), ("d_stream_base", C.c_void_p), ("keep", C.c_int)]
+
+
+class SymbolStream:
+    """dsdneo_b200_symbol_stream: the launches of a Symbolizer joined into one stream per channel (history kept on the device)."""
+
+    def __init__(self, n_channels: int, keep: int, max_new: int):
+        self.n_channels, self.keep, self.max_new = n_channels, keep, max_new
+        self._h = lib().dsdneo_b200_symbol_stream_create(n_channels, keep, max_new)
+        if not self._h:
+            raise B200Error("symbol_stream_create: " + last_error())
+
+    def close(self):
+        if self._h:
+            lib().dsdneo_b200_symbol_stream_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def run(self, symbolizer, d_disc, n_samples, mode=SYM_MODE_GET_DIBIT_SOFT, have_sync=1, stream=None):
+        """begin -> dsdneo_b200_symbolize_batch into the stream's rows -> commit; returns the view (device pointers)."""
+        import torch
+
+        assert d_disc.is_cuda and d_disc.dtype == torch.float32 and d_disc.is_contiguous()
+        assert symbolizer.out_pitch(n_samples) <= self.max_new
+        if stream is None:
+            stream = torch.cuda.current_stream(d_disc.device)
+        out = SymbolOut()
+        check(lib().dsdneo_b200_symbol_stream_begin(self._h, C.byref(out)), "symbol_stream_begin")
+        check(lib().dsdneo_b200_symbolize_batch(symbolizer._h, d_disc.data_ptr(), d_disc.shape[1], n_samples, mode, have_sync,
+                                                C.byref(out), _stream_ptr(stream)), "symbolize_batch")
+        view = SymbolStreamView()
+        check(lib().dsdneo_b200_symbol_stream_commit(self._h, C.byref(view), _stream_ptr(stream)), "symbol_stream_commit")
+        return view
+
+    def fetch(self, view):
+        """Host copies of the joined rows (test helper): dict of numpy arrays."""
+        import numpy as np
+        import torch
+
+        torch.cuda.synchronize()
+        n, p = self.n_channels, int(view.pitch)
+        res = {"symbols": np.zeros((n, p), np.float32), "dibits": np.zeros((n, p), np.uint8), "reliability": np.zeros((n, p), np.uint8),
+               "llr": np.zeros((n, p, 2), np.int16), "valid": np.zeros(n, np.int32), "new": np.zeros(n, np.int32),
+               "stream_base": np.zeros(n, np.int64)}
+        for key, ptr in (("symbols", view.d_symbols), ("dibits", view.d_dibits), ("reliability", view.d_reliability), ("llr", view.d_llr),
+                         ("valid", view.d_valid), ("new", view.d_new), ("stream_base", view.d_stream_base)):
+            check(lib().dsdneo_b200_memcpy_d2h(res[key].ctypes.data, ptr, res[key].nbytes, None), "memcpy_d2h")
+        torch.cuda.synchronize()
+        return res
+
+
 def viterbi_k5_decode(cost, in_len, punct=None, out_pitch=None, out_init=None):
     """cost: uint16 [n, pitch]; returns (out uint8 [n, out_pitch], metric uint32 [n])."""
     import numpy as np

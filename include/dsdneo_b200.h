@@ -809,6 +809,46 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
                                             const uint8_t* h_parity_reliab, int erasure_threshold, int8_t* h_status,
                                             int32_t* h_nac, uint8_t* h_duid, int32_t* h_error_count, int n_words);
 
+/* ---- symbol stream: the launches of one channel joined into one stream --------------------------------------- */
+/*
+ * The reference's frame readers work on ONE sequential dibit stream per channel: they look back into dibits already taken
+ * (DMR: 90 dibits from a rolling buffer at every sync, src/protocol/dmr/dmr_data.c:118-157, src/protocol/dmr/dmr_bs.c:137-148)
+ * and keep reading past the end of whatever block of samples arrived.  A symbol stream keeps the last `keep` symbols, dibits,
+ * reliabilities and LLRs of every channel on the device in front of the next launch's outputs, so that the sync hunt and the
+ * frame cutters see frames that straddle launches whole, once.  Per launch:
+ *     dsdneo_b200_symbol_stream_begin(ss, &out);               // rows the slicer writes this launch's outputs into
+ *     dsdneo_b200_symbolize_batch(y, d_disc, pitch, n, mode, have_sync, &out, stream);
+ *     dsdneo_b200_symbol_stream_commit(ss, &view, stream);     // history moved in front of them, positions counted
+ *     // sync hunt `delay` symbols behind the slicer (delay >= the symbols a frame needs after its sync, keep >= delay + the
+ *     // symbols it needs before it): every stream position is searched exactly once, with its whole frame present
+ *     dsdneo_b200_frame_sync_search_batch(fs, view.d_symbols + (view.keep - delay), view.pitch, view.d_new, d_hits, max_hits, d_n_hits, stream);
+ *     dsdneo_b200_sync_hits_rebase(d_hits, d_n_hits, n_channels, max_hits, view.keep - delay, stream);   // hit positions -> row indices
+ *     dsdneo_b200_dmr_burst_cut_batch(view.d_dibits, view.pitch, view.d_reliability, view.pitch, view.d_valid, d_hits, ...);
+ * Stream position of row index i of channel c = view.d_stream_base[c] + i (negative before the stream's first symbol; the rows
+ * hold zeros there).  `max_new` must cover the symbols one launch can add per channel (the pitch rule of
+ * dsdneo_b200_symbol_out for the longest launch).  The P25 Phase 1 receive bank has the same layout built in.
+ */
+typedef struct dsdneo_b200_symbol_stream dsdneo_b200_symbol_stream;
+typedef struct dsdneo_b200_symbol_stream_view {
+    const float* d_symbols;        /* [n_channels][pitch]: `keep` symbols of history, then this launch's */
+    const uint8_t* d_dibits;       /* [n_channels][pitch] */
+    const uint8_t* d_reliability;  /* [n_channels][pitch] */
+    const int16_t* d_llr;          /* [n_channels][pitch][2] */
+    size_t pitch;
+    const int32_t* d_valid;        /* [n_channels] keep + symbols of this launch = valid row length */
+    const int32_t* d_new;          /* [n_channels] symbols of this launch */
+    const long long* d_stream_base; /* [n_channels] stream position of row index 0 */
+    int keep;
+} dsdneo_b200_symbol_stream_view;
+/** `keep`: multiple of 32.  Rows are zero until written. */
+dsdneo_b200_symbol_stream* dsdneo_b200_symbol_stream_create(int n_channels, int keep, int max_new);
+void dsdneo_b200_symbol_stream_destroy(dsdneo_b200_symbol_stream* ss);
+int dsdneo_b200_symbol_stream_reset(dsdneo_b200_symbol_stream* ss, void* stream);
+int dsdneo_b200_symbol_stream_begin(dsdneo_b200_symbol_stream* ss, dsdneo_b200_symbol_out* out);
+int dsdneo_b200_symbol_stream_commit(dsdneo_b200_symbol_stream* ss, dsdneo_b200_symbol_stream_view* view, void* stream);
+/** Adds `offset` to the position of every reported hit (dsdneo_b200_sync_hit[n_channels][max_hits]). */
+int dsdneo_b200_sync_hits_rebase(void* d_hits, const int32_t* d_n_hits, int n_channels, int max_hits, int offset, void* stream);
+
 /**
  * DMR base-station data burst cutter: the collection phase of `dmr_data_sync` (src/protocol/dmr/dmr_data.c:54-65,118-157,
  * 159-179,218-226,261-268) for every BS DATA sync hit of every channel -- 90 dibits back from the dibit after the sync
@@ -817,11 +857,10 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
  * Hamming(7,4)), info bits [196] in transmitted (interleaved) order = the input of dsdneo_b200_bptc_196x96_batch, per-dibit
  * reliabilities of the 98 info dibits, slot-type bits [20] = the input of Golay(20,8), and whether the channel's stream
  * (d_counts dibits) holds the whole burst.  `inverted_dmr` = opts->inverted_dmr (XOR 2 on the part before the sync's end).
- * The cutters see one launch's dibit buffer: a burst that straddles two launches is reported valid = 0 by both (it needs 90
- * dibits before the end of its sync and 54 after).  A streaming caller keeps the last 143 dibits (and reliabilities) of
- * every channel in front of the next launch's dibits -- the layout the P25 receive bank uses for its own stream history
- * (dsdneo_b200_p25p1_rx_*: 1024 symbols kept, frames decoded 864 symbols behind the slicer) -- and drops hits it has
- * already cut; a DMR bank that does this on the device is not built.
+ * The cutters see the dibit rows they are given: on one launch's rows a burst that straddles two launches is reported
+ * valid = 0 by both (it needs 90 dibits before the end of its sync and 54 after).  A streaming caller hands them the joined
+ * rows of a symbol stream (dsdneo_b200_symbol_stream_*, above: history kept on the device in front of every launch, sync hunt
+ * 64 symbols behind the slicer), which cuts every burst once and whole however the stream is split into launches.
  */
 int dsdneo_b200_dmr_burst_cut_batch(const uint8_t* d_dibits, size_t dibit_pitch, const uint8_t* d_reliability,
                                     size_t reliability_pitch, const int32_t* d_counts, const void* d_hits,

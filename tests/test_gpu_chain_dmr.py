@@ -256,3 +256,103 @@ def test_c4_chain_voice_and_data_on_device(gpu):
         for h in range(voice_hits):
             if v[c, h, 0]:
                 assert np.array_equal(tact[c, h, 0], H.hamming_7_4_encode_bruteforce((1, 0, 0, 0)))
+
+
+def test_dmr_bursts_straddling_launches_are_cut_once_and_whole(gpu):
+    """A DMR BS data stream cut into launches in the middle of bursts.  On one launch's rows alone the cutter has to give up
+    every burst that straddles a boundary; on the joined rows of a symbol stream (dsdneo_b200_symbol_stream_*: 256 symbols of
+    history in front of every launch, sync hunt 64 symbols behind the slicer) every burst of the stream is cut exactly once, at
+    the same stream position and with the same bits as in ONE launch over the whole stream, and its payload decodes."""
+    import torch
+
+    rng = np.random.default_rng(123)
+    n_ch, n_bursts, max_hits, keep, delay = 8, 14, 24, 256, 64
+    taps = _taps()
+    chans, xs = [], []
+    for c in range(n_ch):
+        parts, sent = [rng.integers(0, 4, WARMUP + 7 * c)], []
+        for _ in range(n_bursts):
+            payload = rng.integers(0, 2, 96).astype(np.uint8)
+            burst, _ = H.dmr_build_bs_data_burst(rng, payload, int(rng.integers(0, 16)), int(rng.integers(0, 11)))
+            parts += [burst, rng.integers(0, 4, GAP)]
+            sent.append(payload)
+        parts.append(rng.integers(0, 4, 200))
+        chans.append(sent)
+        xs.append(H.synth_dmr_disc(rng, np.concatenate(parts), taps[1], 10000.0, 0.0 if c % 2 == 0 else 300.0 + 30.0 * c))
+    n = min(x.size for x in xs)
+    xs = np.stack([x[:n] for x in xs])
+    cls = gpu.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)
+    L = gpu.lib()
+
+    def bursts_of(cut_h, hits_h, n_hits_h, base):
+        got = {}
+        for c in range(n_ch):
+            for h in range(min(int(n_hits_h[c]), max_hits)):
+                s = c * max_hits + h
+                if cut_h["valid"][s]:
+                    got[(c, int(base[c]) + int(hits_h[c, h, 0]))] = (cut_h["info196"][s].copy(), cut_h["cach24"][s].copy(),
+                                                                     cut_h["slot_type20"][s].copy(), cut_h["rel98"][s].copy())
+        return got
+
+    # one launch over the whole stream
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([cls] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), n)
+    fs = gpu.FrameSync(n_ch, [(DMR_SYNC, 10)])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=max_hits)
+    cut = gpu.dmr_burst_cut(res["dibits"], res["reliability"], res["count"], hits, n_hits)
+    torch.cuda.synchronize()
+    whole = bursts_of({k: v.cpu().numpy() for k, v in cut.items()}, hits.cpu().numpy(), n_hits.cpu().numpy(), np.zeros(n_ch, np.int64))
+    assert len(whole) >= n_ch * n_bursts
+
+    # the same stream in launches that end in the middle of bursts
+    edges = [0, 5010, 9990, 16470, 20010, n - 2000, n]
+    assert all(b > a for a, b in zip(edges, edges[1:]))
+    sy2 = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy2.set_class([cls] * n_ch)
+    sy3 = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy3.set_class([cls] * n_ch)
+    fs2, fs3 = gpu.FrameSync(n_ch, [(DMR_SYNC, 10)]), gpu.FrameSync(n_ch, [(DMR_SYNC, 10)])
+    ss = gpu.SymbolStream(n_ch, keep, max(sy2.out_pitch(b - a) for a, b in zip(edges, edges[1:])))
+    joined, alone, seen = {}, {}, np.zeros(n_ch, np.int64)
+    for a, b in zip(edges, edges[1:]):
+        d = torch.from_numpy(np.ascontiguousarray(xs[:, a:b])).cuda()
+        # (a) joined rows
+        view = ss.run(sy2, d, b - a)
+        hits2 = torch.zeros((n_ch, max_hits, 2), dtype=torch.int32, device="cuda")
+        n_hits2 = torch.zeros(n_ch, dtype=torch.int32, device="cuda")
+        gpu.check(L.dsdneo_b200_frame_sync_search_batch(fs2._h, view.d_symbols + 4 * (keep - delay), view.pitch, view.d_new,
+                                                        hits2.data_ptr(), max_hits, n_hits2.data_ptr(), None))
+        gpu.check(L.dsdneo_b200_sync_hits_rebase(hits2.data_ptr(), n_hits2.data_ptr(), n_ch, max_hits, keep - delay, None))
+        slots = n_ch * max_hits
+        o = {k: torch.zeros((slots, w) if w else (slots,), dtype=torch.uint8, device="cuda")
+             for k, w in (("cach24", 24), ("info196", 196), ("rel98", 98), ("slot_type20", 20), ("valid", 0))}
+        gpu.check(L.dsdneo_b200_dmr_burst_cut_batch(view.d_dibits, view.pitch, view.d_reliability, view.pitch, view.d_valid,
+                                                    hits2.data_ptr(), n_hits2.data_ptr(), n_ch, max_hits, 0, o["cach24"].data_ptr(),
+                                                    o["info196"].data_ptr(), o["rel98"].data_ptr(), o["slot_type20"].data_ptr(),
+                                                    o["valid"].data_ptr(), None))
+        rows = ss.fetch(view)
+        got = bursts_of({k: v.cpu().numpy() for k, v in o.items()}, hits2.cpu().numpy(), n_hits2.cpu().numpy(), rows["stream_base"])
+        assert not (set(got) & set(joined)), "a burst was cut twice"
+        joined.update(got)
+        # (b) every launch on its own rows
+        r3 = sy3.run(d, b - a)
+        h3, nh3 = fs3.search(r3["symbols"], r3["count"], max_hits=max_hits)
+        c3 = gpu.dmr_burst_cut(r3["dibits"], r3["reliability"], r3["count"], h3, nh3)
+        torch.cuda.synchronize()
+        alone.update(bursts_of({k: v.cpu().numpy() for k, v in c3.items()}, h3.cpu().numpy(), nh3.cpu().numpy(), seen))
+        seen += r3["count"].cpu().numpy()
+    # the hunt trails the slicer by `delay` symbols: bursts whose sync ends in the last `delay` symbols of the stream are still pending
+    total = seen
+    expect = {k: v for k, v in whole.items() if k[1] < total[k[0]] - delay}
+    assert len(expect) >= n_ch * n_bursts
+    assert set(joined) == set(expect), (sorted(set(expect) - set(joined))[:5], sorted(set(joined) - set(expect))[:5])
+    for k in expect:
+        for x, y in zip(joined[k], expect[k]):
+            assert np.array_equal(x, y), k
+    assert len(alone) < len(expect)  # launches on their own lose the bursts at their edges
+    info = np.array([joined[k][0] for k in sorted(joined)])
+    out, _, errs = gpu.bptc_196x96(info, interleaved=True)
+    sent = {c: [p.tobytes() for p in chans[c]] for c in range(n_ch)}
+    ok = sum(1 for (c, _), o96, e in zip(sorted(joined), out, errs) if e == 0 and o96.tobytes() in sent[c])
+    assert ok == n_ch * n_bursts, ok
