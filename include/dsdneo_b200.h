@@ -826,7 +826,9 @@ int dsdneo_b200_p25p1_nid_decode_batch_host(const uint8_t* h_code63, const uint8
  *     dsdneo_b200_dmr_burst_cut_batch(view.d_dibits, view.pitch, view.d_reliability, view.pitch, view.d_valid, d_hits, ...);
  * Stream position of row index i of channel c = view.d_stream_base[c] + i (negative before the stream's first symbol; the rows
  * hold zeros there).  `max_new` must cover the symbols one launch can add per channel (the pitch rule of
- * dsdneo_b200_symbol_out for the longest launch).  The P25 Phase 1 receive bank has the same layout built in.
+ * dsdneo_b200_symbol_out for the longest launch).  DMR data bursts: delay >= 54, keep >= delay + 90 + 24 (e.g. 64 / 256);
+ * DMR voice superframes of n_bursts bursts (dsdneo_b200_dmr_voice_cut_batch): delay >= (n_bursts - 1) * 144 + 54, e.g.
+ * 800 / 1024 for six bursts.  The P25 Phase 1 receive bank has the same layout built in (1024 kept, 864 behind).
  */
 typedef struct dsdneo_b200_symbol_stream dsdneo_b200_symbol_stream;
 typedef struct dsdneo_b200_symbol_stream_view {
