@@ -356,3 +356,87 @@ def test_dmr_bursts_straddling_launches_are_cut_once_and_whole(gpu):
     sent = {c: [p.tobytes() for p in chans[c]] for c in range(n_ch)}
     ok = sum(1 for (c, _), o96, e in zip(sorted(joined), out, errs) if e == 0 and o96.tobytes() in sent[c])
     assert ok == n_ch * n_bursts, ok
+
+
+def test_dmr_voice_superframes_straddling_launches(gpu):
+    """The voice burst cutter on the joined rows of a symbol stream (1024 symbols kept, sync hunt 1536 symbols behind the slicer:
+    eleven 144-dibit bursts after the sync): a slot-1 voice stream cut into launches in the middle of superframes gives, for
+    every BS VOICE sync, the same eleven burst records (CACH, ambe_fr, sync / EMB bits, validity) as ONE launch over the whole
+    stream, exactly once."""
+    import torch
+    from test_mbe_ecc import _o
+
+    Lo = _o()
+    rng = np.random.default_rng(505)
+    n_ch, n_bursts, max_hits, vb, keep, delay = 4, 40, 8, 11, 2048, 1536
+    taps = _taps()
+    xs = []
+    for c in range(n_ch):
+        parts, k = [rng.integers(0, 4, 60 + 11 * c)], 0
+        for b in range(n_bursts):
+            if b % 2 == 0:
+                parts.append(_voice_burst(rng, gpu, Lo, rng.integers(0, 2, (3, 49)).astype(np.uint8), k % 6 == 0, 0))
+                k += 1
+            else:
+                parts.append(H.dmr_build_bs_data_burst(rng, rng.integers(0, 2, 96).astype(np.uint8), 7, 3, tact4=(1, 1, 0, 0))[0])
+        parts.append(rng.integers(0, 4, 1700))
+        xs.append(H.synth_dmr_disc(rng, np.concatenate(parts), taps[1], 10000.0, 0.0 if c % 2 == 0 else 300.0))
+    n = min(x.size for x in xs)
+    xs = np.stack([x[:n] for x in xs])
+    cls = gpu.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)
+    VOICE = ("131111333113313313113313", 12)
+    L = gpu.lib()
+
+    def records(cach, fr, sync, valid, hits_h, n_hits_h, base):
+        cach, fr, sync, valid = (t.cpu().numpy() for t in (cach, fr, sync, valid))
+        got = {}
+        for c in range(n_ch):
+            for h in range(min(int(n_hits_h[c]), max_hits)):
+                r0 = (c * max_hits + h) * vb
+                got[(c, int(base[c]) + int(hits_h[c, h, 0]))] = (valid[r0:r0 + vb].copy(), cach[r0:r0 + vb].copy(), fr[r0:r0 + vb].copy(),
+                                                                  sync[r0:r0 + vb].copy())
+        return got
+
+    sy = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy.set_class([cls] * n_ch)
+    res = sy.run(torch.from_numpy(xs).cuda(), n)
+    fs = gpu.FrameSync(n_ch, [VOICE])
+    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=max_hits)
+    whole = records(*gpu.dmr_voice_cut(res["dibits"], res["count"], hits, n_hits, max_hits, vb), hits.cpu().numpy(), n_hits.cpu().numpy(),
+                    np.zeros(n_ch, np.int64))
+    total = res["count"].cpu().numpy()
+    assert len(whole) >= n_ch * 3
+
+    edges = [0, 7010, 15990, 23330, 30010, 41110, n - 3000, n]
+    assert all(b > a for a, b in zip(edges, edges[1:]))
+    sy2 = gpu.Symbolizer(n_ch, 48000, 4800, filters=taps)
+    sy2.set_class([cls] * n_ch)
+    fs2 = gpu.FrameSync(n_ch, [VOICE])
+    ss = gpu.SymbolStream(n_ch, keep, max(sy2.out_pitch(b - a) for a, b in zip(edges, edges[1:])))
+    joined = {}
+    for a, b in zip(edges, edges[1:]):
+        view = ss.run(sy2, torch.from_numpy(np.ascontiguousarray(xs[:, a:b])).cuda(), b - a)
+        h2 = torch.zeros((n_ch, max_hits, 2), dtype=torch.int32, device="cuda")
+        nh2 = torch.zeros(n_ch, dtype=torch.int32, device="cuda")
+        gpu.check(L.dsdneo_b200_frame_sync_search_batch(fs2._h, view.d_symbols + 4 * (keep - delay), view.pitch, view.d_new, h2.data_ptr(),
+                                                        max_hits, nh2.data_ptr(), None))
+        gpu.check(L.dsdneo_b200_sync_hits_rebase(h2.data_ptr(), nh2.data_ptr(), n_ch, max_hits, keep - delay, None))
+        R = n_ch * max_hits * vb
+        cach = torch.zeros((R, 24), dtype=torch.uint8, device="cuda")
+        fr = torch.zeros((R, 3, 4, 24), dtype=torch.uint8, device="cuda")
+        sync = torch.zeros((R, 48), dtype=torch.uint8, device="cuda")
+        valid = torch.zeros(R, dtype=torch.uint8, device="cuda")
+        gpu.check(L.dsdneo_b200_dmr_voice_cut_batch(view.d_dibits, view.pitch, view.d_valid, h2.data_ptr(), nh2.data_ptr(), n_ch, max_hits, vb, 0,
+                                                    cach.data_ptr(), fr.data_ptr(), sync.data_ptr(), valid.data_ptr(), None))
+        rows = ss.fetch(view)
+        got = records(cach, fr, sync, valid, h2.cpu().numpy(), nh2.cpu().numpy(), rows["stream_base"])
+        assert not (set(got) & set(joined)), "a sync was reported twice"
+        joined.update(got)
+    expect = {k: v for k, v in whole.items() if k[1] < total[k[0]] - delay}
+    assert len(expect) >= n_ch * 3 and set(joined) == set(expect), (sorted(expect)[:4], sorted(joined)[:4])
+    full = 0
+    for k in expect:
+        for x, y in zip(joined[k], expect[k]):
+            assert np.array_equal(x, y), k
+        full += int(expect[k][0].all())
+    assert full >= n_ch * 2  # superframes whose eleven bursts are all present
