@@ -3,7 +3,7 @@
   front (timed on a random cu8 tile: its cost does not depend on the content)
       one wideband cu8 stream of N channels x 48 kS/s -> polyphase channelizer (pfbn_kernel) -> full_demod (channel LPF + discriminator)
   sample side + FEC (synthetic DMR BS traffic at discriminator level: slot 1 = voice superframes A..F, slot 2 = data bursts)
-      dmr matched filter + getSymbol + 4FSK slicer -> BS DATA / BS VOICE sync hunt
+      dmr matched filter + getSymbol + 4FSK slicer -> symbol stream (history on the device, steps joined) -> BS DATA / BS VOICE sync hunt
       -> data burst cutter -> BPTC(196,96), Golay(20,8) slot type
       -> voice burst cutter (6 bursts per superframe) -> AMBE+2 3600x2450 frame ECC (3 frames per burst)
       -> mbe synthesis of as many frames from synthetic parameters (parity unpinned; the parameter dequantiser is not built)
@@ -90,6 +90,8 @@ x = torch.from_numpy(np.stack([base[c % 8][0] for c in range(n_ch)])).to(dev)
 sy = b200.Symbolizer(n_ch, 48000, 4800, filters=taps)
 sy.set_class([b200.sym_class_from_synctype(H.SYNC_DMR_BS_DATA_POS, H.SYNC_DMR_BS_DATA_POS)] * n_ch)
 fs = b200.FrameSync(n_ch, [(DATA_SYNC, 10), (VOICE_SYNC, 12)])
+KEEP, DELAY = 2048, 1536  # symbols of history per channel; the hunt trails the slicer by eleven bursts (10 * 144 + 54 <= 1536)
+ss = b200.SymbolStream(n_ch, KEEP, sy.out_pitch(N_SYM_SAMP))
 MAX_HITS, VOICE_HITS, VB = 40, 8, 11  # sync hits per channel and step: all / voice superframes; bursts cut per superframe
 lib = b200.lib()
 cz = b200.Channelizer(n_ch, 8, True) if n_ch >= 256 and (n_ch & (n_ch - 1)) == 0 else None
@@ -112,13 +114,23 @@ def step(check=False):
     else:
         chan.normal_()
     bank.full_demod(chan, 8192, 6, disc)
-    res = sy.run(x, N_SYM_SAMP)
-    hits, n_hits = fs.search(res["symbols"], res["count"], max_hits=MAX_HITS)
+    # the slicer writes behind the stream history kept on the device; the sync hunt runs DELAY symbols behind it, so bursts and
+    # voice superframes that straddle steps are cut whole, once (dsdneo_b200_symbol_stream_*)
+    view = ss.run(sy, x, N_SYM_SAMP)
+    hits = torch.zeros((n_ch, MAX_HITS, 2), dtype=torch.int32, device=dev)
+    n_hits = torch.zeros(n_ch, dtype=torch.int32, device=dev)
+    b200.check(lib.dsdneo_b200_frame_sync_search_batch(fs._h, view.d_symbols + 4 * (KEEP - DELAY), view.pitch, view.d_new, hits.data_ptr(),
+                                                       MAX_HITS, n_hits.data_ptr(), None))
+    b200.check(lib.dsdneo_b200_sync_hits_rebase(hits.data_ptr(), n_hits.data_ptr(), n_ch, MAX_HITS, KEEP - DELAY, None))
     dh, dn = split(hits, n_hits, 10)
     vh, vn = split(hits, n_hits, 12)
     vh, vn = vh[:, :VOICE_HITS].contiguous(), vn.clamp(max=VOICE_HITS)
-    cut = b200.dmr_burst_cut(res["dibits"], res["reliability"], res["count"], dh, dn)
-    k = cut["valid"].shape[0]
+    k = n_ch * MAX_HITS
+    cut = {name: torch.zeros((k, w) if w else (k,), dtype=torch.uint8, device=dev)
+           for name, w in (("cach24", 24), ("info196", 196), ("rel98", 98), ("slot_type20", 20), ("valid", 0))}
+    b200.check(lib.dsdneo_b200_dmr_burst_cut_batch(view.d_dibits, view.pitch, view.d_reliability, view.pitch, view.d_valid, dh.data_ptr(),
+                                                   dn.data_ptr(), n_ch, MAX_HITS, 0, cut["cach24"].data_ptr(), cut["info196"].data_ptr(),
+                                                   cut["rel98"].data_ptr(), cut["slot_type20"].data_ptr(), cut["valid"].data_ptr(), None))
     out96 = torch.zeros((k, 96), dtype=torch.uint8, device=dev)
     r3 = torch.zeros((k, 3), dtype=torch.uint8, device=dev)
     errs = torch.zeros(k, dtype=torch.int32, device=dev)
@@ -126,7 +138,13 @@ def step(check=False):
     slot_ok = torch.zeros(k, dtype=torch.uint8, device=dev)
     slot8 = torch.zeros((k, 8), dtype=torch.uint8, device=dev)
     b200.check(lib.dsdneo_b200_fec_block_decode_batch(b200.FEC_GOLAY_20_8, cut["slot_type20"].data_ptr(), slot8.data_ptr(), slot_ok.data_ptr(), k, None))
-    cach, fr, sync, valid = b200.dmr_voice_cut(res["dibits"], res["count"], vh, vn, VOICE_HITS, VB)
+    R = n_ch * VOICE_HITS * VB
+    cach = torch.zeros((R, 24), dtype=torch.uint8, device=dev)
+    fr = torch.zeros((R, 3, 4, 24), dtype=torch.uint8, device=dev)
+    sync = torch.zeros((R, 48), dtype=torch.uint8, device=dev)
+    valid = torch.zeros(R, dtype=torch.uint8, device=dev)
+    b200.check(lib.dsdneo_b200_dmr_voice_cut_batch(view.d_dibits, view.pitch, view.d_valid, vh.data_ptr(), vn.data_ptr(), n_ch, VOICE_HITS, VB, 0,
+                                                   cach.data_ptr(), fr.data_ptr(), sync.data_ptr(), valid.data_ptr(), None))
     n_fr = fr.shape[0] * 3
     ambe_d = torch.zeros((n_fr, 49), dtype=torch.uint8, device=dev)
     c0 = torch.zeros(n_fr, dtype=torch.int32, device=dev)
