@@ -1474,6 +1474,20 @@ class Symbolizer:
         return res
 
 
+def sync_hits_select(d_hits, d_n_hits, sync_type: int, out_max_hits: int, stream=None):
+    """The hits of one sync type per channel, in stream order (device tensors in and out): (hits [n_ch, out_max_hits, 2], n [n_ch])."""
+    import torch
+
+    n_ch, max_hits = d_hits.shape[0], d_hits.shape[1]
+    out = torch.zeros((n_ch, out_max_hits, 2), dtype=torch.int32, device=d_hits.device)
+    n_out = torch.zeros(n_ch, dtype=torch.int32, device=d_hits.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(d_hits.device)
+    check(lib().dsdneo_b200_sync_hits_select(d_hits.data_ptr(), d_n_hits.data_ptr(), n_ch, max_hits, sync_type, out.data_ptr(), out_max_hits,
+                                             n_out.data_ptr(), _stream_ptr(stream)), "sync_hits_select")
+    return out, n_out
+
+
 class SymbolStreamView(C.Structure):
     _fields_ = [("d_symbols", C.c_void_p), ("d_dibits", C.c_void_p), ("d_reliability", C.c_void_p), ("d_llr", C.c_void_p),
                 ("pitch", C.c_size_t), ("d_valid", C.c_void_p), ("d_new", C.c_void_p), ("d_stream_base", C.c_void_p), ("keep", C.c_int)]

@@ -58,6 +58,29 @@ symstream_rebase_kernel(int32_t* hits, const int32_t* n_hits, int n_ch, int max_
     }
 }
 
+/* one thread per channel: the hits of one sync type, in stream order */
+__global__ void
+sync_hits_select_kernel(const int32_t* hits, const int32_t* n_hits, int n_ch, int max_hits, int sync_type, int32_t* out, int out_max,
+                        int32_t* n_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_ch) {
+        return;
+    }
+    const int n = min(n_hits[c], max_hits);
+    int k = 0;
+    for (int h = 0; h < n; h++) {
+        const int32_t pos = hits[((size_t)c * max_hits + h) * 2], typ = hits[((size_t)c * max_hits + h) * 2 + 1];
+        if (typ == sync_type) {
+            if (k < out_max) {
+                out[((size_t)c * out_max + k) * 2] = pos;
+                out[((size_t)c * out_max + k) * 2 + 1] = typ;
+            }
+            k++;
+        }
+    }
+    n_out[c] = min(k, out_max);
+}
+
 }  // namespace
 
 struct dsdneo_b200_symbol_stream {
@@ -223,6 +246,28 @@ dsdneo_b200_sync_hits_rebase(void* d_hits, const int32_t* d_n_hits, int n_channe
     {
         KernelTimer kt("symstream_rebase_kernel", s);
         symstream_rebase_kernel<<<(n_channels * max_hits + 255) / 256, 256, 0, s>>>((int32_t*)d_hits, d_n_hits, n_channels, max_hits, offset);
+    }
+    DSDNEO_KERNEL_CHECK();
+    count_launch();
+    return 0;
+}
+
+int
+dsdneo_b200_sync_hits_select(const void* d_hits, const int32_t* d_n_hits, int n_channels, int max_hits, int sync_type, void* d_hits_out,
+                             int out_max_hits, int32_t* d_n_out, void* stream) {
+    if (!d_hits || !d_n_hits || !d_hits_out || !d_n_out || n_channels <= 0 || max_hits <= 0 || out_max_hits <= 0) {
+        set_error("sync_hits_select: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    int rc = ensure_device();
+    if (rc) {
+        return rc;
+    }
+    cudaStream_t s = as_stream(stream);
+    {
+        KernelTimer kt("sync_hits_select_kernel", s);
+        sync_hits_select_kernel<<<(n_channels + 127) / 128, 128, 0, s>>>((const int32_t*)d_hits, d_n_hits, n_channels, max_hits, sync_type,
+                                                                        (int32_t*)d_hits_out, out_max_hits, d_n_out);
     }
     DSDNEO_KERNEL_CHECK();
     count_launch();

@@ -850,6 +850,11 @@ int dsdneo_b200_symbol_stream_begin(dsdneo_b200_symbol_stream* ss, dsdneo_b200_s
 int dsdneo_b200_symbol_stream_commit(dsdneo_b200_symbol_stream* ss, dsdneo_b200_symbol_stream_view* view, void* stream);
 /** Adds `offset` to the position of every reported hit (dsdneo_b200_sync_hit[n_channels][max_hits]). */
 int dsdneo_b200_sync_hits_rebase(void* d_hits, const int32_t* d_n_hits, int n_channels, int max_hits, int offset, void* stream);
+/** The hits of one sync type per channel, in stream order: what the reference's dispatch does when it hands a sync to the
+ * handler of its type (src/engine/dispatch: BS DATA syncs -> dmr_data_sync, BS VOICE syncs -> dmrBSBootstrap).  d_hits_out is
+ * dsdneo_b200_sync_hit[n_channels][out_max_hits]; hits beyond out_max_hits are dropped, d_n_out[c] <= out_max_hits. */
+int dsdneo_b200_sync_hits_select(const void* d_hits, const int32_t* d_n_hits, int n_channels, int max_hits, int sync_type,
+                                 void* d_hits_out, int out_max_hits, int32_t* d_n_out, void* stream);
 
 /**
  * DMR base-station data burst cutter: the collection phase of `dmr_data_sync` (src/protocol/dmr/dmr_data.c:54-65,118-157,

@@ -225,6 +225,13 @@ def test_c4_chain_voice_and_data_on_device(gpu):
 
     dh, dn = split(10, max_hits)
     vh, vn = split(12, voice_hits)
+    for typ, keep_n, (wh, wn) in ((10, max_hits, (dh, dn)), (12, voice_hits, (vh, vn))):  # the library's own selection kernel
+        gh, gn = gpu.sync_hits_select(hits, n_hits, typ, keep_n)
+        assert torch.equal(gn, wn)
+        live = torch.arange(keep_n, device="cuda")[None, :] < gn[:, None]
+        assert torch.equal(gh[live], wh[live])
+    dh, dn = gpu.sync_hits_select(hits, n_hits, 10, max_hits)
+    vh, vn = gpu.sync_hits_select(hits, n_hits, 12, voice_hits)
     cut = gpu.dmr_burst_cut(res["dibits"], res["reliability"], res["count"], dh, dn)
     k = cut["valid"].shape[0]
     out96 = torch.zeros((k, 96), dtype=torch.uint8, device="cuda")

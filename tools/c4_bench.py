@@ -102,12 +102,6 @@ disc = torch.empty((n_ch, N_SAMP), dtype=torch.float32, device=dev)
 ar = torch.arange(MAX_HITS, device=dev)[None, :]
 
 
-def split(hits, n_hits, typ):
-    m = (hits[..., 1] == typ) & (ar < n_hits[:, None])
-    order = torch.argsort((~m).to(torch.int8), dim=1, stable=True)
-    return torch.gather(hits, 1, order[..., None].expand(-1, -1, 2)).contiguous(), m.sum(1).to(torch.int32)
-
-
 def step(check=False):
     if cz is not None:
         cz.channelize(wide, chan)
@@ -122,9 +116,8 @@ def step(check=False):
     b200.check(lib.dsdneo_b200_frame_sync_search_batch(fs._h, view.d_symbols + 4 * (KEEP - DELAY), view.pitch, view.d_new, hits.data_ptr(),
                                                        MAX_HITS, n_hits.data_ptr(), None))
     b200.check(lib.dsdneo_b200_sync_hits_rebase(hits.data_ptr(), n_hits.data_ptr(), n_ch, MAX_HITS, KEEP - DELAY, None))
-    dh, dn = split(hits, n_hits, 10)
-    vh, vn = split(hits, n_hits, 12)
-    vh, vn = vh[:, :VOICE_HITS].contiguous(), vn.clamp(max=VOICE_HITS)
+    dh, dn = b200.sync_hits_select(hits, n_hits, 10, MAX_HITS)
+    vh, vn = b200.sync_hits_select(hits, n_hits, 12, VOICE_HITS)
     k = n_ch * MAX_HITS
     cut = {name: torch.zeros((k, w) if w else (k,), dtype=torch.uint8, device=dev)
            for name, w in (("cach24", 24), ("info196", 196), ("rel98", 98), ("slot_type20", 20), ("valid", 0))}
