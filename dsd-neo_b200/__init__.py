@@ -1147,6 +1147,14 @@ class P25p1Rx:
             ptr = flags.ctypes.data
         check(lib().dsdneo_b200_p25p1_rx_reacquire(self._h, ptr, int(tiles)), "p25p1_rx_reacquire")
 
+    def channel_status(self):
+        """(synchronised flags, idle tiles) per channel as numpy int32 arrays."""
+        import numpy as np
+
+        a, b = np.zeros(self.n_channels, np.int32), np.zeros(self.n_channels, np.int32)
+        check(lib().dsdneo_b200_p25p1_rx_channel_status(self._h, a.ctypes.data, b.ctypes.data), "p25p1_rx_channel_status")
+        return a, b
+
     def input_consumed(self, ticket, stream=None):
         import torch
 

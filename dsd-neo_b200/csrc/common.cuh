@@ -84,6 +84,7 @@ int dsdneo_symbolize_acquire_stage(dsdneo_b200_symbolizer* y, const float* d_dis
                                    int have_sync, const dsdneo_b200_symbol_out* out, dsdneo_b200_acq_info* d_info, int slot,
                                    int hunt_filtered, cudaStream_t s);
 int dsdneo_symbolize_drop_stage(dsdneo_b200_symbolizer* y, int* d_drop, cudaStream_t s);
+int dsdneo_symbolize_get_acquired(dsdneo_b200_symbolizer* y, int* h_acquired);
 
 /* library-internal: the CQPSK chain (cqpsk.cu) behind the channel LPF of the demod bank */
 struct dsdneo_b200_cqpsk_bank;

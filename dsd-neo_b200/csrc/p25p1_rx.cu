@@ -695,6 +695,29 @@ dsdneo_b200_p25p1_rx_reacquire(dsdneo_b200_p25p1_rx* rx, const int* h_synchronis
 }
 
 int
+dsdneo_b200_p25p1_rx_channel_status(dsdneo_b200_p25p1_rx* rx, int* h_synchronised, int* h_idle_tiles) {
+    if (!rx || (!h_synchronised && !h_idle_tiles)) {
+        set_error("p25p1_rx_channel_status: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (h_synchronised) {
+        const int rc = dsdneo_symbolize_get_acquired(rx->sym, h_synchronised);
+        if (rc) {
+            return rc;
+        }
+    }
+    if (h_idle_tiles) {
+        if (rx->d_idle) {
+            DSDNEO_CUDA(cudaDeviceSynchronize());
+            DSDNEO_CUDA(cudaMemcpy(h_idle_tiles, rx->d_idle, (size_t)rx->n_ch * sizeof(int), cudaMemcpyDeviceToHost));
+        } else {
+            memset(h_idle_tiles, 0, (size_t)rx->n_ch * sizeof(int));
+        }
+    }
+    return 0;
+}
+
+int
 dsdneo_b200_p25p1_rx_wait(dsdneo_b200_p25p1_rx* rx, long long ticket, void* stream) {
     if (!rx || !rx->pipe_ready || ticket < 0 || (unsigned long long)ticket >= rx->tiles) {
         set_error("p25p1_rx_wait: unknown ticket");

@@ -2506,6 +2506,24 @@ sym_drop_kernel(int* drop, int* acquired, int* hunt_since, int* hunt_count, int*
     }
 }
 
+/* host copy of the per-channel synchronised (1) / hunting (0) flags; synchronises the device */
+int
+dsdneo_symbolize_get_acquired(dsdneo_b200_symbolizer* y, int* h_acquired) {
+    if (!y || !h_acquired) {
+        set_error("symbolizer: bad argument");
+        return DSDNEO_B200_EINVAL;
+    }
+    if (!y->d_acquired) { /* acquisition never configured: every channel runs the synchronised rules */
+        for (int c = 0; c < y->n_ch; c++) {
+            h_acquired[c] = 1;
+        }
+        return 0;
+    }
+    DSDNEO_CUDA(cudaDeviceSynchronize());
+    DSDNEO_CUDA(cudaMemcpy(h_acquired, y->d_acquired, (size_t)y->n_ch * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int
 dsdneo_symbolize_drop_stage(dsdneo_b200_symbolizer* y, int* d_drop, cudaStream_t s) {
     if (!y || !y->d_acquired || !d_drop) {

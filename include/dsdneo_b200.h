@@ -1191,6 +1191,10 @@ int dsdneo_b200_p25p1_rx_input_consumed(dsdneo_b200_p25p1_rx* rx, long long tick
  * acquiring tiles run their stages one after the other, as at stream start (cfg.acquire_tiles).
  */
 int dsdneo_b200_p25p1_rx_reacquire(dsdneo_b200_p25p1_rx* rx, const int* h_synchronised, int tiles);
+/** Monitoring: per channel whether it is synchronised (1) or hunting (0) -- always 1 when acquisition was never configured --
+ * and, with cfg.auto_reacquire_tiles, the watch's count of tiles without a valid NID (negative while a drop is taking effect).
+ * Either array may be NULL.  Host arrays of n_channels; drains the pipeline (device synchronise). */
+int dsdneo_b200_p25p1_rx_channel_status(dsdneo_b200_p25p1_rx* rx, int* h_synchronised, int* h_idle_tiles);
 /** Host buffers, streaming: returns a ticket >= 0; results are in the caller's buffers once wait_host(ticket) returned.
  * Up to six tickets may be outstanding (H2D, the four pipeline stages and D2H of consecutive tiles overlap); a seventh submit
  * first completes the oldest one.  Input and output buffers of a ticket must stay untouched until its wait_host returned. */

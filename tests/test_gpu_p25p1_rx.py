@@ -379,6 +379,7 @@ def test_rx_bank_auto_reacquire_on_the_device(gpu):
             d = outs[k]["dibits"].cpu().numpy()
             for c in range(n_ch):
                 dibs[c].append(d[c, :cnt[c]].copy())
+        status.append(rx.channel_status())
         return frames, [np.concatenate(x) for x in dibs]
 
     def recovered(frames, c):
@@ -389,8 +390,12 @@ def test_rx_bank_auto_reacquire_on_the_device(gpu):
                 ok += 1
         return ok
 
+    status = []
     plain, dibs_plain = run_bank(0, True)
     auto, dibs_auto = run_bank(2, True)
+    assert status[0][0].tolist() == [1, 1, 1, 1] and status[0][1].tolist() == [0, 0, 0, 0]  # no watch: nothing ever hunts
+    assert status[1][0].tolist() == [1, 1, 1, 1], status[1]  # with the watch: the dropped channels have locked again by the end
+    assert status[1][1][0] <= 1 and status[1][1][1] <= 1, status[1]  # live channels never came near the threshold
     auto_serial, dibs_serial = run_bank(2, False)
     assert len(auto) == len(auto_serial) and all(x.tobytes() == y.tobytes() for x, y in zip(auto, auto_serial))
     for c in range(n_ch):
