@@ -156,8 +156,9 @@ def test_rx_bank_acquires_an_unaligned_stream(gpu):
         noise = rng.integers(96, 160, size=(lead, 2), dtype=np.uint8)
         chans.append((np.concatenate([noise, u8])[:n_tiles * pairs], [(p + lead / 10.0, nac, t) for p, nac, t in truth], lead))
 
-    def run_bank(acquire_tiles):
-        rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=pairs, input_cu8=True, acquire_tiles=acquire_tiles)
+    def run_bank(acquire_tiles, watch=0):
+        rx = gpu.P25p1Rx(n_ch, taps[0], block_pairs=BP, max_pairs_per_call=pairs, input_cu8=True, acquire_tiles=acquire_tiles,
+                         auto_reacquire_tiles=watch)
         out = rx.alloc_device_out("cuda")
         frames, dibs = [], [[] for _ in range(n_ch)]
         for k in range(n_tiles):
@@ -212,6 +213,13 @@ def test_rx_bank_acquires_an_unaligned_stream(gpu):
     assert got >= 0.5 * n_tx and got >= 12, (got, n_tx)
     blind, _ = run_bank(acquire_tiles=0)
     assert recovered(blind) < got, (recovered(blind), got)
+    # acquisition at start together with the loss-of-sync watch: the serialised acquiring tiles hand over to the pipelined form
+    both, _ = run_bank(acquire_tiles=2, watch=2)
+    first_b = {}
+    for f in both:
+        first_b.setdefault(int(f["channel"]), f)
+    assert len(first_b) == n_ch and all(f["nid_status"] > 0 and f["nac"] == chans[c][1][0][1] for c, f in first_b.items())
+    assert recovered(both) >= 12, recovered(both)
 
 
 def test_rx_bank_voice_records_decode_to_the_transmitted_imbe_vectors(gpu):
