@@ -1129,7 +1129,7 @@ typedef struct dsdneo_b200_p25p1_rx_config {
                               * starts never-synchronised and the first k tiles run getFrameSync()'s acquisition on the device
                               * (dsdneo_b200_symbolize_reacquire_batch: hunt on the matched filter's output, timing nudges, sync
                               * warm start), one tile at a time; a channel that has not found the P25 Phase 1 sync by then continues
-                              * with the synchronised rules */
+                              * with the synchronised rules (with auto_reacquire_tiles it keeps hunting, inside the pipeline) */
     int auto_reacquire_tiles; /* 0: off; k > 0: loss-of-sync watch on the device -- a channel none of whose sync hits of the
                                * last k tiles decoded to a valid NID goes back to getFrameSync()'s hunt (warm form, on the matched
                                * filter's output) two tiles later, inside the tile pipeline (no serialised tiles, no host step) and
