@@ -112,3 +112,21 @@ def test_new_entry_points_fail_loudly_without_device(b200):
     assert L.dsdneo_b200_p25_golay_soft_batch_host(b200.P25_WORD_GOLAY_24_6, d.ctypes.data, p.ctypes.data, r.ctypes.data, 1, 64,
                                                    st.ctypes.data, fx.ctypes.data, 2) == b200.ENODEV
     assert b"no CPU fallback" in L.dsdneo_b200_last_error()
+
+
+def test_every_declared_entry_point_has_a_ctypes_prototype(b200):
+    """The Python harness binds every entry point of include/dsdneo_b200.h with explicit argument types (ctypes' default int
+    conversion would truncate 64-bit device pointers), and pointer-returning entry points with a pointer return type."""
+    import ctypes as C
+
+    L = b200.lib()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decl = re.findall(r"^([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dsdneo_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.M | re.S)
+    assert len(decl) > 150
+    for ret, name, args in decl:
+        fn = getattr(L, name)
+        takes_args = args.strip() not in ("", "void")
+        if takes_args:
+            assert fn.argtypes is not None and len(fn.argtypes) == args.count(",") + 1, (name, fn.argtypes, args)
+        if "*" in ret:
+            assert fn.restype in (C.c_void_p, C.c_char_p), (name, fn.restype)
